@@ -1,0 +1,249 @@
+/*
+ * whippet_b200.h — C ABI of the B200-native read -> splice-graph alignment + EM library.
+ *
+ * The reference (timbitz/Whippet.jl v1.6.2) has no FFI: the seams this library replaces are
+ * the ordinary Julia calls made by bin/whippet-quant.jl:143-181.  Every entry point below
+ * cites the reference function whose work it performs; a Julia host binds them with `ccall`
+ * (see INTEGRATION.md).  Plain pointers and sizes only; all host buffers are caller-owned and
+ * borrowed for the duration of a call; every function returns 0 on success and a negative
+ * code on error, with a thread-local message available from wq_last_error().
+ * There is no CPU fallback: wq_index_create fails when no sm_100 device is present.
+ */
+#ifndef WHIPPET_B200_H
+#define WHIPPET_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------------
+ * Flat view of `GraphLib` (src/index.jl:5-15), `SpliceGraph{K}` (src/graph.jl:104-115),
+ * `Edges{K}` (src/edges.jl:10-13) and `FMIndex{2,UInt32}` (FMIndexes 1.0.0; layout pinned by
+ * test/test_index.jls).  Genes/nodes/isoforms are numbered from 1 as in Julia;
+ * arrays are 0-based C arrays, i.e. gene g lives at index g-1.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct wq_index_desc {
+    int32_t   kmer;          /* GraphLib.kmer (K) */
+    uint32_t  n_genes;       /* G */
+    uint32_t  n_nodes;       /* N = sum of nodes over genes */
+    uint32_t  n_isoforms;    /* I = sum of annotated isoforms over genes */
+    uint64_t  text_len;      /* n = sum of graph sequence lengths = FM text length */
+    const uint32_t* gene_offset;  /* [G]   GraphLib.offset: 0-based running text offset */
+    const uint32_t* node_base;    /* [G+1] first node slot of each gene (CSR) */
+    const uint32_t* nodeoffset;   /* [N]   SpliceGraph.nodeoffset, 1-based inside the gene sequence */
+    const uint32_t* nodecoord;    /* [N]   SpliceGraph.nodecoord (genome coordinate; SAM only) */
+    const uint32_t* nodelen;      /* [N]   SpliceGraph.nodelen */
+    const uint8_t*  edgetype;     /* [N+G] SpliceGraph.edgetype; gene g (1-based), edge j at node_base[g-1]+(g-1)+(j-1) */
+    const uint64_t* edgeleft;     /* [N+G] SGKmer bits; meaningful only where is_edge(edgetype,true)  (src/edges.jl:104-107) */
+    const uint64_t* edgeright;    /* [N+G] SGKmer bits; meaningful only where is_edge(edgetype,false) (src/edges.jl:108-111) */
+    const uint8_t*  seq4;         /* [n]   graph sequences back to back, one 4-bit one-hot code per byte (A=1 C=2 G=4 T=8, may be ambiguous) */
+    const uint8_t*  bwt;          /* [n]   stored BWT symbols 0..3 (no `$` row) */
+    uint64_t        sentinel;     /* FMIndex.sentinel: 1-based row of `$` in the (n+1)-row matrix */
+    int64_t         count[4];     /* FMIndex.count */
+    const uint32_t* sa;           /* [n]   FMIndex.samples at r=1 (src/index.jl:97): row i>=2 -> sa[i-2] */
+    const uint32_t* left_ptr;     /* [4^K+1] CSR heads of Edges.left  (an #undef slot is an empty range) */
+    const uint32_t* left_nodes;   /* [2*left_ptr[4^K]]  (gene,node) pairs, sorted as in src/edges.jl:20,91 */
+    const uint32_t* right_ptr;    /* [4^K+1] CSR heads of Edges.right */
+    const uint32_t* right_nodes;  /* [2*right_ptr[4^K]] */
+    const uint32_t* iso_base;     /* [G+1] first isoform slot of each gene (GraphLibQuant.geneidx, src/quant.jl:183-189) */
+    const uint32_t* iso_node_ptr; /* [I+1] CSR heads of SpliceGraph.annopath bitsets */
+    const uint32_t* iso_nodes;    /* ascending 1-based node ids of each annotated path */
+} wq_index_desc;
+
+/* AlignParam, field for field (src/align.jl:2-19). */
+typedef struct wq_align_param {
+    int32_t mismatches;
+    int32_t kmer_size;
+    int32_t seed_try;
+    int32_t seed_tolerate;
+    int32_t seed_min_qual;
+    int32_t seed_length;
+    int32_t seed_buffer;
+    int32_t seed_inc;
+    int32_t seed_pair_range;
+    int32_t _pad;
+    double  score_range;
+    double  score_min;
+    uint8_t is_stranded;
+    uint8_t is_paired;
+    uint8_t is_pair_rc;
+    uint8_t is_trans_ok;
+    uint8_t is_circ_ok;
+    uint8_t _pad2[3];
+} wq_align_param;
+
+/* A batch of FASTQRecords after `fill!` (src/record.jl:13-19): 2-bit sequence + phred bytes. */
+typedef struct wq_read_batch {
+    uint32_t        n_reads;
+    uint32_t        _pad;
+    const uint8_t*  len;        /* [n]   read length (ReadLengthInt = UInt8, src/align.jl:74) */
+    const uint64_t* seq_off;    /* [n]   first 64-bit word of read i inside seq2 */
+    const uint64_t* seq2;       /* 2-bit codes A=0 C=1 G=2 T=3, 32 per word, base j at bits 2*(j%32) */
+    uint64_t        seq2_words;
+    const uint64_t* qual_off;   /* [n]   first byte of read i inside qual */
+    const uint8_t*  qual;       /* phred scores with the FASTQ offset already removed */
+    uint64_t        qual_bytes;
+} wq_read_batch;
+
+/* SGAlignNode + SGAlignScore (src/align.jl:48-62). */
+typedef struct wq_align_node {
+    uint32_t gene;
+    uint32_t node;
+    float    mistolerance;
+    uint8_t  matches;
+    uint8_t  mismatches;
+    uint16_t _pad;
+} wq_align_node;
+
+/* SGAlignment (src/align.jl:76-82); the path is nodes[path_start .. path_start+npath). */
+typedef struct wq_alignment {
+    uint32_t offset;
+    uint32_t path_start;
+    uint8_t  offsetread;
+    uint8_t  strand;
+    uint8_t  isvalid;
+    uint8_t  npath;
+} wq_alignment;
+
+/* Result of `ungapped_align` for a batch (src/align.jl:225-270 / src/paired.jl:42-125):
+ * read i has nhits[i] alignments aln[hit_start[i] ..] in the reference's own hit order.
+ * For paired batches `aln` holds mate-1 alignments and `aln_mate` the index-matched mate-2 ones. */
+typedef struct wq_align_out {
+    uint32_t*      hit_start;   /* [n] */
+    uint8_t*       nhits;       /* [n]  0 = Nullable() */
+    uint8_t*       flipped;     /* [n]  bit0: read 1 was reverse-complemented in place (src/align.jl:231-234); bit1: mate 2 was */
+    wq_alignment*  aln;         /* [aln_cap] */
+    wq_alignment*  aln_mate;    /* [aln_cap] or NULL for single-end */
+    wq_align_node* nodes;       /* [nodes_cap] */
+    uint64_t       aln_cap;
+    uint64_t       nodes_cap;
+    uint64_t       aln_used;    /* out */
+    uint64_t       nodes_used;  /* out */
+} wq_align_out;
+
+/* (mapped, total, mean_readlen) of process_reads! (src/reads.jl:41-80) plus the multi-map total. */
+typedef struct wq_map_stats {
+    uint64_t total;
+    uint64_t mapped;
+    uint64_t multi;           /* reads routed to MultiMapping (length(align) > 1) */
+    uint64_t sum_readlen;     /* sum of mapped read lengths: mean_readlen = sum_readlen / mapped */
+    uint64_t path_overflow;   /* reads whose path exceeded WQ_MAX_PATH (reported, never silently dropped) */
+} wq_map_stats;
+
+#define WQ_MAX_PATH 24        /* device-side bound on nodes per alignment path */
+#define WQ_MAX_TOLERATE 8     /* device-side bound on AlignParam.seed_tolerate */
+
+typedef struct wq_handle wq_handle;
+
+const char* wq_last_error(void);
+int  wq_version(void);
+
+/* Upload + re-layout the index on `device` (GraphLib is the input of bin/whippet-quant.jl:105). */
+int  wq_index_create(const wq_index_desc* desc, int device, wq_handle** out);
+void wq_destroy(wq_handle* h);
+
+/* GraphLibQuant{C,DefaultCounter}(lib) + MultiMapping{C,DefaultCounter}() (bin/whippet-quant.jl:125-126):
+ * zero all device-side count stores. */
+int  wq_quant_reset(wq_handle* h);
+
+/* process_reads! body (src/reads.jl:56-71): ungapped_align (src/align.jl:225-270) for every read of
+ * the batch, then count!/push!(multi) (src/quant.jl:556-594, 456-469) accumulated on the device.
+ * `out` may be NULL (quantification only); when given the alignments are downloaded as well. */
+int  wq_align_se(wq_handle* h, const wq_align_param* p, const wq_read_batch* reads, wq_align_out* out);
+
+/* process_paired_reads! body (src/reads.jl:101-123): paired ungapped_align (src/paired.jl:42-125)
+ * and the paired count! (src/quant.jl:597-653). */
+int  wq_align_pe(wq_handle* h, const wq_align_param* p, const wq_read_batch* fwd, const wq_read_batch* rev,
+                 wq_align_out* out);
+
+/* Same as wq_align_se, but the batch already lives in device memory (pointers inside `reads`
+ * are device pointers).  Used to time the kernels with inputs resident in HBM. */
+int  wq_align_se_device(wq_handle* h, const wq_align_param* p, const wq_read_batch* reads);
+int  wq_align_pe_device(wq_handle* h, const wq_align_param* p, const wq_read_batch* fwd, const wq_read_batch* rev);
+
+int  wq_map_stats_get(wq_handle* h, wq_map_stats* out);
+
+/* Device pointer + element count of the dense count vector (u64 per node, then the scalar
+ * stats) so a host can all-reduce it over NCCL between ranks. */
+int  wq_counts_device_ptr(wq_handle* h, void** dptr, uint64_t* n_u64);
+
+/* Download the count stores filled by count! (src/quant.jl:129-135).  Two-call protocol: call with
+ * NULL buffers to get sizes, then with buffers.  Keys are sorted, which is also the canonical
+ * class order of the EM.
+ *   node_count  [N]              SpliceGraphQuant.node
+ *   edge_key    [n_edge]         (gene<<32 | lnode<<16 | rnode), lnode<rnode  -> SpliceGraphQuant.edge
+ *   circ_key    [n_circ]         same packing, lnode>=rnode                   -> SpliceGraphQuant.circ
+ *   keyed paths: long paths (SpliceGraphQuant.long) and multi-map classes (MultiMapping.map) as
+ *   records of u32 words, see wq_keyed_download. */
+typedef struct wq_counts {
+    uint64_t  n_nodes;   uint64_t* node_count;
+    uint64_t  n_edge;    uint64_t* edge_key;  uint64_t* edge_count;
+    uint64_t  n_circ;    uint64_t* circ_key;  uint64_t* circ_count;
+} wq_counts;
+int  wq_counts_download(wq_handle* h, wq_counts* c);
+
+/* Keyed stores.  kind 0 = long paths, kind 1 = multi-map classes.  A record is
+ *   long  SE: [npath, gene, node_1 .. node_npath]
+ *   long  PE: [npath_fwd | npath_rev<<16, gene, fwd nodes.., rev nodes..]
+ *   multi   : [nhits, then per hit a long-style record]
+ * rec_ptr[i]..rec_ptr[i+1] delimit record i inside `words`; count[i] is its read count.
+ * Records are sorted lexicographically by their words. */
+typedef struct wq_keyed {
+    uint64_t  n_rec;     uint64_t n_words;
+    uint64_t* rec_ptr;   uint32_t* words;  uint64_t* count;
+} wq_keyed;
+int  wq_keyed_download(wq_handle* h, int kind, wq_keyed* k);
+
+/* Merge counts produced by another rank/handle into this handle (host-side exchange of the sparse
+ * stores; the dense vector goes through NCCL). */
+int  wq_counts_merge(wq_handle* h, const wq_counts* c, const wq_keyed* longs, const wq_keyed* multis);
+
+/* build_equivalence_classes! (src/quant.jl:327-389) + MultiCompat construction (src/quant.jl:394-435)
+ * + calculate_tpm! (src/quant.jl:655-667) + gene_em! (src/quant.jl:719-769) + set_gene_tpm!
+ * (src/quant.jl:248-257) on the device.  tpm/count are [I], genetpm is [G]; returns iterations. */
+typedef struct wq_em_param {
+    int64_t readlen;
+    int64_t sig;       /* digits, CLI: 1 */
+    int64_t maxit;     /* CLI: 10000 */
+} wq_em_param;
+int  wq_em_tpm(wq_handle* h, const wq_em_param* p, double* tpm, double* count, double* genetpm, int64_t* iterations);
+
+/* assign_ambig! (src/quant.jl:520-553): after it, node/edge/circ stores hold fractional values.
+ *   node_value [N]; edge/circ as sorted (key,value) lists (two-call protocol). */
+typedef struct wq_values {
+    uint64_t  n_nodes;   double* node_value;
+    uint64_t  n_edge;    uint64_t* edge_key;  double* edge_value;
+    uint64_t  n_circ;    uint64_t* circ_key;  double* circ_value;
+} wq_values;
+int  wq_assign_ambig(wq_handle* h, wq_values* v);
+
+/* Batched PSI EM: spliced_em! (src/events.jl:853-893) and rec_tandem_em! (src/events.jl:895-932),
+ * one event per thread block.  Event e owns paths [path_ptr[e], path_ptr[e+1]) and ambiguous sets
+ * [amb_ptr[e], amb_ptr[e+1]); ambiguous set a lists its member paths (event-local indices) in
+ * amb_paths[amb_path_ptr[a] .. amb_path_ptr[a+1]). */
+typedef struct wq_psi_batch {
+    uint32_t n_events;   uint32_t _pad;
+    const uint32_t* path_ptr;      /* [E+1] */
+    const double*   path_count;    /* [P] unambiguous counts */
+    const double*   path_length;   /* [P] */
+    const uint32_t* amb_ptr;       /* [E+1] */
+    const uint32_t* amb_path_ptr;  /* [A+1] */
+    const uint32_t* amb_paths;     /* event-local path indices */
+    const double*   amb_mult;      /* [A] AmbigCounts.multiplier */
+    const uint8_t*  is_tandem;     /* [E] 1 = tandem-UTR variant (effective length max(len-readlen,1)) */
+    int64_t readlen;
+    int64_t sig;                   /* significant digits, reference: 4 */
+    int64_t maxit;                 /* reference: 1500 */
+    double*   psi;                 /* out [P] */
+    double*   path_total;          /* out [P] counts after EM */
+    int32_t*  iterations;          /* out [E] */
+} wq_psi_batch;
+int  wq_em_psi_batch(wq_handle* h, wq_psi_batch* b);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WHIPPET_B200_H */

@@ -1,0 +1,115 @@
+"""ctypes wrapper of the CPU oracle (oracle/whippet_oracle.cpp) — TEST INFRASTRUCTURE ONLY.
+
+May be imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs, never by the product package."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+import whippet_jl_b200 as wq
+from whippet_jl_b200 import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libwhippet_oracle.so")
+
+
+def build(force=False):
+    src = os.path.join(_HERE, "whippet_oracle.cpp")
+    hdr = os.path.join(_HERE, "..", "include", "whippet_b200.h")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        subprocess.check_call(["make", "-C", _HERE, "-B", "libwhippet_oracle.so"], stdout=subprocess.DEVNULL)
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_SO)
+        _lib.wqo_create.restype = C.c_void_p
+        _lib.wqo_create.argtypes = [C.POINTER(abi.IndexDesc)]
+        _lib.wqo_destroy.argtypes = [C.c_void_p]
+        _lib.wqo_sa_value.restype = C.c_int64
+        _lib.wqo_sa_value.argtypes = [C.c_void_p, C.c_int64]
+        _lib.wqo_result_n_aln.restype = C.c_uint64
+        _lib.wqo_result_n_nodes.restype = C.c_uint64
+        _lib.wqo_result_n_aln.argtypes = [C.c_void_p]
+        _lib.wqo_result_n_nodes.argtypes = [C.c_void_p]
+    return _lib
+
+
+class AlignResult:
+    """Per-read alignments: CSR over `aln`, each alignment owning nodes[path_start:path_start+npath]."""
+
+    def __init__(self, hit_start, nhits, flipped, aln, nodes, aln_mate=None):
+        self.hit_start, self.nhits, self.flipped = hit_start, nhits, flipped
+        self.aln, self.nodes, self.aln_mate = aln, nodes, aln_mate
+
+    def read(self, i, mate=False):
+        """List of (offset, offsetread, strand, isvalid, [(gene,node,matches,mismatches,mistol_bits)...])."""
+        out = []
+        src = self.aln_mate if mate else self.aln
+        for k in range(int(self.hit_start[i]), int(self.hit_start[i]) + int(self.nhits[i])):
+            a = src[k]
+            ns = self.nodes[int(a["path_start"]): int(a["path_start"]) + int(a["npath"])]
+            out.append((int(a["offset"]), int(a["offsetread"]), int(a["strand"]), int(a["isvalid"]),
+                        [(int(n["gene"]), int(n["node"]), int(n["matches"]), int(n["mismatches"]),
+                          int(np.float32(n["mistolerance"]).view(np.uint32))) for n in ns]))
+        return out
+
+
+class Oracle:
+    def __init__(self, index: wq.FlatIndex):
+        self.index = index
+        self._desc = index.desc()
+        self.h = lib().wqo_create(C.byref(self._desc))
+
+    def __del__(self):
+        try:
+            lib().wqo_destroy(C.c_void_p(self.h))
+        except Exception:
+            pass
+
+    def sa_range(self, codes):
+        q = np.ascontiguousarray(codes, "u1")
+        sp, ep = C.c_int64(), C.c_int64()
+        lib().wqo_sa_range(C.c_void_p(self.h), abi.ptr(q, abi.u8p), C.c_int64(len(q)), C.byref(sp), C.byref(ep))
+        return sp.value, ep.value
+
+    def sa_value(self, row):
+        return lib().wqo_sa_value(C.c_void_p(self.h), row)
+
+    def seed_locate(self, param: wq.AlignParam, reads: wq.ReadBatch):
+        out = np.zeros((reads.n, 4), np.int64)
+        p, b = param.c(), reads.c()
+        lib().wqo_seed_locate(C.c_void_p(self.h), C.byref(p), C.byref(b), out.ctypes.data_as(C.c_void_p))
+        return out
+
+    def _collect(self, n, paired):
+        L = lib()
+        na, nn = L.wqo_result_n_aln(C.c_void_p(self.h)), L.wqo_result_n_nodes(C.c_void_p(self.h))
+        hs, nh, fl = np.zeros(n, "<u4"), np.zeros(n, "u1"), np.zeros(n, "u1")
+        aln = np.zeros(na, abi.ALIGNMENT_DT)
+        alm = np.zeros(na, abi.ALIGNMENT_DT) if paired else None
+        nodes = np.zeros(nn, abi.ALIGN_NODE_DT)
+        L.wqo_result_copy(C.c_void_p(self.h), hs.ctypes.data_as(C.c_void_p), nh.ctypes.data_as(C.c_void_p),
+                          fl.ctypes.data_as(C.c_void_p), aln.ctypes.data_as(C.c_void_p),
+                          alm.ctypes.data_as(C.c_void_p) if paired else None, nodes.ctypes.data_as(C.c_void_p))
+        return AlignResult(hs, nh, fl, aln, nodes, alm)
+
+    def align_se(self, param: wq.AlignParam, reads: wq.ReadBatch) -> AlignResult:
+        p, b = param.c(), reads.c()
+        lib().wqo_align_se(C.c_void_p(self.h), C.byref(p), C.byref(b))
+        return self._collect(reads.n, False)
+
+    def align_pe(self, param: wq.AlignParam, fwd: wq.ReadBatch, rev: wq.ReadBatch) -> AlignResult:
+        p, f, r = param.c(), fwd.c(), rev.c()
+        lib().wqo_align_pe(C.c_void_p(self.h), C.byref(p), C.byref(f), C.byref(r))
+        return self._collect(fwd.n, True)

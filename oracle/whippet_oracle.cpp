@@ -1,0 +1,796 @@
+/*
+ * whippet_oracle.cpp — TEST INFRASTRUCTURE ONLY.
+ *
+ * Single-threaded CPU restatement of the read -> splice-graph alignment path of
+ * timbitz/Whippet.jl v1.6.2, used as the parity checker for the CUDA library and as the
+ * timed CPU baseline.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs may load it; the product library never does.
+ *
+ * Each function follows the cited Julia lines statement by statement (1-based indices are
+ * kept, through the at1() helpers).  The FM-index arithmetic lives in the un-vendored
+ * packages FMIndexes 1.0.0 / WaveletMatrices 0.2.0 (Manifest.toml:126-132,400-406); it is
+ * restated from its published semantics and pinned byte-for-byte by test/test_index.jls
+ * (see tests/test_oracle_fixture.py).  Alignment is pinned by the ten reads of
+ * test/runtests.jl:290-330.  EM numerics are "parity unpinned" (no golden TPM/PSI values
+ * exist in the reference); see DESIGN.md.
+ */
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../include/whippet_b200.h"
+
+namespace {
+
+typedef int64_t Int;
+
+// EdgeType codes, src/graph.jl:39-46
+enum : uint8_t { ET_SL = 0, ET_SR = 1, ET_LS = 2, ET_RS = 3, ET_LR = 4, ET_LL = 5, ET_RR = 6 };
+
+struct Score {            // SGAlignScore, src/align.jl:48-52
+    uint8_t matches = 0;
+    uint8_t mismatches = 0;
+    float mistolerance = 0.f;
+};
+struct ANode {            // SGAlignNode, src/align.jl:58-62
+    uint32_t gene, node;
+    Score score;
+};
+struct Align {            // SGAlignment, src/align.jl:76-82
+    uint32_t offset = 0;
+    uint8_t offsetread = 0;
+    std::vector<ANode> path;
+    bool strand = true;
+    bool isvalid = false;
+};
+
+struct Read {             // FASTQRecord after fill!, src/record.jl:2-19
+    std::vector<uint8_t> seq;    // 2-bit codes
+    std::vector<uint8_t> qual;   // phred
+};
+
+struct Lib {
+    const wq_index_desc* d;
+    std::vector<uint32_t> occ;   // occurrence checkpoints every 64 symbols, 4 per block
+    Int n;
+    Int G;
+    // --- 1-based views ---
+    Int gene_offset(Int g) const { return d->gene_offset[g - 1]; }
+    Int nnodes(Int g) const { return d->node_base[g] - d->node_base[g - 1]; }
+    Int seqlen(Int g) const { return (g < G ? (Int)d->gene_offset[g] : n) - (Int)d->gene_offset[g - 1]; }
+    Int nodeoffset(Int g, Int i) const { return d->nodeoffset[d->node_base[g - 1] + i - 1]; }
+    Int nodelen(Int g, Int i) const { return d->nodelen[d->node_base[g - 1] + i - 1]; }
+    size_t eidx(Int g, Int j) const { return (size_t)d->node_base[g - 1] + (g - 1) + (j - 1); }
+    uint8_t edgetype(Int g, Int j) const { return d->edgetype[eidx(g, j)]; }
+    uint64_t edgeleft(Int g, Int j) const { return d->edgeleft[eidx(g, j)]; }
+    uint64_t edgeright(Int g, Int j) const { return d->edgeright[eidx(g, j)]; }
+    uint8_t seq(Int g, Int i) const { return d->seq4[(size_t)d->gene_offset[g - 1] + i - 1]; }
+};
+
+void build_occ(Lib& L) {
+    Int nb = L.n / 64 + 1;
+    L.occ.assign((size_t)nb * 4, 0);
+    uint32_t c[4] = {0, 0, 0, 0};
+    for (Int i = 0; i < L.n; i++) {
+        if (i % 64 == 0) memcpy(&L.occ[(size_t)(i / 64) * 4], c, sizeof c);
+        c[L.d->bwt[i] & 3]++;
+    }
+    if (L.n % 64 == 0) memcpy(&L.occ[(size_t)(L.n / 64) * 4], c, sizeof c);
+}
+
+// WaveletMatrices.rank(char, bwt, i): occurrences of `char` in bwt[1..i]; call site src/fmindex_patch.jl:26-27
+Int rank(const Lib& L, uint8_t ch, Int i) {
+    if (i <= 0) return 0;
+    if (i > L.n) i = L.n;
+    Int b = i / 64;
+    Int r = L.occ[(size_t)b * 4 + ch];
+    for (Int k = b * 64; k < i; k++) r += (L.d->bwt[k] == ch);
+    return r;
+}
+
+// FMIndexes.sa_range override, src/fmindex_patch.jl:19-31 (initial range 1:(n+1))
+void sa_range(const Lib& L, const uint8_t* q, Int len, Int& sp, Int& ep) {
+    sp = 1;
+    ep = L.n + 1;
+    Int sentinel = (Int)L.d->sentinel;
+    Int i = len;
+    while (sp <= ep && i >= 1) {
+        uint8_t ch = q[i - 1];
+        Int c = L.d->count[ch];
+        sp = c + rank(L, ch, (sp > sentinel ? sp - 1 : sp) - 1) + 1;
+        ep = c + rank(L, ch, (ep > sentinel ? ep - 1 : ep));
+        i -= 1;
+    }
+}
+
+// FMIndexes.sa_value at r=1 (call sites src/align.jl:240, src/paired.jl:9): row 1 is `$`
+Int sa_value(const Lib& L, Int i) { return i == 1 ? L.n : (Int)L.d->sa[i - 2]; }
+
+template <class T>
+Int searchsortedlast_u32(const T* a, Int n, Int x) {   // last 1-based index with a[i] <= x, 0 if none
+    Int lo = 0, hi = n + 1;
+    while (lo < hi - 1) {
+        Int m = (lo + hi) >> 1;
+        if ((Int)a[m - 1] <= x) lo = m; else hi = m;
+    }
+    return lo;
+}
+
+// src/align.jl:90-114
+uint8_t matches(const std::vector<ANode>& v, size_t from = 0, size_t to = (size_t)-1) {
+    uint8_t m = 0;
+    if (to > v.size()) to = v.size();
+    for (size_t i = from; i < to; i++) m = (uint8_t)(m + v[i].score.matches);
+    return m;
+}
+float mistolerance(const std::vector<ANode>& v) {
+    float m = 0.f;
+    for (auto& x : v) m += x.score.mistolerance;
+    return m;
+}
+float score(const std::vector<ANode>& v) {
+    float s = 0.f;
+    for (auto& x : v) s += (float)x.score.matches - x.score.mistolerance;
+    return s;
+}
+float score(const Align& a) { return score(a.path); }
+float identity(const Align& a, Int readlen) { return score(a) / (float)readlen; }      // src/align.jl:114
+bool isvalid(const Align& a) {                                                         // src/align.jl:115
+    return a.isvalid && a.path.size() >= 1 && (float)matches(a.path) > mistolerance(a.path);
+}
+
+float PHRED_PROB[256];
+// phred_to_prob, src/align.jl:124: Float32(1 - 10^(-Int8(phred)/10))
+void init_phred() {
+    for (int i = 0; i < 256; i++) PHRED_PROB[i] = (float)(1.0 - std::pow(10.0, -(double)(int8_t)i / 10.0));
+}
+
+// kmer_index(read.sequence[a:b]) for a 2-bit read, src/sgkmer.jl:12-26 (never 0)
+Int read_kmer_index(const Read& r, Int a, Int k) {
+    uint64_t x = 0;
+    for (Int i = a; i < a + k; i++) x = (x << 2) | r.seq[i - 1];
+    return (Int)x + 1;
+}
+
+struct Ctx {
+    const Lib& L;
+    const wq_align_param& p;
+    const Read& read;
+    Int readlen;
+};
+
+const uint32_t* table_slot(const uint32_t* ptr, const uint32_t* nodes, Int kmer_ind, Int& cnt) {
+    // isassigned(lib.edges.X, ind): an #undef slot is an empty CSR range
+    uint32_t a = ptr[kmer_ind - 1], b = ptr[kmer_ind];
+    cnt = (Int)b - (Int)a;
+    return nodes + 2 * (size_t)a;
+}
+
+// intersect_sorted with the gene-only ordering, src/edges.jl:15-18,40-55: returns arrB entries
+void intersect_sorted(const uint32_t* A, Int na, const uint32_t* B, Int nb, std::vector<std::pair<uint32_t, uint32_t>>& res) {
+    Int i = 1, j = 1;
+    while (i <= na && j <= nb) {
+        uint32_t ga = A[2 * (i - 1)], gb = B[2 * (j - 1)];
+        if (ga > gb) j += 1;
+        else if (ga < gb) i += 1;
+        else {
+            res.emplace_back(B[2 * (j - 1)], B[2 * (j - 1) + 1]);
+            i += 1;
+            j += 1;
+        }
+    }
+}
+
+Align ungapped_fwd_extend(const Ctx& c, uint32_t geneind, Int sgidx, Int ridx, Align align, uint32_t nodeidx);
+Align ungapped_rev_extend(const Ctx& c, uint32_t geneind, Int sgidx, Int ridx, Align align, uint32_t nodeidx);
+
+// closure spliced_fwd_extend, src/align.jl:287-311
+Align spliced_fwd_extend(const Ctx& c, uint32_t geneind, uint32_t edgeind, Int ridx, Int right_kmer_ind, const Align& align) {
+    const Lib& L = c.L;
+    Int nr, nl;
+    const uint32_t* R = table_slot(L.d->right_ptr, L.d->right_nodes, right_kmer_ind, nr);
+    if (nr == 0) return align;
+    Int left_kmer_ind = (Int)L.edgeleft(geneind, edgeind) + 1;
+    const uint32_t* Lt = table_slot(L.d->left_ptr, L.d->left_nodes, left_kmer_ind, nl);
+    if (nl == 0) return align;
+    std::vector<std::pair<uint32_t, uint32_t>> right_nodes;
+    intersect_sorted(Lt, nl, R, nr, right_nodes);
+
+    Align best = align;
+    for (auto& rn : right_nodes) {
+        if (rn.first != align.path[0].gene) continue;
+        Int rn_offset = L.nodeoffset(rn.first, rn.second);
+        Align res_align = ungapped_fwd_extend(c, rn.first, rn_offset, ridx, align /*deepcopy*/, rn.second);
+        if (score(res_align) > score(best)) best = res_align;
+    }
+    if (score(best) >= score(align) + (float)c.p.kmer_size) best.isvalid = true;
+    return best;
+}
+
+// ungapped_fwd_extend, src/align.jl:275-418
+Align ungapped_fwd_extend(const Ctx& c, uint32_t geneind, Int sgidx, Int ridx, Align align, uint32_t nodeidx) {
+    const Lib& L = c.L;
+    const wq_align_param& p = c.p;
+    const Int readlen = c.readlen;
+    const Int seqlen = L.seqlen(geneind);
+    const Int nn = L.nnodes(geneind);
+
+    std::vector<uint8_t> passed_edges;
+    bool has_passed = false;
+    float mistol = mistolerance(align.path);
+
+    align.path.push_back(ANode{geneind, nodeidx, Score()});
+
+    while ((double)mistol <= (double)p.mismatches && ridx <= readlen && sgidx <= seqlen) {
+        if ((Int)nodeidx <= nn && sgidx == L.nodeoffset(geneind, nodeidx) + L.nodelen(geneind, nodeidx)) {   // hit next edge
+            uint32_t curedge = nodeidx + 1;
+            uint8_t et = L.edgetype(geneind, curedge);
+            if (et == ET_LR && L.nodelen(geneind, curedge) >= p.kmer_size && readlen - ridx + 1 >= p.kmer_size) {
+                Int rkmer_ind = read_kmer_index(c.read, ridx, p.kmer_size);
+                if (rkmer_ind == 0) break;
+                if ((Int)L.edgeright(geneind, curedge) + 1 == rkmer_ind) {
+                    ridx += p.kmer_size - 1;
+                    sgidx += p.kmer_size - 1;
+                    nodeidx += 1;
+                    Score s;
+                    s.matches = (uint8_t)(p.kmer_size - 1);
+                    align.path.push_back(ANode{geneind, nodeidx, s});
+                    align.isvalid = true;
+                } else {
+                    align = spliced_fwd_extend(c, geneind, curedge, ridx, rkmer_ind, align);
+                    break;
+                }
+            } else if (et == ET_LR || et == ET_LL) {
+                has_passed = true;
+                passed_edges.push_back((uint8_t)align.path.size());
+                nodeidx += 1;
+                align.path.push_back(ANode{geneind, nodeidx, Score()});
+            } else if (et == ET_LS) {
+                if (readlen - ridx + 1 >= p.kmer_size) {
+                    Int rkmer_ind = read_kmer_index(c.read, ridx, p.kmer_size);
+                    if (rkmer_ind == 0) break;
+                    align = spliced_fwd_extend(c, geneind, curedge, ridx, rkmer_ind, align);
+                }
+                break;
+            } else if (et == ET_SR) {
+                break;
+            } else {   // 'RR' || 'SL' || 'RS'
+                nodeidx += 1;
+                if ((Int)nodeidx <= nn) align.path.push_back(ANode{geneind, nodeidx, Score()});
+            }
+        }
+        Score& sc = align.path.back().score;
+        if ((uint8_t)(1u << c.read.seq[ridx - 1]) == L.seq(geneind, sgidx)) {
+            sc.matches += 1;
+        } else {
+            float prob = PHRED_PROB[c.read.qual[ridx - 1]];
+            sc.mistolerance += prob;
+            mistol += prob;
+            sc.mismatches += 1;
+        }
+        ridx += 1;
+        sgidx += 1;
+    }
+
+    // passed-edge backtracking, src/align.jl:382-405
+    if (has_passed) {
+        for (Int ci = (Int)passed_edges.size(); ci >= 1; ci--) {
+            Int cval = passed_edges[ci - 1];
+            if ((Int)matches(align.path, (size_t)cval) >= p.kmer_size + p.mismatches) {
+                align.isvalid = true;
+                break;
+            } else {
+                uint32_t cur_edge = align.path[cval - 1].node + 1;
+                align.path.resize((size_t)cval);   // splice!( path, cval+1:end )
+                Int cur_ridx = ridx - (sgidx - L.nodeoffset(geneind, cur_edge));
+                if (!((cur_ridx + p.kmer_size - 1) <= readlen)) continue;
+                Int rkmer_ind = read_kmer_index(c.read, cur_ridx, p.kmer_size);
+                if (rkmer_ind == 0) continue;
+                Align res_align = spliced_fwd_extend(c, geneind, cur_edge, cur_ridx, rkmer_ind, align);
+                if (res_align.path.size() > align.path.size()) {
+                    if (score(res_align) > score(align)) align = res_align;
+                }
+            }
+        }
+    }
+
+    // clean up bad trailing nodes, src/align.jl:408-412
+    while (align.path.size() >= 1 &&
+           (align.path.back().score.mismatches >= align.path.back().score.matches ||
+            (Int)align.path.back().score.matches - (Int)align.path.back().score.mismatches <= 1)) {
+        align.path.pop_back();
+        if (align.path.size() == 0) align.isvalid = false;
+    }
+
+    if ((double)identity(align, readlen) >= p.score_min) align.isvalid = true;
+    return align;
+}
+
+// closure spliced_rev_extend, src/align.jl:437-461
+Align spliced_rev_extend(const Ctx& c, uint32_t geneind, uint32_t edgeind, Int ridx, Int left_kmer_index, const Align& align) {
+    const Lib& L = c.L;
+    Int nr, nl;
+    const uint32_t* Lt = table_slot(L.d->left_ptr, L.d->left_nodes, left_kmer_index, nl);
+    if (nl == 0) return align;
+    Int right_kmer_ind = (Int)L.edgeright(geneind, edgeind) + 1;
+    const uint32_t* R = table_slot(L.d->right_ptr, L.d->right_nodes, right_kmer_ind, nr);
+    if (nr == 0) return align;
+    std::vector<std::pair<uint32_t, uint32_t>> left_nodes;
+    intersect_sorted(R, nr, Lt, nl, left_nodes);
+
+    Align best = align;
+    for (auto& rn : left_nodes) {
+        if (rn.first != align.path[0].gene) continue;
+        Int rn_offset = L.nodeoffset(rn.first, rn.second - 1) + L.nodelen(rn.first, rn.second - 1) - 1;
+        Align res_align = ungapped_rev_extend(c, rn.first, rn_offset, ridx, align /*deepcopy*/, rn.second - 1);
+        if (score(res_align) > score(best)) best = res_align;
+    }
+    if (score(best) >= score(align) + (float)c.p.kmer_size) best.isvalid = true;
+    return best;
+}
+
+// ungapped_rev_extend, src/align.jl:423-575
+Align ungapped_rev_extend(const Ctx& c, uint32_t geneind, Int sgidx, Int ridx, Align align, uint32_t nodeidx) {
+    const Lib& L = c.L;
+    const wq_align_param& p = c.p;
+    const Int readlen = c.readlen;
+
+    std::vector<uint8_t> passed_edges;
+    bool has_passed = false;
+    float mistol = mistolerance(align.path);
+
+    if (align.path.size() <= 0 || align.path[0].gene != geneind || align.path[0].node != nodeidx)
+        align.path.insert(align.path.begin(), ANode{geneind, nodeidx, Score()});
+
+    while ((double)mistol <= (double)p.mismatches && ridx > 0 && sgidx > 0) {
+        if (sgidx == L.nodeoffset(geneind, nodeidx) - 1) {   // hit right edge
+            uint32_t leftnode = nodeidx - 1;
+            uint8_t et = L.edgetype(geneind, nodeidx);
+            if (et == ET_LR && L.nodelen(geneind, leftnode) >= p.kmer_size && ridx >= p.kmer_size) {
+                Int lkmer_ind = read_kmer_index(c.read, ridx - p.kmer_size + 1, p.kmer_size);
+                if (lkmer_ind == 0) break;
+                if ((Int)L.edgeleft(geneind, nodeidx) + 1 == lkmer_ind) {
+                    ridx -= p.kmer_size - 1;
+                    sgidx -= p.kmer_size - 1;
+                    nodeidx -= 1;
+                    Score s;
+                    s.matches = (uint8_t)(p.kmer_size - 1);
+                    align.path.insert(align.path.begin(), ANode{geneind, nodeidx, s});
+                    align.isvalid = true;
+                } else {
+                    align = spliced_rev_extend(c, geneind, nodeidx, ridx, lkmer_ind, align);
+                    break;
+                }
+            } else if (et == ET_LR || et == ET_RR) {
+                has_passed = true;
+                passed_edges.push_back((uint8_t)(align.path.size() - 1));
+                nodeidx -= 1;
+                align.path.insert(align.path.begin(), ANode{geneind, nodeidx, Score()});
+            } else if (et == ET_SR) {
+                if (ridx >= p.kmer_size) {
+                    Int lkmer_ind = read_kmer_index(c.read, ridx - p.kmer_size + 1, p.kmer_size);
+                    if (lkmer_ind == 0) break;
+                    align = spliced_rev_extend(c, geneind, nodeidx, ridx, lkmer_ind, align);
+                }
+                break;
+            } else if (et == ET_LS) {
+                break;
+            } else {   // 'LL' || 'RS' || 'SL'
+                nodeidx -= 1;
+                if (nodeidx > 0) align.path.insert(align.path.begin(), ANode{geneind, nodeidx, Score()});
+            }
+        }
+        Score& sc = align.path.front().score;
+        if ((uint8_t)(1u << c.read.seq[ridx - 1]) == L.seq(geneind, sgidx)) {
+            sc.matches += 1;
+        } else {
+            float prob = PHRED_PROB[c.read.qual[ridx - 1]];
+            sc.mistolerance += prob;
+            mistol += prob;
+            sc.mismatches += 1;
+        }
+        ridx -= 1;
+        sgidx -= 1;
+    }
+
+    Int cur_ridx = ridx + 1;
+    Int cur_sgidx = sgidx + 1;
+    // passed-edge backtracking, src/align.jl:526-549
+    if (has_passed) {
+        for (Int ci = (Int)passed_edges.size(); ci >= 1; ci--) {
+            Int cval = passed_edges[ci - 1];
+            Int len = (Int)align.path.size();
+            Int upto = len - (cval + 1);   // path[1:(end-(cval+1))]
+            if ((Int)matches(align.path, 0, (size_t)std::max<Int>(upto, 0)) >= p.kmer_size + p.mismatches) {
+                align.isvalid = true;
+                break;
+            } else {
+                uint32_t cur_edge = align.path[len - cval - 1].node;       // path[end-cval]
+                if (upto > 0) align.path.erase(align.path.begin(), align.path.begin() + upto);
+                cur_ridx = ridx + (L.nodeoffset(geneind, cur_edge) - sgidx);
+                cur_sgidx = L.nodeoffset(geneind, cur_edge);
+                if (!((cur_ridx - p.kmer_size) > 0)) continue;
+                Int lkmer_ind = read_kmer_index(c.read, cur_ridx - p.kmer_size, p.kmer_size);
+                if (lkmer_ind == 0) continue;
+                Align res_align = spliced_rev_extend(c, geneind, cur_edge, cur_ridx - 1, lkmer_ind, align);
+                if (res_align.path.size() > align.path.size()) {
+                    if (score(res_align) > score(align)) align = res_align;
+                }
+            }
+        }
+    }
+
+    if ((double)identity(align, readlen) >= p.score_min) align.isvalid = true;
+    if (sgidx < (Int)align.offset) align.offset = (uint32_t)cur_sgidx;
+    if (cur_ridx < (Int)align.offsetread) align.offsetread = (uint8_t)cur_ridx;
+
+    // clean up bad leading nodes, src/align.jl:562-572
+    while (align.path.size() >= 1 &&
+           (align.path.front().score.mismatches >= align.path.front().score.matches ||
+            (Int)align.path.front().score.matches - (Int)align.path.front().score.mismatches <= 1)) {
+        uint8_t offset_change = (uint8_t)(align.path.front().score.matches + align.path.front().score.mismatches);
+        align.path.erase(align.path.begin());
+        if (align.path.size() >= 1) {
+            align.offset = (uint32_t)L.nodeoffset(geneind, align.path.front().node);
+            align.offsetread = (uint8_t)(align.offsetread + offset_change);
+        } else {
+            align.isvalid = false;
+        }
+    }
+    return align;
+}
+
+// _ungapped_align, src/align.jl:209-223
+Align ungapped_align_at(const Ctx& c, Int indx, Int readloc, bool ispos, Int geneind = -1) {
+    const Lib& L = c.L;
+    if (geneind < 0) geneind = searchsortedlast_u32(L.d->gene_offset, L.G, indx);
+    Int sgidx = indx - L.gene_offset(geneind);
+    uint32_t offset_node = (uint32_t)searchsortedlast_u32(L.d->nodeoffset + L.d->node_base[geneind - 1], L.nnodes(geneind), sgidx + 1);
+    Align a;
+    a.offset = (uint32_t)(sgidx + 1);
+    a.offsetread = (uint8_t)(readloc + 1);
+    a.strand = ispos;
+    a.isvalid = false;
+    Align align = ungapped_fwd_extend(c, (uint32_t)geneind, sgidx + 1, readloc + 1, a, offset_node);
+    align = ungapped_rev_extend(c, (uint32_t)geneind, sgidx, readloc, align, offset_node);
+    return align;
+}
+
+struct Seed {
+    Int sp, ep;    // sa range (sp > ep: empty)
+    Int readloc;
+    bool strand;
+};
+
+// seed_locate, src/align.jl:145-185
+Seed seed_locate(const Lib& L, const wq_align_param& p, const Read& read, bool offset_left, bool both_strands) {
+    Int readlen = (Int)read.seq.size();
+    Int ctry = 1;
+    Int increment, increment_sm, curpos;
+    if (offset_left) {
+        increment = p.seed_inc;
+        increment_sm = 1;
+        curpos = p.seed_buffer;
+    } else {
+        increment = -p.seed_inc;
+        increment_sm = -1;
+        curpos = readlen - p.seed_length - p.seed_buffer;
+    }
+    Int maxright = readlen - p.seed_length - p.seed_buffer;
+    std::vector<uint8_t> curseq((size_t)p.seed_length);
+    while (ctry <= p.seed_try && p.seed_buffer <= curpos && curpos <= maxright) {
+        Int minq = 256;
+        for (Int i = curpos; i <= curpos + p.seed_length - 1; i++) minq = std::min<Int>(minq, read.qual[i - 1]);
+        if (minq <= p.seed_min_qual) {
+            curpos += increment_sm;
+            continue;
+        }
+        for (Int i = 0; i < p.seed_length; i++) curseq[i] = read.seq[curpos - 1 + i];
+        Int sp, ep;
+        sa_range(L, curseq.data(), p.seed_length, sp, ep);
+        Int cnt = ep >= sp ? ep - sp + 1 : 0;
+        ctry += 1;
+        if (cnt == 0 || cnt > p.seed_tolerate) {
+            if (both_strands) {
+                std::reverse(curseq.begin(), curseq.end());
+                for (auto& b : curseq) b = 3 - b;
+                Int rsp, rep;
+                sa_range(L, curseq.data(), p.seed_length, rsp, rep);
+                Int rev_cnt = rep >= rsp ? rep - rsp + 1 : 0;
+                if (0 < rev_cnt && rev_cnt <= p.seed_tolerate) {
+                    Int rev_pos = readlen - (curpos + p.seed_length - 1) + 1;
+                    return Seed{rsp, rep, rev_pos, false};
+                }
+            }
+        } else {
+            return Seed{sp, ep, curpos, true};
+        }
+        curpos += increment;
+    }
+    return Seed{2, 1, curpos, true};
+}
+
+// reverse_complement!(rec), src/record.jl:23-26
+void reverse_complement(Read& r) {
+    std::reverse(r.seq.begin(), r.seq.end());
+    for (auto& b : r.seq) b = 3 - b;
+    std::reverse(r.qual.begin(), r.qual.end());
+}
+
+// splice_by_identity!, src/align.jl:198-207
+void splice_by_identity(std::vector<Align>& arr, float threshold, double buffer, Int readlen) {
+    size_t i = 0;
+    while (i < arr.size()) {
+        if ((double)(threshold - identity(arr[i], readlen)) > buffer) arr.erase(arr.begin() + i);
+        else i += 1;
+    }
+}
+
+// ungapped_align (single end), src/align.jl:225-270.  Returns false for a null result.
+bool ungapped_align_se(const Lib& L, const wq_align_param& p, Read& read, std::vector<Align>& res, bool& flipped) {
+    Seed seed = seed_locate(L, p, read, true, !p.is_stranded);
+    Int readlen = (Int)read.seq.size();
+    bool ispos = true;
+    flipped = false;
+    if (!seed.strand) {
+        reverse_complement(read);
+        ispos = false;
+        flipped = true;
+    }
+    bool isnull = true;
+    float maxscore = 0.f;
+    res.clear();
+    Ctx c{L, p, read, readlen};
+    for (Int row = seed.sp; row <= seed.ep; row++) {
+        Int s = sa_value(L, row) + 1;
+        Align align = ungapped_align_at(c, s, seed.readloc, ispos);
+        float scvar = identity(align, readlen);
+        if (isvalid(align)) {
+            if (isnull) {
+                isnull = false;
+                res.push_back(align);
+                maxscore = scvar;
+            } else {
+                if (scvar > maxscore) {
+                    if ((double)(scvar - maxscore) > p.score_range) {
+                        res.clear();
+                    } else {
+                        splice_by_identity(res, scvar, p.score_range, readlen);
+                    }
+                    maxscore = scvar;
+                    res.push_back(align);
+                } else {
+                    if ((double)(maxscore - scvar) <= p.score_range) res.push_back(align);
+                }
+            }
+        }
+    }
+    return !isnull;
+}
+
+// sorted_offsets, src/paired.jl:5-14
+std::vector<Int> sorted_offsets(const Lib& L, const Seed& s) {
+    std::vector<Int> res;
+    for (Int row = s.sp; row <= s.ep; row++) res.push_back(sa_value(L, row) + 1);
+    std::sort(res.begin(), res.end());
+    return res;
+}
+
+// paired identity, src/paired.jl:2-3 (Float32 + Float32, divided by an Int sum)
+float identity_pair(const Align& one, const Align& two, Int onelen, Int twolen) {
+    return (score(one) + score(two)) / (float)(onelen + twolen);
+}
+
+// paired ungapped_align, src/paired.jl:42-125
+bool ungapped_align_pe(const Lib& L, const wq_align_param& p, Read& fwd, Read& rev,
+                       std::vector<Align>& fwd_res, std::vector<Align>& rev_res, uint8_t& flipped) {
+    Seed fs = seed_locate(L, p, fwd, true, !p.is_stranded);
+    bool strand = fs.strand;
+    Seed rs;
+    flipped = 0;
+    if ((p.is_pair_rc && strand) || (!p.is_pair_rc && !strand)) {
+        reverse_complement(rev);
+        flipped |= 2;
+        rs = seed_locate(L, p, rev, false, false);
+    } else {
+        rs = seed_locate(L, p, rev, true, false);
+    }
+    Int fwd_len = (Int)fwd.seq.size();
+    Int rev_len = (Int)rev.seq.size();
+    bool ispos = true;
+    if (!strand) {
+        reverse_complement(fwd);
+        flipped |= 1;
+        ispos = false;
+    }
+    bool isnull = true;
+    float maxscore = 0.f;
+    fwd_res.clear();
+    rev_res.clear();
+    std::vector<Int> fwd_sorted = sorted_offsets(L, fs);
+    std::vector<Int> rev_sorted = sorted_offsets(L, rs);
+    Ctx cf{L, p, fwd, fwd_len};
+    Ctx cr{L, p, rev, rev_len};
+    size_t fidx = 1, ridx = 1;
+    while (fidx <= fwd_sorted.size() && ridx <= rev_sorted.size()) {
+        Int dist = std::llabs(fwd_sorted[fidx - 1] - rev_sorted[ridx - 1]);
+        if (dist < p.seed_pair_range) {
+            Int geneind = searchsortedlast_u32(L.d->gene_offset, L.G, fwd_sorted[fidx - 1]);
+            Int next_offset = geneind < L.G ? L.gene_offset(geneind + 1) : L.gene_offset(geneind) + L.seqlen(geneind);
+            if (L.gene_offset(geneind) <= rev_sorted[ridx - 1] && rev_sorted[ridx - 1] < next_offset) {
+                Align fwd_aln = ungapped_align_at(cf, fwd_sorted[fidx - 1], fs.readloc, ispos, geneind);
+                Align rev_aln = ungapped_align_at(cr, rev_sorted[ridx - 1], rs.readloc, !ispos, geneind);
+                float scvar = identity_pair(fwd_aln, rev_aln, fwd_len, rev_len);
+                if (isvalid(fwd_aln) && isvalid(rev_aln)) {
+                    if (isnull) {
+                        isnull = false;
+                        fwd_res.assign(1, fwd_aln);
+                        rev_res.assign(1, rev_aln);
+                        maxscore = scvar;
+                    } else {
+                        if (scvar > maxscore) {
+                            if ((double)(scvar - maxscore) > p.score_range) {
+                                fwd_res.clear();
+                                rev_res.clear();
+                            } else {
+                                size_t i = 0;   // paired splice_by_identity!, src/paired.jl:29-39
+                                while (i < fwd_res.size()) {
+                                    if ((double)(scvar - identity_pair(fwd_res[i], rev_res[i], fwd_len, rev_len)) > p.score_range) {
+                                        fwd_res.erase(fwd_res.begin() + i);
+                                        rev_res.erase(rev_res.begin() + i);
+                                    } else i += 1;
+                                }
+                            }
+                            maxscore = scvar;
+                            fwd_res.push_back(fwd_aln);
+                            rev_res.push_back(rev_aln);
+                        } else {
+                            if ((double)(maxscore - scvar) <= p.score_range) {
+                                fwd_res.push_back(fwd_aln);
+                                rev_res.push_back(rev_aln);
+                            }
+                        }
+                    }
+                }
+                ridx += 1;
+                fidx += 1;
+                continue;
+            }
+        }
+        if (fwd_sorted[fidx - 1] > rev_sorted[ridx - 1]) ridx += 1;
+        else fidx += 1;
+    }
+    return !isnull;
+}
+
+Read load_read(const wq_read_batch* b, uint32_t i) {
+    Read r;
+    Int len = b->len[i];
+    r.seq.resize(len);
+    r.qual.resize(len);
+    const uint64_t* w = b->seq2 + b->seq_off[i];
+    for (Int j = 0; j < len; j++) r.seq[j] = (uint8_t)((w[j >> 5] >> (2 * (j & 31))) & 3);
+    memcpy(r.qual.data(), b->qual + b->qual_off[i], (size_t)len);
+    return r;
+}
+
+struct Result {
+    std::vector<uint32_t> hit_start;
+    std::vector<uint8_t> nhits, flipped;
+    std::vector<wq_alignment> aln, aln_mate;
+    std::vector<wq_align_node> nodes;
+};
+
+void emit(Result& R, const Align& a, std::vector<wq_alignment>& dst) {
+    wq_alignment o;
+    o.offset = a.offset;
+    o.path_start = (uint32_t)R.nodes.size();
+    o.offsetread = a.offsetread;
+    o.strand = a.strand;
+    o.isvalid = a.isvalid;
+    o.npath = (uint8_t)std::min<size_t>(a.path.size(), 255);
+    dst.push_back(o);
+    for (auto& n : a.path) {
+        wq_align_node x;
+        x.gene = n.gene;
+        x.node = n.node;
+        x.mistolerance = n.score.mistolerance;
+        x.matches = n.score.matches;
+        x.mismatches = n.score.mismatches;
+        x._pad = 0;
+        R.nodes.push_back(x);
+    }
+}
+
+}  // namespace
+
+struct wqo_handle {
+    Lib L;
+    Result R;
+    std::string err;
+};
+
+extern "C" {
+
+wqo_handle* wqo_create(const wq_index_desc* d) {
+    init_phred();
+    wqo_handle* h = new wqo_handle{Lib{d, {}, (Int)d->text_len, (Int)d->n_genes}, {}, {}};
+    build_occ(h->L);
+    return h;
+}
+void wqo_destroy(wqo_handle* h) { delete h; }
+
+// FM search of one 2-bit query: returns sp, ep (src/fmindex_patch.jl:19-31)
+void wqo_sa_range(wqo_handle* h, const uint8_t* q, int64_t len, int64_t* sp, int64_t* ep) {
+    Int a, b;
+    sa_range(h->L, q, len, a, b);
+    *sp = a;
+    *ep = b;
+}
+int64_t wqo_sa_value(wqo_handle* h, int64_t row) { return sa_value(h->L, row); }
+
+// seed_locate for every read of a batch: out[4*i..] = sp, ep, readloc, strand
+void wqo_seed_locate(wqo_handle* h, const wq_align_param* p, const wq_read_batch* b, int64_t* out) {
+    for (uint32_t i = 0; i < b->n_reads; i++) {
+        Read r = load_read(b, i);
+        Seed s = seed_locate(h->L, *p, r, true, !p->is_stranded);
+        out[4 * i] = s.sp;
+        out[4 * i + 1] = s.ep;
+        out[4 * i + 2] = s.readloc;
+        out[4 * i + 3] = s.strand;
+    }
+}
+
+int wqo_align_se(wqo_handle* h, const wq_align_param* p, const wq_read_batch* b) {
+    Result& R = h->R;
+    R = Result();
+    std::vector<Align> res;
+    for (uint32_t i = 0; i < b->n_reads; i++) {
+        Read r = load_read(b, i);
+        bool fl;
+        bool ok = ungapped_align_se(h->L, *p, r, res, fl);
+        R.hit_start.push_back((uint32_t)R.aln.size());
+        R.nhits.push_back(ok ? (uint8_t)res.size() : 0);
+        R.flipped.push_back(fl);
+        if (ok) for (auto& a : res) emit(R, a, R.aln);
+    }
+    return 0;
+}
+
+int wqo_align_pe(wqo_handle* h, const wq_align_param* p, const wq_read_batch* f, const wq_read_batch* rv) {
+    Result& R = h->R;
+    R = Result();
+    std::vector<Align> fr, rr;
+    for (uint32_t i = 0; i < f->n_reads; i++) {
+        Read a = load_read(f, i), b = load_read(rv, i);
+        uint8_t fl;
+        bool ok = ungapped_align_pe(h->L, *p, a, b, fr, rr, fl);
+        R.hit_start.push_back((uint32_t)R.aln.size());
+        R.nhits.push_back(ok ? (uint8_t)fr.size() : 0);
+        R.flipped.push_back(fl);
+        if (ok) for (size_t k = 0; k < fr.size(); k++) {
+            emit(R, fr[k], R.aln);
+            emit(R, rr[k], R.aln_mate);
+        }
+    }
+    return 0;
+}
+
+uint64_t wqo_result_n_aln(wqo_handle* h) { return h->R.aln.size(); }
+uint64_t wqo_result_n_nodes(wqo_handle* h) { return h->R.nodes.size(); }
+void wqo_result_copy(wqo_handle* h, uint32_t* hit_start, uint8_t* nhits, uint8_t* flipped,
+                     wq_alignment* aln, wq_alignment* aln_mate, wq_align_node* nodes) {
+    Result& R = h->R;
+    if (hit_start) memcpy(hit_start, R.hit_start.data(), R.hit_start.size() * 4);
+    if (nhits) memcpy(nhits, R.nhits.data(), R.nhits.size());
+    if (flipped) memcpy(flipped, R.flipped.data(), R.flipped.size());
+    if (aln) memcpy(aln, R.aln.data(), R.aln.size() * sizeof(wq_alignment));
+    if (aln_mate && !R.aln_mate.empty()) memcpy(aln_mate, R.aln_mate.data(), R.aln_mate.size() * sizeof(wq_alignment));
+    if (nodes) memcpy(nodes, R.nodes.data(), R.nodes.size() * sizeof(wq_align_node));
+}
+
+}  // extern "C"
