@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""Headline benchmark: aligned+quantified reads/sec of the read -> splice-graph hot path.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A step = one pass of the hot path (seed, extend, resolve+count[, allreduce]) over one batch of
+synthetic 101-bp single-end reads against a GENCODE-scale synthetic splice-graph index
+(BASELINE.json configs[1]; the GENCODE GTF itself is not available offline).
+`value` is measured with the batch resident in HBM; `e2e` goes through wq_align_se with pinned HOST
+buffers (H2D inside the timed region) and reads the mapping statistics back.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle")]
+
+import numpy as np  # noqa: E402
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--genes", type=int, default=int(os.environ.get("WQ_BENCH_GENES", 40000)))
+    ap.add_argument("--reads", type=int, default=int(os.environ.get("WQ_BENCH_READS", 10_000_000)))
+    ap.add_argument("--readlen", type=int, default=101)
+    ap.add_argument("--cpu-sample", type=int, default=int(os.environ.get("WQ_BENCH_CPU_SAMPLE", 1_500_000)))
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return (f"synthetic GENCODE-scale splice graph ({a.genes} genes, K=9, random-sequence genome; stands in for "
+            f"gencode_hg19.v25.tsl1 which is not available offline) + {a.reads} x {a.readlen}bp SE reads per GPU")
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        self.gpu, self.rows, self.proc = gpu, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_inputs(a, rank):
+    import whippet_jl_b200 as wq
+    from whippet_jl_b200 import synth
+    t0 = time.time()
+    idx = synth.make_index(n_genes=a.genes, K=9, seed=1)
+    t1 = time.time()
+    rb = synth.simulate_reads(idx, a.reads, a.readlen, seed=2 + rank)
+    t2 = time.time()
+    print(f"[bench r{rank}] index n={idx.text_len} N={idx.n_nodes} I={idx.n_isoforms} in {t1 - t0:.1f}s; "
+          f"{a.reads} reads in {t2 - t1:.1f}s", file=sys.stderr, flush=True)
+    return idx, rb
+
+
+def byte_model(ctr, nreads, R):
+    """Algorithmic bytes per read, SURVEY.md section 8d, from oracle-instrumented counters."""
+    S = ctr["fm_steps"] / nreads
+    H = ctr["hits"] / nreads
+    nodes = ctr["nodes_touched"] / max(1, ctr["hits"])
+    r_in = (R + 3) // 4 + R + 8
+    a_out = (8 * ctr["out_alns"] + 16 * ctr["out_nodes"]) / nreads
+    C = ctr["count_updates"] / nreads
+    per_kernel = {"seed": r_in + 64 * S + 4 * H, "extend": H * ((R + 1) // 2 + 25 * nodes) + a_out, "resolve": 8 * C}
+    return per_kernel, dict(S_steps=S, H=H, nodes_per_hit=nodes, R_in=r_in, A_out=a_out, C=C)
+
+
+def cpu_oracle_run(idx, rb, param, nsample, threads):
+    """Times the oracle (CPU restatement) on the first `nsample` reads with `threads` host threads."""
+    from oracle import Oracle, counters
+    nsample = min(nsample, rb.n)
+    per = (nsample + threads - 1) // threads
+    oracles = [Oracle(idx) for _ in range(threads)]
+    slices = [rb.slice(i * per, min(nsample, (i + 1) * per)) for i in range(threads)]
+    counters(reset=True)
+    ctr = {}
+
+    def work(i):
+        oracles[i].process_reads(param, slices[i])
+        if i == 0:
+            ctr.update(counters(reset=True))
+
+    t0 = time.perf_counter()
+    if threads == 1:
+        work(0)
+    else:
+        ts = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+    dt = time.perf_counter() - t0
+    mapped = sum(o.stats()["mapped"] for o in oracles)
+    return nsample / dt, dt, mapped, ctr, slices[0].n
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    import whippet_jl_b200 as wq
+    idx, rb = make_inputs(a, 0)
+    cores = os.cpu_count() or 1
+    threads = max(1, min(cores, 64))
+    param = wq.AlignParam()
+    have_julia = subprocess.call("julia --version", shell=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL) == 0
+    vals = []
+    for i in range(a.warmup + a.steps):
+        nsample = min(rb.n, a.cpu_sample * max(1, threads // 2))
+        v, dt, _, _, _ = cpu_oracle_run(idx, rb, param, nsample, threads)
+        if i >= a.warmup:
+            vals.append((v, dt, nsample))
+        if i == 0 and dt * (a.warmup + a.steps) > 240:   # keep the whole run within a few minutes
+            a.cpu_sample = max(100000, int(a.cpu_sample * 240 / (dt * (a.warmup + a.steps))))
+    v = float(np.mean([x[0] for x in vals]))
+    sample = f"first {vals[-1][2]} reads of the workload per step, sharded over {threads} host threads"
+    print(json.dumps({
+        "impl": "reference", "metric": "aligned+quantified reads/sec", "value": v, "unit": "reads/s",
+        "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1000 * float(np.mean([x[1] for x in vals])),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/u32 integer + f32 scores",
+        "data": "synthetic", "config": {"workload": workload_name(a)},
+        "cpu_baseline": {"value": v, "unit": "reads/s", "cores": threads, "kind": "port", "sample": sample,
+                         "note": "oracle C++ restatement of the Julia path (julia %s on this box)" % ("present but unused" if have_julia else "absent")},
+        "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        return run_reference(a)
+    import torch
+    import torch.distributed as dist
+    import ctypes as C
+    import whippet_jl_b200 as wq
+    from whippet_jl_b200 import abi, lib
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a GPU: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    idx, rb = make_inputs(a, rank)
+    param = wq.AlignParam()
+    q = wq.GraphLibQuant(idx, device=local)
+    L = q.L
+    stream = torch.cuda.current_stream()
+    lib.check(L.wq_set_stream(q.h, C.c_void_p(stream.cuda_stream)))
+
+    # ---- device-resident batch ------------------------------------------------------------------
+    dev = torch.device("cuda", local)
+    t_len = torch.from_numpy(rb.len).to(dev)
+    t_soff = torch.from_numpy(rb.seq_off.view(np.int64)).to(dev)
+    t_seq = torch.from_numpy(rb.seq2.view(np.int64)).to(dev)
+    t_qoff = torch.from_numpy(rb.qual_off.view(np.int64)).to(dev)
+    t_qual = torch.from_numpy(rb.qual).to(dev)
+    db = abi.ReadBatchC()
+    db.n_reads = rb.n
+    db.len = C.cast(t_len.data_ptr(), abi.u8p)
+    db.seq_off = C.cast(t_soff.data_ptr(), abi.u64p)
+    db.seq2 = C.cast(t_seq.data_ptr(), abi.u64p)
+    db.seq2_words = len(rb.seq2)
+    db.qual_off = C.cast(t_qoff.data_ptr(), abi.u64p)
+    db.qual = C.cast(t_qual.data_ptr(), abi.u8p)
+    db.qual_bytes = len(rb.qual)
+    pc = param.c()
+
+    dptr, nd = C.c_void_p(), C.c_uint64()
+    lib.check(L.wq_counts_device_ptr(q.h, C.byref(dptr), C.byref(nd)))
+
+    class _Wrap:   # expose the dense count vector to torch for the NCCL all-reduce
+        __cuda_array_interface__ = {"shape": (int(nd.value),), "typestr": "<i8", "data": (int(dptr.value), False), "version": 2}
+    dense = torch.as_tensor(_Wrap(), device=dev) if world > 1 else None
+
+    def step():
+        lib.check(L.wq_quant_reset(q.h))
+        lib.check(L.wq_align_se_device(q.h, C.byref(pc), C.byref(db)))
+        if world > 1:
+            dist.all_reduce(dense)      # per-node counts + scalar stats, one NCCL all-reduce over NVLink
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(a.warmup):
+        step()
+    kms = np.zeros(3)
+    sync_all()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = L.wq_launch_count(q.h)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(a.steps):
+        step()
+        kms += np.array(q.last_kernel_ms())
+    e1.record(stream)
+    sync_all()
+    ms = e0.elapsed_time(e1) / a.steps
+    launches = int(L.wq_launch_count(q.h) - l0)
+    clocks = sampler.stop()
+    kms /= a.steps
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    stats = q.stats()
+    value = world * rb.n / (ms / 1000.0)
+
+    # ---- end to end: pinned host buffers through wq_align_se ------------------------------------
+    def pinned(arr):
+        return torch.from_numpy(arr).pin_memory()
+    p_len, p_soff, p_seq = pinned(rb.len), pinned(rb.seq_off.view(np.int64)), pinned(rb.seq2.view(np.int64))
+    p_qoff, p_qual = pinned(rb.qual_off.view(np.int64)), pinned(rb.qual)
+    hb = abi.ReadBatchC()
+    hb.n_reads = rb.n
+    hb.len = C.cast(p_len.data_ptr(), abi.u8p)
+    hb.seq_off = C.cast(p_soff.data_ptr(), abi.u64p)
+    hb.seq2 = C.cast(p_seq.data_ptr(), abi.u64p)
+    hb.seq2_words = len(rb.seq2)
+    hb.qual_off = C.cast(p_qoff.data_ptr(), abi.u64p)
+    hb.qual = C.cast(p_qual.data_ptr(), abi.u8p)
+    hb.qual_bytes = len(rb.qual)
+    h2d = int(rb.len.nbytes + rb.seq_off.nbytes + rb.seq2.nbytes + rb.qual_off.nbytes + rb.qual.nbytes)
+    d2h = C.sizeof(abi.MapStatsC)
+
+    def e2e_step():
+        lib.check(L.wq_quant_reset(q.h))
+        lib.check(L.wq_align_se(q.h, C.byref(pc), C.byref(hb), None))
+        if world > 1:
+            dist.all_reduce(dense)
+        return q.stats()
+
+    e2e_step()
+    sync_all()
+    t0 = time.perf_counter()
+    nrep = max(1, min(a.steps, 3))
+    for _ in range(nrep):
+        st2 = e2e_step()
+    sync_all()
+    e2e_ms = (time.perf_counter() - t0) * 1000 / nrep
+    t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * rb.n / (float(t.item()) / 1000.0)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    out = {
+        "metric": "aligned+quantified reads/sec", "value": value, "unit": "reads/s", "n_gpus": world,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8/u32 integer + f32 scores", "data": "synthetic",
+        "config": {"workload": workload_name(a), "l2": "inputs (%.2f GB per step) are larger than the 126 MB L2" % (h2d / 1e9),
+                   "text_len": int(idx.text_len), "nodes": int(idx.n_nodes), "isoforms": int(idx.n_isoforms),
+                   "mapped_frac": stats.mapped / max(1, stats.total), "multi_frac": stats.multi / max(1, stats.total),
+                   "parallelism": f"reads sharded over {world} GPU(s), index replicated" + (", dense counts all-reduced over NCCL" if world > 1 else "")},
+        "clocks": clocks, "gpu_launches": launches,
+        "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "kernel_ms": {"seed": float(kms[0]), "extend": float(kms[1]), "resolve": float(kms[2])},
+    }
+    if world == 1:
+        cpu_v, cpu_dt, _, ctr, n0 = cpu_oracle_run(idx, rb, param, a.cpu_sample, 1)
+        per_kernel, model = byte_model(ctr, n0, a.readlen)
+        names = ["seed", "extend", "resolve"]
+        dom = names[int(np.argmax(kms))]
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        dom_ms = float(kms[names.index(dom)])
+        achieved = per_kernel[dom] * rb.n / (dom_ms / 1000.0) / 1e9 if dom_ms > 0 else 0.0
+        out["roofline"] = {"bound": "hbm", "kernel": "wq_k_" + dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                           "frac": achieved / peak, "traffic": None,
+                           "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6.65 TB/s",
+                           "algorithmic_bytes_per_read": per_kernel, "model": model,
+                           "note": "latency-bound random access (FM occ blocks, SA, node records): the fraction is small by construction"}
+        out["cpu_baseline"] = {"value": cpu_v, "unit": "reads/s", "cores": 1, "kind": "port",
+                               "sample": f"first {min(a.cpu_sample, rb.n)} reads of the workload, oracle restatement on 1 host thread ({cpu_dt:.1f} s)"}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -166,6 +166,17 @@ int  wq_align_pe_device(wq_handle* h, const wq_align_param* p, const wq_read_bat
 
 int  wq_map_stats_get(wq_handle* h, wq_map_stats* out);
 
+/* Plumbing with no reference counterpart: run the handle's work on a caller-owned CUDA stream
+ * (NULL = the handle's own), per-kernel device milliseconds [seed, extend, resolve] of the last
+ * wq_align_*_device call, page-locked host buffers for read batches, and a refresh of the host-side
+ * dense counts after the caller all-reduced wq_counts_device_ptr over NCCL. */
+int  wq_set_stream(wq_handle* h, void* cuda_stream);
+int  wq_last_kernel_ms(wq_handle* h, float* ms3);
+int  wq_pinned_alloc(void** p, uint64_t bytes);
+int  wq_pinned_free(void* p);
+int  wq_counts_refresh_dense(wq_handle* h);
+uint64_t wq_launch_count(wq_handle* h);   /* kernels launched by this handle so far */
+
 /* Device pointer + element count of the dense count vector (u64 per node, then the scalar
  * stats) so a host can all-reduce it over NCCL between ranks. */
 int  wq_counts_device_ptr(wq_handle* h, void** dptr, uint64_t* n_u64);

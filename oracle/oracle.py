@@ -113,3 +113,47 @@ class Oracle:
         p, f, r = param.c(), fwd.c(), rev.c()
         lib().wqo_align_pe(C.c_void_p(self.h), C.byref(p), C.byref(f), C.byref(r))
         return self._collect(fwd.n, True)
+
+    # ---- counting (process_reads!, src/reads.jl:41-80) -------------------------------------------
+    def quant_reset(self):
+        lib().wqo_quant_reset(C.c_void_p(self.h))
+
+    def process_reads(self, param: wq.AlignParam, reads: wq.ReadBatch):
+        p, b = param.c(), reads.c()
+        lib().wqo_process_reads_se(C.c_void_p(self.h), C.byref(p), C.byref(b))
+
+    def stats(self):
+        out = (C.c_uint64 * 5)()
+        m = C.c_double()
+        lib().wqo_stats(C.c_void_p(self.h), out, C.byref(m))
+        return dict(total=out[0], mapped=out[1], multi=out[2], sum_readlen=out[3], mean_readlen=m.value)
+
+    def node_counts(self):
+        a = np.zeros(self.index.n_nodes, "<f8")
+        lib().wqo_node_counts(C.c_void_p(self.h), a.ctypes.data_as(C.c_void_p))
+        return a
+
+    def edges(self):
+        L = lib()
+        L.wqo_edge_count.restype = C.c_uint64
+        n = L.wqo_edge_count(C.c_void_p(self.h))
+        k, v = np.zeros(n, "<u8"), np.zeros(n, "<f8")
+        L.wqo_edges(C.c_void_p(self.h), k.ctypes.data_as(C.c_void_p), v.ctypes.data_as(C.c_void_p))
+        return k, v
+
+    def keyed(self, kind):
+        L = lib()
+        nr, nw = C.c_uint64(), C.c_uint64()
+        L.wqo_keyed(C.c_void_p(self.h), kind, C.byref(nr), C.byref(nw), None, None, None)
+        ptr_, words, vals = np.zeros(nr.value + 1, "<u8"), np.zeros(max(1, nw.value), "<u4"), np.zeros(max(1, nr.value), "<f8")
+        v = lambda a: a.ctypes.data_as(C.c_void_p)
+        L.wqo_keyed(C.c_void_p(self.h), kind, C.byref(nr), C.byref(nw), v(ptr_), v(words), v(vals))
+        return {tuple(int(x) for x in words[int(ptr_[i]):int(ptr_[i + 1])]): float(vals[i]) for i in range(nr.value)}
+
+
+def counters(reset=False):
+    """Instrumentation totals since the last reset: fm_steps, hits, nodes_touched, bases, out_nodes,
+    out_alns, count_updates (process-wide; only meaningful for single-threaded runs)."""
+    out = (C.c_uint64 * 7)()
+    lib().wqo_counters(out, 1 if reset else 0)
+    return dict(zip(("fm_steps", "hits", "nodes_touched", "bases", "out_nodes", "out_alns", "count_updates"), map(int, out)))

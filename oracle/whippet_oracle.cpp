@@ -28,6 +28,11 @@ namespace {
 
 typedef int64_t Int;
 
+// instrumentation for the byte model of SURVEY.md section 8d (not part of the algorithm)
+struct Counters { uint64_t fm_steps = 0, hits = 0, nodes_touched = 0, bases = 0, out_nodes = 0, out_alns = 0, count_updates = 0; };
+thread_local Counters g_ctr;
+
+
 // EdgeType codes, src/graph.jl:39-46
 enum : uint8_t { ET_SL = 0, ET_SR = 1, ET_LS = 2, ET_RS = 3, ET_LR = 4, ET_LL = 5, ET_RR = 6 };
 
@@ -100,6 +105,7 @@ void sa_range(const Lib& L, const uint8_t* q, Int len, Int& sp, Int& ep) {
     Int i = len;
     while (sp <= ep && i >= 1) {
         uint8_t ch = q[i - 1];
+        g_ctr.fm_steps++;
         Int c = L.d->count[ch];
         sp = c + rank(L, ch, (sp > sentinel ? sp - 1 : sp) - 1) + 1;
         ep = c + rank(L, ch, (ep > sentinel ? ep - 1 : ep));
@@ -224,6 +230,7 @@ Align ungapped_fwd_extend(const Ctx& c, uint32_t geneind, Int sgidx, Int ridx, A
     float mistol = mistolerance(align.path);
 
     align.path.push_back(ANode{geneind, nodeidx, Score()});
+    g_ctr.nodes_touched++;
 
     while ((double)mistol <= (double)p.mismatches && ridx <= readlen && sgidx <= seqlen) {
         if ((Int)nodeidx <= nn && sgidx == L.nodeoffset(geneind, nodeidx) + L.nodelen(geneind, nodeidx)) {   // hit next edge
@@ -264,6 +271,7 @@ Align ungapped_fwd_extend(const Ctx& c, uint32_t geneind, Int sgidx, Int ridx, A
             }
         }
         Score& sc = align.path.back().score;
+        g_ctr.bases++;
         if ((uint8_t)(1u << c.read.seq[ridx - 1]) == L.seq(geneind, sgidx)) {
             sc.matches += 1;
         } else {
@@ -385,6 +393,7 @@ Align ungapped_rev_extend(const Ctx& c, uint32_t geneind, Int sgidx, Int ridx, A
             }
         }
         Score& sc = align.path.front().score;
+        g_ctr.bases++;
         if ((uint8_t)(1u << c.read.seq[ridx - 1]) == L.seq(geneind, sgidx)) {
             sc.matches += 1;
         } else {
@@ -547,6 +556,7 @@ bool ungapped_align_se(const Lib& L, const wq_align_param& p, Read& read, std::v
     Ctx c{L, p, read, readlen};
     for (Int row = seed.sp; row <= seed.ep; row++) {
         Int s = sa_value(L, row) + 1;
+        g_ctr.hits++;
         Align align = ungapped_align_at(c, s, seed.readloc, ispos);
         float scvar = identity(align, readlen);
         if (isvalid(align)) {
@@ -706,12 +716,59 @@ void emit(Result& R, const Align& a, std::vector<wq_alignment>& dst) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Counting: SpliceGraphQuant / MultiMapping with DefaultCounter (src/quant.jl:129-144, 439-446,
+// src/bias.jl:66-85: every read adds 1.0).  Stores are kept in ordered maps; the sorted key order is
+// the declared canonical order (Julia Dict order is not reproducible).
+// Keys use the same record format as the library's download (include/whippet_b200.h::wq_keyed).
+struct Quant {
+    std::vector<double> node;                               // by global node index
+    std::map<uint64_t, double> edge;                        // gene<<32 | l<<16 | r  (edge when l<r, circ otherwise)
+    std::map<std::vector<uint32_t>, double> longs;          // [npath, gene, nodes...]  /  PE: [npf | npr<<8 | 2<<28, gene, fwd.., rev..]
+    std::map<std::vector<uint32_t>, double> multi;          // [1<<28 | nhits, per hit: npath, gene, nodes...]
+    uint64_t total = 0, mapped = 0, nmulti = 0, sum_readlen = 0;
+    double mean_readlen = 0.0;                              // running mean in read order, src/reads.jl:69
+};
+
+// count!(quant, align, value), src/quant.jl:556-594
+void count_se(const Lib& L, Quant& Q, const Align& a, double value) {
+    if (!a.isvalid) return;
+    uint32_t init_gene = a.path[0].gene;
+    size_t nb = L.d->node_base[init_gene - 1];
+    if (a.path.size() == 1) {
+        Q.node[nb + a.path[0].node - 1] += value;
+    } else {
+        for (auto& n : a.path) if (n.gene != init_gene) return;
+        if (a.path.size() == 2) {
+            uint32_t l = a.path[0].node, r = a.path[1].node;
+            uint64_t key = ((uint64_t)init_gene << 32) | ((uint64_t)(l & 0xFFFF) << 16) | (r & 0xFFFF);
+            Q.edge[key] += value;     // l < r: edge interval; l >= r: circ tuple (same packed key space)
+        } else {
+            std::vector<uint32_t> key{(uint32_t)a.path.size(), init_gene};
+            for (auto& n : a.path) key.push_back(n.node);
+            Q.longs[key] += value;
+        }
+    }
+}
+
+// push!(multi, alns, value, ...), src/quant.jl:456-469: the key is the ordered vector of node paths
+void push_multi_se(Quant& Q, const std::vector<Align>& alns, double value) {
+    std::vector<uint32_t> key{(1u << 28) | (uint32_t)alns.size()};
+    for (auto& a : alns) {
+        key.push_back((uint32_t)a.path.size());
+        key.push_back(a.path[0].gene);
+        for (auto& n : a.path) key.push_back(n.node);
+    }
+    Q.multi[key] += value;
+}
+
 }  // namespace
 
 struct wqo_handle {
     Lib L;
     Result R;
     std::string err;
+    Quant Q;
 };
 
 extern "C" {
@@ -720,7 +777,67 @@ wqo_handle* wqo_create(const wq_index_desc* d) {
     init_phred();
     wqo_handle* h = new wqo_handle{Lib{d, {}, (Int)d->text_len, (Int)d->n_genes}, {}, {}};
     build_occ(h->L);
+    h->Q.node.assign(d->n_nodes, 0.0);
     return h;
+}
+void wqo_quant_reset(wqo_handle* h) {
+    h->Q = Quant();
+    h->Q.node.assign(h->L.d->n_nodes, 0.0);
+}
+
+// process_reads!, src/reads.jl:41-80 (DefaultBiasMod: biasval = 1.0)
+int wqo_process_reads_se(wqo_handle* h, const wq_align_param* p, const wq_read_batch* b) {
+    Quant& Q = h->Q;
+    std::vector<Align> res;
+    for (uint32_t i = 0; i < b->n_reads; i++) {
+        Read r = load_read(b, i);
+        bool fl;
+        bool ok = ungapped_align_se(h->L, *p, r, res, fl);
+        Q.total += 1;
+        if (ok) {
+            g_ctr.out_alns += res.size();
+            for (auto& a : res) g_ctr.out_nodes += a.path.size();
+            g_ctr.count_updates += 1;
+            if (res.size() > 1) { push_multi_se(Q, res, 1.0); Q.nmulti += 1; }
+            else count_se(h->L, Q, res[0], 1.0);
+            Q.mapped += 1;
+            Q.sum_readlen += r.seq.size();
+            Q.mean_readlen += ((double)r.seq.size() - Q.mean_readlen) / (double)Q.mapped;
+        }
+    }
+    return 0;
+}
+void wqo_stats(wqo_handle* h, uint64_t* out5, double* mean_readlen) {
+    out5[0] = h->Q.total; out5[1] = h->Q.mapped; out5[2] = h->Q.nmulti; out5[3] = h->Q.sum_readlen; out5[4] = 0;
+    *mean_readlen = h->Q.mean_readlen;
+}
+void wqo_counters(uint64_t* out7, int reset) {
+    out7[0] = g_ctr.fm_steps; out7[1] = g_ctr.hits; out7[2] = g_ctr.nodes_touched; out7[3] = g_ctr.bases;
+    out7[4] = g_ctr.out_nodes; out7[5] = g_ctr.out_alns; out7[6] = g_ctr.count_updates;
+    if (reset) g_ctr = Counters();
+}
+void wqo_node_counts(wqo_handle* h, double* out) { memcpy(out, h->Q.node.data(), h->Q.node.size() * 8); }
+uint64_t wqo_edge_count(wqo_handle* h) { return h->Q.edge.size(); }
+void wqo_edges(wqo_handle* h, uint64_t* keys, double* vals) {
+    size_t i = 0;
+    for (auto& kv : h->Q.edge) { keys[i] = kv.first; vals[i] = kv.second; i++; }
+}
+// keyed stores: kind 0 = long, 1 = multi.  First call with NULLs returns sizes.
+void wqo_keyed(wqo_handle* h, int kind, uint64_t* n_rec, uint64_t* n_words, uint64_t* rec_ptr, uint32_t* words, double* vals) {
+    auto& M = kind == 0 ? h->Q.longs : h->Q.multi;
+    uint64_t nr = 0, nw = 0;
+    for (auto& kv : M) {
+        if (rec_ptr) {
+            rec_ptr[nr] = nw;
+            memcpy(words + nw, kv.first.data(), kv.first.size() * 4);
+            vals[nr] = kv.second;
+        }
+        nr++;
+        nw += kv.first.size();
+    }
+    if (rec_ptr) rec_ptr[nr] = nw;
+    *n_rec = nr;
+    *n_words = nw;
 }
 void wqo_destroy(wqo_handle* h) { delete h; }
 

@@ -1,0 +1,94 @@
+"""TEST INFRASTRUCTURE ONLY: ctypes driver of tests/emu/wq_emu.cpp (kernel bodies run on the CPU)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+import whippet_jl_b200 as wq
+from whippet_jl_b200 import abi
+from oracle import AlignResult
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libwq_emu.so")
+_CSRC = os.path.join(_HERE, "..", "..", "whippet.jl_b200", "csrc")
+
+
+def build():
+    srcs = [os.path.join(_HERE, "wq_emu.cpp")] + [os.path.join(_CSRC, f) for f in
+                                                   ("wq_kernels.cuh", "wq_align.cuh", "wq_types.h", "wq_host_index.h")]
+    if not os.path.exists(_SO) or os.path.getmtime(_SO) < max(map(os.path.getmtime, srcs)):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-Wno-unused-function",
+                               "-ffp-contract=off", "-o", _SO, srcs[0]])
+    return _SO
+
+
+class Counters(C.Structure):
+    _fields_ = [(k, C.c_uint64) for k in ("total", "mapped", "multi", "sum_readlen", "path_overflow", "edge_full",
+                                          "keyed_full", "pool_overflow")]
+
+
+class Emu:
+    def __init__(self, index: wq.FlatIndex):
+        build()
+        self.L = C.CDLL(_SO)
+        self.L.emu_create.restype = C.c_void_p
+        self.L.emu_result_sizes.restype = C.c_uint64
+        self.L.emu_node_counts.restype = C.POINTER(C.c_uint64)
+        self.L.emu_counters.restype = C.POINTER(Counters)
+        self.index = index
+        self._d = index.desc()
+        self.h = C.c_void_p(self.L.emu_create(C.byref(self._d)))
+        assert self.h
+
+    def align_se(self, param, reads):
+        p, b = param.c(), reads.c()
+        rc = self.L.emu_align_se(self.h, C.byref(p), C.byref(b))
+        assert rc == 0, rc
+        nn = C.c_uint64()
+        na = self.L.emu_result_sizes(self.h, C.byref(nn))
+        n = reads.n
+        hs, nh, fl = np.zeros(n, "<u4"), np.zeros(n, "u1"), np.zeros(n, "u1")
+        aln, nodes = np.zeros(na, abi.ALIGNMENT_DT), np.zeros(nn.value, abi.ALIGN_NODE_DT)
+        v = lambda a: a.ctypes.data_as(C.c_void_p)
+        self.L.emu_result_copy(self.h, v(hs), v(nh), v(fl), v(aln), v(nodes))
+        return AlignResult(hs, nh, fl, aln, nodes)
+
+    def seeds(self, n):
+        out = np.zeros((n, 4), np.int64)
+        self.L.emu_seeds(self.h, out.ctypes.data_as(C.c_void_p))
+        return out
+
+    def node_counts(self):
+        return np.ctypeslib.as_array(self.L.emu_node_counts(self.h), (self.index.n_nodes,)).copy()
+
+    def counters(self):
+        c = self.L.emu_counters(self.h).contents
+        return {k: getattr(c, k) for k, _ in Counters._fields_}
+
+    def process_reads(self, param, reads):
+        p, b = param.c(), reads.c()
+        rc = self.L.emu_align_se(self.h, C.byref(p), C.byref(b))
+        assert rc == 0, rc
+
+    def edges(self):
+        self.L.emu_edges.restype = C.c_uint64
+        n = self.L.emu_edges(self.h, None, None)
+        k, v = np.zeros(n, "<u8"), np.zeros(n, "<u8")
+        self.L.emu_edges(self.h, k.ctypes.data_as(C.c_void_p), v.ctypes.data_as(C.c_void_p))
+        o = np.argsort(k)
+        return k[o], v[o]
+
+    def keyed(self):
+        self.L.emu_keyed.restype = C.c_uint64
+        n = self.L.emu_keyed(self.h, None)
+        w = np.zeros(max(1, n), "<u4")
+        self.L.emu_keyed(self.h, w.ctypes.data_as(C.c_void_p))
+        longs, multi, i = {}, {}, 0
+        while i < n:
+            nw = int(w[i])
+            key = tuple(int(x) for x in w[i + 1:i + 1 + nw])
+            cnt = int(w[i + 1 + nw]) | (int(w[i + 2 + nw]) << 32)
+            (multi if (key[0] >> 28) & 1 else longs)[key] = cnt
+            i += nw + 3
+        return longs, multi

@@ -1,0 +1,136 @@
+// TEST INFRASTRUCTURE ONLY: drives the per-thread kernel bodies of whippet.jl_b200/csrc/wq_kernels.cuh
+// single-threaded on the CPU so their logic can be checked against the oracle in a container that
+// has no GPU.  Never built into, nor loadable by, the product library (which has no CPU path).
+#include <cstdio>
+#include <vector>
+#include "../../whippet.jl_b200/csrc/wq_kernels.cuh"
+#include "../../whippet.jl_b200/csrc/wq_host_index.h"
+
+struct Emu {
+    WqHostIndex H;
+    WqDevIndex ix;
+    std::vector<uint64_t> node_count;
+    WqCounters counters;
+    std::vector<uint64_t> ekey, ecount, khash, kcount;
+    std::vector<uint32_t> koff, kpool;
+    uint64_t pool_cursor = 0;
+    WqQuantDev q;
+    // last batch
+    std::vector<WqSeed> seeds;
+    std::vector<uint32_t> hit_read, hit_s, pending;
+    std::vector<WqHit> hits;
+    std::vector<wq_align_node> pool;
+    uint32_t cursors[3];
+};
+
+extern "C" {
+
+Emu* emu_create(const wq_index_desc* d) {
+    Emu* e = new Emu();
+    std::string err = wq_build_host_index(d, e->H);
+    if (!err.empty()) { fprintf(stderr, "emu: %s\n", err.c_str()); delete e; return nullptr; }
+    WqHostIndex& H = e->H;
+    WqDevIndex& ix = e->ix;
+    ix.occ = H.occ.data(); ix.sa = d->sa; ix.text2 = H.text2.data(); ix.amb = H.has_amb ? H.amb.data() : nullptr;
+    ix.nodes = H.nodes.data(); ix.genes = H.genes.data(); ix.node_bucket = H.node_bucket.data();
+    ix.left_ptr = d->left_ptr; ix.left_ent = H.left_ent.data(); ix.right_ptr = d->right_ptr; ix.right_ent = H.right_ent.data();
+    ix.n = H.n; ix.sentinel = H.sentinel; for (int i = 0; i < 4; i++) ix.C[i] = H.C[i];
+    ix.N = H.N; ix.G = H.G; ix.K = H.K;
+    e->node_count.assign(H.N, 0);
+    memset(&e->counters, 0, sizeof e->counters);
+    size_t es = 1 << 16, ks = 1 << 16;
+    e->ekey.assign(es, WQ_EMPTY_KEY); e->ecount.assign(es, 0);
+    e->khash.assign(ks, 0); e->kcount.assign(ks, 0); e->koff.assign(ks, WQ_KEYOFF_UNSET); e->kpool.assign(1 << 22, 0);
+    e->q.node_count = e->node_count.data(); e->q.counters = &e->counters;
+    e->q.edges = WqEdgeTable{e->ekey.data(), e->ecount.data(), es - 1};
+    e->q.keyed = WqKeyedTable{e->khash.data(), e->koff.data(), e->kcount.data(), e->kpool.data(), &e->pool_cursor, e->kpool.size(), ks - 1};
+    return e;
+}
+void emu_destroy(Emu* e) { delete e; }
+
+int emu_align_se(Emu* e, const wq_align_param* ap, const wq_read_batch* rb) {
+    WqParams p;
+    std::string err = wq_make_params(ap, e->H.K, p);
+    if (!err.empty()) { fprintf(stderr, "emu: %s\n", err.c_str()); return -1; }
+    WqBatchDev b{rb->n_reads, rb->len, rb->seq_off, rb->seq2, rb->qual_off, rb->qual};
+    uint32_t n = rb->n_reads;
+    e->seeds.assign(n, WqSeed());
+    uint32_t hit_cap = n * p.seed_tolerate + 1;
+    e->hit_read.assign(hit_cap, 0); e->hit_s.assign(hit_cap, 0); e->hits.assign(hit_cap, WqHit());
+    e->pool.assign((size_t)hit_cap * 4 + 64, wq_align_node());
+    e->pending.assign(n + 1, 0);
+    e->cursors[0] = e->cursors[1] = e->cursors[2] = 0;
+    WqWork wk{e->seeds.data(), e->hit_read.data(), e->hit_s.data(), e->hits.data(), e->pool.data(), e->cursors,
+              e->pending.data(), hit_cap, (uint32_t)e->pool.size()};
+    for (uint32_t r = 0; r < n; r++) wq_seed_thread(e->ix, p, b, wk, r);
+    uint32_t nh = e->cursors[0];
+    for (uint32_t s = 0; s < nh; s++) wq_extend_thread(e->ix, p, b, wk, s);
+    uint64_t stats[5] = {0, 0, 0, 0, 0};
+    for (uint32_t r = 0; r < n; r++) wq_resolve_thread(e->ix, p, b, wk, e->q, r, stats);
+    e->counters.total += n; e->counters.mapped += stats[0]; e->counters.multi += stats[1];
+    e->counters.sum_readlen += stats[2]; e->counters.path_overflow += stats[3]; e->counters.pool_overflow += stats[4];
+    return (int)e->cursors[2];   // pending (always 0 single-threaded)
+}
+
+// results of the last batch in the oracle's CSR layout (kept alignments only, reference order)
+uint64_t emu_result_sizes(Emu* e, uint64_t* n_nodes) {
+    uint64_t na = 0, nn = 0;
+    for (auto& s : e->seeds)
+        for (int k = 0; k < s.cnt; k++) {
+            const WqHit& h = e->hits[s.hit_base + k];
+            if (h.flags & 4) { na++; nn += h.npath; }
+        }
+    *n_nodes = nn;
+    return na;
+}
+void emu_result_copy(Emu* e, uint32_t* hit_start, uint8_t* nhits, uint8_t* flipped, wq_alignment* aln, wq_align_node* nodes) {
+    uint64_t na = 0, nn = 0;
+    for (size_t r = 0; r < e->seeds.size(); r++) {
+        const WqSeed& s = e->seeds[r];
+        hit_start[r] = (uint32_t)na;
+        uint8_t c = 0;
+        for (int k = 0; k < s.cnt; k++) {
+            const WqHit& h = e->hits[s.hit_base + k];
+            if (!(h.flags & 4)) continue;
+            wq_alignment a;
+            a.offset = h.offset; a.path_start = (uint32_t)nn; a.offsetread = h.offsetread; a.strand = h.strand;
+            a.isvalid = h.flags & 1; a.npath = h.npath;
+            aln[na++] = a;
+            for (int i = 0; i < h.npath; i++) nodes[nn++] = e->pool[h.path_start + i];
+            c++;
+        }
+        nhits[r] = c;
+        flipped[r] = (s.cnt > 0 && !s.strand) ? 1 : 0;
+    }
+}
+void emu_seeds(Emu* e, int64_t* out) {
+    for (size_t r = 0; r < e->seeds.size(); r++) {
+        const WqSeed& s = e->seeds[r];
+        out[4 * r] = s.sp; out[4 * r + 1] = (int64_t)s.sp + s.cnt - 1; out[4 * r + 2] = s.readloc; out[4 * r + 3] = s.strand;
+    }
+}
+const uint64_t* emu_node_counts(Emu* e) { return e->node_count.data(); }
+uint64_t emu_edges(Emu* e, uint64_t* keys, uint64_t* vals) {
+    uint64_t n = 0;
+    for (size_t i = 0; i < e->ekey.size(); i++)
+        if (e->ekey[i] != WQ_EMPTY_KEY) { if (keys) { keys[n] = e->ekey[i]; vals[n] = e->ecount[i]; } n++; }
+    return n;
+}
+// keyed entries as [nw, words..., count_lo, count_hi] records back to back; returns words written/needed
+uint64_t emu_keyed(Emu* e, uint32_t* out) {
+    uint64_t w = 0;
+    for (size_t i = 0; i < e->khash.size(); i++) {
+        if (!e->khash[i]) continue;
+        uint32_t off = e->koff[i], nw = e->kpool[off];
+        if (out) {
+            out[w] = nw;
+            memcpy(out + w + 1, &e->kpool[off + 1], nw * 4);
+            out[w + 1 + nw] = (uint32_t)e->kcount[i];
+            out[w + 2 + nw] = (uint32_t)(e->kcount[i] >> 32);
+        }
+        w += nw + 3;
+    }
+    return w;
+}
+const WqCounters* emu_counters(Emu* e) { return &e->counters; }
+}

@@ -1,0 +1,72 @@
+"""CPU-side check of the kernel bodies (tests/emu drives csrc/wq_kernels.cuh single-threaded) against
+the oracle.  This is a development aid for a container without a GPU: the shipped library has no CPU
+path, and the parity tests proper are the -m gpu ones."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import whippet_jl_b200 as wq
+from whippet_jl_b200 import synth
+from conftest import GOLDEN
+from data_gen import fixture_random_reads, ragged_reads
+from emu.emu import Emu
+from helpers_cmp import results_equal
+from oracle import Oracle
+
+
+def compare_all(idx, p, rb):
+    o, e = Oracle(idx), Emu(idx)
+    ro, re = o.align_se(p, rb), e.align_se(p, rb)
+    assert results_equal(ro, re, rb.n) == []
+    o.quant_reset()
+    o.process_reads(p, rb)
+    st, c = o.stats(), e.counters()
+    for k in ("total", "mapped", "multi", "sum_readlen"):
+        assert st[k] == c[k], k
+    assert c["path_overflow"] == 0 and c["edge_full"] == 0 and c["keyed_full"] == 0
+    assert np.array_equal(o.node_counts(), e.node_counts().astype(float))
+    ok, ov = o.edges()
+    ek, ev = e.edges()
+    assert np.array_equal(ok, ek) and np.array_equal(ov, ev.astype(float))
+    el, em = e.keyed()
+    assert o.keyed(0) == {k: float(v) for k, v in el.items()}
+    assert o.keyed(1) == {k: float(v) for k, v in em.items()}
+    return ro
+
+
+def test_fixture_known_answer_reads(fixture_index, test_param):
+    kat = json.load(open(os.path.join(GOLDEN, "kat_reads.json")))["reads"]
+    rb = wq.ReadBatch.from_strings([r["seq"] for r in kat], [r["qual"] for r in kat], 33, fill="C")
+    compare_all(fixture_index, test_param, rb)
+
+
+def test_fixture_random_reads(fixture_index, test_param):
+    ro = compare_all(fixture_index, test_param, fixture_random_reads(fixture_index, 20000))
+    assert (ro.nhits > 0).mean() > 0.3 and (ro.nhits > 1).sum() > 50
+
+
+@pytest.mark.parametrize("seed,ng,R", [(1, 300, 101), (2, 300, 50), (3, 200, 255), (4, 300, 76)])
+def test_synthetic(seed, ng, R):
+    idx = synth.make_index(n_genes=ng, K=9, seed=seed, paralog_frac=0.1)
+    rb = synth.simulate_reads(idx, 30000, R, seed=seed + 10, sub_rate=0.01)
+    ro = compare_all(idx, wq.AlignParam(), rb)
+    assert (ro.nhits > 0).mean() > 0.9
+    assert (ro.aln["npath"] >= 3).sum() > 20      # long paths exercised
+
+
+def test_ragged_and_short_reads():
+    idx = synth.make_index(n_genes=150, K=9, seed=9, paralog_frac=0.1)
+    rb = ragged_reads(idx, 20000)
+    compare_all(idx, wq.AlignParam(), rb)
+
+
+def test_stranded_and_small_k():
+    idx = synth.make_index(n_genes=150, K=5, seed=12, paralog_frac=0.2, exon_median=40.0)
+    rb = synth.simulate_reads(idx, 20000, 60, seed=3, sub_rate=0.02)
+    p = wq.AlignParam(mismatches=2, kmer_size=5, seed_try=4, seed_tolerate=6, seed_length=12, seed_buffer=2,
+                      seed_inc=7, is_stranded=True)
+    compare_all(idx, p, rb)
+    p2 = wq.AlignParam(mismatches=4, kmer_size=5, seed_try=2, seed_tolerate=8, seed_length=10, seed_buffer=1, seed_inc=3)
+    compare_all(idx, p2, rb)

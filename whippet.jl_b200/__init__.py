@@ -5,5 +5,6 @@ lives in csrc/ behind the C ABI of include/whippet_b200.h.
 """
 from . import abi, jls, flat
 from .flat import FlatIndex, AlignParam, ReadBatch
+from .quant import GraphLibQuant, AlignResult, MapStats
 
-__all__ = ["abi", "jls", "flat", "FlatIndex", "AlignParam", "ReadBatch"]
+__all__ = ["abi", "jls", "flat", "FlatIndex", "AlignParam", "ReadBatch", "GraphLibQuant", "AlignResult", "MapStats"]

@@ -1,0 +1,611 @@
+// libwhippet_b200.so — C ABI (include/whippet_b200.h) over hand-written sm_100a kernels.
+//
+// Kernels (bodies in wq_kernels.cuh / wq_align.cuh, EM in wq_em.cuh):
+//   wq_k_seed      batched FM-index backward search + locate   (fmindex_patch.jl:19-31, align.jl:145-185)
+//   wq_k_extend    ungapped fwd/rev extension across nodes     (align.jl:209-223, 275-575)
+//   wq_k_resolve   multi-hit resolution + count!/push!(multi)  (align.jl:239-268, quant.jl:456-469, 556-594)
+//   wq_k_retry     second chance for keyed inserts that met an unpublished slot
+// There is no CPU implementation behind this ABI: without an sm_100 device wq_index_create fails.
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "wq_kernels.cuh"
+#include "wq_host_index.h"
+#include "wq_host_quant.h"
+#include "wq_em.cuh"
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(-10, std::string(#call) + ": " + cudaGetErrorString(e_));                  \
+    } while (0)
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = n + n / 4 + 16;
+        cudaError_t e = cudaMalloc(&p, want * sizeof(T));
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct wq_handle {
+    int device = 0;
+    cudaStream_t stream = nullptr, copy_stream = nullptr, own_stream = nullptr;
+    cudaStreamAttrValue l2attr; bool has_l2attr = false;
+    cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+    WqDevIndex dix;
+    WqHostIndex H;               // host mirror (kept for node/gene lookups while building classes)
+    WqIsoIndex iso;              // annotated isoform paths (host)
+    // device index storage
+    DevBuf<WqOccBlock> d_occ; DevBuf<uint32_t> d_sa; DevBuf<uint64_t> d_text2; DevBuf<uint32_t> d_amb;
+    DevBuf<WqNodeRec> d_nodes; DevBuf<WqGeneRec> d_genes; DevBuf<uint32_t> d_bucket;
+    DevBuf<uint32_t> d_lptr, d_rptr; DevBuf<uint2> d_lent, d_rent;
+    // quant stores
+    DevBuf<uint64_t> d_dense;    // [N] node counts followed by WqCounters
+    DevBuf<uint64_t> d_ekey, d_ecount, d_khash, d_kcount; DevBuf<uint32_t> d_koff, d_kpool; DevBuf<uint64_t> d_kcursor;
+    uint64_t edge_slots = 0, keyed_slots = 0, kpool_cap = 0;
+    WqQuantDev q;
+    // per-batch buffers
+    DevBuf<uint8_t> d_len[2], d_qual[2]; DevBuf<uint64_t> d_seqoff[2], d_qualoff[2], d_seq2[2];
+    DevBuf<WqSeed> d_seeds; DevBuf<uint32_t> d_hit_read, d_hit_s, d_pending, d_pending2, d_cursors;
+    DevBuf<WqHit> d_hits; DevBuf<wq_align_node> d_pool;
+    uint32_t* h_cursors = nullptr;   // pinned
+    // host-side quant state (filled by wq_counts_sync / merge; input of EM)
+    WqHostQuant hq;
+    bool hq_valid = false;
+    uint32_t chunk_reads = 1u << 22;
+    float last_kernel_ms[3] = {0, 0, 0};
+    uint64_t launches = 0;       // kernels launched by this handle so far
+};
+
+// ------------------------------------------------------------------------------------------ kernels
+__global__ void __launch_bounds__(128) wq_k_seed(const WqDevIndex ix, const __grid_constant__ WqParams p,
+                                                 const WqBatchDev b, const WqWork wk) {
+    uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= b.n) return;
+    wq_seed_thread(ix, p, b, wk, r);
+}
+
+__global__ void __launch_bounds__(128) wq_k_extend(const WqDevIndex ix, const __grid_constant__ WqParams p,
+                                                   const WqBatchDev b, const WqWork wk) {
+    uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t nh = wk.cursors[0];
+    if (nh > wk.hit_cap) nh = wk.hit_cap;
+    if (slot >= nh) return;
+    wq_extend_thread(ix, p, b, wk, slot);
+}
+
+__global__ void __launch_bounds__(128) wq_k_resolve(const WqDevIndex ix, const __grid_constant__ WqParams p,
+                                                    const WqBatchDev b, const WqWork wk, const WqQuantDev q) {
+    uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t st[5] = {0, 0, 0, 0, 0};
+    if (r < b.n) wq_resolve_thread(ix, p, b, wk, q, r, st);
+    // warp-level reduction of the scalar stats, one atomic per warp and counter
+#pragma unroll
+    for (int i = 0; i < 5; i++) {
+        unsigned long long v = st[i];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        st[i] = v;
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (st[0]) atomicAdd((unsigned long long*)&q.counters->mapped, (unsigned long long)st[0]);
+        if (st[1]) atomicAdd((unsigned long long*)&q.counters->multi, (unsigned long long)st[1]);
+        if (st[2]) atomicAdd((unsigned long long*)&q.counters->sum_readlen, (unsigned long long)st[2]);
+        if (st[3]) atomicAdd((unsigned long long*)&q.counters->path_overflow, (unsigned long long)st[3]);
+        if (st[4]) atomicAdd((unsigned long long*)&q.counters->pool_overflow, (unsigned long long)st[4]);
+    }
+    if (r == 0) atomicAdd((unsigned long long*)&q.counters->total, (unsigned long long)b.n);
+}
+
+__global__ void __launch_bounds__(128) wq_k_retry(const WqDevIndex ix, const WqWork wk, const WqQuantDev q,
+                                                  const uint32_t* list, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    wq_retry_thread(ix, wk, q, list[i]);
+}
+
+__global__ void wq_k_fill_u64(uint64_t* p, uint64_t v, uint64_t n) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) p[i] = v;
+}
+
+// ------------------------------------------------------------------------------------------ helpers
+static uint64_t env_u64(const char* name, uint64_t def) {
+    const char* v = getenv(name);
+    if (!v || !*v) return def;
+    return strtoull(v, nullptr, 10);
+}
+static uint64_t pow2_at_least(uint64_t x) { uint64_t p = 1; while (p < x) p <<= 1; return p; }
+
+template <class T>
+static cudaError_t upload(DevBuf<T>& d, const T* src, size_t n, cudaStream_t s) {
+    cudaError_t e = d.ensure(n ? n : 1);
+    if (e != cudaSuccess) return e;
+    if (n) e = cudaMemcpyAsync(d.p, src, n * sizeof(T), cudaMemcpyHostToDevice, s);
+    return e;
+}
+
+extern "C" {
+
+const char* wq_last_error(void) { return g_err.c_str(); }
+int wq_version(void) { return 100; }
+
+int wq_pinned_alloc(void** p, uint64_t bytes) {
+    CK(cudaHostAlloc(p, bytes ? bytes : 1, cudaHostAllocDefault));
+    return 0;
+}
+int wq_pinned_free(void* p) {
+    CK(cudaFreeHost(p));
+    return 0;
+}
+
+void wq_destroy(wq_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    h->d_occ.release(); h->d_sa.release(); h->d_text2.release(); h->d_amb.release(); h->d_nodes.release();
+    h->d_genes.release(); h->d_bucket.release(); h->d_lptr.release(); h->d_rptr.release(); h->d_lent.release();
+    h->d_rent.release(); h->d_dense.release(); h->d_ekey.release(); h->d_ecount.release(); h->d_khash.release();
+    h->d_kcount.release(); h->d_koff.release(); h->d_kpool.release(); h->d_kcursor.release();
+    for (int i = 0; i < 2; i++) {
+        h->d_len[i].release(); h->d_qual[i].release(); h->d_seqoff[i].release(); h->d_qualoff[i].release(); h->d_seq2[i].release();
+        if (h->ev_copy[i]) cudaEventDestroy(h->ev_copy[i]);
+        if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
+    }
+    h->d_seeds.release(); h->d_hit_read.release(); h->d_hit_s.release(); h->d_pending.release(); h->d_pending2.release();
+    h->d_cursors.release(); h->d_hits.release(); h->d_pool.release();
+    if (h->h_cursors) cudaFreeHost(h->h_cursors);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    delete h;
+}
+
+int wq_quant_reset(wq_handle* h) {
+    if (!h) return fail(-1, "null handle");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    CK(cudaMemsetAsync(h->d_dense.p, 0, (h->H.N + sizeof(WqCounters) / 8) * sizeof(uint64_t), s));
+    wq_k_fill_u64<<<592, 256, 0, s>>>(h->d_ekey.p, WQ_EMPTY_KEY, h->edge_slots);
+    h->launches += 1;
+    CK(cudaMemsetAsync(h->d_ecount.p, 0, h->edge_slots * 8, s));
+    CK(cudaMemsetAsync(h->d_khash.p, 0, h->keyed_slots * 8, s));
+    CK(cudaMemsetAsync(h->d_kcount.p, 0, h->keyed_slots * 8, s));
+    CK(cudaMemsetAsync(h->d_koff.p, 0xFF, h->keyed_slots * 4, s));
+    CK(cudaMemsetAsync(h->d_kcursor.p, 0, 8, s));
+    CK(cudaStreamSynchronize(s));
+    h->hq = WqHostQuant();
+    h->hq_valid = false;
+    return 0;
+}
+
+int wq_index_create(const wq_index_desc* d, int device, wq_handle** out) {
+    if (!d || !out) return fail(-1, "null argument");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e0 = cudaGetDeviceCount(&ndev);
+    if (e0 != cudaSuccess || ndev == 0)
+        return fail(-2, std::string("no CUDA device available (this library has no CPU fallback): ") + cudaGetErrorString(e0));
+    if (device < 0 || device >= ndev) return fail(-2, "device ordinal out of range");
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(-2, std::string("device '") + prop.name + "' is not sm_100-class; the kernels are built for sm_100a only");
+    CK(cudaSetDevice(device));
+    wq_handle* h = new wq_handle();
+    h->device = device;
+    std::string err = wq_build_host_index(d, h->H);
+    if (err.empty()) err = wq_build_iso_index(d, h->iso);
+    if (!err.empty()) { delete h; return fail(-3, err); }
+#define CKH(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { std::string m_ = std::string(#call) + ": " + cudaGetErrorString(e_); wq_destroy(h); return fail(-10, m_); } } while (0)
+    CKH(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    h->stream = h->own_stream;
+    CKH(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+        CKH(cudaEventCreateWithFlags(&h->ev_copy[i], cudaEventDisableTiming));
+        CKH(cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
+    }
+    CKH(cudaHostAlloc((void**)&h->h_cursors, 64, cudaHostAllocDefault));
+    // spliced extensions nest (one level per junction found through the k-mer tables)
+    CKH(cudaDeviceSetLimit(cudaLimitStackSize, env_u64("WQ_STACK_BYTES", 16 * 1024)));
+    WqHostIndex& H = h->H;
+    cudaStream_t s = h->stream;
+    CKH(upload(h->d_occ, H.occ.data(), H.occ.size(), s));
+    CKH(upload(h->d_sa, d->sa, (size_t)H.n, s));
+    CKH(upload(h->d_text2, H.text2.data(), H.text2.size(), s));
+    if (H.has_amb) CKH(upload(h->d_amb, H.amb.data(), H.amb.size(), s));
+    CKH(upload(h->d_nodes, H.nodes.data(), H.nodes.size(), s));
+    CKH(upload(h->d_genes, H.genes.data(), H.genes.size(), s));
+    CKH(upload(h->d_bucket, H.node_bucket.data(), H.node_bucket.size(), s));
+    CKH(upload(h->d_lptr, d->left_ptr, (size_t)H.nslots + 1, s));
+    CKH(upload(h->d_rptr, d->right_ptr, (size_t)H.nslots + 1, s));
+    CKH(upload(h->d_lent, H.left_ent.data(), H.left_ent.size(), s));
+    CKH(upload(h->d_rent, H.right_ent.data(), H.right_ent.size(), s));
+    WqDevIndex& ix = h->dix;
+    ix.occ = h->d_occ.p; ix.sa = h->d_sa.p; ix.text2 = h->d_text2.p; ix.amb = H.has_amb ? h->d_amb.p : nullptr;
+    ix.nodes = h->d_nodes.p; ix.genes = h->d_genes.p; ix.node_bucket = h->d_bucket.p;
+    ix.left_ptr = h->d_lptr.p; ix.left_ent = h->d_lent.p; ix.right_ptr = h->d_rptr.p; ix.right_ent = h->d_rent.p;
+    ix.n = H.n; ix.sentinel = H.sentinel;
+    for (int i = 0; i < 4; i++) ix.C[i] = H.C[i];
+    ix.N = H.N; ix.G = H.G; ix.K = H.K;
+    // free the bulky host mirrors the quant stage does not need
+    std::vector<WqOccBlock>().swap(H.occ);
+    std::vector<uint64_t>().swap(H.text2);
+    std::vector<uint32_t>().swap(H.amb);
+    std::vector<uint32_t>().swap(H.node_bucket);
+    // L2 persisting window over the occurrence blocks (the hot random-access structure of kernel 1)
+    {
+        size_t occ_bytes = h->d_occ.cap * sizeof(WqOccBlock);
+        size_t maxp = (size_t)prop.persistingL2CacheMaxSize;
+        if (maxp > 0 && env_u64("WQ_L2_PERSIST", 1)) {
+            size_t want = std::min(occ_bytes, maxp);
+            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+            cudaStreamAttrValue attr;
+            memset(&attr, 0, sizeof attr);
+            attr.accessPolicyWindow.base_ptr = (void*)h->d_occ.p;
+            attr.accessPolicyWindow.num_bytes = std::min(occ_bytes, (size_t)prop.accessPolicyMaxWindowSize);
+            attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)want / (double)std::max<size_t>(1, attr.accessPolicyWindow.num_bytes));
+            attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+            cudaGetLastError();
+            h->l2attr = attr; h->has_l2attr = true;
+        }
+    }
+    // count stores
+    h->edge_slots = pow2_at_least(env_u64("WQ_EDGE_SLOTS", std::max<uint64_t>(1u << 16, 8ull * H.N)));
+    h->keyed_slots = pow2_at_least(env_u64("WQ_KEYED_SLOTS", std::max<uint64_t>(1u << 16, 16ull * H.N)));
+    h->kpool_cap = env_u64("WQ_KEYED_POOL_WORDS", std::max<uint64_t>(1u << 20, 128ull * H.N));
+    CKH(h->d_dense.ensure(H.N + sizeof(WqCounters) / 8));
+    CKH(h->d_ekey.ensure(h->edge_slots)); CKH(h->d_ecount.ensure(h->edge_slots));
+    CKH(h->d_khash.ensure(h->keyed_slots)); CKH(h->d_kcount.ensure(h->keyed_slots)); CKH(h->d_koff.ensure(h->keyed_slots));
+    CKH(h->d_kpool.ensure(h->kpool_cap)); CKH(h->d_kcursor.ensure(1));
+    CKH(h->d_cursors.ensure(16));
+    h->q.node_count = h->d_dense.p;
+    h->q.counters = reinterpret_cast<WqCounters*>(h->d_dense.p + H.N);
+    h->q.edges = WqEdgeTable{h->d_ekey.p, h->d_ecount.p, h->edge_slots - 1};
+    h->q.keyed = WqKeyedTable{h->d_khash.p, h->d_koff.p, h->d_kcount.p, h->d_kpool.p, h->d_kcursor.p, h->kpool_cap, h->keyed_slots - 1};
+    h->chunk_reads = (uint32_t)env_u64("WQ_CHUNK_READS", 1u << 21);
+    int rc = wq_quant_reset(h);
+    if (rc) { wq_destroy(h); return rc; }
+    CKH(cudaStreamSynchronize(s));
+#undef CKH
+    *out = h;
+    return 0;
+}
+
+// Run the three kernels over reads [0, b.n) already resident on the device.
+static int run_chunk(wq_handle* h, const WqParams& p, const WqBatchDev& b, bool time_kernels) {
+    const uint32_t n = b.n;
+    if (n == 0) return 0;
+    cudaStream_t s = h->stream;
+    const uint32_t hit_cap = n * (uint32_t)p.seed_tolerate;
+    const uint32_t pool_cap = (uint32_t)std::min<uint64_t>((uint64_t)n * 8 + 1024, 0xFFFFFFF0ull);
+    CK(h->d_seeds.ensure(n)); CK(h->d_hit_read.ensure(hit_cap)); CK(h->d_hit_s.ensure(hit_cap)); CK(h->d_hits.ensure(hit_cap));
+    CK(h->d_pool.ensure(pool_cap)); CK(h->d_pending.ensure(n)); CK(h->d_pending2.ensure(n));
+    WqWork wk{h->d_seeds.p, h->d_hit_read.p, h->d_hit_s.p, h->d_hits.p, h->d_pool.p, h->d_cursors.p, h->d_pending.p, hit_cap, pool_cap};
+    CK(cudaMemsetAsync(h->d_cursors.p, 0, 16 * sizeof(uint32_t), s));
+    cudaEvent_t ev[4];
+    if (time_kernels) for (auto& e : ev) CK(cudaEventCreate(&e));
+    const int T = 128;
+    if (time_kernels) CK(cudaEventRecord(ev[0], s));
+    wq_k_seed<<<(n + T - 1) / T, T, 0, s>>>(h->dix, p, b, wk);
+    h->launches += 3;
+    if (time_kernels) CK(cudaEventRecord(ev[1], s));
+    wq_k_extend<<<(hit_cap + T - 1) / T, T, 0, s>>>(h->dix, p, b, wk);
+    if (time_kernels) CK(cudaEventRecord(ev[2], s));
+    wq_k_resolve<<<(n + T - 1) / T, T, 0, s>>>(h->dix, p, b, wk, h->q);
+    if (time_kernels) CK(cudaEventRecord(ev[3], s));
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(h->h_cursors, h->d_cursors.p, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (time_kernels) {
+        for (int i = 0; i < 3; i++) { float ms = 0; cudaEventElapsedTime(&ms, ev[i], ev[i + 1]); h->last_kernel_ms[i] += ms; }
+        for (auto& e : ev) cudaEventDestroy(e);
+    }
+    if (h->h_cursors[1] > pool_cap) return fail(-5, "alignment path pool exhausted for this batch (raise WQ_CHUNK_READS granularity or report)");
+    // keyed inserts that raced with the slot owner: retry until none is left
+    uint32_t pending = h->h_cursors[2];
+    int guard = 0;
+    while (pending) {
+        if (++guard > 64) return fail(-6, "keyed store retry did not converge");
+        CK(cudaMemcpyAsync(h->d_pending2.p, h->d_pending.p, pending * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+        const uint32_t* list = h->d_pending2.p;
+        CK(cudaMemsetAsync(h->d_cursors.p + 2, 0, sizeof(uint32_t), s));
+        wq_k_retry<<<(pending + T - 1) / T, T, 0, s>>>(h->dix, wk, h->q, list, pending);
+        h->launches += 1;
+        CK(cudaMemcpyAsync(h->h_cursors, h->d_cursors.p, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        pending = h->h_cursors[2];
+    }
+    return 0;
+}
+
+static int check_batch(const wq_read_batch* r) {
+    if (!r) return fail(-1, "null read batch");
+    if (r->n_reads && (!r->len || !r->seq_off || !r->seq2 || !r->qual_off || !r->qual)) return fail(-1, "read batch has null arrays");
+    return 0;
+}
+
+// Download the alignments of the chunk just processed (reads [first, first+n) of the caller's batch).
+static int collect_chunk(wq_handle* h, uint32_t first, uint32_t n, wq_align_out* out) {
+    cudaStream_t s = h->stream;
+    uint32_t nh = h->h_cursors[0], np = h->h_cursors[1];
+    std::vector<WqSeed> seeds(n);
+    std::vector<WqHit> hits(nh);
+    std::vector<wq_align_node> pool(np);
+    CK(cudaMemcpyAsync(seeds.data(), h->d_seeds.p, n * sizeof(WqSeed), cudaMemcpyDeviceToHost, s));
+    if (nh) CK(cudaMemcpyAsync(hits.data(), h->d_hits.p, nh * sizeof(WqHit), cudaMemcpyDeviceToHost, s));
+    if (np) CK(cudaMemcpyAsync(pool.data(), h->d_pool.p, np * sizeof(wq_align_node), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    for (uint32_t i = 0; i < n; i++) {
+        const WqSeed& sd = seeds[i];
+        uint32_t r = first + i;
+        out->hit_start[r] = (uint32_t)out->aln_used;
+        uint8_t c = 0;
+        for (int k = 0; k < sd.cnt; k++) {
+            const WqHit& hh = hits[sd.hit_base + k];
+            if (!(hh.flags & 4)) continue;
+            if (out->aln_used >= out->aln_cap || out->nodes_used + hh.npath > out->nodes_cap)
+                return fail(-7, "wq_align_out capacity too small");
+            wq_alignment a;
+            a.offset = hh.offset; a.path_start = (uint32_t)out->nodes_used; a.offsetread = hh.offsetread;
+            a.strand = hh.strand; a.isvalid = hh.flags & 1; a.npath = hh.npath;
+            out->aln[out->aln_used++] = a;
+            memcpy(out->nodes + out->nodes_used, pool.data() + hh.path_start, hh.npath * sizeof(wq_align_node));
+            out->nodes_used += hh.npath;
+            c++;
+        }
+        out->nhits[r] = c;
+        out->flipped[r] = (sd.cnt > 0 && !sd.strand) ? 1 : 0;
+    }
+    return 0;
+}
+
+static int align_se_impl(wq_handle* h, const wq_align_param* ap, const wq_read_batch* reads, wq_align_out* out, bool on_device) {
+    if (!h || !ap) return fail(-1, "null argument");
+    if (int rc = check_batch(reads)) return rc;
+    CK(cudaSetDevice(h->device));
+    WqParams p;
+    std::string err = wq_make_params(ap, h->H.K, p);
+    if (!err.empty()) return fail(-4, err);
+    if (out) { out->aln_used = 0; out->nodes_used = 0; }
+    const uint32_t n = reads->n_reads;
+    if (n == 0) return 0;
+    h->hq_valid = false;
+    for (auto& m : h->last_kernel_ms) m = 0;
+    if (on_device) {
+        for (uint32_t lo = 0; lo < n; lo += h->chunk_reads) {
+            uint32_t m = std::min(h->chunk_reads, n - lo);
+            WqBatchDev b{m, reads->len + lo, reads->seq_off + lo, reads->seq2, reads->qual_off + lo, reads->qual};
+            if (int rc = run_chunk(h, p, b, true)) return rc;
+        }
+        return 0;
+    }
+    // host buffers: copy the packed arrays once, then run chunk by chunk
+    cudaStream_t s = h->stream;
+    CK(h->d_len[0].ensure(n)); CK(h->d_seqoff[0].ensure(n)); CK(h->d_qualoff[0].ensure(n));
+    CK(h->d_seq2[0].ensure(reads->seq2_words + 2)); CK(h->d_qual[0].ensure(reads->qual_bytes + 16));
+    CK(cudaMemcpyAsync(h->d_len[0].p, reads->len, n, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(h->d_seqoff[0].p, reads->seq_off, n * 8ull, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(h->d_qualoff[0].p, reads->qual_off, n * 8ull, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(h->d_seq2[0].p, reads->seq2, reads->seq2_words * 8ull, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(h->d_qual[0].p, reads->qual, reads->qual_bytes, cudaMemcpyHostToDevice, s));
+    for (uint32_t lo = 0; lo < n; lo += h->chunk_reads) {
+        uint32_t m = std::min(h->chunk_reads, n - lo);
+        WqBatchDev b{m, h->d_len[0].p + lo, h->d_seqoff[0].p + lo, h->d_seq2[0].p, h->d_qualoff[0].p + lo, h->d_qual[0].p};
+        if (int rc = run_chunk(h, p, b, false)) return rc;
+        if (out) if (int rc = collect_chunk(h, lo, m, out)) return rc;
+    }
+    return 0;
+}
+
+int wq_align_se(wq_handle* h, const wq_align_param* p, const wq_read_batch* reads, wq_align_out* out) {
+    return align_se_impl(h, p, reads, out, false);
+}
+int wq_align_se_device(wq_handle* h, const wq_align_param* p, const wq_read_batch* reads) {
+    return align_se_impl(h, p, reads, nullptr, true);
+}
+int wq_align_pe(wq_handle*, const wq_align_param*, const wq_read_batch*, const wq_read_batch*, wq_align_out*) {
+    return fail(-99, "paired-end alignment is not built yet");
+}
+int wq_align_pe_device(wq_handle*, const wq_align_param*, const wq_read_batch*, const wq_read_batch*) {
+    return fail(-99, "paired-end alignment is not built yet");
+}
+
+// per-kernel device milliseconds of the last wq_align_*_device call: [seed, extend, resolve]
+int wq_last_kernel_ms(wq_handle* h, float* ms3) {
+    if (!h || !ms3) return fail(-1, "null argument");
+    for (int i = 0; i < 3; i++) ms3[i] = h->last_kernel_ms[i];
+    return 0;
+}
+
+// Run all work of this handle on a caller-owned stream (NULL restores the handle's own stream), so a
+// host that times with its own events, or orders work against its own copies, sees the kernels.
+int wq_set_stream(wq_handle* h, void* stream) {
+    if (!h) return fail(-1, "null handle");
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    h->stream = stream ? (cudaStream_t)stream : h->own_stream;
+    if (h->has_l2attr) { cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &h->l2attr); cudaGetLastError(); }
+    return 0;
+}
+
+uint64_t wq_launch_count(wq_handle* h) { return h ? h->launches : 0; }
+
+int wq_map_stats_get(wq_handle* h, wq_map_stats* out) {
+    if (!h || !out) return fail(-1, "null argument");
+    CK(cudaSetDevice(h->device));
+    WqCounters c;
+    CK(cudaMemcpy(&c, h->q.counters, sizeof c, cudaMemcpyDeviceToHost));
+    out->total = c.total; out->mapped = c.mapped; out->multi = c.multi; out->sum_readlen = c.sum_readlen;
+    out->path_overflow = c.path_overflow;
+    if (c.edge_full) return fail(-8, "edge count table is full (raise WQ_EDGE_SLOTS)");
+    if (c.keyed_full) return fail(-8, "keyed count store is full (raise WQ_KEYED_SLOTS / WQ_KEYED_POOL_WORDS)");
+    if (c.pool_overflow) return fail(-8, "alignment path pool overflowed");
+    return 0;
+}
+
+int wq_counts_device_ptr(wq_handle* h, void** dptr, uint64_t* n_u64) {
+    if (!h || !dptr || !n_u64) return fail(-1, "null argument");
+    *dptr = h->d_dense.p;
+    *n_u64 = h->H.N + 4;     // node counts + total, mapped, multi, sum_readlen
+    return 0;
+}
+
+// Pull the device count stores into the handle's host-side quant state (sorted, canonical order).
+static int sync_host_quant(wq_handle* h) {
+    if (h->hq_valid) return 0;
+    CK(cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    WqHostQuant& Q = h->hq;
+    const uint32_t N = h->H.N;
+    std::vector<uint64_t> dense(N + sizeof(WqCounters) / 8);
+    CK(cudaMemcpyAsync(dense.data(), h->d_dense.p, dense.size() * 8, cudaMemcpyDeviceToHost, s));
+    std::vector<uint64_t> ekey(h->edge_slots), ecount(h->edge_slots), khash(h->keyed_slots), kcount(h->keyed_slots);
+    std::vector<uint32_t> koff(h->keyed_slots);
+    uint64_t kcur = 0;
+    CK(cudaMemcpyAsync(ekey.data(), h->d_ekey.p, h->edge_slots * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(ecount.data(), h->d_ecount.p, h->edge_slots * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(khash.data(), h->d_khash.p, h->keyed_slots * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(kcount.data(), h->d_kcount.p, h->keyed_slots * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(koff.data(), h->d_koff.p, h->keyed_slots * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(&kcur, h->d_kcursor.p, 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    std::vector<uint32_t> kpool(std::min<uint64_t>(kcur, h->kpool_cap));
+    if (!kpool.empty()) CK(cudaMemcpy(kpool.data(), h->d_kpool.p, kpool.size() * 4, cudaMemcpyDeviceToHost));
+    Q = WqHostQuant();
+    Q.node.assign(dense.begin(), dense.begin() + N);
+    memcpy(&Q.stats, dense.data() + N, sizeof(WqCounters));
+    for (uint64_t i = 0; i < h->edge_slots; i++)
+        if (ekey[i] != WQ_EMPTY_KEY) Q.edge[ekey[i]] += (double)ecount[i];
+    for (uint64_t i = 0; i < h->keyed_slots; i++) {
+        if (khash[i] == 0) continue;
+        if (koff[i] >= WQ_KEYOFF_FULL) return fail(-8, "keyed count store overflowed");
+        uint32_t nw = kpool[koff[i]];
+        std::vector<uint32_t> key(kpool.begin() + koff[i] + 1, kpool.begin() + koff[i] + 1 + nw);
+        Q.keyed[key] += kcount[i];
+    }
+    h->hq_valid = true;
+    return 0;
+}
+
+int wq_counts_download(wq_handle* h, wq_counts* c) {
+    if (!h || !c) return fail(-1, "null argument");
+    if (int rc = sync_host_quant(h)) return rc;
+    WqHostQuant& Q = h->hq;
+    uint64_t ne = 0, nc = 0;
+    for (auto& kv : Q.edge) { if (wq_edge_is_circ(kv.first)) nc++; else ne++; }
+    bool sizing = !c->node_count && !c->edge_key && !c->circ_key;
+    if (!sizing && (c->n_nodes < Q.node.size() || c->n_edge < ne || c->n_circ < nc)) return fail(-7, "wq_counts buffers too small");
+    c->n_nodes = Q.node.size(); c->n_edge = ne; c->n_circ = nc;
+    if (sizing) return 0;
+    if (c->node_count) memcpy(c->node_count, Q.node.data(), Q.node.size() * 8);
+    uint64_t ie = 0, ic = 0;
+    for (auto& kv : Q.edge) {
+        if (wq_edge_is_circ(kv.first)) { if (c->circ_key) { c->circ_key[ic] = kv.first; c->circ_count[ic] = (uint64_t)kv.second; } ic++; }
+        else { if (c->edge_key) { c->edge_key[ie] = kv.first; c->edge_count[ie] = (uint64_t)kv.second; } ie++; }
+    }
+    return 0;
+}
+
+int wq_keyed_download(wq_handle* h, int kind, wq_keyed* k) {
+    if (!h || !k) return fail(-1, "null argument");
+    if (kind != 0 && kind != 1) return fail(-1, "kind must be 0 (long paths) or 1 (multi-map classes)");
+    if (int rc = sync_host_quant(h)) return rc;
+    uint64_t nrec = 0, nwords = 0;
+    for (auto& kv : h->hq.keyed)
+        if (wq_key_is_multi(kv.first) == (kind == 1)) { nrec++; nwords += kv.first.size(); }
+    bool sizing = !k->rec_ptr && !k->words && !k->count;
+    if (!sizing && (k->n_rec < nrec || k->n_words < nwords)) return fail(-7, "wq_keyed buffers too small");
+    k->n_rec = nrec; k->n_words = nwords;
+    if (sizing) return 0;
+    uint64_t i = 0, w = 0;
+    for (auto& kv : h->hq.keyed) {
+        if (wq_key_is_multi(kv.first) != (kind == 1)) continue;
+        k->rec_ptr[i] = w;
+        memcpy(k->words + w, kv.first.data(), kv.first.size() * 4);
+        w += kv.first.size();
+        k->count[i] = kv.second;
+        i++;
+    }
+    k->rec_ptr[nrec] = w;
+    return 0;
+}
+
+int wq_counts_merge(wq_handle* h, const wq_counts* c, const wq_keyed* longs, const wq_keyed* multis) {
+    if (!h) return fail(-1, "null handle");
+    if (int rc = sync_host_quant(h)) return rc;
+    WqHostQuant& Q = h->hq;
+    if (c) {
+        if (c->node_count) {
+            if (c->n_nodes != Q.node.size()) return fail(-1, "node count vector has the wrong length");
+            for (size_t i = 0; i < Q.node.size(); i++) Q.node[i] += c->node_count[i];
+        }
+        for (uint64_t i = 0; i < c->n_edge; i++) Q.edge[c->edge_key[i]] += (double)c->edge_count[i];
+        for (uint64_t i = 0; i < c->n_circ; i++) Q.edge[c->circ_key[i]] += (double)c->circ_count[i];
+    }
+    for (const wq_keyed* k : {longs, multis}) {
+        if (!k) continue;
+        for (uint64_t i = 0; i < k->n_rec; i++) {
+            std::vector<uint32_t> key(k->words + k->rec_ptr[i], k->words + k->rec_ptr[i + 1]);
+            Q.keyed[key] += k->count[i];
+        }
+    }
+    return 0;
+}
+
+// Replace the dense part of the host quant state after an NCCL all-reduce of wq_counts_device_ptr.
+int wq_counts_refresh_dense(wq_handle* h) {
+    if (!h) return fail(-1, "null handle");
+    if (int rc = sync_host_quant(h)) return rc;
+    const uint32_t N = h->H.N;
+    std::vector<uint64_t> dense(N + sizeof(WqCounters) / 8);
+    CK(cudaMemcpy(dense.data(), h->d_dense.p, dense.size() * 8, cudaMemcpyDeviceToHost));
+    h->hq.node.assign(dense.begin(), dense.begin() + N);
+    memcpy(&h->hq.stats, dense.data() + N, sizeof(WqCounters));
+    return 0;
+}
+
+int wq_em_tpm(wq_handle* h, const wq_em_param* p, double* tpm, double* count, double* genetpm, int64_t* iterations) {
+    if (!h || !p) return fail(-1, "null argument");
+    if (int rc = sync_host_quant(h)) return rc;
+    CK(cudaSetDevice(h->device));
+    std::string err = wq_run_em_tpm(h->H, h->iso, h->hq, *p, h->stream, tpm, count, genetpm, iterations);
+    if (!err.empty()) return fail(-11, err);
+    return 0;
+}
+
+int wq_assign_ambig(wq_handle* h, wq_values* v) {
+    if (!h || !v) return fail(-1, "null argument");
+    if (int rc = sync_host_quant(h)) return rc;
+    std::string err = wq_host_assign_ambig(h->H, h->iso, h->hq, v);
+    if (!err.empty()) return fail(-12, err);
+    return 0;
+}
+
+int wq_em_psi_batch(wq_handle* h, wq_psi_batch* b) {
+    if (!h || !b) return fail(-1, "null argument");
+    CK(cudaSetDevice(h->device));
+    std::string err = wq_run_em_psi(*b, h->stream);
+    if (!err.empty()) return fail(-13, err);
+    return 0;
+}
+
+}  // extern "C"

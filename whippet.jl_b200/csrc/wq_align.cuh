@@ -1,0 +1,634 @@
+// Device-side seeding and ungapped splice-graph extension.
+//
+// What it computes (bit-exact with the reference, which it cites, but organised for a GPU thread:
+// 2-bit words compared 32 bases at a time with XOR/popc, occurrence blocks of one sector each,
+// node records of one sector each, an explicit per-thread path array instead of heap vectors):
+//   fm_search      FMIndexes.sa_range override        /root/reference/src/fmindex_patch.jl:19-31
+//   seed_locate    seed scheduling                     src/align.jl:145-185
+//   fwd_extend     ungapped_fwd_extend + closure       src/align.jl:275-418
+//   rev_extend     ungapped_rev_extend + closure       src/align.jl:423-575
+//   align_at       _ungapped_align                     src/align.jl:209-223
+#pragma once
+#include "wq_types.h"
+
+#if defined(__CUDA_ARCH__)
+#define WQ_LDG(p) __ldg(p)
+#define WQ_POPCLL(x) __popcll(x)
+#define WQ_CTZLL(x) (__ffsll((long long)(x)) - 1)
+#define WQ_CLZLL(x) __clzll((long long)(x))
+#else
+#define WQ_LDG(p) (*(p))
+#define WQ_POPCLL(x) __builtin_popcountll(x)
+#define WQ_CTZLL(x) __builtin_ctzll(x)
+#define WQ_CLZLL(x) __builtin_clzll(x)
+#endif
+
+struct WqParams {                  // AlignParam in kernel-friendly types
+    int32_t mismatches, K, seed_try, seed_tolerate, seed_min_qual, seed_length, seed_buffer, seed_inc, seed_pair_range;
+    float   mmlimit;               // Float32(mismatches): `mistol <= p.mismatches`
+    float   kf;                    // Float32(kmer_size)
+    double  score_range, score_min;
+    uint8_t is_stranded, is_pair_rc;
+    float   phred_prob[128];       // phred_to_prob, src/align.jl:124 (host-computed table)
+};
+
+struct WqCtx {
+    const WqDevIndex* ix;
+    const WqParams*   p;
+    uint64_t w[WQ_MAX_READ_WORDS + 1];   // read in alignment orientation, zero padded
+    const uint8_t* qual;                 // global, original orientation
+    int32_t  readlen;
+    uint8_t  flipped;
+    uint8_t  overflow;                   // path longer than WQ_MAX_PATH or nesting deeper than WQ_MAX_DEPTH
+    uint8_t  depth;
+    // gene being aligned against
+    uint32_t gene, gstart, seqlen, gbase, nn;
+};
+
+// ---------------------------------------------------------------- read access
+WQ_HD uint32_t wq_rbase(const WqCtx& c, int j) { return (uint32_t)(c.w[j >> 5] >> (2 * (j & 31))) & 3u; }
+WQ_HD float wq_rprob(const WqCtx& c, int j) {   // j 0-based in alignment orientation
+    uint8_t q = WQ_LDG(c.qual + (c.flipped ? c.readlen - 1 - j : j));
+    return c.p->phred_prob[q & 127];
+}
+// 32 bases of the read starting at 0-based j (bases past the end are zero)
+WQ_HD uint64_t wq_rext(const WqCtx& c, int j) {
+    int wi = j >> 5, s = 2 * (j & 31);
+    uint64_t v = c.w[wi] >> s;
+    if (s) v |= c.w[wi + 1] << (64 - s);
+    return v;
+}
+// kmer_index(read.sequence[a:a+K-1]) - 1, first base most significant (src/sgkmer.jl:12-26); a 1-based
+WQ_HD uint32_t wq_read_kmer(const WqCtx& c, int a, int K) {
+    uint32_t x = 0;
+    for (int i = 0; i < K; i++) x = (x << 2) | wq_rbase(c, a - 1 + i);
+    return x;
+}
+// reverse complement of `len` bases held in w[] (reverse_complement!, src/record.jl:23-26)
+WQ_HD void wq_revcomp(uint64_t* w, int len) {
+    uint64_t r[WQ_MAX_READ_WORDS + 1];
+    for (int i = 0; i <= WQ_MAX_READ_WORDS; i++) r[i] = 0;
+    for (int j = 0; j < len; j++) {
+        int s = len - 1 - j;
+        uint64_t b = 3 - ((w[s >> 5] >> (2 * (s & 31))) & 3);
+        r[j >> 5] |= b << (2 * (j & 31));
+    }
+    for (int i = 0; i <= WQ_MAX_READ_WORDS; i++) w[i] = r[i];
+}
+
+// ---------------------------------------------------------------- text access
+// mismatch mask (bit 2k set = base k differs) between 32 read bases and the text at 0-based pos
+WQ_HD uint64_t wq_text_mism(const WqDevIndex& ix, uint64_t pos, uint64_t rword) {
+    uint64_t wi = pos >> 5;
+    int s = 2 * (int)(pos & 31);
+    uint64_t t = WQ_LDG(ix.text2 + wi) >> s;
+    if (s) t |= WQ_LDG(ix.text2 + wi + 1) << (64 - s);
+    uint64_t x = t ^ rword;
+    uint64_t m = (x | (x >> 1)) & 0x5555555555555555ull;
+    if (ix.amb) {   // an ambiguous reference base never equals a read base (DNA `==`, src/align.jl:367)
+        int s1 = (int)(pos & 31);
+        uint64_t a = (uint64_t)WQ_LDG(ix.amb + wi) >> s1;
+        if (s1) a |= (uint64_t)WQ_LDG(ix.amb + wi + 1) << (32 - s1);
+        a &= 0xffffffffull;
+        // spread 32 bits to even bit positions
+        a = (a | (a << 16)) & 0x0000ffff0000ffffull;
+        a = (a | (a << 8)) & 0x00ff00ff00ff00ffull;
+        a = (a | (a << 4)) & 0x0f0f0f0f0f0f0f0full;
+        a = (a | (a << 2)) & 0x3333333333333333ull;
+        a = (a | (a << 1)) & 0x5555555555555555ull;
+        m |= a;
+    }
+    return m;
+}
+
+// ---------------------------------------------------------------- node access (1-based node ids)
+WQ_HD const WqNodeRec* wq_node(const WqCtx& c, uint32_t nodeidx) { return c.ix->nodes + (c.gbase + nodeidx - 1); }
+WQ_HD uint32_t wq_nodeoffset(const WqCtx& c, uint32_t nodeidx) { return WQ_LDG(&wq_node(c, nodeidx)->abs_start) - c.gstart + 1; }
+WQ_HD uint32_t wq_nodelen(const WqCtx& c, uint32_t nodeidx) { return WQ_LDG(&wq_node(c, nodeidx)->len); }
+// edgetype[j] for 1 <= j <= nn+1
+WQ_HD uint8_t wq_edgetype(const WqCtx& c, uint32_t j) {
+    return j <= c.nn ? WQ_LDG(&wq_node(c, j)->et_left) : WQ_LDG(&wq_node(c, c.nn)->et_right);
+}
+
+// ---------------------------------------------------------------- path helpers (src/align.jl:90-115)
+WQ_HD float wq_score(const WqAlign& a) {
+    float s = 0.f;
+    for (int i = 0; i < a.npath; i++) s += (float)a.p[i].m - a.p[i].tol;
+    return s;
+}
+WQ_HD float wq_mistol(const WqAlign& a) {
+    float s = 0.f;
+    for (int i = 0; i < a.npath; i++) s += a.p[i].tol;
+    return s;
+}
+WQ_HD uint8_t wq_matches(const WqAlign& a, int from, int to) {
+    uint8_t m = 0;
+    for (int i = from; i < to; i++) m = (uint8_t)(m + a.p[i].m);
+    return m;
+}
+WQ_HD float wq_identity(const WqAlign& a, int readlen) { return wq_score(a) / (float)readlen; }
+WQ_HD bool wq_isvalid(const WqAlign& a) {
+    return a.isvalid && a.npath >= 1 && (float)wq_matches(a, 0, a.npath) > wq_mistol(a);
+}
+WQ_HD void wq_copy(WqAlign& d, const WqAlign& s) {
+    d.offset = s.offset; d.offsetread = s.offsetread; d.npath = s.npath; d.isvalid = s.isvalid; d.strand = s.strand;
+    for (int i = 0; i < s.npath; i++) d.p[i] = s.p[i];
+}
+WQ_HD void wq_push_back(WqCtx& c, WqAlign& a, uint32_t node, uint8_t m) {
+    if (a.npath >= WQ_MAX_PATH) { c.overflow = 1; return; }
+    WqPNode& n = a.p[a.npath++];
+    n.node = node; n.tol = 0.f; n.m = m; n.mm = 0; n._pad = 0;
+}
+WQ_HD void wq_push_front(WqCtx& c, WqAlign& a, uint32_t node, uint8_t m) {
+    if (a.npath >= WQ_MAX_PATH) { c.overflow = 1; return; }
+    for (int i = a.npath; i > 0; i--) a.p[i] = a.p[i - 1];
+    a.npath++;
+    WqPNode& n = a.p[0];
+    n.node = node; n.tol = 0.f; n.m = m; n.mm = 0; n._pad = 0;
+}
+WQ_HD void wq_erase_front(WqAlign& a, int k) {
+    for (int i = k; i < a.npath; i++) a.p[i - k] = a.p[i];
+    a.npath = (uint8_t)(a.npath - k);
+}
+
+// ---------------------------------------------------------------- FM index
+// occurrences of ch in bwt[0..i)
+WQ_HD uint32_t wq_occ(const WqDevIndex& ix, uint32_t ch, uint64_t i) {
+    const WqOccBlock* b = ix.occ + (i >> 6);
+#if defined(__CUDA_ARCH__)
+    const uint4 planes = __ldg(reinterpret_cast<const uint4*>(&b->lo));
+    uint64_t lo = ((uint64_t)planes.y << 32) | planes.x, hi = ((uint64_t)planes.w << 32) | planes.z;
+    uint32_t base = __ldg(&b->cnt[ch]);
+#else
+    uint64_t lo = b->lo, hi = b->hi;
+    uint32_t base = b->cnt[ch];
+#endif
+    uint64_t m = ((ch & 1) ? lo : ~lo) & ((ch & 2) ? hi : ~hi);
+    uint32_t r = (uint32_t)(i & 63);
+    m &= (r ? (~0ull >> (64 - r)) : 0ull);
+    return base + (uint32_t)WQ_POPCLL(m);
+}
+
+// Backward search of `len` symbols read[start..start+len) (0-based, alignment orientation of c.w).
+// rc = search the reverse complement of that window instead.  Returns rows sp..ep (sp>ep: empty).
+WQ_HD void wq_fm_search(const WqCtx& c, int start, int len, bool rc, int64_t& sp, int64_t& ep) {
+    const WqDevIndex& ix = *c.ix;
+    sp = 1;
+    ep = (int64_t)ix.n + 1;
+    const int64_t sent = (int64_t)ix.sentinel;
+    for (int i = 0; i < len && sp <= ep; i++) {
+        // forward query is consumed last symbol first; the reverse complement consumes the window
+        // first symbol first, complemented
+        uint32_t ch = rc ? 3u - wq_rbase(c, start + i) : wq_rbase(c, start + len - 1 - i);
+        int64_t a = (sp > sent ? sp - 1 : sp) - 1;
+        int64_t b = (ep > sent ? ep - 1 : ep);
+        uint32_t oa = wq_occ(ix, ch, (uint64_t)a);
+        uint32_t ob = wq_occ(ix, ch, (uint64_t)b);
+        sp = (int64_t)ix.C[ch] + oa + 1;
+        ep = (int64_t)ix.C[ch] + ob;
+    }
+}
+
+WQ_HD int64_t wq_sa_value(const WqDevIndex& ix, int64_t row) {
+    return row == 1 ? (int64_t)ix.n : (int64_t)WQ_LDG(ix.sa + (row - 2));
+}
+
+// seed_locate (src/align.jl:145-185).  `badq` has bit j set when quality[j] <= seed_min_qual
+// (0-based, orientation of c.w).  Returns cnt (0 when no seed) and fills sp/readloc/strand.
+WQ_HD int wq_seed_locate(const WqCtx& c, const uint64_t* badq, bool offset_left, bool both_strands,
+                         int64_t& out_sp, int& out_readloc, bool& out_strand) {
+    const WqParams& p = *c.p;
+    const int readlen = c.readlen;
+    int ctry = 1;
+    int increment, increment_sm, curpos;
+    if (offset_left) { increment = p.seed_inc; increment_sm = 1; curpos = p.seed_buffer; }
+    else { increment = -p.seed_inc; increment_sm = -1; curpos = readlen - p.seed_length - p.seed_buffer; }
+    const int maxright = readlen - p.seed_length - p.seed_buffer;
+    out_strand = true;
+    while (ctry <= p.seed_try && p.seed_buffer <= curpos && curpos <= maxright) {
+        // minimum(quality[curpos : curpos+L-1]) <= seed_min_qual  <=>  any bad bit in the window
+        int a = curpos - 1, L = p.seed_length;
+        bool bad = false;
+        for (int j = a; j < a + L;) {
+            int wi = j >> 6, bo = j & 63;
+            int take = 64 - bo;
+            if (take > a + L - j) take = a + L - j;
+            uint64_t mask = (take == 64 ? ~0ull : ((1ull << take) - 1)) << bo;
+            if (badq[wi] & mask) { bad = true; break; }
+            j += take;
+        }
+        if (bad) { curpos += increment_sm; continue; }
+        int64_t sp, ep;
+        wq_fm_search(c, curpos - 1, L, false, sp, ep);
+        int64_t cnt = ep >= sp ? ep - sp + 1 : 0;
+        ctry += 1;
+        if (cnt == 0 || cnt > p.seed_tolerate) {
+            if (both_strands) {
+                int64_t rsp, rep;
+                wq_fm_search(c, curpos - 1, L, true, rsp, rep);
+                int64_t rcnt = rep >= rsp ? rep - rsp + 1 : 0;
+                if (0 < rcnt && rcnt <= p.seed_tolerate) {
+                    out_sp = rsp;
+                    out_readloc = readlen - (curpos + L - 1) + 1;
+                    out_strand = false;
+                    return (int)rcnt;
+                }
+            }
+        } else {
+            out_sp = sp;
+            out_readloc = curpos;
+            out_strand = true;
+            return (int)cnt;
+        }
+        curpos += increment;
+    }
+    out_sp = 2;
+    out_readloc = curpos;
+    return 0;
+}
+
+// ---------------------------------------------------------------- base-by-base walk, 32 at a time
+// Forward: compare read[ridx..] with gene position sgidx.. (both 1-based) for at most `lim` bases
+// with the per-base rules of src/align.jl:367-378; stops after the base that lifts mistol above the
+// limit.  Returns bases consumed.
+WQ_HD int wq_walk_fwd(const WqCtx& c, WqPNode& nd, float& mistol, int ridx, int64_t sgidx, int lim) {
+    int done = 0;
+    uint64_t tpos = (uint64_t)c.gstart + (uint64_t)sgidx - 1;
+    while (done < lim) {
+        int chunk = lim - done < 32 ? lim - done : 32;
+        uint64_t m = wq_text_mism(*c.ix, tpos + done, wq_rext(c, ridx - 1 + done));
+        if (chunk < 32) m &= (1ull << (2 * chunk)) - 1;
+        int prev = 0;
+        while (m) {
+            int b = WQ_CTZLL(m) >> 1;
+            m &= m - 1;
+            nd.m = (uint8_t)(nd.m + (b - prev));
+            float prob = wq_rprob(c, ridx - 1 + done + b);
+            nd.tol += prob;
+            mistol += prob;
+            nd.mm = (uint8_t)(nd.mm + 1);
+            prev = b + 1;
+            if (!(mistol <= c.p->mmlimit)) return done + prev;
+        }
+        nd.m = (uint8_t)(nd.m + (chunk - prev));
+        done += chunk;
+    }
+    return done;
+}
+// Reverse: compare read[ridx], read[ridx-1].. with gene positions sgidx, sgidx-1.. for at most `lim` bases.
+WQ_HD int wq_walk_rev(const WqCtx& c, WqPNode& nd, float& mistol, int ridx, int64_t sgidx, int lim) {
+    int done = 0;
+    while (done < lim) {
+        int chunk = lim - done < 32 ? lim - done : 32;
+        int r0 = ridx - done - chunk;                              // 0-based first read base of the chunk
+        uint64_t t0 = (uint64_t)c.gstart + (uint64_t)(sgidx - done - chunk);   // 0-based text pos of the chunk start
+        uint64_t m = wq_text_mism(*c.ix, t0, wq_rext(c, r0));
+        if (chunk < 32) m &= (1ull << (2 * chunk)) - 1;
+        int prev = chunk;                                          // bases [prev, chunk) already accounted
+        while (m) {
+            int b = (63 - WQ_CLZLL(m)) >> 1;
+            m &= ~(1ull << (2 * b));
+            nd.m = (uint8_t)(nd.m + (prev - 1 - b));
+            float prob = wq_rprob(c, r0 + b);
+            nd.tol += prob;
+            mistol += prob;
+            nd.mm = (uint8_t)(nd.mm + 1);
+            prev = b;
+            if (!(mistol <= c.p->mmlimit)) return done + (chunk - prev);
+        }
+        nd.m = (uint8_t)(nd.m + prev);
+        done += chunk;
+    }
+    return done;
+}
+
+// ---------------------------------------------------------------- extension
+WQ_HDN void wq_fwd_extend(WqCtx& c, int64_t sgidx, int ridx, WqAlign& align, uint32_t nodeidx);
+WQ_HDN void wq_rev_extend(WqCtx& c, int64_t sgidx, int ridx, WqAlign& align, uint32_t nodeidx);
+
+// spliced_fwd_extend (src/align.jl:287-311): candidates = edges.left[kmer(edgeleft[edge])] ∩ edges.right[read kmer]
+// under the gene-only ordering of src/edges.jl:15-18,40-55 (both cursors advance on a gene match,
+// the right-table entry is returned), same gene as the alignment only.
+WQ_HDN void wq_spliced_fwd(WqCtx& c, uint32_t edgeind, int ridx, uint32_t rkmer, WqAlign& align) {
+    const WqDevIndex& ix = *c.ix;
+    uint32_t rb = WQ_LDG(ix.right_ptr + rkmer), re = WQ_LDG(ix.right_ptr + rkmer + 1);
+    if (rb == re) return;
+    uint32_t lk = WQ_LDG(&wq_node(c, edgeind)->kleft);
+    uint32_t lb = WQ_LDG(ix.left_ptr + lk), le = WQ_LDG(ix.left_ptr + lk + 1);
+    if (lb == le) return;
+    if (c.depth >= WQ_MAX_DEPTH) { c.overflow = 1; return; }
+    WqAlign best;
+    wq_copy(best, align);
+    float best_score = wq_score(align);
+    const float base_score = best_score;
+    uint32_t i = lb, j = rb;
+    while (i < le && j < re) {
+        uint32_t ga = WQ_LDG(&ix.left_ent[i].x);
+        uint2 eb = WQ_LDG(&ix.right_ent[j]);
+        if (ga > eb.x) j++;
+        else if (ga < eb.x) i++;
+        else {
+            i++; j++;
+            if (eb.x != c.gene) continue;          // rn.gene == align.path[1].gene || continue
+            uint32_t rn_node = eb.y - c.gbase + 1;
+            int64_t rn_offset = (int64_t)wq_nodeoffset(c, rn_node);
+            WqAlign res;
+            wq_copy(res, align);                   // deepcopy(align)
+            c.depth++;
+            wq_fwd_extend(c, rn_offset, ridx, res, rn_node);
+            c.depth--;
+            float s = wq_score(res);
+            if (s > best_score) { wq_copy(best, res); best_score = s; }
+        }
+    }
+    if (best_score >= base_score + c.p->kf) best.isvalid = 1;
+    wq_copy(align, best);
+}
+
+// ungapped_fwd_extend (src/align.jl:275-418).  sgidx/ridx are 1-based as in the reference.
+WQ_HDN void wq_fwd_extend(WqCtx& c, int64_t sgidx, int ridx, WqAlign& align, uint32_t nodeidx) {
+    const WqParams& p = *c.p;
+    const int readlen = c.readlen;
+    const int K = p.K;
+    uint8_t passed[WQ_MAX_PATH];
+    int npassed = 0;
+    float mistol = wq_mistol(align);
+
+    wq_push_back(c, align, nodeidx, 0);
+
+    while (mistol <= p.mmlimit && ridx <= readlen && sgidx <= (int64_t)c.seqlen && !c.overflow) {
+        int64_t node_end = 0;
+        bool have_node = nodeidx <= c.nn;
+        if (have_node) {
+            const WqNodeRec* nr = wq_node(c, nodeidx);
+            node_end = (int64_t)(WQ_LDG(&nr->abs_start) - c.gstart + 1) + (int64_t)WQ_LDG(&nr->len);
+        }
+        if (have_node && sgidx == node_end) {   // hit next edge
+            uint32_t curedge = nodeidx + 1;
+            uint8_t et = wq_edgetype(c, curedge);
+            if (et == WQ_LR && (int64_t)wq_nodelen(c, curedge) >= K && readlen - ridx + 1 >= K) {
+                uint32_t rkmer = wq_read_kmer(c, ridx, K);
+                if (WQ_LDG(&wq_node(c, curedge)->kright) == rkmer) {
+                    ridx += K - 1;
+                    sgidx += K - 1;
+                    nodeidx += 1;
+                    wq_push_back(c, align, nodeidx, (uint8_t)(K - 1));
+                    align.isvalid = 1;
+                } else {
+                    wq_spliced_fwd(c, curedge, ridx, rkmer, align);
+                    break;
+                }
+            } else if (et == WQ_LR || et == WQ_LL) {
+                if (npassed < WQ_MAX_PATH) passed[npassed++] = align.npath; else c.overflow = 1;
+                nodeidx += 1;
+                wq_push_back(c, align, nodeidx, 0);
+            } else if (et == WQ_LS) {
+                if (readlen - ridx + 1 >= K) {
+                    uint32_t rkmer = wq_read_kmer(c, ridx, K);
+                    wq_spliced_fwd(c, curedge, ridx, rkmer, align);
+                }
+                break;
+            } else if (et == WQ_SR) {
+                break;
+            } else {   // 'RR' || 'SL' || 'RS'
+                nodeidx += 1;
+                if (nodeidx <= c.nn) wq_push_back(c, align, nodeidx, 0);
+            }
+            if (c.overflow) break;
+            // the base at (ridx, sgidx) is compared in this same iteration; the next edge test happens
+            // only after it (an `if`, not a `while`: src/align.jl:314)
+            have_node = nodeidx <= c.nn;
+            if (have_node) {
+                const WqNodeRec* nr = wq_node(c, nodeidx);
+                node_end = (int64_t)(WQ_LDG(&nr->abs_start) - c.gstart + 1) + (int64_t)WQ_LDG(&nr->len);
+            }
+        }
+        int lim = readlen - ridx + 1;
+        int64_t l2 = (int64_t)c.seqlen - sgidx + 1;
+        if (l2 < lim) lim = (int)l2;
+        if (have_node && sgidx < node_end && node_end - sgidx < lim) lim = (int)(node_end - sgidx);
+        int used = wq_walk_fwd(c, align.p[align.npath - 1], mistol, ridx, sgidx, lim);
+        ridx += used;
+        sgidx += used;
+    }
+
+    // passed-edge backtracking (src/align.jl:382-405)
+    for (int ci = npassed; ci >= 1 && !c.overflow; ci--) {
+        int cval = passed[ci - 1];
+        if ((int)wq_matches(align, cval, align.npath) >= K + p.mismatches) {
+            align.isvalid = 1;
+            break;
+        } else {
+            if (cval > align.npath) { c.overflow = 1; break; }      // undefined in the reference (out-of-bounds under @inbounds)
+            uint32_t cur_edge = align.p[cval - 1].node + 1;
+            align.npath = (uint8_t)cval;
+            int64_t cur_ridx = (int64_t)ridx - (sgidx - (int64_t)wq_nodeoffset(c, cur_edge));
+            if (!((cur_ridx + K - 1) <= readlen)) continue;
+            uint32_t rkmer = wq_read_kmer(c, (int)cur_ridx, K);
+            WqAlign res;
+            wq_copy(res, align);
+            wq_spliced_fwd(c, cur_edge, (int)cur_ridx, rkmer, res);
+            if (res.npath > align.npath) {
+                if (wq_score(res) > wq_score(align)) wq_copy(align, res);
+            }
+        }
+    }
+
+    // clean up bad trailing nodes (src/align.jl:408-412)
+    while (align.npath >= 1 && (align.p[align.npath - 1].mm >= align.p[align.npath - 1].m ||
+                                (int)align.p[align.npath - 1].m - (int)align.p[align.npath - 1].mm <= 1)) {
+        align.npath--;
+        if (align.npath == 0) align.isvalid = 0;
+    }
+    if ((double)wq_identity(align, readlen) >= p.score_min) align.isvalid = 1;
+}
+
+// spliced_rev_extend (src/align.jl:437-461): edges.right[kmer(edgeright[edge])] ∩ edges.left[read kmer],
+// returning the left-table entries.
+WQ_HDN void wq_spliced_rev(WqCtx& c, uint32_t edgeind, int ridx, uint32_t lkmer, WqAlign& align) {
+    const WqDevIndex& ix = *c.ix;
+    uint32_t lb = WQ_LDG(ix.left_ptr + lkmer), le = WQ_LDG(ix.left_ptr + lkmer + 1);
+    if (lb == le) return;
+    uint32_t rk = WQ_LDG(&wq_node(c, edgeind)->kright);
+    uint32_t rb = WQ_LDG(ix.right_ptr + rk), re = WQ_LDG(ix.right_ptr + rk + 1);
+    if (rb == re) return;
+    if (c.depth >= WQ_MAX_DEPTH) { c.overflow = 1; return; }
+    WqAlign best;
+    wq_copy(best, align);
+    float best_score = wq_score(align);
+    const float base_score = best_score;
+    uint32_t i = rb, j = lb;     // A = right list, B = left list
+    while (i < re && j < le) {
+        uint32_t ga = WQ_LDG(&ix.right_ent[i].x);
+        uint2 eb = WQ_LDG(&ix.left_ent[j]);
+        if (ga > eb.x) j++;
+        else if (ga < eb.x) i++;
+        else {
+            i++; j++;
+            if (eb.x != c.gene) continue;
+            uint32_t rn_node = eb.y - c.gbase + 1;
+            if (rn_node < 2) { c.overflow = 1; continue; }        // nodeoffset[0] in the reference: undefined
+            int64_t rn_offset = (int64_t)wq_nodeoffset(c, rn_node - 1) + (int64_t)wq_nodelen(c, rn_node - 1) - 1;
+            WqAlign res;
+            wq_copy(res, align);
+            c.depth++;
+            wq_rev_extend(c, rn_offset, ridx, res, rn_node - 1);
+            c.depth--;
+            float s = wq_score(res);
+            if (s > best_score) { wq_copy(best, res); best_score = s; }
+        }
+    }
+    if (best_score >= base_score + c.p->kf) best.isvalid = 1;
+    wq_copy(align, best);
+}
+
+// ungapped_rev_extend (src/align.jl:423-575)
+WQ_HDN void wq_rev_extend(WqCtx& c, int64_t sgidx, int ridx, WqAlign& align, uint32_t nodeidx) {
+    const WqParams& p = *c.p;
+    const int readlen = c.readlen;
+    const int K = p.K;
+    uint8_t passed[WQ_MAX_PATH];
+    int npassed = 0;
+    float mistol = wq_mistol(align);
+
+    if (align.npath == 0 || align.p[0].node != nodeidx) wq_push_front(c, align, nodeidx, 0);
+
+    while (mistol <= p.mmlimit && ridx > 0 && sgidx > 0 && !c.overflow) {
+        int64_t node_start = nodeidx >= 1 ? (int64_t)wq_nodeoffset(c, nodeidx) : -1;
+        if (nodeidx >= 1 && sgidx == node_start - 1) {   // hit right edge
+            uint32_t leftnode = nodeidx - 1;
+            uint8_t et = wq_edgetype(c, nodeidx);
+            if (et == WQ_LR && (int64_t)wq_nodelen(c, leftnode) >= K && ridx >= K) {
+                uint32_t lkmer = wq_read_kmer(c, ridx - K + 1, K);
+                if (WQ_LDG(&wq_node(c, nodeidx)->kleft) == lkmer) {
+                    ridx -= K - 1;
+                    sgidx -= K - 1;
+                    nodeidx -= 1;
+                    wq_push_front(c, align, nodeidx, (uint8_t)(K - 1));
+                    align.isvalid = 1;
+                } else {
+                    wq_spliced_rev(c, nodeidx, ridx, lkmer, align);
+                    break;
+                }
+            } else if (et == WQ_LR || et == WQ_RR) {
+                if (npassed < WQ_MAX_PATH) passed[npassed++] = (uint8_t)(align.npath - 1); else c.overflow = 1;
+                nodeidx -= 1;
+                wq_push_front(c, align, nodeidx, 0);
+            } else if (et == WQ_SR) {
+                if (ridx >= K) {
+                    uint32_t lkmer = wq_read_kmer(c, ridx - K + 1, K);
+                    wq_spliced_rev(c, nodeidx, ridx, lkmer, align);
+                }
+                break;
+            } else if (et == WQ_LS) {
+                break;
+            } else {   // 'LL' || 'RS' || 'SL'
+                nodeidx -= 1;
+                if (nodeidx > 0) wq_push_front(c, align, nodeidx, 0);
+            }
+            if (c.overflow) break;
+            node_start = nodeidx >= 1 ? (int64_t)wq_nodeoffset(c, nodeidx) : -1;
+        }
+        int lim = ridx;
+        if (sgidx < lim) lim = (int)sgidx;
+        // next edge test fires when sgidx == node_start-1, i.e. after sgidx-(node_start-1) more bases
+        if (nodeidx >= 1 && sgidx > node_start - 1 && sgidx - (node_start - 1) < lim) lim = (int)(sgidx - (node_start - 1));
+        int used = wq_walk_rev(c, align.p[0], mistol, ridx, sgidx, lim);
+        ridx -= used;
+        sgidx -= used;
+    }
+
+    int64_t cur_ridx = ridx + 1;
+    int64_t cur_sgidx = sgidx + 1;
+    for (int ci = npassed; ci >= 1 && !c.overflow; ci--) {
+        int cval = passed[ci - 1];
+        int len = align.npath;
+        int upto = len - (cval + 1);
+        if ((int)wq_matches(align, 0, upto > 0 ? upto : 0) >= K + p.mismatches) {
+            align.isvalid = 1;
+            break;
+        } else {
+            if (len - cval - 1 < 0) { c.overflow = 1; break; }      // undefined in the reference
+            uint32_t cur_edge = align.p[len - cval - 1].node;
+            if (upto > 0) wq_erase_front(align, upto);
+            int64_t no = (int64_t)wq_nodeoffset(c, cur_edge);
+            cur_ridx = (int64_t)ridx + (no - sgidx);
+            cur_sgidx = no;
+            if (!((cur_ridx - K) > 0)) continue;
+            uint32_t lkmer = wq_read_kmer(c, (int)(cur_ridx - K), K);
+            WqAlign res;
+            wq_copy(res, align);
+            wq_spliced_rev(c, cur_edge, (int)(cur_ridx - 1), lkmer, res);
+            if (res.npath > align.npath) {
+                if (wq_score(res) > wq_score(align)) wq_copy(align, res);
+            }
+        }
+    }
+
+    if ((double)wq_identity(align, readlen) >= p.score_min) align.isvalid = 1;
+    if (sgidx < (int64_t)align.offset) align.offset = (uint32_t)cur_sgidx;
+    if (cur_ridx < (int64_t)align.offsetread) align.offsetread = (uint8_t)cur_ridx;
+
+    // clean up bad leading nodes (src/align.jl:562-572)
+    while (align.npath >= 1 && (align.p[0].mm >= align.p[0].m || (int)align.p[0].m - (int)align.p[0].mm <= 1)) {
+        uint8_t offset_change = (uint8_t)(align.p[0].m + align.p[0].mm);
+        wq_erase_front(align, 1);
+        if (align.npath >= 1) {
+            align.offset = wq_nodeoffset(c, align.p[0].node);
+            align.offsetread = (uint8_t)(align.offsetread + offset_change);
+        } else {
+            align.isvalid = 0;
+        }
+    }
+}
+
+// Locate gene + node of 1-based text position s (searchsortedlast over GraphLib.offset and
+// SpliceGraph.nodeoffset, src/align.jl:210-213) with one bucket lookup over the globally sorted
+// node starts.  forced_gene > 0 pins the gene (paired call, src/paired.jl:79-80).
+WQ_HD void wq_set_gene(WqCtx& c, uint32_t gene) {
+    const WqGeneRec* g = c.ix->genes + (gene - 1);
+    c.gene = gene;
+    c.gstart = WQ_LDG(&g->text_start);
+    c.seqlen = WQ_LDG(&g->text_end) - c.gstart;
+    c.gbase = WQ_LDG(&g->node_base);
+    c.nn = WQ_LDG(&g->nn);
+}
+WQ_HD uint32_t wq_locate_node(const WqDevIndex& ix, uint64_t s) {
+    // global index of the last node whose abs_start <= s (s is used as a 0-based position: the
+    // reference compares a 1-based position with 0-based gene offsets, src/align.jl:210-212)
+    uint64_t b = s >> WQ_NODE_BUCKET_SHIFT;
+    uint32_t k = WQ_LDG(ix.node_bucket + b);          // #nodes with abs_start <= b<<6  (>= 1)
+    while (k < ix.N && (uint64_t)WQ_LDG(&ix.nodes[k].abs_start) <= s) k++;
+    return k - 1;
+}
+
+// _ungapped_align (src/align.jl:209-223)
+WQ_HDN void wq_align_at(WqCtx& c, int64_t indx, int readloc, bool ispos, uint32_t forced_gene, WqAlign& align) {
+    const WqDevIndex& ix = *c.ix;
+    uint32_t offset_node;
+    if (forced_gene == 0) {
+        uint64_t s = (uint64_t)indx > ix.n ? ix.n : (uint64_t)indx;
+        uint32_t gi = wq_locate_node(ix, s);
+        wq_set_gene(c, WQ_LDG(&ix.nodes[gi].gene));
+        offset_node = gi - c.gbase + 1;
+    } else {
+        wq_set_gene(c, forced_gene);
+        // searchsortedlast(nodeoffset, sgidx+1) inside the pinned gene
+        int64_t target = indx - (int64_t)c.gstart;       // sgidx
+        uint32_t lo = 0, hi = c.nn + 1;
+        while (lo + 1 < hi) {
+            uint32_t mid = (lo + hi) >> 1;
+            if ((int64_t)wq_nodeoffset(c, mid) <= target + 1) lo = mid; else hi = mid;
+        }
+        offset_node = lo;
+    }
+    int64_t sgidx = indx - (int64_t)c.gstart;
+    align.offset = (uint32_t)(sgidx + 1);
+    align.offsetread = (uint8_t)(readloc + 1);
+    align.npath = 0;
+    align.isvalid = 0;
+    align.strand = ispos ? 1 : 0;
+    c.depth = 0;
+    wq_fwd_extend(c, sgidx + 1, readloc + 1, align, offset_node);
+    if (!c.overflow) wq_rev_extend(c, sgidx, readloc, align, offset_node);
+}

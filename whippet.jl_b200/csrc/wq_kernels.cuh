@@ -1,0 +1,361 @@
+// Per-thread bodies of the alignment kernels (one grid thread = one call).  They are written as
+// __host__ __device__ functions so that tests/emu can drive the very same code single-threaded on
+// a CPU while no GPU is attached; the shipped library only ever launches them as CUDA kernels.
+//
+//   wq_seed_thread     kernel 1: one read  -> seed_locate + locate of every SA row of the seed
+//   wq_extend_thread   kernel 2: one hit   -> _ungapped_align (fwd + rev extension)
+//   wq_resolve_thread  kernel 3: one read  -> score filter of ungapped_align (src/align.jl:239-268),
+//                                count! (src/quant.jl:556-594) / push!(multi) (src/quant.jl:456-469)
+#pragma once
+#include "wq_align.cuh"
+
+#if defined(__CUDA_ARCH__)
+#define WQ_ATOMIC_ADD_U32(p, v) atomicAdd((unsigned int*)(p), (unsigned int)(v))
+#define WQ_ATOMIC_ADD_U64(p, v) atomicAdd((unsigned long long*)(p), (unsigned long long)(v))
+#define WQ_ATOMIC_CAS_U64(p, c, v) atomicCAS((unsigned long long*)(p), (unsigned long long)(c), (unsigned long long)(v))
+#define WQ_ATOMIC_EXCH_U32(p, v) atomicExch((unsigned int*)(p), (unsigned int)(v))
+#define WQ_FENCE() __threadfence()
+#define WQ_VLOAD_U32(p) (*(volatile const uint32_t*)(p))
+#define WQ_VLOAD_U64(p) (*(volatile const uint64_t*)(p))
+#else
+template <class T, class V> static inline T wq_emu_add(T* p, V v) { T o = *p; *p = (T)(o + (T)v); return o; }
+static inline uint64_t wq_emu_cas(uint64_t* p, uint64_t c, uint64_t v) { uint64_t o = *p; if (o == c) *p = v; return o; }
+static inline uint32_t wq_emu_exch(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = v; return o; }
+#define WQ_ATOMIC_ADD_U32(p, v) wq_emu_add((uint32_t*)(p), (v))
+#define WQ_ATOMIC_ADD_U64(p, v) wq_emu_add((uint64_t*)(p), (v))
+#define WQ_ATOMIC_CAS_U64(p, c, v) wq_emu_cas((uint64_t*)(p), (c), (v))
+#define WQ_ATOMIC_EXCH_U32(p, v) wq_emu_exch((uint32_t*)(p), (v))
+#define WQ_FENCE() ((void)0)
+#define WQ_VLOAD_U32(p) (*(const uint32_t*)(p))
+#define WQ_VLOAD_U64(p) (*(const uint64_t*)(p))
+#endif
+
+struct WqBatchDev {                // a read batch resident in device memory (wq_read_batch with device pointers)
+    uint32_t n;
+    const uint8_t*  len;
+    const uint64_t* seq_off;
+    const uint64_t* seq2;
+    const uint64_t* qual_off;
+    const uint8_t*  qual;
+};
+
+// ---- count stores -------------------------------------------------------------------------------
+#define WQ_EMPTY_KEY 0xFFFFFFFFFFFFFFFFull
+#define WQ_KEYOFF_UNSET 0xFFFFFFFFu
+#define WQ_KEYOFF_FULL 0xFFFFFFFEu
+
+struct WqEdgeTable {               // SpliceGraphQuant.edge + .circ: key = gene<<32 | lnode<<16 | rnode
+    uint64_t* key;
+    uint64_t* count;
+    uint64_t  mask;                // slots - 1
+};
+struct WqKeyedTable {              // SpliceGraphQuant.long + MultiMapping.map: exact variable-length keys
+    uint64_t* hash;                // 0 = empty
+    uint32_t* keyoff;              // word offset of [nwords, words...] in pool
+    uint64_t* count;
+    uint32_t* pool;
+    uint64_t* pool_cursor;
+    uint64_t  pool_cap;
+    uint64_t  mask;
+};
+struct WqCounters {                // scalar stats, all u64 (kept right behind node_count so one allreduce covers both)
+    uint64_t total, mapped, multi, sum_readlen, path_overflow, edge_full, keyed_full, pool_overflow;
+};
+
+struct WqWork {                    // per-batch scratch
+    WqSeed*   seeds;               // [n]
+    uint32_t* hit_read;            // [hit_cap]
+    uint32_t* hit_s;               // [hit_cap] 1-based text position of the located seed
+    WqHit*    hits;                // [hit_cap]
+    wq_align_node* pool;           // [pool_cap]
+    uint32_t* cursors;             // [0] hit cursor, [1] path-pool cursor, [2] pending cursor
+    uint32_t* pending;             // [n] reads whose keyed insert must be retried
+    uint32_t  hit_cap, pool_cap;
+};
+
+WQ_HD void wq_load_read(WqCtx& c, const WqBatchDev& b, uint32_t r) {
+    int len = WQ_LDG(b.len + r);
+    c.readlen = len;
+    const uint64_t* src = b.seq2 + WQ_LDG(b.seq_off + r);
+    int nw = (len + 31) >> 5;
+    for (int i = 0; i <= WQ_MAX_READ_WORDS; i++) c.w[i] = i < nw ? WQ_LDG(src + i) : 0ull;
+    if (len & 31) c.w[nw - 1] &= (~0ull >> (64 - 2 * (len & 31)));
+    c.qual = b.qual + WQ_LDG(b.qual_off + r);
+    c.flipped = 0;
+    c.overflow = 0;
+    c.depth = 0;
+}
+
+// bit j set when quality[j] <= seed_min_qual (orientation: as stored, or reversed when `rev`)
+WQ_HD void wq_badq(const WqCtx& c, int min_qual, bool rev, uint64_t* badq) {
+    for (int i = 0; i < 4; i++) badq[i] = 0;
+    for (int j = 0; j < c.readlen; j++) {
+        uint8_t q = WQ_LDG(c.qual + j);
+        if ((int)q <= min_qual) {
+            int k = rev ? c.readlen - 1 - j : j;
+            badq[k >> 6] |= 1ull << (k & 63);
+        }
+    }
+}
+
+// ---- kernel 1 -----------------------------------------------------------------------------------
+WQ_HDN void wq_seed_thread(const WqDevIndex& ix, const WqParams& p, const WqBatchDev& b, const WqWork& wk, uint32_t r) {
+    WqCtx c;
+    c.ix = &ix;
+    c.p = &p;
+    wq_load_read(c, b, r);
+    uint64_t badq[4];
+    wq_badq(c, p.seed_min_qual, false, badq);
+    int64_t sp = 2;
+    int readloc = 0;
+    bool strand = true;
+    int cnt = wq_seed_locate(c, badq, true, !p.is_stranded, sp, readloc, strand);
+    WqSeed s;
+    s.sp = (uint32_t)sp;
+    s.cnt = (uint8_t)cnt;
+    s.readloc = (uint8_t)readloc;
+    s.strand = strand ? 1 : 0;
+    s._pad = 0;
+    s.hit_base = 0;
+    if (cnt > 0) {
+        uint32_t base = WQ_ATOMIC_ADD_U32(&wk.cursors[0], cnt);
+        s.hit_base = base;
+        for (int k = 0; k < cnt; k++) {
+            if (base + k < wk.hit_cap) {
+                wk.hit_read[base + k] = r;
+                wk.hit_s[base + k] = (uint32_t)(wq_sa_value(ix, sp + k) + 1);
+            }
+        }
+    }
+    wk.seeds[r] = s;
+}
+
+// ---- kernel 2 -----------------------------------------------------------------------------------
+WQ_HDN void wq_extend_thread(const WqDevIndex& ix, const WqParams& p, const WqBatchDev& b, const WqWork& wk, uint32_t slot) {
+    uint32_t r = wk.hit_read[slot];
+    WqSeed s = wk.seeds[r];
+    WqCtx c;
+    c.ix = &ix;
+    c.p = &p;
+    wq_load_read(c, b, r);
+    if (!s.strand) {                 // reverse_complement!(read), src/align.jl:231-234
+        wq_revcomp(c.w, c.readlen);
+        c.flipped = 1;
+    }
+    WqAlign a;
+    wq_align_at(c, (int64_t)wk.hit_s[slot], s.readloc, s.strand != 0, 0, a);
+    WqHit h;
+    h.identity = wq_identity(a, c.readlen);
+    h.offset = a.offset;
+    h.offsetread = a.offsetread;
+    h.npath = a.npath;
+    h.strand = a.strand;
+    h.flags = (uint8_t)((a.isvalid ? 1 : 0) | (wq_isvalid(a) ? 2 : 0) | (c.overflow ? 8 : 0));
+    if (c.overflow) h.flags &= (uint8_t)~2;
+    uint32_t ps = 0;
+    if (a.npath) {
+        ps = WQ_ATOMIC_ADD_U32(&wk.cursors[1], a.npath);
+        if (ps + a.npath <= wk.pool_cap) {
+            for (int i = 0; i < a.npath; i++) {
+                wq_align_node o;
+                o.gene = c.gene;
+                o.node = a.p[i].node;
+                o.mistolerance = a.p[i].tol;
+                o.matches = a.p[i].m;
+                o.mismatches = a.p[i].mm;
+                o._pad = 0;
+                wk.pool[ps + i] = o;
+            }
+        } else {
+            h.flags |= 16;           // path pool exhausted: reported through WqCounters.pool_overflow
+        }
+    }
+    h.path_start = ps;
+    wk.hits[slot] = h;
+}
+
+// ---- keyed store --------------------------------------------------------------------------------
+WQ_HD uint64_t wq_hash_words(const uint32_t* w, int n) {
+    uint64_t h = 0x9E3779B97F4A7C15ull ^ (uint64_t)n;
+    for (int i = 0; i < n; i++) {
+        h ^= w[i];
+        h *= 0xFF51AFD7ED558CCDull;
+        h ^= h >> 29;
+    }
+    h ^= h >> 32;
+    return h ? h : 1;
+}
+
+// returns 0 = counted, 1 = owner has not published its key yet (retry), 2 = table or pool full
+WQ_HD int wq_keyed_insert(const WqKeyedTable& t, const uint32_t* kw, int nw, uint64_t amount) {
+    uint64_t h = wq_hash_words(kw, nw);
+    uint64_t slot = h & t.mask;
+    for (uint64_t probe = 0; probe <= t.mask; probe++, slot = (slot + 1) & t.mask) {
+        uint64_t cur = WQ_VLOAD_U64(&t.hash[slot]);
+        if (cur == 0) {
+            uint64_t prev = WQ_ATOMIC_CAS_U64(&t.hash[slot], 0ull, h);
+            if (prev == 0) {          // this thread owns the slot: store the key, then publish it
+                uint64_t off = WQ_ATOMIC_ADD_U64(t.pool_cursor, (uint64_t)nw + 1);
+                if (off + nw + 1 > t.pool_cap || off + nw + 1 >= 0xFFFFFFF0ull) {
+                    WQ_ATOMIC_EXCH_U32(&t.keyoff[slot], WQ_KEYOFF_FULL);
+                    return 2;
+                }
+                t.pool[off] = (uint32_t)nw;
+                for (int i = 0; i < nw; i++) t.pool[off + 1 + i] = kw[i];
+                WQ_FENCE();
+                WQ_ATOMIC_EXCH_U32(&t.keyoff[slot], (uint32_t)off);
+                WQ_ATOMIC_ADD_U64(&t.count[slot], amount);
+                return 0;
+            }
+            cur = prev;
+        }
+        if (cur == h) {
+            uint32_t off = WQ_VLOAD_U32(&t.keyoff[slot]);
+            if (off == WQ_KEYOFF_UNSET) return 1;
+            if (off == WQ_KEYOFF_FULL) return 2;
+            WQ_FENCE();
+            bool same = WQ_VLOAD_U32(&t.pool[off]) == (uint32_t)nw;
+            for (int i = 0; same && i < nw; i++) same = WQ_VLOAD_U32(&t.pool[off + 1 + i]) == kw[i];
+            if (same) {
+                WQ_ATOMIC_ADD_U64(&t.count[slot], amount);
+                return 0;
+            }
+        }
+    }
+    return 2;
+}
+
+WQ_HD int wq_edge_insert(const WqEdgeTable& t, uint64_t key, uint64_t amount) {
+    uint64_t h = key * 0x9E3779B97F4A7C15ull;
+    uint64_t slot = (h >> 20) & t.mask;
+    for (uint64_t probe = 0; probe <= t.mask; probe++, slot = (slot + 1) & t.mask) {
+        uint64_t cur = WQ_VLOAD_U64(&t.key[slot]);
+        if (cur == WQ_EMPTY_KEY) {
+            uint64_t prev = WQ_ATOMIC_CAS_U64(&t.key[slot], WQ_EMPTY_KEY, key);
+            cur = prev == WQ_EMPTY_KEY ? key : prev;
+        }
+        if (cur == key) {
+            WQ_ATOMIC_ADD_U64(&t.count[slot], amount);
+            return 0;
+        }
+    }
+    return 2;
+}
+
+// Key words of the alignments a read kept.  SE:
+//   one hit,  >= 3 nodes : [0<<28 | npath, gene, node...]                      (SpliceGraphQuant.long key)
+//   several hits         : [1<<28 | nhits, then per hit: npath, gene, node...] (MultiMapping.map key)
+#define WQ_KEY_WORDS_MAX (1 + WQ_MAX_TOLERATE * (2 + 2 * WQ_MAX_PATH))
+WQ_HD int wq_build_key_se(const WqWork& wk, uint32_t base, int cnt, int nkept, uint32_t* kw) {
+    int n = 0;
+    if (nkept > 1) kw[n++] = (1u << 28) | (uint32_t)nkept;
+    for (int k = 0; k < cnt; k++) {
+        const WqHit h = wk.hits[base + k];
+        if (!(h.flags & 4)) continue;
+        kw[n++] = nkept > 1 ? (uint32_t)h.npath : ((0u << 28) | (uint32_t)h.npath);
+        kw[n++] = wk.pool[h.path_start].gene;
+        for (int i = 0; i < h.npath; i++) kw[n++] = wk.pool[h.path_start + i].node;
+    }
+    return n;
+}
+
+struct WqQuantDev {
+    uint64_t*    node_count;       // [N] SpliceGraphQuant.node, by global node index
+    WqCounters*  counters;
+    WqEdgeTable  edges;
+    WqKeyedTable keyed;
+};
+
+// count!(quant, align, 1.0) for a single kept alignment, or push!(multi, ...) for several.
+// `retry` = only redo the keyed insertion (dense counts were already applied).
+WQ_HD void wq_count_read(const WqDevIndex& ix, const WqWork& wk, const WqQuantDev& q, uint32_t r,
+                         uint32_t base, int cnt, int nkept, bool retry) {
+    uint32_t kw[WQ_KEY_WORDS_MAX];
+    if (nkept == 1) {
+        int k = 0;
+        while (!(wk.hits[base + k].flags & 4)) k++;
+        const WqHit h = wk.hits[base + k];
+        if (!(h.flags & 1)) return;                 // align.isvalid == true || return
+        const wq_align_node n0 = wk.pool[h.path_start];
+        if (h.npath == 1) {
+            if (!retry) WQ_ATOMIC_ADD_U64(&q.node_count[WQ_LDG(&ix.genes[n0.gene - 1].node_base) + n0.node - 1], 1);
+            return;
+        }
+        if (h.npath == 2) {
+            if (!retry) {
+                const wq_align_node n1 = wk.pool[h.path_start + 1];
+                uint64_t key = ((uint64_t)n0.gene << 32) | ((uint64_t)(n0.node & 0xFFFF) << 16) | (uint64_t)(n1.node & 0xFFFF);
+                if (wq_edge_insert(q.edges, key, 1)) WQ_ATOMIC_ADD_U64(&q.counters->edge_full, 1);
+            }
+            return;
+        }
+    }
+    int nw = wq_build_key_se(wk, base, cnt, nkept, kw);
+    int rc = wq_keyed_insert(q.keyed, kw, nw, 1);
+    if (rc == 1) {
+        uint32_t slot = WQ_ATOMIC_ADD_U32(&wk.cursors[2], 1);
+        wk.pending[slot] = r;
+    } else if (rc == 2) {
+        WQ_ATOMIC_ADD_U64(&q.counters->keyed_full, 1);
+    }
+}
+
+// ---- kernel 3 -----------------------------------------------------------------------------------
+WQ_HDN void wq_resolve_thread(const WqDevIndex& ix, const WqParams& p, const WqBatchDev& b, const WqWork& wk,
+                              const WqQuantDev& q, uint32_t r, uint64_t* stats /* [mapped, multi, sum_readlen, overflow, pool_overflow] */) {
+    const WqSeed s = wk.seeds[r];
+    const int cnt = s.cnt;
+    if (cnt == 0) return;
+    const uint32_t base = s.hit_base;
+    const int readlen = WQ_LDG(b.len + r);
+    (void)readlen;
+    // score filter of ungapped_align (src/align.jl:239-268), hits visited in suffix-array row order
+    bool isnull = true;
+    float maxscore = 0.f;
+    uint32_t keep = 0;                  // bit k = hit k is in res.value
+    bool overflow = false, pool_over = false;
+    for (int k = 0; k < cnt; k++) {
+        const WqHit h = wk.hits[base + k];
+        if (h.flags & 8) overflow = true;
+        if (h.flags & 16) pool_over = true;
+        if (!(h.flags & 2)) continue;
+        const float scvar = h.identity;
+        if (isnull) {
+            isnull = false;
+            keep = 1u << k;
+            maxscore = scvar;
+        } else if (scvar > maxscore) {
+            if ((double)(scvar - maxscore) > p.score_range) {
+                keep = 0;
+            } else {                    // splice_by_identity!(res, scvar, score_range, readlen)
+                for (int j = 0; j < k; j++)
+                    if ((keep >> j) & 1)
+                        if ((double)(scvar - wk.hits[base + j].identity) > p.score_range) keep &= ~(1u << j);
+            }
+            maxscore = scvar;
+            keep |= 1u << k;
+        } else if ((double)(maxscore - scvar) <= p.score_range) {
+            keep |= 1u << k;
+        }
+    }
+    if (overflow) stats[3] += 1;
+    if (pool_over) stats[4] += 1;
+    if (isnull || overflow || pool_over) return;
+    int nkept = 0;
+    for (int k = 0; k < cnt; k++)
+        if ((keep >> k) & 1) {
+            wk.hits[base + k].flags |= 4;
+            nkept++;
+        }
+    stats[0] += 1;
+    stats[2] += (uint64_t)WQ_LDG(b.len + r);
+    if (nkept > 1) stats[1] += 1;
+    wq_count_read(ix, wk, q, r, base, cnt, nkept, false);
+}
+
+WQ_HDN void wq_retry_thread(const WqDevIndex& ix, const WqWork& wk, const WqQuantDev& q, uint32_t r) {
+    const WqSeed s = wk.seeds[r];
+    int nkept = 0;
+    for (int k = 0; k < s.cnt; k++) nkept += (wk.hits[s.hit_base + k].flags & 4) ? 1 : 0;
+    wq_count_read(ix, wk, q, r, s.hit_base, s.cnt, nkept, true);
+}

@@ -232,12 +232,15 @@ class ReadBatch:
         n, R = codes.shape
         lens = np.full(n, R, "u1") if lens is None else np.asarray(lens, "u1")
         W = (R + 31) // 32
-        pad = np.zeros((n, W * 32), dtype=np.uint64)
-        pad[:, :R] = codes & 3
-        mask = np.arange(W * 32)[None, :] < lens[:, None].astype(np.int64)
-        pad *= mask
-        shifts = (2 * (np.arange(W * 32) % 32)).astype(np.uint64)
-        words = (pad << shifts[None, :]).reshape(n, W, 32).sum(axis=2, dtype=np.uint64)
+        words = np.zeros((n, W), dtype="<u8")
+        wb = words.view("u1").reshape(n, W * 8)          # little endian: base j -> byte (j//4), bits 2*(j%4)
+        for lo in range(0, n, 1 << 20):
+            hi = min(n, lo + (1 << 20))
+            pad = np.zeros((hi - lo, W * 32), dtype=np.uint8)
+            pad[:, :R] = codes[lo:hi] & 3
+            pad[np.arange(W * 32)[None, :] >= lens[lo:hi, None].astype(np.int64)] = 0
+            p4 = pad.reshape(hi - lo, W * 8, 4)
+            wb[lo:hi] = p4[:, :, 0] | (p4[:, :, 1] << 2) | (p4[:, :, 2] << 4) | (p4[:, :, 3] << 6)
         Q = (R + 15) // 16 * 16
         q = np.zeros((n, Q), dtype=np.uint8)
         q[:, :R] = quals

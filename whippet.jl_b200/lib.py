@@ -1,0 +1,59 @@
+"""ctypes binding of csrc/libwhippet_b200.so (the C ABI of include/whippet_b200.h).
+
+Fails loudly when the CUDA library is missing: there is no CPU path behind it."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import abi
+from .build import CUDA_SO
+
+_lib = None
+
+
+class WhippetB200Error(RuntimeError):
+    pass
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(CUDA_SO):
+        raise WhippetB200Error(f"{CUDA_SO} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(there is no CPU fallback)")
+    L = C.CDLL(CUDA_SO)
+    vp = C.c_void_p
+    L.wq_last_error.restype = C.c_char_p
+    L.wq_index_create.argtypes = [C.POINTER(abi.IndexDesc), C.c_int, C.POINTER(vp)]
+    L.wq_destroy.argtypes = [vp]
+    L.wq_destroy.restype = None
+    L.wq_quant_reset.argtypes = [vp]
+    L.wq_align_se.argtypes = [vp, C.POINTER(abi.AlignParamC), C.POINTER(abi.ReadBatchC), C.POINTER(abi.AlignOutC)]
+    L.wq_align_pe.argtypes = [vp, C.POINTER(abi.AlignParamC), C.POINTER(abi.ReadBatchC), C.POINTER(abi.ReadBatchC),
+                              C.POINTER(abi.AlignOutC)]
+    L.wq_align_se_device.argtypes = [vp, C.POINTER(abi.AlignParamC), C.POINTER(abi.ReadBatchC)]
+    L.wq_align_pe_device.argtypes = [vp, C.POINTER(abi.AlignParamC), C.POINTER(abi.ReadBatchC), C.POINTER(abi.ReadBatchC)]
+    L.wq_map_stats_get.argtypes = [vp, C.POINTER(abi.MapStatsC)]
+    L.wq_counts_device_ptr.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_uint64)]
+    L.wq_counts_download.argtypes = [vp, C.POINTER(abi.CountsC)]
+    L.wq_keyed_download.argtypes = [vp, C.c_int, C.POINTER(abi.KeyedC)]
+    L.wq_counts_merge.argtypes = [vp, C.POINTER(abi.CountsC), C.POINTER(abi.KeyedC), C.POINTER(abi.KeyedC)]
+    L.wq_counts_refresh_dense.argtypes = [vp]
+    L.wq_em_tpm.argtypes = [vp, C.POINTER(abi.EmParamC), abi.f64p, abi.f64p, abi.f64p, C.POINTER(C.c_int64)]
+    L.wq_assign_ambig.argtypes = [vp, C.POINTER(abi.ValuesC)]
+    L.wq_em_psi_batch.argtypes = [vp, C.POINTER(abi.PsiBatchC)]
+    L.wq_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    L.wq_pinned_alloc.argtypes = [C.POINTER(vp), C.c_uint64]
+    L.wq_pinned_free.argtypes = [vp]
+    L.wq_set_stream.argtypes = [vp, vp]
+    L.wq_launch_count.argtypes = [vp]
+    L.wq_launch_count.restype = C.c_uint64
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != 0:
+        raise WhippetB200Error(f"libwhippet_b200 error {rc}: {load().wq_last_error().decode(errors='replace')}")

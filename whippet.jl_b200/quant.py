@@ -1,0 +1,152 @@
+"""Host-side mirror of the reference's quantification interface for the accelerated path.
+
+Names follow the calls bin/whippet-quant.jl:124-181 makes (GraphLibQuant, process_reads!,
+ungapped_align, build_equivalence_classes!/calculate_tpm!/gene_em!, assign_ambig!); each method
+cites the reference function it stands for.  All compute happens behind the C ABI."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import abi, lib
+from .flat import AlignParam, FlatIndex, ReadBatch
+
+
+class AlignResult:
+    """Batch form of `Nullable{Vector{SGAlignment}}` (src/align.jl:86): read i owns
+    aln[hit_start[i] : hit_start[i]+nhits[i]], each alignment owns nodes[path_start : +npath]."""
+
+    def __init__(self, hit_start, nhits, flipped, aln, nodes, aln_mate=None):
+        self.hit_start, self.nhits, self.flipped = hit_start, nhits, flipped
+        self.aln, self.nodes, self.aln_mate = aln, nodes, aln_mate
+
+    def read(self, i, mate=False):
+        out = []
+        src = self.aln_mate if mate else self.aln
+        for k in range(int(self.hit_start[i]), int(self.hit_start[i]) + int(self.nhits[i])):
+            a = src[k]
+            ns = self.nodes[int(a["path_start"]): int(a["path_start"]) + int(a["npath"])]
+            out.append((int(a["offset"]), int(a["offsetread"]), int(a["strand"]), int(a["isvalid"]),
+                        [(int(n["gene"]), int(n["node"]), int(n["matches"]), int(n["mismatches"]),
+                          int(np.float32(n["mistolerance"]).view(np.uint32))) for n in ns]))
+        return out
+
+
+@dataclass
+class MapStats:
+    total: int
+    mapped: int
+    multi: int
+    sum_readlen: int
+    path_overflow: int
+
+    @property
+    def mean_readlen(self):
+        return self.sum_readlen / self.mapped if self.mapped else 0.0
+
+
+class GraphLibQuant:
+    """`GraphLibQuant{C,DefaultCounter}(lib)` + `MultiMapping{C,DefaultCounter}()`
+    (src/quant.jl:165-198, 439-446) living on one GPU."""
+
+    def __init__(self, index: FlatIndex, device: int = 0):
+        self.L = lib.load()
+        self.index = index
+        self._desc = index.desc()
+        h = C.c_void_p()
+        lib.check(self.L.wq_index_create(C.byref(self._desc), int(device), C.byref(h)))
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.wq_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def reset(self):
+        lib.check(self.L.wq_quant_reset(self.h))
+
+    # ---- alignment ------------------------------------------------------------------------------
+    def ungapped_align(self, param: AlignParam, reads: ReadBatch, mate: ReadBatch | None = None) -> AlignResult:
+        """ungapped_align for every read (src/align.jl:225-270; paired: src/paired.jl:42-125).
+        Counts are accumulated as well, exactly as process_reads! does."""
+        n = reads.n
+        T = max(1, param.seed_tolerate)
+        cap = n * T + 1
+        hs, nh, fl = np.zeros(n, "<u4"), np.zeros(n, "u1"), np.zeros(n, "u1")
+        aln = np.zeros(cap, abi.ALIGNMENT_DT)
+        alm = np.zeros(cap, abi.ALIGNMENT_DT) if mate is not None else None
+        nodes = np.zeros(cap * (2 if mate is not None else 1) * abi.WQ_MAX_PATH // 4 + 64, abi.ALIGN_NODE_DT)
+        out = abi.AlignOutC()
+        out.hit_start = abi.ptr(hs, abi.u32p)
+        out.nhits = abi.ptr(nh, abi.u8p)
+        out.flipped = abi.ptr(fl, abi.u8p)
+        out.aln = aln.ctypes.data
+        out.aln_mate = alm.ctypes.data if alm is not None else None
+        out.nodes = nodes.ctypes.data
+        out.aln_cap, out.nodes_cap = len(aln), len(nodes)
+        p, b = param.c(), reads.c()
+        if mate is None:
+            lib.check(self.L.wq_align_se(self.h, C.byref(p), C.byref(b), C.byref(out)))
+        else:
+            m = mate.c()
+            lib.check(self.L.wq_align_pe(self.h, C.byref(p), C.byref(b), C.byref(m), C.byref(out)))
+        na, nn = int(out.aln_used), int(out.nodes_used)
+        return AlignResult(hs, nh, fl, aln[:na], nodes[:nn], alm[:na] if alm is not None else None)
+
+    def process_reads(self, param: AlignParam, reads: ReadBatch) -> MapStats:
+        """process_reads! (src/reads.jl:41-80) over one in-memory batch: align, then count!/push!(multi)
+        on the device.  Returns the running (mapped, total, ...) statistics."""
+        p, b = param.c(), reads.c()
+        lib.check(self.L.wq_align_se(self.h, C.byref(p), C.byref(b), None))
+        return self.stats()
+
+    def process_paired_reads(self, param: AlignParam, fwd: ReadBatch, rev: ReadBatch) -> MapStats:
+        """process_paired_reads! (src/reads.jl:83-129)."""
+        p, f, r = param.c(), fwd.c(), rev.c()
+        lib.check(self.L.wq_align_pe(self.h, C.byref(p), C.byref(f), C.byref(r), None))
+        return self.stats()
+
+    def stats(self) -> MapStats:
+        s = abi.MapStatsC()
+        lib.check(self.L.wq_map_stats_get(self.h, C.byref(s)))
+        return MapStats(s.total, s.mapped, s.multi, s.sum_readlen, s.path_overflow)
+
+    def last_kernel_ms(self):
+        ms = (C.c_float * 3)()
+        lib.check(self.L.wq_last_kernel_ms(self.h, ms))
+        return [float(x) for x in ms]
+
+    # ---- count stores ---------------------------------------------------------------------------
+    def counts(self):
+        """SpliceGraphQuant.node / .edge / .circ (src/quant.jl:129-135) as
+        (node_count[N], edge_key, edge_count, circ_key, circ_count); keys = gene<<32 | l<<16 | r, sorted."""
+        c = abi.CountsC()
+        lib.check(self.L.wq_counts_download(self.h, C.byref(c)))
+        node = np.zeros(c.n_nodes, "<u8")
+        ek, ec = np.zeros(c.n_edge, "<u8"), np.zeros(c.n_edge, "<u8")
+        ck, cc = np.zeros(c.n_circ, "<u8"), np.zeros(c.n_circ, "<u8")
+        c.node_count = abi.ptr(node, abi.u64p)
+        c.edge_key, c.edge_count = abi.ptr(ek, abi.u64p), abi.ptr(ec, abi.u64p)
+        c.circ_key, c.circ_count = abi.ptr(ck, abi.u64p), abi.ptr(cc, abi.u64p)
+        lib.check(self.L.wq_counts_download(self.h, C.byref(c)))
+        return node, ek, ec, ck, cc
+
+    def keyed(self, kind):
+        """kind 0: SpliceGraphQuant.long; kind 1: MultiMapping.map.  Returns {tuple(words): count}."""
+        k = abi.KeyedC()
+        lib.check(self.L.wq_keyed_download(self.h, kind, C.byref(k)))
+        ptr_ = np.zeros(k.n_rec + 1, "<u8")
+        words = np.zeros(max(1, k.n_words), "<u4")
+        cnt = np.zeros(max(1, k.n_rec), "<u8")
+        k.rec_ptr, k.words, k.count = abi.ptr(ptr_, abi.u64p), abi.ptr(words, abi.u32p), abi.ptr(cnt, abi.u64p)
+        lib.check(self.L.wq_keyed_download(self.h, kind, C.byref(k)))
+        return {tuple(int(x) for x in words[int(ptr_[i]):int(ptr_[i + 1])]): int(cnt[i]) for i in range(k.n_rec)}
