@@ -150,6 +150,46 @@ class Oracle:
         L.wqo_keyed(C.c_void_p(self.h), kind, C.byref(nr), C.byref(nw), v(ptr_), v(words), v(vals))
         return {tuple(int(x) for x in words[int(ptr_[i]):int(ptr_[i + 1])]): float(vals[i]) for i in range(nr.value)}
 
+    # ---- quantification (bin/whippet-quant.jl:161-177) --------------------------------------------
+    def add_node(self, gene, node, v):
+        lib().wqo_add_node(C.c_void_p(self.h), C.c_uint32(gene), C.c_uint32(node), C.c_double(v))
+
+    def add_edge(self, gene, l, r, v):
+        lib().wqo_add_edge(C.c_void_p(self.h), C.c_uint32(gene), C.c_uint32(l), C.c_uint32(r), C.c_double(v))
+
+    def add_keyed(self, kind, words, v):
+        w = np.ascontiguousarray(words, "<u4")
+        lib().wqo_add_keyed(C.c_void_p(self.h), kind, w.ctypes.data_as(C.c_void_p), C.c_uint64(len(w)), C.c_double(v))
+
+    def em_tpm(self, readlen, sig=1, maxit=10000):
+        """build_equivalence_classes! + calculate_tpm! + gene_em! + set_gene_tpm!; returns
+        (iterations, tpm[I], count[I], genetpm[G])."""
+        L = lib()
+        L.wqo_em_tpm.restype = C.c_int64
+        it = L.wqo_em_tpm(C.c_void_p(self.h), C.c_int64(readlen), C.c_int64(sig), C.c_int64(maxit))
+        tpm, cnt = np.zeros(self.index.n_isoforms), np.zeros(self.index.n_isoforms)
+        gt = np.zeros(self.index.n_genes)
+        v = lambda a: a.ctypes.data_as(C.c_void_p)
+        L.wqo_em_results(C.c_void_p(self.h), v(tpm), v(cnt), v(gt))
+        return int(it), tpm, cnt, gt
+
+    def classes(self, multi=False):
+        """[(ids, props, count, isdone, postassign)] in canonical order."""
+        L = lib()
+        L.wqo_n_classes.restype = C.c_uint64
+        L.wqo_class.restype = C.c_uint64
+        out = []
+        ids, props = np.zeros(4096, "<i4"), np.zeros(4096, "<f8")
+        for i in range(L.wqo_n_classes(C.c_void_p(self.h), int(multi))):
+            cnt, fl = C.c_double(), C.c_int32()
+            n = L.wqo_class(C.c_void_p(self.h), int(multi), C.c_uint64(i), ids.ctypes.data_as(C.c_void_p),
+                            props.ctypes.data_as(C.c_void_p), C.byref(cnt), C.byref(fl))
+            out.append((ids[:n].tolist(), props[:n].tolist(), cnt.value, bool(fl.value & 1), bool(fl.value & 2)))
+        return out
+
+    def assign_ambig(self):
+        lib().wqo_assign_ambig(C.c_void_p(self.h))
+
 
 def counters(reset=False):
     """Instrumentation totals since the last reset: fm_steps, hits, nodes_touched, bases, out_nodes,

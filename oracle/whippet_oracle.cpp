@@ -762,6 +762,310 @@ void push_multi_se(Quant& Q, const std::vector<Align>& alns, double value) {
     Q.multi[key] += value;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Quantification: isoform compatibility classes, transcript EM, multi-map assignment.
+// Canonical orders (declared, because Julia Dict iteration order cannot be reproduced without
+// Julia): multi-map classes and long paths in lexicographic key order, isoform
+// classes per gene in lexicographic order of their id vectors, edges in (first,last) order (this one
+// IS the reference order: IntervalMap iteration).  sum(quant.tpm) uses the fixed adjacent-pair tree
+// of tree_sum() (Julia's pairwise mapreduce is not reproducible either).  EM numerics: parity unpinned.
+
+struct EqClass {               // IsoCompat / MultiCompat, src/quant.jl:152-162, 422-435
+    std::vector<int32_t> cls;  // 1-based global isoform ids
+    std::vector<double> prop;
+    double prop_sum = 1.0;
+    double count = 0.0;
+    bool isdone = false;
+    bool postassign = false;
+};
+
+struct IsoView {
+    const Lib& L;
+    Int niso(Int g) const { return L.d->iso_base[g] - L.d->iso_base[g - 1]; }
+    Int geneidx(Int g) const { return L.d->iso_base[g - 1]; }
+    // node in annopath[p] of gene g (p 1-based inside the gene)
+    bool has(Int g, Int p, uint32_t node) const {
+        uint32_t i = L.d->iso_base[g - 1] + (uint32_t)p - 1;
+        const uint32_t* b = L.d->iso_nodes + L.d->iso_node_ptr[i];
+        const uint32_t* e = L.d->iso_nodes + L.d->iso_node_ptr[i + 1];
+        return std::binary_search(b, e, node);
+    }
+    // Base.in(first, last, is::BitSet), src/quant.jl:68-79
+    bool edge_in(Int g, Int p, uint32_t first, uint32_t last) const {
+        if (has(g, p, first) && has(g, p, last)) {
+            for (uint32_t i = first + 1; i + 1 <= last && i < last; i++)
+                if (has(g, p, i)) return false;
+            return true;
+        }
+        return false;
+    }
+    // Base.in(path::SGAlignPath, is::BitSet), src/quant.jl:108-121
+    bool path_in(Int g, Int p, const uint32_t* nodes, size_t n) const {
+        if (n == 1) return has(g, p, nodes[0]);
+        for (size_t i = 0; i + 1 < n; i++)
+            if (!edge_in(g, p, nodes[i], nodes[i + 1])) return false;
+        return true;
+    }
+};
+
+struct QuantState {            // GraphLibQuant, src/quant.jl:165-198
+    std::vector<double> tpm, count, genetpm;
+    std::vector<int64_t> length;
+    std::vector<EqClass> classes;                                   // isoform classes, canonical order
+    std::vector<std::pair<std::vector<uint32_t>, EqClass>> multi;   // multi-map classes, canonical (key) order
+};
+
+// a long / multi record holds one or more paths: [npath(|flags), gene, nodes...]
+struct PathRef { uint32_t gene; const uint32_t* nodes; size_t n; const uint32_t* rnodes; size_t rn; };
+size_t parse_path(const std::vector<uint32_t>& k, size_t pos, PathRef& out) {
+    uint32_t hdr = k[pos];
+    bool paired = ((hdr >> 28) & 2) != 0;
+    out.gene = k[pos + 1];
+    if (!paired) {
+        out.n = hdr & 0xFFFF; out.nodes = &k[pos + 2]; out.rnodes = nullptr; out.rn = 0;
+        return pos + 2 + out.n;
+    }
+    out.n = hdr & 0xFF; out.rn = (hdr >> 8) & 0xFF;
+    out.nodes = &k[pos + 2]; out.rnodes = &k[pos + 2 + out.n];
+    return pos + 2 + out.n + out.rn;
+}
+bool pathref_in(const IsoView& V, Int g, Int p, const PathRef& r) {   // src/quant.jl:123-124
+    return V.path_in(g, p, r.nodes, r.n) && (r.rnodes == nullptr || V.path_in(g, p, r.rnodes, r.rn));
+}
+
+void edge_add(Quant& Q, uint32_t gene, uint32_t l, uint32_t r, double v) {
+    Q.edge[((uint64_t)gene << 32) | ((uint64_t)(l & 0xFFFF) << 16) | (r & 0xFFFF)] += v;
+}
+
+// assign_path!, src/quant.jl:263-324 (single and paired)
+void assign_path(const Lib& L, Quant& Q, const PathRef& r, double value) {
+    size_t nb = L.d->node_base[r.gene - 1];
+    std::vector<uint32_t> temp_iset;
+    auto in_set = [&](uint32_t x) { return std::find(temp_iset.begin(), temp_iset.end(), x) != temp_iset.end(); };
+    bool paired = r.rnodes != nullptr;
+    if (r.n == 1) {
+        Q.node[nb + r.nodes[0] - 1] += value;
+        temp_iset.push_back(r.nodes[0]);
+    } else {
+        for (size_t i = 0; i + 1 < r.n; i++) {
+            uint32_t l = r.nodes[i], rr = r.nodes[i + 1];
+            temp_iset.push_back(l);
+            temp_iset.push_back(rr);
+            edge_add(Q, r.gene, l, rr, value);
+        }
+    }
+    if (!paired) return;
+    if (r.rn == 1) {
+        if (!in_set(r.rnodes[0])) Q.node[nb + r.rnodes[0] - 1] += value;
+    } else {
+        for (size_t i = 0; i + 1 < r.rn; i++) {
+            uint32_t l = r.rnodes[i], rr = r.rnodes[i + 1];
+            if (in_set(l) && in_set(rr)) continue;
+            edge_add(Q, r.gene, l, rr, value);
+        }
+    }
+}
+
+// build_equivalence_classes!, src/quant.jl:327-389
+void build_equivalence_classes(const Lib& L, Quant& Q, QuantState& S) {
+    IsoView V{L};
+    const Int G = L.G;
+    auto li = Q.longs.begin();
+    auto ei = Q.edge.begin();
+    std::vector<std::pair<std::vector<uint32_t>, double>> long_snapshot;
+    for (Int g = 1; g <= G; g++) {
+        std::map<std::vector<int32_t>, double> temp;
+        const Int np = V.niso(g), idx = V.geneidx(g), nn = L.nnodes(g);
+        std::vector<int32_t> iset;
+        auto handle = [&](double value) {
+            if (iset.size() == 1) S.count[iset[0] - 1 + idx] += value;
+            else if (iset.size() > 1) temp[iset] += value;
+        };
+        for (Int n = 1; n <= nn; n++) {
+            iset.clear();
+            for (Int p = 1; p <= np; p++) if (V.has(g, p, (uint32_t)n)) iset.push_back((int32_t)p);
+            handle(Q.node[L.d->node_base[g - 1] + n - 1]);
+        }
+        // edges of this gene in (first,last) order; circ entries (l >= r) are not part of .edge
+        ei = Q.edge.lower_bound((uint64_t)g << 32);
+        for (; ei != Q.edge.end() && (ei->first >> 32) == (uint64_t)g; ++ei) {
+            uint32_t l = (ei->first >> 16) & 0xFFFF, r = ei->first & 0xFFFF;
+            if (l >= r) continue;
+            iset.clear();
+            for (Int p = 1; p <= np; p++) if (V.edge_in(g, p, l, r)) iset.push_back((int32_t)p);
+            handle(ei->second);
+        }
+        // long paths of this gene (first path's gene)
+        long_snapshot.clear();
+        for (auto& kv : Q.longs) if (kv.first[1] == (uint32_t)g) long_snapshot.push_back(kv);
+        for (auto& kv : long_snapshot) {
+            PathRef r;
+            parse_path(kv.first, 0, r);
+            iset.clear();
+            for (Int p = 1; p <= np; p++) if (pathref_in(V, g, p, r)) iset.push_back((int32_t)p);
+            handle(kv.second);
+            assign_path(L, Q, r, kv.second);     // assign_long = true
+        }
+        for (auto& kv : temp) {
+            if (kv.second > 0.0) {
+                EqClass c;
+                for (auto p : kv.first) c.cls.push_back((int32_t)(p + idx));
+                c.prop.assign(c.cls.size(), 1.0 / (double)c.cls.size());
+                c.count = kv.second;
+                S.classes.push_back(c);
+            }
+        }
+    }
+    (void)li;
+}
+
+// MultiCompat(graphq, lib, cont), src/quant.jl:431-434 with equivalence_class, :394-417
+EqClass make_multicompat(const Lib& L, const std::vector<uint32_t>& key, double rawcount) {
+    IsoView V{L};
+    EqClass c;
+    uint32_t nh = key[0] & 0xFFFF;
+    size_t pos = 1;
+    std::vector<int32_t> set;
+    bool matches_all = true;
+    for (uint32_t h = 0; h < nh; h++) {
+        PathRef r;
+        pos = parse_path(key, pos, r);
+        Int g = r.gene;
+        bool has_match = false;
+        for (Int p = 1; p <= V.niso(g); p++)
+            if (pathref_in(V, g, p, r)) { set.push_back((int32_t)(p + V.geneidx(g))); has_match = true; }
+        if (!has_match) { matches_all = false; set.clear(); break; }
+    }
+    std::sort(set.begin(), set.end());
+    set.erase(std::unique(set.begin(), set.end()), set.end());
+    c.cls = set;
+    c.prop.assign(set.size(), 1.0 / (double)set.size());
+    c.count = rawcount;              // mc.count = get(mc.raw) after primer_adjust!, src/quant.jl:487-493
+    c.isdone = !matches_all;
+    c.postassign = !matches_all;
+    return c;
+}
+
+// fixed adjacent-pair tree over tiles of 1024 (declared canonical order of sum(quant.tpm))
+double tree_sum(const double* a, size_t n) {
+    if (n == 0) return 0.0;
+    std::vector<double> partial;
+    double buf[1024];
+    for (size_t t = 0; t < n; t += 1024) {
+        size_t m = std::min<size_t>(1024, n - t);
+        for (size_t i = 0; i < 1024; i++) buf[i] = i < m ? a[t + i] : 0.0;
+        for (size_t stride = 1; stride < 1024; stride <<= 1)
+            for (size_t i = 0; i + stride < 1024; i += 2 * stride) buf[i] += buf[i + stride];
+        partial.push_back(buf[0]);
+    }
+    if (partial.size() == 1) return partial[0];
+    return tree_sum(partial.data(), partial.size());
+}
+
+double round_digits(double x, int digits) {   // Base.round(x, digits=d): rint(x*10^d)/10^d, non-finite result -> x
+    double sc = std::pow(10.0, digits);
+    double r = std::nearbyint(x * sc) / sc;
+    if (!std::isfinite(r)) return x;
+    return r;
+}
+
+// calculate_tpm!, src/quant.jl:655-667
+void calculate_tpm(QuantState& S, const std::vector<double>& counts, int64_t readlen, int sig) {
+    const size_t I = S.tpm.size();
+    for (size_t i = 0; i < I; i++) S.tpm[i] = counts[i] / std::max((double)(S.length[i] - readlen), 1.0);
+    double rpk_sum = std::max(tree_sum(S.tpm.data(), I), 1.0);
+    for (size_t i = 0; i < I; i++) {
+        double v = S.tpm[i] * 1000000.0 / rpk_sum;
+        S.tpm[i] = sig > 0 ? round_digits(v, sig) : v;
+    }
+}
+
+// copy_isdone!, src/quant.jl:702-712
+bool copy_isdone(std::vector<double>& dest, const std::vector<double>& src, double denominator, int sig = 4) {
+    bool isdifferent = false;
+    for (size_t i = 0; i < dest.size(); i++) {
+        double val = round_digits(src[i] / denominator, sig);
+        if (val != dest[i]) isdifferent = true;
+        dest[i] = std::isnan(val) ? 0.0 : val;
+    }
+    return !isdifferent || denominator == 0;
+}
+
+// gene_em!, src/quant.jl:719-769
+int64_t gene_em(QuantState& S, int64_t maxit, int sig, int64_t readlen) {
+    int64_t it = 1;
+    const size_t I = S.count.size();
+    std::vector<double> count_temp(I, 1.0), tpm_temp(I, 1.0), prop_temp;
+    auto maximize_and_assign = [&](EqClass& eq, bool maximize) {
+        if (eq.isdone) return;
+        if (maximize) {
+            eq.prop_sum = 0.0;
+            prop_temp.assign(eq.cls.size(), 0.0);
+            for (size_t c = 0; c < eq.cls.size(); c++) {
+                double cur = S.tpm[eq.cls[c] - 1];
+                prop_temp[c] = cur;
+                eq.prop_sum += cur;
+            }
+            eq.isdone = copy_isdone(eq.prop, prop_temp, eq.prop_sum);
+        }
+        for (size_t c = 0; c < eq.cls.size(); c++) {
+            size_t i = eq.cls[c] - 1;
+            if (eq.isdone) S.count[i] += eq.prop[c] * eq.count;
+            count_temp[i] += eq.prop[c] * eq.count;
+        }
+    };
+    while (tpm_temp != S.tpm && it < maxit) {
+        count_temp = S.count;
+        tpm_temp = S.tpm;
+        for (auto& kv : S.multi) maximize_and_assign(kv.second, it > 1);
+        for (auto& eq : S.classes) maximize_and_assign(eq, it > 1);
+        calculate_tpm(S, count_temp, readlen, sig);
+        it += 1;
+    }
+    return it;
+}
+
+// set_gene_tpm!, src/quant.jl:248-257
+void set_gene_tpm(const Lib& L, QuantState& S) {
+    for (Int g = 1; g <= L.G; g++) {
+        double t = 0.0;
+        for (uint32_t i = L.d->iso_base[g - 1]; i < L.d->iso_base[g]; i++) t += S.tpm[i];
+        S.genetpm[g - 1] = t;
+    }
+}
+
+// assign_ambig!, src/quant.jl:520-553
+void assign_ambig(const Lib& L, Quant& Q, QuantState& S) {
+    IsoView V{L};
+    for (auto& kv : S.multi) {
+        const std::vector<uint32_t>& key = kv.first;
+        EqClass& mc = kv.second;
+        uint32_t nh = key[0] & 0xFFFF;
+        std::vector<PathRef> vp(nh);
+        size_t pos = 1;
+        for (uint32_t h = 0; h < nh; h++) pos = parse_path(key, pos, vp[h]);
+        std::vector<double> vals(nh, 0.0);
+        if (mc.postassign) {
+            for (uint32_t i = 0; i < nh; i++) vals[i] = S.genetpm[vp[i].gene - 1];
+        } else {
+            for (uint32_t i = 0; i < nh; i++) {
+                Int g = vp[i].gene;
+                double value = 0.0;      // get_class_value, src/quant.jl:510-518
+                for (size_t c = 0; c < mc.cls.size(); c++) {
+                    Int p = mc.cls[c] - V.geneidx(g);
+                    if (p >= 1 && p <= V.niso(g) && pathref_in(V, g, p, vp[i])) value += mc.prop[c];
+                }
+                vals[i] = value;
+            }
+        }
+        double s = 0.0;
+        for (double v : vals) s += v;
+        for (double& v : vals) v /= s;
+        for (uint32_t i = 0; i < nh; i++) assign_path(L, Q, vp[i], vals[i] * mc.count);
+    }
+}
+
 }  // namespace
 
 struct wqo_handle {
@@ -769,6 +1073,7 @@ struct wqo_handle {
     Result R;
     std::string err;
     Quant Q;
+    QuantState S;
 };
 
 extern "C" {
@@ -811,6 +1116,50 @@ void wqo_stats(wqo_handle* h, uint64_t* out5, double* mean_readlen) {
     out5[0] = h->Q.total; out5[1] = h->Q.mapped; out5[2] = h->Q.nmulti; out5[3] = h->Q.sum_readlen; out5[4] = 0;
     *mean_readlen = h->Q.mean_readlen;
 }
+// direct injection of counts (used by known-answer tests that start from given alignments)
+void wqo_add_node(wqo_handle* h, uint32_t gene, uint32_t node, double v) { h->Q.node[h->L.d->node_base[gene - 1] + node - 1] += v; }
+void wqo_add_edge(wqo_handle* h, uint32_t gene, uint32_t l, uint32_t r, double v) { edge_add(h->Q, gene, l, r, v); }
+void wqo_add_keyed(wqo_handle* h, int kind, const uint32_t* words, uint64_t nw, double v) {
+    std::vector<uint32_t> k(words, words + nw);
+    (kind == 0 ? h->Q.longs : h->Q.multi)[k] += v;
+}
+
+// bin/whippet-quant.jl:161-166: build_equivalence_classes!, calculate_tpm!, gene_em!, set_gene_tpm!
+int64_t wqo_em_tpm(wqo_handle* h, int64_t readlen, int64_t sig, int64_t maxit) {
+    const Lib& L = h->L;
+    QuantState& S = h->S;
+    S = QuantState();
+    const uint32_t I = L.d->n_isoforms;
+    S.tpm.assign(I, 0.0); S.count.assign(I, 0.0); S.genetpm.assign(L.G, 0.0); S.length.assign(I, 0);
+    for (Int g = 1; g <= L.G; g++)
+        for (uint32_t i = L.d->iso_base[g - 1]; i < L.d->iso_base[g]; i++) {
+            int64_t len = 0;
+            for (uint32_t k = L.d->iso_node_ptr[i]; k < L.d->iso_node_ptr[i + 1]; k++) len += L.nodelen(g, L.d->iso_nodes[k]);
+            S.length[i] = len;
+        }
+    for (auto& kv : h->Q.multi) S.multi.emplace_back(kv.first, make_multicompat(L, kv.first, kv.second));
+    build_equivalence_classes(L, h->Q, S);
+    calculate_tpm(S, S.count, readlen, (int)sig);
+    int64_t it = gene_em(S, maxit, (int)sig, readlen);
+    set_gene_tpm(L, S);
+    return it;
+}
+void wqo_em_results(wqo_handle* h, double* tpm, double* count, double* genetpm) {
+    memcpy(tpm, h->S.tpm.data(), h->S.tpm.size() * 8);
+    memcpy(count, h->S.count.data(), h->S.count.size() * 8);
+    memcpy(genetpm, h->S.genetpm.data(), h->S.genetpm.size() * 8);
+}
+uint64_t wqo_n_classes(wqo_handle* h, int multi) { return multi ? h->S.multi.size() : h->S.classes.size(); }
+// class i: ids into out_ids (cap), returns size; props/count/flags through pointers
+uint64_t wqo_class(wqo_handle* h, int multi, uint64_t i, int32_t* ids, double* props, double* count, int32_t* flags) {
+    EqClass& c = multi ? h->S.multi[i].second : h->S.classes[i];
+    for (size_t k = 0; k < c.cls.size(); k++) { ids[k] = c.cls[k]; props[k] = c.prop[k]; }
+    *count = c.count;
+    *flags = (c.isdone ? 1 : 0) | (c.postassign ? 2 : 0);
+    return c.cls.size();
+}
+void wqo_assign_ambig(wqo_handle* h) { assign_ambig(h->L, h->Q, h->S); }
+
 void wqo_counters(uint64_t* out7, int reset) {
     out7[0] = g_ctr.fm_steps; out7[1] = g_ctr.hits; out7[2] = g_ctr.nodes_touched; out7[3] = g_ctr.bases;
     out7[4] = g_ctr.out_nodes; out7[5] = g_ctr.out_alns; out7[6] = g_ctr.count_updates;

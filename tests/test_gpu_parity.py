@@ -114,3 +114,50 @@ def test_larger_index_properties():
     q.close()
     sub = rb.slice(0, 100000)
     compare_all(idx, wq.AlignParam(), sub)
+
+
+def em_parity(idx, p, rb, readlen):
+    """TPM / counts / iterations of the device EM against the oracle.  north_star asks for 1e-6 relative
+    after a fixed iteration count; the implementation reproduces the oracle's operation order, so the
+    comparison is made exact and the tolerance below is only the stated contract."""
+    o = Oracle(idx)
+    o.quant_reset()
+    o.process_reads(p, rb)
+    q = wq.GraphLibQuant(idx)
+    q.process_reads(p, rb)
+    for maxit in (1, 2, 3, 10000):
+        o2 = Oracle(idx)
+        o2.quant_reset()
+        o2.process_reads(p, rb)
+        it_o, tpm_o, cnt_o, gt_o = o2.em_tpm(readlen, 1, maxit)
+        q.reset()
+        q.process_reads(p, rb)
+        it_g, tpm_g, cnt_g, gt_g = q.gene_em(readlen, 1, maxit)
+        assert it_g == it_o, (maxit, it_g, it_o)
+        assert np.allclose(tpm_g, tpm_o, rtol=1e-6, atol=0) and np.allclose(cnt_g, cnt_o, rtol=1e-6, atol=0)
+        assert np.array_equal(tpm_g, tpm_o) and np.array_equal(cnt_g, cnt_o) and np.array_equal(gt_g, gt_o), maxit
+    assert tpm_g.sum() > 0
+    # assign_ambig!: fractional node / edge values
+    o2.assign_ambig()
+    node, ek, ev, ck, cv = q.assign_ambig()
+    assert np.array_equal(node, o2.node_counts())
+    ok, ov = o2.edges()
+    gk, gv = np.concatenate([ek, ck]), np.concatenate([ev, cv])
+    order = np.argsort(gk)
+    assert np.array_equal(ok, gk[order]) and np.array_equal(ov, gv[order])
+    q.close()
+    return it_g, tpm_g
+
+
+def test_em_fixture(fixture_index, test_param):
+    rb = fixture_random_reads(fixture_index, 50000)
+    it, tpm = em_parity(fixture_index, test_param, rb, 15)
+    assert tpm.sum() == 1000000 or abs(tpm.sum() - 1e6) < 1.0
+
+
+@pytest.mark.parametrize("seed,ng,R", [(1, 300, 101), (5, 1500, 76)])
+def test_em_synthetic(seed, ng, R):
+    idx = synth.make_index(n_genes=ng, K=9, seed=seed, paralog_frac=0.1)
+    rb = synth.simulate_reads(idx, 300000, R, seed=seed + 10, sub_rate=0.01)
+    it, tpm = em_parity(idx, wq.AlignParam(), rb, R)
+    assert it > 2

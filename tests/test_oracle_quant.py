@@ -1,0 +1,72 @@
+"""Known answers of the reference's quantification tests, checked on the oracle
+(test/runtests.jl:440-522): isoform/multi-map classes, assign_ambig! split, TPM EM invariants."""
+import json
+import os
+
+import numpy as np
+
+import whippet_jl_b200 as wq
+from conftest import GOLDEN
+from helpers import identity
+from oracle import Oracle
+
+
+def count_kat_reads(o, idx, p):
+    """test/runtests.jl:332-358: count!(gquant, align.value[best_ind], 1.0) for the ten reads."""
+    kat = json.load(open(os.path.join(GOLDEN, "kat_reads.json")))["reads"]
+    rb = wq.ReadBatch.from_strings([r["seq"] for r in kat], [r["qual"] for r in kat], 33, fill="C")
+    res = o.align_se(p, rb)
+    for i, r in enumerate(kat):
+        alns = res.read(i)
+        best = alns[int(np.argmax([identity(a, len(r["seq"])) for a in alns]))]
+        path = best[4]
+        g = path[0][0]
+        if len(path) == 1:
+            o.add_node(g, path[0][1], 1.0)
+        elif len(path) == 2:
+            o.add_edge(g, path[0][1], path[1][1], 1.0)
+        else:
+            o.add_keyed(0, [len(path), g] + [n[1] for n in path], 1.0)
+
+
+def test_multimapping_classes_and_assign_ambig(fixture_index, test_param):
+    """test/runtests.jl:472-511."""
+    idx = fixture_index
+    o = Oracle(idx)
+    o.quant_reset()
+    # alignment to gene 2 nodes [1,7] + gene 4 node [1]: path [1,7] matches no isoform -> isdone, empty class
+    o.add_keyed(1, [(1 << 28) | 2, 2, 2, 1, 7, 1, 4, 1], 1.0)
+    o.em_tpm(20)
+    (ids, props, cnt, isdone, post), = o.classes(multi=True)
+    assert isdone and post and ids == []
+    # gene 2 nodes [1,2] + gene 2 node [1] -> class [3,4,5]
+    o.quant_reset()
+    o.add_keyed(1, [(1 << 28) | 2, 2, 2, 1, 2, 1, 2, 1], 10.0)
+    o.em_tpm(20, maxit=1)        # maxit=1: classes built, no EM iteration
+    (ids, props, cnt, isdone, post), = o.classes(multi=True)
+    assert ids == [3, 4, 5] and not isdone and cnt == 10.0
+    nb = int(idx.node_base[1])
+    prev_node = o.node_counts()[nb]
+    o.assign_ambig()
+    assert o.node_counts()[nb] == prev_node + 7.5
+    k, v = o.edges()
+    assert dict(zip(k.tolist(), v.tolist()))[(2 << 32) | (1 << 16) | 2] == 2.5
+
+
+def test_isoform_classes_and_tpm(fixture_index, test_param):
+    """test/runtests.jl:440-470, 513-522: EM changes TPM, converges in < 5000 iterations, sum(tpm) == 1e6."""
+    idx = fixture_index
+    o = Oracle(idx)
+    o.quant_reset()
+    count_kat_reads(o, idx, test_param)
+    it0, tpm0, cnt0, _ = o.em_tpm(20, sig=1, maxit=1)       # calculate_tpm! only
+    cls = o.classes()
+    assert len(cls) >= 1 and all(len(c[0]) > 1 and c[2] > 0 for c in cls)
+    assert all(2 < i <= 5 for c in cls for i in c[0])          # only gene `one` (isoforms 3..5) has shared nodes
+    o.quant_reset()
+    count_kat_reads(o, idx, test_param)
+    it, tpm, cnt, gtpm = o.em_tpm(20, sig=1, maxit=10000)
+    assert not np.array_equal(tpm0, tpm)
+    assert it < 5000
+    assert tpm.sum() == 1000000
+    assert np.allclose(gtpm, [tpm[0:2].sum(), tpm[2:5].sum(), tpm[5], tpm[6]])

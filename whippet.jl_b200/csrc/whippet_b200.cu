@@ -69,6 +69,7 @@ struct wq_handle {
     uint32_t* h_cursors = nullptr;   // pinned
     // host-side quant state (filled by wq_counts_sync / merge; input of EM)
     WqHostQuant hq;
+    WqHostQuantEx hx;
     bool hq_valid = false;
     uint32_t chunk_reads = 1u << 22;
     float last_kernel_ms[3] = {0, 0, 0};
@@ -192,6 +193,7 @@ int wq_quant_reset(wq_handle* h) {
     CK(cudaMemsetAsync(h->d_kcursor.p, 0, 8, s));
     CK(cudaStreamSynchronize(s));
     h->hq = WqHostQuant();
+    h->hx = WqHostQuantEx();
     h->hq_valid = false;
     return 0;
 }
@@ -389,6 +391,7 @@ static int align_se_impl(wq_handle* h, const wq_align_param* ap, const wq_read_b
     const uint32_t n = reads->n_reads;
     if (n == 0) return 0;
     h->hq_valid = false;
+    h->hx = WqHostQuantEx();
     for (auto& m : h->last_kernel_ms) m = 0;
     if (on_device) {
         for (uint32_t lo = 0; lo < n; lo += h->chunk_reads) {
@@ -553,6 +556,7 @@ int wq_counts_merge(wq_handle* h, const wq_counts* c, const wq_keyed* longs, con
     if (!h) return fail(-1, "null handle");
     if (int rc = sync_host_quant(h)) return rc;
     WqHostQuant& Q = h->hq;
+    h->hx = WqHostQuantEx();
     if (c) {
         if (c->node_count) {
             if (c->n_nodes != Q.node.size()) return fail(-1, "node count vector has the wrong length");
@@ -587,7 +591,7 @@ int wq_em_tpm(wq_handle* h, const wq_em_param* p, double* tpm, double* count, do
     if (!h || !p) return fail(-1, "null argument");
     if (int rc = sync_host_quant(h)) return rc;
     CK(cudaSetDevice(h->device));
-    std::string err = wq_run_em_tpm(h->H, h->iso, h->hq, *p, h->stream, tpm, count, genetpm, iterations);
+    std::string err = wq_run_em_tpm(h->H, h->iso, h->hq, h->hx, *p, h->stream, &h->launches, tpm, count, genetpm, iterations);
     if (!err.empty()) return fail(-11, err);
     return 0;
 }
@@ -595,8 +599,21 @@ int wq_em_tpm(wq_handle* h, const wq_em_param* p, double* tpm, double* count, do
 int wq_assign_ambig(wq_handle* h, wq_values* v) {
     if (!h || !v) return fail(-1, "null argument");
     if (int rc = sync_host_quant(h)) return rc;
-    std::string err = wq_host_assign_ambig(h->H, h->iso, h->hq, v);
+    std::string err = wq_host_assign_ambig_impl(h->H, h->iso, h->hx);
     if (!err.empty()) return fail(-12, err);
+    WqHostQuantEx& X = h->hx;
+    uint64_t ne = 0, nc = 0;
+    for (auto& kv : X.edge_value) { if (wq_edge_is_circ(kv.first)) nc++; else ne++; }
+    bool sizing = !v->node_value && !v->edge_key && !v->circ_key;
+    if (!sizing && (v->n_nodes < X.node_value.size() || v->n_edge < ne || v->n_circ < nc)) return fail(-7, "wq_values buffers too small");
+    v->n_nodes = X.node_value.size(); v->n_edge = ne; v->n_circ = nc;
+    if (sizing) return 0;
+    if (v->node_value) memcpy(v->node_value, X.node_value.data(), X.node_value.size() * 8);
+    uint64_t ie = 0, ic = 0;
+    for (auto& kv : X.edge_value) {
+        if (wq_edge_is_circ(kv.first)) { if (v->circ_key) { v->circ_key[ic] = kv.first; v->circ_value[ic] = kv.second; } ic++; }
+        else { if (v->edge_key) { v->edge_key[ie] = kv.first; v->edge_value[ie] = kv.second; } ie++; }
+    }
     return 0;
 }
 

@@ -15,6 +15,27 @@ struct WqHostQuant {
     WqHostQuant() { memset(&stats, 0, sizeof stats); }
 };
 
+struct WqClassSet {                                         // IsoCompat / MultiCompat in canonical order (multi first)
+    std::vector<uint32_t> ptr;                               // [C+1]
+    std::vector<int32_t>  iso;                               // 0-based global isoform ids
+    std::vector<double>   prop;
+    std::vector<double>   count;                             // [C]
+    std::vector<uint8_t>  state;                             // [C] 0 active, 1/2 finished (isdone)
+    std::vector<uint8_t>  postassign;                        // [C]
+    uint32_t n_multi = 0;
+};
+
+// State of the quant stage after build_equivalence_classes! / gene_em! / assign_ambig!.
+struct WqHostQuantEx {
+    bool built = false, em_done = false, ambig_done = false;
+    std::vector<double> node_value;                          // node store as Float64 (fractional after assign_ambig!)
+    std::map<uint64_t, double> edge_value;                   // edge + circ stores
+    std::vector<double> iso_count, tpm, genetpm;
+    WqClassSet cls;
+    std::vector<const std::vector<uint32_t>*> multi_keys;    // key of each multi-map class (points into WqHostQuant.keyed)
+    int64_t iterations = 0;
+};
+
 static inline bool wq_edge_is_circ(uint64_t key) { return ((key >> 16) & 0xFFFF) >= (key & 0xFFFF); }
 static inline bool wq_key_is_multi(const std::vector<uint32_t>& k) { return !k.empty() && ((k[0] >> 28) & 1); }
 

@@ -150,3 +150,30 @@ class GraphLibQuant:
         k.rec_ptr, k.words, k.count = abi.ptr(ptr_, abi.u64p), abi.ptr(words, abi.u32p), abi.ptr(cnt, abi.u64p)
         lib.check(self.L.wq_keyed_download(self.h, kind, C.byref(k)))
         return {tuple(int(x) for x in words[int(ptr_[i]):int(ptr_[i + 1])]): int(cnt[i]) for i in range(k.n_rec)}
+
+    # ---- quantification -------------------------------------------------------------------------
+    def gene_em(self, readlen: int, sig: int = 1, maxit: int = 10000):
+        """build_equivalence_classes!(quant, lib) + calculate_tpm!(quant, readlen) + gene_em!(quant, multi;
+        sig, readlen, maxit) + set_gene_tpm! (bin/whippet-quant.jl:161-166).  Returns
+        (iterations, tpm[I], count[I], genetpm[G])."""
+        I, G = self.index.n_isoforms, self.index.n_genes
+        tpm, cnt, gt = np.zeros(I), np.zeros(I), np.zeros(G)
+        it = C.c_int64()
+        p = abi.EmParamC(int(readlen), int(sig), int(maxit))
+        lib.check(self.L.wq_em_tpm(self.h, C.byref(p), abi.ptr(tpm, abi.f64p), abi.ptr(cnt, abi.f64p),
+                                   abi.ptr(gt, abi.f64p), C.byref(it)))
+        return int(it.value), tpm, cnt, gt
+
+    def assign_ambig(self):
+        """assign_ambig!(quant, lib, multi) (src/quant.jl:520-553).  Returns the node / edge / circ stores
+        as Float64: (node_value[N], edge_key, edge_value, circ_key, circ_value)."""
+        v = abi.ValuesC()
+        lib.check(self.L.wq_assign_ambig(self.h, C.byref(v)))
+        node = np.zeros(v.n_nodes)
+        ek, ev = np.zeros(v.n_edge, "<u8"), np.zeros(v.n_edge)
+        ck, cv = np.zeros(v.n_circ, "<u8"), np.zeros(v.n_circ)
+        v.node_value = abi.ptr(node, abi.f64p)
+        v.edge_key, v.edge_value = abi.ptr(ek, abi.u64p), abi.ptr(ev, abi.f64p)
+        v.circ_key, v.circ_value = abi.ptr(ck, abi.u64p), abi.ptr(cv, abi.f64p)
+        lib.check(self.L.wq_assign_ambig(self.h, C.byref(v)))
+        return node, ek, ev, ck, cv
