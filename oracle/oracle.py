@@ -122,6 +122,10 @@ class Oracle:
         p, b = param.c(), reads.c()
         lib().wqo_process_reads_se(C.c_void_p(self.h), C.byref(p), C.byref(b))
 
+    def process_paired_reads(self, param: wq.AlignParam, fwd: wq.ReadBatch, rev: wq.ReadBatch):
+        p, f, r = param.c(), fwd.c(), rev.c()
+        lib().wqo_process_reads_pe(C.c_void_p(self.h), C.byref(p), C.byref(f), C.byref(r))
+
     def stats(self):
         out = (C.c_uint64 * 5)()
         m = C.c_double()

@@ -751,6 +751,66 @@ void count_se(const Lib& L, Quant& Q, const Align& a, double value) {
     }
 }
 
+// Base.in(first::SGAlignPath, last::SGAlignPath), src/quant.jl:47-62
+bool path_in_path(const std::vector<ANode>& first, const std::vector<ANode>& last) {
+    for (Int i = 1; i <= (Int)last.size() - (Int)first.size() + 1; i++) {
+        Int offset = i - 1;
+        bool match = true;
+        for (Int j = 1; j <= (Int)first.size(); j++) {
+            const ANode& a = first[j - 1];
+            const ANode& b = last[offset + j - 1];
+            if (!(a.gene == b.gene && a.node == b.node)) { match = false; break; }
+        }
+        if (match) return true;
+    }
+    return false;
+}
+
+std::vector<uint32_t> paired_key(const Align& f, const Align& r) {
+    std::vector<uint32_t> key{(2u << 28) | (uint32_t)f.path.size() | ((uint32_t)r.path.size() << 8), f.path[0].gene};
+    for (auto& n : f.path) key.push_back(n.node);
+    for (auto& n : r.path) key.push_back(n.node);
+    return key;
+}
+
+// count!(quant, fwd, rev, value), src/quant.jl:597-653
+void count_pe(const Lib& L, Quant& Q, const Align& fwd, const Align& rev, double value) {
+    if (!(fwd.isvalid && rev.isvalid)) return;
+    uint32_t init_gene = fwd.path[0].gene, rev_gene = rev.path[0].gene;
+    if (init_gene != rev_gene) return;
+    size_t nb = L.d->node_base[init_gene - 1];
+    bool singlebool = false;
+    const std::vector<ANode>* single = nullptr;
+    if (fwd.path.size() <= rev.path.size()) {
+        if (path_in_path(fwd.path, rev.path)) { singlebool = true; single = &rev.path; }
+    } else {
+        if (path_in_path(rev.path, fwd.path)) { singlebool = true; single = &fwd.path; }
+    }
+    if (singlebool) {
+        if (single->size() == 1) {
+            Q.node[nb + (*single)[0].node - 1] += value;
+        } else {
+            for (auto& n : *single) if (n.gene != init_gene) return;
+            if (single->size() == 2) {
+                uint32_t l = (*single)[0].node, r = (*single)[1].node;
+                Q.edge[((uint64_t)init_gene << 32) | ((uint64_t)(l & 0xFFFF) << 16) | (r & 0xFFFF)] += value;
+            }
+        }
+    } else {
+        Q.longs[paired_key(fwd, rev)] += value;
+    }
+}
+
+// push!(multi, fwd, rev, value, ...), src/quant.jl:471-484
+void push_multi_pe(Quant& Q, const std::vector<Align>& f, const std::vector<Align>& r, double value) {
+    std::vector<uint32_t> key{(3u << 28) | (uint32_t)f.size()};
+    for (size_t i = 0; i < f.size(); i++) {
+        std::vector<uint32_t> k = paired_key(f[i], r[i]);
+        key.insert(key.end(), k.begin(), k.end());
+    }
+    Q.multi[key] += value;
+}
+
 // push!(multi, alns, value, ...), src/quant.jl:456-469: the key is the ordered vector of node paths
 void push_multi_se(Quant& Q, const std::vector<Align>& alns, double value) {
     std::vector<uint32_t> key{(1u << 28) | (uint32_t)alns.size()};
@@ -1108,6 +1168,25 @@ int wqo_process_reads_se(wqo_handle* h, const wq_align_param* p, const wq_read_b
             Q.mapped += 1;
             Q.sum_readlen += r.seq.size();
             Q.mean_readlen += ((double)r.seq.size() - Q.mean_readlen) / (double)Q.mapped;
+        }
+    }
+    return 0;
+}
+// process_paired_reads!, src/reads.jl:83-129
+int wqo_process_reads_pe(wqo_handle* h, const wq_align_param* p, const wq_read_batch* f, const wq_read_batch* rv) {
+    Quant& Q = h->Q;
+    std::vector<Align> fr, rr;
+    for (uint32_t i = 0; i < f->n_reads; i++) {
+        Read a = load_read(f, i), b = load_read(rv, i);
+        uint8_t fl;
+        bool ok = ungapped_align_pe(h->L, *p, a, b, fr, rr, fl);
+        Q.total += 1;
+        if (ok) {
+            if (fr.size() > 1) { push_multi_pe(Q, fr, rr, 1.0); Q.nmulti += 1; }
+            else count_pe(h->L, Q, fr[0], rr[0], 1.0);
+            Q.mapped += 1;
+            Q.sum_readlen += a.seq.size();
+            Q.mean_readlen += ((double)a.seq.size() - Q.mean_readlen) / (double)Q.mapped;
         }
     }
     return 0;

@@ -51,3 +51,27 @@ def ragged_reads(idx, n=20000, seed=5, lo=30, hi=255):
     Q = len(rb.qual) // n
     quals = rb.qual.reshape(n, Q)[:, :hi]
     return wq.ReadBatch.from_codes(codes, quals, lens)
+
+
+def same_strand_mate(r, R):
+    """Turn a head-to-head mate 2 into a same-orientation one (for is_pair_rc = false)."""
+    W = len(r.seq2) // r.n
+    codes = np.zeros((r.n, R), np.uint8)
+    words = r.seq2.reshape(r.n, W)
+    for j in range(R):
+        codes[:, j] = (words[:, j >> 5] >> np.uint64(2 * (j & 31))) & np.uint64(3)
+    Q = len(r.qual) // r.n
+    q = r.qual.reshape(r.n, Q)[:, :R]
+    return wq.ReadBatch.from_codes(np.ascontiguousarray(3 - codes[:, ::-1]), np.ascontiguousarray(q[:, ::-1]))
+
+
+PE_CASES = [(1, 300, 101, 5000, True), (2, 300, 50, 2500, True), (3, 200, 150, 1000, True), (4, 300, 76, 5000, False)]
+
+
+def pe_case(seed, ng, R, pair_range, rc, n):
+    idx = synth.make_index(n_genes=ng, K=9, seed=seed, paralog_frac=0.15)
+    p = wq.AlignParam(seed_pair_range=pair_range, is_paired=True, is_pair_rc=rc)
+    f, r = synth.simulate_reads(idx, n, R, seed=seed + 10, sub_rate=0.01, paired=True)
+    if not rc:
+        r = same_strand_mate(r, R)
+    return idx, p, f, r

@@ -54,6 +54,19 @@ class Emu:
         self.L.emu_result_copy(self.h, v(hs), v(nh), v(fl), v(aln), v(nodes))
         return AlignResult(hs, nh, fl, aln, nodes)
 
+    def align_pe(self, param, fwd, rev):
+        p, f, r = param.c(), fwd.c(), rev.c()
+        rc = self.L.emu_align_pe(self.h, C.byref(p), C.byref(f), C.byref(r))
+        assert rc == 0, rc
+        nn = C.c_uint64()
+        na = self.L.emu_result_sizes(self.h, C.byref(nn))
+        n = fwd.n
+        hs, nh, fl = np.zeros(n, "<u4"), np.zeros(n, "u1"), np.zeros(n, "u1")
+        aln, alm, nodes = np.zeros(na, abi.ALIGNMENT_DT), np.zeros(na, abi.ALIGNMENT_DT), np.zeros(nn.value, abi.ALIGN_NODE_DT)
+        v = lambda a: a.ctypes.data_as(C.c_void_p)
+        self.L.emu_result_copy_pe(self.h, v(hs), v(nh), v(fl), v(aln), v(alm), v(nodes))
+        return AlignResult(hs, nh, fl, aln, nodes, alm)
+
     def seeds(self, n):
         out = np.zeros((n, 4), np.int64)
         self.L.emu_seeds(self.h, out.ctypes.data_as(C.c_void_p))

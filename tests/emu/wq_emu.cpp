@@ -17,7 +17,8 @@ struct Emu {
     WqQuantDev q;
     // last batch
     std::vector<WqSeed> seeds;
-    std::vector<uint32_t> hit_read, hit_s, pending;
+    std::vector<uint32_t> hit_read, hit_s, hit_s2, hit_gene, pending;
+    bool paired = false;
     std::vector<WqHit> hits;
     std::vector<wq_align_node> pool;
     uint32_t cursors[3];
@@ -60,7 +61,8 @@ int emu_align_se(Emu* e, const wq_align_param* ap, const wq_read_batch* rb) {
     e->pool.assign((size_t)hit_cap * 4 + 64, wq_align_node());
     e->pending.assign(n + 1, 0);
     e->cursors[0] = e->cursors[1] = e->cursors[2] = 0;
-    WqWork wk{e->seeds.data(), e->hit_read.data(), e->hit_s.data(), e->hits.data(), e->pool.data(), e->cursors,
+    e->paired = false;
+    WqWork wk{e->seeds.data(), e->hit_read.data(), e->hit_s.data(), nullptr, nullptr, e->hits.data(), e->pool.data(), e->cursors,
               e->pending.data(), hit_cap, (uint32_t)e->pool.size()};
     for (uint32_t r = 0; r < n; r++) wq_seed_thread(e->ix, p, b, wk, r);
     uint32_t nh = e->cursors[0];
@@ -72,16 +74,74 @@ int emu_align_se(Emu* e, const wq_align_param* ap, const wq_read_batch* rb) {
     return (int)e->cursors[2];   // pending (always 0 single-threaded)
 }
 
+int emu_align_pe(Emu* e, const wq_align_param* ap, const wq_read_batch* rf, const wq_read_batch* rr) {
+    WqParams p;
+    std::string err = wq_make_params(ap, e->H.K, p);
+    if (!err.empty()) { fprintf(stderr, "emu: %s\n", err.c_str()); return -1; }
+    WqBatchDev bf{rf->n_reads, rf->len, rf->seq_off, rf->seq2, rf->qual_off, rf->qual};
+    WqBatchDev br{rr->n_reads, rr->len, rr->seq_off, rr->seq2, rr->qual_off, rr->qual};
+    uint32_t n = rf->n_reads;
+    e->seeds.assign(n, WqSeed());
+    uint32_t hit_cap = n * p.seed_tolerate + 1;
+    e->hit_read.assign(hit_cap, 0); e->hit_s.assign(hit_cap, 0); e->hit_s2.assign(hit_cap, 0); e->hit_gene.assign(hit_cap, 0);
+    e->hits.assign((size_t)2 * hit_cap, WqHit());
+    e->pool.assign((size_t)hit_cap * 8 + 64, wq_align_node());
+    e->pending.assign(n + 1, 0);
+    e->cursors[0] = e->cursors[1] = e->cursors[2] = 0;
+    e->paired = true;
+    WqWork wk{e->seeds.data(), e->hit_read.data(), e->hit_s.data(), e->hit_s2.data(), e->hit_gene.data(), e->hits.data(),
+              e->pool.data(), e->cursors, e->pending.data(), hit_cap, (uint32_t)e->pool.size()};
+    for (uint32_t r = 0; r < n; r++) wq_seed_pe_thread(e->ix, p, bf, br, wk, r);
+    uint32_t nh = e->cursors[0];
+    for (uint32_t s = 0; s < nh; s++) { wq_extend_pe_thread(e->ix, p, bf, br, wk, s, 0); wq_extend_pe_thread(e->ix, p, bf, br, wk, s, 1); }
+    uint64_t stats[5] = {0, 0, 0, 0, 0};
+    for (uint32_t r = 0; r < n; r++) wq_resolve_pe_thread(e->ix, p, bf, br, wk, e->q, r, stats);
+    e->counters.total += n; e->counters.mapped += stats[0]; e->counters.multi += stats[1];
+    e->counters.sum_readlen += stats[2]; e->counters.path_overflow += stats[3]; e->counters.pool_overflow += stats[4];
+    return (int)e->cursors[2];
+}
+
 // results of the last batch in the oracle's CSR layout (kept alignments only, reference order)
 uint64_t emu_result_sizes(Emu* e, uint64_t* n_nodes) {
     uint64_t na = 0, nn = 0;
     for (auto& s : e->seeds)
         for (int k = 0; k < s.cnt; k++) {
+            if (e->paired) {
+                const WqHit& hf = e->hits[2 * (s.hit_base + k)];
+                const WqHit& hr = e->hits[2 * (s.hit_base + k) + 1];
+                if (hf.flags & 4) { na++; nn += hf.npath + hr.npath; }
+                continue;
+            }
             const WqHit& h = e->hits[s.hit_base + k];
             if (h.flags & 4) { na++; nn += h.npath; }
         }
     *n_nodes = nn;
     return na;
+}
+static wq_alignment emu_mk(Emu* e, const WqHit& h, wq_align_node* nodes, uint64_t& nn) {
+    wq_alignment a;
+    a.offset = h.offset; a.path_start = (uint32_t)nn; a.offsetread = h.offsetread; a.strand = h.strand;
+    a.isvalid = h.flags & 1; a.npath = h.npath;
+    for (int i = 0; i < h.npath; i++) nodes[nn++] = e->pool[h.path_start + i];
+    return a;
+}
+void emu_result_copy_pe(Emu* e, uint32_t* hit_start, uint8_t* nhits, uint8_t* flipped, wq_alignment* aln, wq_alignment* alm, wq_align_node* nodes) {
+    uint64_t na = 0, nn = 0;
+    for (size_t r = 0; r < e->seeds.size(); r++) {
+        const WqSeed& s = e->seeds[r];
+        hit_start[r] = (uint32_t)na;
+        uint8_t c = 0;
+        for (int k = 0; k < s.cnt; k++) {
+            const WqHit& hf = e->hits[2 * (s.hit_base + k)];
+            const WqHit& hr = e->hits[2 * (s.hit_base + k) + 1];
+            if (!(hf.flags & 4)) continue;
+            aln[na] = emu_mk(e, hf, nodes, nn);
+            alm[na] = emu_mk(e, hr, nodes, nn);
+            na++; c++;
+        }
+        nhits[r] = c;
+        flipped[r] = (uint8_t)((!s.strand ? 1 : 0) | ((s.sp & 0x100u) ? 2 : 0));
+    }
 }
 void emu_result_copy(Emu* e, uint32_t* hit_start, uint8_t* nhits, uint8_t* flipped, wq_alignment* aln, wq_align_node* nodes) {
     uint64_t na = 0, nn = 0;

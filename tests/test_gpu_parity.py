@@ -8,7 +8,7 @@ import pytest
 import whippet_jl_b200 as wq
 from whippet_jl_b200 import synth
 from conftest import GOLDEN
-from data_gen import fixture_random_reads, ragged_reads
+from data_gen import PE_CASES, fixture_random_reads, pe_case, ragged_reads
 from helpers import cigar_string
 from helpers_cmp import results_equal
 from oracle import Oracle
@@ -161,3 +161,37 @@ def test_em_synthetic(seed, ng, R):
     rb = synth.simulate_reads(idx, 300000, R, seed=seed + 10, sub_rate=0.01)
     it, tpm = em_parity(idx, wq.AlignParam(), rb, R)
     assert it > 2
+
+
+@pytest.mark.parametrize("seed,ng,R,pr,rc", PE_CASES)
+def test_paired_end(seed, ng, R, pr, rc):
+    """Paired ungapped_align (src/paired.jl:42-125) + paired count! (src/quant.jl:597-653) + EM."""
+    idx, p, f, r = pe_case(seed, ng, R, pr, rc, 100000)
+    o = Oracle(idx)
+    os.environ["WQ_CHUNK_READS"] = "30000"
+    try:
+        q = wq.GraphLibQuant(idx)
+    finally:
+        os.environ.pop("WQ_CHUNK_READS", None)
+    ro = o.align_pe(p, f, r)
+    rg = q.ungapped_align(p, f, r)
+    assert results_equal(ro, rg, f.n, paired=True) == []
+    o.quant_reset()
+    o.process_paired_reads(p, f, r)
+    st, sg = o.stats(), q.stats()
+    assert (st["total"], st["mapped"], st["multi"], st["sum_readlen"]) == (sg.total, sg.mapped, sg.multi, sg.sum_readlen)
+    node, ek, ec, ck, cc = q.counts()
+    assert np.array_equal(o.node_counts(), node.astype(float))
+    ok, ov = o.edges()
+    gk, gv = np.concatenate([ek, ck]), np.concatenate([ec, cc])
+    order = np.argsort(gk)
+    assert np.array_equal(ok, gk[order]) and np.array_equal(ov, gv[order].astype(float))
+    assert o.keyed(0) == {k: float(v) for k, v in q.keyed(0).items()}
+    assert o.keyed(1) == {k: float(v) for k, v in q.keyed(1).items()}
+    it_o, tpm_o, cnt_o, gt_o = o.em_tpm(R, 1, 10000)
+    it_g, tpm_g, cnt_g, gt_g = q.gene_em(R, 1, 10000)
+    assert it_g == it_o and np.array_equal(tpm_g, tpm_o) and np.array_equal(cnt_g, cnt_o)
+    o.assign_ambig()
+    nodev = q.assign_ambig()[0]
+    assert np.array_equal(nodev, o.node_counts())
+    q.close()

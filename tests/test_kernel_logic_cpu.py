@@ -10,7 +10,7 @@ import pytest
 import whippet_jl_b200 as wq
 from whippet_jl_b200 import synth
 from conftest import GOLDEN
-from data_gen import fixture_random_reads, ragged_reads
+from data_gen import PE_CASES, fixture_random_reads, pe_case, ragged_reads
 from emu.emu import Emu
 from helpers_cmp import results_equal
 from oracle import Oracle
@@ -70,3 +70,24 @@ def test_stranded_and_small_k():
     compare_all(idx, p, rb)
     p2 = wq.AlignParam(mismatches=4, kmer_size=5, seed_try=2, seed_tolerate=8, seed_length=10, seed_buffer=1, seed_inc=3)
     compare_all(idx, p2, rb)
+
+
+@pytest.mark.parametrize("seed,ng,R,pr,rc", PE_CASES)
+def test_paired_end(seed, ng, R, pr, rc):
+    idx, p, f, r = pe_case(seed, ng, R, pr, rc, 20000)
+    o, e = Oracle(idx), Emu(idx)
+    ro, re = o.align_pe(p, f, r), e.align_pe(p, f, r)
+    assert results_equal(ro, re, f.n, paired=True) == []
+    assert (ro.nhits > 0).mean() > 0.85
+    o.quant_reset()
+    o.process_paired_reads(p, f, r)
+    st, c = o.stats(), e.counters()
+    for k in ("total", "mapped", "multi", "sum_readlen"):
+        assert st[k] == c[k], k
+    assert np.array_equal(o.node_counts(), e.node_counts().astype(float))
+    ok, ov = o.edges()
+    ek, ev = e.edges()
+    assert np.array_equal(ok, ek) and np.array_equal(ov, ev.astype(float))
+    el, em = e.keyed()
+    assert o.keyed(0) == {k: float(v) for k, v in el.items()}
+    assert o.keyed(1) == {k: float(v) for k, v in em.items()}

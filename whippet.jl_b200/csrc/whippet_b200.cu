@@ -64,7 +64,7 @@ struct wq_handle {
     WqQuantDev q;
     // per-batch buffers
     DevBuf<uint8_t> d_len[2], d_qual[2]; DevBuf<uint64_t> d_seqoff[2], d_qualoff[2], d_seq2[2];
-    DevBuf<WqSeed> d_seeds; DevBuf<uint32_t> d_hit_read, d_hit_s, d_pending, d_pending2, d_cursors;
+    DevBuf<WqSeed> d_seeds; DevBuf<uint32_t> d_hit_read, d_hit_s, d_hit_s2, d_hit_gene, d_pending, d_pending2, d_cursors;
     DevBuf<WqHit> d_hits; DevBuf<wq_align_node> d_pool;
     uint32_t* h_cursors = nullptr;   // pinned
     // host-side quant state (filled by wq_counts_sync / merge; input of EM)
@@ -86,11 +86,53 @@ __global__ void __launch_bounds__(128) wq_k_seed(const WqDevIndex ix, const __gr
 
 __global__ void __launch_bounds__(128) wq_k_extend(const WqDevIndex ix, const __grid_constant__ WqParams p,
                                                    const WqBatchDev b, const WqWork wk) {
-    uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t nh = wk.cursors[0];
     if (nh > wk.hit_cap) nh = wk.hit_cap;
-    if (slot >= nh) return;
-    wq_extend_thread(ix, p, b, wk, slot);
+    for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < nh; slot += gridDim.x * blockDim.x)
+        wq_extend_thread(ix, p, b, wk, slot);
+}
+
+__global__ void __launch_bounds__(128) wq_k_seed_pe(const WqDevIndex ix, const __grid_constant__ WqParams p,
+                                                    const WqBatchDev bf, const WqBatchDev br, const WqWork wk) {
+    uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= bf.n) return;
+    wq_seed_pe_thread(ix, p, bf, br, wk, r);
+}
+
+__global__ void __launch_bounds__(128) wq_k_extend_pe(const WqDevIndex ix, const __grid_constant__ WqParams p,
+                                                      const WqBatchDev bf, const WqBatchDev br, const WqWork wk) {
+    uint32_t nh = wk.cursors[0];
+    if (nh > wk.hit_cap) nh = wk.hit_cap;
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < 2 * nh; t += gridDim.x * blockDim.x)
+        wq_extend_pe_thread(ix, p, bf, br, wk, t >> 1, (int)(t & 1));
+}
+
+__global__ void __launch_bounds__(128) wq_k_resolve_pe(const WqDevIndex ix, const __grid_constant__ WqParams p,
+                                                       const WqBatchDev bf, const WqBatchDev br, const WqWork wk, const WqQuantDev q) {
+    uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t st[5] = {0, 0, 0, 0, 0};
+    if (r < bf.n) wq_resolve_pe_thread(ix, p, bf, br, wk, q, r, st);
+#pragma unroll
+    for (int i = 0; i < 5; i++) {
+        unsigned long long v = st[i];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        st[i] = v;
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (st[0]) atomicAdd((unsigned long long*)&q.counters->mapped, (unsigned long long)st[0]);
+        if (st[1]) atomicAdd((unsigned long long*)&q.counters->multi, (unsigned long long)st[1]);
+        if (st[2]) atomicAdd((unsigned long long*)&q.counters->sum_readlen, (unsigned long long)st[2]);
+        if (st[3]) atomicAdd((unsigned long long*)&q.counters->path_overflow, (unsigned long long)st[3]);
+        if (st[4]) atomicAdd((unsigned long long*)&q.counters->pool_overflow, (unsigned long long)st[4]);
+    }
+    if (r == 0) atomicAdd((unsigned long long*)&q.counters->total, (unsigned long long)bf.n);
+}
+
+__global__ void __launch_bounds__(128) wq_k_retry_pe(const WqDevIndex ix, const WqWork wk, const WqQuantDev q,
+                                                     const uint32_t* list, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    wq_retry_pe_thread(ix, wk, q, list[i]);
 }
 
 __global__ void __launch_bounds__(128) wq_k_resolve(const WqDevIndex ix, const __grid_constant__ WqParams p,
@@ -171,7 +213,7 @@ void wq_destroy(wq_handle* h) {
         if (h->ev_copy[i]) cudaEventDestroy(h->ev_copy[i]);
         if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
     }
-    h->d_seeds.release(); h->d_hit_read.release(); h->d_hit_s.release(); h->d_pending.release(); h->d_pending2.release();
+    h->d_seeds.release(); h->d_hit_read.release(); h->d_hit_s.release(); h->d_hit_s2.release(); h->d_hit_gene.release(); h->d_pending.release(); h->d_pending2.release();
     h->d_cursors.release(); h->d_hits.release(); h->d_pool.release();
     if (h->h_cursors) cudaFreeHost(h->h_cursors);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -292,27 +334,37 @@ int wq_index_create(const wq_index_desc* d, int device, wq_handle** out) {
     return 0;
 }
 
-// Run the three kernels over reads [0, b.n) already resident on the device.
-static int run_chunk(wq_handle* h, const WqParams& p, const WqBatchDev& b, bool time_kernels) {
+// Run the three kernels over reads [0, b.n) already resident on the device (br != NULL: read pairs).
+static int run_chunk(wq_handle* h, const WqParams& p, const WqBatchDev& b, const WqBatchDev* br, bool time_kernels) {
     const uint32_t n = b.n;
     if (n == 0) return 0;
+    const bool pe = br != nullptr;
     cudaStream_t s = h->stream;
     const uint32_t hit_cap = n * (uint32_t)p.seed_tolerate;
-    const uint32_t pool_cap = (uint32_t)std::min<uint64_t>((uint64_t)n * 8 + 1024, 0xFFFFFFF0ull);
-    CK(h->d_seeds.ensure(n)); CK(h->d_hit_read.ensure(hit_cap)); CK(h->d_hit_s.ensure(hit_cap)); CK(h->d_hits.ensure(hit_cap));
+    const uint32_t pool_cap = (uint32_t)std::min<uint64_t>((uint64_t)n * (pe ? 16 : 8) + 1024, 0xFFFFFFF0ull);
+    CK(h->d_seeds.ensure(n)); CK(h->d_hit_read.ensure(hit_cap)); CK(h->d_hit_s.ensure(hit_cap));
+    CK(h->d_hits.ensure((size_t)hit_cap * (pe ? 2 : 1)));
+    if (pe) { CK(h->d_hit_s2.ensure(hit_cap)); CK(h->d_hit_gene.ensure(hit_cap)); }
     CK(h->d_pool.ensure(pool_cap)); CK(h->d_pending.ensure(n)); CK(h->d_pending2.ensure(n));
-    WqWork wk{h->d_seeds.p, h->d_hit_read.p, h->d_hit_s.p, h->d_hits.p, h->d_pool.p, h->d_cursors.p, h->d_pending.p, hit_cap, pool_cap};
+    WqWork wk{h->d_seeds.p, h->d_hit_read.p, h->d_hit_s.p, h->d_hit_s2.p, h->d_hit_gene.p, h->d_hits.p, h->d_pool.p,
+              h->d_cursors.p, h->d_pending.p, hit_cap, pool_cap};
     CK(cudaMemsetAsync(h->d_cursors.p, 0, 16 * sizeof(uint32_t), s));
     cudaEvent_t ev[4];
     if (time_kernels) for (auto& e : ev) CK(cudaEventCreate(&e));
     const int T = 128;
+    const uint32_t gread = (n + T - 1) / T;
     if (time_kernels) CK(cudaEventRecord(ev[0], s));
-    wq_k_seed<<<(n + T - 1) / T, T, 0, s>>>(h->dix, p, b, wk);
+    if (!pe) wq_k_seed<<<gread, T, 0, s>>>(h->dix, p, b, wk);
+    else wq_k_seed_pe<<<gread, T, 0, s>>>(h->dix, p, b, *br, wk);
     h->launches += 3;
     if (time_kernels) CK(cudaEventRecord(ev[1], s));
-    wq_k_extend<<<(hit_cap + T - 1) / T, T, 0, s>>>(h->dix, p, b, wk);
+    // one thread per located hit; the hit count lives on the device, so the grid is sized for the usual
+    // ~1 hit per read and strides over the rest
+    if (!pe) wq_k_extend<<<gread + gread / 8 + 1, T, 0, s>>>(h->dix, p, b, wk);
+    else wq_k_extend_pe<<<2 * gread + gread / 4 + 1, T, 0, s>>>(h->dix, p, b, *br, wk);
     if (time_kernels) CK(cudaEventRecord(ev[2], s));
-    wq_k_resolve<<<(n + T - 1) / T, T, 0, s>>>(h->dix, p, b, wk, h->q);
+    if (!pe) wq_k_resolve<<<gread, T, 0, s>>>(h->dix, p, b, wk, h->q);
+    else wq_k_resolve_pe<<<gread, T, 0, s>>>(h->dix, p, b, *br, wk, h->q);
     if (time_kernels) CK(cudaEventRecord(ev[3], s));
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(h->h_cursors, h->d_cursors.p, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
@@ -321,7 +373,7 @@ static int run_chunk(wq_handle* h, const WqParams& p, const WqBatchDev& b, bool 
         for (int i = 0; i < 3; i++) { float ms = 0; cudaEventElapsedTime(&ms, ev[i], ev[i + 1]); h->last_kernel_ms[i] += ms; }
         for (auto& e : ev) cudaEventDestroy(e);
     }
-    if (h->h_cursors[1] > pool_cap) return fail(-5, "alignment path pool exhausted for this batch (raise WQ_CHUNK_READS granularity or report)");
+    if (h->h_cursors[1] > pool_cap) return fail(-5, "alignment path pool exhausted for this batch (lower WQ_CHUNK_READS)");
     // keyed inserts that raced with the slot owner: retry until none is left
     uint32_t pending = h->h_cursors[2];
     int guard = 0;
@@ -330,11 +382,12 @@ static int run_chunk(wq_handle* h, const WqParams& p, const WqBatchDev& b, bool 
         CK(cudaMemcpyAsync(h->d_pending2.p, h->d_pending.p, pending * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
         const uint32_t* list = h->d_pending2.p;
         CK(cudaMemsetAsync(h->d_cursors.p + 2, 0, sizeof(uint32_t), s));
-        wq_k_retry<<<(pending + T - 1) / T, T, 0, s>>>(h->dix, wk, h->q, list, pending);
+        if (!pe) wq_k_retry<<<(pending + T - 1) / T, T, 0, s>>>(h->dix, wk, h->q, list, pending);
+        else wq_k_retry_pe<<<(pending + T - 1) / T, T, 0, s>>>(h->dix, wk, h->q, list, pending);
         h->launches += 1;
-        CK(cudaMemcpyAsync(h->h_cursors, h->d_cursors.p, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(h->h_cursors + 4, h->d_cursors.p, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
-        pending = h->h_cursors[2];
+        pending = h->h_cursors[6];
     }
     return 0;
 }
@@ -346,43 +399,72 @@ static int check_batch(const wq_read_batch* r) {
 }
 
 // Download the alignments of the chunk just processed (reads [first, first+n) of the caller's batch).
-static int collect_chunk(wq_handle* h, uint32_t first, uint32_t n, wq_align_out* out) {
+static int collect_chunk(wq_handle* h, uint32_t first, uint32_t n, bool pe, wq_align_out* out) {
     cudaStream_t s = h->stream;
     uint32_t nh = h->h_cursors[0], np = h->h_cursors[1];
+    const uint32_t mult = pe ? 2 : 1;
     std::vector<WqSeed> seeds(n);
-    std::vector<WqHit> hits(nh);
+    std::vector<WqHit> hits((size_t)nh * mult);
     std::vector<wq_align_node> pool(np);
     CK(cudaMemcpyAsync(seeds.data(), h->d_seeds.p, n * sizeof(WqSeed), cudaMemcpyDeviceToHost, s));
-    if (nh) CK(cudaMemcpyAsync(hits.data(), h->d_hits.p, nh * sizeof(WqHit), cudaMemcpyDeviceToHost, s));
+    if (nh) CK(cudaMemcpyAsync(hits.data(), h->d_hits.p, hits.size() * sizeof(WqHit), cudaMemcpyDeviceToHost, s));
     if (np) CK(cudaMemcpyAsync(pool.data(), h->d_pool.p, np * sizeof(wq_align_node), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
+    if (pe && !out->aln_mate) return fail(-1, "wq_align_out.aln_mate is required for paired batches");
+    auto put = [&](const WqHit& hh, wq_alignment* dst) -> bool {
+        if (out->nodes_used + hh.npath > out->nodes_cap) return false;
+        wq_alignment a;
+        a.offset = hh.offset; a.path_start = (uint32_t)out->nodes_used; a.offsetread = hh.offsetread;
+        a.strand = hh.strand; a.isvalid = hh.flags & 1; a.npath = hh.npath;
+        *dst = a;
+        memcpy(out->nodes + out->nodes_used, pool.data() + hh.path_start, hh.npath * sizeof(wq_align_node));
+        out->nodes_used += hh.npath;
+        return true;
+    };
     for (uint32_t i = 0; i < n; i++) {
         const WqSeed& sd = seeds[i];
         uint32_t r = first + i;
         out->hit_start[r] = (uint32_t)out->aln_used;
         uint8_t c = 0;
         for (int k = 0; k < sd.cnt; k++) {
-            const WqHit& hh = hits[sd.hit_base + k];
+            const WqHit& hh = hits[(size_t)(sd.hit_base + k) * mult];
             if (!(hh.flags & 4)) continue;
-            if (out->aln_used >= out->aln_cap || out->nodes_used + hh.npath > out->nodes_cap)
-                return fail(-7, "wq_align_out capacity too small");
-            wq_alignment a;
-            a.offset = hh.offset; a.path_start = (uint32_t)out->nodes_used; a.offsetread = hh.offsetread;
-            a.strand = hh.strand; a.isvalid = hh.flags & 1; a.npath = hh.npath;
-            out->aln[out->aln_used++] = a;
-            memcpy(out->nodes + out->nodes_used, pool.data() + hh.path_start, hh.npath * sizeof(wq_align_node));
-            out->nodes_used += hh.npath;
+            if (out->aln_used >= out->aln_cap) return fail(-7, "wq_align_out capacity too small");
+            if (!put(hh, &out->aln[out->aln_used])) return fail(-7, "wq_align_out capacity too small");
+            if (pe && !put(hits[(size_t)(sd.hit_base + k) * 2 + 1], &out->aln_mate[out->aln_used])) return fail(-7, "wq_align_out capacity too small");
+            out->aln_used++;
             c++;
         }
         out->nhits[r] = c;
-        out->flipped[r] = (sd.cnt > 0 && !sd.strand) ? 1 : 0;
+        if (!pe) out->flipped[r] = (sd.cnt > 0 && !sd.strand) ? 1 : 0;
+        else out->flipped[r] = (uint8_t)((!sd.strand ? 1 : 0) | ((sd.sp & 0x100u) ? 2 : 0));
     }
     return 0;
 }
 
-static int align_se_impl(wq_handle* h, const wq_align_param* ap, const wq_read_batch* reads, wq_align_out* out, bool on_device) {
+struct BatchOnDev { DevBuf<uint8_t>* len; DevBuf<uint64_t>* seqoff; DevBuf<uint64_t>* seq2; DevBuf<uint64_t>* qualoff; DevBuf<uint8_t>* qual; };
+
+static int upload_batch(wq_handle* h, const wq_read_batch* reads, int which, cudaStream_t s) {
+    const uint32_t n = reads->n_reads;
+    CK(h->d_len[which].ensure(n)); CK(h->d_seqoff[which].ensure(n)); CK(h->d_qualoff[which].ensure(n));
+    CK(h->d_seq2[which].ensure(reads->seq2_words + 2)); CK(h->d_qual[which].ensure(reads->qual_bytes + 16));
+    CK(cudaMemcpyAsync(h->d_len[which].p, reads->len, n, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(h->d_seqoff[which].p, reads->seq_off, n * 8ull, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(h->d_qualoff[which].p, reads->qual_off, n * 8ull, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(h->d_seq2[which].p, reads->seq2, reads->seq2_words * 8ull, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(h->d_qual[which].p, reads->qual, reads->qual_bytes, cudaMemcpyHostToDevice, s));
+    return 0;
+}
+
+static int align_impl(wq_handle* h, const wq_align_param* ap, const wq_read_batch* reads, const wq_read_batch* mates,
+                      wq_align_out* out, bool on_device) {
     if (!h || !ap) return fail(-1, "null argument");
     if (int rc = check_batch(reads)) return rc;
+    const bool pe = mates != nullptr;
+    if (pe) {
+        if (int rc = check_batch(mates)) return rc;
+        if (mates->n_reads != reads->n_reads) return fail(-1, "mate batches differ in length");
+    }
     CK(cudaSetDevice(h->device));
     WqParams p;
     std::string err = wq_make_params(ap, h->H.K, p);
@@ -393,43 +475,42 @@ static int align_se_impl(wq_handle* h, const wq_align_param* ap, const wq_read_b
     h->hq_valid = false;
     h->hx = WqHostQuantEx();
     for (auto& m : h->last_kernel_ms) m = 0;
+    const wq_read_batch* src[2] = {reads, mates};
+    WqBatchDev base[2];
     if (on_device) {
-        for (uint32_t lo = 0; lo < n; lo += h->chunk_reads) {
-            uint32_t m = std::min(h->chunk_reads, n - lo);
-            WqBatchDev b{m, reads->len + lo, reads->seq_off + lo, reads->seq2, reads->qual_off + lo, reads->qual};
-            if (int rc = run_chunk(h, p, b, true)) return rc;
+        for (int m = 0; m < (pe ? 2 : 1); m++)
+            base[m] = WqBatchDev{n, src[m]->len, src[m]->seq_off, src[m]->seq2, src[m]->qual_off, src[m]->qual};
+    } else {
+        // host buffers: copy the packed arrays once, then run chunk by chunk
+        for (int m = 0; m < (pe ? 2 : 1); m++) {
+            if (int rc = upload_batch(h, src[m], m, h->stream)) return rc;
+            base[m] = WqBatchDev{n, h->d_len[m].p, h->d_seqoff[m].p, h->d_seq2[m].p, h->d_qualoff[m].p, h->d_qual[m].p};
         }
-        return 0;
     }
-    // host buffers: copy the packed arrays once, then run chunk by chunk
-    cudaStream_t s = h->stream;
-    CK(h->d_len[0].ensure(n)); CK(h->d_seqoff[0].ensure(n)); CK(h->d_qualoff[0].ensure(n));
-    CK(h->d_seq2[0].ensure(reads->seq2_words + 2)); CK(h->d_qual[0].ensure(reads->qual_bytes + 16));
-    CK(cudaMemcpyAsync(h->d_len[0].p, reads->len, n, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(h->d_seqoff[0].p, reads->seq_off, n * 8ull, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(h->d_qualoff[0].p, reads->qual_off, n * 8ull, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(h->d_seq2[0].p, reads->seq2, reads->seq2_words * 8ull, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(h->d_qual[0].p, reads->qual, reads->qual_bytes, cudaMemcpyHostToDevice, s));
     for (uint32_t lo = 0; lo < n; lo += h->chunk_reads) {
         uint32_t m = std::min(h->chunk_reads, n - lo);
-        WqBatchDev b{m, h->d_len[0].p + lo, h->d_seqoff[0].p + lo, h->d_seq2[0].p, h->d_qualoff[0].p + lo, h->d_qual[0].p};
-        if (int rc = run_chunk(h, p, b, false)) return rc;
-        if (out) if (int rc = collect_chunk(h, lo, m, out)) return rc;
+        WqBatchDev b[2];
+        for (int k = 0; k < (pe ? 2 : 1); k++)
+            b[k] = WqBatchDev{m, base[k].len + lo, base[k].seq_off + lo, base[k].seq2, base[k].qual_off + lo, base[k].qual};
+        if (int rc = run_chunk(h, p, b[0], pe ? &b[1] : nullptr, on_device)) return rc;
+        if (out) if (int rc = collect_chunk(h, lo, m, pe, out)) return rc;
     }
     return 0;
 }
 
 int wq_align_se(wq_handle* h, const wq_align_param* p, const wq_read_batch* reads, wq_align_out* out) {
-    return align_se_impl(h, p, reads, out, false);
+    return align_impl(h, p, reads, nullptr, out, false);
 }
 int wq_align_se_device(wq_handle* h, const wq_align_param* p, const wq_read_batch* reads) {
-    return align_se_impl(h, p, reads, nullptr, true);
+    return align_impl(h, p, reads, nullptr, nullptr, true);
 }
-int wq_align_pe(wq_handle*, const wq_align_param*, const wq_read_batch*, const wq_read_batch*, wq_align_out*) {
-    return fail(-99, "paired-end alignment is not built yet");
+int wq_align_pe(wq_handle* h, const wq_align_param* p, const wq_read_batch* fwd, const wq_read_batch* rev, wq_align_out* out) {
+    if (!rev) return fail(-1, "null mate batch");
+    return align_impl(h, p, fwd, rev, out, false);
 }
-int wq_align_pe_device(wq_handle*, const wq_align_param*, const wq_read_batch*, const wq_read_batch*) {
-    return fail(-99, "paired-end alignment is not built yet");
+int wq_align_pe_device(wq_handle* h, const wq_align_param* p, const wq_read_batch* fwd, const wq_read_batch* rev) {
+    if (!rev) return fail(-1, "null mate batch");
+    return align_impl(h, p, fwd, rev, nullptr, true);
 }
 
 // per-kernel device milliseconds of the last wq_align_*_device call: [seed, extend, resolve]

@@ -66,7 +66,9 @@ struct WqWork {                    // per-batch scratch
     WqSeed*   seeds;               // [n]
     uint32_t* hit_read;            // [hit_cap]
     uint32_t* hit_s;               // [hit_cap] 1-based text position of the located seed
-    WqHit*    hits;                // [hit_cap]
+    uint32_t* hit_s2;              // [hit_cap] paired: text position of the mate-2 seed
+    uint32_t* hit_gene;            // [hit_cap] paired: gene both mates are aligned against
+    WqHit*    hits;                // [hit_cap]  (paired: [2*hit_cap], mate m of pair slot s at 2*s+m)
     wq_align_node* pool;           // [pool_cap]
     uint32_t* cursors;             // [0] hit cursor, [1] path-pool cursor, [2] pending cursor
     uint32_t* pending;             // [n] reads whose keyed insert must be retried
@@ -358,4 +360,271 @@ WQ_HDN void wq_retry_thread(const WqDevIndex& ix, const WqWork& wk, const WqQuan
     int nkept = 0;
     for (int k = 0; k < s.cnt; k++) nkept += (wk.hits[s.hit_base + k].flags & 4) ? 1 : 0;
     wq_count_read(ix, wk, q, r, s.hit_base, s.cnt, nkept, true);
+}
+
+
+// =================================================================================================
+// Paired end (src/paired.jl:42-125, src/quant.jl:597-653, src/reads.jl:83-129)
+//   WqSeed reuse: sp = rev_readloc | (mate-2 flipped) << 8, readloc = fwd_readloc, strand = mate-1 strand,
+//   cnt = candidate pairs found by the sorted-offset walk.
+// =================================================================================================
+WQ_HD void wq_sort_small(int64_t* a, int n) {
+    for (int i = 1; i < n; i++) {
+        int64_t v = a[i];
+        int j = i - 1;
+        while (j >= 0 && a[j] > v) { a[j + 1] = a[j]; j--; }
+        a[j + 1] = v;
+    }
+}
+
+// kernel P1: one read pair -> both seeds, sorted offsets, two-pointer walk (src/paired.jl:44-51, 64-77, 112-121)
+WQ_HDN void wq_seed_pe_thread(const WqDevIndex& ix, const WqParams& p, const WqBatchDev& bf, const WqBatchDev& br,
+                              const WqWork& wk, uint32_t r) {
+    WqCtx c;
+    c.ix = &ix;
+    c.p = &p;
+    uint64_t badq[4];
+    // mate 1: both strands unless stranded
+    wq_load_read(c, bf, r);
+    wq_badq(c, p.seed_min_qual, false, badq);
+    int64_t fsp = 2, rsp = 2;
+    int floc = 0, rloc = 0;
+    bool strand = true, dummy = true;
+    int fcnt = wq_seed_locate(c, badq, true, !p.is_stranded, fsp, floc, strand);
+    // mate 2: one strand only; reverse-complemented first when the pair is expected head to head
+    wq_load_read(c, br, r);
+    bool flip2 = (p.is_pair_rc && strand) || (!p.is_pair_rc && !strand);
+    int rcnt;
+    if (flip2) {
+        wq_revcomp(c.w, c.readlen);
+        c.flipped = 1;
+        wq_badq(c, p.seed_min_qual, true, badq);
+        rcnt = wq_seed_locate(c, badq, false, false, rsp, rloc, dummy);
+    } else {
+        wq_badq(c, p.seed_min_qual, false, badq);
+        rcnt = wq_seed_locate(c, badq, true, false, rsp, rloc, dummy);
+    }
+    int64_t fpos[WQ_MAX_TOLERATE], rpos[WQ_MAX_TOLERATE];
+    for (int k = 0; k < fcnt; k++) fpos[k] = wq_sa_value(ix, fsp + k) + 1;
+    for (int k = 0; k < rcnt; k++) rpos[k] = wq_sa_value(ix, rsp + k) + 1;
+    wq_sort_small(fpos, fcnt);
+    wq_sort_small(rpos, rcnt);
+    uint32_t pf[WQ_MAX_TOLERATE], pr[WQ_MAX_TOLERATE], pg[WQ_MAX_TOLERATE];
+    int np = 0;
+    int fi = 0, ri = 0;
+    while (fi < fcnt && ri < rcnt) {
+        int64_t dist = fpos[fi] - rpos[ri];
+        if (dist < 0) dist = -dist;
+        if (dist < p.seed_pair_range) {
+            // geneind = searchsortedlast(lib.offset, fwd_sorted[fidx]) and its text span
+            uint64_t s = (uint64_t)fpos[fi] > ix.n ? ix.n : (uint64_t)fpos[fi];
+            uint32_t gi = wq_locate_node(ix, s);
+            uint32_t gene = WQ_LDG(&ix.nodes[gi].gene);
+            const WqGeneRec* g = ix.genes + (gene - 1);
+            int64_t lo = WQ_LDG(&g->text_start), hi = WQ_LDG(&g->text_end);
+            if (lo <= rpos[ri] && rpos[ri] < hi) {
+                pf[np] = (uint32_t)fpos[fi]; pr[np] = (uint32_t)rpos[ri]; pg[np] = gene; np++;
+                ri++; fi++;
+                continue;
+            }
+        }
+        if (fpos[fi] > rpos[ri]) ri++; else fi++;
+    }
+    WqSeed sd;
+    sd.sp = (uint32_t)rloc | (flip2 ? 0x100u : 0u);
+    sd.cnt = (uint8_t)np;
+    sd.readloc = (uint8_t)floc;
+    sd.strand = strand ? 1 : 0;
+    sd._pad = 0;
+    sd.hit_base = 0;
+    if (np > 0) {
+        uint32_t base = WQ_ATOMIC_ADD_U32(&wk.cursors[0], np);
+        sd.hit_base = base;
+        for (int k = 0; k < np; k++)
+            if (base + k < wk.hit_cap) {
+                wk.hit_read[base + k] = r;
+                wk.hit_s[base + k] = pf[k];
+                wk.hit_s2[base + k] = pr[k];
+                wk.hit_gene[base + k] = pg[k];
+            }
+    }
+    wk.seeds[r] = sd;
+}
+
+// kernel P2: one (pair slot, mate) -> _ungapped_align with the gene pinned (src/paired.jl:79-80)
+WQ_HDN void wq_extend_pe_thread(const WqDevIndex& ix, const WqParams& p, const WqBatchDev& bf, const WqBatchDev& br,
+                                const WqWork& wk, uint32_t slot, int mate) {
+    uint32_t r = wk.hit_read[slot];
+    WqSeed s = wk.seeds[r];
+    WqCtx c;
+    c.ix = &ix;
+    c.p = &p;
+    bool ispos = s.strand != 0;
+    int readloc;
+    int64_t pos;
+    if (mate == 0) {
+        wq_load_read(c, bf, r);
+        if (!ispos) { wq_revcomp(c.w, c.readlen); c.flipped = 1; }      // reverse_complement!(fwd), src/paired.jl:55-58
+        readloc = s.readloc;
+        pos = wk.hit_s[slot];
+    } else {
+        wq_load_read(c, br, r);
+        if (s.sp & 0x100u) { wq_revcomp(c.w, c.readlen); c.flipped = 1; }
+        readloc = (int)(s.sp & 0xFF);
+        pos = wk.hit_s2[slot];
+        ispos = !ispos;
+    }
+    WqAlign a;
+    wq_align_at(c, pos, readloc, ispos, wk.hit_gene[slot], a);
+    WqHit h;
+    h.identity = wq_score(a);            // paired scoring combines the two raw scores (src/paired.jl:2-3)
+    h.offset = a.offset;
+    h.offsetread = a.offsetread;
+    h.npath = a.npath;
+    h.strand = a.strand;
+    h.flags = (uint8_t)((a.isvalid ? 1 : 0) | (wq_isvalid(a) ? 2 : 0) | (c.overflow ? 8 : 0));
+    if (c.overflow) h.flags &= (uint8_t)~2;
+    uint32_t ps = 0;
+    if (a.npath) {
+        ps = WQ_ATOMIC_ADD_U32(&wk.cursors[1], a.npath);
+        if (ps + a.npath <= wk.pool_cap) {
+            for (int i = 0; i < a.npath; i++) {
+                wq_align_node o;
+                o.gene = c.gene; o.node = a.p[i].node; o.mistolerance = a.p[i].tol;
+                o.matches = a.p[i].m; o.mismatches = a.p[i].mm; o._pad = 0;
+                wk.pool[ps + i] = o;
+            }
+        } else {
+            h.flags |= 16;
+        }
+    }
+    h.path_start = ps;
+    wk.hits[2 * slot + mate] = h;
+}
+
+// Base.in(first::SGAlignPath, last::SGAlignPath): contiguous sub-path (src/quant.jl:47-62)
+WQ_HD bool wq_subpath(const wq_align_node* a, int na, const wq_align_node* b, int nb) {
+    for (int i = 0; i + na <= nb; i++) {
+        bool match = true;
+        for (int j = 0; j < na; j++)
+            if (a[j].gene != b[i + j].gene || a[j].node != b[i + j].node) { match = false; break; }
+        if (match) return true;
+    }
+    return false;
+}
+
+// key words of the kept pairs:
+//   one pair, not nested : [2<<28 | npf | npr<<8, gene, fwd nodes.., rev nodes..]               (long, SGAlignPaired)
+//   several pairs        : [3<<28 | npairs, then per pair the record above]                      (MultiMapping)
+#define WQ_KEY_WORDS_MAX_PE (1 + WQ_MAX_TOLERATE * (2 + 2 * WQ_MAX_PATH))
+WQ_HD int wq_build_key_pe(const WqWork& wk, uint32_t base, int cnt, int nkept, uint32_t* kw) {
+    int n = 0;
+    if (nkept > 1) kw[n++] = (3u << 28) | (uint32_t)nkept;
+    for (int k = 0; k < cnt; k++) {
+        const WqHit hf = wk.hits[2 * (base + k)], hr = wk.hits[2 * (base + k) + 1];
+        if (!(hf.flags & 4)) continue;
+        kw[n++] = (2u << 28) | (uint32_t)hf.npath | ((uint32_t)hr.npath << 8);
+        kw[n++] = wk.pool[hf.path_start].gene;
+        for (int i = 0; i < hf.npath; i++) kw[n++] = wk.pool[hf.path_start + i].node;
+        for (int i = 0; i < hr.npath; i++) kw[n++] = wk.pool[hr.path_start + i].node;
+    }
+    return n;
+}
+
+// count!(quant, fwd, rev, 1.0) (src/quant.jl:597-653) or push!(multi, fwd, rev, ...) (:471-484)
+WQ_HD void wq_count_pair(const WqDevIndex& ix, const WqWork& wk, const WqQuantDev& q, uint32_t r,
+                         uint32_t base, int cnt, int nkept, bool retry) {
+    uint32_t kw[WQ_KEY_WORDS_MAX_PE];
+    if (nkept == 1) {
+        int k = 0;
+        while (!(wk.hits[2 * (base + k)].flags & 4)) k++;
+        const WqHit hf = wk.hits[2 * (base + k)], hr = wk.hits[2 * (base + k) + 1];
+        if (!((hf.flags & 1) && (hr.flags & 1))) return;
+        const wq_align_node* pf = wk.pool + hf.path_start;
+        const wq_align_node* pr = wk.pool + hr.path_start;
+        if (pf[0].gene != pr[0].gene) return;
+        const wq_align_node* single = nullptr;
+        int ns = 0;
+        if (hf.npath <= hr.npath) { if (wq_subpath(pf, hf.npath, pr, hr.npath)) { single = pr; ns = hr.npath; } }
+        else { if (wq_subpath(pr, hr.npath, pf, hf.npath)) { single = pf; ns = hf.npath; } }
+        if (single) {
+            if (retry) return;
+            if (ns == 1) {
+                WQ_ATOMIC_ADD_U64(&q.node_count[WQ_LDG(&ix.genes[single[0].gene - 1].node_base) + single[0].node - 1], 1);
+            } else if (ns == 2) {
+                uint64_t key = ((uint64_t)single[0].gene << 32) | ((uint64_t)(single[0].node & 0xFFFF) << 16) | (uint64_t)(single[1].node & 0xFFFF);
+                if (wq_edge_insert(q.edges, key, 1)) WQ_ATOMIC_ADD_U64(&q.counters->edge_full, 1);
+            }                           // a nested path of >= 3 nodes is not counted (no else branch at src/quant.jl:631-640)
+            return;
+        }
+    }
+    int nw = wq_build_key_pe(wk, base, cnt, nkept, kw);
+    int rc = wq_keyed_insert(q.keyed, kw, nw, 1);
+    if (rc == 1) {
+        uint32_t slot = WQ_ATOMIC_ADD_U32(&wk.cursors[2], 1);
+        wk.pending[slot] = r;
+    } else if (rc == 2) {
+        WQ_ATOMIC_ADD_U64(&q.counters->keyed_full, 1);
+    }
+}
+
+// kernel P3: one read pair -> pair score filter (src/paired.jl:82-111) + counting
+WQ_HDN void wq_resolve_pe_thread(const WqDevIndex& ix, const WqParams& p, const WqBatchDev& bf, const WqBatchDev& br,
+                                 const WqWork& wk, const WqQuantDev& q, uint32_t r, uint64_t* stats) {
+    const WqSeed s = wk.seeds[r];
+    const int cnt = s.cnt;
+    if (cnt == 0) return;
+    const uint32_t base = s.hit_base;
+    const float lensum = (float)((int)WQ_LDG(bf.len + r) + (int)WQ_LDG(br.len + r));
+    bool isnull = true;
+    float maxscore = 0.f;
+    uint32_t keep = 0;
+    bool overflow = false, pool_over = false;
+    for (int k = 0; k < cnt; k++) {
+        const WqHit hf = wk.hits[2 * (base + k)], hr = wk.hits[2 * (base + k) + 1];
+        if ((hf.flags | hr.flags) & 8) overflow = true;
+        if ((hf.flags | hr.flags) & 16) pool_over = true;
+        if (!((hf.flags & 2) && (hr.flags & 2))) continue;
+        const float scvar = (hf.identity + hr.identity) / lensum;
+        if (isnull) {
+            isnull = false;
+            keep = 1u << k;
+            maxscore = scvar;
+        } else if (scvar > maxscore) {
+            if ((double)(scvar - maxscore) > p.score_range) {
+                keep = 0;
+            } else {
+                for (int j = 0; j < k; j++)
+                    if ((keep >> j) & 1) {
+                        float sj = (wk.hits[2 * (base + j)].identity + wk.hits[2 * (base + j) + 1].identity) / lensum;
+                        if ((double)(scvar - sj) > p.score_range) keep &= ~(1u << j);
+                    }
+            }
+            maxscore = scvar;
+            keep |= 1u << k;
+        } else if ((double)(maxscore - scvar) <= p.score_range) {
+            keep |= 1u << k;
+        }
+    }
+    if (overflow) stats[3] += 1;
+    if (pool_over) stats[4] += 1;
+    if (isnull || overflow || pool_over) return;
+    int nkept = 0;
+    for (int k = 0; k < cnt; k++)
+        if ((keep >> k) & 1) {
+            wk.hits[2 * (base + k)].flags |= 4;
+            wk.hits[2 * (base + k) + 1].flags |= 4;
+            nkept++;
+        }
+    stats[0] += 1;
+    stats[2] += (uint64_t)WQ_LDG(bf.len + r);
+    if (nkept > 1) stats[1] += 1;
+    wq_count_pair(ix, wk, q, r, base, cnt, nkept, false);
+}
+
+WQ_HDN void wq_retry_pe_thread(const WqDevIndex& ix, const WqWork& wk, const WqQuantDev& q, uint32_t r) {
+    const WqSeed s = wk.seeds[r];
+    int nkept = 0;
+    for (int k = 0; k < s.cnt; k++) nkept += (wk.hits[2 * (s.hit_base + k)].flags & 4) ? 1 : 0;
+    wq_count_pair(ix, wk, q, r, s.hit_base, s.cnt, nkept, true);
 }
