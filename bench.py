@@ -3,7 +3,8 @@
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-A step = one pass of the hot path (seed, extend, resolve+count[, allreduce]) over one batch of
+A step = one pass of the hot path (seed, extend, resolve+count[, exchange], classes + transcript EM +
+multi-map assignment) over one batch of
 synthetic 101-bp single-end reads against a GENCODE-scale synthetic splice-graph index
 (BASELINE.json configs[1]; the GENCODE GTF itself is not available offline).
 `value` is measured with the batch resident in HBM; `e2e` goes through wq_align_se with pinned HOST
@@ -234,18 +235,29 @@ def main():
     db.qual_bytes = len(rb.qual)
     pc = param.c()
 
-    dptr, nd = C.c_void_p(), C.c_uint64()
-    lib.check(L.wq_counts_device_ptr(q.h, C.byref(dptr), C.byref(nd)))
+    em_readlen = a.readlen          # Int(floor(mean_readlen)) of bin/whippet-quant.jl:151 for fixed-length reads
+    phase = {"align": 0.0, "exchange": 0.0, "quant": 0.0, "em_iterations": 0}
 
-    class _Wrap:   # expose the dense count vector to torch for the NCCL all-reduce
-        __cuda_array_interface__ = {"shape": (int(nd.value),), "typestr": "<i8", "data": (int(dptr.value), False), "version": 2}
-    dense = torch.as_tensor(_Wrap(), device=dev) if world > 1 else None
+    def quantify():
+        """Exchange + build_equivalence_classes! + calculate_tpm! + gene_em! + set_gene_tpm! + assign_ambig!"""
+        t0 = time.perf_counter()
+        if world > 1:
+            q.allreduce_counts()        # ONE NCCL all-reduce of the dense counts + all-gather of the sparse stores
+        t1 = time.perf_counter()
+        it, tpm, cnt, gt = q.gene_em(em_readlen, 1, 10000)
+        q.assign_ambig()
+        t2 = time.perf_counter()
+        phase["exchange"] += t1 - t0
+        phase["quant"] += t2 - t1
+        phase["em_iterations"] = it
+        return tpm
 
     def step():
+        t0 = time.perf_counter()
         lib.check(L.wq_quant_reset(q.h))
         lib.check(L.wq_align_se_device(q.h, C.byref(pc), C.byref(db)))
-        if world > 1:
-            dist.all_reduce(dense)      # per-node counts + scalar stats, one NCCL all-reduce over NVLink
+        phase["align"] += time.perf_counter() - t0
+        return quantify()
 
     def sync_all():
         if world > 1:
@@ -254,6 +266,8 @@ def main():
 
     for _ in range(a.warmup):
         step()
+    for k in ("align", "exchange", "quant"):
+        phase[k] = 0.0
     kms = np.zeros(3)
     sync_all()
     sampler = ClockSampler(local)
@@ -292,21 +306,20 @@ def main():
     hb.qual = C.cast(p_qual.data_ptr(), abi.u8p)
     hb.qual_bytes = len(rb.qual)
     h2d = int(rb.len.nbytes + rb.seq_off.nbytes + rb.seq2.nbytes + rb.qual_off.nbytes + rb.qual.nbytes)
-    d2h = C.sizeof(abi.MapStatsC)
+    d2h = C.sizeof(abi.MapStatsC) + 8 * (2 * idx.n_isoforms + idx.n_genes)     # stats + tpm/count/genetpm
 
     def e2e_step():
         lib.check(L.wq_quant_reset(q.h))
         lib.check(L.wq_align_se(q.h, C.byref(pc), C.byref(hb), None))
-        if world > 1:
-            dist.all_reduce(dense)
-        return q.stats()
+        tpm = quantify()
+        return q.stats(), tpm
 
     e2e_step()
     sync_all()
     t0 = time.perf_counter()
     nrep = max(1, min(a.steps, 3))
     for _ in range(nrep):
-        st2 = e2e_step()
+        st2, tpm2 = e2e_step()
     sync_all()
     e2e_ms = (time.perf_counter() - t0) * 1000 / nrep
     t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
@@ -329,6 +342,8 @@ def main():
         "clocks": clocks, "gpu_launches": launches,
         "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "kernel_ms": {"seed": float(kms[0]), "extend": float(kms[1]), "resolve": float(kms[2])},
+        "phase_ms": {"align": 1000 * phase["align"] / a.steps, "exchange": 1000 * phase["exchange"] / a.steps,
+                     "quant": 1000 * phase["quant"] / a.steps, "em_iterations": int(phase["em_iterations"])},
     }
     if world == 1:
         cpu_v, cpu_dt, _, ctr, n0 = cpu_oracle_run(idx, rb, param, a.cpu_sample, 1)

@@ -1,0 +1,70 @@
+"""N>1 exchange path on CPU: world_size-2 gloo processes exchange packed sparse count stores and a dense
+vector, and every rank ends with the union-sum."""
+import os
+import socket
+import sys
+
+import numpy as np
+import torch.multiprocessing as mp
+
+from conftest import ROOT
+
+
+def _stores(rank):
+    rng = np.random.default_rng(100 + rank)
+    ek = np.unique(rng.integers(1, 2000, 300).astype(np.uint64) << np.uint64(16) | rng.integers(1, 50, 300).astype(np.uint64))
+    ec = rng.integers(1, 100, len(ek)).astype(np.uint64)
+    ck = np.unique(rng.integers(1, 50, 20).astype(np.uint64))
+    cc = rng.integers(1, 10, len(ck)).astype(np.uint64)
+    longs = {(3, int(g), 1, 2, 3 + int(g) % 3): int(rng.integers(1, 9)) for g in rng.integers(1, 60, 40)}
+    multis = {((1 << 28) | 2, 1, int(g), 1, 1, int(g) + 1, 2): int(rng.integers(1, 9)) for g in rng.integers(1, 60, 30)}
+    dense = rng.integers(0, 1000, 5000).astype(np.int64)
+    return ek, ec, ck, cc, longs, multis, dense
+
+
+def _worker(rank, world, port, q):
+    sys.path[:0] = [ROOT]
+    import torch
+    import torch.distributed as dist
+    from whippet_jl_b200 import parallel
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ek, ec, ck, cc, longs, multis, dense = _stores(rank)
+    t = torch.from_numpy(dense.copy())
+    dist.all_reduce(t)
+    bufs = parallel.allgather_buffers(parallel.pack_sparse(ek, ec, ck, cc, longs, multis))
+    merged = parallel.merge_sparse([parallel.unpack_sparse(b) for b in bufs])
+    q.put((rank, t.numpy().copy(), merged))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_exchange():
+    world = 2
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    [p.start() for p in procs]
+    res = [q.get(timeout=120) for _ in range(world)]
+    [p.join(timeout=60) for p in procs]
+    from whippet_jl_b200 import parallel
+    parts = [_stores(r) for r in range(world)]
+    want_dense = sum(p[6] for p in parts)
+    want = parallel.merge_sparse([p[:6] for p in parts])
+    for rank, dense, merged in res:
+        assert np.array_equal(dense, want_dense)
+        assert merged == want
+
+
+def test_pack_roundtrip():
+    from whippet_jl_b200 import parallel
+    ek, ec, ck, cc, longs, multis, _ = _stores(0)
+    out = parallel.unpack_sparse(parallel.pack_sparse(ek, ec, ck, cc, longs, multis))
+    assert np.array_equal(out[0], ek) and np.array_equal(out[1], ec) and np.array_equal(out[2], ck) and np.array_equal(out[3], cc)
+    assert out[4] == longs and out[5] == multis
+    empty = parallel.unpack_sparse(parallel.pack_sparse([], [], [], [], {}, {}))
+    assert len(empty[0]) == 0 and empty[4] == {} and empty[5] == {}

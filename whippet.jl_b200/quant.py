@@ -177,3 +177,60 @@ class GraphLibQuant:
         v.circ_key, v.circ_value = abi.ptr(ck, abi.u64p), abi.ptr(cv, abi.f64p)
         lib.check(self.L.wq_assign_ambig(self.h, C.byref(v)))
         return node, ek, ev, ck, cv
+
+    # ---- multi-GPU exchange ---------------------------------------------------------------------
+    def dense_tensor(self):
+        """torch view of the device-resident dense vector (node counts + total/mapped/multi/sum_readlen)."""
+        import torch
+        dptr, nd = C.c_void_p(), C.c_uint64()
+        lib.check(self.L.wq_counts_device_ptr(self.h, C.byref(dptr), C.byref(nd)))
+
+        class _Wrap:
+            __cuda_array_interface__ = {"shape": (int(nd.value),), "typestr": "<i8", "data": (int(dptr.value), False), "version": 2}
+        return torch.as_tensor(_Wrap(), device=torch.device("cuda", self.device))
+
+    def allreduce_counts(self):
+        """Combine the count stores of all ranks (torch.distributed must be initialised): one NCCL all-reduce of
+        the dense vector on the device, one all-gather of the packed sparse stores merged on every rank."""
+        import torch
+        import torch.distributed as dist
+        from . import parallel
+        if not dist.is_initialized() or dist.get_world_size() == 1:
+            return
+        dist.all_reduce(self.dense_tensor())
+        torch.cuda.current_stream().synchronize()
+        node, ek, ec, ck, cc = self.counts()            # host state: all-reduced dense + this rank's sparse stores
+        mine = parallel.pack_sparse(ek, ec, ck, cc, self.keyed(0), self.keyed(1))
+        bufs = parallel.allgather_buffers(mine, torch.device("cuda", self.device))
+        rank = dist.get_rank()
+        for r, b in enumerate(bufs):
+            if r == rank:
+                continue
+            ek, ec, ck, cc, lo, mu = parallel.unpack_sparse(b)
+            self.merge_sparse(ek, ec, ck, cc, lo, mu)
+
+    def merge_sparse(self, ek, ec, ck, cc, longs, multis):
+        c = abi.CountsC()
+        ek, ec, ck, cc = (np.ascontiguousarray(a, "<u8") for a in (ek, ec, ck, cc))
+        c.n_nodes, c.node_count = 0, None
+        c.n_edge, c.edge_key, c.edge_count = len(ek), abi.ptr(ek, abi.u64p), abi.ptr(ec, abi.u64p)
+        c.n_circ, c.circ_key, c.circ_count = len(ck), abi.ptr(ck, abi.u64p), abi.ptr(cc, abi.u64p)
+        ks, keep = [], []
+        for d in (longs, multis):
+            k = abi.KeyedC()
+            keys = sorted(d)
+            ptr_ = np.zeros(len(keys) + 1, "<u8")
+            words = np.zeros(max(1, sum(len(x) for x in keys)), "<u4")
+            cnt = np.zeros(max(1, len(keys)), "<u8")
+            w = 0
+            for i, key in enumerate(keys):
+                ptr_[i] = w
+                words[w:w + len(key)] = key
+                w += len(key)
+                cnt[i] = d[key]
+            ptr_[len(keys)] = w
+            k.n_rec, k.n_words = len(keys), w
+            k.rec_ptr, k.words, k.count = abi.ptr(ptr_, abi.u64p), abi.ptr(words, abi.u32p), abi.ptr(cnt, abi.u64p)
+            ks.append(k)
+            keep.append((ptr_, words, cnt))
+        lib.check(self.L.wq_counts_merge(self.h, C.byref(c), C.byref(ks[0]), C.byref(ks[1])))
