@@ -7,6 +7,7 @@
 //   wq_k_retry     second chance for keyed inserts that met an unpublished slot
 // There is no CPU implementation behind this ABI: without an sm_100 device wq_index_create fails.
 #include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -20,6 +21,12 @@
 #include "wq_host_quant.h"
 #include "wq_em.cuh"
 
+#include <chrono>
+struct WqTimer {
+    const char* name; std::chrono::steady_clock::time_point t0; bool on;
+    explicit WqTimer(const char* n) : name(n), t0(std::chrono::steady_clock::now()) { static int e = getenv("WQ_PROFILE") ? atoi(getenv("WQ_PROFILE")) : 0; on = e != 0; }
+    ~WqTimer() { if (on) fprintf(stderr, "[wq] %-28s %9.3f ms\n", name, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count()); }
+};
 static thread_local std::string g_err;
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
 #define CK(call)                                                                                   \
@@ -70,6 +77,8 @@ struct wq_handle {
     // host-side quant state (filled by wq_counts_sync / merge; input of EM)
     WqHostQuant hq;
     WqHostQuantEx hx;
+    WqEmScratch em_scratch;
+    DevBuf<uint64_t> d_ck, d_cv, d_ck2, d_cv2; DevBuf<uint32_t> d_ckoff; DevBuf<uint8_t> d_cubtmp;
     bool hq_valid = false;
     uint32_t chunk_reads = 1u << 22;
     float last_kernel_ms[3] = {0, 0, 0};
@@ -164,6 +173,28 @@ __global__ void __launch_bounds__(128) wq_k_retry(const WqDevIndex ix, const WqW
     wq_retry_thread(ix, wk, q, list[i]);
 }
 
+// compaction of the open-addressing count tables before download: occupied slots -> dense arrays
+__global__ void wq_k_compact_edges(const uint64_t* key, const uint64_t* count, uint64_t slots, uint64_t* okey, uint64_t* ocount, uint32_t* cursor) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; i < slots; i += stride) {
+        uint64_t k = key[i];
+        if (k == WQ_EMPTY_KEY) continue;
+        uint32_t o = atomicAdd(cursor, 1u);
+        okey[o] = k;
+        ocount[o] = count[i];
+    }
+}
+__global__ void wq_k_compact_keyed(const uint64_t* hash, const uint32_t* keyoff, const uint64_t* count, uint64_t slots,
+                                   uint32_t* ooff, uint64_t* ocount, uint32_t* cursor) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; i < slots; i += stride) {
+        if (hash[i] == 0) continue;
+        uint32_t o = atomicAdd(cursor, 1u);
+        ooff[o] = keyoff[i];
+        ocount[o] = count[i];
+    }
+}
+
 __global__ void wq_k_fill_u64(uint64_t* p, uint64_t v, uint64_t n) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
@@ -215,6 +246,7 @@ void wq_destroy(wq_handle* h) {
     }
     h->d_seeds.release(); h->d_hit_read.release(); h->d_hit_s.release(); h->d_hit_s2.release(); h->d_hit_gene.release(); h->d_pending.release(); h->d_pending2.release();
     h->d_cursors.release(); h->d_hits.release(); h->d_pool.release();
+    h->em_scratch.release(); h->d_ck.release(); h->d_cv.release(); h->d_ck2.release(); h->d_cv2.release(); h->d_ckoff.release(); h->d_cubtmp.release();
     if (h->h_cursors) cudaFreeHost(h->h_cursors);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
@@ -223,6 +255,7 @@ void wq_destroy(wq_handle* h) {
 
 int wq_quant_reset(wq_handle* h) {
     if (!h) return fail(-1, "null handle");
+    WqTimer tm_("quant_reset");
     CK(cudaSetDevice(h->device));
     cudaStream_t s = h->stream;
     CK(cudaMemsetAsync(h->d_dense.p, 0, (h->H.N + sizeof(WqCounters) / 8) * sizeof(uint64_t), s));
@@ -553,39 +586,70 @@ int wq_counts_device_ptr(wq_handle* h, void** dptr, uint64_t* n_u64) {
     return 0;
 }
 
-// Pull the device count stores into the handle's host-side quant state (sorted, canonical order).
+// Pull the device count stores into the handle's host-side quant state: occupied table slots are
+// compacted on the device, edges are radix-sorted there (canonical order), only the dense results
+// cross PCIe.
 static int sync_host_quant(wq_handle* h) {
     if (h->hq_valid) return 0;
+    WqTimer tm_("sync_host_quant");
     CK(cudaSetDevice(h->device));
     cudaStream_t s = h->stream;
     WqHostQuant& Q = h->hq;
+    Q = WqHostQuant();
     const uint32_t N = h->H.N;
     std::vector<uint64_t> dense(N + sizeof(WqCounters) / 8);
     CK(cudaMemcpyAsync(dense.data(), h->d_dense.p, dense.size() * 8, cudaMemcpyDeviceToHost, s));
-    std::vector<uint64_t> ekey(h->edge_slots), ecount(h->edge_slots), khash(h->keyed_slots), kcount(h->keyed_slots);
-    std::vector<uint32_t> koff(h->keyed_slots);
+    // cursors[8] = #edges, cursors[9] = #keyed entries
+    CK(cudaMemsetAsync(h->d_cursors.p + 8, 0, 2 * sizeof(uint32_t), s));
+    CK(h->d_ck.ensure(h->edge_slots)); CK(h->d_cv.ensure(h->edge_slots));
+    wq_k_compact_edges<<<1184, 256, 0, s>>>(h->d_ekey.p, h->d_ecount.p, h->edge_slots, h->d_ck.p, h->d_cv.p, h->d_cursors.p + 8);
+    CK(h->d_ckoff.ensure(h->keyed_slots)); CK(h->d_cv2.ensure(h->keyed_slots));
+    wq_k_compact_keyed<<<1184, 256, 0, s>>>(h->d_khash.p, h->d_koff.p, h->d_kcount.p, h->keyed_slots, h->d_ckoff.p, h->d_cv2.p, h->d_cursors.p + 9);
+    h->launches += 2;
     uint64_t kcur = 0;
-    CK(cudaMemcpyAsync(ekey.data(), h->d_ekey.p, h->edge_slots * 8, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(ecount.data(), h->d_ecount.p, h->edge_slots * 8, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(khash.data(), h->d_khash.p, h->keyed_slots * 8, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(kcount.data(), h->d_kcount.p, h->keyed_slots * 8, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(koff.data(), h->d_koff.p, h->keyed_slots * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(h->h_cursors + 8, h->d_cursors.p + 8, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(&kcur, h->d_kcursor.p, 8, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
-    std::vector<uint32_t> kpool(std::min<uint64_t>(kcur, h->kpool_cap));
-    if (!kpool.empty()) CK(cudaMemcpy(kpool.data(), h->d_kpool.p, kpool.size() * 4, cudaMemcpyDeviceToHost));
-    Q = WqHostQuant();
+    const uint32_t ne = h->h_cursors[8], nk = h->h_cursors[9];
     Q.node.assign(dense.begin(), dense.begin() + N);
     memcpy(&Q.stats, dense.data() + N, sizeof(WqCounters));
-    for (uint64_t i = 0; i < h->edge_slots; i++)
-        if (ekey[i] != WQ_EMPTY_KEY) Q.edge[ekey[i]] += (double)ecount[i];
-    for (uint64_t i = 0; i < h->keyed_slots; i++) {
-        if (khash[i] == 0) continue;
-        if (koff[i] >= WQ_KEYOFF_FULL) return fail(-8, "keyed count store overflowed");
-        uint32_t nw = kpool[koff[i]];
-        std::vector<uint32_t> key(kpool.begin() + koff[i] + 1, kpool.begin() + koff[i] + 1 + nw);
-        Q.keyed[key] += kcount[i];
+    if (Q.stats.keyed_full || kcur > h->kpool_cap) return fail(-8, "keyed count store overflowed (raise WQ_KEYED_SLOTS / WQ_KEYED_POOL_WORDS)");
+    if (Q.stats.edge_full) return fail(-8, "edge count table is full (raise WQ_EDGE_SLOTS)");
+    // edges: device radix sort by key
+    Q.edge_key.resize(ne); Q.edge_count.resize(ne);
+    if (ne) {
+        CK(h->d_ck2.ensure(ne));
+        uint64_t* vals_out = h->d_cv2.p + nk;          // tail of the keyed-count buffer is free
+        if ((size_t)nk + ne > h->d_cv2.cap) { CK(h->d_cubtmp.ensure(1)); }
+        DevBuf<uint64_t> tmpvals;
+        if ((size_t)nk + ne > h->d_cv2.cap) { CK(tmpvals.ensure(ne)); vals_out = tmpvals.p; }
+        size_t tmp_bytes = 0;
+        CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, h->d_ck.p, h->d_ck2.p, h->d_cv.p, vals_out, (int)ne, 0, 64, s));
+        CK(h->d_cubtmp.ensure(tmp_bytes));
+        CK(cub::DeviceRadixSort::SortPairs(h->d_cubtmp.p, tmp_bytes, h->d_ck.p, h->d_ck2.p, h->d_cv.p, vals_out, (int)ne, 0, 64, s));
+        h->launches += 1;
+        CK(cudaMemcpyAsync(Q.edge_key.data(), h->d_ck2.p, ne * 8ull, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(Q.edge_count.data(), vals_out, ne * 8ull, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        tmpvals.release();
     }
+    // keyed entries + the used part of the key pool
+    std::vector<uint32_t> koff(nk), kpool(kcur);
+    std::vector<uint64_t> kcount(nk);
+    if (nk) {
+        CK(cudaMemcpyAsync(koff.data(), h->d_ckoff.p, nk * 4ull, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(kcount.data(), h->d_cv2.p, nk * 8ull, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(kpool.data(), h->d_kpool.p, kcur * 4ull, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+    }
+    Q.longs.words.reserve(kcur);
+    for (uint32_t i = 0; i < nk; i++) {
+        if (koff[i] >= WQ_KEYOFF_FULL) return fail(-8, "keyed count store overflowed");
+        const uint32_t nw = kpool[koff[i]];
+        const uint32_t* w = &kpool[koff[i] + 1];
+        (wq_key_is_multi(w) ? Q.multis : Q.longs).push(w, nw, kcount[i]);
+    }
+    Q.multis.canonicalize();
     h->hq_valid = true;
     return 0;
 }
@@ -595,16 +659,16 @@ int wq_counts_download(wq_handle* h, wq_counts* c) {
     if (int rc = sync_host_quant(h)) return rc;
     WqHostQuant& Q = h->hq;
     uint64_t ne = 0, nc = 0;
-    for (auto& kv : Q.edge) { if (wq_edge_is_circ(kv.first)) nc++; else ne++; }
+    for (uint64_t k : Q.edge_key) { if (wq_edge_is_circ(k)) nc++; else ne++; }
     bool sizing = !c->node_count && !c->edge_key && !c->circ_key;
     if (!sizing && (c->n_nodes < Q.node.size() || c->n_edge < ne || c->n_circ < nc)) return fail(-7, "wq_counts buffers too small");
     c->n_nodes = Q.node.size(); c->n_edge = ne; c->n_circ = nc;
     if (sizing) return 0;
     if (c->node_count) memcpy(c->node_count, Q.node.data(), Q.node.size() * 8);
     uint64_t ie = 0, ic = 0;
-    for (auto& kv : Q.edge) {
-        if (wq_edge_is_circ(kv.first)) { if (c->circ_key) { c->circ_key[ic] = kv.first; c->circ_count[ic] = (uint64_t)kv.second; } ic++; }
-        else { if (c->edge_key) { c->edge_key[ie] = kv.first; c->edge_count[ie] = (uint64_t)kv.second; } ie++; }
+    for (size_t i = 0; i < Q.edge_key.size(); i++) {
+        if (wq_edge_is_circ(Q.edge_key[i])) { if (c->circ_key) { c->circ_key[ic] = Q.edge_key[i]; c->circ_count[ic] = Q.edge_count[i]; } ic++; }
+        else { if (c->edge_key) { c->edge_key[ie] = Q.edge_key[i]; c->edge_count[ie] = Q.edge_count[i]; } ie++; }
     }
     return 0;
 }
@@ -613,23 +677,15 @@ int wq_keyed_download(wq_handle* h, int kind, wq_keyed* k) {
     if (!h || !k) return fail(-1, "null argument");
     if (kind != 0 && kind != 1) return fail(-1, "kind must be 0 (long paths) or 1 (multi-map classes)");
     if (int rc = sync_host_quant(h)) return rc;
-    uint64_t nrec = 0, nwords = 0;
-    for (auto& kv : h->hq.keyed)
-        if (wq_key_is_multi(kv.first) == (kind == 1)) { nrec++; nwords += kv.first.size(); }
+    if (kind == 0) h->hq.longs.canonicalize();        // sorted on demand; the quant stage does not need the order
+    const WqKeyedStore& K = kind == 0 ? h->hq.longs : h->hq.multis;
     bool sizing = !k->rec_ptr && !k->words && !k->count;
-    if (!sizing && (k->n_rec < nrec || k->n_words < nwords)) return fail(-7, "wq_keyed buffers too small");
-    k->n_rec = nrec; k->n_words = nwords;
+    if (!sizing && (k->n_rec < K.size() || k->n_words < K.words.size())) return fail(-7, "wq_keyed buffers too small");
+    k->n_rec = K.size(); k->n_words = K.words.size();
     if (sizing) return 0;
-    uint64_t i = 0, w = 0;
-    for (auto& kv : h->hq.keyed) {
-        if (wq_key_is_multi(kv.first) != (kind == 1)) continue;
-        k->rec_ptr[i] = w;
-        memcpy(k->words + w, kv.first.data(), kv.first.size() * 4);
-        w += kv.first.size();
-        k->count[i] = kv.second;
-        i++;
-    }
-    k->rec_ptr[nrec] = w;
+    memcpy(k->rec_ptr, K.off.data(), K.off.size() * 8);
+    if (!K.words.empty()) memcpy(k->words, K.words.data(), K.words.size() * 4);
+    if (K.size()) memcpy(k->count, K.count.data(), K.size() * 8);
     return 0;
 }
 
@@ -643,15 +699,25 @@ int wq_counts_merge(wq_handle* h, const wq_counts* c, const wq_keyed* longs, con
             if (c->n_nodes != Q.node.size()) return fail(-1, "node count vector has the wrong length");
             for (size_t i = 0; i < Q.node.size(); i++) Q.node[i] += c->node_count[i];
         }
-        for (uint64_t i = 0; i < c->n_edge; i++) Q.edge[c->edge_key[i]] += (double)c->edge_count[i];
-        for (uint64_t i = 0; i < c->n_circ; i++) Q.edge[c->circ_key[i]] += (double)c->circ_count[i];
-    }
-    for (const wq_keyed* k : {longs, multis}) {
-        if (!k) continue;
-        for (uint64_t i = 0; i < k->n_rec; i++) {
-            std::vector<uint32_t> key(k->words + k->rec_ptr[i], k->words + k->rec_ptr[i + 1]);
-            Q.keyed[key] += k->count[i];
+        std::vector<std::pair<uint64_t, uint64_t>> all;
+        all.reserve(Q.edge_key.size() + c->n_edge + c->n_circ);
+        for (size_t i = 0; i < Q.edge_key.size(); i++) all.emplace_back(Q.edge_key[i], Q.edge_count[i]);
+        for (uint64_t i = 0; i < c->n_edge; i++) all.emplace_back(c->edge_key[i], c->edge_count[i]);
+        for (uint64_t i = 0; i < c->n_circ; i++) all.emplace_back(c->circ_key[i], c->circ_count[i]);
+        std::sort(all.begin(), all.end());
+        Q.edge_key.clear(); Q.edge_count.clear();
+        for (auto& kv : all) {
+            if (!Q.edge_key.empty() && Q.edge_key.back() == kv.first) Q.edge_count.back() += kv.second;
+            else { Q.edge_key.push_back(kv.first); Q.edge_count.push_back(kv.second); }
         }
+    }
+    const wq_keyed* in[2] = {longs, multis};
+    WqKeyedStore* dst[2] = {&Q.longs, &Q.multis};
+    for (int t = 0; t < 2; t++) {
+        if (!in[t] || !in[t]->n_rec) continue;
+        for (uint64_t i = 0; i < in[t]->n_rec; i++)
+            dst[t]->push(in[t]->words + in[t]->rec_ptr[i], (size_t)(in[t]->rec_ptr[i + 1] - in[t]->rec_ptr[i]), in[t]->count[i]);
+        dst[t]->canonicalize();
     }
     return 0;
 }
@@ -672,7 +738,8 @@ int wq_em_tpm(wq_handle* h, const wq_em_param* p, double* tpm, double* count, do
     if (!h || !p) return fail(-1, "null argument");
     if (int rc = sync_host_quant(h)) return rc;
     CK(cudaSetDevice(h->device));
-    std::string err = wq_run_em_tpm(h->H, h->iso, h->hq, h->hx, *p, h->stream, &h->launches, tpm, count, genetpm, iterations);
+    WqTimer tm_("em_tpm (classes + kernel)");
+    std::string err = wq_run_em_tpm(h->H, h->iso, h->hq, h->hx, h->em_scratch, *p, h->stream, &h->launches, tpm, count, genetpm, iterations);
     if (!err.empty()) return fail(-11, err);
     return 0;
 }
@@ -680,20 +747,22 @@ int wq_em_tpm(wq_handle* h, const wq_em_param* p, double* tpm, double* count, do
 int wq_assign_ambig(wq_handle* h, wq_values* v) {
     if (!h || !v) return fail(-1, "null argument");
     if (int rc = sync_host_quant(h)) return rc;
-    std::string err = wq_host_assign_ambig_impl(h->H, h->iso, h->hx);
+    WqTimer tm_("assign_ambig");
+    std::string err = wq_host_assign_ambig_impl(h->H, h->iso, h->hq, h->hx);
     if (!err.empty()) return fail(-12, err);
     WqHostQuantEx& X = h->hx;
+    if (!X.edges_final) wq_finalize_edges(h->hq, X);
     uint64_t ne = 0, nc = 0;
-    for (auto& kv : X.edge_value) { if (wq_edge_is_circ(kv.first)) nc++; else ne++; }
+    for (uint64_t k : X.edge_key) { if (wq_edge_is_circ(k)) nc++; else ne++; }
     bool sizing = !v->node_value && !v->edge_key && !v->circ_key;
     if (!sizing && (v->n_nodes < X.node_value.size() || v->n_edge < ne || v->n_circ < nc)) return fail(-7, "wq_values buffers too small");
     v->n_nodes = X.node_value.size(); v->n_edge = ne; v->n_circ = nc;
     if (sizing) return 0;
     if (v->node_value) memcpy(v->node_value, X.node_value.data(), X.node_value.size() * 8);
     uint64_t ie = 0, ic = 0;
-    for (auto& kv : X.edge_value) {
-        if (wq_edge_is_circ(kv.first)) { if (v->circ_key) { v->circ_key[ic] = kv.first; v->circ_value[ic] = kv.second; } ic++; }
-        else { if (v->edge_key) { v->edge_key[ie] = kv.first; v->edge_value[ie] = kv.second; } ie++; }
+    for (size_t i = 0; i < X.edge_key.size(); i++) {
+        if (wq_edge_is_circ(X.edge_key[i])) { if (v->circ_key) { v->circ_key[ic] = X.edge_key[i]; v->circ_value[ic] = X.edge_value[i]; } ic++; }
+        else { if (v->edge_key) { v->edge_key[ie] = X.edge_key[i]; v->edge_value[ie] = X.edge_value[i]; } ie++; }
     }
     return 0;
 }

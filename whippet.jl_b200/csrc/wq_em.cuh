@@ -12,7 +12,10 @@
 // same sequence a sequential sweep would perform them.  sum(tpm) is a fixed adjacent-pair tree.
 #pragma once
 #include <cooperative_groups.h>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <map>
 #include <string>
 #include <vector>
@@ -49,7 +52,7 @@ struct WqGeneBits {                 // annopath bitsets of one gene
 };
 
 struct WqKeyPath { uint32_t gene, n, rn; const uint32_t* nd; const uint32_t* rnd; };
-static inline size_t wq_key_next(const std::vector<uint32_t>& k, size_t pos, WqKeyPath& o) {
+static inline size_t wq_key_next(const uint32_t* k, size_t pos, WqKeyPath& o) {
     uint32_t hdr = k[pos];
     o.gene = k[pos + 1];
     if ((hdr >> 28) & 2) { o.n = hdr & 0xFF; o.rn = (hdr >> 8) & 0xFF; o.nd = &k[pos + 2]; o.rnd = o.nd + o.n; return pos + 2 + o.n + o.rn; }
@@ -65,15 +68,19 @@ static inline bool wq_key_compatible(const WqGeneBits& B, uint32_t p, const WqKe
 static inline void wq_spread_path(const WqHostIndex& H, WqHostQuantEx& Q, const WqKeyPath& kp, double v) {
     const uint32_t nb = H.genes[kp.gene - 1].node_base;
     auto ekey = [&](uint32_t l, uint32_t r) { return ((uint64_t)kp.gene << 32) | ((uint64_t)(l & 0xFFFF) << 16) | (r & 0xFFFF); };
-    std::vector<uint32_t> seen;
-    if (kp.n == 1) { Q.node_value[nb + kp.nd[0] - 1] += v; seen.push_back(kp.nd[0]); }
-    else for (uint32_t i = 0; i + 1 < kp.n; i++) { seen.push_back(kp.nd[i]); seen.push_back(kp.nd[i + 1]); Q.edge_value[ekey(kp.nd[i], kp.nd[i + 1])] += v; }
+    uint32_t seen[2 * WQ_MAX_PATH + 2];
+    int ns = 0;
+    if (kp.n == 1) { Q.node_value[nb + kp.nd[0] - 1] += v; seen[ns++] = kp.nd[0]; }
+    else for (uint32_t i = 0; i + 1 < kp.n; i++) {
+        if (ns + 2 <= (int)(sizeof seen / sizeof seen[0])) { seen[ns++] = kp.nd[i]; seen[ns++] = kp.nd[i + 1]; }
+        Q.edge_adds.emplace_back(ekey(kp.nd[i], kp.nd[i + 1]), v);
+    }
     if (!kp.rnd) return;
-    auto in_seen = [&](uint32_t x) { for (uint32_t s : seen) if (s == x) return true; return false; };
+    auto in_seen = [&](uint32_t x) { for (int i = 0; i < ns; i++) if (seen[i] == x) return true; return false; };
     if (kp.rn == 1) { if (!in_seen(kp.rnd[0])) Q.node_value[nb + kp.rnd[0] - 1] += v; }
     else for (uint32_t i = 0; i + 1 < kp.rn; i++) {
         if (in_seen(kp.rnd[i]) && in_seen(kp.rnd[i + 1])) continue;
-        Q.edge_value[ekey(kp.rnd[i], kp.rnd[i + 1])] += v;
+        Q.edge_adds.emplace_back(ekey(kp.rnd[i], kp.rnd[i + 1]), v);
     }
 }
 
@@ -83,7 +90,6 @@ static inline std::string wq_host_build_classes(const WqHostIndex& H, const WqIs
     const uint32_t G = H.G, I = S.I;
     X = WqHostQuantEx();
     X.node_value.assign(hq.node.begin(), hq.node.end());
-    X.edge_value = hq.edge;
     X.iso_count.assign(I, 0.0);
     WqClassSet& C = X.cls;
     C.ptr.push_back(0);
@@ -94,15 +100,16 @@ static inline std::string wq_host_build_classes(const WqHostIndex& H, const WqIs
         return B;
     };
     // ---- multi-map classes, key order ----
-    for (auto& kv : hq.keyed) {
-        if (!wq_key_is_multi(kv.first)) continue;
-        const uint32_t nh = kv.first[0] & 0xFFFF;
+    std::vector<int32_t> ids;
+    for (size_t m = 0; m < hq.multis.size(); m++) {
+        const uint32_t* key = hq.multis.key(m);
+        const uint32_t nh = key[0] & 0xFFFF;
         size_t pos = 1;
-        std::vector<int32_t> ids;
+        ids.clear();
         bool all = true;
         for (uint32_t h = 0; h < nh && all; h++) {
             WqKeyPath kp;
-            pos = wq_key_next(kv.first, pos, kp);
+            pos = wq_key_next(key, pos, kp);
             const WqGeneBits& b = bits_of(kp.gene);
             bool any = false;
             for (uint32_t p = 0; p < b.np; p++)
@@ -115,56 +122,83 @@ static inline std::string wq_host_build_classes(const WqHostIndex& H, const WqIs
         if (ids.size() > 500) return "multi-map class larger than 500 isoforms (prop_temp = zeros(500), src/quant.jl:725)";
         for (int32_t i : ids) { C.iso.push_back(i); C.prop.push_back(1.0 / (double)ids.size()); }
         C.ptr.push_back((uint32_t)C.iso.size());
-        C.count.push_back((double)kv.second);
+        C.count.push_back((double)hq.multis.count[m]);
         C.state.push_back(all ? 0 : 2);
         C.postassign.push_back(all ? 0 : 1);
-        X.multi_keys.push_back(&kv.first);
     }
     C.n_multi = (uint32_t)C.count.size();
+    // ---- long paths grouped by gene (the order inside a gene does not affect any result) ----
+    std::vector<uint32_t> lptr(G + 2, 0), lidx(hq.longs.size());
+    for (size_t i = 0; i < hq.longs.size(); i++) {
+        uint32_t g = hq.longs.key(i)[1];
+        if (g < 1 || g > G) return "long-path record names a gene out of range";
+        lptr[g + 1]++;
+    }
+    for (uint32_t g = 0; g <= G; g++) lptr[g + 1] += lptr[g];
+    {
+        std::vector<uint32_t> cur(lptr.begin(), lptr.end() - 1);
+        for (size_t i = 0; i < hq.longs.size(); i++) lidx[cur[hq.longs.key(i)[1]]++] = (uint32_t)i;
+    }
     // ---- isoform classes, gene by gene ----
-    auto lit = hq.keyed.begin();
-    std::vector<std::pair<const std::vector<uint32_t>*, uint64_t>> longs_by_gene_sorted;
-    // long keys are sorted by (npath, gene, ...) — group them by gene first, keeping key order inside a gene
-    std::vector<std::vector<std::pair<const std::vector<uint32_t>*, uint64_t>>> longs(G + 1);
-    for (auto& kv : hq.keyed) if (!wq_key_is_multi(kv.first)) longs[kv.first[1]].push_back({&kv.first, kv.second});
-    (void)lit;
+    std::vector<int32_t> setbuf;                 // id lists of this gene's count entries, back to back
+    struct Rec { uint32_t off, len; double value; };
+    std::vector<Rec> recs;
+    std::vector<uint32_t> order;
+    size_t e = 0;
+    const size_t ne = hq.edge_key.size();
     for (uint32_t g = 1; g <= G; g++) {
         const WqGeneBits& b = bits_of(g);
         const uint32_t nn = H.genes[g - 1].nn, nb = H.genes[g - 1].node_base, ib = S.iso_base[g - 1];
-        std::map<std::vector<int32_t>, double> temp;
-        std::vector<int32_t> set;
-        auto account = [&](double value) {
-            if (set.size() == 1) X.iso_count[ib + set[0] - 1] += value;
-            else if (set.size() > 1) temp[set] += value;
+        setbuf.clear();
+        recs.clear();
+        auto account = [&](uint32_t off, double value) {
+            uint32_t len = (uint32_t)setbuf.size() - off;
+            if (len == 1) { X.iso_count[ib + setbuf[off] - 1] += value; setbuf.resize(off); }
+            else if (len > 1) recs.push_back(Rec{off, len, value});
         };
         for (uint32_t n = 1; n <= nn; n++) {
-            set.clear();
-            for (uint32_t p = 0; p < b.np; p++) if (b.has(p, n)) set.push_back((int32_t)p + 1);
-            account((double)hq.node[nb + n - 1]);
+            uint32_t off = (uint32_t)setbuf.size();
+            for (uint32_t p = 0; p < b.np; p++) if (b.has(p, n)) setbuf.push_back((int32_t)p + 1);
+            account(off, (double)hq.node[nb + n - 1]);
         }
-        for (auto it = hq.edge.lower_bound((uint64_t)g << 32); it != hq.edge.end() && (it->first >> 32) == g; ++it) {
-            if (wq_edge_is_circ(it->first)) continue;
-            uint32_t l = (it->first >> 16) & 0xFFFF, r = it->first & 0xFFFF;
-            set.clear();
-            for (uint32_t p = 0; p < b.np; p++) if (b.adjacent(p, l, r)) set.push_back((int32_t)p + 1);
-            account(it->second);
+        while (e < ne && (hq.edge_key[e] >> 32) < g) e++;
+        for (; e < ne && (hq.edge_key[e] >> 32) == g; e++) {
+            if (wq_edge_is_circ(hq.edge_key[e])) continue;
+            uint32_t l = (hq.edge_key[e] >> 16) & 0xFFFF, r = hq.edge_key[e] & 0xFFFF;
+            uint32_t off = (uint32_t)setbuf.size();
+            for (uint32_t p = 0; p < b.np; p++) if (b.adjacent(p, l, r)) setbuf.push_back((int32_t)p + 1);
+            account(off, (double)hq.edge_count[e]);
         }
-        for (auto& lk : longs[g]) {
+        for (uint32_t k = lptr[g]; k < lptr[g + 1]; k++) {
             WqKeyPath kp;
-            wq_key_next(*lk.first, 0, kp);
-            set.clear();
-            for (uint32_t p = 0; p < b.np; p++) if (wq_key_compatible(b, p, kp)) set.push_back((int32_t)p + 1);
-            account((double)lk.second);
-            wq_spread_path(H, X, kp, (double)lk.second);
+            wq_key_next(hq.longs.key(lidx[k]), 0, kp);
+            uint32_t off = (uint32_t)setbuf.size();
+            for (uint32_t p = 0; p < b.np; p++) if (wq_key_compatible(b, p, kp)) setbuf.push_back((int32_t)p + 1);
+            account(off, (double)hq.longs.count[lidx[k]]);
+            wq_spread_path(H, X, kp, (double)hq.longs.count[lidx[k]]);
         }
-        for (auto& kv : temp) {
-            if (!(kv.second > 0.0)) continue;
-            if (kv.first.size() > 500) return "isoform class larger than 500 (prop_temp = zeros(500), src/quant.jl:725)";
-            for (int32_t p : kv.first) { C.iso.push_back((int32_t)(ib + p - 1)); C.prop.push_back(1.0 / (double)kv.first.size()); }
-            C.ptr.push_back((uint32_t)C.iso.size());
-            C.count.push_back(kv.second);
-            C.state.push_back(0);
-            C.postassign.push_back(0);
+        // distinct id sets in lexicographic order, values added up (they are integers: order-free)
+        order.resize(recs.size());
+        for (uint32_t i = 0; i < recs.size(); i++) order[i] = i;
+        auto lt = [&](uint32_t x, uint32_t y) {
+            return std::lexicographical_compare(setbuf.begin() + recs[x].off, setbuf.begin() + recs[x].off + recs[x].len,
+                                                setbuf.begin() + recs[y].off, setbuf.begin() + recs[y].off + recs[y].len);
+        };
+        std::sort(order.begin(), order.end(), lt);
+        for (size_t i = 0; i < order.size();) {
+            size_t j = i;
+            double total = 0.0;
+            while (j < order.size() && !lt(order[i], order[j]) && !lt(order[j], order[i])) { total += recs[order[j]].value; j++; }
+            const Rec& r0 = recs[order[i]];
+            if (total > 0.0) {
+                if (r0.len > 500) return "isoform class larger than 500 (prop_temp = zeros(500), src/quant.jl:725)";
+                for (uint32_t k = 0; k < r0.len; k++) { C.iso.push_back((int32_t)(ib + setbuf[r0.off + k] - 1)); C.prop.push_back(1.0 / (double)r0.len); }
+                C.ptr.push_back((uint32_t)C.iso.size());
+                C.count.push_back(total);
+                C.state.push_back(0);
+                C.postassign.push_back(0);
+            }
+            i = j;
         }
     }
     X.built = true;
@@ -172,19 +206,20 @@ static inline std::string wq_host_build_classes(const WqHostIndex& H, const WqIs
 }
 
 // assign_ambig!, src/quant.jl:520-553 (host: one pass over the multi-map classes)
-static inline std::string wq_host_assign_ambig_impl(const WqHostIndex& H, const WqIsoIndex& S, WqHostQuantEx& X) {
+static inline std::string wq_host_assign_ambig_impl(const WqHostIndex& H, const WqIsoIndex& S, const WqHostQuant& hq, WqHostQuantEx& X) {
     if (!X.built || !X.em_done) return "assign_ambig needs wq_em_tpm first (it uses the EM class proportions and gene TPM)";
     if (X.ambig_done) return "";
     const WqClassSet& C = X.cls;
     WqGeneBits B;
     uint32_t cached = 0;
+    WqKeyPath vp[WQ_MAX_TOLERATE];
+    double w[WQ_MAX_TOLERATE];
     for (uint32_t c = 0; c < C.n_multi; c++) {
-        const std::vector<uint32_t>& key = *X.multi_keys[c];
+        const uint32_t* key = hq.multis.key(c);
         const uint32_t nh = key[0] & 0xFFFF;
-        std::vector<WqKeyPath> vp(nh);
+        if (nh > WQ_MAX_TOLERATE) return "multi-map class with more alignments than WQ_MAX_TOLERATE";
         size_t pos = 1;
         for (uint32_t h = 0; h < nh; h++) pos = wq_key_next(key, pos, vp[h]);
-        std::vector<double> w(nh, 0.0);
         for (uint32_t h = 0; h < nh; h++) {
             if (C.postassign[c]) { w[h] = X.genetpm[vp[h].gene - 1]; continue; }
             if (cached != vp[h].gene) { B.build(S, vp[h].gene - 1, H.genes[vp[h].gene - 1].nn); cached = vp[h].gene; }
@@ -197,10 +232,11 @@ static inline std::string wq_host_assign_ambig_impl(const WqHostIndex& H, const 
             w[h] = acc;
         }
         double tot = 0.0;
-        for (double x : w) tot += x;
+        for (uint32_t h = 0; h < nh; h++) tot += w[h];
         for (uint32_t h = 0; h < nh; h++) wq_spread_path(H, X, vp[h], (w[h] / tot) * C.count[c]);
     }
     X.ambig_done = true;
+    X.edges_final = false;
     return "";
 }
 
@@ -318,37 +354,49 @@ __global__ void __launch_bounds__(1024) wq_k_em_tpm(WqEmDev d) {
     if (gtid == 0) *d.it_out = it;
 }
 
-template <class T>
-struct WqTmpDev {
-    T* p = nullptr;
-    cudaError_t put(const std::vector<T>& v, cudaStream_t s) {
-        cudaError_t e = cudaMalloc(&p, std::max<size_t>(1, v.size()) * sizeof(T));
-        if (e != cudaSuccess) return e;
-        if (!v.empty()) e = cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s);
+// grow-only device scratch kept in the handle (cudaMalloc/cudaFree per call would serialise the device)
+struct WqEmScratch {
+    void* p[16] = {nullptr}; size_t cap[16] = {0};
+    template <class T> cudaError_t get(int slot, size_t n, T** out) {
+        size_t bytes = std::max<size_t>(1, n) * sizeof(T);
+        if (bytes > cap[slot]) {
+            if (p[slot]) cudaFree(p[slot]);
+            p[slot] = nullptr; cap[slot] = 0;
+            cudaError_t e = cudaMalloc(&p[slot], bytes + bytes / 4);
+            if (e != cudaSuccess) return e;
+            cap[slot] = bytes + bytes / 4;
+        }
+        *out = (T*)p[slot];
+        return cudaSuccess;
+    }
+    template <class T> cudaError_t put(int slot, const std::vector<T>& v, T** out, cudaStream_t s) {
+        cudaError_t e = get(slot, v.size(), out);
+        if (e == cudaSuccess && !v.empty()) e = cudaMemcpyAsync(*out, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s);
         return e;
     }
-    cudaError_t zero(size_t n) {
-        cudaError_t e = cudaMalloc(&p, std::max<size_t>(1, n) * sizeof(T));
-        if (e == cudaSuccess) e = cudaMemset(p, 0, std::max<size_t>(1, n) * sizeof(T));
-        return e;
-    }
-    ~WqTmpDev() { if (p) cudaFree(p); }
+    void release() { for (int i = 0; i < 16; i++) { if (p[i]) cudaFree(p[i]); p[i] = nullptr; cap[i] = 0; } }
 };
 
 #define WQ_EMCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return std::string(#call) + ": " + cudaGetErrorString(e_); } while (0)
 
-static inline std::string wq_run_em_tpm(const WqHostIndex& H, const WqIsoIndex& S, WqHostQuant& hq, WqHostQuantEx& X,
+static inline std::string wq_run_em_tpm(const WqHostIndex& H, const WqIsoIndex& S, WqHostQuant& hq, WqHostQuantEx& X, WqEmScratch& M,
                                         const wq_em_param& p, cudaStream_t stream, uint64_t* launches,
                                         double* tpm_out, double* count_out, double* genetpm_out, int64_t* iterations) {
     if (p.sig < 0 || p.sig > 12) return "sig out of range";
-    if (!X.built) { std::string e = wq_host_build_classes(H, S, hq, X); if (!e.empty()) return e; }
+    const bool prof = getenv("WQ_PROFILE") != nullptr;
+    if (!X.built) {
+        auto t0 = std::chrono::steady_clock::now();
+        std::string e = wq_host_build_classes(H, S, hq, X);
+        if (!e.empty()) return e;
+        if (prof) fprintf(stderr, "[wq]   build_classes              %9.3f ms (%zu classes, %u multi)\n",
+            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(), X.cls.count.size(), X.cls.n_multi);
+    }
     if (X.em_done) return "wq_em_tpm was already run on this count state (gene_em! mutates it); call wq_quant_reset first";
     const uint32_t I = S.I;
     WqClassSet& C = X.cls;
     const uint32_t NC = (uint32_t)C.count.size();
     const uint32_t ntiles = (I + 1023) / 1024;
     if (ntiles > 1024) return "more than 1048576 isoforms";
-    // calculate_tpm!(quant, readlen) on the unique counts (host: one pass; same arithmetic as the kernel)
     std::vector<double> leff(I), tpm(I), count = X.iso_count;
     for (uint32_t i = 0; i < I; i++) leff[i] = std::max((double)(S.length[i] - p.readlen), 1.0);
     // contributions (isoform -> class positions) in class order
@@ -360,56 +408,60 @@ static inline std::string wq_run_em_tpm(const WqHostIndex& H, const WqIsoIndex& 
         for (uint32_t c = 0; c < NC; c++)
             for (uint32_t k = C.ptr[c]; k < C.ptr[c + 1]; k++) { uint32_t s = cur[C.iso[k]]++; con_cls[s] = c; con_pos[s] = k; }
     }
-    WqTmpDev<double> d_leff, d_count, d_tpm, d_raw, d_prop, d_ccount, d_partial;
-    WqTmpDev<uint32_t> d_cptr, d_conptr, d_concls, d_conpos;
-    WqTmpDev<int32_t> d_ciso;
-    WqTmpDev<uint8_t> d_state;
-    WqTmpDev<int> d_flags;
-    WqTmpDev<int64_t> d_it;
-    WQ_EMCK(d_leff.put(leff, stream)); WQ_EMCK(d_count.put(count, stream)); WQ_EMCK(d_tpm.zero(I)); WQ_EMCK(d_raw.zero(I));
-    WQ_EMCK(d_prop.put(C.prop, stream)); WQ_EMCK(d_ccount.put(C.count, stream)); WQ_EMCK(d_partial.zero(1024));
-    WQ_EMCK(d_cptr.put(C.ptr, stream)); WQ_EMCK(d_conptr.put(con_ptr, stream)); WQ_EMCK(d_concls.put(con_cls, stream));
-    WQ_EMCK(d_conpos.put(con_pos, stream)); WQ_EMCK(d_ciso.put(C.iso, stream)); WQ_EMCK(d_state.put(C.state, stream));
-    WQ_EMCK(d_flags.zero(4)); WQ_EMCK(d_it.zero(1));
     WqEmDev d;
-    d.I = I; d.C = NC; d.ntiles = ntiles; d.leff = d_leff.p; d.count = d_count.p; d.tpm = d_tpm.p; d.tpm_raw = d_raw.p;
-    d.cls_ptr = d_cptr.p; d.cls_iso = d_ciso.p; d.prop = d_prop.p; d.cls_count = d_ccount.p; d.state = d_state.p;
-    d.con_ptr = d_conptr.p; d.con_cls = d_concls.p; d.con_pos = d_conpos.p; d.partial = d_partial.p; d.flags = d_flags.p;
-    d.it_out = d_it.p; d.sig = (int)p.sig; d.sc_tpm = std::pow(10.0, (double)p.sig); d.sc_prop = 10000.0;
+    double *d_leff, *d_count, *d_tpm, *d_raw, *d_prop, *d_ccount, *d_partial;
+    uint32_t *d_cptr, *d_conptr, *d_concls, *d_conpos;
+    int32_t* d_ciso;
+    uint8_t *d_state, *d_parked;
+    int* d_flags;
+    int64_t* d_it;
+    WQ_EMCK(M.put(0, leff, &d_leff, stream)); WQ_EMCK(M.put(1, count, &d_count, stream));
+    WQ_EMCK(M.get(2, I, &d_tpm)); WQ_EMCK(M.get(3, I, &d_raw));
+    WQ_EMCK(M.put(4, C.prop, &d_prop, stream)); WQ_EMCK(M.put(5, C.count, &d_ccount, stream)); WQ_EMCK(M.get(6, 1024, &d_partial));
+    WQ_EMCK(M.put(7, C.ptr, &d_cptr, stream)); WQ_EMCK(M.put(8, con_ptr, &d_conptr, stream)); WQ_EMCK(M.put(9, con_cls, &d_concls, stream));
+    WQ_EMCK(M.put(10, con_pos, &d_conpos, stream)); WQ_EMCK(M.put(11, C.iso, &d_ciso, stream)); WQ_EMCK(M.put(12, C.state, &d_state, stream));
+    WQ_EMCK(M.get(13, 4, &d_flags)); WQ_EMCK(M.get(14, 1, &d_it));
+    std::vector<uint8_t> parked(NC, 2);
+    WQ_EMCK(M.put(15, parked, &d_parked, stream));
+    WQ_EMCK(cudaMemsetAsync(d_tpm, 0, std::max<size_t>(1, I) * 8, stream));
+    WQ_EMCK(cudaMemsetAsync(d_flags, 0, 4 * sizeof(int), stream));
+    d.I = I; d.C = NC; d.ntiles = ntiles; d.leff = d_leff; d.count = d_count; d.tpm = d_tpm; d.tpm_raw = d_raw;
+    d.cls_ptr = d_cptr; d.cls_iso = d_ciso; d.prop = d_prop; d.cls_count = d_ccount; d.state = d_state;
+    d.con_ptr = d_conptr; d.con_cls = d_concls; d.con_pos = d_conpos; d.partial = d_partial; d.flags = d_flags;
+    d.it_out = d_it; d.sig = (int)p.sig; d.sc_tpm = std::pow(10.0, (double)p.sig); d.sc_prop = 10000.0;
     int dev = 0, sms = 0, per_sm = 0;
     WQ_EMCK(cudaGetDevice(&dev));
     WQ_EMCK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     WQ_EMCK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wq_k_em_tpm, 1024, 0));
     if (per_sm < 1) return "EM kernel does not fit on an SM";
     int grid = sms * per_sm;
-    // pass 0: calculate_tpm!(quant, readlen=...) before gene_em! (bin/whippet-quant.jl:163) = one sweep with no
-    // active class; run it as a 2-iteration call whose classes are all parked, then the real call.
+    // calculate_tpm!(quant, readlen) before gene_em! (bin/whippet-quant.jl:163): one sweep with every class parked
     {
-        std::vector<uint8_t> parked(NC, 2);
-        WqTmpDev<uint8_t> d_parked;
-        WQ_EMCK(d_parked.put(parked, stream));
         WqEmDev d0 = d;
-        d0.state = d_parked.p; d0.maxit = 2; d0.first_differs = 1;
+        d0.state = d_parked; d0.maxit = 2; d0.first_differs = 1;
         void* args0[] = {&d0};
         WQ_EMCK(cudaLaunchCooperativeKernel((void*)wq_k_em_tpm, dim3(grid), dim3(1024), args0, 0, stream));
-        WQ_EMCK(cudaStreamSynchronize(stream));
         if (launches) *launches += 1;
     }
-    WQ_EMCK(cudaMemcpy(tpm.data(), d_tpm.p, I * 8, cudaMemcpyDeviceToHost));
+    WQ_EMCK(cudaMemcpyAsync(tpm.data(), d_tpm, I * 8, cudaMemcpyDeviceToHost, stream));
+    WQ_EMCK(cudaStreamSynchronize(stream));
     bool differs = false;                        // `tpm_temp != quant.tpm` with tpm_temp = ones (src/quant.jl:724,752)
     for (uint32_t i = 0; i < I; i++) if (tpm[i] != 1.0) { differs = true; break; }
     d.maxit = p.maxit; d.first_differs = differs ? 1 : 0;
-    WQ_EMCK(cudaMemset(d_flags.p, 0, 4 * sizeof(int)));
+    WQ_EMCK(cudaMemsetAsync(d_flags, 0, 4 * sizeof(int), stream));
     void* args[] = {&d};
+    auto tk0 = std::chrono::steady_clock::now();
     WQ_EMCK(cudaLaunchCooperativeKernel((void*)wq_k_em_tpm, dim3(grid), dim3(1024), args, 0, stream));
-    WQ_EMCK(cudaStreamSynchronize(stream));
     if (launches) *launches += 1;
     int64_t it = 0;
-    WQ_EMCK(cudaMemcpy(&it, d_it.p, 8, cudaMemcpyDeviceToHost));
-    WQ_EMCK(cudaMemcpy(tpm.data(), d_tpm.p, I * 8, cudaMemcpyDeviceToHost));
-    WQ_EMCK(cudaMemcpy(count.data(), d_count.p, I * 8, cudaMemcpyDeviceToHost));
-    WQ_EMCK(cudaMemcpy(C.prop.data(), d_prop.p, C.prop.size() * 8, cudaMemcpyDeviceToHost));
-    WQ_EMCK(cudaMemcpy(C.state.data(), d_state.p, C.state.size(), cudaMemcpyDeviceToHost));
+    WQ_EMCK(cudaMemcpyAsync(&it, d_it, 8, cudaMemcpyDeviceToHost, stream));
+    WQ_EMCK(cudaMemcpyAsync(tpm.data(), d_tpm, I * 8, cudaMemcpyDeviceToHost, stream));
+    WQ_EMCK(cudaMemcpyAsync(count.data(), d_count, I * 8, cudaMemcpyDeviceToHost, stream));
+    WQ_EMCK(cudaMemcpyAsync(C.prop.data(), d_prop, C.prop.size() * 8, cudaMemcpyDeviceToHost, stream));
+    WQ_EMCK(cudaMemcpyAsync(C.state.data(), d_state, C.state.size(), cudaMemcpyDeviceToHost, stream));
+    WQ_EMCK(cudaStreamSynchronize(stream));
+    if (prof) fprintf(stderr, "[wq]   em kernel (grid %d, %lld it) %9.3f ms\n", grid, (long long)it,
+        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tk0).count());
     X.tpm = tpm; X.iso_count = count;
     X.genetpm.assign(H.G, 0.0);                  // set_gene_tpm!, src/quant.jl:248-257
     for (uint32_t g = 0; g < H.G; g++) {

@@ -1,16 +1,53 @@
 // Host-side quantification state: the count stores downloaded from the device in canonical
 // (sorted) order, the annotated isoform paths, and the host halves of the quant stage.
 #pragma once
+#include <algorithm>
+#include <cstring>
 #include <map>
 #include <string>
 #include <vector>
 #include "wq_types.h"
 #include "wq_kernels.cuh"
 
+struct WqKeyedStore {                                        // variable-length keyed counts (wq_build_key_* records)
+    std::vector<uint32_t> words;                             // key words of all records, back to back
+    std::vector<uint64_t> off;                               // [n+1]
+    std::vector<uint64_t> count;                             // [n]
+    WqKeyedStore() : off(1, 0) {}
+    size_t size() const { return count.size(); }
+    const uint32_t* key(size_t i) const { return words.data() + off[i]; }
+    size_t len(size_t i) const { return (size_t)(off[i + 1] - off[i]); }
+    void push(const uint32_t* w, size_t n, uint64_t c) {
+        words.insert(words.end(), w, w + n);
+        off.push_back(words.size());
+        count.push_back(c);
+    }
+    static bool less(const uint32_t* a, size_t na, const uint32_t* b, size_t nb) {
+        return std::lexicographical_compare(a, a + na, b, b + nb);
+    }
+    // sort lexicographically and add up equal keys (canonical order)
+    void canonicalize() {
+        const size_t n = size();
+        std::vector<uint32_t> idx(n);
+        for (size_t i = 0; i < n; i++) idx[i] = (uint32_t)i;
+        std::sort(idx.begin(), idx.end(), [&](uint32_t x, uint32_t y) { return less(key(x), len(x), key(y), len(y)); });
+        WqKeyedStore out;
+        out.words.reserve(words.size());
+        for (size_t k = 0; k < n; k++) {
+            uint32_t i = idx[k];
+            if (out.size() && out.len(out.size() - 1) == len(i) &&
+                std::equal(key(i), key(i) + len(i), out.key(out.size() - 1))) out.count.back() += count[i];
+            else out.push(key(i), len(i), count[i]);
+        }
+        *this = std::move(out);
+    }
+};
+
 struct WqHostQuant {
     std::vector<uint64_t> node;                              // SpliceGraphQuant.node, by global node index
-    std::map<uint64_t, double> edge;                         // .edge and .circ: gene<<32 | l<<16 | r
-    std::map<std::vector<uint32_t>, uint64_t> keyed;         // .long and MultiMapping.map records (wq_build_key_*)
+    std::vector<uint64_t> edge_key, edge_count;              // .edge and .circ, sorted by gene<<32 | l<<16 | r
+    WqKeyedStore longs;                                      // .long (any order; order does not affect results)
+    WqKeyedStore multis;                                     // MultiMapping.map in canonical (lexicographic) order
     WqCounters stats;
     WqHostQuant() { memset(&stats, 0, sizeof stats); }
 };
@@ -29,15 +66,36 @@ struct WqClassSet {                                         // IsoCompat / Multi
 struct WqHostQuantEx {
     bool built = false, em_done = false, ambig_done = false;
     std::vector<double> node_value;                          // node store as Float64 (fractional after assign_ambig!)
-    std::map<uint64_t, double> edge_value;                   // edge + circ stores
+    std::vector<std::pair<uint64_t, double>> edge_adds;      // additions to the edge/circ stores, in the order made
+    std::vector<uint64_t> edge_key;                          // merged stores (valid after finalize_edges)
+    std::vector<double>   edge_value;
+    bool edges_final = false;
     std::vector<double> iso_count, tpm, genetpm;
     WqClassSet cls;
-    std::vector<const std::vector<uint32_t>*> multi_keys;    // key of each multi-map class (points into WqHostQuant.keyed)
     int64_t iterations = 0;
 };
 
+// base counts + additions (stable by key, so every key sees its additions in the order they were made)
+static inline void wq_finalize_edges(const WqHostQuant& hq, WqHostQuantEx& X) {
+    std::vector<std::pair<uint64_t, double>> adds = X.edge_adds;
+    std::stable_sort(adds.begin(), adds.end(), [](const std::pair<uint64_t, double>& a, const std::pair<uint64_t, double>& b) { return a.first < b.first; });
+    X.edge_key.clear(); X.edge_value.clear();
+    size_t i = 0, j = 0;
+    const size_t ne = hq.edge_key.size(), na = adds.size();
+    while (i < ne || j < na) {
+        uint64_t k;
+        double v = 0.0;
+        if (j >= na || (i < ne && hq.edge_key[i] <= adds[j].first)) { k = hq.edge_key[i]; v = (double)hq.edge_count[i]; i++; }
+        else k = adds[j].first;
+        while (j < na && adds[j].first == k) { v += adds[j].second; j++; }
+        X.edge_key.push_back(k);
+        X.edge_value.push_back(v);
+    }
+    X.edges_final = true;
+}
+
 static inline bool wq_edge_is_circ(uint64_t key) { return ((key >> 16) & 0xFFFF) >= (key & 0xFFFF); }
-static inline bool wq_key_is_multi(const std::vector<uint32_t>& k) { return !k.empty() && ((k[0] >> 28) & 1); }
+static inline bool wq_key_is_multi(const uint32_t* k) { return (k[0] >> 28) & 1; }
 
 struct WqIsoIndex {                                          // SpliceGraph.annopath of every gene
     std::vector<uint32_t> iso_base;                          // [G+1]
