@@ -175,6 +175,10 @@ int  wq_last_kernel_ms(wq_handle* h, float* ms3);
 int  wq_pinned_alloc(void** p, uint64_t bytes);
 int  wq_pinned_free(void* p);
 int  wq_counts_refresh_dense(wq_handle* h);
+/* sparse stores (edges, circ, long paths, multi-map classes) as one flat buffer for an all-gather between ranks;
+ * buf == NULL returns the size.  wq_sparse_merge adds another rank's buffer into this handle. */
+int  wq_sparse_pack(wq_handle* h, void* buf, uint64_t cap, uint64_t* used);
+int  wq_sparse_merge(wq_handle* h, const void* buf, uint64_t len);
 uint64_t wq_launch_count(wq_handle* h);   /* kernels launched by this handle so far */
 
 /* Device pointer + element count of the dense count vector (u64 per node, then the scalar

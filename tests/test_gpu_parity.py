@@ -195,3 +195,29 @@ def test_paired_end(seed, ng, R, pr, rc):
     nodev = q.assign_ambig()[0]
     assert np.array_equal(nodev, o.node_counts())
     q.close()
+
+
+def test_sharded_counts_merge_equals_single_pass():
+    """Multi-GPU exchange emulated on one GPU: two handles each align half of the reads, the sparse stores are
+    packed/merged through the C ABI and the dense vectors added; EM on the merged state equals the single pass."""
+    idx = synth.make_index(n_genes=400, K=9, seed=31, paralog_frac=0.1)
+    rb = synth.simulate_reads(idx, 200000, 101, seed=32, sub_rate=0.01)
+    p = wq.AlignParam()
+    full = wq.GraphLibQuant(idx)
+    full.process_reads(p, rb)
+    a, b = wq.GraphLibQuant(idx), wq.GraphLibQuant(idx)
+    a.process_reads(p, rb.slice(0, 90000))
+    b.process_reads(p, rb.slice(90000, rb.n))
+    ta, tb = a.dense_tensor(), b.dense_tensor()
+    ta += tb                                            # what the NCCL all-reduce does
+    import torch
+    torch.cuda.synchronize()
+    a.sparse_merge(b.sparse_pack())
+    for x, y in zip(full.counts(), a.counts()):
+        assert np.array_equal(x, y)
+    assert full.keyed(0) == a.keyed(0) and full.keyed(1) == a.keyed(1)
+    r1, r2 = full.gene_em(101), a.gene_em(101)
+    assert r1[0] == r2[0] and all(np.array_equal(x, y) for x, y in zip(r1[1:], r2[1:]))
+    assert all(np.array_equal(x, y) for x, y in zip(full.assign_ambig(), a.assign_ambig()))
+    for q in (full, a, b):
+        q.close()

@@ -722,6 +722,76 @@ int wq_counts_merge(wq_handle* h, const wq_counts* c, const wq_keyed* longs, con
     return 0;
 }
 
+// Sparse stores of this handle as one flat byte buffer for an all-gather between ranks:
+//   u64 header[5] = {n_edge, n_long, n_multi, long_words, multi_words}
+//   u64 edge_key[n_edge], u64 edge_count[n_edge]
+//   u64 long_off[n_long+1], u64 long_count[n_long], u32 long_words[] (padded to 8 bytes)
+//   u64 multi_off[n_multi+1], u64 multi_count[n_multi], u32 multi_words[] (padded)
+// Two-call protocol: buf == NULL returns the size in *used.
+int wq_sparse_pack(wq_handle* h, void* buf, uint64_t cap, uint64_t* used) {
+    if (!h || !used) return fail(-1, "null argument");
+    if (int rc = sync_host_quant(h)) return rc;
+    const WqHostQuant& Q = h->hq;
+    auto pad8 = [](uint64_t b) { return (b + 7) & ~7ull; };
+    const uint64_t ne = Q.edge_key.size(), nl = Q.longs.size(), nm = Q.multis.size();
+    uint64_t need = 40 + 16 * ne + 8 * (nl + 1) + 8 * nl + pad8(4 * Q.longs.words.size()) + 8 * (nm + 1) + 8 * nm + pad8(4 * Q.multis.words.size());
+    *used = need;
+    if (!buf) return 0;
+    if (cap < need) return fail(-7, "sparse pack buffer too small");
+    uint8_t* p = (uint8_t*)buf;
+    uint64_t hdr[5] = {ne, nl, nm, Q.longs.words.size(), Q.multis.words.size()};
+    memcpy(p, hdr, 40); p += 40;
+    memcpy(p, Q.edge_key.data(), 8 * ne); p += 8 * ne;
+    memcpy(p, Q.edge_count.data(), 8 * ne); p += 8 * ne;
+    for (const WqKeyedStore* K : {&Q.longs, &Q.multis}) {
+        memcpy(p, K->off.data(), 8 * (K->size() + 1)); p += 8 * (K->size() + 1);
+        memcpy(p, K->count.data(), 8 * K->size()); p += 8 * K->size();
+        memcpy(p, K->words.data(), 4 * K->words.size()); p += pad8(4 * K->words.size());
+    }
+    return 0;
+}
+
+// Merge another rank's wq_sparse_pack buffer into this handle's host-side stores.
+int wq_sparse_merge(wq_handle* h, const void* buf, uint64_t len) {
+    if (!h || !buf) return fail(-1, "null argument");
+    if (len < 40) return fail(-1, "sparse buffer too short");
+    if (int rc = sync_host_quant(h)) return rc;
+    WqHostQuant& Q = h->hq;
+    h->hx = WqHostQuantEx();
+    auto pad8 = [](uint64_t b) { return (b + 7) & ~7ull; };
+    const uint8_t* p = (const uint8_t*)buf;
+    uint64_t hdr[5];
+    memcpy(hdr, p, 40); p += 40;
+    const uint64_t ne = hdr[0];
+    uint64_t need = 40 + 16 * ne + 8 * (hdr[1] + 1) + 8 * hdr[1] + pad8(4 * hdr[3]) + 8 * (hdr[2] + 1) + 8 * hdr[2] + pad8(4 * hdr[4]);
+    if (len < need) return fail(-1, "sparse buffer truncated");
+    const uint64_t* ek = (const uint64_t*)p; p += 8 * ne;
+    const uint64_t* ec = (const uint64_t*)p; p += 8 * ne;
+    {   // both edge lists are sorted: linear merge
+        std::vector<uint64_t> k2, c2;
+        k2.reserve(Q.edge_key.size() + ne); c2.reserve(Q.edge_key.size() + ne);
+        size_t i = 0, j = 0;
+        while (i < Q.edge_key.size() || j < ne) {
+            if (j >= ne || (i < Q.edge_key.size() && Q.edge_key[i] < ek[j])) { k2.push_back(Q.edge_key[i]); c2.push_back(Q.edge_count[i]); i++; }
+            else if (i >= Q.edge_key.size() || ek[j] < Q.edge_key[i]) { k2.push_back(ek[j]); c2.push_back(ec[j]); j++; }
+            else { k2.push_back(ek[j]); c2.push_back(Q.edge_count[i] + ec[j]); i++; j++; }
+        }
+        Q.edge_key.swap(k2); Q.edge_count.swap(c2);
+    }
+    WqKeyedStore* dst[2] = {&Q.longs, &Q.multis};
+    for (int t = 0; t < 2; t++) {
+        const uint64_t n = hdr[1 + t], nw = hdr[3 + t];
+        const uint64_t* off = (const uint64_t*)p; p += 8 * (n + 1);
+        const uint64_t* cnt = (const uint64_t*)p; p += 8 * n;
+        const uint32_t* words = (const uint32_t*)p; p += pad8(4 * nw);
+        for (uint64_t i = 0; i < n; i++) dst[t]->push(words + off[i], (size_t)(off[i + 1] - off[i]), cnt[i]);
+    }
+    // multi-map keys are classes: equal keys must become one record, in canonical order.  Long paths may stay
+    // duplicated and unordered: every use of them is an order-free integer accumulation.
+    Q.multis.canonicalize();
+    return 0;
+}
+
 // Replace the dense part of the host quant state after an NCCL all-reduce of wq_counts_device_ptr.
 int wq_counts_refresh_dense(wq_handle* h) {
     if (!h) return fail(-1, "null handle");

@@ -48,6 +48,8 @@ def load():
     L.wq_pinned_alloc.argtypes = [C.POINTER(vp), C.c_uint64]
     L.wq_pinned_free.argtypes = [vp]
     L.wq_set_stream.argtypes = [vp, vp]
+    L.wq_sparse_pack.argtypes = [vp, vp, C.c_uint64, C.POINTER(C.c_uint64)]
+    L.wq_sparse_merge.argtypes = [vp, vp, C.c_uint64]
     L.wq_launch_count.argtypes = [vp]
     L.wq_launch_count.restype = C.c_uint64
     _lib = L

@@ -199,15 +199,23 @@ class GraphLibQuant:
             return
         dist.all_reduce(self.dense_tensor())
         torch.cuda.current_stream().synchronize()
-        node, ek, ec, ck, cc = self.counts()            # host state: all-reduced dense + this rank's sparse stores
-        mine = parallel.pack_sparse(ek, ec, ck, cc, self.keyed(0), self.keyed(1))
+        mine = self.sparse_pack()                        # host state: all-reduced dense + this rank's sparse stores
         bufs = parallel.allgather_buffers(mine, torch.device("cuda", self.device))
         rank = dist.get_rank()
         for r, b in enumerate(bufs):
-            if r == rank:
-                continue
-            ek, ec, ck, cc, lo, mu = parallel.unpack_sparse(b)
-            self.merge_sparse(ek, ec, ck, cc, lo, mu)
+            if r != rank:
+                self.sparse_merge(b)
+
+    def sparse_pack(self) -> np.ndarray:
+        used = C.c_uint64()
+        lib.check(self.L.wq_sparse_pack(self.h, None, 0, C.byref(used)))
+        buf = np.zeros(used.value // 8, "<u8")
+        lib.check(self.L.wq_sparse_pack(self.h, buf.ctypes.data_as(C.c_void_p), buf.nbytes, C.byref(used)))
+        return buf
+
+    def sparse_merge(self, buf: np.ndarray):
+        buf = np.ascontiguousarray(buf, "<u8")
+        lib.check(self.L.wq_sparse_merge(self.h, buf.ctypes.data_as(C.c_void_p), buf.nbytes))
 
     def merge_sparse(self, ek, ec, ck, cc, longs, multis):
         c = abi.CountsC()
