@@ -64,9 +64,10 @@ int emu_align_se(Emu* e, const wq_align_param* ap, const wq_read_batch* rb) {
     e->paired = false;
     WqWork wk{e->seeds.data(), e->hit_read.data(), e->hit_s.data(), nullptr, nullptr, e->hits.data(), e->pool.data(), e->cursors,
               e->pending.data(), hit_cap, (uint32_t)e->pool.size()};
-    for (uint32_t r = 0; r < n; r++) wq_seed_thread(e->ix, p, b, wk, r);
+    uint64_t wbuf[WQ_MAX_READ_WORDS + 1];
+    for (uint32_t r = 0; r < n; r++) wq_seed_thread(e->ix, p, b, wk, r, wbuf);
     uint32_t nh = e->cursors[0];
-    for (uint32_t s = 0; s < nh; s++) wq_extend_thread(e->ix, p, b, wk, s);
+    for (uint32_t s = 0; s < nh; s++) wq_extend_thread(e->ix, p, b, wk, s, wbuf);
     uint64_t stats[5] = {0, 0, 0, 0, 0};
     for (uint32_t r = 0; r < n; r++) wq_resolve_thread(e->ix, p, b, wk, e->q, r, stats);
     e->counters.total += n; e->counters.mapped += stats[0]; e->counters.multi += stats[1];
@@ -91,9 +92,10 @@ int emu_align_pe(Emu* e, const wq_align_param* ap, const wq_read_batch* rf, cons
     e->paired = true;
     WqWork wk{e->seeds.data(), e->hit_read.data(), e->hit_s.data(), e->hit_s2.data(), e->hit_gene.data(), e->hits.data(),
               e->pool.data(), e->cursors, e->pending.data(), hit_cap, (uint32_t)e->pool.size()};
-    for (uint32_t r = 0; r < n; r++) wq_seed_pe_thread(e->ix, p, bf, br, wk, r);
+    uint64_t wbuf[WQ_MAX_READ_WORDS + 1];
+    for (uint32_t r = 0; r < n; r++) wq_seed_pe_thread(e->ix, p, bf, br, wk, r, wbuf);
     uint32_t nh = e->cursors[0];
-    for (uint32_t s = 0; s < nh; s++) { wq_extend_pe_thread(e->ix, p, bf, br, wk, s, 0); wq_extend_pe_thread(e->ix, p, bf, br, wk, s, 1); }
+    for (uint32_t s = 0; s < nh; s++) { wq_extend_pe_thread(e->ix, p, bf, br, wk, s, 0, wbuf); wq_extend_pe_thread(e->ix, p, bf, br, wk, s, 1, wbuf); }
     uint64_t stats[5] = {0, 0, 0, 0, 0};
     for (uint32_t r = 0; r < n; r++) wq_resolve_pe_thread(e->ix, p, bf, br, wk, e->q, r, stats);
     e->counters.total += n; e->counters.mapped += stats[0]; e->counters.multi += stats[1];

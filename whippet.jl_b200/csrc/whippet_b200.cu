@@ -86,34 +86,44 @@ struct wq_handle {
 };
 
 // ------------------------------------------------------------------------------------------ kernels
-__global__ void __launch_bounds__(128) wq_k_seed(const WqDevIndex ix, const __grid_constant__ WqParams p,
+#ifndef WQ_EXT_MINBLOCKS
+#define WQ_EXT_MINBLOCKS 10
+#endif
+#ifndef WQ_SEED_MINBLOCKS
+#define WQ_SEED_MINBLOCKS 1
+#endif
+__global__ void __launch_bounds__(128, WQ_SEED_MINBLOCKS) wq_k_seed(const WqDevIndex ix, const __grid_constant__ WqParams p,
                                                  const WqBatchDev b, const WqWork wk) {
     uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ uint64_t s_w[128 * (WQ_MAX_READ_WORDS + 1)];
     if (r >= b.n) return;
-    wq_seed_thread(ix, p, b, wk, r);
+    wq_seed_thread(ix, p, b, wk, r, s_w + threadIdx.x * (WQ_MAX_READ_WORDS + 1));
 }
 
-__global__ void __launch_bounds__(128) wq_k_extend(const WqDevIndex ix, const __grid_constant__ WqParams p,
+__global__ void __launch_bounds__(128, WQ_EXT_MINBLOCKS) wq_k_extend(const WqDevIndex ix, const __grid_constant__ WqParams p,
                                                    const WqBatchDev b, const WqWork wk) {
     uint32_t nh = wk.cursors[0];
     if (nh > wk.hit_cap) nh = wk.hit_cap;
+    __shared__ uint64_t s_w[128 * (WQ_MAX_READ_WORDS + 1)];
     for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < nh; slot += gridDim.x * blockDim.x)
-        wq_extend_thread(ix, p, b, wk, slot);
+        wq_extend_thread(ix, p, b, wk, slot, s_w + threadIdx.x * (WQ_MAX_READ_WORDS + 1));
 }
 
 __global__ void __launch_bounds__(128) wq_k_seed_pe(const WqDevIndex ix, const __grid_constant__ WqParams p,
                                                     const WqBatchDev bf, const WqBatchDev br, const WqWork wk) {
     uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ uint64_t s_w[128 * (WQ_MAX_READ_WORDS + 1)];
     if (r >= bf.n) return;
-    wq_seed_pe_thread(ix, p, bf, br, wk, r);
+    wq_seed_pe_thread(ix, p, bf, br, wk, r, s_w + threadIdx.x * (WQ_MAX_READ_WORDS + 1));
 }
 
-__global__ void __launch_bounds__(128) wq_k_extend_pe(const WqDevIndex ix, const __grid_constant__ WqParams p,
+__global__ void __launch_bounds__(128, WQ_EXT_MINBLOCKS) wq_k_extend_pe(const WqDevIndex ix, const __grid_constant__ WqParams p,
                                                       const WqBatchDev bf, const WqBatchDev br, const WqWork wk) {
     uint32_t nh = wk.cursors[0];
     if (nh > wk.hit_cap) nh = wk.hit_cap;
+    __shared__ uint64_t s_w[128 * (WQ_MAX_READ_WORDS + 1)];
     for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < 2 * nh; t += gridDim.x * blockDim.x)
-        wq_extend_pe_thread(ix, p, bf, br, wk, t >> 1, (int)(t & 1));
+        wq_extend_pe_thread(ix, p, bf, br, wk, t >> 1, (int)(t & 1), s_w + threadIdx.x * (WQ_MAX_READ_WORDS + 1));
 }
 
 __global__ void __launch_bounds__(128) wq_k_resolve_pe(const WqDevIndex ix, const __grid_constant__ WqParams p,

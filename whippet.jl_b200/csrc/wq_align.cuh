@@ -35,7 +35,7 @@ struct WqParams {                  // AlignParam in kernel-friendly types
 struct WqCtx {
     const WqDevIndex* ix;
     const WqParams*   p;
-    uint64_t w[WQ_MAX_READ_WORDS + 1];   // read in alignment orientation, zero padded
+    uint64_t* w;                         // [WQ_MAX_READ_WORDS+1] read in alignment orientation, zero padded (shared memory in the kernels)
     const uint8_t* qual;                 // global, original orientation
     int32_t  readlen;
     uint8_t  flipped;
@@ -60,20 +60,34 @@ WQ_HD uint64_t wq_rext(const WqCtx& c, int j) {
 }
 // kmer_index(read.sequence[a:a+K-1]) - 1, first base most significant (src/sgkmer.jl:12-26); a 1-based
 WQ_HD uint32_t wq_read_kmer(const WqCtx& c, int a, int K) {
+    uint64_t v = wq_rext(c, a - 1);          // base a at bits 0..1, a+1 at bits 2..3, ...
     uint32_t x = 0;
-    for (int i = 0; i < K; i++) x = (x << 2) | wq_rbase(c, a - 1 + i);
+    for (int i = 0; i < K; i++) { x = (x << 2) | (uint32_t)(v & 3); v >>= 2; }
     return x;
 }
 // reverse complement of `len` bases held in w[] (reverse_complement!, src/record.jl:23-26)
+WQ_HD uint64_t wq_rev2(uint64_t x) {      // reverse the order of the 32 two-bit groups of a word
+    x = ((x >> 2) & 0x3333333333333333ull) | ((x & 0x3333333333333333ull) << 2);
+    x = ((x >> 4) & 0x0F0F0F0F0F0F0F0Full) | ((x & 0x0F0F0F0F0F0F0F0Full) << 4);
+    x = ((x >> 8) & 0x00FF00FF00FF00FFull) | ((x & 0x00FF00FF00FF00FFull) << 8);
+    x = ((x >> 16) & 0x0000FFFF0000FFFFull) | ((x & 0x0000FFFF0000FFFFull) << 16);
+    return (x >> 32) | (x << 32);
+}
 WQ_HD void wq_revcomp(uint64_t* w, int len) {
+    // complement = bitwise NOT of the 2-bit codes; reverse = reverse words and the groups inside them,
+    // then shift the whole string down by the unused tail of the last word
+    const int nw = (len + 31) >> 5;
+    const int sh = 2 * (32 * nw - len);                 // bits of padding that end up at the bottom
     uint64_t r[WQ_MAX_READ_WORDS + 1];
-    for (int i = 0; i <= WQ_MAX_READ_WORDS; i++) r[i] = 0;
-    for (int j = 0; j < len; j++) {
-        int s = len - 1 - j;
-        uint64_t b = 3 - ((w[s >> 5] >> (2 * (s & 31))) & 3);
-        r[j >> 5] |= b << (2 * (j & 31));
+#pragma unroll
+    for (int i = 0; i <= WQ_MAX_READ_WORDS; i++) r[i] = i < nw ? wq_rev2(~w[nw - 1 - i]) : 0ull;
+#pragma unroll
+    for (int i = 0; i <= WQ_MAX_READ_WORDS; i++) {
+        uint64_t lo = i < nw ? r[i] : 0ull, hi = (i + 1 < nw) ? r[i + 1] : 0ull;
+        uint64_t v = sh ? ((lo >> sh) | (hi << (64 - sh))) : lo;
+        w[i] = i < nw ? v : 0ull;
     }
-    for (int i = 0; i <= WQ_MAX_READ_WORDS; i++) w[i] = r[i];
+    if (len & 31) w[nw - 1] &= (~0ull >> (64 - 2 * (len & 31)));
 }
 
 // ---------------------------------------------------------------- text access
@@ -251,8 +265,9 @@ WQ_HD int wq_seed_locate(const WqCtx& c, const uint64_t* badq, bool offset_left,
 // Forward: compare read[ridx..] with gene position sgidx.. (both 1-based) for at most `lim` bases
 // with the per-base rules of src/align.jl:367-378; stops after the base that lifts mistol above the
 // limit.  Returns bases consumed.
-WQ_HD int wq_walk_fwd(const WqCtx& c, WqPNode& nd, float& mistol, int ridx, int64_t sgidx, int lim) {
+WQ_HD int wq_walk_fwd(const WqCtx& c, WqPNode& ndref, float& mistol, int ridx, int64_t sgidx, int lim) {
     int done = 0;
+    WqPNode nd = ndref;
     uint64_t tpos = (uint64_t)c.gstart + (uint64_t)sgidx - 1;
     while (done < lim) {
         int chunk = lim - done < 32 ? lim - done : 32;
@@ -268,16 +283,18 @@ WQ_HD int wq_walk_fwd(const WqCtx& c, WqPNode& nd, float& mistol, int ridx, int6
             mistol += prob;
             nd.mm = (uint8_t)(nd.mm + 1);
             prev = b + 1;
-            if (!(mistol <= c.p->mmlimit)) return done + prev;
+            if (!(mistol <= c.p->mmlimit)) { ndref = nd; return done + prev; }
         }
         nd.m = (uint8_t)(nd.m + (chunk - prev));
         done += chunk;
     }
+    ndref = nd;
     return done;
 }
 // Reverse: compare read[ridx], read[ridx-1].. with gene positions sgidx, sgidx-1.. for at most `lim` bases.
-WQ_HD int wq_walk_rev(const WqCtx& c, WqPNode& nd, float& mistol, int ridx, int64_t sgidx, int lim) {
+WQ_HD int wq_walk_rev(const WqCtx& c, WqPNode& ndref, float& mistol, int ridx, int64_t sgidx, int lim) {
     int done = 0;
+    WqPNode nd = ndref;
     while (done < lim) {
         int chunk = lim - done < 32 ? lim - done : 32;
         int r0 = ridx - done - chunk;                              // 0-based first read base of the chunk
@@ -294,22 +311,32 @@ WQ_HD int wq_walk_rev(const WqCtx& c, WqPNode& nd, float& mistol, int ridx, int6
             mistol += prob;
             nd.mm = (uint8_t)(nd.mm + 1);
             prev = b;
-            if (!(mistol <= c.p->mmlimit)) return done + (chunk - prev);
+            if (!(mistol <= c.p->mmlimit)) { ndref = nd; return done + (chunk - prev); }
         }
         nd.m = (uint8_t)(nd.m + prev);
         done += chunk;
     }
+    ndref = nd;
     return done;
 }
 
 // ---------------------------------------------------------------- extension
-WQ_HDN void wq_fwd_extend(WqCtx& c, int64_t sgidx, int ridx, WqAlign& align, uint32_t nodeidx);
-WQ_HDN void wq_rev_extend(WqCtx& c, int64_t sgidx, int ridx, WqAlign& align, uint32_t nodeidx);
+// The nested (spliced) calls go through the out-of-line instantiation <false>; the outermost call of a hit is
+// <true> and is inlined into the kernel, so its context and path header live in registers.
+#if defined(__CUDACC__)
+#define WQ_NOINLINE __noinline__
+#else
+#define WQ_NOINLINE
+#endif
+template <bool TOP> WQ_HDN void wq_fwd_extend(WqCtx& c, int64_t sgidx, int ridx, WqAlign& align, uint32_t nodeidx);
+template <bool TOP> WQ_HDN void wq_rev_extend(WqCtx& c, int64_t sgidx, int ridx, WqAlign& align, uint32_t nodeidx);
+WQ_HDN WQ_NOINLINE void wq_fwd_extend_nested(WqCtx& c, int64_t sgidx, int ridx, WqAlign& align, uint32_t nodeidx);
+WQ_HDN WQ_NOINLINE void wq_rev_extend_nested(WqCtx& c, int64_t sgidx, int ridx, WqAlign& align, uint32_t nodeidx);
 
 // spliced_fwd_extend (src/align.jl:287-311): candidates = edges.left[kmer(edgeleft[edge])] ∩ edges.right[read kmer]
 // under the gene-only ordering of src/edges.jl:15-18,40-55 (both cursors advance on a gene match,
 // the right-table entry is returned), same gene as the alignment only.
-WQ_HDN void wq_spliced_fwd(WqCtx& c, uint32_t edgeind, int ridx, uint32_t rkmer, WqAlign& align) {
+WQ_HDN WQ_NOINLINE void wq_spliced_fwd(WqCtx& c, uint32_t edgeind, int ridx, uint32_t rkmer, WqAlign& align) {
     const WqDevIndex& ix = *c.ix;
     uint32_t rb = WQ_LDG(ix.right_ptr + rkmer), re = WQ_LDG(ix.right_ptr + rkmer + 1);
     if (rb == re) return;
@@ -335,7 +362,7 @@ WQ_HDN void wq_spliced_fwd(WqCtx& c, uint32_t edgeind, int ridx, uint32_t rkmer,
             WqAlign res;
             wq_copy(res, align);                   // deepcopy(align)
             c.depth++;
-            wq_fwd_extend(c, rn_offset, ridx, res, rn_node);
+            wq_fwd_extend_nested(c, rn_offset, ridx, res, rn_node);
             c.depth--;
             float s = wq_score(res);
             if (s > best_score) { wq_copy(best, res); best_score = s; }
@@ -346,7 +373,7 @@ WQ_HDN void wq_spliced_fwd(WqCtx& c, uint32_t edgeind, int ridx, uint32_t rkmer,
 }
 
 // ungapped_fwd_extend (src/align.jl:275-418).  sgidx/ridx are 1-based as in the reference.
-WQ_HDN void wq_fwd_extend(WqCtx& c, int64_t sgidx, int ridx, WqAlign& align, uint32_t nodeidx) {
+template <bool TOP> WQ_HDN void wq_fwd_extend(WqCtx& c, int64_t sgidx, int ridx, WqAlign& align, uint32_t nodeidx) {
     const WqParams& p = *c.p;
     const int readlen = c.readlen;
     const int K = p.K;
@@ -445,7 +472,7 @@ WQ_HDN void wq_fwd_extend(WqCtx& c, int64_t sgidx, int ridx, WqAlign& align, uin
 
 // spliced_rev_extend (src/align.jl:437-461): edges.right[kmer(edgeright[edge])] ∩ edges.left[read kmer],
 // returning the left-table entries.
-WQ_HDN void wq_spliced_rev(WqCtx& c, uint32_t edgeind, int ridx, uint32_t lkmer, WqAlign& align) {
+WQ_HDN WQ_NOINLINE void wq_spliced_rev(WqCtx& c, uint32_t edgeind, int ridx, uint32_t lkmer, WqAlign& align) {
     const WqDevIndex& ix = *c.ix;
     uint32_t lb = WQ_LDG(ix.left_ptr + lkmer), le = WQ_LDG(ix.left_ptr + lkmer + 1);
     if (lb == le) return;
@@ -472,7 +499,7 @@ WQ_HDN void wq_spliced_rev(WqCtx& c, uint32_t edgeind, int ridx, uint32_t lkmer,
             WqAlign res;
             wq_copy(res, align);
             c.depth++;
-            wq_rev_extend(c, rn_offset, ridx, res, rn_node - 1);
+            wq_rev_extend_nested(c, rn_offset, ridx, res, rn_node - 1);
             c.depth--;
             float s = wq_score(res);
             if (s > best_score) { wq_copy(best, res); best_score = s; }
@@ -483,7 +510,7 @@ WQ_HDN void wq_spliced_rev(WqCtx& c, uint32_t edgeind, int ridx, uint32_t lkmer,
 }
 
 // ungapped_rev_extend (src/align.jl:423-575)
-WQ_HDN void wq_rev_extend(WqCtx& c, int64_t sgidx, int ridx, WqAlign& align, uint32_t nodeidx) {
+template <bool TOP> WQ_HDN void wq_rev_extend(WqCtx& c, int64_t sgidx, int ridx, WqAlign& align, uint32_t nodeidx) {
     const WqParams& p = *c.p;
     const int readlen = c.readlen;
     const int K = p.K;
@@ -582,6 +609,9 @@ WQ_HDN void wq_rev_extend(WqCtx& c, int64_t sgidx, int ridx, WqAlign& align, uin
     }
 }
 
+WQ_HDN WQ_NOINLINE void wq_fwd_extend_nested(WqCtx& c, int64_t sgidx, int ridx, WqAlign& align, uint32_t nodeidx) { wq_fwd_extend<false>(c, sgidx, ridx, align, nodeidx); }
+WQ_HDN WQ_NOINLINE void wq_rev_extend_nested(WqCtx& c, int64_t sgidx, int ridx, WqAlign& align, uint32_t nodeidx) { wq_rev_extend<false>(c, sgidx, ridx, align, nodeidx); }
+
 // Locate gene + node of 1-based text position s (searchsortedlast over GraphLib.offset and
 // SpliceGraph.nodeoffset, src/align.jl:210-213) with one bucket lookup over the globally sorted
 // node starts.  forced_gene > 0 pins the gene (paired call, src/paired.jl:79-80).
@@ -603,7 +633,7 @@ WQ_HD uint32_t wq_locate_node(const WqDevIndex& ix, uint64_t s) {
 }
 
 // _ungapped_align (src/align.jl:209-223)
-WQ_HDN void wq_align_at(WqCtx& c, int64_t indx, int readloc, bool ispos, uint32_t forced_gene, WqAlign& align) {
+WQ_HD void wq_align_at(WqCtx& c, int64_t indx, int readloc, bool ispos, uint32_t forced_gene, WqAlign& align) {
     const WqDevIndex& ix = *c.ix;
     uint32_t offset_node;
     if (forced_gene == 0) {
@@ -629,6 +659,6 @@ WQ_HDN void wq_align_at(WqCtx& c, int64_t indx, int readloc, bool ispos, uint32_
     align.isvalid = 0;
     align.strand = ispos ? 1 : 0;
     c.depth = 0;
-    wq_fwd_extend(c, sgidx + 1, readloc + 1, align, offset_node);
-    if (!c.overflow) wq_rev_extend(c, sgidx, readloc, align, offset_node);
+    wq_fwd_extend<true>(c, sgidx + 1, readloc + 1, align, offset_node);
+    if (!c.overflow) wq_rev_extend<true>(c, sgidx, readloc, align, offset_node);
 }

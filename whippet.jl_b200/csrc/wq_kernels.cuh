@@ -80,8 +80,12 @@ WQ_HD void wq_load_read(WqCtx& c, const WqBatchDev& b, uint32_t r) {
     c.readlen = len;
     const uint64_t* src = b.seq2 + WQ_LDG(b.seq_off + r);
     int nw = (len + 31) >> 5;
-    for (int i = 0; i <= WQ_MAX_READ_WORDS; i++) c.w[i] = i < nw ? WQ_LDG(src + i) : 0ull;
-    if (len & 31) c.w[nw - 1] &= (~0ull >> (64 - 2 * (len & 31)));
+#pragma unroll
+    for (int i = 0; i <= WQ_MAX_READ_WORDS; i++) {
+        uint64_t v = i < nw ? WQ_LDG(src + i) : 0ull;
+        if (i == nw - 1 && (len & 31)) v &= (~0ull >> (64 - 2 * (len & 31)));
+        c.w[i] = v;
+    }
     c.qual = b.qual + WQ_LDG(b.qual_off + r);
     c.flipped = 0;
     c.overflow = 0;
@@ -89,22 +93,47 @@ WQ_HD void wq_load_read(WqCtx& c, const WqBatchDev& b, uint32_t r) {
 }
 
 // bit j set when quality[j] <= seed_min_qual (orientation: as stored, or reversed when `rev`)
+WQ_HD uint32_t wq_le4(uint32_t v, uint32_t lim) {     // per byte: v <= lim -> 0x01 in that byte
+#if defined(__CUDA_ARCH__)
+    return __vcmpleu4(v, lim) & 0x01010101u;
+#else
+    uint32_t m = 0;
+    for (int i = 0; i < 4; i++) if (((v >> (8 * i)) & 0xFF) <= ((lim >> (8 * i)) & 0xFF)) m |= 1u << (8 * i);
+    return m;
+#endif
+}
 WQ_HD void wq_badq(const WqCtx& c, int min_qual, bool rev, uint64_t* badq) {
-    for (int i = 0; i < 4; i++) badq[i] = 0;
-    for (int j = 0; j < c.readlen; j++) {
-        uint8_t q = WQ_LDG(c.qual + j);
-        if ((int)q <= min_qual) {
-            int k = rev ? c.readlen - 1 - j : j;
-            badq[k >> 6] |= 1ull << (k & 63);
+    uint64_t fw[4] = {0, 0, 0, 0};
+    const int len = c.readlen;
+    if (min_qual >= 0) {
+        const uint32_t lim = (uint32_t)(min_qual > 255 ? 255 : min_qual) * 0x01010101u;
+        int j = 0;
+        if ((((uintptr_t)c.qual) & 3) == 0) {           // 4 phred bytes per load
+            const uint32_t* q4 = reinterpret_cast<const uint32_t*>(c.qual);
+            for (; j + 4 <= len; j += 4) {
+                uint32_t m = wq_le4(WQ_LDG(q4 + (j >> 2)), lim);
+                uint64_t bits = (uint64_t)((m * 0x01020408u) >> 24) & 0xF;
+                fw[j >> 6] |= bits << (j & 63);
+            }
         }
+        for (; j < len; j++)
+            if ((int)WQ_LDG(c.qual + j) <= min_qual) fw[j >> 6] |= 1ull << (j & 63);
+    }
+    if (!rev) { for (int i = 0; i < 4; i++) badq[i] = fw[i]; return; }
+    // reversed orientation: bit k = fw bit (len-1-k)
+    for (int i = 0; i < 4; i++) badq[i] = 0;
+    for (int k = 0; k < len; k++) {
+        int j = len - 1 - k;
+        if ((fw[j >> 6] >> (j & 63)) & 1) badq[k >> 6] |= 1ull << (k & 63);
     }
 }
 
 // ---- kernel 1 -----------------------------------------------------------------------------------
-WQ_HDN void wq_seed_thread(const WqDevIndex& ix, const WqParams& p, const WqBatchDev& b, const WqWork& wk, uint32_t r) {
+WQ_HDN void wq_seed_thread(const WqDevIndex& ix, const WqParams& p, const WqBatchDev& b, const WqWork& wk, uint32_t r, uint64_t* wbuf) {
     WqCtx c;
     c.ix = &ix;
     c.p = &p;
+    c.w = wbuf;
     wq_load_read(c, b, r);
     uint64_t badq[4];
     wq_badq(c, p.seed_min_qual, false, badq);
@@ -133,12 +162,13 @@ WQ_HDN void wq_seed_thread(const WqDevIndex& ix, const WqParams& p, const WqBatc
 }
 
 // ---- kernel 2 -----------------------------------------------------------------------------------
-WQ_HDN void wq_extend_thread(const WqDevIndex& ix, const WqParams& p, const WqBatchDev& b, const WqWork& wk, uint32_t slot) {
+WQ_HDN void wq_extend_thread(const WqDevIndex& ix, const WqParams& p, const WqBatchDev& b, const WqWork& wk, uint32_t slot, uint64_t* wbuf) {
     uint32_t r = wk.hit_read[slot];
     WqSeed s = wk.seeds[r];
     WqCtx c;
     c.ix = &ix;
     c.p = &p;
+    c.w = wbuf;
     wq_load_read(c, b, r);
     if (!s.strand) {                 // reverse_complement!(read), src/align.jl:231-234
         wq_revcomp(c.w, c.readlen);
@@ -379,10 +409,11 @@ WQ_HD void wq_sort_small(int64_t* a, int n) {
 
 // kernel P1: one read pair -> both seeds, sorted offsets, two-pointer walk (src/paired.jl:44-51, 64-77, 112-121)
 WQ_HDN void wq_seed_pe_thread(const WqDevIndex& ix, const WqParams& p, const WqBatchDev& bf, const WqBatchDev& br,
-                              const WqWork& wk, uint32_t r) {
+                              const WqWork& wk, uint32_t r, uint64_t* wbuf) {
     WqCtx c;
     c.ix = &ix;
     c.p = &p;
+    c.w = wbuf;
     uint64_t badq[4];
     // mate 1: both strands unless stranded
     wq_load_read(c, bf, r);
@@ -453,12 +484,13 @@ WQ_HDN void wq_seed_pe_thread(const WqDevIndex& ix, const WqParams& p, const WqB
 
 // kernel P2: one (pair slot, mate) -> _ungapped_align with the gene pinned (src/paired.jl:79-80)
 WQ_HDN void wq_extend_pe_thread(const WqDevIndex& ix, const WqParams& p, const WqBatchDev& bf, const WqBatchDev& br,
-                                const WqWork& wk, uint32_t slot, int mate) {
+                                const WqWork& wk, uint32_t slot, int mate, uint64_t* wbuf) {
     uint32_t r = wk.hit_read[slot];
     WqSeed s = wk.seeds[r];
     WqCtx c;
     c.ix = &ix;
     c.p = &p;
+    c.w = wbuf;
     bool ispos = s.strand != 0;
     int readloc;
     int64_t pos;

@@ -20,10 +20,11 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(CUDA_SO):
+    so = os.environ.get("WQ_LIB", CUDA_SO)      # experiments: alternative builds of the same library
+    if not os.path.exists(so):
         raise WhippetB200Error(f"{CUDA_SO} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                                "(there is no CPU fallback)")
-    L = C.CDLL(CUDA_SO)
+    L = C.CDLL(so)
     vp = C.c_void_p
     L.wq_last_error.restype = C.c_char_p
     L.wq_index_create.argtypes = [C.POINTER(abi.IndexDesc), C.c_int, C.POINTER(vp)]
