@@ -519,26 +519,70 @@ static int align_impl(wq_handle* h, const wq_align_param* ap, const wq_read_batc
     h->hx = WqHostQuantEx();
     for (auto& m : h->last_kernel_ms) m = 0;
     const wq_read_batch* src[2] = {reads, mates};
+    const int nb = pe ? 2 : 1;
     WqBatchDev base[2];
+    const uint32_t nchunks = (n + h->chunk_reads - 1) / h->chunk_reads;
+    std::vector<cudaEvent_t> copied;
     if (on_device) {
-        for (int m = 0; m < (pe ? 2 : 1); m++)
+        for (int m = 0; m < nb; m++)
             base[m] = WqBatchDev{n, src[m]->len, src[m]->seq_off, src[m]->seq2, src[m]->qual_off, src[m]->qual};
     } else {
-        // host buffers: copy the packed arrays once, then run chunk by chunk
-        for (int m = 0; m < (pe ? 2 : 1); m++) {
-            if (int rc = upload_batch(h, src[m], m, h->stream)) return rc;
+        // Host buffers.  The packed arrays of chunk c+1 cross PCIe on the copy stream while chunk c is being
+        // aligned: every chunk's slices are enqueued up front (async when the caller's buffers are page-locked,
+        // e.g. from wq_pinned_alloc) and the compute stream waits on one event per chunk.  Needs ascending
+        // offsets (what any packer produces); otherwise the whole batch is copied first.
+        bool ascending = true;
+        for (int m = 0; m < nb && ascending; m++)
+            for (uint32_t lo = 0; lo < n; lo += h->chunk_reads) {
+                uint32_t hi = std::min(n, lo + h->chunk_reads);
+                uint64_t s0 = src[m]->seq_off[lo], s1 = hi < n ? src[m]->seq_off[hi] : src[m]->seq2_words;
+                uint64_t q0 = src[m]->qual_off[lo], q1 = hi < n ? src[m]->qual_off[hi] : src[m]->qual_bytes;
+                if (s1 < s0 || q1 < q0 || s1 > src[m]->seq2_words || q1 > src[m]->qual_bytes) { ascending = false; break; }
+            }
+        for (int m = 0; m < nb; m++) {
+            CK(h->d_len[m].ensure(n)); CK(h->d_seqoff[m].ensure(n)); CK(h->d_qualoff[m].ensure(n));
+            CK(h->d_seq2[m].ensure(src[m]->seq2_words + 2)); CK(h->d_qual[m].ensure(src[m]->qual_bytes + 16));
             base[m] = WqBatchDev{n, h->d_len[m].p, h->d_seqoff[m].p, h->d_seq2[m].p, h->d_qualoff[m].p, h->d_qual[m].p};
         }
+        if (!ascending || nchunks == 1) {
+            for (int m = 0; m < nb; m++) if (int rc = upload_batch(h, src[m], m, h->stream)) return rc;
+        } else {
+            cudaStream_t cs = h->copy_stream;
+            CK(cudaStreamSynchronize(h->stream));       // buffers may still be read by a previous call's kernels
+            copied.resize(nchunks);
+            for (uint32_t c = 0; c < nchunks; c++) {
+                uint32_t lo = c * h->chunk_reads, hi = std::min(n, lo + h->chunk_reads);
+                for (int m = 0; m < nb; m++) {
+                    const wq_read_batch* r = src[m];
+                    uint64_t s0 = r->seq_off[lo], s1 = hi < n ? r->seq_off[hi] : r->seq2_words;
+                    uint64_t q0 = r->qual_off[lo], q1 = hi < n ? r->qual_off[hi] : r->qual_bytes;
+                    CK(cudaMemcpyAsync(h->d_len[m].p + lo, r->len + lo, hi - lo, cudaMemcpyHostToDevice, cs));
+                    CK(cudaMemcpyAsync(h->d_seqoff[m].p + lo, r->seq_off + lo, (hi - lo) * 8ull, cudaMemcpyHostToDevice, cs));
+                    CK(cudaMemcpyAsync(h->d_qualoff[m].p + lo, r->qual_off + lo, (hi - lo) * 8ull, cudaMemcpyHostToDevice, cs));
+                    CK(cudaMemcpyAsync(h->d_seq2[m].p + s0, r->seq2 + s0, (s1 - s0) * 8ull, cudaMemcpyHostToDevice, cs));
+                    CK(cudaMemcpyAsync(h->d_qual[m].p + q0, r->qual + q0, q1 - q0, cudaMemcpyHostToDevice, cs));
+                }
+                CK(cudaEventCreateWithFlags(&copied[c], cudaEventDisableTiming));
+                CK(cudaEventRecord(copied[c], cs));
+            }
+        }
     }
-    for (uint32_t lo = 0; lo < n; lo += h->chunk_reads) {
+    int rc_all = 0;
+    for (uint32_t c = 0; c < nchunks && !rc_all; c++) {
+        uint32_t lo = c * h->chunk_reads;
         uint32_t m = std::min(h->chunk_reads, n - lo);
         WqBatchDev b[2];
-        for (int k = 0; k < (pe ? 2 : 1); k++)
+        for (int k = 0; k < nb; k++)
             b[k] = WqBatchDev{m, base[k].len + lo, base[k].seq_off + lo, base[k].seq2, base[k].qual_off + lo, base[k].qual};
-        if (int rc = run_chunk(h, p, b[0], pe ? &b[1] : nullptr, on_device)) return rc;
-        if (out) if (int rc = collect_chunk(h, lo, m, pe, out)) return rc;
+        if (!copied.empty()) { cudaError_t e = cudaStreamWaitEvent(h->stream, copied[c], 0); if (e != cudaSuccess) { rc_all = fail(-10, cudaGetErrorString(e)); break; } }
+        rc_all = run_chunk(h, p, b[0], pe ? &b[1] : nullptr, on_device);
+        if (!rc_all && out) rc_all = collect_chunk(h, lo, m, pe, out);
     }
-    return 0;
+    if (!copied.empty()) {
+        cudaStreamSynchronize(h->copy_stream);
+        for (auto& e : copied) if (e) cudaEventDestroy(e);
+    }
+    return rc_all;
 }
 
 int wq_align_se(wq_handle* h, const wq_align_param* p, const wq_read_batch* reads, wq_align_out* out) {

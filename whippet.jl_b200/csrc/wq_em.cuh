@@ -18,6 +18,7 @@
 #include <cstdlib>
 #include <map>
 #include <string>
+#include <thread>
 #include <vector>
 #include "wq_host_quant.h"
 #include "wq_host_index.h"
@@ -65,22 +66,23 @@ static inline bool wq_key_compatible(const WqGeneBits& B, uint32_t p, const WqKe
 
 // add `v` along a path: one node -> node store, otherwise every consecutive pair -> edge/circ store
 // (assign_path!, src/quant.jl:263-324; the paired form skips mate-2 pieces already covered by mate 1)
-static inline void wq_spread_path(const WqHostIndex& H, WqHostQuantEx& Q, const WqKeyPath& kp, double v) {
+static inline void wq_spread_path(const WqHostIndex& H, std::vector<double>& node_value, std::vector<std::pair<uint64_t, double>>& edge_adds,
+                                  const WqKeyPath& kp, double v) {
     const uint32_t nb = H.genes[kp.gene - 1].node_base;
     auto ekey = [&](uint32_t l, uint32_t r) { return ((uint64_t)kp.gene << 32) | ((uint64_t)(l & 0xFFFF) << 16) | (r & 0xFFFF); };
     uint32_t seen[2 * WQ_MAX_PATH + 2];
     int ns = 0;
-    if (kp.n == 1) { Q.node_value[nb + kp.nd[0] - 1] += v; seen[ns++] = kp.nd[0]; }
+    if (kp.n == 1) { node_value[nb + kp.nd[0] - 1] += v; seen[ns++] = kp.nd[0]; }
     else for (uint32_t i = 0; i + 1 < kp.n; i++) {
         if (ns + 2 <= (int)(sizeof seen / sizeof seen[0])) { seen[ns++] = kp.nd[i]; seen[ns++] = kp.nd[i + 1]; }
-        Q.edge_adds.emplace_back(ekey(kp.nd[i], kp.nd[i + 1]), v);
+        edge_adds.emplace_back(ekey(kp.nd[i], kp.nd[i + 1]), v);
     }
     if (!kp.rnd) return;
     auto in_seen = [&](uint32_t x) { for (int i = 0; i < ns; i++) if (seen[i] == x) return true; return false; };
-    if (kp.rn == 1) { if (!in_seen(kp.rnd[0])) Q.node_value[nb + kp.rnd[0] - 1] += v; }
+    if (kp.rn == 1) { if (!in_seen(kp.rnd[0])) node_value[nb + kp.rnd[0] - 1] += v; }
     else for (uint32_t i = 0; i + 1 < kp.rn; i++) {
         if (in_seen(kp.rnd[i]) && in_seen(kp.rnd[i + 1])) continue;
-        Q.edge_adds.emplace_back(ekey(kp.rnd[i], kp.rnd[i + 1]), v);
+        edge_adds.emplace_back(ekey(kp.rnd[i], kp.rnd[i + 1]), v);
     }
 }
 
@@ -139,67 +141,95 @@ static inline std::string wq_host_build_classes(const WqHostIndex& H, const WqIs
         std::vector<uint32_t> cur(lptr.begin(), lptr.end() - 1);
         for (size_t i = 0; i < hq.longs.size(); i++) lidx[cur[hq.longs.key(i)[1]]++] = (uint32_t)i;
     }
-    // ---- isoform classes, gene by gene ----
-    std::vector<int32_t> setbuf;                 // id lists of this gene's count entries, back to back
-    struct Rec { uint32_t off, len; double value; };
-    std::vector<Rec> recs;
-    std::vector<uint32_t> order;
-    size_t e = 0;
-    const size_t ne = hq.edge_key.size();
-    for (uint32_t g = 1; g <= G; g++) {
-        const WqGeneBits& b = bits_of(g);
-        const uint32_t nn = H.genes[g - 1].nn, nb = H.genes[g - 1].node_base, ib = S.iso_base[g - 1];
-        setbuf.clear();
-        recs.clear();
-        auto account = [&](uint32_t off, double value) {
-            uint32_t len = (uint32_t)setbuf.size() - off;
-            if (len == 1) { X.iso_count[ib + setbuf[off] - 1] += value; setbuf.resize(off); }
-            else if (len > 1) recs.push_back(Rec{off, len, value});
-        };
-        for (uint32_t n = 1; n <= nn; n++) {
-            uint32_t off = (uint32_t)setbuf.size();
-            for (uint32_t p = 0; p < b.np; p++) if (b.has(p, n)) setbuf.push_back((int32_t)p + 1);
-            account(off, (double)hq.node[nb + n - 1]);
-        }
-        while (e < ne && (hq.edge_key[e] >> 32) < g) e++;
-        for (; e < ne && (hq.edge_key[e] >> 32) == g; e++) {
-            if (wq_edge_is_circ(hq.edge_key[e])) continue;
-            uint32_t l = (hq.edge_key[e] >> 16) & 0xFFFF, r = hq.edge_key[e] & 0xFFFF;
-            uint32_t off = (uint32_t)setbuf.size();
-            for (uint32_t p = 0; p < b.np; p++) if (b.adjacent(p, l, r)) setbuf.push_back((int32_t)p + 1);
-            account(off, (double)hq.edge_count[e]);
-        }
-        for (uint32_t k = lptr[g]; k < lptr[g + 1]; k++) {
-            WqKeyPath kp;
-            wq_key_next(hq.longs.key(lidx[k]), 0, kp);
-            uint32_t off = (uint32_t)setbuf.size();
-            for (uint32_t p = 0; p < b.np; p++) if (wq_key_compatible(b, p, kp)) setbuf.push_back((int32_t)p + 1);
-            account(off, (double)hq.longs.count[lidx[k]]);
-            wq_spread_path(H, X, kp, (double)hq.longs.count[lidx[k]]);
-        }
-        // distinct id sets in lexicographic order, values added up (they are integers: order-free)
-        order.resize(recs.size());
-        for (uint32_t i = 0; i < recs.size(); i++) order[i] = i;
-        auto lt = [&](uint32_t x, uint32_t y) {
-            return std::lexicographical_compare(setbuf.begin() + recs[x].off, setbuf.begin() + recs[x].off + recs[x].len,
-                                                setbuf.begin() + recs[y].off, setbuf.begin() + recs[y].off + recs[y].len);
-        };
-        std::sort(order.begin(), order.end(), lt);
-        for (size_t i = 0; i < order.size();) {
-            size_t j = i;
-            double total = 0.0;
-            while (j < order.size() && !lt(order[i], order[j]) && !lt(order[j], order[i])) { total += recs[order[j]].value; j++; }
-            const Rec& r0 = recs[order[i]];
-            if (total > 0.0) {
-                if (r0.len > 500) return "isoform class larger than 500 (prop_temp = zeros(500), src/quant.jl:725)";
-                for (uint32_t k = 0; k < r0.len; k++) { C.iso.push_back((int32_t)(ib + setbuf[r0.off + k] - 1)); C.prop.push_back(1.0 / (double)r0.len); }
-                C.ptr.push_back((uint32_t)C.iso.size());
-                C.count.push_back(total);
-                C.state.push_back(0);
-                C.postassign.push_back(0);
+    // ---- isoform classes, gene by gene; genes are independent, so host threads take contiguous gene ranges and
+    //      the fragments are concatenated in gene order ----
+    struct Frag { WqClassSet C; std::vector<std::pair<uint64_t, double>> adds; std::string err; };
+    unsigned nthreads = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    if (const char* ev = getenv("WQ_HOST_THREADS")) nthreads = std::max(1, atoi(ev));
+    if (G < 2048) nthreads = 1;
+    std::vector<Frag> frags(nthreads);
+    auto work = [&](unsigned t) {
+        Frag& F = frags[t];
+        const uint32_t g_lo = 1 + (uint32_t)((uint64_t)G * t / nthreads), g_hi = (uint32_t)((uint64_t)G * (t + 1) / nthreads);
+        WqGeneBits Bt;
+        WqHostQuantEx local;                     // only edge_adds / node_value targets are used through `sink`
+        std::vector<int32_t> setbuf;             // id lists of this gene's count entries, back to back
+        struct Rec { uint32_t off, len; double value; };
+        std::vector<Rec> recs;
+        std::vector<uint32_t> order;
+        const size_t ne = hq.edge_key.size();
+        size_t e = std::lower_bound(hq.edge_key.begin(), hq.edge_key.end(), (uint64_t)g_lo << 32) - hq.edge_key.begin();
+        for (uint32_t g = g_lo; g <= g_hi; g++) {
+            Bt.build(S, g - 1, H.genes[g - 1].nn);
+            const WqGeneBits& b = Bt;
+            const uint32_t nn = H.genes[g - 1].nn, nb = H.genes[g - 1].node_base, ib = S.iso_base[g - 1];
+            setbuf.clear();
+            recs.clear();
+            auto account = [&](uint32_t off, double value) {
+                uint32_t len = (uint32_t)setbuf.size() - off;
+                if (len == 1) { X.iso_count[ib + setbuf[off] - 1] += value; setbuf.resize(off); }
+                else if (len > 1) recs.push_back(Rec{off, len, value});
+            };
+            for (uint32_t n = 1; n <= nn; n++) {
+                uint32_t off = (uint32_t)setbuf.size();
+                for (uint32_t p = 0; p < b.np; p++) if (b.has(p, n)) setbuf.push_back((int32_t)p + 1);
+                account(off, (double)hq.node[nb + n - 1]);
             }
-            i = j;
+            while (e < ne && (hq.edge_key[e] >> 32) < g) e++;
+            for (; e < ne && (hq.edge_key[e] >> 32) == g; e++) {
+                if (wq_edge_is_circ(hq.edge_key[e])) continue;
+                uint32_t l = (hq.edge_key[e] >> 16) & 0xFFFF, r = hq.edge_key[e] & 0xFFFF;
+                uint32_t off = (uint32_t)setbuf.size();
+                for (uint32_t p = 0; p < b.np; p++) if (b.adjacent(p, l, r)) setbuf.push_back((int32_t)p + 1);
+                account(off, (double)hq.edge_count[e]);
+            }
+            for (uint32_t k = lptr[g]; k < lptr[g + 1]; k++) {
+                WqKeyPath kp;
+                wq_key_next(hq.longs.key(lidx[k]), 0, kp);
+                uint32_t off = (uint32_t)setbuf.size();
+                for (uint32_t p = 0; p < b.np; p++) if (wq_key_compatible(b, p, kp)) setbuf.push_back((int32_t)p + 1);
+                account(off, (double)hq.longs.count[lidx[k]]);
+                wq_spread_path(H, X.node_value, F.adds, kp, (double)hq.longs.count[lidx[k]]);
+            }
+            // distinct id sets in lexicographic order, values added up (they are integers: order-free)
+            order.resize(recs.size());
+            for (uint32_t i = 0; i < recs.size(); i++) order[i] = i;
+            auto lt = [&](uint32_t x, uint32_t y) {
+                return std::lexicographical_compare(setbuf.begin() + recs[x].off, setbuf.begin() + recs[x].off + recs[x].len,
+                                                    setbuf.begin() + recs[y].off, setbuf.begin() + recs[y].off + recs[y].len);
+            };
+            std::sort(order.begin(), order.end(), lt);
+            for (size_t i = 0; i < order.size();) {
+                size_t j = i;
+                double total = 0.0;
+                while (j < order.size() && !lt(order[i], order[j]) && !lt(order[j], order[i])) { total += recs[order[j]].value; j++; }
+                const Rec& r0 = recs[order[i]];
+                if (total > 0.0) {
+                    if (r0.len > 500) { F.err = "isoform class larger than 500 (prop_temp = zeros(500), src/quant.jl:725)"; return; }
+                    for (uint32_t k = 0; k < r0.len; k++) { F.C.iso.push_back((int32_t)(ib + setbuf[r0.off + k] - 1)); F.C.prop.push_back(1.0 / (double)r0.len); }
+                    F.C.ptr.push_back((uint32_t)F.C.iso.size());
+                    F.C.count.push_back(total);
+                }
+                i = j;
+            }
         }
+    };
+    if (nthreads == 1) work(0);
+    else {
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < nthreads; t++) th.emplace_back(work, t);
+        for (auto& t : th) t.join();
+    }
+    for (Frag& F : frags) {
+        if (!F.err.empty()) return F.err;
+        const uint32_t base = (uint32_t)C.iso.size();
+        C.iso.insert(C.iso.end(), F.C.iso.begin(), F.C.iso.end());
+        C.prop.insert(C.prop.end(), F.C.prop.begin(), F.C.prop.end());
+        for (uint32_t p : F.C.ptr) C.ptr.push_back(base + p);
+        C.count.insert(C.count.end(), F.C.count.begin(), F.C.count.end());
+        C.state.insert(C.state.end(), F.C.count.size(), 0);
+        C.postassign.insert(C.postassign.end(), F.C.count.size(), 0);
+        X.edge_adds.insert(X.edge_adds.end(), F.adds.begin(), F.adds.end());
     }
     X.built = true;
     return "";
@@ -233,7 +263,7 @@ static inline std::string wq_host_assign_ambig_impl(const WqHostIndex& H, const 
         }
         double tot = 0.0;
         for (uint32_t h = 0; h < nh; h++) tot += w[h];
-        for (uint32_t h = 0; h < nh; h++) wq_spread_path(H, X, vp[h], (w[h] / tot) * C.count[c]);
+        for (uint32_t h = 0; h < nh; h++) wq_spread_path(H, X.node_value, X.edge_adds, vp[h], (w[h] / tot) * C.count[c]);
     }
     X.ambig_done = true;
     X.edges_final = false;
