@@ -242,6 +242,7 @@ int  wq_assign_ambig(wq_handle* h, wq_values* v);
 typedef struct wq_psi_batch {
     uint32_t n_events;   uint32_t _pad;
     const uint32_t* path_ptr;      /* [E+1] */
+    const uint32_t* n_inc;         /* [E] the first n_inc paths of an event are inclusion paths (sums run exclusion first, src/events.jl:838) */
     const double*   path_count;    /* [P] unambiguous counts */
     const double*   path_length;   /* [P] */
     const uint32_t* amb_ptr;       /* [E+1] */
@@ -257,6 +258,31 @@ typedef struct wq_psi_batch {
     int32_t*  iterations;          /* out [E] */
 } wq_psi_batch;
 int  wq_em_psi_batch(wq_handle* h, wq_psi_batch* b);
+
+/* process_events / _process_events (src/events.jl:744-800, isnodeok=false): event construction on the host side
+ * of the library from the stores left by wq_assign_ambig, all EM problems solved by one wq_em_psi_batch launch.
+ * The writers of src/io.jl are not reproduced: every record carries the values they print.
+ *   kind 0 = `output_empty` line, 1 = PSI line, 2 = tandem-UTR lines (n_utr nodes), 3 = no line
+ *   flags bit0 = tandem event without enough reads (NA columns), bit1 = more than 1024 paths (the reference
+ *   subsamples at random there; not reproducible)
+ * values[value_start ..]: kind 2 -> n_utr rounded PSI values; kind 1 -> n_inc + n_exc path PSI values (when both exist)
+ * paths: path_ptr[path_start + k] .. path_ptr[path_start + k + 1] delimit the node ids of path k in path_nodes
+ * (utr paths, or inclusion paths followed by exclusion paths). */
+typedef struct wq_event {
+    uint32_t gene, node;
+    uint8_t  motif, kind, flags, _pad;
+    uint32_t n_utr, n_inc, n_exc;
+    uint32_t value_start, path_start;
+    int32_t  iterations;
+    double   psi, total;
+} wq_event;
+typedef struct wq_events_out {
+    uint64_t n_events;     wq_event* events;
+    uint64_t n_values;     double*   values;
+    uint64_t n_paths;      uint64_t* path_ptr;      /* [n_paths+1] */
+    uint64_t n_path_nodes; uint32_t* path_nodes;
+} wq_events_out;
+int  wq_process_events(wq_handle* h, int64_t readlen, wq_events_out* out);   /* two-call protocol (NULL buffers -> sizes) */
 
 #ifdef __cplusplus
 }

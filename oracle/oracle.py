@@ -194,6 +194,56 @@ class Oracle:
     def assign_ambig(self):
         lib().wqo_assign_ambig(C.c_void_p(self.h))
 
+    # ---- events (src/events.jl) -------------------------------------------------------------------
+    def process_events(self, readlen):
+        """process_events over all genes.  Returns a list of dicts (one per event record, gene/node order)."""
+        L = lib()
+        L.wqo_process_events.restype = C.c_uint64
+        L.wqo_event_path.restype = C.c_uint64
+        n = L.wqo_process_events(C.c_void_p(self.h), C.c_int64(readlen))
+        out = []
+        hdr = (C.c_uint32 * 8)()
+        vals = (C.c_double * 3)()
+        buf = np.zeros(70000, "<u4")
+        for i in range(n):
+            L.wqo_event(C.c_void_p(self.h), C.c_uint64(i), hdr, vals)
+            e = dict(gene=hdr[0], node=hdr[1], motif=hdr[2], kind=hdr[3], flags=hdr[4], psi=vals[0], total=vals[1],
+                     iterations=int(vals[2]), utr_psi=[], inc=[], exc=[])
+            for which, key, cnt in ((0, "utr_psi", hdr[5]), (1, "inc", hdr[6]), (2, "exc", hdr[7])):
+                if not cnt:
+                    continue
+                v = np.zeros(cnt)
+                if which == 0 or e["kind"] == 1 and hdr[6] and hdr[7]:
+                    L.wqo_event_psi(C.c_void_p(self.h), C.c_uint64(i), which, v.ctypes.data_as(C.c_void_p))
+                if which == 0:
+                    e[key] = v.tolist()
+                else:
+                    paths = []
+                    for k in range(cnt):
+                        m = L.wqo_event_path(C.c_void_p(self.h), C.c_uint64(i), which, C.c_uint64(k), buf.ctypes.data_as(C.c_void_p))
+                        paths.append((tuple(int(x) for x in buf[:m]), float(v[k])))
+                    e[key] = paths
+            out.append(e)
+        return out
+
+
+def reduce_graph(edges):
+    """reduce_graph (src/events.jl:223-266) on [(first, last, value)]; returns the list of node sets."""
+    L = lib()
+    L.wqo_reduce_graph.restype = C.c_uint64
+    f = np.array([e[0] for e in edges], "<u4")
+    l = np.array([e[1] for e in edges], "<u4")
+    v = np.array([e[2] for e in edges], "<f8")
+    out = np.zeros(1 << 16, "<u4")
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    n = L.wqo_reduce_graph(p(f), p(l), p(v), C.c_uint64(len(edges)), p(out), C.c_uint64(len(out)))
+    sets, w = [], 0
+    for _ in range(n):
+        k = int(out[w])
+        sets.append(frozenset(int(x) for x in out[w + 1:w + 1 + k]))
+        w += 1 + k
+    return sets
+
 
 def counters(reset=False):
     """Instrumentation totals since the last reset: fm_steps, hits, nodes_touched, bases, out_nodes,

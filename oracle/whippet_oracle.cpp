@@ -18,6 +18,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <iterator>
 #include <map>
 #include <string>
 #include <vector>
@@ -1126,6 +1127,437 @@ void assign_ambig(const Lib& L, Quant& Q, QuantState& S) {
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Events: process_events / _process_events, src/events.jl:744-800 with the CLI settings
+// isnodeok=false (bin/whippet-quant.jl:181).  Writers (src/io.jl) are out of scope: the computed
+// quantities of every output line are returned instead.  Unpinned (no Julia here): IntervalTrees
+// iteration order (taken as (first,last) order), `maximum(sgquant.edge)` (taken as the entry with the
+// greatest (first,last) key, the IntervalValue isless order), sums over more than a handful of paths
+// (sequential here), the random subsampling beyond 1024 paths (flagged, not reproduced).
+enum : uint8_t { M_TXST = 0, M_TXEN = 1, M_ALTF = 2, M_ALTL = 3, M_RETI = 4, M_SKIP = 5, M_ALTD = 6, M_ALTA = 7, M_NONE = 8 };
+
+uint8_t motif_of(uint8_t cur, uint8_t next) {     // MOTIF_TABLE, src/events.jl:41-106
+    static uint8_t table[64];
+    static bool init = false;
+    if (!init) {
+        for (auto& t : table) t = M_NONE;
+        auto set = [&](int idx, uint8_t m) { table[idx] = m; };
+        set(0b000000, M_TXST); set(0b010000, M_TXST);
+        set(0b011011, M_TXEN); set(0b011001, M_TXEN);
+        set(0b010101, M_ALTF); set(0b010100, M_ALTF); set(0b010010, M_ALTF);
+        set(0b110001, M_ALTL); set(0b100001, M_ALTL); set(0b001001, M_ALTL);
+        set(0b101110, M_RETI);
+        set(0b110101, M_SKIP); set(0b110100, M_SKIP); set(0b110010, M_SKIP);
+        set(0b100101, M_SKIP); set(0b100100, M_SKIP); set(0b100010, M_SKIP);
+        set(0b001101, M_SKIP); set(0b001100, M_SKIP); set(0b001010, M_SKIP);
+        set(0b101101, M_ALTD); set(0b101100, M_ALTD); set(0b101010, M_ALTD);
+        set(0b110110, M_ALTA); set(0b100110, M_ALTA); set(0b001110, M_ALTA);
+        init = true;
+    }
+    return table[((cur & 7) << 3) | (next & 7)];
+}
+bool isobligate(uint8_t m) { return m <= 1; }
+bool isaltsplice(uint8_t m) { return (m & 0b110) == 0b110 && m != M_NONE; }
+
+typedef std::vector<uint32_t> NodeSet;          // BitSet as an ascending vector
+struct EdgeIV { uint32_t first, last; double value; };
+struct PsiGraph {                               // src/events.jl:134-141
+    std::vector<double> psi, count, length;
+    std::vector<NodeSet> nodes;
+    uint32_t min = 0, max = 0;
+};
+struct AmbigCounts { std::vector<uint32_t> paths; std::vector<double> prop; double prop_sum = 1.0, multiplier = 0.0; };
+
+bool set_has(const NodeSet& s, uint32_t x) { return std::binary_search(s.begin(), s.end(), x); }
+bool graph_has(const PsiGraph& g, uint32_t x) { for (auto& s : g.nodes) if (set_has(s, x)) return true; return false; }
+bool edge_in_set(const EdgeIV& e, const NodeSet& s) {          // in(edge, is::BitSet), src/quant.jl:68-81
+    if (!set_has(s, e.first) || !set_has(s, e.last)) return false;
+    for (uint32_t i = e.first + 1; i < e.last; i++) if (set_has(s, i)) return false;
+    return true;
+}
+NodeSet set_union(const NodeSet& a, const NodeSet& b) {
+    NodeSet r;
+    std::set_union(a.begin(), a.end(), b.begin(), b.end(), std::back_inserter(r));
+    return r;
+}
+bool hasintersect_terminal(const NodeSet& a, const NodeSet& b) { return a.front() == b.back() || b.front() == a.back(); }
+
+void graph_push_edge(PsiGraph& g, const EdgeIV& e) {           // push!(pgraph, edg; value_bool=false), src/events.jl:284-297
+    g.count.push_back(0.0);
+    g.length.push_back(0.0);
+    g.nodes.push_back(NodeSet{e.first, e.last});
+    if (e.first < g.min) g.min = e.first;
+    if (e.last > g.max) g.max = e.last;
+}
+
+// reduce_graph, src/events.jl:223-266
+PsiGraph reduce_graph(const PsiGraph& edges, bool& subsampled, int maxit = 100, size_t maxiso = 1024) {
+    PsiGraph graph = edges;
+    PsiGraph newgraph;
+    newgraph.min = graph.min; newgraph.max = graph.max;
+    int it = 1;
+    while ((newgraph.nodes != graph.nodes || it == 1) && it <= maxit) {
+        if (it > 1) {
+            std::swap(graph, newgraph);
+            newgraph.nodes.clear(); newgraph.length.clear(); newgraph.count.clear();
+            if (graph.nodes.size() > maxiso) {       // reference: random subsample (unseeded shuffle)
+                subsampled = true;
+                graph.nodes.resize(maxiso); graph.length.resize(maxiso); graph.count.resize(maxiso);
+            }
+        }
+        for (size_t i = 0; i < graph.nodes.size(); i++) {
+            bool push_i = false;
+            for (size_t j = 0; j < edges.nodes.size(); j++) {
+                if (hasintersect_terminal(graph.nodes[i], edges.nodes[j])) {
+                    push_i = true;
+                    NodeSet joint = set_union(graph.nodes[i], edges.nodes[j]);
+                    if (std::find(newgraph.nodes.begin(), newgraph.nodes.end(), joint) != newgraph.nodes.end()) continue;
+                    newgraph.nodes.push_back(joint);
+                    newgraph.length.push_back(graph.length[i] + edges.length[j]);
+                    newgraph.count.push_back(graph.count[i] + edges.count[j]);
+                    newgraph.min = std::min(std::min(graph.nodes[i].front(), edges.nodes[j].front()), newgraph.min);
+                    newgraph.max = std::max(std::max(graph.nodes[i].back(), edges.nodes[j].back()), newgraph.max);
+                }
+            }
+            if (!push_i && std::find(newgraph.nodes.begin(), newgraph.nodes.end(), graph.nodes[i]) == newgraph.nodes.end()) {
+                newgraph.nodes.push_back(graph.nodes[i]);
+                newgraph.length.push_back(graph.length[i]);
+                newgraph.count.push_back(graph.count[i]);
+                newgraph.min = std::min(graph.nodes[i].front(), newgraph.min);
+                newgraph.max = std::max(graph.nodes[i].back(), newgraph.max);
+            }
+        }
+        it += 1;
+    }
+    return newgraph;
+}
+// reduce_graph_simple, src/events.jl:268-282
+PsiGraph reduce_graph_simple(PsiGraph edges, bool& subsampled) {
+    if (edges.nodes.size() == 2) {
+        if (hasintersect_terminal(edges.nodes[0], edges.nodes[1])) {
+            edges.nodes[0] = set_union(edges.nodes[0], edges.nodes[1]);
+            edges.length[0] += edges.length[1];
+            edges.count[0] += edges.count[1];
+            edges.nodes.pop_back(); edges.length.pop_back(); edges.count.pop_back();
+        }
+        return edges;
+    }
+    return reduce_graph(edges, subsampled);
+}
+
+double round_sigdigits(double x, int sig) {    // Base.round(x, sigdigits=n): hidigit via log10, then round to digits
+    if (!std::isfinite(x)) return x;
+    if (x == 0.0) return x;     // hidigit(0) = 0 -> round(0 * 10^sig) / 10^sig = 0
+    int h = 1 + (int)std::floor(std::log10(std::fabs(x)));
+    int digits = sig - h;
+    double r;
+    if (digits >= 0) { double sc = std::pow(10.0, digits); r = std::nearbyint(x * sc) / sc; }
+    else { double sc = std::pow(10.0, -digits); r = std::nearbyint(x / sc) * sc; }
+    if (!std::isfinite(r)) return digits > 0 ? x : r;
+    return r;
+}
+void divsignif(std::vector<double>& arr, double divisor, int sig) {     // src/events.jl:802-812
+    for (auto& a : arr) a = sig > 0 ? round_sigdigits(a / divisor, sig) : a / divisor;
+}
+double seqsum(const std::vector<double>& v) { double s = 0.0; for (double x : v) s += x; return s; }
+
+// calculate_psi! (spliced), src/events.jl:831-841
+void calculate_psi2(PsiGraph& ig, PsiGraph& eg, const std::vector<double>& counts, int sig) {
+    for (size_t i = 0; i < ig.psi.size(); i++) ig.psi[i] = counts[i] / ig.length[i];
+    for (size_t i = 0; i < eg.psi.size(); i++) eg.psi[i] = counts[i + ig.psi.size()] / eg.length[i];
+    double cnt_sum = seqsum(eg.psi) + seqsum(ig.psi);
+    divsignif(ig.psi, cnt_sum, sig);
+    divsignif(eg.psi, cnt_sum, sig);
+}
+// calculate_psi! (tandem), src/events.jl:843-850
+void calculate_psi1(PsiGraph& pg, const std::vector<double>& counts, int sig, int64_t readlen) {
+    for (size_t i = 0; i < pg.psi.size(); i++) pg.psi[i] = counts[i] / std::max(pg.length[i] - (double)readlen, 1.0);
+    divsignif(pg.psi, seqsum(pg.psi), sig);
+}
+void ambig_step(std::vector<AmbigCounts>& ambig, int64_t it, const std::vector<double>& psi_all, std::vector<double>& count_temp) {
+    for (auto& ac : ambig) {
+        if (it > 1) {
+            ac.prop_sum = 0.0;
+            for (size_t k = 0; k < ac.paths.size(); k++) {
+                double prev = psi_all[ac.paths[k] - 1];
+                ac.prop[k] = prev;
+                ac.prop_sum += prev;
+            }
+        }
+        for (size_t k = 0; k < ac.paths.size(); k++) {
+            double prop = ac.prop[k] / ac.prop_sum;
+            ac.prop[k] = prop;
+            count_temp[ac.paths[k] - 1] += prop * ac.multiplier;
+        }
+    }
+}
+// spliced_em!, src/events.jl:853-893
+int64_t spliced_em(PsiGraph& ig, PsiGraph& eg, std::vector<AmbigCounts>& ambig, int sig, int64_t maxit = 1500) {
+    int64_t it = 1;
+    std::vector<double> inc_temp(ig.count.size(), 0.0), exc_temp(eg.count.size(), 0.0), count_temp(ig.count.size() + eg.count.size(), 1.0);
+    while ((inc_temp != ig.psi || eg.psi != exc_temp) && it < maxit) {
+        std::copy(ig.count.begin(), ig.count.end(), count_temp.begin());
+        std::copy(eg.count.begin(), eg.count.end(), count_temp.begin() + ig.count.size());
+        inc_temp = ig.psi;
+        exc_temp = eg.psi;
+        std::vector<double> psi_all = ig.psi;
+        psi_all.insert(psi_all.end(), eg.psi.begin(), eg.psi.end());
+        ambig_step(ambig, it, psi_all, count_temp);
+        calculate_psi2(ig, eg, count_temp, sig);
+        it += 1;
+    }
+    return it;
+}
+// rec_tandem_em!, src/events.jl:895-932 (tail recursion written as a loop)
+int64_t rec_tandem_em(PsiGraph& pg, std::vector<AmbigCounts>& ambig, int sig, int64_t readlen, int64_t maxit = 1500) {
+    int64_t it = 1;
+    std::vector<double> utr_temp(pg.count.size(), 0.0), count_temp(pg.count.size(), 1.0);
+    for (;;) {
+        count_temp = pg.count;
+        utr_temp = pg.psi;
+        ambig_step(ambig, it, pg.psi, count_temp);
+        calculate_psi1(pg, count_temp, sig, readlen);
+        if (utr_temp != pg.psi && it < maxit) it += 1; else break;
+    }
+    return it;
+}
+
+void ambig_account(std::vector<AmbigCounts>& ambig, const std::vector<uint32_t>& iset, double value) {
+    for (auto& am : ambig)
+        if (am.paths == iset) { am.multiplier += value; return; }
+    if (value > 0) {
+        AmbigCounts a;
+        a.paths = iset;
+        a.prop.assign(iset.size(), 1.0 / (double)iset.size());
+        a.prop_sum = 1.0;
+        a.multiplier = value;
+        ambig.push_back(a);
+    }
+}
+
+struct EventOut {
+    uint32_t gene, node; uint8_t motif, kind, flags;     // kind 0 empty line, 1 psi line, 2 utr lines, 3 no line; flags bit0 utr empty, bit1 subsampled
+    double psi = 0.0, total = 0.0;
+    std::vector<double> utr_psi;                         // kind 2: round.(psi, digits=4) per path (zeros when empty)
+    PsiGraph inc, exc;                                   // kind 1 (either may be absent: has_inc / has_exc)
+    bool has_inc = false, has_exc = false;
+    PsiGraph utr; bool has_utr = false;
+    int64_t iterations = 0;
+};
+
+struct GeneView {
+    const Lib& L; const Quant& Q; Int g;
+    std::vector<EdgeIV> edges;                           // sgquant.edge of this gene in (first,last) order
+    double node(Int n) const { return Q.node[L.d->node_base[g - 1] + n - 1]; }
+    double leng(Int n) const { return (double)L.nodelen(g, n); }      // effective_lengths!, src/quant.jl:684-694
+    double edge_value(uint32_t f, uint32_t l) const { for (auto& e : edges) if (e.first == f && e.last == l) return e.value; return 0.0; }
+    Int nedgetype() const { return L.nnodes(g) + 1; }
+    uint8_t et(Int j) const { return L.edgetype(g, j); }
+};
+
+// _process_tandem_utr, src/events.jl:593-645
+void process_tandem_utr(const GeneView& V, uint32_t node, uint8_t motif, int64_t readlen, EventOut& out, size_t& len) {
+    NodeSet used;
+    double total_cnt = 0.0;
+    auto push_used = [&](uint32_t x) { if (!set_has(used, x)) { used.push_back(x); std::sort(used.begin(), used.end()); } };
+    if (motif == M_TXEN) { push_used(node - 1); total_cnt += V.node(node - 1); }
+    Int i = node;
+    uint8_t curmotif = motif;
+    while (curmotif == motif) {
+        push_used((uint32_t)i);
+        total_cnt += V.node(i);
+        if (i > 1) total_cnt += V.edge_value((uint32_t)i - 1, (uint32_t)i);
+        i += 1;
+        if (i < V.nedgetype()) curmotif = motif_of(V.et(i), V.et(i + 1)); else break;
+    }
+    if (motif == M_TXST && i <= V.L.nnodes(V.g)) {     // (the reference would throw a BoundsError past the last node)
+        push_used((uint32_t)i);
+        total_cnt += V.node(i);
+        total_cnt += V.edge_value((uint32_t)i - 1, (uint32_t)i);
+    }
+    len = used.size();
+    if (total_cnt > 2) {
+        PsiGraph g;
+        g.min = used.front(); g.max = used.back();
+        NodeSet nodes = used, curset;
+        while (!nodes.empty()) {                      // build_utr_graph, src/events.jl:570-591
+            uint32_t cur;
+            if (motif == M_TXST) { cur = nodes.back(); nodes.pop_back(); } else { cur = nodes.front(); nodes.erase(nodes.begin()); }
+            curset.push_back(cur);
+            std::sort(curset.begin(), curset.end());
+            g.nodes.push_back(curset); g.psi.push_back(0.0); g.length.push_back(0.0); g.count.push_back(0.0);
+        }
+        std::vector<AmbigCounts> ambig;
+        std::vector<uint32_t> iset;
+        for (uint32_t n = g.min; n <= g.max; n++) {   // add_node_counts! (one graph), src/events.jl:397-435
+            iset.clear();
+            for (size_t k = 0; k < g.nodes.size(); k++) if (set_has(g.nodes[k], n)) { iset.push_back((uint32_t)k + 1); g.length[k] += V.leng(n); }
+            if (iset.empty()) continue;
+            if (iset.size() == 1) g.count[iset[0] - 1] += V.node(n);
+            else ambig_account(ambig, iset, V.node(n));
+        }
+        for (auto& edg : V.edges) {                   // add_edge_counts! (one graph), src/events.jl:490-523
+            iset.clear();
+            for (size_t k = 0; k < g.nodes.size(); k++) if (edge_in_set(edg, g.nodes[k])) iset.push_back((uint32_t)k + 1);
+            if (iset.empty()) continue;
+            if (iset.size() == 1) g.count[iset[0] - 1] += edg.value;
+            else ambig_account(ambig, iset, edg.value);
+        }
+        out.iterations = rec_tandem_em(g, ambig, 4, readlen);
+        out.has_utr = true;
+        double amb = 0.0;
+        for (auto& a : ambig) amb += a.multiplier;
+        out.total = seqsum(g.count) + amb;
+        out.utr = g;
+    }
+}
+
+// _process_spliced, src/events.jl:647-742
+void process_spliced(const GeneView& V, uint32_t node, uint8_t motif, bool isnodeok, EventOut& out, bool& has_psi, double minedgeweight = 0.02) {
+    PsiGraph inc, exc;
+    bool has_inc = false, has_exc = false, has_ambig_edge = false;
+    std::vector<EdgeIV> ambig_edge;
+    std::vector<AmbigCounts> ambig_cnt;
+    double connecting_val = 0.0, spanning_val = 0.0;
+    double maxvalue = V.edges.empty() ? 0.0 : V.edges.back().value;     // maximum(sgquant.edge): greatest (first,last) key
+    for (auto& edg : V.edges) {
+        if (!(edg.first <= node && node <= edg.last)) continue;         // intersect(sgquant.edge, (node,node))
+        if (edg.value / maxvalue < minedgeweight) continue;
+        if (edg.first == node || edg.last == node) {
+            if (!has_inc) { inc = PsiGraph(); inc.min = edg.first; inc.max = edg.last; has_inc = true; }
+            has_ambig_edge = true;
+            graph_push_edge(inc, edg);
+            ambig_edge.push_back(edg);
+            connecting_val += edg.value;
+        } else {
+            if (!has_exc) { exc = PsiGraph(); exc.min = edg.first; exc.max = edg.last; has_exc = true; }
+            has_ambig_edge = true;
+            graph_push_edge(exc, edg);
+            ambig_edge.push_back(edg);
+            spanning_val += edg.value;
+        }
+    }
+    bool sub = false;
+    if (has_exc && has_inc) {
+        // extend_edges!(sgquant.edge, exc, inc, ambig_edge, node), src/events.jl:329-394
+        uint32_t minv = std::min(exc.min, inc.min), maxv = std::max(exc.max, inc.max);
+        Int idx = (Int)node - 1;
+        while (idx > (Int)minv) {
+            for (auto& edg : V.edges) {
+                if (!(edg.first <= idx && idx <= edg.last)) continue;
+                if ((edg.first == idx || edg.last == idx) && edg.last == idx && edg.first >= minv) {
+                    bool shouldpush = false;
+                    if (graph_has(exc, edg.last)) { graph_push_edge(exc, edg); shouldpush = true; }
+                    if (graph_has(inc, edg.last)) { graph_push_edge(inc, edg); shouldpush = true; }
+                    if (shouldpush) { if (edg.first < minv) minv = edg.first; ambig_edge.push_back(edg); }
+                }
+            }
+            idx -= 1;
+        }
+        idx = (Int)node + 1;
+        while (idx < (Int)maxv) {
+            for (auto& edg : V.edges) {
+                if (!(edg.first <= idx && idx <= edg.last)) continue;
+                if ((edg.first == idx || edg.last == idx) && edg.first == idx && edg.last <= maxv) {
+                    bool shouldpush = false;
+                    if (graph_has(exc, edg.first)) { graph_push_edge(exc, edg); shouldpush = true; }
+                    if (graph_has(inc, edg.first)) { graph_push_edge(inc, edg); shouldpush = true; }
+                    if (shouldpush) { if (edg.last > maxv) maxv = edg.last; ambig_edge.push_back(edg); }
+                }
+            }
+            idx += 1;
+        }
+        inc = reduce_graph(inc, sub);
+        exc = reduce_graph(exc, sub);
+        // add_edge_counts! (two graphs), src/events.jl:525-568
+        std::vector<uint32_t> iset;
+        for (auto& edg : ambig_edge) {
+            iset.clear();
+            for (size_t k = 0; k < inc.nodes.size(); k++) if (edge_in_set(edg, inc.nodes[k])) { iset.push_back((uint32_t)k + 1); inc.length[k] += 1; }
+            for (size_t k = 0; k < exc.nodes.size(); k++) if (edge_in_set(edg, exc.nodes[k])) { iset.push_back((uint32_t)(k + 1 + inc.nodes.size())); exc.length[k] += 1; }
+            if (iset.empty()) continue;
+            if (iset.size() == 1) {
+                if (iset[0] <= inc.nodes.size()) inc.count[iset[0] - 1] += edg.value;
+                else exc.count[iset[0] - inc.nodes.size() - 1] += edg.value;
+            } else ambig_account(ambig_cnt, iset, edg.value);
+        }
+        (void)isnodeok;     // CLI: false (bin/whippet-quant.jl:181); node counts are not used for spliced events
+    } else {
+        if (has_inc) inc = reduce_graph_simple(inc, sub);
+        if (has_exc) exc = reduce_graph_simple(exc, sub);
+    }
+    (void)has_ambig_edge;
+    has_psi = false;
+    double psi = 0.0;
+    if (!has_exc) {
+        if (has_inc && (connecting_val >= 2 || (connecting_val >= 1 && isaltsplice(motif)))) { psi = 1.0; has_psi = true; }
+    } else {
+        if (!has_inc) {
+            if (spanning_val >= 1) { psi = 0.0; has_psi = true; }
+        } else {
+            exc.psi.assign(exc.count.size(), 0.0);
+            inc.psi.assign(inc.count.size(), 0.0);
+            std::vector<double> counts = inc.count;
+            counts.insert(counts.end(), exc.count.begin(), exc.count.end());
+            calculate_psi2(inc, exc, counts, 0);
+            out.iterations = spliced_em(inc, exc, ambig_cnt, 4);
+            psi = seqsum(inc.psi);
+            has_psi = true;
+        }
+    }
+    out.psi = psi;
+    out.total = connecting_val + spanning_val;
+    out.inc = inc; out.exc = exc; out.has_inc = has_inc; out.has_exc = has_exc;
+    if (sub) out.flags |= 2;
+}
+
+// _process_events, src/events.jl:760-800
+void process_events_gene(const Lib& L, const Quant& Q, Int g, int64_t readlen, std::vector<EventOut>& outs) {
+    GeneView V{L, Q, g, {}};
+    if (V.nedgetype() <= 2) return;
+    auto lo = Q.edge.lower_bound((uint64_t)g << 32);
+    for (auto it = lo; it != Q.edge.end() && (it->first >> 32) == (uint64_t)g; ++it) {
+        uint32_t l = (it->first >> 16) & 0xFFFF, r = it->first & 0xFFFF;
+        if (l < r) V.edges.push_back(EdgeIV{l, r, it->second});
+    }
+    Int i = 1;
+    const Int ne = V.nedgetype();
+    while (i < ne) {
+        uint8_t motif = motif_of(V.et(i), V.et(i + 1));
+        bool next_istandem = (i + 1 < ne) ? isobligate(motif_of(V.et(i + 1), V.et(i + 2))) : false;
+        EventOut o;
+        o.gene = (uint32_t)g; o.node = (uint32_t)i; o.motif = motif; o.kind = 0; o.flags = 0;
+        if (motif == M_NONE) {
+            o.kind = next_istandem ? 3 : 0;
+            outs.push_back(o);
+        } else if (isobligate(motif)) {
+            size_t len = 0;
+            process_tandem_utr(V, (uint32_t)i, motif, readlen, o, len);
+            o.kind = 2;
+            bool anynan = false;
+            if (o.has_utr) for (double x : o.utr.psi) if (std::isnan(x)) anynan = true;
+            if (o.has_utr && !anynan) {
+                for (double x : o.utr.psi) o.utr_psi.push_back(round_digits(x, 4));
+            } else {
+                o.utr_psi.assign(len, 0.0);
+                o.flags |= 1;
+                o.total = 0.0;
+            }
+            Int st = motif == M_TXST ? i : i - 1;
+            Int en = st + (Int)o.utr_psi.size() - 1;
+            outs.push_back(o);
+            i = en;
+        } else {
+            bool has_psi = false;
+            process_spliced(V, (uint32_t)i, motif, false, o, has_psi);
+            o.kind = (has_psi && 0 <= o.psi && o.psi <= 1 && o.total > 0) ? 1 : 0;
+            outs.push_back(o);
+        }
+        i += 1;
+    }
+}
+
 }  // namespace
 
 struct wqo_handle {
@@ -1134,6 +1566,7 @@ struct wqo_handle {
     std::string err;
     Quant Q;
     QuantState S;
+    std::vector<EventOut> events;
 };
 
 extern "C" {
@@ -1238,6 +1671,53 @@ uint64_t wqo_class(wqo_handle* h, int multi, uint64_t i, int32_t* ids, double* p
     return c.cls.size();
 }
 void wqo_assign_ambig(wqo_handle* h) { assign_ambig(h->L, h->Q, h->S); }
+
+// process_events (src/events.jl:744-758) over all genes, on the stores as they stand (after assign_ambig!)
+uint64_t wqo_process_events(wqo_handle* h, int64_t readlen) {
+    h->events.clear();
+    for (Int g = 1; g <= h->L.G; g++) process_events_gene(h->L, h->Q, g, readlen, h->events);
+    return h->events.size();
+}
+// event i: header[8] = gene, node, motif, kind, flags, n_utr, n_inc, n_exc; vals[3] = psi, total, iterations
+void wqo_event(wqo_handle* h, uint64_t i, uint32_t* header, double* vals) {
+    const EventOut& e = h->events[i];
+    header[0] = e.gene; header[1] = e.node; header[2] = e.motif; header[3] = e.kind; header[4] = e.flags;
+    header[5] = (uint32_t)e.utr_psi.size(); header[6] = e.has_inc ? (uint32_t)e.inc.nodes.size() : 0; header[7] = e.has_exc ? (uint32_t)e.exc.nodes.size() : 0;
+    vals[0] = e.psi; vals[1] = e.total; vals[2] = (double)e.iterations;
+}
+// path psi values: which 0 = utr (rounded psi), 1 = inclusion paths, 2 = exclusion paths
+void wqo_event_psi(wqo_handle* h, uint64_t i, int which, double* out) {
+    const EventOut& e = h->events[i];
+    const std::vector<double>& v = which == 0 ? e.utr_psi : which == 1 ? e.inc.psi : e.exc.psi;
+    memcpy(out, v.data(), v.size() * 8);
+}
+// node set of path k of graph `which` (0 utr, 1 inc, 2 exc): returns size, writes ids
+uint64_t wqo_event_path(wqo_handle* h, uint64_t i, int which, uint64_t k, uint32_t* out) {
+    const EventOut& e = h->events[i];
+    const PsiGraph& g = which == 0 ? e.utr : which == 1 ? e.inc : e.exc;
+    if (k >= g.nodes.size()) return 0;
+    memcpy(out, g.nodes[k].data(), g.nodes[k].size() * 4);
+    return g.nodes[k].size();
+}
+// known-answer hook: reduce_graph on a list of weighted edges (test/runtests.jl:535-580)
+uint64_t wqo_reduce_graph(const uint32_t* first, const uint32_t* last, const double* value, uint64_t n, uint32_t* out_sets, uint64_t cap) {
+    PsiGraph g;
+    g.min = 0xFFFFFFFFu; g.max = 0;
+    for (uint64_t i = 0; i < n; i++) {
+        g.psi.push_back(0.0); g.length.push_back(1.0); g.count.push_back(value[i]);
+        g.nodes.push_back(NodeSet{first[i], last[i]});
+        g.min = std::min(g.min, first[i]); g.max = std::max(g.max, last[i]);
+    }
+    bool sub = false;
+    PsiGraph r = reduce_graph(g, sub);
+    uint64_t w = 0;
+    for (auto& s : r.nodes) {
+        if (w + 1 + s.size() > cap) return 0;
+        out_sets[w++] = (uint32_t)s.size();
+        for (uint32_t x : s) out_sets[w++] = x;
+    }
+    return r.nodes.size();
+}
 
 void wqo_counters(uint64_t* out7, int reset) {
     out7[0] = g_ctr.fm_steps; out7[1] = g_ctr.hits; out7[2] = g_ctr.nodes_touched; out7[3] = g_ctr.bases;

@@ -221,3 +221,58 @@ def test_sharded_counts_merge_equals_single_pass():
     assert all(np.array_equal(x, y) for x, y in zip(full.assign_ambig(), a.assign_ambig()))
     for q in (full, a, b):
         q.close()
+
+
+def events_parity(idx, p, rb, readlen, mate=None):
+    o = Oracle(idx)
+    o.quant_reset()
+    q = wq.GraphLibQuant(idx)
+    if mate is None:
+        o.process_reads(p, rb)
+        q.process_reads(p, rb)
+    else:
+        o.process_paired_reads(p, rb, mate)
+        q.process_paired_reads(p, rb, mate)
+    o.em_tpm(readlen)
+    o.assign_ambig()
+    q.gene_em(readlen)
+    q.assign_ambig()
+    eo, eg = o.process_events(readlen), q.process_events(readlen)
+    assert len(eo) == len(eg) and len(eo) > 0
+    nem = 0
+    for a, b in zip(eo, eg):
+        key = (a["gene"], a["node"])
+        assert (a["gene"], a["node"], a["motif"], a["kind"], a["flags"]) == (b["gene"], b["node"], b["motif"], b["kind"], b["flags"]), key
+        if a["kind"] == 2:
+            assert a["utr_psi"] == b["utr_psi"], key
+            assert a["total"] == b["total"], key
+        elif a["kind"] == 1:
+            # PSI within 1e-6 relative is the contract; the kernel reproduces the oracle's operation order exactly
+            assert abs(a["psi"] - b["psi"]) <= 1e-6 * max(abs(a["psi"]), 1e-300) and a["psi"] == b["psi"], key
+            assert a["total"] == b["total"], key
+            assert a["inc"] == b["inc"] and a["exc"] == b["exc"], key
+            if a["inc"] and a["exc"]:
+                assert a["iterations"] == b["iterations"], key
+                nem += 1
+    q.close()
+    return eo, nem
+
+
+def test_events_fixture(fixture_index, test_param):
+    ev, nem = events_parity(fixture_index, test_param, fixture_random_reads(fixture_index, 50000), 15)
+    assert any(e["kind"] == 1 for e in ev)
+
+
+@pytest.mark.parametrize("seed,ng,R", [(1, 300, 101), (6, 1200, 76)])
+def test_events_synthetic(seed, ng, R):
+    idx = synth.make_index(n_genes=ng, K=9, seed=seed, paralog_frac=0.1)
+    rb = synth.simulate_reads(idx, 300000, R, seed=seed + 10, sub_rate=0.01)
+    ev, nem = events_parity(idx, wq.AlignParam(), rb, R)
+    kinds = [e["kind"] for e in ev]
+    assert kinds.count(1) > 50 and kinds.count(2) > 10 and nem > 20
+
+
+def test_events_paired():
+    idx, p, f, r = pe_case(2, 300, 76, 5000, True, 150000)
+    ev, nem = events_parity(idx, p, f, 76, mate=r)
+    assert nem > 5

@@ -70,3 +70,41 @@ def test_isoform_classes_and_tpm(fixture_index, test_param):
     assert it < 5000
     assert tpm.sum() == 1000000
     assert np.allclose(gtpm, [tpm[0:2].sum(), tpm[2:5].sum(), tpm[5], tpm[6]])
+
+
+def test_graph_enumeration_known_answer():
+    """test/runtests.jl:535-580: 15 weighted edges of ENSMUSG00000038685 node 23 -> exactly 18 minimal paths."""
+    from oracle import reduce_graph
+    edgestr = "1-2:616.0,1-3:4.0,2-3:569.0,2-4:20.0,3-4:629.0,3-6:1.0,3-10:3.0,4-5:1.0,4-6:664.0,5-6:5.0,6-7:789.0,7-8:790.0,8-9:2.0,8-10:606.0,9-10:15.0"
+    edges = []
+    for s in edgestr.split(","):
+        a, rest = s.split("-")
+        b, v = rest.split(":")
+        edges.append((int(a), int(b), float(v)))
+    expected = [[1, 2, 3, 4, 5, 6, 7, 8, 9, 10], [1, 3, 4, 5, 6, 7, 8, 9, 10], [1, 2, 4, 5, 6, 7, 8, 9, 10], [1, 2, 3, 6, 7, 8, 9, 10],
+                [1, 3, 6, 7, 8, 9, 10], [1, 2, 3, 10], [1, 3, 10], [1, 2, 3, 4, 6, 7, 8, 9, 10], [1, 3, 4, 6, 7, 8, 9, 10],
+                [1, 2, 4, 6, 7, 8, 9, 10], [1, 2, 3, 4, 5, 6, 7, 8, 10], [1, 3, 4, 5, 6, 7, 8, 10], [1, 2, 4, 5, 6, 7, 8, 10],
+                [1, 2, 3, 6, 7, 8, 10], [1, 3, 6, 7, 8, 10], [1, 2, 3, 4, 6, 7, 8, 10], [1, 3, 4, 6, 7, 8, 10], [1, 2, 4, 6, 7, 8, 10]]
+    got = reduce_graph(edges)
+    assert len(got) == len(expected) == 18
+    for p in expected:
+        assert frozenset(p) in got
+
+
+def test_event_building_on_fixture(fixture_index, test_param):
+    """test/runtests.jl:582-599 analogue: every node of every multi-node gene yields one event record, PSI in [0,1]."""
+    o = Oracle(fixture_index)
+    o.quant_reset()
+    count_kat_reads(o, fixture_index, test_param)
+    o.em_tpm(20)
+    o.assign_ambig()
+    ev = o.process_events(20)
+    genes = {e["gene"] for e in ev}
+    assert genes == {1, 2}                                  # `single` genes have <= 2 edges: no events
+    for e in ev:
+        assert e["kind"] in (0, 1, 2, 3)
+        if e["kind"] == 1:
+            assert 0.0 <= e["psi"] <= 1.0 and e["total"] > 0
+    # gene `one`: exon2 (node 3) is skipped by the exon1-exon3def and exon1-exon4 reads and included by exon1-exon2
+    e3 = [e for e in ev if e["gene"] == 2 and e["node"] == 3][0]
+    assert e3["motif"] == 5 and e3["kind"] == 1 and 0.0 < e3["psi"] < 1.0

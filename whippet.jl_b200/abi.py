@@ -89,7 +89,7 @@ class ValuesC(C.Structure):
 
 class PsiBatchC(C.Structure):
     _fields_ = [("n_events", C.c_uint32), ("_pad", C.c_uint32),
-                ("path_ptr", u32p), ("path_count", f64p), ("path_length", f64p),
+                ("path_ptr", u32p), ("n_inc", u32p), ("path_count", f64p), ("path_length", f64p),
                 ("amb_ptr", u32p), ("amb_path_ptr", u32p), ("amb_paths", u32p), ("amb_mult", f64p),
                 ("is_tandem", u8p),
                 ("readlen", C.c_int64), ("sig", C.c_int64), ("maxit", C.c_int64),
@@ -102,3 +102,14 @@ def ptr(a: np.ndarray, typ):
         return C.cast(None, typ)
     assert a.flags["C_CONTIGUOUS"]
     return a.ctypes.data_as(typ)
+
+
+EVENT_DT = np.dtype([("gene", "<u4"), ("node", "<u4"), ("motif", "u1"), ("kind", "u1"), ("flags", "u1"), ("_pad", "u1"),
+                     ("n_utr", "<u4"), ("n_inc", "<u4"), ("n_exc", "<u4"), ("value_start", "<u4"), ("path_start", "<u4"),
+                     ("iterations", "<i4"), ("psi", "<f8"), ("total", "<f8")])
+assert EVENT_DT.itemsize == 56
+
+
+class EventsOutC(C.Structure):
+    _fields_ = [("n_events", C.c_uint64), ("events", C.c_void_p), ("n_values", C.c_uint64), ("values", f64p),
+                ("n_paths", C.c_uint64), ("path_ptr", u64p), ("n_path_nodes", C.c_uint64), ("path_nodes", u32p)]

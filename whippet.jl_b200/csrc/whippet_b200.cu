@@ -20,6 +20,7 @@
 #include "wq_host_index.h"
 #include "wq_host_quant.h"
 #include "wq_em.cuh"
+#include "wq_events.h"
 
 #include <chrono>
 struct WqTimer {
@@ -78,6 +79,7 @@ struct wq_handle {
     WqHostQuant hq;
     WqHostQuantEx hx;
     WqEmScratch em_scratch;
+    std::vector<WqEventRec> ev_recs; std::vector<double> ev_values; bool events_done = false;
     DevBuf<uint64_t> d_ck, d_cv, d_ck2, d_cv2; DevBuf<uint32_t> d_ckoff; DevBuf<uint8_t> d_cubtmp;
     bool hq_valid = false;
     uint32_t chunk_reads = 1u << 22;
@@ -278,7 +280,7 @@ int wq_quant_reset(wq_handle* h) {
     CK(cudaMemsetAsync(h->d_kcursor.p, 0, 8, s));
     CK(cudaStreamSynchronize(s));
     h->hq = WqHostQuant();
-    h->hx = WqHostQuantEx();
+    h->hx = WqHostQuantEx(); h->events_done = false;
     h->hq_valid = false;
     return 0;
 }
@@ -516,7 +518,7 @@ static int align_impl(wq_handle* h, const wq_align_param* ap, const wq_read_batc
     const uint32_t n = reads->n_reads;
     if (n == 0) return 0;
     h->hq_valid = false;
-    h->hx = WqHostQuantEx();
+    h->hx = WqHostQuantEx(); h->events_done = false;
     for (auto& m : h->last_kernel_ms) m = 0;
     const wq_read_batch* src[2] = {reads, mates};
     const int nb = pe ? 2 : 1;
@@ -747,7 +749,7 @@ int wq_counts_merge(wq_handle* h, const wq_counts* c, const wq_keyed* longs, con
     if (!h) return fail(-1, "null handle");
     if (int rc = sync_host_quant(h)) return rc;
     WqHostQuant& Q = h->hq;
-    h->hx = WqHostQuantEx();
+    h->hx = WqHostQuantEx(); h->events_done = false;
     if (c) {
         if (c->node_count) {
             if (c->n_nodes != Q.node.size()) return fail(-1, "node count vector has the wrong length");
@@ -811,7 +813,7 @@ int wq_sparse_merge(wq_handle* h, const void* buf, uint64_t len) {
     if (len < 40) return fail(-1, "sparse buffer too short");
     if (int rc = sync_host_quant(h)) return rc;
     WqHostQuant& Q = h->hq;
-    h->hx = WqHostQuantEx();
+    h->hx = WqHostQuantEx(); h->events_done = false;
     auto pad8 = [](uint64_t b) { return (b + 7) & ~7ull; };
     const uint8_t* p = (const uint8_t*)buf;
     uint64_t hdr[5];
@@ -894,8 +896,108 @@ int wq_assign_ambig(wq_handle* h, wq_values* v) {
 int wq_em_psi_batch(wq_handle* h, wq_psi_batch* b) {
     if (!h || !b) return fail(-1, "null argument");
     CK(cudaSetDevice(h->device));
-    std::string err = wq_run_em_psi(*b, h->stream);
+    std::string err = wq_run_em_psi(*b, h->em_scratch, h->stream, &h->launches);
     if (!err.empty()) return fail(-13, err);
+    return 0;
+}
+
+int wq_process_events(wq_handle* h, int64_t readlen, wq_events_out* out) {
+    if (!h || !out) return fail(-1, "null argument");
+    if (!h->hx.built || !h->hx.em_done || !h->hx.ambig_done) return fail(-14, "wq_process_events needs wq_em_tpm and wq_assign_ambig first (bin/whippet-quant.jl:177-181)");
+    CK(cudaSetDevice(h->device));
+    WqHostQuantEx& X = h->hx;
+    if (!X.edges_final) wq_finalize_edges(h->hq, X);
+    if (!h->events_done) {
+        WqTimer tm_("process_events");
+        const uint32_t G = h->H.G;
+        unsigned nt = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+        if (const char* ev = getenv("WQ_HOST_THREADS")) nt = std::max(1, atoi(ev));
+        if (G < 2048) nt = 1;
+        struct Part { std::vector<WqEventRec> recs; WqPsiProblems P; };
+        std::vector<Part> parts(nt);
+        auto work = [&](unsigned t) {
+            const uint32_t g_lo = 1 + (uint32_t)((uint64_t)G * t / nt), g_hi = (uint32_t)((uint64_t)G * (t + 1) / nt);
+            size_t e = std::lower_bound(X.edge_key.begin(), X.edge_key.end(), (uint64_t)g_lo << 32) - X.edge_key.begin();
+            for (uint32_t g = g_lo; g <= g_hi; g++) {
+                WqGeneEvents V{h->H, X.node_value, g, {}};
+                while (e < X.edge_key.size() && (X.edge_key[e] >> 32) < g) e++;
+                for (; e < X.edge_key.size() && (X.edge_key[e] >> 32) == g; e++) {
+                    if (wq_edge_is_circ(X.edge_key[e])) continue;
+                    V.edges.push_back(WqGeneEdge{(uint32_t)((X.edge_key[e] >> 16) & 0xFFFF), (uint32_t)(X.edge_key[e] & 0xFFFF), X.edge_value[e]});
+                }
+                wq_gene_events(V, readlen, parts[t].recs, parts[t].P);
+            }
+        };
+        if (nt == 1) work(0);
+        else { std::vector<std::thread> th; for (unsigned t = 0; t < nt; t++) th.emplace_back(work, t); for (auto& x : th) x.join(); }
+        h->ev_recs.clear();
+        WqPsiProblems P;
+        for (auto& pt : parts) {
+            long shift = 0;
+            P.append(pt.P, shift);
+            for (auto& r : pt.recs) { if (r.problem >= 0) r.problem += shift; h->ev_recs.push_back(std::move(r)); }
+        }
+        // one batched launch for every EM problem
+        std::vector<double> psi(P.count.size());
+        std::vector<int32_t> its(P.size());
+        if (P.size()) {
+            wq_psi_batch b;
+            memset(&b, 0, sizeof b);
+            b.n_events = (uint32_t)P.size();
+            b.path_ptr = P.path_ptr.data(); b.n_inc = P.n_inc.data(); b.path_count = P.count.data(); b.path_length = P.length.data();
+            b.amb_ptr = P.amb_ptr.data(); b.amb_path_ptr = P.amb_path_ptr.data(); b.amb_paths = P.amb_paths.data(); b.amb_mult = P.amb_mult.data();
+            b.is_tandem = P.is_tandem.data(); b.readlen = readlen; b.sig = 4; b.maxit = 1500;
+            b.psi = psi.data(); b.iterations = its.data();
+            std::string err = wq_run_em_psi(b, h->em_scratch, h->stream, &h->launches);
+            if (!err.empty()) return fail(-13, err);
+        }
+        // finish the records (src/events.jl:776-796)
+        h->ev_values.clear();
+        for (auto& r : h->ev_recs) {
+            r.fixed_psi.clear();
+            if (r.kind == 2) {
+                bool ok = r.problem >= 0;
+                if (ok) {
+                    const uint32_t p0 = P.path_ptr[r.problem], p1 = P.path_ptr[r.problem + 1];
+                    for (uint32_t i = p0; i < p1; i++) if (std::isnan(psi[i])) ok = false;
+                    if (ok) for (uint32_t i = p0; i < p1; i++) { double v = std::nearbyint(psi[i] * 10000.0) / 10000.0; r.fixed_psi.push_back(std::isfinite(v) ? v : psi[i]); }
+                    r.iterations_ = its[r.problem];
+                }
+                if (!ok) { r.fixed_psi.assign(r.n_utr, 0.0); r.flags |= 1; r.total = 0.0; }
+            } else if (r.problem >= 0) {
+                const uint32_t p0 = P.path_ptr[r.problem], p1 = P.path_ptr[r.problem + 1], ni = P.n_inc[r.problem];
+                double s = 0.0;
+                for (uint32_t i = p0; i < p0 + ni; i++) s += psi[i];
+                r.psi = s;
+                r.fixed_psi.assign(psi.begin() + p0, psi.begin() + p1);
+                r.iterations_ = its[r.problem];
+                r.kind = (0.0 <= r.psi && r.psi <= 1.0 && r.total > 0) ? 1 : 0;
+            } else if (r.kind == 1) {
+                r.kind = (r.total > 0) ? 1 : 0;
+            }
+        }
+        h->events_done = true;
+    }
+    uint64_t nv = 0, np = 0, npn = 0;
+    for (auto& r : h->ev_recs) { nv += r.fixed_psi.size(); np += r.paths.size(); for (auto& p : r.paths) npn += p.size(); }
+    bool sizing = !out->events && !out->values && !out->path_ptr && !out->path_nodes;
+    if (!sizing && (out->n_events < h->ev_recs.size() || out->n_values < nv || out->n_paths < np || out->n_path_nodes < npn))
+        return fail(-7, "wq_events_out buffers too small");
+    out->n_events = h->ev_recs.size(); out->n_values = nv; out->n_paths = np; out->n_path_nodes = npn;
+    if (sizing) return 0;
+    uint64_t iv = 0, ip = 0, ipn = 0;
+    for (size_t i = 0; i < h->ev_recs.size(); i++) {
+        const WqEventRec& r = h->ev_recs[i];
+        wq_event e;
+        memset(&e, 0, sizeof e);
+        e.gene = r.gene; e.node = r.node; e.motif = r.motif; e.kind = r.kind; e.flags = r.flags;
+        e.n_utr = r.n_utr; e.n_inc = r.n_inc; e.n_exc = r.n_exc; e.value_start = (uint32_t)iv; e.path_start = (uint32_t)ip;
+        e.iterations = r.iterations_; e.psi = r.psi; e.total = r.total;
+        out->events[i] = e;
+        for (double v : r.fixed_psi) out->values[iv++] = v;
+        for (auto& p : r.paths) { out->path_ptr[ip++] = ipn; for (uint32_t x : p) out->path_nodes[ipn++] = x; }
+    }
+    out->path_ptr[np] = ipn;
     return 0;
 }
 

@@ -508,4 +508,138 @@ static inline std::string wq_run_em_tpm(const WqHostIndex& H, const WqIsoIndex& 
     return "";
 }
 
-static inline std::string wq_run_em_psi(wq_psi_batch&, cudaStream_t) { return "PSI EM is not built yet"; }
+// ------------------------------------------------------------------------------------------ PSI EM
+// One event per thread: spliced_em! (src/events.jl:853-893) and rec_tandem_em! (:895-932) with
+// calculate_psi! (:831-850) and divsignif! (:802-812).  Events are tiny (a handful of paths and ambiguous
+// sets) but run up to 1500 strictly sequential sweeps, so the batch dimension is the parallel one.
+struct WqPsiDev {
+    uint32_t n_events;
+    const uint32_t* path_ptr; const uint32_t* n_inc; const double* count; const double* length;
+    const uint32_t* amb_ptr; const uint32_t* amb_path_ptr; const uint32_t* amb_paths; const double* amb_mult;
+    const uint8_t* is_tandem;
+    double readlen; int sig; int64_t maxit;
+    double* psi; double* prev; double* ctemp; double* amb_prop; int32_t* iterations;
+    double p10[23];               // exact powers of ten
+};
+
+__device__ __forceinline__ double wq_pow10(const WqPsiDev& d, int k) { return (k >= 0 && k <= 22) ? d.p10[k] : pow(10.0, (double)k); }
+// Base.round(x, sigdigits = sig)
+__device__ __forceinline__ double wq_round_sig(const WqPsiDev& d, double x, int sig) {
+    if (!isfinite(x) || x == 0.0) return x;
+    int h = 1 + (int)floor(log10(fabs(x)));
+    int digits = sig - h;
+    double r;
+    if (digits >= 0) { double sc = wq_pow10(d, digits); r = __ddiv_rn(rint(__dmul_rn(x, sc)), sc); }
+    else { double sc = wq_pow10(d, -digits); r = __dmul_rn(rint(__ddiv_rn(x, sc)), sc); }
+    if (!isfinite(r)) return digits > 0 ? x : r;
+    return r;
+}
+
+__global__ void __launch_bounds__(128) wq_k_em_psi(const WqPsiDev d) {
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= d.n_events) return;
+    const uint32_t p0 = d.path_ptr[e], p1 = d.path_ptr[e + 1], ni = d.n_inc[e];
+    const uint32_t a0 = d.amb_ptr[e], a1 = d.amb_ptr[e + 1];
+    const bool tandem = d.is_tandem[e] != 0;
+    double* psi = d.psi + p0;
+    double* prev = d.prev + p0;
+    double* ct = d.ctemp + p0;
+    const double* cnt = d.count + p0;
+    const double* len = d.length + p0;
+    const uint32_t np = p1 - p0;
+    for (uint32_t a = a0; a < a1; a++) {
+        const uint32_t b = d.amb_path_ptr[a], n = d.amb_path_ptr[a + 1] - b;
+        for (uint32_t k = 0; k < n; k++) d.amb_prop[b + k] = __ddiv_rn(1.0, (double)n);
+    }
+    auto normalise = [&](int sig) {
+        // psi = counts / effective length; divided by the total and rounded to `sig` significant digits
+        for (uint32_t i = 0; i < np; i++)
+            psi[i] = tandem ? __ddiv_rn(ct[i], fmax(__dsub_rn(len[i], d.readlen), 1.0)) : __ddiv_rn(ct[i], len[i]);
+        double total;
+        if (tandem) { total = 0.0; for (uint32_t i = 0; i < np; i++) total = __dadd_rn(total, psi[i]); }
+        else {
+            double se = 0.0, si = 0.0;
+            for (uint32_t i = ni; i < np; i++) se = __dadd_rn(se, psi[i]);
+            for (uint32_t i = 0; i < ni; i++) si = __dadd_rn(si, psi[i]);
+            total = __dadd_rn(se, si);
+        }
+        for (uint32_t i = 0; i < np; i++) {
+            double q = __ddiv_rn(psi[i], total);
+            psi[i] = sig > 0 ? wq_round_sig(d, q, sig) : q;
+        }
+    };
+    for (uint32_t i = 0; i < np; i++) { prev[i] = 0.0; psi[i] = 0.0; ct[i] = cnt[i]; }
+    if (!tandem) normalise(0);                      // calculate_psi!(inc, exc, counts) before spliced_em!
+    int64_t it = 1;
+    for (;;) {
+        if (!tandem) {
+            bool differs = false;
+            for (uint32_t i = 0; i < np; i++) if (prev[i] != psi[i]) { differs = true; break; }
+            if (!(differs && it < d.maxit)) break;
+        }
+        for (uint32_t i = 0; i < np; i++) { ct[i] = cnt[i]; prev[i] = psi[i]; }
+        for (uint32_t a = a0; a < a1; a++) {
+            const uint32_t b = d.amb_path_ptr[a], n = d.amb_path_ptr[a + 1] - b;
+            double psum = 1.0;
+            if (it > 1) {
+                psum = 0.0;
+                for (uint32_t k = 0; k < n; k++) { double v = psi[d.amb_paths[b + k]]; d.amb_prop[b + k] = v; psum = __dadd_rn(psum, v); }
+            }
+            const double mult = d.amb_mult[a];
+            for (uint32_t k = 0; k < n; k++) {
+                double prop = __ddiv_rn(d.amb_prop[b + k], psum);
+                d.amb_prop[b + k] = prop;
+                const uint32_t pth = d.amb_paths[b + k];
+                ct[pth] = __dadd_rn(ct[pth], __dmul_rn(prop, mult));
+            }
+        }
+        normalise(d.sig);
+        if (tandem) {
+            bool differs = false;
+            for (uint32_t i = 0; i < np; i++) if (prev[i] != psi[i]) { differs = true; break; }
+            if (differs && it < d.maxit) it += 1; else break;
+        } else {
+            it += 1;
+        }
+    }
+    d.iterations[e] = (int32_t)it;
+}
+
+static inline std::string wq_run_em_psi(wq_psi_batch& b, WqEmScratch& M, cudaStream_t stream, uint64_t* launches) {
+    const uint32_t E = b.n_events;
+    if (E == 0) return "";
+    if (!b.path_ptr || !b.n_inc || !b.amb_ptr || !b.amb_path_ptr || !b.is_tandem || !b.psi || !b.iterations) return "wq_psi_batch has null arrays";
+    const uint32_t P = b.path_ptr[E], A = b.amb_ptr[E], AP = b.amb_path_ptr[A];
+    WqPsiDev d;
+    d.n_events = E; d.readlen = (double)b.readlen; d.sig = (int)b.sig; d.maxit = b.maxit;
+    for (int k = 0; k <= 22; k++) d.p10[k] = std::pow(10.0, (double)k);
+    uint32_t *d_pp, *d_ni, *d_ap, *d_app, *d_apaths;
+    double *d_cnt, *d_len, *d_mult, *d_psi, *d_prev, *d_ct, *d_prop;
+    uint8_t* d_tan;
+    int32_t* d_it;
+    auto up = [&](int slot, const void* src, size_t bytes, void** out) -> cudaError_t {
+        uint8_t* p;
+        cudaError_t e = M.get<uint8_t>(slot, bytes, &p);
+        if (e == cudaSuccess && bytes) e = cudaMemcpyAsync(p, src, bytes, cudaMemcpyHostToDevice, stream);
+        *out = p;
+        return e;
+    };
+    WQ_EMCK(up(0, b.path_ptr, (E + 1) * 4ull, (void**)&d_pp)); WQ_EMCK(up(1, b.n_inc, E * 4ull, (void**)&d_ni));
+    WQ_EMCK(up(2, b.amb_ptr, (E + 1) * 4ull, (void**)&d_ap)); WQ_EMCK(up(3, b.amb_path_ptr, (A + 1) * 4ull, (void**)&d_app));
+    WQ_EMCK(up(4, b.amb_paths, AP * 4ull, (void**)&d_apaths)); WQ_EMCK(up(5, b.path_count, P * 8ull, (void**)&d_cnt));
+    WQ_EMCK(up(6, b.path_length, P * 8ull, (void**)&d_len)); WQ_EMCK(up(7, b.amb_mult, A * 8ull, (void**)&d_mult));
+    WQ_EMCK(up(8, b.is_tandem, E, (void**)&d_tan));
+    WQ_EMCK(M.get(9, P, &d_psi)); WQ_EMCK(M.get(10, P, &d_prev)); WQ_EMCK(M.get(11, P, &d_ct)); WQ_EMCK(M.get(12, AP, &d_prop));
+    WQ_EMCK(M.get(13, E, &d_it));
+    d.path_ptr = d_pp; d.n_inc = d_ni; d.count = d_cnt; d.length = d_len; d.amb_ptr = d_ap; d.amb_path_ptr = d_app;
+    d.amb_paths = d_apaths; d.amb_mult = d_mult; d.is_tandem = d_tan; d.psi = d_psi; d.prev = d_prev; d.ctemp = d_ct;
+    d.amb_prop = d_prop; d.iterations = d_it;
+    wq_k_em_psi<<<(E + 127) / 128, 128, 0, stream>>>(d);
+    if (launches) *launches += 1;
+    WQ_EMCK(cudaGetLastError());
+    WQ_EMCK(cudaMemcpyAsync(b.psi, d_psi, P * 8ull, cudaMemcpyDeviceToHost, stream));
+    if (b.path_total) WQ_EMCK(cudaMemcpyAsync(b.path_total, d_ct, P * 8ull, cudaMemcpyDeviceToHost, stream));
+    WQ_EMCK(cudaMemcpyAsync(b.iterations, d_it, E * 4ull, cudaMemcpyDeviceToHost, stream));
+    WQ_EMCK(cudaStreamSynchronize(stream));
+    return "";
+}

@@ -1,0 +1,316 @@
+// Host side of the event stage: turns the node/edge stores of every gene into PSI-EM problems
+// (process_events / _process_events, /root/reference/src/events.jl:744-800 with isnodeok=false as the CLI sets it,
+// bin/whippet-quant.jl:181), which wq_k_em_psi then solves in one batched launch.  Node sets are bit windows
+// over the event's node range.  The writers of src/io.jl are out of scope: every value they would print is
+// returned instead.
+#pragma once
+#include <algorithm>
+#include <cstdint>
+#include <string>
+#include <thread>
+#include <vector>
+#include "wq_host_quant.h"
+#include "wq_host_index.h"
+
+enum : uint8_t { WQM_TXST = 0, WQM_TXEN = 1, WQM_ALTF = 2, WQM_ALTL = 3, WQM_RETI = 4, WQM_SKIP = 5, WQM_ALTD = 6, WQM_ALTA = 7, WQM_NONE = 8 };
+
+// (edgetype[i], edgetype[i+1]) -> motif, src/events.jl:41-106
+static inline uint8_t wq_motif(uint8_t cur, uint8_t next) {
+    // rows: current edge type SL SR LS RS LR LL RR; columns: next edge type
+    static const uint8_t T[7][7] = {
+        /* SL */ {WQM_TXST, WQM_NONE, WQM_NONE, WQM_NONE, WQM_NONE, WQM_NONE, WQM_NONE},
+        /* SR */ {WQM_NONE, WQM_ALTL, WQM_SKIP, WQM_NONE, WQM_SKIP, WQM_SKIP, WQM_ALTA},
+        /* LS */ {WQM_TXST, WQM_NONE, WQM_ALTF, WQM_NONE, WQM_ALTF, WQM_ALTF, WQM_NONE},
+        /* RS */ {WQM_NONE, WQM_TXEN, WQM_NONE, WQM_TXEN, WQM_NONE, WQM_NONE, WQM_NONE},
+        /* LR */ {WQM_NONE, WQM_ALTL, WQM_SKIP, WQM_NONE, WQM_SKIP, WQM_SKIP, WQM_ALTA},
+        /* LL */ {WQM_NONE, WQM_NONE, WQM_ALTD, WQM_NONE, WQM_ALTD, WQM_ALTD, WQM_RETI},
+        /* RR */ {WQM_NONE, WQM_ALTL, WQM_SKIP, WQM_NONE, WQM_SKIP, WQM_SKIP, WQM_ALTA}};
+    if (cur > 6 || next > 6) return WQM_NONE;
+    return T[cur][next];
+}
+
+struct WqBitWin {                       // node set as bits over [lo, lo + 64*words)
+    uint32_t lo = 0;
+    std::vector<uint64_t> w;
+    void init(uint32_t lo_, uint32_t hi_) { lo = lo_; w.assign((hi_ - lo_) / 64 + 1, 0); }
+    void set(uint32_t n) { w[(n - lo) >> 6] |= 1ull << ((n - lo) & 63); }
+    bool has(uint32_t n) const { uint32_t k = n - lo; return n >= lo && (k >> 6) < w.size() && ((w[k >> 6] >> (k & 63)) & 1); }
+    uint32_t first() const { for (size_t i = 0; i < w.size(); i++) if (w[i]) return lo + (uint32_t)(64 * i + __builtin_ctzll(w[i])); return 0; }
+    uint32_t last() const { for (size_t i = w.size(); i-- > 0;) if (w[i]) return lo + (uint32_t)(64 * i + 63 - __builtin_clzll(w[i])); return 0; }
+    bool operator==(const WqBitWin& o) const { return w == o.w; }
+    void unite(const WqBitWin& o) { for (size_t i = 0; i < w.size(); i++) w[i] |= o.w[i]; }
+    // both ends present and nothing strictly between (src/quant.jl:68-79)
+    bool adjacent(uint32_t a, uint32_t b) const {
+        if (!has(a) || !has(b)) return false;
+        for (uint32_t i = a + 1; i < b; i++) if (has(i)) return false;
+        return true;
+    }
+    void list(std::vector<uint32_t>& out) const {
+        for (size_t i = 0; i < w.size(); i++) { uint64_t x = w[i]; while (x) { out.push_back(lo + (uint32_t)(64 * i + __builtin_ctzll(x))); x &= x - 1; } }
+    }
+};
+
+struct WqPathSet {                      // PsiGraph without psi (src/events.jl:134-141)
+    std::vector<WqBitWin> nodes;
+    std::vector<double> count, length;
+    uint32_t mn = 0, mx = 0;
+    size_t size() const { return nodes.size(); }
+    bool covers(uint32_t n) const { for (auto& s : nodes) if (s.has(n)) return true; return false; }
+    long find(const WqBitWin& s) const { for (size_t i = 0; i < nodes.size(); i++) if (nodes[i] == s) return (long)i; return -1; }
+};
+struct WqGeneEdge { uint32_t a, b; double v; };
+
+struct WqAmbSet { std::vector<uint32_t> paths; double mult; };      // AmbigCounts (paths 0-based here)
+
+struct WqEventRec {                     // one record per visited node (include/whippet_b200.h::wq_event)
+    uint32_t gene, node; uint8_t motif, kind, flags;
+    uint32_t n_utr = 0, n_inc = 0, n_exc = 0;
+    double psi = 0.0, total = 0.0;
+    long problem = -1;                  // index into the EM batch, -1 when no EM is needed
+    int32_t iterations_ = 0;
+    std::vector<std::vector<uint32_t>> paths;       // utr paths, or inclusion paths then exclusion paths
+    std::vector<double> fixed_psi;      // utr: zeros when empty
+};
+
+struct WqPsiProblems {                  // flattened wq_psi_batch inputs
+    std::vector<uint32_t> path_ptr{0}, n_inc, amb_ptr{0}, amb_path_ptr{0}, amb_paths;
+    std::vector<double> count, length, amb_mult;
+    std::vector<uint8_t> is_tandem;
+    size_t size() const { return n_inc.size(); }
+    long add(const WqPathSet* inc, const WqPathSet* exc, const std::vector<WqAmbSet>& amb, bool tandem) {
+        for (const WqPathSet* g : {inc, exc}) if (g) { count.insert(count.end(), g->count.begin(), g->count.end()); length.insert(length.end(), g->length.begin(), g->length.end()); }
+        path_ptr.push_back((uint32_t)count.size());
+        n_inc.push_back((uint32_t)(inc ? inc->size() : 0));
+        for (auto& a : amb) { amb_paths.insert(amb_paths.end(), a.paths.begin(), a.paths.end()); amb_path_ptr.push_back((uint32_t)amb_paths.size()); amb_mult.push_back(a.mult); }
+        amb_ptr.push_back((uint32_t)amb_mult.size());
+        is_tandem.push_back(tandem ? 1 : 0);
+        return (long)size() - 1;
+    }
+    void append(const WqPsiProblems& o, long& shift) {
+        shift = (long)size();
+        const uint32_t pb = (uint32_t)count.size(), ab = (uint32_t)amb_mult.size(), apb = (uint32_t)amb_paths.size();
+        count.insert(count.end(), o.count.begin(), o.count.end()); length.insert(length.end(), o.length.begin(), o.length.end());
+        for (size_t i = 1; i < o.path_ptr.size(); i++) path_ptr.push_back(pb + o.path_ptr[i]);
+        n_inc.insert(n_inc.end(), o.n_inc.begin(), o.n_inc.end());
+        for (size_t i = 1; i < o.amb_ptr.size(); i++) amb_ptr.push_back(ab + o.amb_ptr[i]);
+        for (size_t i = 1; i < o.amb_path_ptr.size(); i++) amb_path_ptr.push_back(apb + o.amb_path_ptr[i]);
+        amb_paths.insert(amb_paths.end(), o.amb_paths.begin(), o.amb_paths.end());
+        amb_mult.insert(amb_mult.end(), o.amb_mult.begin(), o.amb_mult.end());
+        is_tandem.insert(is_tandem.end(), o.is_tandem.begin(), o.is_tandem.end());
+    }
+};
+
+static inline void wq_amb_add(std::vector<WqAmbSet>& amb, const std::vector<uint32_t>& set, double v) {
+    for (auto& a : amb) if (a.paths == set) { a.mult += v; return; }
+    if (v > 0) amb.push_back(WqAmbSet{set, v});
+}
+
+// Build minimal node-set paths from edges sharing terminal nodes (reduce_graph, src/events.jl:223-266).
+static inline WqPathSet wq_reduce(const WqPathSet& edges, bool& subsampled) {
+    WqPathSet cur = edges, nxt;
+    nxt.mn = cur.mn; nxt.mx = cur.mx;
+    for (int it = 1; it <= 100; it++) {
+        if (it > 1) {
+            if (nxt.nodes == cur.nodes) break;
+            std::swap(cur, nxt);
+            nxt.nodes.clear(); nxt.count.clear(); nxt.length.clear();
+            if (cur.size() > 1024) { subsampled = true; cur.nodes.resize(1024); cur.count.resize(1024); cur.length.resize(1024); }
+        }
+        for (size_t i = 0; i < cur.size(); i++) {
+            const uint32_t fi = cur.nodes[i].first(), li = cur.nodes[i].last();
+            bool joined = false;
+            for (size_t j = 0; j < edges.size(); j++) {
+                const uint32_t fj = edges.nodes[j].first(), lj = edges.nodes[j].last();
+                if (!(fi == lj || fj == li)) continue;
+                joined = true;
+                WqBitWin u = cur.nodes[i];
+                u.unite(edges.nodes[j]);
+                if (nxt.find(u) >= 0) continue;
+                nxt.nodes.push_back(u);
+                nxt.length.push_back(cur.length[i] + edges.length[j]);
+                nxt.count.push_back(cur.count[i] + edges.count[j]);
+                nxt.mn = std::min(std::min(fi, fj), nxt.mn);
+                nxt.mx = std::max(std::max(li, lj), nxt.mx);
+            }
+            if (!joined && nxt.find(cur.nodes[i]) < 0) {
+                nxt.nodes.push_back(cur.nodes[i]);
+                nxt.length.push_back(cur.length[i]);
+                nxt.count.push_back(cur.count[i]);
+                nxt.mn = std::min(fi, nxt.mn);
+                nxt.mx = std::max(li, nxt.mx);
+            }
+        }
+    }
+    return nxt;
+}
+static inline WqPathSet wq_reduce_simple(const WqPathSet& edges, bool& subsampled) {   // src/events.jl:268-282
+    if (edges.size() != 2) return wq_reduce(edges, subsampled);
+    WqPathSet r = edges;
+    const uint32_t f0 = r.nodes[0].first(), l0 = r.nodes[0].last(), f1 = r.nodes[1].first(), l1 = r.nodes[1].last();
+    if (f0 == l1 || f1 == l0) {
+        r.nodes[0].unite(r.nodes[1]);
+        r.length[0] += r.length[1];
+        r.count[0] += r.count[1];
+        r.nodes.pop_back(); r.length.pop_back(); r.count.pop_back();
+    }
+    return r;
+}
+
+struct WqGeneEvents {
+    const WqHostIndex& H; const std::vector<double>& node_value; uint32_t g;      // g 1-based
+    std::vector<WqGeneEdge> edges;                                                // (first,last) order
+    uint32_t nn() const { return H.genes[g - 1].nn; }
+    uint8_t et(uint32_t j) const { const WqNodeRec* r = &H.nodes[H.genes[g - 1].node_base]; return j <= nn() ? r[j - 1].et_left : r[nn() - 1].et_right; }
+    double nodev(uint32_t n) const { return node_value[H.genes[g - 1].node_base + n - 1]; }
+    double nodelen(uint32_t n) const { return (double)H.nodes[H.genes[g - 1].node_base + n - 1].len; }
+    double edgev(uint32_t a, uint32_t b) const { for (auto& e : edges) if (e.a == a && e.b == b) return e.v; return 0.0; }
+};
+
+static inline void wq_push_edge(WqPathSet& g, const WqGeneEdge& e, uint32_t lo, uint32_t hi) {
+    WqBitWin s;
+    s.init(lo, hi);
+    s.set(e.a); s.set(e.b);
+    g.nodes.push_back(s); g.count.push_back(0.0); g.length.push_back(0.0);
+    g.mn = std::min(g.mn, e.a); g.mx = std::max(g.mx, e.b);
+}
+
+// all events of one gene (src/events.jl:760-800); problems needing EM are appended to P
+static inline void wq_gene_events(const WqGeneEvents& V, int64_t readlen, std::vector<WqEventRec>& out, WqPsiProblems& P) {
+    const uint32_t ne = V.nn() + 1;
+    if (ne <= 2) return;
+    for (uint32_t i = 1; i < ne; i++) {
+        const uint8_t motif = wq_motif(V.et(i), V.et(i + 1));
+        const bool next_tandem = (i + 1 < ne) && wq_motif(V.et(i + 1), V.et(i + 2)) <= 1;
+        WqEventRec R;
+        R.gene = V.g; R.node = i; R.motif = motif; R.kind = 0; R.flags = 0;
+        if (motif == WQM_NONE) { R.kind = next_tandem ? 3 : 0; out.push_back(R); continue; }
+        if (motif <= 1) {
+            // ---- tandem UTR (src/events.jl:593-645) ----
+            std::vector<uint32_t> used;
+            double total = 0.0;
+            if (motif == WQM_TXEN) { used.push_back(i - 1); total += V.nodev(i - 1); }
+            uint32_t k = i;
+            for (;;) {
+                used.push_back(k);
+                total += V.nodev(k);
+                if (k > 1) total += V.edgev(k - 1, k);
+                k++;
+                if (!(k < ne && wq_motif(V.et(k), V.et(k + 1)) == motif)) break;
+            }
+            if (motif == WQM_TXST && k <= V.nn()) { used.push_back(k); total += V.nodev(k); total += V.edgev(k - 1, k); }
+            std::sort(used.begin(), used.end());
+            used.erase(std::unique(used.begin(), used.end()), used.end());
+            R.kind = 2;
+            R.n_utr = (uint32_t)used.size();
+            if (total > 2) {
+                const uint32_t lo = used.front(), hi = used.back();
+                WqPathSet g;
+                g.mn = lo; g.mx = hi;
+                WqBitWin acc;
+                acc.init(lo, hi);
+                for (size_t t = 0; t < used.size(); t++) {      // nested paths growing from the transcript end inwards
+                    acc.set(motif == WQM_TXST ? used[used.size() - 1 - t] : used[t]);
+                    g.nodes.push_back(acc); g.count.push_back(0.0); g.length.push_back(0.0);
+                }
+                std::vector<WqAmbSet> amb;
+                std::vector<uint32_t> set;
+                for (uint32_t n = lo; n <= hi; n++) {
+                    set.clear();
+                    for (size_t p = 0; p < g.size(); p++) if (g.nodes[p].has(n)) { set.push_back((uint32_t)p); g.length[p] += V.nodelen(n); }
+                    if (set.empty()) continue;
+                    if (set.size() == 1) g.count[set[0]] += V.nodev(n); else wq_amb_add(amb, set, V.nodev(n));
+                }
+                for (auto& e : V.edges) {
+                    set.clear();
+                    for (size_t p = 0; p < g.size(); p++) if (e.a >= lo && e.b <= hi && g.nodes[p].adjacent(e.a, e.b)) set.push_back((uint32_t)p);
+                    if (set.empty()) continue;
+                    if (set.size() == 1) g.count[set[0]] += e.v; else wq_amb_add(amb, set, e.v);
+                }
+                double amb_total = 0.0, cnt_total = 0.0;
+                for (auto& a : amb) amb_total += a.mult;
+                for (double c : g.count) cnt_total += c;
+                R.total = cnt_total + amb_total;
+                R.problem = P.add(&g, nullptr, amb, true);
+                for (auto& s : g.nodes) { R.paths.emplace_back(); s.list(R.paths.back()); }
+            } else {
+                R.flags |= 1;
+                R.fixed_psi.assign(used.size(), 0.0);
+            }
+            out.push_back(R);
+            const uint32_t st = motif == WQM_TXST ? i : i - 1;
+            i = st + R.n_utr - 1;         // output_utr returns the last node it printed (src/io.jl:279-316)
+            continue;
+        }
+        // ---- spliced node (src/events.jl:647-742) ----
+        uint32_t lo = 0xFFFFFFFFu, hi = 0;
+        const double maxvalue = V.edges.empty() ? 0.0 : V.edges.back().v;     // maximum(sgquant.edge): greatest (first,last) entry
+        std::vector<const WqGeneEdge*> touch;
+        for (auto& e : V.edges) {
+            if (!(e.a <= i && i <= e.b)) continue;
+            if (e.v / maxvalue < 0.02) continue;
+            touch.push_back(&e);
+            lo = std::min(lo, e.a); hi = std::max(hi, e.b);
+        }
+        WqPathSet inc, exc;
+        inc.mn = exc.mn = 0xFFFFFFFFu;
+        bool has_inc = false, has_exc = false;
+        std::vector<const WqGeneEdge*> amb_edges;
+        double connecting = 0.0, spanning = 0.0;
+        for (const WqGeneEdge* e : touch) {
+            if (e->a == i || e->b == i) { wq_push_edge(inc, *e, lo, hi); has_inc = true; connecting += e->v; }
+            else { wq_push_edge(exc, *e, lo, hi); has_exc = true; spanning += e->v; }
+            amb_edges.push_back(e);
+        }
+        bool sub = false;
+        std::vector<WqAmbSet> amb;
+        if (has_inc && has_exc) {
+            // bridge with neighbouring edges inside [lo, hi] (extend_edges!, src/events.jl:329-394)
+            for (uint32_t idx = i - 1; idx > lo && idx >= 1; idx--)
+                for (auto& e : V.edges) {
+                    if (e.b != idx || e.a < lo) continue;
+                    bool pushed = false;
+                    if (exc.covers(e.b)) { wq_push_edge(exc, e, lo, hi); pushed = true; }
+                    if (inc.covers(e.b)) { wq_push_edge(inc, e, lo, hi); pushed = true; }
+                    if (pushed) amb_edges.push_back(&e);
+                }
+            for (uint32_t idx = i + 1; idx < hi; idx++)
+                for (auto& e : V.edges) {
+                    if (e.a != idx || e.b > hi) continue;
+                    bool pushed = false;
+                    if (exc.covers(e.a)) { wq_push_edge(exc, e, lo, hi); pushed = true; }
+                    if (inc.covers(e.a)) { wq_push_edge(inc, e, lo, hi); pushed = true; }
+                    if (pushed) amb_edges.push_back(&e);
+                }
+            inc = wq_reduce(inc, sub);
+            exc = wq_reduce(exc, sub);
+            std::vector<uint32_t> set;
+            for (const WqGeneEdge* e : amb_edges) {
+                set.clear();
+                for (size_t p = 0; p < inc.size(); p++) if (inc.nodes[p].adjacent(e->a, e->b)) { set.push_back((uint32_t)p); inc.length[p] += 1; }
+                for (size_t p = 0; p < exc.size(); p++) if (exc.nodes[p].adjacent(e->a, e->b)) { set.push_back((uint32_t)(p + inc.size())); exc.length[p] += 1; }
+                if (set.empty()) continue;
+                if (set.size() == 1) { if (set[0] < inc.size()) inc.count[set[0]] += e->v; else exc.count[set[0] - inc.size()] += e->v; }
+                else wq_amb_add(amb, set, e->v);
+            }
+        } else {
+            if (has_inc) inc = wq_reduce_simple(inc, sub);
+            if (has_exc) exc = wq_reduce_simple(exc, sub);
+        }
+        bool has_psi = false;
+        if (!has_exc) {
+            if (has_inc && (connecting >= 2 || (connecting >= 1 && (motif & 6) == 6))) { R.psi = 1.0; has_psi = true; }
+        } else if (!has_inc) {
+            if (spanning >= 1) { R.psi = 0.0; has_psi = true; }
+        } else {
+            R.problem = P.add(&inc, &exc, amb, false);
+            has_psi = true;
+        }
+        R.total = connecting + spanning;
+        R.n_inc = has_inc ? (uint32_t)inc.size() : 0;
+        R.n_exc = has_exc ? (uint32_t)exc.size() : 0;
+        for (const WqPathSet* gph : {&inc, &exc}) for (auto& s : gph->nodes) { R.paths.emplace_back(); s.list(R.paths.back()); }
+        if (sub) R.flags |= 2;
+        R.kind = has_psi ? 1 : 0;         // for EM problems the 0 <= psi <= 1 && total > 0 test is applied after the kernel
+        out.push_back(R);
+    }
+}

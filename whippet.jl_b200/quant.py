@@ -178,6 +178,34 @@ class GraphLibQuant:
         lib.check(self.L.wq_assign_ambig(self.h, C.byref(v)))
         return node, ek, ev, ck, cv
 
+    def process_events(self, readlen: int):
+        """process_events(out, lib, quant; isnodeok=false, readlen) (src/events.jl:744-800) without the writers:
+        returns a list of dicts, one per event record in gene/node order (same shape as the oracle's)."""
+        o = abi.EventsOutC()
+        lib.check(self.L.wq_process_events(self.h, int(readlen), C.byref(o)))
+        ev = np.zeros(o.n_events, abi.EVENT_DT)
+        vals = np.zeros(max(1, o.n_values))
+        pptr = np.zeros(o.n_paths + 1, "<u8")
+        pnodes = np.zeros(max(1, o.n_path_nodes), "<u4")
+        o.events, o.values = ev.ctypes.data, abi.ptr(vals, abi.f64p)
+        o.path_ptr, o.path_nodes = abi.ptr(pptr, abi.u64p), abi.ptr(pnodes, abi.u32p)
+        lib.check(self.L.wq_process_events(self.h, int(readlen), C.byref(o)))
+        out = []
+        for e in ev:
+            d = dict(gene=int(e["gene"]), node=int(e["node"]), motif=int(e["motif"]), kind=int(e["kind"]), flags=int(e["flags"]),
+                     psi=float(e["psi"]), total=float(e["total"]), iterations=int(e["iterations"]), utr_psi=[], inc=[], exc=[])
+            vs, ps = int(e["value_start"]), int(e["path_start"])
+            path = lambda k: tuple(int(x) for x in pnodes[int(pptr[ps + k]):int(pptr[ps + k + 1])])
+            if d["kind"] == 2:
+                d["utr_psi"] = vals[vs:vs + int(e["n_utr"])].tolist()
+            else:
+                ni, nx = int(e["n_inc"]), int(e["n_exc"])
+                have = d["kind"] == 1 and ni and nx
+                d["inc"] = [(path(k), float(vals[vs + k]) if have else 0.0) for k in range(ni)]
+                d["exc"] = [(path(ni + k), float(vals[vs + ni + k]) if have else 0.0) for k in range(nx)]
+            out.append(d)
+        return out
+
     # ---- multi-GPU exchange ---------------------------------------------------------------------
     def dense_tensor(self):
         """torch view of the device-resident dense vector (node counts + total/mapped/multi/sum_readlen)."""
