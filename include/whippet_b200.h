@@ -274,6 +274,7 @@ typedef struct wq_event {
     uint32_t n_utr, n_inc, n_exc;
     uint32_t value_start, path_start;
     int32_t  iterations;
+    uint32_t _pad2;
     double   psi, total;
 } wq_event;
 typedef struct wq_events_out {
