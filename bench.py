@@ -4,7 +4,7 @@
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
 A step = one pass of the hot path (seed, extend, resolve+count[, exchange], classes + transcript EM +
-multi-map assignment) over one batch of
+multi-map assignment + event PSI EM) over one batch of
 synthetic 101-bp single-end reads against a GENCODE-scale synthetic splice-graph index
 (BASELINE.json configs[1]; the GENCODE GTF itself is not available offline).
 `value` is measured with the batch resident in HBM; `e2e` goes through wq_align_se with pinned HOST
@@ -239,13 +239,15 @@ def main():
     phase = {"align": 0.0, "exchange": 0.0, "quant": 0.0, "em_iterations": 0}
 
     def quantify():
-        """Exchange + build_equivalence_classes! + calculate_tpm! + gene_em! + set_gene_tpm! + assign_ambig!"""
+        """Exchange + build_equivalence_classes! + calculate_tpm! + gene_em! + set_gene_tpm! + assign_ambig! + process_events"""
         t0 = time.perf_counter()
         if world > 1:
             q.allreduce_counts()        # ONE NCCL all-reduce of the dense counts + all-gather of the sparse stores
         t1 = time.perf_counter()
         it, tpm, cnt, gt = q.gene_em(em_readlen, 1, 10000)
         q.assign_ambig()
+        ev = q.process_events_raw(em_readlen)       # event construction + batched PSI EM
+        phase["events"] = len(ev[0])
         t2 = time.perf_counter()
         phase["exchange"] += t1 - t0
         phase["quant"] += t2 - t1
@@ -282,6 +284,9 @@ def main():
     sync_all()
     ms = e0.elapsed_time(e1) / a.steps
     launches = int(L.wq_launch_count(q.h) - l0)
+    phase_ms = {"align": 1000 * phase["align"] / a.steps, "exchange": 1000 * phase["exchange"] / a.steps,
+                "quant": 1000 * phase["quant"] / a.steps, "em_iterations": int(phase["em_iterations"]),
+                "events": int(phase.get("events", 0))}
     clocks = sampler.stop()
     kms /= a.steps
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
@@ -342,8 +347,7 @@ def main():
         "clocks": clocks, "gpu_launches": launches,
         "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "kernel_ms": {"seed": float(kms[0]), "extend": float(kms[1]), "resolve": float(kms[2])},
-        "phase_ms": {"align": 1000 * phase["align"] / a.steps, "exchange": 1000 * phase["exchange"] / a.steps,
-                     "quant": 1000 * phase["quant"] / a.steps, "em_iterations": int(phase["em_iterations"])},
+        "phase_ms": phase_ms,
     }
     if world == 1:
         cpu_v, cpu_dt, _, ctr, n0 = cpu_oracle_run(idx, rb, param, a.cpu_sample, 1)

@@ -178,6 +178,20 @@ class GraphLibQuant:
         lib.check(self.L.wq_assign_ambig(self.h, C.byref(v)))
         return node, ek, ev, ck, cv
 
+    def process_events_raw(self, readlen: int):
+        """Same as process_events but returns the flat arrays of wq_events_out:
+        (events[EVENT_DT], values f64, path_ptr u64, path_nodes u32)."""
+        o = abi.EventsOutC()
+        lib.check(self.L.wq_process_events(self.h, int(readlen), C.byref(o)))
+        ev = np.zeros(o.n_events, abi.EVENT_DT)
+        vals = np.zeros(max(1, o.n_values))
+        pptr = np.zeros(o.n_paths + 1, "<u8")
+        pnodes = np.zeros(max(1, o.n_path_nodes), "<u4")
+        o.events, o.values = ev.ctypes.data, abi.ptr(vals, abi.f64p)
+        o.path_ptr, o.path_nodes = abi.ptr(pptr, abi.u64p), abi.ptr(pnodes, abi.u32p)
+        lib.check(self.L.wq_process_events(self.h, int(readlen), C.byref(o)))
+        return ev, vals, pptr, pnodes
+
     def process_events(self, readlen: int):
         """process_events(out, lib, quant; isnodeok=false, readlen) (src/events.jl:744-800) without the writers:
         returns a list of dicts, one per event record in gene/node order (same shape as the oracle's)."""
