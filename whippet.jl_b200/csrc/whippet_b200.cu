@@ -79,7 +79,8 @@ struct wq_handle {
     WqHostQuant hq;
     WqHostQuantEx hx;
     WqEmScratch em_scratch;
-    std::vector<WqEventRec> ev_recs; std::vector<double> ev_values; bool events_done = false;
+    std::vector<WqEventRec> ev_recs; std::vector<double> ev_values; std::vector<uint64_t> ev_path_ptr{0}; std::vector<uint32_t> ev_path_nodes;
+    bool events_done = false;
     DevBuf<uint64_t> d_ck, d_cv, d_ck2, d_cv2; DevBuf<uint32_t> d_ckoff; DevBuf<uint8_t> d_cubtmp;
     bool hq_valid = false;
     uint32_t chunk_reads = 1u << 22;
@@ -913,30 +914,42 @@ int wq_process_events(wq_handle* h, int64_t readlen, wq_events_out* out) {
         unsigned nt = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
         if (const char* ev = getenv("WQ_HOST_THREADS")) nt = std::max(1, atoi(ev));
         if (G < 2048) nt = 1;
-        struct Part { std::vector<WqEventRec> recs; WqPsiProblems P; };
+        struct Part { std::vector<WqEventRec> recs; WqPsiProblems P; WqEventPool pool; };
         std::vector<Part> parts(nt);
         auto work = [&](unsigned t) {
             const uint32_t g_lo = 1 + (uint32_t)((uint64_t)G * t / nt), g_hi = (uint32_t)((uint64_t)G * (t + 1) / nt);
             size_t e = std::lower_bound(X.edge_key.begin(), X.edge_key.end(), (uint64_t)g_lo << 32) - X.edge_key.begin();
+            WqGeneEvents V{h->H, X.node_value, 0, {}};
             for (uint32_t g = g_lo; g <= g_hi; g++) {
-                WqGeneEvents V{h->H, X.node_value, g, {}};
+                V.g = g;
+                V.edges.clear();
                 while (e < X.edge_key.size() && (X.edge_key[e] >> 32) < g) e++;
                 for (; e < X.edge_key.size() && (X.edge_key[e] >> 32) == g; e++) {
                     if (wq_edge_is_circ(X.edge_key[e])) continue;
                     V.edges.push_back(WqGeneEdge{(uint32_t)((X.edge_key[e] >> 16) & 0xFFFF), (uint32_t)(X.edge_key[e] & 0xFFFF), X.edge_value[e]});
                 }
-                wq_gene_events(V, readlen, parts[t].recs, parts[t].P);
+                wq_gene_events(V, readlen, parts[t].recs, parts[t].P, parts[t].pool);
             }
         };
         if (nt == 1) work(0);
         else { std::vector<std::thread> th; for (unsigned t = 0; t < nt; t++) th.emplace_back(work, t); for (auto& x : th) x.join(); }
-        h->ev_recs.clear();
+        if (getenv("WQ_PROFILE")) fprintf(stderr, "[wq]   events: host build        %9.3f ms (%u threads)\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tm_.t0).count(), nt);
+        // concatenate the per-thread parts (flat arrays: a few memcpy-like appends)
+        h->ev_recs.clear(); h->ev_path_ptr.assign(1, 0); h->ev_path_nodes.clear();
+        size_t nrec = 0;
+        for (auto& pt : parts) nrec += pt.recs.size();
+        h->ev_recs.reserve(nrec);
         WqPsiProblems P;
         for (auto& pt : parts) {
             long shift = 0;
             P.append(pt.P, shift);
-            for (auto& r : pt.recs) { if (r.problem >= 0) r.problem += shift; h->ev_recs.push_back(std::move(r)); }
+            const uint32_t pshift = (uint32_t)h->ev_path_ptr.size() - 1;
+            const uint64_t nshift = h->ev_path_nodes.size();
+            for (size_t i = 1; i < pt.pool.path_ptr.size(); i++) h->ev_path_ptr.push_back(nshift + pt.pool.path_ptr[i]);
+            h->ev_path_nodes.insert(h->ev_path_nodes.end(), pt.pool.path_nodes.begin(), pt.pool.path_nodes.end());
+            for (auto& r : pt.recs) { if (r.problem >= 0) r.problem += shift; r.path_first += pshift; h->ev_recs.push_back(r); }
         }
+        if (getenv("WQ_PROFILE")) fprintf(stderr, "[wq]   events: + concat          %9.3f ms (%zu records, %zu EM problems)\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tm_.t0).count(), h->ev_recs.size(), P.size());
         // one batched launch for every EM problem
         std::vector<double> psi(P.count.size());
         std::vector<int32_t> its(P.size());
@@ -951,53 +964,54 @@ int wq_process_events(wq_handle* h, int64_t readlen, wq_events_out* out) {
             std::string err = wq_run_em_psi(b, h->em_scratch, h->stream, &h->launches);
             if (!err.empty()) return fail(-13, err);
         }
+        if (getenv("WQ_PROFILE")) fprintf(stderr, "[wq]   events: + PSI EM kernel   %9.3f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tm_.t0).count());
         // finish the records (src/events.jl:776-796)
         h->ev_values.clear();
+        h->ev_values.reserve(psi.size() + nrec);
         for (auto& r : h->ev_recs) {
-            r.fixed_psi.clear();
+            r.value_start = (uint32_t)h->ev_values.size();
             if (r.kind == 2) {
                 bool ok = r.problem >= 0;
                 if (ok) {
                     const uint32_t p0 = P.path_ptr[r.problem], p1 = P.path_ptr[r.problem + 1];
                     for (uint32_t i = p0; i < p1; i++) if (std::isnan(psi[i])) ok = false;
-                    if (ok) for (uint32_t i = p0; i < p1; i++) { double v = std::nearbyint(psi[i] * 10000.0) / 10000.0; r.fixed_psi.push_back(std::isfinite(v) ? v : psi[i]); }
+                    if (ok) for (uint32_t i = p0; i < p1; i++) { double v = std::nearbyint(psi[i] * 10000.0) / 10000.0; h->ev_values.push_back(std::isfinite(v) ? v : psi[i]); }
                     r.iterations_ = its[r.problem];
                 }
-                if (!ok) { r.fixed_psi.assign(r.n_utr, 0.0); r.flags |= 1; r.total = 0.0; }
+                if (!ok) { h->ev_values.insert(h->ev_values.end(), r.n_utr, 0.0); r.flags |= 1; r.total = 0.0; }
             } else if (r.problem >= 0) {
                 const uint32_t p0 = P.path_ptr[r.problem], p1 = P.path_ptr[r.problem + 1], ni = P.n_inc[r.problem];
                 double s = 0.0;
                 for (uint32_t i = p0; i < p0 + ni; i++) s += psi[i];
                 r.psi = s;
-                r.fixed_psi.assign(psi.begin() + p0, psi.begin() + p1);
+                h->ev_values.insert(h->ev_values.end(), psi.begin() + p0, psi.begin() + p1);
                 r.iterations_ = its[r.problem];
                 r.kind = (0.0 <= r.psi && r.psi <= 1.0 && r.total > 0) ? 1 : 0;
             } else if (r.kind == 1) {
                 r.kind = (r.total > 0) ? 1 : 0;
             }
+            r.n_values = (uint32_t)h->ev_values.size() - r.value_start;
         }
         h->events_done = true;
     }
-    uint64_t nv = 0, np = 0, npn = 0;
-    for (auto& r : h->ev_recs) { nv += r.fixed_psi.size(); np += r.paths.size(); for (auto& p : r.paths) npn += p.size(); }
+    const uint64_t nv = h->ev_values.size(), np = h->ev_path_ptr.size() - 1, npn = h->ev_path_nodes.size();
     bool sizing = !out->events && !out->values && !out->path_ptr && !out->path_nodes;
     if (!sizing && (out->n_events < h->ev_recs.size() || out->n_values < nv || out->n_paths < np || out->n_path_nodes < npn))
         return fail(-7, "wq_events_out buffers too small");
     out->n_events = h->ev_recs.size(); out->n_values = nv; out->n_paths = np; out->n_path_nodes = npn;
     if (sizing) return 0;
-    uint64_t iv = 0, ip = 0, ipn = 0;
     for (size_t i = 0; i < h->ev_recs.size(); i++) {
         const WqEventRec& r = h->ev_recs[i];
         wq_event e;
         memset(&e, 0, sizeof e);
         e.gene = r.gene; e.node = r.node; e.motif = r.motif; e.kind = r.kind; e.flags = r.flags;
-        e.n_utr = r.n_utr; e.n_inc = r.n_inc; e.n_exc = r.n_exc; e.value_start = (uint32_t)iv; e.path_start = (uint32_t)ip;
+        e.n_utr = r.n_utr; e.n_inc = r.n_inc; e.n_exc = r.n_exc; e.value_start = r.value_start; e.path_start = r.path_first;
         e.iterations = r.iterations_; e.psi = r.psi; e.total = r.total;
         out->events[i] = e;
-        for (double v : r.fixed_psi) out->values[iv++] = v;
-        for (auto& p : r.paths) { out->path_ptr[ip++] = ipn; for (uint32_t x : p) out->path_nodes[ipn++] = x; }
     }
-    out->path_ptr[np] = ipn;
+    if (nv) memcpy(out->values, h->ev_values.data(), nv * 8);
+    memcpy(out->path_ptr, h->ev_path_ptr.data(), (np + 1) * 8);
+    if (npn) memcpy(out->path_nodes, h->ev_path_nodes.data(), npn * 4);
     return 0;
 }
 

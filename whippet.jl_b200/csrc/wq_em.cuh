@@ -535,26 +535,34 @@ __device__ __forceinline__ double wq_round_sig(const WqPsiDev& d, double x, int 
     return r;
 }
 
+// One warp per event.  Element-wise work (copies, the division + significant-digit rounding of every path,
+// the additions of one ambiguous set, whose paths are distinct) is spread over the lanes; every sum is formed
+// sequentially in path order by all lanes redundantly, so the arithmetic is the per-event sequential one.
+// Small events keep psi / previous psi / temp counts in a shared-memory slab, larger ones in global scratch.
+#define WQ_PSI_SLAB 48            // paths per warp slab
 __global__ void __launch_bounds__(128) wq_k_em_psi(const WqPsiDev d) {
-    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ double slab[4][3 * WQ_PSI_SLAB];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t e = blockIdx.x * 4 + warp;
     if (e >= d.n_events) return;
     const uint32_t p0 = d.path_ptr[e], p1 = d.path_ptr[e + 1], ni = d.n_inc[e];
     const uint32_t a0 = d.amb_ptr[e], a1 = d.amb_ptr[e + 1];
     const bool tandem = d.is_tandem[e] != 0;
-    double* psi = d.psi + p0;
-    double* prev = d.prev + p0;
-    double* ct = d.ctemp + p0;
+    const uint32_t np = p1 - p0;
+    const bool small = np <= WQ_PSI_SLAB;
+    double* psi = small ? &slab[warp][0] : d.psi + p0;
+    double* prev = small ? &slab[warp][WQ_PSI_SLAB] : d.prev + p0;
+    double* ct = small ? &slab[warp][2 * WQ_PSI_SLAB] : d.ctemp + p0;
     const double* cnt = d.count + p0;
     const double* len = d.length + p0;
-    const uint32_t np = p1 - p0;
     for (uint32_t a = a0; a < a1; a++) {
         const uint32_t b = d.amb_path_ptr[a], n = d.amb_path_ptr[a + 1] - b;
-        for (uint32_t k = 0; k < n; k++) d.amb_prop[b + k] = __ddiv_rn(1.0, (double)n);
+        for (uint32_t k = lane; k < n; k += 32) d.amb_prop[b + k] = __ddiv_rn(1.0, (double)n);
     }
     auto normalise = [&](int sig) {
-        // psi = counts / effective length; divided by the total and rounded to `sig` significant digits
-        for (uint32_t i = 0; i < np; i++)
+        for (uint32_t i = lane; i < np; i += 32)
             psi[i] = tandem ? __ddiv_rn(ct[i], fmax(__dsub_rn(len[i], d.readlen), 1.0)) : __ddiv_rn(ct[i], len[i]);
+        __syncwarp();
         double total;
         if (tandem) { total = 0.0; for (uint32_t i = 0; i < np; i++) total = __dadd_rn(total, psi[i]); }
         else {
@@ -563,46 +571,49 @@ __global__ void __launch_bounds__(128) wq_k_em_psi(const WqPsiDev d) {
             for (uint32_t i = 0; i < ni; i++) si = __dadd_rn(si, psi[i]);
             total = __dadd_rn(se, si);
         }
-        for (uint32_t i = 0; i < np; i++) {
+        __syncwarp();
+        for (uint32_t i = lane; i < np; i += 32) {
             double q = __ddiv_rn(psi[i], total);
             psi[i] = sig > 0 ? wq_round_sig(d, q, sig) : q;
         }
+        __syncwarp();
     };
-    for (uint32_t i = 0; i < np; i++) { prev[i] = 0.0; psi[i] = 0.0; ct[i] = cnt[i]; }
+    auto differs = [&]() {
+        bool diff = false;
+        for (uint32_t i = lane; i < np; i += 32) if (prev[i] != psi[i]) diff = true;
+        return __any_sync(0xffffffffu, diff) != 0;
+    };
+    for (uint32_t i = lane; i < np; i += 32) { prev[i] = 0.0; psi[i] = 0.0; ct[i] = cnt[i]; }
+    __syncwarp();
     if (!tandem) normalise(0);                      // calculate_psi!(inc, exc, counts) before spliced_em!
     int64_t it = 1;
     for (;;) {
-        if (!tandem) {
-            bool differs = false;
-            for (uint32_t i = 0; i < np; i++) if (prev[i] != psi[i]) { differs = true; break; }
-            if (!(differs && it < d.maxit)) break;
-        }
-        for (uint32_t i = 0; i < np; i++) { ct[i] = cnt[i]; prev[i] = psi[i]; }
+        if (!tandem && !(differs() && it < d.maxit)) break;
+        for (uint32_t i = lane; i < np; i += 32) { ct[i] = cnt[i]; prev[i] = psi[i]; }
+        __syncwarp();
         for (uint32_t a = a0; a < a1; a++) {
             const uint32_t b = d.amb_path_ptr[a], n = d.amb_path_ptr[a + 1] - b;
             double psum = 1.0;
             if (it > 1) {
                 psum = 0.0;
-                for (uint32_t k = 0; k < n; k++) { double v = psi[d.amb_paths[b + k]]; d.amb_prop[b + k] = v; psum = __dadd_rn(psum, v); }
+                for (uint32_t k = 0; k < n; k++) psum = __dadd_rn(psum, psi[d.amb_paths[b + k]]);
             }
             const double mult = d.amb_mult[a];
-            for (uint32_t k = 0; k < n; k++) {
-                double prop = __ddiv_rn(d.amb_prop[b + k], psum);
-                d.amb_prop[b + k] = prop;
+            for (uint32_t k = lane; k < n; k += 32) {
                 const uint32_t pth = d.amb_paths[b + k];
+                const double base = it > 1 ? psi[pth] : d.amb_prop[b + k];
+                const double prop = __ddiv_rn(base, psum);
+                d.amb_prop[b + k] = prop;
                 ct[pth] = __dadd_rn(ct[pth], __dmul_rn(prop, mult));
             }
+            __syncwarp();
         }
         normalise(d.sig);
-        if (tandem) {
-            bool differs = false;
-            for (uint32_t i = 0; i < np; i++) if (prev[i] != psi[i]) { differs = true; break; }
-            if (differs && it < d.maxit) it += 1; else break;
-        } else {
-            it += 1;
-        }
+        if (tandem) { if (differs() && it < d.maxit) it += 1; else break; }
+        else it += 1;
     }
-    d.iterations[e] = (int32_t)it;
+    if (small) for (uint32_t i = lane; i < np; i += 32) { d.psi[p0 + i] = psi[i]; d.ctemp[p0 + i] = ct[i]; }
+    if (lane == 0) d.iterations[e] = (int32_t)it;
 }
 
 static inline std::string wq_run_em_psi(wq_psi_batch& b, WqEmScratch& M, cudaStream_t stream, uint64_t* launches) {
@@ -634,7 +645,7 @@ static inline std::string wq_run_em_psi(wq_psi_batch& b, WqEmScratch& M, cudaStr
     d.path_ptr = d_pp; d.n_inc = d_ni; d.count = d_cnt; d.length = d_len; d.amb_ptr = d_ap; d.amb_path_ptr = d_app;
     d.amb_paths = d_apaths; d.amb_mult = d_mult; d.is_tandem = d_tan; d.psi = d_psi; d.prev = d_prev; d.ctemp = d_ct;
     d.amb_prop = d_prop; d.iterations = d_it;
-    wq_k_em_psi<<<(E + 127) / 128, 128, 0, stream>>>(d);
+    wq_k_em_psi<<<(E + 3) / 4, 128, 0, stream>>>(d);
     if (launches) *launches += 1;
     WQ_EMCK(cudaGetLastError());
     WQ_EMCK(cudaMemcpyAsync(b.psi, d_psi, P * 8ull, cudaMemcpyDeviceToHost, stream));

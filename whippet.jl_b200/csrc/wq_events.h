@@ -68,8 +68,14 @@ struct WqEventRec {                     // one record per visited node (include/
     double psi = 0.0, total = 0.0;
     long problem = -1;                  // index into the EM batch, -1 when no EM is needed
     int32_t iterations_ = 0;
-    std::vector<std::vector<uint32_t>> paths;       // utr paths, or inclusion paths then exclusion paths
-    std::vector<double> fixed_psi;      // utr: zeros when empty
+    uint32_t path_first = 0, n_paths = 0;           // into the owning WqEventPool: utr paths, or inclusion then exclusion paths
+    uint32_t value_start = 0, n_values = 0;         // into the finished value array
+};
+
+struct WqEventPool {                    // node ids of all paths of a batch of records, CSR
+    std::vector<uint64_t> path_ptr{0};
+    std::vector<uint32_t> path_nodes;
+    uint32_t add(const WqBitWin& s) { s.list(path_nodes); path_ptr.push_back(path_nodes.size()); return (uint32_t)path_ptr.size() - 2; }
 };
 
 struct WqPsiProblems {                  // flattened wq_psi_batch inputs
@@ -175,7 +181,7 @@ static inline void wq_push_edge(WqPathSet& g, const WqGeneEdge& e, uint32_t lo, 
 }
 
 // all events of one gene (src/events.jl:760-800); problems needing EM are appended to P
-static inline void wq_gene_events(const WqGeneEvents& V, int64_t readlen, std::vector<WqEventRec>& out, WqPsiProblems& P) {
+static inline void wq_gene_events(const WqGeneEvents& V, int64_t readlen, std::vector<WqEventRec>& out, WqPsiProblems& P, WqEventPool& pool) {
     const uint32_t ne = V.nn() + 1;
     if (ne <= 2) return;
     for (uint32_t i = 1; i < ne; i++) {
@@ -231,10 +237,10 @@ static inline void wq_gene_events(const WqGeneEvents& V, int64_t readlen, std::v
                 for (double c : g.count) cnt_total += c;
                 R.total = cnt_total + amb_total;
                 R.problem = P.add(&g, nullptr, amb, true);
-                for (auto& s : g.nodes) { R.paths.emplace_back(); s.list(R.paths.back()); }
+                R.path_first = (uint32_t)pool.path_ptr.size() - 1; R.n_paths = (uint32_t)g.size();
+                for (auto& s : g.nodes) pool.add(s);
             } else {
                 R.flags |= 1;
-                R.fixed_psi.assign(used.size(), 0.0);
             }
             out.push_back(R);
             const uint32_t st = motif == WQM_TXST ? i : i - 1;
@@ -308,7 +314,8 @@ static inline void wq_gene_events(const WqGeneEvents& V, int64_t readlen, std::v
         R.total = connecting + spanning;
         R.n_inc = has_inc ? (uint32_t)inc.size() : 0;
         R.n_exc = has_exc ? (uint32_t)exc.size() : 0;
-        for (const WqPathSet* gph : {&inc, &exc}) for (auto& s : gph->nodes) { R.paths.emplace_back(); s.list(R.paths.back()); }
+        R.path_first = (uint32_t)pool.path_ptr.size() - 1; R.n_paths = R.n_inc + R.n_exc;
+        for (const WqPathSet* gph : {&inc, &exc}) for (auto& s : gph->nodes) pool.add(s);
         if (sub) R.flags |= 2;
         R.kind = has_psi ? 1 : 0;         // for EM problems the 0 <= psi <= 1 && total > 0 test is applied after the kernel
         out.push_back(R);
