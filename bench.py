@@ -134,8 +134,9 @@ def byte_model(ctr, nreads, R):
     return per_kernel, dict(S_steps=S, H=H, nodes_per_hit=nodes, R_in=r_in, A_out=a_out, C=C)
 
 
-def cpu_oracle_run(idx, rb, param, nsample, threads):
-    """Times the oracle (CPU restatement) on the first `nsample` reads with `threads` host threads."""
+def cpu_oracle_run(idx, rb, param, nsample, threads, readlen=101):
+    """Times the oracle (CPU restatement) on the first `nsample` reads: alignment + counting sharded over `threads`
+    host threads, then the merged stores go through classes + transcript EM + multi-map assignment + events once."""
     from oracle import Oracle, counters
     nsample = min(nsample, rb.n)
     per = (nsample + threads - 1) // threads
@@ -156,9 +157,19 @@ def cpu_oracle_run(idx, rb, param, nsample, threads):
         ts = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
         [t.start() for t in ts]
         [t.join() for t in ts]
+    t_align = time.perf_counter() - t0
+    for o in oracles[1:]:
+        oracles[0].merge(o)
+    oracles[0].em_tpm(readlen, 1, 10000)
+    oracles[0].assign_ambig()
+    oracles[0].process_events_count(readlen)
     dt = time.perf_counter() - t0
-    mapped = sum(o.stats()["mapped"] for o in oracles)
-    return nsample / dt, dt, mapped, ctr, slices[0].n
+    mapped = oracles[0].stats()["mapped"]
+    # whole-job rate: alignment scales with the reads, the quant stage is a per-job cost -> extrapolate the sample to the
+    # full workload (this favours the CPU arm compared with dividing the sample by its own wall time)
+    full = rb.n
+    rate = full / (full * t_align / nsample + (dt - t_align))
+    return rate, dt, mapped, ctr, slices[0].n, t_align
 
 
 def run_reference(a):
@@ -174,13 +185,15 @@ def run_reference(a):
     vals = []
     for i in range(a.warmup + a.steps):
         nsample = min(rb.n, a.cpu_sample * max(1, threads // 2))
-        v, dt, _, _, _ = cpu_oracle_run(idx, rb, param, nsample, threads)
+        v, dt, _, _, _, _ = cpu_oracle_run(idx, rb, param, nsample, threads, a.readlen)
         if i >= a.warmup:
             vals.append((v, dt, nsample))
         if i == 0 and dt * (a.warmup + a.steps) > 240:   # keep the whole run within a few minutes
             a.cpu_sample = max(100000, int(a.cpu_sample * 240 / (dt * (a.warmup + a.steps))))
     v = float(np.mean([x[0] for x in vals]))
-    sample = f"first {vals[-1][2]} reads of the workload per step, sharded over {threads} host threads"
+    sample = (f"first {vals[-1][2]} reads of the workload per step aligned+counted on {threads} host threads, then classes + EM + "
+              f"multi-map assignment + events once on the merged counts; value = full-workload rate extrapolated from the sample "
+              f"(alignment time scaled to {rb.n} reads + the per-job quant time)")
     print(json.dumps({
         "impl": "reference", "metric": "aligned+quantified reads/sec", "value": v, "unit": "reads/s",
         "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1000 * float(np.mean([x[1] for x in vals])),
@@ -350,7 +363,7 @@ def main():
         "phase_ms": phase_ms,
     }
     if world == 1:
-        cpu_v, cpu_dt, _, ctr, n0 = cpu_oracle_run(idx, rb, param, a.cpu_sample, 1)
+        cpu_v, cpu_dt, _, ctr, n0, cpu_align = cpu_oracle_run(idx, rb, param, a.cpu_sample, 1, a.readlen)
         per_kernel, model = byte_model(ctr, n0, a.readlen)
         names = ["seed", "extend", "resolve"]
         dom = names[int(np.argmax(kms))]
@@ -368,8 +381,10 @@ def main():
                            "algorithmic_bytes_per_read": per_kernel, "model": model,
                            "note": "latency-bound random access (FM occ blocks, SA, node records): the fraction is small by construction"}
         out["cpu_baseline"] = {"value": cpu_v, "unit": "reads/s", "cores": 1, "kind": "port",
-                               "sample": f"first {min(a.cpu_sample, rb.n)} reads of the workload, oracle restatement on 1 host thread ({cpu_dt:.1f} s)"}
-    print(json.dumps(out))
+                               "sample": f"first {min(a.cpu_sample, rb.n)} reads of the workload, oracle restatement on 1 host thread: "
+                                         f"align+count {cpu_align:.1f} s, then EM + multi-map assignment + events {cpu_dt - cpu_align:.1f} s; "
+                                         f"value = full-workload rate extrapolated (alignment scaled to {rb.n} reads + per-job quant time)"}
+    print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

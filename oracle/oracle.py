@@ -126,6 +126,14 @@ class Oracle:
         p, f, r = param.c(), fwd.c(), rev.c()
         lib().wqo_process_reads_pe(C.c_void_p(self.h), C.byref(p), C.byref(f), C.byref(r))
 
+    def merge(self, other: "Oracle"):
+        lib().wqo_merge(C.c_void_p(self.h), C.c_void_p(other.h))
+
+    def process_events_count(self, readlen):
+        L = lib()
+        L.wqo_process_events.restype = C.c_uint64
+        return L.wqo_process_events(C.c_void_p(self.h), C.c_int64(readlen))
+
     def stats(self):
         out = (C.c_uint64 * 5)()
         m = C.c_double()

@@ -1624,6 +1624,17 @@ int wqo_process_reads_pe(wqo_handle* h, const wq_align_param* p, const wq_read_b
     }
     return 0;
 }
+// add the count stores of `src` into `dst` (reads sharded over host threads for the timed CPU baseline;
+// every read contributes the integer 1, so the merged stores equal a single sequential pass)
+void wqo_merge(wqo_handle* dst, const wqo_handle* src) {
+    Quant& A = dst->Q;
+    const Quant& B = src->Q;
+    for (size_t i = 0; i < A.node.size(); i++) A.node[i] += B.node[i];
+    for (auto& kv : B.edge) A.edge[kv.first] += kv.second;
+    for (auto& kv : B.longs) A.longs[kv.first] += kv.second;
+    for (auto& kv : B.multi) A.multi[kv.first] += kv.second;
+    A.total += B.total; A.mapped += B.mapped; A.nmulti += B.nmulti; A.sum_readlen += B.sum_readlen;
+}
 void wqo_stats(wqo_handle* h, uint64_t* out5, double* mean_readlen) {
     out5[0] = h->Q.total; out5[1] = h->Q.mapped; out5[2] = h->Q.nmulti; out5[3] = h->Q.sum_readlen; out5[4] = 0;
     *mean_readlen = h->Q.mean_readlen;

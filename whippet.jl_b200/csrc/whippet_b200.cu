@@ -911,8 +911,7 @@ int wq_process_events(wq_handle* h, int64_t readlen, wq_events_out* out) {
     if (!h->events_done) {
         WqTimer tm_("process_events");
         const uint32_t G = h->H.G;
-        unsigned nt = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
-        if (const char* ev = getenv("WQ_HOST_THREADS")) nt = std::max(1, atoi(ev));
+        unsigned nt = wq_host_threads();
         if (G < 2048) nt = 1;
         struct Part { std::vector<WqEventRec> recs; WqPsiProblems P; WqEventPool pool; };
         std::vector<Part> parts(nt);

@@ -144,8 +144,7 @@ static inline std::string wq_host_build_classes(const WqHostIndex& H, const WqIs
     // ---- isoform classes, gene by gene; genes are independent, so host threads take contiguous gene ranges and
     //      the fragments are concatenated in gene order ----
     struct Frag { WqClassSet C; std::vector<std::pair<uint64_t, double>> adds; std::string err; };
-    unsigned nthreads = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
-    if (const char* ev = getenv("WQ_HOST_THREADS")) nthreads = std::max(1, atoi(ev));
+    unsigned nthreads = wq_host_threads();
     if (G < 2048) nthreads = 1;
     std::vector<Frag> frags(nthreads);
     auto work = [&](unsigned t) {

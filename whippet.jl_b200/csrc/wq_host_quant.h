@@ -5,9 +5,19 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <thread>
 #include <vector>
 #include "wq_types.h"
 #include "wq_kernels.cuh"
+
+// host threads this process may use: the machine's cores shared between the ranks of one node
+static inline unsigned wq_host_threads() {
+    if (const char* ev = getenv("WQ_HOST_THREADS")) return (unsigned)std::max(1, atoi(ev));
+    unsigned hc = std::max(1u, std::thread::hardware_concurrency());
+    unsigned ranks = 1;
+    if (const char* lw = getenv("LOCAL_WORLD_SIZE")) ranks = (unsigned)std::max(1, atoi(lw));
+    return std::max(1u, std::min(16u, hc / ranks));
+}
 
 struct WqKeyedStore {                                        // variable-length keyed counts (wq_build_key_* records)
     std::vector<uint32_t> words;                             // key words of all records, back to back

@@ -48,7 +48,7 @@ def suffix_array(codes: np.ndarray, threads: int | None = None):
     sa = np.zeros(n, "<u4")
     bwt = np.zeros(n, "u1")
     sent = C.c_uint64(0)
-    threads = threads or min(32, os.cpu_count() or 1)
+    threads = threads or max(1, min(32, (os.cpu_count() or 1) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))))
     L = _hostlib()
     rc = L.wq_build_sa(abi.ptr(codes, abi.u8p), C.c_uint64(n), abi.ptr(sa, abi.u32p), C.c_int(threads))
     assert rc == 0
