@@ -21,7 +21,8 @@ struct Emu {
     bool paired = false;
     std::vector<WqHit> hits;
     std::vector<wq_align_node> pool;
-    uint32_t cursors[3];
+    uint32_t cursors[6];
+    std::vector<uint32_t> pending2;
 };
 
 extern "C" {
@@ -60,14 +61,26 @@ int emu_align_se(Emu* e, const wq_align_param* ap, const wq_read_batch* rb) {
     e->hit_read.assign(hit_cap, 0); e->hit_s.assign(hit_cap, 0); e->hits.assign(hit_cap, WqHit());
     e->pool.assign((size_t)hit_cap * 4 + 64, wq_align_node());
     e->pending.assign(n + 1, 0);
+    e->pending2.assign(n + 1, 0);
     e->cursors[0] = e->cursors[1] = e->cursors[2] = 0;
     e->paired = false;
     WqWork wk{e->seeds.data(), e->hit_read.data(), e->hit_s.data(), nullptr, nullptr, e->hits.data(), e->pool.data(), e->cursors,
-              e->pending.data(), hit_cap, (uint32_t)e->pool.size()};
+              e->pending.data(), e->pending2.data(), hit_cap, (uint32_t)e->pool.size()};
     uint64_t wbuf[WQ_MAX_READ_WORDS + 1];
-    for (uint32_t r = 0; r < n; r++) wq_seed_thread(e->ix, p, b, wk, r, wbuf);
-    uint32_t nh = e->cursors[0];
-    for (uint32_t s = 0; s < nh; s++) wq_extend_thread(e->ix, p, b, wk, s, wbuf);
+    e->cursors[3] = e->cursors[4] = e->cursors[5] = 0;
+    for (uint32_t r = 0; r < n; r++) wq_seed_thread(e->ix, p, b, wk, r, wbuf, 0, wk.pending, &e->cursors[3]);
+    const int npass = 2;
+    for (int k = 1; k < npass; k++) {
+        const uint32_t* qin = (k & 1) ? wk.pending : wk.pending2;
+        uint32_t* qout = (k & 1) ? wk.pending2 : wk.pending;
+        uint32_t m = e->cursors[(k & 1) ? 3 : 4];
+        uint32_t* cur = &e->cursors[(k & 1) ? 4 : 3];
+        *cur = 0;
+        std::vector<uint32_t> list(qin, qin + m);
+        for (uint32_t i = 0; i < m; i++) wq_seed_thread(e->ix, p, b, wk, list[i], wbuf, k, k == npass - 1 ? nullptr : qout, cur);
+    }
+    uint32_t nf = e->cursors[0], nr = e->cursors[5];
+    for (uint32_t t = 0; t < nf + nr; t++) wq_extend_thread(e->ix, p, b, wk, t < nf ? t : hit_cap - 1 - (t - nf), wbuf);
     uint64_t stats[5] = {0, 0, 0, 0, 0};
     for (uint32_t r = 0; r < n; r++) wq_resolve_thread(e->ix, p, b, wk, e->q, r, stats);
     e->counters.total += n; e->counters.mapped += stats[0]; e->counters.multi += stats[1];
@@ -91,7 +104,7 @@ int emu_align_pe(Emu* e, const wq_align_param* ap, const wq_read_batch* rf, cons
     e->cursors[0] = e->cursors[1] = e->cursors[2] = 0;
     e->paired = true;
     WqWork wk{e->seeds.data(), e->hit_read.data(), e->hit_s.data(), e->hit_s2.data(), e->hit_gene.data(), e->hits.data(),
-              e->pool.data(), e->cursors, e->pending.data(), hit_cap, (uint32_t)e->pool.size()};
+              e->pool.data(), e->cursors, e->pending.data(), e->pending.data(), hit_cap, (uint32_t)e->pool.size()};
     uint64_t wbuf[WQ_MAX_READ_WORDS + 1];
     for (uint32_t r = 0; r < n; r++) wq_seed_pe_thread(e->ix, p, bf, br, wk, r, wbuf);
     uint32_t nh = e->cursors[0];

@@ -86,6 +86,7 @@ struct wq_handle {
     uint32_t chunk_reads = 1u << 22;
     float last_kernel_ms[3] = {0, 0, 0};
     uint64_t launches = 0;       // kernels launched by this handle so far
+    uint32_t last_hit_cap = 0;
 };
 
 // ------------------------------------------------------------------------------------------ kernels
@@ -95,21 +96,38 @@ struct wq_handle {
 #ifndef WQ_SEED_MINBLOCKS
 #define WQ_SEED_MINBLOCKS 1
 #endif
+#ifndef WQ_SEED_PASSES
+#define WQ_SEED_PASSES 2      // 1: every read runs seed_locate to completion in one kernel; 2: first window, then a dense pass over the rest
+#endif
 __global__ void __launch_bounds__(128, WQ_SEED_MINBLOCKS) wq_k_seed(const WqDevIndex ix, const __grid_constant__ WqParams p,
                                                  const WqBatchDev b, const WqWork wk) {
     uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     __shared__ uint64_t s_w[128 * (WQ_MAX_READ_WORDS + 1)];
     if (r >= b.n) return;
-    wq_seed_thread(ix, p, b, wk, r, s_w + threadIdx.x * (WQ_MAX_READ_WORDS + 1));
+    wq_seed_thread(ix, p, b, wk, r, s_w + threadIdx.x * (WQ_MAX_READ_WORDS + 1), 0, WQ_SEED_PASSES > 1 ? wk.pending : nullptr, &wk.cursors[3]);
+}
+
+// later seeding passes: one more FM search for the reads queued by the previous pass (queues alternate between
+// wk.pending / cursors[3] and wk.pending2 / cursors[4]); the last pass runs its reads to completion
+__global__ void __launch_bounds__(128, WQ_SEED_MINBLOCKS) wq_k_seed_more(const WqDevIndex ix, const __grid_constant__ WqParams p,
+                                                                        const WqBatchDev b, const WqWork wk, int pass, int last) {
+    __shared__ uint64_t s_w[128 * (WQ_MAX_READ_WORDS + 1)];
+    const uint32_t* qin = (pass & 1) ? wk.pending : wk.pending2;
+    uint32_t* qout = (pass & 1) ? wk.pending2 : wk.pending;
+    const uint32_t n = wk.cursors[(pass & 1) ? 3 : 4];
+    uint32_t* cur = &wk.cursors[(pass & 1) ? 4 : 3];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        wq_seed_thread(ix, p, b, wk, qin[i], s_w + threadIdx.x * (WQ_MAX_READ_WORDS + 1), pass, last ? nullptr : qout, cur);
 }
 
 __global__ void __launch_bounds__(128, WQ_EXT_MINBLOCKS) wq_k_extend(const WqDevIndex ix, const __grid_constant__ WqParams p,
-                                                   const WqBatchDev b, const WqWork wk) {
-    uint32_t nh = wk.cursors[0];
-    if (nh > wk.hit_cap) nh = wk.hit_cap;
+                                                                    const WqBatchDev b, const WqWork wk) {
     __shared__ uint64_t s_w[128 * (WQ_MAX_READ_WORDS + 1)];
-    for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < nh; slot += gridDim.x * blockDim.x)
+    const uint32_t nf = wk.cursors[0], nr = wk.cursors[5];        // forward-strand hits from the front, reverse-strand from the back
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < nf + nr; t += gridDim.x * blockDim.x) {
+        const uint32_t slot = t < nf ? t : wk.hit_cap - 1 - (t - nf);
         wq_extend_thread(ix, p, b, wk, slot, s_w + threadIdx.x * (WQ_MAX_READ_WORDS + 1));
+    }
 }
 
 __global__ void __launch_bounds__(128) wq_k_seed_pe(const WqDevIndex ix, const __grid_constant__ WqParams p,
@@ -393,15 +411,24 @@ static int run_chunk(wq_handle* h, const WqParams& p, const WqBatchDev& b, const
     if (pe) { CK(h->d_hit_s2.ensure(hit_cap)); CK(h->d_hit_gene.ensure(hit_cap)); }
     CK(h->d_pool.ensure(pool_cap)); CK(h->d_pending.ensure(n)); CK(h->d_pending2.ensure(n));
     WqWork wk{h->d_seeds.p, h->d_hit_read.p, h->d_hit_s.p, h->d_hit_s2.p, h->d_hit_gene.p, h->d_hits.p, h->d_pool.p,
-              h->d_cursors.p, h->d_pending.p, hit_cap, pool_cap};
+              h->d_cursors.p, h->d_pending.p, h->d_pending2.p, hit_cap, pool_cap};
     CK(cudaMemsetAsync(h->d_cursors.p, 0, 16 * sizeof(uint32_t), s));
     cudaEvent_t ev[4];
     if (time_kernels) for (auto& e : ev) CK(cudaEventCreate(&e));
     const int T = 128;
     const uint32_t gread = (n + T - 1) / T;
     if (time_kernels) CK(cudaEventRecord(ev[0], s));
-    if (!pe) wq_k_seed<<<gread, T, 0, s>>>(h->dix, p, b, wk);
-    else wq_k_seed_pe<<<gread, T, 0, s>>>(h->dix, p, b, *br, wk);
+    if (!pe) {
+        wq_k_seed<<<gread, T, 0, s>>>(h->dix, p, b, wk);
+        // at most 2*seed_try searches per read: pass 1 is still large (reads from the opposite strand), the rest is a tail
+        const int npass = WQ_SEED_PASSES;
+        for (int k = 1; k < npass; k++) {
+            CK(cudaMemsetAsync(h->d_cursors.p + ((k & 1) ? 4 : 3), 0, sizeof(uint32_t), s));
+            const uint32_t g = gread / 16 + 1;
+            wq_k_seed_more<<<g, T, 0, s>>>(h->dix, p, b, wk, k, k == npass - 1 ? 1 : 0);
+            h->launches += 1;
+        }
+    } else wq_k_seed_pe<<<gread, T, 0, s>>>(h->dix, p, b, *br, wk);
     h->launches += 3;
     if (time_kernels) CK(cudaEventRecord(ev[1], s));
     // one thread per located hit; the hit count lives on the device, so the grid is sized for the usual
@@ -413,8 +440,9 @@ static int run_chunk(wq_handle* h, const WqParams& p, const WqBatchDev& b, const
     else wq_k_resolve_pe<<<gread, T, 0, s>>>(h->dix, p, b, *br, wk, h->q);
     if (time_kernels) CK(cudaEventRecord(ev[3], s));
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(h->h_cursors, h->d_cursors.p, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(h->h_cursors, h->d_cursors.p, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
+    h->last_hit_cap = hit_cap;
     if (time_kernels) {
         for (int i = 0; i < 3; i++) { float ms = 0; cudaEventElapsedTime(&ms, ev[i], ev[i + 1]); h->last_kernel_ms[i] += ms; }
         for (auto& e : ev) cudaEventDestroy(e);
@@ -431,9 +459,9 @@ static int run_chunk(wq_handle* h, const WqParams& p, const WqBatchDev& b, const
         if (!pe) wq_k_retry<<<(pending + T - 1) / T, T, 0, s>>>(h->dix, wk, h->q, list, pending);
         else wq_k_retry_pe<<<(pending + T - 1) / T, T, 0, s>>>(h->dix, wk, h->q, list, pending);
         h->launches += 1;
-        CK(cudaMemcpyAsync(h->h_cursors + 4, h->d_cursors.p, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(h->h_cursors + 8, h->d_cursors.p, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
-        pending = h->h_cursors[6];
+        pending = h->h_cursors[10];
     }
     return 0;
 }
@@ -448,12 +476,19 @@ static int check_batch(const wq_read_batch* r) {
 static int collect_chunk(wq_handle* h, uint32_t first, uint32_t n, bool pe, wq_align_out* out) {
     cudaStream_t s = h->stream;
     uint32_t nh = h->h_cursors[0], np = h->h_cursors[1];
+    const uint32_t nback = pe ? 0 : h->h_cursors[5];          // single-end: reverse-strand hits sit at the back of the array
+    const uint32_t hit_cap = h->last_hit_cap;
+    if (nback) nh = hit_cap;                                     // index space of hit_base
     const uint32_t mult = pe ? 2 : 1;
     std::vector<WqSeed> seeds(n);
     std::vector<WqHit> hits((size_t)nh * mult);
     std::vector<wq_align_node> pool(np);
     CK(cudaMemcpyAsync(seeds.data(), h->d_seeds.p, n * sizeof(WqSeed), cudaMemcpyDeviceToHost, s));
-    if (nh) CK(cudaMemcpyAsync(hits.data(), h->d_hits.p, hits.size() * sizeof(WqHit), cudaMemcpyDeviceToHost, s));
+    if (nback) {
+        const uint32_t nfront = h->h_cursors[0];
+        if (nfront) CK(cudaMemcpyAsync(hits.data(), h->d_hits.p, nfront * sizeof(WqHit), cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(hits.data() + (hit_cap - nback), h->d_hits.p + (hit_cap - nback), nback * sizeof(WqHit), cudaMemcpyDeviceToHost, s));
+    } else if (nh) CK(cudaMemcpyAsync(hits.data(), h->d_hits.p, hits.size() * sizeof(WqHit), cudaMemcpyDeviceToHost, s));
     if (np) CK(cudaMemcpyAsync(pool.data(), h->d_pool.p, np * sizeof(wq_align_node), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     if (pe && !out->aln_mate) return fail(-1, "wq_align_out.aln_mate is required for paired batches");
@@ -657,17 +692,17 @@ static int sync_host_quant(wq_handle* h) {
     std::vector<uint64_t> dense(N + sizeof(WqCounters) / 8);
     CK(cudaMemcpyAsync(dense.data(), h->d_dense.p, dense.size() * 8, cudaMemcpyDeviceToHost, s));
     // cursors[8] = #edges, cursors[9] = #keyed entries
-    CK(cudaMemsetAsync(h->d_cursors.p + 8, 0, 2 * sizeof(uint32_t), s));
+    CK(cudaMemsetAsync(h->d_cursors.p + 12, 0, 2 * sizeof(uint32_t), s));
     CK(h->d_ck.ensure(h->edge_slots)); CK(h->d_cv.ensure(h->edge_slots));
-    wq_k_compact_edges<<<1184, 256, 0, s>>>(h->d_ekey.p, h->d_ecount.p, h->edge_slots, h->d_ck.p, h->d_cv.p, h->d_cursors.p + 8);
+    wq_k_compact_edges<<<1184, 256, 0, s>>>(h->d_ekey.p, h->d_ecount.p, h->edge_slots, h->d_ck.p, h->d_cv.p, h->d_cursors.p + 12);
     CK(h->d_ckoff.ensure(h->keyed_slots)); CK(h->d_cv2.ensure(h->keyed_slots));
-    wq_k_compact_keyed<<<1184, 256, 0, s>>>(h->d_khash.p, h->d_koff.p, h->d_kcount.p, h->keyed_slots, h->d_ckoff.p, h->d_cv2.p, h->d_cursors.p + 9);
+    wq_k_compact_keyed<<<1184, 256, 0, s>>>(h->d_khash.p, h->d_koff.p, h->d_kcount.p, h->keyed_slots, h->d_ckoff.p, h->d_cv2.p, h->d_cursors.p + 13);
     h->launches += 2;
     uint64_t kcur = 0;
-    CK(cudaMemcpyAsync(h->h_cursors + 8, h->d_cursors.p + 8, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(h->h_cursors + 12, h->d_cursors.p + 12, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(&kcur, h->d_kcursor.p, 8, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
-    const uint32_t ne = h->h_cursors[8], nk = h->h_cursors[9];
+    const uint32_t ne = h->h_cursors[12], nk = h->h_cursors[13];
     Q.node.assign(dense.begin(), dense.begin() + N);
     memcpy(&Q.stats, dense.data() + N, sizeof(WqCounters));
     if (Q.stats.keyed_full || kcur > h->kpool_cap) return fail(-8, "keyed count store overflowed (raise WQ_KEYED_SLOTS / WQ_KEYED_POOL_WORDS)");

@@ -464,6 +464,7 @@ static inline std::string wq_run_em_tpm(const WqHostIndex& H, const WqIsoIndex& 
     WQ_EMCK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wq_k_em_tpm, 1024, 0));
     if (per_sm < 1) return "EM kernel does not fit on an SM";
     int grid = sms * per_sm;
+    if (const char* ev = getenv("WQ_EM_BLOCKS")) grid = std::max(1, std::min(grid, atoi(ev)));
     // calculate_tpm!(quant, readlen) before gene_em! (bin/whippet-quant.jl:163): one sweep with every class parked
     {
         WqEmDev d0 = d;
@@ -554,10 +555,6 @@ __global__ void __launch_bounds__(128) wq_k_em_psi(const WqPsiDev d) {
     double* ct = small ? &slab[warp][2 * WQ_PSI_SLAB] : d.ctemp + p0;
     const double* cnt = d.count + p0;
     const double* len = d.length + p0;
-    for (uint32_t a = a0; a < a1; a++) {
-        const uint32_t b = d.amb_path_ptr[a], n = d.amb_path_ptr[a + 1] - b;
-        for (uint32_t k = lane; k < n; k += 32) d.amb_prop[b + k] = __ddiv_rn(1.0, (double)n);
-    }
     auto normalise = [&](int sig) {
         for (uint32_t i = lane; i < np; i += 32)
             psi[i] = tandem ? __ddiv_rn(ct[i], fmax(__dsub_rn(len[i], d.readlen), 1.0)) : __ddiv_rn(ct[i], len[i]);
@@ -600,9 +597,9 @@ __global__ void __launch_bounds__(128) wq_k_em_psi(const WqPsiDev d) {
             const double mult = d.amb_mult[a];
             for (uint32_t k = lane; k < n; k += 32) {
                 const uint32_t pth = d.amb_paths[b + k];
-                const double base = it > 1 ? psi[pth] : d.amb_prop[b + k];
+                // first sweep: ones(n)/n over prop_sum = 1.0; later sweeps: current psi over their sum (src/events.jl:869-886)
+                const double base = it > 1 ? psi[pth] : __ddiv_rn(1.0, (double)n);
                 const double prop = __ddiv_rn(base, psum);
-                d.amb_prop[b + k] = prop;
                 ct[pth] = __dadd_rn(ct[pth], __dmul_rn(prop, mult));
             }
             __syncwarp();

@@ -70,8 +70,9 @@ struct WqWork {                    // per-batch scratch
     uint32_t* hit_gene;            // [hit_cap] paired: gene both mates are aligned against
     WqHit*    hits;                // [hit_cap]  (paired: [2*hit_cap], mate m of pair slot s at 2*s+m)
     wq_align_node* pool;           // [pool_cap]
-    uint32_t* cursors;             // [0] hit cursor, [1] path-pool cursor, [2] pending cursor
-    uint32_t* pending;             // [n] reads whose keyed insert must be retried
+    uint32_t* cursors;             // [0] hit cursor, [1] path-pool cursor, [2] pending keyed inserts, [3]/[4] seed queues, [5] hits of reverse-strand seeds (allocated from the back of the hit arrays)
+    uint32_t* pending;             // [n] reads whose keyed insert must be retried (also: seed queue A)
+    uint32_t* pending2;            // [n] seed queue B
     uint32_t  hit_cap, pool_cap;
 };
 
@@ -129,7 +130,35 @@ WQ_HD void wq_badq(const WqCtx& c, int min_qual, bool rev, uint64_t* badq) {
 }
 
 // ---- kernel 1 -----------------------------------------------------------------------------------
-WQ_HDN void wq_seed_thread(const WqDevIndex& ix, const WqParams& p, const WqBatchDev& b, const WqWork& wk, uint32_t r, uint64_t* wbuf) {
+// Seeding runs as a few dense passes of ONE FM search per thread: pass 0 searches the first window of every read,
+// reads that need another search (reverse complement of the window, or the next window) are queued with their loop
+// state parked in the seed record and taken up by the next pass over that queue.  Same sequence of searches per read
+// as seed_locate, but no lane waits for the rare read that needs six searches.
+WQ_HD void wq_seed_finish(const WqDevIndex& ix, const WqWork& wk, uint32_t r, int cnt, int64_t sp, int readloc, bool strand) {
+    WqSeed s;
+    s.sp = (uint32_t)sp;
+    s.cnt = (uint8_t)cnt;
+    s.readloc = (uint8_t)readloc;
+    s.strand = strand ? 1 : 0;
+    s._pad = 0;
+    s.hit_base = 0;
+    if (cnt > 0) {
+        // hits of forward-strand seeds fill the hit arrays from the front, those of reverse-strand seeds from the back,
+        // so the extension kernel's warps see one kind only (the read is reverse-complemented for the second kind)
+        uint32_t base;
+        if (strand) base = WQ_ATOMIC_ADD_U32(&wk.cursors[0], cnt);
+        else base = wk.hit_cap - WQ_ATOMIC_ADD_U32(&wk.cursors[5], cnt) - cnt;
+        s.hit_base = base;
+        for (int k = 0; k < cnt; k++) {
+            wk.hit_read[base + k] = r;
+            wk.hit_s[base + k] = (uint32_t)(wq_sa_value(ix, sp + k) + 1);
+        }
+    }
+    wk.seeds[r] = s;
+}
+
+WQ_HDN void wq_seed_thread(const WqDevIndex& ix, const WqParams& p, const WqBatchDev& b, const WqWork& wk, uint32_t r, uint64_t* wbuf,
+                           int pass, uint32_t* queue_out, uint32_t* queue_cursor) {
     WqCtx c;
     c.ix = &ix;
     c.p = &p;
@@ -140,25 +169,20 @@ WQ_HDN void wq_seed_thread(const WqDevIndex& ix, const WqParams& p, const WqBatc
     int64_t sp = 2;
     int readloc = 0;
     bool strand = true;
-    int cnt = wq_seed_locate(c, badq, true, !p.is_stranded, sp, readloc, strand);
-    WqSeed s;
-    s.sp = (uint32_t)sp;
-    s.cnt = (uint8_t)cnt;
-    s.readloc = (uint8_t)readloc;
-    s.strand = strand ? 1 : 0;
-    s._pad = 0;
-    s.hit_base = 0;
-    if (cnt > 0) {
-        uint32_t base = WQ_ATOMIC_ADD_U32(&wk.cursors[0], cnt);
-        s.hit_base = base;
-        for (int k = 0; k < cnt; k++) {
-            if (base + k < wk.hit_cap) {
-                wk.hit_read[base + k] = r;
-                wk.hit_s[base + k] = (uint32_t)(wq_sa_value(ix, sp + k) + 1);
-            }
-        }
+    WqSeedState st;
+    if (pass == 0) wq_seed_init(c, true, st);
+    else { const WqSeed q = wk.seeds[r]; st.ctry = q.cnt; st.curpos = (int)q.sp; st.stage = q._pad; }      // parked loop state
+    // pass 0: the first window (forward, then reverse complement if needed); the last pass: everything that is left
+    int cnt = wq_seed_locate(c, badq, true, !p.is_stranded, sp, readloc, strand, st, queue_out ? 2 : 0x7fffffff);
+    if (cnt < 0) {                    // another search is needed: park the loop state and queue the read
+        WqSeed s;
+        s.sp = (uint32_t)st.curpos; s.cnt = (uint8_t)st.ctry; s.readloc = 0; s.strand = 1; s._pad = (uint8_t)st.stage; s.hit_base = 0;
+        wk.seeds[r] = s;
+        uint32_t slot = WQ_ATOMIC_ADD_U32(queue_cursor, 1);
+        queue_out[slot] = r;
+        return;
     }
-    wk.seeds[r] = s;
+    wq_seed_finish(ix, wk, r, cnt, sp, readloc, strand);
 }
 
 // ---- kernel 2 -----------------------------------------------------------------------------------
@@ -421,7 +445,9 @@ WQ_HDN void wq_seed_pe_thread(const WqDevIndex& ix, const WqParams& p, const WqB
     int64_t fsp = 2, rsp = 2;
     int floc = 0, rloc = 0;
     bool strand = true, dummy = true;
-    int fcnt = wq_seed_locate(c, badq, true, !p.is_stranded, fsp, floc, strand);
+    WqSeedState st;
+    wq_seed_init(c, true, st);
+    int fcnt = wq_seed_locate(c, badq, true, !p.is_stranded, fsp, floc, strand, st, 0x7fffffff);
     // mate 2: one strand only; reverse-complemented first when the pair is expected head to head
     wq_load_read(c, br, r);
     bool flip2 = (p.is_pair_rc && strand) || (!p.is_pair_rc && !strand);
@@ -430,10 +456,12 @@ WQ_HDN void wq_seed_pe_thread(const WqDevIndex& ix, const WqParams& p, const WqB
         wq_revcomp(c.w, c.readlen);
         c.flipped = 1;
         wq_badq(c, p.seed_min_qual, true, badq);
-        rcnt = wq_seed_locate(c, badq, false, false, rsp, rloc, dummy);
+        wq_seed_init(c, false, st);
+        rcnt = wq_seed_locate(c, badq, false, false, rsp, rloc, dummy, st, 0x7fffffff);
     } else {
         wq_badq(c, p.seed_min_qual, false, badq);
-        rcnt = wq_seed_locate(c, badq, true, false, rsp, rloc, dummy);
+        wq_seed_init(c, true, st);
+        rcnt = wq_seed_locate(c, badq, true, false, rsp, rloc, dummy, st, 0x7fffffff);
     }
     int64_t fpos[WQ_MAX_TOLERATE], rpos[WQ_MAX_TOLERATE];
     for (int k = 0; k < fcnt; k++) fpos[k] = wq_sa_value(ix, fsp + k) + 1;
