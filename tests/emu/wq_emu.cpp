@@ -68,17 +68,7 @@ int emu_align_se(Emu* e, const wq_align_param* ap, const wq_read_batch* rb) {
               e->pending.data(), e->pending2.data(), hit_cap, (uint32_t)e->pool.size()};
     uint64_t wbuf[WQ_MAX_READ_WORDS + 1];
     e->cursors[3] = e->cursors[4] = e->cursors[5] = 0;
-    for (uint32_t r = 0; r < n; r++) wq_seed_thread(e->ix, p, b, wk, r, wbuf, 0, wk.pending, &e->cursors[3]);
-    const int npass = 2;
-    for (int k = 1; k < npass; k++) {
-        const uint32_t* qin = (k & 1) ? wk.pending : wk.pending2;
-        uint32_t* qout = (k & 1) ? wk.pending2 : wk.pending;
-        uint32_t m = e->cursors[(k & 1) ? 3 : 4];
-        uint32_t* cur = &e->cursors[(k & 1) ? 4 : 3];
-        *cur = 0;
-        std::vector<uint32_t> list(qin, qin + m);
-        for (uint32_t i = 0; i < m; i++) wq_seed_thread(e->ix, p, b, wk, list[i], wbuf, k, k == npass - 1 ? nullptr : qout, cur);
-    }
+    for (uint32_t r = 0; r < n; r++) wq_seed_thread(e->ix, p, b, wk, r, wbuf);
     uint32_t nf = e->cursors[0], nr = e->cursors[5];
     for (uint32_t t = 0; t < nf + nr; t++) wq_extend_thread(e->ix, p, b, wk, t < nf ? t : hit_cap - 1 - (t - nf), wbuf);
     uint64_t stats[5] = {0, 0, 0, 0, 0};

@@ -96,28 +96,12 @@ struct wq_handle {
 #ifndef WQ_SEED_MINBLOCKS
 #define WQ_SEED_MINBLOCKS 1
 #endif
-#ifndef WQ_SEED_PASSES
-#define WQ_SEED_PASSES 2      // 1: every read runs seed_locate to completion in one kernel; 2: first window, then a dense pass over the rest
-#endif
 __global__ void __launch_bounds__(128, WQ_SEED_MINBLOCKS) wq_k_seed(const WqDevIndex ix, const __grid_constant__ WqParams p,
                                                  const WqBatchDev b, const WqWork wk) {
     uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     __shared__ uint64_t s_w[128 * (WQ_MAX_READ_WORDS + 1)];
     if (r >= b.n) return;
-    wq_seed_thread(ix, p, b, wk, r, s_w + threadIdx.x * (WQ_MAX_READ_WORDS + 1), 0, WQ_SEED_PASSES > 1 ? wk.pending : nullptr, &wk.cursors[3]);
-}
-
-// later seeding passes: one more FM search for the reads queued by the previous pass (queues alternate between
-// wk.pending / cursors[3] and wk.pending2 / cursors[4]); the last pass runs its reads to completion
-__global__ void __launch_bounds__(128, WQ_SEED_MINBLOCKS) wq_k_seed_more(const WqDevIndex ix, const __grid_constant__ WqParams p,
-                                                                        const WqBatchDev b, const WqWork wk, int pass, int last) {
-    __shared__ uint64_t s_w[128 * (WQ_MAX_READ_WORDS + 1)];
-    const uint32_t* qin = (pass & 1) ? wk.pending : wk.pending2;
-    uint32_t* qout = (pass & 1) ? wk.pending2 : wk.pending;
-    const uint32_t n = wk.cursors[(pass & 1) ? 3 : 4];
-    uint32_t* cur = &wk.cursors[(pass & 1) ? 4 : 3];
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-        wq_seed_thread(ix, p, b, wk, qin[i], s_w + threadIdx.x * (WQ_MAX_READ_WORDS + 1), pass, last ? nullptr : qout, cur);
+    wq_seed_thread(ix, p, b, wk, r, s_w + threadIdx.x * (WQ_MAX_READ_WORDS + 1));
 }
 
 __global__ void __launch_bounds__(128, WQ_EXT_MINBLOCKS) wq_k_extend(const WqDevIndex ix, const __grid_constant__ WqParams p,
@@ -420,14 +404,6 @@ static int run_chunk(wq_handle* h, const WqParams& p, const WqBatchDev& b, const
     if (time_kernels) CK(cudaEventRecord(ev[0], s));
     if (!pe) {
         wq_k_seed<<<gread, T, 0, s>>>(h->dix, p, b, wk);
-        // at most 2*seed_try searches per read: pass 1 is still large (reads from the opposite strand), the rest is a tail
-        const int npass = WQ_SEED_PASSES;
-        for (int k = 1; k < npass; k++) {
-            CK(cudaMemsetAsync(h->d_cursors.p + ((k & 1) ? 4 : 3), 0, sizeof(uint32_t), s));
-            const uint32_t g = gread / 16 + 1;
-            wq_k_seed_more<<<g, T, 0, s>>>(h->dix, p, b, wk, k, k == npass - 1 ? 1 : 0);
-            h->launches += 1;
-        }
     } else wq_k_seed_pe<<<gread, T, 0, s>>>(h->dix, p, b, *br, wk);
     h->launches += 3;
     if (time_kernels) CK(cudaEventRecord(ev[1], s));

@@ -166,36 +166,8 @@ WQ_HD void wq_erase_front(WqAlign& a, int k) {
 }
 
 // ---------------------------------------------------------------- FM index
-// All row arithmetic is 32-bit (n < 2^32 - 16 is checked at index creation): 64-bit integer ops are emulated on
-// the GPU and the search kernel is issue-bound.
-struct WqOccSel { uint32_t x_lo, x_hi; };           // xor masks turning the bit planes into "symbol == ch" bits
-WQ_HD WqOccSel wq_occ_sel(uint32_t ch) { WqOccSel s; s.x_lo = (ch & 1) ? 0u : ~0u; s.x_hi = (ch & 2) ? 0u : ~0u; return s; }
 // occurrences of ch in bwt[0..i)
-WQ_HD uint32_t wq_occ(const WqDevIndex& ix, uint32_t ch, WqOccSel sel, uint32_t i) {
-    const WqOccBlock* b = ix.occ + (i >> 6);
-#if defined(__CUDA_ARCH__)
-    const uint4 planes = __ldg(reinterpret_cast<const uint4*>(&b->lo));     // lo[0:32], lo[32:64], hi[0:32], hi[32:64]
-    const uint32_t base = __ldg(&b->cnt[ch]);
-    const uint32_t lo0 = planes.x, lo1 = planes.y, hi0 = planes.z, hi1 = planes.w;
-#else
-    const uint32_t lo0 = (uint32_t)b->lo, lo1 = (uint32_t)(b->lo >> 32), hi0 = (uint32_t)b->hi, hi1 = (uint32_t)(b->hi >> 32);
-    const uint32_t base = b->cnt[ch];
-#endif
-    const uint32_t m0 = (lo0 ^ sel.x_lo) & (hi0 ^ sel.x_hi), m1 = (lo1 ^ sel.x_lo) & (hi1 ^ sel.x_hi);
-    const uint32_t r = i & 63;
-    // mask of the first r symbols, split over the two 32-symbol halves
-    const uint32_t k0 = r >= 32 ? ~0u : ((1u << r) - 1u);
-    const uint32_t k1 = r > 32 ? ((1u << (r - 32)) - 1u) : 0u;
-#if defined(__CUDA_ARCH__)
-    return base + __popc(m0 & k0) + __popc(m1 & k1);
-#else
-    return base + (uint32_t)__builtin_popcount(m0 & k0) + (uint32_t)__builtin_popcount(m1 & k1);
-#endif
-}
-
-// one backward-search step for symbol ch (src/fmindex_patch.jl:25-28)
-#ifdef WQ_FM64
-WQ_HD uint32_t wq_occ64(const WqDevIndex& ix, uint32_t ch, uint64_t i) {
+WQ_HD uint32_t wq_occ(const WqDevIndex& ix, uint32_t ch, uint64_t i) {
     const WqOccBlock* b = ix.occ + (i >> 6);
 #if defined(__CUDA_ARCH__)
     const uint4 planes = __ldg(reinterpret_cast<const uint4*>(&b->lo));
@@ -210,41 +182,25 @@ WQ_HD uint32_t wq_occ64(const WqDevIndex& ix, uint32_t ch, uint64_t i) {
     m &= (r ? (~0ull >> (64 - r)) : 0ull);
     return base + (uint32_t)WQ_POPCLL(m);
 }
-WQ_HD void wq_fm_step(const WqDevIndex& ix, uint32_t ch, uint32_t sent32, uint32_t& sp32, uint32_t& ep32) {
-    int64_t sp = sp32, ep = ep32, sent = sent32;
-    int64_t a = (sp > sent ? sp - 1 : sp) - 1;
-    int64_t b = (ep > sent ? ep - 1 : ep);
-    uint32_t oa = wq_occ64(ix, ch, (uint64_t)a);
-    uint32_t ob = wq_occ64(ix, ch, (uint64_t)b);
-    sp32 = (uint32_t)((int64_t)ix.C[ch] + oa + 1);
-    ep32 = (uint32_t)((int64_t)ix.C[ch] + ob);
-}
-#else
-WQ_HD void wq_fm_step(const WqDevIndex& ix, uint32_t ch, uint32_t sent, uint32_t& sp, uint32_t& ep) {
-    const WqOccSel sel = wq_occ_sel(ch);
-    const uint32_t a = (sp > sent ? sp - 1 : sp) - 1;
-    const uint32_t b = (ep > sent ? ep - 1 : ep);
-    const uint32_t oa = wq_occ(ix, ch, sel, a);
-    const uint32_t ob = wq_occ(ix, ch, sel, b);
-    sp = ix.C[ch] + oa + 1;
-    ep = ix.C[ch] + ob;
-}
-#endif
 
 // Backward search of `len` symbols read[start..start+len) (0-based, alignment orientation of c.w).
 // rc = search the reverse complement of that window instead.  Returns rows sp..ep (sp>ep: empty).
-WQ_HD void wq_fm_search(const WqCtx& c, int start, int len, bool rc, int64_t& out_sp, int64_t& out_ep) {
+WQ_HD void wq_fm_search(const WqCtx& c, int start, int len, bool rc, int64_t& sp, int64_t& ep) {
     const WqDevIndex& ix = *c.ix;
-    uint32_t sp = 1, ep = (uint32_t)ix.n + 1;
-    const uint32_t sent = (uint32_t)ix.sentinel;
+    sp = 1;
+    ep = (int64_t)ix.n + 1;
+    const int64_t sent = (int64_t)ix.sentinel;
     for (int i = 0; i < len && sp <= ep; i++) {
         // forward query is consumed last symbol first; the reverse complement consumes the window
         // first symbol first, complemented
         uint32_t ch = rc ? 3u - wq_rbase(c, start + i) : wq_rbase(c, start + len - 1 - i);
-        wq_fm_step(ix, ch, sent, sp, ep);
+        int64_t a = (sp > sent ? sp - 1 : sp) - 1;
+        int64_t b = (ep > sent ? ep - 1 : ep);
+        uint32_t oa = wq_occ(ix, ch, (uint64_t)a);
+        uint32_t ob = wq_occ(ix, ch, (uint64_t)b);
+        sp = (int64_t)ix.C[ch] + oa + 1;
+        ep = (int64_t)ix.C[ch] + ob;
     }
-    out_sp = sp;
-    out_ep = ep;
 }
 
 WQ_HD int64_t wq_sa_value(const WqDevIndex& ix, int64_t row) {
@@ -253,70 +209,55 @@ WQ_HD int64_t wq_sa_value(const WqDevIndex& ix, int64_t row) {
 
 // seed_locate (src/align.jl:145-185).  `badq` has bit j set when quality[j] <= seed_min_qual
 // (0-based, orientation of c.w).  Returns cnt (0 when no seed) and fills sp/readloc/strand.
-// The loop can be paused after `budget` searched windows (state in ctry/curpos, return -1) so that the first
-// window of every read is searched by a dense kernel and only the few reads needing more windows continue in a
-// second one: same sequence of searches, scheduled so that warps do not idle behind their slowest lane.
-struct WqSeedState { int ctry, curpos, stage; };     // stage 1: the forward search of this window failed, its reverse complement is next
-WQ_HD void wq_seed_init(const WqCtx& c, bool offset_left, WqSeedState& st) {
-    st.ctry = 1;
-    st.stage = 0;
-    st.curpos = offset_left ? c.p->seed_buffer : c.readlen - c.p->seed_length - c.p->seed_buffer;
-}
-// `budget` = FM searches this call may run (forward and reverse-complement count separately); -1 is returned with
-// the loop state in `st` when it is used up.
 WQ_HD int wq_seed_locate(const WqCtx& c, const uint64_t* badq, bool offset_left, bool both_strands,
-                         int64_t& out_sp, int& out_readloc, bool& out_strand, WqSeedState& st, int budget) {
+                         int64_t& out_sp, int& out_readloc, bool& out_strand) {
     const WqParams& p = *c.p;
     const int readlen = c.readlen;
-    const int increment = offset_left ? p.seed_inc : -p.seed_inc, increment_sm = offset_left ? 1 : -1;
+    int ctry = 1;
+    int increment, increment_sm, curpos;
+    if (offset_left) { increment = p.seed_inc; increment_sm = 1; curpos = p.seed_buffer; }
+    else { increment = -p.seed_inc; increment_sm = -1; curpos = readlen - p.seed_length - p.seed_buffer; }
     const int maxright = readlen - p.seed_length - p.seed_buffer;
-    const int L = p.seed_length;
     out_strand = true;
-    while ((st.stage == 1 || st.ctry <= p.seed_try) && p.seed_buffer <= st.curpos && st.curpos <= maxright) {
-        const int a = st.curpos - 1;
-        if (st.stage == 0) {
-            // minimum(quality[curpos : curpos+L-1]) <= seed_min_qual  <=>  any bad bit in the window
-            bool bad = false;
-            for (int j = a; j < a + L;) {
-                int wi = j >> 6, bo = j & 63;
-                int take = 64 - bo;
-                if (take > a + L - j) take = a + L - j;
-                uint64_t mask = (take == 64 ? ~0ull : ((1ull << take) - 1)) << bo;
-                if (badq[wi] & mask) { bad = true; break; }
-                j += take;
-            }
-            if (bad) { st.curpos += increment_sm; continue; }
-            if (budget == 0) return -1;
-            budget--;
-            int64_t sp, ep;
-            wq_fm_search(c, a, L, false, sp, ep);
-            const int64_t cnt = ep >= sp ? ep - sp + 1 : 0;
-            st.ctry += 1;
-            if (!(cnt == 0 || cnt > p.seed_tolerate)) {
-                out_sp = sp;
-                out_readloc = st.curpos;
-                out_strand = true;
-                return (int)cnt;
-            }
-            if (!both_strands) { st.curpos += increment; continue; }
-            st.stage = 1;
+    while (ctry <= p.seed_try && p.seed_buffer <= curpos && curpos <= maxright) {
+        // minimum(quality[curpos : curpos+L-1]) <= seed_min_qual  <=>  any bad bit in the window
+        int a = curpos - 1, L = p.seed_length;
+        bool bad = false;
+        for (int j = a; j < a + L;) {
+            int wi = j >> 6, bo = j & 63;
+            int take = 64 - bo;
+            if (take > a + L - j) take = a + L - j;
+            uint64_t mask = (take == 64 ? ~0ull : ((1ull << take) - 1)) << bo;
+            if (badq[wi] & mask) { bad = true; break; }
+            j += take;
         }
-        if (budget == 0) return -1;
-        budget--;
-        int64_t rsp, rep;
-        wq_fm_search(c, a, L, true, rsp, rep);
-        st.stage = 0;
-        const int64_t rcnt = rep >= rsp ? rep - rsp + 1 : 0;
-        if (0 < rcnt && rcnt <= p.seed_tolerate) {
-            out_sp = rsp;
-            out_readloc = readlen - (st.curpos + L - 1) + 1;
-            out_strand = false;
-            return (int)rcnt;
+        if (bad) { curpos += increment_sm; continue; }
+        int64_t sp, ep;
+        wq_fm_search(c, curpos - 1, L, false, sp, ep);
+        int64_t cnt = ep >= sp ? ep - sp + 1 : 0;
+        ctry += 1;
+        if (cnt == 0 || cnt > p.seed_tolerate) {
+            if (both_strands) {
+                int64_t rsp, rep;
+                wq_fm_search(c, curpos - 1, L, true, rsp, rep);
+                int64_t rcnt = rep >= rsp ? rep - rsp + 1 : 0;
+                if (0 < rcnt && rcnt <= p.seed_tolerate) {
+                    out_sp = rsp;
+                    out_readloc = readlen - (curpos + L - 1) + 1;
+                    out_strand = false;
+                    return (int)rcnt;
+                }
+            }
+        } else {
+            out_sp = sp;
+            out_readloc = curpos;
+            out_strand = true;
+            return (int)cnt;
         }
-        st.curpos += increment;
+        curpos += increment;
     }
     out_sp = 2;
-    out_readloc = st.curpos;
+    out_readloc = curpos;
     return 0;
 }
 

@@ -17,6 +17,27 @@
 #define WQ_FENCE() __threadfence()
 #define WQ_VLOAD_U32(p) (*(volatile const uint32_t*)(p))
 #define WQ_VLOAD_U64(p) (*(volatile const uint64_t*)(p))
+// Reserve `cnt` (< 32) consecutive slots behind a global cursor with ONE atomic per warp: the lanes that are here
+// together sum their requests with ballots (one per bit of cnt), the first of them moves the cursor.  A cursor that
+// every thread of a 10-million-read batch bumps on its own would serialise the whole kernel on one L2 atomic unit.
+__device__ __forceinline__ uint32_t wq_warp_alloc(uint32_t* cursor, uint32_t cnt) {
+    const unsigned m = __activemask();
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt = (1u << lane) - 1u;
+    uint32_t prefix = 0, total = 0;
+#pragma unroll
+    for (int b = 0; b < 5; b++) {
+        const unsigned bal = __ballot_sync(m, (cnt >> b) & 1u);
+        prefix += (uint32_t)__popc(bal & lt) << b;
+        total += (uint32_t)__popc(bal) << b;
+    }
+    const int leader = __ffs(m) - 1;
+    uint32_t base = 0;
+    if ((int)lane == leader && total) base = atomicAdd((unsigned int*)cursor, total);
+    base = __shfl_sync(m, base, leader);
+    return base + prefix;
+}
+#define WQ_ALLOC(p, v) wq_warp_alloc((uint32_t*)(p), (uint32_t)(v))
 #else
 template <class T, class V> static inline T wq_emu_add(T* p, V v) { T o = *p; *p = (T)(o + (T)v); return o; }
 static inline uint64_t wq_emu_cas(uint64_t* p, uint64_t c, uint64_t v) { uint64_t o = *p; if (o == c) *p = v; return o; }
@@ -25,6 +46,7 @@ static inline uint32_t wq_emu_exch(uint32_t* p, uint32_t v) { uint32_t o = *p; *
 #define WQ_ATOMIC_ADD_U64(p, v) wq_emu_add((uint64_t*)(p), (v))
 #define WQ_ATOMIC_CAS_U64(p, c, v) wq_emu_cas((uint64_t*)(p), (c), (v))
 #define WQ_ATOMIC_EXCH_U32(p, v) wq_emu_exch((uint32_t*)(p), (v))
+#define WQ_ALLOC(p, v) wq_emu_add((uint32_t*)(p), (v))
 #define WQ_FENCE() ((void)0)
 #define WQ_VLOAD_U32(p) (*(const uint32_t*)(p))
 #define WQ_VLOAD_U64(p) (*(const uint64_t*)(p))
@@ -70,7 +92,7 @@ struct WqWork {                    // per-batch scratch
     uint32_t* hit_gene;            // [hit_cap] paired: gene both mates are aligned against
     WqHit*    hits;                // [hit_cap]  (paired: [2*hit_cap], mate m of pair slot s at 2*s+m)
     wq_align_node* pool;           // [pool_cap]
-    uint32_t* cursors;             // [0] hit cursor, [1] path-pool cursor, [2] pending keyed inserts, [3]/[4] seed queues, [5] hits of reverse-strand seeds (allocated from the back of the hit arrays)
+    uint32_t* cursors;             // [0] hit cursor, [1] path-pool cursor, [2] pending keyed inserts, [5] hits of reverse-strand seeds (allocated from the back of the hit arrays)
     uint32_t* pending;             // [n] reads whose keyed insert must be retried (also: seed queue A)
     uint32_t* pending2;            // [n] seed queue B
     uint32_t  hit_cap, pool_cap;
@@ -130,10 +152,6 @@ WQ_HD void wq_badq(const WqCtx& c, int min_qual, bool rev, uint64_t* badq) {
 }
 
 // ---- kernel 1 -----------------------------------------------------------------------------------
-// Seeding runs as a few dense passes of ONE FM search per thread: pass 0 searches the first window of every read,
-// reads that need another search (reverse complement of the window, or the next window) are queued with their loop
-// state parked in the seed record and taken up by the next pass over that queue.  Same sequence of searches per read
-// as seed_locate, but no lane waits for the rare read that needs six searches.
 WQ_HD void wq_seed_finish(const WqDevIndex& ix, const WqWork& wk, uint32_t r, int cnt, int64_t sp, int readloc, bool strand) {
     WqSeed s;
     s.sp = (uint32_t)sp;
@@ -142,12 +160,12 @@ WQ_HD void wq_seed_finish(const WqDevIndex& ix, const WqWork& wk, uint32_t r, in
     s.strand = strand ? 1 : 0;
     s._pad = 0;
     s.hit_base = 0;
+    // hits of forward-strand seeds fill the hit arrays from the front, those of reverse-strand seeds from the back,
+    // so the extension kernel's warps see one kind only (the read is reverse-complemented for the second kind)
+    const uint32_t bf = WQ_ALLOC(&wk.cursors[0], strand ? cnt : 0);
+    const uint32_t bb = WQ_ALLOC(&wk.cursors[5], strand ? 0 : cnt);
     if (cnt > 0) {
-        // hits of forward-strand seeds fill the hit arrays from the front, those of reverse-strand seeds from the back,
-        // so the extension kernel's warps see one kind only (the read is reverse-complemented for the second kind)
-        uint32_t base;
-        if (strand) base = WQ_ATOMIC_ADD_U32(&wk.cursors[0], cnt);
-        else base = wk.hit_cap - WQ_ATOMIC_ADD_U32(&wk.cursors[5], cnt) - cnt;
+        const uint32_t base = strand ? bf : wk.hit_cap - bb - (uint32_t)cnt;
         s.hit_base = base;
         for (int k = 0; k < cnt; k++) {
             wk.hit_read[base + k] = r;
@@ -157,8 +175,7 @@ WQ_HD void wq_seed_finish(const WqDevIndex& ix, const WqWork& wk, uint32_t r, in
     wk.seeds[r] = s;
 }
 
-WQ_HDN void wq_seed_thread(const WqDevIndex& ix, const WqParams& p, const WqBatchDev& b, const WqWork& wk, uint32_t r, uint64_t* wbuf,
-                           int pass, uint32_t* queue_out, uint32_t* queue_cursor) {
+WQ_HDN void wq_seed_thread(const WqDevIndex& ix, const WqParams& p, const WqBatchDev& b, const WqWork& wk, uint32_t r, uint64_t* wbuf) {
     WqCtx c;
     c.ix = &ix;
     c.p = &p;
@@ -169,19 +186,7 @@ WQ_HDN void wq_seed_thread(const WqDevIndex& ix, const WqParams& p, const WqBatc
     int64_t sp = 2;
     int readloc = 0;
     bool strand = true;
-    WqSeedState st;
-    if (pass == 0) wq_seed_init(c, true, st);
-    else { const WqSeed q = wk.seeds[r]; st.ctry = q.cnt; st.curpos = (int)q.sp; st.stage = q._pad; }      // parked loop state
-    // pass 0: the first window (forward, then reverse complement if needed); the last pass: everything that is left
-    int cnt = wq_seed_locate(c, badq, true, !p.is_stranded, sp, readloc, strand, st, queue_out ? 2 : 0x7fffffff);
-    if (cnt < 0) {                    // another search is needed: park the loop state and queue the read
-        WqSeed s;
-        s.sp = (uint32_t)st.curpos; s.cnt = (uint8_t)st.ctry; s.readloc = 0; s.strand = 1; s._pad = (uint8_t)st.stage; s.hit_base = 0;
-        wk.seeds[r] = s;
-        uint32_t slot = WQ_ATOMIC_ADD_U32(queue_cursor, 1);
-        queue_out[slot] = r;
-        return;
-    }
+    int cnt = wq_seed_locate(c, badq, true, !p.is_stranded, sp, readloc, strand);
     wq_seed_finish(ix, wk, r, cnt, sp, readloc, strand);
 }
 
@@ -208,9 +213,8 @@ WQ_HDN void wq_extend_thread(const WqDevIndex& ix, const WqParams& p, const WqBa
     h.strand = a.strand;
     h.flags = (uint8_t)((a.isvalid ? 1 : 0) | (wq_isvalid(a) ? 2 : 0) | (c.overflow ? 8 : 0));
     if (c.overflow) h.flags &= (uint8_t)~2;
-    uint32_t ps = 0;
+    const uint32_t ps = WQ_ALLOC(&wk.cursors[1], a.npath);
     if (a.npath) {
-        ps = WQ_ATOMIC_ADD_U32(&wk.cursors[1], a.npath);
         if (ps + a.npath <= wk.pool_cap) {
             for (int i = 0; i < a.npath; i++) {
                 wq_align_node o;
@@ -445,9 +449,7 @@ WQ_HDN void wq_seed_pe_thread(const WqDevIndex& ix, const WqParams& p, const WqB
     int64_t fsp = 2, rsp = 2;
     int floc = 0, rloc = 0;
     bool strand = true, dummy = true;
-    WqSeedState st;
-    wq_seed_init(c, true, st);
-    int fcnt = wq_seed_locate(c, badq, true, !p.is_stranded, fsp, floc, strand, st, 0x7fffffff);
+    int fcnt = wq_seed_locate(c, badq, true, !p.is_stranded, fsp, floc, strand);
     // mate 2: one strand only; reverse-complemented first when the pair is expected head to head
     wq_load_read(c, br, r);
     bool flip2 = (p.is_pair_rc && strand) || (!p.is_pair_rc && !strand);
@@ -456,12 +458,10 @@ WQ_HDN void wq_seed_pe_thread(const WqDevIndex& ix, const WqParams& p, const WqB
         wq_revcomp(c.w, c.readlen);
         c.flipped = 1;
         wq_badq(c, p.seed_min_qual, true, badq);
-        wq_seed_init(c, false, st);
-        rcnt = wq_seed_locate(c, badq, false, false, rsp, rloc, dummy, st, 0x7fffffff);
+        rcnt = wq_seed_locate(c, badq, false, false, rsp, rloc, dummy);
     } else {
         wq_badq(c, p.seed_min_qual, false, badq);
-        wq_seed_init(c, true, st);
-        rcnt = wq_seed_locate(c, badq, true, false, rsp, rloc, dummy, st, 0x7fffffff);
+        rcnt = wq_seed_locate(c, badq, true, false, rsp, rloc, dummy);
     }
     int64_t fpos[WQ_MAX_TOLERATE], rpos[WQ_MAX_TOLERATE];
     for (int k = 0; k < fcnt; k++) fpos[k] = wq_sa_value(ix, fsp + k) + 1;
@@ -496,8 +496,8 @@ WQ_HDN void wq_seed_pe_thread(const WqDevIndex& ix, const WqParams& p, const WqB
     sd.strand = strand ? 1 : 0;
     sd._pad = 0;
     sd.hit_base = 0;
+    const uint32_t base = WQ_ALLOC(&wk.cursors[0], np);
     if (np > 0) {
-        uint32_t base = WQ_ATOMIC_ADD_U32(&wk.cursors[0], np);
         sd.hit_base = base;
         for (int k = 0; k < np; k++)
             if (base + k < wk.hit_cap) {
@@ -544,9 +544,8 @@ WQ_HDN void wq_extend_pe_thread(const WqDevIndex& ix, const WqParams& p, const W
     h.strand = a.strand;
     h.flags = (uint8_t)((a.isvalid ? 1 : 0) | (wq_isvalid(a) ? 2 : 0) | (c.overflow ? 8 : 0));
     if (c.overflow) h.flags &= (uint8_t)~2;
-    uint32_t ps = 0;
+    const uint32_t ps = WQ_ALLOC(&wk.cursors[1], a.npath);
     if (a.npath) {
-        ps = WQ_ATOMIC_ADD_U32(&wk.cursors[1], a.npath);
         if (ps + a.npath <= wk.pool_cap) {
             for (int i = 0; i < a.npath; i++) {
                 wq_align_node o;
