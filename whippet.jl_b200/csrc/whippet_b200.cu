@@ -53,6 +53,26 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
+// Events of one gene group.  Group 0 = genes that no multi-map class names: assign_ambig! cannot change their counts, so
+// their events are built on the host threads while the transcript EM kernel runs and their PSI EM launch overlaps
+// assign_ambig!.  Group 1 = the remaining genes, built after assign_ambig!.
+struct WqEvPart { std::vector<WqEventRec> recs; WqPsiProblems P; WqEventPool pool; };
+struct WqEvBatch {
+    std::vector<WqEvPart> parts;         // one per host thread, contiguous gene ranges in gene order
+    WqPsiProblems P;                     // problems of all parts, concatenated
+    std::vector<long> pshift;            // first problem of every part in P
+    WqEmScratch dev;                     // device arrays of this group's PSI launch (the two launches overlap in time)
+    double* psi = nullptr; int32_t* its = nullptr; size_t psi_cap = 0, its_cap = 0;     // pinned results
+    bool built = false, launched = false;
+    int64_t readlen = -1;
+    cudaError_t ensure_pinned(size_t npsi, size_t nits) {
+        if (npsi > psi_cap) { if (psi) cudaFreeHost(psi); psi = nullptr; psi_cap = 0; cudaError_t e = cudaMallocHost(&psi, (npsi + npsi / 4 + 16) * 8); if (e != cudaSuccess) return e; psi_cap = npsi + npsi / 4 + 16; }
+        if (nits > its_cap) { if (its) cudaFreeHost(its); its = nullptr; its_cap = 0; cudaError_t e = cudaMallocHost(&its, (nits + nits / 4 + 16) * 4); if (e != cudaSuccess) return e; its_cap = nits + nits / 4 + 16; }
+        return cudaSuccess;
+    }
+    void release() { dev.release(); if (psi) cudaFreeHost(psi); if (its) cudaFreeHost(its); psi = nullptr; its = nullptr; psi_cap = its_cap = 0; }
+};
+
 struct wq_handle {
     int device = 0;
     cudaStream_t stream = nullptr, copy_stream = nullptr, own_stream = nullptr;
@@ -81,6 +101,7 @@ struct wq_handle {
     WqEmScratch em_scratch;
     std::vector<WqEventRec> ev_recs; std::vector<double> ev_values; std::vector<uint64_t> ev_path_ptr{0}; std::vector<uint32_t> ev_path_nodes;
     bool events_done = false;
+    WqEvBatch ev_batch[2];       // event problems of the genes no multi-map read touches (built while the transcript EM runs) / of the others
     DevBuf<uint64_t> d_ck, d_cv, d_ck2, d_cv2; DevBuf<uint32_t> d_ckoff; DevBuf<uint8_t> d_cubtmp;
     bool hq_valid = false;
     uint32_t chunk_reads = 1u << 22;
@@ -261,11 +282,89 @@ void wq_destroy(wq_handle* h) {
     }
     h->d_seeds.release(); h->d_hit_read.release(); h->d_hit_s.release(); h->d_hit_s2.release(); h->d_hit_gene.release(); h->d_pending.release(); h->d_pending2.release();
     h->d_cursors.release(); h->d_hits.release(); h->d_pool.release();
-    h->em_scratch.release(); h->d_ck.release(); h->d_cv.release(); h->d_ck2.release(); h->d_cv2.release(); h->d_ckoff.release(); h->d_cubtmp.release();
+    h->em_scratch.release(); h->ev_batch[0].release(); h->ev_batch[1].release(); h->d_ck.release(); h->d_cv.release(); h->d_ck2.release(); h->d_cv2.release(); h->d_ckoff.release(); h->d_cubtmp.release();
     if (h->h_cursors) cudaFreeHost(h->h_cursors);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     delete h;
+}
+
+
+// the derived quant state (classes, EM results, event batches) no longer matches the count stores
+static void reset_quant_ex(wq_handle* h) {
+    for (WqEvBatch& B : h->ev_batch) {
+        if (B.launched) cudaStreamSynchronize(h->stream);       // its result copies target B's pinned buffers
+        B.built = B.launched = false;
+    }
+    h->hx = WqHostQuantEx();
+    h->events_done = false;
+}
+
+// Event construction (src/events.jl:760-800) for the genes of one group on the host threads, then the parts' EM problems
+// are concatenated (prefix sums + parallel copies).  Needs finalized edges.
+static void wq_build_event_batch(wq_handle* h, int64_t readlen, int group, WqEvBatch& B) {
+    const WqHostQuantEx& X = h->hx;
+    const uint32_t G = h->H.G;
+    unsigned nt = wq_host_threads();
+    if (G < 2048) nt = 1;
+    B.parts.clear();
+    B.parts.resize(nt);
+    auto run = [&](const std::function<void(unsigned)>& f) {
+        if (nt == 1) { f(0); return; }
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < nt; t++) th.emplace_back(f, t);
+        for (auto& x : th) x.join();
+    };
+    run([&](unsigned t) {
+        const uint32_t g_lo = 1 + (uint32_t)((uint64_t)G * t / nt), g_hi = (uint32_t)((uint64_t)G * (t + 1) / nt);
+        size_t e = std::lower_bound(X.edge_key.begin(), X.edge_key.end(), (uint64_t)g_lo << 32) - X.edge_key.begin();
+        WqGeneEvents V{h->H, X.node_value, 0, {}};
+        WqEvPart& part = B.parts[t];
+        for (uint32_t g = g_lo; g <= g_hi; g++) {
+            if ((int)(X.gene_dirty[g] != 0) != group) continue;
+            V.g = g;
+            V.edges.clear();
+            while (e < X.edge_key.size() && (X.edge_key[e] >> 32) < g) e++;
+            for (; e < X.edge_key.size() && (X.edge_key[e] >> 32) == g; e++) {
+                if (wq_edge_is_circ(X.edge_key[e])) continue;
+                V.edges.push_back(WqGeneEdge{(uint32_t)((X.edge_key[e] >> 16) & 0xFFFF), (uint32_t)(X.edge_key[e] & 0xFFFF), X.edge_value[e]});
+            }
+            wq_gene_events(V, readlen, part.recs, part.P, part.pool);
+        }
+        for (auto& r : part.recs) r.batch = (uint8_t)group;
+    });
+    std::vector<WqPsiProblems::Sizes> at(nt + 1);
+    B.pshift.assign(nt, 0);
+    for (unsigned t = 0; t < nt; t++) {
+        const WqPsiProblems::Sizes z = B.parts[t].P.sizes();
+        at[t + 1].ev = at[t].ev + z.ev; at[t + 1].paths = at[t].paths + z.paths; at[t + 1].amb = at[t].amb + z.amb; at[t + 1].amb_paths = at[t].amb_paths + z.amb_paths;
+        B.pshift[t] = (long)at[t].ev;
+    }
+    B.P.resize_total(at[nt]);
+    run([&](unsigned t) { B.P.place(B.parts[t].P, at[t]); });
+    B.built = true;
+    B.launched = false;
+    B.readlen = readlen;
+}
+
+// one batched PSI EM launch for every problem of the group; results land in the group's pinned buffers when the stream
+// reaches them (no host wait here)
+static int wq_launch_event_batch(wq_handle* h, WqEvBatch& B) {
+    WqPsiProblems& P = B.P;
+    B.launched = false;
+    if (!P.size()) return 0;
+    CK(B.ensure_pinned(P.count.size(), P.size()));
+    wq_psi_batch b;
+    memset(&b, 0, sizeof b);
+    b.n_events = (uint32_t)P.size();
+    b.path_ptr = P.path_ptr.data(); b.n_inc = P.n_inc.data(); b.path_count = P.count.data(); b.path_length = P.length.data();
+    b.amb_ptr = P.amb_ptr.data(); b.amb_path_ptr = P.amb_path_ptr.data(); b.amb_paths = P.amb_paths.data(); b.amb_mult = P.amb_mult.data();
+    b.is_tandem = P.is_tandem.data(); b.readlen = B.readlen; b.sig = 4; b.maxit = 1500;
+    b.psi = B.psi; b.iterations = B.its;
+    std::string err = wq_run_em_psi(b, B.dev, h->stream, &h->launches, /*wait=*/false);
+    if (!err.empty()) return fail(-13, err);
+    B.launched = true;
+    return 0;
 }
 
 int wq_quant_reset(wq_handle* h) {
@@ -283,7 +382,7 @@ int wq_quant_reset(wq_handle* h) {
     CK(cudaMemsetAsync(h->d_kcursor.p, 0, 8, s));
     CK(cudaStreamSynchronize(s));
     h->hq = WqHostQuant();
-    h->hx = WqHostQuantEx(); h->events_done = false;
+    reset_quant_ex(h);
     h->hq_valid = false;
     return 0;
 }
@@ -530,7 +629,7 @@ static int align_impl(wq_handle* h, const wq_align_param* ap, const wq_read_batc
     const uint32_t n = reads->n_reads;
     if (n == 0) return 0;
     h->hq_valid = false;
-    h->hx = WqHostQuantEx(); h->events_done = false;
+    reset_quant_ex(h);
     for (auto& m : h->last_kernel_ms) m = 0;
     const wq_read_batch* src[2] = {reads, mates};
     const int nb = pe ? 2 : 1;
@@ -761,7 +860,7 @@ int wq_counts_merge(wq_handle* h, const wq_counts* c, const wq_keyed* longs, con
     if (!h) return fail(-1, "null handle");
     if (int rc = sync_host_quant(h)) return rc;
     WqHostQuant& Q = h->hq;
-    h->hx = WqHostQuantEx(); h->events_done = false;
+    reset_quant_ex(h);
     if (c) {
         if (c->node_count) {
             if (c->n_nodes != Q.node.size()) return fail(-1, "node count vector has the wrong length");
@@ -825,7 +924,7 @@ int wq_sparse_merge(wq_handle* h, const void* buf, uint64_t len) {
     if (len < 40) return fail(-1, "sparse buffer too short");
     if (int rc = sync_host_quant(h)) return rc;
     WqHostQuant& Q = h->hq;
-    h->hx = WqHostQuantEx(); h->events_done = false;
+    reset_quant_ex(h);
     auto pad8 = [](uint64_t b) { return (b + 7) & ~7ull; };
     const uint8_t* p = (const uint8_t*)buf;
     uint64_t hdr[5];
@@ -877,8 +976,18 @@ int wq_em_tpm(wq_handle* h, const wq_em_param* p, double* tpm, double* count, do
     if (int rc = sync_host_quant(h)) return rc;
     CK(cudaSetDevice(h->device));
     WqTimer tm_("em_tpm (classes + kernel)");
-    std::string err = wq_run_em_tpm(h->H, h->iso, h->hq, h->hx, h->em_scratch, *p, h->stream, &h->launches, tpm, count, genetpm, iterations);
+    // While the EM kernel runs, the host threads build the events of every gene that assign_ambig! cannot touch
+    // (process_events, bin/whippet-quant.jl:181, uses the same read length as the EM, :163-165).
+    static const bool overlap_on = !(getenv("WQ_EVENTS_OVERLAP") && atoi(getenv("WQ_EVENTS_OVERLAP")) == 0);
+    const std::function<void()> overlap = [&]() {
+        WqTimer t2("  events of untouched genes (under the EM kernel)");
+        wq_finalize_edges(h->hq, h->hx);
+        wq_build_event_batch(h, p->readlen, 0, h->ev_batch[0]);
+    };
+    std::string err = wq_run_em_tpm(h->H, h->iso, h->hq, h->hx, h->em_scratch, *p, h->stream, &h->launches, tpm, count, genetpm, iterations,
+                                    overlap_on ? &overlap : nullptr);
     if (!err.empty()) return fail(-11, err);
+    if (h->ev_batch[0].built) { if (int rc = wq_launch_event_batch(h, h->ev_batch[0])) return rc; }     // overlaps assign_ambig!
     return 0;
 }
 
@@ -921,64 +1030,65 @@ int wq_process_events(wq_handle* h, int64_t readlen, wq_events_out* out) {
     if (!X.edges_final) wq_finalize_edges(h->hq, X);
     if (!h->events_done) {
         WqTimer tm_("process_events");
-        const uint32_t G = h->H.G;
-        unsigned nt = wq_host_threads();
-        if (G < 2048) nt = 1;
-        struct Part { std::vector<WqEventRec> recs; WqPsiProblems P; WqEventPool pool; };
-        std::vector<Part> parts(nt);
-        auto work = [&](unsigned t) {
-            const uint32_t g_lo = 1 + (uint32_t)((uint64_t)G * t / nt), g_hi = (uint32_t)((uint64_t)G * (t + 1) / nt);
-            size_t e = std::lower_bound(X.edge_key.begin(), X.edge_key.end(), (uint64_t)g_lo << 32) - X.edge_key.begin();
-            WqGeneEvents V{h->H, X.node_value, 0, {}};
-            for (uint32_t g = g_lo; g <= g_hi; g++) {
-                V.g = g;
-                V.edges.clear();
-                while (e < X.edge_key.size() && (X.edge_key[e] >> 32) < g) e++;
-                for (; e < X.edge_key.size() && (X.edge_key[e] >> 32) == g; e++) {
-                    if (wq_edge_is_circ(X.edge_key[e])) continue;
-                    V.edges.push_back(WqGeneEdge{(uint32_t)((X.edge_key[e] >> 16) & 0xFFFF), (uint32_t)(X.edge_key[e] & 0xFFFF), X.edge_value[e]});
-                }
-                wq_gene_events(V, readlen, parts[t].recs, parts[t].P, parts[t].pool);
+        const bool prof = getenv("WQ_PROFILE") != nullptr;
+        auto lap = [&](const char* what) { if (prof) fprintf(stderr, "[wq]   events: %-22s %9.3f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tm_.t0).count()); };
+        WqEvBatch& B0 = h->ev_batch[0];
+        WqEvBatch& B1 = h->ev_batch[1];
+        if (!B0.built || B0.readlen != readlen) {            // not built under the EM kernel (or for another read length)
+            if (B0.launched) CK(cudaStreamSynchronize(h->stream));
+            wq_build_event_batch(h, readlen, 0, B0);
+            if (int rc = wq_launch_event_batch(h, B0)) return rc;
+        }
+        wq_build_event_batch(h, readlen, 1, B1);
+        if (int rc = wq_launch_event_batch(h, B1)) return rc;
+        lap("+ touched genes built");
+        // records in gene order: per host-thread gene range, merge the two groups' records by gene
+        const size_t nparts = B0.parts.size();
+        if (B1.parts.size() != nparts) return fail(-14, "event batches were built with different host thread counts");
+        std::vector<size_t> rec_at(nparts + 1, 0);
+        std::vector<uint64_t> pool_paths(2 * nparts + 1, 0), pool_nodes(2 * nparts + 1, 0);      // group-major: (group, part)
+        for (size_t t = 0; t < nparts; t++) rec_at[t + 1] = rec_at[t] + B0.parts[t].recs.size() + B1.parts[t].recs.size();
+        for (int g = 0; g < 2; g++) for (size_t t = 0; t < nparts; t++) {
+            const WqEventPool& pl = h->ev_batch[g].parts[t].pool;
+            const size_t k = g * nparts + t;
+            pool_paths[k + 1] = pool_paths[k] + (pl.path_ptr.size() - 1);
+            pool_nodes[k + 1] = pool_nodes[k] + pl.path_nodes.size();
+        }
+        h->ev_recs.resize(rec_at[nparts]);
+        h->ev_path_ptr.resize(pool_paths[2 * nparts] + 1);
+        h->ev_path_nodes.resize(pool_nodes[2 * nparts]);
+        h->ev_path_ptr[0] = 0;
+        auto place = [&](size_t t) {
+            const std::vector<WqEventRec>*rs[2] = {&B0.parts[t].recs, &B1.parts[t].recs};
+            size_t i[2] = {0, 0}, o = rec_at[t];
+            while (i[0] < rs[0]->size() || i[1] < rs[1]->size()) {
+                const int g = (i[1] >= rs[1]->size() || (i[0] < rs[0]->size() && (*rs[0])[i[0]].gene < (*rs[1])[i[1]].gene)) ? 0 : 1;
+                WqEventRec r = (*rs[g])[i[g]++];
+                if (r.problem >= 0) r.problem += h->ev_batch[g].pshift[t];
+                r.path_first += (uint32_t)pool_paths[g * nparts + t];
+                h->ev_recs[o++] = r;
+            }
+            for (int g = 0; g < 2; g++) {
+                const WqEventPool& pl = h->ev_batch[g].parts[t].pool;
+                const size_t k = g * nparts + t;
+                for (size_t q = 1; q < pl.path_ptr.size(); q++) h->ev_path_ptr[pool_paths[k] + q] = pool_nodes[k] + pl.path_ptr[q];
+                std::copy(pl.path_nodes.begin(), pl.path_nodes.end(), h->ev_path_nodes.begin() + pool_nodes[k]);
             }
         };
-        if (nt == 1) work(0);
-        else { std::vector<std::thread> th; for (unsigned t = 0; t < nt; t++) th.emplace_back(work, t); for (auto& x : th) x.join(); }
-        if (getenv("WQ_PROFILE")) fprintf(stderr, "[wq]   events: host build        %9.3f ms (%u threads)\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tm_.t0).count(), nt);
-        // concatenate the per-thread parts (flat arrays: a few memcpy-like appends)
-        h->ev_recs.clear(); h->ev_path_ptr.assign(1, 0); h->ev_path_nodes.clear();
-        size_t nrec = 0;
-        for (auto& pt : parts) nrec += pt.recs.size();
-        h->ev_recs.reserve(nrec);
-        WqPsiProblems P;
-        for (auto& pt : parts) {
-            long shift = 0;
-            P.append(pt.P, shift);
-            const uint32_t pshift = (uint32_t)h->ev_path_ptr.size() - 1;
-            const uint64_t nshift = h->ev_path_nodes.size();
-            for (size_t i = 1; i < pt.pool.path_ptr.size(); i++) h->ev_path_ptr.push_back(nshift + pt.pool.path_ptr[i]);
-            h->ev_path_nodes.insert(h->ev_path_nodes.end(), pt.pool.path_nodes.begin(), pt.pool.path_nodes.end());
-            for (auto& r : pt.recs) { if (r.problem >= 0) r.problem += shift; r.path_first += pshift; h->ev_recs.push_back(r); }
-        }
-        if (getenv("WQ_PROFILE")) fprintf(stderr, "[wq]   events: + concat          %9.3f ms (%zu records, %zu EM problems)\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tm_.t0).count(), h->ev_recs.size(), P.size());
-        // one batched launch for every EM problem
-        std::vector<double> psi(P.count.size());
-        std::vector<int32_t> its(P.size());
-        if (P.size()) {
-            wq_psi_batch b;
-            memset(&b, 0, sizeof b);
-            b.n_events = (uint32_t)P.size();
-            b.path_ptr = P.path_ptr.data(); b.n_inc = P.n_inc.data(); b.path_count = P.count.data(); b.path_length = P.length.data();
-            b.amb_ptr = P.amb_ptr.data(); b.amb_path_ptr = P.amb_path_ptr.data(); b.amb_paths = P.amb_paths.data(); b.amb_mult = P.amb_mult.data();
-            b.is_tandem = P.is_tandem.data(); b.readlen = readlen; b.sig = 4; b.maxit = 1500;
-            b.psi = psi.data(); b.iterations = its.data();
-            std::string err = wq_run_em_psi(b, h->em_scratch, h->stream, &h->launches);
-            if (!err.empty()) return fail(-13, err);
-        }
-        if (getenv("WQ_PROFILE")) fprintf(stderr, "[wq]   events: + PSI EM kernel   %9.3f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tm_.t0).count());
+        if (nparts == 1) place(0);
+        else { std::vector<std::thread> th; for (size_t t = 0; t < nparts; t++) th.emplace_back(place, t); for (auto& x : th) x.join(); }
+        lap("+ records merged");
+        CK(cudaStreamSynchronize(h->stream));                // both PSI launches and their result copies
+        B0.launched = B1.launched = false;
+        lap("+ PSI EM kernels done");
+        if (prof) fprintf(stderr, "[wq]   events: %zu records, %zu + %zu EM problems (untouched + touched genes)\n", h->ev_recs.size(), B0.P.size(), B1.P.size());
         // finish the records (src/events.jl:776-796)
         h->ev_values.clear();
-        h->ev_values.reserve(psi.size() + nrec);
+        h->ev_values.reserve(B0.P.count.size() + B1.P.count.size() + h->ev_recs.size());
         for (auto& r : h->ev_recs) {
+            const WqPsiProblems& P = h->ev_batch[r.batch].P;
+            const double* psi = h->ev_batch[r.batch].psi;
+            const int32_t* its = h->ev_batch[r.batch].its;
             r.value_start = (uint32_t)h->ev_values.size();
             if (r.kind == 2) {
                 bool ok = r.problem >= 0;
@@ -994,7 +1104,7 @@ int wq_process_events(wq_handle* h, int64_t readlen, wq_events_out* out) {
                 double s = 0.0;
                 for (uint32_t i = p0; i < p0 + ni; i++) s += psi[i];
                 r.psi = s;
-                h->ev_values.insert(h->ev_values.end(), psi.begin() + p0, psi.begin() + p1);
+                h->ev_values.insert(h->ev_values.end(), psi + p0, psi + p1);
                 r.iterations_ = its[r.problem];
                 r.kind = (0.0 <= r.psi && r.psi <= 1.0 && r.total > 0) ? 1 : 0;
             } else if (r.kind == 1) {

@@ -16,6 +16,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <functional>
 #include <map>
 #include <string>
 #include <thread>
@@ -103,10 +104,18 @@ static inline std::string wq_host_build_classes(const WqHostIndex& H, const WqIs
     };
     // ---- multi-map classes, key order ----
     std::vector<int32_t> ids;
+    X.gene_dirty.assign(G + 1, 0);
     for (size_t m = 0; m < hq.multis.size(); m++) {
         const uint32_t* key = hq.multis.key(m);
         const uint32_t nh = key[0] & 0xFFFF;
         size_t pos = 1;
+        for (uint32_t h = 0; h < nh; h++) {
+            WqKeyPath kp;
+            pos = wq_key_next(key, pos, kp);
+            if (kp.gene < 1 || kp.gene > G) return "multi-map record names a gene out of range";
+            X.gene_dirty[kp.gene] = 1;
+        }
+        pos = 1;
         ids.clear();
         bool all = true;
         for (uint32_t h = 0; h < nh && all; h++) {
@@ -270,27 +279,38 @@ static inline std::string wq_host_assign_ambig_impl(const WqHostIndex& H, const 
 }
 
 // ------------------------------------------------------------------------------------------ device
+// Device layout of the class set: classes are PERMUTED so that every block of the cooperative grid owns one contiguous
+// range of classes and therefore one contiguous range of class members (multi-map classes, the slow ones to converge, are
+// dealt round-robin over the blocks; isoform classes follow in gene order, balanced by member count).  The canonical class
+// order only matters for the per-isoform accumulation, and that order lives in the contribution lists (con_*).
 struct WqEmDev {
     uint32_t I, C, ntiles;
     const double* leff;          // [I] max(length - readlen, 1)
     double* count;               // [I] unique + finished-class counts (in/out)
-    double* tpm;                 // [I] in: calculate_tpm!(quant) of the unique counts; out: final
+    double* tpm;                 // [I] out: rounded TPM
     double* tpm_raw;             // [I]
-    const uint32_t* cls_ptr;     // [C+1]
-    const int32_t*  cls_iso;
-    double*         prop;
+    const uint32_t* cls_ptr;     // [C+1] member ranges (device class order)
+    const int32_t*  cls_iso;     // [M] member isoforms
+    const uint32_t* mem_cls;     // [M] class of every member
+    double*         prop;        // [M]
     const double*   cls_count;   // [C]
     uint8_t*        state;       // [C] 0 active, 1 finished in this sweep, 2 finished earlier (or never active)
-    const uint32_t* con_ptr;     // [I+1] contributions of each isoform, in class order
-    const uint32_t* con_cls;
-    const uint32_t* con_pos;
+    const uint32_t* blk_cls;     // [grid+1] class range of every block
+    const uint32_t* blk_mem;     // [grid+1] member range of every block
+    double* vals;                // [M] scratch: TPM of every member of an active class
+    double* psum;                // [C] scratch
+    int*    cdiff;               // [C] scratch: some proportion of the class changed
+    const uint32_t* con_ptr;     // [I+1] contributions of each isoform, in canonical class order
+    const uint2*    con_rec;     // [M] (device class, member position)
+    double* w_all;               // [M] scratch: prop * count of unfinished classes, else +0
+    double* w_fin;               // [M] scratch: prop * count of classes finished in this sweep, else +0
     double* partial;             // [ntiles]
-    int*    flags;               // [3] rotating "tpm changed" flags
+    int*    flags;               // [4] rotating "tpm changed" flags + [3] "tpm != ones" of the first calculate_tpm!
     int64_t* it_out;
     int64_t maxit;
     double sc_tpm, sc_prop;      // 10^sig, 10^4
     int    sig;
-    int    first_differs;        // tpm != ones(I) before the first sweep
+    long long* dbg;              // optional [grid][4] clock totals (gather, barrier 1, normalise + sweep, barrier 2) when WQ_EM_TIMING is set
 };
 
 __device__ __forceinline__ double wq_round_sc(double x, double sc) {   // Base.round(x, digits=d)
@@ -298,85 +318,149 @@ __device__ __forceinline__ double wq_round_sc(double x, double sc) {   // Base.r
     return isfinite(r) ? r : x;
 }
 
-// adjacent-pair tree over a 1024-slot shared tile: buf[0] = sum
-__device__ __forceinline__ double wq_tile_tree(double* buf, int t) {
-    for (int stride = 1; stride < 1024; stride <<= 1) {
-        __syncthreads();
-        if ((t & (2 * stride - 1)) == 0) buf[t] = __dadd_rn(buf[t], buf[t + stride]);
-    }
+// adjacent-pair tree over the 1024 values of a block (one per thread), every thread gets the sum.  The pairing is the
+// declared canonical one (v[t] + v[t + stride] for t a multiple of 2*stride): the first five levels are warp shuffles
+// (lane l adds lane l + stride; only lanes that are multiples of 2*stride carry tree nodes), then the 32 warp sums
+// go through shared memory and one more warp-level pass.
+__device__ __forceinline__ double wq_tile_tree(double v, double* buf, int t) {
+    #pragma unroll
+    for (int stride = 1; stride < 32; stride <<= 1) v = __dadd_rn(v, __shfl_down_sync(0xFFFFFFFFu, v, stride));
+    __syncthreads();                                   // buf may still be read from a previous call
+    if ((t & 31) == 0) buf[t >> 5] = v;
     __syncthreads();
-    double r = buf[0];
-    __syncthreads();
-    return r;
+    double w = buf[t & 31];
+    #pragma unroll
+    for (int stride = 1; stride < 32; stride <<= 1) w = __dadd_rn(w, __shfl_down_sync(0xFFFFFFFFu, w, stride));
+    return __shfl_sync(0xFFFFFFFFu, w, 0);
 }
 
+// calculate_tpm!, src/quant.jl:655-667, for one isoform given the raw value count/leff and the folded sum
+__device__ __forceinline__ double wq_tpm_value(const WqEmDev& d, double raw, double rpk) {
+    double v = __ddiv_rn(__dmul_rn(raw, 1000000.0), rpk);
+    if (d.sig > 0) v = wq_round_sc(v, d.sc_tpm);
+    return v;
+}
+
+// Persistent cooperative kernel, TWO grid barriers per EM iteration, every pass parallel over class MEMBERS (the
+// divisions and roundings), with only the order-defining additions left sequential per class / per isoform:
+//   phase B(it)  per tile of 1024 isoforms: (1) every contribution computes prop * count of its class; (2) every isoform
+//                adds its contributions up in canonical class order (temp counts; classes finished in this sweep are
+//                folded into `count`), raw TPM, tile sum                                                    | grid.sync
+//   phase A(it)  every block folds the tile sums, normalises + rounds its isoforms and raises the "changed" flag, then
+//                sweeps its classes FOR ITERATION it+1: (1) TPM of every member, (2) per-class sum in member order,
+//                (3) new rounded proportion of every member (copy_isdone!), (4) class state                 | grid.sync
+// The sweep reads TPM values recomputed from tpm_raw and the folded sum (the same arithmetic as the normalise step, so the
+// same bits) because other blocks are still writing d.tpm in that phase.  The sweep of iteration it+1 is issued before the
+// loop condition of iteration `it` is known; when the loop then ends because the rounded TPM vector did not change, that
+// extra sweep recomputed every proportion from an unchanged TPM vector (identical values) and only moved class states,
+// which nothing reads afterwards.  It is skipped when the loop ends at maxit.
 __global__ void __launch_bounds__(1024) wq_k_em_tpm(WqEmDev d) {
     cg::grid_group grid = cg::this_grid();
-    __shared__ double buf[1024];
-    __shared__ int s_changed;
+    __shared__ double buf[32];
     const int t = threadIdx.x;
     const uint32_t gtid = blockIdx.x * blockDim.x + t, gsz = gridDim.x * blockDim.x;
-    int64_t it = 1;
-    bool differs = d.first_differs != 0;
-    while (differs && it < d.maxit) {
-        // ---- sweep over classes: new proportions from the current TPM (maximize step) ----
-        if (gtid == 0) d.flags[(it + 1) % 3] = 0;
-        for (uint32_t c = gtid; c < d.C; c += gsz) {
-            uint8_t st = d.state[c];
-            if (st == 1) { d.state[c] = 2; continue; }
-            if (st != 0 || it == 1) continue;
-            const uint32_t b = d.cls_ptr[c], e = d.cls_ptr[c + 1];
-            double psum = 0.0;
-            for (uint32_t k = b; k < e; k++) psum = __dadd_rn(psum, d.tpm[d.cls_iso[k]]);
-            bool different = false;
-            for (uint32_t k = b; k < e; k++) {          // copy_isdone!, src/quant.jl:702-712
-                double val = wq_round_sc(__ddiv_rn(d.tpm[d.cls_iso[k]], psum), d.sc_prop);
-                if (val != d.prop[k]) different = true;
-                d.prop[k] = isnan(val) ? 0.0 : val;
-            }
-            if (!different || psum == 0.0) d.state[c] = 1;
+    const uint32_t c_lo = d.blk_cls[blockIdx.x], c_hi = d.blk_cls[blockIdx.x + 1];
+    const uint32_t m_lo = d.blk_mem[blockIdx.x], m_hi = d.blk_mem[blockIdx.x + 1];
+    // ---- calculate_tpm!(quant, readlen) on the unique counts (bin/whippet-quant.jl:163); differs = tpm != ones(I) ----
+    for (uint32_t tile = blockIdx.x; tile < d.ntiles; tile += gridDim.x) {
+        const uint32_t i = tile * 1024 + t;
+        double raw = 0.0;
+        if (i < d.I) { raw = __ddiv_rn(d.count[i], d.leff[i]); d.tpm_raw[i] = raw; }
+        double s = wq_tile_tree(raw, buf, t);
+        if (t == 0) d.partial[tile] = s;
+    }
+    grid.sync();
+    {
+        double rpk = fmax(wq_tile_tree((uint32_t)t < d.ntiles ? d.partial[t] : 0.0, buf, t), 1.0);
+        int mine = 0;
+        for (uint32_t i = gtid; i < d.I; i += gsz) {
+            double v = wq_tpm_value(d, d.tpm_raw[i], rpk);
+            if (v != 1.0) mine = 1;
+            d.tpm[i] = v;
         }
-        grid.sync();
-        // ---- gather per isoform in class order, raw TPM, tile sums ----
+        if (__syncthreads_or(mine) && t == 0) atomicOr(&d.flags[3], 1);
+    }
+    grid.sync();
+    int64_t it = 1;
+    bool differs = d.flags[3] != 0;
+    while (differs && it < d.maxit) {
+        // ---- B: contributions, then the per-isoform sums in class order, raw TPM, tile sums ----
+        long long tk0 = 0, tk1 = 0, tk2 = 0, tk3 = 0;
+        if (d.dbg && t == 0) tk0 = clock64();
+        if (gtid == 0) d.flags[(it + 1) % 3] = 0;
         for (uint32_t tile = blockIdx.x; tile < d.ntiles; tile += gridDim.x) {
-            const uint32_t i = tile * 1024 + t;
+            const uint32_t i = tile * 1024 + t, i_end = min(d.I, tile * 1024 + 1024);
+            const uint32_t j_lo = d.con_ptr[tile * 1024], j_hi = d.con_ptr[i_end];
+            for (uint32_t j = j_lo + t; j < j_hi; j += 1024) {
+                const uint2 rec = d.con_rec[j];
+                const uint8_t st = d.state[rec.x];
+                double v = 0.0;
+                if (st != 2) v = __dmul_rn(d.prop[rec.y], d.cls_count[rec.x]);
+                d.w_all[j] = v;
+                d.w_fin[j] = st == 1 ? v : 0.0;
+            }
+            __syncthreads();
             double raw = 0.0;
             if (i < d.I) {
-                double ct = d.count[i], cn = ct;
-                for (uint32_t k = d.con_ptr[i]; k < d.con_ptr[i + 1]; k++) {
-                    const uint32_t c = d.con_cls[k];
-                    const uint8_t st = d.state[c];
-                    if (st == 2) continue;
-                    const double v = __dmul_rn(d.prop[d.con_pos[k]], d.cls_count[c]);
-                    ct = __dadd_rn(ct, v);
-                    if (st == 1) cn = __dadd_rn(cn, v);
+                const double c0 = d.count[i];
+                double ct = c0, cn = c0;
+                // adding +0.0 for a finished class leaves the (non-negative) sums bit-identical to skipping it
+                for (uint32_t j = d.con_ptr[i], je = d.con_ptr[i + 1]; j < je; j++) {
+                    ct = __dadd_rn(ct, d.w_all[j]);
+                    cn = __dadd_rn(cn, d.w_fin[j]);
                 }
-                d.count[i] = cn;
+                if (cn != c0) d.count[i] = cn;
                 raw = __ddiv_rn(ct, d.leff[i]);
                 d.tpm_raw[i] = raw;
             }
-            buf[t] = raw;
-            double s = wq_tile_tree(buf, t);
+            double s = wq_tile_tree(raw, buf, t);
             if (t == 0) d.partial[tile] = s;
         }
+        if (d.dbg && t == 0) tk1 = clock64();
         grid.sync();
-        // ---- normalise + round (calculate_tpm!, src/quant.jl:655-667); every block folds the tile sums itself ----
-        buf[t] = (uint32_t)t < d.ntiles ? d.partial[t] : 0.0;
-        double rpk = wq_tile_tree(buf, t);
-        rpk = fmax(rpk, 1.0);
-        if (t == 0) s_changed = 0;
-        __syncthreads();
+        if (d.dbg && t == 0) tk2 = clock64();
+        // ---- A: normalise + round (calculate_tpm!); every block folds the tile sums itself ----
+        const double rpk = fmax(wq_tile_tree((uint32_t)t < d.ntiles ? d.partial[t] : 0.0, buf, t), 1.0);
         int mine = 0;
         for (uint32_t i = gtid; i < d.I; i += gsz) {
-            double v = __ddiv_rn(__dmul_rn(d.tpm_raw[i], 1000000.0), rpk);
-            if (d.sig > 0) v = wq_round_sc(v, d.sc_tpm);
+            double v = wq_tpm_value(d, d.tpm_raw[i], rpk);
             if (v != d.tpm[i]) mine = 1;
             d.tpm[i] = v;
         }
-        if (mine) s_changed = 1;
-        __syncthreads();
-        if (t == 0 && s_changed) atomicOr(&d.flags[it % 3], 1);
+        // ---- sweep over this block's classes for iteration it+1 (maximize step, src/quant.jl:726-749) ----
+        if (it + 1 < d.maxit) {
+            for (uint32_t k = m_lo + t; k < m_hi; k += 1024)
+                if (d.state[d.mem_cls[k]] == 0) d.vals[k] = wq_tpm_value(d, d.tpm_raw[d.cls_iso[k]], rpk);
+            __syncthreads();
+            for (uint32_t c = c_lo + t; c < c_hi; c += 1024) {
+                if (d.state[c] != 0) continue;
+                double ps = 0.0;
+                for (uint32_t k = d.cls_ptr[c], ke = d.cls_ptr[c + 1]; k < ke; k++) ps = __dadd_rn(ps, d.vals[k]);
+                d.psum[c] = ps;
+                d.cdiff[c] = 0;
+            }
+            __syncthreads();
+            for (uint32_t k = m_lo + t; k < m_hi; k += 1024) {          // copy_isdone!, src/quant.jl:702-712
+                const uint32_t c = d.mem_cls[k];
+                if (d.state[c] != 0) continue;
+                const double val = wq_round_sc(__ddiv_rn(d.vals[k], d.psum[c]), d.sc_prop);
+                if (val != d.prop[k]) d.cdiff[c] = 1;
+                d.prop[k] = isnan(val) ? 0.0 : val;
+            }
+            __syncthreads();
+            for (uint32_t c = c_lo + t; c < c_hi; c += 1024) {
+                const uint8_t st = d.state[c];
+                if (st == 1) d.state[c] = 2;
+                else if (st == 0 && (!d.cdiff[c] || d.psum[c] == 0.0)) d.state[c] = 1;
+            }
+        }
+        if (__syncthreads_or(mine) && t == 0) atomicOr(&d.flags[it % 3], 1);
+        if (d.dbg && t == 0) tk3 = clock64();
         grid.sync();
+        if (d.dbg && t == 0) {
+            long long* o = d.dbg + 4 * blockIdx.x;
+            o[0] += tk1 - tk0; o[1] += tk2 - tk1; o[2] += tk3 - tk2; o[3] += clock64() - tk3;
+        }
         differs = d.flags[it % 3] != 0;
         it += 1;
     }
@@ -385,7 +469,7 @@ __global__ void __launch_bounds__(1024) wq_k_em_tpm(WqEmDev d) {
 
 // grow-only device scratch kept in the handle (cudaMalloc/cudaFree per call would serialise the device)
 struct WqEmScratch {
-    void* p[16] = {nullptr}; size_t cap[16] = {0};
+    void* p[24] = {nullptr}; size_t cap[24] = {0};
     template <class T> cudaError_t get(int slot, size_t n, T** out) {
         size_t bytes = std::max<size_t>(1, n) * sizeof(T);
         if (bytes > cap[slot]) {
@@ -403,14 +487,33 @@ struct WqEmScratch {
         if (e == cudaSuccess && !v.empty()) e = cudaMemcpyAsync(*out, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s);
         return e;
     }
-    void release() { for (int i = 0; i < 16; i++) { if (p[i]) cudaFree(p[i]); p[i] = nullptr; cap[i] = 0; } }
+    // side streams for kernels that may run next to each other (created on first use, on the current device)
+    cudaStream_t side[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t fork = nullptr, join[3] = {nullptr, nullptr, nullptr};
+    cudaError_t side_streams() {
+        if (fork) return cudaSuccess;
+        for (int i = 0; i < 3; i++) {
+            cudaError_t e = cudaStreamCreateWithFlags(&side[i], cudaStreamNonBlocking);
+            if (e != cudaSuccess) return e;
+            e = cudaEventCreateWithFlags(&join[i], cudaEventDisableTiming);
+            if (e != cudaSuccess) return e;
+        }
+        return cudaEventCreateWithFlags(&fork, cudaEventDisableTiming);
+    }
+    void release() {
+        for (int i = 0; i < 24; i++) { if (p[i]) cudaFree(p[i]); p[i] = nullptr; cap[i] = 0; }
+        for (int i = 0; i < 3; i++) { if (side[i]) cudaStreamDestroy(side[i]); if (join[i]) cudaEventDestroy(join[i]); side[i] = nullptr; join[i] = nullptr; }
+        if (fork) cudaEventDestroy(fork);
+        fork = nullptr;
+    }
 };
 
 #define WQ_EMCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return std::string(#call) + ": " + cudaGetErrorString(e_); } while (0)
 
 static inline std::string wq_run_em_tpm(const WqHostIndex& H, const WqIsoIndex& S, WqHostQuant& hq, WqHostQuantEx& X, WqEmScratch& M,
                                         const wq_em_param& p, cudaStream_t stream, uint64_t* launches,
-                                        double* tpm_out, double* count_out, double* genetpm_out, int64_t* iterations) {
+                                        double* tpm_out, double* count_out, double* genetpm_out, int64_t* iterations,
+                                        const std::function<void()>* while_running = nullptr) {
     if (p.sig < 0 || p.sig > 12) return "sig out of range";
     const bool prof = getenv("WQ_PROFILE") != nullptr;
     if (!X.built) {
@@ -428,68 +531,111 @@ static inline std::string wq_run_em_tpm(const WqHostIndex& H, const WqIsoIndex& 
     if (ntiles > 1024) return "more than 1048576 isoforms";
     std::vector<double> leff(I), tpm(I), count = X.iso_count;
     for (uint32_t i = 0; i < I; i++) leff[i] = std::max((double)(S.length[i] - p.readlen), 1.0);
-    // contributions (isoform -> class positions) in class order
-    std::vector<uint32_t> con_ptr(I + 1, 0), con_cls(C.iso.size()), con_pos(C.iso.size());
-    for (int32_t i : C.iso) con_ptr[i + 1]++;
-    for (uint32_t i = 0; i < I; i++) con_ptr[i + 1] += con_ptr[i];
-    {
-        std::vector<uint32_t> cur(con_ptr.begin(), con_ptr.end() - 1);
-        for (uint32_t c = 0; c < NC; c++)
-            for (uint32_t k = C.ptr[c]; k < C.ptr[c + 1]; k++) { uint32_t s = cur[C.iso[k]]++; con_cls[s] = c; con_pos[s] = k; }
-    }
-    WqEmDev d;
-    double *d_leff, *d_count, *d_tpm, *d_raw, *d_prop, *d_ccount, *d_partial;
-    uint32_t *d_cptr, *d_conptr, *d_concls, *d_conpos;
-    int32_t* d_ciso;
-    uint8_t *d_state, *d_parked;
-    int* d_flags;
-    int64_t* d_it;
-    WQ_EMCK(M.put(0, leff, &d_leff, stream)); WQ_EMCK(M.put(1, count, &d_count, stream));
-    WQ_EMCK(M.get(2, I, &d_tpm)); WQ_EMCK(M.get(3, I, &d_raw));
-    WQ_EMCK(M.put(4, C.prop, &d_prop, stream)); WQ_EMCK(M.put(5, C.count, &d_ccount, stream)); WQ_EMCK(M.get(6, 1024, &d_partial));
-    WQ_EMCK(M.put(7, C.ptr, &d_cptr, stream)); WQ_EMCK(M.put(8, con_ptr, &d_conptr, stream)); WQ_EMCK(M.put(9, con_cls, &d_concls, stream));
-    WQ_EMCK(M.put(10, con_pos, &d_conpos, stream)); WQ_EMCK(M.put(11, C.iso, &d_ciso, stream)); WQ_EMCK(M.put(12, C.state, &d_state, stream));
-    WQ_EMCK(M.get(13, 4, &d_flags)); WQ_EMCK(M.get(14, 1, &d_it));
-    std::vector<uint8_t> parked(NC, 2);
-    WQ_EMCK(M.put(15, parked, &d_parked, stream));
-    WQ_EMCK(cudaMemsetAsync(d_tpm, 0, std::max<size_t>(1, I) * 8, stream));
-    WQ_EMCK(cudaMemsetAsync(d_flags, 0, 4 * sizeof(int), stream));
-    d.I = I; d.C = NC; d.ntiles = ntiles; d.leff = d_leff; d.count = d_count; d.tpm = d_tpm; d.tpm_raw = d_raw;
-    d.cls_ptr = d_cptr; d.cls_iso = d_ciso; d.prop = d_prop; d.cls_count = d_ccount; d.state = d_state;
-    d.con_ptr = d_conptr; d.con_cls = d_concls; d.con_pos = d_conpos; d.partial = d_partial; d.flags = d_flags;
-    d.it_out = d_it; d.sig = (int)p.sig; d.sc_tpm = std::pow(10.0, (double)p.sig); d.sc_prop = 10000.0;
     int dev = 0, sms = 0, per_sm = 0;
     WQ_EMCK(cudaGetDevice(&dev));
     WQ_EMCK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     WQ_EMCK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wq_k_em_tpm, 1024, 0));
     if (per_sm < 1) return "EM kernel does not fit on an SM";
-    int grid = sms * per_sm;
-    if (const char* ev = getenv("WQ_EM_BLOCKS")) grid = std::max(1, std::min(grid, atoi(ev)));
-    // calculate_tpm!(quant, readlen) before gene_em! (bin/whippet-quant.jl:163): one sweep with every class parked
+    int grid = sms;                              // one block per SM: a second resident block only lengthens the grid barrier
+    if (const char* ev = getenv("WQ_EM_BLOCKS")) grid = std::max(1, std::min(sms * per_sm, atoi(ev)));
+    // ---- device class order: block b owns dorder[blk_cls[b] .. blk_cls[b+1]) ----
+    const uint32_t NM = (uint32_t)C.iso.size(), nb = (uint32_t)grid, nmulti = C.n_multi;
+    std::vector<uint32_t> dorder(NC), dinv(NC), blk_cls(nb + 1, 0), blk_mem(nb + 1, 0);
     {
-        WqEmDev d0 = d;
-        d0.state = d_parked; d0.maxit = 2; d0.first_differs = 1;
-        void* args0[] = {&d0};
-        WQ_EMCK(cudaLaunchCooperativeKernel((void*)wq_k_em_tpm, dim3(grid), dim3(1024), args0, 0, stream));
-        if (launches) *launches += 1;
+        // isoform classes: contiguous canonical ranges with ~equal member counts
+        const uint64_t iso_members = NM - C.ptr[nmulti];
+        std::vector<uint32_t> iso_cut(nb + 1, NC);
+        iso_cut[0] = nmulti;
+        uint32_t c = nmulti;
+        for (uint32_t b = 1; b < nb; b++) {
+            const uint64_t want = C.ptr[nmulti] + iso_members * b / nb;
+            while (c < NC && C.ptr[c] < want) c++;
+            iso_cut[b] = c;
+        }
+        uint32_t k = 0;
+        for (uint32_t b = 0; b < nb; b++) {
+            blk_cls[b] = k;
+            for (uint32_t m = b; m < nmulti; m += nb) dorder[k++] = m;
+            for (uint32_t q = iso_cut[b]; q < iso_cut[b + 1]; q++) dorder[k++] = q;
+        }
+        blk_cls[nb] = k;
     }
-    WQ_EMCK(cudaMemcpyAsync(tpm.data(), d_tpm, I * 8, cudaMemcpyDeviceToHost, stream));
-    WQ_EMCK(cudaStreamSynchronize(stream));
-    bool differs = false;                        // `tpm_temp != quant.tpm` with tpm_temp = ones (src/quant.jl:724,752)
-    for (uint32_t i = 0; i < I; i++) if (tpm[i] != 1.0) { differs = true; break; }
-    d.maxit = p.maxit; d.first_differs = differs ? 1 : 0;
+    std::vector<uint32_t> d_cptr_h(NC + 1, 0), mem_cls(NM), mpos(NM);       // mpos: canonical member position -> device position
+    std::vector<int32_t> d_iso_h(NM);
+    std::vector<double> d_prop_h(NM), d_ccount_h(NC);
+    std::vector<uint8_t> d_state_h(NC);
+    for (uint32_t k = 0; k < NC; k++) {
+        const uint32_t c = dorder[k];
+        dinv[c] = k;
+        d_cptr_h[k + 1] = d_cptr_h[k] + (C.ptr[c + 1] - C.ptr[c]);
+        d_ccount_h[k] = C.count[c];
+        d_state_h[k] = C.state[c];
+        for (uint32_t q = C.ptr[c], o = d_cptr_h[k]; q < C.ptr[c + 1]; q++, o++) { d_iso_h[o] = C.iso[q]; d_prop_h[o] = C.prop[q]; mem_cls[o] = k; mpos[q] = o; }
+    }
+    for (uint32_t b = 0; b <= nb; b++) blk_mem[b] = d_cptr_h[blk_cls[b]];
+    // contributions (isoform -> class members) in canonical class order
+    std::vector<uint32_t> con_ptr(I + 1, 0);
+    std::vector<uint2> con_rec(NM);
+    for (int32_t i : C.iso) con_ptr[i + 1]++;
+    for (uint32_t i = 0; i < I; i++) con_ptr[i + 1] += con_ptr[i];
+    {
+        std::vector<uint32_t> cur(con_ptr.begin(), con_ptr.end() - 1);
+        for (uint32_t c = 0; c < NC; c++)
+            for (uint32_t q = C.ptr[c]; q < C.ptr[c + 1]; q++) con_rec[cur[C.iso[q]]++] = make_uint2(dinv[c], mpos[q]);
+    }
+    WqEmDev d;
+    double *d_leff, *d_count, *d_tpm, *d_raw, *d_prop, *d_ccount, *d_partial, *d_vals, *d_psum, *d_wall, *d_wfin;
+    uint32_t *d_cptr, *d_conptr, *d_memcls, *d_blkcls, *d_blkmem;
+    uint2* d_conrec;
+    int32_t* d_ciso;
+    uint8_t* d_state;
+    int *d_flags, *d_cdiff;
+    int64_t* d_it;
+    WQ_EMCK(M.put(0, leff, &d_leff, stream)); WQ_EMCK(M.put(1, count, &d_count, stream));
+    WQ_EMCK(M.get(2, I, &d_tpm)); WQ_EMCK(M.get(3, I, &d_raw));
+    WQ_EMCK(M.put(4, d_prop_h, &d_prop, stream)); WQ_EMCK(M.put(5, d_ccount_h, &d_ccount, stream)); WQ_EMCK(M.get(6, 1024, &d_partial));
+    WQ_EMCK(M.put(7, d_cptr_h, &d_cptr, stream)); WQ_EMCK(M.put(8, con_ptr, &d_conptr, stream)); WQ_EMCK(M.put(9, con_rec, &d_conrec, stream));
+    WQ_EMCK(M.put(10, mem_cls, &d_memcls, stream)); WQ_EMCK(M.put(11, d_iso_h, &d_ciso, stream)); WQ_EMCK(M.put(12, d_state_h, &d_state, stream));
+    WQ_EMCK(M.get(13, 4, &d_flags)); WQ_EMCK(M.get(14, 1, &d_it));
+    WQ_EMCK(M.put(15, blk_cls, &d_blkcls, stream)); WQ_EMCK(M.put(16, blk_mem, &d_blkmem, stream));
+    WQ_EMCK(M.get(17, NM, &d_vals)); WQ_EMCK(M.get(18, NC, &d_psum)); WQ_EMCK(M.get(19, NC, &d_cdiff));
+    WQ_EMCK(M.get(20, NM, &d_wall)); WQ_EMCK(M.get(21, NM, &d_wfin));
+    WQ_EMCK(cudaMemsetAsync(d_tpm, 0, std::max<size_t>(1, I) * 8, stream));
     WQ_EMCK(cudaMemsetAsync(d_flags, 0, 4 * sizeof(int), stream));
+    d.I = I; d.C = NC; d.ntiles = ntiles; d.leff = d_leff; d.count = d_count; d.tpm = d_tpm; d.tpm_raw = d_raw;
+    d.cls_ptr = d_cptr; d.cls_iso = d_ciso; d.mem_cls = d_memcls; d.prop = d_prop; d.cls_count = d_ccount; d.state = d_state;
+    d.blk_cls = d_blkcls; d.blk_mem = d_blkmem; d.vals = d_vals; d.psum = d_psum; d.cdiff = d_cdiff;
+    d.con_ptr = d_conptr; d.con_rec = d_conrec; d.w_all = d_wall; d.w_fin = d_wfin; d.partial = d_partial; d.flags = d_flags;
+    d.it_out = d_it; d.sig = (int)p.sig; d.sc_tpm = std::pow(10.0, (double)p.sig); d.sc_prop = 10000.0;
+    d.maxit = p.maxit;
+    d.dbg = nullptr;
+    const bool timing = getenv("WQ_EM_TIMING") != nullptr;
+    if (timing) { WQ_EMCK(M.get(22, (size_t)grid * 4, &d.dbg)); WQ_EMCK(cudaMemsetAsync(d.dbg, 0, (size_t)grid * 32, stream)); }
     void* args[] = {&d};
     auto tk0 = std::chrono::steady_clock::now();
     WQ_EMCK(cudaLaunchCooperativeKernel((void*)wq_k_em_tpm, dim3(grid), dim3(1024), args, 0, stream));
     if (launches) *launches += 1;
+    if (while_running) (*while_running)();       // host work that does not depend on the EM result overlaps the kernel
     int64_t it = 0;
     WQ_EMCK(cudaMemcpyAsync(&it, d_it, 8, cudaMemcpyDeviceToHost, stream));
     WQ_EMCK(cudaMemcpyAsync(tpm.data(), d_tpm, I * 8, cudaMemcpyDeviceToHost, stream));
     WQ_EMCK(cudaMemcpyAsync(count.data(), d_count, I * 8, cudaMemcpyDeviceToHost, stream));
-    WQ_EMCK(cudaMemcpyAsync(C.prop.data(), d_prop, C.prop.size() * 8, cudaMemcpyDeviceToHost, stream));
-    WQ_EMCK(cudaMemcpyAsync(C.state.data(), d_state, C.state.size(), cudaMemcpyDeviceToHost, stream));
+    WQ_EMCK(cudaMemcpyAsync(d_prop_h.data(), d_prop, (size_t)NM * 8, cudaMemcpyDeviceToHost, stream));
+    WQ_EMCK(cudaMemcpyAsync(d_state_h.data(), d_state, NC, cudaMemcpyDeviceToHost, stream));
     WQ_EMCK(cudaStreamSynchronize(stream));
+    if (timing) {
+        std::vector<long long> dbg((size_t)grid * 4);
+        WQ_EMCK(cudaMemcpy(dbg.data(), d.dbg, dbg.size() * 8, cudaMemcpyDeviceToHost));
+        const char* nm[4] = {"gather", "barrier 1", "normalise+sweep", "barrier 2"};
+        for (int k = 0; k < 4; k++) {
+            long long mn = dbg[k], mx = dbg[k], sum = 0;
+            for (int b = 0; b < grid; b++) { mn = std::min(mn, dbg[4 * b + k]); mx = std::max(mx, dbg[4 * b + k]); sum += dbg[4 * b + k]; }
+            fprintf(stderr, "[wq]     em %-16s cycles/iteration per block: min %8.0f avg %8.0f max %8.0f\n", nm[k],
+                    (double)mn / std::max<int64_t>(1, it - 1), (double)sum / grid / std::max<int64_t>(1, it - 1), (double)mx / std::max<int64_t>(1, it - 1));
+        }
+    }
+    for (uint32_t q = 0; q < NM; q++) C.prop[q] = d_prop_h[mpos[q]];
+    for (uint32_t c = 0; c < NC; c++) C.state[c] = d_state_h[dinv[c]];
     if (prof) fprintf(stderr, "[wq]   em kernel (grid %d, %lld it) %9.3f ms\n", grid, (long long)it,
         std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tk0).count());
     X.tpm = tpm; X.iso_count = count;
@@ -523,10 +669,26 @@ struct WqPsiDev {
 };
 
 __device__ __forceinline__ double wq_pow10(const WqPsiDev& d, int k) { return (k >= 0 && k <= 22) ? d.p10[k] : pow(10.0, (double)k); }
+// hidigit(x, 10) = 1 + floor(log10|x|) (Base.round(x, sigdigits=n)).  The decade is taken from the binary exponent
+// and fixed up against exact powers of ten for |x| >= 1 and correctly rounded ones below; values within an ulp of a
+// power of ten may land in the neighbouring decade compared with a libm log10, which cannot change the rounded
+// result (both decades round such a value to that same power of ten).
+__device__ __forceinline__ int wq_hidigit(const WqPsiDev& d, double ax) {
+    if (ax >= 1e-22 && ax < 1e22) {
+        int e = ilogb(ax);                                   // 2^e <= ax < 2^(e+1)
+        int h = (int)floor((double)e * 0.30102999566398120) + 1;   // candidate: 10^(h-1) <= ax < 10^h, at most one off
+        // pw(k) = 10^k
+        auto pw = [&](int k) { return k >= 0 ? d.p10[k] : __ddiv_rn(1.0, d.p10[-k]); };
+        if (ax >= pw(h)) h += 1;
+        else if (ax < pw(h - 1)) h -= 1;
+        return h;
+    }
+    return 1 + (int)floor(log10(ax));
+}
 // Base.round(x, sigdigits = sig)
 __device__ __forceinline__ double wq_round_sig(const WqPsiDev& d, double x, int sig) {
     if (!isfinite(x) || x == 0.0) return x;
-    int h = 1 + (int)floor(log10(fabs(x)));
+    int h = wq_hidigit(d, fabs(x));
     int digits = sig - h;
     double r;
     if (digits >= 0) { double sc = wq_pow10(d, digits); r = __ddiv_rn(rint(__dmul_rn(x, sc)), sc); }
@@ -535,16 +697,17 @@ __device__ __forceinline__ double wq_round_sig(const WqPsiDev& d, double x, int 
     return r;
 }
 
-// One warp per event.  Element-wise work (copies, the division + significant-digit rounding of every path,
-// the additions of one ambiguous set, whose paths are distinct) is spread over the lanes; every sum is formed
-// sequentially in path order by all lanes redundantly, so the arithmetic is the per-event sequential one.
-// Small events keep psi / previous psi / temp counts in a shared-memory slab, larger ones in global scratch.
+// One warp per event (events with more than 16 paths).  Element-wise work (copies, the division + significant-digit
+// rounding of every path, the additions of one ambiguous set, whose paths are distinct) is spread over the lanes; every sum
+// is formed sequentially in path order by all lanes redundantly, so the arithmetic is the per-event sequential one.
+// Events up to 48 paths keep psi / previous psi / temp counts in a shared-memory slab, larger ones in global scratch.
 #define WQ_PSI_SLAB 48            // paths per warp slab
-__global__ void __launch_bounds__(128) wq_k_em_psi(const WqPsiDev d) {
+__global__ void __launch_bounds__(128) wq_k_em_psi(const WqPsiDev d, const uint32_t* __restrict__ list, const uint32_t n_list) {
     __shared__ double slab[4][3 * WQ_PSI_SLAB];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t e = blockIdx.x * 4 + warp;
-    if (e >= d.n_events) return;
+    const uint32_t slot = blockIdx.x * 4 + warp;
+    if (slot >= n_list) return;
+    const uint32_t e = list[slot];
     const uint32_t p0 = d.path_ptr[e], p1 = d.path_ptr[e + 1], ni = d.n_inc[e];
     const uint32_t a0 = d.amb_ptr[e], a1 = d.amb_ptr[e + 1];
     const bool tandem = d.is_tandem[e] != 0;
@@ -612,7 +775,73 @@ __global__ void __launch_bounds__(128) wq_k_em_psi(const WqPsiDev d) {
     if (lane == 0) d.iterations[e] = (int32_t)it;
 }
 
-static inline std::string wq_run_em_psi(wq_psi_batch& b, WqEmScratch& M, cudaStream_t stream, uint64_t* launches) {
+// G lanes per event, 32/G events per warp, for events with at most G paths (more than 99 % of them have at most 4): lane i of
+// the group OWNS path i, so psi / previous psi / temp count live in registers and there is no shared or global scratch.
+// Sums over paths are formed in path order with group shuffles by every lane redundantly (the per-event sequential
+// arithmetic); an ambiguous set adds its share to the lane that owns the path.  Every loop has a group-uniform trip count
+// and every shuffle / vote names the group's lanes only, so the groups of a warp may diverge freely (an event that needs
+// 1500 sweeps does not hold back its neighbours' lanes beyond the warp's lifetime).
+template <int G>
+__global__ void __launch_bounds__(128) wq_k_em_psi_group(const WqPsiDev d, const uint32_t* __restrict__ list, const uint32_t n_list) {
+    const uint32_t lane = threadIdx.x & 31, sub = lane % G, base = lane - sub;
+    const uint32_t slot = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+    if (slot >= n_list) return;
+    const unsigned gmask = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << base;
+    const uint32_t e = list[slot];
+    const uint32_t p0 = d.path_ptr[e], np = d.path_ptr[e + 1] - p0, ni = d.n_inc[e];
+    const uint32_t a0 = d.amb_ptr[e], a1 = d.amb_ptr[e + 1];
+    const bool tandem = d.is_tandem[e] != 0;
+    const bool own = sub < np;
+    const double cnt = own ? d.count[p0 + sub] : 0.0;
+    const double len = own ? d.length[p0 + sub] : 1.0;
+    const double den = tandem ? fmax(__dsub_rn(len, d.readlen), 1.0) : len;
+    double psi = 0.0, prev = 0.0, ct = cnt;
+    auto normalise = [&](int sig) {
+        const double q = __ddiv_rn(ct, den);
+        double total;
+        if (tandem) { total = 0.0; for (uint32_t i = 0; i < np; i++) total = __dadd_rn(total, __shfl_sync(gmask, q, base + i)); }
+        else {
+            double se = 0.0, si = 0.0;
+            for (uint32_t i = ni; i < np; i++) se = __dadd_rn(se, __shfl_sync(gmask, q, base + i));
+            for (uint32_t i = 0; i < ni; i++) si = __dadd_rn(si, __shfl_sync(gmask, q, base + i));
+            total = __dadd_rn(se, si);
+        }
+        const double r = __ddiv_rn(q, total);
+        psi = sig > 0 ? wq_round_sig(d, r, sig) : r;
+    };
+    auto differs = [&]() { return __any_sync(gmask, own && prev != psi) != 0; };
+    if (!tandem) normalise(0);                      // calculate_psi!(inc, exc, counts) before spliced_em!
+    int64_t it = 1;
+    for (;;) {
+        if (!tandem && !(differs() && it < d.maxit)) break;
+        ct = cnt; prev = psi;
+        for (uint32_t a = a0; a < a1; a++) {
+            const uint32_t b = d.amb_path_ptr[a], n = d.amb_path_ptr[a + 1] - b;
+            double psum = 1.0;
+            bool mine = false;
+            if (it > 1) psum = 0.0;
+            for (uint32_t k = 0; k < n; k++) {
+                const uint32_t pth = d.amb_paths[b + k];
+                if (it > 1) psum = __dadd_rn(psum, __shfl_sync(gmask, psi, base + pth));
+                if (pth == sub) mine = true;
+            }
+            if (mine) {
+                // first sweep: ones(n)/n over prop_sum = 1.0; later sweeps: current psi over their sum (src/events.jl:869-886)
+                const double bs = it > 1 ? psi : __ddiv_rn(1.0, (double)n);
+                ct = __dadd_rn(ct, __dmul_rn(__ddiv_rn(bs, psum), d.amb_mult[a]));
+            }
+        }
+        normalise(d.sig);
+        if (tandem) { if (differs() && it < d.maxit) it += 1; else break; }
+        else it += 1;
+    }
+    if (own) { d.psi[p0 + sub] = psi; d.ctemp[p0 + sub] = ct; }
+    if (sub == 0) d.iterations[e] = (int32_t)it;
+}
+
+// `wait` = false leaves the launch and its result copies in flight on `stream` (the result buffers must then be pinned
+// host memory and stay alive until the stream has been synchronised)
+static inline std::string wq_run_em_psi(wq_psi_batch& b, WqEmScratch& M, cudaStream_t stream, uint64_t* launches, bool wait = true) {
     const uint32_t E = b.n_events;
     if (E == 0) return "";
     if (!b.path_ptr || !b.n_inc || !b.amb_ptr || !b.amb_path_ptr || !b.is_tandem || !b.psi || !b.iterations) return "wq_psi_batch has null arrays";
@@ -641,12 +870,37 @@ static inline std::string wq_run_em_psi(wq_psi_batch& b, WqEmScratch& M, cudaStr
     d.path_ptr = d_pp; d.n_inc = d_ni; d.count = d_cnt; d.length = d_len; d.amb_ptr = d_ap; d.amb_path_ptr = d_app;
     d.amb_paths = d_apaths; d.amb_mult = d_mult; d.is_tandem = d_tan; d.psi = d_psi; d.prev = d_prev; d.ctemp = d_ct;
     d.amb_prop = d_prop; d.iterations = d_it;
-    wq_k_em_psi<<<(E + 3) / 4, 128, 0, stream>>>(d);
-    if (launches) *launches += 1;
-    WQ_EMCK(cudaGetLastError());
+    // events by path count: groups of 4 / 8 / 16 lanes, one warp beyond that.  The classes run concurrently on side streams
+    // (a handful of large events that need all 1500 sweeps would otherwise add their whole latency to the batch).
+    std::vector<uint32_t> order(E);
+    uint32_t nclass[4] = {0, 0, 0, 0}, cbase[5] = {0, 0, 0, 0, 0};
+    auto cls_of = [&](uint32_t e) { const uint32_t np = b.path_ptr[e + 1] - b.path_ptr[e]; return np <= 4 ? 0 : np <= 8 ? 1 : np <= 16 ? 2 : 3; };
+    for (uint32_t e = 0; e < E; e++) nclass[cls_of(e)]++;
+    for (int c = 0; c < 4; c++) cbase[c + 1] = cbase[c] + nclass[c];
+    { uint32_t cur[4] = {cbase[0], cbase[1], cbase[2], cbase[3]}; for (uint32_t e = 0; e < E; e++) order[cur[cls_of(e)]++] = e; }
+    uint32_t* d_list;
+    WQ_EMCK(up(14, order.data(), E * 4ull, (void**)&d_list));
+    WQ_EMCK(M.side_streams());
+    WQ_EMCK(cudaEventRecord(M.fork, stream));
+    int used = 0;
+    for (int c = 0; c < 4; c++) {
+        if (!nclass[c]) continue;
+        cudaStream_t ss = used == 0 ? stream : M.side[used - 1];
+        if (used > 0) WQ_EMCK(cudaStreamWaitEvent(ss, M.fork, 0));
+        const uint32_t n = nclass[c];
+        const uint32_t* lst = d_list + cbase[c];
+        if (c == 0) wq_k_em_psi_group<4><<<(n + 31) / 32, 128, 0, ss>>>(d, lst, n);
+        else if (c == 1) wq_k_em_psi_group<8><<<(n + 15) / 16, 128, 0, ss>>>(d, lst, n);
+        else if (c == 2) wq_k_em_psi_group<16><<<(n + 7) / 8, 128, 0, ss>>>(d, lst, n);
+        else wq_k_em_psi<<<(n + 3) / 4, 128, 0, ss>>>(d, lst, n);
+        if (launches) *launches += 1;
+        WQ_EMCK(cudaGetLastError());
+        if (used > 0) { WQ_EMCK(cudaEventRecord(M.join[used - 1], ss)); WQ_EMCK(cudaStreamWaitEvent(stream, M.join[used - 1], 0)); }
+        used++;
+    }
     WQ_EMCK(cudaMemcpyAsync(b.psi, d_psi, P * 8ull, cudaMemcpyDeviceToHost, stream));
     if (b.path_total) WQ_EMCK(cudaMemcpyAsync(b.path_total, d_ct, P * 8ull, cudaMemcpyDeviceToHost, stream));
     WQ_EMCK(cudaMemcpyAsync(b.iterations, d_it, E * 4ull, cudaMemcpyDeviceToHost, stream));
-    WQ_EMCK(cudaStreamSynchronize(stream));
+    if (wait) WQ_EMCK(cudaStreamSynchronize(stream));
     return "";
 }

@@ -29,16 +29,28 @@ static inline uint8_t wq_motif(uint8_t cur, uint8_t next) {
     return T[cur][next];
 }
 
-struct WqBitWin {                       // node set as bits over [lo, lo + 64*words)
-    uint32_t lo = 0;
-    std::vector<uint64_t> w;
-    void init(uint32_t lo_, uint32_t hi_) { lo = lo_; w.assign((hi_ - lo_) / 64 + 1, 0); }
-    void set(uint32_t n) { w[(n - lo) >> 6] |= 1ull << ((n - lo) & 63); }
-    bool has(uint32_t n) const { uint32_t k = n - lo; return n >= lo && (k >> 6) < w.size() && ((w[k >> 6] >> (k & 63)) & 1); }
-    uint32_t first() const { for (size_t i = 0; i < w.size(); i++) if (w[i]) return lo + (uint32_t)(64 * i + __builtin_ctzll(w[i])); return 0; }
-    uint32_t last() const { for (size_t i = w.size(); i-- > 0;) if (w[i]) return lo + (uint32_t)(64 * i + 63 - __builtin_clzll(w[i])); return 0; }
-    bool operator==(const WqBitWin& o) const { return w == o.w; }
-    void unite(const WqBitWin& o) { for (size_t i = 0; i < w.size(); i++) w[i] |= o.w[i]; }
+struct WqBitWin {                       // node set as bits over [lo, lo + 64*nw); windows up to 128 nodes need no heap
+    uint32_t lo = 0, nw = 0;
+    uint64_t in[2] = {0, 0};
+    std::vector<uint64_t> big;
+    uint64_t* p() { return nw <= 2 ? in : big.data(); }
+    const uint64_t* p() const { return nw <= 2 ? in : big.data(); }
+    void init(uint32_t lo_, uint32_t hi_) {
+        lo = lo_; nw = (hi_ - lo_) / 64 + 1;
+        in[0] = in[1] = 0;
+        if (nw > 2) big.assign(nw, 0); else big.clear();
+    }
+    void set(uint32_t n) { p()[(n - lo) >> 6] |= 1ull << ((n - lo) & 63); }
+    bool has(uint32_t n) const { uint32_t k = n - lo; return n >= lo && (k >> 6) < nw && ((p()[k >> 6] >> (k & 63)) & 1); }
+    uint32_t first() const { const uint64_t* w = p(); for (uint32_t i = 0; i < nw; i++) if (w[i]) return lo + 64 * i + (uint32_t)__builtin_ctzll(w[i]); return 0; }
+    uint32_t last() const { const uint64_t* w = p(); for (uint32_t i = nw; i-- > 0;) if (w[i]) return lo + 64 * i + 63 - (uint32_t)__builtin_clzll(w[i]); return 0; }
+    bool operator==(const WqBitWin& o) const {
+        if (nw != o.nw) return false;
+        const uint64_t *a = p(), *b = o.p();
+        for (uint32_t i = 0; i < nw; i++) if (a[i] != b[i]) return false;
+        return true;
+    }
+    void unite(const WqBitWin& o) { uint64_t* a = p(); const uint64_t* b = o.p(); for (uint32_t i = 0; i < nw; i++) a[i] |= b[i]; }
     // both ends present and nothing strictly between (src/quant.jl:68-79)
     bool adjacent(uint32_t a, uint32_t b) const {
         if (!has(a) || !has(b)) return false;
@@ -46,7 +58,8 @@ struct WqBitWin {                       // node set as bits over [lo, lo + 64*wo
         return true;
     }
     void list(std::vector<uint32_t>& out) const {
-        for (size_t i = 0; i < w.size(); i++) { uint64_t x = w[i]; while (x) { out.push_back(lo + (uint32_t)(64 * i + __builtin_ctzll(x))); x &= x - 1; } }
+        const uint64_t* w = p();
+        for (uint32_t i = 0; i < nw; i++) { uint64_t x = w[i]; while (x) { out.push_back(lo + 64 * i + (uint32_t)__builtin_ctzll(x)); x &= x - 1; } }
     }
 };
 
@@ -70,6 +83,7 @@ struct WqEventRec {                     // one record per visited node (include/
     int32_t iterations_ = 0;
     uint32_t path_first = 0, n_paths = 0;           // into the owning WqEventPool: utr paths, or inclusion then exclusion paths
     uint32_t value_start = 0, n_values = 0;         // into the finished value array
+    uint8_t batch = 0;                              // which gene group built it (0: genes no multi-map read touches, 1: the others)
 };
 
 struct WqEventPool {                    // node ids of all paths of a batch of records, CSR
@@ -91,6 +105,26 @@ struct WqPsiProblems {                  // flattened wq_psi_batch inputs
         amb_ptr.push_back((uint32_t)amb_mult.size());
         is_tandem.push_back(tandem ? 1 : 0);
         return (long)size() - 1;
+    }
+    // parallel concatenation: sizes() of every part -> prefix sums -> resize_total() once -> place() per part (any thread)
+    struct Sizes { size_t ev = 0, paths = 0, amb = 0, amb_paths = 0; };
+    Sizes sizes() const { Sizes z; z.ev = size(); z.paths = count.size(); z.amb = amb_mult.size(); z.amb_paths = amb_paths.size(); return z; }
+    void resize_total(const Sizes& z) {
+        path_ptr.resize(z.ev + 1); n_inc.resize(z.ev); amb_ptr.resize(z.ev + 1); amb_path_ptr.resize(z.amb + 1); amb_paths.resize(z.amb_paths);
+        count.resize(z.paths); length.resize(z.paths); amb_mult.resize(z.amb); is_tandem.resize(z.ev);
+        path_ptr[0] = 0; amb_ptr[0] = 0; amb_path_ptr[0] = 0;
+    }
+    void place(const WqPsiProblems& o, const Sizes& at) {
+        const uint32_t pb = (uint32_t)at.paths, ab = (uint32_t)at.amb, apb = (uint32_t)at.amb_paths;
+        std::copy(o.count.begin(), o.count.end(), count.begin() + at.paths);
+        std::copy(o.length.begin(), o.length.end(), length.begin() + at.paths);
+        for (size_t i = 1; i < o.path_ptr.size(); i++) path_ptr[at.ev + i] = pb + o.path_ptr[i];
+        std::copy(o.n_inc.begin(), o.n_inc.end(), n_inc.begin() + at.ev);
+        for (size_t i = 1; i < o.amb_ptr.size(); i++) amb_ptr[at.ev + i] = ab + o.amb_ptr[i];
+        for (size_t i = 1; i < o.amb_path_ptr.size(); i++) amb_path_ptr[at.amb + i] = apb + o.amb_path_ptr[i];
+        std::copy(o.amb_paths.begin(), o.amb_paths.end(), amb_paths.begin() + at.amb_paths);
+        std::copy(o.amb_mult.begin(), o.amb_mult.end(), amb_mult.begin() + at.amb);
+        std::copy(o.is_tandem.begin(), o.is_tandem.end(), is_tandem.begin() + at.ev);
     }
     void append(const WqPsiProblems& o, long& shift) {
         shift = (long)size();

@@ -81,6 +81,7 @@ struct WqHostQuantEx {
     std::vector<double>   edge_value;
     bool edges_final = false;
     std::vector<double> iso_count, tpm, genetpm;
+    std::vector<uint8_t> gene_dirty;                         // [G+1] gene is named by some multi-map class: assign_ambig! will change its counts
     WqClassSet cls;
     int64_t iterations = 0;
 };
