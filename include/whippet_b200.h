@@ -180,6 +180,12 @@ int  wq_counts_refresh_dense(wq_handle* h);
 int  wq_sparse_pack(wq_handle* h, void* buf, uint64_t cap, uint64_t* used);
 int  wq_sparse_merge(wq_handle* h, const void* buf, uint64_t len);
 uint64_t wq_launch_count(wq_handle* h);   /* kernels launched by this handle so far */
+/* Measurement aid (no reference counterpart): device times of the quant-stage kernels of the last wq_em_tpm /
+ * wq_process_events, taken with CUDA events on the launching stream, and the sizes their algorithmic-byte models use
+ * (EM bytes/iteration = 12 * members + 8 * classes + 24 * isoforms).
+ * out8 = {em_tpm kernel ms, PSI EM kernels ms, EM iterations, classes, class members, isoforms, PSI problems,
+ *         PSI bytes = sum over events of sweeps * (24 * paths + 4 * ambiguous-set members + 8 * ambiguous sets)}. */
+int  wq_quant_kernel_stats(wq_handle* h, double* out8);
 
 /* Device pointer + element count of the dense count vector (u64 per node, then the scalar
  * stats) so a host can all-reduce it over NCCL between ranks. */

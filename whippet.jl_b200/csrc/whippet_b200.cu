@@ -63,14 +63,16 @@ struct WqEvBatch {
     std::vector<long> pshift;            // first problem of every part in P
     WqEmScratch dev;                     // device arrays of this group's PSI launch (the two launches overlap in time)
     double* psi = nullptr; int32_t* its = nullptr; size_t psi_cap = 0, its_cap = 0;     // pinned results
+    cudaStream_t stream = nullptr;       // own stream: the group's uploads, kernels and result copies are ordered against nothing else
     bool built = false, launched = false;
     int64_t readlen = -1;
+    cudaError_t ensure_stream() { return stream ? cudaSuccess : cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking); }
     cudaError_t ensure_pinned(size_t npsi, size_t nits) {
         if (npsi > psi_cap) { if (psi) cudaFreeHost(psi); psi = nullptr; psi_cap = 0; cudaError_t e = cudaMallocHost(&psi, (npsi + npsi / 4 + 16) * 8); if (e != cudaSuccess) return e; psi_cap = npsi + npsi / 4 + 16; }
         if (nits > its_cap) { if (its) cudaFreeHost(its); its = nullptr; its_cap = 0; cudaError_t e = cudaMallocHost(&its, (nits + nits / 4 + 16) * 4); if (e != cudaSuccess) return e; its_cap = nits + nits / 4 + 16; }
         return cudaSuccess;
     }
-    void release() { dev.release(); if (psi) cudaFreeHost(psi); if (its) cudaFreeHost(its); psi = nullptr; its = nullptr; psi_cap = its_cap = 0; }
+    void release() { dev.release(); if (stream) cudaStreamDestroy(stream); stream = nullptr; if (psi) cudaFreeHost(psi); if (its) cudaFreeHost(its); psi = nullptr; its = nullptr; psi_cap = its_cap = 0; }
 };
 
 struct wq_handle {
@@ -101,6 +103,8 @@ struct wq_handle {
     WqEmScratch em_scratch;
     std::vector<WqEventRec> ev_recs; std::vector<double> ev_values; std::vector<uint64_t> ev_path_ptr{0}; std::vector<uint32_t> ev_path_nodes;
     bool events_done = false;
+    float psi_kernel_ms = 0.f;   // device time of the PSI EM launches of the last wq_process_events (CUDA events on the stream)
+    uint64_t psi_sweep_bytes = 0;
     WqEvBatch ev_batch[2];       // event problems of the genes no multi-map read touches (built while the transcript EM runs) / of the others
     DevBuf<uint64_t> d_ck, d_cv, d_ck2, d_cv2; DevBuf<uint32_t> d_ckoff; DevBuf<uint8_t> d_cubtmp;
     bool hq_valid = false;
@@ -293,7 +297,7 @@ void wq_destroy(wq_handle* h) {
 // the derived quant state (classes, EM results, event batches) no longer matches the count stores
 static void reset_quant_ex(wq_handle* h) {
     for (WqEvBatch& B : h->ev_batch) {
-        if (B.launched) cudaStreamSynchronize(h->stream);       // its result copies target B's pinned buffers
+        if (B.launched) cudaStreamSynchronize(B.stream);        // its result copies target B's pinned buffers
         B.built = B.launched = false;
     }
     h->hx = WqHostQuantEx();
@@ -354,6 +358,7 @@ static int wq_launch_event_batch(wq_handle* h, WqEvBatch& B) {
     B.launched = false;
     if (!P.size()) return 0;
     CK(B.ensure_pinned(P.count.size(), P.size()));
+    CK(B.ensure_stream());
     wq_psi_batch b;
     memset(&b, 0, sizeof b);
     b.n_events = (uint32_t)P.size();
@@ -361,7 +366,7 @@ static int wq_launch_event_batch(wq_handle* h, WqEvBatch& B) {
     b.amb_ptr = P.amb_ptr.data(); b.amb_path_ptr = P.amb_path_ptr.data(); b.amb_paths = P.amb_paths.data(); b.amb_mult = P.amb_mult.data();
     b.is_tandem = P.is_tandem.data(); b.readlen = B.readlen; b.sig = 4; b.maxit = 1500;
     b.psi = B.psi; b.iterations = B.its;
-    std::string err = wq_run_em_psi(b, B.dev, h->stream, &h->launches, /*wait=*/false);
+    std::string err = wq_run_em_psi(b, B.dev, B.stream, &h->launches, /*wait=*/false);
     if (!err.empty()) return fail(-13, err);
     B.launched = true;
     return 0;
@@ -733,6 +738,15 @@ int wq_set_stream(wq_handle* h, void* stream) {
 
 uint64_t wq_launch_count(wq_handle* h) { return h ? h->launches : 0; }
 
+int wq_quant_kernel_stats(wq_handle* h, double* out8) {
+    if (!h || !out8) return fail(-1, "null argument");
+    const WqClassSet& C = h->hx.cls;
+    out8[0] = h->hx.em_kernel_ms; out8[1] = h->psi_kernel_ms; out8[2] = (double)h->hx.iterations;
+    out8[3] = (double)C.count.size(); out8[4] = (double)C.iso.size(); out8[5] = (double)h->iso.I;
+    out8[6] = (double)(h->ev_batch[0].P.size() + h->ev_batch[1].P.size()); out8[7] = (double)h->psi_sweep_bytes;
+    return 0;
+}
+
 int wq_map_stats_get(wq_handle* h, wq_map_stats* out) {
     if (!h || !out) return fail(-1, "null argument");
     CK(cudaSetDevice(h->device));
@@ -979,16 +993,19 @@ int wq_em_tpm(wq_handle* h, const wq_em_param* p, double* tpm, double* count, do
     // While the EM kernel runs, the host threads build the events of every gene that assign_ambig! cannot touch
     // (process_events, bin/whippet-quant.jl:181, uses the same read length as the EM, :163-165).
     static const bool overlap_on = !(getenv("WQ_EVENTS_OVERLAP") && atoi(getenv("WQ_EVENTS_OVERLAP")) == 0);
+    int overlap_rc = 0;
     const std::function<void()> overlap = [&]() {
         WqTimer t2("  events of untouched genes (under the EM kernel)");
         wq_finalize_edges(h->hq, h->hx);
         wq_build_event_batch(h, p->readlen, 0, h->ev_batch[0]);
+        // their PSI EM goes to its own stream right away: its blocks fill in beside the EM kernel's and the few events that need
+        // all 1500 sweeps (a pure latency chain) start early
+        overlap_rc = wq_launch_event_batch(h, h->ev_batch[0]);
     };
     std::string err = wq_run_em_tpm(h->H, h->iso, h->hq, h->hx, h->em_scratch, *p, h->stream, &h->launches, tpm, count, genetpm, iterations,
                                     overlap_on ? &overlap : nullptr);
     if (!err.empty()) return fail(-11, err);
-    if (h->ev_batch[0].built) { if (int rc = wq_launch_event_batch(h, h->ev_batch[0])) return rc; }     // overlaps assign_ambig!
-    return 0;
+    return overlap_rc;
 }
 
 int wq_assign_ambig(wq_handle* h, wq_values* v) {
@@ -1035,7 +1052,7 @@ int wq_process_events(wq_handle* h, int64_t readlen, wq_events_out* out) {
         WqEvBatch& B0 = h->ev_batch[0];
         WqEvBatch& B1 = h->ev_batch[1];
         if (!B0.built || B0.readlen != readlen) {            // not built under the EM kernel (or for another read length)
-            if (B0.launched) CK(cudaStreamSynchronize(h->stream));
+            if (B0.launched) CK(cudaStreamSynchronize(B0.stream));
             wq_build_event_batch(h, readlen, 0, B0);
             if (int rc = wq_launch_event_batch(h, B0)) return rc;
         }
@@ -1078,7 +1095,19 @@ int wq_process_events(wq_handle* h, int64_t readlen, wq_events_out* out) {
         if (nparts == 1) place(0);
         else { std::vector<std::thread> th; for (size_t t = 0; t < nparts; t++) th.emplace_back(place, t); for (auto& x : th) x.join(); }
         lap("+ records merged");
-        CK(cudaStreamSynchronize(h->stream));                // both PSI launches and their result copies
+        if (B0.launched) CK(cudaStreamSynchronize(B0.stream));           // PSI launches and their result copies
+        if (B1.launched) CK(cudaStreamSynchronize(B1.stream));
+        h->psi_kernel_ms = (B0.launched ? B0.dev.last_ms() : 0.f) + (B1.launched ? B1.dev.last_ms() : 0.f);
+        h->psi_sweep_bytes = 0;
+        for (WqEvBatch* B : {&B0, &B1}) {
+            if (!B->launched) continue;
+            const WqPsiProblems& P = B->P;
+            for (size_t e = 0; e < P.size(); e++) {
+                const uint64_t np = P.path_ptr[e + 1] - P.path_ptr[e], na = P.amb_ptr[e + 1] - P.amb_ptr[e];
+                const uint64_t ap = P.amb_path_ptr[P.amb_ptr[e + 1]] - P.amb_path_ptr[P.amb_ptr[e]];
+                h->psi_sweep_bytes += (uint64_t)B->its[e] * (24 * np + 4 * ap + 8 * na);
+            }
+        }
         B0.launched = B1.launched = false;
         lap("+ PSI EM kernels done");
         if (prof) fprintf(stderr, "[wq]   events: %zu records, %zu + %zu EM problems (untouched + touched genes)\n", h->ev_recs.size(), B0.P.size(), B1.P.size());

@@ -96,14 +96,7 @@ static inline std::string wq_host_build_classes(const WqHostIndex& H, const WqIs
     X.iso_count.assign(I, 0.0);
     WqClassSet& C = X.cls;
     C.ptr.push_back(0);
-    WqGeneBits B;
-    uint32_t cached_gene = 0;
-    auto bits_of = [&](uint32_t g1) -> const WqGeneBits& {
-        if (cached_gene != g1) { B.build(S, g1 - 1, H.genes[g1 - 1].nn); cached_gene = g1; }
-        return B;
-    };
-    // ---- multi-map classes, key order ----
-    std::vector<int32_t> ids;
+    // ---- genes named by multi-map classes (assign_ambig! will change their counts) ----
     X.gene_dirty.assign(G + 1, 0);
     for (size_t m = 0; m < hq.multis.size(); m++) {
         const uint32_t* key = hq.multis.key(m);
@@ -115,29 +108,37 @@ static inline std::string wq_host_build_classes(const WqHostIndex& H, const WqIs
             if (kp.gene < 1 || kp.gene > G) return "multi-map record names a gene out of range";
             X.gene_dirty[kp.gene] = 1;
         }
-        pos = 1;
-        ids.clear();
-        bool all = true;
-        for (uint32_t h = 0; h < nh && all; h++) {
-            WqKeyPath kp;
-            pos = wq_key_next(key, pos, kp);
-            const WqGeneBits& b = bits_of(kp.gene);
-            bool any = false;
-            for (uint32_t p = 0; p < b.np; p++)
-                if (wq_key_compatible(b, p, kp)) { ids.push_back((int32_t)(S.iso_base[kp.gene - 1] + p)); any = true; }
-            if (!any) all = false;
-        }
-        if (!all) ids.clear();
-        std::sort(ids.begin(), ids.end());
-        ids.erase(std::unique(ids.begin(), ids.end()), ids.end());
-        if (ids.size() > 500) return "multi-map class larger than 500 isoforms (prop_temp = zeros(500), src/quant.jl:725)";
-        for (int32_t i : ids) { C.iso.push_back(i); C.prop.push_back(1.0 / (double)ids.size()); }
-        C.ptr.push_back((uint32_t)C.iso.size());
-        C.count.push_back((double)hq.multis.count[m]);
-        C.state.push_back(all ? 0 : 2);
-        C.postassign.push_back(all ? 0 : 1);
     }
-    C.n_multi = (uint32_t)C.count.size();
+    // ---- multi-map classes in key order: independent of each other, so host threads take contiguous ranges ----
+    struct MFrag { std::vector<int32_t> iso; std::vector<uint32_t> end; std::vector<uint8_t> all; std::string err; };
+    auto multi_work = [&](size_t m_lo, size_t m_hi, MFrag& F) {
+        WqGeneBits B;
+        uint32_t cached_gene = 0;
+        std::vector<int32_t> ids;
+        for (size_t m = m_lo; m < m_hi; m++) {
+            const uint32_t* key = hq.multis.key(m);
+            const uint32_t nh = key[0] & 0xFFFF;
+            size_t pos = 1;
+            ids.clear();
+            bool all = true;
+            for (uint32_t h = 0; h < nh && all; h++) {
+                WqKeyPath kp;
+                pos = wq_key_next(key, pos, kp);
+                if (cached_gene != kp.gene) { B.build(S, kp.gene - 1, H.genes[kp.gene - 1].nn); cached_gene = kp.gene; }
+                bool any = false;
+                for (uint32_t p = 0; p < B.np; p++)
+                    if (wq_key_compatible(B, p, kp)) { ids.push_back((int32_t)(S.iso_base[kp.gene - 1] + p)); any = true; }
+                if (!any) all = false;
+            }
+            if (!all) ids.clear();
+            std::sort(ids.begin(), ids.end());
+            ids.erase(std::unique(ids.begin(), ids.end()), ids.end());
+            if (ids.size() > 500) { F.err = "multi-map class larger than 500 isoforms (prop_temp = zeros(500), src/quant.jl:725)"; return; }
+            F.iso.insert(F.iso.end(), ids.begin(), ids.end());
+            F.end.push_back((uint32_t)F.iso.size());
+            F.all.push_back(all ? 1 : 0);
+        }
+    };
     // ---- long paths grouped by gene (the order inside a gene does not affect any result) ----
     std::vector<uint32_t> lptr(G + 2, 0), lidx(hq.longs.size());
     for (size_t i = 0; i < hq.longs.size(); i++) {
@@ -156,7 +157,10 @@ static inline std::string wq_host_build_classes(const WqHostIndex& H, const WqIs
     unsigned nthreads = wq_host_threads();
     if (G < 2048) nthreads = 1;
     std::vector<Frag> frags(nthreads);
+    std::vector<MFrag> mfrags(nthreads);
+    const size_t NMU = hq.multis.size();
     auto work = [&](unsigned t) {
+        multi_work(NMU * t / nthreads, NMU * (t + 1) / nthreads, mfrags[t]);
         Frag& F = frags[t];
         const uint32_t g_lo = 1 + (uint32_t)((uint64_t)G * t / nthreads), g_hi = (uint32_t)((uint64_t)G * (t + 1) / nthreads);
         WqGeneBits Bt;
@@ -228,6 +232,23 @@ static inline std::string wq_host_build_classes(const WqHostIndex& H, const WqIs
         for (unsigned t = 0; t < nthreads; t++) th.emplace_back(work, t);
         for (auto& t : th) t.join();
     }
+    {
+        size_t m = 0;
+        for (MFrag& F : mfrags) {
+            if (!F.err.empty()) return F.err;
+            uint32_t prev = 0;
+            for (size_t j = 0; j < F.end.size(); j++, m++) {
+                const uint32_t n = F.end[j] - prev;
+                for (uint32_t q = prev; q < F.end[j]; q++) { C.iso.push_back(F.iso[q]); C.prop.push_back(1.0 / (double)n); }
+                prev = F.end[j];
+                C.ptr.push_back((uint32_t)C.iso.size());
+                C.count.push_back((double)hq.multis.count[m]);
+                C.state.push_back(F.all[j] ? 0 : 2);
+                C.postassign.push_back(F.all[j] ? 0 : 1);
+            }
+        }
+        C.n_multi = (uint32_t)C.count.size();
+    }
     for (Frag& F : frags) {
         if (!F.err.empty()) return F.err;
         const uint32_t base = (uint32_t)C.iso.size();
@@ -248,30 +269,52 @@ static inline std::string wq_host_assign_ambig_impl(const WqHostIndex& H, const 
     if (!X.built || !X.em_done) return "assign_ambig needs wq_em_tpm first (it uses the EM class proportions and gene TPM)";
     if (X.ambig_done) return "";
     const WqClassSet& C = X.cls;
-    WqGeneBits B;
-    uint32_t cached = 0;
-    WqKeyPath vp[WQ_MAX_TOLERATE];
-    double w[WQ_MAX_TOLERATE];
+    // the share of every alignment of every class (independent: host threads), then the additions in class order
+    // (sequential: floating-point sums onto one node / edge must see their terms in the reference's order)
+    std::vector<double> share((size_t)C.n_multi * WQ_MAX_TOLERATE, 0.0);
+    unsigned nthreads = wq_host_threads();
+    if (C.n_multi < 1024) nthreads = 1;
+    std::vector<std::string> errs(nthreads);
+    auto work = [&](unsigned t) {
+        WqGeneBits B;
+        uint32_t cached = 0;
+        WqKeyPath vp[WQ_MAX_TOLERATE];
+        double w[WQ_MAX_TOLERATE];
+        const uint32_t c_lo = (uint32_t)((uint64_t)C.n_multi * t / nthreads), c_hi = (uint32_t)((uint64_t)C.n_multi * (t + 1) / nthreads);
+        for (uint32_t c = c_lo; c < c_hi; c++) {
+            const uint32_t* key = hq.multis.key(c);
+            const uint32_t nh = key[0] & 0xFFFF;
+            if (nh > WQ_MAX_TOLERATE) { errs[t] = "multi-map class with more alignments than WQ_MAX_TOLERATE"; return; }
+            size_t pos = 1;
+            for (uint32_t h = 0; h < nh; h++) pos = wq_key_next(key, pos, vp[h]);
+            for (uint32_t h = 0; h < nh; h++) {
+                if (C.postassign[c]) { w[h] = X.genetpm[vp[h].gene - 1]; continue; }
+                if (cached != vp[h].gene) { B.build(S, vp[h].gene - 1, H.genes[vp[h].gene - 1].nn); cached = vp[h].gene; }
+                const uint32_t ib = S.iso_base[vp[h].gene - 1];
+                double acc = 0.0;
+                for (uint32_t k = C.ptr[c]; k < C.ptr[c + 1]; k++) {
+                    int64_t p = (int64_t)C.iso[k] - ib;
+                    if (p >= 0 && p < B.np && wq_key_compatible(B, (uint32_t)p, vp[h])) acc += C.prop[k];
+                }
+                w[h] = acc;
+            }
+            double tot = 0.0;
+            for (uint32_t h = 0; h < nh; h++) tot += w[h];
+            for (uint32_t h = 0; h < nh; h++) share[(size_t)c * WQ_MAX_TOLERATE + h] = (w[h] / tot) * C.count[c];
+        }
+    };
+    if (nthreads == 1) work(0);
+    else { std::vector<std::thread> th; for (unsigned t = 0; t < nthreads; t++) th.emplace_back(work, t); for (auto& x : th) x.join(); }
+    for (auto& e : errs) if (!e.empty()) return e;
     for (uint32_t c = 0; c < C.n_multi; c++) {
         const uint32_t* key = hq.multis.key(c);
         const uint32_t nh = key[0] & 0xFFFF;
-        if (nh > WQ_MAX_TOLERATE) return "multi-map class with more alignments than WQ_MAX_TOLERATE";
         size_t pos = 1;
-        for (uint32_t h = 0; h < nh; h++) pos = wq_key_next(key, pos, vp[h]);
         for (uint32_t h = 0; h < nh; h++) {
-            if (C.postassign[c]) { w[h] = X.genetpm[vp[h].gene - 1]; continue; }
-            if (cached != vp[h].gene) { B.build(S, vp[h].gene - 1, H.genes[vp[h].gene - 1].nn); cached = vp[h].gene; }
-            const uint32_t ib = S.iso_base[vp[h].gene - 1];
-            double acc = 0.0;
-            for (uint32_t k = C.ptr[c]; k < C.ptr[c + 1]; k++) {
-                int64_t p = (int64_t)C.iso[k] - ib;
-                if (p >= 0 && p < B.np && wq_key_compatible(B, (uint32_t)p, vp[h])) acc += C.prop[k];
-            }
-            w[h] = acc;
+            WqKeyPath kp;
+            pos = wq_key_next(key, pos, kp);
+            wq_spread_path(H, X.node_value, X.edge_adds, kp, share[(size_t)c * WQ_MAX_TOLERATE + h]);
         }
-        double tot = 0.0;
-        for (uint32_t h = 0; h < nh; h++) tot += w[h];
-        for (uint32_t h = 0; h < nh; h++) wq_spread_path(H, X.node_value, X.edge_adds, vp[h], (w[h] / tot) * C.count[c]);
     }
     X.ambig_done = true;
     X.edges_final = false;
@@ -490,6 +533,14 @@ struct WqEmScratch {
     // side streams for kernels that may run next to each other (created on first use, on the current device)
     cudaStream_t side[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t fork = nullptr, join[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t tk0 = nullptr, tk1 = nullptr;      // device time of the last kernel (group) launched through this scratch
+    bool timed = false;
+    cudaError_t timing_events() {
+        if (tk0) return cudaSuccess;
+        cudaError_t e = cudaEventCreate(&tk0);
+        return e != cudaSuccess ? e : cudaEventCreate(&tk1);
+    }
+    float last_ms() { float ms = 0.f; if (timed && cudaEventElapsedTime(&ms, tk0, tk1) != cudaSuccess) ms = 0.f; return ms; }
     cudaError_t side_streams() {
         if (fork) return cudaSuccess;
         for (int i = 0; i < 3; i++) {
@@ -504,7 +555,9 @@ struct WqEmScratch {
         for (int i = 0; i < 24; i++) { if (p[i]) cudaFree(p[i]); p[i] = nullptr; cap[i] = 0; }
         for (int i = 0; i < 3; i++) { if (side[i]) cudaStreamDestroy(side[i]); if (join[i]) cudaEventDestroy(join[i]); side[i] = nullptr; join[i] = nullptr; }
         if (fork) cudaEventDestroy(fork);
-        fork = nullptr;
+        if (tk0) cudaEventDestroy(tk0);
+        if (tk1) cudaEventDestroy(tk1);
+        fork = tk0 = tk1 = nullptr; timed = false;
     }
 };
 
@@ -613,7 +666,11 @@ static inline std::string wq_run_em_tpm(const WqHostIndex& H, const WqIsoIndex& 
     if (timing) { WQ_EMCK(M.get(22, (size_t)grid * 4, &d.dbg)); WQ_EMCK(cudaMemsetAsync(d.dbg, 0, (size_t)grid * 32, stream)); }
     void* args[] = {&d};
     auto tk0 = std::chrono::steady_clock::now();
+    WQ_EMCK(M.timing_events());
+    WQ_EMCK(cudaEventRecord(M.tk0, stream));
     WQ_EMCK(cudaLaunchCooperativeKernel((void*)wq_k_em_tpm, dim3(grid), dim3(1024), args, 0, stream));
+    WQ_EMCK(cudaEventRecord(M.tk1, stream));
+    M.timed = true;
     if (launches) *launches += 1;
     if (while_running) (*while_running)();       // host work that does not depend on the EM result overlaps the kernel
     int64_t it = 0;
@@ -647,6 +704,7 @@ static inline std::string wq_run_em_tpm(const WqHostIndex& H, const WqIsoIndex& 
     }
     X.em_done = true;
     X.iterations = it;
+    X.em_kernel_ms = M.last_ms();
     if (tpm_out) memcpy(tpm_out, tpm.data(), I * 8);
     if (count_out) memcpy(count_out, count.data(), I * 8);
     if (genetpm_out) memcpy(genetpm_out, X.genetpm.data(), H.G * 8);
@@ -666,6 +724,7 @@ struct WqPsiDev {
     double readlen; int sig; int64_t maxit;
     double* psi; double* prev; double* ctemp; double* amb_prop; int32_t* iterations;
     double p10[23];               // exact powers of ten
+    double ip10[23];              // 1 / 10^k, correctly rounded (the same bits as an IEEE division on the device)
 };
 
 __device__ __forceinline__ double wq_pow10(const WqPsiDev& d, int k) { return (k >= 0 && k <= 22) ? d.p10[k] : pow(10.0, (double)k); }
@@ -675,10 +734,10 @@ __device__ __forceinline__ double wq_pow10(const WqPsiDev& d, int k) { return (k
 // result (both decades round such a value to that same power of ten).
 __device__ __forceinline__ int wq_hidigit(const WqPsiDev& d, double ax) {
     if (ax >= 1e-22 && ax < 1e22) {
-        int e = ilogb(ax);                                   // 2^e <= ax < 2^(e+1)
+        const int e = ((__double2hiint(ax) >> 20) & 0x7FF) - 1023;  // 2^e <= ax < 2^(e+1) (ax is a normal number here)
         int h = (int)floor((double)e * 0.30102999566398120) + 1;   // candidate: 10^(h-1) <= ax < 10^h, at most one off
         // pw(k) = 10^k
-        auto pw = [&](int k) { return k >= 0 ? d.p10[k] : __ddiv_rn(1.0, d.p10[-k]); };
+        auto pw = [&](int k) { return k >= 0 ? d.p10[k] : d.ip10[-k]; };
         if (ax >= pw(h)) h += 1;
         else if (ax < pw(h - 1)) h -= 1;
         return h;
@@ -848,7 +907,7 @@ static inline std::string wq_run_em_psi(wq_psi_batch& b, WqEmScratch& M, cudaStr
     const uint32_t P = b.path_ptr[E], A = b.amb_ptr[E], AP = b.amb_path_ptr[A];
     WqPsiDev d;
     d.n_events = E; d.readlen = (double)b.readlen; d.sig = (int)b.sig; d.maxit = b.maxit;
-    for (int k = 0; k <= 22; k++) d.p10[k] = std::pow(10.0, (double)k);
+    for (int k = 0; k <= 22; k++) { d.p10[k] = std::pow(10.0, (double)k); d.ip10[k] = 1.0 / d.p10[k]; }
     uint32_t *d_pp, *d_ni, *d_ap, *d_app, *d_apaths;
     double *d_cnt, *d_len, *d_mult, *d_psi, *d_prev, *d_ct, *d_prop;
     uint8_t* d_tan;
@@ -881,6 +940,8 @@ static inline std::string wq_run_em_psi(wq_psi_batch& b, WqEmScratch& M, cudaStr
     uint32_t* d_list;
     WQ_EMCK(up(14, order.data(), E * 4ull, (void**)&d_list));
     WQ_EMCK(M.side_streams());
+    WQ_EMCK(M.timing_events());
+    WQ_EMCK(cudaEventRecord(M.tk0, stream));
     WQ_EMCK(cudaEventRecord(M.fork, stream));
     int used = 0;
     for (int c = 0; c < 4; c++) {
@@ -898,6 +959,8 @@ static inline std::string wq_run_em_psi(wq_psi_batch& b, WqEmScratch& M, cudaStr
         if (used > 0) { WQ_EMCK(cudaEventRecord(M.join[used - 1], ss)); WQ_EMCK(cudaStreamWaitEvent(stream, M.join[used - 1], 0)); }
         used++;
     }
+    WQ_EMCK(cudaEventRecord(M.tk1, stream));
+    M.timed = true;
     WQ_EMCK(cudaMemcpyAsync(b.psi, d_psi, P * 8ull, cudaMemcpyDeviceToHost, stream));
     if (b.path_total) WQ_EMCK(cudaMemcpyAsync(b.path_total, d_ct, P * 8ull, cudaMemcpyDeviceToHost, stream));
     WQ_EMCK(cudaMemcpyAsync(b.iterations, d_it, E * 4ull, cudaMemcpyDeviceToHost, stream));

@@ -84,6 +84,7 @@ struct WqHostQuantEx {
     std::vector<uint8_t> gene_dirty;                         // [G+1] gene is named by some multi-map class: assign_ambig! will change its counts
     WqClassSet cls;
     int64_t iterations = 0;
+    float em_kernel_ms = 0.f;                                // device time of the transcript EM kernel (CUDA events)
 };
 
 // base counts + additions (stable by key, so every key sees its additions in the order they were made)

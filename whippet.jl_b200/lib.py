@@ -54,6 +54,7 @@ def load():
     L.wq_sparse_merge.argtypes = [vp, vp, C.c_uint64]
     L.wq_launch_count.argtypes = [vp]
     L.wq_launch_count.restype = C.c_uint64
+    L.wq_quant_kernel_stats.argtypes = [vp, C.POINTER(C.c_double)]
     _lib = L
     return L
 

@@ -125,6 +125,14 @@ class GraphLibQuant:
         lib.check(self.L.wq_last_kernel_ms(self.h, ms))
         return [float(x) for x in ms]
 
+    def quant_kernel_stats(self):
+        """Device times (CUDA events) of the transcript EM and PSI EM kernels of the last gene_em / process_events and
+        the sizes of their algorithmic-byte models (wq_quant_kernel_stats)."""
+        out = (C.c_double * 8)()
+        lib.check(self.L.wq_quant_kernel_stats(self.h, out))
+        keys = ("em_tpm_ms", "em_psi_ms", "em_iterations", "classes", "class_members", "isoforms", "psi_problems", "psi_bytes")
+        return dict(zip(keys, (float(x) for x in out)))
+
     # ---- count stores ---------------------------------------------------------------------------
     def counts(self):
         """SpliceGraphQuant.node / .edge / .circ (src/quant.jl:129-135) as
