@@ -229,6 +229,8 @@ def main():
     L = q.L
     stream = torch.cuda.current_stream()
     lib.check(L.wq_set_stream(q.h, C.c_void_p(stream.cuda_stream)))
+    if world > 1:
+        q.set_gene_partition(rank, world)       # events (PSI) of gene range `rank` of `world`; the ranks' outputs concatenate
 
     # ---- device-resident batch ------------------------------------------------------------------
     dev = torch.device("cuda", local)
@@ -360,7 +362,7 @@ def main():
         "config": {"workload": workload_name(a), "l2": "inputs (%.2f GB per step) are larger than the 126 MB L2" % (h2d / 1e9),
                    "text_len": int(idx.text_len), "nodes": int(idx.n_nodes), "isoforms": int(idx.n_isoforms),
                    "mapped_frac": stats.mapped / max(1, stats.total), "multi_frac": stats.multi / max(1, stats.total),
-                   "parallelism": f"reads sharded over {world} GPU(s), index replicated" + (", dense counts all-reduced over NCCL" if world > 1 else "")},
+                   "parallelism": f"reads sharded over {world} GPU(s), index replicated" + (", dense counts all-reduced and sparse stores all-gathered over NCCL, transcript EM replicated, event stage partitioned by gene" if world > 1 else "")},
         "clocks": clocks, "gpu_launches": launches,
         "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "kernel_ms": {"seed": float(kms[0]), "extend": float(kms[1]), "resolve": float(kms[2]),

@@ -179,6 +179,16 @@ int  wq_counts_refresh_dense(wq_handle* h);
  * buf == NULL returns the size.  wq_sparse_merge adds another rank's buffer into this handle. */
 int  wq_sparse_pack(wq_handle* h, void* buf, uint64_t cap, uint64_t* used);
 int  wq_sparse_merge(wq_handle* h, const void* buf, uint64_t len);
+/* Device-side form of the same exchange (no reference counterpart): wq_sparse_device_pack compacts
+ * this rank's edge/circ table and keyed stores into one DEVICE buffer owned by the handle (valid until the next pack);
+ * the caller all-gathers the buffers (NCCL) and hands every other rank's buffer (a device pointer) to
+ * wq_sparse_device_merge, which adds its records into this rank's device tables with a kernel.  The host-side stores are
+ * rebuilt from the merged tables on the next download / wq_em_tpm. */
+int  wq_sparse_device_pack(wq_handle* h, void** dptr, uint64_t* bytes);
+int  wq_sparse_device_merge(wq_handle* h, const void* dbuf, uint64_t bytes);
+/* Event stage partitioned by gene across ranks: this handle builds and solves the events of the contiguous gene range
+ * `part` of `nparts` only and wq_process_events returns that range's records; the parts concatenate to the full output. */
+int  wq_set_gene_partition(wq_handle* h, uint32_t part, uint32_t nparts);
 uint64_t wq_launch_count(wq_handle* h);   /* kernels launched by this handle so far */
 /* Measurement aid (no reference counterpart): device times of the quant-stage kernels of the last wq_em_tpm /
  * wq_process_events, taken with CUDA events on the launching stream, and the sizes their algorithmic-byte models use

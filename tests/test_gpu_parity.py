@@ -223,6 +223,52 @@ def test_sharded_counts_merge_equals_single_pass():
         q.close()
 
 
+def test_device_exchange_and_gene_partition():
+    """The NCCL path of the exchange emulated on one GPU: three handles align thirds of the reads, each packs its sparse
+    stores into a device buffer (wq_sparse_device_pack) and the first one merges the other two with the merge kernel
+    (what every rank does after the all-gather); dense vectors are added (the all-reduce).  Counts, keyed stores, EM and
+    multi-map assignment equal the single pass; the event stage run as gene partitions 0/3, 1/3, 2/3 concatenates to
+    the unpartitioned event list."""
+    import ctypes as C
+    import torch
+    from whippet_jl_b200 import lib
+    idx = synth.make_index(n_genes=500, K=9, seed=41, paralog_frac=0.1)
+    rb = synth.simulate_reads(idx, 240000, 101, seed=42, sub_rate=0.01)
+    p = wq.AlignParam()
+    full = wq.GraphLibQuant(idx)
+    full.process_reads(p, rb)
+    hs = [wq.GraphLibQuant(idx) for _ in range(3)]
+    cuts = [0, 70000, 150000, rb.n]
+    for k, q in enumerate(hs):
+        q.process_reads(p, rb.slice(cuts[k], cuts[k + 1]))
+    a = hs[0]
+    ta = a.dense_tensor()
+    for q in hs[1:]:
+        ta += q.dense_tensor()
+    torch.cuda.synchronize()
+    for q in hs[1:]:
+        dptr, nbytes = C.c_void_p(), C.c_uint64()
+        lib.check(q.L.wq_sparse_device_pack(q.h, C.byref(dptr), C.byref(nbytes)))
+        lib.check(a.L.wq_sparse_device_merge(a.h, dptr, nbytes))
+    for x, y in zip(full.counts(), a.counts()):
+        assert np.array_equal(x, y)
+    assert full.keyed(0) == a.keyed(0) and full.keyed(1) == a.keyed(1)
+    st_f, st_a = full.stats(), a.stats()
+    assert (st_f.total, st_f.mapped, st_f.multi) == (st_a.total, st_a.mapped, st_a.multi)
+    r1, r2 = full.gene_em(101), a.gene_em(101)
+    assert r1[0] == r2[0] and all(np.array_equal(x, y) for x, y in zip(r1[1:], r2[1:]))
+    assert all(np.array_equal(x, y) for x, y in zip(full.assign_ambig(), a.assign_ambig()))
+    want = full.process_events(101)
+    got = []
+    for part in range(3):
+        a.set_gene_partition(part, 3)
+        got += a.process_events(101)
+    assert len(want) == len(got) and want == got
+    assert sum(1 for e in want if e["iterations"] > 0) > 20
+    for q in [full] + hs:
+        q.close()
+
+
 def events_parity(idx, p, rb, readlen, mate=None):
     o = Oracle(idx)
     o.quant_reset()

@@ -107,6 +107,8 @@ struct wq_handle {
     uint64_t psi_sweep_bytes = 0;
     WqEvBatch ev_batch[2];       // event problems of the genes no multi-map read touches (built while the transcript EM runs) / of the others
     DevBuf<uint64_t> d_ck, d_cv, d_ck2, d_cv2; DevBuf<uint32_t> d_ckoff; DevBuf<uint8_t> d_cubtmp;
+    DevBuf<uint64_t> d_xpack; DevBuf<uint32_t> d_xpending;      // multi-GPU exchange: this rank's packed sparse stores / merge queue
+    uint32_t part = 0, nparts = 1;                              // gene partition of the event stage (wq_set_gene_partition)
     bool hq_valid = false;
     uint32_t chunk_reads = 1u << 22;
     float last_kernel_ms[3] = {0, 0, 0};
@@ -235,6 +237,31 @@ __global__ void wq_k_compact_keyed(const uint64_t* hash, const uint32_t* keyoff,
     }
 }
 
+// Multi-GPU exchange: another rank's compacted sparse stores (wq_sparse_device_pack layout) are added into this rank's
+// device tables.  Pass 0 queues keyed records whose slot owner has not published its key yet; pass 1 (a later launch, so
+// every owner has published) adds the queued ones.
+__global__ void __launch_bounds__(256) wq_k_merge_sparse(const WqQuantDev q, const uint64_t* __restrict__ buf, uint32_t* pending,
+                                                         uint32_t* cursor, const int pass) {
+    const uint64_t ne = buf[0], nk = buf[1];
+    const uint64_t* ekey = buf + 4;
+    const uint64_t* ecount = ekey + ne;
+    const uint64_t* kcount = ecount + ne;
+    const uint32_t* koff = (const uint32_t*)(kcount + nk);
+    const uint32_t* pool = koff + ((nk + 1) & ~1ull);
+    const uint64_t total = pass == 0 ? ne + nk : (uint64_t)*cursor;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t j;
+        if (pass == 0) {
+            if (i < ne) { if (wq_edge_insert(q.edges, ekey[i], ecount[i])) atomicAdd((unsigned long long*)&q.counters->edge_full, 1ull); continue; }
+            j = i - ne;
+        } else j = pending[i];
+        const uint32_t off = koff[j];
+        const int rc = wq_keyed_insert(q.keyed, pool + off + 1, (int)pool[off], kcount[j]);
+        if (rc == 1 && pass == 0) pending[atomicAdd(cursor, 1u)] = (uint32_t)j;
+        else if (rc != 0) atomicAdd((unsigned long long*)&q.counters->keyed_full, 1ull);
+    }
+}
+
 __global__ void wq_k_fill_u64(uint64_t* p, uint64_t v, uint64_t n) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
@@ -286,7 +313,7 @@ void wq_destroy(wq_handle* h) {
     }
     h->d_seeds.release(); h->d_hit_read.release(); h->d_hit_s.release(); h->d_hit_s2.release(); h->d_hit_gene.release(); h->d_pending.release(); h->d_pending2.release();
     h->d_cursors.release(); h->d_hits.release(); h->d_pool.release();
-    h->em_scratch.release(); h->ev_batch[0].release(); h->ev_batch[1].release(); h->d_ck.release(); h->d_cv.release(); h->d_ck2.release(); h->d_cv2.release(); h->d_ckoff.release(); h->d_cubtmp.release();
+    h->em_scratch.release(); h->ev_batch[0].release(); h->ev_batch[1].release(); h->d_ck.release(); h->d_cv.release(); h->d_ck2.release(); h->d_cv2.release(); h->d_ckoff.release(); h->d_cubtmp.release(); h->d_xpack.release(); h->d_xpending.release();
     if (h->h_cursors) cudaFreeHost(h->h_cursors);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
@@ -319,8 +346,9 @@ static void wq_build_event_batch(wq_handle* h, int64_t readlen, int group, WqEvB
         for (unsigned t = 0; t < nt; t++) th.emplace_back(f, t);
         for (auto& x : th) x.join();
     };
+    const uint32_t p_lo = (uint32_t)((uint64_t)G * h->part / h->nparts), p_n = (uint32_t)((uint64_t)G * (h->part + 1) / h->nparts) - p_lo;
     run([&](unsigned t) {
-        const uint32_t g_lo = 1 + (uint32_t)((uint64_t)G * t / nt), g_hi = (uint32_t)((uint64_t)G * (t + 1) / nt);
+        const uint32_t g_lo = p_lo + 1 + (uint32_t)((uint64_t)p_n * t / nt), g_hi = p_lo + (uint32_t)((uint64_t)p_n * (t + 1) / nt);
         size_t e = std::lower_bound(X.edge_key.begin(), X.edge_key.end(), (uint64_t)g_lo << 32) - X.edge_key.begin();
         WqGeneEvents V{h->H, X.node_value, 0, {}};
         WqEvPart& part = B.parts[t];
@@ -900,6 +928,88 @@ int wq_counts_merge(wq_handle* h, const wq_counts* c, const wq_keyed* longs, con
             dst[t]->push(in[t]->words + in[t]->rec_ptr[i], (size_t)(in[t]->rec_ptr[i + 1] - in[t]->rec_ptr[i]), in[t]->count[i]);
         dst[t]->canonicalize();
     }
+    return 0;
+}
+
+// Device-side exchange of the sparse stores: every rank compacts its edge / circ table and its keyed
+// store (long paths, multi-map classes) into ONE device buffer, the buffers are all-gathered over NCCL by the caller, and
+// every rank adds the other ranks' records into its own device tables with a kernel.  The host-side stores are then pulled
+// once from the merged tables.  Buffer layout (u64 words): {n_edge, n_keyed, pool_words, 0}, edge_key[n_edge],
+// edge_count[n_edge], keyed_count[n_keyed], then u32: keyed_off[n_keyed] (padded to even), pool[pool_words] (padded to even),
+// where pool[off] = number of key words and the words follow.
+int wq_sparse_device_pack(wq_handle* h, void** dptr, uint64_t* bytes) {
+    if (!h || !dptr || !bytes) return fail(-1, "null argument");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    CK(cudaMemsetAsync(h->d_cursors.p + 12, 0, 2 * sizeof(uint32_t), s));
+    CK(h->d_ck.ensure(h->edge_slots)); CK(h->d_cv.ensure(h->edge_slots));
+    wq_k_compact_edges<<<1184, 256, 0, s>>>(h->d_ekey.p, h->d_ecount.p, h->edge_slots, h->d_ck.p, h->d_cv.p, h->d_cursors.p + 12);
+    CK(h->d_ckoff.ensure(h->keyed_slots)); CK(h->d_cv2.ensure(h->keyed_slots));
+    wq_k_compact_keyed<<<1184, 256, 0, s>>>(h->d_khash.p, h->d_koff.p, h->d_kcount.p, h->keyed_slots, h->d_ckoff.p, h->d_cv2.p, h->d_cursors.p + 13);
+    h->launches += 2;
+    uint64_t kcur = 0;
+    CK(cudaMemcpyAsync(h->h_cursors + 12, h->d_cursors.p + 12, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(&kcur, h->d_kcursor.p, 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    const uint64_t ne = h->h_cursors[12], nk = h->h_cursors[13];
+    if (kcur > h->kpool_cap) return fail(-8, "keyed count store overflowed (raise WQ_KEYED_POOL_WORDS)");
+    const uint64_t koff_words = (nk + 1) & ~1ull, pool_words = (kcur + 1) & ~1ull;
+    const uint64_t total = 4 + 2 * ne + nk + koff_words / 2 + pool_words / 2;
+    CK(h->d_xpack.ensure(total));
+    const uint64_t hdr[4] = {ne, nk, kcur, 0};
+    uint64_t* b = h->d_xpack.p;
+    CK(cudaMemcpyAsync(b, hdr, sizeof hdr, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(b + 4, h->d_ck.p, ne * 8, cudaMemcpyDeviceToDevice, s));
+    CK(cudaMemcpyAsync(b + 4 + ne, h->d_cv.p, ne * 8, cudaMemcpyDeviceToDevice, s));
+    CK(cudaMemcpyAsync(b + 4 + 2 * ne, h->d_cv2.p, nk * 8, cudaMemcpyDeviceToDevice, s));
+    uint32_t* w = (uint32_t*)(b + 4 + 2 * ne + nk);
+    CK(cudaMemcpyAsync(w, h->d_ckoff.p, nk * 4, cudaMemcpyDeviceToDevice, s));
+    CK(cudaMemcpyAsync(w + koff_words, h->d_kpool.p, kcur * 4, cudaMemcpyDeviceToDevice, s));
+    CK(cudaStreamSynchronize(s));
+    *dptr = b;
+    *bytes = total * 8;
+    return 0;
+}
+
+int wq_sparse_device_merge(wq_handle* h, const void* dbuf, uint64_t bytes) {
+    if (!h || !dbuf) return fail(-1, "null argument");
+    if (bytes < 32) return fail(-1, "sparse device buffer too short");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    uint64_t hdr[4];
+    CK(cudaMemcpyAsync(hdr, dbuf, sizeof hdr, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    const uint64_t ne = hdr[0], nk = hdr[1], kw = hdr[2];
+    const uint64_t need = (4 + 2 * ne + nk + ((nk + 1) & ~1ull) / 2 + ((kw + 1) & ~1ull) / 2) * 8;
+    if (bytes < need) return fail(-1, "sparse device buffer truncated");
+    CK(h->d_xpending.ensure(nk + 1));
+    CK(cudaMemsetAsync(h->d_cursors.p + 14, 0, sizeof(uint32_t), s));
+    const uint64_t n = ne + nk;
+    if (n) {
+        const unsigned grid = (unsigned)std::min<uint64_t>((n + 255) / 256, 148 * 16);
+        wq_k_merge_sparse<<<grid, 256, 0, s>>>(h->q, (const uint64_t*)dbuf, h->d_xpending.p, h->d_cursors.p + 14, 0);
+        wq_k_merge_sparse<<<148, 256, 0, s>>>(h->q, (const uint64_t*)dbuf, h->d_xpending.p, h->d_cursors.p + 14, 1);
+        h->launches += 2;
+        CK(cudaGetLastError());
+    }
+    CK(cudaStreamSynchronize(s));
+    h->hq = WqHostQuant();
+    h->hq_valid = false;             // the host-side stores are pulled again from the merged tables
+    reset_quant_ex(h);
+    return 0;
+}
+
+// Event stage partitioned by gene (north_star: "EM is then partitioned by gene"): this handle builds and solves the events of
+// the contiguous gene range `part` of `nparts` only; wq_process_events then returns that range's records.  Concatenating
+// the outputs of parts 0..nparts-1 gives the unpartitioned output.
+int wq_set_gene_partition(wq_handle* h, uint32_t part, uint32_t nparts) {
+    if (!h) return fail(-1, "null handle");
+    if (nparts == 0 || part >= nparts) return fail(-1, "gene partition out of range");
+    if (h->part != part || h->nparts != nparts) {
+        for (WqEvBatch& B : h->ev_batch) { if (B.launched) cudaStreamSynchronize(B.stream); B.built = B.launched = false; }
+        h->events_done = false;
+    }
+    h->part = part; h->nparts = nparts;
     return 0;
 }
 

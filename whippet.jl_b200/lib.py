@@ -52,6 +52,9 @@ def load():
     L.wq_set_stream.argtypes = [vp, vp]
     L.wq_sparse_pack.argtypes = [vp, vp, C.c_uint64, C.POINTER(C.c_uint64)]
     L.wq_sparse_merge.argtypes = [vp, vp, C.c_uint64]
+    L.wq_sparse_device_pack.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_uint64)]
+    L.wq_sparse_device_merge.argtypes = [vp, vp, C.c_uint64]
+    L.wq_set_gene_partition.argtypes = [vp, C.c_uint32, C.c_uint32]
     L.wq_launch_count.argtypes = [vp]
     L.wq_launch_count.restype = C.c_uint64
     L.wq_quant_kernel_stats.argtypes = [vp, C.POINTER(C.c_double)]

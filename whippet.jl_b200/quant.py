@@ -247,14 +247,34 @@ class GraphLibQuant:
         from . import parallel
         if not dist.is_initialized() or dist.get_world_size() == 1:
             return
+        world, rank = dist.get_world_size(), dist.get_rank()
+        dev = torch.device("cuda", self.device)
         dist.all_reduce(self.dense_tensor())
+        # sparse stores: compacted on the device, all-gathered over NCCL, merged into the device tables by a kernel
+        dptr, nbytes = C.c_void_p(), C.c_uint64()
+        lib.check(self.L.wq_sparse_device_pack(self.h, C.byref(dptr), C.byref(nbytes)))
+        nw = int(nbytes.value) // 8
+
+        class _Wrap:
+            __cuda_array_interface__ = {"shape": (nw,), "typestr": "<i8", "data": (int(dptr.value), False), "version": 2}
+        mine = torch.as_tensor(_Wrap(), device=dev)
+        sizes = torch.zeros(world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(sizes, torch.tensor([nw], dtype=torch.int64, device=dev))
+        sizes = [int(x) for x in sizes.tolist()]
+        m = max(sizes)
+        padded = torch.zeros(m, dtype=torch.int64, device=dev)
+        padded[:nw] = mine
+        gathered = torch.empty(world * m, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(gathered, padded)
         torch.cuda.current_stream().synchronize()
-        mine = self.sparse_pack()                        # host state: all-reduced dense + this rank's sparse stores
-        bufs = parallel.allgather_buffers(mine, torch.device("cuda", self.device))
-        rank = dist.get_rank()
-        for r, b in enumerate(bufs):
+        for r in range(world):
             if r != rank:
-                self.sparse_merge(b)
+                lib.check(self.L.wq_sparse_device_merge(self.h, C.c_void_p(gathered[r * m:].data_ptr()), C.c_uint64(sizes[r] * 8)))
+
+    def set_gene_partition(self, part: int, nparts: int):
+        """Event stage partitioned by gene: this handle builds and solves the events of gene range `part` of `nparts`;
+        process_events then returns that range only (the parts concatenate to the full output)."""
+        lib.check(self.L.wq_set_gene_partition(self.h, int(part), int(nparts)))
 
     def sparse_pack(self) -> np.ndarray:
         used = C.c_uint64()
