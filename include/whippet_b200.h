@@ -166,6 +166,23 @@ int  wq_align_pe_device(wq_handle* h, const wq_align_param* p, const wq_read_bat
 
 int  wq_map_stats_get(wq_handle* h, wq_map_stats* out);
 
+/* FASTQ ingest: make_fqparser + read_chunk! + fill! (src/reads.jl:2-23, src/record.jl:13-19).  The reader inflates
+ * (gzip or plain), splits 4-line records and packs them into a wq_read_batch on the host threads: every sequence byte
+ * that is not one of ACGTacgt becomes A (FASTQ.Reader(..., fill_ambiguous = DNA_A)), quality = byte - qualoffset in
+ * UInt8 arithmetic.  wq_fastq_next returns at most max_reads records (n_reads == 0 at the end of the input) in
+ * page-locked buffers owned by the reader; they stay valid until the call after the next one.  wq_fastq_names gives the
+ * identifiers of the batch returned last (name i = names[name_off[i] .. name_off[i] + name_len[i])).
+ * wq_process_fastq is process_reads! / process_paired_reads! (src/reads.jl:41-129) over whole files (rev_path NULL =
+ * single end): the next batch is parsed while the device aligns and counts the current one. */
+typedef struct wq_fastq wq_fastq;
+int  wq_fastq_open(const char* path, int qualoffset, wq_fastq** out);
+int  wq_fastq_from_memory(const void* text, uint64_t len, int qualoffset, wq_fastq** out);   /* text must outlive the reader */
+int  wq_fastq_next(wq_fastq* f, uint32_t max_reads, wq_read_batch* out);
+int  wq_fastq_names(wq_fastq* f, const uint64_t** name_off, const uint32_t** name_len, const char** names);
+void wq_fastq_close(wq_fastq* f);
+int  wq_process_fastq(wq_handle* h, const wq_align_param* p, const char* fwd_path, const char* rev_path, int qualoffset,
+                      uint32_t batch_reads, wq_map_stats* st);
+
 /* Plumbing with no reference counterpart: run the handle's work on a caller-owned CUDA stream
  * (NULL = the handle's own), per-kernel device milliseconds [seed, extend, resolve] of the last
  * wq_align_*_device call, page-locked host buffers for read batches, and a refresh of the host-side

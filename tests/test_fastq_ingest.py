@@ -1,0 +1,116 @@
+"""FASTQ ingest (wq_fastq_*): packing equals ReadBatch.from_strings with FASTX's fill_ambiguous = DNA_A
+(src/reads.jl:9) and fill!'s UInt8 quality arithmetic (src/record.jl:13-19).  Host-side code: runs without a GPU."""
+import gzip
+import os
+
+import numpy as np
+import pytest
+
+import whippet_jl_b200 as wq
+from whippet_jl_b200 import lib
+from whippet_jl_b200.fastq import FastqReader
+
+
+def make_records(n, seed, ragged=True):
+    rng = np.random.default_rng(seed)
+    recs = []
+    for i in range(n):
+        L = int(rng.integers(0 if i % 97 == 5 else 1, 256)) if ragged else 101
+        seq = "".join(rng.choice(list("ACGTacgtNRYn."), p=[.22, .22, .22, .22, .02, .02, .02, .02, .01, .01, .005, .005, .01], size=L))
+        qual = "".join(chr(int(q)) for q in rng.integers(33, 75, size=L))
+        recs.append((f"read{i}/1 extra words", seq, qual))
+    return recs
+
+
+def to_text(recs, crlf=False, final_newline=True):
+    nl = "\r\n" if crlf else "\n"
+    t = nl.join(f"@{n}{nl}{s}{nl}+{nl}{q}" for n, s, q in recs)
+    return (t + (nl if final_newline else "")).encode()
+
+
+def expect_batch(recs):
+    return wq.ReadBatch.from_strings([r[1] for r in recs], [r[2] for r in recs], 33, fill="A")
+
+
+def check(rb, names, recs):
+    want = expect_batch(recs)
+    assert rb.n == len(recs) and names == [r[0] for r in recs]
+    assert np.array_equal(rb.len, want.len)
+    for i in range(rb.n):
+        L = int(rb.len[i])
+        nw = (L + 31) // 32
+        a = rb.seq2[int(rb.seq_off[i]):int(rb.seq_off[i]) + nw]
+        b = want.seq2[int(want.seq_off[i]):int(want.seq_off[i]) + nw]
+        assert np.array_equal(a, b), i
+        assert np.array_equal(rb.qual[int(rb.qual_off[i]):int(rb.qual_off[i]) + L],
+                              want.qual[int(want.qual_off[i]):int(want.qual_off[i]) + L]), i
+
+
+@pytest.mark.parametrize("crlf,final_newline", [(False, True), (True, True), (False, False)])
+def test_memory_batches_equal_python_packer(crlf, final_newline):
+    recs = make_records(3000, 7)
+    rd = FastqReader(text=to_text(recs, crlf, final_newline))
+    got = 0
+    for size in (1, 999, 5000):
+        out = rd.next_batch(size)
+        assert out is not None
+        rb, names = out
+        check(rb, names, recs[got:got + rb.n])
+        assert rb.n == min(size, len(recs) - got)
+        got += rb.n
+    assert got == len(recs) and rd.next_batch(10) is None
+    rd.close()
+
+
+def test_gzip_file_and_large_batch(tmp_path):
+    recs = make_records(60000, 8, ragged=False)        # larger than one 8 MB inflate chunk, threaded conversion
+    path = os.path.join(tmp_path, "r.fastq.gz")
+    with gzip.open(path, "wb", compresslevel=1) as f:
+        f.write(to_text(recs))
+    rd = FastqReader(path=path)
+    rb, names = rd.next_batch(1 << 20)
+    check(rb, names, recs)
+    assert rd.next_batch(1) is None
+    rd.close()
+
+
+def test_phred64_and_errors(tmp_path):
+    rd = FastqReader(text=b"@a\nACGT\n+\nhhhh\n", qualoffset=64)
+    rb, _ = rd.next_batch(4)
+    assert rb.qual[:4].tolist() == [40] * 4
+    rd.close()
+    for bad, msg in ((b"@a\nACGT\n+\nhh\n", "lengths differ"), (b"a\nACGT\n+\nhhhh\n", "malformed"), (b"@a\nACGT\n+\n", "truncated"),
+                     (b"@a\n" + b"A" * 256 + b"\n+\n" + b"h" * 256 + b"\n", "longer than 255")):
+        rd = FastqReader(text=bad)
+        with pytest.raises(lib.WhippetB200Error, match=msg):
+            rd.next_batch(4)
+        rd.close()
+    with pytest.raises(lib.WhippetB200Error, match="cannot open"):
+        FastqReader(path=os.path.join(tmp_path, "missing.fastq"))
+
+
+@pytest.mark.gpu
+def test_process_fastq_equals_process_reads(tmp_path):
+    from whippet_jl_b200 import synth
+    idx = synth.make_index(n_genes=300, K=9, seed=51, paralog_frac=0.1)
+    rb = synth.simulate_reads(idx, 50000, 101, seed=52, sub_rate=0.01)
+    # render the packed batch back to FASTQ text
+    recs = []
+    for i in range(rb.n):
+        L = int(rb.len[i])
+        w = rb.seq2[int(rb.seq_off[i]):int(rb.seq_off[i]) + (L + 31) // 32]
+        codes = [(int(w[j // 32]) >> (2 * (j % 32))) & 3 for j in range(L)]
+        q = rb.qual[int(rb.qual_off[i]):int(rb.qual_off[i]) + L]
+        recs.append((f"r{i}", "".join("ACGT"[c] for c in codes), "".join(chr(int(x) + 33) for x in q)))
+    path = os.path.join(tmp_path, "reads.fastq.gz")
+    with gzip.open(path, "wb", compresslevel=1) as f:
+        f.write(to_text(recs))
+    p = wq.AlignParam()
+    a, b = wq.GraphLibQuant(idx), wq.GraphLibQuant(idx)
+    sa = a.process_reads(p, rb)
+    sb = b.process_fastq(p, path, batch_reads=12000)            # several batches, parse overlapped with alignment
+    assert (sa.total, sa.mapped, sa.multi, sa.sum_readlen) == (sb.total, sb.mapped, sb.multi, sb.sum_readlen)
+    for x, y in zip(a.counts(), b.counts()):
+        assert np.array_equal(x, y)
+    assert a.keyed(0) == b.keyed(0) and a.keyed(1) == b.keyed(1)
+    a.close(); b.close()

@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 CUDA_SO = os.path.join(CSRC, "libwhippet_b200.so")
 _CU_DEPS = ["whippet_b200.cu", "wq_align.cuh", "wq_kernels.cuh", "wq_types.h", "wq_host_index.h",
-            "wq_host_quant.h", "wq_em.cuh", "wq_events.h"]
+            "wq_host_quant.h", "wq_em.cuh", "wq_events.h", "wq_fastq.h"]
 
 
 def nvcc_path():
@@ -31,7 +31,7 @@ def build_cuda(force=False, verbose=False):
     if not force and not cuda_stale():
         return CUDA_SO
     cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
-           "-Xcompiler", "-fPIC", "-shared", "-o", CUDA_SO, os.path.join(CSRC, "whippet_b200.cu")]
+           "-Xcompiler", "-fPIC", "-shared", "-o", CUDA_SO, os.path.join(CSRC, "whippet_b200.cu"), "-lz"]
     if verbose:
         cmd[1:1] = ["-Xptxas", "-v"]
     subprocess.check_call(cmd)

@@ -21,6 +21,8 @@
 #include "wq_host_quant.h"
 #include "wq_em.cuh"
 #include "wq_events.h"
+#include "wq_fastq.h"
+#include <future>
 
 #include <chrono>
 struct WqTimer {
@@ -744,6 +746,81 @@ int wq_align_pe(wq_handle* h, const wq_align_param* p, const wq_read_batch* fwd,
 int wq_align_pe_device(wq_handle* h, const wq_align_param* p, const wq_read_batch* fwd, const wq_read_batch* rev) {
     if (!rev) return fail(-1, "null mate batch");
     return align_impl(h, p, fwd, rev, nullptr, true);
+}
+
+// ---- FASTQ ingest (src/reads.jl:2-23, src/record.jl:13-19) -----------------------------------------------
+int wq_fastq_open(const char* path, int qualoffset, wq_fastq** out) {
+    if (!path || !out) return fail(-1, "null argument");
+    *out = nullptr;
+    gzFile gz = gzopen(path, "rb");
+    if (!gz) return fail(-20, std::string("cannot open ") + path);
+    gzbuffer(gz, 1u << 20);
+    wq_fastq* f = new wq_fastq();
+    f->gz = gz; f->qualoffset = qualoffset;
+    *out = f;
+    return 0;
+}
+int wq_fastq_from_memory(const void* text, uint64_t len, int qualoffset, wq_fastq** out) {
+    if ((!text && len) || !out) return fail(-1, "null argument");
+    wq_fastq* f = new wq_fastq();
+    f->mem = (const char*)text; f->mem_len = len; f->qualoffset = qualoffset;
+    *out = f;
+    return 0;
+}
+int wq_fastq_next(wq_fastq* f, uint32_t max_reads, wq_read_batch* out) {
+    if (!f || !out) return fail(-1, "null argument");
+    if (max_reads == 0) return fail(-1, "max_reads must be positive");
+    int rc = wq_fastq_next_impl(f, max_reads, out);
+    if (rc) return fail(rc, f->err);
+    return 0;
+}
+// identifiers (the text after '@' up to the end of the line) of the batch returned by the last wq_fastq_next
+int wq_fastq_names(wq_fastq* f, const uint64_t** name_off, const uint32_t** name_len, const char** names) {
+    if (!f || !name_off || !name_len || !names) return fail(-1, "null argument");
+    const WqFastqSlot& S = f->slot[f->cur];
+    *name_off = S.name_off.data(); *name_len = S.name_len.data(); *names = S.names.data();
+    return 0;
+}
+void wq_fastq_close(wq_fastq* f) {
+    if (!f) return;
+    if (f->gz) gzclose(f->gz);
+    f->slot[0].release(); f->slot[1].release();
+    delete f;
+}
+
+// process_reads! / process_paired_reads! (src/reads.jl:41-129) over FASTQ files: the next batch is inflated, split and
+// packed on the host threads while the device aligns and counts the current one.
+int wq_process_fastq(wq_handle* h, const wq_align_param* p, const char* fwd_path, const char* rev_path, int qualoffset,
+                     uint32_t batch_reads, wq_map_stats* st) {
+    if (!h || !p || !fwd_path) return fail(-1, "null argument");
+    if (batch_reads == 0) batch_reads = 1u << 22;
+    wq_fastq* rd[2] = {nullptr, nullptr};
+    if (int rc = wq_fastq_open(fwd_path, qualoffset, &rd[0])) return rc;
+    if (rev_path) { if (int rc = wq_fastq_open(rev_path, qualoffset, &rd[1])) { wq_fastq_close(rd[0]); return rc; } }
+    struct Pair { wq_read_batch b[2]; int rc = 0; std::string err; };
+    auto parse = [&]() {
+        Pair P;
+        for (int k = 0; k < (rev_path ? 2 : 1) && !P.rc; k++) {
+            P.rc = wq_fastq_next_impl(rd[k], batch_reads, &P.b[k]);
+            if (P.rc) P.err = rd[k]->err;
+        }
+        if (!P.rc && rev_path && P.b[0].n_reads != P.b[1].n_reads) { P.rc = -21; P.err = "paired FASTQ files hold different numbers of records"; }
+        return P;
+    };
+    int rc = 0;
+    std::string err;
+    Pair cur = parse();
+    while (!cur.rc && cur.b[0].n_reads) {
+        std::future<Pair> nxt = std::async(std::launch::async, parse);
+        rc = rev_path ? wq_align_pe(h, p, &cur.b[0], &cur.b[1], nullptr) : wq_align_se(h, p, &cur.b[0], nullptr);
+        if (rc) err = g_err;
+        cur = nxt.get();
+        if (rc) break;
+    }
+    if (!rc && cur.rc) { rc = cur.rc; err = cur.err; }
+    wq_fastq_close(rd[0]); wq_fastq_close(rd[1]);
+    if (rc) return fail(rc, err);
+    return st ? wq_map_stats_get(h, st) : 0;
 }
 
 // per-kernel device milliseconds of the last wq_align_*_device call: [seed, extend, resolve]

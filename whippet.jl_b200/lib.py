@@ -55,6 +55,13 @@ def load():
     L.wq_sparse_device_pack.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_uint64)]
     L.wq_sparse_device_merge.argtypes = [vp, vp, C.c_uint64]
     L.wq_set_gene_partition.argtypes = [vp, C.c_uint32, C.c_uint32]
+    L.wq_fastq_open.argtypes = [C.c_char_p, C.c_int, C.POINTER(vp)]
+    L.wq_fastq_from_memory.argtypes = [C.c_char_p, C.c_uint64, C.c_int, C.POINTER(vp)]
+    L.wq_fastq_next.argtypes = [vp, C.c_uint32, C.POINTER(abi.ReadBatchC)]
+    L.wq_fastq_names.argtypes = [vp, C.POINTER(C.POINTER(C.c_uint64)), C.POINTER(C.POINTER(C.c_uint32)), C.POINTER(vp)]
+    L.wq_fastq_close.argtypes = [vp]
+    L.wq_fastq_close.restype = None
+    L.wq_process_fastq.argtypes = [vp, C.POINTER(abi.AlignParamC), C.c_char_p, C.c_char_p, C.c_int, C.c_uint32, C.POINTER(abi.MapStatsC)]
     L.wq_launch_count.argtypes = [vp]
     L.wq_launch_count.restype = C.c_uint64
     L.wq_quant_kernel_stats.argtypes = [vp, C.POINTER(C.c_double)]

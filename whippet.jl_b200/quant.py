@@ -115,6 +115,16 @@ class GraphLibQuant:
         lib.check(self.L.wq_align_pe(self.h, C.byref(p), C.byref(f), C.byref(r), None))
         return self.stats()
 
+    def process_fastq(self, param: AlignParam, fwd_path: str, rev_path: str | None = None, qualoffset: int = 33,
+                      batch_reads: int = 1 << 22) -> MapStats:
+        """process_reads! / process_paired_reads! over FASTQ files (gzip or plain): the library parses and packs the
+        next batch on its host threads while the device aligns and counts the current one."""
+        p = param.c()
+        s = abi.MapStatsC()
+        lib.check(self.L.wq_process_fastq(self.h, C.byref(p), fwd_path.encode(), rev_path.encode() if rev_path else None,
+                                          int(qualoffset), int(batch_reads), C.byref(s)))
+        return MapStats(s.total, s.mapped, s.multi, s.sum_readlen, s.path_overflow)
+
     def stats(self) -> MapStats:
         s = abi.MapStatsC()
         lib.check(self.L.wq_map_stats_get(self.h, C.byref(s)))
