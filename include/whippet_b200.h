@@ -174,6 +174,19 @@ int  wq_map_stats_get(wq_handle* h, wq_map_stats* out);
  * identifiers of the batch returned last (name i = names[name_off[i] .. name_off[i] + name_len[i])).
  * wq_process_fastq is process_reads! / process_paired_reads! (src/reads.jl:41-129) over whole files (rev_path NULL =
  * single end): the next batch is parsed while the device aligns and counts the current one. */
+/* SAM output from the alignments of a batch: sam_flag, cigar_string, write_sam, write_sam_header (src/io.jl:69-276) as
+ * process_reads! / process_paired_reads! call them with sam=true (src/reads.jl:63-67, 110-121).
+ * wq_index_set_gene_info supplies lib.info (reference sequence name and strand per gene; src/types.jl:33-37), which
+ * only SAM output needs.  wq_sam_batch formats every read of a batch aligned into `out` (in read order, on the host
+ * threads); rev / rname_* are NULL for single-end batches.  buf == NULL returns the size in *used.  The @SQ lines of
+ * the header are written in ascending name order (the reference iterates a Dict). */
+int  wq_index_set_gene_info(wq_handle* h, const char* const* seqname, const uint8_t* strand);
+int  wq_sam_header(wq_handle* h, char* buf, uint64_t cap, uint64_t* used);
+int  wq_sam_batch(wq_handle* h, const wq_read_batch* fwd, const wq_read_batch* rev,
+                  const uint64_t* name_off, const uint32_t* name_len, const char* names,
+                  const uint64_t* rname_off, const uint32_t* rname_len, const char* rnames,
+                  const wq_align_out* out, int qualoffset, char* buf, uint64_t cap, uint64_t* used);
+
 typedef struct wq_fastq wq_fastq;
 int  wq_fastq_open(const char* path, int qualoffset, wq_fastq** out);
 int  wq_fastq_from_memory(const void* text, uint64_t len, int qualoffset, wq_fastq** out);   /* text must outlive the reader */

@@ -22,6 +22,7 @@
 #include "wq_em.cuh"
 #include "wq_events.h"
 #include "wq_fastq.h"
+#include "wq_sam.h"
 #include <future>
 
 #include <chrono>
@@ -85,6 +86,7 @@ struct wq_handle {
     WqDevIndex dix;
     WqHostIndex H;               // host mirror (kept for node/gene lookups while building classes)
     WqIsoIndex iso;              // annotated isoform paths (host)
+    WqSamIndex sam;              // node coordinates + lib.info (SAM output only)
     // device index storage
     DevBuf<WqOccBlock> d_occ; DevBuf<uint32_t> d_sa; DevBuf<uint64_t> d_text2; DevBuf<uint32_t> d_amb;
     DevBuf<WqNodeRec> d_nodes; DevBuf<WqGeneRec> d_genes; DevBuf<uint32_t> d_bucket;
@@ -438,6 +440,12 @@ int wq_index_create(const wq_index_desc* d, int device, wq_handle** out) {
     h->device = device;
     std::string err = wq_build_host_index(d, h->H);
     if (err.empty()) err = wq_build_iso_index(d, h->iso);
+    if (err.empty()) {                                       // SAM output only
+        h->sam.node_base.assign(d->node_base, d->node_base + d->n_genes + 1);
+        h->sam.nodeoffset.assign(d->nodeoffset, d->nodeoffset + d->n_nodes);
+        h->sam.nodecoord.assign(d->nodecoord, d->nodecoord + d->n_nodes);
+        h->sam.nodelen.assign(d->nodelen, d->nodelen + d->n_nodes);
+    }
     if (!err.empty()) { delete h; return fail(-3, err); }
 #define CKH(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { std::string m_ = std::string(#call) + ": " + cudaGetErrorString(e_); wq_destroy(h); return fail(-10, m_); } } while (0)
     CKH(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
@@ -821,6 +829,62 @@ int wq_process_fastq(wq_handle* h, const wq_align_param* p, const char* fwd_path
     wq_fastq_close(rd[0]); wq_fastq_close(rd[1]);
     if (rc) return fail(rc, err);
     return st ? wq_map_stats_get(h, st) : 0;
+}
+
+// ---- SAM output (src/io.jl:69-276) ----------------------------------------------------------------------
+// lib.info (src/index.jl:8, src/types.jl:33-37): reference sequence name and strand of every gene
+int wq_index_set_gene_info(wq_handle* h, const char* const* seqname, const uint8_t* strand) {
+    if (!h || !seqname || !strand) return fail(-1, "null argument");
+    h->sam.seqname.clear(); h->sam.strand.clear();
+    for (uint32_t g = 0; g < h->H.G; g++) {
+        if (!seqname[g]) return fail(-1, "null sequence name");
+        h->sam.seqname.emplace_back(seqname[g]);
+        h->sam.strand.push_back(strand[g] ? 1 : 0);
+    }
+    h->sam.has_info = true;
+    return 0;
+}
+
+int wq_sam_header(wq_handle* h, char* buf, uint64_t cap, uint64_t* used) {
+    if (!h || !used) return fail(-1, "null argument");
+    if (!h->sam.has_info) return fail(-15, "SAM output needs wq_index_set_gene_info (lib.info names and strands)");
+    const std::string t = wq_sam_header_text(h->sam);
+    *used = t.size();
+    if (!buf) return 0;
+    if (cap < t.size()) return fail(-7, "SAM buffer too small");
+    memcpy(buf, t.data(), t.size());
+    return 0;
+}
+
+// write_sam for every read of an aligned batch, in read order (src/reads.jl:63-67, 110-121).  `out` is the wq_align_out the
+// batch was aligned into; names are the FASTQ identifiers (wq_fastq_names layout).  Two-call protocol: buf == NULL
+// returns the size (the text is kept for the second call when the arguments are the same batch).
+int wq_sam_batch(wq_handle* h, const wq_read_batch* fwd, const wq_read_batch* rev,
+                 const uint64_t* name_off, const uint32_t* name_len, const char* names,
+                 const uint64_t* rname_off, const uint32_t* rname_len, const char* rnames,
+                 const wq_align_out* out, int qualoffset, char* buf, uint64_t cap, uint64_t* used) {
+    if (!h || !fwd || !out || !used || !name_off || !name_len || !names) return fail(-1, "null argument");
+    if (rev && (!rname_off || !rname_len || !rnames || !out->aln_mate)) return fail(-1, "paired SAM output needs the mate's names and alignments");
+    if (!h->sam.has_info) return fail(-15, "SAM output needs wq_index_set_gene_info (lib.info names and strands)");
+    if (!out->hit_start || !out->nhits || !out->flipped || !out->aln || !out->nodes) return fail(-1, "wq_align_out has null arrays");
+    const uint32_t n = fwd->n_reads;
+    unsigned nt = wq_host_threads();
+    if (n < 4096) nt = 1;
+    std::vector<std::string> parts(nt);
+    auto work = [&](unsigned t) {
+        wq_sam_range(h->sam, parts[t], fwd, rev, name_off, name_len, names, rname_off, rname_len, rnames, out, qualoffset,
+                     (uint32_t)((uint64_t)n * t / nt), (uint32_t)((uint64_t)n * (t + 1) / nt));
+    };
+    if (nt == 1) work(0);
+    else { std::vector<std::thread> th; for (unsigned t = 0; t < nt; t++) th.emplace_back(work, t); for (auto& x : th) x.join(); }
+    uint64_t total = 0;
+    for (auto& s2 : parts) total += s2.size();
+    *used = total;
+    if (!buf) return 0;
+    if (cap < total) return fail(-7, "SAM buffer too small");
+    uint64_t o = 0;
+    for (auto& s2 : parts) { memcpy(buf + o, s2.data(), s2.size()); o += s2.size(); }
+    return 0;
 }
 
 // per-kernel device milliseconds of the last wq_align_*_device call: [seed, extend, resolve]

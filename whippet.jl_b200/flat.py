@@ -39,7 +39,8 @@ class FlatIndex:
     iso_nodes: np.ndarray       # u32[]
     gene_names: list = field(default_factory=list)
     iso_names: list = field(default_factory=list)
-    gene_strand: np.ndarray | None = None   # u8[G] 1 = '+'
+    gene_strand: np.ndarray | None = None   # u8[G] 1 = '+'  (lib.info[g].strand)
+    gene_seqname: list = field(default_factory=list)      # lib.info[g].name (reference sequence; SAM output only)
 
     _ARRAYS = ["gene_offset", "node_base", "nodeoffset", "nodecoord", "nodelen", "edgetype", "edgeleft",
                "edgeright", "seq4", "bwt", "count", "sa", "left_ptr", "left_nodes", "right_ptr",
@@ -93,6 +94,7 @@ class FlatIndex:
                  gene_names=np.array(self.gene_names),
                  iso_names=np.array(self.iso_names),
                  gene_strand=self.gene_strand if self.gene_strand is not None else np.zeros(0, "u1"),
+                 gene_seqname=np.array(self.gene_seqname),
                  **{k: getattr(self, k) for k in self._ARRAYS})
 
     @classmethod
@@ -101,7 +103,8 @@ class FlatIndex:
         kw = {k: z[k] for k in cls._ARRAYS}
         return cls(kmer=int(z["kmer"]), sentinel=int(z["sentinel"]), gene_names=list(map(str, z["gene_names"])),
                    iso_names=list(map(str, z["iso_names"])),
-                   gene_strand=z["gene_strand"] if len(z["gene_strand"]) else None, **kw)
+                   gene_strand=z["gene_strand"] if len(z["gene_strand"]) else None,
+                   gene_seqname=list(map(str, z["gene_seqname"])) if "gene_seqname" in z.files else [], **kw)
 
     # ---- from the reference's own on-disk format ----
     @classmethod
@@ -159,7 +162,8 @@ class FlatIndex:
                    left_ptr=lp, left_nodes=ln, right_ptr=rp, right_nodes=rn,
                    iso_base=np.array(iso_base), iso_node_ptr=np.array(iso_ptr), iso_nodes=np.array(iso_nodes, "<u4"),
                    gene_names=list(lib.names), iso_names=iso_names,
-                   gene_strand=np.array([1 if i.strand else 0 for i in lib.info], "u1"))
+                   gene_strand=np.array([1 if i.strand else 0 for i in lib.info], "u1"),
+                   gene_seqname=[str(i.name) for i in lib.info])
 
 
 # ------------------------------------------------------------------------------------------

@@ -125,6 +125,56 @@ class GraphLibQuant:
                                           int(qualoffset), int(batch_reads), C.byref(s)))
         return MapStats(s.total, s.mapped, s.multi, s.sum_readlen, s.path_overflow)
 
+    # ---- SAM output (src/io.jl:69-276) -------------------------------------------------------------
+    def set_gene_info(self, seqnames, strands):
+        """lib.info (src/types.jl:33-37): reference sequence name and strand ('+' = True) of every gene."""
+        G = self.index.n_genes
+        assert len(seqnames) == G and len(strands) == G
+        arr = (C.c_char_p * G)(*[str(x).encode() for x in seqnames])
+        st = np.ascontiguousarray([1 if x else 0 for x in strands], "u1")
+        lib.check(self.L.wq_index_set_gene_info(self.h, arr, abi.ptr(st, abi.u8p)))
+
+    def sam_header(self) -> str:
+        used = C.c_uint64()
+        lib.check(self.L.wq_sam_header(self.h, None, 0, C.byref(used)))
+        buf = C.create_string_buffer(int(used.value) + 1)
+        lib.check(self.L.wq_sam_header(self.h, buf, used.value, C.byref(used)))
+        return buf.raw[:used.value].decode()
+
+    def sam_batch(self, reads: ReadBatch, names, res: AlignResult, mate: ReadBatch | None = None, mate_names=None,
+                  qualoffset: int = 33) -> str:
+        """write_sam for every read of an aligned batch in read order (process_reads! with sam=true)."""
+        def pack(nm):
+            enc = [x.encode() for x in nm]
+            ln = np.array([len(x) for x in enc], "<u4")
+            off = np.zeros(len(enc), "<u8")
+            if len(enc) > 1:
+                off[1:] = np.cumsum(ln[:-1])
+            return off, ln, b"".join(enc)
+        out = abi.AlignOutC()
+        out.hit_start = abi.ptr(res.hit_start, abi.u32p)
+        out.nhits = abi.ptr(res.nhits, abi.u8p)
+        out.flipped = abi.ptr(res.flipped, abi.u8p)
+        out.aln = res.aln.ctypes.data
+        out.aln_mate = res.aln_mate.ctypes.data if res.aln_mate is not None else None
+        out.nodes = res.nodes.ctypes.data
+        out.aln_cap, out.nodes_cap = len(res.aln), len(res.nodes)
+        out.aln_used, out.nodes_used = len(res.aln), len(res.nodes)
+        b = reads.c()
+        o1, l1, t1 = pack(names)
+        if mate is not None:
+            m = mate.c()
+            o2, l2, t2 = pack(mate_names)
+            args = (C.byref(b), C.byref(m), abi.ptr(o1, abi.u64p), abi.ptr(l1, abi.u32p), t1,
+                    abi.ptr(o2, abi.u64p), abi.ptr(l2, abi.u32p), t2)
+        else:
+            args = (C.byref(b), None, abi.ptr(o1, abi.u64p), abi.ptr(l1, abi.u32p), t1, None, None, None)
+        used = C.c_uint64()
+        lib.check(self.L.wq_sam_batch(self.h, *args, C.byref(out), int(qualoffset), None, 0, C.byref(used)))
+        buf = C.create_string_buffer(int(used.value) + 1)
+        lib.check(self.L.wq_sam_batch(self.h, *args, C.byref(out), int(qualoffset), buf, used.value, C.byref(used)))
+        return buf.raw[:used.value].decode("latin-1")
+
     def stats(self) -> MapStats:
         s = abi.MapStatsC()
         lib.check(self.L.wq_map_stats_get(self.h, C.byref(s)))
