@@ -322,6 +322,7 @@ typedef struct wq_event {
     int32_t  iterations;
     uint32_t _pad2;
     double   psi, total;
+    double   ci_lo, ci_hi;     /* beta_posterior_ci(psi, total, sig = 3) (src/events.jl:790, 816-828); kind == 1 only */
 } wq_event;
 typedef struct wq_events_out {
     uint64_t n_events;     wq_event* events;

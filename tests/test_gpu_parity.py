@@ -300,6 +300,27 @@ def events_parity(idx, p, rb, readlen, mate=None):
             if a["inc"] and a["exc"]:
                 assert a["iterations"] == b["iterations"], key
                 nem += 1
+    # beta_posterior_ci(psi, total, sig=3), src/events.jl:790: the reference's quantile comes from Rmath (not available);
+    # checked against scipy's Beta quantile rounded to 3 significant digits (1e-6 relative is the stated contract for
+    # PSI-derived values; a 3-digit rounding boundary may move one unit in the last place)
+    from scipy.stats import beta as sbeta
+    ks = [b for b in eg if b["kind"] == 1]
+    assert ks
+    psi = np.array([b["psi"] for b in ks]); tot = np.array([b["total"] for b in ks])
+    want = np.stack([sbeta.ppf(0.05, psi * tot + 1, (1 - psi) * tot + 1), sbeta.ppf(0.95, psi * tot + 1, (1 - psi) * tot + 1)], 1)
+
+    def r3(x):
+        x = np.asarray(x, float)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            mag = np.where(x > 0, np.floor(np.log10(np.where(x > 0, x, 1.0))), 0.0)
+        sc = 10.0 ** (2 - mag)
+        return np.where(x > 0, np.round(x * sc) / sc, x)
+    got = np.array([b["ci"] for b in ks])
+    wr = r3(want)
+    close = np.abs(got - wr) <= 1.01e-2 * np.maximum(np.abs(wr), 1e-300)          # at most one unit of the third digit
+    exact = np.abs(got - wr) <= 1e-12 * np.maximum(np.abs(wr), 1e-300)
+    assert close.all() and exact.mean() > 0.999, (close.mean(), exact.mean())
+    assert (got[:, 0] <= got[:, 1]).all()
     q.close()
     return eo, nem
 

@@ -106,8 +106,9 @@ def ptr(a: np.ndarray, typ):
 
 EVENT_DT = np.dtype([("gene", "<u4"), ("node", "<u4"), ("motif", "u1"), ("kind", "u1"), ("flags", "u1"), ("_pad", "u1"),
                      ("n_utr", "<u4"), ("n_inc", "<u4"), ("n_exc", "<u4"), ("value_start", "<u4"), ("path_start", "<u4"),
-                     ("iterations", "<i4"), ("_pad2", "<u4"), ("psi", "<f8"), ("total", "<f8")])
-assert EVENT_DT.itemsize == 56
+                     ("iterations", "<i4"), ("_pad2", "<u4"), ("psi", "<f8"), ("total", "<f8"),
+                     ("ci_lo", "<f8"), ("ci_hi", "<f8")])
+assert EVENT_DT.itemsize == 72
 
 
 class EventsOutC(C.Structure):

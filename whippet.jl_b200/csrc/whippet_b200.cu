@@ -66,6 +66,9 @@ struct WqEvBatch {
     std::vector<long> pshift;            // first problem of every part in P
     WqEmScratch dev;                     // device arrays of this group's PSI launch (the two launches overlap in time)
     double* psi = nullptr; int32_t* its = nullptr; size_t psi_cap = 0, its_cap = 0;     // pinned results
+    // Beta posterior CI of the events whose psi is known without EM (most of them): launched with the batch
+    std::vector<double> ci_psi, ci_tot;
+    double* ci_out = nullptr; size_t ci_cap = 0;                                         // pinned: lo[n] then hi[n]
     cudaStream_t stream = nullptr;       // own stream: the group's uploads, kernels and result copies are ordered against nothing else
     bool built = false, launched = false;
     int64_t readlen = -1;
@@ -75,7 +78,7 @@ struct WqEvBatch {
         if (nits > its_cap) { if (its) cudaFreeHost(its); its = nullptr; its_cap = 0; cudaError_t e = cudaMallocHost(&its, (nits + nits / 4 + 16) * 4); if (e != cudaSuccess) return e; its_cap = nits + nits / 4 + 16; }
         return cudaSuccess;
     }
-    void release() { dev.release(); if (stream) cudaStreamDestroy(stream); stream = nullptr; if (psi) cudaFreeHost(psi); if (its) cudaFreeHost(its); psi = nullptr; its = nullptr; psi_cap = its_cap = 0; }
+    void release() { dev.release(); if (stream) cudaStreamDestroy(stream); stream = nullptr; if (ci_out) cudaFreeHost(ci_out); ci_out = nullptr; ci_cap = 0; if (psi) cudaFreeHost(psi); if (its) cudaFreeHost(its); psi = nullptr; its = nullptr; psi_cap = its_cap = 0; }
 };
 
 struct wq_handle {
@@ -378,6 +381,15 @@ static void wq_build_event_batch(wq_handle* h, int64_t readlen, int group, WqEvB
     }
     B.P.resize_total(at[nt]);
     run([&](unsigned t) { B.P.place(B.parts[t].P, at[t]); });
+    B.ci_psi.clear(); B.ci_tot.clear();
+    for (unsigned t = 0; t < nt; t++)
+        for (uint32_t i = 0; i < B.parts[t].recs.size(); i++) {
+            const WqEventRec& r = B.parts[t].recs[i];
+            if (r.kind == 1 && r.problem < 0 && r.total > 0 && r.psi >= 0.0 && r.psi <= 1.0) {
+                B.parts[t].recs[i].ci_slot = (int32_t)B.ci_psi.size();
+                B.ci_psi.push_back(r.psi); B.ci_tot.push_back(r.total);
+            }
+        }
     B.built = true;
     B.launched = false;
     B.readlen = readlen;
@@ -388,9 +400,15 @@ static void wq_build_event_batch(wq_handle* h, int64_t readlen, int group, WqEvB
 static int wq_launch_event_batch(wq_handle* h, WqEvBatch& B) {
     WqPsiProblems& P = B.P;
     B.launched = false;
+    CK(B.ensure_stream());
+    if (const size_t nci = B.ci_psi.size()) {
+        if (2 * nci > B.ci_cap) { if (B.ci_out) cudaFreeHost(B.ci_out); B.ci_out = nullptr; B.ci_cap = 0; CK(cudaMallocHost(&B.ci_out, (2 * nci + 64) * 8)); B.ci_cap = 2 * nci + 64; }
+        std::string err = wq_run_beta_ci((uint32_t)nci, B.ci_psi.data(), B.ci_tot.data(), B.ci_out, B.ci_out + nci, B.dev, B.stream, &h->launches, /*wait=*/false);
+        if (!err.empty()) return fail(-13, err);
+        B.launched = true;
+    }
     if (!P.size()) return 0;
     CK(B.ensure_pinned(P.count.size(), P.size()));
-    CK(B.ensure_stream());
     wq_psi_batch b;
     memset(&b, 0, sizeof b);
     b.n_events = (uint32_t)P.size();
@@ -1247,7 +1265,7 @@ int wq_em_tpm(wq_handle* h, const wq_em_param* p, double* tpm, double* count, do
     int overlap_rc = 0;
     const std::function<void()> overlap = [&]() {
         WqTimer t2("  events of untouched genes (under the EM kernel)");
-        wq_finalize_edges(h->hq, h->hx);
+        { WqTimer t3("    finalize edges"); wq_finalize_edges(h->hq, h->hx); }
         wq_build_event_batch(h, p->readlen, 0, h->ev_batch[0]);
         // their PSI EM goes to its own stream right away: its blocks fill in beside the EM kernel's and the few events that need
         // all 1500 sweeps (a pure latency chain) start early
@@ -1313,6 +1331,7 @@ int wq_process_events(wq_handle* h, int64_t readlen, wq_events_out* out) {
         // records in gene order: per host-thread gene range, merge the two groups' records by gene
         const size_t nparts = B0.parts.size();
         if (B1.parts.size() != nparts) return fail(-14, "event batches were built with different host thread counts");
+
         std::vector<size_t> rec_at(nparts + 1, 0);
         std::vector<uint64_t> pool_paths(2 * nparts + 1, 0), pool_nodes(2 * nparts + 1, 0);      // group-major: (group, part)
         for (size_t t = 0; t < nparts; t++) rec_at[t + 1] = rec_at[t] + B0.parts[t].recs.size() + B1.parts[t].recs.size();
@@ -1362,35 +1381,76 @@ int wq_process_events(wq_handle* h, int64_t readlen, wq_events_out* out) {
         B0.launched = B1.launched = false;
         lap("+ PSI EM kernels done");
         if (prof) fprintf(stderr, "[wq]   events: %zu records, %zu + %zu EM problems (untouched + touched genes)\n", h->ev_recs.size(), B0.P.size(), B1.P.size());
-        // finish the records (src/events.jl:776-796)
-        h->ev_values.clear();
-        h->ev_values.reserve(B0.P.count.size() + B1.P.count.size() + h->ev_recs.size());
-        for (auto& r : h->ev_recs) {
-            const WqPsiProblems& P = h->ev_batch[r.batch].P;
-            const double* psi = h->ev_batch[r.batch].psi;
-            const int32_t* its = h->ev_batch[r.batch].its;
-            r.value_start = (uint32_t)h->ev_values.size();
+        // finish the records (src/events.jl:776-796) on the host threads: record ranges as merged above; the value array is
+        // laid out by a counting pass + prefix sums.  Spliced events solved without EM pick up the Beta posterior CI that was
+        // launched with their batch; the EM events' psi is only known now, so theirs is one more (small) launch.
+        auto n_values_of = [&](const WqEventRec& r) -> uint32_t {
             if (r.kind == 2) {
-                bool ok = r.problem >= 0;
-                if (ok) {
-                    const uint32_t p0 = P.path_ptr[r.problem], p1 = P.path_ptr[r.problem + 1];
-                    for (uint32_t i = p0; i < p1; i++) if (std::isnan(psi[i])) ok = false;
-                    if (ok) for (uint32_t i = p0; i < p1; i++) { double v = std::nearbyint(psi[i] * 10000.0) / 10000.0; h->ev_values.push_back(std::isfinite(v) ? v : psi[i]); }
-                    r.iterations_ = its[r.problem];
-                }
-                if (!ok) { h->ev_values.insert(h->ev_values.end(), r.n_utr, 0.0); r.flags |= 1; r.total = 0.0; }
-            } else if (r.problem >= 0) {
-                const uint32_t p0 = P.path_ptr[r.problem], p1 = P.path_ptr[r.problem + 1], ni = P.n_inc[r.problem];
-                double s = 0.0;
-                for (uint32_t i = p0; i < p0 + ni; i++) s += psi[i];
-                r.psi = s;
-                h->ev_values.insert(h->ev_values.end(), psi + p0, psi + p1);
-                r.iterations_ = its[r.problem];
-                r.kind = (0.0 <= r.psi && r.psi <= 1.0 && r.total > 0) ? 1 : 0;
-            } else if (r.kind == 1) {
-                r.kind = (r.total > 0) ? 1 : 0;
+                if (r.problem < 0) return r.n_utr;
+                const WqEvBatch& B = h->ev_batch[r.batch];
+                const uint32_t p0 = B.P.path_ptr[r.problem], p1 = B.P.path_ptr[r.problem + 1];
+                for (uint32_t i = p0; i < p1; i++) if (std::isnan(B.psi[i])) return r.n_utr;
+                return p1 - p0;
             }
-            r.n_values = (uint32_t)h->ev_values.size() - r.value_start;
+            if (r.problem >= 0) { const WqPsiProblems& P = h->ev_batch[r.batch].P; return P.path_ptr[r.problem + 1] - P.path_ptr[r.problem]; }
+            return 0;
+        };
+        std::vector<uint64_t> val_at(nparts + 1, 0);
+        auto par = [&](const std::function<void(size_t)>& f) {
+            if (nparts == 1) { f(0); return; }
+            std::vector<std::thread> th;
+            for (size_t t = 0; t < nparts; t++) th.emplace_back(f, t);
+            for (auto& x : th) x.join();
+        };
+        par([&](size_t t) { uint64_t c = 0; for (size_t i = rec_at[t]; i < rec_at[t + 1]; i++) c += n_values_of(h->ev_recs[i]); val_at[t + 1] = c; });
+        for (size_t t = 0; t < nparts; t++) val_at[t + 1] += val_at[t];
+        h->ev_values.resize(val_at[nparts]);
+        struct CiIn { std::vector<uint32_t> idx; std::vector<double> psi, tot; };
+        std::vector<CiIn> cin(nparts);
+        par([&](size_t t) {
+            uint64_t vo = val_at[t];
+            for (size_t ri = rec_at[t]; ri < rec_at[t + 1]; ri++) {
+                WqEventRec& r = h->ev_recs[ri];
+                const WqEvBatch& B = h->ev_batch[r.batch];
+                const WqPsiProblems& P = B.P;
+                const double* psi = B.psi;
+                const int32_t* its = B.its;
+                r.value_start = (uint32_t)vo;
+                if (r.kind == 2) {
+                    bool ok = r.problem >= 0;
+                    if (ok) {
+                        const uint32_t p0 = P.path_ptr[r.problem], p1 = P.path_ptr[r.problem + 1];
+                        for (uint32_t i = p0; i < p1; i++) if (std::isnan(psi[i])) ok = false;
+                        if (ok) for (uint32_t i = p0; i < p1; i++) { double v = std::nearbyint(psi[i] * 10000.0) / 10000.0; h->ev_values[vo++] = std::isfinite(v) ? v : psi[i]; }
+                        r.iterations_ = its[r.problem];
+                    }
+                    if (!ok) { for (uint32_t k = 0; k < r.n_utr; k++) h->ev_values[vo++] = 0.0; r.flags |= 1; r.total = 0.0; }
+                } else if (r.problem >= 0) {
+                    const uint32_t p0 = P.path_ptr[r.problem], p1 = P.path_ptr[r.problem + 1], ni = P.n_inc[r.problem];
+                    double sm = 0.0;
+                    for (uint32_t i = p0; i < p0 + ni; i++) sm += psi[i];
+                    r.psi = sm;
+                    for (uint32_t i = p0; i < p1; i++) h->ev_values[vo++] = psi[i];
+                    r.iterations_ = its[r.problem];
+                    r.kind = (0.0 <= r.psi && r.psi <= 1.0 && r.total > 0) ? 1 : 0;
+                    if (r.kind == 1) { cin[t].idx.push_back((uint32_t)ri); cin[t].psi.push_back(r.psi); cin[t].tot.push_back(r.total); }
+                } else if (r.kind == 1) {
+                    r.kind = (r.total > 0) ? 1 : 0;
+                    if (r.kind == 1 && r.ci_slot >= 0) { const size_t nci = B.ci_psi.size(); r.ci_lo = B.ci_out[r.ci_slot]; r.ci_hi = B.ci_out[nci + r.ci_slot]; }
+                }
+                r.n_values = (uint32_t)(vo - r.value_start);
+            }
+        });
+        lap("+ records finished");
+        {
+            std::vector<uint32_t> idx;
+            std::vector<double> cpsi, ctot;
+            for (auto& c : cin) { idx.insert(idx.end(), c.idx.begin(), c.idx.end()); cpsi.insert(cpsi.end(), c.psi.begin(), c.psi.end()); ctot.insert(ctot.end(), c.tot.begin(), c.tot.end()); }
+            std::vector<double> lo(idx.size()), hi(idx.size());
+            std::string err = wq_run_beta_ci((uint32_t)idx.size(), cpsi.data(), ctot.data(), lo.data(), hi.data(), h->em_scratch, h->stream, &h->launches);
+            if (!err.empty()) return fail(-13, err);
+            for (size_t k = 0; k < idx.size(); k++) { h->ev_recs[idx[k]].ci_lo = lo[k]; h->ev_recs[idx[k]].ci_hi = hi[k]; }
+            lap("+ Beta posterior CI of the EM events");
         }
         h->events_done = true;
     }
@@ -1406,7 +1466,7 @@ int wq_process_events(wq_handle* h, int64_t readlen, wq_events_out* out) {
         memset(&e, 0, sizeof e);
         e.gene = r.gene; e.node = r.node; e.motif = r.motif; e.kind = r.kind; e.flags = r.flags;
         e.n_utr = r.n_utr; e.n_inc = r.n_inc; e.n_exc = r.n_exc; e.value_start = r.value_start; e.path_start = r.path_first;
-        e.iterations = r.iterations_; e.psi = r.psi; e.total = r.total;
+        e.iterations = r.iterations_; e.psi = r.psi; e.total = r.total; e.ci_lo = r.ci_lo; e.ci_hi = r.ci_hi;
         out->events[i] = e;
     }
     if (nv) memcpy(out->values, h->ev_values.data(), nv * 8);

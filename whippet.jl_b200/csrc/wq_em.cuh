@@ -967,3 +967,134 @@ static inline std::string wq_run_em_psi(wq_psi_batch& b, WqEmScratch& M, cudaStr
     if (wait) WQ_EMCK(cudaStreamSynchronize(stream));
     return "";
 }
+
+
+// ------------------------------------------------------------------------------------------ Beta posterior CI
+// beta_posterior_ci(psi, total; ci = 0.9, sig = 3), src/events.jl:816-828 (call site :790): the 5 % and 95 % quantiles of
+// Beta(psi * n + 1, (1 - psi) * n + 1), rounded to 3 significant digits.  The reference gets the quantile from
+// Distributions 0.24.15 -> Rmath qbeta, which is not available here (parity unpinned); this is the regularised incomplete
+// beta function by Lentz's continued fraction and a bracketed Newton iteration on it, carried to ~1e-14 relative, so the
+// 3-digit rounded values agree with any accurate quantile except within ~1e-11 of a rounding boundary.
+// One thread per quantile (2 per event): independent Float64 work, a few thousand flops each.
+#define WQ_CI_GL 32
+struct WqCiDev { uint32_t n; const double* psi; const double* total; double* lo; double* hi; WqPsiDev tab;
+                 double gl_y[WQ_CI_GL], gl_w[WQ_CI_GL]; };      // Gauss-Legendre nodes / weights on [0, 1]
+
+__device__ inline double wq_betacf(double a, double b, double x) {          // continued fraction of I_x(a, b), modified Lentz
+    const double tiny = 1e-300, eps = 1e-14;     // (machine epsilon is 2.2e-16: a smaller bound may never be met)
+    const double qab = a + b, qap = a + 1.0, qam = a - 1.0;
+    double c = 1.0, d = 1.0 - qab * x / qap;
+    if (fabs(d) < tiny) d = tiny;
+    d = 1.0 / d;
+    double h = d;
+    for (int m = 1; m <= 10000; m++) {
+        const double m2 = 2.0 * m;
+        double aa = m * (b - m) * x / ((qam + m2) * (a + m2));
+        d = 1.0 + aa * d; if (fabs(d) < tiny) d = tiny;
+        c = 1.0 + aa / c; if (fabs(c) < tiny) c = tiny;
+        d = 1.0 / d;
+        h *= d * c;
+        aa = -(a + m) * (qab + m) * x / ((a + m2) * (qap + m2));
+        d = 1.0 + aa * d; if (fabs(d) < tiny) d = tiny;
+        c = 1.0 + aa / c; if (fabs(c) < tiny) c = tiny;
+        d = 1.0 / d;
+        const double del = d * c;
+        h *= del;
+        if (fabs(del - 1.0) < eps) break;
+    }
+    return h;
+}
+// I_x(a, b) for a, b > 3000 by Gauss-Legendre quadrature of the density between x and a point ~10 standard deviations
+// beyond the mean (the continued fraction needs O(sqrt(max(a, b))) terms there); relative error of the resulting
+// quantile below 2e-10 (checked against scipy.special.betaincinv over n = 1e4 .. 1e7)
+__device__ inline double wq_betainc_quad(const WqCiDev& d, double a, double b, double x, double lbeta) {
+    const double a1 = a - 1.0, b1 = b - 1.0, mu = a / (a + b), lnmu = log(mu), lnmuc = log1p(-mu);
+    const double t = sqrt(a * b / ((a + b) * (a + b) * (a + b + 1.0)));
+    double xu;
+    if (x > mu) { if (x >= 1.0) return 1.0; xu = fmin(1.0, fmax(mu + 10.0 * t, x + 5.0 * t)); }
+    else { if (x <= 0.0) return 0.0; xu = fmax(0.0, fmin(mu - 10.0 * t, x - 5.0 * t)); }
+    double sum = 0.0;
+    for (int j = 0; j < WQ_CI_GL; j++) {
+        const double tt = x + (xu - x) * d.gl_y[j];
+        sum += d.gl_w[j] * exp(a1 * (log(tt) - lnmu) + b1 * (log1p(-tt) - lnmuc));
+    }
+    const double ans = sum * (xu - x) * exp(a1 * lnmu + b1 * lnmuc - lbeta);
+    return ans > 0.0 ? 1.0 - ans : -ans;
+}
+// I_x(a, b) and the density at x
+__device__ inline double wq_betainc(const WqCiDev& d, double a, double b, double x, double lbeta, double* pdf) {
+    if (x <= 0.0) { *pdf = 0.0; return 0.0; }
+    if (x >= 1.0) { *pdf = 0.0; return 1.0; }
+    const double lfront = a * log(x) + b * log1p(-x) - lbeta;
+    *pdf = exp(lfront - log(x) - log1p(-x));
+    if (a > 3000.0 && b > 3000.0) return wq_betainc_quad(d, a, b, x, lbeta);
+    const double front = exp(lfront);
+    if (x < (a + 1.0) / (a + b + 2.0)) return front * wq_betacf(a, b, x) / a;
+    return 1.0 - front * wq_betacf(b, a, 1.0 - x) / b;
+}
+__device__ inline double wq_beta_quantile(const WqCiDev& d, double a, double b, double q, double z) {
+    const double lbeta = lgamma(a) + lgamma(b) - lgamma(a + b);
+    double lo = 0.0, hi = 1.0;
+    // start at the normal approximation of the quantile (the continued fraction is slowest at the mean)
+    double x = a / (a + b) + z * sqrt(a * b / ((a + b) * (a + b) * (a + b + 1.0)));
+    if (!(x > 0.0)) x = 0.5 * (a / (a + b));
+    if (!(x < 1.0)) x = 0.5 * (1.0 + a / (a + b));
+    for (int it = 0; it < 200; it++) {
+        double pdf;
+        const double f = wq_betainc(d, a, b, x, lbeta, &pdf) - q;
+        if (f > 0.0) hi = x; else lo = x;
+        double nx = (pdf > 0.0 && isfinite(pdf)) ? x - f / pdf : 0.5 * (lo + hi);
+        if (!(nx >= lo && nx <= hi)) nx = 0.5 * (lo + hi);          // inclusive: a step too small to move x is convergence
+        if (fabs(nx - x) <= 1e-13 * fabs(x) || hi - lo <= 1e-15 * hi) { x = nx; break; }
+        x = nx;
+    }
+    return x;
+}
+__global__ void __launch_bounds__(128) wq_k_beta_ci(const WqCiDev d) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 2 * d.n) return;
+    const uint32_t e = t >> 1;
+    const double p = d.psi[e], n = d.total[e];
+    const double a = __dadd_rn(__dmul_rn(p, n), 1.0), b = __dadd_rn(__dmul_rn(__dsub_rn(1.0, p), n), 1.0);
+    const double q = (t & 1) ? 1.0 - (1.0 - 0.9) / 2 : (1.0 - 0.9) / 2;       // lo_q = (1 - ci) / 2, hi_q = 1 - lo_q
+    const double v = wq_round_sig(d.tab, wq_beta_quantile(d, a, b, q, (t & 1) ? 1.6448536269514722 : -1.6448536269514722), 3);
+    if (t & 1) d.hi[e] = v; else d.lo[e] = v;
+}
+
+// `wait` = false leaves the launch and its result copies in flight (lo / hi must then be pinned host memory)
+static inline std::string wq_run_beta_ci(uint32_t n, const double* psi, const double* total, double* lo, double* hi,
+                                         WqEmScratch& M, cudaStream_t stream, uint64_t* launches, bool wait = true) {
+    if (n == 0) return "";
+    WqCiDev d;
+    d.n = n;
+    for (int k = 0; k <= 22; k++) { d.tab.p10[k] = std::pow(10.0, (double)k); d.tab.ip10[k] = 1.0 / d.tab.p10[k]; }
+    {   // Gauss-Legendre nodes on [-1, 1] by Newton iteration on P_n, mapped to [0, 1]
+        const int n = WQ_CI_GL;
+        for (int i = 0; i < (n + 1) / 2; i++) {
+            double zz = std::cos(3.14159265358979323846 * (i + 0.75) / (n + 0.5)), pp = 1.0;
+            for (int it = 0; it < 100; it++) {
+                double p1 = 1.0, p2 = 0.0;
+                for (int j = 0; j < n; j++) { const double p3 = p2; p2 = p1; p1 = ((2.0 * j + 1.0) * zz * p2 - j * p3) / (j + 1.0); }
+                pp = n * (zz * p1 - p2) / (zz * zz - 1.0);
+                const double z1 = zz;
+                zz = z1 - p1 / pp;
+                if (std::fabs(zz - z1) < 1e-16) break;
+            }
+            const double w = 2.0 / ((1.0 - zz * zz) * pp * pp);
+            d.gl_y[i] = 0.5 * (1.0 - zz); d.gl_y[n - 1 - i] = 0.5 * (1.0 + zz);
+            d.gl_w[i] = 0.5 * w; d.gl_w[n - 1 - i] = 0.5 * w;
+        }
+    }
+    double *d_psi, *d_tot, *d_lo, *d_hi;
+    WQ_EMCK(M.get(15, n, &d_psi)); WQ_EMCK(M.get(16, n, &d_tot)); WQ_EMCK(M.get(17, n, &d_lo)); WQ_EMCK(M.get(18, n, &d_hi));
+    WQ_EMCK(cudaMemcpyAsync(d_psi, psi, n * 8ull, cudaMemcpyHostToDevice, stream));
+    WQ_EMCK(cudaMemcpyAsync(d_tot, total, n * 8ull, cudaMemcpyHostToDevice, stream));
+    d.psi = d_psi; d.total = d_tot; d.lo = d_lo; d.hi = d_hi;
+    wq_k_beta_ci<<<(2 * n + 127) / 128, 128, 0, stream>>>(d);
+    if (launches) *launches += 1;
+    WQ_EMCK(cudaGetLastError());
+    WQ_EMCK(cudaMemcpyAsync(lo, d_lo, n * 8ull, cudaMemcpyDeviceToHost, stream));
+    WQ_EMCK(cudaMemcpyAsync(hi, d_hi, n * 8ull, cudaMemcpyDeviceToHost, stream));
+    if (wait) WQ_EMCK(cudaStreamSynchronize(stream));
+    return "";
+}

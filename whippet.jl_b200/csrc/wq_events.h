@@ -78,11 +78,12 @@ struct WqAmbSet { std::vector<uint32_t> paths; double mult; };      // AmbigCoun
 struct WqEventRec {                     // one record per visited node (include/whippet_b200.h::wq_event)
     uint32_t gene, node; uint8_t motif, kind, flags;
     uint32_t n_utr = 0, n_inc = 0, n_exc = 0;
-    double psi = 0.0, total = 0.0;
+    double psi = 0.0, total = 0.0, ci_lo = 0.0, ci_hi = 0.0;
     long problem = -1;                  // index into the EM batch, -1 when no EM is needed
     int32_t iterations_ = 0;
     uint32_t path_first = 0, n_paths = 0;           // into the owning WqEventPool: utr paths, or inclusion then exclusion paths
     uint32_t value_start = 0, n_values = 0;         // into the finished value array
+    int32_t ci_slot = -1;                           // spliced event solved without EM: its slot in the batch's Beta-CI launch
     uint8_t batch = 0;                              // which gene group built it (0: genes no multi-map read touches, 1: the others)
 };
 

@@ -87,22 +87,54 @@ struct WqHostQuantEx {
     float em_kernel_ms = 0.f;                                // device time of the transcript EM kernel (CUDA events)
 };
 
-// base counts + additions (stable by key, so every key sees its additions in the order they were made)
+// base counts + additions (stable by key, so every key sees its additions in the order they were made).  Keys are
+// gene-major, so host threads take contiguous key ranges: each sorts the additions that fall into its range, merges them
+// with its slice of the base edges, and the slices are concatenated.
 static inline void wq_finalize_edges(const WqHostQuant& hq, WqHostQuantEx& X) {
-    std::vector<std::pair<uint64_t, double>> adds = X.edge_adds;
-    std::stable_sort(adds.begin(), adds.end(), [](const std::pair<uint64_t, double>& a, const std::pair<uint64_t, double>& b) { return a.first < b.first; });
-    X.edge_key.clear(); X.edge_value.clear();
-    size_t i = 0, j = 0;
-    const size_t ne = hq.edge_key.size(), na = adds.size();
-    while (i < ne || j < na) {
-        uint64_t k;
-        double v = 0.0;
-        if (j >= na || (i < ne && hq.edge_key[i] <= adds[j].first)) { k = hq.edge_key[i]; v = (double)hq.edge_count[i]; i++; }
-        else k = adds[j].first;
-        while (j < na && adds[j].first == k) { v += adds[j].second; j++; }
-        X.edge_key.push_back(k);
-        X.edge_value.push_back(v);
+    const size_t ne = hq.edge_key.size(), na = X.edge_adds.size();
+    unsigned nt = wq_host_threads();
+    if (ne + na < (1u << 16)) nt = 1;
+    // split points: equal shares of the base edges, moved to a gene boundary so no key straddles two ranges
+    std::vector<uint64_t> cut(nt + 1, 0);
+    cut[nt] = ~0ull;
+    for (unsigned t = 1; t < nt; t++) {
+        const size_t i = ne * t / nt;
+        cut[t] = i < ne ? (hq.edge_key[i] >> 32) << 32 : ~0ull;
+        if (cut[t] < cut[t - 1]) cut[t] = cut[t - 1];
     }
+    struct Part { std::vector<std::pair<uint64_t, double>> adds; std::vector<uint64_t> key; std::vector<double> value; };
+    std::vector<Part> parts(nt);
+    auto work = [&](unsigned t) {
+        Part& P = parts[t];
+        const uint64_t lo = cut[t], hi = cut[t + 1];
+        for (const auto& a : X.edge_adds) if (a.first >= lo && a.first < hi) P.adds.push_back(a);
+        std::stable_sort(P.adds.begin(), P.adds.end(), [](const std::pair<uint64_t, double>& a, const std::pair<uint64_t, double>& b) { return a.first < b.first; });
+        size_t i = std::lower_bound(hq.edge_key.begin(), hq.edge_key.end(), lo) - hq.edge_key.begin();
+        const size_t ie = hi == ~0ull ? ne : (size_t)(std::lower_bound(hq.edge_key.begin(), hq.edge_key.end(), hi) - hq.edge_key.begin());
+        size_t j = 0;
+        const size_t ja = P.adds.size();
+        P.key.reserve(ie - i + ja); P.value.reserve(ie - i + ja);
+        while (i < ie || j < ja) {
+            uint64_t k;
+            double v = 0.0;
+            if (j >= ja || (i < ie && hq.edge_key[i] <= P.adds[j].first)) { k = hq.edge_key[i]; v = (double)hq.edge_count[i]; i++; }
+            else k = P.adds[j].first;
+            while (j < ja && P.adds[j].first == k) { v += P.adds[j].second; j++; }
+            P.key.push_back(k);
+            P.value.push_back(v);
+        }
+    };
+    if (nt == 1) work(0);
+    else { std::vector<std::thread> th; for (unsigned t = 0; t < nt; t++) th.emplace_back(work, t); for (auto& x : th) x.join(); }
+    std::vector<size_t> at(nt + 1, 0);
+    for (unsigned t = 0; t < nt; t++) at[t + 1] = at[t] + parts[t].key.size();
+    X.edge_key.resize(at[nt]); X.edge_value.resize(at[nt]);
+    auto place = [&](unsigned t) {
+        std::copy(parts[t].key.begin(), parts[t].key.end(), X.edge_key.begin() + at[t]);
+        std::copy(parts[t].value.begin(), parts[t].value.end(), X.edge_value.begin() + at[t]);
+    };
+    if (nt == 1) place(0);
+    else { std::vector<std::thread> th; for (unsigned t = 0; t < nt; t++) th.emplace_back(place, t); for (auto& x : th) x.join(); }
     X.edges_final = true;
 }
 

@@ -275,7 +275,8 @@ class GraphLibQuant:
         out = []
         for e in ev:
             d = dict(gene=int(e["gene"]), node=int(e["node"]), motif=int(e["motif"]), kind=int(e["kind"]), flags=int(e["flags"]),
-                     psi=float(e["psi"]), total=float(e["total"]), iterations=int(e["iterations"]), utr_psi=[], inc=[], exc=[])
+                     psi=float(e["psi"]), total=float(e["total"]), iterations=int(e["iterations"]), utr_psi=[], inc=[], exc=[],
+                     ci=(float(e["ci_lo"]), float(e["ci_hi"])))
             vs, ps = int(e["value_start"]), int(e["path_start"])
             path = lambda k: tuple(int(x) for x in pnodes[int(pptr[ps + k]):int(pptr[ps + k + 1])])
             if d["kind"] == 2:
