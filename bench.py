@@ -261,7 +261,7 @@ def main():
         t1 = time.perf_counter()
         it, tpm, cnt, gt = q.gene_em(em_readlen, 1, 10000)
         q.assign_ambig()
-        ev = q.process_events_raw(em_readlen)       # event construction + batched PSI EM
+        ev = q.process_events_view(em_readlen)      # event construction + batched PSI EM (records lent by the library, no copy)
         phase["events"] = len(ev[0])
         t2 = time.perf_counter()
         phase["exchange"] += t1 - t0

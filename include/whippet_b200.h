@@ -331,6 +331,9 @@ typedef struct wq_events_out {
     uint64_t n_path_nodes; uint32_t* path_nodes;
 } wq_events_out;
 int  wq_process_events(wq_handle* h, int64_t readlen, wq_events_out* out);   /* two-call protocol (NULL buffers -> sizes) */
+/* Same result without the copy: the pointers of `out` are set to arrays owned by the handle, valid until the count state
+ * changes (wq_quant_reset, wq_align_*, merges, wq_set_gene_partition) or the handle is destroyed. */
+int  wq_process_events_view(wq_handle* h, int64_t readlen, wq_events_out* out);
 
 #ifdef __cplusplus
 }

@@ -300,6 +300,8 @@ def events_parity(idx, p, rb, readlen, mate=None):
             if a["inc"] and a["exc"]:
                 assert a["iterations"] == b["iterations"], key
                 nem += 1
+    raw, view = q.process_events_raw(readlen), q.process_events_view(readlen)       # copy and zero-copy forms agree
+    assert all(np.array_equal(a, b) for a, b in zip(raw, view)) and len(raw[0]) == len(eg)
     # beta_posterior_ci(psi, total, sig=3), src/events.jl:790: the reference's quantile comes from Rmath (not available);
     # checked against scipy's Beta quantile rounded to 3 significant digits (1e-6 relative is the stated contract for
     # PSI-derived values; a 3-digit rounding boundary may move one unit in the last place)

@@ -110,6 +110,7 @@ struct wq_handle {
     WqEmScratch em_scratch;
     std::vector<WqEventRec> ev_recs; std::vector<double> ev_values; std::vector<uint64_t> ev_path_ptr{0}; std::vector<uint32_t> ev_path_nodes;
     bool events_done = false;
+    std::vector<wq_event> ev_out;        // the finished records in ABI form (wq_process_events copies them, _view lends them)
     float psi_kernel_ms = 0.f;   // device time of the PSI EM launches of the last wq_process_events (CUDA events on the stream)
     uint64_t psi_sweep_bytes = 0;
     WqEvBatch ev_batch[2];       // event problems of the genes no multi-map read touches (built while the transcript EM runs) / of the others
@@ -1308,7 +1309,10 @@ int wq_em_psi_batch(wq_handle* h, wq_psi_batch* b) {
     return 0;
 }
 
-int wq_process_events(wq_handle* h, int64_t readlen, wq_events_out* out) {
+static int process_events_impl(wq_handle* h, int64_t readlen, wq_events_out* out, bool view);
+int wq_process_events(wq_handle* h, int64_t readlen, wq_events_out* out) { return process_events_impl(h, readlen, out, false); }
+int wq_process_events_view(wq_handle* h, int64_t readlen, wq_events_out* out) { return process_events_impl(h, readlen, out, true); }
+static int process_events_impl(wq_handle* h, int64_t readlen, wq_events_out* out, bool view) {
     if (!h || !out) return fail(-1, "null argument");
     if (!h->hx.built || !h->hx.em_done || !h->hx.ambig_done) return fail(-14, "wq_process_events needs wq_em_tpm and wq_assign_ambig first (bin/whippet-quant.jl:177-181)");
     CK(cudaSetDevice(h->device));
@@ -1452,23 +1456,32 @@ int wq_process_events(wq_handle* h, int64_t readlen, wq_events_out* out) {
             for (size_t k = 0; k < idx.size(); k++) { h->ev_recs[idx[k]].ci_lo = lo[k]; h->ev_recs[idx[k]].ci_hi = hi[k]; }
             lap("+ Beta posterior CI of the EM events");
         }
+        h->ev_out.resize(h->ev_recs.size());
+        par([&](size_t t) {
+            for (size_t i = rec_at[t]; i < rec_at[t + 1]; i++) {
+                const WqEventRec& r = h->ev_recs[i];
+                wq_event e;
+                memset(&e, 0, sizeof e);
+                e.gene = r.gene; e.node = r.node; e.motif = r.motif; e.kind = r.kind; e.flags = r.flags;
+                e.n_utr = r.n_utr; e.n_inc = r.n_inc; e.n_exc = r.n_exc; e.value_start = r.value_start; e.path_start = r.path_first;
+                e.iterations = r.iterations_; e.psi = r.psi; e.total = r.total; e.ci_lo = r.ci_lo; e.ci_hi = r.ci_hi;
+                h->ev_out[i] = e;
+            }
+        });
         h->events_done = true;
     }
     const uint64_t nv = h->ev_values.size(), np = h->ev_path_ptr.size() - 1, npn = h->ev_path_nodes.size();
+    if (view) {                          // lend the library's own arrays (valid until the count state changes or the handle dies)
+        out->n_events = h->ev_out.size(); out->n_values = nv; out->n_paths = np; out->n_path_nodes = npn;
+        out->events = h->ev_out.data(); out->values = h->ev_values.data(); out->path_ptr = h->ev_path_ptr.data(); out->path_nodes = h->ev_path_nodes.data();
+        return 0;
+    }
     bool sizing = !out->events && !out->values && !out->path_ptr && !out->path_nodes;
     if (!sizing && (out->n_events < h->ev_recs.size() || out->n_values < nv || out->n_paths < np || out->n_path_nodes < npn))
         return fail(-7, "wq_events_out buffers too small");
     out->n_events = h->ev_recs.size(); out->n_values = nv; out->n_paths = np; out->n_path_nodes = npn;
     if (sizing) return 0;
-    for (size_t i = 0; i < h->ev_recs.size(); i++) {
-        const WqEventRec& r = h->ev_recs[i];
-        wq_event e;
-        memset(&e, 0, sizeof e);
-        e.gene = r.gene; e.node = r.node; e.motif = r.motif; e.kind = r.kind; e.flags = r.flags;
-        e.n_utr = r.n_utr; e.n_inc = r.n_inc; e.n_exc = r.n_exc; e.value_start = r.value_start; e.path_start = r.path_first;
-        e.iterations = r.iterations_; e.psi = r.psi; e.total = r.total; e.ci_lo = r.ci_lo; e.ci_hi = r.ci_hi;
-        out->events[i] = e;
-    }
+    if (!h->ev_out.empty()) memcpy(out->events, h->ev_out.data(), h->ev_out.size() * sizeof(wq_event));
     if (nv) memcpy(out->values, h->ev_values.data(), nv * 8);
     memcpy(out->path_ptr, h->ev_path_ptr.data(), (np + 1) * 8);
     if (npn) memcpy(out->path_nodes, h->ev_path_nodes.data(), npn * 4);

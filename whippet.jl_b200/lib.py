@@ -46,6 +46,7 @@ def load():
     L.wq_assign_ambig.argtypes = [vp, C.POINTER(abi.ValuesC)]
     L.wq_em_psi_batch.argtypes = [vp, C.POINTER(abi.PsiBatchC)]
     L.wq_process_events.argtypes = [vp, C.c_int64, C.POINTER(abi.EventsOutC)]
+    L.wq_process_events_view.argtypes = [vp, C.c_int64, C.POINTER(abi.EventsOutC)]
     L.wq_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
     L.wq_pinned_alloc.argtypes = [C.POINTER(vp), C.c_uint64]
     L.wq_pinned_free.argtypes = [vp]

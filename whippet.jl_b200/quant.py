@@ -260,6 +260,20 @@ class GraphLibQuant:
         lib.check(self.L.wq_process_events(self.h, int(readlen), C.byref(o)))
         return ev, vals, pptr, pnodes
 
+    def process_events_view(self, readlen: int):
+        """process_events without copies: numpy views of the arrays the library owns (wq_process_events_view), valid
+        until the count state changes or the handle is closed."""
+        o = abi.EventsOutC()
+        lib.check(self.L.wq_process_events_view(self.h, int(readlen), C.byref(o)))
+        n = int(o.n_events)
+        if n == 0:
+            return np.zeros(0, abi.EVENT_DT), np.zeros(0), np.zeros(1, "<u8"), np.zeros(0, "<u4")
+        ev = np.frombuffer((C.c_char * (n * abi.EVENT_DT.itemsize)).from_address(o.events), dtype=abi.EVENT_DT)
+        vals = np.ctypeslib.as_array(o.values, shape=(int(o.n_values),)) if o.n_values else np.zeros(0)
+        pptr = np.ctypeslib.as_array(o.path_ptr, shape=(int(o.n_paths) + 1,))
+        pnodes = np.ctypeslib.as_array(o.path_nodes, shape=(int(o.n_path_nodes),)) if o.n_path_nodes else np.zeros(0, "<u4")
+        return ev, vals, pptr, pnodes
+
     def process_events(self, readlen: int):
         """process_events(out, lib, quant; isnodeok=false, readlen) (src/events.jl:744-800) without the writers:
         returns a list of dicts, one per event record in gene/node order (same shape as the oracle's)."""
