@@ -69,6 +69,8 @@ struct WqEvBatch {
     // Beta posterior CI of the events whose psi is known without EM (most of them): launched with the batch
     std::vector<double> ci_psi, ci_tot;
     double* ci_out = nullptr; size_t ci_cap = 0;                                         // pinned: lo[n] then hi[n]
+    // ... and of the events that need EM: a kernel behind their PSI launch on the same stream (total < 0: no CI)
+    std::vector<double> p_total; double* ci_em = nullptr; size_t ci_em_cap = 0;          // pinned: lo[E] then hi[E]
     cudaStream_t stream = nullptr;       // own stream: the group's uploads, kernels and result copies are ordered against nothing else
     bool built = false, launched = false;
     int64_t readlen = -1;
@@ -78,7 +80,7 @@ struct WqEvBatch {
         if (nits > its_cap) { if (its) cudaFreeHost(its); its = nullptr; its_cap = 0; cudaError_t e = cudaMallocHost(&its, (nits + nits / 4 + 16) * 4); if (e != cudaSuccess) return e; its_cap = nits + nits / 4 + 16; }
         return cudaSuccess;
     }
-    void release() { dev.release(); if (stream) cudaStreamDestroy(stream); stream = nullptr; if (ci_out) cudaFreeHost(ci_out); ci_out = nullptr; ci_cap = 0; if (psi) cudaFreeHost(psi); if (its) cudaFreeHost(its); psi = nullptr; its = nullptr; psi_cap = its_cap = 0; }
+    void release() { dev.release(); if (stream) cudaStreamDestroy(stream); stream = nullptr; if (ci_out) cudaFreeHost(ci_out); ci_out = nullptr; ci_cap = 0; if (ci_em) cudaFreeHost(ci_em); ci_em = nullptr; ci_em_cap = 0; if (psi) cudaFreeHost(psi); if (its) cudaFreeHost(its); psi = nullptr; its = nullptr; psi_cap = its_cap = 0; }
 };
 
 struct wq_handle {
@@ -383,9 +385,11 @@ static void wq_build_event_batch(wq_handle* h, int64_t readlen, int group, WqEvB
     B.P.resize_total(at[nt]);
     run([&](unsigned t) { B.P.place(B.parts[t].P, at[t]); });
     B.ci_psi.clear(); B.ci_tot.clear();
+    B.p_total.assign(B.P.size(), -1.0);
     for (unsigned t = 0; t < nt; t++)
         for (uint32_t i = 0; i < B.parts[t].recs.size(); i++) {
             const WqEventRec& r = B.parts[t].recs[i];
+            if (r.problem >= 0 && r.kind != 2) B.p_total[(size_t)(B.pshift[t] + r.problem)] = r.total;
             if (r.kind == 1 && r.problem < 0 && r.total > 0 && r.psi >= 0.0 && r.psi <= 1.0) {
                 B.parts[t].recs[i].ci_slot = (int32_t)B.ci_psi.size();
                 B.ci_psi.push_back(r.psi); B.ci_tot.push_back(r.total);
@@ -417,7 +421,11 @@ static int wq_launch_event_batch(wq_handle* h, WqEvBatch& B) {
     b.amb_ptr = P.amb_ptr.data(); b.amb_path_ptr = P.amb_path_ptr.data(); b.amb_paths = P.amb_paths.data(); b.amb_mult = P.amb_mult.data();
     b.is_tandem = P.is_tandem.data(); b.readlen = B.readlen; b.sig = 4; b.maxit = 1500;
     b.psi = B.psi; b.iterations = B.its;
-    std::string err = wq_run_em_psi(b, B.dev, B.stream, &h->launches, /*wait=*/false);
+    const size_t E = P.size();
+    if (2 * E > B.ci_em_cap) { if (B.ci_em) cudaFreeHost(B.ci_em); B.ci_em = nullptr; B.ci_em_cap = 0; CK(cudaMallocHost(&B.ci_em, (2 * E + 64) * 8)); B.ci_em_cap = 2 * E + 64; }
+    std::string err = wq_psi_ci_upload((uint32_t)E, B.p_total.data(), B.dev, B.stream);
+    if (err.empty()) err = wq_run_em_psi(b, B.dev, B.stream, &h->launches, /*wait=*/false);
+    if (err.empty()) err = wq_run_psi_ci((uint32_t)E, B.ci_em, B.dev, B.stream, &h->launches);
     if (!err.empty()) return fail(-13, err);
     B.launched = true;
     return 0;
@@ -1409,8 +1417,6 @@ static int process_events_impl(wq_handle* h, int64_t readlen, wq_events_out* out
         par([&](size_t t) { uint64_t c = 0; for (size_t i = rec_at[t]; i < rec_at[t + 1]; i++) c += n_values_of(h->ev_recs[i]); val_at[t + 1] = c; });
         for (size_t t = 0; t < nparts; t++) val_at[t + 1] += val_at[t];
         h->ev_values.resize(val_at[nparts]);
-        struct CiIn { std::vector<uint32_t> idx; std::vector<double> psi, tot; };
-        std::vector<CiIn> cin(nparts);
         par([&](size_t t) {
             uint64_t vo = val_at[t];
             for (size_t ri = rec_at[t]; ri < rec_at[t + 1]; ri++) {
@@ -1437,7 +1443,7 @@ static int process_events_impl(wq_handle* h, int64_t readlen, wq_events_out* out
                     for (uint32_t i = p0; i < p1; i++) h->ev_values[vo++] = psi[i];
                     r.iterations_ = its[r.problem];
                     r.kind = (0.0 <= r.psi && r.psi <= 1.0 && r.total > 0) ? 1 : 0;
-                    if (r.kind == 1) { cin[t].idx.push_back((uint32_t)ri); cin[t].psi.push_back(r.psi); cin[t].tot.push_back(r.total); }
+                    if (r.kind == 1) { const size_t E = P.size(); r.ci_lo = B.ci_em[r.problem]; r.ci_hi = B.ci_em[E + r.problem]; }
                 } else if (r.kind == 1) {
                     r.kind = (r.total > 0) ? 1 : 0;
                     if (r.kind == 1 && r.ci_slot >= 0) { const size_t nci = B.ci_psi.size(); r.ci_lo = B.ci_out[r.ci_slot]; r.ci_hi = B.ci_out[nci + r.ci_slot]; }
@@ -1446,16 +1452,6 @@ static int process_events_impl(wq_handle* h, int64_t readlen, wq_events_out* out
             }
         });
         lap("+ records finished");
-        {
-            std::vector<uint32_t> idx;
-            std::vector<double> cpsi, ctot;
-            for (auto& c : cin) { idx.insert(idx.end(), c.idx.begin(), c.idx.end()); cpsi.insert(cpsi.end(), c.psi.begin(), c.psi.end()); ctot.insert(ctot.end(), c.tot.begin(), c.tot.end()); }
-            std::vector<double> lo(idx.size()), hi(idx.size());
-            std::string err = wq_run_beta_ci((uint32_t)idx.size(), cpsi.data(), ctot.data(), lo.data(), hi.data(), h->em_scratch, h->stream, &h->launches);
-            if (!err.empty()) return fail(-13, err);
-            for (size_t k = 0; k < idx.size(); k++) { h->ev_recs[idx[k]].ci_lo = lo[k]; h->ev_recs[idx[k]].ci_hi = hi[k]; }
-            lap("+ Beta posterior CI of the EM events");
-        }
         h->ev_out.resize(h->ev_recs.size());
         par([&](size_t t) {
             for (size_t i = rec_at[t]; i < rec_at[t + 1]; i++) {

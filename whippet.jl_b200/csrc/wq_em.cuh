@@ -1062,11 +1062,74 @@ __global__ void __launch_bounds__(128) wq_k_beta_ci(const WqCiDev d) {
 }
 
 // `wait` = false leaves the launch and its result copies in flight (lo / hi must then be pinned host memory)
+// CI of the events that needed EM, on the stream of their PSI launch: psi = sum of the inclusion paths' psi in path order
+// (what the host computes for the record, src/events.jl:734-741), then the same quantiles.  total < 0 marks problems
+// without a CI (tandem UTR events).
+__global__ void __launch_bounds__(128) wq_k_psi_ci(const WqCiDev d, const uint32_t* __restrict__ path_ptr, const uint32_t* __restrict__ n_inc,
+                                                   const double* __restrict__ path_psi) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 2 * d.n) return;
+    const uint32_t e = t >> 1;
+    const double n = d.total[e];
+    double p = 0.0;
+    for (uint32_t i = path_ptr[e], ie = path_ptr[e] + n_inc[e]; i < ie; i++) p = __dadd_rn(p, path_psi[i]);
+    double v = 0.0;
+    if (n > 0.0 && p >= 0.0 && p <= 1.0) {
+        const double a = __dadd_rn(__dmul_rn(p, n), 1.0), b = __dadd_rn(__dmul_rn(__dsub_rn(1.0, p), n), 1.0);
+        const double q = (t & 1) ? 1.0 - (1.0 - 0.9) / 2 : (1.0 - 0.9) / 2;
+        v = wq_round_sig(d.tab, wq_beta_quantile(d, a, b, q, (t & 1) ? 1.6448536269514722 : -1.6448536269514722), 3);
+    }
+    if (t & 1) d.hi[e] = v; else d.lo[e] = v;
+}
+
+static inline void wq_ci_tables(WqCiDev& d);
+// The totals go up BEFORE the PSI launch (a copy from pageable memory enqueued behind the kernels would block the host
+// until they finish); the kernel itself goes behind wq_run_em_psi(b, M, stream, ..., wait = false) on the same scratch and
+// stream: out = lo[E] then hi[E] (pinned).
+static inline std::string wq_psi_ci_upload(uint32_t E, const double* total, WqEmScratch& M, cudaStream_t stream) {
+    if (E == 0) return "";
+    double* d_tot;
+    WQ_EMCK(M.get(19, E, &d_tot));
+    WQ_EMCK(cudaMemcpyAsync(d_tot, total, E * 8ull, cudaMemcpyHostToDevice, stream));
+    return "";
+}
+static inline std::string wq_run_psi_ci(uint32_t E, double* out, WqEmScratch& M, cudaStream_t stream, uint64_t* launches) {
+    if (E == 0) return "";
+    WqCiDev d;
+    wq_ci_tables(d);
+    d.n = E;
+    double *d_tot, *d_lo, *d_hi;
+    WQ_EMCK(M.get(19, E, &d_tot)); WQ_EMCK(M.get(20, E, &d_lo)); WQ_EMCK(M.get(21, E, &d_hi));
+    d.psi = nullptr; d.total = d_tot; d.lo = d_lo; d.hi = d_hi;
+    wq_k_psi_ci<<<(2 * E + 127) / 128, 128, 0, stream>>>(d, (const uint32_t*)M.p[0], (const uint32_t*)M.p[1], (const double*)M.p[9]);
+    if (launches) *launches += 1;
+    WQ_EMCK(cudaGetLastError());
+    WQ_EMCK(cudaMemcpyAsync(out, d_lo, E * 8ull, cudaMemcpyDeviceToHost, stream));
+    WQ_EMCK(cudaMemcpyAsync(out + E, d_hi, E * 8ull, cudaMemcpyDeviceToHost, stream));
+    return "";
+}
+
 static inline std::string wq_run_beta_ci(uint32_t n, const double* psi, const double* total, double* lo, double* hi,
                                          WqEmScratch& M, cudaStream_t stream, uint64_t* launches, bool wait = true) {
     if (n == 0) return "";
     WqCiDev d;
+    wq_ci_tables(d);
     d.n = n;
+    double *d_psi, *d_tot, *d_lo, *d_hi;
+    WQ_EMCK(M.get(15, n, &d_psi)); WQ_EMCK(M.get(16, n, &d_tot)); WQ_EMCK(M.get(17, n, &d_lo)); WQ_EMCK(M.get(18, n, &d_hi));
+    WQ_EMCK(cudaMemcpyAsync(d_psi, psi, n * 8ull, cudaMemcpyHostToDevice, stream));
+    WQ_EMCK(cudaMemcpyAsync(d_tot, total, n * 8ull, cudaMemcpyHostToDevice, stream));
+    d.psi = d_psi; d.total = d_tot; d.lo = d_lo; d.hi = d_hi;
+    wq_k_beta_ci<<<(2 * n + 127) / 128, 128, 0, stream>>>(d);
+    if (launches) *launches += 1;
+    WQ_EMCK(cudaGetLastError());
+    WQ_EMCK(cudaMemcpyAsync(lo, d_lo, n * 8ull, cudaMemcpyDeviceToHost, stream));
+    WQ_EMCK(cudaMemcpyAsync(hi, d_hi, n * 8ull, cudaMemcpyDeviceToHost, stream));
+    if (wait) WQ_EMCK(cudaStreamSynchronize(stream));
+    return "";
+}
+
+static inline void wq_ci_tables(WqCiDev& d) {
     for (int k = 0; k <= 22; k++) { d.tab.p10[k] = std::pow(10.0, (double)k); d.tab.ip10[k] = 1.0 / d.tab.p10[k]; }
     {   // Gauss-Legendre nodes on [-1, 1] by Newton iteration on P_n, mapped to [0, 1]
         const int n = WQ_CI_GL;
@@ -1085,16 +1148,4 @@ static inline std::string wq_run_beta_ci(uint32_t n, const double* psi, const do
             d.gl_w[i] = 0.5 * w; d.gl_w[n - 1 - i] = 0.5 * w;
         }
     }
-    double *d_psi, *d_tot, *d_lo, *d_hi;
-    WQ_EMCK(M.get(15, n, &d_psi)); WQ_EMCK(M.get(16, n, &d_tot)); WQ_EMCK(M.get(17, n, &d_lo)); WQ_EMCK(M.get(18, n, &d_hi));
-    WQ_EMCK(cudaMemcpyAsync(d_psi, psi, n * 8ull, cudaMemcpyHostToDevice, stream));
-    WQ_EMCK(cudaMemcpyAsync(d_tot, total, n * 8ull, cudaMemcpyHostToDevice, stream));
-    d.psi = d_psi; d.total = d_tot; d.lo = d_lo; d.hi = d_hi;
-    wq_k_beta_ci<<<(2 * n + 127) / 128, 128, 0, stream>>>(d);
-    if (launches) *launches += 1;
-    WQ_EMCK(cudaGetLastError());
-    WQ_EMCK(cudaMemcpyAsync(lo, d_lo, n * 8ull, cudaMemcpyDeviceToHost, stream));
-    WQ_EMCK(cudaMemcpyAsync(hi, d_hi, n * 8ull, cudaMemcpyDeviceToHost, stream));
-    if (wait) WQ_EMCK(cudaStreamSynchronize(stream));
-    return "";
 }
