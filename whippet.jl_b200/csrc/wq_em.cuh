@@ -510,6 +510,148 @@ __global__ void __launch_bounds__(1024) wq_k_em_tpm(WqEmDev d) {
     if (gtid == 0) *d.it_out = it;
 }
 
+// The same algorithm with the block's working set in SHARED MEMORY.  grid.sync() fences invalidate L1, so the kernel
+// above re-fetches its (constant) index arrays and its block-local scratch from L2 in every iteration, several dependent
+// round trips per phase.  Here every block copies, once, the member / class index of its class range and the
+// contribution records of its isoform tile into dynamic shared memory, keeps the sweep's scratch (member TPM, class sums,
+// proportions, class states) and the gather's products there, and holds each isoform's count, raw and rounded TPM in the
+// registers of the thread that owns it.  Per iteration only three kinds of global traffic remain: state / prop / class
+// count of every contribution (one round trip), the tile sums, and tpm_raw of the class members (one round trip);
+// proportions and states are written through to global memory only when they change.  Same arithmetic in the same order
+// as wq_k_em_tpm, so the same bits.  Requires one isoform tile per block (ntiles <= grid) and a working set within the
+// opt-in shared-memory limit; wq_run_em_tpm falls back to wq_k_em_tpm otherwise.
+struct WqEmSmem { uint32_t max_mem, max_cls, max_con; };
+__global__ void __launch_bounds__(1024) wq_k_em_tpm_smem(WqEmDev d, const WqEmSmem z) {
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* s_vals = reinterpret_cast<double*>(smem_raw);            // [max_mem] TPM of every member of an active class
+    double* s_prop = s_vals + z.max_mem;                             // [max_mem]
+    double* s_psum = s_prop + z.max_mem;                             // [max_cls]
+    double* s_w    = s_psum + z.max_cls;                             // [max_con] prop * count of unfinished classes, else +0
+    uint2*  s_rec  = reinterpret_cast<uint2*>(s_w + z.max_con);      // [max_con] (device class, member position)
+    double* buf    = reinterpret_cast<double*>(s_rec + z.max_con);   // [32]
+    uint32_t* s_iso  = reinterpret_cast<uint32_t*>(buf + 32);        // [max_mem]
+    uint32_t* s_mcls = s_iso + z.max_mem;                            // [max_mem] class of the member, local index
+    uint32_t* s_cptr = s_mcls + z.max_mem;                           // [max_cls + 1] member ranges, local offsets
+    uint8_t* s_state = reinterpret_cast<uint8_t*>(s_cptr + z.max_cls + 1);   // [max_cls]
+    uint8_t* s_cdiff = s_state + z.max_cls;                          // [max_cls]
+    uint8_t* s_wst   = s_cdiff + z.max_cls;                          // [max_con] class state seen by the contribution
+    const int t = threadIdx.x;
+    const uint32_t gtid = blockIdx.x * blockDim.x + t;
+    const uint32_t c_lo = d.blk_cls[blockIdx.x], ncls = d.blk_cls[blockIdx.x + 1] - c_lo;
+    const uint32_t m_lo = d.blk_mem[blockIdx.x], nmem = d.blk_mem[blockIdx.x + 1] - m_lo;
+    const bool has_tile = blockIdx.x < d.ntiles;
+    const uint32_t i = blockIdx.x * 1024 + t;                        // the isoform this thread owns
+    const bool own = has_tile && i < d.I;
+    uint32_t j_lo = 0, ncon = 0, my_j = 0, my_n = 0;
+    if (has_tile) { j_lo = d.con_ptr[blockIdx.x * 1024]; ncon = d.con_ptr[min(d.I, blockIdx.x * 1024 + 1024)] - j_lo; }
+    if (own) { my_j = d.con_ptr[i] - j_lo; my_n = d.con_ptr[i + 1] - d.con_ptr[i]; }
+    // ---- one-time staging ----
+    for (uint32_t k = t; k < nmem; k += 1024) { s_iso[k] = (uint32_t)d.cls_iso[m_lo + k]; s_mcls[k] = d.mem_cls[m_lo + k] - c_lo; s_prop[k] = d.prop[m_lo + k]; }
+    for (uint32_t c = t; c <= ncls; c += 1024) s_cptr[c] = d.cls_ptr[c_lo + c] - m_lo;
+    for (uint32_t c = t; c < ncls; c += 1024) s_state[c] = d.state[c_lo + c];
+    for (uint32_t j = t; j < ncon; j += 1024) s_rec[j] = d.con_rec[j_lo + j];
+    const double leff = own ? d.leff[i] : 1.0;
+    double cnt = own ? d.count[i] : 0.0;                             // unique + finished-class counts of this isoform
+    double raw = 0.0, tpm = 0.0;
+    __syncthreads();
+    // ---- calculate_tpm!(quant, readlen) on the unique counts (bin/whippet-quant.jl:163); differs = tpm != ones(I) ----
+    if (has_tile) {
+        if (own) { raw = __ddiv_rn(cnt, leff); d.tpm_raw[i] = raw; }
+        double sm = wq_tile_tree(raw, buf, t);
+        if (t == 0) d.partial[blockIdx.x] = sm;
+    }
+    grid.sync();
+    {
+        const double rpk = fmax(wq_tile_tree((uint32_t)t < d.ntiles ? d.partial[t] : 0.0, buf, t), 1.0);
+        int mine = 0;
+        if (own) { tpm = wq_tpm_value(d, raw, rpk); if (tpm != 1.0) mine = 1; }
+        if (__syncthreads_or(mine) && t == 0) atomicOr(&d.flags[3], 1);
+    }
+    grid.sync();
+    int64_t it = 1;
+    bool differs = d.flags[3] != 0;
+    while (differs && it < d.maxit) {
+        long long tk0 = 0, tk1 = 0, tk2 = 0, tk3 = 0;
+        if (d.dbg && t == 0) tk0 = clock64();
+        if (gtid == 0) d.flags[(it + 1) % 3] = 0;
+        // ---- B: contributions, then the per-isoform sums in class order, raw TPM, tile sum ----
+        if (has_tile) {
+            for (uint32_t j = t; j < ncon; j += 1024) {
+                const uint2 rec = s_rec[j];
+                const uint8_t st = d.state[rec.x];
+                double v = 0.0;
+                if (st != 2) v = __dmul_rn(d.prop[rec.y], d.cls_count[rec.x]);
+                s_w[j] = v;
+                s_wst[j] = st;
+            }
+            __syncthreads();
+            raw = 0.0;
+            if (own) {
+                double ct = cnt, cn = cnt;
+                // adding +0.0 for a finished class leaves the (non-negative) sums bit-identical to skipping it
+                for (uint32_t j = my_j, je = my_j + my_n; j < je; j++) {
+                    const double v = s_w[j];
+                    ct = __dadd_rn(ct, v);
+                    cn = __dadd_rn(cn, s_wst[j] == 1 ? v : 0.0);
+                }
+                cnt = cn;
+                raw = __ddiv_rn(ct, leff);
+                d.tpm_raw[i] = raw;
+            }
+            double sm = wq_tile_tree(raw, buf, t);
+            if (t == 0) d.partial[blockIdx.x] = sm;
+        }
+        if (d.dbg && t == 0) tk1 = clock64();
+        grid.sync();
+        if (d.dbg && t == 0) tk2 = clock64();
+        // ---- A: normalise + round (calculate_tpm!); every block folds the tile sums itself ----
+        const double rpk = fmax(wq_tile_tree((uint32_t)t < d.ntiles ? d.partial[t] : 0.0, buf, t), 1.0);
+        int mine = 0;
+        if (own) { const double v = wq_tpm_value(d, raw, rpk); if (v != tpm) mine = 1; tpm = v; }
+        // ---- sweep over this block's classes for iteration it+1 (maximize step, src/quant.jl:726-749) ----
+        if (it + 1 < d.maxit) {
+            for (uint32_t k = t; k < nmem; k += 1024)
+                if (s_state[s_mcls[k]] == 0) s_vals[k] = wq_tpm_value(d, d.tpm_raw[s_iso[k]], rpk);
+            __syncthreads();
+            for (uint32_t c = t; c < ncls; c += 1024) {
+                if (s_state[c] != 0) continue;
+                double ps = 0.0;
+                for (uint32_t k = s_cptr[c], ke = s_cptr[c + 1]; k < ke; k++) ps = __dadd_rn(ps, s_vals[k]);
+                s_psum[c] = ps;
+                s_cdiff[c] = 0;
+            }
+            __syncthreads();
+            for (uint32_t k = t; k < nmem; k += 1024) {               // copy_isdone!, src/quant.jl:702-712
+                const uint32_t c = s_mcls[k];
+                if (s_state[c] != 0) continue;
+                const double val = wq_round_sc(__ddiv_rn(s_vals[k], s_psum[c]), d.sc_prop);
+                const double old = s_prop[k];
+                if (val != old) s_cdiff[c] = 1;
+                const double nv = isnan(val) ? 0.0 : val;
+                if (nv != old || isnan(old)) { s_prop[k] = nv; d.prop[m_lo + k] = nv; }
+            }
+            __syncthreads();
+            for (uint32_t c = t; c < ncls; c += 1024) {
+                const uint8_t st = s_state[c];
+                if (st == 1) { s_state[c] = 2; d.state[c_lo + c] = 2; }
+                else if (st == 0 && (!s_cdiff[c] || s_psum[c] == 0.0)) { s_state[c] = 1; d.state[c_lo + c] = 1; }
+            }
+        }
+        if (__syncthreads_or(mine) && t == 0) atomicOr(&d.flags[it % 3], 1);
+        if (d.dbg && t == 0) tk3 = clock64();
+        grid.sync();
+        if (d.dbg && t == 0) {
+            long long* o = d.dbg + 4 * blockIdx.x;
+            o[0] += tk1 - tk0; o[1] += tk2 - tk1; o[2] += tk3 - tk2; o[3] += clock64() - tk3;
+        }
+        differs = d.flags[it % 3] != 0;
+        it += 1;
+    }
+    if (own) { d.count[i] = cnt; d.tpm[i] = tpm; }
+    if (gtid == 0) *d.it_out = it;
+}
+
 // grow-only device scratch kept in the handle (cudaMalloc/cudaFree per call would serialise the device)
 struct WqEmScratch {
     void* p[24] = {nullptr}; size_t cap[24] = {0};
@@ -668,7 +810,27 @@ static inline std::string wq_run_em_tpm(const WqHostIndex& H, const WqIsoIndex& 
     auto tk0 = std::chrono::steady_clock::now();
     WQ_EMCK(M.timing_events());
     WQ_EMCK(cudaEventRecord(M.tk0, stream));
-    WQ_EMCK(cudaLaunchCooperativeKernel((void*)wq_k_em_tpm, dim3(grid), dim3(1024), args, 0, stream));
+    // working set per block for the shared-memory kernel
+    WqEmSmem zs;
+    zs.max_mem = 1; zs.max_cls = 1; zs.max_con = 1;
+    for (uint32_t b = 0; b < nb; b++) { zs.max_mem = std::max(zs.max_mem, blk_mem[b + 1] - blk_mem[b]); zs.max_cls = std::max(zs.max_cls, blk_cls[b + 1] - blk_cls[b]); }
+    for (uint32_t tl = 0; tl < ntiles; tl++) zs.max_con = std::max(zs.max_con, con_ptr[std::min<uint32_t>(I, tl * 1024 + 1024)] - con_ptr[tl * 1024]);
+    zs.max_mem = (zs.max_mem + 1) & ~1u; zs.max_cls = (zs.max_cls + 3) & ~3u; zs.max_con = (zs.max_con + 3) & ~3u;      // keep every array aligned
+    const size_t smem_bytes = 8ull * (2 * (size_t)zs.max_mem + zs.max_cls + 2 * (size_t)zs.max_con + 32) + 4ull * (2 * (size_t)zs.max_mem + zs.max_cls + 1)
+                            + 2ull * zs.max_cls + zs.max_con + 16;
+    int smem_optin = 0;
+    WQ_EMCK(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    static const bool smem_off = getenv("WQ_EM_SMEM") && atoi(getenv("WQ_EM_SMEM")) == 0;
+    const bool use_smem = !smem_off && ntiles <= nb && smem_bytes <= (size_t)smem_optin;
+    if (use_smem) {
+        WQ_EMCK(cudaFuncSetAttribute(wq_k_em_tpm_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+        void* args2[] = {&d, &zs};
+        WQ_EMCK(cudaLaunchCooperativeKernel((void*)wq_k_em_tpm_smem, dim3(grid), dim3(1024), args2, smem_bytes, stream));
+    } else {
+        WQ_EMCK(cudaLaunchCooperativeKernel((void*)wq_k_em_tpm, dim3(grid), dim3(1024), args, 0, stream));
+    }
+    if (prof) fprintf(stderr, "[wq]   em kernel: %s (%zu B shared memory per block; max %u members, %u classes, %u contributions)\n",
+                      use_smem ? "shared-memory working set" : "global working set", smem_bytes, zs.max_mem, zs.max_cls, zs.max_con);
     WQ_EMCK(cudaEventRecord(M.tk1, stream));
     M.timed = true;
     if (launches) *launches += 1;

@@ -285,17 +285,22 @@ static inline void wq_gene_events(const WqGeneEvents& V, int64_t readlen, std::v
         // ---- spliced node (src/events.jl:647-742) ----
         uint32_t lo = 0xFFFFFFFFu, hi = 0;
         const double maxvalue = V.edges.empty() ? 0.0 : V.edges.back().v;     // maximum(sgquant.edge): greatest (first,last) entry
-        std::vector<const WqGeneEdge*> touch;
+        // per-thread scratch, cleared per node (one heap allocation per container and thread instead of per node)
+        static thread_local std::vector<const WqGeneEdge*> touch, amb_edges;
+        static thread_local WqPathSet inc, exc;
+        static thread_local std::vector<WqAmbSet> amb;
+        static thread_local std::vector<uint32_t> set;
+        touch.clear(); amb_edges.clear(); amb.clear();
+        inc.nodes.clear(); inc.count.clear(); inc.length.clear(); inc.mx = 0;
+        exc.nodes.clear(); exc.count.clear(); exc.length.clear(); exc.mx = 0;
         for (auto& e : V.edges) {
             if (!(e.a <= i && i <= e.b)) continue;
             if (e.v / maxvalue < 0.02) continue;
             touch.push_back(&e);
             lo = std::min(lo, e.a); hi = std::max(hi, e.b);
         }
-        WqPathSet inc, exc;
         inc.mn = exc.mn = 0xFFFFFFFFu;
         bool has_inc = false, has_exc = false;
-        std::vector<const WqGeneEdge*> amb_edges;
         double connecting = 0.0, spanning = 0.0;
         for (const WqGeneEdge* e : touch) {
             if (e->a == i || e->b == i) { wq_push_edge(inc, *e, lo, hi); has_inc = true; connecting += e->v; }
@@ -303,7 +308,6 @@ static inline void wq_gene_events(const WqGeneEvents& V, int64_t readlen, std::v
             amb_edges.push_back(e);
         }
         bool sub = false;
-        std::vector<WqAmbSet> amb;
         if (has_inc && has_exc) {
             // bridge with neighbouring edges inside [lo, hi] (extend_edges!, src/events.jl:329-394)
             for (uint32_t idx = i - 1; idx > lo && idx >= 1; idx--)
@@ -324,7 +328,6 @@ static inline void wq_gene_events(const WqGeneEvents& V, int64_t readlen, std::v
                 }
             inc = wq_reduce(inc, sub);
             exc = wq_reduce(exc, sub);
-            std::vector<uint32_t> set;
             for (const WqGeneEdge* e : amb_edges) {
                 set.clear();
                 for (size_t p = 0; p < inc.size(); p++) if (inc.nodes[p].adjacent(e->a, e->b)) { set.push_back((uint32_t)p); inc.length[p] += 1; }
