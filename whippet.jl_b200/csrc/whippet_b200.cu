@@ -59,7 +59,7 @@ struct DevBuf {
 // Events of one gene group.  Group 0 = genes that no multi-map class names: assign_ambig! cannot change their counts, so
 // their events are built on the host threads while the transcript EM kernel runs and their PSI EM launch overlaps
 // assign_ambig!.  Group 1 = the remaining genes, built after assign_ambig!.
-struct WqEvPart { std::vector<WqEventRec> recs; WqPsiProblems P; WqEventPool pool; };
+struct WqEvPart { std::vector<WqEventRec> recs; WqPsiProblems P; WqEventPool pool; std::vector<double> ci_psi, ci_tot, p_total; };
 struct WqEvBatch {
     std::vector<WqEvPart> parts;         // one per host thread, contiguous gene ranges in gene order
     WqPsiProblems P;                     // problems of all parts, concatenated
@@ -345,6 +345,9 @@ static void reset_quant_ex(wq_handle* h) {
 // are concatenated (prefix sums + parallel copies).  Needs finalized edges.
 static void wq_build_event_batch(wq_handle* h, int64_t readlen, int group, WqEvBatch& B) {
     const WqHostQuantEx& X = h->hx;
+    static const bool prof2 = getenv("WQ_PROFILE") && atoi(getenv("WQ_PROFILE")) >= 2;
+    const auto tb0 = std::chrono::steady_clock::now();
+    auto lap2 = [&](const char* what) { if (prof2) fprintf(stderr, "[wq]       batch %d %-20s %9.3f ms\n", group, what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tb0).count()); };
     const uint32_t G = h->H.G;
     unsigned nt = wq_host_threads();
     if (G < 2048) nt = 1;
@@ -373,8 +376,20 @@ static void wq_build_event_batch(wq_handle* h, int64_t readlen, int group, WqEvB
             }
             wq_gene_events(V, readlen, part.recs, part.P, part.pool);
         }
-        for (auto& r : part.recs) r.batch = (uint8_t)group;
+        // Beta-CI inputs of this part: spliced events whose psi is known without EM get a launch slot (part-local for now);
+        // EM problems of spliced events carry their total (tandem UTR problems: -1, no CI)
+        part.ci_psi.clear(); part.ci_tot.clear();
+        part.p_total.assign(part.P.size(), -1.0);
+        for (auto& r : part.recs) {
+            r.batch = (uint8_t)group;
+            if (r.problem >= 0 && r.kind != 2) part.p_total[(size_t)r.problem] = r.total;
+            if (r.kind == 1 && r.problem < 0 && r.total > 0 && r.psi >= 0.0 && r.psi <= 1.0) {
+                r.ci_slot = (int32_t)part.ci_psi.size();
+                part.ci_psi.push_back(r.psi); part.ci_tot.push_back(r.total);
+            }
+        }
     });
+    lap2("genes built");
     std::vector<WqPsiProblems::Sizes> at(nt + 1);
     B.pshift.assign(nt, 0);
     for (unsigned t = 0; t < nt; t++) {
@@ -382,19 +397,21 @@ static void wq_build_event_batch(wq_handle* h, int64_t readlen, int group, WqEvB
         at[t + 1].ev = at[t].ev + z.ev; at[t + 1].paths = at[t].paths + z.paths; at[t + 1].amb = at[t].amb + z.amb; at[t + 1].amb_paths = at[t].amb_paths + z.amb_paths;
         B.pshift[t] = (long)at[t].ev;
     }
+    std::vector<size_t> ci_at(nt + 1, 0);
+    for (unsigned t = 0; t < nt; t++) ci_at[t + 1] = ci_at[t] + B.parts[t].ci_psi.size();
     B.P.resize_total(at[nt]);
-    run([&](unsigned t) { B.P.place(B.parts[t].P, at[t]); });
-    B.ci_psi.clear(); B.ci_tot.clear();
-    B.p_total.assign(B.P.size(), -1.0);
-    for (unsigned t = 0; t < nt; t++)
-        for (uint32_t i = 0; i < B.parts[t].recs.size(); i++) {
-            const WqEventRec& r = B.parts[t].recs[i];
-            if (r.problem >= 0 && r.kind != 2) B.p_total[(size_t)(B.pshift[t] + r.problem)] = r.total;
-            if (r.kind == 1 && r.problem < 0 && r.total > 0 && r.psi >= 0.0 && r.psi <= 1.0) {
-                B.parts[t].recs[i].ci_slot = (int32_t)B.ci_psi.size();
-                B.ci_psi.push_back(r.psi); B.ci_tot.push_back(r.total);
-            }
-        }
+    B.ci_psi.resize(ci_at[nt]); B.ci_tot.resize(ci_at[nt]);
+    B.p_total.resize(at[nt].ev);
+    run([&](unsigned t) {
+        WqEvPart& part = B.parts[t];
+        B.P.place(part.P, at[t]);
+        std::copy(part.ci_psi.begin(), part.ci_psi.end(), B.ci_psi.begin() + ci_at[t]);
+        std::copy(part.ci_tot.begin(), part.ci_tot.end(), B.ci_tot.begin() + ci_at[t]);
+        std::copy(part.p_total.begin(), part.p_total.end(), B.p_total.begin() + at[t].ev);
+        if (ci_at[t]) for (auto& r : part.recs) if (r.ci_slot >= 0) r.ci_slot += (int32_t)ci_at[t];
+    });
+    lap2("problems concatenated");
+    lap2("CI inputs collected");
     B.built = true;
     B.launched = false;
     B.readlen = readlen;
@@ -1278,7 +1295,7 @@ int wq_em_tpm(wq_handle* h, const wq_em_param* p, double* tpm, double* count, do
         wq_build_event_batch(h, p->readlen, 0, h->ev_batch[0]);
         // their PSI EM goes to its own stream right away: its blocks fill in beside the EM kernel's and the few events that need
         // all 1500 sweeps (a pure latency chain) start early
-        overlap_rc = wq_launch_event_batch(h, h->ev_batch[0]);
+        { WqTimer t4("    batch 0 launch (uploads + kernels enqueued)"); overlap_rc = wq_launch_event_batch(h, h->ev_batch[0]); }
     };
     std::string err = wq_run_em_tpm(h->H, h->iso, h->hq, h->hx, h->em_scratch, *p, h->stream, &h->launches, tpm, count, genetpm, iterations,
                                     overlap_on ? &overlap : nullptr);
