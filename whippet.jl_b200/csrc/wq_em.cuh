@@ -53,6 +53,13 @@ struct WqGeneBits {                 // annopath bitsets of one gene
     }
 };
 
+template <class F> static inline void wq_on_threads(unsigned nt, F&& f) {
+    if (nt <= 1) { f(0u); return; }
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; t++) th.emplace_back([&f, t]() { f(t); });
+    for (auto& x : th) x.join();
+}
+
 struct WqKeyPath { uint32_t gene, n, rn; const uint32_t* nd; const uint32_t* rnd; };
 static inline size_t wq_key_next(const uint32_t* k, size_t pos, WqKeyPath& o) {
     uint32_t hdr = k[pos];
@@ -91,11 +98,13 @@ static inline void wq_spread_path(const WqHostIndex& H, std::vector<double>& nod
 // re-counts long paths onto their edges (assign_long=true).
 static inline std::string wq_host_build_classes(const WqHostIndex& H, const WqIsoIndex& S, WqHostQuant& hq, WqHostQuantEx& X) {
     const uint32_t G = H.G, I = S.I;
+    static const bool prof2 = getenv("WQ_PROFILE") && atoi(getenv("WQ_PROFILE")) >= 2;
+    const auto tc0 = std::chrono::steady_clock::now();
+    auto lap2 = [&](const char* what) { if (prof2) fprintf(stderr, "[wq]     classes: %-24s %9.3f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tc0).count()); };
     X = WqHostQuantEx();
     X.node_value.assign(hq.node.begin(), hq.node.end());
     X.iso_count.assign(I, 0.0);
     WqClassSet& C = X.cls;
-    C.ptr.push_back(0);
     // ---- genes named by multi-map classes (assign_ambig! will change their counts) ----
     X.gene_dirty.assign(G + 1, 0);
     for (size_t m = 0; m < hq.multis.size(); m++) {
@@ -153,6 +162,7 @@ static inline std::string wq_host_build_classes(const WqHostIndex& H, const WqIs
     }
     // ---- isoform classes, gene by gene; genes are independent, so host threads take contiguous gene ranges and
     //      the fragments are concatenated in gene order ----
+    lap2("marks + long-path grouping");
     struct Frag { WqClassSet C; std::vector<std::pair<uint64_t, double>> adds; std::string err; };
     unsigned nthreads = wq_host_threads();
     if (G < 2048) nthreads = 1;
@@ -232,34 +242,52 @@ static inline std::string wq_host_build_classes(const WqHostIndex& H, const WqIs
         for (unsigned t = 0; t < nthreads; t++) th.emplace_back(work, t);
         for (auto& t : th) t.join();
     }
-    {
-        size_t m = 0;
-        for (MFrag& F : mfrags) {
-            if (!F.err.empty()) return F.err;
+    lap2("threads done");
+    // concatenate: multi-map fragments first (key order), then the isoform-class fragments (gene order); sizes -> prefix
+    // sums -> every host thread places its own fragment
+    for (MFrag& F : mfrags) if (!F.err.empty()) return F.err;
+    for (Frag& F : frags) if (!F.err.empty()) return F.err;
+    std::vector<size_t> mc_at(nthreads + 1, 0), mm_at(nthreads + 1, 0), fc_at(nthreads + 1, 0), fm_at(nthreads + 1, 0), fa_at(nthreads + 1, 0);
+    for (unsigned t = 0; t < nthreads; t++) { mc_at[t + 1] = mc_at[t] + mfrags[t].end.size(); mm_at[t + 1] = mm_at[t] + mfrags[t].iso.size(); }
+    const size_t nmc = mc_at[nthreads], nmm = mm_at[nthreads];
+    for (unsigned t = 0; t < nthreads; t++) {
+        fc_at[t + 1] = fc_at[t] + frags[t].C.count.size(); fm_at[t + 1] = fm_at[t] + frags[t].C.iso.size(); fa_at[t + 1] = fa_at[t] + frags[t].adds.size();
+    }
+    const size_t ncls = nmc + fc_at[nthreads], nmem = nmm + fm_at[nthreads];
+    C.iso.resize(nmem); C.prop.resize(nmem); C.ptr.resize(ncls + 1); C.count.resize(ncls); C.state.resize(ncls); C.postassign.resize(ncls);
+    C.ptr[0] = 0;
+    C.n_multi = (uint32_t)nmc;
+    X.edge_adds.resize(fa_at[nthreads]);
+    X.frag_cls.assign(nthreads + 1, 0);
+    for (unsigned t = 0; t <= nthreads; t++) X.frag_cls[t] = (uint32_t)(nmc + fc_at[t]);
+    wq_on_threads(nthreads, [&](unsigned t) {
+        {   // multi-map classes of this thread's key range
+            const MFrag& F = mfrags[t];
             uint32_t prev = 0;
-            for (size_t j = 0; j < F.end.size(); j++, m++) {
+            size_t c = mc_at[t], q0 = mm_at[t];
+            for (size_t j = 0; j < F.end.size(); j++, c++) {
                 const uint32_t n = F.end[j] - prev;
-                for (uint32_t q = prev; q < F.end[j]; q++) { C.iso.push_back(F.iso[q]); C.prop.push_back(1.0 / (double)n); }
+                for (uint32_t q = prev; q < F.end[j]; q++) { C.iso[q0 + q] = F.iso[q]; C.prop[q0 + q] = 1.0 / (double)n; }
                 prev = F.end[j];
-                C.ptr.push_back((uint32_t)C.iso.size());
-                C.count.push_back((double)hq.multis.count[m]);
-                C.state.push_back(F.all[j] ? 0 : 2);
-                C.postassign.push_back(F.all[j] ? 0 : 1);
+                C.ptr[c + 1] = (uint32_t)(q0 + F.end[j]);
+                C.count[c] = (double)hq.multis.count[c];
+                C.state[c] = F.all[j] ? 0 : 2;
+                C.postassign[c] = F.all[j] ? 0 : 1;
             }
         }
-        C.n_multi = (uint32_t)C.count.size();
-    }
-    for (Frag& F : frags) {
-        if (!F.err.empty()) return F.err;
-        const uint32_t base = (uint32_t)C.iso.size();
-        C.iso.insert(C.iso.end(), F.C.iso.begin(), F.C.iso.end());
-        C.prop.insert(C.prop.end(), F.C.prop.begin(), F.C.prop.end());
-        for (uint32_t p : F.C.ptr) C.ptr.push_back(base + p);
-        C.count.insert(C.count.end(), F.C.count.begin(), F.C.count.end());
-        C.state.insert(C.state.end(), F.C.count.size(), 0);
-        C.postassign.insert(C.postassign.end(), F.C.count.size(), 0);
-        X.edge_adds.insert(X.edge_adds.end(), F.adds.begin(), F.adds.end());
-    }
+        {   // isoform classes of this thread's gene range
+            const Frag& F = frags[t];
+            const size_t c0 = nmc + fc_at[t], q0 = nmm + fm_at[t];
+            std::copy(F.C.iso.begin(), F.C.iso.end(), C.iso.begin() + q0);
+            std::copy(F.C.prop.begin(), F.C.prop.end(), C.prop.begin() + q0);
+            for (size_t j = 0; j < F.C.ptr.size(); j++) C.ptr[c0 + j + 1] = (uint32_t)(q0 + F.C.ptr[j]);
+            std::copy(F.C.count.begin(), F.C.count.end(), C.count.begin() + c0);
+            std::fill(C.state.begin() + c0, C.state.begin() + c0 + F.C.count.size(), (uint8_t)0);
+            std::fill(C.postassign.begin() + c0, C.postassign.begin() + c0 + F.C.count.size(), (uint8_t)0);
+            std::copy(F.adds.begin(), F.adds.end(), X.edge_adds.begin() + fa_at[t]);
+        }
+    });
+    lap2("fragments concatenated");
     X.built = true;
     return "";
 }
@@ -719,13 +747,21 @@ static inline std::string wq_run_em_tpm(const WqHostIndex& H, const WqIsoIndex& 
             std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(), X.cls.count.size(), X.cls.n_multi);
     }
     if (X.em_done) return "wq_em_tpm was already run on this count state (gene_em! mutates it); call wq_quant_reset first";
+    static const bool prof2 = getenv("WQ_PROFILE") && atoi(getenv("WQ_PROFILE")) >= 2;
+    const auto te0 = std::chrono::steady_clock::now();
+    auto lap2 = [&](const char* what) { if (prof2) fprintf(stderr, "[wq]     em host: %-24s %9.3f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - te0).count()); };
     const uint32_t I = S.I;
     WqClassSet& C = X.cls;
     const uint32_t NC = (uint32_t)C.count.size();
     const uint32_t ntiles = (I + 1023) / 1024;
     if (ntiles > 1024) return "more than 1048576 isoforms";
     std::vector<double> leff(I), tpm(I), count = X.iso_count;
-    for (uint32_t i = 0; i < I; i++) leff[i] = std::max((double)(S.length[i] - p.readlen), 1.0);
+    unsigned hnt = wq_host_threads();
+    if (NC < 4096) hnt = 1;
+    wq_on_threads(hnt, [&](unsigned t) {
+        for (uint32_t i = (uint32_t)((uint64_t)I * t / hnt), ie = (uint32_t)((uint64_t)I * (t + 1) / hnt); i < ie; i++)
+            leff[i] = std::max((double)(S.length[i] - p.readlen), 1.0);
+    });
     int dev = 0, sms = 0, per_sm = 0;
     WQ_EMCK(cudaGetDevice(&dev));
     WQ_EMCK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -759,25 +795,43 @@ static inline std::string wq_run_em_tpm(const WqHostIndex& H, const WqIsoIndex& 
     std::vector<int32_t> d_iso_h(NM);
     std::vector<double> d_prop_h(NM), d_ccount_h(NC);
     std::vector<uint8_t> d_state_h(NC);
-    for (uint32_t k = 0; k < NC; k++) {
+    for (uint32_t k = 0; k < NC; k++) {                      // serial prefix over the device order (cheap), members in parallel below
         const uint32_t c = dorder[k];
         dinv[c] = k;
         d_cptr_h[k + 1] = d_cptr_h[k] + (C.ptr[c + 1] - C.ptr[c]);
-        d_ccount_h[k] = C.count[c];
-        d_state_h[k] = C.state[c];
-        for (uint32_t q = C.ptr[c], o = d_cptr_h[k]; q < C.ptr[c + 1]; q++, o++) { d_iso_h[o] = C.iso[q]; d_prop_h[o] = C.prop[q]; mem_cls[o] = k; mpos[q] = o; }
     }
+    wq_on_threads(hnt, [&](unsigned t) {
+        for (uint32_t k = (uint32_t)((uint64_t)NC * t / hnt), ke = (uint32_t)((uint64_t)NC * (t + 1) / hnt); k < ke; k++) {
+            const uint32_t c = dorder[k];
+            d_ccount_h[k] = C.count[c];
+            d_state_h[k] = C.state[c];
+            for (uint32_t q = C.ptr[c], o = d_cptr_h[k]; q < C.ptr[c + 1]; q++, o++) { d_iso_h[o] = C.iso[q]; d_prop_h[o] = C.prop[q]; mem_cls[o] = k; mpos[q] = o; }
+        }
+    });
     for (uint32_t b = 0; b <= nb; b++) blk_mem[b] = d_cptr_h[blk_cls[b]];
-    // contributions (isoform -> class members) in canonical class order
+    // contributions (isoform -> class members) in canonical class order.  Multi-map classes come first and may name any
+    // isoform (serial, few members); the isoform classes of one class-building fragment only name isoforms of that
+    // fragment's gene range, so the fragments fill disjoint isoform ranges in parallel.
     std::vector<uint32_t> con_ptr(I + 1, 0);
     std::vector<uint2> con_rec(NM);
-    for (int32_t i : C.iso) con_ptr[i + 1]++;
+    const std::vector<uint32_t>& fcl = X.frag_cls;           // [nfrag + 1] class ranges of the fragments
+    const unsigned nfrag = fcl.size() > 1 ? (unsigned)fcl.size() - 1 : 0;
+    const bool frag_ok = nfrag > 0 && fcl[0] == nmulti && fcl[nfrag] == NC;
+    if (frag_ok) {
+        for (uint32_t q = 0; q < C.ptr[nmulti]; q++) con_ptr[C.iso[q] + 1]++;
+        wq_on_threads(nfrag, [&](unsigned t) { for (uint32_t q = C.ptr[fcl[t]]; q < C.ptr[fcl[t + 1]]; q++) con_ptr[C.iso[q] + 1]++; });
+    } else for (int32_t i : C.iso) con_ptr[i + 1]++;
     for (uint32_t i = 0; i < I; i++) con_ptr[i + 1] += con_ptr[i];
     {
         std::vector<uint32_t> cur(con_ptr.begin(), con_ptr.end() - 1);
-        for (uint32_t c = 0; c < NC; c++)
-            for (uint32_t q = C.ptr[c]; q < C.ptr[c + 1]; q++) con_rec[cur[C.iso[q]]++] = make_uint2(dinv[c], mpos[q]);
+        auto fill = [&](uint32_t c_lo, uint32_t c_hi) {
+            for (uint32_t c = c_lo; c < c_hi; c++)
+                for (uint32_t q = C.ptr[c]; q < C.ptr[c + 1]; q++) con_rec[cur[C.iso[q]]++] = make_uint2(dinv[c], mpos[q]);
+        };
+        if (frag_ok) { fill(0, nmulti); wq_on_threads(nfrag, [&](unsigned t) { fill(fcl[t], fcl[t + 1]); }); }
+        else fill(0, NC);
     }
+    lap2("layout built");
     WqEmDev d;
     double *d_leff, *d_count, *d_tpm, *d_raw, *d_prop, *d_ccount, *d_partial, *d_vals, *d_psum, *d_wall, *d_wfin;
     uint32_t *d_cptr, *d_conptr, *d_memcls, *d_blkcls, *d_blkmem;
@@ -808,6 +862,7 @@ static inline std::string wq_run_em_tpm(const WqHostIndex& H, const WqIsoIndex& 
     if (timing) { WQ_EMCK(M.get(22, (size_t)grid * 4, &d.dbg)); WQ_EMCK(cudaMemsetAsync(d.dbg, 0, (size_t)grid * 32, stream)); }
     void* args[] = {&d};
     auto tk0 = std::chrono::steady_clock::now();
+    lap2("uploads enqueued");
     WQ_EMCK(M.timing_events());
     WQ_EMCK(cudaEventRecord(M.tk0, stream));
     // working set per block for the shared-memory kernel
@@ -864,6 +919,7 @@ static inline std::string wq_run_em_tpm(const WqHostIndex& H, const WqIsoIndex& 
         for (uint32_t i = S.iso_base[g]; i < S.iso_base[g + 1]; i++) s += tpm[i];
         X.genetpm[g] = s;
     }
+    lap2("results back + gene TPM");
     X.em_done = true;
     X.iterations = it;
     X.em_kernel_ms = M.last_ms();

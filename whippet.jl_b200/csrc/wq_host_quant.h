@@ -83,6 +83,7 @@ struct WqHostQuantEx {
     std::vector<double> iso_count, tpm, genetpm;
     std::vector<uint8_t> gene_dirty;                         // [G+1] gene is named by some multi-map class: assign_ambig! will change its counts
     WqClassSet cls;
+    std::vector<uint32_t> frag_cls;                          // class ranges of the class-building fragments (disjoint gene ranges)
     int64_t iterations = 0;
     float em_kernel_ms = 0.f;                                // device time of the transcript EM kernel (CUDA events)
 };
