@@ -114,3 +114,33 @@ def test_process_fastq_equals_process_reads(tmp_path):
         assert np.array_equal(x, y)
     assert a.keyed(0) == b.keyed(0) and a.keyed(1) == b.keyed(1)
     a.close(); b.close()
+
+
+@pytest.mark.gpu
+def test_process_fastq_paired(tmp_path):
+    from data_gen import pe_case
+    idx, p, f, r = pe_case(4, 300, 76, 5000, True, 30000)
+
+    def render(rb, tag):
+        recs = []
+        for i in range(rb.n):
+            L = int(rb.len[i])
+            w = rb.seq2[int(rb.seq_off[i]):int(rb.seq_off[i]) + (L + 31) // 32]
+            codes = [(int(w[j // 32]) >> (2 * (j % 32))) & 3 for j in range(L)]
+            q = rb.qual[int(rb.qual_off[i]):int(rb.qual_off[i]) + L]
+            recs.append((f"p{i}/{tag}", "".join("ACGT"[c] for c in codes), "".join(chr(int(x) + 33) for x in q)))
+        return recs
+    paths = []
+    for rb, tag in ((f, 1), (r, 2)):
+        path = os.path.join(tmp_path, f"m{tag}.fastq.gz")
+        with gzip.open(path, "wb", compresslevel=1) as fh:
+            fh.write(to_text(render(rb, tag)))
+        paths.append(path)
+    a, b = wq.GraphLibQuant(idx), wq.GraphLibQuant(idx)
+    sa = a.process_paired_reads(p, f, r)
+    sb = b.process_fastq(p, paths[0], paths[1], batch_reads=7000)
+    assert (sa.total, sa.mapped, sa.multi, sa.sum_readlen) == (sb.total, sb.mapped, sb.multi, sb.sum_readlen) and sa.mapped > 1000
+    for x, y in zip(a.counts(), b.counts()):
+        assert np.array_equal(x, y)
+    assert a.keyed(0) == b.keyed(0) and a.keyed(1) == b.keyed(1)
+    a.close(); b.close()
