@@ -235,6 +235,23 @@ class Oracle:
         return out
 
 
+def em_psi(n_inc, count, length, amb_sets, amb_mult, tandem, readlen, sig=4, maxit=1500):
+    """spliced_em! / rec_tandem_em! (src/events.jl:853-932) on one problem given directly: the first n_inc paths are
+    inclusion paths; amb_sets = list of lists of 0-based path indices.  Returns (psi[np], iterations)."""
+    L = lib()
+    L.wqo_em_psi.restype = C.c_int64
+    cnt, ln = np.ascontiguousarray(count, "<f8"), np.ascontiguousarray(length, "<f8")
+    ptr_ = np.zeros(len(amb_sets) + 1, "<u4")
+    ptr_[1:] = np.cumsum([len(a) for a in amb_sets])
+    paths = np.ascontiguousarray([x for a in amb_sets for x in a] or [0], "<u4")
+    mult = np.ascontiguousarray(list(amb_mult) or [0.0], "<f8")
+    psi = np.zeros(len(cnt))
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    it = L.wqo_em_psi(C.c_uint32(len(cnt)), C.c_uint32(n_inc), p(cnt), p(ln), C.c_uint32(len(amb_sets)), p(ptr_), p(paths), p(mult),
+                      C.c_int(1 if tandem else 0), C.c_int64(readlen), C.c_int(sig), C.c_int64(maxit), p(psi))
+    return psi, int(it)
+
+
 def reduce_graph(edges):
     """reduce_graph (src/events.jl:223-266) on [(first, last, value)]; returns the list of node sets."""
     L = lib()

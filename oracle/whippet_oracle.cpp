@@ -1710,6 +1710,38 @@ uint64_t wqo_event_path(wqo_handle* h, uint64_t i, int which, uint64_t k, uint32
     memcpy(out, g.nodes[k].data(), g.nodes[k].size() * 4);
     return g.nodes[k].size();
 }
+// One EM problem given directly (checker for wq_em_psi_batch): the first n_inc paths are inclusion paths, the rest
+// exclusion paths (spliced_em!, src/events.jl:853-893), or all paths of a tandem-UTR event (rec_tandem_em!, :895-932).
+// AmbigCounts.paths are 1-based here as in the reference.  Returns the iteration count; psi[np] receives the psi values.
+int64_t wqo_em_psi(uint32_t np, uint32_t n_inc, const double* count, const double* length, uint32_t n_amb, const uint32_t* amb_ptr,
+                   const uint32_t* amb_paths, const double* amb_mult, int tandem, int64_t readlen, int sig, int64_t maxit, double* psi) {
+    std::vector<AmbigCounts> ambig(n_amb);
+    for (uint32_t a = 0; a < n_amb; a++) {
+        const uint32_t n = amb_ptr[a + 1] - amb_ptr[a];
+        for (uint32_t k = 0; k < n; k++) ambig[a].paths.push_back(amb_paths[amb_ptr[a] + k] + 1);
+        ambig[a].prop.assign(n, 1.0 / (double)n);           // AmbigCounts(paths, ones(n) / n, 1.0, multiplier), src/events.jl:309-326
+        ambig[a].prop_sum = 1.0;
+        ambig[a].multiplier = amb_mult[a];
+    }
+    int64_t it;
+    if (tandem) {
+        PsiGraph pg;
+        pg.count.assign(count, count + np); pg.length.assign(length, length + np); pg.psi.assign(np, 0.0);
+        it = rec_tandem_em(pg, ambig, sig, readlen, maxit);
+        for (uint32_t i = 0; i < np; i++) psi[i] = pg.psi[i];
+    } else {
+        PsiGraph ig, eg;
+        ig.count.assign(count, count + n_inc); ig.length.assign(length, length + n_inc); ig.psi.assign(n_inc, 0.0);
+        eg.count.assign(count + n_inc, count + np); eg.length.assign(length + n_inc, length + np); eg.psi.assign(np - n_inc, 0.0);
+        std::vector<double> counts(count, count + np);
+        calculate_psi2(ig, eg, counts, 0);                  // calculate_psi!(inc, exc, counts) before spliced_em! (src/events.jl:733)
+        it = spliced_em(ig, eg, ambig, sig, maxit);
+        for (uint32_t i = 0; i < n_inc; i++) psi[i] = ig.psi[i];
+        for (uint32_t i = n_inc; i < np; i++) psi[i] = eg.psi[i - n_inc];
+    }
+    return it;
+}
+
 // known-answer hook: reduce_graph on a list of weighted edges (test/runtests.jl:535-580)
 uint64_t wqo_reduce_graph(const uint32_t* first, const uint32_t* last, const double* value, uint64_t n, uint32_t* out_sets, uint64_t cap) {
     PsiGraph g;

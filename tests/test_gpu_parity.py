@@ -350,3 +350,36 @@ def test_events_paired():
     idx, p, f, r = pe_case(2, 300, 76, 5000, True, 150000)
     ev, nem = events_parity(idx, p, f, 76, mate=r)
     assert nem > 5
+
+
+def test_em_psi_batch_all_event_sizes(fixture_index):
+    """wq_em_psi_batch against the oracle's spliced_em! / rec_tandem_em! on problems given directly, covering every
+    kernel class: 4 / 8 / 16 lanes per event, one warp with the shared-memory slab (<= 48 paths) and with global scratch
+    (config 5 of BASELINE.json: complex events with 64-1024 paths), spliced and tandem, zero-count paths (the slow
+    decay that runs to the 1500-sweep cap) and converging ones."""
+    from oracle import em_psi
+    rng = np.random.default_rng(77)
+    problems = []
+    for np_ in [2, 2, 3, 3, 4, 4, 5, 6, 8, 8, 9, 12, 16, 16, 17, 30, 48, 49, 64, 150, 400, 1024]:
+        for tandem in (False, True):
+            ni = np_ if tandem else int(rng.integers(1, np_))
+            cnt = np.where(rng.random(np_) < 0.3, 0.0, np.round(rng.gamma(1.0, 30.0, np_)))
+            ln = np.round(rng.uniform(2, 400 if tandem else 12, np_))
+            sets, mult = [], []
+            for _ in range(int(rng.integers(0, min(2 * np_, 40) + 1))):
+                k = int(rng.integers(2, min(np_, 12) + 1))
+                a = sorted(int(x) for x in rng.choice(np_, size=k, replace=False))
+                if a in sets:
+                    continue
+                sets.append(a); mult.append(float(np.round(rng.gamma(1.0, 20.0), 1 if rng.random() < 0.3 else 0) + 1))
+            problems.append((ni, cnt, ln, sets, mult, tandem))
+    q = wq.GraphLibQuant(fixture_index)
+    got = q.em_psi_batch(problems, readlen=101)
+    capped = 0
+    for (ni, cnt, ln, sets, mult, tandem), (psi, it) in zip(problems, got):
+        want, wit = em_psi(ni, cnt, ln, sets, mult, tandem, 101)
+        assert it == wit, (len(cnt), tandem, it, wit)
+        assert np.array_equal(psi, want, equal_nan=True), (len(cnt), tandem)
+        capped += it == 1500
+    assert capped > 0 and capped < len(problems)
+    q.close()

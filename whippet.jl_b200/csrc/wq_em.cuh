@@ -731,7 +731,19 @@ struct WqEmScratch {
     }
 };
 
+// powers of ten 10^0 .. 10^308 as the host's libm computes them, uploaded into slot 23 of a scratch
+static inline cudaError_t wq_p10_table(struct WqEmScratch& M, cudaStream_t stream, const double** out);
 #define WQ_EMCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return std::string(#call) + ": " + cudaGetErrorString(e_); } while (0)
+
+static inline cudaError_t wq_p10_table(WqEmScratch& M, cudaStream_t stream, const double** out) {
+    static const std::vector<double> tab = [] { std::vector<double> t(309); for (int k = 0; k <= 308; k++) t[k] = std::pow(10.0, (double)k); return t; }();
+    double* dp = nullptr;
+    const bool fresh = M.cap[23] == 0;
+    cudaError_t e = M.get(23, tab.size(), &dp);
+    if (e == cudaSuccess && fresh) e = cudaMemcpyAsync(dp, tab.data(), tab.size() * 8, cudaMemcpyHostToDevice, stream);
+    *out = dp;
+    return e;
+}
 
 static inline std::string wq_run_em_tpm(const WqHostIndex& H, const WqIsoIndex& S, WqHostQuant& hq, WqHostQuantEx& X, WqEmScratch& M,
                                         const wq_em_param& p, cudaStream_t stream, uint64_t* launches,
@@ -943,9 +955,17 @@ struct WqPsiDev {
     double* psi; double* prev; double* ctemp; double* amb_prop; int32_t* iterations;
     double p10[23];               // exact powers of ten
     double ip10[23];              // 1 / 10^k, correctly rounded (the same bits as an IEEE division on the device)
+    const double* p10big;         // [309] 10^k by the host's libm pow (global memory)
 };
 
-__device__ __forceinline__ double wq_pow10(const WqPsiDev& d, int k) { return (k >= 0 && k <= 22) ? d.p10[k] : pow(10.0, (double)k); }
+// 10^k as the host's libm rounds it (Base.round scales by 10.0^digits computed through libm pow; the device pow may be an
+// ulp or two off, which changes the rounded result of a value as small as 1e-188 — a psi that decayed for 1500 sweeps).
+// Exact for k <= 22 (kernel parameter table), host-computed table up to 10^308, +Inf beyond as in IEEE arithmetic.
+__device__ __forceinline__ double wq_pow10(const WqPsiDev& d, int k) {
+    if (k >= 0 && k <= 22) return d.p10[k];
+    if (k > 22 && k <= 308 && d.p10big) return d.p10big[k];
+    return pow(10.0, (double)k);
+}
 // hidigit(x, 10) = 1 + floor(log10|x|) (Base.round(x, sigdigits=n)).  The decade is taken from the binary exponent
 // and fixed up against exact powers of ten for |x| >= 1 and correctly rounded ones below; values within an ulp of a
 // power of ten may land in the neighbouring decade compared with a libm log10, which cannot change the rounded
@@ -1126,6 +1146,7 @@ static inline std::string wq_run_em_psi(wq_psi_batch& b, WqEmScratch& M, cudaStr
     WqPsiDev d;
     d.n_events = E; d.readlen = (double)b.readlen; d.sig = (int)b.sig; d.maxit = b.maxit;
     for (int k = 0; k <= 22; k++) { d.p10[k] = std::pow(10.0, (double)k); d.ip10[k] = 1.0 / d.p10[k]; }
+    WQ_EMCK(wq_p10_table(M, stream, &d.p10big));
     uint32_t *d_pp, *d_ni, *d_ap, *d_app, *d_apaths;
     double *d_cnt, *d_len, *d_mult, *d_psi, *d_prev, *d_ct, *d_prop;
     uint8_t* d_tan;
@@ -1300,7 +1321,7 @@ __global__ void __launch_bounds__(128) wq_k_psi_ci(const WqCiDev d, const uint32
     if (t & 1) d.hi[e] = v; else d.lo[e] = v;
 }
 
-static inline void wq_ci_tables(WqCiDev& d);
+static inline cudaError_t wq_ci_tables(WqCiDev& d, WqEmScratch& M, cudaStream_t stream);
 // The totals go up BEFORE the PSI launch (a copy from pageable memory enqueued behind the kernels would block the host
 // until they finish); the kernel itself goes behind wq_run_em_psi(b, M, stream, ..., wait = false) on the same scratch and
 // stream: out = lo[E] then hi[E] (pinned).
@@ -1314,7 +1335,7 @@ static inline std::string wq_psi_ci_upload(uint32_t E, const double* total, WqEm
 static inline std::string wq_run_psi_ci(uint32_t E, double* out, WqEmScratch& M, cudaStream_t stream, uint64_t* launches) {
     if (E == 0) return "";
     WqCiDev d;
-    wq_ci_tables(d);
+    WQ_EMCK(wq_ci_tables(d, M, stream));
     d.n = E;
     double *d_tot, *d_lo, *d_hi;
     WQ_EMCK(M.get(19, E, &d_tot)); WQ_EMCK(M.get(20, E, &d_lo)); WQ_EMCK(M.get(21, E, &d_hi));
@@ -1331,7 +1352,7 @@ static inline std::string wq_run_beta_ci(uint32_t n, const double* psi, const do
                                          WqEmScratch& M, cudaStream_t stream, uint64_t* launches, bool wait = true) {
     if (n == 0) return "";
     WqCiDev d;
-    wq_ci_tables(d);
+    WQ_EMCK(wq_ci_tables(d, M, stream));
     d.n = n;
     double *d_psi, *d_tot, *d_lo, *d_hi;
     WQ_EMCK(M.get(15, n, &d_psi)); WQ_EMCK(M.get(16, n, &d_tot)); WQ_EMCK(M.get(17, n, &d_lo)); WQ_EMCK(M.get(18, n, &d_hi));
@@ -1347,8 +1368,10 @@ static inline std::string wq_run_beta_ci(uint32_t n, const double* psi, const do
     return "";
 }
 
-static inline void wq_ci_tables(WqCiDev& d) {
+static inline cudaError_t wq_ci_tables(WqCiDev& d, WqEmScratch& M, cudaStream_t stream) {
     for (int k = 0; k <= 22; k++) { d.tab.p10[k] = std::pow(10.0, (double)k); d.tab.ip10[k] = 1.0 / d.tab.p10[k]; }
+    cudaError_t e0 = wq_p10_table(M, stream, &d.tab.p10big);
+    if (e0 != cudaSuccess) return e0;
     {   // Gauss-Legendre nodes on [-1, 1] by Newton iteration on P_n, mapped to [0, 1]
         const int n = WQ_CI_GL;
         for (int i = 0; i < (n + 1) / 2; i++) {
@@ -1366,4 +1389,5 @@ static inline void wq_ci_tables(WqCiDev& d) {
             d.gl_w[i] = 0.5 * w; d.gl_w[n - 1 - i] = 0.5 * w;
         }
     }
+    return cudaSuccess;
 }

@@ -260,6 +260,33 @@ class GraphLibQuant:
         lib.check(self.L.wq_process_events(self.h, int(readlen), C.byref(o)))
         return ev, vals, pptr, pnodes
 
+    def em_psi_batch(self, problems, readlen: int, sig: int = 4, maxit: int = 1500):
+        """wq_em_psi_batch: spliced_em! / rec_tandem_em! (src/events.jl:853-932) for a list of problems
+        (n_inc, count[np], length[np], amb_sets (lists of 0-based path indices), amb_mult, tandem).
+        Returns [(psi[np], iterations)]."""
+        E = len(problems)
+        path_ptr, amb_ptr, amb_path_ptr = [0], [0], [0]
+        n_inc, cnt, ln, apaths, amult, tan = [], [], [], [], [], []
+        for (ni, c, l, sets, mult, t) in problems:
+            n_inc.append(ni); cnt += list(c); ln += list(l); tan.append(1 if t else 0)
+            path_ptr.append(len(cnt))
+            for a, m in zip(sets, mult):
+                apaths += list(a); amult.append(m); amb_path_ptr.append(len(apaths))
+            amb_ptr.append(len(amult))
+        arr = lambda x, dt: np.ascontiguousarray(x if len(x) else [0], dt)
+        a_pp, a_ni, a_ap, a_app = arr(path_ptr, "<u4"), arr(n_inc, "<u4"), arr(amb_ptr, "<u4"), arr(amb_path_ptr, "<u4")
+        a_paths, a_cnt, a_ln, a_mult, a_tan = arr(apaths, "<u4"), arr(cnt, "<f8"), arr(ln, "<f8"), arr(amult, "<f8"), arr(tan, "u1")
+        psi, its = np.zeros(max(1, len(cnt))), np.zeros(max(1, E), "<i4")
+        b = abi.PsiBatchC()
+        b.n_events = E
+        b.path_ptr, b.n_inc, b.path_count, b.path_length = abi.ptr(a_pp, abi.u32p), abi.ptr(a_ni, abi.u32p), abi.ptr(a_cnt, abi.f64p), abi.ptr(a_ln, abi.f64p)
+        b.amb_ptr, b.amb_path_ptr, b.amb_paths, b.amb_mult = abi.ptr(a_ap, abi.u32p), abi.ptr(a_app, abi.u32p), abi.ptr(a_paths, abi.u32p), abi.ptr(a_mult, abi.f64p)
+        b.is_tandem = abi.ptr(a_tan, abi.u8p)
+        b.readlen, b.sig, b.maxit = int(readlen), int(sig), int(maxit)
+        b.psi, b.path_total, b.iterations = abi.ptr(psi, abi.f64p), None, abi.ptr(its, abi.i32p)
+        lib.check(self.L.wq_em_psi_batch(self.h, C.byref(b)))
+        return [(psi[path_ptr[e]:path_ptr[e + 1]].copy(), int(its[e])) for e in range(E)]
+
     def process_events_view(self, readlen: int):
         """process_events without copies: numpy views of the arrays the library owns (wq_process_events_view), valid
         until the count state changes or the handle is closed."""
