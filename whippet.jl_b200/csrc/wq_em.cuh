@@ -980,6 +980,14 @@ __device__ __forceinline__ int wq_hidigit(const WqPsiDev& d, double ax) {
         else if (ax < pw(h - 1)) h -= 1;
         return h;
     }
+    if (d.p10big && ax >= 1e-300 && ax < 1e300) {               // same scheme over the big table (10^-k as the IEEE quotient 1 / 10^k)
+        const int e = ((__double2hiint(ax) >> 20) & 0x7FF) - 1023;
+        int h = (int)floor((double)e * 0.30102999566398120) + 1;
+        auto pw = [&](int k) { return k >= 0 ? d.p10big[k] : __ddiv_rn(1.0, d.p10big[-k]); };
+        if (ax >= pw(h)) h += 1;
+        else if (ax < pw(h - 1)) h -= 1;
+        return h;
+    }
     return 1 + (int)floor(log10(ax));
 }
 // Base.round(x, sigdigits = sig)
