@@ -259,6 +259,8 @@ def main():
         if world > 1:
             q.allreduce_counts()        # ONE NCCL all-reduce of the dense counts + all-gather of the sparse stores
         t1 = time.perf_counter()
+        if world > 1:
+            q.build_classes_distributed()   # each rank builds the classes of its gene range; shares all-gathered over NCCL
         it, tpm, cnt, gt = q.gene_em(em_readlen, 1, 10000)
         q.assign_ambig()
         ev = q.process_events_view(em_readlen)      # event construction + batched PSI EM (records lent by the library, no copy)
@@ -362,7 +364,7 @@ def main():
         "config": {"workload": workload_name(a), "l2": "inputs (%.2f GB per step) are larger than the 126 MB L2" % (h2d / 1e9),
                    "text_len": int(idx.text_len), "nodes": int(idx.n_nodes), "isoforms": int(idx.n_isoforms),
                    "mapped_frac": stats.mapped / max(1, stats.total), "multi_frac": stats.multi / max(1, stats.total),
-                   "parallelism": f"reads sharded over {world} GPU(s), index replicated" + (", dense counts all-reduced and sparse stores all-gathered over NCCL, transcript EM replicated, event stage partitioned by gene" if world > 1 else "")},
+                   "parallelism": f"reads sharded over {world} GPU(s), index replicated" + (", dense counts all-reduced and sparse stores all-gathered over NCCL, class building and event stage partitioned by gene (shares all-gathered), transcript EM replicated" if world > 1 else "")},
         "clocks": clocks, "gpu_launches": launches,
         "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "kernel_ms": {"seed": float(kms[0]), "extend": float(kms[1]), "resolve": float(kms[2]),

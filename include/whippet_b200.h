@@ -219,6 +219,15 @@ int  wq_sparse_device_merge(wq_handle* h, const void* dbuf, uint64_t bytes);
 /* Event stage partitioned by gene across ranks: this handle builds and solves the events of the contiguous gene range
  * `part` of `nparts` only and wq_process_events returns that range's records; the parts concatenate to the full output. */
 int  wq_set_gene_partition(wq_handle* h, uint32_t part, uint32_t nparts);
+/* Class building (build_equivalence_classes!, src/quant.jl:327-389) partitioned the same way: after the count exchange
+ * every rank holds the same stores; wq_classes_build_local builds this part's share (the multi-map classes of its key
+ * range, the isoform classes of its gene range), wq_classes_pack lends it as a host buffer owned by the handle, the caller
+ * all-gathers the buffers, and wq_classes_assemble (shares of all parts, in part order) completes the class set that
+ * wq_em_tpm then uses.  Node / edge values (wq_assign_ambig) are then complete for this part's genes only.
+ * Without these calls wq_em_tpm builds every class itself. */
+int  wq_classes_build_local(wq_handle* h);
+int  wq_classes_pack(wq_handle* h, const void** ptr, uint64_t* bytes);
+int  wq_classes_assemble(wq_handle* h, const void* const* bufs, const uint64_t* lens, uint32_t n);
 uint64_t wq_launch_count(wq_handle* h);   /* kernels launched by this handle so far */
 /* Measurement aid (no reference counterpart): device times of the quant-stage kernels of the last wq_em_tpm /
  * wq_process_events, taken with CUDA events on the launching stream, and the sizes their algorithmic-byte models use

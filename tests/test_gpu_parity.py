@@ -383,3 +383,41 @@ def test_em_psi_batch_all_event_sizes(fixture_index):
         capped += it == 1500
     assert capped > 0 and capped < len(problems)
     q.close()
+
+
+def test_partitioned_class_building():
+    """Class building partitioned by gene across ranks, emulated on one GPU: three handles hold the same counts (what every
+    rank holds after the exchange), each builds the share of its part, the shares are assembled on every handle; the EM then
+    equals the unpartitioned one bit for bit, assign_ambig! values are complete for each part's own genes, and the parts'
+    events concatenate to the unpartitioned event list."""
+    idx = synth.make_index(n_genes=2500, K=9, seed=61, paralog_frac=0.1)      # >= 2048 genes: the threaded paths run
+    rb = synth.simulate_reads(idx, 400000, 101, seed=62, sub_rate=0.01)
+    p = wq.AlignParam()
+    full = wq.GraphLibQuant(idx)
+    full.process_reads(p, rb)
+    r_full = full.gene_em(101)
+    v_full = full.assign_ambig()
+    ev_full = full.process_events(101)
+    nparts = 3
+    hs = [wq.GraphLibQuant(idx) for _ in range(nparts)]
+    for k, q in enumerate(hs):
+        q.process_reads(p, rb)
+        q.set_gene_partition(k, nparts)
+    shares = [q.classes_share() for q in hs]
+    got_events = []
+    G = idx.n_genes
+    for k, q in enumerate(hs):
+        q.classes_assemble(shares)
+        r = q.gene_em(101)
+        assert r[0] == r_full[0] and all(np.array_equal(a, b) for a, b in zip(r[1:], r_full[1:])), k
+        node, ek, ev, ck, cv = q.assign_ambig()
+        g_lo, g_hi = G * k // nparts, G * (k + 1) // nparts                       # 0-based gene range of the part
+        n_lo, n_hi = int(idx.node_base[g_lo]), int(idx.node_base[g_hi])
+        assert np.array_equal(node[n_lo:n_hi], v_full[0][n_lo:n_hi]), k
+        own = lambda keys: ((keys >> np.uint64(32)) > g_lo) & ((keys >> np.uint64(32)) <= g_hi)
+        m1, m2 = own(ek), own(v_full[1])
+        assert np.array_equal(ek[m1], v_full[1][m2]) and np.array_equal(ev[m1], v_full[2][m2]), k
+        got_events += q.process_events(101)
+    assert got_events == ev_full and sum(1 for e in ev_full if e["iterations"] > 0) > 50
+    for q in [full] + hs:
+        q.close()

@@ -112,6 +112,7 @@ struct wq_handle {
     WqEmScratch em_scratch;
     std::vector<WqEventRec> ev_recs; std::vector<double> ev_values; std::vector<uint64_t> ev_path_ptr{0}; std::vector<uint32_t> ev_path_nodes;
     bool events_done = false;
+    std::vector<uint8_t> class_pack;     // this rank's share of the classes (wq_classes_build_local)
     std::vector<wq_event> ev_out;        // the finished records in ABI form (wq_process_events copies them, _view lends them)
     float psi_kernel_ms = 0.f;   // device time of the PSI EM launches of the last wq_process_events (CUDA events on the stream)
     uint64_t psi_sweep_bytes = 0;
@@ -1277,6 +1278,34 @@ int wq_counts_refresh_dense(wq_handle* h) {
     CK(cudaMemcpy(dense.data(), h->d_dense.p, dense.size() * 8, cudaMemcpyDeviceToHost));
     h->hq.node.assign(dense.begin(), dense.begin() + N);
     memcpy(&h->hq.stats, dense.data() + N, sizeof(WqCounters));
+    return 0;
+}
+
+// Class building partitioned by gene across ranks (multi-GPU: the host threads of a box are shared by its ranks).  After the
+// count exchange every rank holds the same stores; rank `part` (wq_set_gene_partition) builds the multi-map classes of its
+// key range and the isoform classes of its gene range, the shares are all-gathered by the caller, and every rank assembles
+// the complete class set for wq_em_tpm.
+int wq_classes_build_local(wq_handle* h) {
+    if (!h) return fail(-1, "null handle");
+    if (int rc = sync_host_quant(h)) return rc;
+    WqTimer tm_("classes_build_local");
+    std::string err = wq_host_build_classes(h->H, h->iso, h->hq, h->hx, h->part, h->nparts);
+    if (!err.empty()) return fail(-11, err);
+    wq_classes_pack_impl(h->iso, h->hx, h->class_pack);
+    return 0;
+}
+int wq_classes_pack(wq_handle* h, const void** ptr, uint64_t* bytes) {
+    if (!h || !ptr || !bytes) return fail(-1, "null argument");
+    if (!h->hx.local_built) return fail(-11, "wq_classes_pack needs wq_classes_build_local first");
+    *ptr = h->class_pack.data(); *bytes = h->class_pack.size();
+    return 0;
+}
+int wq_classes_assemble(wq_handle* h, const void* const* bufs, const uint64_t* lens, uint32_t n) {
+    if (!h || !bufs || !lens) return fail(-1, "null argument");
+    if (n != h->nparts) return fail(-11, "wq_classes_assemble needs one share per part of wq_set_gene_partition");
+    WqTimer tm_("classes_assemble");
+    std::string err = wq_classes_assemble_impl(h->iso, h->hx, bufs, lens, n);
+    if (!err.empty()) return fail(-11, err);
     return 0;
 }
 

@@ -96,7 +96,11 @@ static inline void wq_spread_path(const WqHostIndex& H, std::vector<double>& nod
 
 // Builds multi-map classes (first) and isoform classes, fills the unique isoform counts, and
 // re-counts long paths onto their edges (assign_long=true).
-static inline std::string wq_host_build_classes(const WqHostIndex& H, const WqIsoIndex& S, WqHostQuant& hq, WqHostQuantEx& X) {
+// With nparts > 1 only the multi-map classes of key range `part` and the isoform classes of gene range `part` are built
+// (the rank's share; wq_classes_pack / wq_classes_assemble exchange the shares), and long paths are re-counted onto the
+// edges of that gene range only.
+static inline std::string wq_host_build_classes(const WqHostIndex& H, const WqIsoIndex& S, WqHostQuant& hq, WqHostQuantEx& X,
+                                                uint32_t part = 0, uint32_t nparts = 1) {
     const uint32_t G = H.G, I = S.I;
     static const bool prof2 = getenv("WQ_PROFILE") && atoi(getenv("WQ_PROFILE")) >= 2;
     const auto tc0 = std::chrono::steady_clock::now();
@@ -168,11 +172,14 @@ static inline std::string wq_host_build_classes(const WqHostIndex& H, const WqIs
     if (G < 2048) nthreads = 1;
     std::vector<Frag> frags(nthreads);
     std::vector<MFrag> mfrags(nthreads);
-    const size_t NMU = hq.multis.size();
+    const size_t NMU_all = hq.multis.size();
+    const size_t M_lo = NMU_all * part / nparts, NMU = NMU_all * (part + 1) / nparts - M_lo;          // this part's multi-map keys
+    const uint32_t Gp_lo = (uint32_t)((uint64_t)G * part / nparts), Gp_n = (uint32_t)((uint64_t)G * (part + 1) / nparts) - Gp_lo;   // and genes
+    X.own_g_lo = Gp_lo + 1; X.own_g_hi = Gp_lo + Gp_n; X.own_m_lo = (uint32_t)M_lo; X.nparts = nparts;
     auto work = [&](unsigned t) {
-        multi_work(NMU * t / nthreads, NMU * (t + 1) / nthreads, mfrags[t]);
+        multi_work(M_lo + NMU * t / nthreads, M_lo + NMU * (t + 1) / nthreads, mfrags[t]);
         Frag& F = frags[t];
-        const uint32_t g_lo = 1 + (uint32_t)((uint64_t)G * t / nthreads), g_hi = (uint32_t)((uint64_t)G * (t + 1) / nthreads);
+        const uint32_t g_lo = Gp_lo + 1 + (uint32_t)((uint64_t)Gp_n * t / nthreads), g_hi = Gp_lo + (uint32_t)((uint64_t)Gp_n * (t + 1) / nthreads);
         WqGeneBits Bt;
         WqHostQuantEx local;                     // only edge_adds / node_value targets are used through `sink`
         std::vector<int32_t> setbuf;             // id lists of this gene's count entries, back to back
@@ -270,7 +277,7 @@ static inline std::string wq_host_build_classes(const WqHostIndex& H, const WqIs
                 for (uint32_t q = prev; q < F.end[j]; q++) { C.iso[q0 + q] = F.iso[q]; C.prop[q0 + q] = 1.0 / (double)n; }
                 prev = F.end[j];
                 C.ptr[c + 1] = (uint32_t)(q0 + F.end[j]);
-                C.count[c] = (double)hq.multis.count[c];
+                C.count[c] = (double)hq.multis.count[M_lo + c];
                 C.state[c] = F.all[j] ? 0 : 2;
                 C.postassign[c] = F.all[j] ? 0 : 1;
             }
@@ -288,6 +295,80 @@ static inline std::string wq_host_build_classes(const WqHostIndex& H, const WqIs
         }
     });
     lap2("fragments concatenated");
+    X.built = nparts == 1;                   // a share is not a class set: wq_classes_assemble completes it
+    X.local_built = true;
+    return "";
+}
+
+// ---- exchange of class shares between ranks (class building partitioned by gene) ----
+// Buffer: u64 hdr[8] = {n_multi, multi_members, n_iso_classes, iso_members, iso_lo, iso_hi, own_m_lo, 0}, then
+// u32 ptr[n_cls + 1] (padded to 8 bytes), i32 iso[n_mem] (padded), f64 count[n_cls], u8 state[n_cls], u8 postassign[n_cls]
+// (padded), f64 iso_count[iso_hi - iso_lo].
+static inline void wq_classes_pack_impl(const WqIsoIndex& S, const WqHostQuantEx& X, std::vector<uint8_t>& out) {
+    const WqClassSet& C = X.cls;
+    const uint64_t ncls = C.count.size(), nmem = C.iso.size();
+    const uint64_t iso_lo = S.iso_base[X.own_g_lo - 1], iso_hi = S.iso_base[X.own_g_hi];
+    auto pad8 = [](uint64_t b) { return (b + 7) & ~7ull; };
+    const uint64_t bytes = 64 + pad8(4 * (ncls + 1)) + pad8(4 * nmem) + 8 * ncls + pad8(2 * ncls) + 8 * (iso_hi - iso_lo);
+    out.assign(bytes, 0);
+    uint8_t* p = out.data();
+    const uint64_t hdr[8] = {C.n_multi, C.n_multi ? C.ptr[C.n_multi] : 0, ncls - C.n_multi, nmem - (C.n_multi ? C.ptr[C.n_multi] : 0), iso_lo, iso_hi, X.own_m_lo, 0};
+    memcpy(p, hdr, 64); p += 64;
+    memcpy(p, C.ptr.data(), 4 * (ncls + 1)); p += pad8(4 * (ncls + 1));
+    memcpy(p, C.iso.data(), 4 * nmem); p += pad8(4 * nmem);
+    memcpy(p, C.count.data(), 8 * ncls); p += 8 * ncls;
+    memcpy(p, C.state.data(), ncls); memcpy(p + ncls, C.postassign.data(), ncls); p += pad8(2 * ncls);
+    memcpy(p, X.iso_count.data() + iso_lo, 8 * (iso_hi - iso_lo));
+}
+
+// All ranks' shares, in rank order -> the complete class set (multi-map classes of every rank first, then the isoform
+// classes: the canonical order) and the unique isoform counts.  The node / edge values stay those of this rank's genes.
+static inline std::string wq_classes_assemble_impl(const WqIsoIndex& S, WqHostQuantEx& X, const void* const* bufs, const uint64_t* lens, uint32_t n) {
+    if (!X.local_built) return "wq_classes_assemble needs wq_classes_build_local first";
+    auto pad8 = [](uint64_t b) { return (b + 7) & ~7ull; };
+    struct View { uint64_t nm, nmm, nc, ncm, iso_lo, iso_hi; const uint32_t* ptr; const int32_t* iso; const double* count; const uint8_t *state, *post; const double* ic; };
+    std::vector<View> V(n);
+    uint64_t tm = 0, tmm = 0, tc = 0, tcm = 0;
+    for (uint32_t r = 0; r < n; r++) {
+        if (!bufs[r] || lens[r] < 64) return "class share buffer too short";
+        const uint8_t* p = (const uint8_t*)bufs[r];
+        uint64_t hdr[8];
+        memcpy(hdr, p, 64); p += 64;
+        View& v = V[r];
+        v.nm = hdr[0]; v.nmm = hdr[1]; v.nc = hdr[2]; v.ncm = hdr[3]; v.iso_lo = hdr[4]; v.iso_hi = hdr[5];
+        const uint64_t ncls = v.nm + v.nc, nmem = v.nmm + v.ncm;
+        if (v.iso_hi < v.iso_lo || v.iso_hi > S.I) return "class share names isoforms out of range";
+        const uint64_t need = 64 + pad8(4 * (ncls + 1)) + pad8(4 * nmem) + 8 * ncls + pad8(2 * ncls) + 8 * (v.iso_hi - v.iso_lo);
+        if (lens[r] < need) return "class share buffer truncated";
+        v.ptr = (const uint32_t*)p; p += pad8(4 * (ncls + 1));
+        v.iso = (const int32_t*)p; p += pad8(4 * nmem);
+        v.count = (const double*)p; p += 8 * ncls;
+        v.state = p; v.post = p + ncls; p += pad8(2 * ncls);
+        v.ic = (const double*)p;
+        tm += v.nm; tmm += v.nmm; tc += v.nc; tcm += v.ncm;
+    }
+    WqClassSet C;
+    C.ptr.resize(tm + tc + 1); C.iso.resize(tmm + tcm); C.prop.resize(tmm + tcm); C.count.resize(tm + tc); C.state.resize(tm + tc); C.postassign.resize(tm + tc);
+    C.ptr[0] = 0;
+    C.n_multi = (uint32_t)tm;
+    X.frag_cls.assign(n + 1, 0);
+    X.iso_count.assign(S.I, 0.0);
+    uint64_t c = 0, q = 0;
+    for (int pass = 0; pass < 2; pass++)
+        for (uint32_t r = 0; r < n; r++) {
+            const View& v = V[r];
+            const uint64_t c0 = pass == 0 ? 0 : v.nm, c1 = pass == 0 ? v.nm : v.nm + v.nc;
+            if (pass == 1) X.frag_cls[r] = (uint32_t)c;
+            for (uint64_t k = c0; k < c1; k++, c++) {
+                const uint32_t b = v.ptr[k], e = v.ptr[k + 1], len = e - b;
+                for (uint32_t j = b; j < e; j++, q++) { C.iso[q] = v.iso[j]; C.prop[q] = 1.0 / (double)len; }
+                C.ptr[c + 1] = (uint32_t)q;
+                C.count[c] = v.count[k]; C.state[c] = v.state[k]; C.postassign[c] = v.post[k];
+            }
+            if (pass == 1) memcpy(X.iso_count.data() + v.iso_lo, v.ic, 8 * (v.iso_hi - v.iso_lo));
+        }
+    X.frag_cls[n] = (uint32_t)c;
+    X.cls = std::move(C);
     X.built = true;
     return "";
 }
@@ -300,6 +381,7 @@ static inline std::string wq_host_assign_ambig_impl(const WqHostIndex& H, const 
     // the share of every alignment of every class (independent: host threads), then the additions in class order
     // (sequential: floating-point sums onto one node / edge must see their terms in the reference's order)
     std::vector<double> share((size_t)C.n_multi * WQ_MAX_TOLERATE, 0.0);
+    std::vector<uint8_t> skip(C.n_multi, 0);
     unsigned nthreads = wq_host_threads();
     if (C.n_multi < 1024) nthreads = 1;
     std::vector<std::string> errs(nthreads);
@@ -315,6 +397,12 @@ static inline std::string wq_host_assign_ambig_impl(const WqHostIndex& H, const 
             if (nh > WQ_MAX_TOLERATE) { errs[t] = "multi-map class with more alignments than WQ_MAX_TOLERATE"; return; }
             size_t pos = 1;
             for (uint32_t h = 0; h < nh; h++) pos = wq_key_next(key, pos, vp[h]);
+            if (X.nparts > 1) {              // partitioned: only classes that touch this rank's genes matter here
+                bool mine = false;
+                for (uint32_t h = 0; h < nh; h++) if (vp[h].gene >= X.own_g_lo && vp[h].gene <= X.own_g_hi) mine = true;
+                skip[c] = mine ? 0 : 1;
+                if (!mine) continue;
+            }
             for (uint32_t h = 0; h < nh; h++) {
                 if (C.postassign[c]) { w[h] = X.genetpm[vp[h].gene - 1]; continue; }
                 if (cached != vp[h].gene) { B.build(S, vp[h].gene - 1, H.genes[vp[h].gene - 1].nn); cached = vp[h].gene; }
@@ -335,12 +423,14 @@ static inline std::string wq_host_assign_ambig_impl(const WqHostIndex& H, const 
     else { std::vector<std::thread> th; for (unsigned t = 0; t < nthreads; t++) th.emplace_back(work, t); for (auto& x : th) x.join(); }
     for (auto& e : errs) if (!e.empty()) return e;
     for (uint32_t c = 0; c < C.n_multi; c++) {
+        if (skip[c]) continue;
         const uint32_t* key = hq.multis.key(c);
         const uint32_t nh = key[0] & 0xFFFF;
         size_t pos = 1;
         for (uint32_t h = 0; h < nh; h++) {
             WqKeyPath kp;
             pos = wq_key_next(key, pos, kp);
+            if (X.nparts > 1 && (kp.gene < X.own_g_lo || kp.gene > X.own_g_hi)) continue;       // another rank's gene
             wq_spread_path(H, X.node_value, X.edge_adds, kp, share[(size_t)c * WQ_MAX_TOLERATE + h]);
         }
     }

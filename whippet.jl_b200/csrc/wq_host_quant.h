@@ -83,6 +83,8 @@ struct WqHostQuantEx {
     std::vector<double> iso_count, tpm, genetpm;
     std::vector<uint8_t> gene_dirty;                         // [G+1] gene is named by some multi-map class: assign_ambig! will change its counts
     WqClassSet cls;
+    bool local_built = false;                                // this rank's share of the classes is built (class building partitioned by gene)
+    uint32_t own_g_lo = 1, own_g_hi = 0xFFFFFFFFu, own_m_lo = 0, nparts = 1;      // the share: gene range, first multi-map key
     std::vector<uint32_t> frag_cls;                          // class ranges of the class-building fragments (disjoint gene ranges)
     int64_t iterations = 0;
     float em_kernel_ms = 0.f;                                // device time of the transcript EM kernel (CUDA events)

@@ -56,6 +56,9 @@ def load():
     L.wq_sparse_device_pack.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_uint64)]
     L.wq_sparse_device_merge.argtypes = [vp, vp, C.c_uint64]
     L.wq_set_gene_partition.argtypes = [vp, C.c_uint32, C.c_uint32]
+    L.wq_classes_build_local.argtypes = [vp]
+    L.wq_classes_pack.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_uint64)]
+    L.wq_classes_assemble.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_uint64), C.c_uint32]
     L.wq_fastq_open.argtypes = [C.c_char_p, C.c_int, C.POINTER(vp)]
     L.wq_fastq_from_memory.argtypes = [C.c_char_p, C.c_uint64, C.c_int, C.POINTER(vp)]
     L.wq_fastq_next.argtypes = [vp, C.c_uint32, C.POINTER(abi.ReadBatchC)]

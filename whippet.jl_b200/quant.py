@@ -373,6 +373,40 @@ class GraphLibQuant:
             if r != rank:
                 lib.check(self.L.wq_sparse_device_merge(self.h, C.c_void_p(gathered[r * m:].data_ptr()), C.c_uint64(sizes[r] * 8)))
 
+    def classes_share(self) -> np.ndarray:
+        """This part's share of the classes (wq_classes_build_local + wq_classes_pack) as a byte array (a copy)."""
+        lib.check(self.L.wq_classes_build_local(self.h))
+        ptr_, n = C.c_void_p(), C.c_uint64()
+        lib.check(self.L.wq_classes_pack(self.h, C.byref(ptr_), C.byref(n)))
+        return np.frombuffer((C.c_char * int(n.value)).from_address(ptr_.value), dtype="u1").copy()
+
+    def classes_assemble(self, shares):
+        """wq_classes_assemble: the shares of all parts, in part order."""
+        shares = [np.ascontiguousarray(s, "u1") for s in shares]
+        bufs = (C.c_void_p * len(shares))(*[s.ctypes.data for s in shares])
+        lens = (C.c_uint64 * len(shares))(*[s.nbytes for s in shares])
+        lib.check(self.L.wq_classes_assemble(self.h, bufs, lens, len(shares)))
+
+    def build_classes_distributed(self):
+        """Class building partitioned by gene across the ranks of torch.distributed (after allreduce_counts and
+        set_gene_partition(rank, world)): local share -> NCCL all-gather -> complete class set on every rank."""
+        import torch
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(), dist.get_rank()
+        dev = torch.device("cuda", self.device)
+        mine = self.classes_share()
+        nb = (len(mine) + 7) // 8 * 8
+        sizes = torch.zeros(world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(sizes, torch.tensor([len(mine)], dtype=torch.int64, device=dev))
+        sizes = [int(x) for x in sizes.tolist()]
+        m = (max(sizes) + 7) // 8 * 8
+        padded = torch.zeros(m, dtype=torch.uint8, device=dev)
+        padded[:len(mine)] = torch.from_numpy(mine).to(dev)
+        gathered = torch.empty(world * m, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(gathered, padded)
+        host = gathered.cpu().numpy()
+        self.classes_assemble([host[r * m:r * m + sizes[r]] for r in range(world)])
+
     def set_gene_partition(self, part: int, nparts: int):
         """Event stage partitioned by gene: this handle builds and solves the events of gene range `part` of `nparts`;
         process_events then returns that range only (the parts concatenate to the full output)."""
