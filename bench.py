@@ -184,7 +184,9 @@ def run_reference(a):
     have_julia = subprocess.call("julia --version", shell=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL) == 0
     vals = []
     for i in range(a.warmup + a.steps):
-        nsample = min(rb.n, a.cpu_sample * max(1, threads // 2))
+        # bounded sample: the per-job quant stage of the restatement is single-threaded (like the reference) and costs ~20 s per
+        # step whatever the sample, so the alignment sample is kept small enough for W + K steps to end within a few minutes
+        nsample = min(rb.n, max(a.cpu_sample * 2 // 3, 125_000 * threads))
         v, dt, _, _, _, _ = cpu_oracle_run(idx, rb, param, nsample, threads, a.readlen)
         if i >= a.warmup:
             vals.append((v, dt, nsample))
