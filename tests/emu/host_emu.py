@@ -1,0 +1,123 @@
+"""TEST INFRASTRUCTURE ONLY: ctypes driver of tests/emu/wq_host_emu.cu (the library's HOST stages run on given count
+stores; no kernel is launched)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+import whippet_jl_b200 as wq
+from whippet_jl_b200.build import nvcc_path
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libwq_host_emu.so")
+_CSRC = os.path.join(_HERE, "..", "..", "whippet.jl_b200", "csrc")
+
+
+def build():
+    srcs = [os.path.join(_HERE, "wq_host_emu.cu")] + [os.path.join(_CSRC, f) for f in
+                                                      ("wq_em.cuh", "wq_events.h", "wq_host_quant.h", "wq_host_index.h", "wq_types.h", "wq_kernels.cuh")]
+    if not os.path.exists(_SO) or os.path.getmtime(_SO) < max(map(os.path.getmtime, srcs)):
+        subprocess.check_call([nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-std=c++17", "-fmad=false",
+                               "-Xcompiler", "-fPIC", "-shared", "-o", _SO, srcs[0]])
+    return _SO
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class HostEmu:
+    def __init__(self, index: wq.FlatIndex):
+        build()
+        self.L = C.CDLL(_SO)
+        self.L.hemu_create.restype = C.c_void_p
+        self.L.hemu_error.restype = C.c_char_p
+        for f in ("hemu_pack", "hemu_n_classes", "hemu_class", "hemu_edge_adds", "hemu_events", "hemu_event_path"):
+            getattr(self.L, f).restype = C.c_uint64
+        self.L.hemu_event.restype = C.c_int64
+        self.index = index
+        self._d = index.desc()
+        self.h = C.c_void_p(self.L.hemu_create(C.byref(self._d)))
+        assert self.h
+
+    def close(self):
+        if self.h:
+            self.L.hemu_destroy(self.h)
+            self.h = None
+
+    def set_counts(self, node, ekey, ecount, longs: dict, multis: dict):
+        def flat(d):
+            keys = list(d)
+            ptr_ = np.zeros(len(keys) + 1, "<u8")
+            ptr_[1:] = np.cumsum([len(k) for k in keys])
+            words = np.array([w for k in keys for w in k] or [0], "<u4")
+            cnt = np.array([int(d[k]) for k in keys] or [0], "<u8")
+            return len(keys), ptr_, words, cnt
+        node = np.ascontiguousarray(node, "<u8")
+        ekey, ecount = np.ascontiguousarray(ekey, "<u8"), np.ascontiguousarray(ecount, "<u8")
+        nl, lp, lw, lc = flat(longs)
+        nm, mp, mw, mc = flat(multis)
+        self.L.hemu_set_counts(self.h, _p(node), C.c_uint64(len(ekey)), _p(ekey), _p(ecount),
+                               C.c_uint64(nl), _p(lp), _p(lw), _p(lc), C.c_uint64(nm), _p(mp), _p(mw), _p(mc))
+
+    def build_classes(self, part=0, nparts=1):
+        rc = self.L.hemu_build_classes(self.h, C.c_uint32(part), C.c_uint32(nparts))
+        assert rc == 0, self.L.hemu_error(self.h)
+
+    def share(self) -> bytes:
+        ptr_ = C.c_void_p()
+        n = self.L.hemu_pack(self.h, C.byref(ptr_))
+        return C.string_at(ptr_, n)
+
+    def assemble(self, shares):
+        keep = [C.create_string_buffer(s, len(s)) for s in shares]
+        bufs = (C.c_void_p * len(shares))(*[C.addressof(k) for k in keep])
+        lens = (C.c_uint64 * len(shares))(*[len(s) for s in shares])
+        rc = self.L.hemu_assemble(self.h, bufs, lens, C.c_uint32(len(shares)))
+        assert rc == 0, self.L.hemu_error(self.h)
+
+    def classes(self):
+        """([(ids, count, isdone, postassign)], n_multi) in canonical order."""
+        nm = C.c_uint32()
+        n = self.L.hemu_n_classes(self.h, C.byref(nm))
+        ids = np.zeros(4096, "<i4")
+        out = []
+        for c in range(n):
+            cnt, fl = C.c_double(), C.c_int32()
+            k = self.L.hemu_class(self.h, C.c_uint64(c), _p(ids), C.c_uint64(len(ids)), C.byref(cnt), C.byref(fl))
+            out.append((ids[:k].tolist(), cnt.value, bool(fl.value & 1), bool(fl.value & 2)))
+        return out, int(nm.value)
+
+    def iso_count(self):
+        a = np.zeros(self.index.n_isoforms)
+        self.L.hemu_iso_count(self.h, _p(a))
+        return a
+
+    def events(self, node_value, ekey, evalue, readlen):
+        """Event construction of every gene.  Returns a list of dicts (gene, node, motif, kind, flags, n_utr, psi, total,
+        problem, inc paths, exc paths / utr paths) and the EM problems as tuples for oracle.em_psi."""
+        node_value = np.ascontiguousarray(node_value, "<f8")
+        ekey, evalue = np.ascontiguousarray(ekey, "<u8"), np.ascontiguousarray(evalue, "<f8")
+        n = self.L.hemu_events(self.h, _p(node_value), C.c_uint64(len(ekey)), _p(ekey), _p(evalue), C.c_int64(readlen))
+        hdr, vals, buf = (C.c_uint32 * 9)(), (C.c_double * 2)(), np.zeros(70000, "<u4")
+        out = []
+        for i in range(n):
+            prob = self.L.hemu_event(self.h, C.c_uint64(i), hdr, vals)
+            paths = []
+            for k in range(hdr[8]):
+                m = self.L.hemu_event_path(self.h, C.c_uint64(i), C.c_uint64(k), _p(buf), C.c_uint64(len(buf)))
+                paths.append(tuple(int(x) for x in buf[:m]))
+            out.append(dict(gene=hdr[0], node=hdr[1], motif=hdr[2], kind=hdr[3], flags=hdr[4], n_utr=hdr[5], n_inc=hdr[6], n_exc=hdr[7],
+                            psi=vals[0], total=vals[1], problem=int(prob), paths=paths))
+        return out
+
+    def problem(self, p):
+        sizes = (C.c_uint32 * 5)()
+        self.L.hemu_problem(self.h, C.c_uint64(p), sizes, None, None, None, None, None)
+        npth, ninc, namb, tandem, nap = (int(x) for x in sizes)
+        cnt, ln = np.zeros(npth), np.zeros(npth)
+        aptr, apaths, amult = np.zeros(namb + 1, "<u4"), np.zeros(max(1, nap), "<u4"), np.zeros(max(1, namb))
+        self.L.hemu_problem(self.h, C.c_uint64(p), sizes, _p(cnt), _p(ln), _p(aptr), _p(apaths), _p(amult))
+        sets = [[int(x) for x in apaths[int(aptr[a]):int(aptr[a + 1])]] for a in range(namb)]
+        return ninc, cnt, ln, sets, amult[:namb].tolist(), bool(tandem)

@@ -1,0 +1,118 @@
+// TEST INFRASTRUCTURE ONLY: drives the HOST stages of the library (class building, class shares, event construction:
+// whippet.jl_b200/csrc/wq_em.cuh host part, wq_events.h) on given count stores, so they can be checked against the oracle
+// in a container without a GPU.  No kernel is launched here and nothing of this file is part of the product library.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <string>
+#include <vector>
+#include "../../whippet.jl_b200/csrc/wq_kernels.cuh"
+#include "../../whippet.jl_b200/csrc/wq_host_index.h"
+#include "../../whippet.jl_b200/csrc/wq_host_quant.h"
+#include "../../whippet.jl_b200/csrc/wq_em.cuh"
+#include "../../whippet.jl_b200/csrc/wq_events.h"
+
+struct HostEmu {
+    WqHostIndex H; WqIsoIndex S; WqHostQuant hq; WqHostQuantEx X;
+    std::vector<uint8_t> pack;
+    std::vector<double> node_value;
+    std::vector<WqEventRec> recs; WqPsiProblems P; WqEventPool pool;
+    std::string err;
+};
+
+extern "C" {
+
+HostEmu* hemu_create(const wq_index_desc* d) {
+    HostEmu* e = new HostEmu();
+    std::string err = wq_build_host_index(d, e->H);
+    if (err.empty()) err = wq_build_iso_index(d, e->S);
+    if (!err.empty()) { fprintf(stderr, "hemu: %s\n", err.c_str()); delete e; return nullptr; }
+    return e;
+}
+void hemu_destroy(HostEmu* e) { delete e; }
+const char* hemu_error(HostEmu* e) { return e->err.c_str(); }
+
+// count stores in the layout of wq_counts / wq_keyed (edges sorted by key; keyed records in any order)
+void hemu_set_counts(HostEmu* e, const uint64_t* node, uint64_t ne, const uint64_t* ekey, const uint64_t* ecount,
+                     uint64_t nl, const uint64_t* lptr, const uint32_t* lwords, const uint64_t* lcount,
+                     uint64_t nm, const uint64_t* mptr, const uint32_t* mwords, const uint64_t* mcount) {
+    e->hq = WqHostQuant();
+    e->hq.node.assign(node, node + e->H.N);
+    e->hq.edge_key.assign(ekey, ekey + ne); e->hq.edge_count.assign(ecount, ecount + ne);
+    for (uint64_t i = 0; i < nl; i++) e->hq.longs.push(lwords + lptr[i], (size_t)(lptr[i + 1] - lptr[i]), lcount[i]);
+    for (uint64_t i = 0; i < nm; i++) e->hq.multis.push(mwords + mptr[i], (size_t)(mptr[i + 1] - mptr[i]), mcount[i]);
+    e->hq.multis.canonicalize();
+}
+
+int hemu_build_classes(HostEmu* e, uint32_t part, uint32_t nparts) {
+    e->err = wq_host_build_classes(e->H, e->S, e->hq, e->X, part, nparts);
+    if (!e->err.empty()) return -1;
+    if (nparts > 1) wq_classes_pack_impl(e->S, e->X, e->pack);
+    return 0;
+}
+uint64_t hemu_pack(HostEmu* e, const void** p) { *p = e->pack.data(); return e->pack.size(); }
+int hemu_assemble(HostEmu* e, const void* const* bufs, const uint64_t* lens, uint32_t n) {
+    e->err = wq_classes_assemble_impl(e->S, e->X, bufs, lens, n);
+    return e->err.empty() ? 0 : -1;
+}
+uint64_t hemu_n_classes(HostEmu* e, uint32_t* n_multi) { *n_multi = e->X.cls.n_multi; return e->X.cls.count.size(); }
+uint64_t hemu_class(HostEmu* e, uint64_t c, int32_t* ids, uint64_t cap, double* count, int32_t* flags) {
+    const WqClassSet& C = e->X.cls;
+    const uint64_t n = C.ptr[c + 1] - C.ptr[c];
+    for (uint64_t k = 0; k < n && k < cap; k++) ids[k] = C.iso[C.ptr[c] + k];
+    *count = C.count[c];
+    *flags = (C.state[c] ? 1 : 0) | (C.postassign[c] ? 2 : 0);
+    return n;
+}
+void hemu_iso_count(HostEmu* e, double* out) { memcpy(out, e->X.iso_count.data(), e->X.iso_count.size() * 8); }
+uint64_t hemu_edge_adds(HostEmu* e, uint64_t* keys, double* vals, uint64_t cap) {
+    const uint64_t n = e->X.edge_adds.size();
+    for (uint64_t i = 0; i < n && i < cap; i++) { keys[i] = e->X.edge_adds[i].first; vals[i] = e->X.edge_adds[i].second; }
+    return n;
+}
+
+// event construction of every gene (src/events.jl:760-800) from the given node / edge values (sorted keys)
+uint64_t hemu_events(HostEmu* e, const double* node_value, uint64_t ne, const uint64_t* ekey, const double* evalue, int64_t readlen) {
+    e->node_value.assign(node_value, node_value + e->H.N);
+    e->recs.clear(); e->P = WqPsiProblems(); e->pool = WqEventPool();
+    WqGeneEvents V{e->H, e->node_value, 0, {}};
+    uint64_t k = 0;
+    for (uint32_t g = 1; g <= e->H.G; g++) {
+        V.g = g;
+        V.edges.clear();
+        while (k < ne && (ekey[k] >> 32) < g) k++;
+        for (; k < ne && (ekey[k] >> 32) == g; k++) {
+            if (wq_edge_is_circ(ekey[k])) continue;
+            V.edges.push_back(WqGeneEdge{(uint32_t)((ekey[k] >> 16) & 0xFFFF), (uint32_t)(ekey[k] & 0xFFFF), evalue[k]});
+        }
+        wq_gene_events(V, readlen, e->recs, e->P, e->pool);
+    }
+    return e->recs.size();
+}
+// header[9] = gene, node, motif, kind, flags, n_utr, n_inc, n_exc, n_paths; vals[2] = psi, total; returns the EM problem index or -1
+int64_t hemu_event(HostEmu* e, uint64_t i, uint32_t* header, double* vals) {
+    const WqEventRec& r = e->recs[i];
+    header[0] = r.gene; header[1] = r.node; header[2] = r.motif; header[3] = r.kind; header[4] = r.flags;
+    header[5] = r.n_utr; header[6] = r.n_inc; header[7] = r.n_exc; header[8] = r.n_paths;
+    vals[0] = r.psi; vals[1] = r.total;
+    return (int64_t)r.problem;
+}
+uint64_t hemu_event_path(HostEmu* e, uint64_t i, uint64_t k, uint32_t* out, uint64_t cap) {
+    const WqEventRec& r = e->recs[i];
+    const uint64_t b = e->pool.path_ptr[r.path_first + k], en = e->pool.path_ptr[r.path_first + k + 1];
+    for (uint64_t j = b; j < en && j - b < cap; j++) out[j - b] = e->pool.path_nodes[j];
+    return en - b;
+}
+// EM problem p: sizes[4] = n_paths, n_inc, n_amb, tandem; then the arrays (two-call: pass NULLs for sizes only)
+void hemu_problem(HostEmu* e, uint64_t p, uint32_t* sizes, double* count, double* length, uint32_t* amb_ptr, uint32_t* amb_paths, double* amb_mult) {
+    const WqPsiProblems& P = e->P;
+    const uint32_t p0 = P.path_ptr[p], p1 = P.path_ptr[p + 1], a0 = P.amb_ptr[p], a1 = P.amb_ptr[p + 1];
+    sizes[0] = p1 - p0; sizes[1] = P.n_inc[p]; sizes[2] = a1 - a0; sizes[3] = P.is_tandem[p];
+    sizes[4] = P.amb_path_ptr[a1] - P.amb_path_ptr[a0];
+    if (!count) return;
+    for (uint32_t i = p0; i < p1; i++) { count[i - p0] = P.count[i]; length[i - p0] = P.length[i]; }
+    for (uint32_t a = a0; a <= a1; a++) amb_ptr[a - a0] = P.amb_path_ptr[a] - P.amb_path_ptr[a0];
+    for (uint32_t a = a0; a < a1; a++) amb_mult[a - a0] = P.amb_mult[a];
+    for (uint32_t j = P.amb_path_ptr[a0]; j < P.amb_path_ptr[a1]; j++) amb_paths[j - P.amb_path_ptr[a0]] = P.amb_paths[j];
+}
+
+}  // extern "C"

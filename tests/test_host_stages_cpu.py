@@ -1,0 +1,107 @@
+"""The library's HOST stages on the CPU (tests/emu/wq_host_emu.cu compiles the same headers the product library uses:
+class building, class shares, event construction) against the oracle.  A development aid for a container without a
+GPU, like test_kernel_logic_cpu.py; the parity tests proper are the -m gpu ones."""
+import numpy as np
+import pytest
+
+import whippet_jl_b200 as wq
+from whippet_jl_b200 import synth
+from emu.host_emu import HostEmu
+from oracle import Oracle, em_psi
+
+
+@pytest.fixture(scope="module")
+def case():
+    idx = synth.make_index(n_genes=2300, K=9, seed=71, paralog_frac=0.1)       # >= 2048 genes: the threaded paths run
+    rb = synth.simulate_reads(idx, 250000, 101, seed=72, sub_rate=0.01)
+    o = Oracle(idx)
+    o.process_reads(wq.AlignParam(), rb)
+    ek, ev = o.edges()
+    counts = dict(node=o.node_counts().astype("<u8"), ekey=ek, ecount=ev.astype("<u8"), longs=o.keyed(0), multis=o.keyed(1))
+    o.em_tpm(101)
+    return idx, o, counts
+
+
+def oracle_classes(o):
+    # the oracle numbers isoforms from 1 (Julia), the library from 0
+    conv = lambda c: ([i - 1 for i in c[0]], c[2], c[3], c[4])
+    return [conv(c) for c in o.classes(multi=True)] + [conv(c) for c in o.classes(multi=False)]
+
+
+def test_class_building_equals_oracle(case):
+    idx, o, counts = case
+    e = HostEmu(idx)
+    e.set_counts(**counts)
+    e.build_classes()
+    got, nm = e.classes()
+    want = oracle_classes(o)
+    assert nm == len(o.classes(multi=True)) and len(got) == len(want)
+    for (gi, gc, gd, gp), (wi, wc, wd, wp) in zip(got, want):
+        assert gi == wi and gc == wc and gp == wp
+    e.close()
+
+
+def test_class_shares_assemble_to_the_same_classes(case):
+    idx, o, counts = case
+    full = HostEmu(idx)
+    full.set_counts(**counts)
+    full.build_classes()
+    want, nm = full.classes()
+    parts = []
+    for k in range(3):
+        e = HostEmu(idx)
+        e.set_counts(**counts)
+        e.build_classes(k, 3)
+        parts.append(e)
+    shares = [e.share() for e in parts]
+    for e in parts:
+        e.assemble(shares)
+        got, gm = e.classes()
+        assert gm == nm and got == want
+        assert np.array_equal(e.iso_count(), full.iso_count())
+        e.close()
+    full.close()
+
+
+def test_event_construction_equals_oracle(case):
+    idx, o, counts = case
+    o.assign_ambig()
+    ek, ev = o.edges()
+    want = o.process_events(101)
+    e = HostEmu(idx)
+    got = e.events(o.node_counts(), ek, ev, 101)
+    assert len(got) == len(want) and len(want) > 5000
+    nem = 0
+    for g, w in zip(got, want):
+        key = (w["gene"], w["node"])
+        assert (g["gene"], g["node"], g["motif"]) == (w["gene"], w["node"], w["motif"]), key
+        if w["kind"] == 2 or g["kind"] == 2:
+            assert g["kind"] == 2 and w["kind"] == 2 and g["n_utr"] == len(w["utr_psi"]), key
+            if g["problem"] >= 0:
+                psi, it = em_psi(*e.problem(g["problem"]), 101)
+                if not np.isnan(psi).any():
+                    assert [float(np.round(x * 10000.0) / 10000.0) for x in psi] == w["utr_psi"] and it == w["iterations"], key
+                    nem += 1
+            continue
+        assert [p for p in g["paths"][:g["n_inc"]]] == [p for p, _ in w["inc"]], key
+        assert [p for p in g["paths"][g["n_inc"]:]] == [p for p, _ in w["exc"]], key
+        assert g["total"] == w["total"], key
+        if g["problem"] >= 0:
+            ninc, cnt, ln, sets, mult, tandem = e.problem(g["problem"])
+            psi, it = em_psi(ninc, cnt, ln, sets, mult, tandem, 101)
+            s = 0.0
+            for x in psi[:ninc]:
+                s += x
+            kind = 1 if (0.0 <= s <= 1.0 and g["total"] > 0) else 0
+            assert kind == w["kind"], key
+            if kind == 1:
+                assert s == w["psi"] and it == w["iterations"], key
+                assert [float(x) for x in psi[:ninc]] == [v for _, v in w["inc"]] and [float(x) for x in psi[ninc:]] == [v for _, v in w["exc"]], key
+            nem += 1
+        else:
+            kind = g["kind"] if g["kind"] != 1 else (1 if g["total"] > 0 else 0)
+            assert kind == w["kind"], key
+            if kind == 1:
+                assert g["psi"] == w["psi"], key
+    assert nem > 100
+    e.close()
