@@ -29,6 +29,9 @@ HostEmu* hemu_create(const wq_index_desc* d) {
     return e;
 }
 void hemu_destroy(HostEmu* e) { delete e; }
+#ifdef WQ_EV_PROF
+void hemu_prof(unsigned long long* out, int reset) { for (int i = 0; i < 8; i++) { out[i] = wq_evp[i]; if (reset) wq_evp[i] = 0; } }
+#endif
 const char* hemu_error(HostEmu* e) { return e->err.c_str(); }
 
 // count stores in the layout of wq_counts / wq_keyed (edges sorted by key; keyed records in any order)

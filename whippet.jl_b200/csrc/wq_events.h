@@ -197,6 +197,16 @@ static inline WqPathSet wq_reduce_simple(const WqPathSet& edges, bool& subsample
     return r;
 }
 
+#ifdef WQ_EV_PROF
+#include <x86intrin.h>
+static unsigned long long wq_evp[8];
+#define WQ_EVP(k) do { unsigned long long t_ = __rdtsc(); wq_evp[k] += t_ - evp_t; evp_t = t_; } while (0)
+#define WQ_EVP_START unsigned long long evp_t = __rdtsc()
+#else
+#define WQ_EVP(k) do { } while (0)
+#define WQ_EVP_START do { } while (0)
+#endif
+
 struct WqGeneEvents {
     const WqHostIndex& H; const std::vector<double>& node_value; uint32_t g;      // g 1-based
     std::vector<WqGeneEdge> edges;                                                // (first,last) order
@@ -219,12 +229,21 @@ static inline void wq_push_edge(WqPathSet& g, const WqGeneEdge& e, uint32_t lo, 
 static inline void wq_gene_events(const WqGeneEvents& V, int64_t readlen, std::vector<WqEventRec>& out, WqPsiProblems& P, WqEventPool& pool) {
     const uint32_t ne = V.nn() + 1;
     if (ne <= 2) return;
+    // thread-local scratch, looked up once per gene (every access to a thread_local of a shared library is a call)
+    struct Scratch { std::vector<const WqGeneEdge*> touch, amb_edges; WqPathSet inc, exc; std::vector<WqAmbSet> amb; std::vector<uint32_t> set; };
+    static thread_local Scratch tl_scratch;
+    Scratch& sc = tl_scratch;
+    std::vector<const WqGeneEdge*>&touch = sc.touch, &amb_edges = sc.amb_edges;
+    WqPathSet &inc = sc.inc, &exc = sc.exc;
+    std::vector<WqAmbSet>& amb = sc.amb;
+    std::vector<uint32_t>& set = sc.set;
     for (uint32_t i = 1; i < ne; i++) {
+        WQ_EVP_START;
         const uint8_t motif = wq_motif(V.et(i), V.et(i + 1));
         const bool next_tandem = (i + 1 < ne) && wq_motif(V.et(i + 1), V.et(i + 2)) <= 1;
         WqEventRec R;
         R.gene = V.g; R.node = i; R.motif = motif; R.kind = 0; R.flags = 0;
-        if (motif == WQM_NONE) { R.kind = next_tandem ? 3 : 0; out.push_back(R); continue; }
+        if (motif == WQM_NONE) { R.kind = next_tandem ? 3 : 0; out.push_back(R); WQ_EVP(0); continue; }
         if (motif <= 1) {
             // ---- tandem UTR (src/events.jl:593-645) ----
             std::vector<uint32_t> used;
@@ -278,6 +297,7 @@ static inline void wq_gene_events(const WqGeneEvents& V, int64_t readlen, std::v
                 R.flags |= 1;
             }
             out.push_back(R);
+            WQ_EVP(1);
             const uint32_t st = motif == WQM_TXST ? i : i - 1;
             i = st + R.n_utr - 1;         // output_utr returns the last node it printed (src/io.jl:279-316)
             continue;
@@ -286,13 +306,10 @@ static inline void wq_gene_events(const WqGeneEvents& V, int64_t readlen, std::v
         uint32_t lo = 0xFFFFFFFFu, hi = 0;
         const double maxvalue = V.edges.empty() ? 0.0 : V.edges.back().v;     // maximum(sgquant.edge): greatest (first,last) entry
         // per-thread scratch, cleared per node (one heap allocation per container and thread instead of per node)
-        static thread_local std::vector<const WqGeneEdge*> touch, amb_edges;
-        static thread_local WqPathSet inc, exc;
-        static thread_local std::vector<WqAmbSet> amb;
-        static thread_local std::vector<uint32_t> set;
         touch.clear(); amb_edges.clear(); amb.clear();
         inc.nodes.clear(); inc.count.clear(); inc.length.clear(); inc.mx = 0;
         exc.nodes.clear(); exc.count.clear(); exc.length.clear(); exc.mx = 0;
+        WQ_EVP(7);
         for (auto& e : V.edges) {
             if (!(e.a <= i && i <= e.b)) continue;
             if (e.v / maxvalue < 0.02) continue;
@@ -308,6 +325,7 @@ static inline void wq_gene_events(const WqGeneEvents& V, int64_t readlen, std::v
             amb_edges.push_back(e);
         }
         bool sub = false;
+        WQ_EVP(2);
         if (has_inc && has_exc) {
             // bridge with neighbouring edges inside [lo, hi] (extend_edges!, src/events.jl:329-394)
             for (uint32_t idx = i - 1; idx > lo && idx >= 1; idx--)
@@ -326,8 +344,10 @@ static inline void wq_gene_events(const WqGeneEvents& V, int64_t readlen, std::v
                     if (inc.covers(e.a)) { wq_push_edge(inc, e, lo, hi); pushed = true; }
                     if (pushed) amb_edges.push_back(&e);
                 }
+            WQ_EVP(3);
             inc = wq_reduce(inc, sub);
             exc = wq_reduce(exc, sub);
+            WQ_EVP(4);
             for (const WqGeneEdge* e : amb_edges) {
                 set.clear();
                 for (size_t p = 0; p < inc.size(); p++) if (inc.nodes[p].adjacent(e->a, e->b)) { set.push_back((uint32_t)p); inc.length[p] += 1; }
@@ -340,6 +360,7 @@ static inline void wq_gene_events(const WqGeneEvents& V, int64_t readlen, std::v
             if (has_inc) inc = wq_reduce_simple(inc, sub);
             if (has_exc) exc = wq_reduce_simple(exc, sub);
         }
+        WQ_EVP(5);
         bool has_psi = false;
         if (!has_exc) {
             if (has_inc && (connecting >= 2 || (connecting >= 1 && (motif & 6) == 6))) { R.psi = 1.0; has_psi = true; }
@@ -357,5 +378,6 @@ static inline void wq_gene_events(const WqGeneEvents& V, int64_t readlen, std::v
         if (sub) R.flags |= 2;
         R.kind = has_psi ? 1 : 0;         // for EM problems the 0 <= psi <= 1 && total > 0 test is applied after the kernel
         out.push_back(R);
+        WQ_EVP(6);
     }
 }
