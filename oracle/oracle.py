@@ -252,6 +252,14 @@ def em_psi(n_inc, count, length, amb_sets, amb_mult, tandem, readlen, sig=4, max
     return psi, int(it)
 
 
+def path_in_path(first, last):
+    """Base.in(first::SGAlignPath, last::SGAlignPath) (src/quant.jl:47-62); paths = [(gene, node), ...]."""
+    a = np.ascontiguousarray([x for p in first for x in p] or [0], "<u4")
+    b = np.ascontiguousarray([x for p in last for x in p] or [0], "<u4")
+    v = lambda x: x.ctypes.data_as(C.c_void_p)
+    return bool(lib().wqo_path_in_path(v(a), C.c_uint64(len(first)), v(b), C.c_uint64(len(last))))
+
+
 def reduce_graph(edges):
     """reduce_graph (src/events.jl:223-266) on [(first, last, value)]; returns the list of node sets."""
     L = lib()

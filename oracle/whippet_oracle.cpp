@@ -1742,6 +1742,14 @@ int64_t wqo_em_psi(uint32_t np, uint32_t n_inc, const double* count, const doubl
     return it;
 }
 
+// known-answer hook: Base.in(first::SGAlignPath, last::SGAlignPath) (test/runtests.jl:421-438); paths as (gene, node) pairs
+int wqo_path_in_path(const uint32_t* first, uint64_t nf, const uint32_t* last, uint64_t nl) {
+    std::vector<ANode> a(nf), b(nl);
+    for (uint64_t i = 0; i < nf; i++) { a[i].gene = first[2 * i]; a[i].node = first[2 * i + 1]; }
+    for (uint64_t i = 0; i < nl; i++) { b[i].gene = last[2 * i]; b[i].node = last[2 * i + 1]; }
+    return path_in_path(a, b) ? 1 : 0;
+}
+
 // known-answer hook: reduce_graph on a list of weighted edges (test/runtests.jl:535-580)
 uint64_t wqo_reduce_graph(const uint32_t* first, const uint32_t* last, const double* value, uint64_t n, uint32_t* out_sets, uint64_t cap) {
     PsiGraph g;

@@ -108,3 +108,15 @@ def test_event_building_on_fixture(fixture_index, test_param):
     # gene `one`: exon2 (node 3) is skipped by the exon1-exon3def and exon1-exon4 reads and included by exon1-exon2
     e3 = [e for e in ev if e["gene"] == 2 and e["node"] == 3][0]
     assert e3["motif"] == 5 and e3["kind"] == 1 and 0.0 < e3["psi"] < 1.0
+
+
+def test_path_overlap_known_answers():
+    """test/runtests.jl:421-438 ("SGAlignPath Overlap"): the sub-path test paired count! relies on (src/quant.jl:47-62)."""
+    from oracle import path_in_path
+    single, single_two = [(1, 1)], [(1, 2)]
+    two_three, larger = [(1, 2), (1, 3)], [(1, 1), (1, 2), (1, 3)]
+    assert path_in_path(single, single)
+    assert not path_in_path(single, single_two)
+    assert path_in_path(single_two, two_three)
+    assert not path_in_path(single, two_three)
+    assert path_in_path(single, larger) and path_in_path(single_two, larger) and path_in_path(two_three, larger)
