@@ -68,3 +68,68 @@ def test_pack_roundtrip():
     assert out[4] == longs and out[5] == multis
     empty = parallel.unpack_sparse(parallel.pack_sparse([], [], [], [], {}, {}))
     assert len(empty[0]) == 0 and empty[4] == {} and empty[5] == {}
+
+
+# ---- class building partitioned by gene: the shares of two gloo ranks assemble to the unpartitioned class set ----
+def _class_counts():
+    """Deterministic count stores from the oracle (every rank computes the same ones: after the count exchange every rank
+    holds identical stores)."""
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")]
+    import whippet_jl_b200 as wq
+    from whippet_jl_b200 import synth
+    from oracle import Oracle
+    idx = synth.make_index(n_genes=400, K=9, seed=81, paralog_frac=0.1)
+    rb = synth.simulate_reads(idx, 60000, 101, seed=82, sub_rate=0.01)
+    o = Oracle(idx)
+    o.process_reads(wq.AlignParam(), rb)
+    ek, ev = o.edges()
+    return idx, dict(node=o.node_counts().astype("<u8"), ekey=ek, ecount=ev.astype("<u8"), longs=o.keyed(0), multis=o.keyed(1))
+
+
+def _class_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    idx, counts = _class_counts()
+    from emu.host_emu import HostEmu
+    e = HostEmu(idx)
+    e.set_counts(**counts)
+    e.build_classes(rank, world)                          # this rank's share (multi-map key range + gene range)
+    mine = np.frombuffer(e.share(), dtype=np.uint8)
+    sizes = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(sizes, torch.tensor([len(mine)], dtype=torch.int64))
+    m = max(int(s.item()) for s in sizes)
+    padded = torch.zeros(m, dtype=torch.uint8)
+    padded[:len(mine)] = torch.from_numpy(mine.copy())
+    outs = [torch.zeros(m, dtype=torch.uint8) for _ in range(world)]
+    dist.all_gather(outs, padded)
+    e.assemble([outs[r][:int(sizes[r].item())].numpy().tobytes() for r in range(world)])
+    classes, nm = e.classes()
+    q.put((rank, classes, nm, e.iso_count()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_class_shares():
+    world = 2
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_class_worker, args=(r, world, port, q)) for r in range(world)]
+    [p.start() for p in procs]
+    res = [q.get(timeout=300) for _ in range(world)]
+    [p.join(timeout=60) for p in procs]
+    idx, counts = _class_counts()
+    from emu.host_emu import HostEmu
+    full = HostEmu(idx)
+    full.set_counts(**counts)
+    full.build_classes()
+    want, nm = full.classes()
+    assert nm > 10 and len(want) > 500
+    for rank, classes, gm, iso_count in res:
+        assert gm == nm and classes == want, rank
+        assert np.array_equal(iso_count, full.iso_count()), rank
