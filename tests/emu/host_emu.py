@@ -16,7 +16,7 @@ _CSRC = os.path.join(_HERE, "..", "..", "whippet.jl_b200", "csrc")
 
 def build():
     srcs = [os.path.join(_HERE, "wq_host_emu.cu")] + [os.path.join(_CSRC, f) for f in
-                                                      ("wq_em.cuh", "wq_events.h", "wq_host_quant.h", "wq_host_index.h", "wq_types.h", "wq_kernels.cuh")]
+                                                      ("wq_em.cuh", "wq_events.h", "wq_sam.h", "wq_host_quant.h", "wq_host_index.h", "wq_types.h", "wq_kernels.cuh")]
     if not os.path.exists(_SO) or os.path.getmtime(_SO) < max(map(os.path.getmtime, srcs)):
         subprocess.check_call([nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-std=c++17", "-fmad=false",
                                "-Xcompiler", "-fPIC", "-shared", "-o", _SO, srcs[0]])
@@ -121,3 +121,58 @@ class HostEmu:
         self.L.hemu_problem(self.h, C.c_uint64(p), sizes, _p(cnt), _p(ln), _p(aptr), _p(apaths), _p(amult))
         sets = [[int(x) for x in apaths[int(aptr[a]):int(aptr[a + 1])]] for a in range(namb)]
         return ninc, cnt, ln, sets, amult[:namb].tolist(), bool(tandem)
+
+
+class HostSam:
+    """wq_sam.h (write_sam, src/io.jl:69-271) on the CPU: SAM text of a batch from given alignments."""
+
+    def __init__(self, index: wq.FlatIndex):
+        from whippet_jl_b200 import abi
+        build()
+        self.abi = abi
+        self.L = C.CDLL(_SO)
+        self.L.hsam_create.restype = C.c_void_p
+        self.L.hsam_batch.restype = C.c_uint64
+        self.L.hsam_header.restype = C.c_uint64
+        self.L.hsam_text.restype = C.c_void_p
+        self._d = index.desc()
+        G = index.n_genes
+        names = (C.c_char_p * G)(*[str(x).encode() for x in index.gene_seqname])
+        st = np.ascontiguousarray(index.gene_strand, "u1")
+        self.h = C.c_void_p(self.L.hsam_create(C.byref(self._d), names, _p(st)))
+
+    def header(self):
+        n = self.L.hsam_header(self.h)
+        return C.string_at(self.L.hsam_text(self.h), n).decode()
+
+    def batch(self, reads, names, res, mate=None, mate_names=None, qualoffset=33):
+        abi = self.abi
+
+        def pack(nm):
+            enc = [x.encode() for x in nm]
+            ln = np.array([len(x) for x in enc], "<u4")
+            off = np.zeros(len(enc), "<u8")
+            if len(enc) > 1:
+                off[1:] = np.cumsum(ln[:-1])
+            return off, ln, b"".join(enc)
+        out = abi.AlignOutC()
+        out.hit_start, out.nhits, out.flipped = abi.ptr(res.hit_start, abi.u32p), abi.ptr(res.nhits, abi.u8p), abi.ptr(res.flipped, abi.u8p)
+        out.aln = res.aln.ctypes.data
+        out.aln_mate = res.aln_mate.ctypes.data if res.aln_mate is not None else None
+        out.nodes = res.nodes.ctypes.data
+        out.aln_cap = out.aln_used = len(res.aln)
+        out.nodes_cap = out.nodes_used = len(res.nodes)
+        b = reads.c()
+        o1, l1, t1 = pack(names)
+        if mate is not None:
+            m = mate.c()
+            o2, l2, t2 = pack(mate_names)
+            n = self.L.hsam_batch(self.h, C.byref(b), C.byref(m), _p(o1), _p(l1), t1, _p(o2), _p(l2), t2, C.byref(out), int(qualoffset))
+        else:
+            n = self.L.hsam_batch(self.h, C.byref(b), None, _p(o1), _p(l1), t1, None, None, None, C.byref(out), int(qualoffset))
+        return C.string_at(self.L.hsam_text(self.h), n).decode("latin-1")
+
+    def close(self):
+        if self.h:
+            self.L.hsam_destroy(self.h)
+            self.h = None

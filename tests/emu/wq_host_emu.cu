@@ -10,6 +10,7 @@
 #include "../../whippet.jl_b200/csrc/wq_host_quant.h"
 #include "../../whippet.jl_b200/csrc/wq_em.cuh"
 #include "../../whippet.jl_b200/csrc/wq_events.h"
+#include "../../whippet.jl_b200/csrc/wq_sam.h"
 
 struct HostEmu {
     WqHostIndex H; WqIsoIndex S; WqHostQuant hq; WqHostQuantEx X;
@@ -117,5 +118,27 @@ void hemu_problem(HostEmu* e, uint64_t p, uint32_t* sizes, double* count, double
     for (uint32_t a = a0; a < a1; a++) amb_mult[a - a0] = P.amb_mult[a];
     for (uint32_t j = P.amb_path_ptr[a0]; j < P.amb_path_ptr[a1]; j++) amb_paths[j - P.amb_path_ptr[a0]] = P.amb_paths[j];
 }
+
+// SAM text of a batch (wq_sam.h: write_sam, src/io.jl:69-271) from given alignments
+struct HostSam { WqSamIndex X; std::string text; };
+HostSam* hsam_create(const wq_index_desc* d, const char* const* seqname, const uint8_t* strand) {
+    HostSam* s = new HostSam();
+    s->X.node_base.assign(d->node_base, d->node_base + d->n_genes + 1);
+    s->X.nodeoffset.assign(d->nodeoffset, d->nodeoffset + d->n_nodes);
+    s->X.nodecoord.assign(d->nodecoord, d->nodecoord + d->n_nodes);
+    s->X.nodelen.assign(d->nodelen, d->nodelen + d->n_nodes);
+    for (uint32_t g = 0; g < d->n_genes; g++) { s->X.seqname.emplace_back(seqname[g]); s->X.strand.push_back(strand[g] ? 1 : 0); }
+    s->X.has_info = true;
+    return s;
+}
+void hsam_destroy(HostSam* s) { delete s; }
+uint64_t hsam_batch(HostSam* s, const wq_read_batch* fwd, const wq_read_batch* rev, const uint64_t* name_off, const uint32_t* name_len, const char* names,
+                    const uint64_t* rname_off, const uint32_t* rname_len, const char* rnames, const wq_align_out* out, int qualoffset) {
+    s->text.clear();
+    wq_sam_range(s->X, s->text, fwd, rev, name_off, name_len, names, rname_off, rname_len, rnames, out, qualoffset, 0, fwd->n_reads);
+    return s->text.size();
+}
+const char* hsam_text(HostSam* s) { return s->text.data(); }
+uint64_t hsam_header(HostSam* s) { s->text = wq_sam_header_text(s->X); return s->text.size(); }
 
 }  // extern "C"

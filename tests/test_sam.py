@@ -41,6 +41,36 @@ def test_known_answer_reads_sam_fields(fixture_index, test_param):
         assert l[2] == "chr0" and len(l[9]) == len(r["seq"]) == len(l[10])
 
 
+def test_sam_formatter_on_cpu(fixture_index, test_param):
+    """The library's SAM formatter (csrc/wq_sam.h, compiled into the host test harness) applied to the oracle's
+    alignments equals the restatement, single-end on the fixture (both gene strands, supplementary entries) and paired-end
+    on a synthetic index with random gene strands."""
+    from emu.host_emu import HostSam
+    rb = fixture_random_reads(fixture_index, 5000)
+    names = [f"r{i} desc" for i in range(rb.n)]
+    res = Oracle(fixture_index).align_se(test_param, rb)
+    hs = HostSam(fixture_index)
+    seqs, quals = batch_text(rb)
+    got, want = hs.batch(rb, names, res), write_sam_reads(fixture_index, names, seqs, quals, res)
+    assert got == want and got.count("\n") > 1000
+    assert {0, 16, 256, 272} <= {int(l.split("\t")[1]) for l in got.splitlines()}
+    assert hs.header().startswith("@HD\tVN:1.0\tSO:unsorted\n@SQ\tSN:chr0\tLN:")
+    hs.close()
+    idx, p, f, r = pe_case(3, 200, 101, 5000, True, 8000)
+    rng = np.random.default_rng(5)
+    idx.gene_strand = rng.integers(0, 2, idx.n_genes).astype("u1")
+    idx.gene_seqname = [f"chr{int(x)}" for x in rng.integers(1, 5, idx.n_genes)]
+    n1, n2 = [f"p{i}/1" for i in range(f.n)], [f"p{i}/2" for i in range(f.n)]
+    s1, q1 = batch_text(f)
+    s2, q2 = batch_text(r)
+    res = Oracle(idx).align_pe(p, f, r)
+    hs = HostSam(idx)
+    got = hs.batch(f, n1, res, mate=r, mate_names=n2)
+    want = write_sam_reads(idx, n1, s1, q1, res, mate=(n2, s2, q2))
+    assert got == want and got.count("\n") > 2000
+    hs.close()
+
+
 @pytest.mark.gpu
 def test_sam_fixture_and_header(fixture_index, test_param):
     rb = fixture_random_reads(fixture_index, 20000)
