@@ -94,6 +94,18 @@ class HostEmu:
         self.L.hemu_iso_count(self.h, _p(a))
         return a
 
+    def assign_ambig(self, props, genetpm):
+        """assign_ambig! with the EM's results given (class proportions flattened in canonical class order, gene TPM).
+        Returns (node_value[N], edge_key, edge_value) with the additions merged."""
+        props, genetpm = np.ascontiguousarray(props, "<f8"), np.ascontiguousarray(genetpm, "<f8")
+        rc = self.L.hemu_assign_ambig(self.h, _p(props), C.c_uint64(len(props)), _p(genetpm))
+        assert rc == 0, self.L.hemu_error(self.h)
+        self.L.hemu_values.restype = C.c_uint64
+        n = self.L.hemu_values(self.h, None, None, None)
+        node, ek, ev = np.zeros(self.index.n_nodes), np.zeros(n, "<u8"), np.zeros(n)
+        self.L.hemu_values(self.h, _p(node), _p(ek), _p(ev))
+        return node, ek, ev
+
     def events(self, node_value, ekey, evalue, readlen):
         """Event construction of every gene.  Returns a list of dicts (gene, node, motif, kind, flags, n_utr, psi, total,
         problem, inc paths, exc paths / utr paths) and the EM problems as tuples for oracle.em_psi."""

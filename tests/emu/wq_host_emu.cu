@@ -119,6 +119,23 @@ void hemu_problem(HostEmu* e, uint64_t p, uint32_t* sizes, double* count, double
     for (uint32_t j = P.amb_path_ptr[a0]; j < P.amb_path_ptr[a1]; j++) amb_paths[j - P.amb_path_ptr[a0]] = P.amb_paths[j];
 }
 
+// assign_ambig! (host stage) given the EM's results: class proportions in canonical order and gene TPM
+int hemu_assign_ambig(HostEmu* e, const double* prop, uint64_t nprop, const double* genetpm) {
+    if (nprop != e->X.cls.prop.size()) { e->err = "prop array has the wrong length"; return -1; }
+    e->X.cls.prop.assign(prop, prop + nprop);
+    e->X.genetpm.assign(genetpm, genetpm + e->H.G);
+    e->X.em_done = true;
+    e->err = wq_host_assign_ambig_impl(e->H, e->S, e->hq, e->X);
+    if (!e->err.empty()) return -1;
+    wq_finalize_edges(e->hq, e->X);
+    return 0;
+}
+uint64_t hemu_values(HostEmu* e, double* node_value, uint64_t* ekey, double* evalue) {
+    if (node_value) memcpy(node_value, e->X.node_value.data(), e->X.node_value.size() * 8);
+    if (ekey) { memcpy(ekey, e->X.edge_key.data(), e->X.edge_key.size() * 8); memcpy(evalue, e->X.edge_value.data(), e->X.edge_value.size() * 8); }
+    return e->X.edge_key.size();
+}
+
 // SAM text of a batch (wq_sam.h: write_sam, src/io.jl:69-271) from given alignments
 struct HostSam { WqSamIndex X; std::string text; };
 HostSam* hsam_create(const wq_index_desc* d, const char* const* seqname, const uint8_t* strand) {

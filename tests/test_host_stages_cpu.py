@@ -22,6 +22,13 @@ def case():
     return idx, o, counts
 
 
+def ensure_ambig(o):
+    """assign_ambig! adds to the oracle's stores: apply it once per fixture."""
+    if not getattr(o, "_ambig_applied", False):
+        o.assign_ambig()
+        o._ambig_applied = True
+
+
 def oracle_classes(o):
     # the oracle numbers isoforms from 1 (Julia), the library from 0
     conv = lambda c: ([i - 1 for i in c[0]], c[2], c[3], c[4])
@@ -63,9 +70,49 @@ def test_class_shares_assemble_to_the_same_classes(case):
     full.close()
 
 
+def test_assign_ambig_equals_oracle(case):
+    """assign_ambig! on the host (with the oracle's EM results injected) equals the oracle's, unpartitioned and as three
+    gene partitions (each complete for its own genes).  Runs before the event test, which moves the oracle on."""
+    idx, o, counts = case
+    props = [x for c in o.classes(multi=True) for x in c[1]] + [x for c in o.classes(multi=False) for x in c[1]]
+    import ctypes as C
+    from oracle import lib
+    tpm, cnt, genetpm = np.zeros(idx.n_isoforms), np.zeros(idx.n_isoforms), np.zeros(idx.n_genes)
+    v = lambda a: a.ctypes.data_as(C.c_void_p)
+    lib().wqo_em_results(C.c_void_p(o.h), v(tpm), v(cnt), v(genetpm))
+    full = HostEmu(idx)
+    full.set_counts(**counts)
+    full.build_classes()
+    node, ek, ev = full.assign_ambig(props, genetpm)
+    ensure_ambig(o)
+    wk, wv = o.edges()
+    assert np.array_equal(node, o.node_counts())
+    assert np.array_equal(ek, wk) and np.array_equal(ev, wv)
+    G = idx.n_genes
+    for k in range(3):
+        parts = []
+        for j in range(3):
+            e = HostEmu(idx)
+            e.set_counts(**counts)
+            e.build_classes(j, 3)
+            parts.append(e)
+        shares = [e.share() for e in parts]
+        e = parts[k]
+        e.assemble(shares)
+        pn, pk, pv = e.assign_ambig(props, genetpm)
+        g_lo, g_hi = G * k // 3, G * (k + 1) // 3
+        n_lo, n_hi = int(idx.node_base[g_lo]), int(idx.node_base[g_hi])
+        assert np.array_equal(pn[n_lo:n_hi], node[n_lo:n_hi]), k
+        own = lambda keys: ((keys >> np.uint64(32)) > g_lo) & ((keys >> np.uint64(32)) <= g_hi)
+        assert np.array_equal(pk[own(pk)], ek[own(ek)]) and np.array_equal(pv[own(pk)], ev[own(ek)]), k
+        for x in parts:
+            x.close()
+    full.close()
+
+
 def test_event_construction_equals_oracle(case):
     idx, o, counts = case
-    o.assign_ambig()
+    ensure_ambig(o)
     ek, ev = o.edges()
     want = o.process_events(101)
     e = HostEmu(idx)
