@@ -47,7 +47,8 @@ def test_fixture_random_reads(fixture_index, test_param):
     assert (ro.nhits > 0).mean() > 0.3 and (ro.nhits > 1).sum() > 50
 
 
-@pytest.mark.parametrize("seed,ng,R", [(1, 300, 101), (2, 300, 50), (3, 200, 255), (4, 300, 76)])
+# read lengths of BASELINE.json config 5's sweep (50-255 bp) and config 4 (150 bp)
+@pytest.mark.parametrize("seed,ng,R", [(1, 300, 101), (2, 300, 50), (3, 200, 255), (4, 300, 76), (5, 200, 125), (6, 200, 150), (7, 200, 200)])
 def test_synthetic(seed, ng, R):
     idx = synth.make_index(n_genes=ng, K=9, seed=seed, paralog_frac=0.1)
     rb = synth.simulate_reads(idx, 30000, R, seed=seed + 10, sub_rate=0.01)
