@@ -74,6 +74,15 @@ def test_gzip_file_and_large_batch(tmp_path):
     rd.close()
 
 
+def test_empty_and_blank_inputs():
+    for text, n in ((b"", 0), (b"\n\r\n", 0), (b"@a\nAC\n+\nII\n\n\n", 1), (b"@a\n\n+\n\n@b\nA\n+a\nI", 2)):
+        rd = FastqReader(text=text)
+        out = rd.next_batch(10)
+        assert (out is None and n == 0) or (out is not None and out[0].n == n), text
+        assert rd.next_batch(10) is None
+        rd.close()
+
+
 def test_phred64_and_errors(tmp_path):
     rd = FastqReader(text=b"@a\nACGT\n+\nhhhh\n", qualoffset=64)
     rb, _ = rd.next_batch(4)
