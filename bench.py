@@ -373,8 +373,7 @@ def main():
                       "em_tpm": float(qms[0]), "em_psi": float(qms[1])},
         "phase_ms": phase_ms,
     }
-    if world == 1:
-        cpu_v, cpu_dt, _, ctr, n0, cpu_align = cpu_oracle_run(idx, rb, param, a.cpu_sample, 1, a.readlen)
+    def roofline(ctr, n0):
         per_kernel, model = byte_model(ctr, n0, a.readlen)
         # per-launch algorithmic bytes of every kernel of the step: alignment kernels from the
         # oracle-instrumented per-read counters, EM kernels from SURVEY.md section 8d's per-iteration figure
@@ -397,20 +396,35 @@ def main():
         dom = max(kt, key=lambda k: kt[k])
         align_ms = float(kms.sum())
         align_bytes = alg["wq_k_seed"] + alg["wq_k_extend"] + alg["wq_k_resolve"]
-        out["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": per[dom]["achieved"], "peak": peak, "unit": "GB/s",
-                           "frac": per[dom]["frac"], "traffic": None,
-                           "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6.65 TB/s",
-                           "kernels": per,
-                           "alignment_path": {"ms": align_ms, "achieved": align_bytes / (align_ms / 1000.0) / 1e9 if align_ms > 0 else 0.0,
-                                              "frac": (align_bytes / (align_ms / 1000.0) / 1e9 / peak) if align_ms > 0 else 0.0},
-                           "algorithmic_bytes_per_read": per_kernel, "model": model,
-                           "note": "dominant kernel = longest device time inside one step; every kernel here is latency-bound "
-                                   "(random access into L2-resident tables, or a chain of grid barriers), so fractions of the HBM "
-                                   "roofline are small by construction"}
+        return {"bound": "hbm", "kernel": dom, "achieved": per[dom]["achieved"], "peak": peak, "unit": "GB/s",
+                "frac": per[dom]["frac"], "traffic": None,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6.65 TB/s",
+                "kernels": per,
+                "alignment_path": {"ms": align_ms, "achieved": align_bytes / (align_ms / 1000.0) / 1e9 if align_ms > 0 else 0.0,
+                                   "frac": (align_bytes / (align_ms / 1000.0) / 1e9 / peak) if align_ms > 0 else 0.0},
+                "algorithmic_bytes_per_read": per_kernel, "model": model,
+                "note": "dominant kernel = longest device time inside one step (rank 0's launches); every kernel here is "
+                        "latency-bound (random access into L2-resident tables, or a chain of grid barriers), so fractions of the "
+                        "HBM roofline are small by construction"}
+
+    if world == 1:
+        cpu_v, cpu_dt, _, ctr, n0, cpu_align = cpu_oracle_run(idx, rb, param, a.cpu_sample, 1, a.readlen)
+        out["roofline"] = roofline(ctr, n0)
         out["cpu_baseline"] = {"value": cpu_v, "unit": "reads/s", "cores": 1, "kind": "port",
                                "sample": f"first {min(a.cpu_sample, rb.n)} reads of the workload, oracle restatement on 1 host thread: "
                                          f"align+count {cpu_align:.1f} s, then EM + multi-map assignment + events {cpu_dt - cpu_align:.1f} s; "
                                          f"value = full-workload rate extrapolated (alignment scaled to {rb.n} reads + per-job quant time)"}
+    else:
+        # N > 1: no CPU baseline (reported at N = 1 only); the byte model of the alignment kernels comes from the oracle's
+        # counters over a small alignment-only sample of rank 0's reads
+        try:
+            from oracle import Oracle, counters
+            n0 = min(200_000, rb.n)
+            counters(reset=True)
+            Oracle(idx).process_reads(param, rb.slice(0, n0))
+            out["roofline"] = roofline(counters(reset=True), n0)
+        except Exception as e:  # noqa: BLE001  (the bench line must not be lost over the explanatory block)
+            out["roofline_error"] = repr(e)
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
