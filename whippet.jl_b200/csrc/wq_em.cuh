@@ -353,21 +353,33 @@ static inline std::string wq_classes_assemble_impl(const WqIsoIndex& S, WqHostQu
     C.n_multi = (uint32_t)tm;
     X.frag_cls.assign(n + 1, 0);
     X.iso_count.assign(S.I, 0.0);
-    uint64_t c = 0, q = 0;
+    // class / member offsets of every (pass, share): multi-map classes of all shares first, then the isoform classes;
+    // the shares are then placed by the host threads (one task per pass and share)
+    std::vector<uint64_t> c_at(2 * (size_t)n + 1, 0), q_at(2 * (size_t)n + 1, 0);
     for (int pass = 0; pass < 2; pass++)
         for (uint32_t r = 0; r < n; r++) {
-            const View& v = V[r];
-            const uint64_t c0 = pass == 0 ? 0 : v.nm, c1 = pass == 0 ? v.nm : v.nm + v.nc;
-            if (pass == 1) X.frag_cls[r] = (uint32_t)c;
-            for (uint64_t k = c0; k < c1; k++, c++) {
-                const uint32_t b = v.ptr[k], e = v.ptr[k + 1], len = e - b;
-                for (uint32_t j = b; j < e; j++, q++) { C.iso[q] = v.iso[j]; C.prop[q] = 1.0 / (double)len; }
-                C.ptr[c + 1] = (uint32_t)q;
-                C.count[c] = v.count[k]; C.state[c] = v.state[k]; C.postassign[c] = v.post[k];
-            }
-            if (pass == 1) memcpy(X.iso_count.data() + v.iso_lo, v.ic, 8 * (v.iso_hi - v.iso_lo));
+            const size_t t = (size_t)pass * n + r;
+            c_at[t + 1] = c_at[t] + (pass == 0 ? V[r].nm : V[r].nc);
+            q_at[t + 1] = q_at[t] + (pass == 0 ? V[r].nmm : V[r].ncm);
         }
-    X.frag_cls[n] = (uint32_t)c;
+    for (uint32_t r = 0; r <= n; r++) X.frag_cls[r] = (uint32_t)c_at[(size_t)n + r];
+    auto place = [&](size_t t) {
+        const int pass = t < n ? 0 : 1;
+        const View& v = V[t - (size_t)pass * n];
+        const uint64_t c0 = pass == 0 ? 0 : v.nm, c1 = pass == 0 ? v.nm : v.nm + v.nc;
+        uint64_t c = c_at[t], q = q_at[t];
+        for (uint64_t k = c0; k < c1; k++, c++) {
+            const uint32_t b = v.ptr[k], e = v.ptr[k + 1], len = e - b;
+            for (uint32_t j = b; j < e; j++, q++) { C.iso[q] = v.iso[j]; C.prop[q] = 1.0 / (double)len; }
+            C.ptr[c + 1] = (uint32_t)q;
+            C.count[c] = v.count[k]; C.state[c] = v.state[k]; C.postassign[c] = v.post[k];
+        }
+        if (pass == 1) memcpy(X.iso_count.data() + v.iso_lo, v.ic, 8 * (v.iso_hi - v.iso_lo));
+    };
+    {
+        const unsigned nt = std::max(1u, std::min<unsigned>(wq_host_threads(), 2 * n));
+        wq_on_threads(nt, [&](unsigned th) { for (size_t t = th; t < 2 * (size_t)n; t += nt) place(t); });
+    }
     X.cls = std::move(C);
     X.built = true;
     return "";
