@@ -113,11 +113,25 @@ def test_assign_ambig_equals_oracle(case):
 def test_event_construction_equals_oracle(case):
     idx, o, counts = case
     ensure_ambig(o)
+    compare_events(idx, o, 101, 5000, 100)
+
+
+def test_event_construction_on_the_fixture(fixture_index, test_param):
+    """The reference's own toy graph (zero-length node, both strands, tiny genes), reads of 11-21 bases."""
+    from data_gen import fixture_random_reads
+    o = Oracle(fixture_index)
+    o.process_reads(test_param, fixture_random_reads(fixture_index, 30000))
+    o.em_tpm(15)
+    o.assign_ambig()
+    compare_events(fixture_index, o, 15, 5, 1)
+
+
+def compare_events(idx, o, readlen, min_records, min_em):
     ek, ev = o.edges()
-    want = o.process_events(101)
+    want = o.process_events(readlen)
     e = HostEmu(idx)
-    got = e.events(o.node_counts(), ek, ev, 101)
-    assert len(got) == len(want) and len(want) > 5000
+    got = e.events(o.node_counts(), ek, ev, readlen)
+    assert len(got) == len(want) and len(want) > min_records
     nem = 0
     for g, w in zip(got, want):
         key = (w["gene"], w["node"])
@@ -125,7 +139,7 @@ def test_event_construction_equals_oracle(case):
         if w["kind"] == 2 or g["kind"] == 2:
             assert g["kind"] == 2 and w["kind"] == 2 and g["n_utr"] == len(w["utr_psi"]), key
             if g["problem"] >= 0:
-                psi, it = em_psi(*e.problem(g["problem"]), 101)
+                psi, it = em_psi(*e.problem(g["problem"]), readlen)
                 if not np.isnan(psi).any():
                     assert [float(np.round(x * 10000.0) / 10000.0) for x in psi] == w["utr_psi"] and it == w["iterations"], key
                     nem += 1
@@ -135,7 +149,7 @@ def test_event_construction_equals_oracle(case):
         assert g["total"] == w["total"], key
         if g["problem"] >= 0:
             ninc, cnt, ln, sets, mult, tandem = e.problem(g["problem"])
-            psi, it = em_psi(ninc, cnt, ln, sets, mult, tandem, 101)
+            psi, it = em_psi(ninc, cnt, ln, sets, mult, tandem, readlen)
             s = 0.0
             for x in psi[:ninc]:
                 s += x
@@ -150,5 +164,5 @@ def test_event_construction_equals_oracle(case):
             assert kind == w["kind"], key
             if kind == 1:
                 assert g["psi"] == w["psi"], key
-    assert nem > 100
+    assert nem >= min_em
     e.close()

@@ -54,8 +54,16 @@ struct WqBitWin {                       // node set as bits over [lo, lo + 64*nw
     // both ends present and nothing strictly between (src/quant.jl:68-79)
     bool adjacent(uint32_t a, uint32_t b) const {
         if (!has(a) || !has(b)) return false;
-        for (uint32_t i = a + 1; i < b; i++) if (has(i)) return false;
-        return true;
+        if (b <= a + 1) return true;
+        // any bit strictly between a and b?  (word masks instead of a per-node probe)
+        const uint32_t x = a + 1 - lo, y = b - 1 - lo;                  // inclusive bit range, inside the window (a, b are set)
+        const uint64_t* w = p();
+        const uint32_t wx = x >> 6, wy = y >> 6;
+        const uint64_t mx = ~0ull << (x & 63), my = ~0ull >> (63 - (y & 63));
+        if (wx == wy) return (w[wx] & mx & my) == 0;
+        if (w[wx] & mx) return false;
+        for (uint32_t i = wx + 1; i < wy; i++) if (w[i]) return false;
+        return (w[wy] & my) == 0;
     }
     void list(std::vector<uint32_t>& out) const {
         const uint64_t* w = p();
@@ -74,6 +82,19 @@ struct WqPathSet {                      // PsiGraph without psi (src/events.jl:1
 struct WqGeneEdge { uint32_t a, b; double v; };
 
 struct WqAmbSet { std::vector<uint32_t> paths; double mult; };      // AmbigCounts (paths 0-based here)
+// the ambiguous sets of one event, flat (no allocation per set): set a = paths[off[a] .. off[a+1]), multiplier mult[a]
+struct WqAmbFlat {
+    std::vector<uint32_t> paths, off{0};
+    std::vector<double> mult;
+    void clear() { paths.clear(); off.resize(1); mult.clear(); }
+    size_t size() const { return mult.size(); }
+    // ambig_add!: a set seen before takes the value, a new one is appended when the value is positive (src/events.jl:299-326)
+    void add(const std::vector<uint32_t>& set, double v) {
+        for (size_t a = 0; a < mult.size(); a++)
+            if (off[a + 1] - off[a] == set.size() && std::equal(set.begin(), set.end(), paths.begin() + off[a])) { mult[a] += v; return; }
+        if (v > 0) { paths.insert(paths.end(), set.begin(), set.end()); off.push_back((uint32_t)paths.size()); mult.push_back(v); }
+    }
+};
 
 struct WqEventRec {                     // one record per visited node (include/whippet_b200.h::wq_event)
     uint32_t gene, node; uint8_t motif, kind, flags;
@@ -126,6 +147,17 @@ struct WqPsiProblems {                  // flattened wq_psi_batch inputs
         std::copy(o.amb_paths.begin(), o.amb_paths.end(), amb_paths.begin() + at.amb_paths);
         std::copy(o.amb_mult.begin(), o.amb_mult.end(), amb_mult.begin() + at.amb);
         std::copy(o.is_tandem.begin(), o.is_tandem.end(), is_tandem.begin() + at.ev);
+    }
+    long add(const WqPathSet* inc, const WqPathSet* exc, const WqAmbFlat& amb, bool tandem) {
+        for (const WqPathSet* g : {inc, exc}) if (g) { count.insert(count.end(), g->count.begin(), g->count.end()); length.insert(length.end(), g->length.begin(), g->length.end()); }
+        path_ptr.push_back((uint32_t)count.size());
+        n_inc.push_back((uint32_t)(inc ? inc->size() : 0));
+        const uint32_t base = (uint32_t)amb_paths.size();
+        amb_paths.insert(amb_paths.end(), amb.paths.begin(), amb.paths.end());
+        for (size_t a = 0; a < amb.size(); a++) { amb_path_ptr.push_back(base + amb.off[a + 1]); amb_mult.push_back(amb.mult[a]); }
+        amb_ptr.push_back((uint32_t)amb_mult.size());
+        is_tandem.push_back(tandem ? 1 : 0);
+        return (long)size() - 1;
     }
     void append(const WqPsiProblems& o, long& shift) {
         shift = (long)size();
@@ -184,19 +216,6 @@ static inline WqPathSet wq_reduce(const WqPathSet& edges, bool& subsampled) {
     }
     return nxt;
 }
-static inline WqPathSet wq_reduce_simple(const WqPathSet& edges, bool& subsampled) {   // src/events.jl:268-282
-    if (edges.size() != 2) return wq_reduce(edges, subsampled);
-    WqPathSet r = edges;
-    const uint32_t f0 = r.nodes[0].first(), l0 = r.nodes[0].last(), f1 = r.nodes[1].first(), l1 = r.nodes[1].last();
-    if (f0 == l1 || f1 == l0) {
-        r.nodes[0].unite(r.nodes[1]);
-        r.length[0] += r.length[1];
-        r.count[0] += r.count[1];
-        r.nodes.pop_back(); r.length.pop_back(); r.count.pop_back();
-    }
-    return r;
-}
-
 #ifdef WQ_EV_PROF
 #include <x86intrin.h>
 static unsigned long long wq_evp[8];
@@ -230,12 +249,12 @@ static inline void wq_gene_events(const WqGeneEvents& V, int64_t readlen, std::v
     const uint32_t ne = V.nn() + 1;
     if (ne <= 2) return;
     // thread-local scratch, looked up once per gene (every access to a thread_local of a shared library is a call)
-    struct Scratch { std::vector<const WqGeneEdge*> touch, amb_edges; WqPathSet inc, exc; std::vector<WqAmbSet> amb; std::vector<uint32_t> set; };
+    struct Scratch { std::vector<const WqGeneEdge*> touch, amb_edges; WqPathSet inc, exc; WqAmbFlat amb; std::vector<uint32_t> set; };
     static thread_local Scratch tl_scratch;
     Scratch& sc = tl_scratch;
     std::vector<const WqGeneEdge*>&touch = sc.touch, &amb_edges = sc.amb_edges;
     WqPathSet &inc = sc.inc, &exc = sc.exc;
-    std::vector<WqAmbSet>& amb = sc.amb;
+    WqAmbFlat& amb = sc.amb;
     std::vector<uint32_t>& set = sc.set;
     for (uint32_t i = 1; i < ne; i++) {
         WQ_EVP_START;
@@ -354,11 +373,22 @@ static inline void wq_gene_events(const WqGeneEvents& V, int64_t readlen, std::v
                 for (size_t p = 0; p < exc.size(); p++) if (exc.nodes[p].adjacent(e->a, e->b)) { set.push_back((uint32_t)(p + inc.size())); exc.length[p] += 1; }
                 if (set.empty()) continue;
                 if (set.size() == 1) { if (set[0] < inc.size()) inc.count[set[0]] += e->v; else exc.count[set[0] - inc.size()] += e->v; }
-                else wq_amb_add(amb, set, e->v);
+                else amb.add(set, e->v);
             }
         } else {
-            if (has_inc) inc = wq_reduce_simple(inc, sub);
-            if (has_exc) exc = wq_reduce_simple(exc, sub);
+            // in place: one edge is already its own path, two edges join when they share a terminal node
+            // (reduce_graph_simple, src/events.jl:268-282); only three or more go through the general reduction
+            for (WqPathSet* g : {&inc, &exc}) {
+                if (g->size() <= 1) continue;
+                if (g->size() > 2) { *g = wq_reduce(*g, sub); continue; }
+                const uint32_t f0 = g->nodes[0].first(), l0 = g->nodes[0].last(), f1 = g->nodes[1].first(), l1 = g->nodes[1].last();
+                if (f0 == l1 || f1 == l0) {
+                    g->nodes[0].unite(g->nodes[1]);
+                    g->length[0] += g->length[1];
+                    g->count[0] += g->count[1];
+                    g->nodes.pop_back(); g->length.pop_back(); g->count.pop_back();
+                }
+            }
         }
         WQ_EVP(5);
         bool has_psi = false;
