@@ -119,6 +119,34 @@ void hemu_problem(HostEmu* e, uint64_t p, uint32_t* sizes, double* count, double
     for (uint32_t j = P.amb_path_ptr[a0]; j < P.amb_path_ptr[a1]; j++) amb_paths[j - P.amb_path_ptr[a0]] = P.amb_paths[j];
 }
 
+// WqBitWin self-test: adjacent() (word masks) against the per-node definition (src/quant.jl:68-79), first() / last() /
+// list() against a plain scan, on random node sets in windows of up to `max_span` nodes.  Returns the number of mismatches.
+uint64_t hemu_bitwin_selftest(uint32_t max_span, uint32_t rounds, uint64_t seed) {
+    uint64_t bad = 0, x = seed | 1;
+    auto rnd = [&]() { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return x; };
+    for (uint32_t r = 0; r < rounds; r++) {
+        const uint32_t lo = 1 + (uint32_t)(rnd() % 50), span = 1 + (uint32_t)(rnd() % max_span), hi = lo + span - 1;
+        WqBitWin w;
+        w.init(lo, hi);
+        std::vector<uint8_t> ref(span, 0);
+        const uint32_t dens = 1 + (uint32_t)(rnd() % 8);
+        for (uint32_t n = lo; n <= hi; n++) if (rnd() % 8 < dens) { w.set(n); ref[n - lo] = 1; }
+        std::vector<uint32_t> lst, want;
+        w.list(lst);
+        for (uint32_t n = lo; n <= hi; n++) if (ref[n - lo]) want.push_back(n);
+        if (lst != want) bad++;
+        if (!want.empty() && (w.first() != want.front() || w.last() != want.back())) bad++;
+        for (int t = 0; t < 64; t++) {
+            uint32_t a = lo + (uint32_t)(rnd() % span), b = lo + (uint32_t)(rnd() % span);
+            if (a > b) std::swap(a, b);
+            bool naive = ref[a - lo] && ref[b - lo];
+            for (uint32_t i = a + 1; naive && i < b; i++) if (ref[i - lo]) naive = false;
+            if (w.adjacent(a, b) != naive) bad++;
+        }
+    }
+    return bad;
+}
+
 // assign_ambig! (host stage) given the EM's results: class proportions in canonical order and gene TPM
 int hemu_assign_ambig(HostEmu* e, const double* prop, uint64_t nprop, const double* genetpm) {
     if (nprop != e->X.cls.prop.size()) { e->err = "prop array has the wrong length"; return -1; }

@@ -166,3 +166,14 @@ def compare_events(idx, o, readlen, min_records, min_em):
                 assert g["psi"] == w["psi"], key
     assert nem >= min_em
     e.close()
+
+
+def test_node_set_windows():
+    """WqBitWin (the node sets of event paths): word-mask adjacency, first / last / list against the per-node definitions,
+    including windows of several 64-bit words (genes with hundreds of nodes)."""
+    import ctypes as C
+    from emu import host_emu
+    L = C.CDLL(host_emu.build())
+    L.hemu_bitwin_selftest.restype = C.c_uint64
+    for span in (5, 64, 65, 128, 129, 400):
+        assert L.hemu_bitwin_selftest(C.c_uint32(span), C.c_uint32(3000), C.c_uint64(12345 + span)) == 0, span
