@@ -166,14 +166,6 @@ int  wq_align_pe_device(wq_handle* h, const wq_align_param* p, const wq_read_bat
 
 int  wq_map_stats_get(wq_handle* h, wq_map_stats* out);
 
-/* FASTQ ingest: make_fqparser + read_chunk! + fill! (src/reads.jl:2-23, src/record.jl:13-19).  The reader inflates
- * (gzip or plain), splits 4-line records and packs them into a wq_read_batch on the host threads: every sequence byte
- * that is not one of ACGTacgt becomes A (FASTQ.Reader(..., fill_ambiguous = DNA_A)), quality = byte - qualoffset in
- * UInt8 arithmetic.  wq_fastq_next returns at most max_reads records (n_reads == 0 at the end of the input) in
- * page-locked buffers owned by the reader; they stay valid until the call after the next one.  wq_fastq_names gives the
- * identifiers of the batch returned last (name i = names[name_off[i] .. name_off[i] + name_len[i])).
- * wq_process_fastq is process_reads! / process_paired_reads! (src/reads.jl:41-129) over whole files (rev_path NULL =
- * single end): the next batch is parsed while the device aligns and counts the current one. */
 /* SAM output from the alignments of a batch: sam_flag, cigar_string, write_sam, write_sam_header (src/io.jl:69-276) as
  * process_reads! / process_paired_reads! call them with sam=true (src/reads.jl:63-67, 110-121).
  * wq_index_set_gene_info supplies lib.info (reference sequence name and strand per gene; src/types.jl:33-37), which
@@ -187,6 +179,14 @@ int  wq_sam_batch(wq_handle* h, const wq_read_batch* fwd, const wq_read_batch* r
                   const uint64_t* rname_off, const uint32_t* rname_len, const char* rnames,
                   const wq_align_out* out, int qualoffset, char* buf, uint64_t cap, uint64_t* used);
 
+/* FASTQ ingest: make_fqparser + read_chunk! + fill! (src/reads.jl:2-23, src/record.jl:13-19).  The reader inflates
+ * (gzip or plain), splits 4-line records and packs them into a wq_read_batch on the host threads: every sequence byte
+ * that is not one of ACGTacgt becomes A (FASTQ.Reader(..., fill_ambiguous = DNA_A)), quality = byte - qualoffset in
+ * UInt8 arithmetic.  wq_fastq_next returns at most max_reads records (n_reads == 0 at the end of the input) in
+ * page-locked buffers owned by the reader; they stay valid until the call after the next one.  wq_fastq_names gives the
+ * identifiers of the batch returned last (name i = names[name_off[i] .. name_off[i] + name_len[i])).
+ * wq_process_fastq is process_reads! / process_paired_reads! (src/reads.jl:41-129) over whole files (rev_path NULL =
+ * single end): the next batch is parsed while the device aligns and counts the current one. */
 typedef struct wq_fastq wq_fastq;
 int  wq_fastq_open(const char* path, int qualoffset, wq_fastq** out);
 int  wq_fastq_from_memory(const void* text, uint64_t len, int qualoffset, wq_fastq** out);   /* text must outlive the reader */
