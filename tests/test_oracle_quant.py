@@ -120,3 +120,18 @@ def test_path_overlap_known_answers():
     assert path_in_path(single_two, two_three)
     assert not path_in_path(single, two_three)
     assert path_in_path(single, larger) and path_in_path(single_two, larger) and path_in_path(two_three, larger)
+
+
+def test_oracle_regression_vectors():
+    """The oracle still computes what it computed when it was pinned (tests/golden/make_oracle_regression.py): counts, EM
+    iterations, TPM and every event record on the reference's fixture index, to the last bit."""
+    import importlib.util
+    import json
+    import os
+    from conftest import GOLDEN
+    spec = importlib.util.spec_from_file_location("make_oracle_regression", os.path.join(GOLDEN, "make_oracle_regression.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    got = mod.compute()
+    want = json.load(open(os.path.join(GOLDEN, "oracle_fixture_regression.json")))
+    assert json.loads(json.dumps(got)) == want
