@@ -900,9 +900,13 @@ void edge_add(Quant& Q, uint32_t gene, uint32_t l, uint32_t r, double v) {
 }
 
 // assign_path!, src/quant.jl:263-324 (single and paired)
-void assign_path(const Lib& L, Quant& Q, const PathRef& r, double value) {
+// `stale`: what temp_iset holds on entry.  assign_ambig! hands the paired method ambig.iset, which set_equivalence_class! left
+// filled with the GLOBAL ISOFORM ids compatible with the class's last alignment (src/quant.jl:493-501, 541-551); the method tests
+// mate-2 NODE ids against it and empties it at its end (:283-323), so only the first alignment of a class sees those ids.
+void assign_path(const Lib& L, Quant& Q, const PathRef& r, double value, const std::vector<uint32_t>* stale = nullptr) {
     size_t nb = L.d->node_base[r.gene - 1];
     std::vector<uint32_t> temp_iset;
+    if (stale && r.rnodes != nullptr) temp_iset = *stale;
     auto in_set = [&](uint32_t x) { return std::find(temp_iset.begin(), temp_iset.end(), x) != temp_iset.end(); };
     bool paired = r.rnodes != nullptr;
     if (r.n == 1) {
@@ -1123,7 +1127,13 @@ void assign_ambig(const Lib& L, Quant& Q, QuantState& S) {
         double s = 0.0;
         for (double v : vals) s += v;
         for (double& v : vals) v /= s;
-        for (uint32_t i = 0; i < nh; i++) assign_path(L, Q, vp[i], vals[i] * mc.count);
+        std::vector<uint32_t> stale;
+        if (!mc.postassign && vp[nh - 1].rnodes != nullptr) {       // ambig.iset after the last set_equivalence_class! of the loop above
+            const Int g = vp[nh - 1].gene;
+            for (Int p = 1; p <= V.niso(g); p++)
+                if (pathref_in(V, g, p, vp[nh - 1])) stale.push_back((uint32_t)(p + V.geneidx(g)));
+        }
+        for (uint32_t i = 0; i < nh; i++) assign_path(L, Q, vp[i], vals[i] * mc.count, i == 0 ? &stale : nullptr);
     }
 }
 

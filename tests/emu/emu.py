@@ -67,6 +67,14 @@ class Emu:
         self.L.emu_result_copy_pe(self.h, v(hs), v(nh), v(fl), v(aln), v(alm), v(nodes))
         return AlignResult(hs, nh, fl, aln, nodes, alm)
 
+    def ext_stats(self):
+        """(deferred tasks, parks, unparks, rollbacks, nested extensions, rollbacks below the checkpoint) since the library was loaded."""
+        self.L.emu_deferred.restype = C.c_uint64
+        self.L.emu_ext_stats.restype = C.POINTER(C.c_uint64)
+        st = self.L.emu_ext_stats()
+        return dict(deferred=int(self.L.emu_deferred(self.h)), parks=int(st[0]), unparks=int(st[1]), rollbacks=int(st[2]),
+                    nested=int(st[3]), rollbacks_below=int(st[4]))
+
     def seeds(self, n):
         out = np.zeros((n, 4), np.int64)
         self.L.emu_seeds(self.h, out.ctypes.data_as(C.c_void_p))

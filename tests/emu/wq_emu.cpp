@@ -1,7 +1,9 @@
 // TEST INFRASTRUCTURE ONLY: drives the per-thread kernel bodies of whippet.jl_b200/csrc/wq_kernels.cuh
 // single-threaded on the CPU so their logic can be checked against the oracle in a container that
 // has no GPU.  Never built into, nor loadable by, the product library (which has no CPU path).
+#define WQ_EMU_STATS 1
 #include <cstdio>
+#include <cstdlib>
 #include <vector>
 #include "../../whippet.jl_b200/csrc/wq_kernels.cuh"
 #include "../../whippet.jl_b200/csrc/wq_host_index.h"
@@ -21,9 +23,17 @@ struct Emu {
     bool paired = false;
     std::vector<WqHit> hits;
     std::vector<wq_align_node> pool;
-    uint32_t cursors[6];
-    std::vector<uint32_t> pending2;
+    uint32_t cursors[8];
+    std::vector<uint32_t> pending2, defer;
+    std::vector<uint2> ftab;
+    std::vector<WqPNode> path, side;     // first pass: WQ_FAST_PATH nodes, no side buffers; second pass: WQ_MAX_PATH + side buffers
+    uint64_t deferred = 0;               // extension tasks that went to the second pass (so tests can see both passes ran)
 };
+static WqPathStore emu_store(Emu* e, bool first) {
+    e->path.assign(WQ_MAX_PATH, WqPNode());
+    e->side.assign((size_t)WQ_MAX_DEPTH * WQ_MAX_PATH, WqPNode());
+    return first ? WqPathStore{e->path.data(), 1, WQ_FAST_PATH, nullptr, 0} : WqPathStore{e->path.data(), 1, WQ_MAX_PATH, e->side.data(), 1};
+}
 
 extern "C" {
 
@@ -38,6 +48,15 @@ Emu* emu_create(const wq_index_desc* d) {
     ix.left_ptr = d->left_ptr; ix.left_ent = H.left_ent.data(); ix.right_ptr = d->right_ptr; ix.right_ent = H.right_ent.data();
     ix.n = H.n; ix.sentinel = H.sentinel; for (int i = 0; i < 4; i++) ix.C[i] = H.C[i];
     ix.N = H.N; ix.G = H.G; ix.K = H.K;
+    // k-mer table of the seeding kernel, built by the same rule the library's wq_k_ftab kernel uses (smaller k: CPU time)
+    ix.ftab = nullptr; ix.ftab_k = 0;
+    const char* fk = getenv("WQ_EMU_FTAB_K");
+    const int k = fk ? atoi(fk) : 7;
+    if (k > 0) {
+        e->ftab.resize((size_t)1 << (2 * k));
+        for (uint32_t i = 0; i < e->ftab.size(); i++) e->ftab[i] = wq_ftab_entry(ix, i, k);
+        ix.ftab = e->ftab.data(); ix.ftab_k = k;
+    }
     e->node_count.assign(H.N, 0);
     memset(&e->counters, 0, sizeof e->counters);
     size_t es = 1 << 16, ks = 1 << 16;
@@ -62,15 +81,18 @@ int emu_align_se(Emu* e, const wq_align_param* ap, const wq_read_batch* rb) {
     e->pool.assign((size_t)hit_cap * 4 + 64, wq_align_node());
     e->pending.assign(n + 1, 0);
     e->pending2.assign(n + 1, 0);
-    e->cursors[0] = e->cursors[1] = e->cursors[2] = 0;
+    for (auto& x : e->cursors) x = 0;
     e->paired = false;
+    e->defer.assign(hit_cap, 0);
     WqWork wk{e->seeds.data(), e->hit_read.data(), e->hit_s.data(), nullptr, nullptr, e->hits.data(), e->pool.data(), e->cursors,
-              e->pending.data(), e->pending2.data(), hit_cap, (uint32_t)e->pool.size()};
+              e->pending.data(), e->pending2.data(), hit_cap, (uint32_t)e->pool.size(), e->defer.data()};
     uint64_t wbuf[WQ_MAX_READ_WORDS + 1];
-    e->cursors[3] = e->cursors[4] = e->cursors[5] = 0;
     for (uint32_t r = 0; r < n; r++) wq_seed_thread(e->ix, p, b, wk, r, wbuf);
     uint32_t nf = e->cursors[0], nr = e->cursors[5];
-    for (uint32_t t = 0; t < nf + nr; t++) wq_extend_thread(e->ix, p, b, wk, t < nf ? t : hit_cap - 1 - (t - nf), wbuf);
+    const WqPathStore st1 = emu_store(e, true), st2 = emu_store(e, false);
+    for (uint32_t t = 0; t < nf + nr; t++) wq_extend_thread(e->ix, p, b, wk, t < nf ? t : hit_cap - 1 - (t - nf), wbuf, st1, true);
+    for (uint32_t t = 0; t < e->cursors[6]; t++) wq_extend_thread(e->ix, p, b, wk, e->defer[t], wbuf, st2, false);
+    e->deferred += e->cursors[6];
     uint64_t stats[5] = {0, 0, 0, 0, 0};
     for (uint32_t r = 0; r < n; r++) wq_resolve_thread(e->ix, p, b, wk, e->q, r, stats);
     e->counters.total += n; e->counters.mapped += stats[0]; e->counters.multi += stats[1];
@@ -91,14 +113,18 @@ int emu_align_pe(Emu* e, const wq_align_param* ap, const wq_read_batch* rf, cons
     e->hits.assign((size_t)2 * hit_cap, WqHit());
     e->pool.assign((size_t)hit_cap * 8 + 64, wq_align_node());
     e->pending.assign(n + 1, 0);
-    e->cursors[0] = e->cursors[1] = e->cursors[2] = 0;
+    for (auto& x : e->cursors) x = 0;
     e->paired = true;
+    e->defer.assign((size_t)2 * hit_cap, 0);
     WqWork wk{e->seeds.data(), e->hit_read.data(), e->hit_s.data(), e->hit_s2.data(), e->hit_gene.data(), e->hits.data(),
-              e->pool.data(), e->cursors, e->pending.data(), e->pending.data(), hit_cap, (uint32_t)e->pool.size()};
+              e->pool.data(), e->cursors, e->pending.data(), e->pending.data(), hit_cap, (uint32_t)e->pool.size(), e->defer.data()};
     uint64_t wbuf[WQ_MAX_READ_WORDS + 1];
     for (uint32_t r = 0; r < n; r++) wq_seed_pe_thread(e->ix, p, bf, br, wk, r, wbuf);
     uint32_t nh = e->cursors[0];
-    for (uint32_t s = 0; s < nh; s++) { wq_extend_pe_thread(e->ix, p, bf, br, wk, s, 0, wbuf); wq_extend_pe_thread(e->ix, p, bf, br, wk, s, 1, wbuf); }
+    const WqPathStore st1 = emu_store(e, true), st2 = emu_store(e, false);
+    for (uint32_t s = 0; s < nh; s++) { wq_extend_pe_thread(e->ix, p, bf, br, wk, s, 0, wbuf, st1, true); wq_extend_pe_thread(e->ix, p, bf, br, wk, s, 1, wbuf, st1, true); }
+    for (uint32_t t = 0; t < e->cursors[6]; t++) wq_extend_pe_thread(e->ix, p, bf, br, wk, e->defer[t] >> 1, (int)(e->defer[t] & 1), wbuf, st2, false);
+    e->deferred += e->cursors[6];
     uint64_t stats[5] = {0, 0, 0, 0, 0};
     for (uint32_t r = 0; r < n; r++) wq_resolve_pe_thread(e->ix, p, bf, br, wk, e->q, r, stats);
     e->counters.total += n; e->counters.mapped += stats[0]; e->counters.multi += stats[1];
@@ -198,4 +224,6 @@ uint64_t emu_keyed(Emu* e, uint32_t* out) {
     return w;
 }
 const WqCounters* emu_counters(Emu* e) { return &e->counters; }
+uint64_t emu_deferred(Emu* e) { return e->deferred; }
+const uint64_t* emu_ext_stats() { return g_wq_emu_stats; }
 }

@@ -95,7 +95,7 @@ struct wq_handle {
     // device index storage
     DevBuf<WqOccBlock> d_occ; DevBuf<uint32_t> d_sa; DevBuf<uint64_t> d_text2; DevBuf<uint32_t> d_amb;
     DevBuf<WqNodeRec> d_nodes; DevBuf<WqGeneRec> d_genes; DevBuf<uint32_t> d_bucket;
-    DevBuf<uint32_t> d_lptr, d_rptr; DevBuf<uint2> d_lent, d_rent;
+    DevBuf<uint32_t> d_lptr, d_rptr; DevBuf<uint2> d_lent, d_rent, d_ftab;
     // quant stores
     DevBuf<uint64_t> d_dense;    // [N] node counts followed by WqCounters
     DevBuf<uint64_t> d_ekey, d_ecount, d_khash, d_kcount; DevBuf<uint32_t> d_koff, d_kpool; DevBuf<uint64_t> d_kcursor;
@@ -104,7 +104,8 @@ struct wq_handle {
     // per-batch buffers
     DevBuf<uint8_t> d_len[2], d_qual[2]; DevBuf<uint64_t> d_seqoff[2], d_qualoff[2], d_seq2[2];
     DevBuf<WqSeed> d_seeds; DevBuf<uint32_t> d_hit_read, d_hit_s, d_hit_s2, d_hit_gene, d_pending, d_pending2, d_cursors;
-    DevBuf<WqHit> d_hits; DevBuf<wq_align_node> d_pool;
+    DevBuf<WqHit> d_hits; DevBuf<wq_align_node> d_pool; DevBuf<uint32_t> d_defer; DevBuf<WqPNode> d_slab;
+    int n_sm = 148; uint64_t pool_nodes_per_read = 8; uint64_t last_deferred = 0;
     uint32_t* h_cursors = nullptr;   // pinned
     // host-side quant state (filled by wq_counts_sync / merge; input of EM)
     WqHostQuant hq;
@@ -129,12 +130,12 @@ struct wq_handle {
 
 // ------------------------------------------------------------------------------------------ kernels
 #ifndef WQ_EXT_MINBLOCKS
-#define WQ_EXT_MINBLOCKS 10
+#define WQ_EXT_MINBLOCKS 8
 #endif
 #ifndef WQ_SEED_MINBLOCKS
 #define WQ_SEED_MINBLOCKS 1
 #endif
-__global__ void __launch_bounds__(128, WQ_SEED_MINBLOCKS) wq_k_seed(const WqDevIndex ix, const __grid_constant__ WqParams p,
+__global__ void __launch_bounds__(128, WQ_SEED_MINBLOCKS) wq_k_seed(const __grid_constant__ WqDevIndex ix, const __grid_constant__ WqParams p,
                                                  const WqBatchDev b, const WqWork wk) {
     uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     __shared__ uint64_t s_w[128 * (WQ_MAX_READ_WORDS + 1)];
@@ -142,17 +143,33 @@ __global__ void __launch_bounds__(128, WQ_SEED_MINBLOCKS) wq_k_seed(const WqDevI
     wq_seed_thread(ix, p, b, wk, r, s_w + threadIdx.x * (WQ_MAX_READ_WORDS + 1));
 }
 
-__global__ void __launch_bounds__(128, WQ_EXT_MINBLOCKS) wq_k_extend(const WqDevIndex ix, const __grid_constant__ WqParams p,
+// First pass: one thread per located hit, working alignment in shared memory (WQ_FAST_PATH nodes per thread, node i of
+// thread t at s_path[i * 128 + t]: conflict-free).  Tasks that need more (a longer path, or a parked candidate) are queued.
+__global__ void __launch_bounds__(128, WQ_EXT_MINBLOCKS) wq_k_extend(const __grid_constant__ WqDevIndex ix, const __grid_constant__ WqParams p,
                                                                     const WqBatchDev b, const WqWork wk) {
     __shared__ uint64_t s_w[128 * (WQ_MAX_READ_WORDS + 1)];
+    __shared__ WqPNode s_path[WQ_FAST_PATH * 128];
+    const WqPathStore st{s_path + threadIdx.x, 128, WQ_FAST_PATH, nullptr, 0};
     const uint32_t nf = wk.cursors[0], nr = wk.cursors[5];        // forward-strand hits from the front, reverse-strand from the back
     for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < nf + nr; t += gridDim.x * blockDim.x) {
         const uint32_t slot = t < nf ? t : wk.hit_cap - 1 - (t - nf);
-        wq_extend_thread(ix, p, b, wk, slot, s_w + threadIdx.x * (WQ_MAX_READ_WORDS + 1));
+        wq_extend_thread(ix, p, b, wk, slot, s_w + threadIdx.x * (WQ_MAX_READ_WORDS + 1), st, true);
     }
 }
+// Second pass over the queued tasks: full-size path store and one side buffer per nesting level in a global slab
+// (thread t: path node i at slab[i * T + t], side buffers behind the T * WQ_MAX_PATH path nodes).
+#define WQ_SLAB_NODES (WQ_MAX_PATH * (1 + WQ_MAX_DEPTH))
+__global__ void __launch_bounds__(128) wq_k_extend2(const __grid_constant__ WqDevIndex ix, const __grid_constant__ WqParams p,
+                                                    const WqBatchDev b, const WqWork wk, WqPNode* slab) {
+    __shared__ uint64_t s_w[128 * (WQ_MAX_READ_WORDS + 1)];
+    const uint32_t T = gridDim.x * blockDim.x, tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const WqPathStore st{slab + tid, (int32_t)T, WQ_MAX_PATH, slab + (size_t)WQ_MAX_PATH * T + tid, (int32_t)T};
+    const uint32_t nd = wk.cursors[6];
+    for (uint32_t t = tid; t < nd; t += T)
+        wq_extend_thread(ix, p, b, wk, wk.defer[t], s_w + threadIdx.x * (WQ_MAX_READ_WORDS + 1), st, false);
+}
 
-__global__ void __launch_bounds__(128) wq_k_seed_pe(const WqDevIndex ix, const __grid_constant__ WqParams p,
+__global__ void __launch_bounds__(128) wq_k_seed_pe(const __grid_constant__ WqDevIndex ix, const __grid_constant__ WqParams p,
                                                     const WqBatchDev bf, const WqBatchDev br, const WqWork wk) {
     uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     __shared__ uint64_t s_w[128 * (WQ_MAX_READ_WORDS + 1)];
@@ -160,19 +177,31 @@ __global__ void __launch_bounds__(128) wq_k_seed_pe(const WqDevIndex ix, const _
     wq_seed_pe_thread(ix, p, bf, br, wk, r, s_w + threadIdx.x * (WQ_MAX_READ_WORDS + 1));
 }
 
-__global__ void __launch_bounds__(128, WQ_EXT_MINBLOCKS) wq_k_extend_pe(const WqDevIndex ix, const __grid_constant__ WqParams p,
+__global__ void __launch_bounds__(128, WQ_EXT_MINBLOCKS) wq_k_extend_pe(const __grid_constant__ WqDevIndex ix, const __grid_constant__ WqParams p,
                                                       const WqBatchDev bf, const WqBatchDev br, const WqWork wk) {
     uint32_t nh = wk.cursors[0];
     if (nh > wk.hit_cap) nh = wk.hit_cap;
     __shared__ uint64_t s_w[128 * (WQ_MAX_READ_WORDS + 1)];
+    __shared__ WqPNode s_path[WQ_FAST_PATH * 128];
+    const WqPathStore st{s_path + threadIdx.x, 128, WQ_FAST_PATH, nullptr, 0};
     for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < 2 * nh; t += gridDim.x * blockDim.x)
-        wq_extend_pe_thread(ix, p, bf, br, wk, t >> 1, (int)(t & 1), s_w + threadIdx.x * (WQ_MAX_READ_WORDS + 1));
+        wq_extend_pe_thread(ix, p, bf, br, wk, t >> 1, (int)(t & 1), s_w + threadIdx.x * (WQ_MAX_READ_WORDS + 1), st, true);
+}
+__global__ void __launch_bounds__(128) wq_k_extend2_pe(const __grid_constant__ WqDevIndex ix, const __grid_constant__ WqParams p,
+                                                       const WqBatchDev bf, const WqBatchDev br, const WqWork wk, WqPNode* slab) {
+    __shared__ uint64_t s_w[128 * (WQ_MAX_READ_WORDS + 1)];
+    const uint32_t T = gridDim.x * blockDim.x, tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const WqPathStore st{slab + tid, (int32_t)T, WQ_MAX_PATH, slab + (size_t)WQ_MAX_PATH * T + tid, (int32_t)T};
+    const uint32_t nd = wk.cursors[6];
+    for (uint32_t t = tid; t < nd; t += T)
+        wq_extend_pe_thread(ix, p, bf, br, wk, wk.defer[t] >> 1, (int)(wk.defer[t] & 1), s_w + threadIdx.x * (WQ_MAX_READ_WORDS + 1), st, false);
 }
 
-__global__ void __launch_bounds__(128) wq_k_resolve_pe(const WqDevIndex ix, const __grid_constant__ WqParams p,
+__global__ void __launch_bounds__(128) wq_k_resolve_pe(const __grid_constant__ WqDevIndex ix, const __grid_constant__ WqParams p,
                                                        const WqBatchDev bf, const WqBatchDev br, const WqWork wk, const WqQuantDev q) {
     uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     uint64_t st[5] = {0, 0, 0, 0, 0};
+    if (wk.cursors[1] > wk.pool_cap) return;      // path pool exhausted: nothing of this chunk is counted, the host re-runs it with a larger pool
     if (r < bf.n) wq_resolve_pe_thread(ix, p, bf, br, wk, q, r, st);
 #pragma unroll
     for (int i = 0; i < 5; i++) {
@@ -190,17 +219,18 @@ __global__ void __launch_bounds__(128) wq_k_resolve_pe(const WqDevIndex ix, cons
     if (r == 0) atomicAdd((unsigned long long*)&q.counters->total, (unsigned long long)bf.n);
 }
 
-__global__ void __launch_bounds__(128) wq_k_retry_pe(const WqDevIndex ix, const WqWork wk, const WqQuantDev q,
+__global__ void __launch_bounds__(128) wq_k_retry_pe(const __grid_constant__ WqDevIndex ix, const WqWork wk, const WqQuantDev q,
                                                      const uint32_t* list, uint32_t n) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     wq_retry_pe_thread(ix, wk, q, list[i]);
 }
 
-__global__ void __launch_bounds__(128) wq_k_resolve(const WqDevIndex ix, const __grid_constant__ WqParams p,
+__global__ void __launch_bounds__(128) wq_k_resolve(const __grid_constant__ WqDevIndex ix, const __grid_constant__ WqParams p,
                                                     const WqBatchDev b, const WqWork wk, const WqQuantDev q) {
     uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     uint64_t st[5] = {0, 0, 0, 0, 0};
+    if (wk.cursors[1] > wk.pool_cap) return;      // path pool exhausted: nothing of this chunk is counted, the host re-runs it with a larger pool
     if (r < b.n) wq_resolve_thread(ix, p, b, wk, q, r, st);
     // warp-level reduction of the scalar stats, one atomic per warp and counter
 #pragma unroll
@@ -219,7 +249,7 @@ __global__ void __launch_bounds__(128) wq_k_resolve(const WqDevIndex ix, const _
     if (r == 0) atomicAdd((unsigned long long*)&q.counters->total, (unsigned long long)b.n);
 }
 
-__global__ void __launch_bounds__(128) wq_k_retry(const WqDevIndex ix, const WqWork wk, const WqQuantDev q,
+__global__ void __launch_bounds__(128) wq_k_retry(const __grid_constant__ WqDevIndex ix, const WqWork wk, const WqQuantDev q,
                                                   const uint32_t* list, uint32_t n) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -273,6 +303,12 @@ __global__ void __launch_bounds__(256) wq_k_merge_sparse(const WqQuantDev q, con
     }
 }
 
+// k-mer table of the seeding kernel: rows of every ftab_k-mer (the first ftab_k steps of any backward search in one lookup)
+__global__ void __launch_bounds__(256) wq_k_ftab(const __grid_constant__ WqDevIndex ix, uint2* out, const int k) {
+    const uint32_t n = 1u << (2 * k);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = wq_ftab_entry(ix, i, k);
+}
+
 __global__ void wq_k_fill_u64(uint64_t* p, uint64_t v, uint64_t n) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
@@ -315,7 +351,7 @@ void wq_destroy(wq_handle* h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     h->d_occ.release(); h->d_sa.release(); h->d_text2.release(); h->d_amb.release(); h->d_nodes.release();
     h->d_genes.release(); h->d_bucket.release(); h->d_lptr.release(); h->d_rptr.release(); h->d_lent.release();
-    h->d_rent.release(); h->d_dense.release(); h->d_ekey.release(); h->d_ecount.release(); h->d_khash.release();
+    h->d_rent.release(); h->d_ftab.release(); h->d_dense.release(); h->d_ekey.release(); h->d_ecount.release(); h->d_khash.release();
     h->d_kcount.release(); h->d_koff.release(); h->d_kpool.release(); h->d_kcursor.release();
     for (int i = 0; i < 2; i++) {
         h->d_len[i].release(); h->d_qual[i].release(); h->d_seqoff[i].release(); h->d_qualoff[i].release(); h->d_seq2[i].release();
@@ -323,7 +359,7 @@ void wq_destroy(wq_handle* h) {
         if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
     }
     h->d_seeds.release(); h->d_hit_read.release(); h->d_hit_s.release(); h->d_hit_s2.release(); h->d_hit_gene.release(); h->d_pending.release(); h->d_pending2.release();
-    h->d_cursors.release(); h->d_hits.release(); h->d_pool.release();
+    h->d_cursors.release(); h->d_hits.release(); h->d_pool.release(); h->d_defer.release(); h->d_slab.release();
     h->em_scratch.release(); h->ev_batch[0].release(); h->ev_batch[1].release(); h->d_ck.release(); h->d_cv.release(); h->d_ck2.release(); h->d_cv2.release(); h->d_ckoff.release(); h->d_cubtmp.release(); h->d_xpack.release(); h->d_xpending.release();
     if (h->h_cursors) cudaFreeHost(h->h_cursors);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -501,8 +537,11 @@ int wq_index_create(const wq_index_desc* d, int device, wq_handle** out) {
         CKH(cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
     }
     CKH(cudaHostAlloc((void**)&h->h_cursors, 64, cudaHostAllocDefault));
-    // spliced extensions nest (one level per junction found through the k-mer tables)
-    CKH(cudaDeviceSetLimit(cudaLimitStackSize, env_u64("WQ_STACK_BYTES", 16 * 1024)));
+    h->n_sm = prop.multiProcessorCount;
+    h->pool_nodes_per_read = env_u64("WQ_POOL_NODES_PER_READ", 8);
+    // spliced extensions nest (one level per junction found through the k-mer tables, at most WQ_MAX_DEPTH); the working alignment
+    // lives in shared memory / a global slab, so a nested frame holds scalars only
+    CKH(cudaDeviceSetLimit(cudaLimitStackSize, env_u64("WQ_STACK_BYTES", 4 * 1024)));
     WqHostIndex& H = h->H;
     cudaStream_t s = h->stream;
     CKH(upload(h->d_occ, H.occ.data(), H.occ.size(), s));
@@ -523,6 +562,18 @@ int wq_index_create(const wq_index_desc* d, int device, wq_handle** out) {
     ix.n = H.n; ix.sentinel = H.sentinel;
     for (int i = 0; i < 4; i++) ix.C[i] = H.C[i];
     ix.N = H.N; ix.G = H.G; ix.K = H.K;
+    ix.ftab = nullptr; ix.ftab_k = 0;
+    {   // k-mer table (default k = 10: 8 MB, resident in L2 beside the occurrence blocks)
+        const int k = (int)env_u64("WQ_FTAB_K", 10);
+        if (k > 0) {
+            if (k > 13) { wq_destroy(h); return fail(-1, "WQ_FTAB_K must be at most 13"); }
+            CKH(h->d_ftab.ensure((size_t)1 << (2 * k)));
+            wq_k_ftab<<<4 * prop.multiProcessorCount, 256, 0, s>>>(ix, h->d_ftab.p, k);
+            CKH(cudaGetLastError());
+            h->launches += 1;
+            ix.ftab = h->d_ftab.p; ix.ftab_k = k;
+        }
+    }
     // free the bulky host mirrors the quant stage does not need
     std::vector<WqOccBlock>().swap(H.occ);
     std::vector<uint64_t>().swap(H.text2);
@@ -569,48 +620,71 @@ int wq_index_create(const wq_index_desc* d, int device, wq_handle** out) {
     return 0;
 }
 
-// Run the three kernels over reads [0, b.n) already resident on the device (br != NULL: read pairs).
+// Run the alignment kernels over reads [0, b.n) already resident on the device (br != NULL: read pairs).
 static int run_chunk(wq_handle* h, const WqParams& p, const WqBatchDev& b, const WqBatchDev* br, bool time_kernels) {
     const uint32_t n = b.n;
     if (n == 0) return 0;
     const bool pe = br != nullptr;
     cudaStream_t s = h->stream;
-    const uint32_t hit_cap = n * (uint32_t)p.seed_tolerate;
-    const uint32_t pool_cap = (uint32_t)std::min<uint64_t>((uint64_t)n * (pe ? 16 : 8) + 1024, 0xFFFFFFF0ull);
+    const uint64_t hit_cap64 = (uint64_t)n * (uint64_t)p.seed_tolerate;
+    if (hit_cap64 >= 0x7FFFFFF0ull) return fail(-1, "chunk too large: reads per chunk x seed_tolerate must stay below 2^31 (lower WQ_CHUNK_READS)");
+    const uint32_t hit_cap = (uint32_t)hit_cap64;
+    const uint32_t ntask = hit_cap * (pe ? 2u : 1u);
     CK(h->d_seeds.ensure(n)); CK(h->d_hit_read.ensure(hit_cap)); CK(h->d_hit_s.ensure(hit_cap));
-    CK(h->d_hits.ensure((size_t)hit_cap * (pe ? 2 : 1)));
+    CK(h->d_hits.ensure((size_t)ntask)); CK(h->d_defer.ensure((size_t)ntask));
     if (pe) { CK(h->d_hit_s2.ensure(hit_cap)); CK(h->d_hit_gene.ensure(hit_cap)); }
-    CK(h->d_pool.ensure(pool_cap)); CK(h->d_pending.ensure(n)); CK(h->d_pending2.ensure(n));
-    WqWork wk{h->d_seeds.p, h->d_hit_read.p, h->d_hit_s.p, h->d_hit_s2.p, h->d_hit_gene.p, h->d_hits.p, h->d_pool.p,
-              h->d_cursors.p, h->d_pending.p, h->d_pending2.p, hit_cap, pool_cap};
-    CK(cudaMemsetAsync(h->d_cursors.p, 0, 16 * sizeof(uint32_t), s));
+    CK(h->d_pending.ensure(n)); CK(h->d_pending2.ensure(n));
+    const unsigned grid2 = 2u * (unsigned)h->n_sm;                    // second-pass extension kernel: small persistent grid
+    CK(h->d_slab.ensure((size_t)grid2 * 128 * WQ_SLAB_NODES));
+    // the path pool is an average budget (a read may legally need seed_tolerate x WQ_MAX_PATH nodes); when a chunk exceeds it nothing of
+    // the chunk is counted (the resolve kernel checks the cursor first) and the chunk runs again with the pool it asked for
+    uint64_t pool_want = std::max<uint64_t>(h->pool_nodes_per_read * (uint64_t)n * (pe ? 2 : 1) + 1024, h->d_pool.cap);
     cudaEvent_t ev[4];
     if (time_kernels) for (auto& e : ev) CK(cudaEventCreate(&e));
-    const int T = 128;
-    const uint32_t gread = (n + T - 1) / T;
-    if (time_kernels) CK(cudaEventRecord(ev[0], s));
-    if (!pe) {
-        wq_k_seed<<<gread, T, 0, s>>>(h->dix, p, b, wk);
-    } else wq_k_seed_pe<<<gread, T, 0, s>>>(h->dix, p, b, *br, wk);
-    h->launches += 3;
-    if (time_kernels) CK(cudaEventRecord(ev[1], s));
-    // one thread per located hit; the hit count lives on the device, so the grid is sized for the usual
-    // ~1 hit per read and strides over the rest
-    if (!pe) wq_k_extend<<<gread + gread / 8 + 1, T, 0, s>>>(h->dix, p, b, wk);
-    else wq_k_extend_pe<<<2 * gread + gread / 4 + 1, T, 0, s>>>(h->dix, p, b, *br, wk);
-    if (time_kernels) CK(cudaEventRecord(ev[2], s));
-    if (!pe) wq_k_resolve<<<gread, T, 0, s>>>(h->dix, p, b, wk, h->q);
-    else wq_k_resolve_pe<<<gread, T, 0, s>>>(h->dix, p, b, *br, wk, h->q);
-    if (time_kernels) CK(cudaEventRecord(ev[3], s));
-    CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(h->h_cursors, h->d_cursors.p, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    h->last_hit_cap = hit_cap;
-    if (time_kernels) {
-        for (int i = 0; i < 3; i++) { float ms = 0; cudaEventElapsedTime(&ms, ev[i], ev[i + 1]); h->last_kernel_ms[i] += ms; }
-        for (auto& e : ev) cudaEventDestroy(e);
+    for (int attempt = 0;; attempt++) {
+        const uint32_t pool_cap = (uint32_t)std::min<uint64_t>(pool_want, 0xFFFFFFF0ull);
+        CK(h->d_pool.ensure(pool_cap));
+        WqWork wk{h->d_seeds.p, h->d_hit_read.p, h->d_hit_s.p, h->d_hit_s2.p, h->d_hit_gene.p, h->d_hits.p, h->d_pool.p,
+                  h->d_cursors.p, h->d_pending.p, h->d_pending2.p, hit_cap, pool_cap, h->d_defer.p};
+        CK(cudaMemsetAsync(h->d_cursors.p, 0, 16 * sizeof(uint32_t), s));
+        const int T = 128;
+        const uint32_t gread = (n + T - 1) / T;
+        if (time_kernels) CK(cudaEventRecord(ev[0], s));
+        if (!pe) wq_k_seed<<<gread, T, 0, s>>>(h->dix, p, b, wk);
+        else wq_k_seed_pe<<<gread, T, 0, s>>>(h->dix, p, b, *br, wk);
+        h->launches += 4;
+        if (time_kernels) CK(cudaEventRecord(ev[1], s));
+        // one thread per located hit; the hit count lives on the device, so the grid is sized for the usual
+        // ~1 hit per read and strides over the rest
+        if (!pe) {
+            wq_k_extend<<<gread + gread / 8 + 1, T, 0, s>>>(h->dix, p, b, wk);
+            wq_k_extend2<<<grid2, T, 0, s>>>(h->dix, p, b, wk, h->d_slab.p);
+        } else {
+            wq_k_extend_pe<<<2 * gread + gread / 4 + 1, T, 0, s>>>(h->dix, p, b, *br, wk);
+            wq_k_extend2_pe<<<grid2, T, 0, s>>>(h->dix, p, b, *br, wk, h->d_slab.p);
+        }
+        if (time_kernels) CK(cudaEventRecord(ev[2], s));
+        if (!pe) wq_k_resolve<<<gread, T, 0, s>>>(h->dix, p, b, wk, h->q);
+        else wq_k_resolve_pe<<<gread, T, 0, s>>>(h->dix, p, b, *br, wk, h->q);
+        if (time_kernels) CK(cudaEventRecord(ev[3], s));
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(h->h_cursors, h->d_cursors.p, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        h->last_hit_cap = hit_cap;
+        h->last_deferred += h->h_cursors[6];
+        if (time_kernels)
+            for (int i = 0; i < 3; i++) { float ms = 0; cudaEventElapsedTime(&ms, ev[i], ev[i + 1]); h->last_kernel_ms[i] += ms; }
+        if (h->h_cursors[1] <= pool_cap) break;
+        if (attempt >= 2 || pool_cap >= 0xFFFFFFF0u) {
+            if (time_kernels) for (auto& e : ev) cudaEventDestroy(e);
+            return fail(-5, "alignment path pool exhausted for this chunk (nothing of the chunk was counted; lower WQ_CHUNK_READS)");
+        }
+        pool_want = (uint64_t)h->h_cursors[1] + 1024;
     }
-    if (h->h_cursors[1] > pool_cap) return fail(-5, "alignment path pool exhausted for this batch (lower WQ_CHUNK_READS)");
+    if (time_kernels) for (auto& e : ev) cudaEventDestroy(e);
+    WqWork wk{h->d_seeds.p, h->d_hit_read.p, h->d_hit_s.p, h->d_hit_s2.p, h->d_hit_gene.p, h->d_hits.p, h->d_pool.p,
+              h->d_cursors.p, h->d_pending.p, h->d_pending2.p, hit_cap, (uint32_t)std::min<uint64_t>(h->d_pool.cap, 0xFFFFFFF0ull), h->d_defer.p};
+    const int T = 128;
     // keyed inserts that raced with the slot owner: retry until none is left
     uint32_t pending = h->h_cursors[2];
     int guard = 0;
@@ -719,6 +793,7 @@ static int align_impl(wq_handle* h, const wq_align_param* ap, const wq_read_batc
     h->hq_valid = false;
     reset_quant_ex(h);
     for (auto& m : h->last_kernel_ms) m = 0;
+    h->last_deferred = 0;
     const wq_read_batch* src[2] = {reads, mates};
     const int nb = pe ? 2 : 1;
     WqBatchDev base[2];

@@ -74,8 +74,10 @@ static inline bool wq_key_compatible(const WqGeneBits& B, uint32_t p, const WqKe
 
 // add `v` along a path: one node -> node store, otherwise every consecutive pair -> edge/circ store
 // (assign_path!, src/quant.jl:263-324; the paired form skips mate-2 pieces already covered by mate 1)
+// `stale`: bit i set = mate-2 node i counts as already seen on entry (assign_ambig! passes the paired method a set that still holds
+// the global isoform ids of the class's last alignment, src/quant.jl:493-501, 541-551; a mate-2 node id equal to one of them is skipped)
 static inline void wq_spread_path(const WqHostIndex& H, std::vector<double>& node_value, std::vector<std::pair<uint64_t, double>>& edge_adds,
-                                  const WqKeyPath& kp, double v) {
+                                  const WqKeyPath& kp, double v, uint32_t stale = 0) {
     const uint32_t nb = H.genes[kp.gene - 1].node_base;
     auto ekey = [&](uint32_t l, uint32_t r) { return ((uint64_t)kp.gene << 32) | ((uint64_t)(l & 0xFFFF) << 16) | (r & 0xFFFF); };
     uint32_t seen[2 * WQ_MAX_PATH + 2];
@@ -86,10 +88,11 @@ static inline void wq_spread_path(const WqHostIndex& H, std::vector<double>& nod
         edge_adds.emplace_back(ekey(kp.nd[i], kp.nd[i + 1]), v);
     }
     if (!kp.rnd) return;
-    auto in_seen = [&](uint32_t x) { for (int i = 0; i < ns; i++) if (seen[i] == x) return true; return false; };
-    if (kp.rn == 1) { if (!in_seen(kp.rnd[0])) node_value[nb + kp.rnd[0] - 1] += v; }
+    auto in_fwd = [&](uint32_t x) { for (int i = 0; i < ns; i++) if (seen[i] == x) return true; return false; };
+    auto in_seen = [&](uint32_t i) { return ((stale >> i) & 1u) != 0 || in_fwd(kp.rnd[i]); };
+    if (kp.rn == 1) { if (!in_seen(0)) node_value[nb + kp.rnd[0] - 1] += v; }
     else for (uint32_t i = 0; i + 1 < kp.rn; i++) {
-        if (in_seen(kp.rnd[i]) && in_seen(kp.rnd[i + 1])) continue;
+        if (in_seen(i) && in_seen(i + 1)) continue;
         edge_adds.emplace_back(ekey(kp.rnd[i], kp.rnd[i + 1]), v);
     }
 }
@@ -394,6 +397,7 @@ static inline std::string wq_host_assign_ambig_impl(const WqHostIndex& H, const 
     // (sequential: floating-point sums onto one node / edge must see their terms in the reference's order)
     std::vector<double> share((size_t)C.n_multi * WQ_MAX_TOLERATE, 0.0);
     std::vector<uint8_t> skip(C.n_multi, 0);
+    std::vector<uint32_t> stale(C.n_multi, 0);      // paired classes: mate-2 nodes of the first alignment that the stale isoform-id set covers
     unsigned nthreads = wq_host_threads();
     if (C.n_multi < 1024) nthreads = 1;
     std::vector<std::string> errs(nthreads);
@@ -429,6 +433,18 @@ static inline std::string wq_host_assign_ambig_impl(const WqHostIndex& H, const 
             double tot = 0.0;
             for (uint32_t h = 0; h < nh; h++) tot += w[h];
             for (uint32_t h = 0; h < nh; h++) share[(size_t)c * WQ_MAX_TOLERATE + h] = (w[h] / tot) * C.count[c];
+            if (!C.postassign[c] && vp[0].rnd) {
+                // ambig.iset still holds {p + geneidx[g]} of the LAST alignment when the first one is spread (see wq_spread_path)
+                const WqKeyPath& last = vp[nh - 1];
+                if (cached != last.gene) { B.build(S, last.gene - 1, H.genes[last.gene - 1].nn); cached = last.gene; }
+                const int64_t ib = S.iso_base[last.gene - 1];
+                uint32_t m = 0;
+                for (uint32_t i = 0; i < vp[0].rn && i < 32; i++) {
+                    const int64_t p = (int64_t)vp[0].rnd[i] - ib - 1;          // node id == p + 1 + geneidx  <=>  0-based isoform p
+                    if (p >= 0 && p < B.np && wq_key_compatible(B, (uint32_t)p, last)) m |= 1u << i;
+                }
+                stale[c] = m;
+            }
         }
     };
     if (nthreads == 1) work(0);
@@ -443,7 +459,7 @@ static inline std::string wq_host_assign_ambig_impl(const WqHostIndex& H, const 
             WqKeyPath kp;
             pos = wq_key_next(key, pos, kp);
             if (X.nparts > 1 && (kp.gene < X.own_g_lo || kp.gene > X.own_g_hi)) continue;       // another rank's gene
-            wq_spread_path(H, X.node_value, X.edge_adds, kp, share[(size_t)c * WQ_MAX_TOLERATE + h]);
+            wq_spread_path(H, X.node_value, X.edge_adds, kp, share[(size_t)c * WQ_MAX_TOLERATE + h], h == 0 ? stale[c] : 0u);
         }
     }
     X.ambig_done = true;

@@ -96,7 +96,50 @@ struct WqWork {                    // per-batch scratch
     uint32_t* pending;             // [n] reads whose keyed insert must be retried (also: seed queue A)
     uint32_t* pending2;            // [n] seed queue B
     uint32_t  hit_cap, pool_cap;
+    uint32_t* defer;               // [hit_cap] extension tasks the first-pass kernel hands to the second pass (count in cursors[6])
 };
+
+// Where a thread keeps its working alignment while extending (WqCtx.path / .side)
+struct WqPathStore {
+    WqPNode* path; int32_t pstride, pcap;
+    WqPNode* side; int32_t sstride;          // NULL in the first-pass kernel
+};
+WQ_HD void wq_bind_store(WqCtx& c, const WqPathStore& st) {
+    c.path = st.path; c.pstride = st.pstride; c.pcap = st.pcap; c.side = st.side; c.sstride = st.sstride;
+}
+
+// result of one extension -> hit header + path nodes in the pool
+WQ_HD void wq_emit_hit(const WqCtx& c, const WqWork& wk, uint32_t hslot, float identity) {
+    WqHit h;
+    h.identity = identity;
+    h.offset = c.offset;
+    h.offsetread = c.offsetread;
+    const int np = c.overflow ? 0 : wq_npath(c);
+    h.npath = (uint8_t)np;
+    h.strand = c.strand;
+    h.flags = (uint8_t)((c.isvalid ? 1 : 0) | (wq_isvalid(c) ? 2 : 0) | (c.overflow ? 8 : 0));
+    if (c.overflow) h.flags &= (uint8_t)~3;
+    const uint32_t ps = WQ_ALLOC(&wk.cursors[1], np);
+    if (np) {
+        if (ps + np <= wk.pool_cap) {
+            for (int i = 0; i < np; i++) {
+                const WqPNode n = wq_pn(c, i);
+                wq_align_node o;
+                o.gene = c.gene;
+                o.node = n.node;
+                o.mistolerance = n.tol;
+                o.matches = n.m;
+                o.mismatches = n.mm;
+                o._pad = 0;
+                wk.pool[ps + i] = o;
+            }
+        } else {
+            h.flags |= 16;           // path pool exhausted: reported through WqCounters.pool_overflow
+        }
+    }
+    h.path_start = ps;
+    wk.hits[hslot] = h;
+}
 
 WQ_HD void wq_load_read(WqCtx& c, const WqBatchDev& b, uint32_t r) {
     int len = WQ_LDG(b.len + r);
@@ -191,47 +234,28 @@ WQ_HDN void wq_seed_thread(const WqDevIndex& ix, const WqParams& p, const WqBatc
 }
 
 // ---- kernel 2 -----------------------------------------------------------------------------------
-WQ_HDN void wq_extend_thread(const WqDevIndex& ix, const WqParams& p, const WqBatchDev& b, const WqWork& wk, uint32_t slot, uint64_t* wbuf) {
+// `first_pass`: a task that overflows the small path store (or would have to park a candidate) is queued for the second pass,
+// which runs the same code with the full WQ_MAX_PATH store and side buffers.
+WQ_HDN void wq_extend_thread(const WqDevIndex& ix, const WqParams& p, const WqBatchDev& b, const WqWork& wk, uint32_t slot, uint64_t* wbuf,
+                             const WqPathStore& st, bool first_pass) {
     uint32_t r = wk.hit_read[slot];
     WqSeed s = wk.seeds[r];
     WqCtx c;
     c.ix = &ix;
     c.p = &p;
     c.w = wbuf;
+    wq_bind_store(c, st);
     wq_load_read(c, b, r);
     if (!s.strand) {                 // reverse_complement!(read), src/align.jl:231-234
         wq_revcomp(c.w, c.readlen);
         c.flipped = 1;
     }
-    WqAlign a;
-    wq_align_at(c, (int64_t)wk.hit_s[slot], s.readloc, s.strand != 0, 0, a);
-    WqHit h;
-    h.identity = wq_identity(a, c.readlen);
-    h.offset = a.offset;
-    h.offsetread = a.offsetread;
-    h.npath = a.npath;
-    h.strand = a.strand;
-    h.flags = (uint8_t)((a.isvalid ? 1 : 0) | (wq_isvalid(a) ? 2 : 0) | (c.overflow ? 8 : 0));
-    if (c.overflow) h.flags &= (uint8_t)~2;
-    const uint32_t ps = WQ_ALLOC(&wk.cursors[1], a.npath);
-    if (a.npath) {
-        if (ps + a.npath <= wk.pool_cap) {
-            for (int i = 0; i < a.npath; i++) {
-                wq_align_node o;
-                o.gene = c.gene;
-                o.node = a.p[i].node;
-                o.mistolerance = a.p[i].tol;
-                o.matches = a.p[i].m;
-                o.mismatches = a.p[i].mm;
-                o._pad = 0;
-                wk.pool[ps + i] = o;
-            }
-        } else {
-            h.flags |= 16;           // path pool exhausted: reported through WqCounters.pool_overflow
-        }
+    wq_align_at(c, (int64_t)wk.hit_s[slot], s.readloc, s.strand != 0, 0);
+    if (c.overflow && first_pass) {
+        wk.defer[WQ_ATOMIC_ADD_U32(&wk.cursors[6], 1)] = slot;
+        return;
     }
-    h.path_start = ps;
-    wk.hits[slot] = h;
+    wq_emit_hit(c, wk, slot, wq_identity(c));
 }
 
 // ---- keyed store --------------------------------------------------------------------------------
@@ -510,15 +534,16 @@ WQ_HDN void wq_seed_pe_thread(const WqDevIndex& ix, const WqParams& p, const WqB
     wk.seeds[r] = sd;
 }
 
-// kernel P2: one (pair slot, mate) -> _ungapped_align with the gene pinned (src/paired.jl:79-80)
+// kernel P2: one (pair slot, mate) -> _ungapped_align with the gene pinned (src/paired.jl:79-80); task = 2*slot + mate
 WQ_HDN void wq_extend_pe_thread(const WqDevIndex& ix, const WqParams& p, const WqBatchDev& bf, const WqBatchDev& br,
-                                const WqWork& wk, uint32_t slot, int mate, uint64_t* wbuf) {
+                                const WqWork& wk, uint32_t slot, int mate, uint64_t* wbuf, const WqPathStore& st, bool first_pass) {
     uint32_t r = wk.hit_read[slot];
     WqSeed s = wk.seeds[r];
     WqCtx c;
     c.ix = &ix;
     c.p = &p;
     c.w = wbuf;
+    wq_bind_store(c, st);
     bool ispos = s.strand != 0;
     int readloc;
     int64_t pos;
@@ -534,31 +559,12 @@ WQ_HDN void wq_extend_pe_thread(const WqDevIndex& ix, const WqParams& p, const W
         pos = wk.hit_s2[slot];
         ispos = !ispos;
     }
-    WqAlign a;
-    wq_align_at(c, pos, readloc, ispos, wk.hit_gene[slot], a);
-    WqHit h;
-    h.identity = wq_score(a);            // paired scoring combines the two raw scores (src/paired.jl:2-3)
-    h.offset = a.offset;
-    h.offsetread = a.offsetread;
-    h.npath = a.npath;
-    h.strand = a.strand;
-    h.flags = (uint8_t)((a.isvalid ? 1 : 0) | (wq_isvalid(a) ? 2 : 0) | (c.overflow ? 8 : 0));
-    if (c.overflow) h.flags &= (uint8_t)~2;
-    const uint32_t ps = WQ_ALLOC(&wk.cursors[1], a.npath);
-    if (a.npath) {
-        if (ps + a.npath <= wk.pool_cap) {
-            for (int i = 0; i < a.npath; i++) {
-                wq_align_node o;
-                o.gene = c.gene; o.node = a.p[i].node; o.mistolerance = a.p[i].tol;
-                o.matches = a.p[i].m; o.mismatches = a.p[i].mm; o._pad = 0;
-                wk.pool[ps + i] = o;
-            }
-        } else {
-            h.flags |= 16;
-        }
+    wq_align_at(c, pos, readloc, ispos, wk.hit_gene[slot]);
+    if (c.overflow && first_pass) {
+        wk.defer[WQ_ATOMIC_ADD_U32(&wk.cursors[6], 1)] = 2 * slot + (uint32_t)mate;
+        return;
     }
-    h.path_start = ps;
-    wk.hits[2 * slot + mate] = h;
+    wq_emit_hit(c, wk, 2 * slot + (uint32_t)mate, wq_score(c));     // paired scoring combines the two raw scores (src/paired.jl:2-3)
 }
 
 // Base.in(first::SGAlignPath, last::SGAlignPath): contiguous sub-path (src/quant.jl:47-62)

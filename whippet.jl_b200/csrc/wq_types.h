@@ -62,6 +62,8 @@ struct WqDevIndex {
     const uint2*      left_ent;    // (gene, global node index)
     const uint32_t*   right_ptr;
     const uint2*      right_ent;
+    const uint2*      ftab;        // [4^ftab_k] rows (sp, ep) of every ftab_k-mer (sp > ep: absent); NULL = no table
+    int32_t           ftab_k;
     uint64_t n;
     uint64_t sentinel;
     uint32_t C[4];
@@ -69,23 +71,17 @@ struct WqDevIndex {
     int32_t  K;
 };
 
-// Alignment path node kept in thread-local memory while extending.
-struct WqPNode {
-    uint32_t node;     // 1-based node id inside the gene
-    float    tol;      // SGAlignScore.mistolerance
+// Alignment path node of the working alignment (8 bytes).  A gene has at most 65535 nodes (ExonInt = UInt16,
+// src/types.jl:20; enforced when the index is created), so the node id fits 16 bits.
+struct __attribute__((aligned(8))) WqPNode {
+    uint16_t node;     // 1-based node id inside the gene
     uint8_t  m;        // matches
     uint8_t  mm;       // mismatches
-    uint16_t _pad;
+    float    tol;      // SGAlignScore.mistolerance
 };
 
-struct WqAlign {       // SGAlignment (src/align.jl:76-82), single gene
-    uint32_t offset;
-    uint8_t  offsetread;
-    uint8_t  npath;
-    uint8_t  isvalid;
-    uint8_t  strand;
-    WqPNode  p[WQ_MAX_PATH];
-};
+#define WQ_FAST_PATH 12            // path capacity of the first-pass extension kernel (shared memory); longer paths and
+                                   // extensions that must park a candidate go to the second-pass kernel (WQ_MAX_PATH)
 
 // Per-read seed result (seed_locate, src/align.jl:145-185)
 struct WqSeed {
