@@ -111,7 +111,7 @@ class ClockSampler:
 
 def make_inputs(a, rank):
     import whippet_jl_b200 as wq
-    from whippet_jl_b200 import synth
+    from wq_inputs import synth
     t0 = time.time()
     idx = synth.make_index(n_genes=a.genes, K=9, seed=1)
     t1 = time.time()

@@ -124,13 +124,19 @@ typedef struct wq_align_out {
     uint64_t       nodes_used;  /* out */
 } wq_align_out;
 
-/* (mapped, total, mean_readlen) of process_reads! (src/reads.jl:41-80) plus the multi-map total. */
+/* (mapped, total, mean_readlen) of process_reads! (src/reads.jl:41-80) plus the multi-map total.
+ * mean_readlen is the reference's RUNNING mean, `mean += (len - mean) / mapped` over the mapped reads in read order
+ * (src/reads.jl:69, :121; floored by the caller, bin/whippet-quant.jl:145,151), not sum / mapped: the two can floor
+ * differently at an integer boundary.  Fixed-length input keeps it equal to that length at no cost; for ragged input the
+ * library replays the recurrence on the host from a per-read mapped bit (reads of this handle only: with reads sharded
+ * over several handles the caller chains the shards in read order, or uses fixed-length input). */
 typedef struct wq_map_stats {
     uint64_t total;
     uint64_t mapped;
     uint64_t multi;           /* reads routed to MultiMapping (length(align) > 1) */
-    uint64_t sum_readlen;     /* sum of mapped read lengths: mean_readlen = sum_readlen / mapped */
+    uint64_t sum_readlen;     /* sum of mapped read lengths */
     uint64_t path_overflow;   /* reads whose path exceeded WQ_MAX_PATH (reported, never silently dropped) */
+    double   mean_readlen;    /* running mean as defined above (0 when nothing mapped) */
 } wq_map_stats;
 
 #define WQ_MAX_PATH 24        /* device-side bound on nodes per alignment path */

@@ -46,7 +46,7 @@ mutable struct AlignOut     # wq_align_out
 end
 
 struct MapStats             # wq_map_stats
-   total::UInt64; mapped::UInt64; multi::UInt64; sum_readlen::UInt64; path_overflow::UInt64
+   total::UInt64; mapped::UInt64; multi::UInt64; sum_readlen::UInt64; path_overflow::UInt64; mean_readlen::Float64
 end
 
 struct EmParam; readlen::Int64; sig::Int64; maxit::Int64; end          # wq_em_param
@@ -103,17 +103,17 @@ align_se(h, p::AlignParamC, b::ReadBatch, out = C_NULL) =
 align_pe(h, p::AlignParamC, f::ReadBatch, r::ReadBatch, out = C_NULL) =
    check(ccall((:wq_align_pe, LIB), Cint, (Ptr{Cvoid}, Ref{AlignParamC}, Ref{ReadBatch}, Ref{ReadBatch}, Ptr{Cvoid}), h, p, f, r, out))
 function map_stats(h)
-   st = Ref(MapStats(0, 0, 0, 0, 0))
+   st = Ref(MapStats(0, 0, 0, 0, 0, 0.0))
    check(ccall((:wq_map_stats_get, LIB), Cint, (Ptr{Cvoid}, Ref{MapStats}), h, st))
    st[]
 end
 """Whole files (gzip or plain); `rev = nothing` for single end.  Returns (mapped, total, mean_readlen)."""
 function process_fastq(h, p::AlignParamC, fwd::String, rev::Union{String,Nothing} = nothing; qualoffset = 33, batch_reads = 1 << 22)
-   st = Ref(MapStats(0, 0, 0, 0, 0))
+   st = Ref(MapStats(0, 0, 0, 0, 0, 0.0))
    check(ccall((:wq_process_fastq, LIB), Cint, (Ptr{Cvoid}, Ref{AlignParamC}, Cstring, Cstring, Cint, UInt32, Ref{MapStats}),
                h, p, fwd, rev === nothing ? C_NULL : rev, qualoffset, batch_reads, st))
    s = st[]
-   s.mapped, s.total, s.sum_readlen / max(s.mapped, 1)
+   s.mapped, s.total, s.mean_readlen      # the running mean of src/reads.jl:69, floored by the caller as bin/whippet-quant.jl:145 does
 end
 
 # ---- count stores (refill SpliceGraphQuant.node/edge/circ/long and MultiMapping.map for the writers) ----------------

@@ -3,7 +3,7 @@ import os, sys, time
 sys.path[:0] = [os.path.dirname(os.path.dirname(os.path.abspath(__file__)))]
 import numpy as np
 import whippet_jl_b200 as wq
-from whippet_jl_b200 import synth
+from wq_inputs import synth
 idx = synth.make_index(n_genes=int(os.environ.get("WQ_BENCH_GENES", 40000)), K=9, seed=1)
 rb = synth.simulate_reads(idx, int(os.environ.get("WQ_BENCH_READS", 4000000)), 101, seed=2)
 q = wq.GraphLibQuant(idx)

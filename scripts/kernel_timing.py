@@ -7,7 +7,8 @@ sys.path[:0] = [os.path.dirname(os.path.dirname(os.path.abspath(__file__)))]
 import numpy as np
 import torch
 import whippet_jl_b200 as wq
-from whippet_jl_b200 import abi, lib, synth
+from whippet_jl_b200 import abi, lib
+from wq_inputs import synth
 
 genes = int(os.environ.get("WQ_BENCH_GENES", 40000))
 nreads = int(os.environ.get("WQ_BENCH_READS", 4000000))

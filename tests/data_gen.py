@@ -2,7 +2,7 @@
 import numpy as np
 
 import whippet_jl_b200 as wq
-from whippet_jl_b200 import synth
+from wq_inputs import synth
 
 
 def fixture_random_reads(idx, n=20000, seed=7):

@@ -85,7 +85,7 @@ int emu_align_se(Emu* e, const wq_align_param* ap, const wq_read_batch* rb) {
     e->paired = false;
     e->defer.assign(hit_cap, 0);
     WqWork wk{e->seeds.data(), e->hit_read.data(), e->hit_s.data(), nullptr, nullptr, e->hits.data(), e->pool.data(), e->cursors,
-              e->pending.data(), e->pending2.data(), hit_cap, (uint32_t)e->pool.size(), e->defer.data()};
+              e->pending.data(), e->pending2.data(), hit_cap, (uint32_t)e->pool.size(), e->defer.data(), nullptr};
     uint64_t wbuf[WQ_MAX_READ_WORDS + 1];
     for (uint32_t r = 0; r < n; r++) wq_seed_thread(e->ix, p, b, wk, r, wbuf);
     uint32_t nf = e->cursors[0], nr = e->cursors[5];
@@ -117,7 +117,7 @@ int emu_align_pe(Emu* e, const wq_align_param* ap, const wq_read_batch* rf, cons
     e->paired = true;
     e->defer.assign((size_t)2 * hit_cap, 0);
     WqWork wk{e->seeds.data(), e->hit_read.data(), e->hit_s.data(), e->hit_s2.data(), e->hit_gene.data(), e->hits.data(),
-              e->pool.data(), e->cursors, e->pending.data(), e->pending.data(), hit_cap, (uint32_t)e->pool.size(), e->defer.data()};
+              e->pool.data(), e->cursors, e->pending.data(), e->pending.data(), hit_cap, (uint32_t)e->pool.size(), e->defer.data(), nullptr};
     uint64_t wbuf[WQ_MAX_READ_WORDS + 1];
     for (uint32_t r = 0; r < n; r++) wq_seed_pe_thread(e->ix, p, bf, br, wk, r, wbuf);
     uint32_t nh = e->cursors[0];

@@ -100,7 +100,7 @@ def test_phred64_and_errors(tmp_path):
 
 @pytest.mark.gpu
 def test_process_fastq_equals_process_reads(tmp_path):
-    from whippet_jl_b200 import synth
+    from wq_inputs import synth
     idx = synth.make_index(n_genes=300, K=9, seed=51, paralog_frac=0.1)
     rb = synth.simulate_reads(idx, 50000, 101, seed=52, sub_rate=0.01)
     # render the packed batch back to FASTQ text

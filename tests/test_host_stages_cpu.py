@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 import whippet_jl_b200 as wq
-from whippet_jl_b200 import synth
+from wq_inputs import synth
 from emu.host_emu import HostEmu
 from oracle import Oracle, em_psi
 

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 import whippet_jl_b200 as wq
-from whippet_jl_b200 import synth
+from wq_inputs import synth
 from conftest import GOLDEN
 from data_gen import PE_CASES, fixture_random_reads, pe_case, ragged_reads
 from emu.emu import Emu

@@ -76,7 +76,7 @@ def _class_counts():
     holds identical stores)."""
     sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")]
     import whippet_jl_b200 as wq
-    from whippet_jl_b200 import synth
+    from wq_inputs import synth
     from oracle import Oracle
     idx = synth.make_index(n_genes=400, K=9, seed=81, paralog_frac=0.1)
     rb = synth.simulate_reads(idx, 60000, 101, seed=82, sub_rate=0.01)

@@ -99,7 +99,7 @@ def test_sam_fixture_and_header(fixture_index, test_param):
 
 @pytest.mark.gpu
 def test_sam_synthetic_single_and_paired():
-    from whippet_jl_b200 import synth
+    from wq_inputs import synth
     idx, p, f, r = pe_case(3, 300, 101, 5000, True, 40000)
     rng = np.random.default_rng(5)
     idx.gene_strand = rng.integers(0, 2, idx.n_genes).astype("u1")

@@ -63,7 +63,7 @@ class AlignOutC(C.Structure):
 
 class MapStatsC(C.Structure):
     _fields_ = [("total", C.c_uint64), ("mapped", C.c_uint64), ("multi", C.c_uint64),
-                ("sum_readlen", C.c_uint64), ("path_overflow", C.c_uint64)]
+                ("sum_readlen", C.c_uint64), ("path_overflow", C.c_uint64), ("mean_readlen", C.c_double)]
 
 
 class CountsC(C.Structure):

@@ -1,4 +1,4 @@
-"""In-tree builds: the CUDA library (nvcc, sm_100a) and the host-side index helper (g++)."""
+"""In-tree build of the CUDA library (nvcc, sm_100a)."""
 from __future__ import annotations
 
 import os
@@ -39,6 +39,4 @@ def build_cuda(force=False, verbose=False):
 
 
 def build_all(force=False):
-    from . import synth
-    synth.build_host_lib(force)
     return build_cuda(force)

@@ -106,6 +106,8 @@ struct wq_handle {
     DevBuf<WqSeed> d_seeds; DevBuf<uint32_t> d_hit_read, d_hit_s, d_hit_s2, d_hit_gene, d_pending, d_pending2, d_cursors;
     DevBuf<WqHit> d_hits; DevBuf<wq_align_node> d_pool; DevBuf<uint32_t> d_defer; DevBuf<WqPNode> d_slab;
     int n_sm = 148; uint64_t pool_nodes_per_read = 8; uint64_t last_deferred = 0;
+    DevBuf<uint32_t> d_mapped_bits;
+    double rl_mean = 0.0; uint64_t rl_mapped = 0;      // running mean_readlen over the mapped reads in read order (src/reads.jl:69)
     uint32_t* h_cursors = nullptr;   // pinned
     // host-side quant state (filled by wq_counts_sync / merge; input of EM)
     WqHostQuant hq;
@@ -169,6 +171,17 @@ __global__ void __launch_bounds__(128) wq_k_extend2(const __grid_constant__ WqDe
         wq_extend_thread(ix, p, b, wk, wk.defer[t], s_w + threadIdx.x * (WQ_MAX_READ_WORDS + 1), st, false);
 }
 
+// what the running mean_readlen needs from a chunk: a mapped bit per read, and whether all mapped reads have one length
+__device__ __forceinline__ void wq_note_mapped(const WqWork& wk, uint32_t r, bool mapped, uint32_t len) {
+    const unsigned bal = __ballot_sync(0xffffffffu, mapped);
+    const unsigned lmax = __reduce_max_sync(0xffffffffu, mapped ? len : 0u);
+    const unsigned lmin = __reduce_max_sync(0xffffffffu, mapped ? 255u - len : 0u);
+    if ((threadIdx.x & 31) == 0) {
+        wk.mapped_bits[r >> 5] = bal;
+        if (bal) { atomicMax(&wk.cursors[3], lmin); atomicMax(&wk.cursors[4], lmax); atomicAdd(&wk.cursors[7], (unsigned)__popc(bal)); }
+    }
+}
+
 __global__ void __launch_bounds__(128) wq_k_seed_pe(const __grid_constant__ WqDevIndex ix, const __grid_constant__ WqParams p,
                                                     const WqBatchDev bf, const WqBatchDev br, const WqWork wk) {
     uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -203,6 +216,7 @@ __global__ void __launch_bounds__(128) wq_k_resolve_pe(const __grid_constant__ W
     uint64_t st[5] = {0, 0, 0, 0, 0};
     if (wk.cursors[1] > wk.pool_cap) return;      // path pool exhausted: nothing of this chunk is counted, the host re-runs it with a larger pool
     if (r < bf.n) wq_resolve_pe_thread(ix, p, bf, br, wk, q, r, st);
+    wq_note_mapped(wk, r, st[0] != 0, (uint32_t)st[2]);
 #pragma unroll
     for (int i = 0; i < 5; i++) {
         unsigned long long v = st[i];
@@ -232,6 +246,7 @@ __global__ void __launch_bounds__(128) wq_k_resolve(const __grid_constant__ WqDe
     uint64_t st[5] = {0, 0, 0, 0, 0};
     if (wk.cursors[1] > wk.pool_cap) return;      // path pool exhausted: nothing of this chunk is counted, the host re-runs it with a larger pool
     if (r < b.n) wq_resolve_thread(ix, p, b, wk, q, r, st);
+    wq_note_mapped(wk, r, st[0] != 0, (uint32_t)st[2]);
     // warp-level reduction of the scalar stats, one atomic per warp and counter
 #pragma unroll
     for (int i = 0; i < 5; i++) {
@@ -359,7 +374,7 @@ void wq_destroy(wq_handle* h) {
         if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
     }
     h->d_seeds.release(); h->d_hit_read.release(); h->d_hit_s.release(); h->d_hit_s2.release(); h->d_hit_gene.release(); h->d_pending.release(); h->d_pending2.release();
-    h->d_cursors.release(); h->d_hits.release(); h->d_pool.release(); h->d_defer.release(); h->d_slab.release();
+    h->d_cursors.release(); h->d_hits.release(); h->d_pool.release(); h->d_defer.release(); h->d_slab.release(); h->d_mapped_bits.release();
     h->em_scratch.release(); h->ev_batch[0].release(); h->ev_batch[1].release(); h->d_ck.release(); h->d_cv.release(); h->d_ck2.release(); h->d_cv2.release(); h->d_ckoff.release(); h->d_cubtmp.release(); h->d_xpack.release(); h->d_xpending.release();
     if (h->h_cursors) cudaFreeHost(h->h_cursors);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -502,6 +517,7 @@ int wq_quant_reset(wq_handle* h) {
     h->hq = WqHostQuant();
     reset_quant_ex(h);
     h->hq_valid = false;
+    h->rl_mean = 0.0; h->rl_mapped = 0;
     return 0;
 }
 
@@ -633,7 +649,7 @@ static int run_chunk(wq_handle* h, const WqParams& p, const WqBatchDev& b, const
     CK(h->d_seeds.ensure(n)); CK(h->d_hit_read.ensure(hit_cap)); CK(h->d_hit_s.ensure(hit_cap));
     CK(h->d_hits.ensure((size_t)ntask)); CK(h->d_defer.ensure((size_t)ntask));
     if (pe) { CK(h->d_hit_s2.ensure(hit_cap)); CK(h->d_hit_gene.ensure(hit_cap)); }
-    CK(h->d_pending.ensure(n)); CK(h->d_pending2.ensure(n));
+    CK(h->d_pending.ensure(n)); CK(h->d_pending2.ensure(n)); CK(h->d_mapped_bits.ensure(((size_t)n + 127) / 128 * 4));
     const unsigned grid2 = 2u * (unsigned)h->n_sm;                    // second-pass extension kernel: small persistent grid
     CK(h->d_slab.ensure((size_t)grid2 * 128 * WQ_SLAB_NODES));
     // the path pool is an average budget (a read may legally need seed_tolerate x WQ_MAX_PATH nodes); when a chunk exceeds it nothing of
@@ -645,7 +661,7 @@ static int run_chunk(wq_handle* h, const WqParams& p, const WqBatchDev& b, const
         const uint32_t pool_cap = (uint32_t)std::min<uint64_t>(pool_want, 0xFFFFFFF0ull);
         CK(h->d_pool.ensure(pool_cap));
         WqWork wk{h->d_seeds.p, h->d_hit_read.p, h->d_hit_s.p, h->d_hit_s2.p, h->d_hit_gene.p, h->d_hits.p, h->d_pool.p,
-                  h->d_cursors.p, h->d_pending.p, h->d_pending2.p, hit_cap, pool_cap, h->d_defer.p};
+                  h->d_cursors.p, h->d_pending.p, h->d_pending2.p, hit_cap, pool_cap, h->d_defer.p, h->d_mapped_bits.p};
         CK(cudaMemsetAsync(h->d_cursors.p, 0, 16 * sizeof(uint32_t), s));
         const int T = 128;
         const uint32_t gread = (n + T - 1) / T;
@@ -682,8 +698,29 @@ static int run_chunk(wq_handle* h, const WqParams& p, const WqBatchDev& b, const
         pool_want = (uint64_t)h->h_cursors[1] + 1024;
     }
     if (time_kernels) for (auto& e : ev) cudaEventDestroy(e);
+    // mean_readlen (src/reads.jl:69): `mean += (len - mean) / mapped` over the mapped reads in read order.  When every mapped read
+    // of the chunk has the length the mean already has (fixed-length input), the recurrence adds exact zeros; otherwise it is
+    // replayed here from the chunk's mapped bits.
+    if (const uint32_t mc = h->h_cursors[7]) {
+        const uint32_t lmin = 255u - h->h_cursors[3], lmax = h->h_cursors[4];
+        if (lmin == lmax && (h->rl_mapped == 0 || h->rl_mean == (double)lmin)) {
+            h->rl_mean = (double)lmin;
+            h->rl_mapped += mc;
+        } else {
+            std::vector<uint32_t> bits(((size_t)n + 31) / 32);
+            std::vector<uint8_t> lens(n);
+            CK(cudaMemcpyAsync(bits.data(), h->d_mapped_bits.p, bits.size() * 4, cudaMemcpyDeviceToHost, s));
+            CK(cudaMemcpyAsync(lens.data(), b.len, n, cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+            double mean = h->rl_mean;
+            uint64_t mapped = h->rl_mapped;
+            for (uint32_t r = 0; r < n; r++)
+                if ((bits[r >> 5] >> (r & 31)) & 1u) { mapped += 1; mean += ((double)lens[r] - mean) / (double)mapped; }
+            h->rl_mean = mean; h->rl_mapped = mapped;
+        }
+    }
     WqWork wk{h->d_seeds.p, h->d_hit_read.p, h->d_hit_s.p, h->d_hit_s2.p, h->d_hit_gene.p, h->d_hits.p, h->d_pool.p,
-              h->d_cursors.p, h->d_pending.p, h->d_pending2.p, hit_cap, (uint32_t)std::min<uint64_t>(h->d_pool.cap, 0xFFFFFFF0ull), h->d_defer.p};
+              h->d_cursors.p, h->d_pending.p, h->d_pending2.p, hit_cap, (uint32_t)std::min<uint64_t>(h->d_pool.cap, 0xFFFFFFF0ull), h->d_defer.p, h->d_mapped_bits.p};
     const int T = 128;
     // keyed inserts that raced with the slot owner: retry until none is left
     uint32_t pending = h->h_cursors[2];
@@ -1043,6 +1080,7 @@ int wq_map_stats_get(wq_handle* h, wq_map_stats* out) {
     CK(cudaMemcpy(&c, h->q.counters, sizeof c, cudaMemcpyDeviceToHost));
     out->total = c.total; out->mapped = c.mapped; out->multi = c.multi; out->sum_readlen = c.sum_readlen;
     out->path_overflow = c.path_overflow;
+    out->mean_readlen = h->rl_mean;
     if (c.edge_full) return fail(-8, "edge count table is full (raise WQ_EDGE_SLOTS)");
     if (c.keyed_full) return fail(-8, "keyed count store is full (raise WQ_KEYED_SLOTS / WQ_KEYED_POOL_WORDS)");
     if (c.pool_overflow) return fail(-8, "alignment path pool overflowed");

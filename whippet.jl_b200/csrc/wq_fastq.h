@@ -112,11 +112,11 @@ static inline int wq_fastq_next_impl(wq_fastq* f, uint32_t max_reads, wq_read_ba
         }
         const char* ln[5];
         ln[0] = p;
-        bool complete = true;
+        bool complete = true, open_end = false;      // open_end: the last line of the file has no newline (ln[4] = end, nothing to strip)
         for (int k = 1; k <= 4; k++) {
             const char* nl = (const char*)memchr(ln[k - 1], '\n', (size_t)(end - ln[k - 1]));
             if (!nl) {
-                if (f->eof && k == 4 && ln[3] < end) { ln[4] = end + 1; break; }     // last line without a newline
+                if (f->eof && k == 4 && ln[3] < end) { ln[4] = end; open_end = true; break; }
                 complete = false; break;
             }
             ln[k] = nl + 1;
@@ -126,13 +126,13 @@ static inline int wq_fastq_next_impl(wq_fastq* f, uint32_t max_reads, wq_read_ba
             if (!wq_fastq_fill(f, (f->text.size() - f->text_pos) + (1u << 20), false)) return -20;
             continue;
         }
-        auto line_len = [&](int k) { size_t n = (size_t)(ln[k + 1] - 1 - ln[k]); if (n && ln[k][n - 1] == '\r') n--; return n; };
+        auto line_len = [&](int k) { size_t n = (size_t)(ln[k + 1] - ln[k]) - ((k == 3 && open_end) ? 0 : 1); if (n && ln[k][n - 1] == '\r') n--; return n; };
         const size_t nl = line_len(0), sl = line_len(1), ql = line_len(3);
         if (ln[0][0] != '@' || ln[2][0] != '+') { f->err = "malformed FASTQ record " + std::to_string(f->records + recs.size() + 1) + " (expected '@' / '+' lines)"; return -21; }
         if (sl != ql) { f->err = "FASTQ record " + std::to_string(f->records + recs.size() + 1) + ": sequence and quality lengths differ"; return -21; }
         if (sl > 255) { f->err = "FASTQ record " + std::to_string(f->records + recs.size() + 1) + ": read longer than 255 (ReadLengthInt = UInt8, src/align.jl:74)"; return -21; }
         recs.push_back(Rec{(size_t)(ln[0] + 1 - base), (size_t)(ln[1] - base), (size_t)(ln[3] - base), (uint32_t)(nl - 1), (uint32_t)sl});
-        f->text_pos = (size_t)(std::min(ln[4], end) - base);
+        f->text_pos = (size_t)(ln[4] - base);
     }
     const char* text = f->text.data();
     f->cur ^= 1;
@@ -145,6 +145,7 @@ static inline int wq_fastq_next_impl(wq_fastq* f, uint32_t max_reads, wq_read_ba
     uint8_t* len = (uint8_t*)S.len.ensure(n);
     uint64_t* seq_off = (uint64_t*)S.seq_off.ensure((size_t)n * 8);
     uint64_t* qual_off = (uint64_t*)S.qual_off.ensure((size_t)n * 8);
+    if (!len || !seq_off || !qual_off) { f->err = "out of memory"; return -22; }
     S.name_off.resize(n); S.name_len.resize(n);
     uint64_t w = 0, q = 0, nm = 0;
     for (uint32_t i = 0; i < n; i++) {
@@ -154,7 +155,6 @@ static inline int wq_fastq_next_impl(wq_fastq* f, uint32_t max_reads, wq_read_ba
         q += (recs[i].len + 3) & ~3u;
         nm += recs[i].name_len;
     }
-    if (!len || !seq_off || !qual_off) { f->err = "out of memory"; return -22; }
     S.seq2_words = w; S.qual_bytes = q;
     uint64_t* seq2 = (uint64_t*)S.seq2.ensure((size_t)std::max<uint64_t>(w, 1) * 8);
     uint8_t* qual = (uint8_t*)S.qual.ensure((size_t)std::max<uint64_t>(q, 4));

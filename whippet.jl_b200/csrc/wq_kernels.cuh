@@ -97,6 +97,8 @@ struct WqWork {                    // per-batch scratch
     uint32_t* pending2;            // [n] seed queue B
     uint32_t  hit_cap, pool_cap;
     uint32_t* defer;               // [hit_cap] extension tasks the first-pass kernel hands to the second pass (count in cursors[6])
+    uint32_t* mapped_bits;         // [(n + 31) / 32] bit r = read r was mapped (running mean_readlen of src/reads.jl:69); cursors[3] = max(255 - len),
+                                   // cursors[4] = max(len), cursors[7] = mapped reads of the chunk
 };
 
 // Where a thread keeps its working alignment while extending (WqCtx.path / .side)
@@ -210,10 +212,11 @@ WQ_HD void wq_seed_finish(const WqDevIndex& ix, const WqWork& wk, uint32_t r, in
     if (cnt > 0) {
         const uint32_t base = strand ? bf : wk.hit_cap - bb - (uint32_t)cnt;
         s.hit_base = base;
-        for (int k = 0; k < cnt; k++) {
-            wk.hit_read[base + k] = r;
-            wk.hit_s[base + k] = (uint32_t)(wq_sa_value(ix, sp + k) + 1);
-        }
+        for (int k = 0; k < cnt; k++)
+            if (base + k < wk.hit_cap) {    // hit_cap = reads x seed_tolerate, so this always holds; a guard against a mis-sized launch
+                wk.hit_read[base + k] = r;
+                wk.hit_s[base + k] = (uint32_t)(wq_sa_value(ix, sp + k) + 1);
+            }
     }
     wk.seeds[r] = s;
 }

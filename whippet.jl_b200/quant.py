@@ -41,10 +41,7 @@ class MapStats:
     multi: int
     sum_readlen: int
     path_overflow: int
-
-    @property
-    def mean_readlen(self):
-        return self.sum_readlen / self.mapped if self.mapped else 0.0
+    mean_readlen: float = 0.0      # the reference's running mean in read order (src/reads.jl:69), floored by the caller
 
 
 class GraphLibQuant:
@@ -123,7 +120,7 @@ class GraphLibQuant:
         s = abi.MapStatsC()
         lib.check(self.L.wq_process_fastq(self.h, C.byref(p), fwd_path.encode(), rev_path.encode() if rev_path else None,
                                           int(qualoffset), int(batch_reads), C.byref(s)))
-        return MapStats(s.total, s.mapped, s.multi, s.sum_readlen, s.path_overflow)
+        return MapStats(s.total, s.mapped, s.multi, s.sum_readlen, s.path_overflow, s.mean_readlen)
 
     # ---- SAM output (src/io.jl:69-276) -------------------------------------------------------------
     def set_gene_info(self, seqnames, strands):
@@ -178,7 +175,7 @@ class GraphLibQuant:
     def stats(self) -> MapStats:
         s = abi.MapStatsC()
         lib.check(self.L.wq_map_stats_get(self.h, C.byref(s)))
-        return MapStats(s.total, s.mapped, s.multi, s.sum_readlen, s.path_overflow)
+        return MapStats(s.total, s.mapped, s.multi, s.sum_readlen, s.path_overflow, s.mean_readlen)
 
     def last_kernel_ms(self):
         ms = (C.c_float * 3)()

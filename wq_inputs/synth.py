@@ -5,7 +5,7 @@ inputs are fabricated: random-sequence genes whose node/edge structure follows t
 SpliceGraph (src/graph.jl:104-220: edge codes SL/SR/LS/RS/LR/LL/RR of src/graph.jl:39-46, nodes
 contiguous inside the gene sequence), the k-mer edge tables of build_edges (src/edges.jl:96-116)
 and the FM index of trans_index! (src/index.jl:64-110, sigma=4, r=1).  Index construction is
-outside the accelerated path; this module exists to feed it.
+outside the accelerated path; this module exists to feed it (test / benchmark infrastructure, not product code).
 """
 from __future__ import annotations
 
@@ -15,16 +15,16 @@ import subprocess
 
 import numpy as np
 
-from . import abi
-from .flat import FlatIndex, ReadBatch
+from whippet_jl_b200 import abi
+from whippet_jl_b200.flat import FlatIndex, ReadBatch
 
 SL, SR, LS, RS, LR, LL, RR = 0, 1, 2, 3, 4, 5, 6
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_HOST_SO = os.path.join(_HERE, "csrc", "libwq_host.so")
+_HOST_SO = os.path.join(_HERE, "libwq_host.so")
 
 
 def build_host_lib(force=False):
-    src = os.path.join(_HERE, "csrc", "sa_build.cpp")
+    src = os.path.join(_HERE, "sa_build.cpp")
     if force or not os.path.exists(_HOST_SO) or os.path.getmtime(_HOST_SO) < os.path.getmtime(src):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-o", _HOST_SO, src])
     return _HOST_SO
@@ -64,8 +64,9 @@ def _is_edge(et, left):
     return (et == LR) | (et == SR) | (et == RR)
 
 
-def build_edges(K, gene_offset, node_base, nodeoffset, edgetype, codes):
-    """build_edges / add_kmer_edge!, src/edges.jl:58-116, for all-ACGT graph sequences."""
+def build_edges(K, gene_offset, node_base, nodeoffset, edgetype, codes, seq4=None):
+    """build_edges / add_kmer_edge!, src/edges.jl:58-116.  A window that leaves the gene sequence or holds an ambiguous base
+    (seq4 not one-hot; `N` -> no table entry, k-mer value 0, :65-67) adds nothing."""
     G = len(gene_offset)
     N = len(nodeoffset)
     n = len(codes)
@@ -77,10 +78,17 @@ def build_edges(K, gene_offset, node_base, nodeoffset, edgetype, codes):
     off = nodeoffset.astype(np.int64)
     base = gene_offset.astype(np.int64)[gene_of_node]
     pw = (4 ** np.arange(K - 1, -1, -1)).astype(np.uint64)
+    ambcum = None
+    if seq4 is not None:
+        amb = ~np.isin(np.asarray(seq4), (1, 2, 4, 8))
+        if amb.any():
+            ambcum = np.concatenate([[0], np.cumsum(amb)])
 
     def kmers(start1):   # k-mer beginning at 1-based in-gene position start1
         ok = (start1 >= 1) & (start1 + K - 1 <= seqlen)
         pos = np.where(ok, base + start1 - 1, 0)
+        if ambcum is not None:
+            ok &= (ambcum[np.minimum(pos + K, n)] - ambcum[pos]) == 0
         v = np.zeros(N, np.uint64)
         for t in range(K):
             v += codes[np.minimum(pos + t, n - 1)].astype(np.uint64) * pw[t]
