@@ -222,6 +222,23 @@ int  wq_sparse_merge(wq_handle* h, const void* buf, uint64_t len);
  * rebuilt from the merged tables on the next download / wq_em_tpm. */
 int  wq_sparse_device_pack(wq_handle* h, void** dptr, uint64_t* bytes);
 int  wq_sparse_device_merge(wq_handle* h, const void* dbuf, uint64_t bytes);
+/* The exchange step of the path on several GPUs (`*_counts_sync (NCCL)`), inside the library so that a
+ * host without torch (the Julia CLI, one process per GPU) can run it.  libnccl.so.2 is opened at run time (no link-time
+ * dependency; single-GPU use never touches it).
+ *   wq_comm_unique_id   rank 0 fills 128 bytes (ncclUniqueId) and hands them to the other ranks by any means
+ *   wq_comm_init_rank   every rank: communicator of this handle (its device, its stream)
+ *   wq_counts_sync      after the last batch: ONE ncclAllReduce over the dense vector (node counts + statistics: every read
+ *                       adds the integer 1, so the sum is exact) and ONE ncclAllGather of the compacted sparse stores (edge /
+ *                       circ table, long paths, multi-map classes), merged into the device tables by kernels; one stream
+ *                       synchronisation, nothing staged through the host.  Afterwards every rank holds the whole job's counts.
+ *   wq_classes_sync     wq_classes_build_local + all-gather of the shares + wq_classes_assemble (see below)
+ * Every rank must call these in the same order.  wq_set_gene_partition(rank, nranks) is implied by wq_comm_init_rank. */
+int  wq_comm_unique_id(void* id128);
+int  wq_comm_init_rank(wq_handle* h, int nranks, int rank, const void* id128);
+int  wq_counts_sync(wq_handle* h);
+int  wq_classes_sync(wq_handle* h);
+int  wq_comm_destroy(wq_handle* h);
+
 /* Event stage partitioned by gene across ranks: this handle builds and solves the events of the contiguous gene range
  * `part` of `nparts` only and wq_process_events returns that range's records; the parts concatenate to the full output. */
 int  wq_set_gene_partition(wq_handle* h, uint32_t part, uint32_t nparts);
@@ -235,6 +252,8 @@ int  wq_classes_build_local(wq_handle* h);
 int  wq_classes_pack(wq_handle* h, const void** ptr, uint64_t* bytes);
 int  wq_classes_assemble(wq_handle* h, const void* const* bufs, const uint64_t* lens, uint32_t n);
 uint64_t wq_launch_count(wq_handle* h);   /* kernels launched by this handle so far */
+uint64_t wq_last_deferred(wq_handle* h);  /* extension tasks of the last wq_align_* call that went to the second-pass kernel (paths
+                                           * longer than the first pass's shared-memory store, or a parked candidate) */
 /* Measurement aid (no reference counterpart): device times of the quant-stage kernels of the last wq_em_tpm /
  * wq_process_events, taken with CUDA events on the launching stream, and the sizes their algorithmic-byte models use
  * (EM bytes/iteration = 12 * members + 8 * classes + 24 * isoforms).

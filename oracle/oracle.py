@@ -203,6 +203,20 @@ class Oracle:
         lib().wqo_assign_ambig(C.c_void_p(self.h))
 
     # ---- events (src/events.jl) -------------------------------------------------------------------
+    def events_flat(self, readlen):
+        """process_events over all genes, every record in the canonical flat form (see canonical_events):
+        (hdr[E,8] u32, dbl[E,3] f64, values f64, path_len u32, path_nodes u32)."""
+        L = lib()
+        L.wqo_process_events.restype = C.c_uint64
+        E = int(L.wqo_process_events(C.c_void_p(self.h), C.c_int64(readlen)))
+        n = (C.c_uint64 * 3)()
+        L.wqo_events_flat(C.c_void_p(self.h), n, None, None, None, None, None)
+        hdr, dbl = np.zeros((E, 8), "<u4"), np.zeros((E, 3), "<f8")
+        values, plen, nodes = np.zeros(int(n[0]), "<f8"), np.zeros(int(n[1]), "<u4"), np.zeros(int(n[2]), "<u4")
+        v = lambda a: a.ctypes.data_as(C.c_void_p)
+        L.wqo_events_flat(C.c_void_p(self.h), n, v(hdr), v(dbl), v(values), v(plen), v(nodes))
+        return hdr, dbl, values, plen, nodes
+
     def process_events(self, readlen):
         """process_events over all genes.  Returns a list of dicts (one per event record, gene/node order)."""
         L = lib()
@@ -233,6 +247,32 @@ class Oracle:
                     e[key] = paths
             out.append(e)
         return out
+
+
+def canonical_events(ev, vals, pptr, pnodes):
+    """The library's wq_events_out arrays (abi.EVENT_DT records, values, path_ptr, path_nodes) in the canonical flat form of
+    Oracle.events_flat, so that two numpy comparisons check every record: (hdr[E,8], dbl[E,3], values, path_len, path_nodes)."""
+    E = len(ev)
+    hdr = np.zeros((E, 8), "<u4")
+    for k, f in enumerate(("gene", "node", "motif", "kind", "flags", "n_utr", "n_inc", "n_exc")):
+        hdr[:, k] = ev[f]
+    dbl = np.stack([ev["psi"], ev["total"], ev["iterations"].astype("<f8")], axis=1) if E else np.zeros((0, 3))
+    kind, n_utr, n_inc, n_exc = hdr[:, 3], hdr[:, 5].astype(np.int64), hdr[:, 6].astype(np.int64), hdr[:, 7].astype(np.int64)
+    nv = np.where(kind == 2, n_utr, np.where((kind == 1) & (n_inc > 0) & (n_exc > 0), n_inc + n_exc, 0))
+
+    def expand(start, cnt):          # concatenated ranges start[i] .. start[i] + cnt[i]
+        tot = int(cnt.sum())
+        if tot == 0:
+            return np.zeros(0, np.int64)
+        first = np.cumsum(cnt) - cnt
+        return np.arange(tot, dtype=np.int64) - np.repeat(first, cnt) + np.repeat(start, cnt)
+    values = np.asarray(vals, "<f8")[expand(ev["value_start"].astype(np.int64), nv)] if E else np.zeros(0)
+    npaths = np.where(kind == 2, 0, n_inc + n_exc)
+    pidx = expand(ev["path_start"].astype(np.int64), npaths) if E else np.zeros(0, np.int64)
+    pptr = np.asarray(pptr, np.int64)
+    plen = (pptr[pidx + 1] - pptr[pidx]).astype("<u4") if len(pidx) else np.zeros(0, "<u4")
+    nodes = np.asarray(pnodes, "<u4")[expand(pptr[pidx], plen.astype(np.int64))] if len(pidx) else np.zeros(0, "<u4")
+    return hdr, dbl, values, plen, nodes
 
 
 def em_psi(n_inc, count, length, amb_sets, amb_mult, tandem, readlen, sig=4, maxit=1500):
@@ -282,5 +322,9 @@ def counters(reset=False):
     """Instrumentation totals since the last reset: fm_steps, hits, nodes_touched, bases, out_nodes,
     out_alns, count_updates (process-wide; only meaningful for single-threaded runs)."""
     out = (C.c_uint64 * 7)()
+    hist = (C.c_uint64 * 34)()
+    lib().wqo_steps_hist(hist)            # before the reset below
     lib().wqo_counters(out, 1 if reset else 0)
-    return dict(zip(("fm_steps", "hits", "nodes_touched", "bases", "out_nodes", "out_alns", "count_updates"), map(int, out)))
+    d = dict(zip(("fm_steps", "hits", "nodes_touched", "bases", "out_nodes", "out_alns", "count_updates"), map(int, out)))
+    d["steps_hist"] = [int(x) for x in hist]     # steps_hist[s] = backward searches that executed s steps
+    return d

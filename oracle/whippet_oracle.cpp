@@ -30,7 +30,8 @@ namespace {
 typedef int64_t Int;
 
 // instrumentation for the byte model of SURVEY.md section 8d (not part of the algorithm)
-struct Counters { uint64_t fm_steps = 0, hits = 0, nodes_touched = 0, bases = 0, out_nodes = 0, out_alns = 0, count_updates = 0; };
+struct Counters { uint64_t fm_steps = 0, hits = 0, nodes_touched = 0, bases = 0, out_nodes = 0, out_alns = 0, count_updates = 0;
+                  uint64_t steps_hist[34] = {0}; };      // steps_hist[s] = backward searches that executed s steps (byte model of a k-mer table start)
 thread_local Counters g_ctr;
 
 
@@ -104,14 +105,17 @@ void sa_range(const Lib& L, const uint8_t* q, Int len, Int& sp, Int& ep) {
     ep = L.n + 1;
     Int sentinel = (Int)L.d->sentinel;
     Int i = len;
+    Int steps = 0;
     while (sp <= ep && i >= 1) {
         uint8_t ch = q[i - 1];
         g_ctr.fm_steps++;
+        steps++;
         Int c = L.d->count[ch];
         sp = c + rank(L, ch, (sp > sentinel ? sp - 1 : sp) - 1) + 1;
         ep = c + rank(L, ch, (ep > sentinel ? ep - 1 : ep));
         i -= 1;
     }
+    g_ctr.steps_hist[steps > 33 ? 33 : steps]++;
 }
 
 // FMIndexes.sa_value at r=1 (call sites src/align.jl:240, src/paired.jl:9): row 1 is `$`
@@ -1627,6 +1631,10 @@ int wqo_process_reads_pe(wqo_handle* h, const wq_align_param* p, const wq_read_b
         if (ok) {
             if (fr.size() > 1) { push_multi_pe(Q, fr, rr, 1.0); Q.nmulti += 1; }
             else count_pe(h->L, Q, fr[0], rr[0], 1.0);
+            g_ctr.out_alns += 2 * fr.size();
+            for (auto& a2 : fr) g_ctr.out_nodes += a2.path.size();
+            for (auto& a2 : rr) g_ctr.out_nodes += a2.path.size();
+            g_ctr.count_updates += 1;
             Q.mapped += 1;
             Q.sum_readlen += a.seq.size();
             Q.mean_readlen += ((double)a.seq.size() - Q.mean_readlen) / (double)Q.mapped;
@@ -1705,6 +1713,41 @@ void wqo_event(wqo_handle* h, uint64_t i, uint32_t* header, double* vals) {
     header[0] = e.gene; header[1] = e.node; header[2] = e.motif; header[3] = e.kind; header[4] = e.flags;
     header[5] = (uint32_t)e.utr_psi.size(); header[6] = e.has_inc ? (uint32_t)e.inc.nodes.size() : 0; header[7] = e.has_exc ? (uint32_t)e.exc.nodes.size() : 0;
     vals[0] = e.psi; vals[1] = e.total; vals[2] = (double)e.iterations;
+}
+// All event records at once in a canonical flat form (what the writers of src/io.jl would print from):
+//   hdr[8 * i ..]  gene, node, motif, kind, flags, n_utr, n_inc, n_exc      dbl[3 * i ..]  psi, total, iterations
+//   values: kind 2 -> the n_utr rounded psi values; kind 1 with both graphs -> inclusion then exclusion path psi values
+//   paths (kind != 2): inclusion then exclusion node sets: path_len[] per path, path_nodes[] concatenated
+// Two calls: with NULL arrays the sizes come back in n[0..2] = {values, paths, path nodes}.
+void wqo_events_flat(wqo_handle* h, uint64_t* n, uint32_t* hdr, double* dbl, double* values, uint32_t* path_len, uint32_t* path_nodes) {
+    uint64_t nv = 0, np = 0, nn = 0;
+    for (size_t i = 0; i < h->events.size(); i++) {
+        const EventOut& e = h->events[i];
+        const uint32_t n_utr = (uint32_t)e.utr_psi.size(), n_inc = e.has_inc ? (uint32_t)e.inc.nodes.size() : 0, n_exc = e.has_exc ? (uint32_t)e.exc.nodes.size() : 0;
+        if (hdr) {
+            uint32_t* x = hdr + 8 * i;
+            x[0] = e.gene; x[1] = e.node; x[2] = e.motif; x[3] = e.kind; x[4] = e.flags; x[5] = n_utr; x[6] = n_inc; x[7] = n_exc;
+            dbl[3 * i] = e.psi; dbl[3 * i + 1] = e.total; dbl[3 * i + 2] = (double)e.iterations;
+        }
+        if (e.kind == 2) {
+            if (values) memcpy(values + nv, e.utr_psi.data(), 8 * (size_t)n_utr);
+            nv += n_utr;
+            continue;
+        }
+        if (e.kind == 1 && n_inc && n_exc) {
+            if (values) { memcpy(values + nv, e.inc.psi.data(), 8 * (size_t)n_inc); memcpy(values + nv + n_inc, e.exc.psi.data(), 8 * (size_t)n_exc); }
+            nv += n_inc + n_exc;
+        }
+        for (int w = 0; w < 2; w++) {
+            if (!(w == 0 ? e.has_inc : e.has_exc)) continue;
+            const PsiGraph& g = w == 0 ? e.inc : e.exc;
+            for (auto& st : g.nodes) {
+                if (path_len) { path_len[np] = (uint32_t)st.size(); memcpy(path_nodes + nn, st.data(), 4 * st.size()); }
+                np++; nn += st.size();
+            }
+        }
+    }
+    n[0] = nv; n[1] = np; n[2] = nn;
 }
 // path psi values: which 0 = utr (rounded psi), 1 = inclusion paths, 2 = exclusion paths
 void wqo_event_psi(wqo_handle* h, uint64_t i, int which, double* out) {
@@ -1785,6 +1828,7 @@ void wqo_counters(uint64_t* out7, int reset) {
     out7[4] = g_ctr.out_nodes; out7[5] = g_ctr.out_alns; out7[6] = g_ctr.count_updates;
     if (reset) g_ctr = Counters();
 }
+void wqo_steps_hist(uint64_t* out34) { memcpy(out34, g_ctr.steps_hist, sizeof g_ctr.steps_hist); }
 void wqo_node_counts(wqo_handle* h, double* out) { memcpy(out, h->Q.node.data(), h->Q.node.size() * 8); }
 uint64_t wqo_edge_count(wqo_handle* h) { return h->Q.edge.size(); }
 void wqo_edges(wqo_handle* h, uint64_t* keys, double* vals) {

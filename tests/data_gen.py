@@ -75,3 +75,41 @@ def pe_case(seed, ng, R, pair_range, rc, n):
     if not rc:
         r = same_strand_mate(r, R)
     return idx, p, f, r
+
+
+# ---- inputs for the branches round 1 left untested (VERDICT weak item 3) ----------------------------------------
+def refseq_subset(n_genes=600, seed=3, n_frac=0.0, paralog_families=0, K=9):
+    """The first `n_genes` loci of the refFlat-derived structure fixture ('+' and '-' strand genes, retained introns,
+    zero-length nodes), optionally with runs of N in the graph sequence (ambiguity mask of wq_text_mism)."""
+    from wq_inputs import graphbuild
+    return graphbuild.index_from_structure(graphbuild.load_structure(), K=K, seed=seed, n_genes=n_genes, n_frac=n_frac,
+                                           paralog_families=paralog_families)
+
+
+def tiny_node_index(n_chain_genes=6, chain_nodes=70, node_len=6, seed=11, K=9):
+    """Genes made of MANY tiny contiguous nodes (alternating alt-5' / alt-3' boundaries, LL / RR) next to ordinary genes:
+    a 255-bp read crosses far more than WQ_MAX_PATH = 24 nodes there, which the library must report as path_overflow
+    (the reference's path vectors are unbounded)."""
+    from wq_inputs import graphbuild as gb
+    rng = np.random.default_rng(seed)
+    node_base, nodelen, nodecoord, edgetype = [0], [], [], []
+    iso_base, iso_ptr, iso_nodes, strands, names = [0], [0], [], [], []
+    coord = 1000
+    for g in range(n_chain_genes):
+        nn = chain_nodes
+        for j in range(nn):
+            nodelen.append(node_len + int(rng.integers(0, 3)))
+            nodecoord.append(coord)
+            coord += nodelen[-1]
+        edgetype += [gb.SL] + [gb.LL if j % 2 == 0 else gb.RR for j in range(nn - 1)] + [gb.RS]
+        iso_nodes += list(range(1, nn + 1))
+        iso_ptr.append(len(iso_nodes))
+        iso_base.append(iso_base[-1] + 1)
+        node_base.append(node_base[-1] + nn)
+        strands.append(1)
+        names.append(f"chain{g}")
+        coord += 5000
+    S = dict(node_base=np.array(node_base, "<u4"), nodelen=np.array(nodelen, "<u4"), nodecoord=np.array(nodecoord, "<u4"),
+             edgetype=np.array(edgetype, "u1"), iso_base=np.array(iso_base, "<u4"), iso_ptr=np.array(iso_ptr, "<u4"),
+             iso_nodes=np.array(iso_nodes, "<u2"), strand=np.array(strands, "u1"), names=np.array(names))
+    return gb.index_from_structure(S, K=K, seed=seed)

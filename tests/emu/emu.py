@@ -18,7 +18,7 @@ def build():
     srcs = [os.path.join(_HERE, "wq_emu.cpp")] + [os.path.join(_CSRC, f) for f in
                                                    ("wq_kernels.cuh", "wq_align.cuh", "wq_types.h", "wq_host_index.h")]
     if not os.path.exists(_SO) or os.path.getmtime(_SO) < max(map(os.path.getmtime, srcs)):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-Wno-unused-function",
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-Wno-unused-function", "-Wno-unknown-pragmas",
                                "-ffp-contract=off", "-o", _SO, srcs[0]])
     return _SO
 

@@ -177,3 +177,33 @@ def test_node_set_windows():
     L.hemu_bitwin_selftest.restype = C.c_uint64
     for span in (5, 64, 65, 128, 129, 400):
         assert L.hemu_bitwin_selftest(C.c_uint32(span), C.c_uint32(3000), C.c_uint64(12345 + span)) == 0, span
+
+
+def test_paired_assign_ambig_stale_iset_equals_oracle():
+    """Paired multi-map classes: the library's host stage and the oracle both hand the FIRST alignment of a class the isoform
+    ids left in ambig.iset by the last one (src/quant.jl:493-501, 541-551); few genes and many paralogs make the collision
+    of mate-2 node ids with small isoform ids common."""
+    idx = synth.make_index(n_genes=12, K=9, seed=31, paralog_frac=1.0)
+    f, r = synth.simulate_reads(idx, 40000, 76, seed=32, sub_rate=0.005, paired=True)
+    p = wq.AlignParam(seed_pair_range=5000, is_paired=True, is_pair_rc=True)
+    o = Oracle(idx)
+    o.process_paired_reads(p, f, r)
+    ek, ev = o.edges()
+    counts = dict(node=o.node_counts().astype("<u8"), ekey=ek, ecount=ev.astype("<u8"), longs=o.keyed(0), multis=o.keyed(1))
+    assert len(counts["multis"]) > 50
+    o.em_tpm(76)
+    props = [x for c in o.classes(multi=True) for x in c[1]] + [x for c in o.classes(multi=False) for x in c[1]]
+    import ctypes as C
+    from oracle import lib
+    tpm, cnt, genetpm = np.zeros(idx.n_isoforms), np.zeros(idx.n_isoforms), np.zeros(idx.n_genes)
+    v = lambda a: a.ctypes.data_as(C.c_void_p)
+    lib().wqo_em_results(C.c_void_p(o.h), v(tpm), v(cnt), v(genetpm))
+    e = HostEmu(idx)
+    e.set_counts(**counts)
+    e.build_classes()
+    node, gk, gv = e.assign_ambig(props, genetpm)
+    o.assign_ambig()
+    wk, wv = o.edges()
+    assert np.array_equal(node, o.node_counts())
+    assert np.array_equal(gk, wk) and np.array_equal(gv, wv)
+    e.close()

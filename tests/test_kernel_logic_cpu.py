@@ -10,7 +10,7 @@ import pytest
 import whippet_jl_b200 as wq
 from wq_inputs import synth
 from conftest import GOLDEN
-from data_gen import PE_CASES, fixture_random_reads, pe_case, ragged_reads
+from data_gen import PE_CASES, fixture_random_reads, pe_case, ragged_reads, refseq_subset, tiny_node_index
 from emu.emu import Emu
 from helpers_cmp import results_equal
 from oracle import Oracle
@@ -92,3 +92,44 @@ def test_paired_end(seed, ng, R, pr, rc):
     el, em = e.keyed()
     assert o.keyed(0) == {k: float(v) for k, v in el.items()}
     assert o.keyed(1) == {k: float(v) for k, v in em.items()}
+
+
+def test_real_structure_minus_strand_and_ambiguous_bases():
+    """'-' strand genes, retained introns and zero-length nodes of the refFlat-derived structures; runs of N in the graph text
+    (the ambiguity mask of wq_text_mism, which no round-1 input reached)."""
+    idx = refseq_subset(600, seed=3, n_frac=0.002)
+    assert (np.asarray(idx.gene_strand) == 0).sum() > 200 and (~np.isin(idx.seq4, (1, 2, 4, 8))).sum() > 1000
+    rb = synth.simulate_reads(idx, 30000, 101, seed=4, sub_rate=0.01)
+    ro = compare_all(idx, wq.AlignParam(), rb)
+    assert (ro.nhits > 0).mean() > 0.9
+
+
+def test_path_overflow_reported_and_second_pass():
+    idx = tiny_node_index()
+    p = wq.AlignParam()
+    rb = synth.simulate_reads(idx, 5000, 101, seed=5, sub_rate=0.002)
+    o, e = Oracle(idx), Emu(idx)
+    d0 = e.ext_stats()["deferred"]
+    ro, re = o.align_se(p, rb), e.align_se(p, rb)
+    assert results_equal(ro, re, rb.n) == [] and ro.aln["npath"].max() > 12
+    assert e.ext_stats()["deferred"] - d0 > 500 and e.counters()["path_overflow"] == 0
+    rb = synth.simulate_reads(idx, 5000, 255, seed=6, sub_rate=0.002)
+    o, e = Oracle(idx), Emu(idx)
+    ro, re = o.align_se(p, rb), e.align_se(p, rb)
+    assert ro.aln["npath"].max() > 24 and e.counters()["path_overflow"] > 1000
+    for i in range(rb.n):
+        if any(len(a[4]) > 24 for a in ro.read(i)):
+            assert re.nhits[i] == 0
+        if re.nhits[i]:
+            assert re.read(i) == ro.read(i)
+
+
+def test_small_k_parked_candidates():
+    idx = synth.make_index(n_genes=100, K=2, seed=23, paralog_frac=0.2, exon_median=12.0, utr_median=36.0)
+    rb = synth.simulate_reads(idx, 20000, 40, seed=24, sub_rate=0.02)
+    p = wq.AlignParam(mismatches=3, kmer_size=2, seed_try=3, seed_tolerate=6, seed_length=12, seed_buffer=2, seed_inc=7)
+    e = Emu(idx)
+    s0 = e.ext_stats()
+    compare_all(idx, p, rb)
+    s1 = Emu(idx).ext_stats()
+    assert s1["parks"] - s0["parks"] > 100 and s1["unparks"] - s0["unparks"] > 50

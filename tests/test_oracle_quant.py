@@ -53,6 +53,29 @@ def test_multimapping_classes_and_assign_ambig(fixture_index, test_param):
     assert dict(zip(k.tolist(), v.tolist()))[(2 << 32) | (1 << 16) | 2] == 2.5
 
 
+def test_paired_assign_ambig_stale_iset_known_answer(fixture_index):
+    """Hand-worked: a paired multi-map class of two alignments in gene `one` (geneidx 2, isoform ids 3,4,5),
+    A1 = (mate 1 [node 1], mate 2 [node 3]) and A2 = (mate 1 [node 1], mate 2 [node 5]), count 10.  Both are compatible with all
+    three isoforms, so each gets 5.  assign_ambig! (src/quant.jl:520-553) leaves ambig.iset = {3,4,5} (the isoform ids of A2, set
+    by the last set_equivalence_class!, :499-508) when it spreads A1: assign_path! (:283-323) adds node 1 to the set, then finds
+    mate-2 node 3 `in temp_iset` -- it is isoform id 3 -- and SKIPS it; the set is emptied, A2 then adds node 1 and node 5.
+    Expected: node 1 += 10, node 3 += 0 (5 without the stale ids), node 5 += 5."""
+    idx = fixture_index
+    o = Oracle(idx)
+    o.quant_reset()
+    pair = lambda f, r: [(2 << 28) | len(f) | (len(r) << 8), 2] + f + r
+    o.add_keyed(1, [(3 << 28) | 2] + pair([1], [3]) + pair([1], [5]), 10.0)
+    o.em_tpm(20, maxit=1)
+    (ids, props, cnt, isdone, post), = o.classes(multi=True)
+    assert ids == [3, 4, 5] and not post and cnt == 10.0
+    nb = int(idx.node_base[1])
+    before = o.node_counts().copy()
+    o.assign_ambig()
+    d = o.node_counts() - before
+    assert d[nb + 0] == 10.0 and d[nb + 2] == 0.0 and d[nb + 4] == 5.0
+    assert d.sum() == 15.0
+
+
 def test_isoform_classes_and_tpm(fixture_index, test_param):
     """test/runtests.jl:440-470, 513-522: EM changes TPM, converges in < 5000 iterations, sum(tpm) == 1e6."""
     idx = fixture_index

@@ -12,6 +12,7 @@ f64p = C.POINTER(C.c_double)
 i32p = C.POINTER(C.c_int32)
 
 WQ_MAX_PATH = 24
+WQ_FAST_PATH = 12      # path capacity of the first-pass extension kernel (csrc/wq_types.h)
 WQ_MAX_TOLERATE = 8
 
 

@@ -31,7 +31,7 @@ def build_cuda(force=False, verbose=False):
     if not force and not cuda_stale():
         return CUDA_SO
     cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
-           "-Xcompiler", "-fPIC", "-shared", "-o", CUDA_SO, os.path.join(CSRC, "whippet_b200.cu"), "-lz"]
+           "-Xcompiler", "-fPIC", "-shared", "-o", CUDA_SO, os.path.join(CSRC, "whippet_b200.cu"), "-lz", "-ldl"]
     if verbose:
         cmd[1:1] = ["-Xptxas", "-v"]
     subprocess.check_call(cmd)

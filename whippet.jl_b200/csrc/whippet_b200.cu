@@ -24,6 +24,7 @@
 #include "wq_fastq.h"
 #include "wq_sam.h"
 #include <future>
+#include <dlfcn.h>
 
 #include <chrono>
 struct WqTimer {
@@ -123,6 +124,11 @@ struct wq_handle {
     DevBuf<uint64_t> d_ck, d_cv, d_ck2, d_cv2; DevBuf<uint32_t> d_ckoff; DevBuf<uint8_t> d_cubtmp;
     DevBuf<uint64_t> d_xpack; DevBuf<uint32_t> d_xpending;      // multi-GPU exchange: this rank's packed sparse stores / merge queue
     uint32_t part = 0, nparts = 1;                              // gene partition of the event stage (wq_set_gene_partition)
+    // multi-GPU exchange inside the library (wq_comm_init_rank / wq_counts_sync / wq_classes_sync)
+    void* nccl_comm = nullptr; int comm_rank = 0, comm_size = 1;
+    DevBuf<uint64_t> d_xgather; uint64_t xcap = 1ull << 20;    // words per rank of the sparse all-gather (same on every rank: derived from shared headers)
+    uint64_t* h_xhdr = nullptr;                                // pinned: the ranks' pack headers
+    DevBuf<uint8_t> d_cshare, d_cgather; uint64_t ccap = 1ull << 20; uint8_t* h_cgather = nullptr; size_t h_cgather_cap = 0;
     bool hq_valid = false;
     uint32_t chunk_reads = 1u << 22;
     float last_kernel_ms[3] = {0, 0, 0};
@@ -324,6 +330,59 @@ __global__ void __launch_bounds__(256) wq_k_ftab(const __grid_constant__ WqDevIn
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = wq_ftab_entry(ix, i, k);
 }
 
+// Sparse stores of this rank, compacted (wq_k_compact_*), laid out as ONE record for the all-gather without the host knowing
+// the sizes: {n_edge, n_keyed, pool_words, total_words}, edge_key[ne], edge_count[ne], keyed_count[nk], then u32 keyed_off[nk]
+// (padded to even) and pool[pool_words] (padded to even).  A record longer than `cap` words carries its header only.
+__device__ __forceinline__ uint64_t wq_pack_words(uint64_t ne, uint64_t nk, uint64_t kw) {
+    return 4 + 2 * ne + nk + ((nk + 1) & ~1ull) / 2 + ((kw + 1) & ~1ull) / 2;
+}
+__global__ void __launch_bounds__(256) wq_k_pack_sparse(uint64_t* __restrict__ buf, const uint64_t cap, const uint32_t* __restrict__ counts,
+                                                        const uint64_t* __restrict__ kcursor, const uint64_t* __restrict__ ck,
+                                                        const uint64_t* __restrict__ cv, const uint64_t* __restrict__ kcnt,
+                                                        const uint32_t* __restrict__ koff, const uint32_t* __restrict__ pool) {
+    const uint64_t ne = counts[0], nk = counts[1], kw = *kcursor;
+    const uint64_t total = wq_pack_words(ne, nk, kw);
+    const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, T = (uint64_t)gridDim.x * blockDim.x;
+    if (tid == 0) { buf[0] = ne; buf[1] = nk; buf[2] = kw; buf[3] = total; }
+    if (total > cap) return;
+    uint64_t* ekey = buf + 4;
+    uint64_t* ecount = ekey + ne;
+    uint64_t* kcount = ecount + ne;
+    uint32_t* ko = (uint32_t*)(kcount + nk);
+    uint32_t* pl = ko + ((nk + 1) & ~1ull);
+    for (uint64_t i = tid; i < ne; i += T) { ekey[i] = ck[i]; ecount[i] = cv[i]; }
+    for (uint64_t i = tid; i < nk; i += T) { kcount[i] = kcnt[i]; ko[i] = koff[i]; }
+    for (uint64_t i = tid; i < kw; i += T) pl[i] = pool[i];
+}
+// every rank's header says its record fits: the merge of all peers happens, or none of it (all ranks see the same headers)
+__device__ __forceinline__ bool wq_gather_ok(const uint64_t* g, uint64_t cap, int world) {
+    for (int r = 0; r < world; r++) if (g[(uint64_t)r * cap + 3] > cap) return false;
+    return true;
+}
+__global__ void __launch_bounds__(256) wq_k_merge_gathered(const WqQuantDev q, const uint64_t* __restrict__ g, const uint64_t cap, const int world,
+                                                           const int peer, uint32_t* pending, uint32_t* cursor, const int pass) {
+    if (!wq_gather_ok(g, cap, world)) return;
+    const uint64_t* buf = g + (uint64_t)peer * cap;
+    const uint64_t ne = buf[0], nk = buf[1];
+    const uint64_t* ekey = buf + 4;
+    const uint64_t* ecount = ekey + ne;
+    const uint64_t* kcount = ecount + ne;
+    const uint32_t* koff = (const uint32_t*)(kcount + nk);
+    const uint32_t* pool = koff + ((nk + 1) & ~1ull);
+    const uint64_t total = pass == 0 ? ne + nk : (uint64_t)*cursor;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t j;
+        if (pass == 0) {
+            if (i < ne) { if (wq_edge_insert(q.edges, ekey[i], ecount[i])) atomicAdd((unsigned long long*)&q.counters->edge_full, 1ull); continue; }
+            j = i - ne;
+        } else j = pending[i];
+        const uint32_t off = koff[j];
+        const int rc = wq_keyed_insert(q.keyed, pool + off + 1, (int)pool[off], kcount[j]);
+        if (rc == 1 && pass == 0) pending[atomicAdd(cursor, 1u)] = (uint32_t)j;
+        else if (rc != 0) atomicAdd((unsigned long long*)&q.counters->keyed_full, 1ull);
+    }
+}
+
 __global__ void wq_k_fill_u64(uint64_t* p, uint64_t v, uint64_t n) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
@@ -348,6 +407,7 @@ static cudaError_t upload(DevBuf<T>& d, const T* src, size_t n, cudaStream_t s) 
 
 extern "C" {
 
+int wq_comm_destroy(wq_handle* h);
 const char* wq_last_error(void) { return g_err.c_str(); }
 int wq_version(void) { return 100; }
 
@@ -376,6 +436,10 @@ void wq_destroy(wq_handle* h) {
     h->d_seeds.release(); h->d_hit_read.release(); h->d_hit_s.release(); h->d_hit_s2.release(); h->d_hit_gene.release(); h->d_pending.release(); h->d_pending2.release();
     h->d_cursors.release(); h->d_hits.release(); h->d_pool.release(); h->d_defer.release(); h->d_slab.release(); h->d_mapped_bits.release();
     h->em_scratch.release(); h->ev_batch[0].release(); h->ev_batch[1].release(); h->d_ck.release(); h->d_cv.release(); h->d_ck2.release(); h->d_cv2.release(); h->d_ckoff.release(); h->d_cubtmp.release(); h->d_xpack.release(); h->d_xpending.release();
+    wq_comm_destroy(h);
+    h->d_xgather.release(); h->d_cshare.release(); h->d_cgather.release();
+    if (h->h_xhdr) cudaFreeHost(h->h_xhdr);
+    if (h->h_cgather) cudaFreeHost(h->h_cgather);
     if (h->h_cursors) cudaFreeHost(h->h_cursors);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
@@ -1063,6 +1127,7 @@ int wq_set_stream(wq_handle* h, void* stream) {
 }
 
 uint64_t wq_launch_count(wq_handle* h) { return h ? h->launches : 0; }
+uint64_t wq_last_deferred(wq_handle* h) { return h ? h->last_deferred : 0; }
 
 int wq_quant_kernel_stats(wq_handle* h, double* out8) {
     if (!h || !out8) return fail(-1, "null argument");
@@ -1296,6 +1361,158 @@ int wq_sparse_device_merge(wq_handle* h, const void* dbuf, uint64_t bytes) {
     h->hq_valid = false;             // the host-side stores are pulled again from the merged tables
     reset_quant_ex(h);
     return 0;
+}
+
+// ---- multi-GPU exchange inside the library --------------------------------------------------------------------------------
+// libnccl.so.2 is opened at run time: the few entry points used have had the same signatures since NCCL 2.0.
+struct WqNcclId { char internal[128]; };
+struct WqNccl {
+    void* lib = nullptr;
+    int (*GetUniqueId)(void*) = nullptr;
+    int (*CommInitRank)(void**, int, /* ncclUniqueId by value: 128 bytes */ WqNcclId, int) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+static WqNccl g_nccl;
+static std::string wq_nccl_load() {
+    if (g_nccl.lib) return "";
+    const char* names[] = {getenv("WQ_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    void* lib = nullptr;
+    for (const char* n : names) if (n && *n && (lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL))) break;
+    if (!lib) return std::string("cannot open libnccl.so.2 (set WQ_NCCL_LIB): ") + (dlerror() ? dlerror() : "");
+    auto sym = [&](const char* n) { return dlsym(lib, n); };
+    g_nccl.GetUniqueId = (int (*)(void*))sym("ncclGetUniqueId");
+    g_nccl.CommInitRank = (int (*)(void**, int, WqNcclId, int))sym("ncclCommInitRank");
+    g_nccl.CommDestroy = (int (*)(void*))sym("ncclCommDestroy");
+    g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))sym("ncclAllReduce");
+    g_nccl.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))sym("ncclAllGather");
+    g_nccl.GetErrorString = (const char* (*)(int))sym("ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.AllReduce || !g_nccl.AllGather) return "libnccl.so.2 lacks an expected entry point";
+    g_nccl.lib = lib;
+    return "";
+}
+#define NK(call)                                                                                                    \
+    do {                                                                                                            \
+        int r_ = (call);                                                                                            \
+        if (r_ != 0) return fail(-30, std::string(#call) + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r_) : "NCCL error")); \
+    } while (0)
+enum { WQ_NCCL_UINT8 = 1, WQ_NCCL_UINT64 = 5, WQ_NCCL_SUM = 0 };
+
+int wq_comm_unique_id(void* id128) {
+    if (!id128) return fail(-1, "null argument");
+    std::string e = wq_nccl_load();
+    if (!e.empty()) return fail(-30, e);
+    NK(g_nccl.GetUniqueId(id128));
+    return 0;
+}
+int wq_comm_init_rank(wq_handle* h, int nranks, int rank, const void* id128) {
+    if (!h || !id128) return fail(-1, "null argument");
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail(-1, "rank out of range");
+    std::string e = wq_nccl_load();
+    if (!e.empty()) return fail(-30, e);
+    CK(cudaSetDevice(h->device));
+    wq_comm_destroy(h);
+    WqNcclId id;
+    memcpy(&id, id128, sizeof id);
+    NK(g_nccl.CommInitRank(&h->nccl_comm, nranks, id, rank));
+    h->comm_rank = rank; h->comm_size = nranks;
+    if (!h->h_xhdr) CK(cudaHostAlloc((void**)&h->h_xhdr, 1024 * 4 * sizeof(uint64_t), cudaHostAllocDefault));
+    return wq_set_gene_partition(h, (uint32_t)rank, (uint32_t)nranks);
+}
+int wq_comm_destroy(wq_handle* h) {
+    if (!h || !h->nccl_comm) return 0;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (g_nccl.CommDestroy) g_nccl.CommDestroy(h->nccl_comm);
+    h->nccl_comm = nullptr; h->comm_rank = 0; h->comm_size = 1;
+    return 0;
+}
+
+int wq_counts_sync(wq_handle* h) {
+    if (!h) return fail(-1, "null handle");
+    if (!h->nccl_comm) return fail(-31, "wq_counts_sync needs wq_comm_init_rank first");
+    if (h->comm_size > 1024) return fail(-31, "more than 1024 ranks");
+    WqTimer tm_("counts_sync");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    const int W = h->comm_size;
+    CK(h->d_ck.ensure(h->edge_slots)); CK(h->d_cv.ensure(h->edge_slots));
+    CK(h->d_ckoff.ensure(h->keyed_slots)); CK(h->d_cv2.ensure(h->keyed_slots));
+    for (int attempt = 0;; attempt++) {
+        const uint64_t cap = h->xcap;
+        CK(h->d_xpack.ensure(cap)); CK(h->d_xgather.ensure(cap * (uint64_t)W)); CK(h->d_xpending.ensure(cap));
+        CK(cudaMemsetAsync(h->d_cursors.p + 12, 0, 2 * sizeof(uint32_t), s));
+        wq_k_compact_edges<<<1184, 256, 0, s>>>(h->d_ekey.p, h->d_ecount.p, h->edge_slots, h->d_ck.p, h->d_cv.p, h->d_cursors.p + 12);
+        wq_k_compact_keyed<<<1184, 256, 0, s>>>(h->d_khash.p, h->d_koff.p, h->d_kcount.p, h->keyed_slots, h->d_ckoff.p, h->d_cv2.p, h->d_cursors.p + 13);
+        wq_k_pack_sparse<<<592, 256, 0, s>>>(h->d_xpack.p, cap, h->d_cursors.p + 12, h->d_kcursor.p, h->d_ck.p, h->d_cv.p, h->d_cv2.p, h->d_ckoff.p, h->d_kpool.p);
+        h->launches += 3;
+        CK(cudaGetLastError());
+        NK(g_nccl.AllGather(h->d_xpack.p, h->d_xgather.p, cap, WQ_NCCL_UINT64, h->nccl_comm, s));
+        for (int r = 0; r < W; r++) {
+            if (r == h->comm_rank) continue;
+            CK(cudaMemsetAsync(h->d_cursors.p + 14, 0, sizeof(uint32_t), s));
+            wq_k_merge_gathered<<<592, 256, 0, s>>>(h->q, h->d_xgather.p, cap, W, r, h->d_xpending.p, h->d_cursors.p + 14, 0);
+            wq_k_merge_gathered<<<148, 256, 0, s>>>(h->q, h->d_xgather.p, cap, W, r, h->d_xpending.p, h->d_cursors.p + 14, 1);
+            h->launches += 2;
+        }
+        CK(cudaGetLastError());
+        // the ranks' headers (4 words each, `cap` words apart) in one strided copy, then the only synchronisation of the exchange
+        CK(cudaMemcpy2DAsync(h->h_xhdr, 4 * sizeof(uint64_t), h->d_xgather.p, cap * sizeof(uint64_t), 4 * sizeof(uint64_t), (size_t)W, cudaMemcpyDeviceToHost, s));
+        if (attempt == 0)       // dense vector: node counts + the scalar statistics (exact integer sums), once
+            NK(g_nccl.AllReduce(h->d_dense.p, h->d_dense.p, h->H.N + sizeof(WqCounters) / 8, WQ_NCCL_UINT64, WQ_NCCL_SUM, h->nccl_comm, s));
+        CK(cudaStreamSynchronize(s));
+        uint64_t need = 0;
+        for (int r = 0; r < W; r++) need = std::max(need, h->h_xhdr[4 * r + 3]);
+        const bool fits = need <= cap;
+        // next capacity: a quarter above the largest record seen (identical on every rank: all ranks read the same headers)
+        h->xcap = std::max<uint64_t>(1ull << 16, need + need / 4 + 1024);
+        if (fits) break;
+        if (attempt >= 2) return fail(-31, "sparse exchange did not fit after growing the buffers");
+    }
+    h->hq = WqHostQuant();
+    h->hq_valid = false;             // the host-side stores are pulled from the merged tables
+    reset_quant_ex(h);
+    return 0;
+}
+
+int wq_classes_sync(wq_handle* h) {
+    if (!h) return fail(-1, "null handle");
+    if (!h->nccl_comm) return fail(-31, "wq_classes_sync needs wq_comm_init_rank first");
+    if (int rc = wq_classes_build_local(h)) return rc;
+    WqTimer tm_("classes_sync (exchange + assemble)");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    const int W = h->comm_size;
+    const uint64_t mine = h->class_pack.size();
+    for (int attempt = 0;; attempt++) {
+        const uint64_t cap = h->ccap;                    // bytes per rank, multiple of 16: [u64 length][bytes]
+        CK(h->d_cshare.ensure(cap)); CK(h->d_cgather.ensure(cap * (uint64_t)W));
+        if (cap * (uint64_t)W > h->h_cgather_cap) {
+            if (h->h_cgather) cudaFreeHost(h->h_cgather);
+            h->h_cgather = nullptr; h->h_cgather_cap = 0;
+            CK(cudaHostAlloc((void**)&h->h_cgather, cap * (uint64_t)W, cudaHostAllocDefault));
+            h->h_cgather_cap = cap * (uint64_t)W;
+        }
+        CK(cudaMemcpyAsync(h->d_cshare.p, &mine, 8, cudaMemcpyHostToDevice, s));
+        if (mine + 8 <= cap && mine) CK(cudaMemcpyAsync(h->d_cshare.p + 8, h->class_pack.data(), mine, cudaMemcpyHostToDevice, s));
+        NK(g_nccl.AllGather(h->d_cshare.p, h->d_cgather.p, cap, WQ_NCCL_UINT8, h->nccl_comm, s));
+        CK(cudaMemcpyAsync(h->h_cgather, h->d_cgather.p, cap * (uint64_t)W, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        uint64_t need = 0;
+        for (int r = 0; r < W; r++) { uint64_t len; memcpy(&len, h->h_cgather + (uint64_t)r * cap, 8); need = std::max(need, len + 8); }
+        const bool fits = need <= cap;
+        h->ccap = (std::max<uint64_t>(1ull << 16, need + need / 4 + 1024) + 15) & ~15ull;
+        if (fits) {
+            std::vector<const void*> bufs(W);
+            std::vector<uint64_t> lens(W);
+            for (int r = 0; r < W; r++) { memcpy(&lens[r], h->h_cgather + (uint64_t)r * cap, 8); bufs[r] = h->h_cgather + (uint64_t)r * cap + 8; }
+            // wq_classes_assemble updates ccap-independent state only; the next call's capacity was fixed above from the shared lengths
+            return wq_classes_assemble(h, bufs.data(), lens.data(), (uint32_t)W);
+        }
+        if (attempt >= 2) return fail(-31, "class exchange did not fit after growing the buffers");
+    }
 }
 
 // Event stage partitioned by gene (north_star: "EM is then partitioned by gene"): this handle builds and solves the events of

@@ -71,8 +71,15 @@ def load():
     L.wq_sam_batch.argtypes = [vp, C.POINTER(abi.ReadBatchC), C.POINTER(abi.ReadBatchC),
                                abi.u64p, abi.u32p, C.c_char_p, abi.u64p, abi.u32p, C.c_char_p,
                                C.POINTER(abi.AlignOutC), C.c_int, C.c_char_p, C.c_uint64, C.POINTER(C.c_uint64)]
+    L.wq_comm_unique_id.argtypes = [vp]
+    L.wq_comm_init_rank.argtypes = [vp, C.c_int, C.c_int, C.c_char_p]
+    L.wq_counts_sync.argtypes = [vp]
+    L.wq_classes_sync.argtypes = [vp]
+    L.wq_comm_destroy.argtypes = [vp]
     L.wq_launch_count.argtypes = [vp]
     L.wq_launch_count.restype = C.c_uint64
+    L.wq_last_deferred.argtypes = [vp]
+    L.wq_last_deferred.restype = C.c_uint64
     L.wq_quant_kernel_stats.argtypes = [vp, C.POINTER(C.c_double)]
     _lib = L
     return L

@@ -177,6 +177,10 @@ class GraphLibQuant:
         lib.check(self.L.wq_map_stats_get(self.h, C.byref(s)))
         return MapStats(s.total, s.mapped, s.multi, s.sum_readlen, s.path_overflow, s.mean_readlen)
 
+    def last_deferred(self) -> int:
+        """Extension tasks of the last alignment call that went to the second-pass kernel."""
+        return int(self.L.wq_last_deferred(self.h))
+
     def last_kernel_ms(self):
         ms = (C.c_float * 3)()
         lib.check(self.L.wq_last_kernel_ms(self.h, ms))
@@ -242,6 +246,11 @@ class GraphLibQuant:
         v.circ_key, v.circ_value = abi.ptr(ck, abi.u64p), abi.ptr(cv, abi.f64p)
         lib.check(self.L.wq_assign_ambig(self.h, C.byref(v)))
         return node, ek, ev, ck, cv
+
+    def assign_ambig_inplace(self):
+        """assign_ambig! without copying the stores out (the event stage reads them inside the library)."""
+        v = abi.ValuesC()
+        lib.check(self.L.wq_assign_ambig(self.h, C.byref(v)))
 
     def process_events_raw(self, readlen: int):
         """Same as process_events but returns the flat arrays of wq_events_out:
@@ -328,6 +337,31 @@ class GraphLibQuant:
         return out
 
     # ---- multi-GPU exchange ---------------------------------------------------------------------
+    def comm_init(self, dist=None, nranks=None, rank=None, unique_id: bytes | None = None):
+        """NCCL communicator of this handle inside the library (wq_comm_unique_id / wq_comm_init_rank).  With a
+        torch.distributed module the 128-byte id is made on rank 0 and broadcast over that process group; a host without
+        torch passes (nranks, rank, unique_id) obtained by any other means."""
+        if dist is not None:
+            nranks, rank = dist.get_world_size(), dist.get_rank()
+            box = [None]
+            if rank == 0:
+                buf = C.create_string_buffer(128)
+                lib.check(self.L.wq_comm_unique_id(buf))
+                box[0] = buf.raw
+            dist.broadcast_object_list(box, src=0)
+            unique_id = box[0]
+        lib.check(self.L.wq_comm_init_rank(self.h, int(nranks), int(rank), C.c_char_p(unique_id)))
+        self._lib_comm = True
+
+    def counts_sync(self):
+        """wq_counts_sync: ONE ncclAllReduce of the dense counts + ONE ncclAllGather of the compacted sparse stores, merged on
+        the device, one stream synchronisation."""
+        lib.check(self.L.wq_counts_sync(self.h))
+
+    def classes_sync(self):
+        """wq_classes_sync: this rank's share of the classes, all-gathered over the library's communicator, assembled."""
+        lib.check(self.L.wq_classes_sync(self.h))
+
     def dense_tensor(self):
         """torch view of the device-resident dense vector (node counts + total/mapped/multi/sum_readlen)."""
         import torch
@@ -385,8 +419,11 @@ class GraphLibQuant:
         lib.check(self.L.wq_classes_assemble(self.h, bufs, lens, len(shares)))
 
     def build_classes_distributed(self):
-        """Class building partitioned by gene across the ranks of torch.distributed (after allreduce_counts and
-        set_gene_partition(rank, world)): local share -> NCCL all-gather -> complete class set on every rank."""
+        """Class building partitioned by gene across ranks: inside the library when it has a communicator (comm_init),
+        else over torch.distributed (after allreduce_counts and set_gene_partition(rank, world)): local share -> NCCL
+        all-gather -> complete class set on every rank."""
+        if getattr(self, "_lib_comm", False):
+            return self.classes_sync()
         import torch
         import torch.distributed as dist
         world, rank = dist.get_world_size(), dist.get_rank()

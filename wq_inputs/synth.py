@@ -274,19 +274,25 @@ def make_index(n_genes=2000, K=9, seed=1, mean_exons=8.0, paralog_frac=0.02, thr
 # read simulation
 # ------------------------------------------------------------------------------------------
 class Transcriptome:
-    """Isoform sequences (concatenated node sequences of each annotated path)."""
+    """Sequences of node paths (by default the annotated isoforms): concatenated node sequences of each path.
+    `paths` = (gene_of_path 0-based [P], ptr [P+1], nodes 1-based within the gene) samples reads from arbitrary paths,
+    e.g. every exon-skipping combination of a stress gene, annotated or not."""
 
-    def __init__(self, idx: FlatIndex):
+    def __init__(self, idx: FlatIndex, paths=None):
         codes = np.zeros(len(idx.seq4), np.uint8)
         for v, c in ((1, 0), (2, 1), (4, 2), (8, 3)):
             codes[idx.seq4 == v] = c
-        I = idx.n_isoforms
-        gene_of_iso = np.repeat(np.arange(idx.n_genes), np.diff(idx.iso_base))
-        iso_of_entry = np.repeat(np.arange(I), np.diff(idx.iso_node_ptr))
+        if paths is None:
+            gene_of_iso = np.repeat(np.arange(idx.n_genes), np.diff(idx.iso_base))
+            ptr, nodes = np.asarray(idx.iso_node_ptr, np.int64), np.asarray(idx.iso_nodes, np.int64)
+        else:
+            gene_of_iso, ptr, nodes = (np.asarray(x, np.int64) for x in paths)
+        I = len(ptr) - 1
+        iso_of_entry = np.repeat(np.arange(I), np.diff(ptr))
         g = gene_of_iso[iso_of_entry]
-        slot = idx.node_base[g].astype(np.int64) + idx.iso_nodes.astype(np.int64) - 1
-        start = idx.gene_offset[g].astype(np.int64) + idx.nodeoffset[slot].astype(np.int64) - 1
-        ln = idx.nodelen[slot].astype(np.int64)
+        slot = np.asarray(idx.node_base, np.int64)[g] + nodes - 1
+        start = np.asarray(idx.gene_offset, np.int64)[g] + np.asarray(idx.nodeoffset, np.int64)[slot] - 1
+        ln = np.asarray(idx.nodelen, np.int64)[slot]
         tot = int(ln.sum())
         # expand (start, len) runs into positions
         run_start = np.cumsum(ln) - ln
@@ -356,3 +362,102 @@ def simulate_reads(idx: FlatIndex, n_reads: int, readlen: int = 101, seed: int =
         lens = np.asarray(lens, "u1")
     batches = [ReadBatch.from_codes(c, q, lens) for c, q in zip(out_codes, out_qual)]
     return batches[0] if not paired else tuple(batches)
+
+
+# ------------------------------------------------------------------------------------------
+# BASELINE config 5: "complex-event PSI EM stress (high-entropy AS events)"
+# ------------------------------------------------------------------------------------------
+def make_stress_index(n_genes=2000, K=9, seed=5, cassettes=(6, 10), exon_len=(60, 140), threads=None):
+    """Genes of one first exon, c consecutive cassette exons (c in `cassettes`) and one last exon, every boundary an intron
+    (LR).  Two isoforms are annotated (all cassettes in / all out); the reads come from random subsets (stress_paths), so
+    every skip junction is expressed and the events of a cassette node have 2^6 .. 2^10 = 64 .. 1024 paths, the bound below
+    which the reference does not subsample at random (src/events.jl:234-238)."""
+    rng = np.random.default_rng(seed)
+    node_base, nodelen, nodecoord, edgetype = [0], [], [], []
+    iso_base, iso_ptr, iso_nodes = [0], [0], []
+    coord = 1000
+    for g in range(n_genes):
+        c = int(rng.integers(cassettes[0], cassettes[1] + 1))
+        nn = c + 2
+        nl = rng.integers(exon_len[0], exon_len[1] + 1, nn)
+        nl[0] += 150
+        nl[-1] += 150
+        for j in range(nn):
+            nodelen.append(int(nl[j]))
+            nodecoord.append(coord)
+            coord += int(nl[j]) + int(rng.integers(100, 2000))
+        edgetype += [SL] + [LR] * (nn - 1) + [RS]
+        for pth in (list(range(1, nn + 1)), [1, nn]):
+            iso_nodes.extend(pth)
+            iso_ptr.append(len(iso_nodes))
+        iso_base.append(iso_base[-1] + 2)
+        node_base.append(node_base[-1] + nn)
+        coord += 5000
+    nodelen = np.array(nodelen, np.int64)
+    node_base = np.array(node_base, np.int64)
+    G = n_genes
+    gene_of_node = np.repeat(np.arange(G), np.diff(node_base))
+    glen = np.zeros(G, np.int64)
+    np.add.at(glen, gene_of_node, nodelen)
+    gene_offset = np.cumsum(glen) - glen
+    text_len = int(glen.sum())
+    nodeoffset = (np.cumsum(nodelen) - nodelen) - gene_offset[gene_of_node] + 1
+    codes = rng.integers(0, 4, text_len, dtype=np.uint8)
+    edgetype = np.array(edgetype, "u1")
+    el, er, (lp, ln_), (rp, rn) = build_edges(K, gene_offset, node_base, nodeoffset, edgetype, codes)
+    sa, bwt, sentinel = suffix_array(codes, threads)
+    cnt = np.bincount(codes, minlength=4)
+    count = np.array([1, 1 + cnt[0], 1 + cnt[0] + cnt[1], 1 + cnt[0] + cnt[1] + cnt[2]], np.int64)
+    return FlatIndex(kmer=K, gene_offset=gene_offset, node_base=node_base, nodeoffset=nodeoffset,
+                     nodecoord=np.array(nodecoord), nodelen=nodelen, edgetype=edgetype, edgeleft=el, edgeright=er,
+                     seq4=(1 << codes).astype("u1"), bwt=bwt, sentinel=sentinel, count=count, sa=sa,
+                     left_ptr=lp, left_nodes=ln_, right_ptr=rp, right_nodes=rn,
+                     iso_base=np.array(iso_base), iso_node_ptr=np.array(iso_ptr), iso_nodes=np.array(iso_nodes, "<u4"),
+                     gene_names=[f"S{g}" for g in range(G)], iso_names=[], gene_strand=np.ones(G, "u1"))
+
+
+def stress_paths(idx: FlatIndex, per_gene=48, seed=6):
+    """Random exon-skipping combinations of every stress gene (first and last exon always in) as Transcriptome paths."""
+    rng = np.random.default_rng(seed)
+    gene, ptr, nodes = [], [0], []
+    nb = np.asarray(idx.node_base, np.int64)
+    for g in range(idx.n_genes):
+        nn = int(nb[g + 1] - nb[g])
+        for _ in range(per_gene):
+            keep = rng.random(nn - 2) < rng.uniform(0.25, 0.75)
+            pth = [1] + [j + 2 for j in range(nn - 2) if keep[j]] + [nn]
+            gene.append(g)
+            nodes.extend(pth)
+            ptr.append(len(nodes))
+    return np.array(gene), np.array(ptr), np.array(nodes)
+
+
+def fixture_reads(idx: FlatIndex, n=100000, seed=20261019, lo=11, hi=21):
+    """BASELINE config 1 as SURVEY.md section 8d restates it: reads of length lo..hi (the fixture's own read-length range) sampled
+    from the annotated isoform paths of test/test_index.jls, strand 50/50, 1 % substitutions (phred '#' = 2 there, 'B' = 33
+    elsewhere), first base N -> A with p = 0.1 (src/reads.jl:9)."""
+    rng = np.random.default_rng(seed)
+    tx = Transcriptome(idx)
+    lens = rng.integers(lo, hi + 1, n)
+    cands = np.nonzero(tx.iso_len >= lo)[0]
+    iso = cands[rng.integers(0, len(cands), n)]
+    lens = np.minimum(lens, tx.iso_len[iso]).astype(np.int64)
+    st = (rng.random(n) * (tx.iso_len[iso] - lens + 1)).astype(np.int64)
+    ar = np.arange(hi, dtype=np.int64)
+    pos = tx.iso_start[iso][:, None] + st[:, None] + np.minimum(ar[None, :], lens[:, None] - 1)
+    c = tx.seq[pos]
+    valid = ar[None, :] < lens[:, None]
+    flip = rng.random(n) < 0.5
+    # reverse complement inside each read's own length
+    rc_idx = np.clip(lens[:, None] - 1 - ar[None, :], 0, hi - 1)
+    rc = 3 - np.take_along_axis(c, rc_idx, axis=1)
+    c = np.where(flip[:, None], rc, c)
+    q = np.full((n, hi), 33, np.uint8)
+    sub = (rng.random((n, hi)) < 0.01) & valid
+    c = np.where(sub, (c + rng.integers(1, 4, (n, hi))) % 4, c).astype(np.uint8)
+    q[sub] = 2
+    firstn = rng.random(n) < 0.1
+    c[firstn, 0] = 0
+    q[firstn, 0] = 2
+    c[~valid] = 0
+    return ReadBatch.from_codes(np.ascontiguousarray(c), q, lens.astype("u1"))
