@@ -275,6 +275,25 @@ def canonical_events(ev, vals, pptr, pnodes):
     return hdr, dbl, values, plen, nodes
 
 
+def gene_em_direct(lengths, count, multi, classes, readlen, sig=1, maxit=10000, trace_n=0):
+    """The oracle's calculate_tpm! + gene_em! on a problem given directly: multi / classes = [(ids 1-based, count)], visited in
+    that order (multi-map classes first).  Returns (iterations, tpm, count, trace[trace_n][I])."""
+    L = lib()
+    L.wqo_gene_em_direct.restype = C.c_int64
+    I = len(lengths)
+    ln, cnt = np.ascontiguousarray(lengths, "<i8"), np.ascontiguousarray(count, "<f8")
+    allc = list(multi) + list(classes)
+    ptr_ = np.zeros(len(allc) + 1, "<u4")
+    ptr_[1:] = np.cumsum([len(c[0]) for c in allc])
+    ids = np.ascontiguousarray([i for c in allc for i in c[0]] or [0], "<i4")
+    cc = np.ascontiguousarray([c[1] for c in allc] or [0.0], "<f8")
+    tpm, cout, trace = np.zeros(I), np.zeros(I), np.zeros((max(1, trace_n), I))
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    it = L.wqo_gene_em_direct(C.c_uint32(I), p(ln), p(cnt), C.c_uint32(len(multi)), C.c_uint32(len(allc)), p(ptr_), p(ids), p(cc),
+                              C.c_int64(readlen), C.c_int64(sig), C.c_int64(maxit), p(tpm), p(cout), p(trace), C.c_uint32(trace_n))
+    return int(it), tpm, cout, trace[:trace_n]
+
+
 def em_psi(n_inc, count, length, amb_sets, amb_mult, tandem, readlen, sig=4, maxit=1500):
     """spliced_em! / rec_tandem_em! (src/events.jl:853-932) on one problem given directly: the first n_inc paths are
     inclusion paths; amb_sets = list of lists of 0-based path indices.  Returns (psi[np], iterations)."""

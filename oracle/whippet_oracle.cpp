@@ -1685,6 +1685,41 @@ int64_t wqo_em_tpm(wqo_handle* h, int64_t readlen, int64_t sig, int64_t maxit) {
     set_gene_tpm(L, S);
     return it;
 }
+// The transcript EM on a problem given directly (known-answer tests): I isoforms with lengths and unique counts, n_multi multi-map
+// classes followed by the isoform classes (cls_ptr / cls_ids 1-based / cls_count), visited in that order.  The same
+// calculate_tpm / gene_em as wqo_em_tpm runs (initial TPM with calculate_tpm!'s own default sig = 1, bin/whippet-quant.jl:163).
+// trace (optional) receives the TPM vector after each of the first trace_n iterations.
+int64_t wqo_gene_em_direct(uint32_t I, const int64_t* length, const double* count, uint32_t n_multi, uint32_t n_cls, const uint32_t* cls_ptr,
+                           const int32_t* cls_ids, const double* cls_count, int64_t readlen, int64_t sig, int64_t maxit,
+                           double* tpm_out, double* count_out, double* trace, uint32_t trace_n) {
+    QuantState S;
+    S.tpm.assign(I, 0.0); S.count.assign(count, count + I); S.genetpm.clear(); S.length.assign(length, length + I);
+    for (uint32_t c = 0; c < n_cls; c++) {
+        EqClass q;
+        q.cls.assign(cls_ids + cls_ptr[c], cls_ids + cls_ptr[c + 1]);
+        q.prop.assign(q.cls.size(), 1.0 / (double)q.cls.size());
+        q.count = cls_count[c];
+        if (c < n_multi) S.multi.emplace_back(std::vector<uint32_t>{c}, q); else S.classes.push_back(q);
+    }
+    calculate_tpm(S, S.count, readlen, 1);
+    int64_t it = 1;
+    if (trace && trace_n) {            // iteration by iteration: gene_em with maxit = it + 1 runs exactly one more sweep
+        for (uint32_t t = 0; t < trace_n; t++) {
+            QuantState T = S;
+            // re-run from the start with a bounded iteration count (the class state lives inside S)
+            T = QuantState();
+            T.tpm.assign(I, 0.0); T.count.assign(count, count + I); T.length = S.length;
+            T.multi = S.multi; T.classes = S.classes;
+            calculate_tpm(T, T.count, readlen, 1);
+            gene_em(T, (int64_t)t + 2, (int)sig, readlen);
+            memcpy(trace + (size_t)t * I, T.tpm.data(), 8 * (size_t)I);
+        }
+    }
+    it = gene_em(S, maxit, (int)sig, readlen);
+    memcpy(tpm_out, S.tpm.data(), 8 * (size_t)I);
+    memcpy(count_out, S.count.data(), 8 * (size_t)I);
+    return it;
+}
 void wqo_em_results(wqo_handle* h, double* tpm, double* count, double* genetpm) {
     memcpy(tpm, h->S.tpm.data(), h->S.tpm.size() * 8);
     memcpy(count, h->S.count.data(), h->S.count.size() * 8);

@@ -106,6 +106,10 @@ class HostEmu:
         self.L.hemu_values(self.h, _p(node), _p(ek), _p(ev))
         return node, ek, ev
 
+    def set_event_pieces(self, k):
+        """Build every gene in pieces of k visited nodes (0 = whole genes), as the library does for genes with many nodes."""
+        self.L.hemu_set_event_pieces(int(k))
+
     def events(self, node_value, ekey, evalue, readlen):
         """Event construction of every gene.  Returns a list of dicts (gene, node, motif, kind, flags, n_utr, psi, total,
         problem, inc paths, exc paths / utr paths) and the EM problems as tuples for oracle.em_psi."""

@@ -3,6 +3,7 @@
 // in a container without a GPU.  No kernel is launched here and nothing of this file is part of the product library.
 #include <cuda_runtime.h>
 #include <cstdio>
+#include <cstdlib>
 #include <string>
 #include <vector>
 #include "../../whippet.jl_b200/csrc/wq_kernels.cuh"
@@ -22,6 +23,8 @@ struct HostEmu {
 
 extern "C" {
 
+static int g_event_pieces = 0;
+void hemu_set_event_pieces(int k) { g_event_pieces = k; }
 HostEmu* hemu_create(const wq_index_desc* d) {
     HostEmu* e = new HostEmu();
     std::string err = wq_build_host_index(d, e->H);
@@ -32,6 +35,7 @@ HostEmu* hemu_create(const wq_index_desc* d) {
 void hemu_destroy(HostEmu* e) { delete e; }
 #ifdef WQ_EV_PROF
 void hemu_prof(unsigned long long* out, int reset) { for (int i = 0; i < 8; i++) { out[i] = wq_evp[i]; if (reset) wq_evp[i] = 0; } }
+void hemu_prof_counts(unsigned long long* out, int reset) { for (int i = 0; i < 8; i++) { out[i] = wq_evc[i]; if (reset) wq_evc[i] = 0; } }
 #endif
 const char* hemu_error(HostEmu* e) { return e->err.c_str(); }
 
@@ -88,7 +92,15 @@ uint64_t hemu_events(HostEmu* e, const double* node_value, uint64_t ne, const ui
             if (wq_edge_is_circ(ekey[k])) continue;
             V.edges.push_back(WqGeneEdge{(uint32_t)((ekey[k] >> 16) & 0xFFFF), (uint32_t)(ekey[k] & 0xFFFF), evalue[k]});
         }
-        wq_gene_events(V, readlen, e->recs, e->P, e->pool);
+        // hemu_set_event_pieces(k): build every gene in pieces of k visited nodes, the way the library cuts genes with many nodes
+        // over its host threads (wq_gene_visits); the records must not depend on the cut
+        const int pieces = g_event_pieces;
+        if (pieces > 0) {
+            std::vector<uint32_t> visits;
+            wq_gene_visits(V, visits);
+            for (size_t v = 0; v < visits.size(); v += (size_t)pieces)
+                wq_gene_events(V, readlen, e->recs, e->P, e->pool, visits[v], visits[std::min(visits.size(), v + (size_t)pieces) - 1]);
+        } else wq_gene_events(V, readlen, e->recs, e->P, e->pool);
     }
     return e->recs.size();
 }

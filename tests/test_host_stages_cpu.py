@@ -126,11 +126,26 @@ def test_event_construction_on_the_fixture(fixture_index, test_param):
     compare_events(fixture_index, o, 15, 5, 1)
 
 
-def compare_events(idx, o, readlen, min_records, min_em):
+def test_event_construction_in_pieces_and_on_real_structures():
+    """Genes of the RefSeq-derived structures ('-' strand, retained introns, many isoforms), built whole and in pieces of 1 and 5
+    visited nodes (the way the library spreads a gene with many nodes over its host threads): same records either way."""
+    from data_gen import refseq_subset
+    idx = refseq_subset(400, seed=3)
+    o = Oracle(idx)
+    o.process_reads(wq.AlignParam(), synth.simulate_reads(idx, 150000, 101, seed=4, sub_rate=0.01))
+    o.em_tpm(101)
+    o.assign_ambig()
+    for pieces in (0, 1, 5):
+        compare_events(idx, o, 101, 2000, 50, pieces=pieces)
+
+
+def compare_events(idx, o, readlen, min_records, min_em, pieces=0):
     ek, ev = o.edges()
     want = o.process_events(readlen)
     e = HostEmu(idx)
+    e.set_event_pieces(pieces)
     got = e.events(o.node_counts(), ek, ev, readlen)
+    e.set_event_pieces(0)
     assert len(got) == len(want) and len(want) > min_records
     nem = 0
     for g, w in zip(got, want):

@@ -24,6 +24,7 @@
 #include "wq_fastq.h"
 #include "wq_sam.h"
 #include <future>
+#include <atomic>
 #include <dlfcn.h>
 
 #include <chrono>
@@ -467,17 +468,47 @@ static void wq_build_event_batch(wq_handle* h, int64_t readlen, int group, WqEvB
     const uint32_t G = h->H.G;
     unsigned nt = wq_host_threads();
     if (G < 2048) nt = 1;
+    // The gene range is cut into many more contiguous pieces than there are host threads and the threads pull pieces as they
+    // finish: the cost of a gene goes from nothing to hundreds of path enumerations (TTN: 365 nodes), so a gene with many nodes is
+    // itself cut into pieces at visited nodes (every node's event is independent of the others).  The pieces depend on the index
+    // and the partition only, so both gene groups and every call see the same list.
+    const uint32_t p_lo = (uint32_t)((uint64_t)G * h->part / h->nparts), p_n = (uint32_t)((uint64_t)G * (h->part + 1) / h->nparts) - p_lo;
+    struct Piece { uint32_t g_lo, g_hi, node_lo, node_hi; };
+    std::vector<Piece> pieces;
+    {
+        const uint32_t per_piece = nt == 1 ? p_n : std::max<uint32_t>(8, p_n / (16 * nt) + 1), big_gene = 48, visits_per_piece = 12;
+        std::vector<uint32_t> visits;
+        WqGeneEvents Vv{h->H, X.node_value, 0, {}};
+        uint32_t start = p_lo + 1;
+        auto flush = [&](uint32_t upto) { if (upto >= start) pieces.push_back(Piece{start, upto, 1, 0xFFFFFFFFu}); start = upto + 1; };
+        for (uint32_t g = p_lo + 1; g <= p_lo + p_n; g++) {
+            if (nt > 1 && h->H.genes[g - 1].nn >= big_gene) {
+                flush(g - 1);
+                Vv.g = g;
+                wq_gene_visits(Vv, visits);
+                for (size_t v = 0; v < visits.size(); v += visits_per_piece) {
+                    const size_t ve = std::min(visits.size(), v + visits_per_piece);
+                    pieces.push_back(Piece{g, g, visits[v], visits[ve - 1]});
+                }
+                start = g + 1;
+            } else if (g - start + 1 >= per_piece) flush(g);
+        }
+        flush(p_lo + p_n);
+    }
+    const unsigned npieces = (unsigned)std::max<size_t>(1, pieces.size());
+    if (pieces.empty()) pieces.push_back(Piece{1, 0, 1, 0});
     B.parts.clear();
-    B.parts.resize(nt);
+    B.parts.resize(npieces);
     auto run = [&](const std::function<void(unsigned)>& f) {
-        if (nt == 1) { f(0); return; }
+        if (nt == 1) { for (unsigned t = 0; t < npieces; t++) f(t); return; }
+        std::atomic<unsigned> next{0};
         std::vector<std::thread> th;
-        for (unsigned t = 0; t < nt; t++) th.emplace_back(f, t);
+        for (unsigned k = 0; k < nt; k++) th.emplace_back([&]() { for (unsigned t; (t = next.fetch_add(1)) < npieces;) f(t); });
         for (auto& x : th) x.join();
     };
-    const uint32_t p_lo = (uint32_t)((uint64_t)G * h->part / h->nparts), p_n = (uint32_t)((uint64_t)G * (h->part + 1) / h->nparts) - p_lo;
     run([&](unsigned t) {
-        const uint32_t g_lo = p_lo + 1 + (uint32_t)((uint64_t)p_n * t / nt), g_hi = p_lo + (uint32_t)((uint64_t)p_n * (t + 1) / nt);
+        const Piece pc = pieces[t];
+        const uint32_t g_lo = pc.g_lo, g_hi = pc.g_hi;
         size_t e = std::lower_bound(X.edge_key.begin(), X.edge_key.end(), (uint64_t)g_lo << 32) - X.edge_key.begin();
         WqGeneEvents V{h->H, X.node_value, 0, {}};
         WqEvPart& part = B.parts[t];
@@ -490,7 +521,7 @@ static void wq_build_event_batch(wq_handle* h, int64_t readlen, int group, WqEvB
                 if (wq_edge_is_circ(X.edge_key[e])) continue;
                 V.edges.push_back(WqGeneEdge{(uint32_t)((X.edge_key[e] >> 16) & 0xFFFF), (uint32_t)(X.edge_key[e] & 0xFFFF), X.edge_value[e]});
             }
-            wq_gene_events(V, readlen, part.recs, part.P, part.pool);
+            wq_gene_events(V, readlen, part.recs, part.P, part.pool, pc.node_lo, pc.node_hi);
         }
         // Beta-CI inputs of this part: spliced events whose psi is known without EM get a launch slot (part-local for now);
         // EM problems of spliced events carry their total (tandem UTR problems: -1, no CI)
@@ -506,18 +537,18 @@ static void wq_build_event_batch(wq_handle* h, int64_t readlen, int group, WqEvB
         }
     });
     lap2("genes built");
-    std::vector<WqPsiProblems::Sizes> at(nt + 1);
-    B.pshift.assign(nt, 0);
-    for (unsigned t = 0; t < nt; t++) {
+    std::vector<WqPsiProblems::Sizes> at(npieces + 1);
+    B.pshift.assign(npieces, 0);
+    for (unsigned t = 0; t < npieces; t++) {
         const WqPsiProblems::Sizes z = B.parts[t].P.sizes();
         at[t + 1].ev = at[t].ev + z.ev; at[t + 1].paths = at[t].paths + z.paths; at[t + 1].amb = at[t].amb + z.amb; at[t + 1].amb_paths = at[t].amb_paths + z.amb_paths;
         B.pshift[t] = (long)at[t].ev;
     }
-    std::vector<size_t> ci_at(nt + 1, 0);
-    for (unsigned t = 0; t < nt; t++) ci_at[t + 1] = ci_at[t] + B.parts[t].ci_psi.size();
-    B.P.resize_total(at[nt]);
-    B.ci_psi.resize(ci_at[nt]); B.ci_tot.resize(ci_at[nt]);
-    B.p_total.resize(at[nt].ev);
+    std::vector<size_t> ci_at(npieces + 1, 0);
+    for (unsigned t = 0; t < npieces; t++) ci_at[t + 1] = ci_at[t] + B.parts[t].ci_psi.size();
+    B.P.resize_total(at[npieces]);
+    B.ci_psi.resize(ci_at[npieces]); B.ci_tot.resize(ci_at[npieces]);
+    B.p_total.resize(at[npieces].ev);
     run([&](unsigned t) {
         WqEvPart& part = B.parts[t];
         B.P.place(part.P, at[t]);
@@ -1750,8 +1781,15 @@ static int process_events_impl(wq_handle* h, int64_t readlen, wq_events_out* out
                 std::copy(pl.path_nodes.begin(), pl.path_nodes.end(), h->ev_path_nodes.begin() + pool_nodes[k]);
             }
         };
-        if (nparts == 1) place(0);
-        else { std::vector<std::thread> th; for (size_t t = 0; t < nparts; t++) th.emplace_back(place, t); for (auto& x : th) x.join(); }
+        auto par = [&](const std::function<void(size_t)>& f) {          // pieces pulled by the host threads
+            const unsigned nthr = (unsigned)std::min<size_t>(nparts, wq_host_threads());
+            if (nthr <= 1) { for (size_t t = 0; t < nparts; t++) f(t); return; }
+            std::atomic<size_t> next{0};
+            std::vector<std::thread> th;
+            for (unsigned k = 0; k < nthr; k++) th.emplace_back([&]() { for (size_t t; (t = next.fetch_add(1)) < nparts;) f(t); });
+            for (auto& x : th) x.join();
+        };
+        par(place);
         lap("+ records merged");
         if (B0.launched) CK(cudaStreamSynchronize(B0.stream));           // PSI launches and their result copies
         if (B1.launched) CK(cudaStreamSynchronize(B1.stream));
@@ -1784,12 +1822,6 @@ static int process_events_impl(wq_handle* h, int64_t readlen, wq_events_out* out
             return 0;
         };
         std::vector<uint64_t> val_at(nparts + 1, 0);
-        auto par = [&](const std::function<void(size_t)>& f) {
-            if (nparts == 1) { f(0); return; }
-            std::vector<std::thread> th;
-            for (size_t t = 0; t < nparts; t++) th.emplace_back(f, t);
-            for (auto& x : th) x.join();
-        };
         par([&](size_t t) { uint64_t c = 0; for (size_t i = rec_at[t]; i < rec_at[t + 1]; i++) c += n_values_of(h->ev_recs[i]); val_at[t + 1] = c; });
         for (size_t t = 0; t < nparts; t++) val_at[t + 1] += val_at[t];
         h->ev_values.resize(val_at[nparts]);

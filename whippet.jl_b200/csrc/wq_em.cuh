@@ -1120,30 +1120,54 @@ __device__ __forceinline__ double wq_round_sig(const WqPsiDev& d, double x, int 
     return r;
 }
 
-// One warp per event (events with more than 16 paths).  Element-wise work (copies, the division + significant-digit
-// rounding of every path, the additions of one ambiguous set, whose paths are distinct) is spread over the lanes; every sum
-// is formed sequentially in path order by all lanes redundantly, so the arithmetic is the per-event sequential one.
-// Events up to 48 paths keep psi / previous psi / temp counts in a shared-memory slab, larger ones in global scratch.
-#define WQ_PSI_SLAB 48            // paths per warp slab
-__global__ void __launch_bounds__(128) wq_k_em_psi(const WqPsiDev d, const uint32_t* __restrict__ list, const uint32_t n_list) {
-    __shared__ double slab[4][3 * WQ_PSI_SLAB];
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t slot = blockIdx.x * 4 + warp;
+// One warp per event (events with more than 16 paths), the event's whole working set in shared memory.
+//
+// What bounds an event is latency, not arithmetic: up to 1500 sweeps, each a chain of sums the reference forms sequentially
+// (`ac.prop_sum += prev_psi` over the members of every ambiguous set, src/events.jl:869-876; the sum of all path psi in
+// calculate_psi!, :838); a CPU core runs a 50-path event's sweep in ~3 us.  So everything a sweep reads is staged once in the
+// warp's shared memory (psi / previous psi / temp counts / denominators / unambiguous counts per path, the member lists of the
+// ambiguous sets as 16-bit path indices, one prop_sum per set), and the independent chains run side by side: every lane owns
+// ambiguous sets and forms their prop_sum sequentially in member order (different sets on different lanes), the additions
+// `count_temp[p] += prop * multiplier` then go set by set (two sets may touch one path: their order is the reference's) with
+// the members of a set spread over the lanes, and the divisions / significant-digit roundings of the paths are lane-parallel.
+// The sum over all paths stays one sequential chain in path order (every lane forms it from shared memory).
+// Shared memory per event: 40 * paths + 16 * sets + 4 * (sets + 1) + 2 * members bytes, rounded up; the launch classes
+// group events by that size.  Events whose member lists do not fit (> ~100 k members) read them from global memory.
+struct WqPsiWarpCfg { uint32_t smem_bytes; uint32_t members_in_smem; };
+__global__ void __launch_bounds__(32) wq_k_em_psi(const WqPsiDev d, const uint32_t* __restrict__ list, const uint32_t n_list, const WqPsiWarpCfg cfg) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const uint32_t lane = threadIdx.x;
+    const uint32_t slot = blockIdx.x;
     if (slot >= n_list) return;
     const uint32_t e = list[slot];
-    const uint32_t p0 = d.path_ptr[e], p1 = d.path_ptr[e + 1], ni = d.n_inc[e];
-    const uint32_t a0 = d.amb_ptr[e], a1 = d.amb_ptr[e + 1];
+    const uint32_t p0 = d.path_ptr[e], np = d.path_ptr[e + 1] - p0, ni = d.n_inc[e];
+    const uint32_t a0 = d.amb_ptr[e], na = d.amb_ptr[e + 1] - a0;
+    const uint32_t m0 = d.amb_path_ptr[a0], nm = d.amb_path_ptr[a0 + na] - m0;
     const bool tandem = d.is_tandem[e] != 0;
-    const uint32_t np = p1 - p0;
-    const bool small = np <= WQ_PSI_SLAB;
-    double* psi = small ? &slab[warp][0] : d.psi + p0;
-    double* prev = small ? &slab[warp][WQ_PSI_SLAB] : d.prev + p0;
-    double* ct = small ? &slab[warp][2 * WQ_PSI_SLAB] : d.ctemp + p0;
-    const double* cnt = d.count + p0;
-    const double* len = d.length + p0;
+    double* psi = reinterpret_cast<double*>(smem_raw);
+    double* prev = psi + np;
+    double* ct = prev + np;
+    double* den = ct + np;
+    double* cnt = den + np;
+    double* psum = cnt + np;                                      // [na]
+    double* mult = psum + na;                                     // [na]
+    uint32_t* moff = reinterpret_cast<uint32_t*>(mult + na);      // [na + 1] member offsets of the sets, event-local
+    uint16_t* mem = reinterpret_cast<uint16_t*>(moff + na + 1);   // [nm] event-local path index of every member (when staged)
+    const bool staged = cfg.members_in_smem != 0;
+    const uint32_t* gmem = d.amb_paths + m0;
+    for (uint32_t i = lane; i < np; i += 32) {
+        const double len = d.length[p0 + i];
+        cnt[i] = d.count[p0 + i];
+        den[i] = tandem ? fmax(__dsub_rn(len, d.readlen), 1.0) : len;
+        prev[i] = 0.0; psi[i] = 0.0; ct[i] = cnt[i];
+    }
+    for (uint32_t a = lane; a <= na; a += 32) moff[a] = d.amb_path_ptr[a0 + a] - m0;
+    for (uint32_t a = lane; a < na; a += 32) mult[a] = d.amb_mult[a0 + a];
+    if (staged) for (uint32_t k = lane; k < nm; k += 32) mem[k] = (uint16_t)gmem[k];
+    __syncwarp();
+    auto member = [&](uint32_t k) -> uint32_t { return staged ? (uint32_t)mem[k] : gmem[k]; };
     auto normalise = [&](int sig) {
-        for (uint32_t i = lane; i < np; i += 32)
-            psi[i] = tandem ? __ddiv_rn(ct[i], fmax(__dsub_rn(len[i], d.readlen), 1.0)) : __ddiv_rn(ct[i], len[i]);
+        for (uint32_t i = lane; i < np; i += 32) psi[i] = __ddiv_rn(ct[i], den[i]);
         __syncwarp();
         double total;
         if (tandem) { total = 0.0; for (uint32_t i = 0; i < np; i++) total = __dadd_rn(total, psi[i]); }
@@ -1165,28 +1189,30 @@ __global__ void __launch_bounds__(128) wq_k_em_psi(const WqPsiDev d, const uint3
         for (uint32_t i = lane; i < np; i += 32) if (prev[i] != psi[i]) diff = true;
         return __any_sync(0xffffffffu, diff) != 0;
     };
-    for (uint32_t i = lane; i < np; i += 32) { prev[i] = 0.0; psi[i] = 0.0; ct[i] = cnt[i]; }
-    __syncwarp();
     if (!tandem) normalise(0);                      // calculate_psi!(inc, exc, counts) before spliced_em!
     int64_t it = 1;
     for (;;) {
         if (!tandem && !(differs() && it < d.maxit)) break;
         for (uint32_t i = lane; i < np; i += 32) { ct[i] = cnt[i]; prev[i] = psi[i]; }
         __syncwarp();
-        for (uint32_t a = a0; a < a1; a++) {
-            const uint32_t b = d.amb_path_ptr[a], n = d.amb_path_ptr[a + 1] - b;
-            double psum = 1.0;
-            if (it > 1) {
-                psum = 0.0;
-                for (uint32_t k = 0; k < n; k++) psum = __dadd_rn(psum, psi[d.amb_paths[b + k]]);
+        // prop_sum of every set: sequential in member order, the sets side by side on the lanes
+        if (it > 1) {
+            for (uint32_t a = lane; a < na; a += 32) {
+                double s = 0.0;
+                const uint32_t kb = moff[a], ke = moff[a + 1];
+                for (uint32_t k = kb; k < ke; k++) s = __dadd_rn(s, psi[member(k)]);
+                psum[a] = s;
             }
-            const double mult = d.amb_mult[a];
+            __syncwarp();
+        }
+        for (uint32_t a = 0; a < na; a++) {
+            const uint32_t kb = moff[a], n = moff[a + 1] - kb;
+            const double ps = it > 1 ? psum[a] : 1.0, mu = mult[a];
             for (uint32_t k = lane; k < n; k += 32) {
-                const uint32_t pth = d.amb_paths[b + k];
+                const uint32_t pth = member(kb + k);
                 // first sweep: ones(n)/n over prop_sum = 1.0; later sweeps: current psi over their sum (src/events.jl:869-886)
                 const double base = it > 1 ? psi[pth] : __ddiv_rn(1.0, (double)n);
-                const double prop = __ddiv_rn(base, psum);
-                ct[pth] = __dadd_rn(ct[pth], __dmul_rn(prop, mult));
+                ct[pth] = __dadd_rn(ct[pth], __dmul_rn(__ddiv_rn(base, ps), mu));
             }
             __syncwarp();
         }
@@ -1194,8 +1220,12 @@ __global__ void __launch_bounds__(128) wq_k_em_psi(const WqPsiDev d, const uint3
         if (tandem) { if (differs() && it < d.maxit) it += 1; else break; }
         else it += 1;
     }
-    if (small) for (uint32_t i = lane; i < np; i += 32) { d.psi[p0 + i] = psi[i]; d.ctemp[p0 + i] = ct[i]; }
+    for (uint32_t i = lane; i < np; i += 32) { d.psi[p0 + i] = psi[i]; d.ctemp[p0 + i] = ct[i]; }
     if (lane == 0) d.iterations[e] = (int32_t)it;
+}
+static inline size_t wq_psi_warp_smem(uint32_t np, uint32_t na, uint32_t nm, bool staged) {
+    size_t b = 40ull * np + 16ull * na + 4ull * (na + 1) + (staged ? 2ull * nm : 0);
+    return (b + 15) & ~15ull;
 }
 
 // G lanes per event, 32/G events per warp, for events with at most G paths (more than 99 % of them have at most 4): lane i of
@@ -1294,34 +1324,66 @@ static inline std::string wq_run_em_psi(wq_psi_batch& b, WqEmScratch& M, cudaStr
     d.path_ptr = d_pp; d.n_inc = d_ni; d.count = d_cnt; d.length = d_len; d.amb_ptr = d_ap; d.amb_path_ptr = d_app;
     d.amb_paths = d_apaths; d.amb_mult = d_mult; d.is_tandem = d_tan; d.psi = d_psi; d.prev = d_prev; d.ctemp = d_ct;
     d.amb_prop = d_prop; d.iterations = d_it;
-    // events by path count: groups of 4 / 8 / 16 lanes, one warp beyond that.  The classes run concurrently on side streams
-    // (a handful of large events that need all 1500 sweeps would otherwise add their whole latency to the batch).
+    // events by path count: groups of 4 / 8 / 16 lanes; beyond that one warp per event, grouped by the shared memory the event
+    // needs (launch classes of 6 / 24 / 96 / 200 KB per warp; the last one also takes events whose member lists stay in
+    // global memory).  The classes run concurrently on side streams (a handful of large events that need all 1500 sweeps would
+    // otherwise add their whole latency to the batch).
+    static const size_t kWarpSmem[4] = {6 * 1024, 24 * 1024, 96 * 1024, 200 * 1024};
+    const int NC = 7;
     std::vector<uint32_t> order(E);
-    uint32_t nclass[4] = {0, 0, 0, 0}, cbase[5] = {0, 0, 0, 0, 0};
-    auto cls_of = [&](uint32_t e) { const uint32_t np = b.path_ptr[e + 1] - b.path_ptr[e]; return np <= 4 ? 0 : np <= 8 ? 1 : np <= 16 ? 2 : 3; };
-    for (uint32_t e = 0; e < E; e++) nclass[cls_of(e)]++;
-    for (int c = 0; c < 4; c++) cbase[c + 1] = cbase[c] + nclass[c];
-    { uint32_t cur[4] = {cbase[0], cbase[1], cbase[2], cbase[3]}; for (uint32_t e = 0; e < E; e++) order[cur[cls_of(e)]++] = e; }
+    std::vector<uint8_t> cls(E);
+    uint32_t nclass[NC] = {0}, cbase[NC + 1] = {0};
+    bool unstaged_any = false;
+    auto cls_of = [&](uint32_t e) -> int {
+        const uint32_t np = b.path_ptr[e + 1] - b.path_ptr[e];
+        if (np <= 4) return 0;
+        if (np <= 8) return 1;
+        if (np <= 16) return 2;
+        const uint32_t na = b.amb_ptr[e + 1] - b.amb_ptr[e], nm = b.amb_path_ptr[b.amb_ptr[e + 1]] - b.amb_path_ptr[b.amb_ptr[e]];
+        const size_t need = wq_psi_warp_smem(np, na, nm, true);
+        for (int k = 0; k < 4; k++) if (need <= kWarpSmem[k]) return 3 + k;
+        return -1;
+    };
+    for (uint32_t e = 0; e < E; e++) {
+        int c = cls_of(e);
+        if (c < 0) {            // member lists too long for shared memory: the paths must still fit
+            const uint32_t np = b.path_ptr[e + 1] - b.path_ptr[e], na = b.amb_ptr[e + 1] - b.amb_ptr[e];
+            if (np > 65535 || wq_psi_warp_smem(np, na, 0, false) > kWarpSmem[3]) return "PSI event too large for the device kernel (more than ~4000 paths)";
+            unstaged_any = true;
+            c = 6;
+        }
+        cls[e] = (uint8_t)c;
+        nclass[c]++;
+    }
+    for (int c = 0; c < NC; c++) cbase[c + 1] = cbase[c] + nclass[c];
+    { uint32_t cur[NC]; for (int c = 0; c < NC; c++) cur[c] = cbase[c]; for (uint32_t e = 0; e < E; e++) order[cur[cls[e]]++] = e; }
     uint32_t* d_list;
     WQ_EMCK(up(14, order.data(), E * 4ull, (void**)&d_list));
     WQ_EMCK(M.side_streams());
     WQ_EMCK(M.timing_events());
+    static bool smem_attr_set = false;
+    if (!smem_attr_set) {
+        WQ_EMCK(cudaFuncSetAttribute(wq_k_em_psi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWarpSmem[3]));
+        smem_attr_set = true;
+    }
     WQ_EMCK(cudaEventRecord(M.tk0, stream));
     WQ_EMCK(cudaEventRecord(M.fork, stream));
     int used = 0;
-    for (int c = 0; c < 4; c++) {
+    for (int c = NC - 1; c >= 0; c--) {             // the large events first: their sweeps are the long pole
         if (!nclass[c]) continue;
-        cudaStream_t ss = used == 0 ? stream : M.side[used - 1];
+        cudaStream_t ss = used == 0 ? stream : M.side[(used - 1) % 3];
         if (used > 0) WQ_EMCK(cudaStreamWaitEvent(ss, M.fork, 0));
         const uint32_t n = nclass[c];
         const uint32_t* lst = d_list + cbase[c];
         if (c == 0) wq_k_em_psi_group<4><<<(n + 31) / 32, 128, 0, ss>>>(d, lst, n);
         else if (c == 1) wq_k_em_psi_group<8><<<(n + 15) / 16, 128, 0, ss>>>(d, lst, n);
         else if (c == 2) wq_k_em_psi_group<16><<<(n + 7) / 8, 128, 0, ss>>>(d, lst, n);
-        else wq_k_em_psi<<<(n + 3) / 4, 128, 0, ss>>>(d, lst, n);
+        else if (c == 6 && unstaged_any)            // a class that holds events with member lists in global memory reads them from there for all
+            wq_k_em_psi<<<n, 32, kWarpSmem[3], ss>>>(d, lst, n, WqPsiWarpCfg{(uint32_t)kWarpSmem[3], 0u});
+        else wq_k_em_psi<<<n, 32, kWarpSmem[c - 3], ss>>>(d, lst, n, WqPsiWarpCfg{(uint32_t)kWarpSmem[c - 3], 1u});
         if (launches) *launches += 1;
         WQ_EMCK(cudaGetLastError());
-        if (used > 0) { WQ_EMCK(cudaEventRecord(M.join[used - 1], ss)); WQ_EMCK(cudaStreamWaitEvent(stream, M.join[used - 1], 0)); }
+        if (used > 0) { WQ_EMCK(cudaEventRecord(M.join[(used - 1) % 3], ss)); WQ_EMCK(cudaStreamWaitEvent(stream, M.join[(used - 1) % 3], 0)); }
         used++;
     }
     WQ_EMCK(cudaEventRecord(M.tk1, stream));

@@ -29,16 +29,17 @@ static inline uint8_t wq_motif(uint8_t cur, uint8_t next) {
     return T[cur][next];
 }
 
-struct WqBitWin {                       // node set as bits over [lo, lo + 64*nw); windows up to 128 nodes need no heap
+#define WQ_WIN_INLINE 6                 // 384 nodes: the widest gene of the RefSeq annotation (TTN, 365 nodes) needs no heap per set
+struct WqBitWin {                       // node set as bits over [lo, lo + 64*nw); windows up to 64 * WQ_WIN_INLINE nodes need no heap
     uint32_t lo = 0, nw = 0;
-    uint64_t in[2] = {0, 0};
+    uint64_t in[WQ_WIN_INLINE] = {0};
     std::vector<uint64_t> big;
-    uint64_t* p() { return nw <= 2 ? in : big.data(); }
-    const uint64_t* p() const { return nw <= 2 ? in : big.data(); }
+    uint64_t* p() { return nw <= WQ_WIN_INLINE ? in : big.data(); }
+    const uint64_t* p() const { return nw <= WQ_WIN_INLINE ? in : big.data(); }
     void init(uint32_t lo_, uint32_t hi_) {
         lo = lo_; nw = (hi_ - lo_) / 64 + 1;
-        in[0] = in[1] = 0;
-        if (nw > 2) big.assign(nw, 0); else big.clear();
+        for (auto& w : in) w = 0;
+        if (nw > WQ_WIN_INLINE) big.assign(nw, 0); else big.clear();
     }
     void set(uint32_t n) { p()[(n - lo) >> 6] |= 1ull << ((n - lo) & 63); }
     bool has(uint32_t n) const { uint32_t k = n - lo; return n >= lo && (k >> 6) < nw && ((p()[k >> 6] >> (k & 63)) & 1); }
@@ -178,34 +179,122 @@ static inline void wq_amb_add(std::vector<WqAmbSet>& amb, const std::vector<uint
     if (v > 0) amb.push_back(WqAmbSet{set, v});
 }
 
+#ifdef WQ_EV_PROF
+#include <x86intrin.h>
+static unsigned long long wq_evp[8];
+static unsigned long long wq_evc[8];     // [0] reductions, [1] rounds, [2] unions, [3] largest path set before truncation, [4] paths visited
+#define WQ_EVC(k, v) (wq_evc[k] += (v))
+#define WQ_EVC_MAX(k, v) do { if ((unsigned long long)(v) > wq_evc[k]) wq_evc[k] = (v); } while (0)
+#define WQ_EVP(k) do { unsigned long long t_ = __rdtsc(); wq_evp[k] += t_ - evp_t; evp_t = t_; } while (0)
+#define WQ_EVP_START unsigned long long evp_t = __rdtsc()
+#else
+#define WQ_EVC(k, v) do { } while (0)
+#define WQ_EVC_MAX(k, v) do { } while (0)
+#define WQ_EVP(k) do { } while (0)
+#define WQ_EVP_START do { } while (0)
+#endif
+
+// Membership index over the node sets of a WqPathSet (open addressing on a hash of the window words): the reference asks
+// `jointset in newgraph.nodes` with a linear scan (src/events.jl:246,254), which is quadratic in the number of paths; an event
+// of a complex gene reaches the 1024-path bound with tens of edges, i.e. millions of set comparisons per round.  Only membership
+// is asked, so the index changes no result: paths keep their order of first appearance.
+struct WqSetIndex {
+    std::vector<int32_t> slot;          // -1 = empty, else index into the path set
+    size_t used = 0;
+    static uint64_t hash(const WqBitWin& s) {
+        const uint64_t* w = s.p();
+        uint64_t h = 0x9E3779B97F4A7C15ull;
+        for (uint32_t i = 0; i < s.nw; i++) { h ^= w[i]; h *= 0xFF51AFD7ED558CCDull; h ^= h >> 31; }
+        return h;
+    }
+    void reset(size_t expect) {
+        size_t cap = 64;
+        while (cap < 4 * expect) cap <<= 1;
+        slot.assign(cap, -1);
+        used = 0;
+    }
+    // index of an equal set, or -1 after remembering `idx` (the position the caller is about to push the set at)
+    long find_or_add(const std::vector<WqBitWin>& nodes, const WqBitWin& s, size_t idx) {
+        if (2 * (used + 1) > slot.size()) {                     // grow, re-inserting what is there
+            std::vector<int32_t> old;
+            old.swap(slot);
+            slot.assign(old.size() * 2, -1);
+            for (int32_t k : old) if (k >= 0) { size_t h = hash(nodes[k]) & (slot.size() - 1); while (slot[h] >= 0) h = (h + 1) & (slot.size() - 1); slot[h] = k; }
+        }
+        size_t h = hash(s) & (slot.size() - 1);
+        while (slot[h] >= 0) {
+            if (nodes[slot[h]] == s) return slot[h];
+            h = (h + 1) & (slot.size() - 1);
+        }
+        slot[h] = (int32_t)idx;
+        used++;
+        return -1;
+    }
+};
+
 // Build minimal node-set paths from edges sharing terminal nodes (reduce_graph, src/events.jl:223-266).
 static inline WqPathSet wq_reduce(const WqPathSet& edges, bool& subsampled) {
     WqPathSet cur = edges, nxt;
     nxt.mn = cur.mn; nxt.mx = cur.mx;
+    static thread_local WqSetIndex index;
+    // An edge joins a path when its last node is the path's first or its first node is the path's last (hasintersect_terminal).
+    // The reference scans every edge for every path (src/events.jl:242-243); here the edges are grouped by first and by last node
+    // once (an edge set never changes during the reduction) and a path visits its two groups merged in ascending edge order, which
+    // is the order the scan would have met them in.
+    const size_t E = edges.size();
+    static thread_local std::vector<uint32_t> ef, el, by_first, by_last, off_first, off_last, cand;
+    ef.resize(E); el.resize(E);
+    uint32_t lo = 0xFFFFFFFFu, hi = 0;
+    for (size_t j = 0; j < E; j++) { ef[j] = edges.nodes[j].first(); el[j] = edges.nodes[j].last(); lo = std::min(lo, ef[j]); hi = std::max(hi, el[j]); }
+    const uint32_t span = E ? hi - lo + 1 : 0;
+    off_first.assign(span + 1, 0); off_last.assign(span + 1, 0);
+    for (size_t j = 0; j < E; j++) { off_first[ef[j] - lo + 1]++; off_last[el[j] - lo + 1]++; }
+    for (uint32_t k = 0; k < span; k++) { off_first[k + 1] += off_first[k]; off_last[k + 1] += off_last[k]; }
+    by_first.resize(E); by_last.resize(E);
+    {
+        std::vector<uint32_t> cf(off_first.begin(), off_first.end() - (span ? 1 : 0)), cl(off_last.begin(), off_last.end() - (span ? 1 : 0));
+        for (size_t j = 0; j < E; j++) { by_first[cf[ef[j] - lo]++] = (uint32_t)j; by_last[cl[el[j] - lo]++] = (uint32_t)j; }     // ascending j inside a group
+    }
+    WQ_EVC(0, 1);
     for (int it = 1; it <= 100; it++) {
+        WQ_EVC(1, 1);
         if (it > 1) {
             if (nxt.nodes == cur.nodes) break;
             std::swap(cur, nxt);
             nxt.nodes.clear(); nxt.count.clear(); nxt.length.clear();
+            WQ_EVC_MAX(3, cur.size());
             if (cur.size() > 1024) { subsampled = true; cur.nodes.resize(1024); cur.count.resize(1024); cur.length.resize(1024); }
         }
+        index.reset(cur.size());
         for (size_t i = 0; i < cur.size(); i++) {
             const uint32_t fi = cur.nodes[i].first(), li = cur.nodes[i].last();
-            bool joined = false;
-            for (size_t j = 0; j < edges.size(); j++) {
-                const uint32_t fj = edges.nodes[j].first(), lj = edges.nodes[j].last();
-                if (!(fi == lj || fj == li)) continue;
-                joined = true;
+            // edges with last == fi, merged with edges with first == li, ascending, without duplicates
+            cand.clear();
+            {
+                const uint32_t *a = nullptr, *ae = nullptr, *b = nullptr, *be = nullptr;
+                if (fi >= lo && fi <= hi) { a = by_last.data() + off_last[fi - lo]; ae = by_last.data() + off_last[fi - lo + 1]; }
+                if (li >= lo && li <= hi) { b = by_first.data() + off_first[li - lo]; be = by_first.data() + off_first[li - lo + 1]; }
+                while (a != ae || b != be) {
+                    uint32_t j;
+                    if (b == be || (a != ae && *a <= *b)) { j = *a++; if (b != be && *b == j) b++; }
+                    else j = *b++;
+                    cand.push_back(j);
+                }
+            }
+            WQ_EVC(4, 1);
+            for (const uint32_t j : cand) {
+                WQ_EVC(2, 1);
+                const uint32_t fj = ef[j], lj = el[j];
                 WqBitWin u = cur.nodes[i];
                 u.unite(edges.nodes[j]);
-                if (nxt.find(u) >= 0) continue;
+                if (index.find_or_add(nxt.nodes, u, nxt.nodes.size()) >= 0) continue;
                 nxt.nodes.push_back(u);
                 nxt.length.push_back(cur.length[i] + edges.length[j]);
                 nxt.count.push_back(cur.count[i] + edges.count[j]);
                 nxt.mn = std::min(std::min(fi, fj), nxt.mn);
                 nxt.mx = std::max(std::max(li, lj), nxt.mx);
             }
-            if (!joined && nxt.find(cur.nodes[i]) < 0) {
+            if (cand.empty() && index.find_or_add(nxt.nodes, cur.nodes[i], nxt.nodes.size()) < 0) {
                 nxt.nodes.push_back(cur.nodes[i]);
                 nxt.length.push_back(cur.length[i]);
                 nxt.count.push_back(cur.count[i]);
@@ -216,16 +305,6 @@ static inline WqPathSet wq_reduce(const WqPathSet& edges, bool& subsampled) {
     }
     return nxt;
 }
-#ifdef WQ_EV_PROF
-#include <x86intrin.h>
-static unsigned long long wq_evp[8];
-#define WQ_EVP(k) do { unsigned long long t_ = __rdtsc(); wq_evp[k] += t_ - evp_t; evp_t = t_; } while (0)
-#define WQ_EVP_START unsigned long long evp_t = __rdtsc()
-#else
-#define WQ_EVP(k) do { } while (0)
-#define WQ_EVP_START do { } while (0)
-#endif
-
 struct WqGeneEvents {
     const WqHostIndex& H; const std::vector<double>& node_value; uint32_t g;      // g 1-based
     std::vector<WqGeneEdge> edges;                                                // (first,last) order
@@ -244,8 +323,32 @@ static inline void wq_push_edge(WqPathSet& g, const WqGeneEdge& e, uint32_t lo, 
     g.mn = std::min(g.mn, e.a); g.mx = std::max(g.mx, e.b);
 }
 
-// all events of one gene (src/events.jl:760-800); problems needing EM are appended to P
-static inline void wq_gene_events(const WqGeneEvents& V, int64_t readlen, std::vector<WqEventRec>& out, WqPsiProblems& P, WqEventPool& pool) {
+// The nodes the loop of _process_events visits (src/events.jl:760-800): every node, except that a tandem-UTR event consumes the
+// run of nodes it prints (src/io.jl:279-316).  The runs depend on the edge types only, so the visit list is known without any
+// counts; a gene with hundreds of nodes is cut at visited nodes into pieces that different host threads build.
+static inline void wq_gene_visits(const WqGeneEvents& V, std::vector<uint32_t>& visits) {
+    const uint32_t ne = V.nn() + 1;
+    visits.clear();
+    if (ne <= 2) return;
+    for (uint32_t i = 1; i < ne; i++) {
+        visits.push_back(i);
+        const uint8_t motif = wq_motif(V.et(i), V.et(i + 1));
+        if (motif > 1) continue;
+        uint32_t lo = i, hi = i;
+        if (motif == WQM_TXEN) lo = i - 1;
+        uint32_t k = i;
+        for (;;) { hi = k; k++; if (!(k < ne && wq_motif(V.et(k), V.et(k + 1)) == motif)) break; }
+        if (motif == WQM_TXST && k <= V.nn()) hi = k;
+        const uint32_t n_utr = hi - lo + 1;                  // the used nodes are the contiguous run lo..hi
+        const uint32_t st = motif == WQM_TXST ? i : i - 1;
+        i = st + n_utr - 1;
+    }
+}
+
+// all events of one gene (src/events.jl:760-800), or of its visited nodes in [node_lo, node_hi] (node_lo must be a visited node);
+// problems needing EM are appended to P
+static inline void wq_gene_events(const WqGeneEvents& V, int64_t readlen, std::vector<WqEventRec>& out, WqPsiProblems& P, WqEventPool& pool,
+                                  uint32_t node_lo = 1, uint32_t node_hi = 0xFFFFFFFFu) {
     const uint32_t ne = V.nn() + 1;
     if (ne <= 2) return;
     // thread-local scratch, looked up once per gene (every access to a thread_local of a shared library is a call)
@@ -256,7 +359,7 @@ static inline void wq_gene_events(const WqGeneEvents& V, int64_t readlen, std::v
     WqPathSet &inc = sc.inc, &exc = sc.exc;
     WqAmbFlat& amb = sc.amb;
     std::vector<uint32_t>& set = sc.set;
-    for (uint32_t i = 1; i < ne; i++) {
+    for (uint32_t i = node_lo; i < ne && i <= node_hi; i++) {
         WQ_EVP_START;
         const uint8_t motif = wq_motif(V.et(i), V.et(i + 1));
         const bool next_tandem = (i + 1 < ne) && wq_motif(V.et(i + 1), V.et(i + 2)) <= 1;
