@@ -160,6 +160,7 @@ __global__ void __launch_bounds__(128, WQ_EXT_MINBLOCKS) wq_k_extend(const __gri
     __shared__ WqPNode s_path[WQ_FAST_PATH * 128];
     const WqPathStore st{s_path + threadIdx.x, 128, WQ_FAST_PATH, nullptr, 0};
     const uint32_t nf = wk.cursors[0], nr = wk.cursors[5];        // forward-strand hits from the front, reverse-strand from the back
+#pragma unroll 1
     for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < nf + nr; t += gridDim.x * blockDim.x) {
         const uint32_t slot = t < nf ? t : wk.hit_cap - 1 - (t - nf);
         wq_extend_thread(ix, p, b, wk, slot, s_w + threadIdx.x * (WQ_MAX_READ_WORDS + 1), st, true);
@@ -204,6 +205,7 @@ __global__ void __launch_bounds__(128, WQ_EXT_MINBLOCKS) wq_k_extend_pe(const __
     __shared__ uint64_t s_w[128 * (WQ_MAX_READ_WORDS + 1)];
     __shared__ WqPNode s_path[WQ_FAST_PATH * 128];
     const WqPathStore st{s_path + threadIdx.x, 128, WQ_FAST_PATH, nullptr, 0};
+#pragma unroll 1
     for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < 2 * nh; t += gridDim.x * blockDim.x)
         wq_extend_pe_thread(ix, p, bf, br, wk, t >> 1, (int)(t & 1), s_w + threadIdx.x * (WQ_MAX_READ_WORDS + 1), st, true);
 }

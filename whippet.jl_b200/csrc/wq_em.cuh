@@ -1127,12 +1127,15 @@ __device__ __forceinline__ double wq_round_sig(const WqPsiDev& d, double x, int 
 // calculate_psi!, :838); a CPU core runs a 50-path event's sweep in ~3 us.  So everything a sweep reads is staged once in the
 // warp's shared memory (psi / previous psi / temp counts / denominators / unambiguous counts per path, the member lists of the
 // ambiguous sets as 16-bit path indices, one prop_sum per set), and the independent chains run side by side: every lane owns
-// ambiguous sets and forms their prop_sum sequentially in member order (different sets on different lanes), the additions
-// `count_temp[p] += prop * multiplier` then go set by set (two sets may touch one path: their order is the reference's) with
-// the members of a set spread over the lanes, and the divisions / significant-digit roundings of the paths are lane-parallel.
-// The sum over all paths stays one sequential chain in path order (every lane forms it from shared memory).
-// Shared memory per event: 40 * paths + 16 * sets + 4 * (sets + 1) + 2 * members bytes, rounded up; the launch classes
-// group events by that size.  Events whose member lists do not fit (> ~100 k members) read them from global memory.
+// ambiguous sets and forms their prop_sum sequentially in member order (different sets on different lanes); the additions
+// `count_temp[p] += prop * multiplier` are then made by the lane that OWNS path p, over the sets that contain p in set order
+// (the order the reference's loop over `ambig` adds them in): an inverted index path -> sets, built once per event, replaces a
+// warp barrier per set and puts the divisions of different paths side by side.  The divisions / significant-digit roundings
+// of the paths are lane-parallel; the sum over all paths stays one sequential chain in path order (every lane forms it from
+// shared memory).
+// Shared memory per event: 44 * paths + 16 * sets + 4 * (sets + 1) + 4 * members bytes (+4), rounded up; the launch classes
+// group events by that size.  Events whose member lists do not fit (> ~50 k members) keep the set-by-set form with the
+// lists in global memory.
 struct WqPsiWarpCfg { uint32_t smem_bytes; uint32_t members_in_smem; };
 __global__ void __launch_bounds__(32) wq_k_em_psi(const WqPsiDev d, const uint32_t* __restrict__ list, const uint32_t n_list, const WqPsiWarpCfg cfg) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1152,7 +1155,9 @@ __global__ void __launch_bounds__(32) wq_k_em_psi(const WqPsiDev d, const uint32
     double* psum = cnt + np;                                      // [na]
     double* mult = psum + na;                                     // [na]
     uint32_t* moff = reinterpret_cast<uint32_t*>(mult + na);      // [na + 1] member offsets of the sets, event-local
-    uint16_t* mem = reinterpret_cast<uint16_t*>(moff + na + 1);   // [nm] event-local path index of every member (when staged)
+    uint32_t* poff = moff + na + 1;                               // [np + 1] staged: offsets of the inverted index (path -> its sets, in set order)
+    uint16_t* mem = reinterpret_cast<uint16_t*>(poff + np + 1);   // [nm] staged: event-local path index of every member
+    uint16_t* pset = mem + nm;                                    // [nm] staged: the sets of every path
     const bool staged = cfg.members_in_smem != 0;
     const uint32_t* gmem = d.amb_paths + m0;
     for (uint32_t i = lane; i < np; i += 32) {
@@ -1163,7 +1168,19 @@ __global__ void __launch_bounds__(32) wq_k_em_psi(const WqPsiDev d, const uint32
     }
     for (uint32_t a = lane; a <= na; a += 32) moff[a] = d.amb_path_ptr[a0 + a] - m0;
     for (uint32_t a = lane; a < na; a += 32) mult[a] = d.amb_mult[a0 + a];
-    if (staged) for (uint32_t k = lane; k < nm; k += 32) mem[k] = (uint16_t)gmem[k];
+    if (staged) {
+        for (uint32_t k = lane; k < nm; k += 32) mem[k] = (uint16_t)gmem[k];
+        for (uint32_t i = lane; i <= np; i += 32) poff[i] = 0;
+        __syncwarp();
+        if (lane == 0) {            // counting sort of the (set, path) pairs by path, stable in the set order; once per event
+            for (uint32_t k = 0; k < nm; k++) poff[mem[k] + 1]++;
+            for (uint32_t i = 0; i < np; i++) poff[i + 1] += poff[i];
+            for (uint32_t a = 0; a < na; a++)
+                for (uint32_t k = moff[a]; k < moff[a + 1]; k++) pset[poff[mem[k]]++] = (uint16_t)a;
+            for (uint32_t i = np; i > 0; i--) poff[i] = poff[i - 1];
+            poff[0] = 0;
+        }
+    }
     __syncwarp();
     auto member = [&](uint32_t k) -> uint32_t { return staged ? (uint32_t)mem[k] : gmem[k]; };
     auto normalise = [&](int sig) {
@@ -1205,16 +1222,32 @@ __global__ void __launch_bounds__(32) wq_k_em_psi(const WqPsiDev d, const uint32
             }
             __syncwarp();
         }
-        for (uint32_t a = 0; a < na; a++) {
-            const uint32_t kb = moff[a], n = moff[a + 1] - kb;
-            const double ps = it > 1 ? psum[a] : 1.0, mu = mult[a];
-            for (uint32_t k = lane; k < n; k += 32) {
-                const uint32_t pth = member(kb + k);
-                // first sweep: ones(n)/n over prop_sum = 1.0; later sweeps: current psi over their sum (src/events.jl:869-886)
-                const double base = it > 1 ? psi[pth] : __ddiv_rn(1.0, (double)n);
-                ct[pth] = __dadd_rn(ct[pth], __dmul_rn(__ddiv_rn(base, ps), mu));
+        if (staged) {
+            // every path by its owner lane: the shares of the sets that contain it, added in set order
+            for (uint32_t i = lane; i < np; i += 32) {
+                double c = ct[i];
+                const double pi = psi[i];
+                for (uint32_t k = poff[i]; k < poff[i + 1]; k++) {
+                    const uint32_t a = pset[k];
+                    // first sweep: ones(n)/n over prop_sum = 1.0; later sweeps: current psi over their sum (src/events.jl:869-886)
+                    const double base = it > 1 ? pi : __ddiv_rn(1.0, (double)(moff[a + 1] - moff[a]));
+                    const double ps = it > 1 ? psum[a] : 1.0;
+                    c = __dadd_rn(c, __dmul_rn(__ddiv_rn(base, ps), mult[a]));
+                }
+                ct[i] = c;
             }
             __syncwarp();
+        } else {
+            for (uint32_t a = 0; a < na; a++) {
+                const uint32_t kb = moff[a], n = moff[a + 1] - kb;
+                const double ps = it > 1 ? psum[a] : 1.0, mu = mult[a];
+                for (uint32_t k = lane; k < n; k += 32) {
+                    const uint32_t pth = member(kb + k);
+                    const double base = it > 1 ? psi[pth] : __ddiv_rn(1.0, (double)n);
+                    ct[pth] = __dadd_rn(ct[pth], __dmul_rn(__ddiv_rn(base, ps), mu));
+                }
+                __syncwarp();
+            }
         }
         normalise(d.sig);
         if (tandem) { if (differs() && it < d.maxit) it += 1; else break; }
@@ -1224,7 +1257,7 @@ __global__ void __launch_bounds__(32) wq_k_em_psi(const WqPsiDev d, const uint32
     if (lane == 0) d.iterations[e] = (int32_t)it;
 }
 static inline size_t wq_psi_warp_smem(uint32_t np, uint32_t na, uint32_t nm, bool staged) {
-    size_t b = 40ull * np + 16ull * na + 4ull * (na + 1) + (staged ? 2ull * nm : 0);
+    size_t b = 40ull * np + 16ull * na + 4ull * (na + 1) + 4ull * (np + 1) + (staged ? 4ull * nm : 0);
     return (b + 15) & ~15ull;
 }
 

@@ -16,7 +16,7 @@ static inline unsigned wq_host_threads() {
     unsigned hc = std::max(1u, std::thread::hardware_concurrency());
     unsigned ranks = 1;
     if (const char* lw = getenv("LOCAL_WORLD_SIZE")) ranks = (unsigned)std::max(1, atoi(lw));
-    return std::max(1u, std::min(16u, hc / ranks));
+    return std::max(1u, std::min(32u, hc / ranks));
 }
 
 struct WqKeyedStore {                                        // variable-length keyed counts (wq_build_key_* records)
