@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--reads", type=int, default=int(os.environ.get("WQ_BENCH_READS", 0)), help="override the config's read count")
     ap.add_argument("--cpu-sample", type=int, default=int(os.environ.get("WQ_BENCH_CPU_SAMPLE", 1_500_000)))
     ap.add_argument("--no-parity", action="store_true", help="skip the parity check (profiling runs only; the line says so)")
+    ap.add_argument("--no-fastq", action="store_true", help="skip the file -> result measurement (e2e_fastq)")
     return ap.parse_args()
 
 
@@ -416,6 +417,49 @@ def quantify(q, part, world, phase=None):
     return it, tpm, cnt, gt, ev, rl
 
 
+def fastq_e2e(run, world):
+    """File -> result through wq_process_fastq (inflate / map, newline scan, 2-bit + phred packing on the host threads, pipelined with
+    the alignment of the previous batch) + the same quant stage, on FASTQ renderings of a prefix of the bench reads: a plain
+    file, a blocked-gzip (BGZF) file and an ordinary single-member gzip file (serial inflate).  Files live in /dev/shm or the
+    temp directory and are in the page cache (just written)."""
+    import gzip
+    import tempfile
+    from wq_inputs import synth
+    part, q = run.part, run.q
+    rb = part.reads
+    d = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else tempfile.gettempdir()
+    res = {"unit": "reads/s", "note": "reads / (wq_quant_reset + wq_process_fastq + classes + EM + multi-map assignment + events), one GPU; "
+                                      "the text is a rendering of the first reads of the bench batch"}
+    plan = [("plain", min(rb.n, 4_000_000)), ("bgzf", min(rb.n, 2_000_000)), ("gzip", min(rb.n, 1_000_000))]
+    text = synth.fastq_bytes(rb, 0, plan[0][1])
+    rec = len(text) // plan[0][1]
+    for kind, n in plan:
+        path = os.path.join(d, f"wq_bench_{os.getpid()}_{kind}.fastq" + ("" if kind == "plain" else ".gz"))
+        t = text[:n * rec]
+        try:
+            if kind == "plain":
+                open(path, "wb").write(t)
+            elif kind == "bgzf":
+                open(path, "wb").write(synth.bgzf_compress(t, threads=min(32, os.cpu_count() or 8)))
+            else:
+                with gzip.open(path, "wb", compresslevel=1) as fh:
+                    fh.write(t)
+            best = None
+            for rep in range(2):
+                t0 = time.perf_counter()
+                q.reset()
+                st = q.process_fastq(part.param, path)
+                quantify(q, part, world)
+                dt = time.perf_counter() - t0
+                best = dt if best is None else min(best, dt)
+            assert st.total == n, (st.total, n)
+            res[kind] = {"value": n / best, "reads": n, "file_bytes": os.path.getsize(path), "text_bytes": len(t), "seconds": best}
+        finally:
+            if os.path.exists(path):
+                os.remove(path)
+    return res
+
+
 def bits_equal(a, b):
     a, b = np.ascontiguousarray(a), np.ascontiguousarray(b)
     return a.shape == b.shape and a.dtype.itemsize == b.dtype.itemsize and np.array_equal(a.view(np.uint8), b.view(np.uint8))
@@ -625,6 +669,11 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = total_reads / (float(t.item()) / 1000.0)
 
+    # ---- file -> result: the closest equal of the reference's process_reads!, which parses (src/reads.jl:54-57) ----------
+    e2e_fastq = None
+    if world == 1 and a.config == 2 and not a.no_fastq:
+        e2e_fastq = fastq_e2e(main_run, world)
+
     # ---- CPU baseline (N = 1 only) and the parity check (every run) -------------------------------------------
     oracle_runs = {}
     cpu = None
@@ -669,6 +718,8 @@ def main():
         "phase_ms": phase_ms,
         "parity_check": parity if parity is not None else "skipped (--no-parity)",
     }
+    if e2e_fastq is not None:
+        out["e2e_fastq"] = e2e_fastq
 
     def roofline(ctr, n0):
         R = mp.readlen or 101

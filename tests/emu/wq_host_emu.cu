@@ -2,6 +2,7 @@
 // whippet.jl_b200/csrc/wq_em.cuh host part, wq_events.h) on given count stores, so they can be checked against the oracle
 // in a container without a GPU.  No kernel is launched here and nothing of this file is part of the product library.
 #include <cuda_runtime.h>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <string>
@@ -24,6 +25,8 @@ struct HostEmu {
 extern "C" {
 
 static int g_event_pieces = 0;
+static double* g_gene_times = nullptr;      // optional [G + 1] milliseconds per gene of the last hemu_events (profiling aid)
+void hemu_set_gene_times(double* p) { g_gene_times = p; }
 void hemu_set_event_pieces(int k) { g_event_pieces = k; }
 HostEmu* hemu_create(const wq_index_desc* d) {
     HostEmu* e = new HostEmu();
@@ -95,12 +98,14 @@ uint64_t hemu_events(HostEmu* e, const double* node_value, uint64_t ne, const ui
         // hemu_set_event_pieces(k): build every gene in pieces of k visited nodes, the way the library cuts genes with many nodes
         // over its host threads (wq_gene_visits); the records must not depend on the cut
         const int pieces = g_event_pieces;
+        const auto tg0 = std::chrono::steady_clock::now();
         if (pieces > 0) {
             std::vector<uint32_t> visits;
             wq_gene_visits(V, visits);
             for (size_t v = 0; v < visits.size(); v += (size_t)pieces)
                 wq_gene_events(V, readlen, e->recs, e->P, e->pool, visits[v], visits[std::min(visits.size(), v + (size_t)pieces) - 1]);
         } else wq_gene_events(V, readlen, e->recs, e->P, e->pool);
+        if (g_gene_times) g_gene_times[g] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tg0).count();
     }
     return e->recs.size();
 }

@@ -153,3 +153,69 @@ def test_process_fastq_paired(tmp_path):
         assert np.array_equal(x, y)
     assert a.keyed(0) == b.keyed(0) and a.keyed(1) == b.keyed(1)
     a.close(); b.close()
+
+
+def _batches(path_or_text, batch, from_memory=False):
+    """All batches of a reader as (lens, seq words per read, qual bytes per read, names)."""
+    import ctypes as C
+    from whippet_jl_b200 import abi, lib
+    L = lib.load()
+    h = C.c_void_p()
+    if from_memory:
+        lib.check(L.wq_fastq_from_memory(path_or_text, len(path_or_text), 33, C.byref(h)))
+    else:
+        lib.check(L.wq_fastq_open(str(path_or_text).encode(), 33, C.byref(h)))
+    out = []
+    while True:
+        b = abi.ReadBatchC()
+        lib.check(L.wq_fastq_next(h, batch, C.byref(b)))
+        if b.n_reads == 0:
+            break
+        n = b.n_reads
+        lens = np.ctypeslib.as_array(b.len, (n,)).copy()
+        seq = np.ctypeslib.as_array(b.seq2, (int(b.seq2_words),)).copy()
+        qual = np.ctypeslib.as_array(b.qual, (int(b.qual_bytes),)).copy()
+        so = np.ctypeslib.as_array(b.seq_off, (n,)).copy()
+        qo = np.ctypeslib.as_array(b.qual_off, (n,)).copy()
+        out.append((lens, seq, qual, so, qo))
+    L.wq_fastq_close(h)
+    return out
+
+
+def test_large_plain_file_blocked_gzip_and_plain_gzip_agree(tmp_path):
+    """The three input forms of one text -- mapped plain file (parallel newline scan over a window of many MB), blocked gzip
+    (BGZF: parallel inflate) and ordinary gzip (serial zlib) -- give the same batches as the in-memory reader, across batch
+    boundaries that fall inside scan pieces and inflate windows."""
+    import gzip
+    from wq_inputs import synth
+    idx = synth.make_index(n_genes=60, K=9, seed=3)
+    rb = synth.simulate_reads(idx, 120_000, 101, seed=4)
+    text = synth.fastq_bytes(rb)
+    assert len(text) > 20 * (1 << 20)
+    plain, bg, gz = tmp_path / "r.fastq", tmp_path / "r.bgzf.fastq.gz", tmp_path / "r.fastq.gz"
+    plain.write_bytes(text)
+    bg.write_bytes(synth.bgzf_compress(text))
+    with gzip.open(gz, "wb", compresslevel=1) as fh:
+        fh.write(text)
+    assert gzip.decompress(bg.read_bytes()) == text             # a BGZF file is a valid multi-member gzip file
+    want = _batches(text, 50_000, from_memory=True)
+    assert sum(len(b[0]) for b in want) == rb.n
+    # the packed form equals the batch the text was rendered from
+    lens = np.concatenate([b[0] for b in want])
+    assert np.array_equal(lens, rb.len) and np.array_equal(np.concatenate([b[1] for b in want]), rb.seq2)
+    for path in (plain, bg, gz):
+        got = _batches(path, 50_000)
+        assert len(got) == len(want), path
+        for g, w in zip(got, want):
+            assert all(np.array_equal(a, b) for a, b in zip(g, w)), path
+
+
+def test_truncated_and_malformed_files_are_errors(tmp_path):
+    from whippet_jl_b200.lib import WhippetB200Error
+    good = b"@a\nACGT\n+\nIIII\n@b\nAC\n+\nII\n"
+    for bad in (good[:-4], good.replace(b"+\nII", b"-\nII"), good.replace(b"IIII", b"III")):
+        with pytest.raises(WhippetB200Error):
+            _batches(bad, 10, from_memory=True)
+    # blank lines at the end of the file are not records
+    assert sum(len(b[0]) for b in _batches(good + b"\n\r\n\n", 10, from_memory=True)) == 2
+    assert sum(len(b[0]) for b in _batches(good[:-1], 10, from_memory=True)) == 2          # last line without a newline

@@ -478,7 +478,7 @@ static void wq_build_event_batch(wq_handle* h, int64_t readlen, int group, WqEvB
     struct Piece { uint32_t g_lo, g_hi, node_lo, node_hi; };
     std::vector<Piece> pieces;
     {
-        const uint32_t per_piece = nt == 1 ? p_n : std::max<uint32_t>(8, p_n / (16 * nt) + 1), big_gene = 48, visits_per_piece = 12;
+        const uint32_t per_piece = nt == 1 ? p_n : std::max<uint32_t>(8, p_n / (16 * nt) + 1), big_gene = 32;
         std::vector<uint32_t> visits;
         WqGeneEvents Vv{h->H, X.node_value, 0, {}};
         uint32_t start = p_lo + 1;
@@ -488,6 +488,7 @@ static void wq_build_event_batch(wq_handle* h, int64_t readlen, int group, WqEvB
                 flush(g - 1);
                 Vv.g = g;
                 wq_gene_visits(Vv, visits);
+                const size_t visits_per_piece = h->H.genes[g - 1].nn >= 128 ? 2 : 8;      // the widest genes have the costliest nodes
                 for (size_t v = 0; v < visits.size(); v += visits_per_piece) {
                     const size_t ve = std::min(visits.size(), v + visits_per_piece);
                     pieces.push_back(Piece{g, g, visits[v], visits[ve - 1]});
@@ -1014,18 +1015,17 @@ int wq_align_pe_device(wq_handle* h, const wq_align_param* p, const wq_read_batc
 int wq_fastq_open(const char* path, int qualoffset, wq_fastq** out) {
     if (!path || !out) return fail(-1, "null argument");
     *out = nullptr;
-    gzFile gz = gzopen(path, "rb");
-    if (!gz) return fail(-20, std::string("cannot open ") + path);
-    gzbuffer(gz, 1u << 20);
     wq_fastq* f = new wq_fastq();
-    f->gz = gz; f->qualoffset = qualoffset;
+    f->qualoffset = qualoffset;
+    if (int rc = wq_fastq_open_impl(f, path)) { std::string e = f->err; delete f; return fail(rc, e); }
     *out = f;
     return 0;
 }
 int wq_fastq_from_memory(const void* text, uint64_t len, int qualoffset, wq_fastq** out) {
     if ((!text && len) || !out) return fail(-1, "null argument");
     wq_fastq* f = new wq_fastq();
-    f->mem = (const char*)text; f->mem_len = len; f->qualoffset = qualoffset;
+    f->map = (const char*)text; f->map_len = len; f->map_owned = false; f->qualoffset = qualoffset;
+    f->wbase = f->map; f->woff = 0; f->wlen = len; f->eof = true;
     *out = f;
     return 0;
 }
@@ -1045,8 +1045,7 @@ int wq_fastq_names(wq_fastq* f, const uint64_t** name_off, const uint32_t** name
 }
 void wq_fastq_close(wq_fastq* f) {
     if (!f) return;
-    if (f->gz) gzclose(f->gz);
-    f->slot[0].release(); f->slot[1].release();
+    wq_fastq_release(f);
     delete f;
 }
 

@@ -1416,6 +1416,15 @@ static inline std::string wq_run_em_psi(wq_psi_batch& b, WqEmScratch& M, cudaStr
         else wq_k_em_psi<<<n, 32, kWarpSmem[c - 3], ss>>>(d, lst, n, WqPsiWarpCfg{(uint32_t)kWarpSmem[c - 3], 1u});
         if (launches) *launches += 1;
         WQ_EMCK(cudaGetLastError());
+        static const bool class_timing = getenv("WQ_PSI_CLASS_TIMING") != nullptr;     // diagnostic: serialises the classes
+        if (class_timing) {
+            const auto t0 = std::chrono::steady_clock::now();
+            WQ_EMCK(cudaStreamSynchronize(ss));
+            uint64_t np_max = 0;
+            for (uint32_t k = 0; k < n; k++) { const uint32_t e = order[cbase[c] + k]; np_max = std::max<uint64_t>(np_max, b.path_ptr[e + 1] - b.path_ptr[e]); }
+            fprintf(stderr, "[wq]       psi class %d: %u events (max %llu paths) %9.3f ms\n", c, n, (unsigned long long)np_max,
+                    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+        }
         if (used > 0) { WQ_EMCK(cudaEventRecord(M.join[(used - 1) % 3], ss)); WQ_EMCK(cudaStreamWaitEvent(stream, M.join[(used - 1) % 3], 0)); }
         used++;
     }

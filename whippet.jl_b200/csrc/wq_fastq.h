@@ -4,12 +4,24 @@
 //   make_fqparser            FASTQ.Reader(stream, fill_ambiguous = DNA_A): every sequence byte that is not one of
 //                            ACGTacgt becomes 'A' before the 2-bit conversion (FASTX 1.1.3 generate_fill_ambiguous)
 //   fill!(rec, offset)       sequence -> 2-bit BioSequence, quality = raw quality bytes .- offset (UInt8 arithmetic)
-// The reference parses one record at a time on one thread through Libz; here the serial part is only the inflate and
-// the newline scan, the conversion of the records of a batch is spread over the host threads, and the batch is written
-// into page-locked buffers so the H2D copies of wq_align_se / wq_align_pe run at full PCIe rate.
+// The reference parses one record at a time on one thread through Libz.  Here every stage that can be is spread over the
+// host threads, because at the device's alignment rate (> 100 M reads/s) the text side is what bounds file -> result:
+//   * plain files are mapped, not read: the newline scan and the conversion work on the mapping directly;
+//   * blocked gzip (BGZF: bgzip, bcl2fastq output -- independent deflate blocks that announce their size) is inflated block
+//     by block on all threads straight into the text window; an ordinary single-member gzip stream has no entry points and
+//     is inflated serially by zlib (about 0.3-0.4 GB/s), overlapped with the alignment of the previous batch;
+//   * the newline scan runs in parallel over pieces of the window (records are strictly four lines, so a record boundary is
+//     a line number, not a guess about '@'), then lengths / validation / offsets by a two-pass prefix sum, then the 2-bit and
+//     phred conversion of the records;
+//   * the batch is written into page-locked buffers so the H2D copies of wq_align_se / wq_align_pe run at full PCIe rate.
 // Host-only code (no kernel): it is the stage in front of the device path, SURVEY.md section 8f row 1.
 #pragma once
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <zlib.h>
+#include <atomic>
 #include <cstdint>
 #include <cstring>
 #include <string>
@@ -41,15 +53,24 @@ struct WqFastqSlot {                 // one packed batch + the record names (for
 };
 
 struct wq_fastq {
-    gzFile gz = nullptr;                          // file input (gzread is transparent for uncompressed files)
-    const char* mem = nullptr; uint64_t mem_len = 0, mem_pos = 0;     // or an in-memory text
+    // ---- input: exactly one of these ----
+    const char* map = nullptr; size_t map_len = 0; int fd = -1; bool map_owned = false;     // plain text, mapped (or caller's memory)
+    gzFile gz = nullptr;                                                                   // single-member gzip: serial inflate
+    bool bgzf = false; size_t bgzf_pos = 0;                                                 // blocked gzip: `map` holds the COMPRESSED file
     int qualoffset = 33;
-    std::vector<char> text;                       // inflated text not yet consumed
-    size_t text_pos = 0;
-    bool eof = false;
+    // ---- text window: stream offsets [woff, woff + wlen) are in memory at wbase ----
+    std::vector<char> text;            // owns the window for the gzip modes
+    const char* wbase = nullptr; uint64_t woff = 0, wlen = 0;
+    bool eof = false;                  // no more text will be appended to the window
+    // ---- line index: stream offsets of the newlines found so far, nl_pos = first one not yet consumed by a batch ----
+    std::vector<uint64_t> nl; size_t nl_pos = 0;
+    uint64_t scanned = 0;              // the window has been scanned up to this stream offset
+    uint64_t line_start = 0;           // stream offset of the first line not yet consumed
+    bool closed_tail = false;          // the virtual newline after an unterminated last line has been added
     WqFastqSlot slot[2];
     int cur = 0;
-    uint64_t records = 0;                         // records returned so far (for error messages)
+    uint64_t records = 0;              // records returned so far (for error messages)
+    double avg_rec = 300.0;            // bytes per record seen so far (sizes the next scan)
     std::string err;
 };
 
@@ -64,97 +85,249 @@ static inline const uint8_t* wq_fastq_code_table() {
     return T;
 }
 
-// pull more text until at least `want` bytes are buffered after text_pos or the input ends
-static inline bool wq_fastq_fill(wq_fastq* f, size_t want, bool compact) {
-    if (compact && f->text_pos > 0) {                                    // drop the consumed prefix (only between batches:
-        f->text.erase(f->text.begin(), f->text.begin() + f->text_pos);   //  records of the current batch are offsets into text)
-        f->text_pos = 0;
+template <class F> static inline void wq_fq_parallel(unsigned nt, F&& f) {
+    if (nt <= 1) { f(0u); return; }
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; t++) th.emplace_back([&f, t]() { f(t); });
+    for (auto& x : th) x.join();
+}
+
+// BGZF block at `p` (RFC 1952 member with FEXTRA subfield 'B','C'): total block size, or 0 when it is not one
+static inline size_t wq_bgzf_block_size(const unsigned char* p, size_t avail) {
+    if (avail < 18 || p[0] != 0x1f || p[1] != 0x8b || p[2] != 8 || !(p[3] & 4)) return 0;
+    const size_t xlen = p[10] | ((size_t)p[11] << 8);
+    if (avail < 12 + xlen) return 0;
+    for (size_t o = 12; o + 4 <= 12 + xlen;) {
+        const size_t slen = p[o + 2] | ((size_t)p[o + 3] << 8);
+        if (p[o] == 'B' && p[o + 1] == 'C' && slen == 2) return (size_t)(p[o + 4] | ((size_t)p[o + 5] << 8)) + 1;
+        o += 4 + slen;
     }
-    while (!f->eof && f->text.size() - f->text_pos < want) {
-        const size_t chunk = 8u << 20;
+    return 0;
+}
+
+static inline int wq_fastq_open_impl(wq_fastq* f, const char* path) {
+    int fd = open(path, O_RDONLY);
+    if (fd < 0) { f->err = std::string("cannot open ") + path; return -20; }
+    struct stat st;
+    if (fstat(fd, &st) != 0) { close(fd); f->err = std::string("cannot stat ") + path; return -20; }
+    unsigned char head[32];
+    const ssize_t got = pread(fd, head, sizeof head, 0);
+    const bool is_gz = got >= 2 && head[0] == 0x1f && head[1] == 0x8b;
+    const bool is_bgzf = is_gz && wq_bgzf_block_size(head, (size_t)got) != 0;
+    if (is_gz && !is_bgzf) {
+        close(fd);
+        f->gz = gzopen(path, "rb");
+        if (!f->gz) { f->err = std::string("cannot open ") + path; return -20; }
+        gzbuffer(f->gz, 1u << 20);
+        return 0;
+    }
+    if (st.st_size > 0) {
+        void* m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+        if (m == MAP_FAILED) { close(fd); f->err = std::string("cannot map ") + path; return -20; }
+        madvise(m, (size_t)st.st_size, MADV_SEQUENTIAL);
+        f->map = (const char*)m; f->map_len = (size_t)st.st_size; f->map_owned = true;
+    }
+    f->fd = fd;
+    f->bgzf = is_bgzf;
+    if (!is_bgzf) { f->wbase = f->map; f->woff = 0; f->wlen = f->map_len; f->eof = true; }      // the whole text is the window
+    return 0;
+}
+
+static inline void wq_fastq_release(wq_fastq* f) {
+    if (f->gz) gzclose(f->gz);
+    if (f->map_owned && f->map) munmap((void*)f->map, f->map_len);
+    if (f->fd >= 0) close(f->fd);
+    f->slot[0].release(); f->slot[1].release();
+}
+
+// gzip modes: drop the consumed prefix of the window (between batches only) and append more inflated text
+static inline bool wq_fastq_pull(wq_fastq* f, size_t want) {
+    if (f->eof) return true;
+    const uint64_t keep_from = f->line_start;                       // everything before the first unconsumed line can go
+    if (keep_from > f->woff) {
+        f->text.erase(f->text.begin(), f->text.begin() + (size_t)(keep_from - f->woff));
+        f->woff = keep_from;
+    }
+    if (f->gz) {
         const size_t old = f->text.size();
-        f->text.resize(old + chunk);
+        f->text.resize(old + want);
         size_t got = 0;
-        if (f->gz) {
-            int r = gzread(f->gz, f->text.data() + old, (unsigned)chunk);
+        while (got < want) {
+            int r = gzread(f->gz, f->text.data() + old + got, (unsigned)std::min<size_t>(want - got, 1u << 30));
             if (r < 0) { int en = 0; f->err = std::string("gzread: ") + gzerror(f->gz, &en); f->text.resize(old); return false; }
-            got = (size_t)r;
-        } else {
-            got = (size_t)std::min<uint64_t>(chunk, f->mem_len - f->mem_pos);
-            memcpy(f->text.data() + old, f->mem + f->mem_pos, got);
-            f->mem_pos += got;
+            if (r == 0) { f->eof = true; break; }
+            got += (size_t)r;
         }
         f->text.resize(old + got);
-        if (got == 0) f->eof = true;
+    } else if (f->bgzf) {
+        // blocks up to ~want bytes of text: sizes from the block trailers (ISIZE), then every block inflated by some thread
+        struct Blk { size_t off, csize, hdr; uint32_t isize; size_t out; };
+        std::vector<Blk> blks;
+        size_t total = 0;
+        const unsigned char* base = (const unsigned char*)f->map;
+        while (f->bgzf_pos < f->map_len && total < want) {
+            const size_t bs = wq_bgzf_block_size(base + f->bgzf_pos, f->map_len - f->bgzf_pos);
+            if (bs < 26 || f->bgzf_pos + bs > f->map_len) { f->err = "malformed BGZF block"; return false; }
+            const unsigned char* p = base + f->bgzf_pos;
+            const size_t xlen = p[10] | ((size_t)p[11] << 8);
+            uint32_t isize;
+            memcpy(&isize, p + bs - 4, 4);
+            blks.push_back(Blk{f->bgzf_pos, bs, 12 + xlen, isize, total});
+            total += isize;
+            f->bgzf_pos += bs;
+        }
+        if (f->bgzf_pos >= f->map_len) f->eof = true;
+        const size_t old = f->text.size();
+        f->text.resize(old + total);
+        char* dst = f->text.data() + old;
+        std::atomic<size_t> next{0};
+        std::atomic<int> bad{0};
+        const unsigned nt = blks.size() < 8 ? 1u : wq_host_threads();
+        wq_fq_parallel(nt, [&](unsigned) {
+            z_stream zs;
+            memset(&zs, 0, sizeof zs);
+            if (inflateInit2(&zs, -15) != Z_OK) { bad = 1; return; }
+            for (size_t b; (b = next.fetch_add(1)) < blks.size();) {
+                const Blk& k = blks[b];
+                if (k.isize == 0) continue;
+                inflateReset(&zs);
+                zs.next_in = (Bytef*)(base + k.off + k.hdr);
+                zs.avail_in = (uInt)(k.csize - k.hdr - 8);
+                zs.next_out = (Bytef*)(dst + k.out);
+                zs.avail_out = k.isize;
+                const int r = inflate(&zs, Z_FINISH);
+                if (r != Z_STREAM_END || zs.avail_out != 0) bad = 1;
+            }
+            inflateEnd(&zs);
+        });
+        if (bad) { f->err = "BGZF block failed to inflate"; return false; }
     }
+    f->wbase = f->text.data();
+    f->wlen = f->text.size();
     return true;
+}
+
+// newline offsets of the window part [from, to) appended to f->nl, scanned in parallel
+static inline void wq_fastq_scan(wq_fastq* f, uint64_t from, uint64_t to) {
+    if (to <= from) return;
+    const uint64_t span = to - from;
+    unsigned nt = span < (4u << 20) ? 1u : wq_host_threads();
+    std::vector<std::vector<uint64_t>> found(nt);
+    const char* base = f->wbase - f->woff;                         // base + stream offset = address
+    wq_fq_parallel(nt, [&](unsigned t) {
+        const uint64_t a = from + span * t / nt, b = from + span * (t + 1) / nt;
+        std::vector<uint64_t>& v = found[t];
+        v.reserve((size_t)((b - a) / 60 + 16));
+        const char* p = base + a;
+        const char* e = base + b;
+        while (p < e) {
+            const char* q = (const char*)memchr(p, '\n', (size_t)(e - p));
+            if (!q) break;
+            v.push_back((uint64_t)(q - base));
+            p = q + 1;
+        }
+    });
+    size_t add = 0;
+    for (auto& v : found) add += v.size();
+    const size_t old = f->nl.size();
+    f->nl.resize(old + add);
+    size_t at = old;
+    for (auto& v : found) { memcpy(f->nl.data() + at, v.data(), v.size() * 8); at += v.size(); }
 }
 
 // Next batch of at most max_reads records.  out->n_reads == 0 at end of input.  The buffers belong to the reader and
 // stay valid until the call after the next one (two slots alternate, so a batch can be aligned while the next is parsed).
 static inline int wq_fastq_next_impl(wq_fastq* f, uint32_t max_reads, wq_read_batch* out) {
-    struct Rec { size_t name, seq, qual; uint32_t name_len, len; };          // offsets into f->text (it may be reallocated)
-    std::vector<Rec> recs;
-    recs.reserve(max_reads);
-    // ---- serial: split lines; more text is appended as needed ----
-    if (!wq_fastq_fill(f, 1u << 20, true)) return -20;
-    while (recs.size() < max_reads) {
-        const char* base = f->text.data();
-        const char* end = base + f->text.size();
-        const char* p = base + f->text_pos;
-        // skip blank lines between records (a trailing newline at the end of the file)
-        while (p < end && (*p == '\n' || *p == '\r')) p++;
-        f->text_pos = (size_t)(p - base);
-        if (p >= end) {
-            if (f->eof) break;
-            if (!wq_fastq_fill(f, 1u << 20, false)) return -20;
+    memset(out, 0, sizeof *out);
+    // ---- forget the consumed part of the line index ----
+    if (f->nl_pos > 0) { f->nl.erase(f->nl.begin(), f->nl.begin() + f->nl_pos); f->nl_pos = 0; }
+    // ---- enough lines for the batch, or the end of the input ----
+    const size_t need = (size_t)max_reads * 4;
+    for (;;) {
+        if (f->nl.size() >= need) break;
+        const uint64_t wend = f->woff + f->wlen;
+        if (f->scanned < wend) {
+            const uint64_t want = (uint64_t)((double)(need - f->nl.size()) / 4.0 * f->avg_rec * 1.05) + (1u << 16);
+            const uint64_t to = std::min(wend, f->scanned + want);
+            wq_fastq_scan(f, f->scanned, to);
+            f->scanned = to;
             continue;
         }
-        const char* ln[5];
-        ln[0] = p;
-        bool complete = true, open_end = false;      // open_end: the last line of the file has no newline (ln[4] = end, nothing to strip)
-        for (int k = 1; k <= 4; k++) {
-            const char* nl = (const char*)memchr(ln[k - 1], '\n', (size_t)(end - ln[k - 1]));
-            if (!nl) {
-                if (f->eof && k == 4 && ln[3] < end) { ln[4] = end; open_end = true; break; }
-                complete = false; break;
-            }
-            ln[k] = nl + 1;
-        }
-        if (!complete) {
-            if (f->eof) { f->err = "truncated FASTQ record after record " + std::to_string(f->records + recs.size()); return -21; }
-            if (!wq_fastq_fill(f, (f->text.size() - f->text_pos) + (1u << 20), false)) return -20;
+        if (!f->eof) {
+            const size_t want = (size_t)std::max<double>(32.0 * (1 << 20), (double)(need - f->nl.size()) / 4.0 * f->avg_rec * 1.05);
+            if (!wq_fastq_pull(f, want)) return -20;
             continue;
         }
-        auto line_len = [&](int k) { size_t n = (size_t)(ln[k + 1] - ln[k]) - ((k == 3 && open_end) ? 0 : 1); if (n && ln[k][n - 1] == '\r') n--; return n; };
-        const size_t nl = line_len(0), sl = line_len(1), ql = line_len(3);
-        if (ln[0][0] != '@' || ln[2][0] != '+') { f->err = "malformed FASTQ record " + std::to_string(f->records + recs.size() + 1) + " (expected '@' / '+' lines)"; return -21; }
-        if (sl != ql) { f->err = "FASTQ record " + std::to_string(f->records + recs.size() + 1) + ": sequence and quality lengths differ"; return -21; }
-        if (sl > 255) { f->err = "FASTQ record " + std::to_string(f->records + recs.size() + 1) + ": read longer than 255 (ReadLengthInt = UInt8, src/align.jl:74)"; return -21; }
-        recs.push_back(Rec{(size_t)(ln[0] + 1 - base), (size_t)(ln[1] - base), (size_t)(ln[3] - base), (uint32_t)(nl - 1), (uint32_t)sl});
-        f->text_pos = (size_t)(ln[4] - base);
+        // end of input: an unterminated last line counts as a line
+        if (!f->closed_tail) {
+            f->closed_tail = true;
+            const uint64_t last_start = f->nl.empty() ? f->line_start : f->nl.back() + 1;
+            if (wend > last_start) f->nl.push_back(wend);
+        }
+        break;
     }
-    const char* text = f->text.data();
+    // trailing blank lines at the end of the file are not records
+    size_t nlines = std::min(f->nl.size(), need);
+    const char* base = f->wbase - f->woff;
+    if (f->nl.size() < need) {
+        auto blank = [&](size_t k) {
+            const uint64_t s = k == 0 ? f->line_start : f->nl[k - 1] + 1, e = f->nl[k];
+            return e == s || (e == s + 1 && base[s] == '\r');
+        };
+        while (nlines > 0 && blank(nlines - 1)) nlines--;
+        if (nlines % 4 != 0) { f->err = "truncated FASTQ record after record " + std::to_string(f->records + nlines / 4); return -21; }
+    }
+    const uint32_t n = (uint32_t)(nlines / 4);
     f->cur ^= 1;
     WqFastqSlot& S = f->slot[f->cur];
-    const uint32_t n = (uint32_t)recs.size();
     S.n = n;
-    memset(out, 0, sizeof *out);
-    if (n == 0) return 0;
-    // ---- offsets (serial prefix), then conversion on the host threads ----
+    if (n == 0) { f->nl_pos = f->nl.size(); return 0; }
     uint8_t* len = (uint8_t*)S.len.ensure(n);
     uint64_t* seq_off = (uint64_t*)S.seq_off.ensure((size_t)n * 8);
     uint64_t* qual_off = (uint64_t*)S.qual_off.ensure((size_t)n * 8);
     if (!len || !seq_off || !qual_off) { f->err = "out of memory"; return -22; }
     S.name_off.resize(n); S.name_len.resize(n);
-    uint64_t w = 0, q = 0, nm = 0;
-    for (uint32_t i = 0; i < n; i++) {
-        len[i] = (uint8_t)recs[i].len;
-        seq_off[i] = w; qual_off[i] = q; S.name_off[i] = nm; S.name_len[i] = recs[i].name_len;
-        w += (recs[i].len + 31) / 32 + (recs[i].len == 0 ? 1 : 0);
-        q += (recs[i].len + 3) & ~3u;
-        nm += recs[i].name_len;
-    }
+    const uint64_t first = f->line_start;
+    const uint64_t* nl = f->nl.data();
+    auto lstart = [&](size_t k) -> uint64_t { return k == 0 ? first : nl[k - 1] + 1; };
+    auto llen = [&](size_t k) -> size_t {              // without the newline and a carriage return before it
+        const uint64_t s = lstart(k), e = nl[k];
+        size_t m = (size_t)(e - s);
+        if (m && base[e - 1] == '\r') m--;
+        return m;
+    };
+    unsigned nt = n < 4096 ? 1u : wq_host_threads();
+    // ---- pass 1: lengths + validation + per-thread totals ----
+    std::vector<uint64_t> tw(nt + 1, 0), tq(nt + 1, 0), tn(nt + 1, 0);
+    std::vector<int64_t> bad(nt, -1);
+    std::vector<int> why(nt, 0);
+    wq_fq_parallel(nt, [&](unsigned t) {
+        const uint32_t lo = (uint32_t)((uint64_t)n * t / nt), hi = (uint32_t)((uint64_t)n * (t + 1) / nt);
+        uint64_t w = 0, q = 0, nm = 0;
+        for (uint32_t i = lo; i < hi; i++) {
+            const size_t k = (size_t)i * 4;
+            const size_t l0 = llen(k), sl = llen(k + 1), l2 = llen(k + 2), ql = llen(k + 3);
+            if (l0 == 0 || base[lstart(k)] != '@' || l2 == 0 || base[lstart(k + 2)] != '+') { if (bad[t] < 0) { bad[t] = i; why[t] = 1; } continue; }
+            if (sl != ql) { if (bad[t] < 0) { bad[t] = i; why[t] = 2; } continue; }
+            if (sl > 255) { if (bad[t] < 0) { bad[t] = i; why[t] = 3; } continue; }
+            len[i] = (uint8_t)sl;
+            S.name_len[i] = (uint32_t)(l0 - 1);
+            w += (sl + 31) / 32 + (sl == 0 ? 1 : 0);
+            q += (sl + 3) & ~(size_t)3;
+            nm += l0 - 1;
+        }
+        tw[t + 1] = w; tq[t + 1] = q; tn[t + 1] = nm;
+    });
+    for (unsigned t = 0; t < nt; t++)
+        if (bad[t] >= 0) {
+            const std::string r = std::to_string(f->records + (uint64_t)bad[t] + 1);
+            f->err = why[t] == 1 ? "malformed FASTQ record " + r + " (expected '@' / '+' lines)"
+                   : why[t] == 2 ? "FASTQ record " + r + ": sequence and quality lengths differ"
+                                 : "FASTQ record " + r + ": read longer than 255 (ReadLengthInt = UInt8, src/align.jl:74)";
+            return -21;
+        }
+    for (unsigned t = 0; t < nt; t++) { tw[t + 1] += tw[t]; tq[t + 1] += tq[t]; tn[t + 1] += tn[t]; }
+    const uint64_t w = tw[nt], q = tq[nt], nm = tn[nt];
     S.seq2_words = w; S.qual_bytes = q;
     uint64_t* seq2 = (uint64_t*)S.seq2.ensure((size_t)std::max<uint64_t>(w, 1) * 8);
     uint8_t* qual = (uint8_t*)S.qual.ensure((size_t)std::max<uint64_t>(q, 4));
@@ -162,29 +335,39 @@ static inline int wq_fastq_next_impl(wq_fastq* f, uint32_t max_reads, wq_read_ba
     S.names.resize(nm);
     const uint8_t* T = wq_fastq_code_table();
     const uint8_t qo = (uint8_t)f->qualoffset;
-    unsigned nt = wq_host_threads();
-    if (n < 4096) nt = 1;
-    auto work = [&](unsigned t) {
+    // ---- pass 2: offsets of the thread's range, then the conversion of its records ----
+    wq_fq_parallel(nt, [&](unsigned t) {
         const uint32_t lo = (uint32_t)((uint64_t)n * t / nt), hi = (uint32_t)((uint64_t)n * (t + 1) / nt);
+        uint64_t wo = tw[t], qo_ = tq[t], no = tn[t];
         for (uint32_t i = lo; i < hi; i++) {
-            const Rec& r = recs[i];
-            uint64_t* wd = seq2 + seq_off[i];
-            const uint32_t nw = (r.len + 31) / 32;
-            for (uint32_t k = 0; k < nw; k++) {
+            const size_t k = (size_t)i * 4;
+            const uint32_t L = len[i];
+            seq_off[i] = wo; qual_off[i] = qo_; S.name_off[i] = no;
+            const char* sp = base + lstart(k + 1);
+            const char* qp = base + lstart(k + 3);
+            uint64_t* wd = seq2 + wo;
+            const uint32_t nw = (L + 31) / 32;
+            for (uint32_t kk = 0; kk < nw; kk++) {
                 uint64_t acc = 0;
-                const uint32_t b0 = k * 32, b1 = std::min(r.len, b0 + 32);
-                for (uint32_t j = b0; j < b1; j++) acc |= (uint64_t)T[(uint8_t)text[r.seq + j]] << (2 * (j - b0));
-                wd[k] = acc;
+                const uint32_t b0 = kk * 32, b1 = std::min(L, b0 + 32);
+                for (uint32_t j = b0; j < b1; j++) acc |= (uint64_t)T[(uint8_t)sp[j]] << (2 * (j - b0));
+                wd[kk] = acc;
             }
-            if (r.len == 0) wd[0] = 0;
-            uint8_t* qd = qual + qual_off[i];
-            for (uint32_t j = 0; j < r.len; j++) qd[j] = (uint8_t)((uint8_t)text[r.qual + j] - qo);       // UInt8 arithmetic (src/record.jl:17)
-            for (uint32_t j = r.len; j < ((r.len + 3) & ~3u); j++) qd[j] = 0;
-            memcpy(S.names.data() + S.name_off[i], text + r.name, r.name_len);
+            if (L == 0) wd[0] = 0;
+            uint8_t* qd = qual + qo_;
+            for (uint32_t j = 0; j < L; j++) qd[j] = (uint8_t)((uint8_t)qp[j] - qo);       // UInt8 arithmetic (src/record.jl:17)
+            for (uint32_t j = L; j < ((L + 3) & ~3u); j++) qd[j] = 0;
+            memcpy(S.names.data() + no, base + lstart(k) + 1, S.name_len[i]);
+            wo += nw + (L == 0 ? 1 : 0);
+            qo_ += (L + 3) & ~3u;
+            no += S.name_len[i];
         }
-    };
-    if (nt == 1) work(0);
-    else { std::vector<std::thread> th; for (unsigned t = 0; t < nt; t++) th.emplace_back(work, t); for (auto& x : th) x.join(); }
+    });
+    // ---- consume ----
+    const uint64_t consumed_to = nl[nlines - 1] + 1;
+    f->avg_rec = std::max(16.0, (double)(consumed_to - f->line_start) / (double)n);
+    f->line_start = std::min<uint64_t>(consumed_to, f->woff + f->wlen);
+    f->nl_pos = f->nl.size() < need ? f->nl.size() : nlines;      // at the end of the input the blank tail is dropped too
     f->records += n;
     out->n_reads = n; out->len = len; out->seq_off = seq_off; out->seq2 = seq2; out->seq2_words = w;
     out->qual_off = qual_off; out->qual = qual; out->qual_bytes = q;

@@ -461,3 +461,56 @@ def fixture_reads(idx: FlatIndex, n=100000, seed=20261019, lo=11, hi=21):
     q[firstn, 0] = 2
     c[~valid] = 0
     return ReadBatch.from_codes(np.ascontiguousarray(c), q, lens.astype("u1"))
+
+
+# ------------------------------------------------------------------------------------------
+# FASTQ text of a read batch (the file -> result measurements and tests of the ingest path)
+# ------------------------------------------------------------------------------------------
+def fastq_bytes(rb: ReadBatch, lo=0, hi=None, qualoffset=33, tag="r") -> bytes:
+    """4-line FASTQ records of reads [lo, hi) of a FIXED-length batch, names `<tag><9 digits>` (vectorised)."""
+    hi = rb.n if hi is None else hi
+    n = hi - lo
+    R = int(rb.len[lo]) if n else 0
+    assert n == 0 or (np.asarray(rb.len[lo:hi]) == R).all(), "fastq_bytes needs fixed-length reads"
+    W = (R + 31) // 32
+    so = np.asarray(rb.seq_off[lo:hi]).astype(np.int64)
+    qo = np.asarray(rb.qual_off[lo:hi]).astype(np.int64)
+    name_w = len(tag) + 10
+    reclen = name_w + 1 + R + 3 + R + 1
+    out = np.empty((n, reclen), np.uint8)
+    out[:, 0] = ord("@")
+    for k, ch in enumerate(tag.encode()):
+        out[:, 1 + k] = ch
+    idx = np.arange(lo, hi, dtype=np.int64)
+    for d in range(9):
+        out[:, name_w - 1 - d] = 48 + (idx // (10 ** d)) % 10
+    out[:, name_w] = 10
+    lut = np.frombuffer(b"ACGT", np.uint8)
+    words = rb.seq2[(so[:, None] + np.arange(W)[None, :]).ravel()].reshape(n, W)
+    for j in range(R):
+        out[:, name_w + 1 + j] = lut[((words[:, j >> 5] >> np.uint64(2 * (j & 31))) & np.uint64(3)).astype(np.int64)]
+    p = name_w + 1 + R
+    out[:, p] = 10
+    out[:, p + 1] = ord("+")
+    out[:, p + 2] = 10
+    out[:, p + 3:p + 3 + R] = rb.qual[(qo[:, None] + np.arange(R)[None, :]).ravel()].reshape(n, R) + np.uint8(qualoffset)
+    out[:, p + 3 + R] = 10
+    return out.tobytes()
+
+
+def bgzf_compress(data: bytes, level=1, block=65280, threads=8) -> bytes:
+    """Blocked gzip (BGZF, as bgzip / bcl2fastq write it): independent deflate blocks with their size in a 'BC' extra field."""
+    import struct
+    import zlib
+    from concurrent.futures import ThreadPoolExecutor
+
+    def one(i):
+        chunk = data[i:i + block]
+        co = zlib.compressobj(level, zlib.DEFLATED, -15)
+        comp = co.compress(chunk) + co.flush()
+        hdr = struct.pack("<BBBBIBBHBBHH", 0x1F, 0x8B, 8, 4, 0, 0, 0xFF, 6, ord("B"), ord("C"), 2, len(comp) + 25)
+        return hdr + comp + struct.pack("<II", zlib.crc32(chunk) & 0xFFFFFFFF, len(chunk))
+    with ThreadPoolExecutor(threads) as ex:
+        parts = list(ex.map(one, range(0, len(data), block)))
+    eof = bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000")
+    return b"".join(parts) + eof
