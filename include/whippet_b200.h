@@ -201,6 +201,11 @@ int  wq_fastq_names(wq_fastq* f, const uint64_t** name_off, const uint32_t** nam
 void wq_fastq_close(wq_fastq* f);
 int  wq_process_fastq(wq_handle* h, const wq_align_param* p, const char* fwd_path, const char* rev_path, int qualoffset,
                       uint32_t batch_reads, wq_map_stats* st);
+/* The same with sam = true (src/reads.jl:49-52, 63-67, 110-121; `whippet-quant.jl --sam` writes to stdout): the header
+ * (write_sam_header) and then the records of every batch, in read order, are written to the file descriptor sam_fd while
+ * the next batch is being parsed (sam_fd < 0: no SAM output, i.e. wq_process_fastq).  Needs wq_index_set_gene_info. */
+int  wq_process_fastq_sam(wq_handle* h, const wq_align_param* p, const char* fwd_path, const char* rev_path, int qualoffset,
+                          uint32_t batch_reads, int sam_fd, wq_map_stats* st);
 
 /* Plumbing with no reference counterpart: run the handle's work on a caller-owned CUDA stream
  * (NULL = the handle's own), per-kernel device milliseconds [seed, extend, resolve] of the last

@@ -108,10 +108,12 @@ function map_stats(h)
    st[]
 end
 """Whole files (gzip or plain); `rev = nothing` for single end.  Returns (mapped, total, mean_readlen)."""
-function process_fastq(h, p::AlignParamC, fwd::String, rev::Union{String,Nothing} = nothing; qualoffset = 33, batch_reads = 1 << 22)
+function process_fastq(h, p::AlignParamC, fwd::String, rev::Union{String,Nothing} = nothing; qualoffset = 33, batch_reads = 0,
+                       sam::Bool = false)
    st = Ref(MapStats(0, 0, 0, 0, 0, 0.0))
-   check(ccall((:wq_process_fastq, LIB), Cint, (Ptr{Cvoid}, Ref{AlignParamC}, Cstring, Cstring, Cint, UInt32, Ref{MapStats}),
-               h, p, fwd, rev === nothing ? C_NULL : rev, qualoffset, batch_reads, st))
+   samfd = sam ? Cint(1) : Cint(-1)          # `--sam` writes to stdout (src/reads.jl:49-52); needs set_gene_info first
+   check(ccall((:wq_process_fastq_sam, LIB), Cint, (Ptr{Cvoid}, Ref{AlignParamC}, Cstring, Cstring, Cint, UInt32, Cint, Ref{MapStats}),
+               h, p, fwd, rev === nothing ? C_NULL : rev, qualoffset, batch_reads, samfd, st))
    s = st[]
    s.mapped, s.total, s.mean_readlen      # the running mean of src/reads.jl:69, floored by the caller as bin/whippet-quant.jl:145 does
 end

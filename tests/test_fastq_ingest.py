@@ -155,6 +155,69 @@ def test_process_fastq_paired(tmp_path):
     a.close(); b.close()
 
 
+def _render(rb, fmt):
+    recs = []
+    for i in range(rb.n):
+        L = int(rb.len[i])
+        w = rb.seq2[int(rb.seq_off[i]):int(rb.seq_off[i]) + (L + 31) // 32]
+        codes = [(int(w[j // 32]) >> (2 * (j % 32))) & 3 for j in range(L)]
+        q = rb.qual[int(rb.qual_off[i]):int(rb.qual_off[i]) + L]
+        recs.append((fmt.format(i=i), "".join("ACGT"[c] for c in codes), "".join(chr(int(x) + 33) for x in q)))
+    return recs
+
+
+@pytest.mark.gpu
+def test_process_fastq_streams_sam(tmp_path):
+    """sam = true of process_reads! / process_paired_reads! (src/reads.jl:49-52, 63-67, 110-121): header, then the records
+    of every batch in read order, written while the next batch is parsed; equal to wq_sam_header + wq_sam_batch over the
+    whole input, with the counts unchanged.  Single end (plain file, many batches) and paired (gzip)."""
+    from data_gen import pe_case
+    idx, p, f, r = pe_case(6, 300, 101, 5000, True, 30000)
+    rng = np.random.default_rng(8)
+    idx.gene_strand = rng.integers(0, 2, idx.n_genes).astype("u1")
+    idx.gene_seqname = [f"chr{int(x)}" for x in rng.integers(1, 4, idx.n_genes)]
+    n1, n2 = [f"p{i}/1 x" for i in range(f.n)], [f"p{i}/2 x" for i in range(f.n)]
+    paths = []
+    for rb, tag in ((f, 1), (r, 2)):
+        path = os.path.join(tmp_path, f"s{tag}.fastq" + (".gz" if tag == 2 else ""))
+        text = to_text(_render(rb, "p{i}/%d x" % tag))
+        with (gzip.open(path, "wb", compresslevel=1) if tag == 2 else open(path, "wb")) as fh:
+            fh.write(text)
+        paths.append(path)
+    gz1 = os.path.join(tmp_path, "s1.fastq.gz")
+    with gzip.open(gz1, "wb", compresslevel=1) as fh:
+        fh.write(open(paths[0], "rb").read())
+    for paired in (False, True):
+        a, b = wq.GraphLibQuant(idx), wq.GraphLibQuant(idx)
+        for q in (a, b):
+            q.set_gene_info(idx.gene_seqname, idx.gene_strand)
+        pp = p if paired else wq.AlignParam()
+        if paired:
+            res = a.ungapped_align(pp, f, r)
+            want = a.sam_header() + a.sam_batch(f, n1, res, mate=r, mate_names=n2)
+            a.reset(); sa = a.process_paired_reads(pp, f, r)
+        else:
+            res = a.ungapped_align(pp, f)
+            want = a.sam_header() + a.sam_batch(f, n1, res)
+            a.reset(); sa = a.process_reads(pp, f)
+        out = os.path.join(tmp_path, f"out{int(paired)}.sam")
+        fd = os.open(out, os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o600)
+        try:
+            sb = b.process_fastq(pp, gz1 if paired else paths[0], paths[1] if paired else None, batch_reads=4321, sam_fd=fd)
+        finally:
+            os.close(fd)
+        got = open(out).read()
+        assert got == want and got.count("\n") > 20000
+        assert (sa.total, sa.mapped, sa.multi, sa.sum_readlen) == (sb.total, sb.mapped, sb.multi, sb.sum_readlen)
+        for x, y in zip(a.counts(), b.counts()):
+            assert np.array_equal(x, y)
+        assert a.keyed(0) == b.keyed(0) and a.keyed(1) == b.keyed(1)
+        c = wq.GraphLibQuant(idx)                        # without lib.info the call refuses before touching the counts
+        with pytest.raises(lib.WhippetB200Error, match="wq_index_set_gene_info"):
+            c.process_fastq(pp, paths[0], sam_fd=1)
+        a.close(); b.close(); c.close()
+
+
 def _batches(path_or_text, batch, from_memory=False):
     """All batches of a reader as (lens, seq words per read, qual bytes per read, names)."""
     import ctypes as C

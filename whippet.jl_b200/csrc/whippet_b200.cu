@@ -844,6 +844,26 @@ static int check_batch(const wq_read_batch* r) {
     return 0;
 }
 
+// wq_align_out whose arrays the library owns and may grow (streaming SAM output of wq_process_fastq_sam)
+struct WqOwnedOut {
+    std::vector<uint32_t> hit_start; std::vector<uint8_t> nhits, flipped;
+    std::vector<wq_alignment> aln, aln_mate; std::vector<wq_align_node> nodes;
+    wq_align_out v;
+    void bind(bool pe) {
+        v.hit_start = hit_start.data(); v.nhits = nhits.data(); v.flipped = flipped.data();
+        v.aln = aln.data(); v.aln_mate = pe ? aln_mate.data() : nullptr; v.nodes = nodes.data();
+        v.aln_cap = aln.size(); v.nodes_cap = nodes.size();
+    }
+    void start(uint32_t n, bool pe) {
+        hit_start.resize(n); nhits.resize(n); flipped.resize(n);
+        if (aln.size() < (size_t)n * 2) aln.resize((size_t)n * 2);
+        if (pe && aln_mate.size() < aln.size()) aln_mate.resize(aln.size());
+        if (nodes.size() < (size_t)n * 4) nodes.resize((size_t)n * 4);
+        bind(pe); v.aln_used = 0; v.nodes_used = 0;
+    }
+};
+static thread_local WqOwnedOut* g_owned_out = nullptr;     // set by wq_process_fastq_sam around its wq_align_* calls
+
 // Download the alignments of the chunk just processed (reads [first, first+n) of the caller's batch).
 static int collect_chunk(wq_handle* h, uint32_t first, uint32_t n, bool pe, wq_align_out* out) {
     cudaStream_t s = h->stream;
@@ -864,6 +884,16 @@ static int collect_chunk(wq_handle* h, uint32_t first, uint32_t n, bool pe, wq_a
     if (np) CK(cudaMemcpyAsync(pool.data(), h->d_pool.p, np * sizeof(wq_align_node), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     if (pe && !out->aln_mate) return fail(-1, "wq_align_out.aln_mate is required for paired batches");
+    if (g_owned_out && out == &g_owned_out->v) {               // library-owned output: make room for this chunk's worst case
+        WqOwnedOut& O = *g_owned_out;
+        const size_t need_nodes = (size_t)out->nodes_used + (size_t)np;       // every path of the chunk lies in the pool
+        size_t need_aln = (size_t)out->aln_used;
+        for (uint32_t i = 0; i < n; i++) need_aln += seeds[i].cnt;
+        if (need_aln > O.aln.size()) O.aln.resize(need_aln + need_aln / 2);
+        if (pe && O.aln_mate.size() < O.aln.size()) O.aln_mate.resize(O.aln.size());
+        if (need_nodes > O.nodes.size()) O.nodes.resize(need_nodes + need_nodes / 2);
+        O.bind(pe);
+    }
     auto put = [&](const WqHit& hh, wq_alignment* dst) -> bool {
         if (out->nodes_used + hh.npath > out->nodes_cap) return false;
         wq_alignment a;
@@ -1050,31 +1080,65 @@ void wq_fastq_close(wq_fastq* f) {
 }
 
 // process_reads! / process_paired_reads! (src/reads.jl:41-129) over FASTQ files: the next batch is inflated, split and
-// packed on the host threads while the device aligns and counts the current one.
-int wq_process_fastq(wq_handle* h, const wq_align_param* p, const char* fwd_path, const char* rev_path, int qualoffset,
-                     uint32_t batch_reads, wq_map_stats* st) {
+// packed on the host threads while the device aligns and counts the current one.  With sam_fd >= 0 the SAM header and the
+// records of every batch are written to that descriptor in read order (sam = true: src/reads.jl:49-52, 63-67, 110-121).
+static int wq_sam_format(wq_handle* h, const wq_read_batch* fwd, const wq_read_batch* rev,
+                         const uint64_t* name_off, const uint32_t* name_len, const char* names,
+                         const uint64_t* rname_off, const uint32_t* rname_len, const char* rnames,
+                         const wq_align_out* out, int qualoffset, std::vector<std::string>& parts);
+static int wq_write_all(int fd, const char* p, size_t n) {
+    while (n) {
+        const ssize_t w = write(fd, p, n);
+        if (w < 0) { if (errno == EINTR) continue; return -1; }
+        p += w; n -= (size_t)w;
+    }
+    return 0;
+}
+int wq_process_fastq_sam(wq_handle* h, const wq_align_param* p, const char* fwd_path, const char* rev_path, int qualoffset,
+                         uint32_t batch_reads, int sam_fd, wq_map_stats* st) {
     if (!h || !p || !fwd_path) return fail(-1, "null argument");
-    if (batch_reads == 0) batch_reads = 1u << 22;
+    const bool sam = sam_fd >= 0;
+    if (sam && !h->sam.has_info) return fail(-15, "SAM output needs wq_index_set_gene_info (lib.info names and strands)");
+    if (batch_reads == 0) batch_reads = 1u << 19;      // small enough that parsing batch k+1 hides behind aligning batch k from the first batch on
     wq_fastq* rd[2] = {nullptr, nullptr};
     if (int rc = wq_fastq_open(fwd_path, qualoffset, &rd[0])) return rc;
     if (rev_path) { if (int rc = wq_fastq_open(rev_path, qualoffset, &rd[1])) { wq_fastq_close(rd[0]); return rc; } }
-    struct Pair { wq_read_batch b[2]; int rc = 0; std::string err; };
+    struct Pair { wq_read_batch b[2]; const WqFastqSlot* names[2] = {nullptr, nullptr}; int rc = 0; std::string err; };
     auto parse = [&]() {
         Pair P;
         for (int k = 0; k < (rev_path ? 2 : 1) && !P.rc; k++) {
             P.rc = wq_fastq_next_impl(rd[k], batch_reads, &P.b[k]);
             if (P.rc) P.err = rd[k]->err;
+            P.names[k] = &rd[k]->slot[rd[k]->cur];             // this slot is not touched again until the parse after the next
         }
         if (!P.rc && rev_path && P.b[0].n_reads != P.b[1].n_reads) { P.rc = -21; P.err = "paired FASTQ files hold different numbers of records"; }
         return P;
     };
     int rc = 0;
     std::string err;
+    if (sam) {
+        const std::string hd = wq_sam_header_text(h->sam);
+        if (wq_write_all(sam_fd, hd.data(), hd.size())) { wq_fastq_close(rd[0]); wq_fastq_close(rd[1]); return fail(-22, "cannot write SAM output"); }
+    }
+    WqOwnedOut own;
+    std::vector<std::string> parts;
     Pair cur = parse();
     while (!cur.rc && cur.b[0].n_reads) {
         std::future<Pair> nxt = std::async(std::launch::async, parse);
-        rc = rev_path ? wq_align_pe(h, p, &cur.b[0], &cur.b[1], nullptr) : wq_align_se(h, p, &cur.b[0], nullptr);
+        wq_align_out* out = nullptr;
+        if (sam) { own.start(cur.b[0].n_reads, rev_path != nullptr); out = &own.v; g_owned_out = &own; }
+        rc = rev_path ? wq_align_pe(h, p, &cur.b[0], &cur.b[1], out) : wq_align_se(h, p, &cur.b[0], out);
+        g_owned_out = nullptr;
         if (rc) err = g_err;
+        if (!rc && sam) {
+            const WqFastqSlot* N0 = cur.names[0]; const WqFastqSlot* N1 = cur.names[1];
+            rc = wq_sam_format(h, &cur.b[0], rev_path ? &cur.b[1] : nullptr, N0->name_off.data(), N0->name_len.data(), N0->names.data(),
+                               N1 ? N1->name_off.data() : nullptr, N1 ? N1->name_len.data() : nullptr, N1 ? N1->names.data() : nullptr,
+                               &own.v, qualoffset, parts);
+            if (rc) err = g_err;
+            for (size_t t = 0; t < parts.size() && !rc; t++)
+                if (wq_write_all(sam_fd, parts[t].data(), parts[t].size())) { rc = -22; err = "cannot write SAM output"; }
+        }
         cur = nxt.get();
         if (rc) break;
     }
@@ -1082,6 +1146,10 @@ int wq_process_fastq(wq_handle* h, const wq_align_param* p, const char* fwd_path
     wq_fastq_close(rd[0]); wq_fastq_close(rd[1]);
     if (rc) return fail(rc, err);
     return st ? wq_map_stats_get(h, st) : 0;
+}
+int wq_process_fastq(wq_handle* h, const wq_align_param* p, const char* fwd_path, const char* rev_path, int qualoffset,
+                     uint32_t batch_reads, wq_map_stats* st) {
+    return wq_process_fastq_sam(h, p, fwd_path, rev_path, qualoffset, batch_reads, -1, st);
 }
 
 // ---- SAM output (src/io.jl:69-276) ----------------------------------------------------------------------
@@ -1120,16 +1188,8 @@ int wq_sam_batch(wq_handle* h, const wq_read_batch* fwd, const wq_read_batch* re
     if (rev && (!rname_off || !rname_len || !rnames || !out->aln_mate)) return fail(-1, "paired SAM output needs the mate's names and alignments");
     if (!h->sam.has_info) return fail(-15, "SAM output needs wq_index_set_gene_info (lib.info names and strands)");
     if (!out->hit_start || !out->nhits || !out->flipped || !out->aln || !out->nodes) return fail(-1, "wq_align_out has null arrays");
-    const uint32_t n = fwd->n_reads;
-    unsigned nt = wq_host_threads();
-    if (n < 4096) nt = 1;
-    std::vector<std::string> parts(nt);
-    auto work = [&](unsigned t) {
-        wq_sam_range(h->sam, parts[t], fwd, rev, name_off, name_len, names, rname_off, rname_len, rnames, out, qualoffset,
-                     (uint32_t)((uint64_t)n * t / nt), (uint32_t)((uint64_t)n * (t + 1) / nt));
-    };
-    if (nt == 1) work(0);
-    else { std::vector<std::thread> th; for (unsigned t = 0; t < nt; t++) th.emplace_back(work, t); for (auto& x : th) x.join(); }
+    std::vector<std::string> parts;
+    if (int rc = wq_sam_format(h, fwd, rev, name_off, name_len, names, rname_off, rname_len, rnames, out, qualoffset, parts)) return rc;
     uint64_t total = 0;
     for (auto& s2 : parts) total += s2.size();
     *used = total;
@@ -1137,6 +1197,24 @@ int wq_sam_batch(wq_handle* h, const wq_read_batch* fwd, const wq_read_batch* re
     if (cap < total) return fail(-7, "SAM buffer too small");
     uint64_t o = 0;
     for (auto& s2 : parts) { memcpy(buf + o, s2.data(), s2.size()); o += s2.size(); }
+    return 0;
+}
+
+// the reads of a batch split over the host threads; parts concatenate to the text in read order
+static int wq_sam_format(wq_handle* h, const wq_read_batch* fwd, const wq_read_batch* rev,
+                         const uint64_t* name_off, const uint32_t* name_len, const char* names,
+                         const uint64_t* rname_off, const uint32_t* rname_len, const char* rnames,
+                         const wq_align_out* out, int qualoffset, std::vector<std::string>& parts) {
+    const uint32_t n = fwd->n_reads;
+    unsigned nt = wq_host_threads();
+    if (n < 4096) nt = 1;
+    parts.assign(nt, std::string());
+    auto work = [&](unsigned t) {
+        wq_sam_range(h->sam, parts[t], fwd, rev, name_off, name_len, names, rname_off, rname_len, rnames, out, qualoffset,
+                     (uint32_t)((uint64_t)n * t / nt), (uint32_t)((uint64_t)n * (t + 1) / nt));
+    };
+    if (nt == 1) work(0);
+    else { std::vector<std::thread> th; for (unsigned t = 0; t < nt; t++) th.emplace_back(work, t); for (auto& x : th) x.join(); }
     return 0;
 }
 

@@ -16,12 +16,17 @@
 //   * the batch is written into page-locked buffers so the H2D copies of wq_align_se / wq_align_pe run at full PCIe rate.
 // Host-only code (no kernel): it is the stage in front of the device path, SURVEY.md section 8f row 1.
 #pragma once
+#include <chrono>
 #include <fcntl.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
 #include <zlib.h>
 #include <atomic>
+#include <algorithm>
+#include <condition_variable>
+#include <emmintrin.h>
+#include <mutex>
 #include <cstdint>
 #include <cstring>
 #include <string>
@@ -30,19 +35,67 @@
 #include "wq_host_quant.h"          // wq_host_threads
 #include "../../include/whippet_b200.h"
 
+// Page-locked blocks released by a reader are kept for the next one (process lifetime, bounded): cudaHostAlloc costs about
+// as much as parsing the batch that goes into the block, and wq_process_fastq opens a reader per call.
+struct WqPinnedCache {
+    struct Blk { void* p; size_t cap; };
+    std::mutex mu; std::vector<Blk> free_; size_t bytes = 0;
+    static WqPinnedCache& get() { static WqPinnedCache* c = new WqPinnedCache(); return *c; }     // never destroyed (no CUDA calls at exit)
+    void* take(size_t want, size_t* cap) {
+        std::lock_guard<std::mutex> g(mu);
+        size_t best = free_.size();
+        for (size_t i = 0; i < free_.size(); i++)
+            if (free_[i].cap >= want && (best == free_.size() || free_[i].cap < free_[best].cap)) best = i;
+        if (best == free_.size() || free_[best].cap > 4 * want + (1u << 20)) return nullptr;
+        void* p = free_[best].p; *cap = free_[best].cap; bytes -= *cap;
+        free_.erase(free_.begin() + best);
+        return p;
+    }
+    bool give(void* p, size_t cap) {
+        std::lock_guard<std::mutex> g(mu);
+        if (free_.size() >= 32 || bytes + cap > (size_t)4 << 30) return false;
+        free_.push_back(Blk{p, cap}); bytes += cap;
+        return true;
+    }
+};
+
 struct WqPinned {                    // grow-only page-locked buffer (plain memory when no CUDA device is usable)
     void* p = nullptr; size_t cap = 0; bool pinned = false;
     void* ensure(size_t bytes) {
         if (bytes <= cap) return p;
         release();
         size_t want = bytes + bytes / 4 + 4096;
-        void* q = nullptr;
+        void* q = WqPinnedCache::get().take(want, &cap);
+        if (q) { p = q; pinned = true; return p; }
         if (cudaHostAlloc(&q, want, cudaHostAllocDefault) == cudaSuccess) { p = q; pinned = true; }
         else { (void)cudaGetLastError(); p = aligned_alloc(4096, (want + 4095) & ~(size_t)4095); pinned = false; }
         cap = p ? want : 0;
         return p;
     }
-    void release() { if (p) { if (pinned) cudaFreeHost(p); else free(p); } p = nullptr; cap = 0; }
+    void release() {
+        if (p) {
+            if (pinned) { if (!WqPinnedCache::get().give(p, cap)) cudaFreeHost(p); }
+            else free(p);
+        }
+        p = nullptr; cap = 0;
+    }
+};
+
+// text window of the gzip modes: raw storage that is never zero-filled (std::vector::resize would touch every byte first)
+struct WqTextBuf {
+    char* p = nullptr; size_t len = 0, cap = 0;
+    ~WqTextBuf() { free(p); }
+    size_t size() const { return len; }
+    char* data() { return p; }
+    bool reserve_more(size_t add) {
+        if (len + add <= cap) return true;
+        size_t nc = std::max(len + add, cap + cap / 2);
+        char* q = (char*)realloc(p, nc);
+        if (!q) return false;
+        p = q; cap = nc;
+        return true;
+    }
+    void drop_front(size_t n) { if (n >= len) { len = 0; return; } memmove(p, p + n, len - n); len -= n; }
 };
 
 struct WqFastqSlot {                 // one packed batch + the record names (for SAM output)
@@ -59,7 +112,7 @@ struct wq_fastq {
     bool bgzf = false; size_t bgzf_pos = 0;                                                 // blocked gzip: `map` holds the COMPRESSED file
     int qualoffset = 33;
     // ---- text window: stream offsets [woff, woff + wlen) are in memory at wbase ----
-    std::vector<char> text;            // owns the window for the gzip modes
+    WqTextBuf text;                    // owns the window for the gzip modes
     const char* wbase = nullptr; uint64_t woff = 0, wlen = 0;
     bool eof = false;                  // no more text will be appended to the window
     // ---- line index: stream offsets of the newlines found so far, nl_pos = first one not yet consumed by a batch ----
@@ -83,6 +136,26 @@ static inline const uint8_t* wq_fastq_code_table() {
         init = true;
     }
     return T;
+}
+
+// 16 sequence bytes -> 16 two-bit codes in 32 bits (base j in bits 2j..2j+1).  For ACGTacgt the code is ((c >> 1) ^ (c >> 2)) & 3
+// (A 0, C 1, G 2, T 3 in either case); every other byte becomes 0 = A (fill_ambiguous = DNA_A).
+static inline uint32_t wq_fastq_pack16(const char* p) {
+    const __m128i v = _mm_loadu_si128((const __m128i*)p);
+    const __m128i u = _mm_and_si128(v, _mm_set1_epi8((char)0xDF));                    // fold the case bit
+    const __m128i ok = _mm_or_si128(_mm_or_si128(_mm_cmpeq_epi8(u, _mm_set1_epi8('A')), _mm_cmpeq_epi8(u, _mm_set1_epi8('C'))),
+                                    _mm_or_si128(_mm_cmpeq_epi8(u, _mm_set1_epi8('G')), _mm_cmpeq_epi8(u, _mm_set1_epi8('T'))));
+    __m128i c = _mm_xor_si128(_mm_srli_epi16(v, 1), _mm_srli_epi16(v, 2));            // bits leaking across bytes are masked next
+    c = _mm_and_si128(_mm_and_si128(c, _mm_set1_epi8(3)), ok);
+    // fold pairs: 16 x 2 bits (one per byte) -> 8 x 4 bits -> 4 x 8 bits -> 2 x 16 bits per 64-bit half
+    uint64_t lo = (uint64_t)_mm_cvtsi128_si64(c), hi = (uint64_t)_mm_cvtsi128_si64(_mm_unpackhi_epi64(c, c));
+    auto fold = [](uint64_t y) -> uint32_t {
+        y = (y | (y >> 6)) & 0x000F000F000F000Full;
+        y = (y | (y >> 12)) & 0x000000FF000000FFull;
+        y = (y | (y >> 24)) & 0xFFFFull;
+        return (uint32_t)y;
+    };
+    return fold(lo) | (fold(hi) << 16);
 }
 
 template <class F> static inline void wq_fq_parallel(unsigned nt, F&& f) {
@@ -145,20 +218,20 @@ static inline bool wq_fastq_pull(wq_fastq* f, size_t want) {
     if (f->eof) return true;
     const uint64_t keep_from = f->line_start;                       // everything before the first unconsumed line can go
     if (keep_from > f->woff) {
-        f->text.erase(f->text.begin(), f->text.begin() + (size_t)(keep_from - f->woff));
+        f->text.drop_front((size_t)(keep_from - f->woff));
         f->woff = keep_from;
     }
     if (f->gz) {
         const size_t old = f->text.size();
-        f->text.resize(old + want);
+        if (!f->text.reserve_more(want)) { f->err = "out of memory"; return false; }
         size_t got = 0;
         while (got < want) {
             int r = gzread(f->gz, f->text.data() + old + got, (unsigned)std::min<size_t>(want - got, 1u << 30));
-            if (r < 0) { int en = 0; f->err = std::string("gzread: ") + gzerror(f->gz, &en); f->text.resize(old); return false; }
+            if (r < 0) { int en = 0; f->err = std::string("gzread: ") + gzerror(f->gz, &en); return false; }
             if (r == 0) { f->eof = true; break; }
             got += (size_t)r;
         }
-        f->text.resize(old + got);
+        f->text.len = old + got;
     } else if (f->bgzf) {
         // blocks up to ~want bytes of text: sizes from the block trailers (ISIZE), then every block inflated by some thread
         struct Blk { size_t off, csize, hdr; uint32_t isize; size_t out; };
@@ -178,7 +251,8 @@ static inline bool wq_fastq_pull(wq_fastq* f, size_t want) {
         }
         if (f->bgzf_pos >= f->map_len) f->eof = true;
         const size_t old = f->text.size();
-        f->text.resize(old + total);
+        if (!f->text.reserve_more(total)) { f->err = "out of memory"; return false; }
+        f->text.len = old + total;
         char* dst = f->text.data() + old;
         std::atomic<size_t> next{0};
         std::atomic<int> bad{0};
@@ -220,12 +294,19 @@ static inline void wq_fastq_scan(wq_fastq* f, uint64_t from, uint64_t to) {
         v.reserve((size_t)((b - a) / 60 + 16));
         const char* p = base + a;
         const char* e = base + b;
-        while (p < e) {
-            const char* q = (const char*)memchr(p, '\n', (size_t)(e - p));
-            if (!q) break;
-            v.push_back((uint64_t)(q - base));
-            p = q + 1;
+        // 64 bytes per step: four 16-byte compares folded into one 64-bit mask (lines are short, a memchr call per line costs more)
+        const __m128i nlv = _mm_set1_epi8('\n');
+        while (p + 64 <= e) {
+            const uint64_t m0 = (uint32_t)_mm_movemask_epi8(_mm_cmpeq_epi8(_mm_loadu_si128((const __m128i*)p), nlv));
+            const uint64_t m1 = (uint32_t)_mm_movemask_epi8(_mm_cmpeq_epi8(_mm_loadu_si128((const __m128i*)(p + 16)), nlv));
+            const uint64_t m2 = (uint32_t)_mm_movemask_epi8(_mm_cmpeq_epi8(_mm_loadu_si128((const __m128i*)(p + 32)), nlv));
+            const uint64_t m3 = (uint32_t)_mm_movemask_epi8(_mm_cmpeq_epi8(_mm_loadu_si128((const __m128i*)(p + 48)), nlv));
+            uint64_t m = m0 | (m1 << 16) | (m2 << 32) | (m3 << 48);
+            const uint64_t at = (uint64_t)(p - base);
+            while (m) { v.push_back(at + (uint64_t)__builtin_ctzll(m)); m &= m - 1; }
+            p += 64;
         }
+        for (; p < e; p++) if (*p == '\n') v.push_back((uint64_t)(p - base));
     });
     size_t add = 0;
     for (auto& v : found) add += v.size();
@@ -239,6 +320,10 @@ static inline void wq_fastq_scan(wq_fastq* f, uint64_t from, uint64_t to) {
 // stay valid until the call after the next one (two slots alternate, so a batch can be aligned while the next is parsed).
 static inline int wq_fastq_next_impl(wq_fastq* f, uint32_t max_reads, wq_read_batch* out) {
     memset(out, 0, sizeof *out);
+    static const bool prof = getenv("WQ_FASTQ_PROF") != nullptr;
+    auto now = []() { return std::chrono::steady_clock::now(); };
+    auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+    const auto t_begin = now();
     // ---- forget the consumed part of the line index ----
     if (f->nl_pos > 0) { f->nl.erase(f->nl.begin(), f->nl.begin() + f->nl_pos); f->nl_pos = 0; }
     // ---- enough lines for the batch, or the end of the input ----
@@ -266,6 +351,7 @@ static inline int wq_fastq_next_impl(wq_fastq* f, uint32_t max_reads, wq_read_ba
         }
         break;
     }
+    const auto t_lines = now();
     // trailing blank lines at the end of the file are not records
     size_t nlines = std::min(f->nl.size(), need);
     const char* base = f->wbase - f->woff;
@@ -318,6 +404,7 @@ static inline int wq_fastq_next_impl(wq_fastq* f, uint32_t max_reads, wq_read_ba
         }
         tw[t + 1] = w; tq[t + 1] = q; tn[t + 1] = nm;
     });
+    const auto t_pass1 = now();
     for (unsigned t = 0; t < nt; t++)
         if (bad[t] >= 0) {
             const std::string r = std::to_string(f->records + (uint64_t)bad[t] + 1);
@@ -335,6 +422,7 @@ static inline int wq_fastq_next_impl(wq_fastq* f, uint32_t max_reads, wq_read_ba
     S.names.resize(nm);
     const uint8_t* T = wq_fastq_code_table();
     const uint8_t qo = (uint8_t)f->qualoffset;
+    const auto t_alloc = now();
     // ---- pass 2: offsets of the thread's range, then the conversion of its records ----
     wq_fq_parallel(nt, [&](unsigned t) {
         const uint32_t lo = (uint32_t)((uint64_t)n * t / nt), hi = (uint32_t)((uint64_t)n * (t + 1) / nt);
@@ -348,14 +436,20 @@ static inline int wq_fastq_next_impl(wq_fastq* f, uint32_t max_reads, wq_read_ba
             uint64_t* wd = seq2 + wo;
             const uint32_t nw = (L + 31) / 32;
             for (uint32_t kk = 0; kk < nw; kk++) {
-                uint64_t acc = 0;
                 const uint32_t b0 = kk * 32, b1 = std::min(L, b0 + 32);
+                if (b1 - b0 == 32) { wd[kk] = (uint64_t)wq_fastq_pack16(sp + b0) | ((uint64_t)wq_fastq_pack16(sp + b0 + 16) << 32); continue; }
+                uint64_t acc = 0;
                 for (uint32_t j = b0; j < b1; j++) acc |= (uint64_t)T[(uint8_t)sp[j]] << (2 * (j - b0));
                 wd[kk] = acc;
             }
             if (L == 0) wd[0] = 0;
             uint8_t* qd = qual + qo_;
-            for (uint32_t j = 0; j < L; j++) qd[j] = (uint8_t)((uint8_t)qp[j] - qo);       // UInt8 arithmetic (src/record.jl:17)
+            {   // UInt8 arithmetic (src/record.jl:17), 16 bytes at a time
+                const __m128i qov = _mm_set1_epi8((char)qo);
+                uint32_t j = 0;
+                for (; j + 16 <= L; j += 16) _mm_storeu_si128((__m128i*)(qd + j), _mm_sub_epi8(_mm_loadu_si128((const __m128i*)(qp + j)), qov));
+                for (; j < L; j++) qd[j] = (uint8_t)((uint8_t)qp[j] - qo);
+            }
             for (uint32_t j = L; j < ((L + 3) & ~3u); j++) qd[j] = 0;
             memcpy(S.names.data() + no, base + lstart(k) + 1, S.name_len[i]);
             wo += nw + (L == 0 ? 1 : 0);
@@ -363,6 +457,9 @@ static inline int wq_fastq_next_impl(wq_fastq* f, uint32_t max_reads, wq_read_ba
             no += S.name_len[i];
         }
     });
+    if (prof)
+        fprintf(stderr, "[wq] fastq batch %u reads: lines (inflate + scan) %.2f ms, pass 1 %.2f ms, buffers %.2f ms, pass 2 %.2f ms\n", n,
+                ms(t_begin, t_lines), ms(t_lines, t_pass1), ms(t_pass1, t_alloc), ms(t_alloc, now()));
     // ---- consume ----
     const uint64_t consumed_to = nl[nlines - 1] + 1;
     f->avg_rec = std::max(16.0, (double)(consumed_to - f->line_start) / (double)n);

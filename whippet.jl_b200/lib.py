@@ -66,6 +66,7 @@ def load():
     L.wq_fastq_close.argtypes = [vp]
     L.wq_fastq_close.restype = None
     L.wq_process_fastq.argtypes = [vp, C.POINTER(abi.AlignParamC), C.c_char_p, C.c_char_p, C.c_int, C.c_uint32, C.POINTER(abi.MapStatsC)]
+    L.wq_process_fastq_sam.argtypes = [vp, C.POINTER(abi.AlignParamC), C.c_char_p, C.c_char_p, C.c_int, C.c_uint32, C.c_int, C.POINTER(abi.MapStatsC)]
     L.wq_index_set_gene_info.argtypes = [vp, C.POINTER(C.c_char_p), abi.u8p]
     L.wq_sam_header.argtypes = [vp, C.c_char_p, C.c_uint64, C.POINTER(C.c_uint64)]
     L.wq_sam_batch.argtypes = [vp, C.POINTER(abi.ReadBatchC), C.POINTER(abi.ReadBatchC),

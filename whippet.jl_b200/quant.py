@@ -113,13 +113,15 @@ class GraphLibQuant:
         return self.stats()
 
     def process_fastq(self, param: AlignParam, fwd_path: str, rev_path: str | None = None, qualoffset: int = 33,
-                      batch_reads: int = 1 << 22) -> MapStats:
+                      batch_reads: int = 0, sam_fd: int = -1) -> MapStats:
         """process_reads! / process_paired_reads! over FASTQ files (gzip or plain): the library parses and packs the
-        next batch on its host threads while the device aligns and counts the current one."""
+        next batch on its host threads while the device aligns and counts the current one.  sam_fd >= 0 is `sam=true`
+        (src/reads.jl:49-52, 63-67): header + records of every batch go to that file descriptor in read order.
+        batch_reads = 0 takes the library's default (512 k records: parsing batch k+1 hides behind aligning batch k)."""
         p = param.c()
         s = abi.MapStatsC()
-        lib.check(self.L.wq_process_fastq(self.h, C.byref(p), fwd_path.encode(), rev_path.encode() if rev_path else None,
-                                          int(qualoffset), int(batch_reads), C.byref(s)))
+        lib.check(self.L.wq_process_fastq_sam(self.h, C.byref(p), fwd_path.encode(), rev_path.encode() if rev_path else None,
+                                              int(qualoffset), int(batch_reads), int(sam_fd), C.byref(s)))
         return MapStats(s.total, s.mapped, s.multi, s.sum_readlen, s.path_overflow, s.mean_readlen)
 
     # ---- SAM output (src/io.jl:69-276) -------------------------------------------------------------
