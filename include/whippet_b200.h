@@ -151,6 +151,16 @@ int  wq_version(void);
 int  wq_index_create(const wq_index_desc* desc, int device, wq_handle** out);
 void wq_destroy(wq_handle* h);
 
+/* The index in the library's native on-disk form.  The reference serialises GraphLib with Julia's
+ * Serialization (bin/whippet-index.jl:97-101) and deserialises all of it on every start (bin/whippet-quant.jl:105, its first
+ * @timer line).  wq_index_write stores the RE-LAID index instead (occurrence blocks, suffix array, 2-bit text, node / gene
+ * records, bucket table, k-mer edge tables, annotation paths, and lib.info when seqname / strand are given) in one file of
+ * page-aligned, checksummed sections; it is host-only and builds the sections with the same code wq_index_create uploads from.
+ * wq_index_load maps such a file and copies the sections to the device: a handle equal to the one wq_index_create makes from
+ * the same wq_index_desc (+ wq_index_set_gene_info).  WQ_INDEX_VERIFY=1 also checks the checksums of the large sections. */
+int  wq_index_write(const wq_index_desc* desc, const char* const* seqname, const uint8_t* strand, const char* path);
+int  wq_index_load(const char* path, int device, wq_handle** out);
+
 /* GraphLibQuant{C,DefaultCounter}(lib) + MultiMapping{C,DefaultCounter}() (bin/whippet-quant.jl:125-126):
  * zero all device-side count stores. */
 int  wq_quant_reset(wq_handle* h);

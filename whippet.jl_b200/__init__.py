@@ -5,6 +5,6 @@ lives in csrc/ behind the C ABI of include/whippet_b200.h.
 """
 from . import abi, jls, flat
 from .flat import FlatIndex, AlignParam, ReadBatch
-from .quant import GraphLibQuant, AlignResult, MapStats
+from .quant import GraphLibQuant, AlignResult, MapStats, write_index
 
-__all__ = ["abi", "jls", "flat", "FlatIndex", "AlignParam", "ReadBatch", "GraphLibQuant", "AlignResult", "MapStats"]
+__all__ = ["abi", "jls", "flat", "FlatIndex", "AlignParam", "ReadBatch", "GraphLibQuant", "AlignResult", "MapStats", "write_index"]

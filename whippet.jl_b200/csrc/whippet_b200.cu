@@ -23,6 +23,7 @@
 #include "wq_events.h"
 #include "wq_fastq.h"
 #include "wq_sam.h"
+#include "wq_index_file.h"
 #include <future>
 #include <atomic>
 #include <dlfcn.h>
@@ -619,29 +620,27 @@ int wq_quant_reset(wq_handle* h) {
     return 0;
 }
 
-int wq_index_create(const wq_index_desc* d, int device, wq_handle** out) {
-    if (!d || !out) return fail(-1, "null argument");
-    *out = nullptr;
+// the large arrays of the index as they are uploaded: views into WqHostIndex + the caller's wq_index_desc (wq_index_create), or into
+// a mapped index file (wq_index_load)
+struct WqBigArrays {
+    const WqOccBlock* occ; size_t n_occ; const uint32_t* sa; const uint64_t* text2; size_t n_text2; const uint32_t* amb; size_t n_amb;
+    const uint32_t* bucket; size_t n_bucket; const uint32_t* lptr; const uint32_t* rptr;
+};
+
+static int index_device_check(int device, cudaDeviceProp& prop) {
     int ndev = 0;
     cudaError_t e0 = cudaGetDeviceCount(&ndev);
     if (e0 != cudaSuccess || ndev == 0)
         return fail(-2, std::string("no CUDA device available (this library has no CPU fallback): ") + cudaGetErrorString(e0));
     if (device < 0 || device >= ndev) return fail(-2, "device ordinal out of range");
-    cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10) return fail(-2, std::string("device '") + prop.name + "' is not sm_100-class; the kernels are built for sm_100a only");
     CK(cudaSetDevice(device));
-    wq_handle* h = new wq_handle();
-    h->device = device;
-    std::string err = wq_build_host_index(d, h->H);
-    if (err.empty()) err = wq_build_iso_index(d, h->iso);
-    if (err.empty()) {                                       // SAM output only
-        h->sam.node_base.assign(d->node_base, d->node_base + d->n_genes + 1);
-        h->sam.nodeoffset.assign(d->nodeoffset, d->nodeoffset + d->n_nodes);
-        h->sam.nodecoord.assign(d->nodecoord, d->nodecoord + d->n_nodes);
-        h->sam.nodelen.assign(d->nodelen, d->nodelen + d->n_nodes);
-    }
-    if (!err.empty()) { delete h; return fail(-3, err); }
+    return 0;
+}
+
+// h->H (nodes, genes, edge-table entries, scalars), h->iso and h->sam are filled; upload everything and set up the count stores
+static int index_finish(wq_handle* h, const cudaDeviceProp& prop, const WqBigArrays& A, wq_handle** out) {
 #define CKH(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { std::string m_ = std::string(#call) + ": " + cudaGetErrorString(e_); wq_destroy(h); return fail(-10, m_); } } while (0)
     CKH(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
     h->stream = h->own_stream;
@@ -658,15 +657,15 @@ int wq_index_create(const wq_index_desc* d, int device, wq_handle** out) {
     CKH(cudaDeviceSetLimit(cudaLimitStackSize, env_u64("WQ_STACK_BYTES", 4 * 1024)));
     WqHostIndex& H = h->H;
     cudaStream_t s = h->stream;
-    CKH(upload(h->d_occ, H.occ.data(), H.occ.size(), s));
-    CKH(upload(h->d_sa, d->sa, (size_t)H.n, s));
-    CKH(upload(h->d_text2, H.text2.data(), H.text2.size(), s));
-    if (H.has_amb) CKH(upload(h->d_amb, H.amb.data(), H.amb.size(), s));
+    CKH(upload(h->d_occ, A.occ, A.n_occ, s));
+    CKH(upload(h->d_sa, A.sa, (size_t)H.n, s));
+    CKH(upload(h->d_text2, A.text2, A.n_text2, s));
+    if (H.has_amb) CKH(upload(h->d_amb, A.amb, A.n_amb, s));
     CKH(upload(h->d_nodes, H.nodes.data(), H.nodes.size(), s));
     CKH(upload(h->d_genes, H.genes.data(), H.genes.size(), s));
-    CKH(upload(h->d_bucket, H.node_bucket.data(), H.node_bucket.size(), s));
-    CKH(upload(h->d_lptr, d->left_ptr, (size_t)H.nslots + 1, s));
-    CKH(upload(h->d_rptr, d->right_ptr, (size_t)H.nslots + 1, s));
+    CKH(upload(h->d_bucket, A.bucket, A.n_bucket, s));
+    CKH(upload(h->d_lptr, A.lptr, (size_t)H.nslots + 1, s));
+    CKH(upload(h->d_rptr, A.rptr, (size_t)H.nslots + 1, s));
     CKH(upload(h->d_lent, H.left_ent.data(), H.left_ent.size(), s));
     CKH(upload(h->d_rent, H.right_ent.data(), H.right_ent.size(), s));
     WqDevIndex& ix = h->dix;
@@ -726,12 +725,92 @@ int wq_index_create(const wq_index_desc* d, int device, wq_handle** out) {
     h->q.edges = WqEdgeTable{h->d_ekey.p, h->d_ecount.p, h->edge_slots - 1};
     h->q.keyed = WqKeyedTable{h->d_khash.p, h->d_koff.p, h->d_kcount.p, h->d_kpool.p, h->d_kcursor.p, h->kpool_cap, h->keyed_slots - 1};
     h->chunk_reads = (uint32_t)env_u64("WQ_CHUNK_READS", 1u << 21);
+    CKH(cudaStreamSynchronize(s));                           // the uploads read caller / mapped memory: done before it goes away
     int rc = wq_quant_reset(h);
     if (rc) { wq_destroy(h); return rc; }
-    CKH(cudaStreamSynchronize(s));
 #undef CKH
     *out = h;
     return 0;
+}
+
+
+int wq_index_create(const wq_index_desc* d, int device, wq_handle** out) {
+    if (!d || !out) return fail(-1, "null argument");
+    *out = nullptr;
+    cudaDeviceProp prop;
+    if (int rc = index_device_check(device, prop)) return rc;
+    wq_handle* h = new wq_handle();
+    h->device = device;
+    std::string err = wq_build_host_index(d, h->H);
+    if (err.empty()) err = wq_build_iso_index(d, h->iso);
+    if (err.empty()) {                                       // SAM output only
+        h->sam.node_base.assign(d->node_base, d->node_base + d->n_genes + 1);
+        h->sam.nodeoffset.assign(d->nodeoffset, d->nodeoffset + d->n_nodes);
+        h->sam.nodecoord.assign(d->nodecoord, d->nodecoord + d->n_nodes);
+        h->sam.nodelen.assign(d->nodelen, d->nodelen + d->n_nodes);
+    }
+    if (!err.empty()) { delete h; return fail(-3, err); }
+    const WqHostIndex& H = h->H;
+    const WqBigArrays A{H.occ.data(), H.occ.size(), d->sa, H.text2.data(), H.text2.size(), H.amb.data(), H.amb.size(),
+                        H.node_bucket.data(), H.node_bucket.size(), d->left_ptr, d->right_ptr};
+    return index_finish(h, prop, A, out);
+}
+
+// The index in its native on-disk form (csrc/wq_index_file.h): wq_index_write is host-only; wq_index_load maps the file and copies
+// the sections to the device (no re-layout, no deserialisation).
+int wq_index_write(const wq_index_desc* d, const char* const* seqname, const uint8_t* strand, const char* path) {
+    if (!d || !path) return fail(-1, "null argument");
+    const std::string err = wq_index_write_impl(d, seqname, strand, path);
+    if (!err.empty()) return fail(-3, err);
+    return 0;
+}
+
+int wq_index_load(const char* path, int device, wq_handle** out) {
+    if (!path || !out) return fail(-1, "null argument");
+    *out = nullptr;
+    WqIdxMapped M;
+    {
+        const std::string err = wq_index_map(path, M, env_u64("WQ_INDEX_VERIFY", 0) != 0);
+        if (!err.empty()) return fail(-3, err);
+    }
+    cudaDeviceProp prop;
+    if (int rc = index_device_check(device, prop)) return rc;
+    wq_handle* h = new wq_handle();
+    h->device = device;
+    const WqIdxHeader& hd = M.hd;
+    WqHostIndex& H = h->H;
+    H.n = hd.n; H.sentinel = hd.sentinel; H.nslots = hd.nslots; H.N = hd.N; H.G = hd.G; H.K = hd.K; H.has_amb = hd.has_amb != 0;
+    for (int i = 0; i < 4; i++) H.C[i] = hd.C[i];
+    H.nodes.assign(M.ptr<WqNodeRec>(WQ_SEC_NODES), M.ptr<WqNodeRec>(WQ_SEC_NODES) + hd.N);
+    H.genes.assign(M.ptr<WqGeneRec>(WQ_SEC_GENES), M.ptr<WqGeneRec>(WQ_SEC_GENES) + hd.G);
+    H.left_ent.assign(M.ptr<uint2>(WQ_SEC_LENT), M.ptr<uint2>(WQ_SEC_LENT) + M.count(WQ_SEC_LENT));
+    H.right_ent.assign(M.ptr<uint2>(WQ_SEC_RENT), M.ptr<uint2>(WQ_SEC_RENT) + M.count(WQ_SEC_RENT));
+    wq_index_desc d;                                         // the fields the annotation index reads
+    memset(&d, 0, sizeof d);
+    d.n_genes = hd.G; d.n_nodes = hd.N; d.n_isoforms = hd.I;
+    d.node_base = M.ptr<uint32_t>(WQ_SEC_NODE_BASE); d.nodelen = M.ptr<uint32_t>(WQ_SEC_NODELEN);
+    d.iso_base = M.ptr<uint32_t>(WQ_SEC_ISO_BASE); d.iso_node_ptr = M.ptr<uint32_t>(WQ_SEC_ISO_NODE_PTR); d.iso_nodes = M.ptr<uint32_t>(WQ_SEC_ISO_NODES);
+    for (uint32_t g = 0; g < hd.G; g++)
+        if (d.node_base[g + 1] < d.node_base[g] || d.node_base[g + 1] > hd.N) { delete h; return fail(-3, std::string(path) + ": node_base is not a CSR over the nodes"); }
+    const std::string err = wq_build_iso_index(&d, h->iso);
+    if (!err.empty()) { delete h; return fail(-3, err); }
+    h->sam.node_base.assign(d.node_base, d.node_base + hd.G + 1);
+    h->sam.nodeoffset.assign(M.ptr<uint32_t>(WQ_SEC_NODEOFFSET), M.ptr<uint32_t>(WQ_SEC_NODEOFFSET) + hd.N);
+    h->sam.nodecoord.assign(M.ptr<uint32_t>(WQ_SEC_NODECOORD), M.ptr<uint32_t>(WQ_SEC_NODECOORD) + hd.N);
+    h->sam.nodelen.assign(d.nodelen, d.nodelen + hd.N);
+    if (hd.has_info) {
+        const uint64_t* no = M.ptr<uint64_t>(WQ_SEC_NAME_OFF); const char* nm = M.ptr<char>(WQ_SEC_NAMES); const uint8_t* st = M.ptr<uint8_t>(WQ_SEC_STRAND);
+        for (uint32_t g = 0; g < hd.G; g++) {
+            if (no[g + 1] < no[g] || no[g + 1] > M.count(WQ_SEC_NAMES)) { delete h; return fail(-3, std::string(path) + ": malformed name table"); }
+            h->sam.seqname.emplace_back(nm + no[g], (size_t)(no[g + 1] - no[g]));
+            h->sam.strand.push_back(st[g] ? 1 : 0);
+        }
+        h->sam.has_info = true;
+    }
+    const WqBigArrays A{M.ptr<WqOccBlock>(WQ_SEC_OCC), (size_t)M.count(WQ_SEC_OCC), M.ptr<uint32_t>(WQ_SEC_SA), M.ptr<uint64_t>(WQ_SEC_TEXT2),
+                        (size_t)M.count(WQ_SEC_TEXT2), M.ptr<uint32_t>(WQ_SEC_AMB), (size_t)M.count(WQ_SEC_AMB), M.ptr<uint32_t>(WQ_SEC_BUCKET),
+                        (size_t)M.count(WQ_SEC_BUCKET), M.ptr<uint32_t>(WQ_SEC_LPTR), M.ptr<uint32_t>(WQ_SEC_RPTR)};
+    return index_finish(h, prop, A, out);                    // synchronises before M unmaps the file
 }
 
 // Run the alignment kernels over reads [0, b.n) already resident on the device (br != NULL: read pairs).

@@ -1137,7 +1137,7 @@ __device__ __forceinline__ double wq_round_sig(const WqPsiDev& d, double x, int 
 // group events by that size.  Events whose member lists do not fit (> ~50 k members) keep the set-by-set form with the
 // lists in global memory.
 struct WqPsiWarpCfg { uint32_t smem_bytes; uint32_t members_in_smem; };
-__global__ void __launch_bounds__(32) wq_k_em_psi(const WqPsiDev d, const uint32_t* __restrict__ list, const uint32_t n_list, const WqPsiWarpCfg cfg) {
+__global__ void __launch_bounds__(32) wq_k_em_psi_big(const WqPsiDev d, const uint32_t* __restrict__ list, const uint32_t n_list, const WqPsiWarpCfg cfg) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t lane = threadIdx.x;
     const uint32_t slot = blockIdx.x;
@@ -1261,35 +1261,200 @@ static inline size_t wq_psi_warp_smem(uint32_t np, uint32_t na, uint32_t nm, boo
     return (b + 15) & ~15ull;
 }
 
-// G lanes per event, 32/G events per warp, for events with at most G paths (more than 99 % of them have at most 4): lane i of
-// the group OWNS path i, so psi / previous psi / temp count live in registers and there is no shared or global scratch.
-// Sums over paths are formed in path order with group shuffles by every lane redundantly (the per-event sequential
-// arithmetic); an ambiguous set adds its share to the lane that owns the path.  Every loop has a group-uniform trip count
-// and every shuffle / vote names the group's lanes only, so the groups of a warp may diverge freely (an event that needs
-// 1500 sweeps does not hold back its neighbours' lanes beyond the warp's lifetime).
-template <int G>
-__global__ void __launch_bounds__(128) wq_k_em_psi_group(const WqPsiDev d, const uint32_t* __restrict__ list, const uint32_t n_list) {
-    const uint32_t lane = threadIdx.x & 31, sub = lane % G, base = lane - sub;
-    const uint32_t slot = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+// One event per block of T = 32 * W threads (events with more than 4 paths), written for the LATENCY of one sweep:
+// a fifth of the events never converge under the 4-significant-digit rounding and run all 1500 sweeps, so the launch lasts
+// 1500 x (the dependent chain of one sweep of its slowest event).  Per sweep:
+//   (1) prop_sum of every set: sequential in member order (the reference's `ac.prop_sum += prev_psi`), the sets side by side on the threads;
+//   (2) every (set, path) share `prop / prop_sum * multiplier`: independent IEEE divisions, spread evenly over ALL threads (a path that
+//       belongs to many sets does not serialise its divisions on one lane) and stored in the order of the inverted index path -> sets;
+//   (3) every path by its owner thread: unambiguous count + its shares added in set order (the order the reference's loop over `ambig`
+//       adds them in), then count / length;
+//   (4) the sum over all paths as ONE sequential chain in path order (every thread forms it from shared memory), division + rounding.
+// Only additions are chained; loads feeding them do not depend on the running sum and are unrolled so that they overlap.
+// Shared memory per event: 40 * paths + 16 * sets + 4 * (sets + 1) + 4 * (paths + 1) + 14 * members bytes.
+__device__ __forceinline__ void wq_psi_sync(const bool one_warp) { if (one_warp) __syncwarp(); else __syncthreads(); }
+__global__ void __launch_bounds__(128) wq_k_em_psi(const WqPsiDev d, const uint32_t* __restrict__ list, const uint32_t n_list) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const uint32_t tid = threadIdx.x, T = blockDim.x;
+    const bool one_warp = T == 32;
+    const uint32_t slot = blockIdx.x;
     if (slot >= n_list) return;
-    const unsigned gmask = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << base;
     const uint32_t e = list[slot];
     const uint32_t p0 = d.path_ptr[e], np = d.path_ptr[e + 1] - p0, ni = d.n_inc[e];
-    const uint32_t a0 = d.amb_ptr[e], a1 = d.amb_ptr[e + 1];
+    const uint32_t a0 = d.amb_ptr[e], na = d.amb_ptr[e + 1] - a0;
+    const uint32_t m0 = d.amb_path_ptr[a0], nm = d.amb_path_ptr[a0 + na] - m0;
+    const bool tandem = d.is_tandem[e] != 0;
+    double* psi = reinterpret_cast<double*>(smem_raw);
+    double* prev = psi + np;
+    double* ct = prev + np;
+    double* den = ct + np;
+    double* cnt = den + np;
+    double* psum = cnt + np;                                      // [na]
+    double* mult = psum + na;                                     // [na]
+    double* quo = mult + na;                                      // [nm] shares, in inverted-index order
+    uint32_t* moff = reinterpret_cast<uint32_t*>(quo + nm);       // [na + 1] member offsets of the sets, event-local
+    uint32_t* poff = moff + na + 1;                               // [np + 1] offsets of the inverted index (path -> its sets, in set order)
+    uint16_t* mem = reinterpret_cast<uint16_t*>(poff + np + 1);   // [nm] event-local path index of every member
+    uint16_t* pset = mem + nm;                                    // [nm] inverted index: the set of every slot
+    uint16_t* ppath = pset + nm;                                  // [nm] inverted index: the path of every slot
+    const uint32_t* gmem = d.amb_paths + m0;
+    for (uint32_t i = tid; i < np; i += T) {
+        const double len = d.length[p0 + i];
+        cnt[i] = d.count[p0 + i];
+        den[i] = tandem ? fmax(__dsub_rn(len, d.readlen), 1.0) : len;
+        prev[i] = 0.0; psi[i] = 0.0; ct[i] = cnt[i];
+    }
+    for (uint32_t a = tid; a <= na; a += T) moff[a] = d.amb_path_ptr[a0 + a] - m0;
+    for (uint32_t a = tid; a < na; a += T) mult[a] = d.amb_mult[a0 + a];
+    for (uint32_t k = tid; k < nm; k += T) mem[k] = (uint16_t)gmem[k];
+    for (uint32_t i = tid; i <= np; i += T) poff[i] = 0;
+    wq_psi_sync(one_warp);
+    if (tid == 0) {                 // counting sort of the (set, path) pairs by path, stable in the set order; once per event
+        for (uint32_t k = 0; k < nm; k++) poff[mem[k] + 1]++;
+        for (uint32_t i = 0; i < np; i++) poff[i + 1] += poff[i];
+        for (uint32_t a = 0; a < na; a++)
+            for (uint32_t k = moff[a]; k < moff[a + 1]; k++) { const uint32_t at = poff[mem[k]]++; pset[at] = (uint16_t)a; ppath[at] = mem[k]; }
+        for (uint32_t i = np; i > 0; i--) poff[i] = poff[i - 1];
+        poff[0] = 0;
+    }
+    wq_psi_sync(one_warp);
+    // sum of psi over the paths in the reference's order (exclusion paths, then inclusion paths, then their sum; tandem: all paths)
+    auto total_of = [&]() -> double {
+        if (tandem) {
+            double t = 0.0;
+            #pragma unroll 8
+            for (uint32_t i = 0; i < np; i++) t = __dadd_rn(t, psi[i]);
+            return t;
+        }
+        double se = 0.0, si = 0.0;
+        #pragma unroll 8
+        for (uint32_t i = ni; i < np; i++) se = __dadd_rn(se, psi[i]);
+        #pragma unroll 4
+        for (uint32_t i = 0; i < ni; i++) si = __dadd_rn(si, psi[i]);
+        return __dadd_rn(se, si);
+    };
+    auto divide = [&](int sig) {            // psi[] holds count / length on entry
+        const double total = total_of();
+        wq_psi_sync(one_warp);
+        for (uint32_t i = tid; i < np; i += T) {
+            const double q = __ddiv_rn(psi[i], total);
+            psi[i] = sig > 0 ? wq_round_sig(d, q, sig) : q;
+        }
+        wq_psi_sync(one_warp);
+    };
+    auto differs = [&]() -> bool {
+        bool diff = false;
+        for (uint32_t i = tid; i < np; i += T) if (prev[i] != psi[i]) diff = true;
+        return one_warp ? __any_sync(0xffffffffu, diff) != 0 : __syncthreads_or(diff) != 0;
+    };
+    if (!tandem) {                          // calculate_psi!(inc, exc, counts) before spliced_em!
+        for (uint32_t i = tid; i < np; i += T) psi[i] = __ddiv_rn(ct[i], den[i]);
+        wq_psi_sync(one_warp);
+        divide(0);
+    }
+    int64_t it = 1;
+    for (;;) {
+        if (!tandem && !(differs() && it < d.maxit)) break;
+        // (1) prop_sum of every set (psi is stable here: the last write was followed by a barrier)
+        if (it > 1) {
+            for (uint32_t a = tid; a < na; a += T) {
+                double sm = 0.0;
+                const uint32_t kb = moff[a], ke = moff[a + 1];
+                #pragma unroll 4
+                for (uint32_t k = kb; k < ke; k++) sm = __dadd_rn(sm, psi[mem[k]]);
+                psum[a] = sm;
+            }
+            wq_psi_sync(one_warp);
+        }
+        // (2) the shares: first sweep ones(n)/n over prop_sum = 1.0, later sweeps the current psi over their sum (src/events.jl:869-886)
+        if (it > 1) {
+            #pragma unroll 2
+            for (uint32_t k = tid; k < nm; k += T) {
+                const uint32_t a = pset[k];
+                quo[k] = __dmul_rn(__ddiv_rn(psi[ppath[k]], psum[a]), mult[a]);
+            }
+        } else {
+            for (uint32_t k = tid; k < nm; k += T) {
+                const uint32_t a = pset[k];
+                quo[k] = __dmul_rn(__ddiv_rn(1.0, (double)(moff[a + 1] - moff[a])), mult[a]);      // (1 / n) / 1.0 = 1 / n
+            }
+        }
+        wq_psi_sync(one_warp);
+        // (3) every path by its owner
+        for (uint32_t i = tid; i < np; i += T) {
+            double c = cnt[i];
+            const uint32_t kb = poff[i], ke = poff[i + 1];
+            #pragma unroll 4
+            for (uint32_t k = kb; k < ke; k++) c = __dadd_rn(c, quo[k]);
+            ct[i] = c;
+            prev[i] = psi[i];
+            psi[i] = __ddiv_rn(c, den[i]);
+        }
+        wq_psi_sync(one_warp);
+        // (4)
+        divide(d.sig);
+        if (tandem) { if (differs() && it < d.maxit) it += 1; else break; }
+        else it += 1;
+    }
+    for (uint32_t i = tid; i < np; i += T) { d.psi[p0 + i] = psi[i]; d.ctemp[p0 + i] = ct[i]; }
+    if (tid == 0) d.iterations[e] = (int32_t)it;
+}
+static inline size_t wq_psi_block_smem(uint32_t np, uint32_t na, uint32_t nm) {
+    size_t b = 40ull * np + 16ull * na + 4ull * (na + 1) + 4ull * (np + 1) + 14ull * nm;
+    return (b + 15) & ~15ull;
+}
+
+// Events with at most 4 paths (more than 90 % of them), at most WQ_PSI4_SETS ambiguous sets of at most 4 members: 4 lanes per
+// event, 8 events per warp.  Lane i of the group OWNS path i (psi / previous psi / temp count in registers); once per sweep the
+// four psi values are exchanged with four shuffles, after which every lane forms every set's prop_sum from registers (the same
+// sequential additions, redundantly) and adds its own shares; the set descriptors (member list as 4-bit path indices, count,
+// multiplier) sit in shared memory, written once per event.  The divisions of up to four sets are issued together (they do not
+// depend on each other; only the additions into the temp count are chained, in set order).  Every loop has a group-uniform trip
+// count and every shuffle / vote names the group's lanes only, so the groups of a warp diverge freely.
+#define WQ_PSI4_SETS 12
+__global__ void __launch_bounds__(128) wq_k_em_psi4(const WqPsiDev d, const uint32_t* __restrict__ list, const uint32_t n_list) {
+    __shared__ double s_mult[32][WQ_PSI4_SETS];
+    __shared__ uint32_t s_desc[32][WQ_PSI4_SETS];      // bits 0..15: four 4-bit path indices in member order; bits 16..18: member count
+    const uint32_t lane = threadIdx.x & 31, sub = lane & 3, base = lane - sub, grp = threadIdx.x >> 2;
+    const uint32_t slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+    if (slot >= n_list) return;
+    const unsigned gmask = 0xFu << base;
+    const uint32_t e = list[slot];
+    const uint32_t p0 = d.path_ptr[e], np = d.path_ptr[e + 1] - p0, ni = d.n_inc[e];
+    const uint32_t a0 = d.amb_ptr[e], na = d.amb_ptr[e + 1] - a0;
     const bool tandem = d.is_tandem[e] != 0;
     const bool own = sub < np;
     const double cnt = own ? d.count[p0 + sub] : 0.0;
     const double len = own ? d.length[p0 + sub] : 1.0;
     const double den = tandem ? fmax(__dsub_rn(len, d.readlen), 1.0) : len;
+    for (uint32_t a = sub; a < na; a += 4) {
+        const uint32_t b = d.amb_path_ptr[a0 + a], n = d.amb_path_ptr[a0 + a + 1] - b;
+        uint32_t desc = n << 16;
+        for (uint32_t k = 0; k < n; k++) desc |= (d.amb_paths[b + k] & 15u) << (4 * k);
+        s_desc[grp][a] = desc;
+        s_mult[grp][a] = d.amb_mult[a0 + a];
+    }
+    __syncwarp(gmask);
     double psi = 0.0, prev = 0.0, ct = cnt;
     auto normalise = [&](int sig) {
         const double q = __ddiv_rn(ct, den);
+        const double q0 = __shfl_sync(gmask, q, base), q1 = __shfl_sync(gmask, q, base + 1), q2 = __shfl_sync(gmask, q, base + 2), q3 = __shfl_sync(gmask, q, base + 3);
         double total;
-        if (tandem) { total = 0.0; for (uint32_t i = 0; i < np; i++) total = __dadd_rn(total, __shfl_sync(gmask, q, base + i)); }
-        else {
+        if (tandem) {
+            total = __dadd_rn(0.0, q0);
+            if (np > 1) total = __dadd_rn(total, q1);
+            if (np > 2) total = __dadd_rn(total, q2);
+            if (np > 3) total = __dadd_rn(total, q3);
+        } else {
             double se = 0.0, si = 0.0;
-            for (uint32_t i = ni; i < np; i++) se = __dadd_rn(se, __shfl_sync(gmask, q, base + i));
-            for (uint32_t i = 0; i < ni; i++) si = __dadd_rn(si, __shfl_sync(gmask, q, base + i));
+            if (ni <= 0 && np > 0) se = __dadd_rn(se, q0);
+            if (ni <= 1 && np > 1) se = __dadd_rn(se, q1);
+            if (ni <= 2 && np > 2) se = __dadd_rn(se, q2);
+            if (ni <= 3 && np > 3) se = __dadd_rn(se, q3);
+            if (ni > 0) si = __dadd_rn(si, q0);
+            if (ni > 1) si = __dadd_rn(si, q1);
+            if (ni > 2) si = __dadd_rn(si, q2);
+            if (ni > 3) si = __dadd_rn(si, q3);
             total = __dadd_rn(se, si);
         }
         const double r = __ddiv_rn(q, total);
@@ -1301,21 +1466,33 @@ __global__ void __launch_bounds__(128) wq_k_em_psi_group(const WqPsiDev d, const
     for (;;) {
         if (!tandem && !(differs() && it < d.maxit)) break;
         ct = cnt; prev = psi;
-        for (uint32_t a = a0; a < a1; a++) {
-            const uint32_t b = d.amb_path_ptr[a], n = d.amb_path_ptr[a + 1] - b;
-            double psum = 1.0;
-            bool mine = false;
-            if (it > 1) psum = 0.0;
-            for (uint32_t k = 0; k < n; k++) {
-                const uint32_t pth = d.amb_paths[b + k];
-                if (it > 1) psum = __dadd_rn(psum, __shfl_sync(gmask, psi, base + pth));
-                if (pth == sub) mine = true;
+        const double v0 = __shfl_sync(gmask, psi, base), v1 = __shfl_sync(gmask, psi, base + 1), v2 = __shfl_sync(gmask, psi, base + 2), v3 = __shfl_sync(gmask, psi, base + 3);
+        for (uint32_t ab = 0; ab < na; ab += 4) {
+            double share[4];
+            uint32_t member_of = 0;                                                              // bit u: this lane's path is in set ab + u
+            #pragma unroll
+            for (int u = 0; u < 4; u++) {
+                share[u] = 0.0;
+                const uint32_t a = ab + u;
+                if (a < na) {
+                    const uint32_t desc = s_desc[grp][a], n = desc >> 16;
+                    double psum = 1.0;
+                    bool mine = false;
+                    if (it > 1) psum = 0.0;
+                    #pragma unroll
+                    for (uint32_t k = 0; k < 4; k++) {
+                        if (k < n) {
+                            const uint32_t pth = (desc >> (4 * k)) & 15u;
+                            if (it > 1) psum = __dadd_rn(psum, pth == 0 ? v0 : pth == 1 ? v1 : pth == 2 ? v2 : v3);
+                            if (pth == sub) mine = true;
+                        }
+                    }
+                    // first sweep: ones(n)/n over prop_sum = 1.0; later sweeps: current psi over their sum (src/events.jl:869-886)
+                    if (mine) { share[u] = __dmul_rn(__ddiv_rn(it > 1 ? psi : __ddiv_rn(1.0, (double)n), psum), s_mult[grp][a]); member_of |= 1u << u; }
+                }
             }
-            if (mine) {
-                // first sweep: ones(n)/n over prop_sum = 1.0; later sweeps: current psi over their sum (src/events.jl:869-886)
-                const double bs = it > 1 ? psi : __ddiv_rn(1.0, (double)n);
-                ct = __dadd_rn(ct, __dmul_rn(__ddiv_rn(bs, psum), d.amb_mult[a]));
-            }
+            #pragma unroll
+            for (int u = 0; u < 4; u++) if (member_of & (1u << u)) ct = __dadd_rn(ct, share[u]);
         }
         normalise(d.sig);
         if (tandem) { if (differs() && it < d.maxit) it += 1; else break; }
@@ -1357,33 +1534,35 @@ static inline std::string wq_run_em_psi(wq_psi_batch& b, WqEmScratch& M, cudaStr
     d.path_ptr = d_pp; d.n_inc = d_ni; d.count = d_cnt; d.length = d_len; d.amb_ptr = d_ap; d.amb_path_ptr = d_app;
     d.amb_paths = d_apaths; d.amb_mult = d_mult; d.is_tandem = d_tan; d.psi = d_psi; d.prev = d_prev; d.ctemp = d_ct;
     d.amb_prop = d_prop; d.iterations = d_it;
-    // events by path count: groups of 4 / 8 / 16 lanes; beyond that one warp per event, grouped by the shared memory the event
-    // needs (launch classes of 6 / 24 / 96 / 200 KB per warp; the last one also takes events whose member lists stay in
-    // global memory).  The classes run concurrently on side streams (a handful of large events that need all 1500 sweeps would
-    // otherwise add their whole latency to the batch).
-    static const size_t kWarpSmem[4] = {6 * 1024, 24 * 1024, 96 * 1024, 200 * 1024};
-    const int NC = 7;
+    // Launch classes: 0 = at most 4 paths with small sets (4 lanes per event); 1..4 = one block per event, grouped by the shared memory the
+    // event needs (4 / 16 / 64 / 200 KB, with 32 / 64 / 128 / 128 threads: more threads shorten the share divisions of a large event);
+    // 5 = events whose member lists do not fit in shared memory (set-by-set form, lists in global memory).  The classes run concurrently on
+    // side streams (a handful of large events that need all 1500 sweeps would otherwise add their whole latency to the batch).
+    static const size_t kBlockSmem[4] = {4 * 1024, 16 * 1024, 64 * 1024, 200 * 1024};
+    static const unsigned kBlockThreads[4] = {32, 64, 128, 128};
+    const int NC = 6;
     std::vector<uint32_t> order(E);
     std::vector<uint8_t> cls(E);
     uint32_t nclass[NC] = {0}, cbase[NC + 1] = {0};
-    bool unstaged_any = false;
     auto cls_of = [&](uint32_t e) -> int {
         const uint32_t np = b.path_ptr[e + 1] - b.path_ptr[e];
-        if (np <= 4) return 0;
-        if (np <= 8) return 1;
-        if (np <= 16) return 2;
-        const uint32_t na = b.amb_ptr[e + 1] - b.amb_ptr[e], nm = b.amb_path_ptr[b.amb_ptr[e + 1]] - b.amb_path_ptr[b.amb_ptr[e]];
-        const size_t need = wq_psi_warp_smem(np, na, nm, true);
-        for (int k = 0; k < 4; k++) if (need <= kWarpSmem[k]) return 3 + k;
+        const uint32_t a_lo = b.amb_ptr[e], a_hi = b.amb_ptr[e + 1], na = a_hi - a_lo, nm = b.amb_path_ptr[a_hi] - b.amb_path_ptr[a_lo];
+        if (np <= 4 && na <= WQ_PSI4_SETS) {
+            bool small = true;
+            for (uint32_t a = a_lo; a < a_hi && small; a++) if (b.amb_path_ptr[a + 1] - b.amb_path_ptr[a] > 4) small = false;
+            if (small) return 0;
+        }
+        if (np > 65535 || na > 65535) return -1;
+        const size_t need = wq_psi_block_smem(np, na, nm);
+        for (int k = 0; k < 4; k++) if (need <= kBlockSmem[k]) return 1 + k;
         return -1;
     };
     for (uint32_t e = 0; e < E; e++) {
         int c = cls_of(e);
         if (c < 0) {            // member lists too long for shared memory: the paths must still fit
             const uint32_t np = b.path_ptr[e + 1] - b.path_ptr[e], na = b.amb_ptr[e + 1] - b.amb_ptr[e];
-            if (np > 65535 || wq_psi_warp_smem(np, na, 0, false) > kWarpSmem[3]) return "PSI event too large for the device kernel (more than ~4000 paths)";
-            unstaged_any = true;
-            c = 6;
+            if (np > 65535 || wq_psi_warp_smem(np, na, 0, false) > kBlockSmem[3]) return "PSI event too large for the device kernel (more than ~4000 paths)";
+            c = 5;
         }
         cls[e] = (uint8_t)c;
         nclass[c]++;
@@ -1396,7 +1575,8 @@ static inline std::string wq_run_em_psi(wq_psi_batch& b, WqEmScratch& M, cudaStr
     WQ_EMCK(M.timing_events());
     static bool smem_attr_set = false;
     if (!smem_attr_set) {
-        WQ_EMCK(cudaFuncSetAttribute(wq_k_em_psi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWarpSmem[3]));
+        WQ_EMCK(cudaFuncSetAttribute(wq_k_em_psi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBlockSmem[3]));
+        WQ_EMCK(cudaFuncSetAttribute(wq_k_em_psi_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBlockSmem[3]));
         smem_attr_set = true;
     }
     WQ_EMCK(cudaEventRecord(M.tk0, stream));
@@ -1408,22 +1588,25 @@ static inline std::string wq_run_em_psi(wq_psi_batch& b, WqEmScratch& M, cudaStr
         if (used > 0) WQ_EMCK(cudaStreamWaitEvent(ss, M.fork, 0));
         const uint32_t n = nclass[c];
         const uint32_t* lst = d_list + cbase[c];
-        if (c == 0) wq_k_em_psi_group<4><<<(n + 31) / 32, 128, 0, ss>>>(d, lst, n);
-        else if (c == 1) wq_k_em_psi_group<8><<<(n + 15) / 16, 128, 0, ss>>>(d, lst, n);
-        else if (c == 2) wq_k_em_psi_group<16><<<(n + 7) / 8, 128, 0, ss>>>(d, lst, n);
-        else if (c == 6 && unstaged_any)            // a class that holds events with member lists in global memory reads them from there for all
-            wq_k_em_psi<<<n, 32, kWarpSmem[3], ss>>>(d, lst, n, WqPsiWarpCfg{(uint32_t)kWarpSmem[3], 0u});
-        else wq_k_em_psi<<<n, 32, kWarpSmem[c - 3], ss>>>(d, lst, n, WqPsiWarpCfg{(uint32_t)kWarpSmem[c - 3], 1u});
+        if (c == 0) wq_k_em_psi4<<<(n + 31) / 32, 128, 0, ss>>>(d, lst, n);
+        else if (c == 5) wq_k_em_psi_big<<<n, 32, kBlockSmem[3], ss>>>(d, lst, n, WqPsiWarpCfg{(uint32_t)kBlockSmem[3], 0u});
+        else wq_k_em_psi<<<n, kBlockThreads[c - 1], kBlockSmem[c - 1], ss>>>(d, lst, n);
         if (launches) *launches += 1;
         WQ_EMCK(cudaGetLastError());
         static const bool class_timing = getenv("WQ_PSI_CLASS_TIMING") != nullptr;     // diagnostic: serialises the classes
         if (class_timing) {
             const auto t0 = std::chrono::steady_clock::now();
             WQ_EMCK(cudaStreamSynchronize(ss));
-            uint64_t np_max = 0;
-            for (uint32_t k = 0; k < n; k++) { const uint32_t e = order[cbase[c] + k]; np_max = std::max<uint64_t>(np_max, b.path_ptr[e + 1] - b.path_ptr[e]); }
-            fprintf(stderr, "[wq]       psi class %d: %u events (max %llu paths) %9.3f ms\n", c, n, (unsigned long long)np_max,
-                    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+            uint64_t np_max = 0, sweeps = 0, capped = 0;
+            std::vector<int32_t> its(E);
+            WQ_EMCK(cudaMemcpy(its.data(), d_it, E * 4ull, cudaMemcpyDeviceToHost));
+            for (uint32_t k = 0; k < n; k++) {
+                const uint32_t e = order[cbase[c] + k];
+                np_max = std::max<uint64_t>(np_max, b.path_ptr[e + 1] - b.path_ptr[e]);
+                sweeps += (uint64_t)its[e]; if (its[e] >= b.maxit) capped++;
+            }
+            fprintf(stderr, "[wq]       psi class %d: %u events (max %llu paths, %llu sweeps, %llu at the cap) %9.3f ms\n", c, n, (unsigned long long)np_max,
+                    (unsigned long long)sweeps, (unsigned long long)capped, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
         }
         if (used > 0) { WQ_EMCK(cudaEventRecord(M.join[(used - 1) % 3], ss)); WQ_EMCK(cudaStreamWaitEvent(stream, M.join[(used - 1) % 3], 0)); }
         used++;

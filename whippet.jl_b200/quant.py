@@ -6,6 +6,7 @@ cites the reference function it stands for.  All compute happens behind the C AB
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 
 import numpy as np
@@ -44,16 +45,36 @@ class MapStats:
     mean_readlen: float = 0.0      # the reference's running mean in read order (src/reads.jl:69), floored by the caller
 
 
+def write_index(index: FlatIndex, path: str, with_info: bool = True):
+    """wq_index_write: the re-laid index of `index` as one file (host only, no GPU needed).  lib.info (sequence name and
+    strand of every gene, SAM output) is stored when the FlatIndex carries it."""
+    L = lib.load()
+    d = index.desc()
+    names = getattr(index, "gene_seqname", None)
+    strands = getattr(index, "gene_strand", None)
+    if with_info and names is not None and strands is not None:
+        arr = (C.c_char_p * index.n_genes)(*[str(x).encode() for x in names])
+        st = np.ascontiguousarray([1 if x else 0 for x in strands], "u1")
+        lib.check(L.wq_index_write(C.byref(d), arr, abi.ptr(st, abi.u8p), os.fsencode(path)))
+    else:
+        lib.check(L.wq_index_write(C.byref(d), None, None, os.fsencode(path)))
+
+
 class GraphLibQuant:
     """`GraphLibQuant{C,DefaultCounter}(lib)` + `MultiMapping{C,DefaultCounter}()`
     (src/quant.jl:165-198, 439-446) living on one GPU."""
 
-    def __init__(self, index: FlatIndex, device: int = 0):
+    def __init__(self, index: FlatIndex, device: int = 0, index_file: str | None = None):
+        """From the flat arrays of a GraphLib (wq_index_create), or, with `index_file`, from the library's native on-disk
+        index (wq_index_load; `index` then only serves the host-side helpers that look at the annotation)."""
         self.L = lib.load()
         self.index = index
-        self._desc = index.desc()
         h = C.c_void_p()
-        lib.check(self.L.wq_index_create(C.byref(self._desc), int(device), C.byref(h)))
+        if index_file is not None:
+            lib.check(self.L.wq_index_load(os.fsencode(index_file), int(device), C.byref(h)))
+        else:
+            self._desc = index.desc()
+            lib.check(self.L.wq_index_create(C.byref(self._desc), int(device), C.byref(h)))
         self.h = h
         self.device = device
 
