@@ -577,16 +577,44 @@ def main():
     parts = build_parts(a, rank, world)
     stream = torch.cuda.current_stream()
     handles, runs = {}, []
+    # The product handles come from the library's native on-disk index (wq_index_write once, by rank 0, host only; wq_index_load on every
+    # rank: map + copy, no re-layout), so the in-run parity check also covers the file path.  index_create_s (rank 0, N = 1) is the same
+    # handle made from the flat GraphLib arrays (wq_index_create: re-layout on the host), for comparison.
+    import tempfile
+    idx_dir = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else tempfile.gettempdir()
+    idx_files, index_write_s, index_create_s = {}, 0.0, None
+    for p in parts:
+        if p.idx_key not in idx_files:
+            idx_files[p.idx_key] = os.path.join(idx_dir, f"wq_bench_{os.environ.get('MASTER_PORT', '0')}_{os.getppid() if world > 1 else os.getpid()}_{p.idx_key.replace('+', '_')}.wqx")
+            if rank == 0:
+                t0 = time.perf_counter()
+                wq.write_index(p.idx, idx_files[p.idx_key])
+                index_write_s += time.perf_counter() - t0
+    if world > 1:
+        dist.barrier()
+    if world == 1 and not a.no_parity:
+        t0 = time.perf_counter()
+        for key in idx_files:
+            qq = wq.GraphLibQuant(next(p.idx for p in parts if p.idx_key == key), device=local)
+            qq.close()
+        index_create_s = time.perf_counter() - t0
     t0 = time.perf_counter()
     for p in parts:
         if p.idx_key not in handles:
-            q = wq.GraphLibQuant(p.idx, device=local)
+            q = wq.GraphLibQuant(p.idx, device=local, index_file=idx_files[p.idx_key])
             lib.check(q.L.wq_set_stream(q.h, C.c_void_p(stream.cuda_stream)))
             if world > 1:
                 q.comm_init(dist)               # NCCL communicator inside the library (unique id broadcast over the process group)
             handles[p.idx_key] = q
         runs.append(PartRun(p, handles[p.idx_key], dev, torch))
     index_load_s = time.perf_counter() - t0
+    index_file_bytes = sum(os.path.getsize(f) for f in idx_files.values())
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        for f in idx_files.values():
+            if os.path.exists(f):
+                os.remove(f)
     phase = {"align": 0.0, "exchange": 0.0, "quant": 0.0, "em_iterations": 0}
 
     def set_partition():
@@ -709,7 +737,8 @@ def main():
                          "inputs are %.1f MB per step (smaller than L2); every step rewrites the count tables, hit lists and path pool (> L2) between passes" % (h2d / 1e6),
                    "text_len": int(mp.idx.text_len), "nodes": int(mp.idx.n_nodes), "isoforms": int(mp.idx.n_isoforms), "genes": int(mp.idx.n_genes),
                    "mapped_frac": stats.mapped / max(1, stats.total), "multi_frac": stats.multi / max(1, stats.total),
-                   "index_load_s": index_load_s,
+                   "index_load_s": index_load_s, "index_load": "wq_index_load of the native index file (written by wq_index_write in "
+                   f"{index_write_s:.2f} s, {index_file_bytes} bytes)", "index_create_s": index_create_s,
                    "parallelism": f"reads sharded over {world} GPU(s), index replicated" + (", dense counts all-reduced and sparse stores all-gathered over NCCL inside the library (wq_counts_sync), class building and event stage partitioned by gene (shares all-gathered), transcript EM replicated" if world > 1 else "")},
         "clocks": clocks, "gpu_launches": launches,
         "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},

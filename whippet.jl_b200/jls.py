@@ -54,9 +54,12 @@ _PRIM = {
 
 @dataclass(frozen=True)
 class JType:
-    """A (possibly parametric) Julia DataType as it appears in the stream."""
+    """A (possibly parametric) Julia DataType as it appears in the stream.  `module` = (package UUID as an int or None, module
+    name) as read; `unionall` marks a type that was wrapped in a UnionAll (an abstract element type such as SpliceGraph)."""
     name: str
     params: tuple = ()
+    module: tuple = field(default=(), compare=False)
+    unionall: bool = field(default=False, compare=False)
 
     def __repr__(self):
         return self.name + ("{" + ",".join(map(repr, self.params)) + "}" if self.params else "")
@@ -77,6 +80,11 @@ class JObject:
 class Undef:
     def __repr__(self):
         return "#undef"
+
+
+class JArray(list):
+    """A Julia Vector of non-bits elements: the elements as a list, plus the element type the stream declared."""
+    eltype: Any = None
 
 
 UNDEF = Undef()
@@ -202,7 +210,8 @@ class JLSReader:
             if flag != 1:
                 raise ValueError("unsupported UnionAll form")
             self.raw(2)  # number of wrapped type variables
-            return self.value()
+            t = self.value()
+            return JType(t.name, t.params, t.module, True) if isinstance(t, JType) else t
         if b == T_MODULE:
             return self.module()
         if b == T_TUPLE:
@@ -235,14 +244,14 @@ class JLSReader:
     def datatype(self):
         s = self.slot()
         name = self.value()
-        self.value()  # module path
+        mod = self.value()  # module path
         params = ()
         if name in _PARAMETRIC:
             n = self.i32()
             params = tuple(self.value() for _ in range(n))
         elif name not in _STRUCTS and name not in _RAW:
             raise ValueError(f"unknown DataType {name!r} in .jls stream (not part of the GraphLib tree)")
-        t = JType(name, params)
+        t = JType(name, params, mod if isinstance(mod, tuple) else ())
         self.table[s] = t
         return t
 
@@ -282,7 +291,8 @@ class JLSReader:
             a = np.frombuffer(self.raw(n * dt.itemsize), dtype=dt).copy()
             self.table[s] = a
             return a
-        lst: list = []
+        lst = JArray()
+        lst.eltype = elty
         self.table[s] = lst
         for _ in range(n):
             lst.append(self.value())
@@ -336,3 +346,336 @@ def decode_seq4(seq: JObject) -> np.ndarray:
     nib[0::2] = data & 0x0F
     nib[1::2] = data >> 4
     return nib[seq.part.start - 1: seq.part.stop].copy()
+
+
+# ---------- writer (test / conversion infrastructure; NOT authoritative) ----------
+# The inverse of JLSReader for the same type tree.  Tag usage, slot numbering and module paths were taken from the one
+# stream available offline (test/test_index.jls): re-serialising the parsed fixture reproduces the
+# file byte for byte (tests/test_jls_roundtrip.py), which pins the writer on everything that file contains.  Forms the
+# fixture does not contain (Int64 values beyond 32 bits, back-references beyond 65535 slots, FMIndex{2,UInt32}) follow
+# Julia's documented widening of the same tags and are only checked against this module's own reader.
+
+_MUTABLE = {"BitSet", "LongSequence"}                      # serialised as 0x35 (reference objects), everything else 0x34
+_PKG_UUID = {                                             # module paths of the package-defined types, as read from the fixture
+    "BioSequences": 168037684205929904788751793060242390617,
+    "FMIndexes": 296814024326595212326055432692074177461,
+    "WaveletMatrices": 255668952536537837259247064549473942047,
+    "IndexableBitVectors": 38151570902576313188594203416082802253,
+}
+_TYPE_MODULE = {
+    "GraphLib": (None, "Main"), "GeneInfo": (None, "Main"), "SpliceGraph": (None, "Main"), "EdgeType": (None, "Main"),
+    "Edges": (None, "Main"), "SGNode": (None, "Main"), "BitSet": (None, "Base"), "UnitRange": (None, "Base"),
+    "Array": (None, "Core"), "Mer": ("BioSequences",), "DNAAlphabet": ("BioSequences",), "LongSequence": ("BioSequences",),
+    "FMIndex": ("FMIndexes",), "WaveletMatrix": ("WaveletMatrices",), "SucVector": ("IndexableBitVectors",),
+    "Block": ("IndexableBitVectors",),
+}
+_PRIM_NAME_TAG = {"Int8": T_INT8, "UInt8": T_UINT8, "Int16": T_INT16, "UInt16": T_UINT16, "Int32": T_INT32, "UInt32": T_UINT32,
+                  "Int64": T_INT64, "UInt64": T_UINT64, "Float16": T_FLOAT16, "Float32": T_FLOAT32, "Float64": T_FLOAT64, "String": T_STRING}
+_NP_ELTYPE = {"int8": "Int8", "uint8": "UInt8", "int16": "Int16", "uint16": "UInt16", "int32": "Int32", "uint32": "UInt32",
+              "int64": "Int64", "uint64": "UInt64", "float16": "Float16", "float32": "Float32", "float64": "Float64"}
+
+
+def jtype(name, *params):
+    mod = _TYPE_MODULE.get(name, ())
+    if len(mod) == 1:
+        mod = (_PKG_UUID[mod[0]], mod[0])
+    return JType(name, tuple(params), mod)
+
+
+class JLSWriter:
+    def __init__(self):
+        self.out = bytearray()
+        self.table: dict = {}
+        self.counter = 0
+
+    def slot(self):
+        s = self.counter
+        self.counter += 1
+        return s
+
+    def backref(self, s):
+        if s <= 0xFFFF:
+            self.out += bytes([T_SHORTBACKREF]) + struct.pack("<H", s)
+        elif s <= 0x7FFFFFFF:
+            self.out += bytes([T_BACKREF]) + struct.pack("<i", s)
+        else:
+            self.out += bytes([T_LONGBACKREF]) + struct.pack("<q", s)
+
+    def header(self):
+        self.out += b"7JL\x0d\x04\x00\x00\x00"
+
+    def int64(self, v):
+        v = int(v)
+        if 0 <= v <= 32:
+            self.out.append(T_INT64_ZERO + v)
+        elif -(1 << 31) <= v < (1 << 31):
+            self.out += bytes([T_SHORTINT64]) + struct.pack("<i", v)
+        else:
+            self.out += bytes([T_INT64]) + struct.pack("<q", v)
+
+    def symbol(self, s: str):
+        if s == "Array":                                 # a symbol with a tag of its own
+            self.out.append(T_SYM_ARRAY)
+            return
+        b = s.encode()
+        if len(b) > 7:
+            key = ("sym", s)
+            if key in self.table:
+                return self.backref(self.table[key])
+            self.table[key] = self.slot()
+        self.out += bytes([T_SYMBOL, len(b)]) + b
+
+    def string(self, s: str):
+        b = s.encode()
+        if len(b) > 7:                                   # tracked by identity in Julia; here: equal long strings share one object
+            key = ("str", s)
+            if key in self.table:
+                return self.backref(self.table[key])
+            self.table[key] = self.slot()
+            self.out.append(T_SHARED_REF)
+        if len(b) <= 255:
+            self.out += bytes([T_STRING, len(b)]) + b
+        else:
+            self.out += bytes([T_LONGSTRING]) + struct.pack("<q", len(b)) + b
+
+    def module(self, mod):
+        uuid, name = mod
+        self.out.append(T_MODULE)
+        if uuid is None:
+            self.out.append(T_NOTHING)
+        else:
+            self.out += bytes([T_UINT128]) + int(uuid).to_bytes(16, "little")
+        if name in ("Core", "Base"):
+            self.out.append({"Core": 0x9B, "Base": 0x9E}[name])
+        else:
+            self.symbol(name)
+        self.out.append(T_EMPTYTUPLE)
+
+    def type_value(self, t):
+        """A type in value position (array element types, type parameters)."""
+        if isinstance(t, JType) and t.name in _PRIM_NAME_TAG and not t.params:
+            self.out += bytes([0x00, _PRIM_NAME_TAG[t.name]])
+        elif isinstance(t, JType):
+            self.datatype(t)
+        else:
+            self.value(t)
+
+    def datatype(self, t: JType):
+        key = ("type", t.name, t.params)
+        if key in self.table:
+            return self.backref(self.table[key])
+        if t.unionall:
+            self.out += bytes([T_UNIONALL, 1, 1, 0])
+        self.out.append(T_DATATYPE)
+        self.table[key] = self.slot()
+        self.symbol(t.name)
+        mod = t.module or _TYPE_MODULE.get(t.name)
+        if len(mod) == 1:
+            mod = (_PKG_UUID[mod[0]], mod[0])
+        self.module(mod)
+        if t.name in _PARAMETRIC:
+            self.out += struct.pack("<i", len(t.params))
+            for p in t.params:
+                self.type_value(p)
+
+    def array_raw(self, a: np.ndarray, elty):
+        self.slot()
+        self.out.append(T_ARRAY)
+        if not (isinstance(elty, JType) and elty.name == "UInt8"):
+            self.type_value(elty)
+        self.int64(len(a))
+        self.out += np.ascontiguousarray(a).tobytes()
+
+    def value(self, v, elty_hint=None):
+        if v is None:
+            self.out.append(T_NOTHING)
+        elif v is UNDEF or isinstance(v, Undef):
+            self.out.append(T_UNDEFREF)
+        elif isinstance(v, (bool, np.bool_)):
+            self.out.append(T_TRUE if v else T_FALSE)
+        elif isinstance(v, (int, np.integer)):
+            self.int64(v)
+        elif isinstance(v, str):
+            self.string(v)
+        elif isinstance(v, JType):
+            self.type_value(v)
+        elif isinstance(v, tuple):
+            if len(v) == 0:
+                self.out.append(T_EMPTYTUPLE)
+            else:
+                self.out += bytes([T_TUPLE, len(v)])
+                for x in v:
+                    self.value(x)
+        elif isinstance(v, np.ndarray):
+            elty = elty_hint
+            if elty is None:
+                if v.dtype.names == ("gene", "node"):
+                    elty = jtype("SGNode")
+                elif v.dtype.names is not None and "chunks" in v.dtype.names:
+                    elty = jtype("Block")
+                else:
+                    elty = JType(_NP_ELTYPE[v.dtype.name])
+            self.array_raw(v, elty)
+        elif isinstance(v, list):
+            elty = getattr(v, "eltype", None) or elty_hint
+            if elty is None:
+                raise ValueError("a list needs its Julia element type (JArray.eltype)")
+            self.slot()
+            self.out.append(T_ARRAY)
+            self.type_value(elty)
+            self.int64(len(v))
+            inner = elty.params[0] if isinstance(elty, JType) and elty.name == "Array" and elty.params else None
+            for x in v:
+                self.value(x, elty_hint=inner)
+        elif isinstance(v, JObject):
+            if v.type.name in _MUTABLE:
+                self.slot()
+                self.out.append(T_REF_OBJECT)
+            else:
+                self.out.append(T_OBJECT)
+            self.datatype(v.type)
+            for f in _STRUCTS[v.type.name][1]:
+                self.value(v.fields[f], elty_hint=_FIELD_ELTYPE.get((v.type.name, f)))
+        else:
+            raise ValueError(f"cannot serialise {type(v).__name__}")
+
+
+# element types of the raw arrays that numpy cannot tell apart from plain integers
+_FIELD_ELTYPE: dict = {}
+
+
+def _init_field_eltypes():
+    mer = lambda k: jtype("Mer", jtype("DNAAlphabet", 2), k)
+    _FIELD_ELTYPE[("SpliceGraph", "edgetype")] = jtype("EdgeType")
+    return mer
+
+
+_mer_of = _init_field_eltypes()
+
+
+def dump_jls(lib: JObject) -> bytes:
+    """Serialise a GraphLib tree (as load_jls returns it, or as graphlib_tree builds it)."""
+    w = JLSWriter()
+    w.header()
+    K = int(lib.kmer)
+    _FIELD_ELTYPE[("SpliceGraph", "edgeleft")] = _mer_of(K)
+    _FIELD_ELTYPE[("SpliceGraph", "edgeright")] = _mer_of(K)
+    w.value(lib)
+    return bytes(w.out)
+
+
+# ---- a GraphLib tree from flat arrays ----
+def sucvector_from_bits(bits: np.ndarray) -> JObject:
+    """SucVector(blocks, len): 256 bits per block = 4 chunks; `large` = ones before the block, smalls[j] = ones before chunk j
+    inside the block (IndexableBitVectors 1.0.0; layout observed in the fixture)."""
+    n = len(bits)
+    nblk = (n + 255) // 256 if n else 0
+    # the fixture stores ceil((len + 1) / 256) blocks when len is a multiple of 256?  It holds 105 bits in one block; keep ceil(n / 256), min 1
+    nblk = max(1, nblk)
+    padded = np.zeros(nblk * 256, np.uint8)
+    padded[:n] = bits
+    chunks = np.packbits(padded, bitorder="little").view("<u8").reshape(nblk, 4)
+    pc = padded.reshape(nblk, 4, 64).sum(axis=2, dtype=np.int64)
+    cum = np.cumsum(pc, axis=1)
+    smalls = np.zeros((nblk, 4), np.uint8)
+    smalls[:, 1:] = cum[:, :3]
+    # past the end of the data the fixture repeats the running count (chunks are empty, so the cumulative form does that by itself)
+    large = np.zeros(nblk, np.int64)
+    large[1:] = np.cumsum(cum[:, 3])[:-1]
+    blocks = np.zeros(nblk, _RAW["Block"])
+    blocks["large"] = large.astype("<u4")
+    blocks["smalls"] = smalls
+    blocks["chunks"] = chunks
+    return JObject(jtype("SucVector"), {"blocks": blocks, "len": int(n)})
+
+
+def wavelet_encode(sym: np.ndarray, w: int = 2) -> JObject:
+    """WaveletMatrix{w,UInt8,SucVector} of the symbols (inverse of wavelet_decode)."""
+    n = len(sym)
+    cur = np.asarray(sym, np.uint8)
+    levels, nzeros = [], []
+    for lv in range(w):
+        b = (cur >> (w - 1 - lv)) & 1
+        levels.append(sucvector_from_bits(b.astype(np.uint8)))
+        nzeros.append(int(n - int(b.sum())))
+        cur = np.concatenate([cur[b == 0], cur[b == 1]])           # stable: zeros first
+    # sps[c] = start of symbol c's run in the final order (sorted by bit-reversed symbol)
+    counts = np.bincount(np.asarray(sym, np.int64), minlength=1 << w)
+    order = sorted(range(1 << w), key=lambda c: int(format(c, f"0{w}b")[::-1], 2))
+    sps = np.zeros(1 << w, "<i8")
+    run = 0
+    for c in order:
+        sps[c] = run
+        run += int(counts[c])
+    return JObject(jtype("WaveletMatrix", w, JType("UInt8"), jtype("SucVector")),
+                   {"bits": tuple(levels), "nzeros": tuple(nzeros), "sps": sps})
+
+
+def encode_seq4(nib: np.ndarray) -> JObject:
+    """One nibble per base -> LongSequence{DNAAlphabet{4}} (16 bases per word, low nibble first)."""
+    n = len(nib)
+    pad = np.zeros(((n + 15) // 16) * 16, np.uint8)
+    pad[:n] = nib
+    data = (pad[0::2] | (pad[1::2] << 4)).astype(np.uint8).view("<u8").copy()
+    return JObject(jtype("LongSequence", jtype("DNAAlphabet", 4)),
+                   {"data": data, "part": JObject(jtype("UnitRange", JType("Int64")), {"start": 1, "stop": int(n)}), "shared": False})
+
+
+def bitset_of(ids) -> JObject:
+    """Base.BitSet holding the (ascending, positive) ids: value v is bit (v & 63) of chunk (v >> 6) - offset."""
+    ids = np.asarray(ids, np.int64)
+    off = int(ids.min() >> 6) if len(ids) else 0
+    nch = int(ids.max() >> 6) - off + 1 if len(ids) else 0
+    bits = np.zeros(nch, "<u8")
+    np.bitwise_or.at(bits, (ids >> 6) - off, np.uint64(1) << (ids & 63).astype(np.uint64))
+    return JObject(jtype("BitSet"), {"bits": bits, "offset": off})
+
+
+def graphlib_tree(idx) -> JObject:
+    """A GraphLib tree (src/index.jl:5-15) from a FlatIndex, shaped like the reference's own stream: FMIndex{2,T} with
+    T the narrowest unsigned type that holds the text length (UInt8 in the fixture, UInt32 at annotation scale,
+    src/index.jl:57,97), Edges{K} with #undef holes, one SpliceGraph{K} per gene.  Fields the flat bundle does not carry are
+    filled with neutral values: annobias (20 zero bins per isoform), GraphLib.lengths (sum of node lengths)."""
+    G, K, n = idx.n_genes, int(idx.kmer), idx.text_len
+    nb, ib = idx.node_base.astype(np.int64), idx.iso_base.astype(np.int64)
+    ends = np.append(idx.gene_offset[1:].astype(np.int64), n)
+    names = list(idx.gene_names) if len(idx.gene_names) == G else [f"gene{g + 1}" for g in range(G)]
+    seqn = list(idx.gene_seqname) if len(idx.gene_seqname) == G else ["chr0"] * G
+    strand = idx.gene_strand if idx.gene_strand is not None and len(idx.gene_strand) == G else np.ones(G, "u1")
+    iso_names = list(idx.iso_names) if len(idx.iso_names) == idx.n_isoforms else [f"iso{i + 1}" for i in range(idx.n_isoforms)]
+    info = JArray(JObject(jtype("GeneInfo"), {"gene": names[g], "name": str(seqn[g]), "strand": bool(strand[g])}) for g in range(G))
+    info.eltype = jtype("GeneInfo")
+    sg_t = jtype("SpliceGraph", K)
+    graphs = JArray()
+    graphs.eltype = JType("SpliceGraph", (), _TYPE_MODULE["SpliceGraph"], True)
+    zero_bias = np.zeros(20, "<f2")
+    for g in range(G):
+        a, b, e0 = int(nb[g]), int(nb[g + 1]), int(nb[g]) + g
+        ne = b - a + 1
+        paths = JArray(bitset_of(idx.iso_nodes[int(idx.iso_node_ptr[i]):int(idx.iso_node_ptr[i + 1])]) for i in range(int(ib[g]), int(ib[g + 1])))
+        paths.eltype = jtype("BitSet")
+        an = JArray(iso_names[int(ib[g]):int(ib[g + 1])])
+        an.eltype = JType("String")
+        bias = JArray(zero_bias.copy() for _ in range(int(ib[g + 1] - ib[g])))
+        bias.eltype = jtype("Array", JType("Float16"), 1)
+        graphs.append(JObject(sg_t, {
+            "nodeoffset": idx.nodeoffset[a:b].copy(), "nodecoord": idx.nodecoord[a:b].copy(), "nodelen": idx.nodelen[a:b].copy(),
+            "edgetype": idx.edgetype[e0:e0 + ne].copy(), "edgeleft": idx.edgeleft[e0:e0 + ne].copy(), "edgeright": idx.edgeright[e0:e0 + ne].copy(),
+            "annopath": paths, "annoname": an, "annobias": bias, "seq": encode_seq4(idx.seq4[int(idx.gene_offset[g]):int(ends[g])])}))
+
+    def table(ptr_, nodes):
+        pairs = np.zeros(len(nodes) // 2, _RAW["SGNode"])
+        pairs["gene"], pairs["node"] = nodes[0::2], nodes[1::2]
+        t = JArray(UNDEF if ptr_[k] == ptr_[k + 1] else pairs[int(ptr_[k]):int(ptr_[k + 1])] for k in range(len(ptr_) - 1))
+        t.eltype = jtype("Array", jtype("SGNode"), 1)
+        return t
+    edges = JObject(jtype("Edges", K), {"left": table(idx.left_ptr, idx.left_nodes), "right": table(idx.right_ptr, idx.right_nodes)})
+    st = "UInt8" if n < (1 << 8) else "UInt16" if n < (1 << 16) else "UInt32" if n < (1 << 32) else "UInt64"
+    fm = JObject(jtype("FMIndex", 2, JType(st)), {
+        "bwt": wavelet_encode(idx.bwt, 2), "sentinel": int(idx.sentinel), "samples": idx.sa.astype(_PRIM[_PRIM_NAME_TAG[st]][0]),
+        "sampled": sucvector_from_bits(np.ones(n, np.uint8)), "count": idx.count.astype("<i8")})
+    nm = JArray(names)
+    nm.eltype = JType("String")
+    lengths = np.add.reduceat(idx.nodelen.astype(np.float64), nb[:-1]) if G else np.zeros(0)
+    return JObject(jtype("GraphLib"), {"offset": idx.gene_offset.copy(), "names": nm, "info": info, "lengths": lengths.astype("<f8"),
+                                        "graphs": graphs, "edges": edges, "index": fm, "sorted": True, "kmer": K})

@@ -52,7 +52,7 @@ def write_index(index: FlatIndex, path: str, with_info: bool = True):
     d = index.desc()
     names = getattr(index, "gene_seqname", None)
     strands = getattr(index, "gene_strand", None)
-    if with_info and names is not None and strands is not None:
+    if with_info and names is not None and strands is not None and len(names) == index.n_genes and len(strands) == index.n_genes:
         arr = (C.c_char_p * index.n_genes)(*[str(x).encode() for x in names])
         st = np.ascontiguousarray([1 if x else 0 for x in strands], "u1")
         lib.check(L.wq_index_write(C.byref(d), arr, abi.ptr(st, abi.u8p), os.fsencode(path)))
