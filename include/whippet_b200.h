@@ -165,6 +165,29 @@ int  wq_index_load(const char* path, int device, wq_handle** out);
  * zero all device-side count stores. */
 int  wq_quant_reset(wq_handle* h);
 
+/* `--biascorrect` (bin/whippet-quant.jl:116-122: CounterType = JointBiasCounter, BiasModelType = JointBiasMod; src/bias.jl:103-270).
+ * wq_set_biascorrect(h, 1) before the first batch (it resets the count stores).  From then on every mapped read also feeds the 5' hexamer /
+ * GC-window model (count!(mod, read.sequence), src/reads.jl:59, 108) and files its hexamers and GC bins under the counter it is counted
+ * in (push!, src/bias.jl:222-235); the quant stage then works with the Float64 counts of primer_adjust! (classes, EM) and, from
+ * assign_ambig! on, of gc_adjust! (bin/whippet-quant.jl:156-169), inside wq_em_tpm / wq_assign_ambig / wq_process_events as before.
+ * Everything is tallied in integers on the device and turned into Float64 in one fixed order per counter (ascending hexamer, then
+ * ascending bin: the declared canonical order of the reference's Dict iteration), so results do not depend on thread timing.
+ * Mapped reads must be at least 37 bases long (the reference throws BoundsError otherwise); one GPU per job in this version.
+ * wq_bias_download returns, aligned with wq_counts_download and wq_keyed_download (kinds 0 and 1), every counter's count after
+ * primer_adjust! and the factor gc_adjust! multiplies it by (< 0: the counter saw no GC window and is left alone), plus the
+ * normalised model tables mod.fore / mod.back (4096 each; NULL to skip).  NULL arrays = sizes only. */
+typedef struct wq_bias_counts {
+    uint64_t n_nodes, n_edge, n_circ, n_long, n_multi;
+    double *node_primer, *node_gc;
+    double *edge_primer, *edge_gc;
+    double *circ_primer, *circ_gc;
+    double *long_primer, *long_gc;
+    double *multi_primer, *multi_gc;
+    double *fore, *back;
+} wq_bias_counts;
+int  wq_set_biascorrect(wq_handle* h, int on);
+int  wq_bias_download(wq_handle* h, wq_bias_counts* out);
+
 /* process_reads! body (src/reads.jl:56-71): ungapped_align (src/align.jl:225-270) for every read of
  * the batch, then count!/push!(multi) (src/quant.jl:556-594, 456-469) accumulated on the device.
  * `out` may be NULL (quantification only); when given the alignments are downloaded as well. */

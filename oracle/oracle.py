@@ -120,11 +120,33 @@ class Oracle:
 
     def process_reads(self, param: wq.AlignParam, reads: wq.ReadBatch):
         p, b = param.c(), reads.c()
-        lib().wqo_process_reads_se(C.c_void_p(self.h), C.byref(p), C.byref(b))
+        rc = lib().wqo_process_reads_se(C.c_void_p(self.h), C.byref(p), C.byref(b))
+        if rc == -2:
+            raise ValueError("bias correction: a mapped read is shorter than 37 bases (the reference throws BoundsError, src/bias.jl:163-165)")
 
     def process_paired_reads(self, param: wq.AlignParam, fwd: wq.ReadBatch, rev: wq.ReadBatch):
         p, f, r = param.c(), fwd.c(), rev.c()
-        lib().wqo_process_reads_pe(C.c_void_p(self.h), C.byref(p), C.byref(f), C.byref(r))
+        rc = lib().wqo_process_reads_pe(C.c_void_p(self.h), C.byref(p), C.byref(f), C.byref(r))
+        if rc == -2:
+            raise ValueError("bias correction: a mapped read is shorter than 37 bases (the reference throws BoundsError, src/bias.jl:163-165)")
+
+    # ---- --biascorrect (JointBiasMod / JointBiasCounter, src/bias.jl:103-270; bin/whippet-quant.jl:116-122, 156-169) ----
+    def set_bias(self, on=True):
+        """CounterType = JointBiasCounter, BiasModelType = JointBiasMod; takes effect at the next quant_reset()."""
+        lib().wqo_set_bias(C.c_void_p(self.h), int(bool(on)))
+
+    def bias_primer_adjust(self):
+        """primer_normalize!(mod); primer_adjust!(quant, mod); primer_adjust!(multi, mod) -- before build_equivalence_classes!."""
+        lib().wqo_bias_primer_adjust(C.c_void_p(self.h))
+
+    def bias_gc_adjust(self):
+        """gc_adjust!(quant, mod); gc_adjust!(multi, mod) -- after gene_em! / set_gene_tpm!, before assign_ambig!."""
+        lib().wqo_bias_gc_adjust(C.c_void_p(self.h))
+
+    def bias_model(self):
+        fore, back, short = np.zeros(4096), np.zeros(4096), C.c_uint64()
+        lib().wqo_bias_model(C.c_void_p(self.h), fore.ctypes.data_as(C.c_void_p), back.ctypes.data_as(C.c_void_p), C.byref(short))
+        return fore, back, short.value
 
     def merge(self, other: "Oracle"):
         lib().wqo_merge(C.c_void_p(self.h), C.c_void_p(other.h))

@@ -726,7 +726,83 @@ void emit(Result& R, const Align& a, std::vector<wq_alignment>& dst) {
 // src/bias.jl:66-85: every read adds 1.0).  Stores are kept in ordered maps; the sorted key order is
 // the declared canonical order (Julia Dict order is not reproducible).
 // Keys use the same record format as the library's download (include/whippet_b200.h::wq_keyed).
+// --biascorrect (bin/whippet-quant.jl:116-122): JointBiasMod / JointBiasCounter, src/bias.jl:103-270.
+// Julia's div for floats is exact floor-toward-zero division, round((x - rem(x, y)) / y) (Base; the reference's own test
+// `length(ExpectedGC(seq)) == 20`, test/runtests.jl:101, holds only under it: div(1.0, 0.05) == 19.0).
+double jl_div(double x, double y) { return std::nearbyint((x - std::fmod(x, y)) / y); }
+struct BiasTemp {               // JointBiasTemp, src/bias.jl:103-106
+    uint16_t primer[2];
+    int32_t gc[100];
+};
+struct BiasMod {                // JointBiasMod(), src/bias.jl:108-143 with the defaults of the constructor
+    std::vector<double> fore, back;                                    // 4^6
+    Int size = 6, backoffset = 23, backnpos = 10, foreoffset = 1, forenpos = 2;
+    std::vector<double> gcfore, gcback;                                // Int(ceil(1.0 / 0.05) + 1) = 21
+    Int gcsize = 50; double gcwidth = 0.05; Int gcoffset = 5, gcincrement = 10;
+    BiasTemp temp;
+    BiasMod() : fore(4096, 0.0), back(4096, 0.0), gcfore(21, 0.0), gcback(21, 0.0) { memset(&temp, 0, sizeof temp); }
+};
+struct BiasCounter {            // JointBiasCounter without `count` (that is the Float64 of the Quant store), src/bias.jl:207-218
+    std::map<uint16_t, int32_t> map;       // Dict{UInt16,Int32}: iterated in ascending key order (canonical; Julia Dict order is unspecified)
+    int32_t gc[21];
+    BiasCounter() { memset(gc, 0, sizeof gc); }
+};
+// kmer_index_trailing(UInt16, seq[i:i+size-1]), src/sgkmer.jl:17-28 (reads hold no ambiguous symbols after fill_ambiguous)
+uint16_t kmer_trailing(const std::vector<uint8_t>& seq, Int i1, Int size) {
+    uint16_t x = 0;
+    for (Int k = 0; k < size; k++) x = (uint16_t)((x << 2) | seq[(size_t)(i1 - 1 + k)]);
+    return x;
+}
+// primer_count!, src/bias.jl:154-167.  false = the read is too short for the background window (the reference throws BoundsError)
+bool primer_count(BiasMod& m, const std::vector<uint8_t>& seq) {
+    if ((Int)seq.size() < m.backoffset + m.backnpos - 1 + m.size - 1) return false;
+    Int idx = 1;
+    for (Int i = m.foreoffset; i <= m.foreoffset + m.forenpos - 1; i++) {
+        uint16_t hept = kmer_trailing(seq, i, m.size);
+        m.fore[hept] += 1.0;
+        m.temp.primer[idx - 1] = hept;
+        idx += 1;
+    }
+    for (Int i = m.backoffset; i <= m.backoffset + m.backnpos - 1; i++) m.back[kmer_trailing(seq, i, m.size)] += 1.0;
+    return true;
+}
+// gc_count!, src/bias.jl:169-181 (idx restarts at 1 on every call: in the paired form the mate's bins overwrite the first entries)
+void gc_count(BiasMod& m, const std::vector<uint8_t>& seq) {
+    Int idx = 1;
+    for (Int i = m.gcoffset; i <= (Int)seq.size() - m.gcsize; i += m.gcincrement) {
+        Int ngc = 0;
+        for (Int k = 0; k < m.gcsize; k++) { uint8_t c = seq[(size_t)(i - 1 + k)]; ngc += (c == 1 || c == 2); }
+        double gc = (double)ngc / (double)m.gcsize;                    // gc_content(seq[i:i+gcsize-1])
+        Int bin = (Int)(jl_div(gc, m.gcwidth) + 1);
+        m.gcfore[(size_t)bin - 1] += 1.0;
+        m.temp.gc[idx - 1] = (int32_t)bin;
+        idx += 1;
+    }
+}
+// count!(mod, seq) / count!(mod, fwd, rev), src/bias.jl:183-203
+bool bias_count(BiasMod& m, const std::vector<uint8_t>& seq, const std::vector<uint8_t>* rev = nullptr) {
+    if (!primer_count(m, seq)) return false;
+    memset(m.temp.gc, 0, sizeof m.temp.gc);
+    gc_count(m, seq);
+    if (rev) gc_count(m, *rev);
+    return true;
+}
+// push!(cnt::JointBiasCounter, temp), src/bias.jl:222-235
+void bias_push(BiasCounter& c, const BiasTemp& t) {
+    for (int i = 0; i < 2; i++) c.map[t.primer[i]] += 1;
+    for (int i = 0; i < 100; i++) {
+        if (t.gc[i] > 0) c.gc[t.gc[i] - 1] += 1;
+        else return;
+    }
+}
+
 struct Quant {
+    bool bias = false;                                      // CounterType = JointBiasCounter, BiasModelType = JointBiasMod
+    BiasMod mod;
+    std::vector<BiasCounter> bnode;
+    std::map<uint64_t, BiasCounter> bedge;
+    std::map<std::vector<uint32_t>, BiasCounter> blongs, bmulti;
+    uint64_t bias_short = 0;
     std::vector<double> node;                               // by global node index
     std::map<uint64_t, double> edge;                        // gene<<32 | l<<16 | r  (edge when l<r, circ otherwise)
     std::map<std::vector<uint32_t>, double> longs;          // [npath, gene, nodes...]  /  PE: [npf | npr<<8 | 2<<28, gene, fwd.., rev..]
@@ -736,22 +812,28 @@ struct Quant {
 };
 
 // count!(quant, align, value), src/quant.jl:556-594
-void count_se(const Lib& L, Quant& Q, const Align& a, double value) {
+// With a JointBiasTemp as `value` push! files the read's hexamers and GC bins in the counter and leaves its count alone
+// (src/bias.jl:222-235); the stores' Float64 stay 0.0 until primer_adjust!.
+void count_se(const Lib& L, Quant& Q, const Align& a, double value, const BiasTemp* bt = nullptr) {
     if (!a.isvalid) return;
     uint32_t init_gene = a.path[0].gene;
     size_t nb = L.d->node_base[init_gene - 1];
+    if (bt) value = 0.0;
     if (a.path.size() == 1) {
         Q.node[nb + a.path[0].node - 1] += value;
+        if (bt) bias_push(Q.bnode[nb + a.path[0].node - 1], *bt);
     } else {
         for (auto& n : a.path) if (n.gene != init_gene) return;
         if (a.path.size() == 2) {
             uint32_t l = a.path[0].node, r = a.path[1].node;
             uint64_t key = ((uint64_t)init_gene << 32) | ((uint64_t)(l & 0xFFFF) << 16) | (r & 0xFFFF);
             Q.edge[key] += value;     // l < r: edge interval; l >= r: circ tuple (same packed key space)
+            if (bt) bias_push(Q.bedge[key], *bt);
         } else {
             std::vector<uint32_t> key{(uint32_t)a.path.size(), init_gene};
             for (auto& n : a.path) key.push_back(n.node);
             Q.longs[key] += value;
+            if (bt) bias_push(Q.blongs[key], *bt);
         }
     }
 }
@@ -779,8 +861,9 @@ std::vector<uint32_t> paired_key(const Align& f, const Align& r) {
 }
 
 // count!(quant, fwd, rev, value), src/quant.jl:597-653
-void count_pe(const Lib& L, Quant& Q, const Align& fwd, const Align& rev, double value) {
+void count_pe(const Lib& L, Quant& Q, const Align& fwd, const Align& rev, double value, const BiasTemp* bt = nullptr) {
     if (!(fwd.isvalid && rev.isvalid)) return;
+    if (bt) value = 0.0;
     uint32_t init_gene = fwd.path[0].gene, rev_gene = rev.path[0].gene;
     if (init_gene != rev_gene) return;
     size_t nb = L.d->node_base[init_gene - 1];
@@ -794,37 +877,88 @@ void count_pe(const Lib& L, Quant& Q, const Align& fwd, const Align& rev, double
     if (singlebool) {
         if (single->size() == 1) {
             Q.node[nb + (*single)[0].node - 1] += value;
+            if (bt) bias_push(Q.bnode[nb + (*single)[0].node - 1], *bt);
         } else {
             for (auto& n : *single) if (n.gene != init_gene) return;
             if (single->size() == 2) {
                 uint32_t l = (*single)[0].node, r = (*single)[1].node;
-                Q.edge[((uint64_t)init_gene << 32) | ((uint64_t)(l & 0xFFFF) << 16) | (r & 0xFFFF)] += value;
+                const uint64_t key = ((uint64_t)init_gene << 32) | ((uint64_t)(l & 0xFFFF) << 16) | (r & 0xFFFF);
+                Q.edge[key] += value;
+                if (bt) bias_push(Q.bedge[key], *bt);
             }
         }
     } else {
-        Q.longs[paired_key(fwd, rev)] += value;
+        const std::vector<uint32_t> key = paired_key(fwd, rev);
+        Q.longs[key] += value;
+        if (bt) bias_push(Q.blongs[key], *bt);
     }
 }
 
 // push!(multi, fwd, rev, value, ...), src/quant.jl:471-484
-void push_multi_pe(Quant& Q, const std::vector<Align>& f, const std::vector<Align>& r, double value) {
+void push_multi_pe(Quant& Q, const std::vector<Align>& f, const std::vector<Align>& r, double value, const BiasTemp* bt = nullptr) {
     std::vector<uint32_t> key{(3u << 28) | (uint32_t)f.size()};
     for (size_t i = 0; i < f.size(); i++) {
         std::vector<uint32_t> k = paired_key(f[i], r[i]);
         key.insert(key.end(), k.begin(), k.end());
     }
-    Q.multi[key] += value;
+    Q.multi[key] += bt ? 0.0 : value;
+    if (bt) bias_push(Q.bmulti[key], *bt);
 }
 
 // push!(multi, alns, value, ...), src/quant.jl:456-469: the key is the ordered vector of node paths
-void push_multi_se(Quant& Q, const std::vector<Align>& alns, double value) {
+void push_multi_se(Quant& Q, const std::vector<Align>& alns, double value, const BiasTemp* bt = nullptr) {
     std::vector<uint32_t> key{(1u << 28) | (uint32_t)alns.size()};
     for (auto& a : alns) {
         key.push_back((uint32_t)a.path.size());
         key.push_back(a.path[0].gene);
         for (auto& n : a.path) key.push_back(n.node);
     }
-    Q.multi[key] += value;
+    Q.multi[key] += bt ? 0.0 : value;
+    if (bt) bias_push(Q.bmulti[key], *bt);
+}
+
+// primer_normalize!(mod) (src/bias.jl:145-152) + primer_adjust!(quant, mod) + primer_adjust!(multi, mod) (src/quant.jl:200-221, 486-495;
+// bin/whippet-quant.jl:156-158).  value!(mod, hept) = back[hept+1] / fore[hept+1] (src/bias.jl:205).
+double primer_value(const BiasCounter& c, const BiasMod& m) {
+    double count = 0.0;                                     // JointBiasCounter() starts at 0.0
+    for (auto& kv : c.map) count += (m.back[kv.first] / m.fore[kv.first]) * (double)kv.second;
+    count /= (double)m.forenpos;
+    return count;
+}
+void bias_primer_adjust(Quant& Q) {
+    BiasMod& m = Q.mod;
+    double foresum = 0.0, backsum = 0.0;                    // integer-valued addends: exact in any order
+    for (size_t i = 0; i < m.fore.size(); i++) { foresum += m.fore[i]; backsum += m.back[i]; }
+    for (size_t i = 0; i < m.fore.size(); i++) { m.fore[i] = m.fore[i] / foresum; m.back[i] = m.back[i] / backsum; }
+    static const BiasCounter none;
+    for (size_t i = 0; i < Q.node.size(); i++) Q.node[i] = primer_value(Q.bnode[i], m);
+    auto get = [&](auto& store, const auto& key) -> const BiasCounter& { auto it = store.find(key); return it == store.end() ? none : it->second; };
+    for (auto& kv : Q.edge) kv.second = primer_value(get(Q.bedge, kv.first), m);
+    for (auto& kv : Q.longs) kv.second = primer_value(get(Q.blongs, kv.first), m);
+    for (auto& kv : Q.multi) kv.second = primer_value(get(Q.bmulti, kv.first), m);       // mc.count = get(mc.raw)
+}
+// gc_adjust!(quant, mod) + gc_adjust!(multi, mod) (src/bias.jl:258-269, bin/whippet-quant.jl:167-169).  `value!(mod, i)` with i::Int
+// dispatches to the method that reads mod.fore / mod.back -- the normalised HEXAMER tables -- at index `bin` (src/bias.jl:206), not
+// gcfore / gcback; gc_normalize! (src/quant.jl:223-238) therefore changes nothing that is read later and is not restated.
+double gc_weight(const BiasCounter& c, const BiasMod& m, bool& has) {
+    double weight = 0.0;
+    int64_t total = 0;
+    for (int i = 1; i <= 21; i++) {
+        const double v = m.fore[i - 1] > 0.0 ? m.back[i - 1] / m.fore[i - 1] : 1.0;
+        weight += v * (double)c.gc[i - 1];
+        total += c.gc[i - 1];
+    }
+    has = total > 0;
+    if (has) weight /= (double)total;
+    return weight;
+}
+void bias_gc_adjust(Quant& Q) {
+    const BiasMod& m = Q.mod;
+    bool has;
+    for (size_t i = 0; i < Q.node.size(); i++) { double w = gc_weight(Q.bnode[i], m, has); if (has) Q.node[i] *= w; }
+    for (auto& kv : Q.edge) { auto it = Q.bedge.find(kv.first); if (it != Q.bedge.end()) { double w = gc_weight(it->second, m, has); if (has) kv.second *= w; } }
+    for (auto& kv : Q.longs) { auto it = Q.blongs.find(kv.first); if (it != Q.blongs.end()) { double w = gc_weight(it->second, m, has); if (has) kv.second *= w; } }
+    for (auto& kv : Q.multi) { auto it = Q.bmulti.find(kv.first); if (it != Q.bmulti.end()) { double w = gc_weight(it->second, m, has); if (has) kv.second *= w; } }
 }
 
 
@@ -1593,9 +1727,30 @@ wqo_handle* wqo_create(const wq_index_desc* d) {
     return h;
 }
 void wqo_quant_reset(wqo_handle* h) {
+    const bool bias = h->Q.bias;
     h->Q = Quant();
     h->Q.node.assign(h->L.d->n_nodes, 0.0);
+    h->Q.bias = bias;
+    if (bias) h->Q.bnode.assign(h->L.d->n_nodes, BiasCounter());
 }
+// CounterType / BiasModelType of bin/whippet-quant.jl:116-122; takes effect at the next wqo_quant_reset
+void wqo_set_bias(wqo_handle* h, int on) { h->Q.bias = on != 0; }
+void wqo_bias_primer_adjust(wqo_handle* h) { if (h->Q.bias) bias_primer_adjust(h->Q); }
+void wqo_bias_gc_adjust(wqo_handle* h) {
+    if (!h->Q.bias) return;
+    bias_gc_adjust(h->Q);
+    for (auto& kv : h->S.multi) {                           // mc.count = get(mc.raw), src/quant.jl:486-495: the classes of the EM see the new count
+        auto it = h->Q.multi.find(kv.first);
+        if (it != h->Q.multi.end()) kv.second.count = it->second;
+    }
+}
+void wqo_bias_model(wqo_handle* h, double* fore4096, double* back4096, uint64_t* short_reads) {
+    memcpy(fore4096, h->Q.mod.fore.data(), 4096 * 8); memcpy(back4096, h->Q.mod.back.data(), 4096 * 8);
+    *short_reads = h->Q.bias_short;
+}
+// known-answer helpers (test/runtests.jl:62-103): the GC bin of a window with k G/C bases out of n, a counter holding `hept` twice
+int64_t wqo_bias_gc_bin(int64_t k, int64_t n, double width) { return (int64_t)(jl_div((double)k / (double)n, width) + 1); }
+int64_t wqo_bias_expected_gc_bins(double width) { return (int64_t)(jl_div(1.0, width) + 1); }
 
 // process_reads!, src/reads.jl:41-80 (DefaultBiasMod: biasval = 1.0)
 int wqo_process_reads_se(wqo_handle* h, const wq_align_param* p, const wq_read_batch* b) {
@@ -1610,8 +1765,13 @@ int wqo_process_reads_se(wqo_handle* h, const wq_align_param* p, const wq_read_b
             g_ctr.out_alns += res.size();
             for (auto& a : res) g_ctr.out_nodes += a.path.size();
             g_ctr.count_updates += 1;
-            if (res.size() > 1) { push_multi_se(Q, res, 1.0); Q.nmulti += 1; }
-            else count_se(h->L, Q, res[0], 1.0);
+            const BiasTemp* bt = nullptr;
+            if (Q.bias) {                                    // biasval = count!(mod, reads[i].sequence): the read as ungapped_align left it
+                if (!bias_count(Q.mod, r.seq)) { Q.bias_short += 1; return -2; }
+                bt = &Q.mod.temp;
+            }
+            if (res.size() > 1) { push_multi_se(Q, res, 1.0, bt); Q.nmulti += 1; }
+            else count_se(h->L, Q, res[0], 1.0, bt);
             Q.mapped += 1;
             Q.sum_readlen += r.seq.size();
             Q.mean_readlen += ((double)r.seq.size() - Q.mean_readlen) / (double)Q.mapped;
@@ -1629,8 +1789,13 @@ int wqo_process_reads_pe(wqo_handle* h, const wq_align_param* p, const wq_read_b
         bool ok = ungapped_align_pe(h->L, *p, a, b, fr, rr, fl);
         Q.total += 1;
         if (ok) {
-            if (fr.size() > 1) { push_multi_pe(Q, fr, rr, 1.0); Q.nmulti += 1; }
-            else count_pe(h->L, Q, fr[0], rr[0], 1.0);
+            const BiasTemp* bt = nullptr;
+            if (Q.bias) {                                    // biasval = count!(mod, fwd.sequence, rev.sequence)
+                if (!bias_count(Q.mod, a.seq, &b.seq)) { Q.bias_short += 1; return -2; }
+                bt = &Q.mod.temp;
+            }
+            if (fr.size() > 1) { push_multi_pe(Q, fr, rr, 1.0, bt); Q.nmulti += 1; }
+            else count_pe(h->L, Q, fr[0], rr[0], 1.0, bt);
             g_ctr.out_alns += 2 * fr.size();
             for (auto& a2 : fr) g_ctr.out_nodes += a2.path.size();
             for (auto& a2 : rr) g_ctr.out_nodes += a2.path.size();

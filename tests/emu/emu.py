@@ -16,7 +16,7 @@ _CSRC = os.path.join(_HERE, "..", "..", "whippet.jl_b200", "csrc")
 
 def build():
     srcs = [os.path.join(_HERE, "wq_emu.cpp")] + [os.path.join(_CSRC, f) for f in
-                                                   ("wq_kernels.cuh", "wq_align.cuh", "wq_types.h", "wq_host_index.h")]
+                                                   ("wq_kernels.cuh", "wq_align.cuh", "wq_types.h", "wq_host_index.h", "wq_bias.cuh")]
     if not os.path.exists(_SO) or os.path.getmtime(_SO) < max(map(os.path.getmtime, srcs)):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-Wno-unused-function", "-Wno-unknown-pragmas",
                                "-ffp-contract=off", "-o", _SO, srcs[0]])
@@ -91,6 +91,42 @@ class Emu:
         p, b = param.c(), reads.c()
         rc = self.L.emu_align_se(self.h, C.byref(p), C.byref(b))
         assert rc == 0, rc
+
+    # ---- --biascorrect: per-counter values in the oracle's form ----
+    def set_bias(self, on=True):
+        self.L.emu_set_bias(self.h, int(bool(on)))
+
+    def bias_values(self):
+        """After all reads: ({node: (p, g)} as arrays, {edge key: (p, g)}, {long key: (p, g)}, {multi key: (p, g)}, fore, back, short) with
+        p = the count after primer_adjust!, g = the gc_adjust! factor (< 0: none)."""
+        self.L.emu_bias_finish.restype = C.c_uint64
+        short = int(self.L.emu_bias_finish(self.h))
+        v = lambda a: a.ctypes.data_as(C.c_void_p)
+        N = self.index.n_nodes
+        np_, ng = np.zeros(N), np.zeros(N)
+        self.L.emu_bias_nodes(self.h, v(np_), v(ng))
+        self.L.emu_edges.restype = C.c_uint64
+        ne = self.L.emu_edges(self.h, None, None)
+        k, c, ep, eg = np.zeros(ne, "<u8"), np.zeros(ne, "<u8"), np.zeros(ne), np.zeros(ne)
+        self.L.emu_edges(self.h, v(k), v(c))
+        self.L.emu_bias_edges(self.h, v(ep), v(eg))
+        edges = {int(k[i]): (ep[i], eg[i]) for i in range(ne)}
+        self.L.emu_keyed.restype = C.c_uint64
+        n = self.L.emu_keyed(self.h, None)
+        w = np.zeros(max(1, n), "<u4")
+        self.L.emu_keyed(self.h, v(w))
+        keys, i = [], 0
+        while i < n:
+            nw = int(w[i])
+            keys.append(tuple(int(x) for x in w[i + 1:i + 1 + nw]))
+            i += nw + 3
+        kp, kg = np.zeros(max(1, len(keys))), np.zeros(max(1, len(keys)))
+        self.L.emu_bias_keyed(self.h, v(kp), v(kg))
+        longs = {key: (kp[j], kg[j]) for j, key in enumerate(keys) if not (key[0] >> 28) & 1}
+        multi = {key: (kp[j], kg[j]) for j, key in enumerate(keys) if (key[0] >> 28) & 1}
+        fore, back = np.zeros(4096), np.zeros(4096)
+        self.L.emu_bias_model(self.h, v(fore), v(back))
+        return (np_, ng), edges, longs, multi, fore, back, short
 
     def edges(self):
         self.L.emu_edges.restype = C.c_uint64

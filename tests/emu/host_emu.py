@@ -61,6 +61,11 @@ class HostEmu:
         self.L.hemu_set_counts(self.h, _p(node), C.c_uint64(len(ekey)), _p(ekey), _p(ecount),
                                C.c_uint64(nl), _p(lp), _p(lw), _p(lc), C.c_uint64(nm), _p(mp), _p(mw), _p(mc))
 
+    def set_bias(self, node_pg, edge_pg, long_pg, multi_pg):
+        """--biascorrect: (primer-adjusted count, gc factor) arrays in the orders given to set_counts (multi-map records in sorted key order)."""
+        arrs = [np.ascontiguousarray(a, "<f8") for pg in (node_pg, edge_pg, long_pg, multi_pg) for a in pg]
+        self.L.hemu_set_bias(self.h, *[_p(a if len(a) else np.zeros(1)) for a in arrs])
+
     def build_classes(self, part=0, nparts=1):
         rc = self.L.hemu_build_classes(self.h, C.c_uint32(part), C.c_uint32(nparts))
         assert rc == 0, self.L.hemu_error(self.h)

@@ -7,6 +7,8 @@
 #include <vector>
 #include "../../whippet.jl_b200/csrc/wq_kernels.cuh"
 #include "../../whippet.jl_b200/csrc/wq_host_index.h"
+#include "../../whippet.jl_b200/csrc/wq_bias.cuh"
+#include <algorithm>
 
 struct Emu {
     WqHostIndex H;
@@ -28,6 +30,18 @@ struct Emu {
     std::vector<uint2> ftab;
     std::vector<WqPNode> path, side;     // first pass: WQ_FAST_PATH nodes, no side buffers; second pass: WQ_MAX_PATH + side buffers
     uint64_t deferred = 0;               // extension tasks that went to the second pass (so tests can see both passes ran)
+    // --biascorrect (csrc/wq_bias.cuh)
+    bool bias = false;
+    std::vector<uint64_t> bias_tab, bias_rec;      // fore[4096] back[4096] cursor[2]; records
+    std::vector<double> node_p, node_g, edge_p, edge_g, keyed_p, keyed_g, fore_n, back_n;
+    WqBiasDev bias_dev(uint32_t n) {
+        const uint64_t used = bias_tab[2 * WQ_BIAS_NHEX];
+        if (bias_rec.size() < used + (uint64_t)n * WQ_BIAS_MAX_REC) bias_rec.resize(used + (uint64_t)n * WQ_BIAS_MAX_REC);
+        WqBiasDev B;
+        B.fore = bias_tab.data(); B.back = B.fore + WQ_BIAS_NHEX; B.cursor = B.back + WQ_BIAS_NHEX; B.rec = bias_rec.data(); B.cap = bias_rec.size();
+        wq_bias_gc_table(B.gcbin);
+        return B;
+    }
 };
 static WqPathStore emu_store(Emu* e, bool first) {
     e->path.assign(WQ_MAX_PATH, WqPNode());
@@ -95,6 +109,7 @@ int emu_align_se(Emu* e, const wq_align_param* ap, const wq_read_batch* rb) {
     e->deferred += e->cursors[6];
     uint64_t stats[5] = {0, 0, 0, 0, 0};
     for (uint32_t r = 0; r < n; r++) wq_resolve_thread(e->ix, p, b, wk, e->q, r, stats);
+    if (e->bias) { const WqBiasDev B = e->bias_dev(n); for (uint32_t r = 0; r < n; r++) wq_bias_thread(e->ix, b, wk, e->q, B, r); }
     e->counters.total += n; e->counters.mapped += stats[0]; e->counters.multi += stats[1];
     e->counters.sum_readlen += stats[2]; e->counters.path_overflow += stats[3]; e->counters.pool_overflow += stats[4];
     return (int)e->cursors[2];   // pending (always 0 single-threaded)
@@ -127,6 +142,7 @@ int emu_align_pe(Emu* e, const wq_align_param* ap, const wq_read_batch* rf, cons
     e->deferred += e->cursors[6];
     uint64_t stats[5] = {0, 0, 0, 0, 0};
     for (uint32_t r = 0; r < n; r++) wq_resolve_pe_thread(e->ix, p, bf, br, wk, e->q, r, stats);
+    if (e->bias) { const WqBiasDev B = e->bias_dev(n); for (uint32_t r = 0; r < n; r++) wq_bias_pe_thread(e->ix, bf, br, wk, e->q, B, r); }
     e->counters.total += n; e->counters.mapped += stats[0]; e->counters.multi += stats[1];
     e->counters.sum_readlen += stats[2]; e->counters.path_overflow += stats[3]; e->counters.pool_overflow += stats[4];
     return (int)e->cursors[2];
@@ -223,6 +239,46 @@ uint64_t emu_keyed(Emu* e, uint32_t* out) {
     }
     return w;
 }
+// ---- --biascorrect: the per-read tallies (same bodies as wq_k_bias / wq_k_bias_pe), then sort + run lengths + the adjust arithmetic
+// of wq_k_bias_model / wq_k_bias_adjust on the host
+void emu_set_bias(Emu* e, int on) { e->bias = on != 0; e->bias_tab.assign(2 * WQ_BIAS_NHEX + 2, 0); e->bias_rec.clear(); }
+uint64_t emu_bias_finish(Emu* e) {
+    const uint64_t nrec = e->bias_tab[2 * WQ_BIAS_NHEX];
+    std::vector<uint64_t> rec(e->bias_rec.begin(), e->bias_rec.begin() + nrec), ukey;
+    std::vector<uint32_t> ucnt;
+    std::sort(rec.begin(), rec.end());
+    for (uint64_t i = 0; i < nrec; i++) { if (ukey.empty() || ukey.back() != rec[i]) { ukey.push_back(rec[i]); ucnt.push_back(1); } else ucnt.back()++; }
+    const uint64_t* fore = e->bias_tab.data(); const uint64_t* back = fore + WQ_BIAS_NHEX;
+    uint64_t fs = 0, bs = 0;
+    for (int k = 0; k < WQ_BIAS_NHEX; k++) { fs += fore[k]; bs += back[k]; }
+    std::vector<double> ratio(WQ_BIAS_NHEX), gcval(32);
+    e->fore_n.assign(WQ_BIAS_NHEX, 0.0); e->back_n.assign(WQ_BIAS_NHEX, 0.0);
+    for (int k = 0; k < WQ_BIAS_NHEX; k++) wq_bias_model_entry(fore, back, (double)fs, (double)bs, k, ratio.data(), gcval.data(), e->fore_n.data(), e->back_n.data());
+    e->node_p.assign(e->H.N, 0.0); e->node_g.assign(e->H.N, -1.0);
+    e->edge_p.assign(e->ekey.size(), 0.0); e->edge_g.assign(e->ekey.size(), -1.0);
+    e->keyed_p.assign(e->khash.size(), 0.0); e->keyed_g.assign(e->khash.size(), -1.0);
+    const uint32_t n = (uint32_t)ukey.size();
+    for (uint32_t i = 0; i < n; i++) {
+        const uint64_t id = ukey[i] >> 13;
+        if (i > 0 && (ukey[i - 1] >> 13) == id) continue;
+        double c, g;
+        wq_bias_adjust_run(ukey.data(), ucnt.data(), n, i, ratio.data(), gcval.data(), c, g);
+        const uint32_t kind = (uint32_t)(id >> 32), slot = (uint32_t)id;
+        (kind == 0 ? e->node_p : kind == 1 ? e->edge_p : e->keyed_p)[slot] = c;
+        (kind == 0 ? e->node_g : kind == 1 ? e->edge_g : e->keyed_g)[slot] = g;
+    }
+    return e->bias_tab[2 * WQ_BIAS_NHEX + 1];      // mapped reads that were too short
+}
+void emu_bias_nodes(Emu* e, double* p, double* g) { memcpy(p, e->node_p.data(), e->node_p.size() * 8); memcpy(g, e->node_g.data(), e->node_g.size() * 8); }
+void emu_bias_edges(Emu* e, double* p, double* g) {       // same order as emu_edges
+    uint64_t n = 0;
+    for (size_t i = 0; i < e->ekey.size(); i++) if (e->ekey[i] != WQ_EMPTY_KEY) { p[n] = e->edge_p[i]; g[n] = e->edge_g[i]; n++; }
+}
+void emu_bias_keyed(Emu* e, double* p, double* g) {       // same order as emu_keyed
+    uint64_t n = 0;
+    for (size_t i = 0; i < e->khash.size(); i++) if (e->khash[i]) { p[n] = e->keyed_p[i]; g[n] = e->keyed_g[i]; n++; }
+}
+void emu_bias_model(Emu* e, double* fore, double* back) { memcpy(fore, e->fore_n.data(), WQ_BIAS_NHEX * 8); memcpy(back, e->back_n.data(), WQ_BIAS_NHEX * 8); }
 const WqCounters* emu_counters(Emu* e) { return &e->counters; }
 uint64_t emu_deferred(Emu* e) { return e->deferred; }
 const uint64_t* emu_ext_stats() { return g_wq_emu_stats; }

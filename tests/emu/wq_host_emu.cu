@@ -54,6 +54,17 @@ void hemu_set_counts(HostEmu* e, const uint64_t* node, uint64_t ne, const uint64
     e->hq.multis.canonicalize();
 }
 
+// --biascorrect: the Float64 side of the stores just set (same orders; the multi-map records must have been given in canonical order)
+void hemu_set_bias(HostEmu* e, const double* node_p, const double* node_g, const double* edge_p, const double* edge_g,
+                   const double* long_p, const double* long_g, const double* multi_p, const double* multi_g) {
+    WqHostQuant& Q = e->hq;
+    Q.bias = true;
+    Q.node_p.assign(node_p, node_p + Q.node.size()); Q.node_g.assign(node_g, node_g + Q.node.size());
+    Q.edge_p.assign(edge_p, edge_p + Q.edge_key.size()); Q.edge_g.assign(edge_g, edge_g + Q.edge_key.size());
+    Q.longs.bias_p.assign(long_p, long_p + Q.longs.size()); Q.longs.bias_g.assign(long_g, long_g + Q.longs.size());
+    Q.multis.bias_p.assign(multi_p, multi_p + Q.multis.size()); Q.multis.bias_g.assign(multi_g, multi_g + Q.multis.size());
+}
+
 int hemu_build_classes(HostEmu* e, uint32_t part, uint32_t nparts) {
     e->err = wq_host_build_classes(e->H, e->S, e->hq, e->X, part, nparts);
     if (!e->err.empty()) return -1;

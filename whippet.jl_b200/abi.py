@@ -73,6 +73,12 @@ class CountsC(C.Structure):
                 ("n_circ", C.c_uint64), ("circ_key", u64p), ("circ_count", u64p)]
 
 
+class BiasCountsC(C.Structure):
+    _fields_ = [(k, C.c_uint64) for k in ("n_nodes", "n_edge", "n_circ", "n_long", "n_multi")] + \
+               [(k, C.POINTER(C.c_double)) for k in ("node_primer", "node_gc", "edge_primer", "edge_gc", "circ_primer", "circ_gc",
+                                                     "long_primer", "long_gc", "multi_primer", "multi_gc", "fore", "back")]
+
+
 class KeyedC(C.Structure):
     _fields_ = [("n_rec", C.c_uint64), ("n_words", C.c_uint64),
                 ("rec_ptr", u64p), ("words", u32p), ("count", u64p)]

@@ -24,6 +24,7 @@
 #include "wq_fastq.h"
 #include "wq_sam.h"
 #include "wq_index_file.h"
+#include "wq_bias.cuh"
 #include <future>
 #include <atomic>
 #include <dlfcn.h>
@@ -131,6 +132,13 @@ struct wq_handle {
     DevBuf<uint64_t> d_xgather; uint64_t xcap = 1ull << 20;    // words per rank of the sparse all-gather (same on every rank: derived from shared headers)
     uint64_t* h_xhdr = nullptr;                                // pinned: the ranks' pack headers
     DevBuf<uint8_t> d_cshare, d_cgather; uint64_t ccap = 1ull << 20; uint8_t* h_cgather = nullptr; size_t h_cgather_cap = 0;
+    // --biascorrect (csrc/wq_bias.cuh): model tallies, record buffer (grows, contents kept), per-slot results
+    bool bias_on = false;
+    DevBuf<uint64_t> d_bias_tab;                                // fore[4096], back[4096], cursor[2]
+    uint64_t* d_bias_rec = nullptr; uint64_t bias_rec_cap = 0, bias_rec_used = 0;
+    DevBuf<double> d_bias_model;                                // ratio[4096], gcval[32], fore_n[4096], back_n[4096]
+    DevBuf<double> d_bias_slot;                                 // node_p[N] node_g[N] edge_p[S] edge_g[S] keyed_p[K] keyed_g[K]
+    uint8_t bias_gcbin[WQ_BIAS_GC_SIZE + 1];
     bool hq_valid = false;
     uint32_t chunk_reads = 1u << 22;
     float last_kernel_ms[3] = {0, 0, 0};
@@ -282,7 +290,9 @@ __global__ void __launch_bounds__(128) wq_k_retry(const __grid_constant__ WqDevI
 }
 
 // compaction of the open-addressing count tables before download: occupied slots -> dense arrays
-__global__ void wq_k_compact_edges(const uint64_t* key, const uint64_t* count, uint64_t slots, uint64_t* okey, uint64_t* ocount, uint32_t* cursor) {
+// (oslot, when given, receives the table slot of every compacted record: the identity the bias tallies are filed under)
+__global__ void wq_k_compact_edges(const uint64_t* key, const uint64_t* count, uint64_t slots, uint64_t* okey, uint64_t* ocount, uint32_t* cursor,
+                                   uint32_t* oslot = nullptr) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (uint64_t)gridDim.x * blockDim.x;
     for (; i < slots; i += stride) {
         uint64_t k = key[i];
@@ -290,16 +300,18 @@ __global__ void wq_k_compact_edges(const uint64_t* key, const uint64_t* count, u
         uint32_t o = atomicAdd(cursor, 1u);
         okey[o] = k;
         ocount[o] = count[i];
+        if (oslot) oslot[o] = (uint32_t)i;
     }
 }
 __global__ void wq_k_compact_keyed(const uint64_t* hash, const uint32_t* keyoff, const uint64_t* count, uint64_t slots,
-                                   uint32_t* ooff, uint64_t* ocount, uint32_t* cursor) {
+                                   uint32_t* ooff, uint64_t* ocount, uint32_t* cursor, uint32_t* oslot = nullptr) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (uint64_t)gridDim.x * blockDim.x;
     for (; i < slots; i += stride) {
         if (hash[i] == 0) continue;
         uint32_t o = atomicAdd(cursor, 1u);
         ooff[o] = keyoff[i];
         ocount[o] = count[i];
+        if (oslot) oslot[o] = (uint32_t)i;
     }
 }
 
@@ -441,6 +453,8 @@ void wq_destroy(wq_handle* h) {
     h->d_cursors.release(); h->d_hits.release(); h->d_pool.release(); h->d_defer.release(); h->d_slab.release(); h->d_mapped_bits.release();
     h->em_scratch.release(); h->ev_batch[0].release(); h->ev_batch[1].release(); h->d_ck.release(); h->d_cv.release(); h->d_ck2.release(); h->d_cv2.release(); h->d_ckoff.release(); h->d_cubtmp.release(); h->d_xpack.release(); h->d_xpending.release();
     wq_comm_destroy(h);
+    h->d_bias_tab.release(); h->d_bias_model.release(); h->d_bias_slot.release();
+    if (h->d_bias_rec) cudaFree(h->d_bias_rec);
     h->d_xgather.release(); h->d_cshare.release(); h->d_cgather.release();
     if (h->h_xhdr) cudaFreeHost(h->h_xhdr);
     if (h->h_cgather) cudaFreeHost(h->h_cgather);
@@ -612,12 +626,26 @@ int wq_quant_reset(wq_handle* h) {
     CK(cudaMemsetAsync(h->d_kcount.p, 0, h->keyed_slots * 8, s));
     CK(cudaMemsetAsync(h->d_koff.p, 0xFF, h->keyed_slots * 4, s));
     CK(cudaMemsetAsync(h->d_kcursor.p, 0, 8, s));
+    if (h->bias_on) { CK(cudaMemsetAsync(h->d_bias_tab.p, 0, (2 * WQ_BIAS_NHEX + 2) * 8, s)); h->bias_rec_used = 0; }
     CK(cudaStreamSynchronize(s));
     h->hq = WqHostQuant();
     reset_quant_ex(h);
     h->hq_valid = false;
     h->rl_mean = 0.0; h->rl_mapped = 0;
     return 0;
+}
+
+// CounterType = JointBiasCounter, BiasModelType = JointBiasMod (bin/whippet-quant.jl:116-122): chosen before the first read
+int wq_set_biascorrect(wq_handle* h, int on) {
+    if (!h) return fail(-1, "null handle");
+    CK(cudaSetDevice(h->device));
+    if (on && h->nccl_comm) return fail(-16, "bias correction is single-GPU in this version: the per-counter tallies are keyed by table slot, which differs between ranks");
+    h->bias_on = on != 0;
+    if (h->bias_on) {
+        CK(h->d_bias_tab.ensure(2 * WQ_BIAS_NHEX + 2));
+        wq_bias_gc_table(h->bias_gcbin);
+    }
+    return wq_quant_reset(h);
 }
 
 // the large arrays of the index as they are uploaded: views into WqHostIndex + the caller's wq_index_desc (wq_index_create), or into
@@ -913,6 +941,33 @@ static int run_chunk(wq_handle* h, const WqParams& p, const WqBatchDev& b, const
         CK(cudaMemcpyAsync(h->h_cursors + 8, h->d_cursors.p, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
         pending = h->h_cursors[10];
+    }
+    if (h->bias_on) {
+        // biasval = count!(mod, read.sequence) + push! into the read's counter (src/reads.jl:59-66, 108-118), after every insertion of the
+        // chunk is in: the kernel looks each mapped read's counter up and appends its (counter, hexamer) / (counter, GC bin) records
+        const uint64_t need = h->bias_rec_used + (uint64_t)n * WQ_BIAS_MAX_REC;
+        if (need > h->bias_rec_cap) {                          // grow, keeping the records of earlier chunks
+            const uint64_t want = need + need / 2;
+            uint64_t* nb = nullptr;
+            CK(cudaMalloc(&nb, want * 8));
+            if (h->bias_rec_used) CK(cudaMemcpyAsync(nb, h->d_bias_rec, h->bias_rec_used * 8, cudaMemcpyDeviceToDevice, s));
+            CK(cudaStreamSynchronize(s));
+            if (h->d_bias_rec) cudaFree(h->d_bias_rec);
+            h->d_bias_rec = nb; h->bias_rec_cap = want;
+        }
+        WqBiasDev B;
+        B.fore = h->d_bias_tab.p; B.back = B.fore + WQ_BIAS_NHEX; B.cursor = B.back + WQ_BIAS_NHEX; B.rec = h->d_bias_rec; B.cap = h->bias_rec_cap;
+        memcpy(B.gcbin, h->bias_gcbin, sizeof B.gcbin);
+        const unsigned gread = (n + T - 1) / T;
+        if (!pe) wq_k_bias<<<gread, T, 0, s>>>(h->dix, b, wk, h->q, B);
+        else wq_k_bias_pe<<<gread, T, 0, s>>>(h->dix, b, *br, wk, h->q, B);
+        h->launches += 1;
+        CK(cudaGetLastError());
+        uint64_t cur[2];
+        CK(cudaMemcpyAsync(cur, B.cursor, 16, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        h->bias_rec_used = cur[0];
+        if (cur[1]) return fail(-17, "bias correction: a mapped read is shorter than 37 bases (the reference throws BoundsError in primer_count!, src/bias.jl:163-165)");
     }
     return 0;
 }
@@ -1364,15 +1419,57 @@ static int sync_host_quant(wq_handle* h) {
     // cursors[8] = #edges, cursors[9] = #keyed entries
     CK(cudaMemsetAsync(h->d_cursors.p + 12, 0, 2 * sizeof(uint32_t), s));
     CK(h->d_ck.ensure(h->edge_slots)); CK(h->d_cv.ensure(h->edge_slots));
-    wq_k_compact_edges<<<1184, 256, 0, s>>>(h->d_ekey.p, h->d_ecount.p, h->edge_slots, h->d_ck.p, h->d_cv.p, h->d_cursors.p + 12);
+    DevBuf<uint32_t> eslot, kslot, eslot_sorted;                 // --biascorrect: table slots of the compacted records
+    if (h->bias_on) { CK(eslot.ensure(h->edge_slots)); CK(kslot.ensure(h->keyed_slots)); }
+    wq_k_compact_edges<<<1184, 256, 0, s>>>(h->d_ekey.p, h->d_ecount.p, h->edge_slots, h->d_ck.p, h->d_cv.p, h->d_cursors.p + 12, eslot.p);
     CK(h->d_ckoff.ensure(h->keyed_slots)); CK(h->d_cv2.ensure(h->keyed_slots));
-    wq_k_compact_keyed<<<1184, 256, 0, s>>>(h->d_khash.p, h->d_koff.p, h->d_kcount.p, h->keyed_slots, h->d_ckoff.p, h->d_cv2.p, h->d_cursors.p + 13);
+    wq_k_compact_keyed<<<1184, 256, 0, s>>>(h->d_khash.p, h->d_koff.p, h->d_kcount.p, h->keyed_slots, h->d_ckoff.p, h->d_cv2.p, h->d_cursors.p + 13, kslot.p);
     h->launches += 2;
     uint64_t kcur = 0;
     CK(cudaMemcpyAsync(h->h_cursors + 12, h->d_cursors.p + 12, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(&kcur, h->d_kcursor.p, 8, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     const uint32_t ne = h->h_cursors[12], nk = h->h_cursors[13];
+    // --biascorrect: primer_normalize! / primer_adjust! / the factors of gc_adjust! for every counter, on the device (csrc/wq_bias.cuh)
+    const uint64_t ES = h->edge_slots, KS = h->keyed_slots;
+    double *d_node_p = nullptr, *d_node_g = nullptr, *d_edge_p = nullptr, *d_edge_g = nullptr, *d_keyed_p = nullptr, *d_keyed_g = nullptr;
+    if (h->bias_on) {
+        CK(h->d_bias_slot.ensure(2ull * N + 2 * ES + 2 * KS));
+        d_node_p = h->d_bias_slot.p; d_node_g = d_node_p + N; d_edge_p = d_node_g + N; d_edge_g = d_edge_p + ES; d_keyed_p = d_edge_g + ES; d_keyed_g = d_keyed_p + KS;
+        CK(cudaMemsetAsync(d_node_p, 0, N * 8ull, s)); CK(cudaMemsetAsync(d_edge_p, 0, ES * 8ull, s)); CK(cudaMemsetAsync(d_keyed_p, 0, KS * 8ull, s));
+        wq_k_fill_f64<<<592, 256, 0, s>>>(d_node_g, -1.0, N);
+        wq_k_fill_f64<<<592, 256, 0, s>>>(d_edge_g, -1.0, ES);
+        wq_k_fill_f64<<<592, 256, 0, s>>>(d_keyed_g, -1.0, KS);
+        CK(h->d_bias_model.ensure(3 * WQ_BIAS_NHEX + 32));
+        double* ratio = h->d_bias_model.p; double* gcval = ratio + WQ_BIAS_NHEX; double* fore_n = gcval + 32; double* back_n = fore_n + WQ_BIAS_NHEX;
+        wq_k_bias_model<<<1, 1024, 0, s>>>(h->d_bias_tab.p, h->d_bias_tab.p + WQ_BIAS_NHEX, ratio, gcval, fore_n, back_n);
+        h->launches += 4;
+        const uint64_t nrec = h->bias_rec_used;
+        if (nrec >= (1ull << 31)) return fail(-18, "bias correction: more than 2^31 tally records in one job (about 250 M mapped reads); split the input");
+        if (nrec) {
+            DevBuf<uint64_t> sorted, ukey; DevBuf<uint32_t> ucnt, nuniq;
+            CK(sorted.ensure(nrec)); CK(ukey.ensure(nrec)); CK(ucnt.ensure(nrec)); CK(nuniq.ensure(1));
+            size_t t1 = 0, t2 = 0;
+            CK(cub::DeviceRadixSort::SortKeys(nullptr, t1, h->d_bias_rec, sorted.p, (int)nrec, 0, 47, s));
+            CK(cub::DeviceRunLengthEncode::Encode(nullptr, t2, sorted.p, ukey.p, ucnt.p, nuniq.p, (int)nrec, s));
+            CK(h->d_cubtmp.ensure(std::max(t1, t2)));
+            size_t tb = h->d_cubtmp.cap;
+            CK(cub::DeviceRadixSort::SortKeys(h->d_cubtmp.p, tb, h->d_bias_rec, sorted.p, (int)nrec, 0, 47, s));
+            tb = h->d_cubtmp.cap;
+            CK(cub::DeviceRunLengthEncode::Encode(h->d_cubtmp.p, tb, sorted.p, ukey.p, ucnt.p, nuniq.p, (int)nrec, s));
+            wq_k_bias_adjust<<<1184, 256, 0, s>>>(ukey.p, ucnt.p, nuniq.p, ratio, gcval, d_node_p, d_node_g, d_edge_p, d_edge_g, d_keyed_p, d_keyed_g);
+            h->launches += 3;
+            cudaError_t e1 = cudaGetLastError();
+            cudaError_t e2 = cudaStreamSynchronize(s);
+            sorted.release(); ukey.release(); ucnt.release(); nuniq.release();
+            CK(e1); CK(e2);
+        }
+        Q.bias = true;
+        Q.node_p.resize(N); Q.node_g.resize(N);
+        CK(cudaMemcpyAsync(Q.node_p.data(), d_node_p, N * 8ull, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(Q.node_g.data(), d_node_g, N * 8ull, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+    }
     Q.node.assign(dense.begin(), dense.begin() + N);
     memcpy(&Q.stats, dense.data() + N, sizeof(WqCounters));
     if (Q.stats.keyed_full || kcur > h->kpool_cap) return fail(-8, "keyed count store overflowed (raise WQ_KEYED_SLOTS / WQ_KEYED_POOL_WORDS)");
@@ -1392,24 +1489,53 @@ static int sync_host_quant(wq_handle* h) {
         h->launches += 1;
         CK(cudaMemcpyAsync(Q.edge_key.data(), h->d_ck2.p, ne * 8ull, cudaMemcpyDeviceToHost, s));
         CK(cudaMemcpyAsync(Q.edge_count.data(), vals_out, ne * 8ull, cudaMemcpyDeviceToHost, s));
+        if (h->bias_on) {                                   // the same sort carrying the slots, then the slots' results in key order
+            DevBuf<uint64_t> keys2; DevBuf<double> pg;
+            CK(eslot_sorted.ensure(ne)); CK(keys2.ensure(ne)); CK(pg.ensure(2ull * ne));
+            size_t tb2 = 0;
+            CK(cub::DeviceRadixSort::SortPairs(nullptr, tb2, h->d_ck.p, keys2.p, eslot.p, eslot_sorted.p, (int)ne, 0, 64, s));
+            CK(h->d_cubtmp.ensure(tb2));
+            CK(cub::DeviceRadixSort::SortPairs(h->d_cubtmp.p, tb2, h->d_ck.p, keys2.p, eslot.p, eslot_sorted.p, (int)ne, 0, 64, s));
+            wq_k_bias_gather<<<592, 256, 0, s>>>(eslot_sorted.p, ne, d_edge_p, d_edge_g, pg.p, pg.p + ne);
+            h->launches += 2;
+            Q.edge_p.resize(ne); Q.edge_g.resize(ne);
+            CK(cudaMemcpyAsync(Q.edge_p.data(), pg.p, ne * 8ull, cudaMemcpyDeviceToHost, s));
+            CK(cudaMemcpyAsync(Q.edge_g.data(), pg.p + ne, ne * 8ull, cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+            keys2.release(); pg.release();
+        }
         CK(cudaStreamSynchronize(s));
         tmpvals.release();
     }
     // keyed entries + the used part of the key pool
     std::vector<uint32_t> koff(nk), kpool(kcur);
     std::vector<uint64_t> kcount(nk);
+    std::vector<double> kpg;
     if (nk) {
         CK(cudaMemcpyAsync(koff.data(), h->d_ckoff.p, nk * 4ull, cudaMemcpyDeviceToHost, s));
         CK(cudaMemcpyAsync(kcount.data(), h->d_cv2.p, nk * 8ull, cudaMemcpyDeviceToHost, s));
         CK(cudaMemcpyAsync(kpool.data(), h->d_kpool.p, kcur * 4ull, cudaMemcpyDeviceToHost, s));
+        if (h->bias_on) {
+            DevBuf<double> pg;
+            CK(pg.ensure(2ull * nk));
+            wq_k_bias_gather<<<592, 256, 0, s>>>(kslot.p, nk, d_keyed_p, d_keyed_g, pg.p, pg.p + nk);
+            h->launches += 1;
+            kpg.resize(2ull * nk);
+            CK(cudaMemcpyAsync(kpg.data(), pg.p, 2ull * nk * 8, cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+            pg.release();
+        }
         CK(cudaStreamSynchronize(s));
     }
+    eslot.release(); kslot.release(); eslot_sorted.release();
     Q.longs.words.reserve(kcur);
     for (uint32_t i = 0; i < nk; i++) {
         if (koff[i] >= WQ_KEYOFF_FULL) return fail(-8, "keyed count store overflowed");
         const uint32_t nw = kpool[koff[i]];
         const uint32_t* w = &kpool[koff[i] + 1];
-        (wq_key_is_multi(w) ? Q.multis : Q.longs).push(w, nw, kcount[i]);
+        WqKeyedStore& K = wq_key_is_multi(w) ? Q.multis : Q.longs;
+        K.push(w, nw, kcount[i]);
+        if (h->bias_on) { K.bias_p.push_back(kpg[i]); K.bias_g.push_back(kpg[nk + i]); }
     }
     Q.multis.canonicalize();
     h->hq_valid = true;
@@ -1448,6 +1574,39 @@ int wq_keyed_download(wq_handle* h, int kind, wq_keyed* k) {
     memcpy(k->rec_ptr, K.off.data(), K.off.size() * 8);
     if (!K.words.empty()) memcpy(k->words, K.words.data(), K.words.size() * 4);
     if (K.size()) memcpy(k->count, K.count.data(), K.size() * 8);
+    return 0;
+}
+
+// --biascorrect: the Float64 side of every counter, aligned with wq_counts_download / wq_keyed_download
+int wq_bias_download(wq_handle* h, wq_bias_counts* o) {
+    if (!h || !o) return fail(-1, "null argument");
+    if (!h->bias_on) return fail(-16, "bias correction is off (wq_set_biascorrect)");
+    if (int rc = sync_host_quant(h)) return rc;
+    WqHostQuant& Q = h->hq;
+    Q.longs.canonicalize();
+    uint64_t ne = 0, nc = 0;
+    for (uint64_t k : Q.edge_key) { if (wq_edge_is_circ(k)) nc++; else ne++; }
+    const bool sizing = !o->node_primer && !o->edge_primer && !o->circ_primer && !o->long_primer && !o->multi_primer;
+    if (!sizing && (o->n_nodes < Q.node_p.size() || o->n_edge < ne || o->n_circ < nc || o->n_long < Q.longs.size() || o->n_multi < Q.multis.size()))
+        return fail(-7, "wq_bias_counts buffers too small");
+    o->n_nodes = Q.node_p.size(); o->n_edge = ne; o->n_circ = nc; o->n_long = Q.longs.size(); o->n_multi = Q.multis.size();
+    if (sizing) return 0;
+    auto put = [](double* dst, const std::vector<double>& v) { if (dst && !v.empty()) memcpy(dst, v.data(), v.size() * 8); };
+    put(o->node_primer, Q.node_p); put(o->node_gc, Q.node_g);
+    uint64_t ie = 0, ic = 0;
+    for (size_t i = 0; i < Q.edge_key.size(); i++) {
+        if (wq_edge_is_circ(Q.edge_key[i])) { if (o->circ_primer) o->circ_primer[ic] = Q.edge_p[i]; if (o->circ_gc) o->circ_gc[ic] = Q.edge_g[i]; ic++; }
+        else { if (o->edge_primer) o->edge_primer[ie] = Q.edge_p[i]; if (o->edge_gc) o->edge_gc[ie] = Q.edge_g[i]; ie++; }
+    }
+    put(o->long_primer, Q.longs.bias_p); put(o->long_gc, Q.longs.bias_g);
+    put(o->multi_primer, Q.multis.bias_p); put(o->multi_gc, Q.multis.bias_g);
+    if (o->fore || o->back) {
+        CK(cudaSetDevice(h->device));
+        const double* fore_n = h->d_bias_model.p + WQ_BIAS_NHEX + 32;
+        if (o->fore) CK(cudaMemcpyAsync(o->fore, fore_n, WQ_BIAS_NHEX * 8, cudaMemcpyDeviceToHost, h->stream));
+        if (o->back) CK(cudaMemcpyAsync(o->back, fore_n + WQ_BIAS_NHEX, WQ_BIAS_NHEX * 8, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
     return 0;
 }
 
@@ -1597,6 +1756,7 @@ int wq_comm_unique_id(void* id128) {
     return 0;
 }
 int wq_comm_init_rank(wq_handle* h, int nranks, int rank, const void* id128) {
+    if (h && h->bias_on && nranks > 1) return fail(-16, "bias correction is single-GPU in this version: the per-counter tallies are keyed by table slot, which differs between ranks");
     if (!h || !id128) return fail(-1, "null argument");
     if (nranks < 1 || rank < 0 || rank >= nranks) return fail(-1, "rank out of range");
     std::string e = wq_nccl_load();

@@ -109,7 +109,15 @@ static inline std::string wq_host_build_classes(const WqHostIndex& H, const WqIs
     const auto tc0 = std::chrono::steady_clock::now();
     auto lap2 = [&](const char* what) { if (prof2) fprintf(stderr, "[wq]     classes: %-24s %9.3f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tc0).count()); };
     X = WqHostQuantEx();
-    X.node_value.assign(hq.node.begin(), hq.node.end());
+    if (!hq.bias) X.node_value.assign(hq.node.begin(), hq.node.end());
+    else {
+        // --biascorrect: this store is first read after gc_adjust! (assign_ambig! / events), so it starts at the gc-adjusted count; the
+        // primer-adjusted counts that build_equivalence_classes! needs are read through hq.nodec().  Long paths must be visited in
+        // canonical (key) order now: their counts are no longer integers, so the order of the additions shows in the result.
+        X.node_value.resize(hq.node.size());
+        for (size_t i = 0; i < hq.node.size(); i++) X.node_value[i] = WqHostQuant::gc_apply(hq.node_p[i], hq.node_g[i]);
+        hq.longs.canonicalize();
+    }
     X.iso_count.assign(I, 0.0);
     WqClassSet& C = X.cls;
     // ---- genes named by multi-map classes (assign_ambig! will change their counts) ----
@@ -205,7 +213,7 @@ static inline std::string wq_host_build_classes(const WqHostIndex& H, const WqIs
             for (uint32_t n = 1; n <= nn; n++) {
                 uint32_t off = (uint32_t)setbuf.size();
                 for (uint32_t p = 0; p < b.np; p++) if (b.has(p, n)) setbuf.push_back((int32_t)p + 1);
-                account(off, (double)hq.node[nb + n - 1]);
+                account(off, hq.nodec(nb + n - 1));
             }
             while (e < ne && (hq.edge_key[e] >> 32) < g) e++;
             for (; e < ne && (hq.edge_key[e] >> 32) == g; e++) {
@@ -213,24 +221,25 @@ static inline std::string wq_host_build_classes(const WqHostIndex& H, const WqIs
                 uint32_t l = (hq.edge_key[e] >> 16) & 0xFFFF, r = hq.edge_key[e] & 0xFFFF;
                 uint32_t off = (uint32_t)setbuf.size();
                 for (uint32_t p = 0; p < b.np; p++) if (b.adjacent(p, l, r)) setbuf.push_back((int32_t)p + 1);
-                account(off, (double)hq.edge_count[e]);
+                account(off, hq.edgec(e));
             }
             for (uint32_t k = lptr[g]; k < lptr[g + 1]; k++) {
                 WqKeyPath kp;
                 wq_key_next(hq.longs.key(lidx[k]), 0, kp);
                 uint32_t off = (uint32_t)setbuf.size();
                 for (uint32_t p = 0; p < b.np; p++) if (wq_key_compatible(b, p, kp)) setbuf.push_back((int32_t)p + 1);
-                account(off, (double)hq.longs.count[lidx[k]]);
-                wq_spread_path(H, X.node_value, F.adds, kp, (double)hq.longs.count[lidx[k]]);
+                account(off, hq.longc(lidx[k]));
+                wq_spread_path(H, X.node_value, F.adds, kp, hq.longc(lidx[k]));
             }
-            // distinct id sets in lexicographic order, values added up (they are integers: order-free)
+            // distinct id sets in lexicographic order, values added up in the order met (nodes, edges, long paths: the order the
+            // reference's temp[arr] += value sees them in, src/quant.jl:333-343; it only shows with --biascorrect, where they are not integers)
             order.resize(recs.size());
             for (uint32_t i = 0; i < recs.size(); i++) order[i] = i;
             auto lt = [&](uint32_t x, uint32_t y) {
                 return std::lexicographical_compare(setbuf.begin() + recs[x].off, setbuf.begin() + recs[x].off + recs[x].len,
                                                     setbuf.begin() + recs[y].off, setbuf.begin() + recs[y].off + recs[y].len);
             };
-            std::sort(order.begin(), order.end(), lt);
+            std::stable_sort(order.begin(), order.end(), lt);
             for (size_t i = 0; i < order.size();) {
                 size_t j = i;
                 double total = 0.0;
@@ -280,7 +289,7 @@ static inline std::string wq_host_build_classes(const WqHostIndex& H, const WqIs
                 for (uint32_t q = prev; q < F.end[j]; q++) { C.iso[q0 + q] = F.iso[q]; C.prop[q0 + q] = 1.0 / (double)n; }
                 prev = F.end[j];
                 C.ptr[c + 1] = (uint32_t)(q0 + F.end[j]);
-                C.count[c] = (double)hq.multis.count[M_lo + c];
+                C.count[c] = hq.multic(M_lo + c);
                 C.state[c] = F.all[j] ? 0 : 2;
                 C.postassign[c] = F.all[j] ? 0 : 1;
             }
@@ -298,6 +307,7 @@ static inline std::string wq_host_build_classes(const WqHostIndex& H, const WqIs
         }
     });
     lap2("fragments concatenated");
+    X.adds_before_gc = X.edge_adds.size();
     X.built = nparts == 1;                   // a share is not a class set: wq_classes_assemble completes it
     X.local_built = true;
     return "";
@@ -432,7 +442,9 @@ static inline std::string wq_host_assign_ambig_impl(const WqHostIndex& H, const 
             }
             double tot = 0.0;
             for (uint32_t h = 0; h < nh; h++) tot += w[h];
-            for (uint32_t h = 0; h < nh; h++) share[(size_t)c * WQ_MAX_TOLERATE + h] = (w[h] / tot) * C.count[c];
+            // mc.count: with --biascorrect gc_adjust!(multi, mod) has scaled it since the EM (src/quant.jl:486-495, bin/whippet-quant.jl:169)
+            const double mcount = hq.bias ? WqHostQuant::gc_apply(C.count[c], hq.multis.bias_g[c]) : C.count[c];
+            for (uint32_t h = 0; h < nh; h++) share[(size_t)c * WQ_MAX_TOLERATE + h] = (w[h] / tot) * mcount;
             if (!C.postassign[c] && vp[0].rnd) {
                 // ambig.iset still holds {p + geneidx[g]} of the LAST alignment when the first one is spread (see wq_spread_path)
                 const WqKeyPath& last = vp[nh - 1];
@@ -1536,11 +1548,13 @@ static inline std::string wq_run_em_psi(wq_psi_batch& b, WqEmScratch& M, cudaStr
     d.amb_prop = d_prop; d.iterations = d_it;
     // Launch classes: 0 = at most 4 paths with small sets (4 lanes per event); 1..4 = one block per event, grouped by the shared memory the
     // event needs (4 / 16 / 64 / 200 KB, with 32 / 64 / 128 / 128 threads: more threads shorten the share divisions of a large event);
-    // 5 = events whose member lists do not fit in shared memory (set-by-set form, lists in global memory).  The classes run concurrently on
-    // side streams (a handful of large events that need all 1500 sweeps would otherwise add their whole latency to the batch).
+    // 5 = events too large for that layout (14 bytes per set member) that still fit the compact one of wq_k_em_psi_big (4 bytes per member,
+    // one warp, shares divided by the owner lanes); 6 = events whose member lists do not fit in shared memory at all (set-by-set form, lists
+    // in global memory).  The classes run concurrently on side streams (a handful of large events that need all 1500 sweeps would
+    // otherwise add their whole latency to the batch).
     static const size_t kBlockSmem[4] = {4 * 1024, 16 * 1024, 64 * 1024, 200 * 1024};
     static const unsigned kBlockThreads[4] = {32, 64, 128, 128};
-    const int NC = 6;
+    const int NC = 7;
     std::vector<uint32_t> order(E);
     std::vector<uint8_t> cls(E);
     uint32_t nclass[NC] = {0}, cbase[NC + 1] = {0};
@@ -1555,6 +1569,7 @@ static inline std::string wq_run_em_psi(wq_psi_batch& b, WqEmScratch& M, cudaStr
         if (np > 65535 || na > 65535) return -1;
         const size_t need = wq_psi_block_smem(np, na, nm);
         for (int k = 0; k < 4; k++) if (need <= kBlockSmem[k]) return 1 + k;
+        if (wq_psi_warp_smem(np, na, nm, true) <= kBlockSmem[3]) return 5;
         return -1;
     };
     for (uint32_t e = 0; e < E; e++) {
@@ -1562,7 +1577,7 @@ static inline std::string wq_run_em_psi(wq_psi_batch& b, WqEmScratch& M, cudaStr
         if (c < 0) {            // member lists too long for shared memory: the paths must still fit
             const uint32_t np = b.path_ptr[e + 1] - b.path_ptr[e], na = b.amb_ptr[e + 1] - b.amb_ptr[e];
             if (np > 65535 || wq_psi_warp_smem(np, na, 0, false) > kBlockSmem[3]) return "PSI event too large for the device kernel (more than ~4000 paths)";
-            c = 5;
+            c = 6;
         }
         cls[e] = (uint8_t)c;
         nclass[c]++;
@@ -1589,7 +1604,8 @@ static inline std::string wq_run_em_psi(wq_psi_batch& b, WqEmScratch& M, cudaStr
         const uint32_t n = nclass[c];
         const uint32_t* lst = d_list + cbase[c];
         if (c == 0) wq_k_em_psi4<<<(n + 31) / 32, 128, 0, ss>>>(d, lst, n);
-        else if (c == 5) wq_k_em_psi_big<<<n, 32, kBlockSmem[3], ss>>>(d, lst, n, WqPsiWarpCfg{(uint32_t)kBlockSmem[3], 0u});
+        else if (c == 5) wq_k_em_psi_big<<<n, 32, kBlockSmem[3], ss>>>(d, lst, n, WqPsiWarpCfg{(uint32_t)kBlockSmem[3], 1u});
+        else if (c == 6) wq_k_em_psi_big<<<n, 32, kBlockSmem[3], ss>>>(d, lst, n, WqPsiWarpCfg{(uint32_t)kBlockSmem[3], 0u});
         else wq_k_em_psi<<<n, kBlockThreads[c - 1], kBlockSmem[c - 1], ss>>>(d, lst, n);
         if (launches) *launches += 1;
         WQ_EMCK(cudaGetLastError());

@@ -23,6 +23,7 @@ struct WqKeyedStore {                                        // variable-length 
     std::vector<uint32_t> words;                             // key words of all records, back to back
     std::vector<uint64_t> off;                               // [n+1]
     std::vector<uint64_t> count;                             // [n]
+    std::vector<double> bias_p, bias_g;                      // [n] or empty: primer-adjusted count and GC factor (< 0: none) with --biascorrect
     WqKeyedStore() : off(1, 0) {}
     size_t size() const { return count.size(); }
     const uint32_t* key(size_t i) const { return words.data() + off[i]; }
@@ -43,11 +44,12 @@ struct WqKeyedStore {                                        // variable-length 
         std::sort(idx.begin(), idx.end(), [&](uint32_t x, uint32_t y) { return less(key(x), len(x), key(y), len(y)); });
         WqKeyedStore out;
         out.words.reserve(words.size());
+        const bool fp = !bias_p.empty();                     // one device: every key sits in one slot, so equal keys never meet here
         for (size_t k = 0; k < n; k++) {
             uint32_t i = idx[k];
             if (out.size() && out.len(out.size() - 1) == len(i) &&
                 std::equal(key(i), key(i) + len(i), out.key(out.size() - 1))) out.count.back() += count[i];
-            else out.push(key(i), len(i), count[i]);
+            else { out.push(key(i), len(i), count[i]); if (fp) { out.bias_p.push_back(bias_p[i]); out.bias_g.push_back(bias_g[i]); } }
         }
         *this = std::move(out);
     }
@@ -59,7 +61,17 @@ struct WqHostQuant {
     WqKeyedStore longs;                                      // .long (any order; order does not affect results)
     WqKeyedStore multis;                                     // MultiMapping.map in canonical (lexicographic) order
     WqCounters stats;
+    // --biascorrect (JointBiasCounter, src/bias.jl:207-270): the counts the quant stage works with are Float64.  *_p = the count after
+    // primer_adjust! (what build_equivalence_classes! and the EM see), *_g = the factor gc_adjust! multiplies it by afterwards (< 0: the
+    // counter saw no GC window and is left alone); same order as node / edge_key.  The integer arrays still hold the raw read tallies.
+    bool bias = false;
+    std::vector<double> node_p, node_g, edge_p, edge_g;
     WqHostQuant() { memset(&stats, 0, sizeof stats); }
+    double nodec(size_t i) const { return bias ? node_p[i] : (double)node[i]; }
+    double edgec(size_t i) const { return bias ? edge_p[i] : (double)edge_count[i]; }
+    double longc(size_t i) const { return bias ? longs.bias_p[i] : (double)longs.count[i]; }
+    double multic(size_t i) const { return bias ? multis.bias_p[i] : (double)multis.count[i]; }
+    static double gc_apply(double v, double g) { return g < 0.0 ? v : v * g; }       // cnt.count *= weight (src/bias.jl:264-268)
 };
 
 struct WqClassSet {                                         // IsoCompat / MultiCompat in canonical order (multi first)
@@ -77,6 +89,7 @@ struct WqHostQuantEx {
     bool built = false, em_done = false, ambig_done = false;
     std::vector<double> node_value;                          // node store as Float64 (fractional after assign_ambig!)
     std::vector<std::pair<uint64_t, double>> edge_adds;      // additions to the edge/circ stores, in the order made
+    size_t adds_before_gc = 0;                               // --biascorrect: edge_adds[0 .. adds_before_gc) were made before gc_adjust! (the long-path re-count)
     std::vector<uint64_t> edge_key;                          // merged stores (valid after finalize_edges)
     std::vector<double>   edge_value;
     bool edges_final = false;
@@ -105,13 +118,20 @@ static inline void wq_finalize_edges(const WqHostQuant& hq, WqHostQuantEx& X) {
         cut[t] = i < ne ? (hq.edge_key[i] >> 32) << 32 : ~0ull;
         if (cut[t] < cut[t - 1]) cut[t] = cut[t - 1];
     }
-    struct Part { std::vector<std::pair<uint64_t, double>> adds; std::vector<uint64_t> key; std::vector<double> value; };
+    struct Part { std::vector<std::pair<uint64_t, double>> adds; std::vector<size_t> seq; std::vector<uint64_t> key; std::vector<double> value; };
     std::vector<Part> parts(nt);
     auto work = [&](unsigned t) {
         Part& P = parts[t];
         const uint64_t lo = cut[t], hi = cut[t + 1];
-        for (const auto& a : X.edge_adds) if (a.first >= lo && a.first < hi) P.adds.push_back(a);
-        std::stable_sort(P.adds.begin(), P.adds.end(), [](const std::pair<uint64_t, double>& a, const std::pair<uint64_t, double>& b) { return a.first < b.first; });
+        if (!hq.bias) {
+            for (const auto& a : X.edge_adds) if (a.first >= lo && a.first < hi) P.adds.push_back(a);
+            std::stable_sort(P.adds.begin(), P.adds.end(), [](const std::pair<uint64_t, double>& a, const std::pair<uint64_t, double>& b) { return a.first < b.first; });
+        } else {                                             // the same, remembering every addition's position in the order made
+            std::vector<size_t> ord;
+            for (size_t q = 0; q < X.edge_adds.size(); q++) if (X.edge_adds[q].first >= lo && X.edge_adds[q].first < hi) ord.push_back(q);
+            std::stable_sort(ord.begin(), ord.end(), [&](size_t a, size_t b) { return X.edge_adds[a].first < X.edge_adds[b].first; });
+            for (size_t q : ord) { P.adds.push_back(X.edge_adds[q]); P.seq.push_back(q); }
+        }
         size_t i = std::lower_bound(hq.edge_key.begin(), hq.edge_key.end(), lo) - hq.edge_key.begin();
         const size_t ie = hi == ~0ull ? ne : (size_t)(std::lower_bound(hq.edge_key.begin(), hq.edge_key.end(), hi) - hq.edge_key.begin());
         size_t j = 0;
@@ -120,8 +140,15 @@ static inline void wq_finalize_edges(const WqHostQuant& hq, WqHostQuantEx& X) {
         while (i < ie || j < ja) {
             uint64_t k;
             double v = 0.0;
-            if (j >= ja || (i < ie && hq.edge_key[i] <= P.adds[j].first)) { k = hq.edge_key[i]; v = (double)hq.edge_count[i]; i++; }
+            double g = -1.0;                                 // gc_adjust! acts on counters that exist when it runs: the base edges
+            if (j >= ja || (i < ie && hq.edge_key[i] <= P.adds[j].first)) { k = hq.edge_key[i]; v = hq.edgec(i); if (hq.bias) g = hq.edge_g[i]; i++; }
             else k = P.adds[j].first;
+            // with bias correction the additions made before gc_adjust! (long paths re-counted onto their edges by
+            // build_equivalence_classes!) are inside the count it scales; the later ones (assign_ambig!) are not
+            if (hq.bias) {
+                while (j < ja && P.adds[j].first == k && P.seq[j] < X.adds_before_gc) { v += P.adds[j].second; j++; }
+                v = WqHostQuant::gc_apply(v, g);
+            }
             while (j < ja && P.adds[j].first == k) { v += P.adds[j].second; j++; }
             P.key.push_back(k);
             P.value.push_back(v);

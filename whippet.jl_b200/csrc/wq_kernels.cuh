@@ -329,6 +329,34 @@ WQ_HD int wq_edge_insert(const WqEdgeTable& t, uint64_t key, uint64_t amount) {
     return 2;
 }
 
+// read-only lookups of a counter's slot (after every insertion of the chunk has completed): -1 = not present
+WQ_HD int64_t wq_edge_find(const WqEdgeTable& t, uint64_t key) {
+    uint64_t h = key * 0x9E3779B97F4A7C15ull;
+    uint64_t slot = (h >> 20) & t.mask;
+    for (uint64_t probe = 0; probe <= t.mask; probe++, slot = (slot + 1) & t.mask) {
+        const uint64_t cur = WQ_VLOAD_U64(&t.key[slot]);
+        if (cur == key) return (int64_t)slot;
+        if (cur == WQ_EMPTY_KEY) return -1;
+    }
+    return -1;
+}
+WQ_HD int64_t wq_keyed_find(const WqKeyedTable& t, const uint32_t* kw, int nw) {
+    const uint64_t h = wq_hash_words(kw, nw);
+    uint64_t slot = h & t.mask;
+    for (uint64_t probe = 0; probe <= t.mask; probe++, slot = (slot + 1) & t.mask) {
+        const uint64_t cur = WQ_VLOAD_U64(&t.hash[slot]);
+        if (cur == 0) return -1;
+        if (cur == h) {
+            const uint32_t off = WQ_VLOAD_U32(&t.keyoff[slot]);
+            if (off >= WQ_KEYOFF_FULL) continue;
+            bool same = WQ_VLOAD_U32(&t.pool[off]) == (uint32_t)nw;
+            for (int i = 0; same && i < nw; i++) same = WQ_VLOAD_U32(&t.pool[off + 1 + i]) == kw[i];
+            if (same) return (int64_t)slot;
+        }
+    }
+    return -1;
+}
+
 // Key words of the alignments a read kept.  SE:
 //   one hit,  >= 3 nodes : [0<<28 | npath, gene, node...]                      (SpliceGraphQuant.long key)
 //   several hits         : [1<<28 | nhits, then per hit: npath, gene, node...] (MultiMapping.map key)
@@ -353,32 +381,41 @@ struct WqQuantDev {
     WqKeyedTable keyed;
 };
 
+// Which counter a read's kept alignments go to (the branch structure of count!, src/quant.jl:556-594, and of the `length(align) > 1`
+// test of process_reads!, src/reads.jl:60-66): kind -1 = counted nowhere, 0 = node store (node_idx), 1 = edge / circ table (ekey),
+// 2 = keyed store (long path or multi-map class; kw[0..nw) holds the key).
+struct WqTarget { int kind; uint32_t node_idx; uint64_t ekey; int nw; };
+WQ_HD WqTarget wq_target_se(const WqDevIndex& ix, const WqWork& wk, uint32_t base, int cnt, int nkept, uint32_t* kw) {
+    WqTarget t{-1, 0u, 0ull, 0};
+    if (nkept == 1) {
+        int k = 0;
+        while (!(wk.hits[base + k].flags & 4)) k++;
+        const WqHit h = wk.hits[base + k];
+        if (!(h.flags & 1)) return t;               // align.isvalid == true || return
+        const wq_align_node n0 = wk.pool[h.path_start];
+        if (h.npath == 1) { t.kind = 0; t.node_idx = WQ_LDG(&ix.genes[n0.gene - 1].node_base) + n0.node - 1; return t; }
+        if (h.npath == 2) {
+            const wq_align_node n1 = wk.pool[h.path_start + 1];
+            t.kind = 1;
+            t.ekey = ((uint64_t)n0.gene << 32) | ((uint64_t)(n0.node & 0xFFFF) << 16) | (uint64_t)(n1.node & 0xFFFF);
+            return t;
+        }
+    }
+    t.nw = wq_build_key_se(wk, base, cnt, nkept, kw);
+    t.kind = 2;
+    return t;
+}
+
 // count!(quant, align, 1.0) for a single kept alignment, or push!(multi, ...) for several.
 // `retry` = only redo the keyed insertion (dense counts were already applied).
 WQ_HD void wq_count_read(const WqDevIndex& ix, const WqWork& wk, const WqQuantDev& q, uint32_t r,
                          uint32_t base, int cnt, int nkept, bool retry) {
     uint32_t kw[WQ_KEY_WORDS_MAX];
-    if (nkept == 1) {
-        int k = 0;
-        while (!(wk.hits[base + k].flags & 4)) k++;
-        const WqHit h = wk.hits[base + k];
-        if (!(h.flags & 1)) return;                 // align.isvalid == true || return
-        const wq_align_node n0 = wk.pool[h.path_start];
-        if (h.npath == 1) {
-            if (!retry) WQ_ATOMIC_ADD_U64(&q.node_count[WQ_LDG(&ix.genes[n0.gene - 1].node_base) + n0.node - 1], 1);
-            return;
-        }
-        if (h.npath == 2) {
-            if (!retry) {
-                const wq_align_node n1 = wk.pool[h.path_start + 1];
-                uint64_t key = ((uint64_t)n0.gene << 32) | ((uint64_t)(n0.node & 0xFFFF) << 16) | (uint64_t)(n1.node & 0xFFFF);
-                if (wq_edge_insert(q.edges, key, 1)) WQ_ATOMIC_ADD_U64(&q.counters->edge_full, 1);
-            }
-            return;
-        }
-    }
-    int nw = wq_build_key_se(wk, base, cnt, nkept, kw);
-    int rc = wq_keyed_insert(q.keyed, kw, nw, 1);
+    const WqTarget t = wq_target_se(ix, wk, base, cnt, nkept, kw);
+    if (t.kind < 0) return;
+    if (t.kind == 0) { if (!retry) WQ_ATOMIC_ADD_U64(&q.node_count[t.node_idx], 1); return; }
+    if (t.kind == 1) { if (!retry && wq_edge_insert(q.edges, t.ekey, 1)) WQ_ATOMIC_ADD_U64(&q.counters->edge_full, 1); return; }
+    int rc = wq_keyed_insert(q.keyed, kw, t.nw, 1);
     if (rc == 1) {
         uint32_t slot = WQ_ATOMIC_ADD_U32(&wk.cursors[2], 1);
         wk.pending[slot] = r;
@@ -599,35 +636,44 @@ WQ_HD int wq_build_key_pe(const WqWork& wk, uint32_t base, int cnt, int nkept, u
     return n;
 }
 
-// count!(quant, fwd, rev, 1.0) (src/quant.jl:597-653) or push!(multi, fwd, rev, ...) (:471-484)
-WQ_HD void wq_count_pair(const WqDevIndex& ix, const WqWork& wk, const WqQuantDev& q, uint32_t r,
-                         uint32_t base, int cnt, int nkept, bool retry) {
-    uint32_t kw[WQ_KEY_WORDS_MAX_PE];
+// the paired form of the same decision: count!(quant, fwd, rev, value), src/quant.jl:597-653
+WQ_HD WqTarget wq_target_pe(const WqDevIndex& ix, const WqWork& wk, uint32_t base, int cnt, int nkept, uint32_t* kw) {
+    WqTarget t{-1, 0u, 0ull, 0};
     if (nkept == 1) {
         int k = 0;
         while (!(wk.hits[2 * (base + k)].flags & 4)) k++;
         const WqHit hf = wk.hits[2 * (base + k)], hr = wk.hits[2 * (base + k) + 1];
-        if (!((hf.flags & 1) && (hr.flags & 1))) return;
+        if (!((hf.flags & 1) && (hr.flags & 1))) return t;
         const wq_align_node* pf = wk.pool + hf.path_start;
         const wq_align_node* pr = wk.pool + hr.path_start;
-        if (pf[0].gene != pr[0].gene) return;
+        if (pf[0].gene != pr[0].gene) return t;
         const wq_align_node* single = nullptr;
         int ns = 0;
         if (hf.npath <= hr.npath) { if (wq_subpath(pf, hf.npath, pr, hr.npath)) { single = pr; ns = hr.npath; } }
         else { if (wq_subpath(pr, hr.npath, pf, hf.npath)) { single = pf; ns = hf.npath; } }
         if (single) {
-            if (retry) return;
-            if (ns == 1) {
-                WQ_ATOMIC_ADD_U64(&q.node_count[WQ_LDG(&ix.genes[single[0].gene - 1].node_base) + single[0].node - 1], 1);
-            } else if (ns == 2) {
-                uint64_t key = ((uint64_t)single[0].gene << 32) | ((uint64_t)(single[0].node & 0xFFFF) << 16) | (uint64_t)(single[1].node & 0xFFFF);
-                if (wq_edge_insert(q.edges, key, 1)) WQ_ATOMIC_ADD_U64(&q.counters->edge_full, 1);
-            }                           // a nested path of >= 3 nodes is not counted (no else branch at src/quant.jl:631-640)
-            return;
+            if (ns == 1) { t.kind = 0; t.node_idx = WQ_LDG(&ix.genes[single[0].gene - 1].node_base) + single[0].node - 1; }
+            else if (ns == 2) {
+                t.kind = 1;
+                t.ekey = ((uint64_t)single[0].gene << 32) | ((uint64_t)(single[0].node & 0xFFFF) << 16) | (uint64_t)(single[1].node & 0xFFFF);
+            }                               // a nested path of >= 3 nodes is not counted (no else branch at src/quant.jl:631-640)
+            return t;
         }
     }
-    int nw = wq_build_key_pe(wk, base, cnt, nkept, kw);
-    int rc = wq_keyed_insert(q.keyed, kw, nw, 1);
+    t.nw = wq_build_key_pe(wk, base, cnt, nkept, kw);
+    t.kind = 2;
+    return t;
+}
+
+// count!(quant, fwd, rev, 1.0) (src/quant.jl:597-653) or push!(multi, fwd, rev, ...) (:471-484)
+WQ_HD void wq_count_pair(const WqDevIndex& ix, const WqWork& wk, const WqQuantDev& q, uint32_t r,
+                         uint32_t base, int cnt, int nkept, bool retry) {
+    uint32_t kw[WQ_KEY_WORDS_MAX_PE];
+    const WqTarget t = wq_target_pe(ix, wk, base, cnt, nkept, kw);
+    if (t.kind < 0) return;
+    if (t.kind == 0) { if (!retry) WQ_ATOMIC_ADD_U64(&q.node_count[t.node_idx], 1); return; }
+    if (t.kind == 1) { if (!retry && wq_edge_insert(q.edges, t.ekey, 1)) WQ_ATOMIC_ADD_U64(&q.counters->edge_full, 1); return; }
+    int rc = wq_keyed_insert(q.keyed, kw, t.nw, 1);
     if (rc == 1) {
         uint32_t slot = WQ_ATOMIC_ADD_U32(&wk.cursors[2], 1);
         wk.pending[slot] = r;

@@ -28,6 +28,8 @@ def load():
     vp = C.c_void_p
     L.wq_last_error.restype = C.c_char_p
     L.wq_index_create.argtypes = [C.POINTER(abi.IndexDesc), C.c_int, C.POINTER(vp)]
+    L.wq_set_biascorrect.argtypes = [vp, C.c_int]
+    L.wq_bias_download.argtypes = [vp, C.POINTER(abi.BiasCountsC)]
     L.wq_index_write.argtypes = [C.POINTER(abi.IndexDesc), C.POINTER(C.c_char_p), abi.u8p, C.c_char_p]
     L.wq_index_load.argtypes = [C.c_char_p, C.c_int, C.POINTER(vp)]
     L.wq_destroy.argtypes = [vp]

@@ -92,6 +92,30 @@ class GraphLibQuant:
     def reset(self):
         lib.check(self.L.wq_quant_reset(self.h))
 
+    # ---- --biascorrect (JointBiasMod / JointBiasCounter, src/bias.jl:103-270; bin/whippet-quant.jl:116-122, 156-169) ----
+    def set_biascorrect(self, on: bool = True):
+        """CounterType = JointBiasCounter, BiasModelType = JointBiasMod: call before the first batch (it resets the count stores).  From then
+        on gene_em / assign_ambig / process_events work with the primer- and GC-adjusted Float64 counts."""
+        lib.check(self.L.wq_set_biascorrect(self.h, int(bool(on))))
+
+    def bias_download(self):
+        """Every counter's count after primer_adjust! and gc_adjust! factor (< 0: none), aligned with counts() and keyed(kind), plus the
+        normalised model tables: dict(node=(p, g), edge=(p, g), circ=(p, g), long=(p, g), multi=(p, g), fore, back)."""
+        o = abi.BiasCountsC()
+        lib.check(self.L.wq_bias_download(self.h, C.byref(o)))
+        dp = C.POINTER(C.c_double)
+        arrs = {k: (np.zeros(max(1, n)), np.zeros(max(1, n))) for k, n in
+                (("node", o.n_nodes), ("edge", o.n_edge), ("circ", o.n_circ), ("long", o.n_long), ("multi", o.n_multi))}
+        sizes = dict(node=o.n_nodes, edge=o.n_edge, circ=o.n_circ, long=o.n_long, multi=o.n_multi)
+        for k, (p, g) in arrs.items():
+            setattr(o, k + "_primer", p.ctypes.data_as(dp)); setattr(o, k + "_gc", g.ctypes.data_as(dp))
+        fore, back = np.zeros(4096), np.zeros(4096)
+        o.fore, o.back = fore.ctypes.data_as(dp), back.ctypes.data_as(dp)
+        lib.check(self.L.wq_bias_download(self.h, C.byref(o)))
+        out = {k: (p[:sizes[k]], g[:sizes[k]]) for k, (p, g) in arrs.items()}
+        out["fore"], out["back"] = fore, back
+        return out
+
     # ---- alignment ------------------------------------------------------------------------------
     def ungapped_align(self, param: AlignParam, reads: ReadBatch, mate: ReadBatch | None = None) -> AlignResult:
         """ungapped_align for every read (src/align.jl:225-270; paired: src/paired.jl:42-125).
