@@ -92,7 +92,49 @@ function index_create(desc::IndexDesc, device::Integer = 0)
    check(ccall((:wq_index_create, LIB), Cint, (Ref{IndexDesc}, Cint, Ref{Ptr{Cvoid}}), desc, device, h))
    h[]
 end
+"""The index in the library's native on-disk form (csrc/wq_index_file.h).  `index_write` is host-only (no GPU needed): run it once after
+`whippet-index.jl` has built the GraphLib; `index_load` then replaces `open(deserialize, indexname)` + `index_create` at the start of
+every `whippet-quant.jl` run (bin/whippet-quant.jl:105).  `seqnames` / `strands` = lib.info[g].name / .strand ('+' = 1), for SAM output."""
+function index_write(desc::IndexDesc, path::String, seqnames::Union{Vector{String},Nothing} = nothing, strands::Union{Vector{UInt8},Nothing} = nothing)
+   if seqnames === nothing || strands === nothing
+      check(ccall((:wq_index_write, LIB), Cint, (Ref{IndexDesc}, Ptr{Cstring}, Ptr{UInt8}, Cstring), desc, C_NULL, C_NULL, path))
+   else
+      check(ccall((:wq_index_write, LIB), Cint, (Ref{IndexDesc}, Ptr{Cstring}, Ptr{UInt8}, Cstring), desc, seqnames, strands, path))
+   end
+end
+function index_load(path::String, device::Integer = 0)
+   h = Ref{Ptr{Cvoid}}(C_NULL)
+   check(ccall((:wq_index_load, LIB), Cint, (Cstring, Cint, Ref{Ptr{Cvoid}}), path, device, h))
+   h[]
+end
 destroy(h) = ccall((:wq_destroy, LIB), Cvoid, (Ptr{Cvoid},), h)
+
+# ---- --biascorrect (bin/whippet-quant.jl:116-122: CounterType = JointBiasCounter, BiasModelType = JointBiasMod) ----
+"""Call before the first batch.  The quant stage calls (em_tpm, assign_ambig, process_events) then work with the Float64 counts of
+primer_adjust! / gc_adjust! (bin/whippet-quant.jl:156-169) without further calls from the host."""
+set_biascorrect(h, on::Bool = true) = check(ccall((:wq_set_biascorrect, LIB), Cint, (Ptr{Cvoid}, Cint), h, on ? 1 : 0))
+mutable struct BiasCounts   # wq_bias_counts
+   n_nodes::UInt64; n_edge::UInt64; n_circ::UInt64; n_long::UInt64; n_multi::UInt64
+   node_primer::Ptr{Float64}; node_gc::Ptr{Float64}; edge_primer::Ptr{Float64}; edge_gc::Ptr{Float64}
+   circ_primer::Ptr{Float64}; circ_gc::Ptr{Float64}; long_primer::Ptr{Float64}; long_gc::Ptr{Float64}
+   multi_primer::Ptr{Float64}; multi_gc::Ptr{Float64}; fore::Ptr{Float64}; back::Ptr{Float64}
+end
+"""Every counter's `count` after primer_adjust! and the factor gc_adjust! multiplies it by (< 0: none), in the orders of
+counts_download / keyed_download, for refilling JointBiasCounter.count of SpliceGraphQuant / MultiMapping before the writers run."""
+function bias_download(h)
+   o = BiasCounts(0, 0, 0, 0, 0, ntuple(_ -> Ptr{Float64}(C_NULL), 12)...)
+   check(ccall((:wq_bias_download, LIB), Cint, (Ptr{Cvoid}, Ref{BiasCounts}), h, o))             # sizes
+   mk(n) = (Vector{Float64}(undef, n), Vector{Float64}(undef, n))
+   node, edge, circ, long, multi = mk(o.n_nodes), mk(o.n_edge), mk(o.n_circ), mk(o.n_long), mk(o.n_multi)
+   fore, back = Vector{Float64}(undef, 4096), Vector{Float64}(undef, 4096)
+   GC.@preserve node edge circ long multi fore back begin
+      o.node_primer, o.node_gc = pointer(node[1]), pointer(node[2]); o.edge_primer, o.edge_gc = pointer(edge[1]), pointer(edge[2])
+      o.circ_primer, o.circ_gc = pointer(circ[1]), pointer(circ[2]); o.long_primer, o.long_gc = pointer(long[1]), pointer(long[2])
+      o.multi_primer, o.multi_gc = pointer(multi[1]), pointer(multi[2]); o.fore, o.back = pointer(fore), pointer(back)
+      check(ccall((:wq_bias_download, LIB), Cint, (Ptr{Cvoid}, Ref{BiasCounts}), h, o))
+   end
+   (node = node, edge = edge, circ = circ, long = long, multi = multi, fore = fore, back = back)
+end
 quant_reset(h) = check(ccall((:wq_quant_reset, LIB), Cint, (Ptr{Cvoid},), h))
 set_gene_info(h, seqnames::Vector{String}, strands::Vector{UInt8}) =
    check(ccall((:wq_index_set_gene_info, LIB), Cint, (Ptr{Cvoid}, Ptr{Cstring}, Ptr{UInt8}), h, seqnames, strands))
@@ -173,7 +215,22 @@ function process_events_view(h, readlen::Integer)
    # values[value_start+1 ...]); kind 2 -> tandem-UTR lines; kind 0 -> output_empty; kind 3 -> no line
 end
 
-# ---- multi-GPU (one process per GPU; NCCL calls are the host's) -----------------------------------------------------
+# ---- multi-GPU, exchange inside the library (one process per GPU; libnccl.so.2 is opened at run time) ------------------
+"""Rank 0: 128 bytes (ncclUniqueId) to hand to the other ranks by any means (a file, a socket, MPI)."""
+function comm_unique_id()
+   id = Vector{UInt8}(undef, 128)
+   check(ccall((:wq_comm_unique_id, LIB), Cint, (Ptr{UInt8},), id))
+   id
+end
+comm_init(h, nranks::Integer, rank::Integer, id::Vector{UInt8}) =
+   check(ccall((:wq_comm_init_rank, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{UInt8}), h, nranks, rank, id))
+"""After the last batch: one ncclAllReduce of the dense counts, one ncclAllGather of the sparse stores, merged on the device."""
+counts_sync(h) = check(ccall((:wq_counts_sync, LIB), Cint, (Ptr{Cvoid},), h))
+"""Class building partitioned by gene: this rank's share, all-gathered, assembled.  Then em_tpm! / assign_ambig / process_events."""
+classes_sync(h) = check(ccall((:wq_classes_sync, LIB), Cint, (Ptr{Cvoid},), h))
+comm_destroy(h) = check(ccall((:wq_comm_destroy, LIB), Cint, (Ptr{Cvoid},), h))
+
+# ---- multi-GPU, step by step (for a host that runs its own NCCL calls) ---------------------------------------------------
 function counts_device_ptr(h)
    p = Ref{Ptr{Cvoid}}(C_NULL); n = Ref{UInt64}(0)
    check(ccall((:wq_counts_device_ptr, LIB), Cint, (Ptr{Cvoid}, Ref{Ptr{Cvoid}}, Ref{UInt64}), h, p, n))

@@ -87,20 +87,29 @@ def test_kernel_bodies_on_cpu(paired):
     assert with_gc > 50 and len(edges) > 50 and (len(multi) > 10 or paired)
 
 
-def test_host_stages_with_bias_on_cpu():
+@pytest.mark.parametrize("paired", [False, True])
+def test_host_stages_with_bias_on_cpu(paired):
     """Class building, the long-path re-count, gc_adjust! and assign_ambig! of the library's host code (tests/emu/wq_host_emu.cu) fed with
-    the tallies of the kernel bodies, against the oracle in the reference's order (bin/whippet-quant.jl:156-176)."""
+    the tallies of the kernel bodies, against the oracle in the reference's order (bin/whippet-quant.jl:156-176).  Paired: a "long path"
+    may be two single-node mates, whose re-count lands on NODE counters before gc_adjust! scales them."""
     import ctypes as C
     from emu.emu import Emu
     from emu.host_emu import HostEmu
     from oracle import lib as olib_
     from wq_inputs import synth
-    idx = synth.make_index(n_genes=2300, K=9, seed=71, paralog_frac=0.1)       # >= 2048 genes: the threaded paths run
-    rb = synth.simulate_reads(idx, 120000, 101, seed=72, sub_rate=0.01)
-    p = wq.AlignParam()
+    if paired:
+        from data_gen import pe_case
+        idx, p, rb, rb2 = pe_case(5, 2300, 101, 5000, True, 60000)
+    else:
+        idx = synth.make_index(n_genes=2300, K=9, seed=71, paralog_frac=0.1)       # >= 2048 genes: the threaded paths run
+        rb, rb2 = synth.simulate_reads(idx, 120000, 101, seed=72, sub_rate=0.01), None
+        p = wq.AlignParam()
     e = Emu(idx)
     e.set_bias(True)
-    e.process_reads(p, rb)
+    if paired:
+        e.align_pe(p, rb, rb2)
+    else:
+        e.process_reads(p, rb)
     node_pg, edges, longs, multi, fore, back, short = e.bias_values()
     ek, ec = e.edges()
     kl, km = e.keyed()
@@ -114,13 +123,13 @@ def test_host_stages_with_bias_on_cpu():
     o = Oracle(idx)
     o.set_bias(True)
     o.quant_reset()
-    o.process_reads(p, rb)
+    (o.process_paired_reads(p, rb, rb2) if paired else o.process_reads(p, rb))
     o.bias_primer_adjust()
     o.em_tpm(101)
     conv = lambda c: ([i - 1 for i in c[0]], c[2], c[3], c[4])
     want = [conv(c) for c in o.classes(multi=True)] + [conv(c) for c in o.classes(multi=False)]
     got, nm = he.classes()
-    assert nm == len(o.classes(multi=True)) and len(got) == len(want) and nm > 100
+    assert nm == len(o.classes(multi=True)) and len(got) == len(want) and nm > (10 if paired else 100)
     for (gi, gc, gd, gp), (wi, wc, wd, wp) in zip(got, want):
         assert gi == wi and np.float64(gc).tobytes() == np.float64(wc).tobytes() and gp == wp
     assert any(gc != round(gc) for _, gc, _, _ in got)                          # the counts really are fractional
@@ -188,9 +197,11 @@ def full_bias_parity(q, o, p, f, r):
     vals_q = np.concatenate([vq[2], vq[4]])
     order = np.argsort(keys_q, kind="stable")
     assert np.array_equal(keys_q[order], ek_o) and bits_equal(vals_q[order], ev_o)
-    ev_q, ev_oo = q.process_events(readlen), o.process_events(readlen)
-    assert canonical_events(ev_q) == canonical_events(ev_oo) and len(ev_q) > 100
-    return dict(with_gc=with_gc, iterations=it_q, events=len(ev_q), multi=len(multi), longs=len(longs))
+    got = canonical_events(*q.process_events_raw(readlen))
+    want = o.events_flat(readlen)
+    for name, x, y in zip(("hdr", "psi/total/iterations", "values", "path lengths", "path nodes"), got, want):
+        assert bits_equal(x, y), f"event records differ in {name}"
+    return dict(with_gc=with_gc, iterations=it_q, events=len(want[0]), multi=len(multi), longs=len(longs))
 
 
 @pytest.mark.gpu

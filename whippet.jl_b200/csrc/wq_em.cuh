@@ -111,11 +111,11 @@ static inline std::string wq_host_build_classes(const WqHostIndex& H, const WqIs
     X = WqHostQuantEx();
     if (!hq.bias) X.node_value.assign(hq.node.begin(), hq.node.end());
     else {
-        // --biascorrect: this store is first read after gc_adjust! (assign_ambig! / events), so it starts at the gc-adjusted count; the
-        // primer-adjusted counts that build_equivalence_classes! needs are read through hq.nodec().  Long paths must be visited in
-        // canonical (key) order now: their counts are no longer integers, so the order of the additions shows in the result.
-        X.node_value.resize(hq.node.size());
-        for (size_t i = 0; i < hq.node.size(); i++) X.node_value[i] = WqHostQuant::gc_apply(hq.node_p[i], hq.node_g[i]);
+        // --biascorrect: the store starts at the primer-adjusted counts, takes the long-path re-count below (a paired "long path" may
+        // be two single-node mates, which add to nodes), and is scaled by gc_adjust! at the end of this function: nothing reads it
+        // before assign_ambig! / the events.  Long paths must be visited in canonical (key) order now: their counts are no longer
+        // integers, so the order of the additions shows in the result.
+        X.node_value = hq.node_p;
         hq.longs.canonicalize();
     }
     X.iso_count.assign(I, 0.0);
@@ -308,6 +308,8 @@ static inline std::string wq_host_build_classes(const WqHostIndex& H, const WqIs
     });
     lap2("fragments concatenated");
     X.adds_before_gc = X.edge_adds.size();
+    if (hq.bias)                                             // gc_adjust!(quant, mod) on the node counters (the edge counters: wq_finalize_edges)
+        for (size_t i = 0; i < X.node_value.size(); i++) X.node_value[i] = WqHostQuant::gc_apply(X.node_value[i], hq.node_g[i]);
     X.built = nparts == 1;                   // a share is not a class set: wq_classes_assemble completes it
     X.local_built = true;
     return "";
@@ -812,7 +814,7 @@ __global__ void __launch_bounds__(1024) wq_k_em_tpm_smem(WqEmDev d, const WqEmSm
 
 // grow-only device scratch kept in the handle (cudaMalloc/cudaFree per call would serialise the device)
 struct WqEmScratch {
-    void* p[24] = {nullptr}; size_t cap[24] = {0};
+    void* p[26] = {nullptr}; size_t cap[26] = {0};
     template <class T> cudaError_t get(int slot, size_t n, T** out) {
         size_t bytes = std::max<size_t>(1, n) * sizeof(T);
         if (bytes > cap[slot]) {
@@ -852,7 +854,7 @@ struct WqEmScratch {
         return cudaEventCreateWithFlags(&fork, cudaEventDisableTiming);
     }
     void release() {
-        for (int i = 0; i < 24; i++) { if (p[i]) cudaFree(p[i]); p[i] = nullptr; cap[i] = 0; }
+        for (int i = 0; i < 26; i++) { if (p[i]) cudaFree(p[i]); p[i] = nullptr; cap[i] = 0; }
         for (int i = 0; i < 3; i++) { if (side[i]) cudaStreamDestroy(side[i]); if (join[i]) cudaEventDestroy(join[i]); side[i] = nullptr; join[i] = nullptr; }
         if (fork) cudaEventDestroy(fork);
         if (tk0) cudaEventDestroy(tk0);
@@ -1132,147 +1134,6 @@ __device__ __forceinline__ double wq_round_sig(const WqPsiDev& d, double x, int 
     return r;
 }
 
-// One warp per event (events with more than 16 paths), the event's whole working set in shared memory.
-//
-// What bounds an event is latency, not arithmetic: up to 1500 sweeps, each a chain of sums the reference forms sequentially
-// (`ac.prop_sum += prev_psi` over the members of every ambiguous set, src/events.jl:869-876; the sum of all path psi in
-// calculate_psi!, :838); a CPU core runs a 50-path event's sweep in ~3 us.  So everything a sweep reads is staged once in the
-// warp's shared memory (psi / previous psi / temp counts / denominators / unambiguous counts per path, the member lists of the
-// ambiguous sets as 16-bit path indices, one prop_sum per set), and the independent chains run side by side: every lane owns
-// ambiguous sets and forms their prop_sum sequentially in member order (different sets on different lanes); the additions
-// `count_temp[p] += prop * multiplier` are then made by the lane that OWNS path p, over the sets that contain p in set order
-// (the order the reference's loop over `ambig` adds them in): an inverted index path -> sets, built once per event, replaces a
-// warp barrier per set and puts the divisions of different paths side by side.  The divisions / significant-digit roundings
-// of the paths are lane-parallel; the sum over all paths stays one sequential chain in path order (every lane forms it from
-// shared memory).
-// Shared memory per event: 44 * paths + 16 * sets + 4 * (sets + 1) + 4 * members bytes (+4), rounded up; the launch classes
-// group events by that size.  Events whose member lists do not fit (> ~50 k members) keep the set-by-set form with the
-// lists in global memory.
-struct WqPsiWarpCfg { uint32_t smem_bytes; uint32_t members_in_smem; };
-__global__ void __launch_bounds__(32) wq_k_em_psi_big(const WqPsiDev d, const uint32_t* __restrict__ list, const uint32_t n_list, const WqPsiWarpCfg cfg) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const uint32_t lane = threadIdx.x;
-    const uint32_t slot = blockIdx.x;
-    if (slot >= n_list) return;
-    const uint32_t e = list[slot];
-    const uint32_t p0 = d.path_ptr[e], np = d.path_ptr[e + 1] - p0, ni = d.n_inc[e];
-    const uint32_t a0 = d.amb_ptr[e], na = d.amb_ptr[e + 1] - a0;
-    const uint32_t m0 = d.amb_path_ptr[a0], nm = d.amb_path_ptr[a0 + na] - m0;
-    const bool tandem = d.is_tandem[e] != 0;
-    double* psi = reinterpret_cast<double*>(smem_raw);
-    double* prev = psi + np;
-    double* ct = prev + np;
-    double* den = ct + np;
-    double* cnt = den + np;
-    double* psum = cnt + np;                                      // [na]
-    double* mult = psum + na;                                     // [na]
-    uint32_t* moff = reinterpret_cast<uint32_t*>(mult + na);      // [na + 1] member offsets of the sets, event-local
-    uint32_t* poff = moff + na + 1;                               // [np + 1] staged: offsets of the inverted index (path -> its sets, in set order)
-    uint16_t* mem = reinterpret_cast<uint16_t*>(poff + np + 1);   // [nm] staged: event-local path index of every member
-    uint16_t* pset = mem + nm;                                    // [nm] staged: the sets of every path
-    const bool staged = cfg.members_in_smem != 0;
-    const uint32_t* gmem = d.amb_paths + m0;
-    for (uint32_t i = lane; i < np; i += 32) {
-        const double len = d.length[p0 + i];
-        cnt[i] = d.count[p0 + i];
-        den[i] = tandem ? fmax(__dsub_rn(len, d.readlen), 1.0) : len;
-        prev[i] = 0.0; psi[i] = 0.0; ct[i] = cnt[i];
-    }
-    for (uint32_t a = lane; a <= na; a += 32) moff[a] = d.amb_path_ptr[a0 + a] - m0;
-    for (uint32_t a = lane; a < na; a += 32) mult[a] = d.amb_mult[a0 + a];
-    if (staged) {
-        for (uint32_t k = lane; k < nm; k += 32) mem[k] = (uint16_t)gmem[k];
-        for (uint32_t i = lane; i <= np; i += 32) poff[i] = 0;
-        __syncwarp();
-        if (lane == 0) {            // counting sort of the (set, path) pairs by path, stable in the set order; once per event
-            for (uint32_t k = 0; k < nm; k++) poff[mem[k] + 1]++;
-            for (uint32_t i = 0; i < np; i++) poff[i + 1] += poff[i];
-            for (uint32_t a = 0; a < na; a++)
-                for (uint32_t k = moff[a]; k < moff[a + 1]; k++) pset[poff[mem[k]]++] = (uint16_t)a;
-            for (uint32_t i = np; i > 0; i--) poff[i] = poff[i - 1];
-            poff[0] = 0;
-        }
-    }
-    __syncwarp();
-    auto member = [&](uint32_t k) -> uint32_t { return staged ? (uint32_t)mem[k] : gmem[k]; };
-    auto normalise = [&](int sig) {
-        for (uint32_t i = lane; i < np; i += 32) psi[i] = __ddiv_rn(ct[i], den[i]);
-        __syncwarp();
-        double total;
-        if (tandem) { total = 0.0; for (uint32_t i = 0; i < np; i++) total = __dadd_rn(total, psi[i]); }
-        else {
-            double se = 0.0, si = 0.0;
-            for (uint32_t i = ni; i < np; i++) se = __dadd_rn(se, psi[i]);
-            for (uint32_t i = 0; i < ni; i++) si = __dadd_rn(si, psi[i]);
-            total = __dadd_rn(se, si);
-        }
-        __syncwarp();
-        for (uint32_t i = lane; i < np; i += 32) {
-            double q = __ddiv_rn(psi[i], total);
-            psi[i] = sig > 0 ? wq_round_sig(d, q, sig) : q;
-        }
-        __syncwarp();
-    };
-    auto differs = [&]() {
-        bool diff = false;
-        for (uint32_t i = lane; i < np; i += 32) if (prev[i] != psi[i]) diff = true;
-        return __any_sync(0xffffffffu, diff) != 0;
-    };
-    if (!tandem) normalise(0);                      // calculate_psi!(inc, exc, counts) before spliced_em!
-    int64_t it = 1;
-    for (;;) {
-        if (!tandem && !(differs() && it < d.maxit)) break;
-        for (uint32_t i = lane; i < np; i += 32) { ct[i] = cnt[i]; prev[i] = psi[i]; }
-        __syncwarp();
-        // prop_sum of every set: sequential in member order, the sets side by side on the lanes
-        if (it > 1) {
-            for (uint32_t a = lane; a < na; a += 32) {
-                double s = 0.0;
-                const uint32_t kb = moff[a], ke = moff[a + 1];
-                for (uint32_t k = kb; k < ke; k++) s = __dadd_rn(s, psi[member(k)]);
-                psum[a] = s;
-            }
-            __syncwarp();
-        }
-        if (staged) {
-            // every path by its owner lane: the shares of the sets that contain it, added in set order
-            for (uint32_t i = lane; i < np; i += 32) {
-                double c = ct[i];
-                const double pi = psi[i];
-                for (uint32_t k = poff[i]; k < poff[i + 1]; k++) {
-                    const uint32_t a = pset[k];
-                    // first sweep: ones(n)/n over prop_sum = 1.0; later sweeps: current psi over their sum (src/events.jl:869-886)
-                    const double base = it > 1 ? pi : __ddiv_rn(1.0, (double)(moff[a + 1] - moff[a]));
-                    const double ps = it > 1 ? psum[a] : 1.0;
-                    c = __dadd_rn(c, __dmul_rn(__ddiv_rn(base, ps), mult[a]));
-                }
-                ct[i] = c;
-            }
-            __syncwarp();
-        } else {
-            for (uint32_t a = 0; a < na; a++) {
-                const uint32_t kb = moff[a], n = moff[a + 1] - kb;
-                const double ps = it > 1 ? psum[a] : 1.0, mu = mult[a];
-                for (uint32_t k = lane; k < n; k += 32) {
-                    const uint32_t pth = member(kb + k);
-                    const double base = it > 1 ? psi[pth] : __ddiv_rn(1.0, (double)n);
-                    ct[pth] = __dadd_rn(ct[pth], __dmul_rn(__ddiv_rn(base, ps), mu));
-                }
-                __syncwarp();
-            }
-        }
-        normalise(d.sig);
-        if (tandem) { if (differs() && it < d.maxit) it += 1; else break; }
-        else it += 1;
-    }
-    for (uint32_t i = lane; i < np; i += 32) { d.psi[p0 + i] = psi[i]; d.ctemp[p0 + i] = ct[i]; }
-    if (lane == 0) d.iterations[e] = (int32_t)it;
-}
-static inline size_t wq_psi_warp_smem(uint32_t np, uint32_t na, uint32_t nm, bool staged) {
-    size_t b = 40ull * np + 16ull * na + 4ull * (na + 1) + 4ull * (np + 1) + (staged ? 4ull * nm : 0);
-    return (b + 15) & ~15ull;
-}
-
 // One event per block of T = 32 * W threads (events with more than 4 paths), written for the LATENCY of one sweep:
 // a fifth of the events never converge under the 4-significant-digit rounding and run all 1500 sweeps, so the launch lasts
 // 1500 x (the dependent chain of one sweep of its slowest event).  Per sweep:
@@ -1283,9 +1144,16 @@ static inline size_t wq_psi_warp_smem(uint32_t np, uint32_t na, uint32_t nm, boo
 //       adds them in), then count / length;
 //   (4) the sum over all paths as ONE sequential chain in path order (every thread forms it from shared memory), division + rounding.
 // Only additions are chained; loads feeding them do not depend on the running sum and are unrolled so that they overlap.
-// Shared memory per event: 40 * paths + 16 * sets + 4 * (sets + 1) + 4 * (paths + 1) + 14 * members bytes.
+// Shared memory per event: 40 * paths + 16 * sets + 4 * (sets + 1) + 4 * (paths + 1) + 14 * members bytes.  Events too large for that
+// (hundreds of paths, tens of thousands of set members: the stress genes of BASELINE config 5, deeply covered paralog families) keep
+// only the per-path arrays in shared memory; the per-set and per-member arrays live in a global scratch (`big`, L2-resident) and the
+// block has 1024 threads, so that the share divisions of a sweep are ~40 per thread instead of ~1000 per lane of one warp.
+struct WqPsiBigCfg {                  // quo == nullptr: everything in shared memory
+    double* quo; double* psum; double* mult; uint32_t* moff; uint16_t* mem; uint16_t* pset; uint16_t* ppath;
+    const uint64_t* mbase; const uint64_t* abase;      // per launch slot: first member / first set of the event inside the scratch
+};
 __device__ __forceinline__ void wq_psi_sync(const bool one_warp) { if (one_warp) __syncwarp(); else __syncthreads(); }
-__global__ void __launch_bounds__(128) wq_k_em_psi(const WqPsiDev d, const uint32_t* __restrict__ list, const uint32_t n_list) {
+__global__ void __launch_bounds__(1024) wq_k_em_psi(const WqPsiDev d, const uint32_t* __restrict__ list, const uint32_t n_list, const WqPsiBigCfg big) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t tid = threadIdx.x, T = blockDim.x;
     const bool one_warp = T == 32;
@@ -1301,14 +1169,22 @@ __global__ void __launch_bounds__(128) wq_k_em_psi(const WqPsiDev d, const uint3
     double* ct = prev + np;
     double* den = ct + np;
     double* cnt = den + np;
-    double* psum = cnt + np;                                      // [na]
-    double* mult = psum + na;                                     // [na]
-    double* quo = mult + na;                                      // [nm] shares, in inverted-index order
-    uint32_t* moff = reinterpret_cast<uint32_t*>(quo + nm);       // [na + 1] member offsets of the sets, event-local
-    uint32_t* poff = moff + na + 1;                               // [np + 1] offsets of the inverted index (path -> its sets, in set order)
-    uint16_t* mem = reinterpret_cast<uint16_t*>(poff + np + 1);   // [nm] event-local path index of every member
-    uint16_t* pset = mem + nm;                                    // [nm] inverted index: the set of every slot
-    uint16_t* ppath = pset + nm;                                  // [nm] inverted index: the path of every slot
+    double* psum; double* mult; double* quo; uint32_t* moff; uint32_t* poff; uint16_t* mem; uint16_t* pset; uint16_t* ppath;
+    if (big.quo == nullptr) {
+        psum = cnt + np;                                          // [na]
+        mult = psum + na;                                         // [na]
+        quo = mult + na;                                          // [nm] shares, in inverted-index order
+        moff = reinterpret_cast<uint32_t*>(quo + nm);             // [na + 1] member offsets of the sets, event-local
+        poff = moff + na + 1;                                     // [np + 1] offsets of the inverted index (path -> its sets, in set order)
+        mem = reinterpret_cast<uint16_t*>(poff + np + 1);         // [nm] event-local path index of every member
+        pset = mem + nm;                                          // [nm] inverted index: the set of every slot
+        ppath = pset + nm;                                        // [nm] inverted index: the path of every slot
+    } else {
+        const uint64_t mb = big.mbase[slot], ab = big.abase[slot];
+        poff = reinterpret_cast<uint32_t*>(cnt + np);
+        psum = big.psum + ab; mult = big.mult + ab; moff = big.moff + ab + slot;
+        quo = big.quo + mb; mem = big.mem + mb; pset = big.pset + mb; ppath = big.ppath + mb;
+    }
     const uint32_t* gmem = d.amb_paths + m0;
     for (uint32_t i = tid; i < np; i += T) {
         const double len = d.length[p0 + i];
@@ -1415,6 +1291,7 @@ static inline size_t wq_psi_block_smem(uint32_t np, uint32_t na, uint32_t nm) {
     size_t b = 40ull * np + 16ull * na + 4ull * (na + 1) + 4ull * (np + 1) + 14ull * nm;
     return (b + 15) & ~15ull;
 }
+static inline size_t wq_psi_big_smem(uint32_t np) { return (40ull * np + 4ull * (np + 1) + 15) & ~15ull; }      // per-path arrays only
 
 // Events with at most 4 paths (more than 90 % of them), at most WQ_PSI4_SETS ambiguous sets of at most 4 members: 4 lanes per
 // event, 8 events per warp.  Lane i of the group OWNS path i (psi / previous psi / temp count in registers); once per sweep the
@@ -1547,14 +1424,12 @@ static inline std::string wq_run_em_psi(wq_psi_batch& b, WqEmScratch& M, cudaStr
     d.amb_paths = d_apaths; d.amb_mult = d_mult; d.is_tandem = d_tan; d.psi = d_psi; d.prev = d_prev; d.ctemp = d_ct;
     d.amb_prop = d_prop; d.iterations = d_it;
     // Launch classes: 0 = at most 4 paths with small sets (4 lanes per event); 1..4 = one block per event, grouped by the shared memory the
-    // event needs (4 / 16 / 64 / 200 KB, with 32 / 64 / 128 / 128 threads: more threads shorten the share divisions of a large event);
-    // 5 = events too large for that layout (14 bytes per set member) that still fit the compact one of wq_k_em_psi_big (4 bytes per member,
-    // one warp, shares divided by the owner lanes); 6 = events whose member lists do not fit in shared memory at all (set-by-set form, lists
-    // in global memory).  The classes run concurrently on side streams (a handful of large events that need all 1500 sweeps would
-    // otherwise add their whole latency to the batch).
+    // event needs (4 / 16 / 64 / 200 KB, with 32 / 64 / 128 / 256 threads: more threads shorten the share divisions of a large event);
+    // 5 = events too large for that: per-path arrays in shared memory, the rest in a global scratch, 1024 threads.  The classes run
+    // concurrently on side streams (a handful of large events that need all 1500 sweeps would otherwise add their whole latency to the batch).
     static const size_t kBlockSmem[4] = {4 * 1024, 16 * 1024, 64 * 1024, 200 * 1024};
-    static const unsigned kBlockThreads[4] = {32, 64, 128, 128};
-    const int NC = 7;
+    static const unsigned kBlockThreads[4] = {32, 64, 128, 256};
+    const int NC = 6;
     std::vector<uint32_t> order(E);
     std::vector<uint8_t> cls(E);
     uint32_t nclass[NC] = {0}, cbase[NC + 1] = {0};
@@ -1569,16 +1444,14 @@ static inline std::string wq_run_em_psi(wq_psi_batch& b, WqEmScratch& M, cudaStr
         if (np > 65535 || na > 65535) return -1;
         const size_t need = wq_psi_block_smem(np, na, nm);
         for (int k = 0; k < 4; k++) if (need <= kBlockSmem[k]) return 1 + k;
-        if (wq_psi_warp_smem(np, na, nm, true) <= kBlockSmem[3]) return 5;
+        if (wq_psi_big_smem(np) <= kBlockSmem[3]) return 5;
         return -1;
     };
+    size_t big_smem = 0;
     for (uint32_t e = 0; e < E; e++) {
-        int c = cls_of(e);
-        if (c < 0) {            // member lists too long for shared memory: the paths must still fit
-            const uint32_t np = b.path_ptr[e + 1] - b.path_ptr[e], na = b.amb_ptr[e + 1] - b.amb_ptr[e];
-            if (np > 65535 || wq_psi_warp_smem(np, na, 0, false) > kBlockSmem[3]) return "PSI event too large for the device kernel (more than ~4000 paths)";
-            c = 6;
-        }
+        const int c = cls_of(e);
+        if (c < 0) return "PSI event too large for the device kernel (more than ~4600 paths or 65535 ambiguous sets)";
+        if (c == 5) big_smem = std::max(big_smem, wq_psi_big_smem(b.path_ptr[e + 1] - b.path_ptr[e]));
         cls[e] = (uint8_t)c;
         nclass[c]++;
     }
@@ -1586,12 +1459,36 @@ static inline std::string wq_run_em_psi(wq_psi_batch& b, WqEmScratch& M, cudaStr
     { uint32_t cur[NC]; for (int c = 0; c < NC; c++) cur[c] = cbase[c]; for (uint32_t e = 0; e < E; e++) order[cur[cls[e]]++] = e; }
     uint32_t* d_list;
     WQ_EMCK(up(14, order.data(), E * 4ull, (void**)&d_list));
+    WqPsiBigCfg big;
+    memset(&big, 0, sizeof big);
+    const WqPsiBigCfg staged = big;
+    if (nclass[5]) {                                          // global scratch of the large events: members and sets back to back in launch order
+        std::vector<uint64_t> base(2ull * nclass[5]);
+        uint64_t mtot = 0, atot = 0;
+        for (uint32_t k = 0; k < nclass[5]; k++) {
+            const uint32_t e = order[cbase[5] + k];
+            const uint32_t a_lo = b.amb_ptr[e], a_hi = b.amb_ptr[e + 1];
+            base[k] = mtot; base[nclass[5] + k] = atot;
+            mtot += b.amb_path_ptr[a_hi] - b.amb_path_ptr[a_lo];
+            atot += a_hi - a_lo;
+        }
+        uint64_t* d_base;
+        WQ_EMCK(up(24, base.data(), base.size() * 8ull, (void**)&d_base));
+        uint8_t* scratch;
+        const size_t m8 = (mtot + 3) & ~3ull, a8 = (atot + nclass[5] + 1) & ~1ull;
+        WQ_EMCK(M.get<uint8_t>(25, 8 * m8 + 3 * 2 * m8 + 16 * atot + 4 * a8 + 64, &scratch));
+        big.quo = reinterpret_cast<double*>(scratch);
+        big.psum = big.quo + m8; big.mult = big.psum + atot;
+        big.moff = reinterpret_cast<uint32_t*>(big.mult + atot);
+        big.mem = reinterpret_cast<uint16_t*>(big.moff + a8);
+        big.pset = big.mem + m8; big.ppath = big.pset + m8;
+        big.mbase = d_base; big.abase = d_base + nclass[5];
+    }
     WQ_EMCK(M.side_streams());
     WQ_EMCK(M.timing_events());
     static bool smem_attr_set = false;
     if (!smem_attr_set) {
         WQ_EMCK(cudaFuncSetAttribute(wq_k_em_psi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBlockSmem[3]));
-        WQ_EMCK(cudaFuncSetAttribute(wq_k_em_psi_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBlockSmem[3]));
         smem_attr_set = true;
     }
     WQ_EMCK(cudaEventRecord(M.tk0, stream));
@@ -1604,9 +1501,8 @@ static inline std::string wq_run_em_psi(wq_psi_batch& b, WqEmScratch& M, cudaStr
         const uint32_t n = nclass[c];
         const uint32_t* lst = d_list + cbase[c];
         if (c == 0) wq_k_em_psi4<<<(n + 31) / 32, 128, 0, ss>>>(d, lst, n);
-        else if (c == 5) wq_k_em_psi_big<<<n, 32, kBlockSmem[3], ss>>>(d, lst, n, WqPsiWarpCfg{(uint32_t)kBlockSmem[3], 1u});
-        else if (c == 6) wq_k_em_psi_big<<<n, 32, kBlockSmem[3], ss>>>(d, lst, n, WqPsiWarpCfg{(uint32_t)kBlockSmem[3], 0u});
-        else wq_k_em_psi<<<n, kBlockThreads[c - 1], kBlockSmem[c - 1], ss>>>(d, lst, n);
+        else if (c == 5) wq_k_em_psi<<<n, 1024, big_smem, ss>>>(d, lst, n, big);
+        else wq_k_em_psi<<<n, kBlockThreads[c - 1], kBlockSmem[c - 1], ss>>>(d, lst, n, staged);
         if (launches) *launches += 1;
         WQ_EMCK(cudaGetLastError());
         static const bool class_timing = getenv("WQ_PSI_CLASS_TIMING") != nullptr;     // diagnostic: serialises the classes

@@ -194,115 +194,156 @@ static unsigned long long wq_evc[8];     // [0] reductions, [1] rounds, [2] unio
 #define WQ_EVP_START do { } while (0)
 #endif
 
-// Membership index over the node sets of a WqPathSet (open addressing on a hash of the window words): the reference asks
-// `jointset in newgraph.nodes` with a linear scan (src/events.jl:246,254), which is quadratic in the number of paths; an event
-// of a complex gene reaches the 1024-path bound with tens of edges, i.e. millions of set comparisons per round.  Only membership
-// is asked, so the index changes no result: paths keep their order of first appearance.
-struct WqSetIndex {
-    std::vector<int32_t> slot;          // -1 = empty, else index into the path set
-    size_t used = 0;
-    static uint64_t hash(const WqBitWin& s) {
-        const uint64_t* w = s.p();
-        uint64_t h = 0x9E3779B97F4A7C15ull;
-        for (uint32_t i = 0; i < s.nw; i++) { h ^= w[i]; h *= 0xFF51AFD7ED558CCDull; h ^= h >> 31; }
-        return h;
-    }
-    void reset(size_t expect) {
-        size_t cap = 64;
-        while (cap < 4 * expect) cap <<= 1;
-        slot.assign(cap, -1);
-        used = 0;
-    }
-    // index of an equal set, or -1 after remembering `idx` (the position the caller is about to push the set at)
-    long find_or_add(const std::vector<WqBitWin>& nodes, const WqBitWin& s, size_t idx) {
-        if (2 * (used + 1) > slot.size()) {                     // grow, re-inserting what is there
-            std::vector<int32_t> old;
-            old.swap(slot);
-            slot.assign(old.size() * 2, -1);
-            for (int32_t k : old) if (k >= 0) { size_t h = hash(nodes[k]) & (slot.size() - 1); while (slot[h] >= 0) h = (h + 1) & (slot.size() - 1); slot[h] = k; }
-        }
-        size_t h = hash(s) & (slot.size() - 1);
-        while (slot[h] >= 0) {
-            if (nodes[slot[h]] == s) return slot[h];
-            h = (h + 1) & (slot.size() - 1);
-        }
-        slot[h] = (int32_t)idx;
-        used++;
-        return -1;
-    }
-};
-
 // Build minimal node-set paths from edges sharing terminal nodes (reduce_graph, src/events.jl:223-266).
+//
+// The rounds run on FLAT storage: a node set is `nw` consecutive 64-bit words of one array (nw = words of the event's node window,
+// 1 for nearly every gene), so a union is nw ORs into the tail of the array, no set owns heap memory, and membership (`jointset in
+// newgraph.nodes`, a linear scan in the reference, src/events.jl:246,254, i.e. quadratic in the number of paths) is an open-addressing
+// table of set indices keyed by a hash of the words.  Only membership is asked, so the table changes no result: paths keep their
+// order of first appearance.  An edge joins a path when its last node is the path's first or its first node is the path's last
+// (hasintersect_terminal); the reference scans every edge for every path (:242-243), here the edges are grouped by first and by last
+// node once (the edge set never changes during the reduction) and a path visits its two groups merged in ascending edge order, which
+// is the order the scan would have met them in.
 static inline WqPathSet wq_reduce(const WqPathSet& edges, bool& subsampled) {
-    WqPathSet cur = edges, nxt;
-    nxt.mn = cur.mn; nxt.mx = cur.mx;
-    static thread_local WqSetIndex index;
-    // An edge joins a path when its last node is the path's first or its first node is the path's last (hasintersect_terminal).
-    // The reference scans every edge for every path (src/events.jl:242-243); here the edges are grouped by first and by last node
-    // once (an edge set never changes during the reduction) and a path visits its two groups merged in ascending edge order, which
-    // is the order the scan would have met them in.
+#ifdef WQ_EV_PROF
+    const unsigned long long t_enter = __rdtsc();
+#endif
+    WqPathSet nxt;
+    nxt.mn = edges.mn; nxt.mx = edges.mx;
     const size_t E = edges.size();
-    static thread_local std::vector<uint32_t> ef, el, by_first, by_last, off_first, off_last, cand;
-    ef.resize(E); el.resize(E);
+    if (E == 0) return nxt;
+    struct Scratch {
+        std::vector<uint32_t> ef, el, by_first, by_last, off_first, off_last, cf, cl;
+        std::vector<uint64_t> ew, cs, ns;            // edge sets, current paths, next paths: nw words each
+        std::vector<double> clen, ccnt, nlen, ncnt;
+        std::vector<uint32_t> tab;                   // 0 = empty, else 1 + index of a set in ns
+    };
+    static thread_local Scratch* scratch = nullptr;  // one TLS lookup per call (every access to a thread_local of a shared library is a call)
+    if (!scratch) scratch = new Scratch();
+    Scratch& S = *scratch;
+    const uint32_t nw = edges.nodes[0].nw, wlo = edges.nodes[0].lo;
+    for (size_t j = 0; j < E; j++)
+        if (edges.nodes[j].nw != nw || edges.nodes[j].lo != wlo) { nxt = edges; return nxt; }       // cannot happen: one window per event
+    S.ef.resize(E); S.el.resize(E); S.ew.resize(E * nw);
     uint32_t lo = 0xFFFFFFFFu, hi = 0;
-    for (size_t j = 0; j < E; j++) { ef[j] = edges.nodes[j].first(); el[j] = edges.nodes[j].last(); lo = std::min(lo, ef[j]); hi = std::max(hi, el[j]); }
-    const uint32_t span = E ? hi - lo + 1 : 0;
-    off_first.assign(span + 1, 0); off_last.assign(span + 1, 0);
-    for (size_t j = 0; j < E; j++) { off_first[ef[j] - lo + 1]++; off_last[el[j] - lo + 1]++; }
-    for (uint32_t k = 0; k < span; k++) { off_first[k + 1] += off_first[k]; off_last[k + 1] += off_last[k]; }
-    by_first.resize(E); by_last.resize(E);
-    {
-        std::vector<uint32_t> cf(off_first.begin(), off_first.end() - (span ? 1 : 0)), cl(off_last.begin(), off_last.end() - (span ? 1 : 0));
-        for (size_t j = 0; j < E; j++) { by_first[cf[ef[j] - lo]++] = (uint32_t)j; by_last[cl[el[j] - lo]++] = (uint32_t)j; }     // ascending j inside a group
+    for (size_t j = 0; j < E; j++) {
+        const uint64_t* w = edges.nodes[j].p();
+        for (uint32_t k = 0; k < nw; k++) S.ew[j * nw + k] = w[k];
+        S.ef[j] = edges.nodes[j].first(); S.el[j] = edges.nodes[j].last();
+        lo = std::min(lo, S.ef[j]); hi = std::max(hi, S.el[j]);
     }
+    const uint32_t span = hi - lo + 1;
+    S.off_first.assign(span + 1, 0); S.off_last.assign(span + 1, 0);
+    for (size_t j = 0; j < E; j++) { S.off_first[S.ef[j] - lo + 1]++; S.off_last[S.el[j] - lo + 1]++; }
+    for (uint32_t k = 0; k < span; k++) { S.off_first[k + 1] += S.off_first[k]; S.off_last[k + 1] += S.off_last[k]; }
+    S.by_first.resize(E); S.by_last.resize(E);
+    S.cf.assign(S.off_first.begin(), S.off_first.end() - 1); S.cl.assign(S.off_last.begin(), S.off_last.end() - 1);
+    for (size_t j = 0; j < E; j++) { S.by_first[S.cf[S.ef[j] - lo]++] = (uint32_t)j; S.by_last[S.cl[S.el[j] - lo]++] = (uint32_t)j; }     // ascending j inside a group
     WQ_EVC(0, 1);
+#ifdef WQ_EV_PROF
+    const unsigned long long t_pre = __rdtsc();
+    wq_evc[6] += t_pre - t_enter;
+#endif
+    S.cs.assign(S.ew.begin(), S.ew.end());
+    S.clen.assign(edges.length.begin(), edges.length.end()); S.ccnt.assign(edges.count.begin(), edges.count.end());
+    S.ns.clear(); S.nlen.clear(); S.ncnt.clear();
+    uint32_t nmn = edges.mn, nmx = edges.mx;
+    size_t used = 0;
+    auto hash = [nw](const uint64_t* w) -> uint64_t {
+        uint64_t h = 0x9E3779B97F4A7C15ull;
+        for (uint32_t k = 0; k < nw; k++) { h ^= w[k]; h *= 0xFF51AFD7ED558CCDull; h ^= h >> 31; }
+        return h;
+    };
+    auto place = [&](uint32_t idx1) { const size_t mask = S.tab.size() - 1; size_t h = (size_t)hash(&S.ns[(size_t)(idx1 - 1) * nw]) & mask; while (S.tab[h]) h = (h + 1) & mask; S.tab[h] = idx1; };
+    // the candidate set sits at the tail of ns (index `at`): true when an equal set is already there, else it stays and is indexed
+    auto seen_or_keep = [&](size_t at) -> bool {
+        if (2 * (used + 1) > S.tab.size()) {            // grow, re-inserting what is there
+            S.tab.assign(S.tab.size() * 2, 0);
+            for (size_t i = 0; i < at; i++) place((uint32_t)i + 1);
+        }
+        const uint64_t* w = &S.ns[at * nw];
+        const size_t mask = S.tab.size() - 1;
+        size_t h = (size_t)hash(w) & mask;
+        while (S.tab[h]) {
+            const uint64_t* o = &S.ns[(size_t)(S.tab[h] - 1) * nw];
+            bool eq = true;
+            for (uint32_t k = 0; k < nw && eq; k++) eq = o[k] == w[k];
+            if (eq) return true;
+            h = (h + 1) & mask;
+        }
+        S.tab[h] = (uint32_t)at + 1;
+        used++;
+        return false;
+    };
+    auto first_of = [&](const uint64_t* w) -> uint32_t { for (uint32_t k = 0; k < nw; k++) if (w[k]) return wlo + 64 * k + (uint32_t)__builtin_ctzll(w[k]); return 0; };
+    auto last_of = [&](const uint64_t* w) -> uint32_t { for (uint32_t k = nw; k-- > 0;) if (w[k]) return wlo + 64 * k + 63 - (uint32_t)__builtin_clzll(w[k]); return 0; };
     for (int it = 1; it <= 100; it++) {
         WQ_EVC(1, 1);
         if (it > 1) {
-            if (nxt.nodes == cur.nodes) break;
-            std::swap(cur, nxt);
-            nxt.nodes.clear(); nxt.count.clear(); nxt.length.clear();
-            WQ_EVC_MAX(3, cur.size());
-            if (cur.size() > 1024) { subsampled = true; cur.nodes.resize(1024); cur.count.resize(1024); cur.length.resize(1024); }
+            if (S.ns == S.cs) break;
+            S.cs.swap(S.ns); S.clen.swap(S.nlen); S.ccnt.swap(S.ncnt);
+            S.ns.clear(); S.nlen.clear(); S.ncnt.clear();
+            WQ_EVC_MAX(3, S.clen.size());
+            if (S.clen.size() > 1024) { subsampled = true; S.cs.resize((size_t)1024 * nw); S.clen.resize(1024); S.ccnt.resize(1024); }
         }
-        index.reset(cur.size());
-        for (size_t i = 0; i < cur.size(); i++) {
-            const uint32_t fi = cur.nodes[i].first(), li = cur.nodes[i].last();
+        const size_t ncur = S.clen.size();
+        {
+            size_t cap = 64;
+            while (cap < 8 * ncur + 32) cap <<= 1;
+            S.tab.assign(cap, 0);
+            used = 0;
+        }
+        for (size_t i = 0; i < ncur; i++) {
+            const uint64_t* w = &S.cs[i * nw];
+            const uint32_t fi = first_of(w), li = last_of(w);
             // edges with last == fi, merged with edges with first == li, ascending, without duplicates
-            cand.clear();
-            {
-                const uint32_t *a = nullptr, *ae = nullptr, *b = nullptr, *be = nullptr;
-                if (fi >= lo && fi <= hi) { a = by_last.data() + off_last[fi - lo]; ae = by_last.data() + off_last[fi - lo + 1]; }
-                if (li >= lo && li <= hi) { b = by_first.data() + off_first[li - lo]; be = by_first.data() + off_first[li - lo + 1]; }
-                while (a != ae || b != be) {
-                    uint32_t j;
-                    if (b == be || (a != ae && *a <= *b)) { j = *a++; if (b != be && *b == j) b++; }
-                    else j = *b++;
-                    cand.push_back(j);
-                }
-            }
+            const uint32_t *a = nullptr, *ae = nullptr, *b = nullptr, *be = nullptr;
+            if (fi >= lo && fi <= hi) { a = S.by_last.data() + S.off_last[fi - lo]; ae = S.by_last.data() + S.off_last[fi - lo + 1]; }
+            if (li >= lo && li <= hi) { b = S.by_first.data() + S.off_first[li - lo]; be = S.by_first.data() + S.off_first[li - lo + 1]; }
+            const bool none = a == ae && b == be;
             WQ_EVC(4, 1);
-            for (const uint32_t j : cand) {
+            while (a != ae || b != be) {
+                uint32_t j;
+                if (b == be || (a != ae && *a <= *b)) { j = *a++; if (b != be && *b == j) b++; }
+                else j = *b++;
                 WQ_EVC(2, 1);
-                const uint32_t fj = ef[j], lj = el[j];
-                WqBitWin u = cur.nodes[i];
-                u.unite(edges.nodes[j]);
-                if (index.find_or_add(nxt.nodes, u, nxt.nodes.size()) >= 0) continue;
-                nxt.nodes.push_back(u);
-                nxt.length.push_back(cur.length[i] + edges.length[j]);
-                nxt.count.push_back(cur.count[i] + edges.count[j]);
-                nxt.mn = std::min(std::min(fi, fj), nxt.mn);
-                nxt.mx = std::max(std::max(li, lj), nxt.mx);
+                const size_t at = S.nlen.size();
+                S.ns.resize((at + 1) * nw);
+                w = &S.cs[i * nw];
+                for (uint32_t k = 0; k < nw; k++) S.ns[at * nw + k] = w[k] | S.ew[(size_t)j * nw + k];
+                if (seen_or_keep(at)) { S.ns.resize(at * nw); continue; }
+                S.nlen.push_back(S.clen[i] + edges.length[j]);
+                S.ncnt.push_back(S.ccnt[i] + edges.count[j]);
+                nmn = std::min(std::min(fi, S.ef[j]), nmn);
+                nmx = std::max(std::max(li, S.el[j]), nmx);
             }
-            if (cand.empty() && index.find_or_add(nxt.nodes, cur.nodes[i], nxt.nodes.size()) < 0) {
-                nxt.nodes.push_back(cur.nodes[i]);
-                nxt.length.push_back(cur.length[i]);
-                nxt.count.push_back(cur.count[i]);
-                nxt.mn = std::min(fi, nxt.mn);
-                nxt.mx = std::max(li, nxt.mx);
+            if (none) {
+                const size_t at = S.nlen.size();
+                S.ns.resize((at + 1) * nw);
+                w = &S.cs[i * nw];
+                for (uint32_t k = 0; k < nw; k++) S.ns[at * nw + k] = w[k];
+                if (seen_or_keep(at)) { S.ns.resize(at * nw); continue; }
+                S.nlen.push_back(S.clen[i]);
+                S.ncnt.push_back(S.ccnt[i]);
+                nmn = std::min(fi, nmn);
+                nmx = std::max(li, nmx);
             }
         }
     }
+#ifdef WQ_EV_PROF
+    wq_evc[7] += __rdtsc() - t_pre;
+#endif
+    nxt.mn = nmn; nxt.mx = nmx;
+    const size_t nout = S.nlen.size();
+    nxt.nodes.resize(nout);
+    for (size_t i = 0; i < nout; i++) {
+        WqBitWin& s = nxt.nodes[i];
+        s.lo = wlo; s.nw = nw;
+        if (nw > WQ_WIN_INLINE) s.big.assign(S.ns.begin() + i * nw, S.ns.begin() + (i + 1) * nw);
+        else for (uint32_t k = 0; k < nw; k++) s.in[k] = S.ns[i * nw + k];
+    }
+    nxt.count.assign(S.ncnt.begin(), S.ncnt.end());
+    nxt.length.assign(S.nlen.begin(), S.nlen.end());
     return nxt;
 }
 struct WqGeneEvents {
