@@ -773,8 +773,12 @@ def main():
         dom = max(kt, key=lambda k: kt[k])           # the longest SINGLE kernel of the step
         traffic = None
         try:    # dram__bytes_read + write per launch of that kernel from the committed ncu --set full capture of this round, if any
+            # (captured at `reads_per_alignment_launch` reads; the alignment kernels' traffic grows with the reads of the launch)
             tr = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")))
-            traffic = tr.get(dom, {}).get("dram_bytes_per_launch")
+            k = tr["kernels"].get(dom) or tr["kernels"].get(dom + "_smem")
+            if k and a.config == 2 and mp.mate is None:
+                scale = mp.n / float(tr["reads_per_alignment_launch"]) if dom in ("wq_k_seed", "wq_k_extend", "wq_k_resolve") else 1.0
+                traffic = (k["dram_bytes_read"] + k["dram_bytes_write"]) * scale
         except Exception:
             pass
         align_ms = float(kms.sum())

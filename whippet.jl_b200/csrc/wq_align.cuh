@@ -776,12 +776,20 @@ WQ_HD void wq_align_at(WqCtx& c, int64_t indx, int readloc, bool ispos, uint32_t
     c.isvalid = 0;
     c.strand = ispos ? 1 : 0;
     c.depth = 0;
+#ifdef WQ_TOP_NESTED
+    wq_fwd_extend_nested(c, sgidx + 1, readloc + 1, offset_node);
+#else
     wq_fwd_extend<true>(c, sgidx + 1, readloc + 1, offset_node);
+#endif
     if (c.overflow) return;
     // the reverse extension grows the path at its front: move it to the end of the buffer once, so that a push at the
     // front is a store below `lo` instead of a shift of every node
     const int k = c.hi;
     for (int i = k - 1; i >= 0; i--) c.path[(c.pcap - k + i) * c.pstride] = c.path[i * c.pstride];
     c.lo = c.pcap - k; c.hi = c.pcap;
+#ifdef WQ_TOP_NESTED
+    wq_rev_extend_nested(c, sgidx, readloc, offset_node);
+#else
     wq_rev_extend<true>(c, sgidx, readloc, offset_node);
+#endif
 }
