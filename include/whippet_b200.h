@@ -75,10 +75,13 @@ typedef struct wq_align_param {
     uint8_t _pad2[3];
 } wq_align_param;
 
-/* A batch of FASTQRecords after `fill!` (src/record.jl:13-19): 2-bit sequence + phred bytes. */
+/* A batch of FASTQRecords after `fill!` (src/record.jl:13-19): 2-bit sequence + phred bytes.
+ * fixed_len = 0: seq_off / qual_off give the position of every read.  fixed_len = L > 0 (a batch of equal-capacity records, the usual
+ * case for Illumina runs): read i starts at word i * ceil(L / 32) of seq2 and at byte i * ((L + 3) & ~3) of qual, len[i] <= L, and
+ * seq_off / qual_off may be NULL -- the 16 bytes per read of offsets then never cross PCIe (the device derives them). */
 typedef struct wq_read_batch {
     uint32_t        n_reads;
-    uint32_t        _pad;
+    uint32_t        fixed_len;
     const uint8_t*  len;        /* [n]   read length (ReadLengthInt = UInt8, src/align.jl:74) */
     const uint64_t* seq_off;    /* [n]   first 64-bit word of read i inside seq2 */
     const uint64_t* seq2;       /* 2-bit codes A=0 C=1 G=2 T=3, 32 per word, base j at bits 2*(j%32) */

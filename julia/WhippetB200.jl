@@ -26,7 +26,7 @@ struct AlignParamC          # wq_align_param (AlignParam, src/align.jl:2-19)
 end
 
 struct ReadBatch            # wq_read_batch
-   n_reads::UInt32; _pad::UInt32
+   n_reads::UInt32; fixed_len::UInt32      # fixed_len = L > 0: read i at word i * cld(L, 32) / quality byte i * ((L + 3) & ~3); offsets may be C_NULL
    len::Ptr{UInt8}; seq_off::Ptr{UInt64}; seq2::Ptr{UInt64}; seq2_words::UInt64
    qual_off::Ptr{UInt64}; qual::Ptr{UInt8}; qual_bytes::UInt64
 end

@@ -3,6 +3,7 @@
 text, path-capacity overflow and its reporting, the second-pass extension kernel (long paths, parked candidates), the
 seed_tolerate bound, events beyond 1024 paths, the stale iset of the paired assign_ambig!, the running mean_readlen, and the
 all-or-nothing re-run of a chunk whose path pool was too small."""
+import ctypes as C
 import os
 
 import numpy as np
@@ -136,4 +137,50 @@ def test_path_pool_regrows_without_double_counting():
         os.environ.pop("WQ_POOL_NODES_PER_READ", None)
     o = Oracle(idx)
     full_pipeline_parity(q, o, wq.AlignParam(), rb, readlen=101)
+    q.close()
+
+
+@pytest.mark.gpu
+def test_fixed_len_batches_equal_offset_batches(monkeypatch):
+    """wq_read_batch.fixed_len: a batch handed over without its offset arrays (the device derives them) gives the same alignments, counts
+    and SAM text as the same reads with explicit offsets -- single end with ragged lengths below the capacity, paired end, several chunks
+    per call (the chunked H2D path computes its slices from the strides) and the one-chunk path."""
+    from data_gen import pe_case
+    from helpers_cmp import results_equal
+    from wq_inputs import synth
+    idx, p, f, r = pe_case(8, 200, 101, 5000, True, 30000)
+    rng = np.random.default_rng(4)
+    rag = synth.simulate_reads(idx, 30000, 101, seed=12, lens=rng.integers(37, 102, 30000))
+    idx.gene_strand = rng.integers(0, 2, idx.n_genes).astype("u1")
+    idx.gene_seqname = [f"chr{int(x)}" for x in rng.integers(1, 4, idx.n_genes)]
+    for chunk in ("7000", "4194304"):
+        monkeypatch.setenv("WQ_CHUNK_READS", chunk)
+        a, b = wq.GraphLibQuant(idx), wq.GraphLibQuant(idx)
+        for q in (a, b):
+            q.set_gene_info(idx.gene_seqname, idx.gene_strand)
+        fx = rag.to_fixed()
+        assert fx is not None and fx.c().fixed_len == 101 and not fx.c().seq_off and not fx.c().qual_off
+        ra, rb_ = a.ungapped_align(wq.AlignParam(), rag), b.ungapped_align(wq.AlignParam(), fx)
+        assert results_equal(ra, rb_, rag.n) == []
+        names = [f"r{i}" for i in range(rag.n)]
+        assert a.sam_batch(rag, names, ra) == b.sam_batch(fx, names, rb_)
+        a.reset(); b.reset()
+        a.process_reads(wq.AlignParam(), rag); b.process_reads(wq.AlignParam(), fx)
+        for x, y in zip(a.counts(), b.counts()):
+            assert np.array_equal(x, y)
+        assert a.keyed(0) == b.keyed(0) and a.keyed(1) == b.keyed(1)
+        a.reset(); b.reset()
+        ff, rr = f.to_fixed(), r.to_fixed()
+        sa, sb = a.process_paired_reads(p, f, r), b.process_paired_reads(p, ff, rr)
+        assert (sa.total, sa.mapped, sa.multi, sa.sum_readlen) == (sb.total, sb.mapped, sb.multi, sb.sum_readlen) and sa.mapped > 1000
+        for x, y in zip(a.counts(), b.counts()):
+            assert np.array_equal(x, y)
+        assert a.keyed(0) == b.keyed(0) and a.keyed(1) == b.keyed(1)
+        a.close(); b.close()
+    from whippet_jl_b200 import lib
+    bad = fx.c()
+    bad.seq2_words = 10                                            # smaller than n_reads strides: refused before anything is read
+    q = wq.GraphLibQuant(idx)
+    with pytest.raises(lib.WhippetB200Error, match="fixed_len"):
+        lib.check(q.L.wq_align_se(q.h, C.byref(wq.AlignParam().c()), C.byref(bad), None))
     q.close()

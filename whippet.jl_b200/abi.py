@@ -41,7 +41,7 @@ class AlignParamC(C.Structure):
 
 class ReadBatchC(C.Structure):
     _fields_ = [
-        ("n_reads", C.c_uint32), ("_pad", C.c_uint32),
+        ("n_reads", C.c_uint32), ("fixed_len", C.c_uint32),
         ("len", u8p), ("seq_off", u64p), ("seq2", u64p), ("seq2_words", C.c_uint64),
         ("qual_off", u64p), ("qual", u8p), ("qual_bytes", C.c_uint64),
     ]

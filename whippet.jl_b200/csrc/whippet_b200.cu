@@ -974,7 +974,13 @@ static int run_chunk(wq_handle* h, const WqParams& p, const WqBatchDev& b, const
 
 static int check_batch(const wq_read_batch* r) {
     if (!r) return fail(-1, "null read batch");
-    if (r->n_reads && (!r->len || !r->seq_off || !r->seq2 || !r->qual_off || !r->qual)) return fail(-1, "read batch has null arrays");
+    if (r->n_reads && (!r->len || !r->seq2 || !r->qual)) return fail(-1, "read batch has null arrays");
+    if (r->n_reads && r->fixed_len == 0 && (!r->seq_off || !r->qual_off)) return fail(-1, "read batch has null offset arrays (allowed only with fixed_len)");
+    if (r->fixed_len > 255) return fail(-1, "wq_read_batch.fixed_len must be at most 255 (ReadLengthInt = UInt8)");
+    if (r->n_reads && r->fixed_len) {
+        const uint64_t ws = (r->fixed_len + 31) / 32, qs = (r->fixed_len + 3) & ~3u;
+        if ((uint64_t)r->n_reads * ws > r->seq2_words || (uint64_t)r->n_reads * qs > r->qual_bytes) return fail(-1, "fixed_len batch: seq2_words / qual_bytes smaller than n_reads strides");
+    }
     return 0;
 }
 
@@ -1061,13 +1067,34 @@ static int collect_chunk(wq_handle* h, uint32_t first, uint32_t n, bool pe, wq_a
 
 struct BatchOnDev { DevBuf<uint8_t>* len; DevBuf<uint64_t>* seqoff; DevBuf<uint64_t>* seq2; DevBuf<uint64_t>* qualoff; DevBuf<uint8_t>* qual; };
 
+// position of read i of a batch (explicit offsets, or the strides of a fixed_len batch)
+static inline uint64_t batch_soff(const wq_read_batch* r, uint64_t i) { return r->fixed_len ? i * ((r->fixed_len + 31) / 32) : r->seq_off[i]; }
+static inline uint64_t batch_qoff(const wq_read_batch* r, uint64_t i) { return r->fixed_len ? i * ((r->fixed_len + 3) & ~3u) : r->qual_off[i]; }
+// offsets of reads [lo, hi) of a fixed_len batch, written on the device instead of copied from the host
+__global__ void wq_k_fill_offsets(uint64_t* seq_off, uint64_t* qual_off, uint32_t lo, uint32_t hi, uint32_t wstride, uint32_t qstride) {
+    for (uint64_t i = lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (uint64_t)gridDim.x * blockDim.x) {
+        seq_off[i] = i * wstride;
+        qual_off[i] = i * qstride;
+    }
+}
+static int put_offsets(wq_handle* h, const wq_read_batch* r, int which, uint32_t lo, uint32_t hi, cudaStream_t s) {
+    if (r->fixed_len) {
+        wq_k_fill_offsets<<<296, 256, 0, s>>>(h->d_seqoff[which].p, h->d_qualoff[which].p, lo, hi, (r->fixed_len + 31) / 32, (r->fixed_len + 3) & ~3u);
+        h->launches += 1;
+        CK(cudaGetLastError());
+    } else {
+        CK(cudaMemcpyAsync(h->d_seqoff[which].p + lo, r->seq_off + lo, (hi - lo) * 8ull, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(h->d_qualoff[which].p + lo, r->qual_off + lo, (hi - lo) * 8ull, cudaMemcpyHostToDevice, s));
+    }
+    return 0;
+}
+
 static int upload_batch(wq_handle* h, const wq_read_batch* reads, int which, cudaStream_t s) {
     const uint32_t n = reads->n_reads;
     CK(h->d_len[which].ensure(n)); CK(h->d_seqoff[which].ensure(n)); CK(h->d_qualoff[which].ensure(n));
     CK(h->d_seq2[which].ensure(reads->seq2_words + 2)); CK(h->d_qual[which].ensure(reads->qual_bytes + 16));
     CK(cudaMemcpyAsync(h->d_len[which].p, reads->len, n, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(h->d_seqoff[which].p, reads->seq_off, n * 8ull, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(h->d_qualoff[which].p, reads->qual_off, n * 8ull, cudaMemcpyHostToDevice, s));
+    if (int rc = put_offsets(h, reads, which, 0, n, s)) return rc;
     CK(cudaMemcpyAsync(h->d_seq2[which].p, reads->seq2, reads->seq2_words * 8ull, cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(h->d_qual[which].p, reads->qual, reads->qual_bytes, cudaMemcpyHostToDevice, s));
     return 0;
@@ -1099,8 +1126,13 @@ static int align_impl(wq_handle* h, const wq_align_param* ap, const wq_read_batc
     const uint32_t nchunks = (n + h->chunk_reads - 1) / h->chunk_reads;
     std::vector<cudaEvent_t> copied;
     if (on_device) {
-        for (int m = 0; m < nb; m++)
-            base[m] = WqBatchDev{n, src[m]->len, src[m]->seq_off, src[m]->seq2, src[m]->qual_off, src[m]->qual};
+        for (int m = 0; m < nb; m++) {
+            if (src[m]->fixed_len && (!src[m]->seq_off || !src[m]->qual_off)) {       // device-resident fixed_len batch without offsets: derive them
+                CK(h->d_seqoff[m].ensure(n)); CK(h->d_qualoff[m].ensure(n));
+                if (int rc = put_offsets(h, src[m], m, 0, n, h->stream)) return rc;
+                base[m] = WqBatchDev{n, src[m]->len, h->d_seqoff[m].p, src[m]->seq2, h->d_qualoff[m].p, src[m]->qual};
+            } else base[m] = WqBatchDev{n, src[m]->len, src[m]->seq_off, src[m]->seq2, src[m]->qual_off, src[m]->qual};
+        }
     } else {
         // Host buffers.  The packed arrays of chunk c+1 cross PCIe on the copy stream while chunk c is being
         // aligned: every chunk's slices are enqueued up front (async when the caller's buffers are page-locked,
@@ -1110,8 +1142,8 @@ static int align_impl(wq_handle* h, const wq_align_param* ap, const wq_read_batc
         for (int m = 0; m < nb && ascending; m++)
             for (uint32_t lo = 0; lo < n; lo += h->chunk_reads) {
                 uint32_t hi = std::min(n, lo + h->chunk_reads);
-                uint64_t s0 = src[m]->seq_off[lo], s1 = hi < n ? src[m]->seq_off[hi] : src[m]->seq2_words;
-                uint64_t q0 = src[m]->qual_off[lo], q1 = hi < n ? src[m]->qual_off[hi] : src[m]->qual_bytes;
+                uint64_t s0 = batch_soff(src[m], lo), s1 = hi < n ? batch_soff(src[m], hi) : src[m]->seq2_words;
+                uint64_t q0 = batch_qoff(src[m], lo), q1 = hi < n ? batch_qoff(src[m], hi) : src[m]->qual_bytes;
                 if (s1 < s0 || q1 < q0 || s1 > src[m]->seq2_words || q1 > src[m]->qual_bytes) { ascending = false; break; }
             }
         for (int m = 0; m < nb; m++) {
@@ -1129,11 +1161,10 @@ static int align_impl(wq_handle* h, const wq_align_param* ap, const wq_read_batc
                 uint32_t lo = c * h->chunk_reads, hi = std::min(n, lo + h->chunk_reads);
                 for (int m = 0; m < nb; m++) {
                     const wq_read_batch* r = src[m];
-                    uint64_t s0 = r->seq_off[lo], s1 = hi < n ? r->seq_off[hi] : r->seq2_words;
-                    uint64_t q0 = r->qual_off[lo], q1 = hi < n ? r->qual_off[hi] : r->qual_bytes;
+                    uint64_t s0 = batch_soff(r, lo), s1 = hi < n ? batch_soff(r, hi) : r->seq2_words;
+                    uint64_t q0 = batch_qoff(r, lo), q1 = hi < n ? batch_qoff(r, hi) : r->qual_bytes;
                     CK(cudaMemcpyAsync(h->d_len[m].p + lo, r->len + lo, hi - lo, cudaMemcpyHostToDevice, cs));
-                    CK(cudaMemcpyAsync(h->d_seqoff[m].p + lo, r->seq_off + lo, (hi - lo) * 8ull, cudaMemcpyHostToDevice, cs));
-                    CK(cudaMemcpyAsync(h->d_qualoff[m].p + lo, r->qual_off + lo, (hi - lo) * 8ull, cudaMemcpyHostToDevice, cs));
+                    if (int rc = put_offsets(h, r, m, lo, hi, cs)) return rc;
                     CK(cudaMemcpyAsync(h->d_seq2[m].p + s0, r->seq2 + s0, (s1 - s0) * 8ull, cudaMemcpyHostToDevice, cs));
                     CK(cudaMemcpyAsync(h->d_qual[m].p + q0, r->qual + q0, q1 - q0, cudaMemcpyHostToDevice, cs));
                 }

@@ -28,10 +28,15 @@ struct WqSamRead {                        // FASTQRecord as write_sam sees it (a
     // base j (0-based) of the current orientation, as a 2-bit code
     uint8_t code(uint32_t j, bool rc) const {
         const uint32_t L = len(), k = rc ? L - 1 - j : j;
-        const uint8_t c = (uint8_t)((b->seq2[b->seq_off[i] + (k >> 5)] >> (2 * (k & 31))) & 3);
+        const uint64_t so = b->fixed_len ? (uint64_t)i * ((b->fixed_len + 31) / 32) : b->seq_off[i];
+        const uint8_t c = (uint8_t)((b->seq2[so + (k >> 5)] >> (2 * (k & 31))) & 3);
         return rc ? (uint8_t)(3 - c) : c;
     }
-    uint8_t qual(uint32_t j, bool rc) const { const uint32_t L = len(); return b->qual[b->qual_off[i] + (rc ? L - 1 - j : j)]; }
+    uint8_t qual(uint32_t j, bool rc) const {
+        const uint32_t L = len();
+        const uint64_t qo = b->fixed_len ? (uint64_t)i * ((b->fixed_len + 3) & ~3u) : b->qual_off[i];
+        return b->qual[qo + (rc ? L - 1 - j : j)];
+    }
 };
 
 static inline void wq_sam_uint(std::string& o, uint64_t v) { char t[24]; int n = snprintf(t, sizeof t, "%llu", (unsigned long long)v); o.append(t, (size_t)n); }

@@ -270,16 +270,59 @@ class ReadBatch:
             lens[i] = len(s)
         return cls.from_codes(codes, q, lens)
 
-    def c(self) -> abi.ReadBatchC:
+    def fixed_stride(self):
+        """L when every read sits at the strides of a fixed_len = L batch (read i at word i * ceil(L / 32) and quality byte
+        i * ((L + 3) & ~3)), i.e. when the offsets need not be handed over; 0 otherwise."""
+        if self.n == 0:
+            return 0
+        L = int(self.len.max())
+        i = np.arange(self.n, dtype=np.uint64)
+        ok = L > 0 and np.array_equal(self.seq_off, i * np.uint64((L + 31) // 32)) and np.array_equal(self.qual_off, i * np.uint64((L + 3) & ~3))
+        return L if ok else 0
+
+    def to_fixed(self):
+        """The same reads in the fixed_len layout (rows of ceil(L / 32) words and (L + 3) & ~3 quality bytes, L = the longest read), or
+        None when the batch is not stored at constant strides already (e.g. ragged FASTQ input)."""
+        n = self.n
+        if n == 0:
+            return None
+        L = int(self.len.max())
+        ws, qs = (L + 31) // 32, (L + 3) & ~3
+        if n > 1:
+            sw, sq = int(self.seq_off[1] - self.seq_off[0]), int(self.qual_off[1] - self.qual_off[0])
+            i = np.arange(n, dtype=np.uint64)
+            if sw < ws or sq < L or not (np.array_equal(self.seq_off, self.seq_off[0] + i * np.uint64(sw))
+                                         and np.array_equal(self.qual_off, self.qual_off[0] + i * np.uint64(sq))):
+                return None
+        else:
+            sw, sq = ws, max(qs, L)
+        s0, q0 = int(self.seq_off[0]), int(self.qual_off[0])
+        seq = np.ascontiguousarray(np.lib.stride_tricks.as_strided(self.seq2[s0:], (n, ws), (8 * sw, 8)))
+        qual = np.zeros((n, qs), "u1")
+        src = np.lib.stride_tricks.as_strided(self.qual[q0:], (n, min(qs, sq)), (sq, 1))
+        qual[:, :src.shape[1]] = src
+        if qs > L:                                             # padding bytes beyond the longest read are zero, as every packer leaves them
+            qual[:, L:] = 0
+        i = np.arange(n, dtype=np.uint64)
+        out = ReadBatch(self.len, i * np.uint64(ws), seq.reshape(-1), i * np.uint64(qs), qual.reshape(-1))
+        out.prefer_fixed = True                                # c() then hands the batch over without its offset arrays
+        return out
+
+    def c(self, fixed_len: int = 0) -> abi.ReadBatchC:
+        """The C struct.  fixed_len = L > 0 (see fixed_stride) leaves seq_off / qual_off NULL: the library derives them on the device."""
+        if not fixed_len and getattr(self, "prefer_fixed", False):
+            fixed_len = self.fixed_stride()
         b = abi.ReadBatchC()
         b.n_reads = self.n
+        b.fixed_len = int(fixed_len)
         b.len = abi.ptr(self.len, abi.u8p)
-        b.seq_off = abi.ptr(self.seq_off, abi.u64p)
         b.seq2 = abi.ptr(self.seq2, abi.u64p)
         b.seq2_words = len(self.seq2)
-        b.qual_off = abi.ptr(self.qual_off, abi.u64p)
         b.qual = abi.ptr(self.qual, abi.u8p)
         b.qual_bytes = len(self.qual)
+        if not fixed_len:
+            b.seq_off = abi.ptr(self.seq_off, abi.u64p)
+            b.qual_off = abi.ptr(self.qual_off, abi.u64p)
         b._keepalive = self
         return b
 
