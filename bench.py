@@ -364,8 +364,9 @@ class PartRun:
 
         def batch(rb, to, fixed):
             # fixed > 0: an equal-length batch at the strides of wq_read_batch.fixed_len; its offsets stay on the host (16 B per read less H2D)
+            q4 = getattr(rb, "qual4", None) if fixed else None         # 4-bit quality indices (binned qualities): half the quality bytes
             t = [to(rb.len), None if fixed else to(rb.seq_off.view(np.int64)), to(rb.seq2.view(np.int64)),
-                 None if fixed else to(rb.qual_off.view(np.int64)), to(rb.qual)]
+                 None if fixed else to(rb.qual_off.view(np.int64)), to(rb.qual if q4 is None else q4)]
             self.keep.append(t)
             b = abi.ReadBatchC()
             b.n_reads = rb.n
@@ -374,7 +375,11 @@ class PartRun:
             b.seq2 = C.cast(t[2].data_ptr(), abi.u64p)
             b.seq2_words = len(rb.seq2)
             b.qual = C.cast(t[4].data_ptr(), abi.u8p)
-            b.qual_bytes = len(rb.qual)
+            b.qual_bytes = len(rb.qual) if q4 is None else len(q4)
+            if q4 is not None:
+                b.qual_bits = 4
+                for k in range(16):
+                    b.qual_dict[k] = int(rb.qual_dict[k])
             if not fixed:
                 b.seq_off = C.cast(t[1].data_ptr(), abi.u64p)
                 b.qual_off = C.cast(t[3].data_ptr(), abi.u64p)
@@ -384,11 +389,14 @@ class PartRun:
         rbs = [part.reads] + ([part.mate] if part.mate is not None else [])
         self.dev = [batch(rb, on_dev, 0) for rb in rbs]
         # the host-side (e2e) copies: equal-capacity batches go in the fixed_len layout of the ABI (no offset arrays, quality rows padded to 4)
-        hrbs = [rb.to_fixed() or rb for rb in rbs]
+        hrbs = [rb.to_fixed(pack_qual=True) or rb for rb in rbs]
         fixed = [rb.fixed_stride() for rb in hrbs]
         self.fixed_len = fixed
         self.host = [batch(rb, pinned, f) for rb, f in zip(hrbs, fixed)]
-        self.h2d = int(sum(rb.len.nbytes + rb.seq2.nbytes + rb.qual.nbytes + (0 if f else rb.seq_off.nbytes + rb.qual_off.nbytes) for rb, f in zip(hrbs, fixed)))
+        qbytes = lambda rb, f: rb.qual4.nbytes if f and getattr(rb, "qual4", None) is not None else rb.qual.nbytes
+        self.h2d = int(sum(rb.len.nbytes + rb.seq2.nbytes + qbytes(rb, f) + (0 if f else rb.seq_off.nbytes + rb.qual_off.nbytes) for rb, f in zip(hrbs, fixed)))
+        self.layout = [("fixed_len %d rows without offset arrays" % f + (", qualities as 4-bit dictionary indices" if getattr(rb, "qual4", None) is not None else ""))
+                       if f else "per-read offset arrays, phred bytes" for rb, f in zip(hrbs, fixed)]
         self.pc = part.param.c()
 
     def align(self, host):
@@ -750,7 +758,8 @@ def main():
                    f"{index_write_s:.2f} s, {index_file_bytes} bytes)", "index_create_s": index_create_s,
                    "parallelism": f"reads sharded over {world} GPU(s), index replicated" + (", dense counts all-reduced and sparse stores all-gathered over NCCL inside the library (wq_counts_sync), class building and event stage partitioned by gene (shares all-gathered), transcript EM replicated" if world > 1 else "")},
         "clocks": clocks, "gpu_launches": launches,
-        "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "host_batch_layout": sorted(set(x for r in runs for x in r.layout))},
         "kernel_ms": {"seed": float(kms[0]), "extend": float(kms[1]), "resolve": float(kms[2]),
                       "em_tpm": float(qms[0]), "em_psi_span": float(qms[1])},
         "phase_ms": phase_ms,

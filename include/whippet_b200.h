@@ -78,7 +78,11 @@ typedef struct wq_align_param {
 /* A batch of FASTQRecords after `fill!` (src/record.jl:13-19): 2-bit sequence + phred bytes.
  * fixed_len = 0: seq_off / qual_off give the position of every read.  fixed_len = L > 0 (a batch of equal-capacity records, the usual
  * case for Illumina runs): read i starts at word i * ceil(L / 32) of seq2 and at byte i * ((L + 3) & ~3) of qual, len[i] <= L, and
- * seq_off / qual_off may be NULL -- the 16 bytes per read of offsets then never cross PCIe (the device derives them). */
+ * seq_off / qual_off may be NULL -- the 16 bytes per read of offsets then never cross PCIe (the device derives them).
+ * qual_bits = 0 or 8: one phred byte per base.  qual_bits = 4 (fixed_len batches only): `qual` holds 4-bit indices into qual_dict, two per
+ * byte (base j of read i in byte i * ((ceil(L / 2) + 3) & ~3) + j / 2, even j in the low nibble) -- instruments that bin their qualities
+ * (4 or 8 distinct values per run) then move half the quality bytes; the device expands them to phred bytes before the kernels run, so
+ * every result is that of the expanded batch. */
 typedef struct wq_read_batch {
     uint32_t        n_reads;
     uint32_t        fixed_len;
@@ -89,6 +93,9 @@ typedef struct wq_read_batch {
     const uint64_t* qual_off;   /* [n]   first byte of read i inside qual */
     const uint8_t*  qual;       /* phred scores with the FASTQ offset already removed */
     uint64_t        qual_bytes;
+    uint8_t         qual_bits;  /* 0 / 8: bytes; 4: dictionary indices (see above) */
+    uint8_t         qual_dict[16];
+    uint8_t         _pad2[7];
 } wq_read_batch;
 
 /* SGAlignNode + SGAlignScore (src/align.jl:48-62). */

@@ -29,7 +29,10 @@ struct ReadBatch            # wq_read_batch
    n_reads::UInt32; fixed_len::UInt32      # fixed_len = L > 0: read i at word i * cld(L, 32) / quality byte i * ((L + 3) & ~3); offsets may be C_NULL
    len::Ptr{UInt8}; seq_off::Ptr{UInt64}; seq2::Ptr{UInt64}; seq2_words::UInt64
    qual_off::Ptr{UInt64}; qual::Ptr{UInt8}; qual_bytes::UInt64
+   qual_bits::UInt8; qual_dict::NTuple{16,UInt8}; _pad2::NTuple{7,UInt8}      # qual_bits = 4: two 4-bit indices into qual_dict per byte (fixed_len batches)
 end
+ReadBatch(n, fixed_len, len, seq_off, seq2, seq2_words, qual_off, qual, qual_bytes) =
+   ReadBatch(n, fixed_len, len, seq_off, seq2, seq2_words, qual_off, qual, qual_bytes, 0x00, ntuple(_ -> 0x00, 16), ntuple(_ -> 0x00, 7))
 
 struct AlignNode            # wq_align_node (SGAlignNode + SGAlignScore)
    gene::UInt32; node::UInt32; mistolerance::Float32; matches::UInt8; mismatches::UInt8; _pad::UInt16

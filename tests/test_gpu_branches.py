@@ -164,13 +164,20 @@ def test_fixed_len_batches_equal_offset_batches(monkeypatch):
         assert results_equal(ra, rb_, rag.n) == []
         names = [f"r{i}" for i in range(rag.n)]
         assert a.sam_batch(rag, names, ra) == b.sam_batch(fx, names, rb_)
+        # qualities as 4-bit dictionary indices (qual_bits = 4): expanded on the device, decoded by the SAM formatter
+        pk = rag.to_fixed(pack_qual=True)
+        assert pk.c().qual_bits == 4 and pk.c().qual_bytes == rag.n * 52 and sorted(set(pk.qual_dict[:2])) == [2, 40]
+        rc_ = b.ungapped_align(wq.AlignParam(), pk)
+        assert results_equal(ra, rc_, rag.n) == []
+        assert a.sam_batch(rag, names, ra) == b.sam_batch(pk, names, rc_)
         a.reset(); b.reset()
         a.process_reads(wq.AlignParam(), rag); b.process_reads(wq.AlignParam(), fx)
         for x, y in zip(a.counts(), b.counts()):
             assert np.array_equal(x, y)
         assert a.keyed(0) == b.keyed(0) and a.keyed(1) == b.keyed(1)
         a.reset(); b.reset()
-        ff, rr = f.to_fixed(), r.to_fixed()
+        ff, rr = f.to_fixed(pack_qual=True), r.to_fixed(pack_qual=True)
+        assert ff.c().qual_bits == 4
         sa, sb = a.process_paired_reads(p, f, r), b.process_paired_reads(p, ff, rr)
         assert (sa.total, sa.mapped, sa.multi, sa.sum_readlen) == (sb.total, sb.mapped, sb.multi, sb.sum_readlen) and sa.mapped > 1000
         for x, y in zip(a.counts(), b.counts()):

@@ -44,6 +44,7 @@ class ReadBatchC(C.Structure):
         ("n_reads", C.c_uint32), ("fixed_len", C.c_uint32),
         ("len", u8p), ("seq_off", u64p), ("seq2", u64p), ("seq2_words", C.c_uint64),
         ("qual_off", u64p), ("qual", u8p), ("qual_bytes", C.c_uint64),
+        ("qual_bits", C.c_uint8), ("qual_dict", C.c_uint8 * 16), ("_pad2", C.c_uint8 * 7),
     ]
 
 

@@ -63,6 +63,7 @@ struct DevBuf {
 // Events of one gene group.  Group 0 = genes that no multi-map class names: assign_ambig! cannot change their counts, so
 // their events are built on the host threads while the transcript EM kernel runs and their PSI EM launch overlaps
 // assign_ambig!.  Group 1 = the remaining genes, built after assign_ambig!.
+struct WqEvPiece { uint32_t g_lo, g_hi, node_lo, node_hi; };      // a contiguous gene range, or a range of visited nodes of one gene with many nodes
 struct WqEvPart { std::vector<WqEventRec> recs; WqPsiProblems P; WqEventPool pool; std::vector<double> ci_psi, ci_tot, p_total; };
 struct WqEvBatch {
     std::vector<WqEvPart> parts;         // one per host thread, contiguous gene ranges in gene order
@@ -106,7 +107,7 @@ struct wq_handle {
     uint64_t edge_slots = 0, keyed_slots = 0, kpool_cap = 0;
     WqQuantDev q;
     // per-batch buffers
-    DevBuf<uint8_t> d_len[2], d_qual[2]; DevBuf<uint64_t> d_seqoff[2], d_qualoff[2], d_seq2[2];
+    DevBuf<uint8_t> d_len[2], d_qual[2], d_qualpk[2]; DevBuf<uint64_t> d_seqoff[2], d_qualoff[2], d_seq2[2];
     DevBuf<WqSeed> d_seeds; DevBuf<uint32_t> d_hit_read, d_hit_s, d_hit_s2, d_hit_gene, d_pending, d_pending2, d_cursors;
     DevBuf<WqHit> d_hits; DevBuf<wq_align_node> d_pool; DevBuf<uint32_t> d_defer; DevBuf<WqPNode> d_slab;
     int n_sm = 148; uint64_t pool_nodes_per_read = 8; uint64_t last_deferred = 0;
@@ -123,6 +124,7 @@ struct wq_handle {
     std::vector<wq_event> ev_out;        // the finished records in ABI form (wq_process_events copies them, _view lends them)
     float psi_kernel_ms = 0.f;   // device time of the PSI EM launches of the last wq_process_events (CUDA events on the stream)
     uint64_t psi_sweep_bytes = 0;
+    std::vector<WqEvPiece> ev_pieces; uint32_t ev_pieces_key[3] = {0xFFFFFFFFu, 0, 0};      // work list of the event build (index + partition only)
     WqEvBatch ev_batch[2];       // event problems of the genes no multi-map read touches (built while the transcript EM runs) / of the others
     DevBuf<uint64_t> d_ck, d_cv, d_ck2, d_cv2; DevBuf<uint32_t> d_ckoff; DevBuf<uint8_t> d_cubtmp;
     DevBuf<uint64_t> d_xpack; DevBuf<uint32_t> d_xpending;      // multi-GPU exchange: this rank's packed sparse stores / merge queue
@@ -445,7 +447,7 @@ void wq_destroy(wq_handle* h) {
     h->d_rent.release(); h->d_ftab.release(); h->d_dense.release(); h->d_ekey.release(); h->d_ecount.release(); h->d_khash.release();
     h->d_kcount.release(); h->d_koff.release(); h->d_kpool.release(); h->d_kcursor.release();
     for (int i = 0; i < 2; i++) {
-        h->d_len[i].release(); h->d_qual[i].release(); h->d_seqoff[i].release(); h->d_qualoff[i].release(); h->d_seq2[i].release();
+        h->d_len[i].release(); h->d_qual[i].release(); h->d_qualpk[i].release(); h->d_seqoff[i].release(); h->d_qualoff[i].release(); h->d_seq2[i].release();
         if (h->ev_copy[i]) cudaEventDestroy(h->ev_copy[i]);
         if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
     }
@@ -490,14 +492,15 @@ static void wq_build_event_batch(wq_handle* h, int64_t readlen, int group, WqEvB
     // itself cut into pieces at visited nodes (every node's event is independent of the others).  The pieces depend on the index
     // and the partition only, so both gene groups and every call see the same list.
     const uint32_t p_lo = (uint32_t)((uint64_t)G * h->part / h->nparts), p_n = (uint32_t)((uint64_t)G * (h->part + 1) / h->nparts) - p_lo;
-    struct Piece { uint32_t g_lo, g_hi, node_lo, node_hi; };
-    std::vector<Piece> pieces;
-    {
+    typedef WqEvPiece Piece;
+    if (h->ev_pieces_key[0] != h->part || h->ev_pieces_key[1] != h->nparts || h->ev_pieces_key[2] != nt || h->ev_pieces.empty()) {
+        std::vector<Piece>& mk = h->ev_pieces;               // cached in the handle: built once per partition
+        mk.clear();
         const uint32_t per_piece = nt == 1 ? p_n : std::max<uint32_t>(8, p_n / (16 * nt) + 1), big_gene = 32;
         std::vector<uint32_t> visits;
         WqGeneEvents Vv{h->H, X.node_value, 0, {}};
         uint32_t start = p_lo + 1;
-        auto flush = [&](uint32_t upto) { if (upto >= start) pieces.push_back(Piece{start, upto, 1, 0xFFFFFFFFu}); start = upto + 1; };
+        auto flush = [&](uint32_t upto) { if (upto >= start) mk.push_back(Piece{start, upto, 1, 0xFFFFFFFFu}); start = upto + 1; };
         for (uint32_t g = p_lo + 1; g <= p_lo + p_n; g++) {
             if (nt > 1 && h->H.genes[g - 1].nn >= big_gene) {
                 flush(g - 1);
@@ -506,15 +509,29 @@ static void wq_build_event_batch(wq_handle* h, int64_t readlen, int group, WqEvB
                 const size_t visits_per_piece = h->H.genes[g - 1].nn >= 128 ? 2 : 8;      // the widest genes have the costliest nodes
                 for (size_t v = 0; v < visits.size(); v += visits_per_piece) {
                     const size_t ve = std::min(visits.size(), v + visits_per_piece);
-                    pieces.push_back(Piece{g, g, visits[v], visits[ve - 1]});
+                    mk.push_back(Piece{g, g, visits[v], visits[ve - 1]});
                 }
                 start = g + 1;
             } else if (g - start + 1 >= per_piece) flush(g);
         }
         flush(p_lo + p_n);
+        if (mk.empty()) mk.push_back(Piece{1, 0, 1, 0});
+        h->ev_pieces_key[0] = h->part; h->ev_pieces_key[1] = h->nparts; h->ev_pieces_key[2] = nt;
     }
-    const unsigned npieces = (unsigned)std::max<size_t>(1, pieces.size());
-    if (pieces.empty()) pieces.push_back(Piece{1, 0, 1, 0});
+    const std::vector<Piece>& pieces = h->ev_pieces;
+    const unsigned npieces = (unsigned)pieces.size();
+    // the group of genes that multi-map classes name is often empty (no multi-mapping reads in the job): nothing to build or launch then
+    bool any = group == 0;
+    if (group == 1) for (uint32_t g = p_lo + 1; g <= p_lo + p_n && !any; g++) any = X.gene_dirty[g] != 0;
+    if (!any) {
+        B.parts.clear();
+        B.parts.resize(npieces);
+        B.P = WqPsiProblems();
+        B.pshift.assign(npieces, 0);
+        B.ci_psi.clear(); B.ci_tot.clear(); B.p_total.clear();
+        B.built = true; B.launched = false; B.readlen = readlen;
+        return;
+    }
     B.parts.clear();
     B.parts.resize(npieces);
     auto run = [&](const std::function<void(unsigned)>& f) {
@@ -972,13 +989,19 @@ static int run_chunk(wq_handle* h, const WqParams& p, const WqBatchDev& b, const
     return 0;
 }
 
+// bytes of one read's row in wq_read_batch.qual of a fixed_len batch (phred bytes, or 4-bit dictionary indices)
+static inline uint64_t batch_qrow(const wq_read_batch* r) {
+    return r->qual_bits == 4 ? ((((uint64_t)r->fixed_len + 1) / 2 + 3) & ~3ull) : (((uint64_t)r->fixed_len + 3) & ~3ull);
+}
 static int check_batch(const wq_read_batch* r) {
     if (!r) return fail(-1, "null read batch");
     if (r->n_reads && (!r->len || !r->seq2 || !r->qual)) return fail(-1, "read batch has null arrays");
     if (r->n_reads && r->fixed_len == 0 && (!r->seq_off || !r->qual_off)) return fail(-1, "read batch has null offset arrays (allowed only with fixed_len)");
     if (r->fixed_len > 255) return fail(-1, "wq_read_batch.fixed_len must be at most 255 (ReadLengthInt = UInt8)");
+    if (r->qual_bits != 0 && r->qual_bits != 8 && r->qual_bits != 4) return fail(-1, "wq_read_batch.qual_bits must be 0, 8 or 4");
+    if (r->qual_bits == 4 && r->fixed_len == 0) return fail(-1, "4-bit quality indices need a fixed_len batch");
     if (r->n_reads && r->fixed_len) {
-        const uint64_t ws = (r->fixed_len + 31) / 32, qs = (r->fixed_len + 3) & ~3u;
+        const uint64_t ws = (r->fixed_len + 31) / 32, qs = batch_qrow(r);
         if ((uint64_t)r->n_reads * ws > r->seq2_words || (uint64_t)r->n_reads * qs > r->qual_bytes) return fail(-1, "fixed_len batch: seq2_words / qual_bytes smaller than n_reads strides");
     }
     return 0;
@@ -1069,7 +1092,43 @@ struct BatchOnDev { DevBuf<uint8_t>* len; DevBuf<uint64_t>* seqoff; DevBuf<uint6
 
 // position of read i of a batch (explicit offsets, or the strides of a fixed_len batch)
 static inline uint64_t batch_soff(const wq_read_batch* r, uint64_t i) { return r->fixed_len ? i * ((r->fixed_len + 31) / 32) : r->seq_off[i]; }
-static inline uint64_t batch_qoff(const wq_read_batch* r, uint64_t i) { return r->fixed_len ? i * ((r->fixed_len + 3) & ~3u) : r->qual_off[i]; }
+static inline uint64_t batch_qoff(const wq_read_batch* r, uint64_t i) { return r->fixed_len ? i * batch_qrow(r) : r->qual_off[i]; }      // in the caller's `qual`
+struct WqQualDict { uint8_t v[16]; };
+// 4-bit quality indices of reads [lo, hi) -> phred bytes in the layout the kernels read (rows of (L + 3) & ~3 bytes, zero beyond the read)
+__global__ void wq_k_unpack_qual(const uint8_t* __restrict__ packed, uint8_t* __restrict__ out, const uint8_t* __restrict__ len, uint32_t lo, uint32_t hi,
+                                 uint32_t prow, uint32_t qrow, const WqQualDict d) {
+    const uint32_t groups = qrow / 4;
+    const uint64_t total = (uint64_t)(hi - lo) * groups;
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t i = lo + (uint32_t)(t / groups), g = (uint32_t)(t % groups);
+        const uint32_t L = len[i];
+        const uint8_t* src = packed + (uint64_t)i * prow + 2 * g;
+        uint32_t w = 0;
+        for (uint32_t k = 0; k < 4; k++) {
+            const uint32_t j = 4 * g + k;
+            if (j < L) { const uint8_t b = src[k >> 1]; w |= (uint32_t)d.v[(k & 1) ? (b >> 4) : (b & 15)] << (8 * k); }
+        }
+        *reinterpret_cast<uint32_t*>(out + (uint64_t)i * qrow + 4 * g) = w;
+    }
+}
+// quality bytes of reads [lo, hi) of batch `which` onto the device: a plain copy, or (4-bit indices) the packed rows + the expansion kernel
+static int put_quals(wq_handle* h, const wq_read_batch* r, int which, uint32_t lo, uint32_t hi, uint64_t q0, uint64_t q1, cudaStream_t s) {
+    if (r->qual_bits != 4) { CK(cudaMemcpyAsync(h->d_qual[which].p + q0, r->qual + q0, q1 - q0, cudaMemcpyHostToDevice, s)); return 0; }
+    CK(cudaMemcpyAsync(h->d_qualpk[which].p + q0, r->qual + q0, q1 - q0, cudaMemcpyHostToDevice, s));
+    WqQualDict d;
+    memcpy(d.v, r->qual_dict, 16);
+    wq_k_unpack_qual<<<592, 256, 0, s>>>(h->d_qualpk[which].p, h->d_qual[which].p, h->d_len[which].p, lo, hi, (uint32_t)batch_qrow(r), (r->fixed_len + 3) & ~3u, d);
+    h->launches += 1;
+    CK(cudaGetLastError());
+    return 0;
+}
+static int ensure_quals(wq_handle* h, const wq_read_batch* r, int which) {
+    if (r->qual_bits == 4) {
+        CK(h->d_qualpk[which].ensure(r->qual_bytes + 16));
+        CK(h->d_qual[which].ensure((uint64_t)r->n_reads * ((r->fixed_len + 3) & ~3u) + 16));
+    } else CK(h->d_qual[which].ensure(r->qual_bytes + 16));
+    return 0;
+}
 // offsets of reads [lo, hi) of a fixed_len batch, written on the device instead of copied from the host
 __global__ void wq_k_fill_offsets(uint64_t* seq_off, uint64_t* qual_off, uint32_t lo, uint32_t hi, uint32_t wstride, uint32_t qstride) {
     for (uint64_t i = lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (uint64_t)gridDim.x * blockDim.x) {
@@ -1092,11 +1151,12 @@ static int put_offsets(wq_handle* h, const wq_read_batch* r, int which, uint32_t
 static int upload_batch(wq_handle* h, const wq_read_batch* reads, int which, cudaStream_t s) {
     const uint32_t n = reads->n_reads;
     CK(h->d_len[which].ensure(n)); CK(h->d_seqoff[which].ensure(n)); CK(h->d_qualoff[which].ensure(n));
-    CK(h->d_seq2[which].ensure(reads->seq2_words + 2)); CK(h->d_qual[which].ensure(reads->qual_bytes + 16));
+    CK(h->d_seq2[which].ensure(reads->seq2_words + 2));
+    if (int rc = ensure_quals(h, reads, which)) return rc;
     CK(cudaMemcpyAsync(h->d_len[which].p, reads->len, n, cudaMemcpyHostToDevice, s));
     if (int rc = put_offsets(h, reads, which, 0, n, s)) return rc;
     CK(cudaMemcpyAsync(h->d_seq2[which].p, reads->seq2, reads->seq2_words * 8ull, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(h->d_qual[which].p, reads->qual, reads->qual_bytes, cudaMemcpyHostToDevice, s));
+    if (int rc = put_quals(h, reads, which, 0, n, 0, reads->qual_bytes, s)) return rc;
     return 0;
 }
 
@@ -1126,6 +1186,7 @@ static int align_impl(wq_handle* h, const wq_align_param* ap, const wq_read_batc
     const uint32_t nchunks = (n + h->chunk_reads - 1) / h->chunk_reads;
     std::vector<cudaEvent_t> copied;
     if (on_device) {
+        for (int m = 0; m < nb; m++) if (src[m]->qual_bits == 4) return fail(-1, "device-resident batches take phred bytes (qual_bits 4 is a transfer format for host batches)");
         for (int m = 0; m < nb; m++) {
             if (src[m]->fixed_len && (!src[m]->seq_off || !src[m]->qual_off)) {       // device-resident fixed_len batch without offsets: derive them
                 CK(h->d_seqoff[m].ensure(n)); CK(h->d_qualoff[m].ensure(n));
@@ -1148,7 +1209,8 @@ static int align_impl(wq_handle* h, const wq_align_param* ap, const wq_read_batc
             }
         for (int m = 0; m < nb; m++) {
             CK(h->d_len[m].ensure(n)); CK(h->d_seqoff[m].ensure(n)); CK(h->d_qualoff[m].ensure(n));
-            CK(h->d_seq2[m].ensure(src[m]->seq2_words + 2)); CK(h->d_qual[m].ensure(src[m]->qual_bytes + 16));
+            CK(h->d_seq2[m].ensure(src[m]->seq2_words + 2));
+            if (int rc = ensure_quals(h, src[m], m)) return rc;
             base[m] = WqBatchDev{n, h->d_len[m].p, h->d_seqoff[m].p, h->d_seq2[m].p, h->d_qualoff[m].p, h->d_qual[m].p};
         }
         if (!ascending || nchunks == 1) {
@@ -1166,7 +1228,7 @@ static int align_impl(wq_handle* h, const wq_align_param* ap, const wq_read_batc
                     CK(cudaMemcpyAsync(h->d_len[m].p + lo, r->len + lo, hi - lo, cudaMemcpyHostToDevice, cs));
                     if (int rc = put_offsets(h, r, m, lo, hi, cs)) return rc;
                     CK(cudaMemcpyAsync(h->d_seq2[m].p + s0, r->seq2 + s0, (s1 - s0) * 8ull, cudaMemcpyHostToDevice, cs));
-                    CK(cudaMemcpyAsync(h->d_qual[m].p + q0, r->qual + q0, q1 - q0, cudaMemcpyHostToDevice, cs));
+                    if (int rc = put_quals(h, r, m, lo, hi, q0, q1, cs)) return rc;
                 }
                 CK(cudaEventCreateWithFlags(&copied[c], cudaEventDisableTiming));
                 CK(cudaEventRecord(copied[c], cs));

@@ -34,8 +34,13 @@ struct WqSamRead {                        // FASTQRecord as write_sam sees it (a
     }
     uint8_t qual(uint32_t j, bool rc) const {
         const uint32_t L = len();
+        const uint32_t k = rc ? L - 1 - j : j;
+        if (b->qual_bits == 4) {                               // 4-bit dictionary indices (fixed_len batches)
+            const uint8_t v = b->qual[(uint64_t)i * ((((uint64_t)b->fixed_len + 1) / 2 + 3) & ~3ull) + (k >> 1)];
+            return b->qual_dict[(k & 1) ? (v >> 4) : (v & 15)];
+        }
         const uint64_t qo = b->fixed_len ? (uint64_t)i * ((b->fixed_len + 3) & ~3u) : b->qual_off[i];
-        return b->qual[qo + (rc ? L - 1 - j : j)];
+        return b->qual[qo + k];
     }
 };
 

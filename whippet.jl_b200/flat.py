@@ -280,9 +280,11 @@ class ReadBatch:
         ok = L > 0 and np.array_equal(self.seq_off, i * np.uint64((L + 31) // 32)) and np.array_equal(self.qual_off, i * np.uint64((L + 3) & ~3))
         return L if ok else 0
 
-    def to_fixed(self):
+    def to_fixed(self, pack_qual=False):
         """The same reads in the fixed_len layout (rows of ceil(L / 32) words and (L + 3) & ~3 quality bytes, L = the longest read), or
-        None when the batch is not stored at constant strides already (e.g. ragged FASTQ input)."""
+        None when the batch is not stored at constant strides already (e.g. ragged FASTQ input).  pack_qual: when the batch holds at most
+        16 distinct quality values (binned instrument qualities), c() hands the qualities over as 4-bit dictionary indices
+        (wq_read_batch.qual_bits = 4); `qual` keeps the phred bytes for everything that reads them on the host."""
         n = self.n
         if n == 0:
             return None
@@ -306,6 +308,19 @@ class ReadBatch:
         i = np.arange(n, dtype=np.uint64)
         out = ReadBatch(self.len, i * np.uint64(ws), seq.reshape(-1), i * np.uint64(qs), qual.reshape(-1))
         out.prefer_fixed = True                                # c() then hands the batch over without its offset arrays
+        if pack_qual:
+            valid = np.arange(qs)[None, :] < self.len[:, None]
+            vals = np.unique(qual[valid])
+            if len(vals) <= 16:
+                lut = np.zeros(256, "u1")
+                lut[vals] = np.arange(len(vals), dtype="u1")
+                idx = np.where(valid, lut[qual], 0).astype("u1")
+                prow = ((L + 1) // 2 + 3) & ~3
+                even = np.zeros((n, prow * 2), "u1")
+                even[:, :qs] = idx
+                out.qual4 = np.ascontiguousarray((even[:, 0::2] | (even[:, 1::2] << 4)).reshape(-1))
+                out.qual_dict = np.zeros(16, "u1")
+                out.qual_dict[:len(vals)] = vals
         return out
 
     def c(self, fixed_len: int = 0) -> abi.ReadBatchC:
@@ -318,8 +333,15 @@ class ReadBatch:
         b.len = abi.ptr(self.len, abi.u8p)
         b.seq2 = abi.ptr(self.seq2, abi.u64p)
         b.seq2_words = len(self.seq2)
-        b.qual = abi.ptr(self.qual, abi.u8p)
-        b.qual_bytes = len(self.qual)
+        if fixed_len and getattr(self, "qual4", None) is not None:
+            b.qual = abi.ptr(self.qual4, abi.u8p)
+            b.qual_bytes = len(self.qual4)
+            b.qual_bits = 4
+            for k in range(16):
+                b.qual_dict[k] = int(self.qual_dict[k])
+        else:
+            b.qual = abi.ptr(self.qual, abi.u8p)
+            b.qual_bytes = len(self.qual)
         if not fixed_len:
             b.seq_off = abi.ptr(self.seq_off, abi.u64p)
             b.qual_off = abi.ptr(self.qual_off, abi.u64p)
