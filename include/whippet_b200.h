@@ -349,7 +349,7 @@ int  wq_counts_merge(wq_handle* h, const wq_counts* c, const wq_keyed* longs, co
  * (src/quant.jl:248-257) on the device.  tpm/count are [I], genetpm is [G]; returns iterations. */
 typedef struct wq_em_param {
     int64_t readlen;
-    int64_t sig;       /* digits, CLI: 1 */
+    int64_t sig;       /* digits of gene_em!, CLI: 1 (the calculate_tpm! call before the loop rounds with its own default, 1: bin/whippet-quant.jl:163) */
     int64_t maxit;     /* CLI: 10000 */
 } wq_em_param;
 int  wq_em_tpm(wq_handle* h, const wq_em_param* p, double* tpm, double* count, double* genetpm, int64_t* iterations);

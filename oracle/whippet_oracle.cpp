@@ -1845,7 +1845,7 @@ int64_t wqo_em_tpm(wqo_handle* h, int64_t readlen, int64_t sig, int64_t maxit) {
         }
     for (auto& kv : h->Q.multi) S.multi.emplace_back(kv.first, make_multicompat(L, kv.first, kv.second));
     build_equivalence_classes(L, h->Q, S);
-    calculate_tpm(S, S.count, readlen, (int)sig);
+    calculate_tpm(S, S.count, readlen, 1);       // calculate_tpm!(quant, readlen = readlen): its own default sig = 1 (bin/whippet-quant.jl:163)
     int64_t it = gene_em(S, maxit, (int)sig, readlen);
     set_gene_tpm(L, S);
     return it;

@@ -544,6 +544,12 @@ __device__ __forceinline__ double wq_tpm_value(const WqEmDev& d, double raw, dou
     return v;
 }
 
+// the call before gene_em! is calculate_tpm!(quant, readlen = readlen) with calculate_tpm!'s OWN default sig = 1 (bin/whippet-quant.jl:163,
+// src/quant.jl:655), whatever sig gene_em! is given
+__device__ __forceinline__ double wq_tpm_value_init(double raw, double rpk) {
+    return wq_round_sc(__ddiv_rn(__dmul_rn(raw, 1000000.0), rpk), 10.0);
+}
+
 // Persistent cooperative kernel, TWO grid barriers per EM iteration, every pass parallel over class MEMBERS (the
 // divisions and roundings), with only the order-defining additions left sequential per class / per isoform:
 //   phase B(it)  per tile of 1024 isoforms: (1) every contribution computes prop * count of its class; (2) every isoform
@@ -577,7 +583,7 @@ __global__ void __launch_bounds__(1024) wq_k_em_tpm(WqEmDev d) {
         double rpk = fmax(wq_tile_tree((uint32_t)t < d.ntiles ? d.partial[t] : 0.0, buf, t), 1.0);
         int mine = 0;
         for (uint32_t i = gtid; i < d.I; i += gsz) {
-            double v = wq_tpm_value(d, d.tpm_raw[i], rpk);
+            double v = wq_tpm_value_init(d.tpm_raw[i], rpk);
             if (v != 1.0) mine = 1;
             d.tpm[i] = v;
         }
@@ -725,7 +731,7 @@ __global__ void __launch_bounds__(1024) wq_k_em_tpm_smem(WqEmDev d, const WqEmSm
     {
         const double rpk = fmax(wq_tile_tree((uint32_t)t < d.ntiles ? d.partial[t] : 0.0, buf, t), 1.0);
         int mine = 0;
-        if (own) { tpm = wq_tpm_value(d, raw, rpk); if (tpm != 1.0) mine = 1; }
+        if (own) { tpm = wq_tpm_value_init(raw, rpk); if (tpm != 1.0) mine = 1; }
         if (__syncthreads_or(mine) && t == 0) atomicOr(&d.flags[3], 1);
     }
     grid.sync();
@@ -815,6 +821,18 @@ __global__ void __launch_bounds__(1024) wq_k_em_tpm_smem(WqEmDev d, const WqEmSm
 // grow-only device scratch kept in the handle (cudaMalloc/cudaFree per call would serialise the device)
 struct WqEmScratch {
     void* p[26] = {nullptr}; size_t cap[26] = {0};
+    void* hp = nullptr; size_t hcap = 0;               // page-locked staging for results (a copy into pageable memory is staged by the driver, copy by copy)
+    cudaError_t pinned(size_t bytes, void** out) {
+        if (bytes > hcap) {
+            if (hp) cudaFreeHost(hp);
+            hp = nullptr; hcap = 0;
+            cudaError_t e = cudaMallocHost(&hp, bytes + bytes / 4 + 4096);
+            if (e != cudaSuccess) return e;
+            hcap = bytes + bytes / 4 + 4096;
+        }
+        *out = hp;
+        return cudaSuccess;
+    }
     template <class T> cudaError_t get(int slot, size_t n, T** out) {
         size_t bytes = std::max<size_t>(1, n) * sizeof(T);
         if (bytes > cap[slot]) {
@@ -855,6 +873,8 @@ struct WqEmScratch {
     }
     void release() {
         for (int i = 0; i < 26; i++) { if (p[i]) cudaFree(p[i]); p[i] = nullptr; cap[i] = 0; }
+        if (hp) cudaFreeHost(hp);
+        hp = nullptr; hcap = 0;
         for (int i = 0; i < 3; i++) { if (side[i]) cudaStreamDestroy(side[i]); if (join[i]) cudaEventDestroy(join[i]); side[i] = nullptr; join[i] = nullptr; }
         if (fork) cudaEventDestroy(fork);
         if (tk0) cudaEventDestroy(tk0);
@@ -1035,12 +1055,23 @@ static inline std::string wq_run_em_tpm(const WqHostIndex& H, const WqIsoIndex& 
     if (launches) *launches += 1;
     if (while_running) (*while_running)();       // host work that does not depend on the EM result overlaps the kernel
     int64_t it = 0;
-    WQ_EMCK(cudaMemcpyAsync(&it, d_it, 8, cudaMemcpyDeviceToHost, stream));
-    WQ_EMCK(cudaMemcpyAsync(tpm.data(), d_tpm, I * 8, cudaMemcpyDeviceToHost, stream));
-    WQ_EMCK(cudaMemcpyAsync(count.data(), d_count, I * 8, cudaMemcpyDeviceToHost, stream));
-    WQ_EMCK(cudaMemcpyAsync(d_prop_h.data(), d_prop, (size_t)NM * 8, cudaMemcpyDeviceToHost, stream));
-    WQ_EMCK(cudaMemcpyAsync(d_state_h.data(), d_state, NC, cudaMemcpyDeviceToHost, stream));
-    WQ_EMCK(cudaStreamSynchronize(stream));
+    {   // results through one page-locked staging block: five copies in flight, one synchronisation
+        const size_t o_tpm = 8, o_cnt = o_tpm + (size_t)I * 8, o_prop = o_cnt + (size_t)I * 8, o_state = o_prop + (size_t)NM * 8, total = o_state + NC;
+        void* stg;
+        WQ_EMCK(M.pinned(total, &stg));
+        uint8_t* sb = (uint8_t*)stg;
+        WQ_EMCK(cudaMemcpyAsync(sb, d_it, 8, cudaMemcpyDeviceToHost, stream));
+        WQ_EMCK(cudaMemcpyAsync(sb + o_tpm, d_tpm, (size_t)I * 8, cudaMemcpyDeviceToHost, stream));
+        WQ_EMCK(cudaMemcpyAsync(sb + o_cnt, d_count, (size_t)I * 8, cudaMemcpyDeviceToHost, stream));
+        WQ_EMCK(cudaMemcpyAsync(sb + o_prop, d_prop, (size_t)NM * 8, cudaMemcpyDeviceToHost, stream));
+        WQ_EMCK(cudaMemcpyAsync(sb + o_state, d_state, NC, cudaMemcpyDeviceToHost, stream));
+        WQ_EMCK(cudaStreamSynchronize(stream));
+        memcpy(&it, sb, 8);
+        memcpy(tpm.data(), sb + o_tpm, (size_t)I * 8);
+        memcpy(count.data(), sb + o_cnt, (size_t)I * 8);
+        memcpy(d_prop_h.data(), sb + o_prop, (size_t)NM * 8);
+        memcpy(d_state_h.data(), sb + o_state, NC);
+    }
     if (timing) {
         std::vector<long long> dbg((size_t)grid * 4);
         WQ_EMCK(cudaMemcpy(dbg.data(), d.dbg, dbg.size() * 8, cudaMemcpyDeviceToHost));
