@@ -1177,11 +1177,15 @@ __device__ __forceinline__ double wq_round_sig(const WqPsiDev& d, double x, int 
 // Only additions are chained; loads feeding them do not depend on the running sum and are unrolled so that they overlap.
 // Shared memory per event: 40 * paths + 16 * sets + 4 * (sets + 1) + 4 * (paths + 1) + 14 * members bytes.  Events too large for that
 // (hundreds of paths, tens of thousands of set members: the stress genes of BASELINE config 5, deeply covered paralog families) keep
-// only the per-path arrays in shared memory; the per-set and per-member arrays live in a global scratch (`big`, L2-resident) and the
-// block has 1024 threads, so that the share divisions of a sweep are ~40 per thread instead of ~1000 per lane of one warp.
-struct WqPsiBigCfg {                  // quo == nullptr: everything in shared memory
-    double* quo; double* psum; double* mult; uint32_t* moff; uint16_t* mem; uint16_t* pset; uint16_t* ppath;
+// the per-path arrays in shared memory, the per-set arrays (prop_sum, multiplier, member offsets) there as well when they fit, and the
+// member lists (set -> paths, path -> sets: 2 bytes per member each) in a global scratch (`big`, L2-resident).  The block has 1024
+// threads and every path's owner divides its own shares (a path of such an event belongs to hundreds of sets, so the owners are
+// as evenly loaded as a pair-parallel split would be, and no share array has to go through memory: 4 bytes of traffic per member
+// and sweep instead of 38 -- with 168 such events in flight the sweep is bound by L2 bandwidth, not by the divisions).
+struct WqPsiBigCfg {                  // mem == nullptr: everything in shared memory
+    double* psum; double* mult; uint32_t* moff; uint16_t* mem; uint16_t* pset;
     const uint64_t* mbase; const uint64_t* abase;      // per launch slot: first member / first set of the event inside the scratch
+    uint32_t sets_smem;               // the per-set arrays sit in shared memory behind the per-path ones
 };
 __device__ __forceinline__ void wq_psi_sync(const bool one_warp) { if (one_warp) __syncwarp(); else __syncthreads(); }
 __global__ void __launch_bounds__(1024) wq_k_em_psi(const WqPsiDev d, const uint32_t* __restrict__ list, const uint32_t n_list, const WqPsiBigCfg big) {
@@ -1201,7 +1205,8 @@ __global__ void __launch_bounds__(1024) wq_k_em_psi(const WqPsiDev d, const uint
     double* den = ct + np;
     double* cnt = den + np;
     double* psum; double* mult; double* quo; uint32_t* moff; uint32_t* poff; uint16_t* mem; uint16_t* pset; uint16_t* ppath;
-    if (big.quo == nullptr) {
+    const bool is_big = big.mem != nullptr;
+    if (!is_big) {
         psum = cnt + np;                                          // [na]
         mult = psum + na;                                         // [na]
         quo = mult + na;                                          // [nm] shares, in inverted-index order
@@ -1212,9 +1217,16 @@ __global__ void __launch_bounds__(1024) wq_k_em_psi(const WqPsiDev d, const uint
         ppath = pset + nm;                                        // [nm] inverted index: the path of every slot
     } else {
         const uint64_t mb = big.mbase[slot], ab = big.abase[slot];
-        poff = reinterpret_cast<uint32_t*>(cnt + np);
-        psum = big.psum + ab; mult = big.mult + ab; moff = big.moff + ab + slot;
-        quo = big.quo + mb; mem = big.mem + mb; pset = big.pset + mb; ppath = big.ppath + mb;
+        if (big.sets_smem) {
+            psum = cnt + np; mult = psum + na;
+            moff = reinterpret_cast<uint32_t*>(mult + na);
+            poff = moff + na + 1;
+        } else {
+            poff = reinterpret_cast<uint32_t*>(cnt + np);
+            psum = big.psum + ab; mult = big.mult + ab; moff = big.moff + ab + slot;
+        }
+        quo = nullptr; ppath = nullptr;
+        mem = big.mem + mb; pset = big.pset + mb;
     }
     const uint32_t* gmem = d.amb_paths + m0;
     for (uint32_t i = tid; i < np; i += T) {
@@ -1232,7 +1244,7 @@ __global__ void __launch_bounds__(1024) wq_k_em_psi(const WqPsiDev d, const uint
         for (uint32_t k = 0; k < nm; k++) poff[mem[k] + 1]++;
         for (uint32_t i = 0; i < np; i++) poff[i + 1] += poff[i];
         for (uint32_t a = 0; a < na; a++)
-            for (uint32_t k = moff[a]; k < moff[a + 1]; k++) { const uint32_t at = poff[mem[k]]++; pset[at] = (uint16_t)a; ppath[at] = mem[k]; }
+            for (uint32_t k = moff[a]; k < moff[a + 1]; k++) { const uint32_t at = poff[mem[k]]++; pset[at] = (uint16_t)a; if (ppath) ppath[at] = mem[k]; }
         for (uint32_t i = np; i > 0; i--) poff[i] = poff[i - 1];
         poff[0] = 0;
     }
@@ -1252,9 +1264,15 @@ __global__ void __launch_bounds__(1024) wq_k_em_psi(const WqPsiDev d, const uint
         for (uint32_t i = 0; i < ni; i++) si = __dadd_rn(si, psi[i]);
         return __dadd_rn(se, si);
     };
+    __shared__ double s_total;
     auto divide = [&](int sig) {            // psi[] holds count / length on entry
-        const double total = total_of();
-        wq_psi_sync(one_warp);
+        double total;
+        if (one_warp) { total = total_of(); __syncwarp(); }
+        else {                              // one warp forms the chain (a broadcast read per path and warp), the others take the result
+            if (tid < 32) { const double t = total_of(); if (tid == 0) s_total = t; }
+            __syncthreads();
+            total = s_total;
+        }
         for (uint32_t i = tid; i < np; i += T) {
             const double q = __ddiv_rn(psi[i], total);
             psi[i] = sig > 0 ? wq_round_sig(d, q, sig) : q;
@@ -1286,6 +1304,29 @@ __global__ void __launch_bounds__(1024) wq_k_em_psi(const WqPsiDev d, const uint
             wq_psi_sync(one_warp);
         }
         // (2) the shares: first sweep ones(n)/n over prop_sum = 1.0, later sweeps the current psi over their sum (src/events.jl:869-886)
+        if (is_big) {
+            // (2 + 3) large events: every owner divides its own shares and adds them in set order
+            for (uint32_t i = tid; i < np; i += T) {
+                double c = cnt[i];
+                const double pi = psi[i];
+                const uint32_t kb = poff[i], ke = poff[i + 1];
+                if (it > 1) {
+                    #pragma unroll 4
+                    for (uint32_t k = kb; k < ke; k++) { const uint32_t a = pset[k]; c = __dadd_rn(c, __dmul_rn(__ddiv_rn(pi, psum[a]), mult[a])); }
+                } else {
+                    #pragma unroll 4
+                    for (uint32_t k = kb; k < ke; k++) { const uint32_t a = pset[k]; c = __dadd_rn(c, __dmul_rn(__ddiv_rn(1.0, (double)(moff[a + 1] - moff[a])), mult[a])); }
+                }
+                ct[i] = c;
+                prev[i] = pi;
+                psi[i] = __ddiv_rn(c, den[i]);            // no other thread reads psi[i] in this step (prop_sum is done, shares are the owner's)
+            }
+            wq_psi_sync(one_warp);
+            divide(d.sig);
+            if (tandem) { if (differs() && it < d.maxit) it += 1; else break; }
+            else it += 1;
+            continue;
+        }
         if (it > 1) {
             #pragma unroll 2
             for (uint32_t k = tid; k < nm; k += T) {
@@ -1322,7 +1363,9 @@ static inline size_t wq_psi_block_smem(uint32_t np, uint32_t na, uint32_t nm) {
     size_t b = 40ull * np + 16ull * na + 4ull * (na + 1) + 4ull * (np + 1) + 14ull * nm;
     return (b + 15) & ~15ull;
 }
-static inline size_t wq_psi_big_smem(uint32_t np) { return (40ull * np + 4ull * (np + 1) + 15) & ~15ull; }      // per-path arrays only
+static inline size_t wq_psi_big_smem(uint32_t np, uint32_t na, bool sets) {      // per-path arrays (+ the per-set ones)
+    return (40ull * np + 4ull * (np + 1) + (sets ? 16ull * na + 4ull * (na + 1) : 0ull) + 15) & ~15ull;
+}
 
 // Events with at most 4 paths (more than 90 % of them), at most WQ_PSI4_SETS ambiguous sets of at most 4 members: 4 lanes per
 // event, 8 events per warp.  Lane i of the group OWNS path i (psi / previous psi / temp count in registers); once per sweep the
@@ -1456,11 +1499,21 @@ static inline std::string wq_run_em_psi(wq_psi_batch& b, WqEmScratch& M, cudaStr
     d.amb_prop = d_prop; d.iterations = d_it;
     // Launch classes: 0 = at most 4 paths with small sets (4 lanes per event); 1..4 = one block per event, grouped by the shared memory the
     // event needs (4 / 16 / 64 / 200 KB, with 32 / 64 / 128 / 256 threads: more threads shorten the share divisions of a large event);
-    // 5 = events too large for that: per-path arrays in shared memory, the rest in a global scratch, 1024 threads.  The classes run
-    // concurrently on side streams (a handful of large events that need all 1500 sweeps would otherwise add their whole latency to the batch).
+    // 5 / 6 = events too large for that: per-path arrays (5: and per-set arrays) in shared memory, member lists in a global scratch, 1024
+    // threads.  The classes run concurrently on side streams (a handful of large events that need all 1500 sweeps would otherwise add
+    // their whole latency to the batch).
     static const size_t kBlockSmem[4] = {4 * 1024, 16 * 1024, 64 * 1024, 200 * 1024};
-    static const unsigned kBlockThreads[4] = {32, 64, 128, 256};
-    const int NC = 6;
+    static unsigned kBlockThreads[4] = {32, 64, 128, 256};
+    static bool threads_env = false;
+    if (!threads_env) {                                       // experiment knob: WQ_PSI_THREADS="32,64,128,256"
+        threads_env = true;
+        if (const char* ev = getenv("WQ_PSI_THREADS")) {
+            unsigned v[4];
+            if (sscanf(ev, "%u,%u,%u,%u", &v[0], &v[1], &v[2], &v[3]) == 4)
+                for (int k = 0; k < 4; k++) if (v[k] >= 32 && v[k] <= 1024 && v[k] % 32 == 0) kBlockThreads[k] = v[k];
+        }
+    }
+    const int NC = 7;
     std::vector<uint32_t> order(E);
     std::vector<uint8_t> cls(E);
     uint32_t nclass[NC] = {0}, cbase[NC + 1] = {0};
@@ -1475,14 +1528,15 @@ static inline std::string wq_run_em_psi(wq_psi_batch& b, WqEmScratch& M, cudaStr
         if (np > 65535 || na > 65535) return -1;
         const size_t need = wq_psi_block_smem(np, na, nm);
         for (int k = 0; k < 4; k++) if (need <= kBlockSmem[k]) return 1 + k;
-        if (wq_psi_big_smem(np) <= kBlockSmem[3]) return 5;
+        if (wq_psi_big_smem(np, na, true) <= kBlockSmem[3]) return 5;
+        if (wq_psi_big_smem(np, na, false) <= kBlockSmem[3]) return 6;
         return -1;
     };
-    size_t big_smem = 0;
+    size_t big_smem[2] = {0, 0};
     for (uint32_t e = 0; e < E; e++) {
         const int c = cls_of(e);
         if (c < 0) return "PSI event too large for the device kernel (more than ~4600 paths or 65535 ambiguous sets)";
-        if (c == 5) big_smem = std::max(big_smem, wq_psi_big_smem(b.path_ptr[e + 1] - b.path_ptr[e]));
+        if (c >= 5) big_smem[c - 5] = std::max(big_smem[c - 5], wq_psi_big_smem(b.path_ptr[e + 1] - b.path_ptr[e], b.amb_ptr[e + 1] - b.amb_ptr[e], c == 5));
         cls[e] = (uint8_t)c;
         nclass[c]++;
     }
@@ -1490,30 +1544,41 @@ static inline std::string wq_run_em_psi(wq_psi_batch& b, WqEmScratch& M, cudaStr
     { uint32_t cur[NC]; for (int c = 0; c < NC; c++) cur[c] = cbase[c]; for (uint32_t e = 0; e < E; e++) order[cur[cls[e]]++] = e; }
     uint32_t* d_list;
     WQ_EMCK(up(14, order.data(), E * 4ull, (void**)&d_list));
-    WqPsiBigCfg big;
-    memset(&big, 0, sizeof big);
-    const WqPsiBigCfg staged = big;
-    if (nclass[5]) {                                          // global scratch of the large events: members and sets back to back in launch order
-        std::vector<uint64_t> base(2ull * nclass[5]);
+    WqPsiBigCfg bigc[2];
+    memset(bigc, 0, sizeof bigc);
+    WqPsiBigCfg staged;
+    memset(&staged, 0, sizeof staged);
+    const uint32_t nbig = nclass[5] + nclass[6];
+    if (nbig) {                                               // global scratch of the large events (classes 5 and 6 are adjacent in `order`): members and sets back to back
+        std::vector<uint64_t> base(2ull * nbig);
         uint64_t mtot = 0, atot = 0;
-        for (uint32_t k = 0; k < nclass[5]; k++) {
+        for (uint32_t k = 0; k < nbig; k++) {
             const uint32_t e = order[cbase[5] + k];
             const uint32_t a_lo = b.amb_ptr[e], a_hi = b.amb_ptr[e + 1];
-            base[k] = mtot; base[nclass[5] + k] = atot;
+            base[k] = mtot; base[nbig + k] = atot;
             mtot += b.amb_path_ptr[a_hi] - b.amb_path_ptr[a_lo];
             atot += a_hi - a_lo;
         }
         uint64_t* d_base;
         WQ_EMCK(up(24, base.data(), base.size() * 8ull, (void**)&d_base));
         uint8_t* scratch;
-        const size_t m8 = (mtot + 3) & ~3ull, a8 = (atot + nclass[5] + 1) & ~1ull;
-        WQ_EMCK(M.get<uint8_t>(25, 8 * m8 + 3 * 2 * m8 + 16 * atot + 4 * a8 + 64, &scratch));
-        big.quo = reinterpret_cast<double*>(scratch);
-        big.psum = big.quo + m8; big.mult = big.psum + atot;
-        big.moff = reinterpret_cast<uint32_t*>(big.mult + atot);
-        big.mem = reinterpret_cast<uint16_t*>(big.moff + a8);
-        big.pset = big.mem + m8; big.ppath = big.pset + m8;
-        big.mbase = d_base; big.abase = d_base + nclass[5];
+        const size_t m8 = (mtot + 3) & ~3ull, a8 = (atot + nbig + 1) & ~1ull;
+        WQ_EMCK(M.get<uint8_t>(25, 2 * 2 * m8 + 16 * atot + 4 * a8 + 64, &scratch));
+        WqPsiBigCfg g;
+        memset(&g, 0, sizeof g);
+        g.psum = reinterpret_cast<double*>(scratch);
+        g.mult = g.psum + atot;
+        g.moff = reinterpret_cast<uint32_t*>(g.mult + atot);
+        g.mem = reinterpret_cast<uint16_t*>(g.moff + a8);
+        g.pset = g.mem + m8;
+        for (int k = 0; k < 2; k++) {                         // class 5 uses slots [0, nclass[5]), class 6 the ones behind
+            bigc[k] = g;
+            bigc[k].mbase = d_base + (k ? nclass[5] : 0);
+            bigc[k].abase = d_base + nbig + (k ? nclass[5] : 0);
+            bigc[k].sets_smem = k == 0 ? 1u : 0u;
+        }
+        // class 6's moff base: big.moff + ab + slot with slot counted inside its own launch; shift so the regions do not overlap with class 5's
+        bigc[1].moff = g.moff + nclass[5];
     }
     WQ_EMCK(M.side_streams());
     WQ_EMCK(M.timing_events());
@@ -1532,7 +1597,7 @@ static inline std::string wq_run_em_psi(wq_psi_batch& b, WqEmScratch& M, cudaStr
         const uint32_t n = nclass[c];
         const uint32_t* lst = d_list + cbase[c];
         if (c == 0) wq_k_em_psi4<<<(n + 31) / 32, 128, 0, ss>>>(d, lst, n);
-        else if (c == 5) wq_k_em_psi<<<n, 1024, big_smem, ss>>>(d, lst, n, big);
+        else if (c >= 5) wq_k_em_psi<<<n, 1024, big_smem[c - 5], ss>>>(d, lst, n, bigc[c - 5]);
         else wq_k_em_psi<<<n, kBlockThreads[c - 1], kBlockSmem[c - 1], ss>>>(d, lst, n, staged);
         if (launches) *launches += 1;
         WQ_EMCK(cudaGetLastError());
