@@ -287,14 +287,18 @@ int  wq_counts_sync(wq_handle* h);
 int  wq_classes_sync(wq_handle* h);
 int  wq_comm_destroy(wq_handle* h);
 
-/* Event stage partitioned by gene across ranks: this handle builds and solves the events of the contiguous gene range
- * `part` of `nparts` only and wq_process_events returns that range's records; the parts concatenate to the full output. */
+/* Event stage partitioned across ranks: this handle builds and solves the events of part `part` of `nparts` only and wq_process_events
+ * returns that part's records; the parts concatenate to the full output.  A part is a contiguous range of the event work list (gene
+ * ranges, and ranges of nodes inside a gene with many nodes), cut where the estimated cost -- nodes + (expressed edges)^2 per gene --
+ * reaches part / nparts of the total, so that one gene with hundreds of expressed junctions is shared by several ranks.  Every rank
+ * holds the same counts after wq_counts_sync and therefore computes the same cuts; node / edge values (wq_assign_ambig) are complete
+ * for every gene on every rank. */
 int  wq_set_gene_partition(wq_handle* h, uint32_t part, uint32_t nparts);
 /* Class building (build_equivalence_classes!, src/quant.jl:327-389) partitioned the same way: after the count exchange
  * every rank holds the same stores; wq_classes_build_local builds this part's share (the multi-map classes of its key
  * range, the isoform classes of its gene range), wq_classes_pack lends it as a host buffer owned by the handle, the caller
  * all-gathers the buffers, and wq_classes_assemble (shares of all parts, in part order) completes the class set that
- * wq_em_tpm then uses.  Node / edge values (wq_assign_ambig) are then complete for this part's genes only.
+ * wq_em_tpm then uses.
  * Without these calls wq_em_tpm builds every class itself. */
 int  wq_classes_build_local(wq_handle* h);
 int  wq_classes_pack(wq_handle* h, const void** ptr, uint64_t* bytes);

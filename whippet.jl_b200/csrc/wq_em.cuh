@@ -307,6 +307,18 @@ static inline std::string wq_host_build_classes(const WqHostIndex& H, const WqIs
         }
     });
     lap2("fragments concatenated");
+    if (nparts > 1) {
+        // assign_long for the genes whose classes another rank builds: their edge values must be complete here too (see assign_ambig);
+        // a key belongs to one gene, so the order of the additions to any one edge is the order inside that gene's long paths
+        for (uint32_t g = 1; g <= G; g++) {
+            if (g >= X.own_g_lo && g <= X.own_g_hi) continue;
+            for (uint32_t k = lptr[g]; k < lptr[g + 1]; k++) {
+                WqKeyPath kp;
+                wq_key_next(hq.longs.key(lidx[k]), 0, kp);
+                wq_spread_path(H, X.node_value, X.edge_adds, kp, hq.longc(lidx[k]));
+            }
+        }
+    }
     X.adds_before_gc = X.edge_adds.size();
     if (hq.bias)                                             // gc_adjust!(quant, mod) on the node counters (the edge counters: wq_finalize_edges)
         for (size_t i = 0; i < X.node_value.size(); i++) X.node_value[i] = WqHostQuant::gc_apply(X.node_value[i], hq.node_g[i]);
@@ -425,12 +437,8 @@ static inline std::string wq_host_assign_ambig_impl(const WqHostIndex& H, const 
             if (nh > WQ_MAX_TOLERATE) { errs[t] = "multi-map class with more alignments than WQ_MAX_TOLERATE"; return; }
             size_t pos = 1;
             for (uint32_t h = 0; h < nh; h++) pos = wq_key_next(key, pos, vp[h]);
-            if (X.nparts > 1) {              // partitioned: only classes that touch this rank's genes matter here
-                bool mine = false;
-                for (uint32_t h = 0; h < nh; h++) if (vp[h].gene >= X.own_g_lo && vp[h].gene <= X.own_g_hi) mine = true;
-                skip[c] = mine ? 0 : 1;
-                if (!mine) continue;
-            }
+            // (with the quant stage partitioned over ranks every rank still applies every class: the event stage is partitioned by
+            // pieces of work, not by gene range, so a rank may build events of any gene and needs complete node / edge values)
             for (uint32_t h = 0; h < nh; h++) {
                 if (C.postassign[c]) { w[h] = X.genetpm[vp[h].gene - 1]; continue; }
                 if (cached != vp[h].gene) { B.build(S, vp[h].gene - 1, H.genes[vp[h].gene - 1].nn); cached = vp[h].gene; }
@@ -472,7 +480,6 @@ static inline std::string wq_host_assign_ambig_impl(const WqHostIndex& H, const 
         for (uint32_t h = 0; h < nh; h++) {
             WqKeyPath kp;
             pos = wq_key_next(key, pos, kp);
-            if (X.nparts > 1 && (kp.gene < X.own_g_lo || kp.gene > X.own_g_hi)) continue;       // another rank's gene
             wq_spread_path(H, X.node_value, X.edge_adds, kp, share[(size_t)c * WQ_MAX_TOLERATE + h], h == 0 ? stale[c] : 0u);
         }
     }
