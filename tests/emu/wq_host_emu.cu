@@ -147,6 +147,19 @@ void hemu_problem(HostEmu* e, uint64_t p, uint32_t* sizes, double* count, double
     for (uint32_t j = P.amb_path_ptr[a0]; j < P.amb_path_ptr[a1]; j++) amb_paths[j - P.amb_path_ptr[a0]] = P.amb_paths[j];
 }
 
+// all EM problems of the last hemu_events call as the flat arrays of wq_psi_batch (sizes first: out == NULL)
+void hemu_problems_flat(HostEmu* e, uint64_t* sizes4, uint32_t* path_ptr, uint32_t* n_inc, double* count, double* length, uint32_t* amb_ptr,
+                        uint32_t* amb_path_ptr, uint32_t* amb_paths, double* amb_mult, uint8_t* is_tandem) {
+    const WqPsiProblems& P = e->P;
+    sizes4[0] = P.size(); sizes4[1] = P.count.size(); sizes4[2] = P.amb_mult.size(); sizes4[3] = P.amb_paths.size();
+    if (!path_ptr) return;
+    memcpy(path_ptr, P.path_ptr.data(), P.path_ptr.size() * 4); memcpy(n_inc, P.n_inc.data(), P.n_inc.size() * 4);
+    memcpy(count, P.count.data(), P.count.size() * 8); memcpy(length, P.length.data(), P.length.size() * 8);
+    memcpy(amb_ptr, P.amb_ptr.data(), P.amb_ptr.size() * 4); memcpy(amb_path_ptr, P.amb_path_ptr.data(), P.amb_path_ptr.size() * 4);
+    memcpy(amb_paths, P.amb_paths.data(), P.amb_paths.size() * 4); memcpy(amb_mult, P.amb_mult.data(), P.amb_mult.size() * 8);
+    memcpy(is_tandem, P.is_tandem.data(), P.is_tandem.size());
+}
+
 // WqBitWin self-test: adjacent() (word masks) against the per-node definition (src/quant.jl:68-79), first() / last() /
 // list() against a plain scan, on random node sets in windows of up to `max_span` nodes.  Returns the number of mismatches.
 uint64_t hemu_bitwin_selftest(uint32_t max_span, uint32_t rounds, uint64_t seed) {
