@@ -115,6 +115,16 @@ class HostEmu:
         """Build every gene in pieces of k visited nodes (0 = whole genes), as the library does for genes with many nodes."""
         self.L.hemu_set_event_pieces(int(k))
 
+    def event_cuts(self, ekey, evalue, nparts, threads=4):
+        """The event stage's work list and the ranks' cuts (wq_event_make_pieces / wq_event_cuts) for sorted edge keys and their
+        values.  Returns (pieces[n, 4] = g_lo, g_hi, node_lo, node_hi; cum[n + 1] running cost estimate; cuts[nparts + 1])."""
+        ekey, evalue = np.ascontiguousarray(ekey, "<u8"), np.ascontiguousarray(evalue, "<f8")
+        self.L.hemu_event_cuts.restype = C.c_uint64
+        n = self.L.hemu_event_cuts(self.h, C.c_uint64(len(ekey)), _p(ekey), _p(evalue), int(threads), int(nparts), None, None, None)
+        pieces, cum, cuts = np.zeros((n, 4), "<u4"), np.zeros(n + 1), np.zeros(nparts + 1, "<u4")
+        self.L.hemu_event_cuts(self.h, C.c_uint64(len(ekey)), _p(ekey), _p(evalue), int(threads), int(nparts), _p(pieces), _p(cum), _p(cuts))
+        return pieces, cum, cuts
+
     def events(self, node_value, ekey, evalue, readlen):
         """Event construction of every gene.  Returns a list of dicts (gene, node, motif, kind, flags, n_utr, psi, total,
         problem, inc paths, exc paths / utr paths) and the EM problems as tuples for oracle.em_psi."""

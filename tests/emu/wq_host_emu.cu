@@ -120,6 +120,22 @@ uint64_t hemu_events(HostEmu* e, const double* node_value, uint64_t ne, const ui
     }
     return e->recs.size();
 }
+// the event stage's work list and the ranks' cuts for the edges given (sorted keys): pieces as rows (g_lo, g_hi, node_lo, node_hi),
+// cum[npieces + 1] the running cost estimate, cuts[nparts + 1].  Returns the number of pieces (call with out == NULL first).
+uint64_t hemu_event_cuts(HostEmu* e, uint64_t ne, const uint64_t* ekey, const double* evalue, unsigned nt, uint32_t nparts, uint32_t* pieces_out, double* cum_out, uint32_t* cuts_out) {
+    std::vector<WqEvPiece> pieces;
+    if (e->node_value.size() != e->H.N) e->node_value.assign(e->H.N, 0.0);
+    wq_event_make_pieces(e->H, e->node_value, nt, nparts, pieces);
+    if (!pieces_out) return pieces.size();
+    std::vector<uint64_t> keys(ekey, ekey + ne);
+    std::vector<double> vals(evalue, evalue + ne);
+    std::vector<unsigned> cuts; std::vector<double> cum;
+    wq_event_cuts(e->H, keys, vals, pieces, nparts, cuts, &cum);
+    for (size_t t = 0; t < pieces.size(); t++) { pieces_out[4 * t] = pieces[t].g_lo; pieces_out[4 * t + 1] = pieces[t].g_hi; pieces_out[4 * t + 2] = pieces[t].node_lo; pieces_out[4 * t + 3] = pieces[t].node_hi; }
+    for (size_t t = 0; t < cum.size(); t++) cum_out[t] = cum[t];
+    for (size_t r = 0; r < cuts.size(); r++) cuts_out[r] = cuts[r];
+    return pieces.size();
+}
 // header[9] = gene, node, motif, kind, flags, n_utr, n_inc, n_exc, n_paths; vals[2] = psi, total; returns the EM problem index or -1
 int64_t hemu_event(HostEmu* e, uint64_t i, uint32_t* header, double* vals) {
     const WqEventRec& r = e->recs[i];

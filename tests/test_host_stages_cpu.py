@@ -183,6 +183,43 @@ def compare_events(idx, o, readlen, min_records, min_em, pieces=0):
     e.close()
 
 
+def test_event_cuts_spread_one_wide_gene_over_the_ranks():
+    """Partition of the event stage (wq_event_cuts): the cuts are monotone and cover the work list; a gene of 200 nodes whose middle
+    100 nodes sit under one long exon-skipping junction beside a dozen shorter ones (the shape of the titin-like gene that holds nearly
+    every 1000-path event of a deep human job) is shared by all ranks, each getting about the same number of those nodes, while
+    its nodes outside the junction and the junction-free genes cost next to nothing."""
+    idx = synth.make_index(n_genes=40, K=9, seed=5, paralog_frac=0.0, mean_exons=150.0)
+    nn = np.diff(idx.node_base)
+    g = int(np.argmax(nn)) + 1                              # 1-based gene id
+    assert nn[g - 1] >= 200
+    others = [int(x) + 1 for x in np.argsort(nn)[:2]]
+    e = HostEmu(idx)
+    keys, vals = [], []
+    for n in range(1, 200):
+        keys.append((g << 32) | (n << 16) | (n + 1)); vals.append(50.0)
+    keys.append((g << 32) | (50 << 16) | 151); vals.append(20.0)
+    for a in range(60, 140, 7):
+        keys.append((g << 32) | (a << 16) | (a + 3)); vals.append(10.0)
+    for gg in others:                                       # two ordinary genes: adjacent edges only
+        for n in range(1, 30):
+            keys.append((gg << 32) | (n << 16) | (n + 1)); vals.append(30.0)
+    order = np.argsort(np.array(keys, "<u8"))
+    ek, ev = np.array(keys, "<u8")[order], np.array(vals)[order]
+    for nparts in (2, 4, 8):
+        pieces, cum, cuts = e.event_cuts(ek, ev, nparts)
+        assert cuts[0] == 0 and cuts[-1] == len(pieces) and np.all(np.diff(cuts.astype(np.int64)) >= 0)
+        assert np.all(np.diff(cum) > 0)
+        under = []                                          # nodes 51..150 of gene 7 per rank
+        for r in range(nparts):
+            k = 0
+            for g_lo, g_hi, n_lo, n_hi in pieces[cuts[r]:cuts[r + 1]]:
+                if g_lo == g and g_hi == g and n_hi != 0xFFFFFFFF:
+                    k += len([n for n in range(int(n_lo), int(n_hi) + 1) if 51 <= n <= 150])
+            under.append(k)
+        assert sum(under) == 100 and min(under) >= 100 // nparts - 4 and max(under) <= 100 // nparts + 4, (nparts, under)
+    e.close()
+
+
 def test_node_set_windows():
     """WqBitWin (the node sets of event paths): word-mask adjacency, first / last / list against the per-node definitions,
     including windows of several 64-bit words (genes with hundreds of nodes)."""

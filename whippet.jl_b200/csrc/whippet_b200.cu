@@ -63,7 +63,6 @@ struct DevBuf {
 // Events of one gene group.  Group 0 = genes that no multi-map class names: assign_ambig! cannot change their counts, so
 // their events are built on the host threads while the transcript EM kernel runs and their PSI EM launch overlaps
 // assign_ambig!.  Group 1 = the remaining genes, built after assign_ambig!.
-struct WqEvPiece { uint32_t g_lo, g_hi, node_lo, node_hi; };      // a contiguous gene range, or a range of visited nodes of one gene with many nodes
 struct WqEvPart { std::vector<WqEventRec> recs; WqPsiProblems P; WqEventPool pool; std::vector<double> ci_psi, ci_tot, p_total; };
 struct WqEvBatch {
     std::vector<WqEvPart> parts;         // one per host thread, contiguous gene ranges in gene order
@@ -487,67 +486,21 @@ static void wq_build_event_batch(wq_handle* h, int64_t readlen, int group, WqEvB
     const uint32_t G = h->H.G;
     unsigned nt = wq_host_threads();
     if (G < 2048) nt = 1;
-    // The gene range is cut into many more contiguous pieces than there are host threads and the threads pull pieces as they
-    // finish: the cost of a gene goes from nothing to hundreds of path enumerations (TTN: 365 nodes), so a gene with many nodes is
-    // itself cut into pieces at visited nodes (every node's event is independent of the others).  The pieces depend on the index
-    // and the partition only, so both gene groups and every call see the same list.
-    const uint32_t p_lo = 0, p_n = G;                        // the work list covers every gene; a rank takes a contiguous range of its pieces
+    // work list: see wq_event_make_pieces
     typedef WqEvPiece Piece;
     if (h->ev_pieces_key[2] != nt || h->ev_pieces_key[1] != h->nparts || h->ev_pieces.empty()) {
-        std::vector<Piece>& mk = h->ev_pieces;               // cached in the handle: depends on the index and the host thread count only
-        mk.clear();
-        const uint32_t per_piece = nt == 1 && h->nparts == 1 ? p_n : std::max<uint32_t>(8, p_n / (16 * std::max(nt, 4u)) + 1), big_gene = 32;
-        std::vector<uint32_t> visits;
-        WqGeneEvents Vv{h->H, X.node_value, 0, {}};
-        uint32_t start = p_lo + 1;
-        auto flush = [&](uint32_t upto) { if (upto >= start) mk.push_back(Piece{start, upto, 1, 0xFFFFFFFFu}); start = upto + 1; };
-        for (uint32_t g = p_lo + 1; g <= p_lo + p_n; g++) {
-            if ((nt > 1 || h->nparts > 1) && h->H.genes[g - 1].nn >= big_gene) {
-                flush(g - 1);
-                Vv.g = g;
-                wq_gene_visits(Vv, visits);
-                const size_t visits_per_piece = h->H.genes[g - 1].nn >= 128 ? 2 : 8;      // the widest genes have the costliest nodes
-                for (size_t v = 0; v < visits.size(); v += visits_per_piece) {
-                    const size_t ve = std::min(visits.size(), v + visits_per_piece);
-                    mk.push_back(Piece{g, g, visits[v], visits[ve - 1]});
-                }
-                start = g + 1;
-            } else if (g - start + 1 >= per_piece) flush(g);
-        }
-        flush(p_lo + p_n);
-        if (mk.empty()) mk.push_back(Piece{1, 0, 1, 0});
+        wq_event_make_pieces(h->H, X.node_value, nt, h->nparts, h->ev_pieces);      // cached in the handle: depends on the index, the host thread count and the partition only
         h->ev_pieces_key[0] = 0; h->ev_pieces_key[1] = h->nparts; h->ev_pieces_key[2] = nt;
     }
     const std::vector<Piece>& pieces = h->ev_pieces;
     const unsigned npieces = (unsigned)pieces.size();
-    // This rank's range of pieces (wq_set_gene_partition): contiguous, so the ranks' records concatenate to the whole output, and cut
-    // where the estimated cost reaches part / nparts of the total.  The estimate is (nodes + expressed edges squared) per gene -- the
-    // path enumeration of an event grows with the alternative edges around it -- and a gene that is cut into node pieces spreads its
-    // cost over them, so a single gene with hundreds of expressed edges (one titin-like gene holds nearly all the 1024-path events of
-    // a deep human data set) is shared by several ranks instead of landing on one.  Every rank holds the same counts after
-    // wq_counts_sync and the same piece list, so every rank computes the same cuts.
+    // This rank's range of pieces (wq_set_gene_partition): contiguous, so the ranks' records concatenate to the whole output; every rank
+    // holds the same counts after wq_counts_sync and the same piece list, so every rank computes the same cuts (wq_event_cuts).
     unsigned pc_lo = 0, pc_hi = npieces;
     if (h->nparts > 1) {
-        std::vector<double> gcost(G + 2, 0.0);
-        for (uint64_t k : h->hq.edge_key) { const uint64_t g = k >> 32; if (g >= 1 && g <= G && !wq_edge_is_circ(k)) gcost[g] += 1.0; }
-        for (uint32_t g = 1; g <= G; g++) gcost[g] = (double)h->H.genes[g - 1].nn + gcost[g] * gcost[g];
-        std::vector<uint32_t> per_gene(G + 2, 0);
-        for (const Piece& pc : pieces) if (pc.g_lo == pc.g_hi && pc.node_hi != 0xFFFFFFFFu) per_gene[pc.g_lo]++;
-        std::vector<double> cum(npieces + 1, 0.0);
-        for (unsigned t = 0; t < npieces; t++) {
-            const Piece& pc = pieces[t];
-            double c = 0.0;
-            if (pc.g_lo == pc.g_hi && pc.node_hi != 0xFFFFFFFFu) c = gcost[pc.g_lo] / (double)per_gene[pc.g_lo];
-            else for (uint32_t g = pc.g_lo; g <= pc.g_hi && g <= G; g++) c += gcost[g];
-            cum[t + 1] = cum[t] + c;
-        }
-        auto cut = [&](uint32_t r) -> unsigned {
-            if (r == 0) return 0;
-            if (r >= h->nparts) return npieces;
-            const double target = cum[npieces] * (double)r / (double)h->nparts;
-            return (unsigned)(std::lower_bound(cum.begin(), cum.end(), target) - cum.begin());
-        };
-        pc_lo = std::min(cut(h->part), npieces); pc_hi = std::min(std::max(cut(h->part + 1), pc_lo), npieces);
+        std::vector<unsigned> cuts;
+        wq_event_cuts(h->H, X.edge_key, X.edge_value, pieces, h->nparts, cuts);
+        pc_lo = cuts[h->part]; pc_hi = cuts[h->part + 1];
     }
     // the group of genes that multi-map classes name is often empty (no multi-mapping reads in the job): nothing to build or launch then
     bool any = group == 0;

@@ -386,6 +386,103 @@ static inline void wq_gene_visits(const WqGeneEvents& V, std::vector<uint32_t>& 
     }
 }
 
+// Estimated cost of the events of nodes node_lo..node_hi of one gene, from its expressed edges (el[k], er[k]): the paths of node n's
+// event are drawn from the edges inside the hull of the edges that span or touch n and carry at least 2 % of the gene's reference
+// edge value (src/events.jl:647-742 collects exactly those before reduce_graph enumerates; a node without both an inclusion and an
+// exclusion edge has no enumeration at all), and the work grows roughly with the cube of their number e_n up to the 1024-path cap
+// (measured on the counts of an 80 M-read job: paths x ambiguous sets = 18 at e ~ 12, 1.1 k at e ~ 48, 135 k at e ~ 170 and beyond).
+// Used only to place the cuts of the event stage between ranks; any estimate gives the same records.
+static inline double wq_piece_cost(const std::vector<uint32_t>& el, const std::vector<uint32_t>& er, const std::vector<double>& ev, uint32_t node_lo, uint32_t node_hi) {
+    double c = 0.0;
+    const size_t E = el.size();
+    const double maxvalue = E ? ev[E - 1] : 0.0;              // the same reading of maximum(sgquant.edge) as the event build
+    for (uint32_t n = node_lo; n <= node_hi; n++) {
+        uint32_t lo = 0xFFFFFFFFu, hi = 0;
+        bool has_inc = false, has_exc = false;
+        for (size_t k = 0; k < E; k++) {
+            if (!(el[k] <= n && n <= er[k]) || ev[k] / maxvalue < 0.02) continue;
+            lo = std::min(lo, el[k]); hi = std::max(hi, er[k]);
+            if (el[k] == n || er[k] == n) has_inc = true; else has_exc = true;
+        }
+        double e = 0.0;
+        if (has_inc && has_exc) for (size_t k = 0; k < E; k++) if (el[k] >= lo && er[k] <= hi) e += 1.0;
+        e = std::min(e, 128.0);                               // beyond ~128 edges the enumeration stops at the 1024-path cap
+        c += 1.0 + e * e * e;
+        if (n == 0xFFFFFFFFu) break;
+    }
+    return c;
+}
+
+// Work list of the event stage.  The gene range is cut into many more contiguous pieces than there are host threads and the threads
+// pull pieces as they finish: the cost of a gene goes from nothing to hundreds of path enumerations (TTN: 365 nodes), so a gene with
+// many nodes is itself cut into pieces at visited nodes (every node's event is independent of the others).  The pieces depend on the
+// index, the thread count and the partition only, so both gene groups and every call see the same list.
+struct WqEvPiece { uint32_t g_lo, g_hi, node_lo, node_hi; };      // a contiguous gene range, or a range of visited nodes of one gene with many nodes
+static inline void wq_event_make_pieces(const WqHostIndex& H, const std::vector<double>& node_value, unsigned nt, uint32_t nparts, std::vector<WqEvPiece>& mk) {
+    const uint32_t G = H.G;
+    mk.clear();
+    const uint32_t per_piece = nt == 1 && nparts == 1 ? G : std::max<uint32_t>(8, G / (16 * std::max(nt, 4u)) + 1), big_gene = 32;
+    std::vector<uint32_t> visits;
+    WqGeneEvents Vv{H, node_value, 0, {}};
+    uint32_t start = 1;
+    auto flush = [&](uint32_t upto) { if (upto >= start) mk.push_back(WqEvPiece{start, upto, 1, 0xFFFFFFFFu}); start = upto + 1; };
+    for (uint32_t g = 1; g <= G; g++) {
+        if ((nt > 1 || nparts > 1) && H.genes[g - 1].nn >= big_gene) {
+            flush(g - 1);
+            Vv.g = g;
+            wq_gene_visits(Vv, visits);
+            const size_t visits_per_piece = H.genes[g - 1].nn >= 128 ? 2 : 8;      // the widest genes have the costliest nodes
+            for (size_t v = 0; v < visits.size(); v += visits_per_piece) {
+                const size_t ve = std::min(visits.size(), v + visits_per_piece);
+                mk.push_back(WqEvPiece{g, g, visits[v], visits[ve - 1]});
+            }
+            start = g + 1;
+        } else if (g - start + 1 >= per_piece) flush(g);
+    }
+    flush(G);
+    if (mk.empty()) mk.push_back(WqEvPiece{1, 0, 1, 0});
+}
+// The ranks' ranges of pieces (wq_set_gene_partition): rank r takes pieces [cuts[r], cuts[r + 1]), cut where the estimated cost reaches
+// r / nparts of the total.  Whole-gene pieces cost nodes + E^3 (E = the gene's expressed edges); a gene cut into node pieces costs
+// wq_piece_cost of each piece, so the ~170 events of one titin-like gene that sit under one long exon-skipping junction (each
+// ~1000-1900 paths: nearly all of the stage once a human job has tens of millions of reads) are spread over nearly all ranks instead
+// of landing on the one or two that hold the middle of the gene.  edge_key must be sorted (gene, first, last).
+static inline void wq_event_cuts(const WqHostIndex& H, const std::vector<uint64_t>& edge_key, const std::vector<double>& edge_value, const std::vector<WqEvPiece>& pieces, uint32_t nparts,
+                                 std::vector<unsigned>& cuts, std::vector<double>* cum_out = nullptr) {
+    const uint32_t G = H.G;
+    const unsigned npieces = (unsigned)pieces.size();
+    std::vector<double> gcost(G + 2, 0.0);
+    for (uint64_t k : edge_key) { const uint64_t g = k >> 32; if (g >= 1 && g <= G && !wq_edge_is_circ(k)) gcost[g] += 1.0; }
+    for (uint32_t g = 1; g <= G; g++) gcost[g] = (double)H.genes[g - 1].nn + gcost[g] * gcost[g] * gcost[g];
+    std::vector<double> cum(npieces + 1, 0.0);
+    std::vector<uint32_t> el, er;
+    std::vector<double> ev;
+    uint32_t el_gene = 0;
+    for (unsigned t = 0; t < npieces; t++) {
+        const WqEvPiece& pc = pieces[t];
+        double c = 0.0;
+        if (pc.g_lo == pc.g_hi && pc.node_hi != 0xFFFFFFFFu) {
+            const uint32_t g = pc.g_lo;
+            if (el_gene != g) {
+                el.clear(); er.clear(); ev.clear(); el_gene = g;
+                for (size_t e = std::lower_bound(edge_key.begin(), edge_key.end(), (uint64_t)g << 32) - edge_key.begin(); e < edge_key.size() && (edge_key[e] >> 32) == g; e++) {
+                    if (wq_edge_is_circ(edge_key[e])) continue;
+                    el.push_back((uint32_t)((edge_key[e] >> 16) & 0xFFFF)); er.push_back((uint32_t)(edge_key[e] & 0xFFFF)); ev.push_back(edge_value[e]);
+                }
+            }
+            c = wq_piece_cost(el, er, ev, pc.node_lo, pc.node_hi);
+        } else for (uint32_t g = pc.g_lo; g <= pc.g_hi && g <= G; g++) c += gcost[g];
+        cum[t + 1] = cum[t] + c;
+    }
+    cuts.assign(nparts + 1, npieces);
+    cuts[0] = 0;
+    for (uint32_t r = 1; r < nparts; r++) {
+        const double target = cum[npieces] * (double)r / (double)nparts;
+        cuts[r] = std::max(cuts[r - 1], std::min(npieces, (unsigned)(std::lower_bound(cum.begin(), cum.end(), target) - cum.begin())));
+    }
+    if (cum_out) *cum_out = cum;
+}
+
 // all events of one gene (src/events.jl:760-800), or of its visited nodes in [node_lo, node_hi] (node_lo must be a visited node);
 // problems needing EM are appended to P
 static inline void wq_gene_events(const WqGeneEvents& V, int64_t readlen, std::vector<WqEventRec>& out, WqPsiProblems& P, WqEventPool& pool,
