@@ -154,6 +154,31 @@ class HostEmu:
         return ninc, cnt, ln, sets, amult[:namb].tolist(), bool(tandem)
 
 
+def psi_cluster(problems, C_blocks, threads, readlen, sig=4, maxit=1500):
+    """The cluster PSI kernel's phases (wq_k_em_psi_cl, csrc/wq_em.cuh) run on the CPU for `C_blocks` blocks of `threads` threads.
+    problems as for GraphLibQuant.em_psi_batch.  Returns [(psi, iterations)], or None when the layout does not fit / a set names a
+    path twice (the library keeps such events on the block kernel); also the shared-memory bytes one block needs."""
+    L = C.CDLL(build())
+    E = len(problems)
+    path_ptr, amb_ptr, amb_path_ptr = [0], [0], [0]
+    n_inc, cnt, ln, apaths, amult, tan = [], [], [], [], [], []
+    for (ni, c, l, sets, mult, t) in problems:
+        n_inc.append(ni); cnt += list(c); ln += list(l); tan.append(1 if t else 0)
+        path_ptr.append(len(cnt))
+        for a, m in zip(sets, mult):
+            apaths += list(a); amult.append(m); amb_path_ptr.append(len(apaths))
+        amb_ptr.append(len(amult))
+    arr = lambda x, dt: np.ascontiguousarray(x if len(x) else [0], dt)
+    a = [arr(path_ptr, "<u4"), arr(n_inc, "<u4"), arr(cnt, "<f8"), arr(ln, "<f8"), arr(amb_ptr, "<u4"), arr(amb_path_ptr, "<u4"),
+         arr(apaths, "<u4"), arr(amult, "<f8"), arr(tan, "u1")]
+    psi, ct, its, need = np.zeros(max(1, len(cnt))), np.zeros(max(1, len(cnt))), np.zeros(max(1, E), "<i4"), C.c_uint64()
+    rc = L.hemu_psi_cluster(C.c_uint32(E), *[_p(x) for x in a], C.c_int64(readlen), C.c_int(sig), C.c_int64(maxit), C.c_uint32(C_blocks),
+                            C.c_uint32(threads), _p(psi), _p(ct), _p(its), C.byref(need))
+    if rc != 0:
+        return None, int(need.value)
+    return [(psi[path_ptr[e]:path_ptr[e + 1]].copy(), int(its[e])) for e in range(E)], int(need.value)
+
+
 class HostSam:
     """wq_sam.h (write_sam, src/io.jl:69-271) on the CPU: SAM text of a batch from given alignments."""
 

@@ -5,6 +5,9 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <functional>
+#include <cmath>
+#include <cstring>
 #include <string>
 #include <vector>
 #include "../../whippet.jl_b200/csrc/wq_kernels.cuh"
@@ -174,6 +177,78 @@ void hemu_problems_flat(HostEmu* e, uint64_t* sizes4, uint32_t* path_ptr, uint32
     memcpy(amb_ptr, P.amb_ptr.data(), P.amb_ptr.size() * 4); memcpy(amb_path_ptr, P.amb_path_ptr.data(), P.amb_path_ptr.size() * 4);
     memcpy(amb_paths, P.amb_paths.data(), P.amb_paths.size() * 4); memcpy(amb_mult, P.amb_mult.data(), P.amb_mult.size() * 8);
     memcpy(is_tandem, P.is_tandem.data(), P.is_tandem.size());
+}
+
+// The cluster PSI kernel (wq_k_em_psi_cl) on the CPU: the same phase functions the kernel calls, run for every block of the cluster
+// and every thread in turn, a phase at a time (a cluster barrier separates the phases on the device; within a phase no thread reads
+// what another writes -- that part only the GPU run can show).  Remote shared-memory writes go to the other blocks' buffers.
+// Returns 0, or -1 when the layout does not fit the device's shared memory / a set names a path twice (the library would then keep
+// these events on the block kernel).
+int hemu_psi_cluster(uint32_t E, const uint32_t* path_ptr, const uint32_t* n_inc, const double* count, const double* length, const uint32_t* amb_ptr,
+                     const uint32_t* amb_path_ptr, const uint32_t* amb_paths, const double* amb_mult, const uint8_t* is_tandem, int64_t readlen,
+                     int sig, int64_t maxit, uint32_t C, uint32_t T, double* psi, double* ctemp, int32_t* iterations, uint64_t* smem_bytes) {
+    wq_psi_batch b;
+    memset(&b, 0, sizeof b);
+    b.n_events = E; b.path_ptr = path_ptr; b.n_inc = n_inc; b.path_count = count; b.path_length = length; b.amb_ptr = amb_ptr;
+    b.amb_path_ptr = amb_path_ptr; b.amb_paths = amb_paths; b.amb_mult = amb_mult; b.is_tandem = is_tandem;
+    std::vector<uint32_t> events(E);
+    for (uint32_t e = 0; e < E; e++) events[e] = e;
+    if (!wq_psi_cl_unique(b, events.data(), E)) return -1;
+    WqPsiClCfg z;
+    const size_t need = wq_psi_cl_config(b, events.data(), E, C, z);
+    if (smem_bytes) *smem_bytes = need;
+    if (need > 227 * 1024) return -1;
+    static const std::vector<double> big = [] { std::vector<double> t(309); for (int k = 0; k <= 308; k++) t[k] = std::pow(10.0, (double)k); return t; }();
+    WqPsiDev d;
+    memset(&d, 0, sizeof d);
+    d.n_events = E; d.path_ptr = path_ptr; d.n_inc = n_inc; d.count = count; d.length = length; d.amb_ptr = amb_ptr; d.amb_path_ptr = amb_path_ptr;
+    d.amb_paths = amb_paths; d.amb_mult = amb_mult; d.is_tandem = is_tandem; d.readlen = (double)readlen; d.sig = sig; d.maxit = maxit;
+    d.psi = psi; d.ctemp = ctemp; d.iterations = iterations; d.p10big = big.data();
+    for (int k = 0; k <= 22; k++) { d.p10[k] = std::pow(10.0, (double)k); d.ip10[k] = 1.0 / d.p10[k]; }
+    std::vector<std::vector<unsigned char>> buf(C, std::vector<unsigned char>(need + 16, 0xAB));      // poisoned: nothing may rely on zeroed shared memory
+    unsigned char* all[8];
+    for (uint32_t r = 0; r < C; r++) all[r] = buf[r].data();
+    std::vector<WqClCtx> ctx(C);
+    for (uint32_t r = 0; r < C; r++) { ctx[r].r = r; ctx[r].C = C; ctx[r].T = T; ctx[r].self = all[r]; ctx[r].all = all; wq_psi_cl_layout(z, all[r], &ctx[r].S); }
+    auto each = [&](const std::function<void(const WqClCtx&, uint32_t)>& f) { for (uint32_t r = 0; r < C; r++) for (uint32_t t = 0; t < T; t++) f(ctx[r], t); };
+    for (uint32_t e = 0; e < E; e++) {
+        const WqPsiClEv ev = wq_psi_cl_event(d, e);
+        each([&](const WqClCtx& c, uint32_t t) { wq_cl_init_a(d, ev, c, t); });
+        each([&](const WqClCtx& c, uint32_t t) { wq_cl_init_b(d, ev, c, t); });
+        for (uint32_t r = 0; r < C; r++) wq_cl_init_c(ev, ctx[r]);
+        for (uint32_t a = 0; a < ev.na; a++) each([&](const WqClCtx& c, uint32_t t) { wq_cl_init_d(d, ev, c, t, a); });
+        bool differs = false;
+        auto norm = [&](int sg) {
+            for (uint32_t r = 0; r < C; r++) {
+                bool any = false;
+                for (uint32_t t = 0; t < T; t++) any |= wq_cl_phase_norm(d, ev, ctx[r], t, sg);
+                for (uint32_t rr = 0; rr < C; rr++) *wq_cl_remote(ctx[r], ctx[r].S.flags + r, rr) = any ? 1u : 0u;
+            }
+            differs = false;
+            for (uint32_t r = 0; r < C; r++) {                       // every block must see the same answer
+                uint32_t f = 0;
+                for (uint32_t rr = 0; rr < C; rr++) f |= ctx[r].S.flags[rr];
+                if (r == 0) differs = f != 0; else if (differs != (f != 0)) abort();
+            }
+        };
+        if (!ev.tandem) {
+            each([&](const WqClCtx& c, uint32_t t) { wq_cl_phase_pre(ev, c, t); });
+            each([&](const WqClCtx& c, uint32_t t) { wq_cl_phase_total(ev, c, t); });
+            norm(0);
+        }
+        int64_t it = 1;
+        for (;;) {
+            if (!ev.tandem && !(differs && it < d.maxit)) break;
+            if (it > 1) each([&](const WqClCtx& c, uint32_t t) { wq_cl_phase_psum(ev, c, t); });
+            each([&](const WqClCtx& c, uint32_t t) { wq_cl_phase_shares(d, ev, c, t, it == 1); });
+            each([&](const WqClCtx& c, uint32_t t) { wq_cl_phase_total(ev, c, t); });
+            norm(d.sig);
+            if (ev.tandem) { if (differs && it < d.maxit) it += 1; else break; }
+            else it += 1;
+        }
+        each([&](const WqClCtx& c, uint32_t t) { wq_cl_write_out(d, ev, c, t, it); });
+    }
+    return 0;
 }
 
 // WqBitWin self-test: adjacent() (word masks) against the per-node definition (src/quant.jl:68-79), first() / last() /

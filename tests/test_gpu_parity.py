@@ -385,6 +385,31 @@ def test_em_psi_batch_all_event_sizes(fixture_index):
     q.close()
 
 
+def test_em_psi_large_events_block_and_cluster_kernels(fixture_index, monkeypatch):
+    """Large events (1000-1900 paths, 60-140 k set members; all run to the 1500-sweep cap) through wq_em_psi_batch on the block kernel
+    (WQ_PSI_CLUSTER=0: one block per event, member lists in a global scratch) and on the cluster kernel with 8 and 4 blocks per event
+    (everything in distributed shared memory), and as the library chooses by itself: every psi value and iteration count equals
+    the oracle's spliced_em! (src/events.jl:853-893).  The problems are tests/golden/psi_large_events.npz (inputs only)."""
+    from oracle import em_psi
+    from test_psi_cluster_cpu import large_events
+    problems = large_events()
+    ni, cnt, ln, sets, mult, _ = problems[3]
+    problems.append((len(cnt), cnt, ln + 150.0, sets, mult, True))           # the same structure as a tandem-UTR problem
+    want = [em_psi(ni, cnt, ln, sets, mult, tandem, 101) for (ni, cnt, ln, sets, mult, tandem) in problems]
+    assert all(it == 1500 for _, it in want[:4])
+    q = wq.GraphLibQuant(fixture_index)
+    for mode in ("0", "8", "4", None):
+        if mode is None:
+            monkeypatch.delenv("WQ_PSI_CLUSTER", raising=False)
+        else:
+            monkeypatch.setenv("WQ_PSI_CLUSTER", mode)
+        got = q.em_psi_batch(problems, readlen=101)
+        for k, ((psi, it), (wpsi, wit)) in enumerate(zip(got, want)):
+            assert it == wit, (mode, k, it, wit)
+            assert psi.tobytes() == wpsi.tobytes(), (mode, k)
+    q.close()
+
+
 def test_partitioned_class_building():
     """Class building partitioned by gene across ranks, emulated on one GPU: three handles hold the same counts (what every
     rank holds after the exchange), each builds the share of its part, the shares are assembled on every handle; the EM then

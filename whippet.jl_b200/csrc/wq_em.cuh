@@ -16,6 +16,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <functional>
 #include <map>
 #include <string>
@@ -1128,10 +1129,27 @@ struct WqPsiDev {
     const double* p10big;         // [309] 10^k by the host's libm pow (global memory)
 };
 
+// IEEE operations that the compiler must not contract or reassociate: intrinsics on the device, plain operators in the host build of
+// the same functions (tests/emu drives the cluster kernel's phases on the CPU; host code is compiled without FMA contraction).
+#ifdef __CUDA_ARCH__
+#define WQ_EM_DADD(a, b) __dadd_rn((a), (b))
+#define WQ_EM_DSUB(a, b) __dsub_rn((a), (b))
+#define WQ_EM_DMUL(a, b) __dmul_rn((a), (b))
+#define WQ_EM_DDIV(a, b) __ddiv_rn((a), (b))
+#define WQ_HIINT(x) __double2hiint(x)
+#else
+#define WQ_EM_DADD(a, b) ((a) + (b))
+#define WQ_EM_DSUB(a, b) ((a) - (b))
+#define WQ_EM_DMUL(a, b) ((a) * (b))
+#define WQ_EM_DDIV(a, b) ((a) / (b))
+static inline int wq_hiint_host(double x) { unsigned long long u; memcpy(&u, &x, 8); return (int)(u >> 32); }
+#define WQ_HIINT(x) wq_hiint_host(x)
+#endif
+
 // 10^k as the host's libm rounds it (Base.round scales by 10.0^digits computed through libm pow; the device pow may be an
 // ulp or two off, which changes the rounded result of a value as small as 1e-188 — a psi that decayed for 1500 sweeps).
 // Exact for k <= 22 (kernel parameter table), host-computed table up to 10^308, +Inf beyond as in IEEE arithmetic.
-__device__ __forceinline__ double wq_pow10(const WqPsiDev& d, int k) {
+__host__ __device__ __forceinline__ double wq_pow10(const WqPsiDev& d, int k) {
     if (k >= 0 && k <= 22) return d.p10[k];
     if (k > 22 && k <= 308 && d.p10big) return d.p10big[k];
     return pow(10.0, (double)k);
@@ -1140,9 +1158,9 @@ __device__ __forceinline__ double wq_pow10(const WqPsiDev& d, int k) {
 // and fixed up against exact powers of ten for |x| >= 1 and correctly rounded ones below; values within an ulp of a
 // power of ten may land in the neighbouring decade compared with a libm log10, which cannot change the rounded
 // result (both decades round such a value to that same power of ten).
-__device__ __forceinline__ int wq_hidigit(const WqPsiDev& d, double ax) {
+__host__ __device__ __forceinline__ int wq_hidigit(const WqPsiDev& d, double ax) {
     if (ax >= 1e-22 && ax < 1e22) {
-        const int e = ((__double2hiint(ax) >> 20) & 0x7FF) - 1023;  // 2^e <= ax < 2^(e+1) (ax is a normal number here)
+        const int e = ((WQ_HIINT(ax) >> 20) & 0x7FF) - 1023;  // 2^e <= ax < 2^(e+1) (ax is a normal number here)
         int h = (int)floor((double)e * 0.30102999566398120) + 1;   // candidate: 10^(h-1) <= ax < 10^h, at most one off
         // pw(k) = 10^k
         auto pw = [&](int k) { return k >= 0 ? d.p10[k] : d.ip10[-k]; };
@@ -1151,9 +1169,9 @@ __device__ __forceinline__ int wq_hidigit(const WqPsiDev& d, double ax) {
         return h;
     }
     if (d.p10big && ax >= 1e-300 && ax < 1e300) {               // same scheme over the big table (10^-k as the IEEE quotient 1 / 10^k)
-        const int e = ((__double2hiint(ax) >> 20) & 0x7FF) - 1023;
+        const int e = ((WQ_HIINT(ax) >> 20) & 0x7FF) - 1023;
         int h = (int)floor((double)e * 0.30102999566398120) + 1;
-        auto pw = [&](int k) { return k >= 0 ? d.p10big[k] : __ddiv_rn(1.0, d.p10big[-k]); };
+        auto pw = [&](int k) { return k >= 0 ? d.p10big[k] : WQ_EM_DDIV(1.0, d.p10big[-k]); };
         if (ax >= pw(h)) h += 1;
         else if (ax < pw(h - 1)) h -= 1;
         return h;
@@ -1161,13 +1179,13 @@ __device__ __forceinline__ int wq_hidigit(const WqPsiDev& d, double ax) {
     return 1 + (int)floor(log10(ax));
 }
 // Base.round(x, sigdigits = sig)
-__device__ __forceinline__ double wq_round_sig(const WqPsiDev& d, double x, int sig) {
+__host__ __device__ __forceinline__ double wq_round_sig(const WqPsiDev& d, double x, int sig) {
     if (!isfinite(x) || x == 0.0) return x;
     int h = wq_hidigit(d, fabs(x));
     int digits = sig - h;
     double r;
-    if (digits >= 0) { double sc = wq_pow10(d, digits); r = __ddiv_rn(rint(__dmul_rn(x, sc)), sc); }
-    else { double sc = wq_pow10(d, -digits); r = __dmul_rn(rint(__ddiv_rn(x, sc)), sc); }
+    if (digits >= 0) { double sc = wq_pow10(d, digits); r = WQ_EM_DDIV(rint(WQ_EM_DMUL(x, sc)), sc); }
+    else { double sc = wq_pow10(d, -digits); r = WQ_EM_DMUL(rint(WQ_EM_DDIV(x, sc)), sc); }
     if (!isfinite(r)) return digits > 0 ? x : r;
     return r;
 }
@@ -1374,6 +1392,292 @@ static inline size_t wq_psi_big_smem(uint32_t np, uint32_t na, bool sets) {     
     return (40ull * np + 4ull * (np + 1) + (sets ? 16ull * na + 4ull * (na + 1) : 0ull) + 15) & ~15ull;
 }
 
+
+// ---- large events on a thread-block cluster ----
+// An event of ~1000-1900 paths, ~150 ambiguous sets and ~60-140 k set members runs all 1500 sweeps, and a deep human job has ~170 of
+// them (the nodes of one titin-like gene under one long exon-skipping junction).  One block per event leaves such a sweep at ~100 us:
+// 0.6 MB of member lists streamed from L2, 140 k IEEE divisions on one SM's Float64 pipe, and most SMs idle when the events are shared
+// between the ranks of a multi-GPU job.  Here C = 2 / 4 / 8 blocks of a cluster share one event.  Paths are dealt to the blocks in
+// groups of 32 (block r owns the paths i with (i / 32) % C == r), sets round-robin (a % C == r); a block keeps ONLY the member lists
+// of its own sets and the inverted index of its own paths -- with the lists divided by C the whole working set sits in shared
+// memory and a sweep touches no global memory at all.  Per sweep, three cluster barriers:
+//   (1) prop_sum of the block's sets (sequential in member order, a lane per set), written into every block's psum[] through
+//       distributed shared memory;                                                                                  -- barrier
+//   (2) the block's paths: unambiguous count + shares in set order (the owner divides its own shares), count / length written into
+//       every block's raw[];                                                                                        -- barrier
+//   (3) every block forms the same total from raw[] (the reference's order: exclusion paths, inclusion paths, their sum -- two
+//       chains on two warps), then normalises + rounds its own paths, writes them into every block's psi[] and its "changed" flag
+//       into every block's flag word.                                                                               -- barrier
+// The arithmetic of every path and set is the block kernel's, operation for operation; only who does it changed.  The phases are
+// __host__ __device__ so that tests/emu can run the same code for all blocks and threads on the CPU against the oracle.
+struct WqPsiClCfg {
+    uint32_t C;                                   // blocks per cluster
+    uint32_t np_cap, na_cap, npl_cap, nal_cap;    // over the launch's events: paths, sets, path slots of one block, sets of one block
+    uint32_t mem_cap, inv_cap;                    // entries of one block's member lists / inverted index
+};
+struct WqPsiClSmem {                              // one block's arrays; the layout is identical in every block of the launch
+    double *psi, *raw, *psum, *mult;              // complete copies: [np] rounded psi, [np] count / length, [na], [na]
+    double *prev, *ct, *den, *cnt, *tot;          // the block's own path slots; tot[2] = the two partial sums of the total
+    uint32_t *lmoff, *poff, *cur, *flags;         // [nal + 1] member offsets of the own sets, [npl + 1] inverted index, build cursor, [8] changed flags
+    uint16_t *lmem, *lpset;                       // members of the own sets (event-local path ids); sets of the own paths, in set order
+};
+WQ_HDN inline size_t wq_psi_cl_layout(const WqPsiClCfg& z, unsigned char* base, WqPsiClSmem* o) {
+    size_t at = 0;
+    auto take = [&](size_t bytes) { const size_t p = at; at += (bytes + 15) & ~(size_t)15; return p; };
+    const size_t o_psi = take(8ull * z.np_cap), o_raw = take(8ull * z.np_cap), o_psum = take(8ull * z.na_cap), o_mult = take(8ull * z.na_cap);
+    const size_t o_prev = take(8ull * z.npl_cap), o_ct = take(8ull * z.npl_cap), o_den = take(8ull * z.npl_cap), o_cnt = take(8ull * z.npl_cap), o_tot = take(16);
+    const size_t o_lmoff = take(4ull * (z.nal_cap + 1)), o_poff = take(4ull * (z.npl_cap + 1)), o_cur = take(4ull * z.npl_cap), o_flags = take(32);
+    const size_t o_lmem = take(2ull * z.mem_cap), o_lpset = take(2ull * z.inv_cap);
+    if (o) {
+        o->psi = reinterpret_cast<double*>(base + o_psi); o->raw = reinterpret_cast<double*>(base + o_raw);
+        o->psum = reinterpret_cast<double*>(base + o_psum); o->mult = reinterpret_cast<double*>(base + o_mult);
+        o->prev = reinterpret_cast<double*>(base + o_prev); o->ct = reinterpret_cast<double*>(base + o_ct);
+        o->den = reinterpret_cast<double*>(base + o_den); o->cnt = reinterpret_cast<double*>(base + o_cnt); o->tot = reinterpret_cast<double*>(base + o_tot);
+        o->lmoff = reinterpret_cast<uint32_t*>(base + o_lmoff); o->poff = reinterpret_cast<uint32_t*>(base + o_poff);
+        o->cur = reinterpret_cast<uint32_t*>(base + o_cur); o->flags = reinterpret_cast<uint32_t*>(base + o_flags);
+        o->lmem = reinterpret_cast<uint16_t*>(base + o_lmem); o->lpset = reinterpret_cast<uint16_t*>(base + o_lpset);
+    }
+    return at;
+}
+// ownership: paths in groups of 32 round-robin over the blocks, sets round-robin
+WQ_HDN inline uint32_t wq_cl_owner(uint32_t i, uint32_t C) { return (i >> 5) % C; }
+WQ_HDN inline uint32_t wq_cl_slot(uint32_t i, uint32_t C) { return ((i >> 5) / C) * 32u + (i & 31u); }
+WQ_HDN inline uint32_t wq_cl_path(uint32_t s, uint32_t r, uint32_t C) { return ((((s >> 5) * C) + r) << 5) + (s & 31u); }
+WQ_HDN inline uint32_t wq_cl_nslots(uint32_t np, uint32_t r, uint32_t C) { const uint32_t w = (np + 31u) >> 5; return w > r ? ((w - r + C - 1) / C) * 32u : 0u; }
+WQ_HDN inline uint32_t wq_cl_nsets(uint32_t na, uint32_t r, uint32_t C) { return na > r ? (na - r + C - 1) / C : 0u; }
+
+struct WqPsiClEv { uint32_t e, p0, np, ni, a0, na, m0, nm; bool tandem; };
+WQ_HDN inline WqPsiClEv wq_psi_cl_event(const WqPsiDev& d, uint32_t e) {
+    WqPsiClEv v;
+    v.e = e; v.p0 = d.path_ptr[e]; v.np = d.path_ptr[e + 1] - v.p0; v.ni = d.n_inc[e];
+    v.a0 = d.amb_ptr[e]; v.na = d.amb_ptr[e + 1] - v.a0;
+    v.m0 = d.amb_path_ptr[v.a0]; v.nm = d.amb_path_ptr[v.a0 + v.na] - v.m0;
+    v.tandem = d.is_tandem[e] != 0;
+    return v;
+}
+struct WqClCtx {
+    uint32_t r, C, T;                             // this block's rank in the cluster, blocks per cluster, threads per block
+    WqPsiClSmem S;
+    unsigned char* self;                          // host emulation only: this block's buffer and every block's
+    unsigned char* const* all;
+};
+// the same array element in block rr's shared memory
+template <class Tp> WQ_HDN inline Tp* wq_cl_remote(const WqClCtx& c, Tp* p, uint32_t rr) {
+#ifdef __CUDA_ARCH__
+    return cg::this_cluster().map_shared_rank(p, rr);
+#else
+    return reinterpret_cast<Tp*>(c.all[rr] + (reinterpret_cast<unsigned char*>(p) - c.self));
+#endif
+}
+// -- build, once per event.  a: own path slots, complete arrays, own set offsets.
+WQ_HDN inline void wq_cl_init_a(const WqPsiDev& d, const WqPsiClEv& ev, const WqClCtx& c, uint32_t tid) {
+    const WqPsiClSmem& S = c.S;
+    const uint32_t nsl = wq_cl_nslots(ev.np, c.r, c.C);
+    for (uint32_t s = tid; s < nsl; s += c.T) {
+        const uint32_t i = wq_cl_path(s, c.r, c.C);
+        if (i < ev.np) {
+            const double len = d.length[ev.p0 + i];
+            S.cnt[s] = d.count[ev.p0 + i];
+            S.den[s] = ev.tandem ? fmax(WQ_EM_DSUB(len, d.readlen), 1.0) : len;
+            S.prev[s] = 0.0; S.ct[s] = S.cnt[s];
+        }
+    }
+    for (uint32_t s = tid; s <= nsl; s += c.T) S.poff[s] = 0;
+    for (uint32_t i = tid; i < ev.np; i += c.T) { S.psi[i] = 0.0; S.raw[i] = 0.0; }
+    for (uint32_t a = tid; a < ev.na; a += c.T) { S.mult[a] = d.amb_mult[ev.a0 + a]; S.psum[a] = 1.0; }
+    if (tid < 8) S.flags[tid] = 0;
+    if (tid == 0) {
+        const uint32_t nal = wq_cl_nsets(ev.na, c.r, c.C);
+        uint32_t acc = 0;
+        for (uint32_t al = 0; al < nal; al++) {
+            const uint32_t a = c.r + c.C * al;
+            S.lmoff[al] = acc;
+            acc += d.amb_path_ptr[ev.a0 + a + 1] - d.amb_path_ptr[ev.a0 + a];
+        }
+        S.lmoff[nal] = acc;
+    }
+}
+// b: the members of the own sets; how many sets every own path belongs to
+WQ_HDN inline void wq_cl_init_b(const WqPsiDev& d, const WqPsiClEv& ev, const WqClCtx& c, uint32_t tid) {
+    const WqPsiClSmem& S = c.S;
+    const uint32_t nal = wq_cl_nsets(ev.na, c.r, c.C);
+    for (uint32_t al = 0; al < nal; al++) {
+        const uint32_t a = c.r + c.C * al;
+        const uint32_t gb = d.amb_path_ptr[ev.a0 + a], n = d.amb_path_ptr[ev.a0 + a + 1] - gb, lb = S.lmoff[al];
+        for (uint32_t k = tid; k < n; k += c.T) S.lmem[lb + k] = (uint16_t)d.amb_paths[gb + k];
+    }
+    for (uint32_t k = tid; k < ev.nm; k += c.T) {
+        const uint32_t m = d.amb_paths[ev.m0 + k];
+        if (wq_cl_owner(m, c.C) != c.r) continue;
+#ifdef __CUDA_ARCH__
+        atomicAdd(&S.poff[wq_cl_slot(m, c.C) + 1], 1u);
+#else
+        S.poff[wq_cl_slot(m, c.C) + 1] += 1u;
+#endif
+    }
+}
+// c (one thread): offsets of the inverted index
+WQ_HDN inline void wq_cl_init_c(const WqPsiClEv& ev, const WqClCtx& c) {
+    const WqPsiClSmem& S = c.S;
+    const uint32_t nsl = wq_cl_nslots(ev.np, c.r, c.C);
+    for (uint32_t s = 0; s < nsl; s++) { S.poff[s + 1] += S.poff[s]; S.cur[s] = S.poff[s]; }
+}
+// d, set by set with a block barrier in between: the own paths' entries in set order.  A path occurs at most once in a set
+// (checked on the host before this kernel is chosen), so no two threads of one step share a cursor.
+WQ_HDN inline void wq_cl_init_d(const WqPsiDev& d, const WqPsiClEv& ev, const WqClCtx& c, uint32_t tid, uint32_t a) {
+    const WqPsiClSmem& S = c.S;
+    const uint32_t gb = d.amb_path_ptr[ev.a0 + a], ge = d.amb_path_ptr[ev.a0 + a + 1];
+    for (uint32_t k = gb + tid; k < ge; k += c.T) {
+        const uint32_t m = d.amb_paths[k];
+        if (wq_cl_owner(m, c.C) != c.r) continue;
+        const uint32_t at = S.cur[wq_cl_slot(m, c.C)]++;
+        S.lpset[at] = (uint16_t)a;
+    }
+}
+// -- sweep.  (1) prop_sum of the own sets, to every block
+WQ_HDN inline void wq_cl_phase_psum(const WqPsiClEv& ev, const WqClCtx& c, uint32_t tid) {
+    const WqPsiClSmem& S = c.S;
+    const uint32_t nal = wq_cl_nsets(ev.na, c.r, c.C);
+    for (uint32_t al = tid; al < nal; al += c.T) {
+        double sm = 0.0;
+        const uint32_t kb = S.lmoff[al], ke = S.lmoff[al + 1];
+        #pragma unroll 8
+        for (uint32_t k = kb; k < ke; k++) sm = WQ_EM_DADD(sm, S.psi[S.lmem[k]]);
+        const uint32_t a = c.r + c.C * al;
+        for (uint32_t rr = 0; rr < c.C; rr++) *wq_cl_remote(c, S.psum + a, rr) = sm;
+    }
+}
+// calculate_psi!(inc, exc, counts) before spliced_em!: count / length of the own paths, to every block
+WQ_HDN inline void wq_cl_phase_pre(const WqPsiClEv& ev, const WqClCtx& c, uint32_t tid) {
+    const WqPsiClSmem& S = c.S;
+    const uint32_t nsl = wq_cl_nslots(ev.np, c.r, c.C);
+    for (uint32_t s = tid; s < nsl; s += c.T) {
+        const uint32_t i = wq_cl_path(s, c.r, c.C);
+        if (i >= ev.np) continue;
+        const double rv = WQ_EM_DDIV(S.ct[s], S.den[s]);
+        for (uint32_t rr = 0; rr < c.C; rr++) *wq_cl_remote(c, S.raw + i, rr) = rv;
+    }
+}
+// (2) the own paths: count + shares in set order (first sweep: ones(n) / n over prop_sum = 1.0), count / length to every block
+WQ_HDN inline void wq_cl_phase_shares(const WqPsiDev& d, const WqPsiClEv& ev, const WqClCtx& c, uint32_t tid, bool first) {
+    const WqPsiClSmem& S = c.S;
+    const uint32_t nsl = wq_cl_nslots(ev.np, c.r, c.C);
+    for (uint32_t s = tid; s < nsl; s += c.T) {
+        const uint32_t i = wq_cl_path(s, c.r, c.C);
+        if (i >= ev.np) continue;
+        double cc = S.cnt[s];
+        const double pi = S.psi[i];
+        const uint32_t kb = S.poff[s], ke = S.poff[s + 1];
+        if (!first) {
+            #pragma unroll 4
+            for (uint32_t k = kb; k < ke; k++) { const uint32_t a = S.lpset[k]; cc = WQ_EM_DADD(cc, WQ_EM_DMUL(WQ_EM_DDIV(pi, S.psum[a]), S.mult[a])); }
+        } else {
+            for (uint32_t k = kb; k < ke; k++) {
+                const uint32_t a = S.lpset[k];
+                const uint32_t n = d.amb_path_ptr[ev.a0 + a + 1] - d.amb_path_ptr[ev.a0 + a];
+                cc = WQ_EM_DADD(cc, WQ_EM_DMUL(WQ_EM_DDIV(1.0, (double)n), S.mult[a]));
+            }
+        }
+        S.ct[s] = cc;
+        S.prev[s] = pi;
+        const double rv = WQ_EM_DDIV(cc, S.den[s]);
+        for (uint32_t rr = 0; rr < c.C; rr++) *wq_cl_remote(c, S.raw + i, rr) = rv;
+    }
+}
+// (3a) the total in the reference's order, by every block for itself: warp 0 the exclusion paths (tandem: all paths), warp 1 the inclusion paths
+WQ_HDN inline void wq_cl_phase_total(const WqPsiClEv& ev, const WqClCtx& c, uint32_t tid) {
+    const WqPsiClSmem& S = c.S;
+    const uint32_t warp = tid >> 5;
+    if (warp > 1) return;
+    uint32_t lo, hi;
+    if (ev.tandem) { if (warp == 1) return; lo = 0; hi = ev.np; }
+    else if (warp == 0) { lo = ev.ni; hi = ev.np; }
+    else { lo = 0; hi = ev.ni; }
+    double t = 0.0;
+    #pragma unroll 8
+    for (uint32_t i = lo; i < hi; i++) t = WQ_EM_DADD(t, S.raw[i]);
+    if ((tid & 31u) == 0) S.tot[warp] = t;
+}
+// (3b) divsignif! of the own paths, to every block; returns whether one of this thread's paths changed
+WQ_HDN inline bool wq_cl_phase_norm(const WqPsiDev& d, const WqPsiClEv& ev, const WqClCtx& c, uint32_t tid, int sig) {
+    const WqPsiClSmem& S = c.S;
+    const double total = ev.tandem ? S.tot[0] : WQ_EM_DADD(S.tot[0], S.tot[1]);
+    const uint32_t nsl = wq_cl_nslots(ev.np, c.r, c.C);
+    bool diff = false;
+    for (uint32_t s = tid; s < nsl; s += c.T) {
+        const uint32_t i = wq_cl_path(s, c.r, c.C);
+        if (i >= ev.np) continue;
+        double q = WQ_EM_DDIV(S.raw[i], total);
+        if (sig > 0) q = wq_round_sig(d, q, sig);
+        if (S.prev[s] != q) diff = true;
+        for (uint32_t rr = 0; rr < c.C; rr++) *wq_cl_remote(c, S.psi + i, rr) = q;
+    }
+    return diff;
+}
+WQ_HDN inline void wq_cl_write_out(const WqPsiDev& d, const WqPsiClEv& ev, const WqClCtx& c, uint32_t tid, int64_t it) {
+    const WqPsiClSmem& S = c.S;
+    const uint32_t nsl = wq_cl_nslots(ev.np, c.r, c.C);
+    for (uint32_t s = tid; s < nsl; s += c.T) {
+        const uint32_t i = wq_cl_path(s, c.r, c.C);
+        if (i >= ev.np) continue;
+        d.psi[ev.p0 + i] = S.psi[i];
+        d.ctemp[ev.p0 + i] = S.ct[s];
+    }
+    if (c.r == 0 && tid == 0) d.iterations[ev.e] = (int32_t)it;
+}
+
+__global__ void __launch_bounds__(1024) wq_k_em_psi_cl(const WqPsiDev d, const uint32_t* __restrict__ list, const uint32_t n_list, const WqPsiClCfg z) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cg::cluster_group cl = cg::this_cluster();
+    WqClCtx c;
+    c.r = cl.block_rank(); c.C = z.C; c.T = blockDim.x; c.self = nullptr; c.all = nullptr;
+    wq_psi_cl_layout(z, smem_raw, &c.S);
+    const uint32_t tid = threadIdx.x;
+    const uint32_t ncl = gridDim.x / z.C, cid = blockIdx.x / z.C;
+    for (uint32_t slot = cid; slot < n_list; slot += ncl) {          // every block of a cluster walks the same events
+        const WqPsiClEv ev = wq_psi_cl_event(d, list[slot]);
+        wq_cl_init_a(d, ev, c, tid);
+        __syncthreads();
+        wq_cl_init_b(d, ev, c, tid);
+        __syncthreads();
+        if (tid == 0) wq_cl_init_c(ev, c);
+        __syncthreads();
+        for (uint32_t a = 0; a < ev.na; a++) { wq_cl_init_d(d, ev, c, tid, a); __syncthreads(); }
+        cl.sync();
+        bool differs = false;
+        auto norm = [&](int sig) {
+            const bool df = wq_cl_phase_norm(d, ev, c, tid, sig);
+            const int any = __syncthreads_or(df ? 1 : 0);
+            if (tid == 0) for (uint32_t rr = 0; rr < c.C; rr++) *wq_cl_remote(c, c.S.flags + c.r, rr) = (uint32_t)(any != 0);
+            cl.sync();
+            uint32_t f = 0;
+            for (uint32_t rr = 0; rr < c.C; rr++) f |= c.S.flags[rr];
+            differs = f != 0;
+        };
+        if (!ev.tandem) {
+            wq_cl_phase_pre(ev, c, tid);
+            cl.sync();
+            wq_cl_phase_total(ev, c, tid);
+            __syncthreads();
+            norm(0);
+        }
+        int64_t it = 1;
+        for (;;) {
+            if (!ev.tandem && !(differs && it < d.maxit)) break;
+            if (it > 1) { wq_cl_phase_psum(ev, c, tid); cl.sync(); }
+            wq_cl_phase_shares(d, ev, c, tid, it == 1);
+            cl.sync();
+            wq_cl_phase_total(ev, c, tid);
+            __syncthreads();
+            norm(d.sig);
+            if (ev.tandem) { if (differs && it < d.maxit) it += 1; else break; }
+            else it += 1;
+        }
+        wq_cl_write_out(d, ev, c, tid, it);
+        cl.sync();                                                   // no block rebuilds its arrays while another still reads them
+    }
+}
+
 // Events with at most 4 paths (more than 90 % of them), at most WQ_PSI4_SETS ambiguous sets of at most 4 members: 4 lanes per
 // event, 8 events per warp.  Lane i of the group OWNS path i (psi / previous psi / temp count in registers); once per sweep the
 // four psi values are exchanged with four shuffles, after which every lane forms every set's prop_sum from registers (the same
@@ -1474,6 +1778,40 @@ __global__ void __launch_bounds__(128) wq_k_em_psi4(const WqPsiDev d, const uint
 
 // `wait` = false leaves the launch and its result copies in flight on `stream` (the result buffers must then be pinned
 // host memory and stay alive until the stream has been synchronised)
+// capacities of the cluster kernel's shared-memory layout over the given events; returns the bytes one block needs
+static inline size_t wq_psi_cl_config(const wq_psi_batch& b, const uint32_t* events, uint32_t n, uint32_t C, WqPsiClCfg& z) {
+    memset(&z, 0, sizeof z);
+    z.C = C;
+    for (uint32_t k = 0; k < n; k++) {
+        const uint32_t e = events[k];
+        const uint32_t np = b.path_ptr[e + 1] - b.path_ptr[e], a_lo = b.amb_ptr[e], na = b.amb_ptr[e + 1] - a_lo;
+        z.np_cap = std::max(z.np_cap, np); z.na_cap = std::max(z.na_cap, na);
+        z.npl_cap = std::max(z.npl_cap, wq_cl_nslots(np, 0, C)); z.nal_cap = std::max(z.nal_cap, wq_cl_nsets(na, 0, C));
+        uint32_t own_mem[8] = {0}, own_inv[8] = {0};
+        for (uint32_t a = 0; a < na; a++) {
+            own_mem[a % C] += b.amb_path_ptr[a_lo + a + 1] - b.amb_path_ptr[a_lo + a];
+            for (uint32_t j = b.amb_path_ptr[a_lo + a]; j < b.amb_path_ptr[a_lo + a + 1]; j++) own_inv[wq_cl_owner(b.amb_paths[j], C)]++;
+        }
+        for (uint32_t r = 0; r < C; r++) { z.mem_cap = std::max(z.mem_cap, own_mem[r]); z.inv_cap = std::max(z.inv_cap, own_inv[r]); }
+    }
+    return wq_psi_cl_layout(z, nullptr, nullptr);
+}
+// the cluster kernel's inverted-index build needs every path at most once per set (and every member inside the event)
+static inline bool wq_psi_cl_unique(const wq_psi_batch& b, const uint32_t* events, uint32_t n) {
+    std::vector<uint32_t> stamp;
+    for (uint32_t k = 0; k < n; k++) {
+        const uint32_t e = events[k];
+        stamp.assign(b.path_ptr[e + 1] - b.path_ptr[e], 0xFFFFFFFFu);
+        for (uint32_t a = b.amb_ptr[e]; a < b.amb_ptr[e + 1]; a++)
+            for (uint32_t j = b.amb_path_ptr[a]; j < b.amb_path_ptr[a + 1]; j++) {
+                const uint32_t m = b.amb_paths[j];
+                if (m >= stamp.size() || stamp[m] == a) return false;
+                stamp[m] = a;
+            }
+    }
+    return true;
+}
+
 static inline std::string wq_run_em_psi(wq_psi_batch& b, WqEmScratch& M, cudaStream_t stream, uint64_t* launches, bool wait = true) {
     const uint32_t E = b.n_events;
     if (E == 0) return "";
@@ -1556,7 +1894,52 @@ static inline std::string wq_run_em_psi(wq_psi_batch& b, WqEmScratch& M, cudaStr
     WqPsiBigCfg staged;
     memset(&staged, 0, sizeof staged);
     const uint32_t nbig = nclass[5] + nclass[6];
-    if (nbig) {                                               // global scratch of the large events (classes 5 and 6 are adjacent in `order`): members and sets back to back
+    // Large events on a cluster of C blocks (wq_k_em_psi_cl) when the device can hold them in at most two rounds: C = 8 when all of them
+    // are resident at once, else C = 4.  More events than that (a single GPU holding every large event of a deep job) stay on the block
+    // kernel, where every SM already has an event of its own.  WQ_PSI_CLUSTER = 0 / 2 / 4 / 8 overrides (0: never).
+    WqPsiClCfg clz;
+    memset(&clz, 0, sizeof clz);
+    size_t cl_smem = 0;
+    uint32_t cl_clusters = 0;
+    if (nbig) {
+        const int cl_env = getenv("WQ_PSI_CLUSTER") ? atoi(getenv("WQ_PSI_CLUSTER")) : -1;      // read per call: tests switch it
+        static bool cl_attr_set = false;
+        const size_t smem_max = 227 * 1024;
+        const bool unique = wq_psi_cl_unique(b, order.data() + cbase[5], nbig);
+        auto config = [&](uint32_t C, WqPsiClCfg& z) -> size_t { return wq_psi_cl_config(b, order.data() + cbase[5], nbig, C, z); };
+        auto resident = [&](uint32_t C, size_t smem) -> uint32_t {       // clusters of C blocks the device holds at once
+            cudaLaunchConfig_t cfg;
+            memset(&cfg, 0, sizeof cfg);
+            cfg.gridDim = dim3(C * nbig); cfg.blockDim = dim3(1024); cfg.dynamicSmemBytes = smem;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            int n = 0;
+            if (cudaOccupancyMaxActiveClusters(&n, wq_k_em_psi_cl, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
+            return n > 0 ? (uint32_t)n : 0u;
+        };
+        if (unique && cl_env != 0) {
+            if (!cl_attr_set) {
+                if (cudaFuncSetAttribute(wq_k_em_psi_cl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max) == cudaSuccess) cl_attr_set = true;
+                else cudaGetLastError();
+            }
+            const uint32_t tryC[2] = {8, 4};
+            for (int t = 0; t < 2 && cl_attr_set && !cl_clusters; t++) {
+                const uint32_t C = cl_env > 0 ? (uint32_t)cl_env : tryC[t];
+                if (C != 2 && C != 4 && C != 8) break;
+                WqPsiClCfg z;
+                const size_t need = config(C, z);
+                if (need <= smem_max) {
+                    const uint32_t res = resident(C, need);
+                    const bool take = cl_env > 0 ? res > 0 : (C == 8 ? nbig <= res : nbig <= 2 * res);
+                    if (take) { clz = z; cl_smem = need; cl_clusters = std::min(nbig, res); }
+                }
+                if (cl_env > 0) break;
+            }
+        }
+    }
+    if (nbig && !cl_clusters) {                                               // global scratch of the large events (classes 5 and 6 are adjacent in `order`): members and sets back to back
         std::vector<uint64_t> base(2ull * nbig);
         uint64_t mtot = 0, atot = 0;
         for (uint32_t k = 0; k < nbig; k++) {
@@ -1599,11 +1982,22 @@ static inline std::string wq_run_em_psi(wq_psi_batch& b, WqEmScratch& M, cudaStr
     int used = 0;
     for (int c = NC - 1; c >= 0; c--) {             // the large events first: their sweeps are the long pole
         if (!nclass[c]) continue;
+        if (c == 5 && cl_clusters && nclass[6]) continue;         // went out with class 6's cluster launch
         cudaStream_t ss = used == 0 ? stream : M.side[(used - 1) % 3];
         if (used > 0) WQ_EMCK(cudaStreamWaitEvent(ss, M.fork, 0));
         const uint32_t n = nclass[c];
         const uint32_t* lst = d_list + cbase[c];
         if (c == 0) wq_k_em_psi4<<<(n + 31) / 32, 128, 0, ss>>>(d, lst, n);
+        else if (c >= 5 && cl_clusters) {                     // classes 5 and 6 are adjacent in `order`: one cluster launch covers both
+            cudaLaunchConfig_t cfg;
+            memset(&cfg, 0, sizeof cfg);
+            cfg.gridDim = dim3(clz.C * cl_clusters); cfg.blockDim = dim3(1024); cfg.dynamicSmemBytes = cl_smem; cfg.stream = ss;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = clz.C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            WQ_EMCK(cudaLaunchKernelEx(&cfg, wq_k_em_psi_cl, d, (const uint32_t*)(d_list + cbase[5]), nbig, clz));
+        }
         else if (c >= 5) wq_k_em_psi<<<n, 1024, big_smem[c - 5], ss>>>(d, lst, n, bigc[c - 5]);
         else wq_k_em_psi<<<n, kBlockThreads[c - 1], kBlockSmem[c - 1], ss>>>(d, lst, n, staged);
         if (launches) *launches += 1;
@@ -1620,6 +2014,7 @@ static inline std::string wq_run_em_psi(wq_psi_batch& b, WqEmScratch& M, cudaStr
                 np_max = std::max<uint64_t>(np_max, b.path_ptr[e + 1] - b.path_ptr[e]);
                 sweeps += (uint64_t)its[e]; if (its[e] >= b.maxit) capped++;
             }
+            if (c >= 5 && cl_clusters) fprintf(stderr, "[wq]       psi classes 5+6 on %u clusters of %u blocks (%zu B shared memory each), %u events; next line: class %d's share\n", cl_clusters, clz.C, cl_smem, nbig, c);
             fprintf(stderr, "[wq]       psi class %d: %u events (max %llu paths, %llu sweeps, %llu at the cap) %9.3f ms\n", c, n, (unsigned long long)np_max,
                     (unsigned long long)sweeps, (unsigned long long)capped, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
         }
