@@ -124,6 +124,7 @@ struct wq_handle {
     float psi_kernel_ms = 0.f;   // device time of the PSI EM launches of the last wq_process_events (CUDA events on the stream)
     uint64_t psi_sweep_bytes = 0;
     std::vector<WqEvPiece> ev_pieces; uint32_t ev_pieces_key[3] = {0xFFFFFFFFu, 0, 0};      // work list of the event build (index + partition only)
+    std::vector<unsigned> ev_cuts;                              // the ranks' ranges of that list for the current counts (empty: not computed yet)
     WqEvBatch ev_batch[2];       // event problems of the genes no multi-map read touches (built while the transcript EM runs) / of the others
     DevBuf<uint64_t> d_ck, d_cv, d_ck2, d_cv2; DevBuf<uint32_t> d_ckoff; DevBuf<uint8_t> d_cubtmp;
     DevBuf<uint64_t> d_xpack; DevBuf<uint32_t> d_xpending;      // multi-GPU exchange: this rank's packed sparse stores / merge queue
@@ -473,6 +474,7 @@ static void reset_quant_ex(wq_handle* h) {
         B.built = B.launched = false;
     }
     h->hx = WqHostQuantEx();
+    h->ev_cuts.clear();
     h->events_done = false;
 }
 
@@ -498,9 +500,14 @@ static void wq_build_event_batch(wq_handle* h, int64_t readlen, int group, WqEvB
     // holds the same counts after wq_counts_sync and the same piece list, so every rank computes the same cuts (wq_event_cuts).
     unsigned pc_lo = 0, pc_hi = npieces;
     if (h->nparts > 1) {
-        std::vector<unsigned> cuts;
-        wq_event_cuts(h->H, X.edge_key, X.edge_value, pieces, h->nparts, cuts);
-        pc_lo = cuts[h->part]; pc_hi = cuts[h->part + 1];
+        // from the RAW count store (identical on every rank after the exchange, and the same for both gene groups of a job: the merged
+        // values in X change when assign_ambig! runs between the two builds), once per job
+        if (h->ev_cuts.size() != (size_t)h->nparts + 1) {
+            std::vector<double> raw(h->hq.edge_count.size());
+            for (size_t i = 0; i < raw.size(); i++) raw[i] = (double)h->hq.edge_count[i];
+            wq_event_cuts(h->H, h->hq.edge_key, raw, pieces, h->nparts, h->ev_cuts);
+        }
+        pc_lo = h->ev_cuts[h->part]; pc_hi = h->ev_cuts[h->part + 1];
     }
     // the group of genes that multi-map classes name is often empty (no multi-mapping reads in the job): nothing to build or launch then
     bool any = group == 0;
@@ -1949,6 +1956,7 @@ int wq_set_gene_partition(wq_handle* h, uint32_t part, uint32_t nparts) {
     if (h->part != part || h->nparts != nparts) {
         for (WqEvBatch& B : h->ev_batch) { if (B.launched) cudaStreamSynchronize(B.stream); B.built = B.launched = false; }
         h->events_done = false;
+        h->ev_cuts.clear();
     }
     h->part = part; h->nparts = nparts;
     return 0;

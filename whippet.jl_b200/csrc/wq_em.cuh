@@ -1414,6 +1414,8 @@ struct WqPsiClCfg {
     uint32_t C;                                   // blocks per cluster
     uint32_t np_cap, na_cap, npl_cap, nal_cap;    // over the launch's events: paths, sets, path slots of one block, sets of one block
     uint32_t mem_cap, inv_cap;                    // entries of one block's member lists / inverted index
+    uint32_t split;                               // 1: several lanes share a path's divisions in phase (2) when the block has threads to spare
+    long long* dbg;                               // optional [8] clock totals of cluster 0, block 0 (WQ_PSI_CL_TIMING): build, prop_sum, barrier, shares, barrier, total, normalise + barrier, sweeps
 };
 struct WqPsiClSmem {                              // one block's arrays; the layout is identical in every block of the launch
     double *psi, *raw, *psum, *mult;              // complete copies: [np] rounded psi, [np] count / length, [na], [na]
@@ -1534,15 +1536,34 @@ WQ_HDN inline void wq_cl_init_d(const WqPsiDev& d, const WqPsiClEv& ev, const Wq
         S.lpset[at] = (uint16_t)a;
     }
 }
-// -- sweep.  (1) prop_sum of the own sets, to every block
+// -- sweep.  (1) prop_sum of the own sets, to every block.  The chain of additions is the set's member order; what can overlap is
+// the two dependent shared-memory loads per member (index, then psi), so the loop is software-pipelined by hand: the values of the
+// next eight members are fetched while the current eight are added (measured before: 55 clocks per member of the longest set, the
+// largest item of a sweep; the additions alone need ~8).
 WQ_HDN inline void wq_cl_phase_psum(const WqPsiClEv& ev, const WqClCtx& c, uint32_t tid) {
     const WqPsiClSmem& S = c.S;
     const uint32_t nal = wq_cl_nsets(ev.na, c.r, c.C);
     for (uint32_t al = tid; al < nal; al += c.T) {
         double sm = 0.0;
-        const uint32_t kb = S.lmoff[al], ke = S.lmoff[al + 1];
-        #pragma unroll 8
-        for (uint32_t k = kb; k < ke; k++) sm = WQ_EM_DADD(sm, S.psi[S.lmem[k]]);
+        uint32_t k = S.lmoff[al];
+        const uint32_t ke = S.lmoff[al + 1];
+        if (ke - k >= 8) {
+            double va[8], vb[8];
+            #pragma unroll
+            for (int j = 0; j < 8; j++) va[j] = S.psi[S.lmem[k + j]];
+            k += 8;
+            for (; ke - k >= 8; k += 8) {
+                #pragma unroll
+                for (int j = 0; j < 8; j++) vb[j] = S.psi[S.lmem[k + j]];
+                #pragma unroll
+                for (int j = 0; j < 8; j++) sm = WQ_EM_DADD(sm, va[j]);
+                #pragma unroll
+                for (int j = 0; j < 8; j++) va[j] = vb[j];
+            }
+            #pragma unroll
+            for (int j = 0; j < 8; j++) sm = WQ_EM_DADD(sm, va[j]);
+        }
+        for (; k < ke; k++) sm = WQ_EM_DADD(sm, S.psi[S.lmem[k]]);
         const uint32_t a = c.r + c.C * al;
         for (uint32_t rr = 0; rr < c.C; rr++) *wq_cl_remote(c, S.psum + a, rr) = sm;
     }
@@ -1594,8 +1615,24 @@ WQ_HDN inline void wq_cl_phase_total(const WqPsiClEv& ev, const WqClCtx& c, uint
     else if (warp == 0) { lo = ev.ni; hi = ev.np; }
     else { lo = 0; hi = ev.ni; }
     double t = 0.0;
-    #pragma unroll 8
-    for (uint32_t i = lo; i < hi; i++) t = WQ_EM_DADD(t, S.raw[i]);
+    uint32_t i = lo;
+    if (hi - i >= 8) {                                               // pipelined like prop_sum: the next eight values are on their way while these are added
+        double va[8], vb[8];
+        #pragma unroll
+        for (int j = 0; j < 8; j++) va[j] = S.raw[i + j];
+        i += 8;
+        for (; hi - i >= 8; i += 8) {
+            #pragma unroll
+            for (int j = 0; j < 8; j++) vb[j] = S.raw[i + j];
+            #pragma unroll
+            for (int j = 0; j < 8; j++) t = WQ_EM_DADD(t, va[j]);
+            #pragma unroll
+            for (int j = 0; j < 8; j++) va[j] = vb[j];
+        }
+        #pragma unroll
+        for (int j = 0; j < 8; j++) t = WQ_EM_DADD(t, va[j]);
+    }
+    for (; i < hi; i++) t = WQ_EM_DADD(t, S.raw[i]);
     if ((tid & 31u) == 0) S.tot[warp] = t;
 }
 // (3b) divsignif! of the own paths, to every block; returns whether one of this thread's paths changed
@@ -1626,6 +1663,57 @@ WQ_HDN inline void wq_cl_write_out(const WqPsiDev& d, const WqPsiClEv& ev, const
     if (c.r == 0 && tid == 0) d.iterations[ev.e] = (int32_t)it;
 }
 
+// Phase (2) with L = 2 / 4 / 8 lanes per path (device only; the arithmetic and its order are those of wq_cl_phase_shares).  A block of a
+// cluster owns a quarter or an eighth of the paths, fewer than it has threads, and what bounds the phase is the path that belongs to
+// the most sets: its IEEE divisions run one after the other on one lane (the division's special-case branch keeps the compiler from
+// overlapping them: ~125 clocks per set measured).  Here lane h of a group divides the shares k0 + h of every round of L sets, and
+// every lane of the group adds the L quotients in set order (shuffles that name the group's lanes only, so the groups of a warp
+// diverge freely); lane 0 writes.
+template <int L>
+__device__ __forceinline__ void wq_cl_phase_shares_split(const WqPsiDev& d, const WqPsiClEv& ev, const WqClCtx& c, uint32_t tid, bool first) {
+    const WqPsiClSmem& S = c.S;
+    const uint32_t nsl = wq_cl_nslots(ev.np, c.r, c.C);
+    const uint32_t lane = tid & 31u, h = lane & (uint32_t)(L - 1), base = lane & ~(uint32_t)(L - 1);
+    const unsigned gmask = (L == 32 ? 0xFFFFFFFFu : ((1u << L) - 1u)) << base;
+    for (uint32_t s = tid / L; s < nsl; s += c.T / L) {              // s is the same for the L lanes of a group
+        const uint32_t i = wq_cl_path(s, c.r, c.C);
+        if (i >= ev.np) continue;
+        double cc = S.cnt[s];
+        const double pi = S.psi[i];
+        const uint32_t kb = S.poff[s], ke = S.poff[s + 1];
+        for (uint32_t k0 = kb; k0 < ke; k0 += L) {
+            const uint32_t k = k0 + h;
+            double q = 0.0;
+            if (k < ke) {
+                const uint32_t a = S.lpset[k];
+                if (!first) q = WQ_EM_DMUL(WQ_EM_DDIV(pi, S.psum[a]), S.mult[a]);
+                else {
+                    const uint32_t n = d.amb_path_ptr[ev.a0 + a + 1] - d.amb_path_ptr[ev.a0 + a];
+                    q = WQ_EM_DMUL(WQ_EM_DDIV(1.0, (double)n), S.mult[a]);
+                }
+            }
+            #pragma unroll
+            for (int j = 0; j < L; j++) {
+                const double qj = __shfl_sync(gmask, q, (int)base + j);
+                if (k0 + (uint32_t)j < ke) cc = WQ_EM_DADD(cc, qj);
+            }
+        }
+        if (h == 0) {
+            S.ct[s] = cc;
+            S.prev[s] = pi;
+            const double rv = WQ_EM_DDIV(cc, S.den[s]);
+            for (uint32_t rr = 0; rr < c.C; rr++) *wq_cl_remote(c, S.raw + i, rr) = rv;
+        }
+    }
+}
+__device__ __forceinline__ void wq_cl_phase_shares_dev(const WqPsiDev& d, const WqPsiClEv& ev, const WqClCtx& c, uint32_t tid, bool first, bool split) {
+    const uint32_t nsl = wq_cl_nslots(ev.np, c.r, c.C);
+    if (split && nsl * 8u <= c.T) wq_cl_phase_shares_split<8>(d, ev, c, tid, first);
+    else if (split && nsl * 4u <= c.T) wq_cl_phase_shares_split<4>(d, ev, c, tid, first);
+    else if (split && nsl * 2u <= c.T) wq_cl_phase_shares_split<2>(d, ev, c, tid, first);
+    else wq_cl_phase_shares(d, ev, c, tid, first);
+}
+
 __global__ void __launch_bounds__(1024) wq_k_em_psi_cl(const WqPsiDev d, const uint32_t* __restrict__ list, const uint32_t n_list, const WqPsiClCfg z) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cg::cluster_group cl = cg::this_cluster();
@@ -1634,8 +1722,12 @@ __global__ void __launch_bounds__(1024) wq_k_em_psi_cl(const WqPsiDev d, const u
     wq_psi_cl_layout(z, smem_raw, &c.S);
     const uint32_t tid = threadIdx.x;
     const uint32_t ncl = gridDim.x / z.C, cid = blockIdx.x / z.C;
+    const bool timing = z.dbg != nullptr && blockIdx.x == 0 && tid == 0;
+    long long tk[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t0 = 0;
+    auto lap = [&](int k) { if (timing) { const long long t1 = clock64(); tk[k] += t1 - t0; t0 = t1; } };
     for (uint32_t slot = cid; slot < n_list; slot += ncl) {          // every block of a cluster walks the same events
         const WqPsiClEv ev = wq_psi_cl_event(d, list[slot]);
+        if (timing) t0 = clock64();
         wq_cl_init_a(d, ev, c, tid);
         __syncthreads();
         wq_cl_init_b(d, ev, c, tid);
@@ -1644,6 +1736,7 @@ __global__ void __launch_bounds__(1024) wq_k_em_psi_cl(const WqPsiDev d, const u
         __syncthreads();
         for (uint32_t a = 0; a < ev.na; a++) { wq_cl_init_d(d, ev, c, tid, a); __syncthreads(); }
         cl.sync();
+        lap(0);
         bool differs = false;
         auto norm = [&](int sig) {
             const bool df = wq_cl_phase_norm(d, ev, c, tid, sig);
@@ -1664,18 +1757,25 @@ __global__ void __launch_bounds__(1024) wq_k_em_psi_cl(const WqPsiDev d, const u
         int64_t it = 1;
         for (;;) {
             if (!ev.tandem && !(differs && it < d.maxit)) break;
-            if (it > 1) { wq_cl_phase_psum(ev, c, tid); cl.sync(); }
-            wq_cl_phase_shares(d, ev, c, tid, it == 1);
+            if (timing) t0 = clock64();
+            if (it > 1) { wq_cl_phase_psum(ev, c, tid); lap(1); cl.sync(); lap(2); }
+            wq_cl_phase_shares_dev(d, ev, c, tid, it == 1, z.split != 0);
+            lap(3);
             cl.sync();
+            lap(4);
             wq_cl_phase_total(ev, c, tid);
             __syncthreads();
+            lap(5);
             norm(d.sig);
+            lap(6);
+            if (timing) tk[7] += 1;                                  // slot 7 counts sweeps
             if (ev.tandem) { if (differs && it < d.maxit) it += 1; else break; }
             else it += 1;
         }
         wq_cl_write_out(d, ev, c, tid, it);
         cl.sync();                                                   // no block rebuilds its arrays while another still reads them
     }
+    if (timing) for (int k = 0; k < 8; k++) z.dbg[k] = tk[k];
 }
 
 // Events with at most 4 paths (more than 90 % of them), at most WQ_PSI4_SETS ambiguous sets of at most 4 members: 4 lanes per
@@ -1933,7 +2033,7 @@ static inline std::string wq_run_em_psi(wq_psi_batch& b, WqEmScratch& M, cudaStr
                 if (need <= smem_max) {
                     const uint32_t res = resident(C, need);
                     const bool take = cl_env > 0 ? res > 0 : (C == 8 ? nbig <= res : nbig <= 2 * res);
-                    if (take) { clz = z; cl_smem = need; cl_clusters = std::min(nbig, res); }
+                    if (take) { clz = z; cl_smem = need; cl_clusters = std::min(nbig, res); clz.split = getenv("WQ_PSI_CL_SPLIT") ? (uint32_t)(atoi(getenv("WQ_PSI_CL_SPLIT")) != 0) : 1u; }
                 }
                 if (cl_env > 0) break;
             }
@@ -1996,7 +2096,17 @@ static inline std::string wq_run_em_psi(wq_psi_batch& b, WqEmScratch& M, cudaStr
             at[0].id = cudaLaunchAttributeClusterDimension;
             at[0].val.clusterDim.x = clz.C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
             cfg.attrs = at; cfg.numAttrs = 1;
+            const bool cl_timing = getenv("WQ_PSI_CL_TIMING") != nullptr;      // diagnostic: per-phase clocks of cluster 0, block 0; waits for the launch
+            if (cl_timing) { WQ_EMCK(M.get<long long>(24, 8, &clz.dbg)); WQ_EMCK(cudaMemsetAsync(clz.dbg, 0, 64, ss)); }
             WQ_EMCK(cudaLaunchKernelEx(&cfg, wq_k_em_psi_cl, d, (const uint32_t*)(d_list + cbase[5]), nbig, clz));
+            if (cl_timing) {
+                long long tk[8];
+                WQ_EMCK(cudaStreamSynchronize(ss));
+                WQ_EMCK(cudaMemcpy(tk, clz.dbg, 64, cudaMemcpyDeviceToHost));
+                const double sw = tk[7] > 0 ? (double)tk[7] : 1.0;
+                fprintf(stderr, "[wq]       psi cluster kernel (%u events, %u clusters of %u): build %.0f clocks per event-walk; per sweep of cluster 0 (%lld sweeps): prop_sum %.0f, barrier %.0f, shares %.0f, "
+                        "barrier %.0f, total %.0f, normalise + barrier %.0f clocks\n", nbig, cl_clusters, clz.C, (double)tk[0], tk[7], tk[1] / sw, tk[2] / sw, tk[3] / sw, tk[4] / sw, tk[5] / sw, tk[6] / sw);
+            }
         }
         else if (c >= 5) wq_k_em_psi<<<n, 1024, big_smem[c - 5], ss>>>(d, lst, n, bigc[c - 5]);
         else wq_k_em_psi<<<n, kBlockThreads[c - 1], kBlockSmem[c - 1], ss>>>(d, lst, n, staged);
