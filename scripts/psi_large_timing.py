@@ -3,7 +3,7 @@ weak-scaling job holds, and to 48 / 96): block kernel (WQ_PSI_CLUSTER=0) against
 the library's own choice.  The kernel time is the library's per-class diagnostic (WQ_PSI_CLASS_TIMING: host clock around a stream
 synchronisation after the launch, printed on stderr as "psi class 5"); the wall time of the Python call is dominated by building the
 argument arrays and only given for completeness.  One more call per cluster mode prints the per-phase clocks of one block
-(WQ_PSI_CL_TIMING).  WQ_PSI_CL_SPLIT=0 switches the lane-split shares phase off.  The results of every mode are compared with the block kernel's bit for bit."""
+(WQ_PSI_CL_TIMING).  WQ_PSI_CL_SPLIT=1 switches the lane-split shares phase on.  The results of every mode are compared with the block kernel's bit for bit."""
 import os
 import sys
 import time
@@ -20,7 +20,7 @@ base = large_events()
 for reps in [int(x) for x in sys.argv[1:]] or [6, 12, 24]:
     problems = base * reps
     ref = None
-    for mode, split in (("0", None), ("4", "0"), ("4", None), ("8", "0"), ("8", None), (None, None)):
+    for mode, split in (("0", None), ("2", None), ("4", None), ("4", "1"), ("8", None), (None, None)):
         for name, val in (("WQ_PSI_CLUSTER", mode), ("WQ_PSI_CL_SPLIT", split)):
             if val is None:
                 os.environ.pop(name, None)
@@ -35,7 +35,7 @@ for reps in [int(x) for x in sys.argv[1:]] or [6, 12, 24]:
         if ref is None:
             ref = sig
         print(f"{len(problems):3d} large events, WQ_PSI_CLUSTER={mode} WQ_PSI_CL_SPLIT={split}: call {wall * 1e3:8.1f} ms  equal_to_block_kernel={sig == ref}", flush=True)
-        if mode in ("4", "8") and reps == 6:
+        if mode in ("2", "4", "8") and split is None and reps == 6:
             os.environ["WQ_PSI_CL_TIMING"] = "1"
             q.em_psi_batch(problems, readlen=101)
             os.environ.pop("WQ_PSI_CL_TIMING")

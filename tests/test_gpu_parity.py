@@ -387,7 +387,7 @@ def test_em_psi_batch_all_event_sizes(fixture_index):
 
 def test_em_psi_large_events_block_and_cluster_kernels(fixture_index, monkeypatch):
     """Large events (1000-1900 paths, 60-140 k set members; all run to the 1500-sweep cap) through wq_em_psi_batch on the block kernel
-    (WQ_PSI_CLUSTER=0: one block per event, member lists in a global scratch) and on the cluster kernel with 8 and 4 blocks per event
+    (WQ_PSI_CLUSTER=0: one block per event, member lists in a global scratch) and on the cluster kernel with 8, 4 and 2 blocks per event
     (everything in distributed shared memory; with and without the lane-split shares phase), and as the library chooses by itself: every psi value and iteration count equals
     the oracle's spliced_em! (src/events.jl:853-893).  The problems are tests/golden/psi_large_events.npz (inputs only)."""
     from oracle import em_psi
@@ -398,9 +398,8 @@ def test_em_psi_large_events_block_and_cluster_kernels(fixture_index, monkeypatc
     want = [em_psi(ni, cnt, ln, sets, mult, tandem, 101) for (ni, cnt, ln, sets, mult, tandem) in problems]
     assert all(it == 1500 for _, it in want[:4])
     q = wq.GraphLibQuant(fixture_index)
-    # WQ_PSI_CL_SPLIT=0: one lane per path in the shares phase of the cluster kernel instead of 2 / 4 / 8 (the default when a block has
-    # threads to spare)
-    for mode, split in (("0", None), ("8", None), ("8", "0"), ("4", None), ("4", "0"), (None, None)):
+    # WQ_PSI_CL_SPLIT=1: 2 / 4 / 8 lanes per path in the shares phase of the cluster kernel (off by default: measured slower)
+    for mode, split in (("0", None), ("8", None), ("8", "1"), ("4", None), ("4", "1"), ("2", None), (None, None)):
         for name, val in (("WQ_PSI_CLUSTER", mode), ("WQ_PSI_CL_SPLIT", split)):
             if val is None:
                 monkeypatch.delenv(name, raising=False)

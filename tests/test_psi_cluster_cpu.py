@@ -75,12 +75,19 @@ def test_cluster_phases_equal_oracle_large_events(blocks):
 
 
 def test_cluster_layout_limits():
-    """Two blocks cannot hold the member lists of a 1900-path event in shared memory, and a set that names a path twice would race in
-    the inverted-index build: both are refused (the library then keeps the events on the block kernel)."""
+    """What the host refuses (the library then keeps the events on the block kernel): a layout beyond the 227 KB of shared memory a
+    block can have -- a synthetic event of 20 000 paths in 40 sets on two blocks -- and member lists that are not in ascending path
+    order (the bit-mask walk of phase 1 would add them in another order than the reference; a path twice would also race in the
+    inverted-index build).  Two blocks do hold a 1900-path event."""
     problems = large_events()[:1]
     got, need = psi_cluster(problems, 2, 64, readlen=101, maxit=3)
+    assert got is not None and need <= 227 * 1024
+    assert check(problems, got, 101, 3) == 1
+    n = 20000
+    huge = (n // 2, np.ones(n), np.full(n, 100.0), [np.arange(k, n, 2, dtype=np.uint32) for k in range(40)], np.ones(40), False)
+    got, need = psi_cluster([huge], 2, 64, readlen=101, maxit=2)
     assert got is None and need > 227 * 1024
     ni, cnt, ln, sets, mult, t = random_problems(9, [40])[0]
-    sets = [list(sets[0]) + [sets[0][0]]] + sets[1:]
-    got, _ = psi_cluster([(ni, cnt, ln, sets, mult, t)], 4, 64, readlen=101)
-    assert got is None
+    for bad in ([list(sets[0]) + [sets[0][0]]], [list(sets[0])[::-1]]):
+        got, _ = psi_cluster([(ni, cnt, ln, bad + sets[1:], mult, t)], 4, 64, readlen=101)
+        assert got is None

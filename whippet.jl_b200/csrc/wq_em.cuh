@@ -1398,11 +1398,11 @@ static inline size_t wq_psi_big_smem(uint32_t np, uint32_t na, bool sets) {     
 // them (the nodes of one titin-like gene under one long exon-skipping junction).  One block per event leaves such a sweep at ~100 us:
 // 0.6 MB of member lists streamed from L2, 140 k IEEE divisions on one SM's Float64 pipe, and most SMs idle when the events are shared
 // between the ranks of a multi-GPU job.  Here C = 2 / 4 / 8 blocks of a cluster share one event.  Paths are dealt to the blocks in
-// groups of 32 (block r owns the paths i with (i / 32) % C == r), sets round-robin (a % C == r); a block keeps ONLY the member lists
-// of its own sets and the inverted index of its own paths -- with the lists divided by C the whole working set sits in shared
-// memory and a sweep touches no global memory at all.  Per sweep, three cluster barriers:
-//   (1) prop_sum of the block's sets (sequential in member order, a lane per set), written into every block's psum[] through
-//       distributed shared memory;                                                                                  -- barrier
+// groups of 32 (block r owns the paths i with (i / 32) % C == r), sets round-robin (a % C == r); a block keeps ONLY the members of
+// its own sets (as bit masks over the paths) and the inverted index of its own paths -- divided by C the whole working set sits in
+// shared memory and a sweep touches no global memory at all.  Per sweep, three cluster barriers:
+//   (1) prop_sum of the block's sets (sequential in member order = ascending path order, a lane per set walking the set's bit mask
+//       over broadcast reads of psi), written into every block's psum[] through distributed shared memory;                                                                                  -- barrier
 //   (2) the block's paths: unambiguous count + shares in set order (the owner divides its own shares), count / length written into
 //       every block's raw[];                                                                                        -- barrier
 //   (3) every block forms the same total from raw[] (the reference's order: exclusion paths, inclusion paths, their sum -- two
@@ -1413,31 +1413,32 @@ static inline size_t wq_psi_big_smem(uint32_t np, uint32_t na, bool sets) {     
 struct WqPsiClCfg {
     uint32_t C;                                   // blocks per cluster
     uint32_t np_cap, na_cap, npl_cap, nal_cap;    // over the launch's events: paths, sets, path slots of one block, sets of one block
-    uint32_t mem_cap, inv_cap;                    // entries of one block's member lists / inverted index
-    uint32_t split;                               // 1: several lanes share a path's divisions in phase (2) when the block has threads to spare
+    uint32_t inv_cap;                             // entries of one block's inverted index
+    uint32_t split;                               // 1: several lanes share a path's divisions in phase (2) when the block has threads to spare (WQ_PSI_CL_SPLIT=1; slower as measured)
     long long* dbg;                               // optional [8] clock totals of cluster 0, block 0 (WQ_PSI_CL_TIMING): build, prop_sum, barrier, shares, barrier, total, normalise + barrier, sweeps
 };
 struct WqPsiClSmem {                              // one block's arrays; the layout is identical in every block of the launch
     double *psi, *raw, *psum, *mult;              // complete copies: [np] rounded psi, [np] count / length, [na], [na]
     double *prev, *ct, *den, *cnt, *tot;          // the block's own path slots; tot[2] = the two partial sums of the total
-    uint32_t *lmoff, *poff, *cur, *flags;         // [nal + 1] member offsets of the own sets, [npl + 1] inverted index, build cursor, [8] changed flags
-    uint16_t *lmem, *lpset;                       // members of the own sets (event-local path ids); sets of the own paths, in set order
+    uint32_t *lmask, *poff, *cur, *flags;         // [nal][ceil(np / 32)] member bit masks of the own sets, [npl + 1] inverted index, build cursor, [8] changed flags
+    uint16_t *lpset;                              // sets of the own paths, in set order
 };
 WQ_HDN inline size_t wq_psi_cl_layout(const WqPsiClCfg& z, unsigned char* base, WqPsiClSmem* o) {
     size_t at = 0;
     auto take = [&](size_t bytes) { const size_t p = at; at += (bytes + 15) & ~(size_t)15; return p; };
-    const size_t o_psi = take(8ull * z.np_cap), o_raw = take(8ull * z.np_cap), o_psum = take(8ull * z.na_cap), o_mult = take(8ull * z.na_cap);
+    const uint32_t nwords = (z.np_cap + 31u) >> 5;               // psi[] is padded to whole mask words: phase (1) reads 32 values per word
+    const size_t o_psi = take(8ull * 32u * nwords), o_raw = take(8ull * z.np_cap), o_psum = take(8ull * z.na_cap), o_mult = take(8ull * z.na_cap);
     const size_t o_prev = take(8ull * z.npl_cap), o_ct = take(8ull * z.npl_cap), o_den = take(8ull * z.npl_cap), o_cnt = take(8ull * z.npl_cap), o_tot = take(16);
-    const size_t o_lmoff = take(4ull * (z.nal_cap + 1)), o_poff = take(4ull * (z.npl_cap + 1)), o_cur = take(4ull * z.npl_cap), o_flags = take(32);
-    const size_t o_lmem = take(2ull * z.mem_cap), o_lpset = take(2ull * z.inv_cap);
+    const size_t o_lmask = take(4ull * z.nal_cap * nwords), o_poff = take(4ull * (z.npl_cap + 1)), o_cur = take(4ull * z.npl_cap), o_flags = take(32);
+    const size_t o_lpset = take(2ull * z.inv_cap);
     if (o) {
         o->psi = reinterpret_cast<double*>(base + o_psi); o->raw = reinterpret_cast<double*>(base + o_raw);
         o->psum = reinterpret_cast<double*>(base + o_psum); o->mult = reinterpret_cast<double*>(base + o_mult);
         o->prev = reinterpret_cast<double*>(base + o_prev); o->ct = reinterpret_cast<double*>(base + o_ct);
         o->den = reinterpret_cast<double*>(base + o_den); o->cnt = reinterpret_cast<double*>(base + o_cnt); o->tot = reinterpret_cast<double*>(base + o_tot);
-        o->lmoff = reinterpret_cast<uint32_t*>(base + o_lmoff); o->poff = reinterpret_cast<uint32_t*>(base + o_poff);
+        o->lmask = reinterpret_cast<uint32_t*>(base + o_lmask); o->poff = reinterpret_cast<uint32_t*>(base + o_poff);
         o->cur = reinterpret_cast<uint32_t*>(base + o_cur); o->flags = reinterpret_cast<uint32_t*>(base + o_flags);
-        o->lmem = reinterpret_cast<uint16_t*>(base + o_lmem); o->lpset = reinterpret_cast<uint16_t*>(base + o_lpset);
+        o->lpset = reinterpret_cast<uint16_t*>(base + o_lpset);
     }
     return at;
 }
@@ -1485,28 +1486,29 @@ WQ_HDN inline void wq_cl_init_a(const WqPsiDev& d, const WqPsiClEv& ev, const Wq
         }
     }
     for (uint32_t s = tid; s <= nsl; s += c.T) S.poff[s] = 0;
-    for (uint32_t i = tid; i < ev.np; i += c.T) { S.psi[i] = 0.0; S.raw[i] = 0.0; }
+    const uint32_t nw = (ev.np + 31u) >> 5;
+    for (uint32_t i = tid; i < 32u * nw; i += c.T) S.psi[i] = 0.0;                  // including the padding of the last mask word
+    for (uint32_t i = tid; i < ev.np; i += c.T) S.raw[i] = 0.0;
     for (uint32_t a = tid; a < ev.na; a += c.T) { S.mult[a] = d.amb_mult[ev.a0 + a]; S.psum[a] = 1.0; }
+    const uint32_t nal = wq_cl_nsets(ev.na, c.r, c.C);
+    for (uint32_t k = tid; k < nal * nw; k += c.T) S.lmask[k] = 0u;
     if (tid < 8) S.flags[tid] = 0;
-    if (tid == 0) {
-        const uint32_t nal = wq_cl_nsets(ev.na, c.r, c.C);
-        uint32_t acc = 0;
-        for (uint32_t al = 0; al < nal; al++) {
-            const uint32_t a = c.r + c.C * al;
-            S.lmoff[al] = acc;
-            acc += d.amb_path_ptr[ev.a0 + a + 1] - d.amb_path_ptr[ev.a0 + a];
-        }
-        S.lmoff[nal] = acc;
-    }
 }
-// b: the members of the own sets; how many sets every own path belongs to
+// b: the members of the own sets as bit masks; how many sets every own path belongs to
 WQ_HDN inline void wq_cl_init_b(const WqPsiDev& d, const WqPsiClEv& ev, const WqClCtx& c, uint32_t tid) {
     const WqPsiClSmem& S = c.S;
-    const uint32_t nal = wq_cl_nsets(ev.na, c.r, c.C);
+    const uint32_t nal = wq_cl_nsets(ev.na, c.r, c.C), nw = (ev.np + 31u) >> 5;
     for (uint32_t al = 0; al < nal; al++) {
         const uint32_t a = c.r + c.C * al;
-        const uint32_t gb = d.amb_path_ptr[ev.a0 + a], n = d.amb_path_ptr[ev.a0 + a + 1] - gb, lb = S.lmoff[al];
-        for (uint32_t k = tid; k < n; k += c.T) S.lmem[lb + k] = (uint16_t)d.amb_paths[gb + k];
+        const uint32_t gb = d.amb_path_ptr[ev.a0 + a], n = d.amb_path_ptr[ev.a0 + a + 1] - gb;
+        for (uint32_t k = tid; k < n; k += c.T) {
+            const uint32_t m = d.amb_paths[gb + k];
+#ifdef __CUDA_ARCH__
+            atomicOr(&S.lmask[al * nw + (m >> 5)], 1u << (m & 31u));
+#else
+            S.lmask[al * nw + (m >> 5)] |= 1u << (m & 31u);
+#endif
+        }
     }
     for (uint32_t k = tid; k < ev.nm; k += c.T) {
         const uint32_t m = d.amb_paths[ev.m0 + k];
@@ -1536,34 +1538,24 @@ WQ_HDN inline void wq_cl_init_d(const WqPsiDev& d, const WqPsiClEv& ev, const Wq
         S.lpset[at] = (uint16_t)a;
     }
 }
-// -- sweep.  (1) prop_sum of the own sets, to every block.  The chain of additions is the set's member order; what can overlap is
-// the two dependent shared-memory loads per member (index, then psi), so the loop is software-pipelined by hand: the values of the
-// next eight members are fetched while the current eight are added (measured before: 55 clocks per member of the longest set, the
-// largest item of a sweep; the additions alone need ~8).
+// -- sweep.  (1) prop_sum of the own sets, to every block.  The reference adds a set's members in list order, and the lists are in
+// ascending path order (checked on the host before this kernel is chosen), so a lane walks ITS set's bit mask over the paths in
+// order and adds psi[i] where the bit is set.  Every lane reads the same psi[i] at the same time -- a broadcast, one shared-memory
+// wavefront -- where a gather through member lists cost a bank-conflicted access per member (measured: 26 clocks per member of the
+// longest set, against ~11 for the dependent addition itself; the longest set of a large event names all paths but one, so the
+// chain of ~np additions is the floor of this phase either way).
 WQ_HDN inline void wq_cl_phase_psum(const WqPsiClEv& ev, const WqClCtx& c, uint32_t tid) {
     const WqPsiClSmem& S = c.S;
-    const uint32_t nal = wq_cl_nsets(ev.na, c.r, c.C);
+    const uint32_t nal = wq_cl_nsets(ev.na, c.r, c.C), nw = (ev.np + 31u) >> 5;
     for (uint32_t al = tid; al < nal; al += c.T) {
         double sm = 0.0;
-        uint32_t k = S.lmoff[al];
-        const uint32_t ke = S.lmoff[al + 1];
-        if (ke - k >= 8) {
-            double va[8], vb[8];
+        const uint32_t* mk = S.lmask + al * nw;
+        for (uint32_t w = 0; w < nw; w++) {
+            const uint32_t bits = mk[w];
+            const double* v = S.psi + 32u * w;
             #pragma unroll
-            for (int j = 0; j < 8; j++) va[j] = S.psi[S.lmem[k + j]];
-            k += 8;
-            for (; ke - k >= 8; k += 8) {
-                #pragma unroll
-                for (int j = 0; j < 8; j++) vb[j] = S.psi[S.lmem[k + j]];
-                #pragma unroll
-                for (int j = 0; j < 8; j++) sm = WQ_EM_DADD(sm, va[j]);
-                #pragma unroll
-                for (int j = 0; j < 8; j++) va[j] = vb[j];
-            }
-            #pragma unroll
-            for (int j = 0; j < 8; j++) sm = WQ_EM_DADD(sm, va[j]);
+            for (int b = 0; b < 32; b++) if (bits & (1u << b)) sm = WQ_EM_DADD(sm, v[b]);
         }
-        for (; k < ke; k++) sm = WQ_EM_DADD(sm, S.psi[S.lmem[k]]);
         const uint32_t a = c.r + c.C * al;
         for (uint32_t rr = 0; rr < c.C; rr++) *wq_cl_remote(c, S.psum + a, rr) = sm;
     }
@@ -1668,7 +1660,9 @@ WQ_HDN inline void wq_cl_write_out(const WqPsiDev& d, const WqPsiClEv& ev, const
 // the most sets: its IEEE divisions run one after the other on one lane (the division's special-case branch keeps the compiler from
 // overlapping them: ~125 clocks per set measured).  Here lane h of a group divides the shares k0 + h of every round of L sets, and
 // every lane of the group adds the L quotients in set order (shuffles that name the group's lanes only, so the groups of a warp
-// diverge freely); lane 0 writes.
+// diverge freely); lane 0 writes.  MEASURED SLOWER than one lane per path (L = 2: 45.9 k against 18.9 k clocks per sweep, L = 4: 17.6 k
+// against 16.2 k: the partial-mask shuffles and the groups' divergence cost more than the halved chain saves), so it is OFF unless
+// WQ_PSI_CL_SPLIT=1; kept as a tested variant.
 template <int L>
 __device__ __forceinline__ void wq_cl_phase_shares_split(const WqPsiDev& d, const WqPsiClEv& ev, const WqClCtx& c, uint32_t tid, bool first) {
     const WqPsiClSmem& S = c.S;
@@ -1887,26 +1881,23 @@ static inline size_t wq_psi_cl_config(const wq_psi_batch& b, const uint32_t* eve
         const uint32_t np = b.path_ptr[e + 1] - b.path_ptr[e], a_lo = b.amb_ptr[e], na = b.amb_ptr[e + 1] - a_lo;
         z.np_cap = std::max(z.np_cap, np); z.na_cap = std::max(z.na_cap, na);
         z.npl_cap = std::max(z.npl_cap, wq_cl_nslots(np, 0, C)); z.nal_cap = std::max(z.nal_cap, wq_cl_nsets(na, 0, C));
-        uint32_t own_mem[8] = {0}, own_inv[8] = {0};
-        for (uint32_t a = 0; a < na; a++) {
-            own_mem[a % C] += b.amb_path_ptr[a_lo + a + 1] - b.amb_path_ptr[a_lo + a];
+        uint32_t own_inv[8] = {0};
+        for (uint32_t a = 0; a < na; a++)
             for (uint32_t j = b.amb_path_ptr[a_lo + a]; j < b.amb_path_ptr[a_lo + a + 1]; j++) own_inv[wq_cl_owner(b.amb_paths[j], C)]++;
-        }
-        for (uint32_t r = 0; r < C; r++) { z.mem_cap = std::max(z.mem_cap, own_mem[r]); z.inv_cap = std::max(z.inv_cap, own_inv[r]); }
+        for (uint32_t r = 0; r < C; r++) z.inv_cap = std::max(z.inv_cap, own_inv[r]);
     }
     return wq_psi_cl_layout(z, nullptr, nullptr);
 }
-// the cluster kernel's inverted-index build needs every path at most once per set (and every member inside the event)
+// the cluster kernel walks a set's members as a bit mask in ascending path order, which is the reference's order of additions only
+// when the member list is ascending (it is, as the event construction writes it: inclusion paths, then exclusion paths, each in
+// order); ascending also means no path twice (the inverted-index build relies on that) and every member inside the event
 static inline bool wq_psi_cl_unique(const wq_psi_batch& b, const uint32_t* events, uint32_t n) {
-    std::vector<uint32_t> stamp;
     for (uint32_t k = 0; k < n; k++) {
-        const uint32_t e = events[k];
-        stamp.assign(b.path_ptr[e + 1] - b.path_ptr[e], 0xFFFFFFFFu);
+        const uint32_t e = events[k], np = b.path_ptr[e + 1] - b.path_ptr[e];
         for (uint32_t a = b.amb_ptr[e]; a < b.amb_ptr[e + 1]; a++)
             for (uint32_t j = b.amb_path_ptr[a]; j < b.amb_path_ptr[a + 1]; j++) {
-                const uint32_t m = b.amb_paths[j];
-                if (m >= stamp.size() || stamp[m] == a) return false;
-                stamp[m] = a;
+                if (b.amb_paths[j] >= np) return false;
+                if (j > b.amb_path_ptr[a] && b.amb_paths[j] <= b.amb_paths[j - 1]) return false;
             }
     }
     return true;
@@ -1995,8 +1986,8 @@ static inline std::string wq_run_em_psi(wq_psi_batch& b, WqEmScratch& M, cudaStr
     memset(&staged, 0, sizeof staged);
     const uint32_t nbig = nclass[5] + nclass[6];
     // Large events on a cluster of C blocks (wq_k_em_psi_cl) when the device can hold them in at most two rounds: C = 8 when all of them
-    // are resident at once, else C = 4.  More events than that (a single GPU holding every large event of a deep job) stay on the block
-    // kernel, where every SM already has an event of its own.  WQ_PSI_CLUSTER = 0 / 2 / 4 / 8 overrides (0: never).
+    // are resident at once, else C = 4, else C = 2.  More events than that (a single GPU holding every large event of a deep job) stay
+    // on the block kernel, where every SM already has an event of its own.  WQ_PSI_CLUSTER = 0 / 2 / 4 / 8 overrides (0: never).
     WqPsiClCfg clz;
     memset(&clz, 0, sizeof clz);
     size_t cl_smem = 0;
@@ -2024,8 +2015,8 @@ static inline std::string wq_run_em_psi(wq_psi_batch& b, WqEmScratch& M, cudaStr
                 if (cudaFuncSetAttribute(wq_k_em_psi_cl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max) == cudaSuccess) cl_attr_set = true;
                 else cudaGetLastError();
             }
-            const uint32_t tryC[2] = {8, 4};
-            for (int t = 0; t < 2 && cl_attr_set && !cl_clusters; t++) {
+            const uint32_t tryC[3] = {8, 4, 2};
+            for (int t = 0; t < 3 && cl_attr_set && !cl_clusters; t++) {
                 const uint32_t C = cl_env > 0 ? (uint32_t)cl_env : tryC[t];
                 if (C != 2 && C != 4 && C != 8) break;
                 WqPsiClCfg z;
@@ -2033,7 +2024,7 @@ static inline std::string wq_run_em_psi(wq_psi_batch& b, WqEmScratch& M, cudaStr
                 if (need <= smem_max) {
                     const uint32_t res = resident(C, need);
                     const bool take = cl_env > 0 ? res > 0 : (C == 8 ? nbig <= res : nbig <= 2 * res);
-                    if (take) { clz = z; cl_smem = need; cl_clusters = std::min(nbig, res); clz.split = getenv("WQ_PSI_CL_SPLIT") ? (uint32_t)(atoi(getenv("WQ_PSI_CL_SPLIT")) != 0) : 1u; }
+                    if (take) { clz = z; cl_smem = need; cl_clusters = std::min(nbig, res); clz.split = getenv("WQ_PSI_CL_SPLIT") ? (uint32_t)(atoi(getenv("WQ_PSI_CL_SPLIT")) != 0) : 0u; }
                 }
                 if (cl_env > 0) break;
             }
