@@ -1540,7 +1540,7 @@ WQ_HDN inline void wq_cl_init_d(const WqPsiDev& d, const WqPsiClEv& ev, const Wq
 }
 // -- sweep.  (1) prop_sum of the own sets, to every block.  The reference adds a set's members in list order, and the lists are in
 // ascending path order (checked on the host before this kernel is chosen), so a lane walks ITS set's bit mask over the paths in
-// order and adds psi[i] where the bit is set.  Every lane reads the same psi[i] at the same time -- a broadcast, one shared-memory
+// order and adds psi[i] where the bit is set (+0.0 elsewhere: an exact identity on these non-negative sums).  Every lane reads the same psi[i] at the same time -- a broadcast, one shared-memory
 // wavefront -- where a gather through member lists cost a bank-conflicted access per member (measured: 26 clocks per member of the
 // longest set, against ~11 for the dependent addition itself; the longest set of a large event names all paths but one, so the
 // chain of ~np additions is the floor of this phase either way).
@@ -1552,9 +1552,15 @@ WQ_HDN inline void wq_cl_phase_psum(const WqPsiClEv& ev, const WqClCtx& c, uint3
         const uint32_t* mk = S.lmask + al * nw;
         for (uint32_t w = 0; w < nw; w++) {
             const uint32_t bits = mk[w];
-            const double* v = S.psi + 32u * w;
+            const double2* v2 = reinterpret_cast<const double2*>(S.psi + 32u * w);
+            // a path outside the set adds +0.0, which leaves the sum as it is bit for bit (psi >= +0, the sum starts at +0.0, NaN stays NaN);
+            // written as a select so that the 16 loads of a word are unconditional and issued ahead of the chain of additions
             #pragma unroll
-            for (int b = 0; b < 32; b++) if (bits & (1u << b)) sm = WQ_EM_DADD(sm, v[b]);
+            for (int b2 = 0; b2 < 16; b2++) {
+                const double2 v = v2[b2];
+                sm = WQ_EM_DADD(sm, (bits >> (2 * b2)) & 1u ? v.x : 0.0);
+                sm = WQ_EM_DADD(sm, (bits >> (2 * b2 + 1)) & 1u ? v.y : 0.0);
+            }
         }
         const uint32_t a = c.r + c.C * al;
         for (uint32_t rr = 0; rr < c.C; rr++) *wq_cl_remote(c, S.psum + a, rr) = sm;
