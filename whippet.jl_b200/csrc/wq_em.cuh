@@ -1991,9 +1991,8 @@ static inline std::string wq_run_em_psi(wq_psi_batch& b, WqEmScratch& M, cudaStr
     WqPsiBigCfg staged;
     memset(&staged, 0, sizeof staged);
     const uint32_t nbig = nclass[5] + nclass[6];
-    // Large events on a cluster of C blocks (wq_k_em_psi_cl) when the device can hold them in at most two rounds: C = 8 when all of them
-    // are resident at once, else C = 4, else C = 2.  More events than that (a single GPU holding every large event of a deep job) stay
-    // on the block kernel, where every SM already has an event of its own.  WQ_PSI_CLUSTER = 0 / 2 / 4 / 8 overrides (0: never).
+    // Large events on clusters of C = 8 / 4 / 2 blocks (wq_k_em_psi_cl) or on the block kernel, whichever needs the least time for
+    // this many events (see below).  WQ_PSI_CLUSTER = 0 / 2 / 4 / 8 overrides (0: never).
     WqPsiClCfg clz;
     memset(&clz, 0, sizeof clz);
     size_t cl_smem = 0;
@@ -2021,18 +2020,27 @@ static inline std::string wq_run_em_psi(wq_psi_batch& b, WqEmScratch& M, cudaStr
                 if (cudaFuncSetAttribute(wq_k_em_psi_cl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max) == cudaSuccess) cl_attr_set = true;
                 else cudaGetLastError();
             }
+            // the cheapest of: C = 8 / 4 / 2 blocks per event in rounds of the clusters the device holds at once, or the block kernel in
+            // rounds of one event per SM.  Relative cost of one round, measured on 24 events of 1000-1900 paths (profiles/r02_psi_large_events.txt):
+            // block kernel 272 ms, C = 2: 55 ms, C = 4: 46 ms, C = 8: ~35 ms.
+            int sms = 148;
+            { int dev = 0; if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) { cudaGetLastError(); sms = 148; } }
             const uint32_t tryC[3] = {8, 4, 2};
-            for (int t = 0; t < 3 && cl_attr_set && !cl_clusters; t++) {
-                const uint32_t C = cl_env > 0 ? (uint32_t)cl_env : tryC[t];
-                if (C != 2 && C != 4 && C != 8) break;
+            const double round_cost[3] = {0.75, 1.0, 1.2};
+            double best = cl_env > 0 ? 1e300 : 5.9 * (double)((nbig + (uint32_t)sms - 1) / (uint32_t)sms);
+            for (int t = 0; t < 3 && cl_attr_set; t++) {
+                const uint32_t C = tryC[t];
+                if (cl_env > 0 && C != (uint32_t)cl_env) continue;
                 WqPsiClCfg z;
                 const size_t need = config(C, z);
-                if (need <= smem_max) {
-                    const uint32_t res = resident(C, need);
-                    const bool take = cl_env > 0 ? res > 0 : (C == 8 ? nbig <= res : nbig <= 2 * res);
-                    if (take) { clz = z; cl_smem = need; cl_clusters = std::min(nbig, res); clz.split = getenv("WQ_PSI_CL_SPLIT") ? (uint32_t)(atoi(getenv("WQ_PSI_CL_SPLIT")) != 0) : 0u; }
+                if (need > smem_max) continue;
+                const uint32_t res = resident(C, need);
+                if (!res) continue;
+                const double cost = round_cost[t] * (double)((nbig + res - 1) / res);
+                if (cost < best) {
+                    best = cost; clz = z; cl_smem = need; cl_clusters = std::min(nbig, res);
+                    clz.split = getenv("WQ_PSI_CL_SPLIT") ? (uint32_t)(atoi(getenv("WQ_PSI_CL_SPLIT")) != 0) : 0u;
                 }
-                if (cl_env > 0) break;
             }
         }
     }
