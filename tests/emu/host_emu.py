@@ -174,6 +174,7 @@ def psi_cluster(problems, C_blocks, threads, readlen, sig=4, maxit=1500):
     psi, ct, its, need = np.zeros(max(1, len(cnt))), np.zeros(max(1, len(cnt))), np.zeros(max(1, E), "<i4"), C.c_uint64()
     rc = L.hemu_psi_cluster(C.c_uint32(E), *[_p(x) for x in a], C.c_int64(readlen), C.c_int(sig), C.c_int64(maxit), C.c_uint32(C_blocks),
                             C.c_uint32(threads), _p(psi), _p(ct), _p(its), C.byref(need))
+    assert rc in (0, -1), f"hemu_psi_cluster: the layout's capacities do not cover the build (rc {rc})"
     if rc != 0:
         return None, int(need.value)
     return [(psi[path_ptr[e]:path_ptr[e + 1]].copy(), int(its[e])) for e in range(E)], int(need.value)

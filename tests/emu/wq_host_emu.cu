@@ -216,6 +216,8 @@ int hemu_psi_cluster(uint32_t E, const uint32_t* path_ptr, const uint32_t* n_inc
         each([&](const WqClCtx& c, uint32_t t) { wq_cl_init_a(d, ev, c, t); });
         each([&](const WqClCtx& c, uint32_t t) { wq_cl_init_b(d, ev, c, t); });
         for (uint32_t r = 0; r < C; r++) wq_cl_init_c(ev, ctx[r]);
+        for (uint32_t r = 0; r < C; r++)                                 // the layout's capacities must cover what the build produced
+            if (ctx[r].S.poff[wq_cl_nslots(ev.np, r, C)] > z.inv_cap || wq_cl_nslots(ev.np, r, C) > z.npl_cap || wq_cl_nsets(ev.na, r, C) > z.nal_cap || ev.np > z.np_cap || ev.na > z.na_cap) return -2;
         for (uint32_t a = 0; a < ev.na; a++) each([&](const WqClCtx& c, uint32_t t) { wq_cl_init_d(d, ev, c, t, a); });
         bool differs = false;
         auto norm = [&](int sg) {

@@ -1878,36 +1878,47 @@ __global__ void __launch_bounds__(128) wq_k_em_psi4(const WqPsiDev d, const uint
 
 // `wait` = false leaves the launch and its result copies in flight on `stream` (the result buffers must then be pinned
 // host memory and stay alive until the stream has been synchronised)
+// One pass over the member lists of the given events for the cluster kernel: are they all in ascending path order (the kernel walks a
+// set's members as a bit mask in path order, which is the reference's order of additions only then; the event construction writes
+// them that way: inclusion paths, then exclusion paths, each in order; ascending also means no path twice -- the inverted-index build
+// relies on that -- and every member inside the event), and how many inverted-index entries the fullest block holds with 8 / 4 / 2
+// blocks per event (a path's owner with C blocks is its owner with 8 blocks modulo C).
+struct WqPsiClScan { bool ascending = true; uint32_t inv_cap[3] = {0, 0, 0}; };
+static inline WqPsiClScan wq_psi_cl_scan(const wq_psi_batch& b, const uint32_t* events, uint32_t n) {
+    WqPsiClScan sc;
+    for (uint32_t k = 0; k < n; k++) {
+        const uint32_t e = events[k], np = b.path_ptr[e + 1] - b.path_ptr[e];
+        uint32_t own8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (uint32_t a = b.amb_ptr[e]; a < b.amb_ptr[e + 1]; a++) {
+            const uint32_t jb = b.amb_path_ptr[a], je = b.amb_path_ptr[a + 1];
+            for (uint32_t j = jb; j < je; j++) {
+                const uint32_t m = b.amb_paths[j];
+                if (m >= np || (j > jb && m <= b.amb_paths[j - 1])) sc.ascending = false;
+                own8[(m >> 5) & 7u]++;
+            }
+        }
+        for (uint32_t r = 0; r < 8; r++) sc.inv_cap[0] = std::max(sc.inv_cap[0], own8[r]);
+        for (uint32_t r = 0; r < 4; r++) sc.inv_cap[1] = std::max(sc.inv_cap[1], own8[r] + own8[r + 4]);
+        for (uint32_t r = 0; r < 2; r++) sc.inv_cap[2] = std::max(sc.inv_cap[2], own8[r] + own8[r + 2] + own8[r + 4] + own8[r + 6]);
+    }
+    return sc;
+}
 // capacities of the cluster kernel's shared-memory layout over the given events; returns the bytes one block needs
-static inline size_t wq_psi_cl_config(const wq_psi_batch& b, const uint32_t* events, uint32_t n, uint32_t C, WqPsiClCfg& z) {
+static inline size_t wq_psi_cl_config(const wq_psi_batch& b, const uint32_t* events, uint32_t n, uint32_t C, WqPsiClCfg& z, const WqPsiClScan* scan = nullptr) {
+    WqPsiClScan local;
+    if (!scan) { local = wq_psi_cl_scan(b, events, n); scan = &local; }
     memset(&z, 0, sizeof z);
     z.C = C;
+    z.inv_cap = scan->inv_cap[C == 8 ? 0 : C == 4 ? 1 : 2];
     for (uint32_t k = 0; k < n; k++) {
         const uint32_t e = events[k];
-        const uint32_t np = b.path_ptr[e + 1] - b.path_ptr[e], a_lo = b.amb_ptr[e], na = b.amb_ptr[e + 1] - a_lo;
+        const uint32_t np = b.path_ptr[e + 1] - b.path_ptr[e], na = b.amb_ptr[e + 1] - b.amb_ptr[e];
         z.np_cap = std::max(z.np_cap, np); z.na_cap = std::max(z.na_cap, na);
         z.npl_cap = std::max(z.npl_cap, wq_cl_nslots(np, 0, C)); z.nal_cap = std::max(z.nal_cap, wq_cl_nsets(na, 0, C));
-        uint32_t own_inv[8] = {0};
-        for (uint32_t a = 0; a < na; a++)
-            for (uint32_t j = b.amb_path_ptr[a_lo + a]; j < b.amb_path_ptr[a_lo + a + 1]; j++) own_inv[wq_cl_owner(b.amb_paths[j], C)]++;
-        for (uint32_t r = 0; r < C; r++) z.inv_cap = std::max(z.inv_cap, own_inv[r]);
     }
     return wq_psi_cl_layout(z, nullptr, nullptr);
 }
-// the cluster kernel walks a set's members as a bit mask in ascending path order, which is the reference's order of additions only
-// when the member list is ascending (it is, as the event construction writes it: inclusion paths, then exclusion paths, each in
-// order); ascending also means no path twice (the inverted-index build relies on that) and every member inside the event
-static inline bool wq_psi_cl_unique(const wq_psi_batch& b, const uint32_t* events, uint32_t n) {
-    for (uint32_t k = 0; k < n; k++) {
-        const uint32_t e = events[k], np = b.path_ptr[e + 1] - b.path_ptr[e];
-        for (uint32_t a = b.amb_ptr[e]; a < b.amb_ptr[e + 1]; a++)
-            for (uint32_t j = b.amb_path_ptr[a]; j < b.amb_path_ptr[a + 1]; j++) {
-                if (b.amb_paths[j] >= np) return false;
-                if (j > b.amb_path_ptr[a] && b.amb_paths[j] <= b.amb_paths[j - 1]) return false;
-            }
-    }
-    return true;
-}
+static inline bool wq_psi_cl_unique(const wq_psi_batch& b, const uint32_t* events, uint32_t n) { return wq_psi_cl_scan(b, events, n).ascending; }
 
 static inline std::string wq_run_em_psi(wq_psi_batch& b, WqEmScratch& M, cudaStream_t stream, uint64_t* launches, bool wait = true) {
     const uint32_t E = b.n_events;
@@ -2001,8 +2012,9 @@ static inline std::string wq_run_em_psi(wq_psi_batch& b, WqEmScratch& M, cudaStr
         const int cl_env = getenv("WQ_PSI_CLUSTER") ? atoi(getenv("WQ_PSI_CLUSTER")) : -1;      // read per call: tests switch it
         static bool cl_attr_set = false;
         const size_t smem_max = 227 * 1024;
-        const bool unique = wq_psi_cl_unique(b, order.data() + cbase[5], nbig);
-        auto config = [&](uint32_t C, WqPsiClCfg& z) -> size_t { return wq_psi_cl_config(b, order.data() + cbase[5], nbig, C, z); };
+        const WqPsiClScan scan = cl_env != 0 ? wq_psi_cl_scan(b, order.data() + cbase[5], nbig) : WqPsiClScan();
+        const bool unique = scan.ascending;
+        auto config = [&](uint32_t C, WqPsiClCfg& z) -> size_t { return wq_psi_cl_config(b, order.data() + cbase[5], nbig, C, z, &scan); };
         auto resident = [&](uint32_t C, size_t smem) -> uint32_t {       // clusters of C blocks the device holds at once
             cudaLaunchConfig_t cfg;
             memset(&cfg, 0, sizeof cfg);
