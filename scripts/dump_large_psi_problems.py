@@ -1,7 +1,8 @@
 """EM problems of the large PSI events of an 80 M-read job (provenance of tmp_psi/big169.npz, which tests/golden/make_psi_large_events.py selects from):
 the host harness (tests/emu) builds the events from the counts written by scripts/make_depth_counts.py and the problems are dumped in decreasing
 order of member count.  CPU only."""
-sys.path[:0] = ['/root/repo', '/root/repo/oracle', '/root/repo/tests']
+import os, sys, time, ctypes as C
+sys.path[:0] = [__import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__)))] + [__import__('os').path.join(__import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))), d) for d in ('oracle', 'tests')]
 import numpy as np
 import whippet_jl_b200 as wq
 from wq_inputs import graphbuild

@@ -1,7 +1,8 @@
 """Counts of deep jobs over the hg19-scale annotation (provenance of tmp_psi/counts_depth80M.npz and of tests/golden/psi_large_events.npz):
 the oracle aligns 8 x 10 M simulated reads (seeds as the ranks of an 8-GPU weak-scaling bench use them) and the node / edge counts are saved after
 every 10 M.  CPU only, about twelve minutes.  Output: /tmp/evprof_counts_depth{10..80}M.npz (copy the 80M one to tmp_psi/counts_depth80M.npz)."""
-sys.path[:0] = ['/root/repo', '/root/repo/oracle', '/root/repo/tests']
+import os, sys, time, ctypes as C
+sys.path[:0] = [__import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__)))] + [__import__('os').path.join(__import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))), d) for d in ('oracle', 'tests')]
 import numpy as np
 import whippet_jl_b200 as wq
 from wq_inputs import synth, graphbuild
