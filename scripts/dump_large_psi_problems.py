@@ -2,7 +2,8 @@
 the host harness (tests/emu) builds the events from the counts written by scripts/make_depth_counts.py and the problems are dumped in decreasing
 order of member count.  CPU only."""
 import os, sys, time, ctypes as C
-sys.path[:0] = [__import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__)))] + [__import__('os').path.join(__import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))), d) for d in ('oracle', 'tests')]
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, 'oracle'), os.path.join(ROOT, 'tests')]
 import numpy as np
 import whippet_jl_b200 as wq
 from wq_inputs import graphbuild
@@ -28,7 +29,7 @@ def subset(sel):
     cat=lambda k,dt: np.concatenate(o[k]).astype(dt) if o[k] else np.zeros(0,dt)
     return dict(path_ptr=np.array(o['path_ptr'],'<u4'),n_inc=np.array(o['n_inc'],'<u4'),count=cat('count','<f8'),length=cat('length','<f8'),amb_ptr=np.array(o['amb_ptr'],'<u4'),
                 amb_path_ptr=np.array(o['amb_path_ptr'],'<u4'),amb_paths=cat('amb_paths','<u4'),amb_mult=cat('amb_mult','<f8'),is_tandem=np.array(o['is_tandem'],'u1'))
-os.makedirs('/root/repo/tmp_psi',exist_ok=True)
+os.makedirs(os.path.join(ROOT, 'tmp_psi'),exist_ok=True)
 for name,sel in (('big24',order[:24]),('big169',order[:169]),('mid',order[169:169+600])):
-    d=subset(sel); np.savez_compressed(f'/root/repo/tmp_psi/{name}.npz',**d)
-    print(name, len(sel), 'paths', int(d['path_ptr'][-1]), 'sets', int(d['amb_ptr'][-1]), 'members', int(d['amb_path_ptr'][-1]), os.path.getsize(f'/root/repo/tmp_psi/{name}.npz'))
+    d=subset(sel); np.savez_compressed(os.path.join(ROOT, 'tmp_psi', name + '.npz'),**d)
+    print(name, len(sel), 'paths', int(d['path_ptr'][-1]), 'sets', int(d['amb_ptr'][-1]), 'members', int(d['amb_path_ptr'][-1]), os.path.getsize(os.path.join(ROOT, 'tmp_psi', name + '.npz')))

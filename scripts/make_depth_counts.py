@@ -2,7 +2,8 @@
 the oracle aligns 8 x 10 M simulated reads (seeds as the ranks of an 8-GPU weak-scaling bench use them) and the node / edge counts are saved after
 every 10 M.  CPU only, about twelve minutes.  Output: /tmp/evprof_counts_depth{10..80}M.npz (copy the 80M one to tmp_psi/counts_depth80M.npz)."""
 import os, sys, time, ctypes as C
-sys.path[:0] = [__import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__)))] + [__import__('os').path.join(__import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))), d) for d in ('oracle', 'tests')]
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, 'oracle'), os.path.join(ROOT, 'tests')]
 import numpy as np
 import whippet_jl_b200 as wq
 from wq_inputs import synth, graphbuild
