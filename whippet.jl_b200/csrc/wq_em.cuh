@@ -2039,7 +2039,12 @@ static inline std::string wq_run_em_psi(wq_psi_batch& b, WqEmScratch& M, cudaStr
             { int dev = 0; if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) { cudaGetLastError(); sms = 148; } }
             const uint32_t tryC[3] = {8, 4, 2};
             const double round_cost[3] = {0.75, 1.0, 1.2};
-            double best = cl_env > 0 ? 1e300 : 5.9 * (double)((nbig + (uint32_t)sms - 1) / (uint32_t)sms);
+            // (that ratio holds for events of ~100 k set members; for the smaller ones of these classes -- a few hundred paths, ~15 k members --
+            // nothing was measured, and the block kernel keeps them unless the clusters need no more rounds than it does)
+            uint64_t members = 0;
+            for (uint32_t k = 0; k < nbig; k++) { const uint32_t e = order[cbase[5] + k]; members += b.amb_path_ptr[b.amb_ptr[e + 1]] - b.amb_path_ptr[b.amb_ptr[e]]; }
+            const double block_round = members / nbig >= 30000 ? 5.9 : 1.5;
+            double best = cl_env > 0 ? 1e300 : block_round * (double)((nbig + (uint32_t)sms - 1) / (uint32_t)sms);
             for (int t = 0; t < 3 && cl_attr_set; t++) {
                 const uint32_t C = tryC[t];
                 if (cl_env > 0 && C != (uint32_t)cl_env) continue;
