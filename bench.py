@@ -756,7 +756,7 @@ def main():
                    "mapped_frac": stats.mapped / max(1, stats.total), "multi_frac": stats.multi / max(1, stats.total),
                    "index_load_s": index_load_s, "index_load": "wq_index_load of the native index file (written by wq_index_write in "
                    f"{index_write_s:.2f} s, {index_file_bytes} bytes)", "index_create_s": index_create_s,
-                   "parallelism": f"reads sharded over {world} GPU(s), index replicated" + (", dense counts all-reduced and sparse stores all-gathered over NCCL inside the library (wq_counts_sync), class building and event stage partitioned by gene (shares all-gathered), transcript EM replicated" if world > 1 else "")},
+                   "parallelism": f"reads sharded over {world} GPU(s), index replicated" + (", dense counts all-reduced and sparse stores all-gathered over NCCL inside the library (wq_counts_sync), class building partitioned by gene (shares all-gathered), event stage by cost-balanced ranges of the event work list (genes, and node ranges of genes with many nodes), transcript EM replicated" if world > 1 else "")},
         "clocks": clocks, "gpu_launches": launches,
         "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "host_batch_layout": sorted(set(x for r in runs for x in r.layout))},
