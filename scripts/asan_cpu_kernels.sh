@@ -20,11 +20,11 @@ cp /tmp/libwq_emu.so.keep $SO 2>/dev/null || true
 HSO=tests/emu/libwq_host_emu.so
 cp $HSO /tmp/libwq_host_emu.so.keep 2>/dev/null || true
 nvcc -gencode arch=compute_100a,code=sm_100a -O1 -g -std=c++17 -fmad=false -Xcompiler -fPIC,-fsanitize=address,-fsanitize=undefined,-fno-sanitize-recover=undefined,-fno-omit-frame-pointer \
-    -shared -o $HSO tests/emu/wq_host_emu.cu -lasan -lubsan
+    -shared -o $HSO tests/emu/wq_host_emu.cu -lasan -lubsan -lz
 touch $HSO
 echo "instrumented: $(nm -D $HSO | grep -c __asan_) __asan_ symbols, $(nm -D $HSO | grep -c __ubsan_) __ubsan_ symbols in $HSO"
 ASAN_OPTIONS=detect_leaks=0:abort_on_error=0:halt_on_error=1:protect_shadow_gap=0 UBSAN_OPTIONS=print_stacktrace=1 LD_PRELOAD=$(/usr/bin/gcc -print-file-name=libasan.so):$(/usr/bin/gcc -print-file-name=libubsan.so) \
-    python -m pytest tests/test_host_stages_cpu.py tests/test_events_flat.py tests/test_psi_cluster_cpu.py "tests/test_bias.py::test_host_stages_with_bias_on_cpu" "tests/test_sam.py::test_sam_formatter_on_cpu" -q -x -p no:cacheprovider 2>&1 | tail -15
+    python -m pytest tests/test_host_stages_cpu.py tests/test_events_flat.py tests/test_psi_cluster_cpu.py tests/test_inflate_cpu.py "tests/test_bias.py::test_host_stages_with_bias_on_cpu" "tests/test_sam.py::test_sam_formatter_on_cpu" -q -x -p no:cacheprovider 2>&1 | tail -15
 rc2=${PIPESTATUS[0]}
 rm -f $HSO
 cp /tmp/libwq_host_emu.so.keep $HSO 2>/dev/null || true

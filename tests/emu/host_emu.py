@@ -16,10 +16,10 @@ _CSRC = os.path.join(_HERE, "..", "..", "whippet.jl_b200", "csrc")
 
 def build():
     srcs = [os.path.join(_HERE, "wq_host_emu.cu")] + [os.path.join(_CSRC, f) for f in
-                                                      ("wq_em.cuh", "wq_events.h", "wq_sam.h", "wq_host_quant.h", "wq_host_index.h", "wq_types.h", "wq_kernels.cuh")]
+                                                      ("wq_em.cuh", "wq_events.h", "wq_sam.h", "wq_host_quant.h", "wq_host_index.h", "wq_types.h", "wq_kernels.cuh", "wq_inflate.h")]
     if not os.path.exists(_SO) or os.path.getmtime(_SO) < max(map(os.path.getmtime, srcs)):
         subprocess.check_call([nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-std=c++17", "-fmad=false",
-                               "-Xcompiler", "-fPIC", "-shared", "-o", _SO, srcs[0]])
+                               "-Xcompiler", "-fPIC", "-shared", "-o", _SO, srcs[0], "-lz"])
     return _SO
 
 
@@ -178,6 +178,20 @@ def psi_cluster(problems, C_blocks, threads, readlen, sig=4, maxit=1500):
     if rc != 0:
         return None, int(need.value)
     return [(psi[path_ptr[e]:path_ptr[e + 1]].copy(), int(its[e])) for e in range(E)], int(need.value)
+
+
+def inflate(data: bytes, piece: int = 1 << 20, cap: int | None = None):
+    """WqInflate (csrc/wq_inflate.h) on a gzip file image.  Returns (text, error message or "", members)."""
+    L = C.CDLL(build())
+    L.hemu_inflate.restype = C.c_int64
+    cap = cap if cap is not None else max(64, 1100 * len(data) + 1024)
+    out = np.zeros(cap, "u1")
+    src = np.frombuffer(data, "u1") if len(data) else np.zeros(1, "u1")
+    err = C.create_string_buffer(256)
+    members = C.c_uint64()
+    r = L.hemu_inflate(_p(src), C.c_uint64(len(data)), _p(out), C.c_uint64(cap), C.c_uint64(piece), err, C.c_uint64(256), C.byref(members))
+    n = r if r >= 0 else -1 - r
+    return out[:n].tobytes(), (err.value.decode() if r < 0 else ""), int(members.value)
 
 
 class HostSam:

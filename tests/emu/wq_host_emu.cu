@@ -16,6 +16,7 @@
 #include "../../whippet.jl_b200/csrc/wq_em.cuh"
 #include "../../whippet.jl_b200/csrc/wq_events.h"
 #include "../../whippet.jl_b200/csrc/wq_sam.h"
+#include "../../whippet.jl_b200/csrc/wq_inflate.h"
 
 struct HostEmu {
     WqHostIndex H; WqIsoIndex S; WqHostQuant hq; WqHostQuantEx X;
@@ -251,6 +252,24 @@ int hemu_psi_cluster(uint32_t E, const uint32_t* path_ptr, const uint32_t* n_inc
         each([&](const WqClCtx& c, uint32_t t) { wq_cl_write_out(d, ev, c, t, it); });
     }
     return 0;
+}
+
+// WqInflate (csrc/wq_inflate.h) on a gzip file image: the text is read in pieces of `piece` bytes into out[cap].  Returns the
+// number of bytes produced, or -1 - (bytes produced) when the stream ended in an error (message in errbuf).
+int64_t hemu_inflate(const uint8_t* data, uint64_t n, uint8_t* out, uint64_t cap, uint64_t piece, char* errbuf, uint64_t errcap, uint64_t* members) {
+    WqInflate z;
+    z.open(data, (size_t)n);
+    uint64_t got = 0;
+    for (;;) {
+        const size_t want = (size_t)std::min<uint64_t>(piece, cap - got);
+        if (!want) break;
+        const size_t r = z.read(out + got, want);
+        got += r;
+        if (r < want) break;
+    }
+    if (members) *members = z.members;
+    if (errbuf && errcap) { strncpy(errbuf, z.err.c_str(), errcap - 1); errbuf[errcap - 1] = 0; }
+    return z.failed() ? -1 - (int64_t)got : (int64_t)got;
 }
 
 // WqBitWin self-test: adjacent() (word masks) against the per-node definition (src/quant.jl:68-79), first() / last() /

@@ -247,7 +247,7 @@ def _batches(path_or_text, batch, from_memory=False):
 
 def test_large_plain_file_blocked_gzip_and_plain_gzip_agree(tmp_path):
     """The three input forms of one text -- mapped plain file (parallel newline scan over a window of many MB), blocked gzip
-    (BGZF: parallel inflate) and ordinary gzip (serial zlib) -- give the same batches as the in-memory reader, across batch
+    (BGZF: parallel inflate) and ordinary gzip (serial, the library's own inflate) -- give the same batches as the in-memory reader, across batch
     boundaries that fall inside scan pieces and inflate windows."""
     import gzip
     from wq_inputs import synth
@@ -271,6 +271,41 @@ def test_large_plain_file_blocked_gzip_and_plain_gzip_agree(tmp_path):
         assert len(got) == len(want), path
         for g, w in zip(got, want):
             assert all(np.array_equal(a, b) for a, b in zip(g, w)), path
+
+
+def test_ordinary_gzip_own_inflate_zlib_switch_and_damaged_files(tmp_path, monkeypatch):
+    """Ordinary gzip goes through the library's own inflate (csrc/wq_inflate.h; tests/test_inflate_cpu.py checks it against zlib): the
+    batches equal those through zlib's gzread (WQ_GZ_ZLIB=1) for a best-compression, two-member file; a file cut short or with a
+    flipped bit is an error of the reader (the member's CRC-32 and length are verified), not wrong reads."""
+    import gzip
+    from whippet_jl_b200.lib import WhippetB200Error
+    from wq_inputs import synth
+    idx = synth.make_index(n_genes=40, K=9, seed=13)
+    rb = synth.simulate_reads(idx, 30_000, 101, seed=14)
+    text = synth.fastq_bytes(rb)
+    cut = text.index(b"\n@", len(text) // 2) + 1                # a record boundary
+    gz = tmp_path / "two.fastq.gz"
+    gz.write_bytes(gzip.compress(text[:cut], 9) + gzip.compress(text[cut:], 9))
+    want = _batches(text, 7000, from_memory=True)
+    got = _batches(gz, 7000)
+    monkeypatch.setenv("WQ_GZ_ZLIB", "1")
+    via_zlib = _batches(gz, 7000)
+    monkeypatch.delenv("WQ_GZ_ZLIB")
+    for other in (got, via_zlib):
+        assert len(other) == len(want)
+        for g, w in zip(other, want):
+            assert all(np.array_equal(a, b) for a, b in zip(g, w))
+    whole = gzip.compress(text, 6)
+    short = tmp_path / "short.fastq.gz"
+    short.write_bytes(whole[:len(whole) * 2 // 3])
+    with pytest.raises(WhippetB200Error):
+        _batches(short, 7000)
+    flipped = bytearray(whole)
+    flipped[len(whole) // 2] ^= 0x40
+    bad = tmp_path / "flipped.fastq.gz"
+    bad.write_bytes(bytes(flipped))
+    with pytest.raises(WhippetB200Error):
+        _batches(bad, 7000)
 
 
 def test_truncated_and_malformed_files_are_errors(tmp_path):

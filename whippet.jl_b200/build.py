@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 CUDA_SO = os.path.join(CSRC, "libwhippet_b200.so")
 _CU_DEPS = ["whippet_b200.cu", "wq_align.cuh", "wq_kernels.cuh", "wq_types.h", "wq_host_index.h",
-            "wq_host_quant.h", "wq_em.cuh", "wq_events.h", "wq_fastq.h", "wq_sam.h", "wq_index_file.h"]
+            "wq_host_quant.h", "wq_em.cuh", "wq_events.h", "wq_fastq.h", "wq_sam.h", "wq_index_file.h", "wq_inflate.h", "wq_bias.cuh"]
 
 
 def nvcc_path():

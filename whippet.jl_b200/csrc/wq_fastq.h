@@ -9,7 +9,7 @@
 //   * plain files are mapped, not read: the newline scan and the conversion work on the mapping directly;
 //   * blocked gzip (BGZF: bgzip, bcl2fastq output -- independent deflate blocks that announce their size) is inflated block
 //     by block on all threads straight into the text window; an ordinary single-member gzip stream has no entry points and
-//     is inflated serially by zlib (about 0.3-0.4 GB/s), overlapped with the alignment of the previous batch;
+//     is inflated serially (wq_inflate.h, about twice zlib's rate on FASTQ text), overlapped with the alignment of the previous batch;
 //   * the newline scan runs in parallel over pieces of the window (records are strictly four lines, so a record boundary is
 //     a line number, not a guess about '@'), then lengths / validation / offsets by a two-pass prefix sum, then the 2-bit and
 //     phred conversion of the records;
@@ -34,6 +34,7 @@
 #include <vector>
 #include "wq_host_quant.h"          // wq_host_threads
 #include "../../include/whippet_b200.h"
+#include "wq_inflate.h"
 
 // Page-locked blocks released by a reader are kept for the next one (process lifetime, bounded): cudaHostAlloc costs about
 // as much as parsing the batch that goes into the block, and wq_process_fastq opens a reader per call.
@@ -108,7 +109,8 @@ struct WqFastqSlot {                 // one packed batch + the record names (for
 struct wq_fastq {
     // ---- input: exactly one of these ----
     const char* map = nullptr; size_t map_len = 0; int fd = -1; bool map_owned = false;     // plain text, mapped (or caller's memory)
-    gzFile gz = nullptr;                                                                   // single-member gzip: serial inflate
+    gzFile gz = nullptr;                                                                   // ordinary gzip through zlib's gzread (WQ_GZ_ZLIB=1, or the file cannot be mapped)
+    WqInflate* inf = nullptr;                                                              // ordinary gzip: `map` holds the COMPRESSED file, inflated serially by wq_inflate.h
     bool bgzf = false; size_t bgzf_pos = 0;                                                 // blocked gzip: `map` holds the COMPRESSED file
     int qualoffset = 33;
     // ---- text window: stream offsets [woff, woff + wlen) are in memory at wbase ----
@@ -187,6 +189,17 @@ static inline int wq_fastq_open_impl(wq_fastq* f, const char* path) {
     const ssize_t got = pread(fd, head, sizeof head, 0);
     const bool is_gz = got >= 2 && head[0] == 0x1f && head[1] == 0x8b;
     const bool is_bgzf = is_gz && wq_bgzf_block_size(head, (size_t)got) != 0;
+    const bool use_zlib = getenv("WQ_GZ_ZLIB") && atoi(getenv("WQ_GZ_ZLIB")) != 0;
+    if (is_gz && !is_bgzf && !use_zlib && st.st_size > 0) {
+        void* m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+        if (m != MAP_FAILED) {
+            madvise(m, (size_t)st.st_size, MADV_SEQUENTIAL);
+            f->map = (const char*)m; f->map_len = (size_t)st.st_size; f->map_owned = true; f->fd = fd;
+            f->inf = new WqInflate();
+            f->inf->open(m, (size_t)st.st_size);
+            return 0;
+        }
+    }
     if (is_gz && !is_bgzf) {
         close(fd);
         f->gz = gzopen(path, "rb");
@@ -208,6 +221,7 @@ static inline int wq_fastq_open_impl(wq_fastq* f, const char* path) {
 
 static inline void wq_fastq_release(wq_fastq* f) {
     if (f->gz) gzclose(f->gz);
+    delete f->inf; f->inf = nullptr;
     if (f->map_owned && f->map) munmap((void*)f->map, f->map_len);
     if (f->fd >= 0) close(f->fd);
     f->slot[0].release(); f->slot[1].release();
@@ -221,7 +235,14 @@ static inline bool wq_fastq_pull(wq_fastq* f, size_t want) {
         f->text.drop_front((size_t)(keep_from - f->woff));
         f->woff = keep_from;
     }
-    if (f->gz) {
+    if (f->inf) {
+        const size_t old = f->text.size();
+        if (!f->text.reserve_more(want)) { f->err = "out of memory"; return false; }
+        const size_t got = f->inf->read((uint8_t*)f->text.data() + old, want);
+        if (f->inf->failed()) { f->err = f->inf->err; return false; }
+        if (got < want) f->eof = true;
+        f->text.len = old + got;
+    } else if (f->gz) {
         const size_t old = f->text.size();
         if (!f->text.reserve_more(want)) { f->err = "out of memory"; return false; }
         size_t got = 0;
