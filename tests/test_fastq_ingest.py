@@ -308,6 +308,35 @@ def test_ordinary_gzip_own_inflate_zlib_switch_and_damaged_files(tmp_path, monke
         _batches(bad, 7000)
 
 
+def test_two_readers_side_by_side(tmp_path):
+    """wq_process_fastq reads the two files of a paired input on two threads (an ordinary .fastq.gz is inflated serially, so one file
+    after the other would halve the rate): two readers running at the same time -- gzip and blocked gzip, several batches, many
+    repetitions so that the page-locked block cache is taken and given back concurrently -- return what they return alone."""
+    import gzip
+    import threading
+    from wq_inputs import synth
+    idx = synth.make_index(n_genes=40, K=9, seed=23)
+    f, r = synth.simulate_reads(idx, 40_000, 101, seed=24, paired=True)
+    t1, t2 = synth.fastq_bytes(f), synth.fastq_bytes(r)
+    p1, p2 = tmp_path / "m1.fastq.gz", tmp_path / "m2.fastq.gz"
+    p1.write_bytes(gzip.compress(t1, 4))
+    p2.write_bytes(synth.bgzf_compress(t2))
+    alone = [_batches(p1, 9000), _batches(p2, 9000)]
+    for _ in range(6):
+        got = [None, None]
+        def work(k, path):
+            got[k] = _batches(path, 9000)
+        th = [threading.Thread(target=work, args=(k, path)) for k, path in enumerate((p1, p2))]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        for k in range(2):
+            assert len(got[k]) == len(alone[k])
+            for g, w in zip(got[k], alone[k]):
+                assert all(np.array_equal(a, b) for a, b in zip(g, w)), k
+
+
 def test_truncated_and_malformed_files_are_errors(tmp_path):
     from whippet_jl_b200.lib import WhippetB200Error
     good = b"@a\nACGT\n+\nIIII\n@b\nAC\n+\nII\n"

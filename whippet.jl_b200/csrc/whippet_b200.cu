@@ -1321,13 +1321,24 @@ int wq_process_fastq_sam(wq_handle* h, const wq_align_param* p, const char* fwd_
     if (int rc = wq_fastq_open(fwd_path, qualoffset, &rd[0])) return rc;
     if (rev_path) { if (int rc = wq_fastq_open(rev_path, qualoffset, &rd[1])) { wq_fastq_close(rd[0]); return rc; } }
     struct Pair { wq_read_batch b[2]; const WqFastqSlot* names[2] = {nullptr, nullptr}; int rc = 0; std::string err; };
+    (void)wq_fastq_code_table();                               // initialised before two readers run side by side
     auto parse = [&]() {
         Pair P;
-        for (int k = 0; k < (rev_path ? 2 : 1) && !P.rc; k++) {
-            P.rc = wq_fastq_next_impl(rd[k], batch_reads, &P.b[k]);
-            if (P.rc) P.err = rd[k]->err;
-            P.names[k] = &rd[k]->slot[rd[k]->cur];             // this slot is not touched again until the parse after the next
+        if (!rev_path) {
+            P.rc = wq_fastq_next_impl(rd[0], batch_reads, &P.b[0]);
+            if (P.rc) P.err = rd[0]->err;
+        } else {
+            // the two files side by side: an ordinary .fastq.gz is inflated serially, so the mates' files one after the other would halve
+            // the rate of the usual paired input (readers share nothing but the page-locked block cache, which has its own lock)
+            int rc1 = 0;
+            std::thread mate([&]() { rc1 = wq_fastq_next_impl(rd[1], batch_reads, &P.b[1]); });
+            const int rc0 = wq_fastq_next_impl(rd[0], batch_reads, &P.b[0]);
+            mate.join();
+            if (rc0) { P.rc = rc0; P.err = rd[0]->err; }
+            else if (rc1) { P.rc = rc1; P.err = rd[1]->err; }
         }
+        for (int k = 0; k < (rev_path ? 2 : 1); k++) P.names[k] = &rd[k]->slot[rd[k]->cur];      // these slots are not touched again until the parse after the next
+
         if (!P.rc && rev_path && P.b[0].n_reads != P.b[1].n_reads) { P.rc = -21; P.err = "paired FASTQ files hold different numbers of records"; }
         return P;
     };
