@@ -194,6 +194,18 @@ def inflate(data: bytes, piece: int = 1 << 20, cap: int | None = None):
     return out[:n].tobytes(), (err.value.decode() if r < 0 else ""), int(members.value)
 
 
+def inflate_raw(data: bytes, out_len: int):
+    """WqInflate::raw_into on a raw deflate stream.  Returns (text or None, error message, canary intact): the output buffer is followed
+    by 64 canary bytes that the inflater must not touch."""
+    L = C.CDLL(build())
+    out = np.full(out_len + 64, 0xA5, "u1")
+    src = np.frombuffer(data, "u1") if len(data) else np.zeros(1, "u1")
+    err = C.create_string_buffer(256)
+    rc = L.hemu_inflate_raw(_p(src), C.c_uint64(len(data)), _p(out), C.c_uint64(out_len), err, C.c_uint64(256))
+    intact = bool(np.all(out[out_len:] == 0xA5))
+    return (out[:out_len].tobytes() if rc == 0 else None), err.value.decode(), intact
+
+
 class HostSam:
     """wq_sam.h (write_sam, src/io.jl:69-271) on the CPU: SAM text of a batch from given alignments."""
 

@@ -272,6 +272,16 @@ int64_t hemu_inflate(const uint8_t* data, uint64_t n, uint8_t* out, uint64_t cap
     return z.failed() ? -1 - (int64_t)got : (int64_t)got;
 }
 
+// WqInflate::raw_into: one raw deflate stream into exactly out[0 .. out_len) (the way the blocked-gzip reader inflates a block next to
+// its neighbours).  Returns 0, or -1 with the message in errbuf.
+int hemu_inflate_raw(const uint8_t* data, uint64_t n, uint8_t* out, uint64_t out_len, char* errbuf, uint64_t errcap) {
+    static thread_local WqInflate* z = nullptr;
+    if (!z) z = new WqInflate();
+    const bool ok = z->raw_into(data, (size_t)n, out, (size_t)out_len);
+    if (errbuf && errcap) { strncpy(errbuf, z->err.c_str(), errcap - 1); errbuf[errcap - 1] = 0; }
+    return ok ? 0 : -1;
+}
+
 // WqBitWin self-test: adjacent() (word masks) against the per-node definition (src/quant.jl:68-79), first() / last() /
 // list() against a plain scan, on random node sets in windows of up to `max_span` nodes.  Returns the number of mismatches.
 uint64_t hemu_bitwin_selftest(uint32_t max_span, uint32_t rounds, uint64_t seed) {

@@ -9,7 +9,7 @@ import zlib
 import numpy as np
 import pytest
 
-from emu.host_emu import inflate
+from emu.host_emu import inflate, inflate_raw
 
 
 def gz(data: bytes, level=6, strategy=zlib.Z_DEFAULT_STRATEGY, wbits=31, memlevel=8) -> bytes:
@@ -127,3 +127,31 @@ def test_malformed_input_is_an_error_not_a_crash():
         junk = comp[:10] + rng.integers(0, 256, int(rng.integers(1, 400)), dtype=np.uint8).tobytes()
         got, err, _ = inflate(junk, cap=1 << 22)
         assert err != ""
+
+
+def test_raw_stream_into_exact_destination():
+    """raw_into (one deflate stream straight into the caller's memory, as the blocked-gzip reader inflates a block between its
+    neighbours): right text for block-sized and larger inputs of every kind, nothing written behind the announced length (canary), and
+    a wrong announced length, truncation or damage is an error."""
+    rng = np.random.default_rng(21)
+    cases = [b"", b"A", fastq_text(280, 11)[:65280], fastq_text(30, 12), bytes(5000), b"abc" * 700, rng.integers(0, 256, 3000, dtype=np.uint8).tobytes(),
+             fastq_text(2500, 13), b"x" * 299, b"y" * 300, b"z" * 301, fastq_text(2, 14)[:150]]
+    for data in cases:
+        for level, strategy in ((6, zlib.Z_DEFAULT_STRATEGY), (1, zlib.Z_DEFAULT_STRATEGY), (9, zlib.Z_DEFAULT_STRATEGY), (0, zlib.Z_DEFAULT_STRATEGY),
+                                (6, zlib.Z_FIXED), (6, zlib.Z_HUFFMAN_ONLY), (6, zlib.Z_RLE)):
+            comp = gz(data, level, strategy, wbits=-15)
+            got, err, intact = inflate_raw(comp, len(data))
+            assert intact and err == "" and got == data, (len(data), level, strategy, err)
+            if len(data) > 1:
+                for wrong in (len(data) - 1, len(data) + 1):
+                    got, err, intact = inflate_raw(comp, wrong)
+                    assert intact and got is None and err != "", (len(data), wrong)
+                got, err, intact = inflate_raw(comp[:max(1, len(comp) * 2 // 3)], len(data))
+                assert intact and got is None
+    data = fastq_text(250, 15)
+    comp = gz(data, 6, wbits=-15)
+    for _ in range(300):
+        bad = bytearray(comp)
+        bad[int(rng.integers(0, len(comp)))] ^= 1 << int(rng.integers(0, 8))
+        got, err, intact = inflate_raw(bytes(bad), len(data))
+        assert intact                                  # no checksum at this level (the reader compares the block's announced length): wrong text is possible, overrun is not

@@ -8,7 +8,7 @@
 // host threads, because at the device's alignment rate (> 100 M reads/s) the text side is what bounds file -> result:
 //   * plain files are mapped, not read: the newline scan and the conversion work on the mapping directly;
 //   * blocked gzip (BGZF: bgzip, bcl2fastq output -- independent deflate blocks that announce their size) is inflated block
-//     by block on all threads straight into the text window; an ordinary single-member gzip stream has no entry points and
+//     by block on all threads straight into the text window (wq_inflate.h, no intermediate copy); an ordinary single-member gzip stream has no entry points and
 //     is inflated serially (wq_inflate.h, about twice zlib's rate on FASTQ text), overlapped with the alignment of the previous batch;
 //   * the newline scan runs in parallel over pieces of the window (records are strictly four lines, so a record boundary is
 //     a line number, not a guess about '@'), then lengths / validation / offsets by a two-pass prefix sum, then the 2-bit and
@@ -264,6 +264,7 @@ static inline bool wq_fastq_pull(wq_fastq* f, size_t want) {
             if (bs < 26 || f->bgzf_pos + bs > f->map_len) { f->err = "malformed BGZF block"; return false; }
             const unsigned char* p = base + f->bgzf_pos;
             const size_t xlen = p[10] | ((size_t)p[11] << 8);
+            if (12 + xlen + 8 > bs) { f->err = "malformed BGZF block"; return false; }
             uint32_t isize;
             memcpy(&isize, p + bs - 4, 4);
             blks.push_back(Blk{f->bgzf_pos, bs, 12 + xlen, isize, total});
@@ -278,7 +279,18 @@ static inline bool wq_fastq_pull(wq_fastq* f, size_t want) {
         std::atomic<size_t> next{0};
         std::atomic<int> bad{0};
         const unsigned nt = blks.size() < 8 ? 1u : wq_host_threads();
+        static const bool bgzf_zlib = getenv("WQ_GZ_ZLIB") && atoi(getenv("WQ_GZ_ZLIB")) != 0;
         wq_fq_parallel(nt, [&](unsigned) {
+            if (!bgzf_zlib) {                                // the library's own inflate, straight into the block's place in the window
+                WqInflate* z = new WqInflate();
+                for (size_t b; (b = next.fetch_add(1)) < blks.size();) {
+                    const Blk& k = blks[b];
+                    if (k.isize == 0) continue;
+                    if (!z->raw_into(base + k.off + k.hdr, k.csize - k.hdr - 8, (uint8_t*)dst + k.out, k.isize)) bad = 1;
+                }
+                delete z;
+                return;
+            }
             z_stream zs;
             memset(&zs, 0, sizeof zs);
             if (inflateInit2(&zs, -15) != Z_OK) { bad = 1; return; }

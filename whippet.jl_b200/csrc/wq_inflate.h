@@ -32,6 +32,7 @@ struct WqInflate {
     const uint8_t* in = nullptr; const uint8_t* in_end = nullptr; const uint8_t* p = nullptr;
     uint64_t bitbuf = 0; uint32_t bitcnt = 0;
     std::vector<uint8_t> buf;              // [history | fresh output | slack]
+    uint8_t* obase = nullptr;              // where the output goes: buf, or the caller's memory in raw_into()
     size_t out_pos = 0, read_pos = 0, crc_pos = 0, win_lo = 0;      // offsets into buf; win_lo = first byte of the current member's history
     int state = S_HEADER;
     bool last_block = false;
@@ -45,6 +46,7 @@ struct WqInflate {
         in = p = (const uint8_t*)data; in_end = in + n;
         bitbuf = 0; bitcnt = 0;
         buf.assign(HIST + CHUNK + SLACK, 0);
+        obase = buf.data();
         out_pos = read_pos = crc_pos = win_lo = 0;
         state = S_HEADER; last_block = false; stored_left = 0; crc = 0; member_out = 0; members = 0; err.clear();
     }
@@ -65,6 +67,30 @@ struct WqInflate {
             decode_some();
         }
         return got;
+    }
+
+    // One raw deflate stream (RFC 1951, e.g. the payload of a blocked-gzip block) straight into dst[0 .. out_len): no window, no copy.
+    // The fast loop may write a little past the symbol it is decoding, so it stops 300 bytes before the end and an exact loop
+    // finishes -- the bytes behind dst + out_len belong to somebody else (the next block, inflated by another thread).
+    bool raw_into(const void* data, size_t n, uint8_t* dst, size_t out_len) {
+        in = p = (const uint8_t*)data; in_end = in + n;
+        bitbuf = 0; bitcnt = 0; obase = dst; out_pos = read_pos = crc_pos = win_lo = 0;
+        state = S_BLOCK; last_block = false; stored_left = 0; err.clear();
+        while (state != S_TRAILER && state != S_ERROR) {
+            if (state == S_BLOCK) block_header();
+            else if (state == S_STORED) {
+                if (stored_left > out_len - out_pos) { fail("more output than announced"); break; }
+                if (stored_left > (size_t)(in_end - p)) { fail("truncated stored block"); break; }
+                memcpy(dst + out_pos, p, stored_left);
+                p += stored_left; out_pos += stored_left; stored_left = 0;
+                state = last_block ? S_TRAILER : S_BLOCK;
+            } else if (state == S_HUFF) {
+                if (out_len - out_pos > 300) huffman<false>(out_len - 300);
+                if (state == S_HUFF) huffman<true>(out_len);
+            } else break;
+        }
+        if (state == S_TRAILER && out_pos != out_len) fail("less output than announced");
+        return state == S_TRAILER;
     }
 
 private:
@@ -238,26 +264,27 @@ private:
         return true;
     }
 
+    void block_header() {
+        if (!need(3)) return;
+        last_block = take(1) != 0;
+        const uint32_t type = take(2);
+        if (type == 0) {
+            align_to_byte();
+            if (in_end - p < 4) { fail("truncated stored block"); return; }
+            const uint32_t len = p[0] | (uint32_t)p[1] << 8, nlen = p[2] | (uint32_t)p[3] << 8;
+            if ((len ^ 0xFFFF) != nlen) { fail("stored block length check"); return; }
+            p += 4; stored_left = len; state = S_STORED;
+        } else if (type == 1) { if (fixed_tables()) state = S_HUFF; }
+        else if (type == 2) { if (dynamic_tables()) state = S_HUFF; }
+        else fail("reserved block type");
+    }
+
     // one step of the state machine; returns when the output window is full, a member ended, or the state changed
     void decode_some() {
         const size_t out_limit = HIST + CHUNK;            // decoding stops once out_pos passes this (SLACK bytes remain behind it)
         switch (state) {
         case S_HEADER: if (header()) state = S_BLOCK; return;
-        case S_BLOCK: {
-            if (!need(3)) return;
-            last_block = take(1) != 0;
-            const uint32_t type = take(2);
-            if (type == 0) {
-                align_to_byte();
-                if (in_end - p < 4) { fail("truncated stored block"); return; }
-                const uint32_t len = p[0] | (uint32_t)p[1] << 8, nlen = p[2] | (uint32_t)p[3] << 8;
-                if ((len ^ 0xFFFF) != nlen) { fail("stored block length check"); return; }
-                p += 4; stored_left = len; state = S_STORED;
-            } else if (type == 1) { if (fixed_tables()) state = S_HUFF; }
-            else if (type == 2) { if (dynamic_tables()) state = S_HUFF; }
-            else fail("reserved block type");
-            return;
-        }
+        case S_BLOCK: block_header(); return;
         case S_STORED: {
             if (out_pos >= out_limit) return;
             const size_t n = std::min<size_t>(stored_left, std::min<size_t>(out_limit + SLACK / 2 - out_pos, (size_t)(in_end - p)));
@@ -267,7 +294,7 @@ private:
             if (!stored_left) state = last_block ? S_TRAILER : S_BLOCK;
             return;
         }
-        case S_HUFF: huffman(out_limit); return;
+        case S_HUFF: huffman<false>(out_limit); return;
         case S_TRAILER: trailer(); return;
         default: return;
         }
@@ -275,8 +302,10 @@ private:
 
     // The bit reader's state lives in locals here: the output is written through a byte pointer, which may alias anything, so members
     // would be reloaded after every literal.
-    void huffman(size_t out_limit) {
-        uint8_t* const base = buf.data();
+    // EXACT: nothing is written behind base + out_limit (one byte at a time, every write checked); the loop then ends only at the end of
+    // the block, and output beyond the limit is an error.
+    template <bool EXACT> void huffman(size_t out_limit) {
+        uint8_t* const base = obase;
         uint8_t* out = base + out_pos;
         uint8_t* const out_stop = base + out_limit;
         const uint8_t* const lo = base + win_lo;
@@ -287,10 +316,10 @@ private:
         #define WQ_INF_REFILL() do { if (qe - q >= 8) { bb |= load64(q) << bc; q += 7 - (bc >> 3); bc |= 56; } \
                                      else while (bc <= 56 && q < qe) { bb |= (uint64_t)*q++ << bc; bc += 8; } } while (0)
         for (;;) {
-            if (out >= out_stop) break;                                        // window full: the caller reads, slides, and comes back
+            if (!EXACT && out >= out_stop) break;                              // window full: the caller reads, slides, and comes back
             WQ_INF_REFILL();
             uint32_t e = LT[bb & lmask];
-            if (__builtin_expect((e & 0xE0) == (K_BASE << 5) && bc >= 56, 1)) {
+            if (!EXACT && __builtin_expect((e & 0xE0) == (K_BASE << 5) && bc >= 56, 1)) {
                 // a match with its length and distance codes in the main tables and a distance of 8 or more: the bulk of FASTQ text (sequence
                 // lines come out as matches of 4-10 bases against the last 32 KB).  Nothing is committed until all of that is known; anything
                 // else falls through to the general path below with the reader untouched.
@@ -309,7 +338,7 @@ private:
                     continue;
                 }
             }
-            if (((e & 0xE0) == 0 || (e & 0xE0) == (K_LIT2 << 5)) && (e & 31) <= bc) {      // one or two literals of the main table, the common case
+            if (!EXACT && ((e & 0xE0) == 0 || (e & 0xE0) == (K_LIT2 << 5)) && (e & 31) <= bc) {      // one or two literals of the main table, the common case
                 // up to four lookups from the same refill (56 bits were there when input remains; each needs at most 11)
                 for (int k = 0;; k++) {
                     bb >>= (e & 31); bc -= (e & 31);
@@ -331,7 +360,13 @@ private:
             if (nb > bc) { bad = "truncated input"; break; }
             const uint64_t lsaved = bb;
             bb >>= nb; bc -= nb;                                               // past the code and its extra bits in one step
-            if (kind == K_LIT) { *out++ = (uint8_t)(e >> 12); continue; }
+            if (kind == K_LIT || kind == K_LIT2) {
+                const uint32_t nlit = kind == K_LIT2 ? 2u : 1u;
+                if (EXACT && nlit > (size_t)(out_stop - out)) { bad = "more output than announced"; break; }
+                *out++ = (uint8_t)(e >> 12);
+                if (nlit == 2) *out++ = (uint8_t)(e >> 20);
+                continue;
+            }
             if (kind == K_EOB) { state = last_block ? S_TRAILER : S_BLOCK; break; }
             if (kind != K_BASE) { bad = "invalid literal / length code"; break; }
             const uint32_t lcl = (e >> 8) & 15;
@@ -350,6 +385,13 @@ private:
             const uint32_t dd = (d >> 12) + (uint32_t)((bb >> dcl) & ((1u << (dn - dcl)) - 1));
             bb >>= dn; bc -= dn;
             if (dd > (size_t)(out - lo)) { bad = "distance beyond the start of the member"; break; }
+            if (EXACT) {
+                if (len > (size_t)(out_stop - out)) { bad = "more output than announced"; break; }
+                const uint8_t* sx = out - dd;
+                for (uint32_t k = 0; k < len; k++) out[k] = sx[k];
+                out += len;
+                continue;
+            }
             const uint8_t* src = out - dd;
             uint8_t* dst = out;
             out += len;                                                        // len <= 258 and out < out_stop before: inside the slack
