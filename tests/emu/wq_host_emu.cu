@@ -272,6 +272,9 @@ int64_t hemu_inflate(const uint8_t* data, uint64_t n, uint8_t* out, uint64_t cap
     return z.failed() ? -1 - (int64_t)got : (int64_t)got;
 }
 
+// wq_crc32 (csrc/wq_inflate.h: carry-less-multiplication CRC-32 with zlib for the tail), zlib's calling convention
+uint32_t hemu_crc32(uint32_t crc, const uint8_t* p, uint64_t n) { return wq_crc32(crc, p, (size_t)n); }
+
 // WqInflate::raw_into: one raw deflate stream into exactly out[0 .. out_len) (the way the blocked-gzip reader inflates a block next to
 // its neighbours).  Returns 0, or -1 with the message in errbuf.
 int hemu_inflate_raw(const uint8_t* data, uint64_t n, uint8_t* out, uint64_t out_len, char* errbuf, uint64_t errcap) {

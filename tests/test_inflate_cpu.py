@@ -155,3 +155,26 @@ def test_raw_stream_into_exact_destination():
         bad[int(rng.integers(0, len(comp)))] ^= 1 << int(rng.integers(0, 8))
         got, err, intact = inflate_raw(bytes(bad), len(data))
         assert intact                                  # no checksum at this level (the reader compares the block's announced length): wrong text is possible, overrun is not
+
+
+def test_crc32_by_carryless_multiplication_equals_zlib():
+    """The trailer check's CRC-32 (wq_crc32: PCLMULQDQ folding for the bulk, zlib for the tail) against zlib.crc32: every length around
+    the 16- and 64-byte steps, odd alignments, running values carried from piece to piece."""
+    import ctypes as C
+    from emu import host_emu
+    L = C.CDLL(host_emu.build())
+    L.hemu_crc32.restype = C.c_uint32
+    rng = np.random.default_rng(31)
+    buf = rng.integers(0, 256, 300000, dtype=np.uint8)
+    base = buf.ctypes.data
+    for n in list(range(0, 200)) + [255, 256, 257, 1000, 4095, 4096, 65537, 299000]:
+        for off in (0, 1, 7, 13):
+            want = zlib.crc32(buf[off:off + n].tobytes())
+            assert L.hemu_crc32(C.c_uint32(0), C.c_void_p(base + off), C.c_uint64(n)) == want, (n, off)
+    crc, want, pos = 0, 0, 0
+    while pos < len(buf):
+        n = int(rng.integers(1, 5000))
+        crc = L.hemu_crc32(C.c_uint32(crc), C.c_void_p(base + pos), C.c_uint64(min(n, len(buf) - pos)))
+        want = zlib.crc32(buf[pos:pos + n].tobytes(), want)
+        pos += n
+        assert crc == want
