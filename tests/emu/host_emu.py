@@ -143,6 +143,20 @@ class HostEmu:
                             psi=vals[0], total=vals[1], problem=int(prob), paths=paths))
         return out
 
+    def events_part(self, node_value, ekey, evalue, readlen, part, nparts, threads=4):
+        """Event construction of rank `part` of `nparts` (its range of the work list, as the library cuts it).  Returns the records as
+        (gene, node, motif, kind, flags, n_paths, psi, total) tuples."""
+        node_value = np.ascontiguousarray(node_value, "<f8")
+        ekey, evalue = np.ascontiguousarray(ekey, "<u8"), np.ascontiguousarray(evalue, "<f8")
+        self.L.hemu_events_part.restype = C.c_uint64
+        n = self.L.hemu_events_part(self.h, _p(node_value), C.c_uint64(len(ekey)), _p(ekey), _p(evalue), C.c_int64(readlen), int(threads), int(nparts), int(part))
+        hdr, vals = (C.c_uint32 * 9)(), (C.c_double * 2)()
+        out = []
+        for i in range(n):
+            self.L.hemu_event(self.h, C.c_uint64(i), hdr, vals)
+            out.append((hdr[0], hdr[1], hdr[2], hdr[3], hdr[4], hdr[8], vals[0], vals[1]))
+        return out
+
     def problem(self, p):
         sizes = (C.c_uint32 * 5)()
         self.L.hemu_problem(self.h, C.c_uint64(p), sizes, None, None, None, None, None)

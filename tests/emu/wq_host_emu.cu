@@ -140,6 +140,35 @@ uint64_t hemu_event_cuts(HostEmu* e, uint64_t ne, const uint64_t* ekey, const do
     for (size_t r = 0; r < cuts.size(); r++) cuts_out[r] = cuts[r];
     return pieces.size();
 }
+// event construction of ONE rank's range of the work list, the way wq_build_event_batch walks it (pieces from wq_event_make_pieces, cuts
+// from wq_event_cuts on the given edges, gene ranges and node ranges of genes with many nodes); replaces the records of the last call
+uint64_t hemu_events_part(HostEmu* e, const double* node_value, uint64_t ne, const uint64_t* ekey, const double* evalue, int64_t readlen,
+                          unsigned nt, uint32_t nparts, uint32_t part) {
+    e->node_value.assign(node_value, node_value + e->H.N);
+    e->recs.clear(); e->P = WqPsiProblems(); e->pool = WqEventPool();
+    std::vector<WqEvPiece> pieces;
+    wq_event_make_pieces(e->H, e->node_value, nt, nparts, pieces);
+    std::vector<uint64_t> keys(ekey, ekey + ne);
+    std::vector<double> vals(evalue, evalue + ne);
+    std::vector<unsigned> cuts;
+    wq_event_cuts(e->H, keys, vals, pieces, nparts, cuts);
+    WqGeneEvents V{e->H, e->node_value, 0, {}};
+    for (unsigned t = cuts[part]; t < cuts[part + 1]; t++) {
+        const WqEvPiece pc = pieces[t];
+        size_t k = std::lower_bound(keys.begin(), keys.end(), (uint64_t)pc.g_lo << 32) - keys.begin();
+        for (uint32_t g = pc.g_lo; g <= pc.g_hi && g <= e->H.G; g++) {
+            V.g = g;
+            V.edges.clear();
+            while (k < ne && (keys[k] >> 32) < g) k++;
+            for (; k < ne && (keys[k] >> 32) == g; k++) {
+                if (wq_edge_is_circ(keys[k])) continue;
+                V.edges.push_back(WqGeneEdge{(uint32_t)((keys[k] >> 16) & 0xFFFF), (uint32_t)(keys[k] & 0xFFFF), vals[k]});
+            }
+            wq_gene_events(V, readlen, e->recs, e->P, e->pool, pc.node_lo, pc.node_hi);
+        }
+    }
+    return e->recs.size();
+}
 // header[9] = gene, node, motif, kind, flags, n_utr, n_inc, n_exc, n_paths; vals[2] = psi, total; returns the EM problem index or -1
 int64_t hemu_event(HostEmu* e, uint64_t i, uint32_t* header, double* vals) {
     const WqEventRec& r = e->recs[i];

@@ -133,3 +133,57 @@ def test_two_rank_class_shares():
     for rank, classes, gm, iso_count in res:
         assert gm == nm and classes == want, rank
         assert np.array_equal(iso_count, full.iso_count()), rank
+
+
+# ---- event stage partitioned by cost-balanced ranges of the work list: two gloo ranks, each builds its range, the ranges concatenate ----
+def _event_case():
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")]
+    import whippet_jl_b200 as wq
+    from wq_inputs import synth
+    from oracle import Oracle
+    idx = synth.make_index(n_genes=2200, K=9, seed=91, mean_exons=14.0)          # some genes with 32 nodes or more: cut into node pieces
+    rb = synth.simulate_reads(idx, 150000, 101, seed=92, sub_rate=0.01)
+    o = Oracle(idx)
+    o.process_reads(wq.AlignParam(), rb)
+    ek, ev = o.edges()
+    return idx, o.node_counts().astype("<f8"), ek, ev.astype("<f8")
+
+
+def _event_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    idx, node, ek, ev = _event_case()
+    # the ranks agree on the counts the cuts are computed from (on the GPUs: after wq_counts_sync); checked with a checksum
+    chk = torch.tensor([float(node.sum()), float(ev.sum()), float(len(ek))], dtype=torch.float64)
+    both = [torch.zeros(3, dtype=torch.float64) for _ in range(world)]
+    dist.all_gather(both, chk)
+    assert all(torch.equal(b, chk) for b in both)
+    from emu.host_emu import HostEmu
+    e = HostEmu(idx)
+    recs = e.events_part(node, ek, ev, 101, rank, world)
+    q.put((rank, recs))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_event_ranges_concatenate():
+    world = 2
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_event_worker, args=(r, world, port, q)) for r in range(world)]
+    [p.start() for p in procs]
+    res = dict(q.get(timeout=300) for _ in range(world))
+    [p.join(timeout=60) for p in procs]
+    idx, node, ek, ev = _event_case()
+    from emu.host_emu import HostEmu
+    full = HostEmu(idx)
+    want = full.events_part(node, ek, ev, 101, 0, 1)
+    assert int((np.diff(idx.node_base) >= 32).sum()) >= 3 and len(want) > 10000
+    assert min(len(res[0]), len(res[1])) > len(want) // 20                       # both ranks have work
+    assert res[0] + res[1] == want
