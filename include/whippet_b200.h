@@ -289,8 +289,9 @@ int  wq_comm_destroy(wq_handle* h);
 
 /* Event stage partitioned across ranks: this handle builds and solves the events of part `part` of `nparts` only and wq_process_events
  * returns that part's records; the parts concatenate to the full output.  A part is a contiguous range of the event work list (gene
- * ranges, and ranges of nodes inside a gene with many nodes), cut where the estimated cost -- nodes + (expressed edges)^2 per gene --
- * reaches part / nparts of the total, so that one gene with hundreds of expressed junctions is shared by several ranks.  Every rank
+ * ranges, and ranges of nodes inside a gene with many nodes), cut where the estimated cost of the path enumeration -- per node, from the
+ * expressed edges inside the hull of the edges that span or touch it -- reaches part / nparts of the total, so that one gene whose nodes
+ * sit under a long exon-skipping junction (the bulk of the stage in a deep human job) is shared by all ranks.  Every rank
  * holds the same counts after wq_counts_sync and therefore computes the same cuts; node / edge values (wq_assign_ambig) are complete
  * for every gene on every rank. */
 int  wq_set_gene_partition(wq_handle* h, uint32_t part, uint32_t nparts);
